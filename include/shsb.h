@@ -1,0 +1,321 @@
+/*
+ * shsb.h -- C-ABI of the B200-native rasterization hot path ("shsb" = SHS renderer, B200).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and POD
+ * structs, no C++ / torch types.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/cpp-folders/src/shs-renderer-lib/include/shs/).
+ *
+ * Conventions kept from the reference:
+ *   - matrices are column-major float[16] exactly like glm::mat4 (m[col*4+row]);
+ *   - render targets are row-major, origin bottom-left, data[y*w+x]    (gfx/rt_types.hpp:35-59);
+ *   - asset / RT handles are 1-based uint32_t, 0 = invalid             (gfx/rt_handle.hpp:19-20,
+ *                                                                        resources/resource_registry.hpp:29);
+ *   - no exceptions: the reference silently returns zero stats on bad input
+ *     (sw_render/rasterizer.hpp:190-194); here every call returns an int32 status, SHSB_OK = 0,
+ *     and shsb_last_error_string() explains a failure.
+ *   - one host thread per context; calls are asynchronous on the context's CUDA stream until
+ *     shsb_sync / a download.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable shsb_context_create fails with
+ * SHSB_E_NO_DEVICE, and arbitrary host std::function shaders are rejected with
+ * SHSB_E_UNSUPPORTED_SHADER (only the reference's builtin programs exist on the device).
+ */
+#ifndef SHSB_H
+#define SHSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SHSB_API
+#else
+#define SHSB_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ status codes */
+enum
+{
+    SHSB_OK = 0,
+    SHSB_E_INVALID_ARGUMENT = 1,
+    SHSB_E_INVALID_HANDLE = 2,
+    SHSB_E_NO_DEVICE = 3,
+    SHSB_E_CUDA = 4,
+    SHSB_E_UNSUPPORTED_SHADER = 5,
+    SHSB_E_OUT_OF_MEMORY = 6,
+    SHSB_E_SIZE_MISMATCH = 7,
+    SHSB_E_UNSUPPORTED = 8
+};
+
+typedef struct shsb_context_t* shsb_ctx; /* opaque */
+typedef uint32_t shsb_mesh;              /* MeshAssetHandle     resources/mesh.hpp:21          */
+typedef uint32_t shsb_tex;               /* TextureAssetHandle  resources/texture.hpp:21       */
+typedef uint32_t shsb_rt;                /* RTHandle::id        gfx/rt_handle.hpp:17           */
+
+/* ------------------------------------------------------------------ enums mirrored from the reference */
+enum /* RasterizerCullMode, sw_render/rasterizer.hpp:26-31 == CullMode, frame/frame_params.hpp */
+{
+    SHSB_CULL_NONE = 0,
+    SHSB_CULL_BACK = 1,
+    SHSB_CULL_FRONT = 2
+};
+
+enum /* device shader programs == the reference's builtin ShaderProgram factories */
+{
+    SHSB_SHADER_PBR_MR = 0,       /* make_pbr_mr_program        shader/builtin_shaders.hpp:154 */
+    SHSB_SHADER_BLINN_PHONG = 1,  /* make_blinn_phong_program   shader/builtin_shaders.hpp:105 */
+    SHSB_SHADER_DEBUG_ALBEDO = 2, /* make_debug_view_shader_program(Albedo)            :221   */
+    SHSB_SHADER_DEBUG_NORMAL = 3, /* ...(Normal)                                               */
+    SHSB_SHADER_DEBUG_DEPTH = 4,  /* ...(Depth)                                                */
+    SHSB_SHADER_DEPTH_ONLY = 5,   /* detail::make_depth_prepass_program  pipeline/pass_adapters.hpp:335 */
+    SHSB_SHADER_COUNT = 6
+};
+
+enum /* ShadingModel, frame/frame_params.hpp */
+{
+    SHSB_SHADING_PBR_METAL_ROUGH = 0,
+    SHSB_SHADING_BLINN_PHONG = 1
+};
+
+enum /* DebugViewMode, frame/frame_params.hpp */
+{
+    SHSB_DEBUG_FINAL = 0,
+    SHSB_DEBUG_ALBEDO = 1,
+    SHSB_DEBUG_NORMAL = 2,
+    SHSB_DEBUG_DEPTH = 3
+};
+
+enum /* render-target kinds, gfx/rt_types.hpp:61-157, gfx/rt_shadow.hpp:18 */
+{
+    SHSB_RT_COLOR_HDR = 1,    /* RT_ColorHDR: RGBA32F                                         */
+    SHSB_RT_COLOR_LDR = 2,    /* RT_ColorLDR: RGBA8                                           */
+    SHSB_RT_DEPTH_MOTION = 3, /* RT_ColorDepthVelocity: depth f32 (+ motion 2xf32), zn/zf     */
+    SHSB_RT_SHADOW = 4        /* RT_ShadowDepth: f32                                          */
+};
+
+enum /* planes of a render target for clear / upload / download / device_ptr */
+{
+    SHSB_PLANE_COLOR = 0,  /* HDR: float4; LDR: uchar4                                        */
+    SHSB_PLANE_DEPTH = 1,  /* f32 (DEPTH_MOTION, SHADOW)                                      */
+    SHSB_PLANE_MOTION = 2, /* 2 x f32 (DEPTH_MOTION)                                          */
+    SHSB_PLANE_TRI_ID = 3, /* u32 AOV: draw-order key of the winning fragment, 0xFFFFFFFF none */
+    SHSB_PLANE_COVERAGE = 4 /* u32 AOV: number of fragments that passed coverage+1/w test      */
+};
+
+#define SHSB_TRI_ID_NONE 0xFFFFFFFFu
+#define SHSB_LIGHT_RECORD_BYTES 160u /* sizeof(CullingLightGPU), lighting/light_types.hpp:141-167 */
+
+/* ------------------------------------------------------------------ POD mirrors of reference structs */
+
+typedef struct ShsbStats /* RasterizerStats, sw_render/rasterizer.hpp:48-53 (+ fragment counters) */
+{
+    uint64_t tri_input;
+    uint64_t tri_after_clip;
+    uint64_t tri_raster;
+    uint64_t frag_covered; /* fragments passing coverage and 1/w tests (rasterizer.hpp:338,342) */
+    uint64_t frag_shaded;  /* pixels whose final colour came from a fragment of this call       */
+} ShsbStats;
+
+typedef struct ShsbRasterCfg /* RasterizerConfig, sw_render/rasterizer.hpp:33-40 */
+{
+    int32_t cull_mode;      /* SHSB_CULL_*                                                    */
+    int32_t front_face_ccw; /* bool                                                           */
+    int32_t write_aovs;     /* extension: also fill the TRI_ID / COVERAGE planes of the HDR RT */
+    int32_t reserved;       /* job_system / parallel_min_* have no meaning on the device      */
+} ShsbRasterCfg;
+
+typedef struct ShsbUniforms /* device-visible subset of ShaderUniforms, shader/types.hpp:82-116 */
+{
+    float model[16];
+    float viewproj[16];
+    float light_viewproj[16];
+    float light_dir_ws[3];
+    float light_intensity;
+    float light_color[3];
+    float metallic;
+    float camera_pos[3];
+    float roughness;
+    float base_color[3];
+    float ao;
+    shsb_tex base_color_tex; /* 0 = none (sampler returns 1,1,1; builtin_shaders.hpp:35)     */
+    shsb_rt shadow_map;      /* 0 = none (shadow_vis = 1)                                     */
+    float shadow_bias_const;
+    float shadow_bias_slope;
+    int32_t shadow_pcf_radius;
+    float shadow_pcf_step;
+    float shadow_strength;
+    int32_t reserved;
+} ShsbUniforms;
+
+typedef struct ShsbTransform /* Transform, scene/scene_types.hpp:26-31 */
+{
+    float pos[3];
+    float rot_euler[3];
+    float scl[3];
+} ShsbTransform;
+
+typedef struct ShsbRenderItem /* RenderItem (scene/scene_types.hpp:62-70) with its MaterialData resolved */
+{
+    ShsbTransform tr;
+    shsb_mesh mesh;
+    uint32_t has_material; /* 0: reference defaults (0.8,0.5,0.2) m=0.1 r=0.5 ao=1; pass_pbr_forward.hpp:179-184 */
+    float base_color[3];
+    float metallic;
+    float roughness;
+    float ao;
+    shsb_tex base_color_tex;
+    uint32_t casts_shadow;
+    uint32_t visible;
+} ShsbRenderItem;
+
+typedef struct ShsbScene /* Scene, scene/scene_types.hpp:92-104 (camera + sun + items) */
+{
+    float cam_viewproj[16];
+    float cam_pos[3];
+    float sun_intensity;
+    float sun_dir_ws[3];
+    uint32_t n_items;
+    float sun_color[3];
+    uint32_t reserved;
+    const ShsbRenderItem* items;
+} ShsbScene;
+
+typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/frame_params.hpp:117-171 */
+{
+    int32_t shading_model;  /* SHSB_SHADING_*                                                 */
+    int32_t debug_view;     /* SHSB_DEBUG_*                                                   */
+    int32_t cull_mode;      /* SHSB_CULL_*                                                    */
+    int32_t front_face_ccw;
+    int32_t shadow_enable;  /* pass.shadow.enable                                             */
+    float shadow_bias_const;
+    float shadow_bias_slope;
+    int32_t shadow_pcf_radius;
+    float shadow_pcf_step;
+    float shadow_strength;
+    float exposure;         /* pass.tonemap.exposure                                          */
+    float gamma;            /* pass.tonemap.gamma                                             */
+    int32_t light_culling;  /* technique.light_culling: Forward+ local-light loop on/off      */
+    uint32_t tile_size;     /* technique.tile_size (16)                                       */
+    uint32_t max_lights_per_tile; /* technique.max_lights_per_tile (128)                      */
+    int32_t write_aovs;
+} ShsbFrameParams;
+
+/* ------------------------------------------------------------------ context */
+
+/* Creates a device context on CUDA device `device_ordinal`.  Replaces the reference's
+ * Context + ThreadPoolJobSystem set-up (core/context.hpp:116, job/thread_pool_job_system.hpp:26):
+ * the job-system fan-out becomes kernel launches on one CUDA stream. */
+SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx);
+SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx);
+SHSB_API const char* shsb_last_error_string(shsb_ctx ctx);
+SHSB_API int32_t shsb_sync(shsb_ctx ctx);
+/* CUDA stream handle (cudaStream_t as void*) so callers can record their own events on it. */
+SHSB_API int32_t shsb_stream(shsb_ctx ctx, void** out_stream);
+/* Number of kernels this context launched since creation (bench.py's gpu_launches). */
+SHSB_API int32_t shsb_launch_count(shsb_ctx ctx, uint64_t* out_count);
+/* Library build info string (arch, flags). */
+SHSB_API const char* shsb_version(void);
+
+/* ------------------------------------------------------------------ resources */
+
+/* MeshData (resources/mesh.hpp:23-44): SoA positions(vec3) normals(vec3) uvs(vec2) + u32 indices.
+ * n_normals / n_uvs may be shorter than n_positions (defaults (0,1,0) / (0,0), rasterizer.hpp:196-202);
+ * n_indices == 0 means non-indexed (rasterizer.hpp:204-205). */
+SHSB_API int32_t shsb_mesh_upload(shsb_ctx ctx,
+                                  const float* positions, uint32_t n_positions,
+                                  const float* normals, uint32_t n_normals,
+                                  const float* uvs, uint32_t n_uvs,
+                                  const uint32_t* indices, uint32_t n_indices,
+                                  shsb_mesh* out_mesh);
+SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh);
+
+/* Texture2DData (resources/texture.hpp:23-50): RGBA8, row-major. */
+SHSB_API int32_t shsb_texture_upload(shsb_ctx ctx, const uint8_t* rgba, int32_t w, int32_t h, shsb_tex* out_tex);
+SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex);
+
+/* ------------------------------------------------------------------ render targets */
+
+/* RT_ColorHDR / RT_ColorLDR / RT_ColorDepthVelocity / RT_ShadowDepth constructors
+ * (gfx/rt_types.hpp:61-157, gfx/rt_shadow.hpp:18-40).  Storage is device-resident; initial
+ * contents equal the reference constructors' (colour 0,0,0,1; depth 1.0; motion 0). */
+SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h, float zn, float zf, shsb_rt* out_rt);
+SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt);
+/* PixelBuffer2D::clear (rt_types.hpp:53-56): `value` points at one pixel of the plane's type. */
+SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* value);
+SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* src, size_t bytes);
+SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst, size_t bytes);
+/* Raw device pointer of a plane (for NCCL frame gather through torch.distributed). */
+SHSB_API int32_t shsb_rt_device_ptr(shsb_ctx ctx, shsb_rt rt, int32_t plane, void** out_ptr, size_t* out_bytes);
+
+/* ------------------------------------------------------------------ host helpers (bit-exact restatements) */
+
+/* model = T * Rx * Ry * Rz * S via successive glm::translate/rotate/scale
+ * (passes/pass_pbr_forward.hpp:136-141, passes/pass_shadow_map.hpp:57-65). */
+SHSB_API int32_t shsb_model_from_transform(const ShsbTransform* tr, float out_model[16]);
+/* viewproj = perspective_lh_no(fovy, aspect, zn, zf) * look_at_lh(eye, target, up)
+ * (camera/convention.hpp:19-27; every reference demo builds Camera::viewproj this way). */
+SHSB_API int32_t shsb_camera_viewproj(const float eye[3], const float target[3], const float up[3],
+                                      float fovy_radians, float aspect, float znear, float zfar,
+                                      float out_viewproj[16]);
+
+/* ------------------------------------------------------------------ the hot path */
+
+/* rasterize_mesh (sw_render/rasterizer.hpp:181-442): one mesh draw with a builtin program.
+ * depth_motion_rt == 0 reproduces the "no depth target" painter behaviour (rasterizer.hpp:348). */
+SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh, int32_t shader_id,
+                                     const ShsbUniforms* uniforms,
+                                     shsb_rt hdr_rt, shsb_rt depth_motion_rt,
+                                     const ShsbRasterCfg* cfg, ShsbStats* out_stats);
+
+/* PassPBRForward::execute (passes/pass_pbr_forward.hpp:49-214): background gradient fill, depth
+ * clear policy, per-item model matrix + uniforms, all draws in item order.  With
+ * fp->light_culling != 0 the fragment program additionally walks the tile light lists built by
+ * the last shsb_light_cull (Forward+). */
+SHSB_API int32_t shsb_pass_pbr_forward(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                       shsb_rt hdr_rt, shsb_rt depth_motion_rt, shsb_rt shadow_rt,
+                                       const float* shadow_light_viewproj, /* ctx.shadow.light_viewproj or NULL */
+                                       int32_t preserve_existing_depth, ShsbStats* out_stats);
+
+/* PassDepthPrepassAdapter (pipeline/pass_adapters.hpp:401-528): depth-only draw of all items. */
+SHSB_API int32_t shsb_pass_depth_prepass(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                         shsb_rt depth_motion_rt, ShsbStats* out_stats);
+
+/* PassShadowMap::execute (passes/pass_shadow_map.hpp:44-205): scene AABB -> texel-snapped ortho
+ * light camera (camera/light_camera.hpp:33-99) -> depth-only, unclipped, uncull'd raster.
+ * out_light_viewproj receives ctx.shadow.light_viewproj. */
+SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                      shsb_rt shadow_rt, float out_light_viewproj[16]);
+
+/* PassTonemap::execute (passes/pass_tonemap.hpp:37-84). */
+SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt, float exposure, float gamma);
+
+/* Local lights: n records of CullingLightGPU (lighting/light_types.hpp:141-167, 160 B each). */
+SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t n_lights);
+
+/* cull_lights_tiled (lighting/jolt_light_culling.hpp:135-187): per 2-D screen tile, the ascending
+ * list of lights whose cull_sphere / cull_aabb is not Outside the tile's 6-plane cell.  Lists are
+ * kept on the device for the Forward+ pass: counts[T] (uncapped) and indices[T*max_per_tile]
+ * (first max_per_tile entries, LightCullingRuntimePayload pipeline/render_pass.hpp:32-50). */
+SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t viewport_w, uint32_t viewport_h,
+                                 uint32_t tile_size, uint32_t max_per_tile);
+SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts,
+                                           uint32_t* indices, size_t n_indices);
+
+/* Fused Forward+ frame = light cull + PassPBRForward (Forward+) + PassTonemap in one submission
+ * with HDR, depth and LDR each written once (SURVEY.md section 8d B_frame). */
+SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                         shsb_rt hdr_rt, shsb_rt depth_motion_rt, shsb_rt ldr_rt,
+                                         ShsbStats* out_stats);
+
+/* Last frame's per-stage device times in milliseconds (CUDA events on the context stream):
+ * [0] vertex+setup, [1] binning, [2] tile raster+shade, [3] light cull, [4] tonemap, [5] total. */
+SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SHSB_H */

@@ -1,0 +1,164 @@
+"""ctypes binding of the C-ABI in include/shsb.h (the drop-in boundary).
+
+Only the shared library built from leisure_software_renderer_b200/csrc is loaded here.  There is
+no CPU fallback: if the library is missing or no CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshsb.so")
+
+# ---------------------------------------------------------------- enums (include/shsb.h)
+OK = 0
+CULL_NONE, CULL_BACK, CULL_FRONT = 0, 1, 2
+SHADER_PBR_MR, SHADER_BLINN_PHONG, SHADER_DEBUG_ALBEDO, SHADER_DEBUG_NORMAL, SHADER_DEBUG_DEPTH, SHADER_DEPTH_ONLY = range(6)
+SHADING_PBR, SHADING_BLINN = 0, 1
+DEBUG_FINAL, DEBUG_ALBEDO, DEBUG_NORMAL, DEBUG_DEPTH = 0, 1, 2, 3
+RT_COLOR_HDR, RT_COLOR_LDR, RT_DEPTH_MOTION, RT_SHADOW = 1, 2, 3, 4
+PLANE_COLOR, PLANE_DEPTH, PLANE_MOTION, PLANE_TRI_ID, PLANE_COVERAGE = 0, 1, 2, 3, 4
+TRI_ID_NONE = 0xFFFFFFFF
+LIGHT_RECORD_BYTES = 160
+
+F16 = C.c_float * 16
+F3 = C.c_float * 3
+
+
+class Stats(C.Structure):
+    _fields_ = [("tri_input", C.c_uint64), ("tri_after_clip", C.c_uint64), ("tri_raster", C.c_uint64),
+                ("frag_covered", C.c_uint64), ("frag_shaded", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class RasterCfg(C.Structure):
+    _fields_ = [("cull_mode", C.c_int32), ("front_face_ccw", C.c_int32), ("write_aovs", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Uniforms(C.Structure):
+    _fields_ = [("model", F16), ("viewproj", F16), ("light_viewproj", F16),
+                ("light_dir_ws", F3), ("light_intensity", C.c_float),
+                ("light_color", F3), ("metallic", C.c_float),
+                ("camera_pos", F3), ("roughness", C.c_float),
+                ("base_color", F3), ("ao", C.c_float),
+                ("base_color_tex", C.c_uint32), ("shadow_map", C.c_uint32),
+                ("shadow_bias_const", C.c_float), ("shadow_bias_slope", C.c_float),
+                ("shadow_pcf_radius", C.c_int32), ("shadow_pcf_step", C.c_float),
+                ("shadow_strength", C.c_float), ("reserved", C.c_int32)]
+
+
+class Transform(C.Structure):
+    _fields_ = [("pos", F3), ("rot_euler", F3), ("scl", F3)]
+
+
+class RenderItem(C.Structure):
+    _fields_ = [("tr", Transform), ("mesh", C.c_uint32), ("has_material", C.c_uint32),
+                ("base_color", F3), ("metallic", C.c_float), ("roughness", C.c_float), ("ao", C.c_float),
+                ("base_color_tex", C.c_uint32), ("casts_shadow", C.c_uint32), ("visible", C.c_uint32)]
+
+
+class Scene(C.Structure):
+    _fields_ = [("cam_viewproj", F16), ("cam_pos", F3), ("sun_intensity", C.c_float),
+                ("sun_dir_ws", F3), ("n_items", C.c_uint32),
+                ("sun_color", F3), ("reserved", C.c_uint32),
+                ("items", C.POINTER(RenderItem))]
+
+
+class FrameParams(C.Structure):
+    _fields_ = [("shading_model", C.c_int32), ("debug_view", C.c_int32), ("cull_mode", C.c_int32), ("front_face_ccw", C.c_int32),
+                ("shadow_enable", C.c_int32), ("shadow_bias_const", C.c_float), ("shadow_bias_slope", C.c_float),
+                ("shadow_pcf_radius", C.c_int32), ("shadow_pcf_step", C.c_float), ("shadow_strength", C.c_float),
+                ("exposure", C.c_float), ("gamma", C.c_float),
+                ("light_culling", C.c_int32), ("tile_size", C.c_uint32), ("max_lights_per_tile", C.c_uint32),
+                ("write_aovs", C.c_int32)]
+
+
+def default_frame_params(**kw) -> FrameParams:
+    """FrameParams defaults of the reference (frame/frame_params.hpp:117-171, :20-31, :73-85)."""
+    fp = FrameParams(shading_model=SHADING_PBR, debug_view=DEBUG_FINAL, cull_mode=CULL_BACK, front_face_ccw=1,
+                     shadow_enable=1, shadow_bias_const=0.0008, shadow_bias_slope=0.0015, shadow_pcf_radius=2,
+                     shadow_pcf_step=1.0, shadow_strength=1.0, exposure=1.0, gamma=2.2,
+                     light_culling=0, tile_size=16, max_lights_per_tile=128, write_aovs=0)
+    for k, v in kw.items():
+        setattr(fp, k, v)
+    return fp
+
+
+def fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def u32ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def set_f(arr, values):
+    for i, v in enumerate(np.asarray(values, dtype=np.float32).reshape(-1)):
+        arr[i] = float(v)
+
+
+class ShsbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Loads libshsb.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ShsbError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for the raster path)")
+    lib = C.CDLL(p)
+    P = C.POINTER
+    vp = C.c_void_p
+    sigs = {
+        "shsb_context_create": [C.c_int32, P(vp)],
+        "shsb_context_destroy": [vp],
+        "shsb_sync": [vp],
+        "shsb_stream": [vp, P(vp)],
+        "shsb_launch_count": [vp, P(C.c_uint64)],
+        "shsb_mesh_upload": [vp, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32)],
+        "shsb_mesh_destroy": [vp, C.c_uint32],
+        "shsb_texture_upload": [vp, P(C.c_uint8), C.c_int32, C.c_int32, P(C.c_uint32)],
+        "shsb_texture_destroy": [vp, C.c_uint32],
+        "shsb_rt_create": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, P(C.c_uint32)],
+        "shsb_rt_destroy": [vp, C.c_uint32],
+        "shsb_rt_clear": [vp, C.c_uint32, C.c_int32, vp],
+        "shsb_rt_upload": [vp, C.c_uint32, C.c_int32, vp, C.c_size_t],
+        "shsb_rt_download": [vp, C.c_uint32, C.c_int32, vp, C.c_size_t],
+        "shsb_rt_device_ptr": [vp, C.c_uint32, C.c_int32, P(vp), P(C.c_size_t)],
+        "shsb_model_from_transform": [P(Transform), P(C.c_float)],
+        "shsb_camera_viewproj": [P(C.c_float), P(C.c_float), P(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, P(C.c_float)],
+        "shsb_rasterize_mesh": [vp, C.c_uint32, C.c_int32, P(Uniforms), C.c_uint32, C.c_uint32, P(RasterCfg), P(Stats)],
+        "shsb_pass_pbr_forward": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float), C.c_int32, P(Stats)],
+        "shsb_pass_depth_prepass": [vp, P(Scene), P(FrameParams), C.c_uint32, P(Stats)],
+        "shsb_pass_shadow_map": [vp, P(Scene), P(FrameParams), C.c_uint32, P(C.c_float)],
+        "shsb_pass_tonemap": [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float],
+        "shsb_lights_upload": [vp, vp, C.c_uint32],
+        "shsb_light_cull": [vp, P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32],
+        "shsb_light_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
+        "shsb_frame_forward_plus": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(Stats)],
+        "shsb_last_stage_ms": [vp, P(C.c_float)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here = the library does not export what shsb.h declares
+        fn.argtypes = args
+        fn.restype = C.c_int32
+    lib.shsb_last_error_string.argtypes = [vp]
+    lib.shsb_last_error_string.restype = C.c_char_p
+    lib.shsb_version.argtypes = []
+    lib.shsb_version.restype = C.c_char_p
+    lib._shsb_symbols = sorted(list(sigs) + ["shsb_last_error_string", "shsb_version"])
+    if path is None:
+        _lib = lib
+    return lib

@@ -1,0 +1,206 @@
+"""Thin, numpy-facing wrapper over the C-ABI (include/shsb.h).
+
+Names follow the reference's pass / render-target vocabulary (RT_ColorHDR, PassPBRForward ...).
+Everything here forwards to libshsb.so; nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (FrameParams, RasterCfg, RenderItem, Scene, Stats, Transform, Uniforms)
+
+
+def _check(lib, ctx, rc, what):
+    if rc != capi.OK:
+        msg = lib.shsb_last_error_string(ctx) if ctx else b""
+        raise capi.ShsbError(f"{what} failed: status {rc}: {(msg or b'').decode(errors='replace')}")
+
+
+class Context:
+    """shsb_ctx: one CUDA device, one stream; replaces Context + ThreadPoolJobSystem of the reference."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.shsb_context_create(device, C.byref(self.h))
+        if rc != capi.OK:
+            raise capi.ShsbError(f"shsb_context_create(device={device}) failed with status {rc} "
+                                 "(3 = no usable CUDA device; there is no CPU fallback)")
+        self._rt_shape = {}
+
+    def close(self):
+        if self.h:
+            self.lib.shsb_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- resources
+    def mesh_upload(self, positions, normals=None, uvs=None, indices=None) -> int:
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals if normals is not None else np.zeros((0, 3)), dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs if uvs is not None else np.zeros((0, 2)), dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(indices if indices is not None else np.zeros((0,)), dtype=np.uint32).reshape(-1)
+        out = C.c_uint32()
+        rc = self.lib.shsb_mesh_upload(self.h, capi.fptr(pos), len(pos), capi.fptr(nrm), len(nrm), capi.fptr(uv), len(uv),
+                                       capi.u32ptr(idx), len(idx), C.byref(out))
+        _check(self.lib, self.h, rc, "shsb_mesh_upload")
+        return out.value
+
+    def texture_upload(self, rgba) -> int:
+        t = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = t.shape[0], t.shape[1]
+        out = C.c_uint32()
+        rc = self.lib.shsb_texture_upload(self.h, t.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, C.byref(out))
+        _check(self.lib, self.h, rc, "shsb_texture_upload")
+        return out.value
+
+    # ---- render targets
+    def rt_create(self, kind, w, h, zn=0.1, zf=1000.0) -> int:
+        out = C.c_uint32()
+        rc = self.lib.shsb_rt_create(self.h, kind, w, h, zn, zf, C.byref(out))
+        _check(self.lib, self.h, rc, "shsb_rt_create")
+        self._rt_shape[out.value] = (kind, w, h)
+        return out.value
+
+    def rt_destroy(self, rt):
+        _check(self.lib, self.h, self.lib.shsb_rt_destroy(self.h, rt), "shsb_rt_destroy")
+        self._rt_shape.pop(rt, None)
+
+    def _plane_array(self, rt, plane):
+        kind, w, h = self._rt_shape[rt]
+        if plane == capi.PLANE_COLOR:
+            return np.empty((h, w, 4), dtype=np.float32 if kind == capi.RT_COLOR_HDR else np.uint8)
+        if plane == capi.PLANE_DEPTH:
+            return np.empty((h, w), dtype=np.float32)
+        if plane == capi.PLANE_MOTION:
+            return np.empty((h, w, 2), dtype=np.float32)
+        return np.empty((h, w), dtype=np.uint32)
+
+    def rt_download(self, rt, plane=capi.PLANE_COLOR) -> np.ndarray:
+        a = self._plane_array(rt, plane)
+        rc = self.lib.shsb_rt_download(self.h, rt, plane, a.ctypes.data_as(C.c_void_p), a.nbytes)
+        _check(self.lib, self.h, rc, "shsb_rt_download")
+        return a
+
+    def rt_download_into(self, rt, plane, dst_ptr, nbytes):
+        _check(self.lib, self.h, self.lib.shsb_rt_download(self.h, rt, plane, C.c_void_p(dst_ptr), nbytes), "shsb_rt_download")
+
+    def rt_upload(self, rt, plane, array):
+        a = np.ascontiguousarray(array)
+        rc = self.lib.shsb_rt_upload(self.h, rt, plane, a.ctypes.data_as(C.c_void_p), a.nbytes)
+        _check(self.lib, self.h, rc, "shsb_rt_upload")
+
+    def rt_clear(self, rt, plane, value):
+        v = np.ascontiguousarray(value)
+        _check(self.lib, self.h, self.lib.shsb_rt_clear(self.h, rt, plane, v.ctypes.data_as(C.c_void_p)), "shsb_rt_clear")
+
+    def rt_device_ptr(self, rt, plane):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        _check(self.lib, self.h, self.lib.shsb_rt_device_ptr(self.h, rt, plane, C.byref(p), C.byref(n)), "shsb_rt_device_ptr")
+        return p.value, n.value
+
+    # ---- passes
+    def rasterize_mesh(self, mesh, shader_id, uniforms: Uniforms, hdr_rt, depth_rt=0, cull_mode=capi.CULL_BACK,
+                       front_face_ccw=True, write_aovs=False) -> Stats:
+        cfg = RasterCfg(cull_mode, int(front_face_ccw), int(write_aovs), 0)
+        st = Stats()
+        rc = self.lib.shsb_rasterize_mesh(self.h, mesh, shader_id, C.byref(uniforms), hdr_rt, depth_rt, C.byref(cfg), C.byref(st))
+        _check(self.lib, self.h, rc, "shsb_rasterize_mesh")
+        return st
+
+    def pass_pbr_forward(self, scene: Scene, fp: FrameParams, hdr_rt, depth_rt=0, shadow_rt=0, shadow_light_viewproj=None,
+                         preserve_existing_depth=False) -> Stats:
+        st = Stats()
+        lvp = None
+        if shadow_light_viewproj is not None:
+            lvp = np.ascontiguousarray(shadow_light_viewproj, dtype=np.float32).reshape(16)
+        rc = self.lib.shsb_pass_pbr_forward(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, shadow_rt,
+                                            capi.fptr(lvp) if lvp is not None else None, int(preserve_existing_depth), C.byref(st))
+        _check(self.lib, self.h, rc, "shsb_pass_pbr_forward")
+        return st
+
+    def pass_depth_prepass(self, scene: Scene, fp: FrameParams, depth_rt) -> Stats:
+        st = Stats()
+        _check(self.lib, self.h, self.lib.shsb_pass_depth_prepass(self.h, C.byref(scene), C.byref(fp), depth_rt, C.byref(st)),
+               "shsb_pass_depth_prepass")
+        return st
+
+    def pass_shadow_map(self, scene: Scene, fp: FrameParams, shadow_rt) -> np.ndarray:
+        lvp = np.zeros(16, dtype=np.float32)
+        _check(self.lib, self.h, self.lib.shsb_pass_shadow_map(self.h, C.byref(scene), C.byref(fp), shadow_rt, capi.fptr(lvp)),
+               "shsb_pass_shadow_map")
+        return lvp
+
+    def pass_tonemap(self, hdr_rt, ldr_rt, exposure=1.0, gamma=2.2):
+        _check(self.lib, self.h, self.lib.shsb_pass_tonemap(self.h, hdr_rt, ldr_rt, exposure, gamma), "shsb_pass_tonemap")
+
+    def lights_upload(self, records: np.ndarray):
+        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
+        _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")
+
+    def light_cull(self, view_proj, w, h, tile_size=16, max_per_tile=128):
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        _check(self.lib, self.h, self.lib.shsb_light_cull(self.h, capi.fptr(vp), w, h, tile_size, max_per_tile), "shsb_light_cull")
+        self._tiles = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        self._max_per_tile = max_per_tile
+
+    def light_lists_download(self):
+        counts = np.zeros(self._tiles, dtype=np.uint32)
+        indices = np.zeros(self._tiles * self._max_per_tile, dtype=np.uint32)
+        rc = self.lib.shsb_light_lists_download(self.h, capi.u32ptr(counts), counts.size, capi.u32ptr(indices), indices.size)
+        _check(self.lib, self.h, rc, "shsb_light_lists_download")
+        return counts, indices.reshape(self._tiles, self._max_per_tile)
+
+    def frame_forward_plus(self, scene: Scene, fp: FrameParams, hdr_rt, depth_rt, ldr_rt) -> Stats:
+        st = Stats()
+        rc = self.lib.shsb_frame_forward_plus(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, ldr_rt, C.byref(st))
+        _check(self.lib, self.h, rc, "shsb_frame_forward_plus")
+        return st
+
+    def sync(self):
+        _check(self.lib, self.h, self.lib.shsb_sync(self.h), "shsb_sync")
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        _check(self.lib, self.h, self.lib.shsb_stream(self.h, C.byref(p)), "shsb_stream")
+        return p.value or 0
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib, self.h, self.lib.shsb_launch_count(self.h, C.byref(n)), "shsb_launch_count")
+        return n.value
+
+    def last_stage_ms(self):
+        a = np.zeros(8, dtype=np.float32)
+        _check(self.lib, self.h, self.lib.shsb_last_stage_ms(self.h, capi.fptr(a)), "shsb_last_stage_ms")
+        return a
+
+
+def model_from_transform(pos, rot, scl) -> np.ndarray:
+    lib = capi.load_library()
+    tr = Transform()
+    capi.set_f(tr.pos, pos)
+    capi.set_f(tr.rot_euler, rot)
+    capi.set_f(tr.scl, scl)
+    out = np.zeros(16, dtype=np.float32)
+    lib.shsb_model_from_transform(C.byref(tr), capi.fptr(out))
+    return out
+
+
+def camera_viewproj(eye, target, up, fovy, aspect, zn, zf) -> np.ndarray:
+    lib = capi.load_library()
+    e = np.asarray(eye, dtype=np.float32)
+    t = np.asarray(target, dtype=np.float32)
+    u = np.asarray(up, dtype=np.float32)
+    out = np.zeros(16, dtype=np.float32)
+    lib.shsb_camera_viewproj(capi.fptr(e), capi.fptr(t), capi.fptr(u), fovy, aspect, zn, zf, capi.fptr(out))
+    return out

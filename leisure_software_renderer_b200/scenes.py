@@ -1,0 +1,329 @@
+"""Deterministic synthetic scenes of the shapes BASELINE.json names.
+
+A scene is plain host data (numpy arrays + the POD structs of include/shsb.h): the same bytes are
+fed to the CUDA path, to the CPU oracle and to the compiled reference.  Camera matrices and light
+records are INPUTS of the path, so they are built here once (numpy float32) and shared.
+
+Hash RNG = the reference's own pseudo_random01 (exp-plumbing/hello_light_types_culling_sw.cpp:156-165).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import FrameParams, RenderItem, Scene
+
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def pseudo_random01(seed) -> np.ndarray:
+    x = np.asarray(seed, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    m = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & m
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & m
+    x ^= x >> np.uint64(16)
+    return ((x & np.uint64(0x00FFFFFF)).astype(np.float32) / np.float32(0x01000000)).astype(np.float32)
+
+
+def load_suzanne() -> dict:
+    """Suzanne (967 triangles), derived from the reference fixture by tests/golden/make_assets.py."""
+    z = np.load(os.path.join(_ASSETS, "suzanne.npz"))
+    return {k: z[k] for k in ("positions", "normals", "uvs", "indices")}
+
+
+def make_grid_plane(extent=64.0, n=32) -> dict:
+    """(n x n)-quad floor in the XZ plane, CCW seen from +Y in the LH/y-up convention."""
+    xs = np.linspace(-extent / 2, extent / 2, n + 1, dtype=np.float32)
+    gx, gz = np.meshgrid(xs, xs, indexing="xy")
+    pos = np.stack([gx.ravel(), np.zeros_like(gx).ravel(), gz.ravel()], axis=1).astype(np.float32)
+    nrm = np.tile(np.array([[0, 1, 0]], np.float32), (len(pos), 1))
+    uv = np.stack([(gx.ravel() / extent + 0.5) * 8.0, (gz.ravel() / extent + 0.5) * 8.0], axis=1).astype(np.float32)
+    idx = []
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i
+            b, c, d = a + 1, a + (n + 1), a + (n + 1) + 1
+            idx += [a, b, c, b, d, c]
+    return {"positions": pos, "normals": nrm, "uvs": uv, "indices": np.asarray(idx, np.uint32)}
+
+
+def make_checker_texture(size=64, seed=7) -> np.ndarray:
+    y, x = np.mgrid[0:size, 0:size]
+    r = (pseudo_random01((y * size + x + seed).astype(np.uint64)) * 60).astype(np.int32)
+    base = np.where(((x // 8) + (y // 8)) % 2 == 0, 200, 90).astype(np.int32)
+    t = np.zeros((size, size, 4), np.uint8)
+    t[..., 0] = np.clip(base + r, 0, 255)
+    t[..., 1] = np.clip(base - r // 2 + 20, 0, 255)
+    t[..., 2] = np.clip(255 - base + r, 0, 255)
+    t[..., 3] = 255
+    return t
+
+
+# ---------------------------------------------------------------- camera (inputs; numpy float32)
+def _norm(v):
+    v = np.asarray(v, np.float32)
+    return v / np.float32(math.sqrt(float(np.dot(v, v))))
+
+
+def look_at_lh(eye, target, up) -> np.ndarray:
+    eye = np.asarray(eye, np.float32)
+    f = _norm(np.asarray(target, np.float32) - eye)
+    s = _norm(np.cross(np.asarray(up, np.float32), f))
+    u = np.cross(f, s)
+    m = np.eye(4, dtype=np.float32)  # m[row, col]
+    m[0, :3], m[1, :3], m[2, :3] = s, u, f
+    m[0, 3], m[1, 3], m[2, 3] = -np.dot(s, eye), -np.dot(u, eye), -np.dot(f, eye)
+    return m
+
+
+def perspective_lh_no(fovy, aspect, zn, zf) -> np.ndarray:
+    t = math.tan(fovy / 2.0)
+    m = np.zeros((4, 4), np.float32)
+    m[0, 0] = 1.0 / (aspect * t)
+    m[1, 1] = 1.0 / t
+    m[2, 2] = (zf + zn) / (zf - zn)
+    m[3, 2] = 1.0
+    m[2, 3] = -(2.0 * zf * zn) / (zf - zn)
+    return m
+
+
+def camera_viewproj(eye, target, up, fovy, aspect, zn, zf) -> np.ndarray:
+    """Column-major float32[16] like glm::mat4 (proj * view)."""
+    vp = (perspective_lh_no(fovy, aspect, zn, zf) @ look_at_lh(eye, target, up)).astype(np.float32)
+    return np.ascontiguousarray(vp.T).reshape(16)
+
+
+# ---------------------------------------------------------------- lights (CullingLightGPU, 160 B)
+LIGHT_DTYPE = np.dtype([
+    ("position_range", np.float32, 4), ("color_intensity", np.float32, 4), ("direction_spot", np.float32, 4),
+    ("axis_spot_outer", np.float32, 4), ("up_shape_x", np.float32, 4), ("shape_attenuation", np.float32, 4),
+    ("type_shape_flags", np.uint32, 4), ("cull_sphere", np.float32, 4), ("cull_aabb_min", np.float32, 4),
+    ("cull_aabb_max", np.float32, 4)])
+assert LIGHT_DTYPE.itemsize == capi.LIGHT_RECORD_BYTES
+
+LIGHT_POINT, LIGHT_SPOT = 1, 2
+ATTEN_LINEAR, ATTEN_SMOOTH, ATTEN_INVERSE_SQUARE = 0, 1, 2
+
+
+def pack_lights(pos, rng, color, intensity, kind, direction=None, inner=None, outer=None,
+                atten_model=ATTEN_SMOOTH, atten_power=1.25, atten_bias=0.05, atten_cutoff=0.0, jolt_bounds=False) -> np.ndarray:
+    """Layout of make_point_culling_light / make_spot_culling_light (lighting/light_types.hpp:327-379)."""
+    n = len(pos)
+    r = np.zeros(n, LIGHT_DTYPE)
+    pos = np.asarray(pos, np.float32)
+    rng = np.maximum(np.asarray(rng, np.float32), 0)
+    kind = np.broadcast_to(np.asarray(kind, np.uint32), (n,))
+    r["position_range"][:, :3] = pos
+    r["position_range"][:, 3] = rng
+    r["color_intensity"][:, :3] = np.maximum(np.asarray(color, np.float32), 0)
+    r["color_intensity"][:, 3] = np.maximum(np.asarray(intensity, np.float32), 0)
+    r["direction_spot"][:] = (0, -1, 0, 1)
+    r["axis_spot_outer"][:] = (1, 0, 0, 0)
+    r["up_shape_x"][:] = (0, 1, 0, 0)
+    r["shape_attenuation"][:] = (0, max(atten_power, 0.001), max(atten_bias, 1e-5), max(atten_cutoff, 0.0))
+    r["type_shape_flags"][:, 0] = kind
+    r["type_shape_flags"][:, 1] = kind  # Sphere = 1 for points, Cone = 2 for spots
+    r["type_shape_flags"][:, 2] = 7     # LightFlagsDefault
+    r["type_shape_flags"][:, 3] = atten_model
+    spot = kind == LIGHT_SPOT
+    if spot.any():
+        d = np.asarray(direction, np.float32)
+        d = d / np.sqrt((d * d).sum(axis=1, keepdims=True)).astype(np.float32)
+        r["direction_spot"][spot, :3] = d[spot]
+        r["direction_spot"][spot, 3] = np.cos(np.asarray(inner, np.float32))[spot]
+        r["axis_spot_outer"][spot, 3] = np.cos(np.asarray(outer, np.float32))[spot]
+    r["cull_sphere"][:, :3] = pos
+    r["cull_sphere"][:, 3] = rng * np.float32(math.sqrt(3.0)) if jolt_bounds else rng
+    r["cull_aabb_min"][:, :3] = pos - rng[:, None]
+    r["cull_aabb_max"][:, :3] = pos + rng[:, None]
+    r["cull_aabb_min"][:, 3] = 1
+    r["cull_aabb_max"][:, 3] = 1
+    return r
+
+
+def make_lights(n_point, n_spot, lo, hi, seed=0, range_lo=2.0, range_hi=5.0, jolt_bounds=False) -> np.ndarray:
+    """Local lights uniform in the box [lo, hi]; ranges / intensities / cone angles in the spirit of
+    exp-plumbing/hello_light_types_culling_sw.cpp:600-627."""
+    n = n_point + n_spot
+    i = np.arange(n, dtype=np.uint64) + np.uint64(seed * 7919)
+    r = [pseudo_random01(i * np.uint64(k) + np.uint64(c)) for k, c in
+         ((747796405, 13), (2891336453, 17), (1181783497, 19), (2246822519, 23), (3266489917, 29), (668265263, 31), (374761393, 37), (2654435761, 41))]
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    pos = np.stack([lo[k] + (hi[k] - lo[k]) * r[k] for k in range(3)], axis=1).astype(np.float32)
+    rng = (range_lo + (range_hi - range_lo) * r[3]).astype(np.float32)
+    palette = np.array([[1.0, 0.55, 0.30], [0.35, 0.70, 1.0], [0.60, 1.0, 0.45], [1.0, 0.35, 0.75], [1.0, 0.90, 0.50]], np.float32)
+    color = palette[(np.arange(n) * 3) % len(palette)] * (0.82 + 0.30 * r[4])[:, None]
+    intensity = (2.0 + 1.0 * r[5]).astype(np.float32)
+    kind = np.where(np.arange(n) < n_point, LIGHT_POINT, LIGHT_SPOT).astype(np.uint32)
+    direction = np.stack([r[6] * 2 - 1, -np.ones(n, np.float32) * 1.5, r[7] * 2 - 1], axis=1).astype(np.float32)
+    inner = np.radians(12.0 + 8.0 * r[6]).astype(np.float32)
+    outer = (inner + np.radians(8.0 + 12.0 * r[7])).astype(np.float32)
+    return pack_lights(pos, rng, color.astype(np.float32), intensity, kind, direction, inner, outer, jolt_bounds=jolt_bounds)
+
+
+# ---------------------------------------------------------------- scene container
+@dataclass
+class SceneData:
+    name: str
+    w: int
+    h: int
+    zn: float
+    zf: float
+    meshes: list
+    textures: list
+    items: list          # list of dicts: pos, rot, scl, mesh (1-based), material or None
+    cam_pos: tuple
+    cam_target: tuple
+    fovy: float
+    sun_dir: tuple
+    sun_color: tuple
+    sun_intensity: float
+    fp: FrameParams = field(default_factory=capi.default_frame_params)
+    lights: np.ndarray | None = None
+    aspect: float | None = None
+    shadow_size: int = 0
+    viewproj: np.ndarray | None = None
+
+    def __post_init__(self):
+        if self.viewproj is None:
+            asp = self.aspect if self.aspect is not None else self.w / self.h
+            self.viewproj = camera_viewproj(self.cam_pos, self.cam_target, (0, 1, 0), self.fovy, asp, self.zn, self.zf)
+        self._items_c = (RenderItem * max(1, len(self.items)))()
+        for i, it in enumerate(self.items):
+            ri = self._items_c[i]
+            capi.set_f(ri.tr.pos, it["pos"])
+            capi.set_f(ri.tr.rot_euler, it.get("rot", (0, 0, 0)))
+            capi.set_f(ri.tr.scl, it.get("scl", (1, 1, 1)))
+            ri.mesh = it["mesh"]
+            mat = it.get("material")
+            ri.has_material = 1 if mat else 0
+            if mat:
+                capi.set_f(ri.base_color, mat["base_color"])
+                ri.metallic, ri.roughness, ri.ao = mat["metallic"], mat["roughness"], mat.get("ao", 1.0)
+                ri.base_color_tex = mat.get("tex", 0)
+            ri.casts_shadow = 1 if it.get("casts_shadow", True) else 0
+            ri.visible = 1 if it.get("visible", True) else 0
+        self.scene = Scene()
+        capi.set_f(self.scene.cam_viewproj, self.viewproj)
+        capi.set_f(self.scene.cam_pos, self.cam_pos)
+        capi.set_f(self.scene.sun_dir_ws, self.sun_dir)
+        capi.set_f(self.scene.sun_color, self.sun_color)
+        self.scene.sun_intensity = self.sun_intensity
+        self.scene.n_items = len(self.items)
+        self.scene.items = C.cast(self._items_c, C.POINTER(RenderItem))
+
+    @property
+    def n_triangles(self) -> int:
+        return int(sum(len(self.meshes[it["mesh"] - 1]["indices"]) // 3 for it in self.items if it.get("visible", True)))
+
+    def with_camera(self, cam_pos, cam_target):
+        return SceneData(self.name, self.w, self.h, self.zn, self.zf, self.meshes, self.textures, self.items, tuple(cam_pos),
+                         tuple(cam_target), self.fovy, self.sun_dir, self.sun_color, self.sun_intensity, self.fp, self.lights,
+                         self.aspect, self.shadow_size)
+
+
+_SUN_DIR = tuple(_norm((-0.35, -1.0, -0.25)))  # exp-plumbing/hello_pass_basics.cpp:669-671
+_SUN_COLOR = (1.0, 0.97, 0.92)
+_MATERIALS = [
+    {"base_color": (240 / 255, 195 / 255, 75 / 255), "metallic": 0.95, "roughness": 0.20},  # gold (hello_pass_basics.cpp:703)
+    {"base_color": (0.42, 0.44, 0.48), "metallic": 0.0, "roughness": 0.96},                 # plastic
+    {"base_color": (0.80, 0.25, 0.20), "metallic": 0.28, "roughness": 0.44},
+    {"base_color": (0.25, 0.55, 0.85), "metallic": 0.60, "roughness": 0.35},
+]
+
+
+def scene_c1(w=640, h=480) -> SceneData:
+    """BASELINE config 1: one Suzanne, Blinn-Phong, 1 directional light, z-buffer, 640x480
+    (placement per hello-3d-primitives/hello_pipeline_blinn_phong_shading.cpp:152-153,384; aspect 4/3)."""
+    fp = capi.default_frame_params(shading_model=capi.SHADING_BLINN, shadow_enable=0)
+    return SceneData("C1_suzanne_blinn", w, h, 0.1, 1000.0, [load_suzanne()], [],
+                     [{"pos": (0, 0, 10), "rot": (0, math.pi, 0), "scl": (4, 4, 4), "mesh": 1,
+                       "material": {"base_color": (60 / 255, 100 / 255, 200 / 255), "metallic": 0.0, "roughness": 0.5}}],
+                     (0, 5, -20), (0, 5, -19), math.radians(60.0), tuple(_norm((-1, -0.4, 1))), (1, 1, 1), 1.0, fp, aspect=4 / 3)
+
+
+def _suzanne_grid(nx, nz, spacing, scale=1.0, mesh=1, y=0.0):
+    items = []
+    for j in range(nz):
+        for i in range(nx):
+            k = j * nx + i
+            rot = float(2.0 * math.pi * pseudo_random01(np.uint64(k * 2654435761 + 101)))
+            items.append({"pos": ((i - (nx - 1) / 2) * spacing, y, (j - (nz - 1) / 2) * spacing), "rot": (0, rot, 0),
+                          "scl": (scale, scale, scale), "mesh": mesh, "material": _MATERIALS[k % len(_MATERIALS)]})
+    return items
+
+
+def scene_c2(w=1920, h=1080, grid=10, n_point=768, n_spot=256, seed=0) -> SceneData:
+    """BASELINE config 2: 1080p Forward+, grid x grid Suzanne instances (~100k tris), 1024 point/spot
+    lights, 16-px tiles, <=128 lights per tile (frame/frame_params.hpp:83-84)."""
+    items = _suzanne_grid(grid, grid, 3.0)
+    ext = (grid - 1) * 3.0 / 2 + 1.5
+    lights = make_lights(n_point, n_spot, (-ext, 0.5, -ext), (ext, 3.0, ext), seed=seed)
+    fp = capi.default_frame_params(shading_model=capi.SHADING_PBR, shadow_enable=0, light_culling=1, tile_size=16, max_lights_per_tile=128)
+    return SceneData(f"C2_forward_plus_{w}x{h}_{grid * grid}inst_{n_point + n_spot}lights", w, h, 0.1, 200.0, [load_suzanne()], [], items,
+                     (0, 12, -28), (0, 0, 0), math.radians(60.0), _SUN_DIR, _SUN_COLOR, 2.2, fp, lights)
+
+
+def scene_c3(w=2560, h=1440, nx=32, nz=33, shadow_size=4096) -> SceneData:
+    """BASELINE config 3: shadow-map depth pass (4096^2) + PCF lit pass at 1440p, ~1M triangles."""
+    items = [{"pos": (0, -1.0, 0), "mesh": 2, "material": _MATERIALS[1], "casts_shadow": False}] + _suzanne_grid(nx, nz, 3.0)
+    fp = capi.default_frame_params(shading_model=capi.SHADING_PBR, shadow_enable=1)
+    ext = max(nx, nz) * 3.0
+    return SceneData(f"C3_shadow_{w}x{h}_{nx * nz}inst", w, h, 0.1, 400.0, [load_suzanne(), make_grid_plane(ext * 1.2, 64)], [], items,
+                     (0, ext * 0.35, -ext * 0.75), (0, 0, 0), math.radians(60.0), _SUN_DIR, _SUN_COLOR, 2.2, fp, shadow_size=shadow_size)
+
+
+def scene_c4(w=3840, h=2160, nx=44, nz=47) -> SceneData:
+    """BASELINE config 4 (library flavour): PBR-MR with eval_fake_ibl and an albedo texture at 4K, ~2M triangles.
+    Normal mapping has no reference semantics and the cubemap skybox is a 'next' row (8f-3)."""
+    mats = [dict(m, tex=1) for m in _MATERIALS]
+    items = _suzanne_grid(nx, nz, 3.0)
+    for k, it in enumerate(items):
+        it["material"] = mats[k % len(mats)]
+    fp = capi.default_frame_params(shading_model=capi.SHADING_PBR, shadow_enable=0)
+    ext = max(nx, nz) * 3.0
+    return SceneData(f"C4_pbr_{w}x{h}_{nx * nz}inst", w, h, 0.1, 600.0, [load_suzanne()], [make_checker_texture(256)], items,
+                     (0, ext * 0.35, -ext * 0.75), (0, 0, 0), math.radians(60.0), _SUN_DIR, _SUN_COLOR, 2.2, fp)
+
+
+def scene_c5(w=7680, h=4320, nx=101, nz=102, n_point=768, n_spot=256) -> SceneData:
+    """BASELINE config 5: 8K Forward+, ~10M triangles (sort-first split across GPUs)."""
+    items = _suzanne_grid(nx, nz, 3.0)
+    ext = max(nx, nz) * 3.0 / 2
+    lights = make_lights(n_point, n_spot, (-ext, 0.5, -ext), (ext, 3.0, ext), seed=5, range_lo=4.0, range_hi=10.0)
+    fp = capi.default_frame_params(shading_model=capi.SHADING_PBR, shadow_enable=0, light_culling=1)
+    return SceneData(f"C5_8k_{nx * nz}inst", w, h, 0.1, 1000.0, [load_suzanne()], [], items,
+                     (0, ext * 0.7, -ext * 1.5), (0, 0, 0), math.radians(60.0), _SUN_DIR, _SUN_COLOR, 2.2, fp, lights)
+
+
+def camera_ring(scene: SceneData, n_cameras: int, radius=28.0, height=12.0):
+    """64-camera batch of config 5b: cameras on a circle looking at the origin."""
+    out = []
+    for c in range(n_cameras):
+        a = 2.0 * math.pi * c / n_cameras
+        out.append(scene.with_camera((radius * math.sin(a), height, -radius * math.cos(a)), (0, 0, 0)))
+    return out
+
+
+def scene_small(w=160, h=120, shading=capi.SHADING_PBR, n_inst=3, lights=0, tex=False, seed=1, near_clip=False) -> SceneData:
+    """Small parity scene: a few Suzannes + floor; optional texture, lights and a camera that forces frustum clipping."""
+    meshes = [load_suzanne(), make_grid_plane(24.0, 8)]
+    textures = [make_checker_texture(32)] if tex else []
+    items = [{"pos": (0, -1.0, 0), "mesh": 2, "material": dict(_MATERIALS[1], tex=1 if tex else 0), "casts_shadow": False}]
+    for k in range(n_inst):
+        r = pseudo_random01(np.arange(4, dtype=np.uint64) + np.uint64(seed * 131 + k * 17))
+        items.append({"pos": (float(r[0] * 8 - 4), float(r[1] * 1.5), float(r[2] * 8 - 4)), "rot": (0.1 * k, float(r[3] * 6.28), 0.05 * k),
+                      "scl": (1.0 + 0.3 * k, 1.0 + 0.3 * k, 1.0 + 0.3 * k), "mesh": 1,
+                      "material": (dict(_MATERIALS[k % 4], tex=1) if (tex and k % 2 == 0) else (_MATERIALS[k % 4] if k % 3 else None))})
+    lt = make_lights(max(1, lights * 3 // 4), lights - max(1, lights * 3 // 4), (-6, 0.2, -6), (6, 3.0, 6), seed=seed) if lights else None
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=0, light_culling=1 if lights else 0)
+    cam = (0.5, 1.2, -2.2) if near_clip else (0, 4, -8)
+    return SceneData(f"small_{w}x{h}", w, h, 0.1, 100.0, meshes, textures, items, cam, (0, 0.5, 0), math.radians(60.0),
+                     _SUN_DIR, _SUN_COLOR, 2.2, fp, lt, shadow_size=256)

@@ -1,0 +1,200 @@
+"""oracle/bindings.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes bindings of the two CPU checkers declared in oracle/oracle_abi.h:
+  Oracle("port")      -> oracle/liboracle.so        (this repo's restatement, shso_*)
+  Oracle("reference") -> oracle/_ref/libshs_ref.so  (the reference's own headers, shsref_*)
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from leisure_software_renderer_b200 import capi
+from leisure_software_renderer_b200.capi import FrameParams, RasterCfg, Scene, Stats, Transform, Uniforms
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_LIB = os.path.join(_HERE, "liboracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libshs_ref.so")
+
+
+class Mesh(C.Structure):
+    _fields_ = [("positions", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("uvs", C.POINTER(C.c_float)),
+                ("indices", C.POINTER(C.c_uint32)), ("n_positions", C.c_uint32), ("n_normals", C.c_uint32),
+                ("n_uvs", C.c_uint32), ("n_indices", C.c_uint32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("rgba", C.POINTER(C.c_uint8)), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+class Assets(C.Structure):
+    _fields_ = [("meshes", C.POINTER(Mesh)), ("textures", C.POINTER(Texture)), ("n_meshes", C.c_uint32), ("n_textures", C.c_uint32)]
+
+
+class Target(C.Structure):
+    _fields_ = [("hdr", C.POINTER(C.c_float)), ("depth", C.POINTER(C.c_float)), ("shadow", C.POINTER(C.c_float)),
+                ("tri_id", C.POINTER(C.c_uint32)), ("coverage", C.POINTER(C.c_uint32)),
+                ("w", C.c_int32), ("h", C.c_int32), ("shadow_w", C.c_int32), ("shadow_h", C.c_int32),
+                ("zn", C.c_float), ("zf", C.c_float)]
+
+
+def build(kind: str = "port") -> None:
+    subprocess.run(["make", "-C", _HERE, "oracle" if kind == "port" else "ref"], check=True, capture_output=True)
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(PORT_LIB if kind == "port" else REF_LIB)
+
+
+class HostAssets:
+    """Keeps numpy arrays alive behind a ShsoAssets block (1-based handles like ResourceRegistry)."""
+
+    def __init__(self, meshes, textures=()):
+        self._keep = []
+        self.meshes = (Mesh * max(1, len(meshes)))()
+        for i, m in enumerate(meshes):
+            pos = np.ascontiguousarray(m["positions"], dtype=np.float32).reshape(-1, 3)
+            nrm = np.ascontiguousarray(m.get("normals", np.zeros((0, 3))), dtype=np.float32).reshape(-1, 3)
+            uv = np.ascontiguousarray(m.get("uvs", np.zeros((0, 2))), dtype=np.float32).reshape(-1, 2)
+            idx = np.ascontiguousarray(m.get("indices", np.zeros((0,))), dtype=np.uint32).reshape(-1)
+            self._keep += [pos, nrm, uv, idx]
+            self.meshes[i] = Mesh(capi.fptr(pos), capi.fptr(nrm), capi.fptr(uv), capi.u32ptr(idx), len(pos), len(nrm), len(uv), len(idx))
+        self.textures = (Texture * max(1, len(textures)))()
+        for i, t in enumerate(textures):
+            a = np.ascontiguousarray(t, dtype=np.uint8)
+            self._keep.append(a)
+            self.textures[i] = Texture(a.ctypes.data_as(C.POINTER(C.c_uint8)), a.shape[1], a.shape[0])
+        self.block = Assets(self.meshes, self.textures, len(meshes), len(textures))
+
+
+class Oracle:
+    def __init__(self, kind: str = "port"):
+        assert kind in ("port", "reference")
+        self.kind = kind
+        path = PORT_LIB if kind == "port" else REF_LIB
+        if not os.path.exists(path):
+            build(kind)
+        self.lib = C.CDLL(path)
+        self.prefix = "shso_" if kind == "port" else "shsref_"
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    # ---- helpers
+    def model_from_transform(self, pos, rot, scl):
+        tr = Transform()
+        capi.set_f(tr.pos, pos); capi.set_f(tr.rot_euler, rot); capi.set_f(tr.scl, scl)
+        out = np.zeros(16, dtype=np.float32)
+        f = self.fn("model_from_transform"); f.restype = None
+        f(C.byref(tr), capi.fptr(out))
+        return out
+
+    def camera_viewproj(self, eye, target, up, fovy, aspect, zn, zf):
+        e, t, u = (np.asarray(v, dtype=np.float32) for v in (eye, target, up))
+        out = np.zeros(16, dtype=np.float32)
+        f = self.fn("camera_viewproj"); f.restype = None
+        f(capi.fptr(e), capi.fptr(t), capi.fptr(u), C.c_float(fovy), C.c_float(aspect), C.c_float(zn), C.c_float(zf), capi.fptr(out))
+        return out
+
+    def pack_point_light(self, pos, rng, color, intensity, model=1, power=1.0, bias=0.05, cutoff=0.0, jolt_bounds=False):
+        p, c = np.asarray(pos, dtype=np.float32), np.asarray(color, dtype=np.float32)
+        out = np.zeros(160, dtype=np.uint8)
+        f = self.fn("pack_point_light"); f.restype = None
+        f(capi.fptr(p), C.c_float(rng), capi.fptr(c), C.c_float(intensity), C.c_uint32(model), C.c_float(power), C.c_float(bias),
+          C.c_float(cutoff), C.c_int32(int(jolt_bounds)), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def pack_spot_light(self, pos, rng, color, intensity, direction, inner, outer, model=1, power=1.0, bias=0.05, cutoff=0.0):
+        p, c, d = (np.asarray(v, dtype=np.float32) for v in (pos, color, direction))
+        out = np.zeros(160, dtype=np.uint8)
+        f = self.fn("pack_spot_light"); f.restype = None
+        f(capi.fptr(p), C.c_float(rng), capi.fptr(c), C.c_float(intensity), capi.fptr(d), C.c_float(inner), C.c_float(outer),
+          C.c_uint32(model), C.c_float(power), C.c_float(bias), C.c_float(cutoff), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def set_threads(self, n):
+        if self.kind == "reference":
+            self.lib.shsref_set_threads(C.c_int32(n))
+
+    # ---- target plumbing
+    @staticmethod
+    def make_target(w, h, hdr, depth=None, shadow=None, tri_id=None, coverage=None, zn=0.1, zf=1000.0):
+        t = Target()
+        t.hdr = capi.fptr(hdr)
+        t.depth = capi.fptr(depth) if depth is not None else None
+        if shadow is not None:
+            t.shadow = capi.fptr(shadow)
+            t.shadow_h, t.shadow_w = shadow.shape
+        t.tri_id = capi.u32ptr(tri_id) if tri_id is not None else None
+        t.coverage = capi.u32ptr(coverage) if coverage is not None else None
+        t.w, t.h, t.zn, t.zf = w, h, zn, zf
+        return t
+
+    # ---- passes
+    def rasterize_mesh(self, assets: HostAssets, mesh, shader_id, u: Uniforms, tgt: Target, cull_mode=capi.CULL_BACK,
+                       front_face_ccw=True, key_base=0):
+        cfg = RasterCfg(cull_mode, int(front_face_ccw), 0, 0)
+        st = Stats()
+        rc = self.fn("rasterize_mesh")(C.byref(assets.block), C.c_uint32(mesh), C.c_int32(shader_id), C.byref(u), C.byref(tgt),
+                                       C.byref(cfg), C.c_uint32(key_base), C.byref(st))
+        assert rc == 0, rc
+        return st
+
+    def pass_pbr_forward(self, assets: HostAssets, scene: Scene, fp: FrameParams, tgt: Target, shadow_lvp=None, preserve_depth=False):
+        st = Stats()
+        lvp = np.ascontiguousarray(shadow_lvp, dtype=np.float32) if shadow_lvp is not None else None
+        rc = self.fn("pass_pbr_forward")(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt),
+                                         capi.fptr(lvp) if lvp is not None else None, C.c_int32(int(preserve_depth)), C.byref(st))
+        assert rc == 0, rc
+        return st
+
+    def pass_shadow_map(self, assets: HostAssets, scene: Scene, fp: FrameParams, sw, sh):
+        shadow = np.zeros((sh, sw), dtype=np.float32)
+        lvp = np.zeros(16, dtype=np.float32)
+        rc = self.fn("pass_shadow_map")(C.byref(assets.block), C.byref(scene), C.byref(fp), capi.fptr(shadow), C.c_int32(sw), C.c_int32(sh), capi.fptr(lvp))
+        assert rc == 0, rc
+        return shadow, lvp
+
+    def pass_tonemap(self, hdr, exposure=1.0, gamma=2.2):
+        h, w = hdr.shape[:2]
+        ldr = np.zeros((h, w, 4), dtype=np.uint8)
+        rc = self.fn("pass_tonemap")(capi.fptr(hdr), C.c_int32(w), C.c_int32(h), C.c_float(exposure), C.c_float(gamma),
+                                     ldr.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert rc == 0, rc
+        return ldr
+
+    # ---- restatement-only
+    def light_cull(self, records, view_proj, w, h, tile_size=16, max_per_tile=128):
+        assert self.kind == "port"
+        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, 160)
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32)
+        tiles = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        counts = np.zeros(tiles, dtype=np.uint32)
+        indices = np.zeros((tiles, max_per_tile), dtype=np.uint32)
+        rc = self.lib.shso_light_cull(r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), capi.fptr(vp), C.c_uint32(w), C.c_uint32(h),
+                                      C.c_uint32(tile_size), C.c_uint32(max_per_tile), capi.u32ptr(counts), capi.u32ptr(indices))
+        assert rc == 0, rc
+        return counts, indices
+
+    def pass_pbr_forward_plus(self, assets, scene, fp, tgt, records, counts, indices, shadow_lvp=None, preserve_depth=False):
+        assert self.kind == "port"
+        st = Stats()
+        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, 160)
+        lvp = np.ascontiguousarray(shadow_lvp, dtype=np.float32) if shadow_lvp is not None else None
+        rc = self.lib.shso_pass_pbr_forward_plus(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt),
+                                                 capi.fptr(lvp) if lvp is not None else None, C.c_int32(int(preserve_depth)),
+                                                 r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), capi.u32ptr(counts), capi.u32ptr(indices),
+                                                 C.byref(st))
+        assert rc == 0, rc
+        return st
+
+    def pass_depth_prepass(self, assets, scene, fp, tgt):
+        assert self.kind == "port"
+        st = Stats()
+        rc = self.lib.shso_pass_depth_prepass(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt), C.byref(st))
+        assert rc == 0, rc
+        return st

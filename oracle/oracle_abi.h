@@ -1,0 +1,125 @@
+/*
+ * oracle/oracle_abi.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Shared C interface of the two CPU checkers:
+ *   shso_*   : oracle/oracle.cpp      -- this repo's CPU restatement of the reference algorithm
+ *   shsref_* : oracle/ref_harness.cpp -- the reference's OWN headers compiled from /root/reference
+ *                                        against oracle/glm_shim (built into oracle/_ref/)
+ * Both take host pointers and the POD structs of include/shsb.h, so a test feeds the same bytes to
+ * the reference, the restatement and the CUDA path.  Nothing in the product may include this.
+ */
+#ifndef SHS_ORACLE_ABI_H
+#define SHS_ORACLE_ABI_H
+
+#include "../include/shsb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ShsoMesh /* MeshData, resources/mesh.hpp:23 */
+{
+    const float* positions;
+    const float* normals;
+    const float* uvs;
+    const uint32_t* indices;
+    uint32_t n_positions;
+    uint32_t n_normals;
+    uint32_t n_uvs;
+    uint32_t n_indices;
+} ShsoMesh;
+
+typedef struct ShsoTexture /* Texture2DData, resources/texture.hpp:23 */
+{
+    const uint8_t* rgba;
+    int32_t w;
+    int32_t h;
+} ShsoTexture;
+
+typedef struct ShsoAssets /* what ResourceRegistry resolves handles against (1-based) */
+{
+    const ShsoMesh* meshes;
+    const ShsoTexture* textures;
+    uint32_t n_meshes;
+    uint32_t n_textures;
+} ShsoAssets;
+
+typedef struct ShsoTarget /* RasterizerTarget + the RTs behind it, all host memory */
+{
+    float* hdr;          /* W*H*4, required                                                    */
+    float* depth;        /* W*H or NULL (no depth target => painter)                           */
+    const float* shadow; /* shadow map (sw*sh) or NULL                                         */
+    uint32_t* tri_id;    /* optional AOV: draw-order key of the winning fragment               */
+    uint32_t* coverage;  /* optional AOV: per-pixel count of fragments passing coverage + 1/w  */
+    int32_t w, h;
+    int32_t shadow_w, shadow_h;
+    float zn, zf;
+} ShsoTarget;
+
+#define SHSO_FN(ret, name, args) ret shso_##name args; ret shsref_##name args
+
+/* glm::translate/rotate/scale chain, pass_pbr_forward.hpp:136-141 */
+SHSO_FN(void, model_from_transform, (const ShsbTransform* tr, float out_model[16]));
+/* look_at_lh / perspective_lh_no / proj*view, camera/convention.hpp:19-33 */
+SHSO_FN(void, camera_viewproj, (const float eye[3], const float target[3], const float up[3],
+                                float fovy_radians, float aspect, float znear, float zfar, float out_viewproj[16]));
+/* make_point_culling_light / make_spot_culling_light, lighting/light_types.hpp:327-379;
+ * jolt_bounds != 0 applies the Jolt sphere-shape bounds of scene_shape.hpp:56-81 (radius = |vec3(range)|). */
+SHSO_FN(void, pack_point_light, (const float pos[3], float range, const float color[3], float intensity,
+                                 uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff,
+                                 int32_t jolt_bounds, void* out_record160));
+SHSO_FN(void, pack_spot_light, (const float pos[3], float range, const float color[3], float intensity,
+                                const float dir[3], float inner_rad, float outer_rad,
+                                uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff,
+                                void* out_record160));
+
+/* rasterize_mesh, sw_render/rasterizer.hpp:181.  key_base: draw-order key of triangle 0, fan 0
+ * (key = key_base + tri*8 + fan_k; the reference harness cannot see fan_k and reports fan 0). */
+SHSO_FN(int32_t, rasterize_mesh, (const ShsoAssets* assets, shsb_mesh mesh, int32_t shader_id,
+                                  const ShsbUniforms* u, const ShsoTarget* tgt, const ShsbRasterCfg* cfg,
+                                  uint32_t key_base, ShsbStats* out_stats));
+
+/* PassPBRForward::execute, passes/pass_pbr_forward.hpp:49 */
+SHSO_FN(int32_t, pass_pbr_forward, (const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                    const ShsoTarget* tgt, const float* shadow_light_viewproj,
+                                    int32_t preserve_existing_depth, ShsbStats* out_stats));
+
+/* PassShadowMap::execute, passes/pass_shadow_map.hpp:44 */
+SHSO_FN(int32_t, pass_shadow_map, (const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                   float* shadow, int32_t sw, int32_t sh, float out_light_viewproj[16]));
+
+/* PassTonemap::execute, passes/pass_tonemap.hpp:37 */
+SHSO_FN(int32_t, pass_tonemap, (const float* hdr, int32_t w, int32_t h, float exposure, float gamma, uint8_t* out_ldr));
+
+#undef SHSO_FN
+
+/* ---- restatement-only entry points (no compilable reference: Jolt-guarded headers / GLSL spec) ---- */
+
+/* cull_lights_tiled, lighting/jolt_light_culling.hpp:135-187 over CullingLightGPU cull_sphere/cull_aabb.
+ * counts[T] uncapped; indices[T*max_per_tile] first max_per_tile entries, ascending. */
+int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float view_proj[16],
+                        uint32_t viewport_w, uint32_t viewport_h, uint32_t tile_size, uint32_t max_per_tile,
+                        uint32_t* counts, uint32_t* indices);
+
+/* Forward+ frame: PassPBRForward with the local-light loop of fp_stress_scene.frag:644-678 added to
+ * the builtin fragment program.  counts/indices as produced by shso_light_cull. */
+int32_t shso_pass_pbr_forward_plus(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                   const ShsoTarget* tgt, const float* shadow_light_viewproj,
+                                   int32_t preserve_existing_depth,
+                                   const void* records160, uint32_t n_lights,
+                                   const uint32_t* counts, const uint32_t* indices,
+                                   ShsbStats* out_stats);
+
+/* PassDepthPrepassAdapter, pipeline/pass_adapters.hpp:401-528 */
+int32_t shso_pass_depth_prepass(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                const ShsoTarget* tgt, ShsbStats* out_stats);
+
+/* ThreadPoolJobSystem(n) handed to the reference passes as ctx.job_system / RasterizerConfig::job_system
+ * (exp-plumbing/hello_pass_basics.cpp:629-630); n <= 1 means no job system (serial). */
+int32_t shsref_set_threads(int32_t n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
