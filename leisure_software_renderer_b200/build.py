@@ -1,0 +1,81 @@
+"""Builds leisure_software_renderer_b200/libshsb.so (sm_100a only) with nvcc, in-tree.
+
+nvcc cross-compiles without a GPU, so this runs on the CPU build box; the .so travels to the GPU box.
+Per-file flags:
+  geometry.cu, light_cull.cu   --fmad=false   (every expression decides coverage / depth / list bits)
+  tile_raster.cu, binning.cu   FMA allowed; exact expressions use __fmul_rn/__fadd_rn/__fdiv_rn explicitly
+  api.cu                       host code with -ffp-contract=off (host float math must equal the reference's)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libshsb.so")
+OBJ = os.path.join(HERE, "build")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+SOURCES = {
+    "geometry.cu": ["--fmad=false"],
+    "light_cull.cu": ["--fmad=false"],
+    "binning.cu": [],
+    "tile_raster.cu": [],
+    "api.cu": [],
+}
+
+
+def nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "shsb.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    os.makedirs(OBJ, exist_ok=True)
+    cc = nvcc()
+    objs = []
+    procs = []
+    for src, extra in SOURCES.items():
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        cmd = [cc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", o]
+        if ptxas_info:
+            cmd += ["-Xptxas", "-v"]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed on {src}\n{out}\n")
+        elif (verbose or ptxas_info) and out.strip():
+            print(f"--- {src}\n{out}")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [cc, *ARCH, "-shared", "-o", OUT, *objs, "-Xcompiler", "-fPIC"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_info="--ptxas" in sys.argv))

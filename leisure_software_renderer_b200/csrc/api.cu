@@ -1,0 +1,1011 @@
+// api.cu -- the C-ABI of include/shsb.h: context, device-resident resources / render targets and the
+// pass entry points.  This is the host half of the path; it replaces the reference's job-system dispatch
+// (job/parallel_for.hpp:23-59, job/thread_pool_job_system.hpp:26-110) with kernel launches on one CUDA
+// stream per context, and its std::vector render targets (gfx/rt_types.hpp:35-157) with HBM buffers.
+//
+// There is no CPU raster path in this file: every pass either launches the kernels or returns an error.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/shsb.h"
+#include "host_math.hpp"
+#include "shsb_dev.cuh"
+
+using namespace shsb;
+namespace hm = shsb_host;
+
+namespace
+{
+    constexpr int NUM_STAGE_EVENTS = 6; // begin, after geometry, after binning, after raster, (cull begin, cull end)
+
+    struct MeshSlot
+    {
+        bool live = false;
+        float* positions = nullptr;
+        float* normals = nullptr;
+        float* uvs = nullptr;
+        uint32_t* indices = nullptr;
+        uint32_t n_positions = 0, n_normals = 0, n_uvs = 0, n_indices = 0;
+        hm::vec3f bmin{0, 0, 0}, bmax{0, 0, 0}; // local bounds (PassShadowMap mesh_bounds_cache, pass_shadow_map.hpp:96-110)
+    };
+
+    struct TexSlot
+    {
+        bool live = false;
+        uchar4* texels = nullptr;
+        int w = 0, h = 0;
+    };
+
+    struct RtSlot
+    {
+        bool live = false;
+        int kind = 0, w = 0, h = 0;
+        float zn = 0.1f, zf = 1000.0f;
+        void* color = nullptr;    // float4 (HDR) or uchar4 (LDR)
+        float* depth = nullptr;   // DEPTH_MOTION, SHADOW
+        float2* motion = nullptr; // DEPTH_MOTION
+        uint32_t* tri_id = nullptr;
+        uint32_t* coverage = nullptr;
+    };
+
+    template <typename T>
+    struct DevBuf
+    {
+        T* p = nullptr;
+        size_t cap = 0;
+    };
+
+    template <typename T>
+    struct PinnedBuf
+    {
+        T* p = nullptr;
+        size_t cap = 0;
+    };
+}
+
+struct shsb_context_t
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    std::vector<MeshSlot> meshes;
+    std::vector<TexSlot> textures;
+    std::vector<RtSlot> rts;
+    DevBuf<DevMesh> d_meshes;
+    DevBuf<DevTexture> d_textures;
+    bool mesh_table_dirty = true, tex_table_dirty = true;
+    float* d_srgb_lut = nullptr;
+
+    // lights + tile lists
+    DevBuf<DevLightRec> d_lights;
+    uint32_t n_lights = 0;
+    DevBuf<uint8_t> d_light_visible;
+    DevBuf<uint32_t> d_tile_counts, d_tile_indices;
+    uint32_t lists_w = 0, lists_h = 0, lists_ts = 0, lists_max = 0;
+    bool lists_valid = false;
+
+    // per-frame arena
+    DevBuf<DevItem> d_items;
+    DevBuf<uint2> d_blocks;
+    PinnedBuf<DevItem> h_items;
+    PinnedBuf<uint2> h_blocks;
+    DevBuf<RasterRec> d_rrecs;
+    DevBuf<ShadeRec> d_srecs;
+    DevBuf<uint2> d_clipq;
+    DevBuf<uint32_t> d_tile_count, d_tile_offset, d_tile_fill, d_tile_list;
+    uint32_t* d_counters = nullptr; // [0] rec_count, [1] clipq_count
+    DevStats* d_stats = nullptr;
+    DevStats* h_stats = nullptr;    // pinned
+    double rec_growth = 1.0;        // multiplier learned from overflow reruns
+
+    cudaEvent_t ev[NUM_STAGE_EVENTS]{};
+    bool ev_valid[NUM_STAGE_EVENTS]{};
+};
+
+namespace
+{
+    int fail(shsb_ctx c, int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        if (c) c->error = buf;
+        return code;
+    }
+
+#define CK(call)                                                                                                \
+    do                                                                                                          \
+    {                                                                                                           \
+        const cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(ctx, SHSB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+    template <typename T>
+    int ensure_dev(shsb_ctx ctx, DevBuf<T>& b, size_t n)
+    {
+        if (n <= b.cap) return SHSB_OK;
+        const size_t want = std::max(n, b.cap + b.cap / 2);
+        T* np = nullptr;
+        const cudaError_t e = cudaMalloc(&np, want * sizeof(T));
+        if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        if (b.p)
+        {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(b.p);
+        }
+        b.p = np;
+        b.cap = want;
+        return SHSB_OK;
+    }
+
+    template <typename T>
+    int ensure_pinned(shsb_ctx ctx, PinnedBuf<T>& b, size_t n)
+    {
+        if (n <= b.cap) return SHSB_OK;
+        const size_t want = std::max(n, b.cap + b.cap / 2);
+        T* np = nullptr;
+        const cudaError_t e = cudaHostAlloc(&np, want * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaHostAlloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        if (b.p)
+        {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFreeHost(b.p);
+        }
+        b.p = np;
+        b.cap = want;
+        return SHSB_OK;
+    }
+
+    RtSlot* get_rt(shsb_ctx ctx, shsb_rt h, int kind = 0)
+    {
+        if (h == 0 || h > ctx->rts.size()) return nullptr;
+        RtSlot* r = &ctx->rts[h - 1];
+        if (!r->live) return nullptr;
+        if (kind && r->kind != kind) return nullptr;
+        return r;
+    }
+
+    MeshSlot* get_mesh(shsb_ctx ctx, shsb_mesh h)
+    {
+        if (h == 0 || h > ctx->meshes.size()) return nullptr;
+        MeshSlot* m = &ctx->meshes[h - 1];
+        return m->live ? m : nullptr;
+    }
+
+    size_t plane_bytes(const RtSlot& r, int plane, void** ptr)
+    {
+        const size_t n = (size_t)r.w * (size_t)r.h;
+        switch (plane)
+        {
+        case SHSB_PLANE_COLOR:
+            *ptr = r.color;
+            if (r.kind == SHSB_RT_COLOR_HDR) return n * 16;
+            if (r.kind == SHSB_RT_COLOR_LDR) return n * 4;
+            return 0;
+        case SHSB_PLANE_DEPTH: *ptr = r.depth; return r.depth ? n * 4 : 0;
+        case SHSB_PLANE_MOTION: *ptr = r.motion; return r.motion ? n * 8 : 0;
+        case SHSB_PLANE_TRI_ID: *ptr = r.tri_id; return r.tri_id ? n * 4 : 0;
+        case SHSB_PLANE_COVERAGE: *ptr = r.coverage; return r.coverage ? n * 4 : 0;
+        default: *ptr = nullptr; return 0;
+        }
+    }
+
+    int sync_tables(shsb_ctx ctx)
+    {
+        if (ctx->mesh_table_dirty)
+        {
+            std::vector<DevMesh> t(std::max<size_t>(1, ctx->meshes.size()));
+            for (size_t i = 0; i < ctx->meshes.size(); ++i)
+            {
+                const MeshSlot& m = ctx->meshes[i];
+                t[i] = DevMesh{m.positions, m.normals, m.uvs, m.indices, m.n_positions, m.n_normals, m.n_uvs, m.n_indices};
+            }
+            if (int rc = ensure_dev(ctx, ctx->d_meshes, t.size())) return rc;
+            CK(cudaMemcpyAsync(ctx->d_meshes.p, t.data(), t.size() * sizeof(DevMesh), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->mesh_table_dirty = false;
+        }
+        if (ctx->tex_table_dirty)
+        {
+            std::vector<DevTexture> t(std::max<size_t>(1, ctx->textures.size()));
+            for (size_t i = 0; i < ctx->textures.size(); ++i) t[i] = DevTexture{ctx->textures[i].texels, ctx->textures[i].w, ctx->textures[i].h};
+            if (int rc = ensure_dev(ctx, ctx->d_textures, t.size())) return rc;
+            CK(cudaMemcpyAsync(ctx->d_textures.p, t.data(), t.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->tex_table_dirty = false;
+        }
+        return SHSB_OK;
+    }
+
+    struct HostItem
+    {
+        DevItem dev;
+    };
+
+    struct FrameJob
+    {
+        FrameConst fc{};
+        FrameBuffers fb{};
+        std::vector<DevItem>* items = nullptr; // in h_items after staging
+        uint32_t n_items = 0;
+        uint64_t n_src_tris = 0;
+        uint32_t n_blocks = 0;
+    };
+
+    void record(shsb_ctx ctx, int i)
+    {
+        if (cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess) ctx->ev_valid[i] = true;
+    }
+
+    // Runs geometry -> binning -> tile raster for the draws staged in ctx->h_items[0..n_items).
+    int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats)
+    {
+        FrameConst& fc = job.fc;
+        fc.tiles_x = (fc.W + TILE - 1) / TILE;
+        fc.tiles_y = (fc.H + TILE - 1) / TILE;
+        const uint32_t n_tiles = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
+        if (fc.W > 65535 || fc.H > 65535) return fail(ctx, SHSB_E_UNSUPPORTED, "render target larger than 65535 pixels on a side");
+        if ((job.n_src_tris + 1) * 8ull >= 0xFFFFFFFFull) return fail(ctx, SHSB_E_UNSUPPORTED, "more than 2^29 source triangles in one submission");
+        if (int rc = sync_tables(ctx)) return rc;
+
+        for (int attempt = 0; attempt < 4; ++attempt)
+        {
+            // capacities: every source triangle may emit one record; clipped ones up to 7
+            const size_t clipq_cap = std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth));
+            const size_t rec_cap = std::max<size_t>(4096, (size_t)(((double)job.n_src_tris + 6.0 * (double)std::min<size_t>(clipq_cap, job.n_src_tris)) * 1.0));
+            const size_t list_cap = std::max<size_t>((size_t)n_tiles + 65536, (size_t)((double)rec_cap * 4.0 * ctx->rec_growth) + (size_t)n_tiles * 2);
+            if (int rc = ensure_dev(ctx, ctx->d_rrecs, rec_cap)) return rc;
+            if (!fc.shadow_mode) { if (int rc = ensure_dev(ctx, ctx->d_srecs, rec_cap)) return rc; }
+            if (int rc = ensure_dev(ctx, ctx->d_clipq, clipq_cap)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_tile_count, n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_tile_offset, n_tiles + 2)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_tile_fill, n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_tile_list, list_cap)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_items, std::max<size_t>(1, job.n_items))) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_blocks, std::max<size_t>(1, job.n_blocks))) return rc;
+
+            if (job.n_items)
+            {
+                CK(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items.p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks.p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            }
+            CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_tile_count.p, 0, (size_t)(n_tiles + 1) * sizeof(uint32_t), ctx->stream));
+
+            Geometry g{};
+            g.meshes = ctx->d_meshes.p;
+            g.items = ctx->d_items.p;
+            g.block_table = ctx->d_blocks.p;
+            g.n_blocks = job.n_blocks;
+            g.rrecs = ctx->d_rrecs.p;
+            g.srecs = ctx->d_srecs.p;
+            g.rec_capacity = (uint32_t)std::min<size_t>(ctx->d_rrecs.cap, fc.shadow_mode ? ctx->d_rrecs.cap : ctx->d_srecs.cap);
+            g.rec_count = ctx->d_counters + 0;
+            g.clip_queue = ctx->d_clipq.p;
+            g.clipq_capacity = (uint32_t)ctx->d_clipq.cap;
+            g.clipq_count = ctx->d_counters + 1;
+            g.tile_count = ctx->d_tile_count.p;
+            g.tile_offset = ctx->d_tile_offset.p;
+            g.tile_fill = ctx->d_tile_fill.p;
+            g.tile_list = ctx->d_tile_list.p;
+            g.list_capacity = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFFFull);
+            g.stats = ctx->d_stats;
+
+            record(ctx, 0);
+            launch_geometry(fc, g, ctx->stream, &ctx->launches);
+            record(ctx, 1);
+            launch_binning(fc, g, ctx->stream, &ctx->launches);
+            record(ctx, 2);
+            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, ctx->stream, &ctx->launches);
+            record(ctx, 3);
+            CK(cudaGetLastError());
+
+            if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
+            CK(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const DevStats& st = *ctx->h_stats;
+            if (st.overflow_recs || st.overflow_lists || st.overflow_clipq)
+            {
+                ctx->rec_growth *= 4.0; // arena too small for this scene: grow and re-run the frame
+                continue;
+            }
+            out_stats->tri_input += st.tri_input;
+            out_stats->tri_after_clip += st.tri_after_clip;
+            out_stats->tri_raster += st.tri_raster;
+            out_stats->frag_covered += st.frag_covered;
+            out_stats->frag_shaded += st.frag_shaded;
+            return SHSB_OK;
+        }
+        return fail(ctx, SHSB_E_OUT_OF_MEMORY, "per-frame arena overflow persisted after regrowth");
+    }
+
+    // Stages one draw into the pinned item / block tables.
+    int stage_item(shsb_ctx ctx, std::vector<DevItem>& items, std::vector<uint2>& blocks, uint64_t& tri_cursor,
+                   const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
+                   const float base_color[3], float metallic, float roughness, float ao, uint32_t tex)
+    {
+        DevItem it{};
+        hm::store(model, it.model);
+        hm::normal_matrix(model, it.nrm);
+        it.base_color[0] = base_color[0]; it.base_color[1] = base_color[1]; it.base_color[2] = base_color[2];
+        it.metallic = metallic; it.roughness = roughness; it.ao = ao;
+        it.tex = (tex >= 1 && tex <= ctx->textures.size() && ctx->textures[tex - 1].live) ? tex : 0u;
+        it.mesh = mesh_index;
+        it.tri_offset = (uint32_t)tri_cursor;
+        it.tri_count = mesh.n_indices ? mesh.n_indices / 3 : mesh.n_positions / 3;
+        const uint32_t item_index = (uint32_t)items.size();
+        items.push_back(it);
+        for (uint32_t t = 0; t < it.tri_count; t += 128) blocks.push_back(make_uint2(item_index, t));
+        tri_cursor += it.tri_count;
+        return SHSB_OK;
+    }
+
+    int upload_staging(shsb_ctx ctx, const std::vector<DevItem>& items, const std::vector<uint2>& blocks)
+    {
+        if (int rc = ensure_pinned(ctx, ctx->h_items, std::max<size_t>(1, items.size()))) return rc;
+        if (int rc = ensure_pinned(ctx, ctx->h_blocks, std::max<size_t>(1, blocks.size()))) return rc;
+        // the previous frame's H2D copy out of these pinned buffers must have completed
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!items.empty()) std::memcpy(ctx->h_items.p, items.data(), items.size() * sizeof(DevItem));
+        if (!blocks.empty()) std::memcpy(ctx->h_blocks.p, blocks.data(), blocks.size() * sizeof(uint2));
+        return SHSB_OK;
+    }
+
+    int shader_from_params(const ShsbFrameParams* fp)
+    {
+        int shader = (fp->shading_model == SHSB_SHADING_BLINN_PHONG) ? SHSB_SHADER_BLINN_PHONG : SHSB_SHADER_PBR_MR; // pass_pbr_forward.hpp:100-108
+        if (fp->debug_view == SHSB_DEBUG_ALBEDO) shader = SHSB_SHADER_DEBUG_ALBEDO;
+        else if (fp->debug_view == SHSB_DEBUG_NORMAL) shader = SHSB_SHADER_DEBUG_NORMAL;
+        else if (fp->debug_view == SHSB_DEBUG_DEPTH) shader = SHSB_SHADER_DEBUG_DEPTH;
+        return shader;
+    }
+
+    int ensure_aovs(shsb_ctx ctx, RtSlot* r)
+    {
+        const size_t n = (size_t)r->w * r->h;
+        if (!r->tri_id) CK(cudaMalloc(&r->tri_id, n * 4));
+        if (!r->coverage) CK(cudaMalloc(&r->coverage, n * 4));
+        return SHSB_OK;
+    }
+
+    void fill_camera_sun(FrameConst& fc, const ShsbScene* s)
+    {
+        std::memcpy(fc.viewproj, s->cam_viewproj, 64);
+        std::memcpy(fc.camera_pos, s->cam_pos, 12);
+        std::memcpy(fc.sun_dir, s->sun_dir_ws, 12);
+        std::memcpy(fc.sun_color, s->sun_color, 12);
+        fc.sun_intensity = s->sun_intensity;
+    }
+
+    int forward_common(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt hdr_rt, shsb_rt depth_rt, shsb_rt shadow_rt,
+                       const float* shadow_lvp, int preserve_depth, bool depth_only, shsb_rt ldr_rt, ShsbStats* out_stats)
+    {
+        if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
+        if (scene->n_items && !scene->items) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene->items is null");
+        RtSlot* hdr = depth_only ? nullptr : get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+        if (!depth_only && !hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR");
+        RtSlot* dm = depth_rt ? get_rt(ctx, depth_rt, SHSB_RT_DEPTH_MOTION) : nullptr;
+        if (depth_rt && !dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth_motion_rt is not a live RT_ColorDepthMotion");
+        if (depth_only && !dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth prepass needs a depth target");
+        // the reference ignores a motion RT whose size differs from the HDR target (pass_pbr_forward.hpp:87,111)
+        if (hdr && dm && (dm->w != hdr->w || dm->h != hdr->h)) dm = nullptr;
+        const int W = hdr ? hdr->w : dm->w, H = hdr ? hdr->h : dm->h;
+        RtSlot* ldr = ldr_rt ? get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR) : nullptr;
+        if (ldr_rt && (!ldr || ldr->w != W || ldr->h != H)) return fail(ctx, SHSB_E_INVALID_HANDLE, "ldr_rt is not a live RT_ColorLDR of the HDR target's size");
+
+        FrameJob job;
+        FrameConst& fc = job.fc;
+        fill_camera_sun(fc, scene);
+        fc.W = W; fc.H = H;
+        fc.zn = dm ? dm->zn : 0.1f;
+        fc.zf = dm ? dm->zf : 1000.0f;
+        fc.shader_id = depth_only ? SHSB_SHADER_DEPTH_ONLY : shader_from_params(fp);
+        fc.cull_mode = fp->cull_mode;
+        fc.front_face_ccw = fp->front_face_ccw;
+        fc.has_depth = dm ? 1 : 0;
+        fc.linear_depth = (dm && (dm->zf > dm->zn + 1e-6f)) ? 1 : 0;
+        fc.load_depth = (!depth_only && preserve_depth) ? 1 : 0;
+        fc.load_color = 0;
+        fc.write_aovs = fp->write_aovs;
+        fc.shadow_mode = 0;
+
+        RtSlot* sh = (!depth_only && shadow_rt) ? get_rt(ctx, shadow_rt, SHSB_RT_SHADOW) : nullptr;
+        if (fp->shadow_enable && sh && shadow_lvp) // pass_pbr_forward.hpp:185-194
+        {
+            fc.shadow_map = sh->depth;
+            fc.shadow_w = sh->w; fc.shadow_h = sh->h;
+            std::memcpy(fc.light_viewproj, shadow_lvp, 64);
+            fc.bias_const = fp->shadow_bias_const;
+            fc.bias_slope = fp->shadow_bias_slope;
+            fc.pcf_radius = fp->shadow_pcf_radius;
+            fc.pcf_step = fp->shadow_pcf_step;
+            fc.shadow_strength = fp->shadow_strength;
+        }
+        if (!depth_only && fp->light_culling && ctx->n_lights > 0)
+        {
+            if (!ctx->lists_valid || ctx->lists_w != (uint32_t)W || ctx->lists_h != (uint32_t)H)
+                return fail(ctx, SHSB_E_INVALID_ARGUMENT, "light_culling is on but shsb_light_cull has not been run for a %dx%d viewport", W, H);
+            fc.forward_plus = 1;
+            fc.lights = ctx->d_lights.p;
+            fc.n_lights = ctx->n_lights;
+            fc.tile_counts = ctx->d_tile_counts.p;
+            fc.tile_indices = ctx->d_tile_indices.p;
+            fc.light_tile_size = ctx->lists_ts;
+            fc.max_per_tile = ctx->lists_max;
+            fc.light_tiles_x = (W + ctx->lists_ts - 1) / ctx->lists_ts;
+            fc.light_tiles_y = (H + ctx->lists_ts - 1) / ctx->lists_ts;
+        }
+        if (ldr)
+        {
+            fc.fuse_tonemap = 1;
+            fc.exposure = std::max(0.0001f, fp->exposure);            // pass_tonemap.hpp:49-50
+            fc.inv_gamma = 1.0f / std::max(0.001f, fp->gamma);
+        }
+
+        job.fb.hdr = hdr ? (float4*)hdr->color : nullptr;
+        job.fb.depth = dm ? dm->depth : nullptr;
+        job.fb.ldr = ldr ? (uchar4*)ldr->color : nullptr;
+        if (fp->write_aovs)
+        {
+            RtSlot* host = hdr ? hdr : dm;
+            if (int rc = ensure_aovs(ctx, host)) return rc;
+            job.fb.aov_tri_id = host->tri_id;
+            job.fb.aov_coverage = host->coverage;
+        }
+
+        std::vector<DevItem> items;
+        std::vector<uint2> blocks;
+        items.reserve(scene->n_items);
+        uint64_t tri_cursor = 0;
+        for (uint32_t i = 0; i < scene->n_items; ++i)
+        {
+            const ShsbRenderItem& it = scene->items[i];
+            if (!it.visible) continue;
+            const MeshSlot* mesh = get_mesh(ctx, it.mesh);
+            if (!mesh || mesh->n_positions == 0 || mesh->n_indices == 0) continue; // MeshData::empty(), resources/mesh.hpp:32-35
+            const hm::mat4f model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
+            const float def_color[3] = {0.8f, 0.5f, 0.2f}; // pass_pbr_forward.hpp:179-184
+            if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex);
+            else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u);
+        }
+        if (int rc = upload_staging(ctx, items, blocks)) return rc;
+        job.n_items = (uint32_t)items.size();
+        job.n_blocks = (uint32_t)blocks.size();
+        job.n_src_tris = tri_cursor;
+        return run_frame(ctx, job, out_stats);
+    }
+}
+
+// ======================================================================================== C ABI
+extern "C" {
+
+SHSB_API const char* shsb_version(void)
+{
+    return "shsb 0.1 (sm_100a; geometry/light-cull: --fmad=false; raster: exact intrinsics)";
+}
+
+SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
+{
+    if (!out_ctx) return SHSB_E_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_ordinal < 0 || device_ordinal >= n)
+    {
+        cudaGetLastError();
+        return SHSB_E_NO_DEVICE;
+    }
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return SHSB_E_NO_DEVICE;
+    shsb_ctx ctx = new shsb_context_t();
+    ctx->device = device_ordinal;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counters, 4 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_stats, sizeof(DevStats)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
+    for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    if (ok)
+    {
+        // srgb_to_linear_rgb (shader/builtin_shaders.hpp:25-31) evaluated by the host libm, as the reference does per tap
+        float lut[256];
+        for (int i = 0; i < 256; ++i) lut[i] = std::pow((float)i / 255.0f, 2.2f);
+        ok = cudaMemcpy(ctx->d_srgb_lut, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok)
+    {
+        delete ctx;
+        return SHSB_E_CUDA;
+    }
+    *out_ctx = ctx;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& m : ctx->meshes) { cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.indices); }
+    for (auto& t : ctx->textures) cudaFree(t.texels);
+    for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
+    cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
+    cudaFree(ctx->d_lights.p); cudaFree(ctx->d_light_visible.p); cudaFree(ctx->d_tile_counts.p); cudaFree(ctx->d_tile_indices.p);
+    cudaFree(ctx->d_items.p); cudaFree(ctx->d_blocks.p); cudaFree(ctx->d_rrecs.p); cudaFree(ctx->d_srecs.p); cudaFree(ctx->d_clipq.p);
+    cudaFree(ctx->d_tile_count.p); cudaFree(ctx->d_tile_offset.p); cudaFree(ctx->d_tile_fill.p); cudaFree(ctx->d_tile_list.p);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_stats);
+    cudaFreeHost(ctx->h_stats); cudaFreeHost(ctx->h_items.p); cudaFreeHost(ctx->h_blocks.p);
+    for (int i = 0; i < NUM_STAGE_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SHSB_OK;
+}
+
+SHSB_API const char* shsb_last_error_string(shsb_ctx ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+SHSB_API int32_t shsb_sync(shsb_ctx ctx)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_stream(shsb_ctx ctx, void** out_stream)
+{
+    if (!ctx || !out_stream) return SHSB_E_INVALID_ARGUMENT;
+    *out_stream = (void*)ctx->stream;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_launch_count(shsb_ctx ctx, uint64_t* out_count)
+{
+    if (!ctx || !out_count) return SHSB_E_INVALID_ARGUMENT;
+    *out_count = ctx->launches;
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- resources
+SHSB_API int32_t shsb_mesh_upload(shsb_ctx ctx, const float* positions, uint32_t n_positions, const float* normals, uint32_t n_normals,
+                                  const float* uvs, uint32_t n_uvs, const uint32_t* indices, uint32_t n_indices, shsb_mesh* out_mesh)
+{
+    if (!ctx || !out_mesh) return SHSB_E_INVALID_ARGUMENT;
+    if (n_positions && !positions) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "positions is null");
+    if ((n_normals && !normals) || (n_uvs && !uvs) || (n_indices && !indices)) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null attribute stream with non-zero count");
+    CK(cudaSetDevice(ctx->device));
+    MeshSlot m;
+    m.live = true;
+    m.n_positions = n_positions; m.n_normals = n_normals; m.n_uvs = n_uvs; m.n_indices = n_indices;
+    auto up = [&](auto** dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!bytes) { *dst = nullptr; return cudaSuccess; }
+        cudaError_t e = cudaMalloc((void**)dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    CK(up(&m.positions, positions, (size_t)n_positions * 12));
+    CK(up(&m.normals, normals, (size_t)n_normals * 12));
+    CK(up(&m.uvs, uvs, (size_t)n_uvs * 8));
+    CK(up(&m.indices, indices, (size_t)n_indices * 4));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_positions)
+    {
+        hm::vec3f mn{3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx{-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+        for (uint32_t v = 0; v < n_positions; ++v)
+        {
+            const float* p = positions + (size_t)v * 3;
+            mn = {hm::gmin(mn.x, p[0]), hm::gmin(mn.y, p[1]), hm::gmin(mn.z, p[2])};
+            mx = {hm::gmax(mx.x, p[0]), hm::gmax(mx.y, p[1]), hm::gmax(mx.z, p[2])};
+        }
+        m.bmin = mn; m.bmax = mx;
+    }
+    ctx->meshes.push_back(m);
+    ctx->mesh_table_dirty = true;
+    *out_mesh = (shsb_mesh)ctx->meshes.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    MeshSlot* m = get_mesh(ctx, mesh);
+    if (!m) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(m->positions); cudaFree(m->normals); cudaFree(m->uvs); cudaFree(m->indices);
+    *m = MeshSlot{};
+    ctx->mesh_table_dirty = true;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_texture_upload(shsb_ctx ctx, const uint8_t* rgba, int32_t w, int32_t h, shsb_tex* out_tex)
+{
+    if (!ctx || !out_tex || !rgba || w <= 0 || h <= 0) return ctx ? fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad texture arguments") : SHSB_E_INVALID_ARGUMENT;
+    TexSlot t;
+    t.live = true; t.w = w; t.h = h;
+    CK(cudaMalloc(&t.texels, (size_t)w * h * 4));
+    CK(cudaMemcpyAsync(t.texels, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->textures.push_back(t);
+    ctx->tex_table_dirty = true;
+    *out_tex = (shsb_tex)ctx->textures.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (tex == 0 || tex > ctx->textures.size() || !ctx->textures[tex - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", tex);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->textures[tex - 1].texels);
+    ctx->textures[tex - 1] = TexSlot{};
+    ctx->tex_table_dirty = true;
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- render targets
+SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h, float zn, float zf, shsb_rt* out_rt)
+{
+    if (!ctx || !out_rt) return SHSB_E_INVALID_ARGUMENT;
+    if (w <= 0 || h <= 0 || kind < SHSB_RT_COLOR_HDR || kind > SHSB_RT_SHADOW) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad render-target description");
+    RtSlot r;
+    r.live = true; r.kind = kind; r.w = w; r.h = h; r.zn = zn; r.zf = zf;
+    const size_t n = (size_t)w * h;
+    if (kind == SHSB_RT_COLOR_HDR)
+    {
+        CK(cudaMalloc(&r.color, n * 16));
+        launch_fill_f4((float4*)r.color, make_float4(0, 0, 0, 1), n, ctx->stream, &ctx->launches); // RT_ColorHDR ctor, rt_types.hpp:85
+    }
+    else if (kind == SHSB_RT_COLOR_LDR)
+    {
+        CK(cudaMalloc(&r.color, n * 4));
+        launch_fill_u32((uint32_t*)r.color, 0xFF000000u, n, ctx->stream, &ctx->launches);          // {0,0,0,255}, rt_types.hpp:68
+    }
+    else if (kind == SHSB_RT_DEPTH_MOTION)
+    {
+        CK(cudaMalloc(&r.depth, n * 4));
+        CK(cudaMalloc(&r.motion, n * 8));
+        launch_fill_u32((uint32_t*)r.depth, 0x3F800000u, n, ctx->stream, &ctx->launches);          // depth 1.0, rt_types.hpp:144
+        CK(cudaMemsetAsync(r.motion, 0, n * 8, ctx->stream));
+    }
+    else
+    {
+        CK(cudaMalloc(&r.depth, n * 4));
+        launch_fill_u32((uint32_t*)r.depth, 0x3F800000u, n, ctx->stream, &ctx->launches);          // rt_shadow.hpp:26-29
+    }
+    CK(cudaGetLastError());
+    ctx->rts.push_back(r);
+    *out_rt = (shsb_rt)ctx->rts.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(r->color); cudaFree(r->depth); cudaFree(r->motion); cudaFree(r->tri_id); cudaFree(r->coverage);
+    *r = RtSlot{};
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* value)
+{
+    if (!ctx || !value) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t bytes = plane_bytes(*r, plane, &p);
+    if (!bytes) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    const size_t n = (size_t)r->w * r->h;
+    if (bytes == n * 16) { float4 v; std::memcpy(&v, value, 16); launch_fill_f4((float4*)p, v, n, ctx->stream, &ctx->launches); }
+    else if (bytes == n * 8) { uint32_t v[2]; std::memcpy(v, value, 8); if (v[0] == v[1]) launch_fill_u32((uint32_t*)p, v[0], n * 2, ctx->stream, &ctx->launches); else return fail(ctx, SHSB_E_UNSUPPORTED, "motion clear needs x == y"); }
+    else { uint32_t v; std::memcpy(&v, value, 4); launch_fill_u32((uint32_t*)p, v, n, ctx->stream, &ctx->launches); }
+    CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* src, size_t bytes)
+{
+    if (!ctx || !src) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t want = plane_bytes(*r, plane, &p);
+    if (!want) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
+    CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst, size_t bytes)
+{
+    if (!ctx || !dst) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t want = plane_bytes(*r, plane, &p);
+    if (!want) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
+    CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_device_ptr(shsb_ctx ctx, shsb_rt rt, int32_t plane, void** out_ptr, size_t* out_bytes)
+{
+    if (!ctx || !out_ptr) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t bytes = plane_bytes(*r, plane, &p);
+    if (!bytes) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    *out_ptr = p;
+    if (out_bytes) *out_bytes = bytes;
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- host helpers
+SHSB_API int32_t shsb_model_from_transform(const ShsbTransform* tr, float out_model[16])
+{
+    if (!tr || !out_model) return SHSB_E_INVALID_ARGUMENT;
+    hm::store(hm::model_from_transform(tr->pos, tr->rot_euler, tr->scl), out_model);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_camera_viewproj(const float eye[3], const float target[3], const float up[3],
+                                      float fovy_radians, float aspect, float znear, float zfar, float out_viewproj[16])
+{
+    if (!eye || !target || !up || !out_viewproj) return SHSB_E_INVALID_ARGUMENT;
+    const hm::mat4f view = hm::look_at_lh({eye[0], eye[1], eye[2]}, {target[0], target[1], target[2]}, {up[0], up[1], up[2]});
+    const hm::mat4f proj = hm::perspective_lh_no(fovy_radians, aspect, znear, zfar);
+    hm::store(hm::mul(proj, view), out_viewproj);
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- passes
+SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh_h, int32_t shader_id, const ShsbUniforms* u,
+                                     shsb_rt hdr_rt, shsb_rt depth_motion_rt, const ShsbRasterCfg* cfg, ShsbStats* out_stats)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!u || !cfg) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "uniforms / config are null");
+    if (shader_id < 0 || shader_id >= SHSB_SHADER_COUNT)
+        return fail(ctx, SHSB_E_UNSUPPORTED_SHADER, "shader id %d is not a builtin program; host std::function shaders cannot run on the device", shader_id);
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* hdr = get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+    if (!hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR"); // rasterizer.hpp:190
+    RtSlot* dm = depth_motion_rt ? get_rt(ctx, depth_motion_rt, SHSB_RT_DEPTH_MOTION) : nullptr;
+    if (depth_motion_rt && !dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth_motion_rt is not a live RT_ColorDepthMotion");
+    if (dm && (dm->w != hdr->w || dm->h != hdr->h)) return fail(ctx, SHSB_E_SIZE_MISMATCH, "depth target size differs from the HDR target");
+    const MeshSlot* mesh = get_mesh(ctx, mesh_h);
+    if (!mesh) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh_h);
+    if (mesh->n_positions == 0) return SHSB_OK; // rasterizer.hpp:191
+
+    FrameJob job;
+    FrameConst& fc = job.fc;
+    std::memcpy(fc.viewproj, u->viewproj, 64);
+    std::memcpy(fc.camera_pos, u->camera_pos, 12);
+    std::memcpy(fc.sun_dir, u->light_dir_ws, 12);
+    std::memcpy(fc.sun_color, u->light_color, 12);
+    fc.sun_intensity = u->light_intensity;
+    fc.W = hdr->w; fc.H = hdr->h;
+    fc.zn = dm ? dm->zn : 0.1f;
+    fc.zf = dm ? dm->zf : 1000.0f;
+    fc.shader_id = shader_id;
+    fc.cull_mode = cfg->cull_mode;
+    fc.front_face_ccw = cfg->front_face_ccw;
+    fc.has_depth = dm ? 1 : 0;
+    fc.linear_depth = (dm && (dm->zf > dm->zn + 1e-6f)) ? 1 : 0;
+    fc.load_depth = 1;
+    fc.load_color = 1;
+    fc.write_aovs = cfg->write_aovs;
+    RtSlot* sh = u->shadow_map ? get_rt(ctx, u->shadow_map, SHSB_RT_SHADOW) : nullptr;
+    if (u->shadow_map && !sh) return fail(ctx, SHSB_E_INVALID_HANDLE, "uniforms.shadow_map is not a live RT_ShadowDepth");
+    if (sh)
+    {
+        fc.shadow_map = sh->depth;
+        fc.shadow_w = sh->w; fc.shadow_h = sh->h;
+        std::memcpy(fc.light_viewproj, u->light_viewproj, 64);
+        fc.bias_const = u->shadow_bias_const;
+        fc.bias_slope = u->shadow_bias_slope;
+        fc.pcf_radius = u->shadow_pcf_radius;
+        fc.pcf_step = u->shadow_pcf_step;
+        fc.shadow_strength = u->shadow_strength;
+    }
+    job.fb.hdr = (float4*)hdr->color;
+    job.fb.depth = dm ? dm->depth : nullptr;
+    if (cfg->write_aovs)
+    {
+        if (int rc = ensure_aovs(ctx, hdr)) return rc;
+        job.fb.aov_tri_id = hdr->tri_id;
+        job.fb.aov_coverage = hdr->coverage;
+    }
+    std::vector<DevItem> items;
+    std::vector<uint2> blocks;
+    uint64_t tri_cursor = 0;
+    stage_item(ctx, items, blocks, tri_cursor, hm::load(u->model), *mesh, mesh_h - 1, u->base_color, u->metallic, u->roughness, u->ao, u->base_color_tex);
+    if (int rc = upload_staging(ctx, items, blocks)) return rc;
+    job.n_items = 1;
+    job.n_blocks = (uint32_t)blocks.size();
+    job.n_src_tris = tri_cursor;
+    return run_frame(ctx, job, out_stats);
+}
+
+SHSB_API int32_t shsb_pass_pbr_forward(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt hdr_rt, shsb_rt depth_motion_rt,
+                                       shsb_rt shadow_rt, const float* shadow_light_viewproj, int32_t preserve_existing_depth, ShsbStats* out_stats)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    if (out_stats) *out_stats = ShsbStats{}; // ctx.debug.tri_* = 0, pass_pbr_forward.hpp:53-55
+    return forward_common(ctx, scene, fp, hdr_rt, depth_motion_rt, shadow_rt, shadow_light_viewproj, preserve_existing_depth, false, 0, out_stats);
+}
+
+SHSB_API int32_t shsb_pass_depth_prepass(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt depth_motion_rt, ShsbStats* out_stats)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    if (out_stats) *out_stats = ShsbStats{};
+    return forward_common(ctx, scene, fp, 0, depth_motion_rt, 0, nullptr, 0, true, 0, out_stats);
+}
+
+SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt hdr_rt, shsb_rt depth_motion_rt,
+                                         shsb_rt ldr_rt, ShsbStats* out_stats)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* hdr = get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+    if (!hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR");
+    if (fp->light_culling && ctx->n_lights > 0)
+    {
+        if (int rc = shsb_light_cull(ctx, scene->cam_viewproj, (uint32_t)hdr->w, (uint32_t)hdr->h, std::max(1u, fp->tile_size), std::max(1u, fp->max_lights_per_tile))) return rc;
+    }
+    if (out_stats) *out_stats = ShsbStats{};
+    return forward_common(ctx, scene, fp, hdr_rt, depth_motion_rt, 0, nullptr, 0, false, ldr_rt, out_stats);
+}
+
+SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt shadow_rt, float out_light_viewproj[16])
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* sh = get_rt(ctx, shadow_rt, SHSB_RT_SHADOW);
+    if (!sh) return fail(ctx, SHSB_E_INVALID_HANDLE, "shadow_rt is not a live RT_ShadowDepth");
+    if (!fp->shadow_enable) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "pass.shadow.enable is false (pass_shadow_map.hpp:50)");
+
+    // scene AABB over the transformed corners of each caster's local bounds, pass_shadow_map.hpp:80-131
+    hm::Aabb box;
+    bool any = false;
+    std::vector<DevItem> items;
+    std::vector<uint2> blocks;
+    uint64_t tri_cursor = 0;
+    const float white[3] = {1, 1, 1};
+    for (uint32_t i = 0; i < scene->n_items; ++i)
+    {
+        const ShsbRenderItem& it = scene->items[i];
+        if (!it.visible || !it.casts_shadow) continue;
+        const MeshSlot* mesh = get_mesh(ctx, it.mesh);
+        if (mesh && mesh->n_positions)
+        {
+            const hm::mat4f model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
+            for (int c = 0; c < 8; ++c)
+            {
+                const hm::vec4f p = hm::mul_v(model, {(c & 1) ? mesh->bmax.x : mesh->bmin.x, (c & 2) ? mesh->bmax.y : mesh->bmin.y, (c & 4) ? mesh->bmax.z : mesh->bmin.z, 1.0f});
+                box.expand({p.x, p.y, p.z});
+            }
+            stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, white, 0, 0, 1, 0);
+        }
+        else box.expand({it.tr.pos[0], it.tr.pos[1], it.tr.pos[2]});
+        any = true;
+    }
+    if (!any) { box.expand({-1, -1, -1}); box.expand({1, 1, 1}); }
+    const hm::mat4f lvp = hm::light_camera_viewproj({scene->sun_dir_ws[0], scene->sun_dir_ws[1], scene->sun_dir_ws[2]}, box, 10.0f, (unsigned)std::max(sh->w, 1));
+    if (out_light_viewproj) hm::store(lvp, out_light_viewproj);
+
+    FrameJob job;
+    FrameConst& fc = job.fc;
+    hm::store(lvp, fc.viewproj);
+    fc.W = sh->w; fc.H = sh->h;
+    fc.shadow_mode = 1;
+    fc.shader_id = SHSB_SHADER_DEPTH_ONLY;
+    fc.load_depth = 0; // shadow->clear(1.0f), pass_shadow_map.hpp:55
+    job.fb.depth = sh->depth;
+    if (int rc = upload_staging(ctx, items, blocks)) return rc;
+    job.n_items = (uint32_t)items.size();
+    job.n_blocks = (uint32_t)blocks.size();
+    job.n_src_tris = tri_cursor;
+    ShsbStats st{};
+    return run_frame(ctx, job, &st);
+}
+
+SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt, float exposure, float gamma)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* hdr = get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+    RtSlot* ldr = get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR);
+    if (!hdr || !ldr) return fail(ctx, SHSB_E_INVALID_HANDLE, "tonemap needs a live RT_ColorHDR and RT_ColorLDR");
+    if (hdr->w != ldr->w || hdr->h != ldr->h) return fail(ctx, SHSB_E_SIZE_MISMATCH, "tonemap targets differ in size"); // reference crops to min(w,h); not needed on this path
+    record(ctx, 4);
+    launch_tonemap((const float4*)hdr->color, (uchar4*)ldr->color, hdr->w * hdr->h, std::max(0.0001f, exposure), 1.0f / std::max(0.001f, gamma), ctx->stream, &ctx->launches);
+    record(ctx, 5);
+    CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t n_lights)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (n_lights && !records) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "records is null");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_dev(ctx, ctx->d_lights, std::max(1u, n_lights))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_light_visible, std::max(1u, n_lights))) return rc;
+    if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights.p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_lights = n_lights;
+    ctx->lists_valid = false;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!view_proj || vw == 0 || vh == 0 || ts == 0 || max_per_tile == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad light-cull arguments");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t tiles = ((vw + ts - 1) / ts) * ((vh + ts - 1) / ts);
+    if (int rc = ensure_dev(ctx, ctx->d_tile_counts, tiles)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_tile_indices, (size_t)tiles * max_per_tile)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_lights, 1)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_light_visible, 1)) return rc;
+    const hm::mat4f vp = hm::load(view_proj);
+    const hm::mat4f inv = hm::inverse(vp);
+    float planes[24];
+    hm::frustum_planes(vp, planes);
+    record(ctx, 4);
+    launch_light_cull(ctx->d_lights.p, ctx->n_lights, planes, &inv.col[0].x, vw, vh, ts, max_per_tile, ctx->d_light_visible.p,
+                      ctx->d_tile_counts.p, ctx->d_tile_indices.p, ctx->stream, &ctx->launches);
+    record(ctx, 5);
+    CK(cudaGetLastError());
+    ctx->lists_w = vw; ctx->lists_h = vh; ctx->lists_ts = ts; ctx->lists_max = max_per_tile;
+    ctx->lists_valid = true;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!ctx->lists_valid) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile light lists: call shsb_light_cull first");
+    const size_t tiles = (size_t)((ctx->lists_w + ctx->lists_ts - 1) / ctx->lists_ts) * ((ctx->lists_h + ctx->lists_ts - 1) / ctx->lists_ts);
+    if (counts && n_counts != tiles) return fail(ctx, SHSB_E_SIZE_MISMATCH, "counts has %zu entries, lists have %zu tiles", n_counts, tiles);
+    if (indices && n_indices != tiles * ctx->lists_max) return fail(ctx, SHSB_E_SIZE_MISMATCH, "indices has %zu entries, expected %zu", n_indices, tiles * ctx->lists_max);
+    if (counts) CK(cudaMemcpyAsync(counts, ctx->d_tile_counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices) CK(cudaMemcpyAsync(indices, ctx->d_tile_indices.p, tiles * ctx->lists_max * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
+{
+    if (!ctx || !out_ms) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) out_ms[i] = 0.0f;
+    auto span = [&](int a, int b) -> float {
+        float ms = 0.0f;
+        if (ctx->ev_valid[a] && ctx->ev_valid[b] && cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) == cudaSuccess) return ms;
+        cudaGetLastError();
+        return 0.0f;
+    };
+    out_ms[0] = span(0, 1);
+    out_ms[1] = span(1, 2);
+    out_ms[2] = span(2, 3);
+    out_ms[3] = span(4, 5); // light cull or standalone tonemap, whichever ran last
+    out_ms[5] = span(0, 3);
+    return SHSB_OK;
+}
+
+} // extern "C"

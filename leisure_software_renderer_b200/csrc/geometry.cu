@@ -1,0 +1,407 @@
+// geometry.cu -- K1: vertex transform, frustum clip, triangle setup.
+//
+// Replaces the serial per-triangle front half of rasterize_mesh (sw_render/rasterizer.hpp:206-328):
+// VS x3 (builtin make_default_vertex_out, shader/builtin_shaders.hpp:87-103), trivially-inside test
+// (:232-249), Sutherland-Hodgman clip against the 6 homogeneous planes (:69-164), fan triangulation
+// (:253-258), NDC -> screen map (:260-269), signed-area cull (:271-278), clamped bbox (:280-290) and the
+// 1/w pre-multiplication of attributes (:292-328) -- one CUDA thread per source triangle, all draws of a
+// frame in one launch.  Set-up triangles are appended (warp-aggregated atomic) to the RasterRec/ShadeRec
+// arrays; their position in memory is arbitrary because every record carries its draw-order key and the
+// tile kernel resolves visibility by (depth, key), which reproduces "earliest draw wins a depth tie"
+// (rasterizer.hpp:359) without ordered lists.
+//
+// Compiled with --fmad=false AND written with the exact helpers: every expression here decides bits of
+// coverage, depth or clip topology.
+#include "shsb_dev.cuh"
+
+namespace shsb
+{
+    namespace
+    {
+        constexpr int GEOM_THREADS = 128;
+        constexpr int NATTR = 8;      // WorldPos.xyz, NormalWS.xyz, UV0.xy (the varyings the builtin programs read)
+        constexpr int MAX_POLY = 10;  // a triangle clipped by 6 planes has at most 9 corners
+
+        struct Corner
+        {
+            float clip[4];
+            float a[NATTR];
+        };
+
+        __device__ __forceinline__ Corner run_vs(const DevItem& it, const DevMesh& mesh, uint32_t idx, const FrameConst& fc, bool varyings)
+        {
+            const float px = mesh.positions[(size_t)idx * 3 + 0];
+            const float py = mesh.positions[(size_t)idx * 3 + 1];
+            const float pz = mesh.positions[(size_t)idx * 3 + 2];
+            Corner o;
+            const float4 wp = xmat4_mul(it.model, px, py, pz, 1.0f);
+            const float4 cl = xmat4_mul(fc.viewproj, wp.x, wp.y, wp.z, wp.w);
+            o.clip[0] = cl.x; o.clip[1] = cl.y; o.clip[2] = cl.z; o.clip[3] = cl.w;
+            if (varyings)
+            {
+                float nx = 0.0f, ny = 1.0f, nz = 0.0f, tu = 0.0f, tv = 0.0f; // read_v defaults, rasterizer.hpp:196-202
+                if (idx < mesh.n_normals) { nx = mesh.normals[(size_t)idx * 3 + 0]; ny = mesh.normals[(size_t)idx * 3 + 1]; nz = mesh.normals[(size_t)idx * 3 + 2]; }
+                if (idx < mesh.n_uvs) { tu = mesh.uvs[(size_t)idx * 2 + 0]; tv = mesh.uvs[(size_t)idx * 2 + 1]; }
+                const float* n = it.nrm;
+                F3 nn;
+                nn.x = xadd(xadd(xmul(n[0], nx), xmul(n[3], ny)), xmul(n[6], nz));
+                nn.y = xadd(xadd(xmul(n[1], nx), xmul(n[4], ny)), xmul(n[7], nz));
+                nn.z = xadd(xadd(xmul(n[2], nx), xmul(n[5], ny)), xmul(n[8], nz));
+                nn = xnormalize3(nn);
+                o.a[0] = wp.x; o.a[1] = wp.y; o.a[2] = wp.z;
+                o.a[3] = nn.x; o.a[4] = nn.y; o.a[5] = nn.z;
+                o.a[6] = tu; o.a[7] = tv;
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < NATTR; ++i) o.a[i] = 0.0f;
+            }
+            return o;
+        }
+
+        __device__ __forceinline__ bool corner_inside(const Corner& c)
+        {
+            const float x = c.clip[0], y = c.clip[1], z = c.clip[2], w = c.clip[3];
+            if (!(w > 0.0f)) return false;
+            return (x >= -w && x <= w) && (y >= -w && y <= w) && (z >= -w && z <= w);
+        }
+
+        __device__ __forceinline__ float plane_dist(const Corner& c, int plane)
+        {
+            switch (plane)
+            {
+            case 0: return xadd(c.clip[0], c.clip[3]);
+            case 1: return xsub(c.clip[3], c.clip[0]);
+            case 2: return xadd(c.clip[1], c.clip[3]);
+            case 3: return xsub(c.clip[3], c.clip[1]);
+            case 4: return xadd(c.clip[2], c.clip[3]);
+            default: return xsub(c.clip[3], c.clip[2]);
+            }
+        }
+
+        __device__ __forceinline__ float xmix(float a, float b, float t, float one_minus_t) { return xadd(xmul(a, one_minus_t), xmul(b, t)); }
+
+        __device__ Corner lerp_corner(const Corner& a, const Corner& b, float t)
+        {
+            Corner o;
+            const float omt = xsub(1.0f, t);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o.clip[i] = xmix(a.clip[i], b.clip[i], t, omt);
+#pragma unroll
+            for (int i = 0; i < NATTR; ++i) o.a[i] = xmix(a.a[i], b.a[i], t, omt);
+            return o;
+        }
+
+        // Projects one fan triangle, applies the cull / bbox rules and, if it survives, fills the two records.
+        // Returns: bit0 = counted in tri_raster, bit1 = record must be emitted.
+        __device__ __forceinline__ int setup_triangle(const Corner& c0, const Corner& c1, const Corner& c2, const FrameConst& fc,
+                                                      uint32_t key, uint32_t item_index, RasterRec& rr, ShadeRec& sr)
+        {
+            const Corner* c[3] = {&c0, &c1, &c2};
+            float sx[3], sy[3];
+            const float fw1 = (float)(fc.W - 1), fh1 = (float)(fc.H - 1);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+                const float w = c[j]->clip[3];
+                const float nx = xdiv(c[j]->clip[0], w), ny = xdiv(c[j]->clip[1], w), nz = xdiv(c[j]->clip[2], w);
+                if (!isfinite(nx) || !isfinite(ny) || !isfinite(nz)) return 0;
+                sx[j] = xmul(xadd(xmul(nx, 0.5f), 0.5f), fw1);
+                sy[j] = xmul(xadd(xmul(ny, 0.5f), 0.5f), fh1);
+            }
+            const float v0x = xsub(sx[1], sx[0]), v0y = xsub(sy[1], sy[0]);
+            const float v1x = xsub(sx[2], sx[0]), v1y = xsub(sy[2], sy[0]);
+            const float area2 = xsub(xmul(v0x, v1y), xmul(v0y, v1x)); // == barycentric den (v1x*v0y commutes)
+            if (fabsf(area2) < 1e-10f) return 0;
+            const bool ccw = area2 > 0.0f;
+            const bool is_front = (ccw == (fc.front_face_ccw != 0));
+            if (fc.cull_mode == 1 && !is_front) return 0;
+            if (fc.cull_mode == 2 && is_front) return 0;
+
+            const float minxf = fminf(fminf(sx[0], sx[1]), sx[2]), maxxf = fmaxf(fmaxf(sx[0], sx[1]), sx[2]);
+            const float minyf = fminf(fminf(sy[0], sy[1]), sy[2]), maxyf = fmaxf(fmaxf(sy[0], sy[1]), sy[2]);
+            const int minx = max(0, (int)floorf(minxf));
+            const int maxx = min(fc.W - 1, (int)ceilf(maxxf));
+            const int miny = max(0, (int)floorf(minyf));
+            const int maxy = min(fc.H - 1, (int)ceilf(maxyf));
+            if (minx > maxx || miny > maxy) return 0;
+            if (fabsf(area2) < 1e-8f) return 1; // barycentric_2d returns (-1,-1,-1): counted, covers nothing (rasterizer.hpp:173)
+
+            float iw[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) iw[j] = xrcp(c[j]->clip[3]);
+            rr.ax = sx[0]; rr.ay = sy[0];
+            rr.v0x = v0x; rr.v0y = v0y; rr.v1x = v1x; rr.v1y = v1y;
+            rr.inv_den = xrcp(area2);
+            rr.iw0 = iw[0]; rr.iw1 = iw[1]; rr.iw2 = iw[2];
+            rr.zw0 = xmul(c0.clip[2], iw[0]); rr.zw1 = xmul(c1.clip[2], iw[1]); rr.zw2 = xmul(c2.clip[2], iw[2]);
+            rr.bbox_x = (uint32_t)minx | ((uint32_t)maxx << 16);
+            rr.bbox_y = (uint32_t)miny | ((uint32_t)maxy << 16);
+            rr.key = key + 1u;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+                sr.wp[j][0] = xmul(c[j]->a[0], iw[j]); sr.wp[j][1] = xmul(c[j]->a[1], iw[j]); sr.wp[j][2] = xmul(c[j]->a[2], iw[j]);
+                sr.n[j][0] = xmul(c[j]->a[3], iw[j]); sr.n[j][1] = xmul(c[j]->a[4], iw[j]); sr.n[j][2] = xmul(c[j]->a[5], iw[j]);
+                sr.uv[j][0] = xmul(c[j]->a[6], iw[j]); sr.uv[j][1] = xmul(c[j]->a[7], iw[j]);
+            }
+            sr.item = item_index;
+            return 3;
+        }
+
+        __device__ __forceinline__ void store_records(const Geometry& g, uint32_t slot, const RasterRec& rr, const ShadeRec& sr)
+        {
+            float4* d = reinterpret_cast<float4*>(g.rrecs + slot);
+            const float4* s = reinterpret_cast<const float4*>(&rr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = s[i];
+            float4* d2 = reinterpret_cast<float4*>(g.srecs + slot);
+            const float4* s2 = reinterpret_cast<const float4*>(&sr);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) d2[i] = s2[i]; // 25 words used; the pad tail is never read
+        }
+
+        __device__ __forceinline__ void block_add_stats(DevStats* st, unsigned tri_input, unsigned after_clip, unsigned raster)
+        {
+            // warp reduce, then one atomic per warp and counter
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                tri_input += __shfl_down_sync(0xffffffffu, tri_input, o);
+                after_clip += __shfl_down_sync(0xffffffffu, after_clip, o);
+                raster += __shfl_down_sync(0xffffffffu, raster, o);
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                if (tri_input) atomicAdd(&st->tri_input, (unsigned long long)tri_input);
+                if (after_clip) atomicAdd(&st->tri_after_clip, (unsigned long long)after_clip);
+                if (raster) atomicAdd(&st->tri_raster, (unsigned long long)raster);
+            }
+        }
+
+        __global__ void __launch_bounds__(GEOM_THREADS) geometry_kernel(const FrameConst fc, const Geometry g)
+        {
+            const uint2 blk = g.block_table[blockIdx.x];
+            const DevItem& it = g.items[blk.x];
+            const DevMesh mesh = g.meshes[it.mesh];
+            const uint32_t ti = blk.y + threadIdx.x;
+            const bool active = ti < it.tri_count;
+            const bool varyings = fc.shader_id != 5; // SHSB_SHADER_DEPTH_ONLY: pass_adapters.hpp:335-353 sets no varyings
+
+            unsigned n_input = 0, n_after = 0, n_raster = 0;
+            bool emit = false;
+            RasterRec rr;
+            ShadeRec sr;
+            if (active)
+            {
+                n_input = 1;
+                uint32_t i0, i1, i2;
+                if (mesh.n_indices) { i0 = mesh.indices[(size_t)ti * 3]; i1 = mesh.indices[(size_t)ti * 3 + 1]; i2 = mesh.indices[(size_t)ti * 3 + 2]; }
+                else { i0 = ti * 3; i1 = i0 + 1; i2 = i0 + 2; }
+                if (i0 < mesh.n_positions && i1 < mesh.n_positions && i2 < mesh.n_positions)
+                {
+                    const Corner c0 = run_vs(it, mesh, i0, fc, varyings);
+                    const Corner c1 = run_vs(it, mesh, i1, fc, varyings);
+                    const Corner c2 = run_vs(it, mesh, i2, fc, varyings);
+                    if (corner_inside(c0) && corner_inside(c1) && corner_inside(c2))
+                    {
+                        n_after = 1;
+                        const int r = setup_triangle(c0, c1, c2, fc, (it.tri_offset + ti) * 8u, blk.x, rr, sr);
+                        n_raster = r & 1;
+                        emit = (r & 2) != 0;
+                    }
+                    else
+                    {
+                        const uint32_t q = atomicAdd(g.clipq_count, 1u);
+                        if (q < g.clipq_capacity) g.clip_queue[q] = make_uint2(blk.x, ti);
+                        else atomicAdd(&g.stats->overflow_clipq, 1u);
+                    }
+                }
+            }
+            // warp-aggregated append
+            const unsigned mask = __ballot_sync(0xffffffffu, emit);
+            if (mask)
+            {
+                const int lane = threadIdx.x & 31;
+                uint32_t base = 0;
+                if (lane == (__ffs(mask) - 1)) base = atomicAdd(g.rec_count, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                if (emit)
+                {
+                    const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
+                    else atomicAdd(&g.stats->overflow_recs, 1u);
+                }
+            }
+            block_add_stats(g.stats, n_input, n_after, n_raster);
+        }
+
+        // Rare path: triangles with at least one corner outside the clip volume.
+        __global__ void __launch_bounds__(GEOM_THREADS) clip_kernel(const FrameConst fc, const Geometry g)
+        {
+            const uint32_t n = min(*g.clipq_count, g.clipq_capacity);
+            const bool varyings = fc.shader_id != 5;
+            unsigned n_after = 0, n_raster = 0;
+            for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+            {
+                const uint2 e = g.clip_queue[q];
+                const DevItem& it = g.items[e.x];
+                const DevMesh mesh = g.meshes[it.mesh];
+                const uint32_t ti = e.y;
+                uint32_t i0, i1, i2;
+                if (mesh.n_indices) { i0 = mesh.indices[(size_t)ti * 3]; i1 = mesh.indices[(size_t)ti * 3 + 1]; i2 = mesh.indices[(size_t)ti * 3 + 2]; }
+                else { i0 = ti * 3; i1 = i0 + 1; i2 = i0 + 2; }
+
+                Corner bufA[MAX_POLY], bufB[MAX_POLY];
+                Corner* src = bufA;
+                Corner* dst = bufB;
+                src[0] = run_vs(it, mesh, i0, fc, varyings);
+                src[1] = run_vs(it, mesh, i1, fc, varyings);
+                src[2] = run_vs(it, mesh, i2, fc, varyings);
+                int np = 3;
+                for (int plane = 0; plane < 6 && np > 0; ++plane)
+                {
+                    int m = 0;
+                    for (int i = 0; i < np; ++i)
+                    {
+                        const Corner& cur = src[i];
+                        const Corner& nxt = src[(i + 1 == np) ? 0 : i + 1];
+                        const float da = plane_dist(cur, plane);
+                        const float db = plane_dist(nxt, plane);
+                        const bool cur_in = da >= 0.0f, nxt_in = db >= 0.0f;
+                        if (m + 2 > MAX_POLY) break;
+                        if (cur_in && nxt_in) dst[m++] = nxt;
+                        else if (cur_in != nxt_in)
+                        {
+                            const float denom = xsub(da, db);
+                            if (fabsf(denom) > 1e-8f) dst[m++] = lerp_corner(cur, nxt, xdiv(da, denom));
+                            if (nxt_in) dst[m++] = nxt;
+                        }
+                    }
+                    Corner* t = src; src = dst; dst = t;
+                    np = m;
+                }
+                if (np < 3) continue;
+                for (int k = 1; k + 1 < np; ++k)
+                {
+                    ++n_after;
+                    RasterRec rr;
+                    ShadeRec sr;
+                    const int r = setup_triangle(src[0], src[k], src[k + 1], fc, (it.tri_offset + ti) * 8u + (uint32_t)(k - 1), e.x, rr, sr);
+                    n_raster += r & 1;
+                    if (r & 2)
+                    {
+                        const uint32_t slot = atomicAdd(g.rec_count, 1u);
+                        if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
+                        else atomicAdd(&g.stats->overflow_recs, 1u);
+                    }
+                }
+            }
+            block_add_stats(g.stats, 0, n_after, n_raster);
+        }
+
+        // PassShadowMap set-up rules (passes/pass_shadow_map.hpp:155-190): world = vec3(model * p), clip = light_vp * (world, 1),
+        // reject |w| < 1e-8, reject only if all three corners are beyond the same NDC bound, NO clipping, NO culling.
+        __global__ void __launch_bounds__(GEOM_THREADS) shadow_geometry_kernel(const FrameConst fc, const Geometry g)
+        {
+            const uint2 blk = g.block_table[blockIdx.x];
+            const DevItem& it = g.items[blk.x];
+            const DevMesh mesh = g.meshes[it.mesh];
+            const uint32_t ti = blk.y + threadIdx.x;
+            bool emit = false;
+            RasterRec rr;
+            if (ti < it.tri_count)
+            {
+                uint32_t id[3];
+                if (mesh.n_indices) { id[0] = mesh.indices[(size_t)ti * 3]; id[1] = mesh.indices[(size_t)ti * 3 + 1]; id[2] = mesh.indices[(size_t)ti * 3 + 2]; }
+                else { id[0] = ti * 3; id[1] = id[0] + 1; id[2] = id[0] + 2; }
+                if (id[0] < mesh.n_positions && id[1] < mesh.n_positions && id[2] < mesh.n_positions)
+                {
+                    float nx[3], ny[3], nz[3];
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                    {
+                        const float* p = mesh.positions + (size_t)id[j] * 3;
+                        const float4 wp = xmat4_mul(it.model, p[0], p[1], p[2], 1.0f);
+                        const float4 c = xmat4_mul(fc.viewproj, wp.x, wp.y, wp.z, 1.0f);
+                        if (fabsf(c.w) < 1e-8f) ok = false;
+                        nx[j] = xdiv(c.x, c.w); ny[j] = xdiv(c.y, c.w); nz[j] = xdiv(c.z, c.w);
+                    }
+                    if (ok &&
+                        !((nx[0] < -1.0f && nx[1] < -1.0f && nx[2] < -1.0f) || (nx[0] > 1.0f && nx[1] > 1.0f && nx[2] > 1.0f)) &&
+                        !((ny[0] < -1.0f && ny[1] < -1.0f && ny[2] < -1.0f) || (ny[0] > 1.0f && ny[1] > 1.0f && ny[2] > 1.0f)) &&
+                        !((nz[0] < -1.0f && nz[1] < -1.0f && nz[2] < -1.0f) || (nz[0] > 1.0f && nz[1] > 1.0f && nz[2] > 1.0f)))
+                    {
+                        const float fw1 = (float)(fc.W - 1), fh1 = (float)(fc.H - 1);
+                        float sx[3], sy[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                        {
+                            sx[j] = xmul(xadd(xmul(nx[j], 0.5f), 0.5f), fw1);
+                            sy[j] = xmul(xadd(xmul(ny[j], 0.5f), 0.5f), fh1);
+                        }
+                        // floor/ceil of +-inf/NaN are UB on the CPU side as well; a sane light camera never produces them.
+                        const float minxf = fminf(fminf(sx[0], sx[1]), sx[2]), maxxf = fmaxf(fmaxf(sx[0], sx[1]), sx[2]);
+                        const float minyf = fminf(fminf(sy[0], sy[1]), sy[2]), maxyf = fmaxf(fmaxf(sy[0], sy[1]), sy[2]);
+                        const int minx = max(0, (int)floorf(minxf));
+                        const int maxx = min(fc.W - 1, (int)ceilf(maxxf));
+                        const int miny = max(0, (int)floorf(minyf));
+                        const int maxy = min(fc.H - 1, (int)ceilf(maxyf));
+                        const float v0x = xsub(sx[1], sx[0]), v0y = xsub(sy[1], sy[0]);
+                        const float v1x = xsub(sx[2], sx[0]), v1y = xsub(sy[2], sy[0]);
+                        const float den = xsub(xmul(v0x, v1y), xmul(v1x, v0y));
+                        if (minx <= maxx && miny <= maxy && !(fabsf(den) < 1e-8f))
+                        {
+                            rr.ax = sx[0]; rr.ay = sy[0];
+                            rr.v0x = v0x; rr.v0y = v0y; rr.v1x = v1x; rr.v1y = v1y;
+                            rr.inv_den = xrcp(den);
+                            rr.iw0 = rr.iw1 = rr.iw2 = 1.0f;
+                            rr.zw0 = nz[0]; rr.zw1 = nz[1]; rr.zw2 = nz[2];
+                            rr.bbox_x = (uint32_t)minx | ((uint32_t)maxx << 16);
+                            rr.bbox_y = (uint32_t)miny | ((uint32_t)maxy << 16);
+                            rr.key = (it.tri_offset + ti) * 8u + 1u;
+                            emit = true;
+                        }
+                    }
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, emit);
+            if (mask)
+            {
+                const int lane = threadIdx.x & 31;
+                uint32_t base = 0;
+                if (lane == (__ffs(mask) - 1)) base = atomicAdd(g.rec_count, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                if (emit)
+                {
+                    const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    if (slot < g.rec_capacity)
+                    {
+                        float4* d = reinterpret_cast<float4*>(g.rrecs + slot);
+                        const float4* s = reinterpret_cast<const float4*>(&rr);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[i] = s[i];
+                    }
+                    else atomicAdd(&g.stats->overflow_recs, 1u);
+                }
+            }
+        }
+    }
+
+    void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches)
+    {
+        if (g.n_blocks == 0) return;
+        if (fc.shadow_mode)
+        {
+            shadow_geometry_kernel<<<g.n_blocks, GEOM_THREADS, 0, s>>>(fc, g);
+            *launches += 1;
+            return;
+        }
+        geometry_kernel<<<g.n_blocks, GEOM_THREADS, 0, s>>>(fc, g);
+        // The clip queue length lives on the device; a fixed persistent-style grid (4 CTAs per SM) strides over it.
+        clip_kernel<<<148 * 4, GEOM_THREADS, 0, s>>>(fc, g);
+        *launches += 2;
+    }
+}

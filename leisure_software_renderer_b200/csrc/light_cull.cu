@@ -1,0 +1,186 @@
+// light_cull.cu -- K4: Forward+ tile light-list builder.
+//
+// Replaces cull_lights_tiled (lighting/jolt_light_culling.hpp:135-187): per 2-D screen tile, build the
+// 6-plane cell from 8 unprojected NDC corners (make_screen_tile_cell, :95-133) and keep, in ASCENDING
+// light index, every frustum-visible light whose bounding sphere is not Outside the cell and -- if the
+// sphere only intersects -- whose AABB p-vertex is not Outside either (classify_vs_cell,
+// geometry/jolt_culling.hpp:239-257; sphere :129-147; AABB :152-181; eps 1e-5 :118-122).  Bounds come from
+// the CullingLightGPU record's cull_sphere / cull_aabb_min / cull_aabb_max (lighting/light_types.hpp:141-167).
+//
+// One CTA per tile; lights are strided over the CTA's threads 256 at a time and compacted with warp
+// ballots + a per-warp prefix so the list order is the ascending order of the serial reference loop.
+// Output: counts[T] (uncapped) and indices[T * max_per_tile] (first max_per_tile survivors).
+//
+// Every expression decides list membership => exact helpers only (and the TU is built with --fmad=false).
+#include "shsb_dev.cuh"
+
+namespace shsb
+{
+    namespace
+    {
+        constexpr int CULL_THREADS = 256;
+
+        struct Planes6 { float4 p[6]; };
+
+        __device__ __forceinline__ float plane_dist(const float4& pl, float x, float y, float z)
+        {
+            return xadd(xadd(xadd(xmul(pl.x, x), xmul(pl.y, y)), xmul(pl.z, z)), pl.w); // dot(n, p) + d
+        }
+
+        // 0 = Outside, 1 = Intersecting, 2 = Inside
+        __device__ __forceinline__ int classify(const float4* __restrict__ planes, const float4 sphere, const float4 bmin, const float4 bmax)
+        {
+            const float r = fmaxf(sphere.w, 0.0f);
+            const float r_eps = xadd(r, 1e-5f);
+            bool inside = true;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+            {
+                const float d = plane_dist(planes[i], sphere.x, sphere.y, sphere.z);
+                if (d < -r_eps) return 0;
+                if (d < r_eps) inside = false;
+            }
+            if (inside) return 2;
+            inside = true;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+            {
+                const float4 pl = planes[i];
+                const float d = plane_dist(pl, (pl.x >= 0.0f) ? bmax.x : bmin.x, (pl.y >= 0.0f) ? bmax.y : bmin.y, (pl.z >= 0.0f) ? bmax.z : bmin.z);
+                if (d < -1e-5f) return 0;
+                const float dn = plane_dist(pl, (pl.x >= 0.0f) ? bmin.x : bmax.x, (pl.y >= 0.0f) ? bmin.y : bmax.y, (pl.z >= 0.0f) ? bmin.z : bmax.z);
+                if (dn < 1e-5f) inside = false;
+            }
+            return inside ? 2 : 1;
+        }
+
+        // camera-frustum pre-filter, jolt_light_culling.hpp:152-161
+        __global__ void light_visible_kernel(const DevLightRec* __restrict__ lights, uint32_t n, const Planes6 frustum, uint8_t* __restrict__ visible)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            const float4 sp = *reinterpret_cast<const float4*>(lights[i].cull_sphere);
+            const float4 mn = *reinterpret_cast<const float4*>(lights[i].cull_aabb_min);
+            const float4 mx = *reinterpret_cast<const float4*>(lights[i].cull_aabb_max);
+            visible[i] = classify(frustum.p, sp, mn, mx) != 0 ? 1 : 0;
+        }
+
+        struct CullParams
+        {
+            float inv_vp[16];
+            uint32_t vw, vh, ts, max_per_tile, tiles_x, tiles_y, n_lights;
+        };
+
+        __global__ void __launch_bounds__(CULL_THREADS) tile_cull_kernel(const DevLightRec* __restrict__ lights, const uint8_t* __restrict__ visible,
+                                                                         const CullParams cp, uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
+        {
+            __shared__ float s_corner[8][3];
+            __shared__ float4 s_plane[6];
+            __shared__ uint32_t s_warp_count[CULL_THREADS / 32];
+
+            const uint32_t tile = blockIdx.x;
+            const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+            if (threadIdx.x < 8)
+            {
+                // make_screen_tile_cell, jolt_light_culling.hpp:103-117: corner order nbl nbr ntl ntr fbl fbr ftl ftr
+                const float fw = (float)cp.vw, fh = (float)cp.vh;
+                const float x0 = xsub(xmul(xdiv((float)(tx * cp.ts), fw), 2.0f), 1.0f);
+                const float x1 = xsub(xmul(xdiv((float)min((tx + 1u) * cp.ts, cp.vw), fw), 2.0f), 1.0f);
+                const float y_top = xsub(1.0f, xmul(xdiv((float)(ty * cp.ts), fh), 2.0f));
+                const float y_bottom = xsub(1.0f, xmul(xdiv((float)min((ty + 1u) * cp.ts, cp.vh), fh), 2.0f));
+                const int c = threadIdx.x;
+                const float x = (c & 1) ? x1 : x0;
+                const float y = (c & 2) ? y_top : y_bottom;
+                const float z = (c & 4) ? 1.0f : -1.0f;
+                const float4 q = xmat4_mul(cp.inv_vp, x, y, z, 1.0f);
+                s_corner[c][0] = xdiv(q.x, q.w);
+                s_corner[c][1] = xdiv(q.y, q.w);
+                s_corner[c][2] = xdiv(q.z, q.w);
+            }
+            __syncthreads();
+            if (threadIdx.x < 6)
+            {
+                enum { NBL = 0, NBR = 1, NTL = 2, NTR = 3, FBL = 4, FBR = 5, FTL = 6, FTR = 7 };
+                // plane vertex triples, jolt_light_culling.hpp:125-130: near far left right bottom top
+                const int tri[6][3] = {{NBL, NBR, NTR}, {FBR, FBL, FTL}, {NBL, NTL, FTL}, {NBR, FBR, FTR}, {NBL, FBL, FBR}, {NTL, NTR, FTR}};
+                const int i = threadIdx.x;
+                const float* A = s_corner[tri[i][0]];
+                const float* B = s_corner[tri[i][1]];
+                const float* Cc = s_corner[tri[i][2]];
+                // inside = (nbl + ntr + fbl + ftr) * 0.25
+                F3 in;
+                in.x = xmul(xadd(xadd(xadd(s_corner[NBL][0], s_corner[NTR][0]), s_corner[FBL][0]), s_corner[FTR][0]), 0.25f);
+                in.y = xmul(xadd(xadd(xadd(s_corner[NBL][1], s_corner[NTR][1]), s_corner[FBL][1]), s_corner[FTR][1]), 0.25f);
+                in.z = xmul(xadd(xadd(xadd(s_corner[NBL][2], s_corner[NTR][2]), s_corner[FBL][2]), s_corner[FTR][2]), 0.25f);
+                // make_oriented_plane_from_points, :53-68
+                const F3 e1{xsub(B[0], A[0]), xsub(B[1], A[1]), xsub(B[2], A[2])};
+                const F3 e2{xsub(Cc[0], A[0]), xsub(Cc[1], A[1]), xsub(Cc[2], A[2])};
+                F3 nrm{xsub(xmul(e1.y, e2.z), xmul(e2.y, e1.z)), xsub(xmul(e1.z, e2.x), xmul(e2.z, e1.x)), xsub(xmul(e1.x, e2.y), xmul(e2.x, e1.y))};
+                nrm = xnormalize3(nrm);
+                float d = -xdot3(nrm, F3{A[0], A[1], A[2]});
+                if (xadd(xdot3(nrm, in), d) < 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; d = -d; }
+                s_plane[i] = make_float4(nrm.x, nrm.y, nrm.z, d);
+            }
+            __syncthreads();
+            float4 planes[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) planes[i] = s_plane[i];
+
+            uint32_t total = 0;
+            for (uint32_t base = 0; base < cp.n_lights; base += CULL_THREADS)
+            {
+                const uint32_t li = base + threadIdx.x;
+                bool keep = false;
+                if (li < cp.n_lights && visible[li])
+                {
+                    const float4 sp = __ldg(reinterpret_cast<const float4*>(lights[li].cull_sphere));
+                    const float4 mn = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_min));
+                    const float4 mx = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_max));
+                    keep = classify(planes, sp, mn, mx) != 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                __syncthreads(); // previous iteration's readers are done with s_warp_count
+                if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
+                __syncthreads();
+                uint32_t before = 0, chunk_total = 0;
+#pragma unroll
+                for (int w = 0; w < CULL_THREADS / 32; ++w)
+                {
+                    const uint32_t c = s_warp_count[w];
+                    if (w < warp) before += c;
+                    chunk_total += c;
+                }
+                if (keep)
+                {
+                    const uint32_t pos = total + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (pos < cp.max_per_tile) indices[(size_t)tile * cp.max_per_tile + pos] = li;
+                }
+                total += chunk_total;
+            }
+            if (threadIdx.x == 0) counts[tile] = total;
+        }
+    }
+
+    void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
+                           uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
+                           uint8_t* visible_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches)
+    {
+        CullParams cp;
+        for (int i = 0; i < 16; ++i) cp.inv_vp[i] = inv_view_proj[i];
+        cp.vw = vw; cp.vh = vh; cp.ts = ts; cp.max_per_tile = max_per_tile;
+        cp.tiles_x = (vw + ts - 1) / ts;
+        cp.tiles_y = (vh + ts - 1) / ts;
+        cp.n_lights = n_lights;
+        Planes6 fr;
+        for (int i = 0; i < 6; ++i) fr.p[i] = make_float4(frustum_planes24[i * 4], frustum_planes24[i * 4 + 1], frustum_planes24[i * 4 + 2], frustum_planes24[i * 4 + 3]);
+        if (n_lights)
+        {
+            light_visible_kernel<<<(n_lights + 255) / 256, 256, 0, s>>>(lights, n_lights, fr, visible_scratch);
+            *launches += 1;
+        }
+        tile_cull_kernel<<<cp.tiles_x * cp.tiles_y, CULL_THREADS, 0, s>>>(lights, visible_scratch, cp, counts, indices);
+        *launches += 1;
+    }
+}

@@ -1,0 +1,208 @@
+// shsb_dev.cuh -- device-side data layout and exact-arithmetic helpers shared by all kernels.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   DevMesh      SoA vertex streams exactly as MeshData (resources/mesh.hpp:23): float3 / float3 / float2 / u32
+//   DevItem      one per draw (RenderItem + resolved material + host-computed model / normal matrix), 192 B
+//   RasterRec    one per set-up fan triangle, 64 B = 4 x 16-B loads: everything the per-pixel coverage +
+//                depth test needs (rasterizer.hpp:167-179, 336-361)
+//   ShadeRec     one per set-up fan triangle, 128 B: attributes pre-multiplied by 1/w, read only for the
+//                winning fragment of a pixel (rasterizer.hpp:309-328, 363-387)
+//   tile lists   u32 RasterRec indices, CSR over 16x16-px screen tiles (tile rows are TOP-anchored so
+//                that a raster tile is exactly a light tile of jolt_light_culling.hpp:103-107)
+//
+// Exactness: everything that decides coverage, depth, clip topology or light lists must reproduce the
+// reference's IEEE-754 binary32, round-to-nearest, NO-FMA arithmetic (x86-64 -O3 without -mfma).  Those
+// expressions are written with the xmul/xadd/xsub/xdiv helpers below (__fmul_rn & co are never contracted
+// into FMA by nvcc) so they stay exact even in translation units compiled with FMA enabled.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace shsb
+{
+    constexpr int TILE = 16;           // raster tile edge in pixels (== Forward+ light tile of the reference default)
+    constexpr int TILE_PIXELS = TILE * TILE;
+    constexpr uint32_t KEY_NONE = 0u;  // internal draw-order key = public key + 1; 0 = "no fragment yet"
+
+    // ---------------------------------------------------------------- exact binary32 ops (never fused)
+    __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+    __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+    __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+    __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+    __device__ __forceinline__ float xrcp(float a) { return __fdiv_rn(1.0f, a); }
+    __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+    // glm::max / std::max: (a < b) ? b : a      glm::min / std::min: (b < a) ? b : a
+    __device__ __forceinline__ float gmax(float a, float b) { return (a < b) ? b : a; }
+    __device__ __forceinline__ float gmin(float a, float b) { return (b < a) ? b : a; }
+    __device__ __forceinline__ float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }          // glm::clamp
+    __device__ __forceinline__ float sclamp(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); } // std::clamp
+
+    struct F3 { float x, y, z; };
+    __device__ __forceinline__ float xdot3(F3 a, F3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+    __device__ __forceinline__ F3 xnormalize3(F3 v)
+    {
+        const float k = xrcp(xsqrt(xdot3(v, v)));
+        return F3{xmul(v.x, k), xmul(v.y, k), xmul(v.z, k)};
+    }
+    // column-major mat4 * (x,y,z,w): (m0*x + m1*y) + (m2*z + m3*w)   [GLM scalar order]
+    __device__ __forceinline__ float4 xmat4_mul(const float* __restrict__ m, float x, float y, float z, float w)
+    {
+        float4 r;
+        r.x = xadd(xadd(xmul(m[0], x), xmul(m[4], y)), xadd(xmul(m[8], z), xmul(m[12], w)));
+        r.y = xadd(xadd(xmul(m[1], x), xmul(m[5], y)), xadd(xmul(m[9], z), xmul(m[13], w)));
+        r.z = xadd(xadd(xmul(m[2], x), xmul(m[6], y)), xadd(xmul(m[10], z), xmul(m[14], w)));
+        r.w = xadd(xadd(xmul(m[3], x), xmul(m[7], y)), xadd(xmul(m[11], z), xmul(m[15], w)));
+        return r;
+    }
+
+    // ---------------------------------------------------------------- device records
+    struct DevMesh
+    {
+        const float* positions; // n_positions * 3
+        const float* normals;   // n_normals * 3
+        const float* uvs;       // n_uvs * 2
+        const uint32_t* indices;
+        uint32_t n_positions, n_normals, n_uvs, n_indices;
+    };
+
+    struct __align__(16) DevItem
+    {
+        float model[16];
+        float nrm[9];          // transpose(inverse(mat3(model))) or mat3(model), builtin_shaders.hpp:92-95 (host-computed)
+        float base_color[3];
+        float metallic, roughness, ao;
+        uint32_t tex;          // 1-based, 0 = none
+        uint32_t mesh;         // index into the context's DevMesh table
+        uint32_t tri_offset;   // global index of this draw's triangle 0 (draw-order key = (tri_offset + ti) * 8 + fan)
+        uint32_t tri_count;
+        uint32_t pad[10];
+    };
+    static_assert(sizeof(DevItem) == 192, "DevItem is 192 bytes");
+
+    struct __align__(16) RasterRec
+    {
+        float ax, ay;          // s0 (screen position of corner 0)
+        float v0x, v0y;        // s1 - s0
+        float v1x, v1y;        // s2 - s0
+        float inv_den;         // 1 / (v0x*v1y - v1x*v0y)
+        float iw0, iw1, iw2;   // 1 / clip.w per corner
+        float zw0, zw1, zw2;   // clip.z * (1/w) per corner   (shadow pass: NDC z per corner)
+        uint32_t bbox_x;       // minx | maxx << 16   (clamped bbox, rasterizer.hpp:285-289)
+        uint32_t bbox_y;       // miny | maxy << 16
+        uint32_t key;          // draw-order key + 1
+    };
+    static_assert(sizeof(RasterRec) == 64, "RasterRec is 64 bytes");
+
+    struct __align__(16) ShadeRec
+    {
+        float wp[3][3];        // world_pos * (1/w) per corner     (semantic varying 0)
+        float n[3][3];         // normal_ws * (1/w) per corner     (semantic varying 1)
+        float uv[3][2];        // uv * (1/w) per corner            (semantic varying 2)
+        uint32_t item;
+        uint32_t pad[7];
+    };
+    static_assert(sizeof(ShadeRec) == 128, "ShadeRec is 128 bytes");
+
+    struct DevStats // device mirror of ShsbStats
+    {
+        unsigned long long tri_input, tri_after_clip, tri_raster, frag_covered, frag_shaded;
+        unsigned int overflow_recs, overflow_lists, overflow_clipq, pad;
+    };
+
+    struct DevLightRec // CullingLightGPU, lighting/light_types.hpp:141-167
+    {
+        float position_range[4], color_intensity[4], direction_spot[4], axis_spot_outer[4], up_shape_x[4], shape_attenuation[4];
+        uint32_t type_shape_flags[4];
+        float cull_sphere[4], cull_aabb_min[4], cull_aabb_max[4];
+    };
+    static_assert(sizeof(DevLightRec) == 160, "CullingLightGPU is 160 bytes");
+
+    // Everything a frame's kernels need, passed by value as a kernel parameter.
+    struct FrameConst
+    {
+        float viewproj[16];
+        float light_viewproj[16];
+        float camera_pos[3];
+        float sun_intensity;
+        float sun_dir[3];
+        float zn;
+        float sun_color[3];
+        float zf;
+        int W, H;
+        int tiles_x, tiles_y;
+        int shader_id;
+        int cull_mode;
+        int front_face_ccw;
+        int has_depth;          // depth target bound (rasterizer.hpp:348)
+        int linear_depth;       // zf > zn + 1e-6 (rasterizer.hpp:354)
+        int load_depth;         // 1: initial depth comes from the RT (preserve_existing_depth / separate draws); 0: clear to 1.0 in-tile
+        int load_color;         // 1: keep RT colour where nothing is drawn; 0: write the background gradient (pass_pbr_forward.hpp:69-85)
+        int write_aovs;
+        int shadow_mode;        // PassShadowMap raster rules (pass_shadow_map.hpp:144-203)
+        // shadow sampling (shadow_sample.hpp)
+        const float* shadow_map;
+        int shadow_w, shadow_h;
+        float bias_const, bias_slope, pcf_step, shadow_strength;
+        int pcf_radius;
+        // Forward+
+        int forward_plus;
+        const DevLightRec* lights;
+        uint32_t n_lights;
+        const uint32_t* tile_counts;
+        const uint32_t* tile_indices;
+        uint32_t light_tile_size, max_per_tile, light_tiles_x, light_tiles_y;
+        // fused tonemap (PassTonemap, pass_tonemap.hpp:49-81)
+        int fuse_tonemap;
+        float exposure, inv_gamma;
+    };
+
+    struct FrameBuffers
+    {
+        float4* hdr;              // W*H RGBA32F or null (depth-only)
+        float* depth;             // W*H or null
+        uchar4* ldr;              // W*H or null
+        uint32_t* aov_tri_id;     // W*H or null
+        uint32_t* aov_coverage;   // W*H or null
+    };
+
+    struct Geometry // per-frame transient arena
+    {
+        const DevMesh* meshes;
+        const DevItem* items;
+        const uint2* block_table;   // per geometry CTA: (item index, first triangle)
+        uint32_t n_blocks;
+        RasterRec* rrecs;
+        ShadeRec* srecs;
+        uint32_t rec_capacity;
+        uint32_t* rec_count;
+        uint2* clip_queue;          // (item, triangle) pairs that need frustum clipping
+        uint32_t clipq_capacity;
+        uint32_t* clipq_count;
+        uint32_t* tile_count;       // per tile
+        uint32_t* tile_offset;      // exclusive scan of tile_count (+1 entry: total)
+        uint32_t* tile_fill;        // per tile write cursor
+        uint32_t* tile_list;        // RasterRec indices
+        uint32_t list_capacity;
+        DevStats* stats;
+    };
+
+    struct DevTexture
+    {
+        const uchar4* texels;
+        int w, h;
+    };
+
+    // ---------------------------------------------------------------- kernel launchers (one per .cu)
+    void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
+    void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
+    void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
+                            const float* srgb_lut, cudaStream_t s, uint64_t* launches);
+    void launch_tonemap(const float4* hdr, uchar4* ldr, int n_pixels, float exposure, float inv_gamma, cudaStream_t s, uint64_t* launches);
+    void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s, uint64_t* launches);
+    void launch_fill_f4(float4* p, float4 v, size_t n, cudaStream_t s, uint64_t* launches);
+    // frustum_planes24: the 6 normalised camera-frustum planes (nx, ny, nz, d) computed on the host
+    void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
+                           uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
+                           uint8_t* visible_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+}

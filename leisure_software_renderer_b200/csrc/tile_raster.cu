@@ -1,0 +1,670 @@
+// tile_raster.cu -- K3: per-tile scan conversion, depth test, deferred fragment shading, resolve.
+//
+// Replaces raster_rows (sw_render/rasterizer.hpp:330-422), the fragment programs it calls
+// (shader/builtin_shaders.hpp:105-245), PCF lookup (lighting/shadow_sample.hpp:65-104), the background
+// fill / depth clear of PassPBRForward (passes/pass_pbr_forward.hpp:64-98), the inline depth raster of
+// PassShadowMap (passes/pass_shadow_map.hpp:191-201) and -- when fused -- PassTonemap
+// (passes/pass_tonemap.hpp:52-81).
+//
+// One CTA of 256 threads owns one 16x16-pixel tile; one thread owns one pixel.  The colour / depth tile
+// lives in registers (one pixel each), triangle records are staged through shared memory 256 at a time
+// and broadcast to all pixels.  Per pixel the kernel keeps only the WINNING fragment:
+//     depth target bound : minimum z01, ties broken by the smallest draw-order key
+//                          (== the reference's strict "z01 >= zbuf -> skip", rasterizer.hpp:359)
+//     no depth target    : the largest draw-order key (painter, rasterizer.hpp:348,419)
+// and runs the fragment program ONCE for it.  This equals the reference's serial result because the
+// builtin fragment programs are pure functions of (FragmentIn, uniforms) and never discard.
+// Each output byte (HDR, depth, LDR) is written exactly once, with 128-bit / full-sector stores.
+#include "shsb_dev.cuh"
+
+namespace shsb
+{
+    namespace
+    {
+        constexpr int TILE_THREADS = 256;
+        constexpr float PI_F = 3.14159265358979323846f;
+        constexpr int MAX_SMEM_LIGHTS = 128;
+
+        struct V3 { float x, y, z; };
+        __device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+        __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+        __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+        __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+        __device__ __forceinline__ V3 operator*(V3 a, float k) { return V3{a.x * k, a.y * k, a.z * k}; }
+        __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+        __device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
+        __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+        __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+        __device__ __forceinline__ V3 normalize_fast(V3 v) { return v * rsqrtf(dot(v, v)); }
+        __device__ __forceinline__ V3 toV3(F3 v) { return V3{v.x, v.y, v.z}; }
+        __device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
+
+        struct SmLight // compact per-tile copy of the CullingLightGPU fields the point/spot path reads
+        {
+            float4 pos_range;     // xyz, max(range, 0.001)
+            float4 radiance;      // color * intensity, w = range^2
+            float4 dir_cos;       // normalised spot direction, inner cos
+            float4 params;        // outer cos, attenuation power, bias, cutoff
+            uint32_t type, model, index, flags;
+        };
+
+        struct Surface
+        {
+            V3 P, N, V, albedo;
+            float metallic, roughness;
+            bool blinn;
+        };
+
+        // ---- eval_pbr_light / eval_blinn_phong_light, shaders/vulkan/fp_stress_scene.frag:132-165
+        __device__ __forceinline__ V3 eval_brdf(const Surface& s, V3 L, V3 radiance)
+        {
+            const float NdotL = fmaxf(dot(s.N, L), 0.0f);
+            if (NdotL <= 0.0f) return v3(0, 0, 0);
+            const V3 H = normalize_fast(s.V + L);
+            if (s.blinn)
+            {
+                const float smooth = 1.0f - sat(s.roughness);
+                const float shininess = mixf(10.0f, 96.0f, smooth);
+                const float spec = __powf(fmaxf(dot(s.N, H), 0.0f), shininess);
+                const V3 spec_color = mix3(v3(0.04f, 0.04f, 0.04f), s.albedo, s.metallic);
+                const float spec_strength = mixf(0.15f, 0.65f, smooth);
+                return radiance * (s.albedo * ((1.0f / PI_F) * NdotL) + spec_color * (spec * spec_strength));
+            }
+            const V3 F0 = mix3(v3(0.04f, 0.04f, 0.04f), s.albedo, s.metallic);
+            const float fres = pow5(1.0f - fmaxf(dot(H, s.V), 0.0f));
+            const V3 F = F0 + (v3(1, 1, 1) - F0) * fres;
+            const float a = s.roughness * s.roughness, a2 = a * a;
+            const float NdotH = fmaxf(dot(s.N, H), 0.0f);
+            const float dd = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+            const float NDF = __fdividef(a2, fmaxf(PI_F * dd * dd, 1e-6f));
+            const float NdotV = fmaxf(dot(s.N, s.V), 0.0f);
+            const float rr = s.roughness + 1.0f, k = rr * rr * 0.125f;
+            const float g1 = __fdividef(NdotV, fmaxf(NdotV * (1.0f - k) + k, 1e-6f));
+            const float g2 = __fdividef(NdotL, fmaxf(NdotL * (1.0f - k) + k, 1e-6f));
+            const float inv_denom = __fdividef(1.0f, fmaxf(4.0f * NdotV * NdotL, 1e-6f));
+            const V3 specular = F * (NDF * g1 * g2 * inv_denom);
+            const V3 kD = (v3(1, 1, 1) - F) * (1.0f - s.metallic);
+            return (kD * s.albedo * (1.0f / PI_F) + specular) * radiance * NdotL;
+        }
+
+        // ---- shs_eval_light_attenuation_quadratic, shaders/vulkan/common/light_math.glsl:44-78
+        __device__ __forceinline__ float attenuation_quadratic(float dist, float range, uint32_t model, float power, float bias, float cutoff)
+        {
+            const float safe_range = fmaxf(range, 1e-4f);
+            const float t = sat(__fdividef(dist, safe_range));
+            const float edge = 1.0f - t;
+            float falloff;
+            if (model == 0u) falloff = edge;
+            else if (model == 2u)
+            {
+                const float denom = fmaxf(dist * dist, fmaxf(bias, 1e-5f));
+                falloff = __fdividef(safe_range * safe_range, denom) * edge * edge;
+            }
+            else falloff = edge * edge;
+            falloff = fmaxf(falloff, 0.0f);
+            const float p = fmaxf(power, 0.001f);
+            if (p != 1.0f) falloff = (falloff > 0.0f) ? __powf(falloff, p) : 0.0f;
+            return (falloff <= fmaxf(cutoff, 0.0f)) ? 0.0f : falloff;
+        }
+
+        // point / spot lights from the shared-memory copy -- eval_local_light, fp_stress_scene.frag:421-523
+        __device__ __forceinline__ V3 eval_point_spot(const Surface& s, const SmLight& lt)
+        {
+            const V3 d = v3(lt.pos_range.x, lt.pos_range.y, lt.pos_range.z) - s.P;
+            const float dist2 = dot(d, d);
+            if (!(dist2 < lt.radiance.w) || dist2 <= 1e-10f) return v3(0, 0, 0);
+            const float inv_dist = rsqrtf(dist2);
+            const float dist = dist2 * inv_dist;
+            const V3 L = d * inv_dist;
+            float atten = attenuation_quadratic(dist, lt.pos_range.w, lt.model, lt.params.y, lt.params.z, lt.params.w);
+            if (atten <= 0.0f) return v3(0, 0, 0);
+            if (lt.type == 2u)
+            {
+                const float inner_cos = fminf(fmaxf(lt.dir_cos.w, -1.0f), 1.0f);
+                const float outer_cos = fminf(fmaxf(lt.params.x, -1.0f), inner_cos);
+                const float cone_cos = -(lt.dir_cos.x * L.x + lt.dir_cos.y * L.y + lt.dir_cos.z * L.z);
+                const float t = sat(__fdividef(cone_cos - outer_cos, fmaxf(inner_cos - outer_cos, 1e-6f)));
+                const float spot = t * t * (3.0f - 2.0f * t);
+                if (spot <= 0.0f) return v3(0, 0, 0);
+                atten *= spot;
+            }
+            return eval_brdf(s, L, v3(lt.radiance.x, lt.radiance.y, lt.radiance.z) * atten);
+        }
+
+        // Any light type straight from the 160-B record (saturated tiles, non-16 light tiles, rect / tube lights).
+        __device__ __noinline__ V3 eval_light_record(const Surface& s, const DevLightRec* __restrict__ rec)
+        {
+            const uint32_t type = rec->type_shape_flags[0], flags = rec->type_shape_flags[2], model = rec->type_shape_flags[3];
+            const V3 zero = v3(0, 0, 0);
+            if ((flags & 1u) == 0u || type < 1u || type > 4u) return zero;
+            const V3 lpos = v3(rec->position_range[0], rec->position_range[1], rec->position_range[2]);
+            const float range = fmaxf(rec->position_range[3], 0.001f);
+            V3 to_light = lpos - s.P;
+            float dist = sqrtf(dot(to_light, to_light));
+            float rect_forward = 0.0f;
+            if (type == 3u)
+            {
+                const V3 right = normalize_fast(v3(rec->axis_spot_outer[0], rec->axis_spot_outer[1], rec->axis_spot_outer[2]));
+                const V3 up = normalize_fast(v3(rec->up_shape_x[0], rec->up_shape_x[1], rec->up_shape_x[2]));
+                const V3 emit = normalize_fast(v3(rec->direction_spot[0], rec->direction_spot[1], rec->direction_spot[2]));
+                const float hx = fmaxf(rec->up_shape_x[3], 1e-4f), hy = fmaxf(rec->shape_attenuation[0], 1e-4f);
+                const V3 rel = s.P - lpos;
+                rect_forward = dot(rel, emit);
+                if (rect_forward <= 1e-4f || rect_forward >= range) return zero;
+                const float lx = dot(rel, right), ly = dot(rel, up);
+                const float x = fminf(fmaxf(lx, -hx), hx), y = fminf(fmaxf(ly, -hy), hy);
+                const float dx = fmaxf(fabsf(lx) - hx, 0.0f), dy = fmaxf(fabsf(ly) - hy, 0.0f);
+                if (sqrtf(dx * dx + dy * dy + rect_forward * rect_forward) >= range) return zero;
+                to_light = (lpos + right * x + up * y) - s.P;
+                dist = sqrtf(dot(to_light, to_light));
+            }
+            else if (type == 4u)
+            {
+                const V3 axis = normalize_fast(v3(rec->axis_spot_outer[0], rec->axis_spot_outer[1], rec->axis_spot_outer[2]));
+                const float half_len = fmaxf(rec->up_shape_x[3], 1e-4f);
+                const V3 p0 = lpos - axis * half_len, p1 = lpos + axis * half_len;
+                const V3 seg = p1 - p0;
+                const float u = sat(dot(s.P - p0, seg) / fmaxf(dot(seg, seg), 1e-6f));
+                to_light = (p0 + seg * u) - s.P;
+                dist = sqrtf(dot(to_light, to_light));
+            }
+            if (dist <= 1e-5f || dist >= range) return zero;
+            const V3 L = to_light * (1.0f / fmaxf(dist, 1e-5f));
+            float atten = attenuation_quadratic(dist, range, model, rec->shape_attenuation[1], rec->shape_attenuation[2], rec->shape_attenuation[3]);
+            if (atten <= 0.0f) return zero;
+            if (type == 2u)
+            {
+                const V3 sd = normalize_fast(v3(rec->direction_spot[0], rec->direction_spot[1], rec->direction_spot[2]));
+                const float inner_cos = fminf(fmaxf(rec->direction_spot[3], -1.0f), 1.0f);
+                const float outer_cos = fminf(fmaxf(rec->axis_spot_outer[3], -1.0f), inner_cos);
+                const float t = sat((-dot(sd, L) - outer_cos) / fmaxf(inner_cos - outer_cos, 1e-6f));
+                const float spot = t * t * (3.0f - 2.0f * t);
+                if (spot <= 0.0f) return zero;
+                atten *= spot;
+            }
+            else if (type == 3u)
+            {
+                const V3 emit = normalize_fast(v3(rec->direction_spot[0], rec->direction_spot[1], rec->direction_spot[2]));
+                const float one_sided = fmaxf(-dot(emit, L), 0.0f);
+                if (one_sided <= 0.0f) return zero;
+                atten *= one_sided * sat(1.0f - rect_forward / fmaxf(range, 1e-4f));
+            }
+            else if (type == 4u)
+            {
+                const float edge_soften = fminf(fmaxf(fmaxf(rec->shape_attenuation[0], 1e-4f) / fmaxf(range, 1e-4f), 0.05f), 1.0f);
+                atten *= mixf(0.65f, 1.0f, edge_soften);
+            }
+            const V3 radiance = v3(rec->color_intensity[0], rec->color_intensity[1], rec->color_intensity[2]) * (rec->color_intensity[3] * atten);
+            return eval_brdf(s, L, radiance);
+        }
+
+        // ---- eval_fake_ibl, shader/builtin_shaders.hpp:57-85
+        __device__ __forceinline__ V3 fake_ibl(V3 N, V3 V, V3 base_color, float metallic, float roughness, float ao)
+        {
+            const V3 n = normalize_fast(N), v = normalize_fast(V);
+            const V3 mv = v * -1.0f;
+            const V3 r = mv - n * (dot(n, mv) * 2.0f);
+            const V3 zen = v3(0.32f, 0.46f, 0.72f), hor = v3(0.62f, 0.66f, 0.72f), gnd = v3(0.16f, 0.15f, 0.14f);
+            const float up_n = sat(n.y * 0.5f + 0.5f), up_r = sat(r.y * 0.5f + 0.5f);
+            const V3 env_n = mix3(gnd, mix3(hor, zen, up_n), up_n);
+            const V3 env_r = mix3(gnd, mix3(hor, zen, up_r), up_r);
+            const float m = sat(metallic), rgh = sat(roughness);
+            const V3 F0 = mix3(v3(0.04f, 0.04f, 0.04f), v3(fmaxf(base_color.x, 0.0f), fmaxf(base_color.y, 0.0f), fmaxf(base_color.z, 0.0f)), m);
+            const float fres = pow5(1.0f - fmaxf(0.0f, dot(n, v)));
+            const V3 F = F0 + (v3(1, 1, 1) - F0) * fres;
+            const V3 kd = (v3(1, 1, 1) - F) * (1.0f - m);
+            const V3 diffuse_ibl = kd * base_color * env_n * 0.12f;
+            const float spec_strength = 0.02f + (1.0f - rgh) * 0.18f;
+            return (diffuse_ibl + env_r * F * spec_strength) * sat(ao);
+        }
+
+        // ---- sample_texture2d_bilinear_repeat_linear, shader/builtin_shaders.hpp:33-55.
+        // Addressing is exact (it selects texels); srgb_lut[i] = powf(i/255, 2.2) computed on the host by libm.
+        __device__ __forceinline__ V3 sample_texture(const DevTexture& tex, const float* __restrict__ lut, float uvx, float uvy)
+        {
+            const float u = xsub(uvx, floorf(uvx)), v = xsub(uvy, floorf(uvy));
+            const float fx = xmul(u, (float)(tex.w - 1)), fy = xmul(v, (float)(tex.h - 1));
+            const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+            const int x1 = min(x0 + 1, tex.w - 1), y1 = min(y0 + 1, tex.h - 1);
+            const float tx = xsub(fx, (float)x0), ty = xsub(fy, (float)y0);
+            const uchar4 t00 = tex.texels[(size_t)y0 * tex.w + x0], t10 = tex.texels[(size_t)y0 * tex.w + x1];
+            const uchar4 t01 = tex.texels[(size_t)y1 * tex.w + x0], t11 = tex.texels[(size_t)y1 * tex.w + x1];
+            const V3 c00 = v3(lut[t00.x], lut[t00.y], lut[t00.z]), c10 = v3(lut[t10.x], lut[t10.y], lut[t10.z]);
+            const V3 c01 = v3(lut[t01.x], lut[t01.y], lut[t01.z]), c11 = v3(lut[t11.x], lut[t11.y], lut[t11.z]);
+            return mix3(mix3(c00, c10, tx), mix3(c01, c11, tx), ty);
+        }
+
+        // ---- shadow_visibility_dir, lighting/shadow_sample.hpp:65-104 (exact: it selects texels and compares depths)
+        __device__ __forceinline__ float shadow_visibility(const FrameConst& fc, F3 pos_ws, float ndotl)
+        {
+            const float4 p = xmat4_mul(fc.light_viewproj, pos_ws.x, pos_ws.y, pos_ws.z, 1.0f);
+            if (fabsf(p.w) < 1e-8f) return 1.0f;
+            const float u = xadd(xmul(xdiv(p.x, p.w), 0.5f), 0.5f);
+            const float v = xadd(xmul(xdiv(p.y, p.w), 0.5f), 0.5f);
+            const float z = xadd(xmul(xdiv(p.z, p.w), 0.5f), 0.5f);
+            if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return 1.0f;
+            const float slope = xsub(1.0f, sclamp(ndotl, 0.0f, 1.0f));
+            const float z_test = xsub(z, xadd(fc.bias_const, xmul(fc.bias_slope, slope)));
+            const int cx = (int)roundf(xmul(u, (float)(fc.shadow_w - 1)));
+            const int cy = (int)roundf(xmul(v, (float)(fc.shadow_h - 1)));
+            const int r = max(0, fc.pcf_radius);
+            if (r == 0)
+            {
+                const int x = min(max(cx, 0), fc.shadow_w - 1), y = min(max(cy, 0), fc.shadow_h - 1);
+                return (z_test <= fc.shadow_map[(size_t)y * fc.shadow_w + x]) ? 1.0f : 0.0f;
+            }
+            const int step = max(1, (int)roundf(fmaxf(1.0f, fc.pcf_step)));
+            int lit = 0;
+            for (int oy = -r; oy <= r; ++oy)
+            {
+                const int y = min(max(cy + oy * step, 0), fc.shadow_h - 1);
+                for (int ox = -r; ox <= r; ++ox)
+                {
+                    const int x = min(max(cx + ox * step, 0), fc.shadow_w - 1);
+                    lit += (z_test <= fc.shadow_map[(size_t)y * fc.shadow_w + x]) ? 1 : 0;
+                }
+            }
+            const int count = (2 * r + 1) * (2 * r + 1);
+            return xdiv((float)lit, (float)count);
+        }
+
+        __device__ __forceinline__ uchar4 tonemap_pixel(float r, float g, float b, float exposure, float inv_gamma)
+        {
+            // PassTonemap, passes/pass_tonemap.hpp:58-80
+            float c[3] = {r, g, b};
+            unsigned char o[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                float v = fmaxf(0.0f, c[i] * exposure);
+                v = v / (1.0f + v);
+                v = powf(v, inv_gamma);
+                const long q = lroundf(v * 255.0f);
+                o[i] = (unsigned char)min(max(q, 0l), 255l);
+            }
+            return make_uchar4(o[0], o[1], o[2], 255);
+        }
+
+        __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
+                                                                    const DevTexture* __restrict__ textures,
+                                                                    const float* __restrict__ srgb_lut)
+        {
+            __shared__ __align__(16) RasterRec s_rec[TILE_THREADS];
+            __shared__ uint32_t s_idx[TILE_THREADS];
+            __shared__ __align__(16) SmLight s_light[MAX_SMEM_LIGHTS];
+            __shared__ unsigned long long s_frag[2];
+
+            const int tile = blockIdx.x;
+            const int tx = tile % fc.tiles_x, ty = tile / fc.tiles_x;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            // a warp owns an 8x4-pixel block: 128 contiguous bytes of HDR per row
+            const int wx0 = tx * TILE + (warp & 1) * 8;
+            const int wfy0 = ty * TILE + (warp >> 1) * 4;
+            const int px = wx0 + (lane & 7);
+            const int fy = wfy0 + (lane >> 3);
+            const int py = fc.H - 1 - fy;
+            const bool valid = px < fc.W && fy < fc.H;
+            const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
+            // warp rectangle in RT coordinates (y up)
+            const int wx1 = wx0 + 7;
+            const int wy_hi = fc.H - 1 - wfy0, wy_lo = wy_hi - 3;
+
+            if (threadIdx.x < 2) s_frag[threadIdx.x] = 0ull;
+            __syncthreads();
+
+            float bz = 1.0f;
+            if (fc.has_depth && fc.load_depth && valid) bz = fb.depth[pix];
+            uint32_t bkey = KEY_NONE, bidx = 0;
+            uint32_t n_cov = 0;
+            const float pxf = xadd((float)px, 0.5f), pyf = xadd((float)py, 0.5f);
+            const float zrange = xsub(fc.zf, fc.zn);
+
+            const uint32_t off0 = g.tile_offset[tile];
+            const uint32_t off1 = min(g.tile_offset[tile + 1], g.list_capacity);
+            for (uint32_t base = off0; base < off1; base += TILE_THREADS)
+            {
+                __syncthreads();
+                const uint32_t n = min((uint32_t)TILE_THREADS, off1 - base);
+                if (threadIdx.x < n)
+                {
+                    const uint32_t rec = g.tile_list[base + threadIdx.x];
+                    const float4* src = reinterpret_cast<const float4*>(g.rrecs + rec);
+                    float4* dst = reinterpret_cast<float4*>(&s_rec[threadIdx.x]);
+                    dst[0] = __ldg(src + 0); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+                    s_idx[threadIdx.x] = rec;
+                }
+                __syncthreads();
+                for (uint32_t j = 0; j < n; ++j)
+                {
+                    const RasterRec& r = s_rec[j];
+                    const int minx = (int)(r.bbox_x & 0xffffu), maxx = (int)(r.bbox_x >> 16);
+                    const int miny = (int)(r.bbox_y & 0xffffu), maxy = (int)(r.bbox_y >> 16);
+                    if (maxx < wx0 || minx > wx1 || maxy < wy_lo || miny > wy_hi) continue; // warp-uniform reject
+                    if (!valid || px < minx || px > maxx || py < miny || py > maxy) continue;  // the reference's bbox loop bounds
+                    // barycentric_2d, rasterizer.hpp:167-179
+                    const float v2x = xsub(pxf, r.ax), v2y = xsub(pyf, r.ay);
+                    const float bv = xmul(xsub(xmul(v2x, r.v1y), xmul(r.v1x, v2y)), r.inv_den);
+                    const float bw = xmul(xsub(xmul(r.v0x, v2y), xmul(v2x, r.v0y)), r.inv_den);
+                    const float bu = xsub(xsub(1.0f, bv), bw);
+                    if (bu < 0.0f || bv < 0.0f || bw < 0.0f) continue;
+                    if (fc.shadow_mode)
+                    {
+                        // pass_shadow_map.hpp:197-200: affine NDC z, keep the minimum
+                        const float z_ndc = xadd(xadd(xmul(bu, r.zw0), xmul(bv, r.zw1)), xmul(bw, r.zw2));
+                        const float z01 = sclamp(xadd(xmul(z_ndc, 0.5f), 0.5f), 0.0f, 1.0f);
+                        ++n_cov;
+                        if (z01 < bz) { bz = z01; bkey = r.key; }
+                        continue;
+                    }
+                    const float denom = xadd(xadd(xmul(bu, r.iw0), xmul(bv, r.iw1)), xmul(bw, r.iw2));
+                    if (denom <= 1e-10f) continue;
+                    ++n_cov;
+                    if (fc.has_depth)
+                    {
+                        float z01;
+                        if (fc.linear_depth)
+                        {
+                            const float view_z = xrcp(denom);
+                            z01 = gclamp(xdiv(xsub(view_z, fc.zn), zrange), 0.0f, 1.0f);
+                        }
+                        else
+                        {
+                            const float z_clip = xadd(xadd(xmul(bu, r.zw0), xmul(bv, r.zw1)), xmul(bw, r.zw2));
+                            z01 = gclamp(xadd(xmul(xmul(z_clip, xrcp(denom)), 0.5f), 0.5f), 0.0f, 1.0f);
+                        }
+                        if (z01 < bz || (z01 == bz && r.key < bkey)) { bz = z01; bkey = r.key; bidx = s_idx[j]; }
+                    }
+                    else if (r.key > bkey) { bkey = r.key; bidx = s_idx[j]; }
+                }
+            }
+
+            // ---------------- resolve: depth + AOVs
+            if (valid)
+            {
+                if (fb.depth && (fc.has_depth || fc.shadow_mode) && (bkey != KEY_NONE || !fc.load_depth)) fb.depth[pix] = bz;
+                if (fb.aov_tri_id) fb.aov_tri_id[pix] = (bkey != KEY_NONE) ? (bkey - 1u) : 0xFFFFFFFFu;
+                if (fb.aov_coverage) fb.aov_coverage[pix] = n_cov;
+            }
+            // fragment counters: warp reduce -> shared -> one global atomic per CTA
+            {
+                uint32_t c = n_cov, sh = (bkey != KEY_NONE) ? 1u : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); sh += __shfl_down_sync(0xffffffffu, sh, o); }
+                if (lane == 0) { atomicAdd(&s_frag[0], (unsigned long long)c); atomicAdd(&s_frag[1], (unsigned long long)sh); }
+            }
+
+            if (fc.shadow_mode || fc.shader_id == 5 || !fb.hdr)
+            {
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    if (s_frag[0]) atomicAdd(&g.stats->frag_covered, s_frag[0]);
+                    if (s_frag[1]) atomicAdd(&g.stats->frag_shaded, s_frag[1]);
+                }
+                return;
+            }
+
+            // ---------------- Forward+: stage this tile's light list (light tile == raster tile when tile_size is 16)
+            const bool use_lights = fc.forward_plus && (fc.shader_id == 0 || fc.shader_id == 1) && fc.n_lights > 0;
+            const bool tile_lights = use_lights && fc.light_tile_size == (uint32_t)TILE;
+            uint32_t light_count = 0;
+            bool saturated = false;
+            if (tile_lights)
+            {
+                const uint32_t list_id = (uint32_t)min(ty, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
+                light_count = min(fc.tile_counts[list_id], fc.max_per_tile);
+                saturated = light_count >= fc.max_per_tile;
+                if (!saturated)
+                {
+                    for (uint32_t i = threadIdx.x; i < light_count; i += TILE_THREADS)
+                    {
+                        const uint32_t idx = fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
+                        SmLight sl;
+                        sl.type = 0u; sl.model = 0u; sl.index = idx; sl.flags = 0u;
+                        sl.pos_range = make_float4(0, 0, 0, 0); sl.radiance = make_float4(0, 0, 0, 0);
+                        sl.dir_cos = make_float4(0, -1, 0, 1); sl.params = make_float4(0, 1, 0.05f, 0);
+                        if (idx < fc.n_lights)
+                        {
+                            const DevLightRec* rec = fc.lights + idx;
+                            const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
+                            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
+                            const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
+                            const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
+                            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
+                            const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
+                            const float range = fmaxf(pr.w, 0.001f);
+                            sl.pos_range = make_float4(pr.x, pr.y, pr.z, range);
+                            sl.radiance = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, range * range);
+                            const float dl = rsqrtf(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
+                            sl.dir_cos = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, ds.w);
+                            sl.params = make_float4(ax.w, sa.y, sa.z, sa.w);
+                            sl.type = tf.x; sl.flags = tf.z; sl.model = tf.w;
+                        }
+                        s_light[i] = sl;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                if (s_frag[0]) atomicAdd(&g.stats->frag_covered, s_frag[0]);
+                if (s_frag[1]) atomicAdd(&g.stats->frag_shaded, s_frag[1]);
+            }
+            if (!valid) return;
+
+            float out_r, out_g, out_b;
+            if (bkey == KEY_NONE)
+            {
+                if (fc.load_color)
+                {
+                    if (!(fc.fuse_tonemap && fb.ldr)) return;
+                    const float4 c = fb.hdr[pix];
+                    fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
+                    return;
+                }
+                // background gradient, pass_pbr_forward.hpp:73-81
+                const float t = xdiv((float)py, (float)max(1, fc.H - 1));
+                out_r = xadd(0.06f, xmul(0.08f, t));
+                out_g = xadd(0.08f, xmul(0.10f, t));
+                out_b = xadd(0.12f, xmul(0.12f, t));
+            }
+            else
+            {
+                // ---------------- re-derive the winning fragment (bit-identical to the test above)
+                const float4* rsrc = reinterpret_cast<const float4*>(g.rrecs + bidx);
+                const float4 r0 = __ldg(rsrc + 0), r1 = __ldg(rsrc + 1), r2 = __ldg(rsrc + 2), r3 = __ldg(rsrc + 3);
+                const float v2x = xsub(pxf, r0.x), v2y = xsub(pyf, r0.y);
+                const float bv = xmul(xsub(xmul(v2x, r1.y), xmul(r1.x, v2y)), r1.z);
+                const float bw = xmul(xsub(xmul(r0.z, v2y), xmul(v2x, r0.w)), r1.z);
+                const float bu = xsub(xsub(1.0f, bv), bw);
+                const float denom = xadd(xadd(xmul(bu, r1.w), xmul(bv, r2.x)), xmul(bw, r2.y));
+                const float inv_denom = xrcp(denom);
+                float depth01 = bz;
+                if (!fc.has_depth)
+                {
+                    const float z_clip = xadd(xadd(xmul(bu, r2.z), xmul(bv, r2.w)), xmul(bw, r3.x));
+                    depth01 = gclamp(xadd(xmul(xmul(z_clip, inv_denom), 0.5f), 0.5f), 0.0f, 1.0f);
+                }
+                const ShadeRec* sr = g.srecs + bidx;
+                const float4* ssrc = reinterpret_cast<const float4*>(sr);
+                float a[28];
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+                {
+                    const float4 q = __ldg(ssrc + i);
+                    a[i * 4 + 0] = q.x; a[i * 4 + 1] = q.y; a[i * 4 + 2] = q.z; a[i * 4 + 3] = q.w;
+                }
+                // layout: wp[3][3] = a[0..8], n[3][3] = a[9..17], uv[3][2] = a[18..23], item = a[24]
+                auto interp = [&](float c0, float c1, float c2) {
+                    return xmul(xadd(xadd(xmul(bu, c0), xmul(bv, c1)), xmul(bw, c2)), inv_denom); // rasterizer.hpp:368
+                };
+                const F3 wpos{interp(a[0], a[3], a[6]), interp(a[1], a[4], a[7]), interp(a[2], a[5], a[8])};
+                const F3 nrm_i{interp(a[9], a[12], a[15]), interp(a[10], a[13], a[16]), interp(a[11], a[14], a[17])};
+                const float uvx = interp(a[18], a[20], a[22]), uvy = interp(a[19], a[21], a[23]);
+                const uint32_t item_index = __float_as_uint(a[24]);
+                const DevItem& it = g.items[item_index];
+                const F3 n_ws = xnormalize3(nrm_i); // rasterizer.hpp:381
+
+                if (fc.shader_id == 2) { out_r = it.base_color[0]; out_g = it.base_color[1]; out_b = it.base_color[2]; }
+                else if (fc.shader_id == 3)
+                {
+                    const F3 n = xnormalize3(n_ws);
+                    out_r = xadd(xmul(n.x, 0.5f), 0.5f); out_g = xadd(xmul(n.y, 0.5f), 0.5f); out_b = xadd(xmul(n.z, 0.5f), 0.5f);
+                }
+                else if (fc.shader_id == 4) { const float d = sclamp(depth01, 0.0f, 1.0f); out_r = out_g = out_b = d; }
+                else
+                {
+                    // ---- builtin lit programs.  N, L, NdotL stay exact: they feed the shadow bias and the NdotL > 0 branches.
+                    const F3 Nx = xnormalize3(n_ws);
+                    const F3 Lx = xnormalize3(F3{-fc.sun_dir[0], -fc.sun_dir[1], -fc.sun_dir[2]});
+                    const F3 Vx = xnormalize3(F3{xsub(fc.camera_pos[0], wpos.x), xsub(fc.camera_pos[1], wpos.y), xsub(fc.camera_pos[2], wpos.z)});
+                    const float NdotL = fmaxf(0.0f, xdot3(Nx, Lx));
+                    const V3 N = toV3(Nx), L = toV3(Lx), V = toV3(Vx);
+                    V3 albedo_tex = v3(1, 1, 1);
+                    if (it.tex != 0u) albedo_tex = sample_texture(textures[it.tex - 1u], srgb_lut, uvx, uvy);
+                    const V3 base = v3(it.base_color[0], it.base_color[1], it.base_color[2]);
+                    const V3 albedo = v3(fmaxf(base.x * albedo_tex.x, 0.0f), fmaxf(base.y * albedo_tex.y, 0.0f), fmaxf(base.z * albedo_tex.z, 0.0f));
+                    float shadow_vis = 1.0f;
+                    if (fc.shadow_map && NdotL > 0.0f)
+                    {
+                        shadow_vis = shadow_visibility(fc, wpos, NdotL);
+                        shadow_vis = mixf(1.0f, shadow_vis, sat(fc.shadow_strength));
+                    }
+                    const V3 light_color = v3(fc.sun_color[0], fc.sun_color[1], fc.sun_color[2]);
+                    const V3 H = normalize_fast(V + L);
+                    V3 c;
+                    Surface surf;
+                    surf.P = toV3(wpos); surf.N = N; surf.V = V; surf.albedo = albedo;
+                    if (fc.shader_id == 1)
+                    {
+                        // make_blinn_phong_program, builtin_shaders.hpp:105-152
+                        const float NdotH = fmaxf(0.0f, dot(N, H));
+                        const float rough = sat(it.roughness), metal = sat(it.metallic);
+                        const float spec_pow = fmaxf(4.0f, 8.0f + (1.0f - rough) * 120.0f);
+                        const float spec_norm = (spec_pow + 2.0f) / (2.0f * PI_F);
+                        const float spec = powf(NdotH, spec_pow) * spec_norm * (0.04f + 0.96f * metal) * NdotL;
+                        const V3 diffuse = albedo * ((1.0f - metal) * (NdotL / PI_F));
+                        const V3 direct = (diffuse + v3(spec, spec, spec)) * light_color * (fc.sun_intensity * shadow_vis);
+                        c = direct + fake_ibl(N, V, albedo, it.metallic, it.roughness, it.ao);
+                        surf.metallic = metal; surf.roughness = rough; surf.blinn = true;
+                    }
+                    else
+                    {
+                        // make_pbr_mr_program, builtin_shaders.hpp:154-214
+                        const float NdotV = fmaxf(0.0f, dot(N, V)), NdotH = fmaxf(0.0f, dot(N, H)), VdotH = fmaxf(0.0f, dot(V, H));
+                        const float rough = fminf(fmaxf(it.roughness, 0.04f), 1.0f), metal = sat(it.metallic);
+                        const V3 F0 = mix3(v3(0.04f, 0.04f, 0.04f), albedo, metal);
+                        const float aa = rough * rough, a2 = aa * aa;
+                        const float denomD = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+                        const float D = a2 / (PI_F * denomD * denomD + 1e-7f);
+                        const float k = (aa + 1.0f) * (aa + 1.0f) * 0.125f;
+                        const float G = (NdotV / (NdotV * (1.0f - k) + k + 1e-7f)) * (NdotL / (NdotL * (1.0f - k) + k + 1e-7f));
+                        const V3 F = F0 + (v3(1, 1, 1) - F0) * pow5(1.0f - VdotH);
+                        const V3 spec = F * ((D * G) / fmaxf(4.0f * NdotL * NdotV, 1e-6f));
+                        const V3 kd = (v3(1, 1, 1) - F) * (1.0f - metal);
+                        const V3 diff = kd * albedo * (1.0f / PI_F);
+                        V3 direct = v3(0, 0, 0);
+                        if (NdotL > 0.0f && NdotV > 0.0f) direct = (diff + spec) * light_color * (fc.sun_intensity * NdotL * shadow_vis);
+                        c = direct + fake_ibl(N, V, albedo, metal, rough, it.ao);
+                        surf.metallic = metal; surf.roughness = rough; surf.blinn = false;
+                    }
+                    if (use_lights)
+                    {
+                        // Forward+ local lights in ascending list order, fp_stress_scene.frag:644-678
+                        V3 sum = v3(0, 0, 0);
+                        if (tile_lights && !saturated)
+                        {
+                            for (uint32_t i = 0; i < light_count; ++i)
+                            {
+                                const SmLight& lt = s_light[i];
+                                if ((lt.flags & 1u) == 0u) continue;
+                                if (lt.type == 1u || lt.type == 2u) sum = sum + eval_point_spot(surf, lt);
+                                else if (lt.index < fc.n_lights) sum = sum + eval_light_record(surf, fc.lights + lt.index);
+                            }
+                        }
+                        else if (tile_lights)
+                        {
+                            for (uint32_t i = 0; i < fc.n_lights; ++i) sum = sum + eval_light_record(surf, fc.lights + i);
+                        }
+                        else
+                        {
+                            // generic light-tile size: per-pixel list lookup, tile_y counted from the top
+                            const uint32_t ltx = min((uint32_t)px / fc.light_tile_size, fc.light_tiles_x - 1u);
+                            const uint32_t lty = min((uint32_t)fy / fc.light_tile_size, fc.light_tiles_y - 1u);
+                            const uint32_t list_id = lty * fc.light_tiles_x + ltx;
+                            const uint32_t cnt = min(fc.tile_counts[list_id], fc.max_per_tile);
+                            if (cnt >= fc.max_per_tile)
+                            {
+                                for (uint32_t i = 0; i < fc.n_lights; ++i) sum = sum + eval_light_record(surf, fc.lights + i);
+                            }
+                            else
+                            {
+                                for (uint32_t i = 0; i < cnt; ++i)
+                                {
+                                    const uint32_t idx = fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
+                                    if (idx < fc.n_lights) sum = sum + eval_light_record(surf, fc.lights + idx);
+                                }
+                            }
+                        }
+                        c = c + sum;
+                    }
+                    out_r = c.x; out_g = c.y; out_b = c.z;
+                }
+            }
+            fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
+            if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);
+        }
+
+        __global__ void __launch_bounds__(256) tonemap_kernel(const float4* __restrict__ hdr, uchar4* __restrict__ ldr, int n, float exposure, float inv_gamma)
+        {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            {
+                const float4 c = __ldg(hdr + i);
+                ldr[i] = tonemap_pixel(c.x, c.y, c.z, exposure, inv_gamma);
+            }
+        }
+
+        __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n)
+        {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+        }
+
+        __global__ void fill_f4_kernel(float4* p, float4 v, size_t n)
+        {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+        }
+    }
+
+    void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
+                            const float* srgb_lut, cudaStream_t s, uint64_t* launches)
+    {
+        const int n_tiles = fc.tiles_x * fc.tiles_y;
+        if (n_tiles <= 0) return;
+        tile_kernel<<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        *launches += 1;
+    }
+
+    void launch_tonemap(const float4* hdr, uchar4* ldr, int n_pixels, float exposure, float inv_gamma, cudaStream_t s, uint64_t* launches)
+    {
+        if (n_pixels <= 0) return;
+        const int grid = min((n_pixels + 255) / 256, 148 * 16);
+        tonemap_kernel<<<grid, 256, 0, s>>>(hdr, ldr, n_pixels, exposure, inv_gamma);
+        *launches += 1;
+    }
+
+    void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s, uint64_t* launches)
+    {
+        if (!n) return;
+        const int grid = (int)min((n + 255) / 256, (size_t)148 * 16);
+        fill_u32_kernel<<<grid, 256, 0, s>>>(p, v, n);
+        *launches += 1;
+    }
+
+    void launch_fill_f4(float4* p, float4 v, size_t n, cudaStream_t s, uint64_t* launches)
+    {
+        if (!n) return;
+        const int grid = (int)min((n + 255) / 256, (size_t)148 * 16);
+        fill_f4_kernel<<<grid, 256, 0, s>>>(p, v, n);
+        *launches += 1;
+    }
+}

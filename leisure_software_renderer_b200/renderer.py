@@ -144,7 +144,7 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_pass_tonemap(self.h, hdr_rt, ldr_rt, exposure, gamma), "shsb_pass_tonemap")
 
     def lights_upload(self, records: np.ndarray):
-        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
+        r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")
 
     def light_cull(self, view_proj, w, h, tile_size=16, max_per_tile=128):
@@ -164,6 +164,11 @@ class Context:
         st = Stats()
         rc = self.lib.shsb_frame_forward_plus(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, ldr_rt, C.byref(st))
         _check(self.lib, self.h, rc, "shsb_frame_forward_plus")
+        if fp.light_culling:
+            _, w, h = self._rt_shape[hdr_rt]
+            ts = max(1, fp.tile_size)
+            self._tiles = ((w + ts - 1) // ts) * ((h + ts - 1) // ts)
+            self._max_per_tile = max(1, fp.max_lights_per_tile)
         return st
 
     def sync(self):

@@ -42,6 +42,12 @@ class Target(C.Structure):
                 ("zn", C.c_float), ("zf", C.c_float)]
 
 
+def _records_u8(records) -> np.ndarray:
+    """CullingLightGPU records (structured or raw) as a contiguous (n, 160) uint8 array."""
+    r = np.ascontiguousarray(records)
+    return r.view(np.uint8).reshape(-1, 160)
+
+
 def build(kind: str = "port") -> None:
     subprocess.run(["make", "-C", _HERE, "oracle" if kind == "port" else "ref"], check=True, capture_output=True)
 
@@ -170,7 +176,7 @@ class Oracle:
     # ---- restatement-only
     def light_cull(self, records, view_proj, w, h, tile_size=16, max_per_tile=128):
         assert self.kind == "port"
-        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, 160)
+        r = _records_u8(records)
         vp = np.ascontiguousarray(view_proj, dtype=np.float32)
         tiles = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
         counts = np.zeros(tiles, dtype=np.uint32)
@@ -183,7 +189,7 @@ class Oracle:
     def pass_pbr_forward_plus(self, assets, scene, fp, tgt, records, counts, indices, shadow_lvp=None, preserve_depth=False):
         assert self.kind == "port"
         st = Stats()
-        r = np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, 160)
+        r = _records_u8(records)
         lvp = np.ascontiguousarray(shadow_lvp, dtype=np.float32) if shadow_lvp is not None else None
         rc = self.lib.shso_pass_pbr_forward_plus(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt),
                                                  capi.fptr(lvp) if lvp is not None else None, C.c_int32(int(preserve_depth)),
