@@ -314,6 +314,12 @@ SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, c
  * [0] vertex+setup, [1] binning, [2] tile raster+shade, [3] light cull, [4] tonemap, [5] total. */
 SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8]);
 
+/* Per-frame stage timing history for benchmarks: while enabled every frame submission records four CUDA
+ * events on the context stream (no host synchronisation).  shsb_timing_collect synchronises, writes
+ * {vertex+setup, binning, tile raster+shade, total} milliseconds per frame and clears the history. */
+SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable);
+SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,8 +93,14 @@ struct shsb_context_t
     // per-frame arena
     DevBuf<DevItem> d_items;
     DevBuf<uint2> d_blocks;
-    PinnedBuf<DevItem> h_items;
-    PinnedBuf<uint2> h_blocks;
+    // pinned staging ring: a frame's item / block tables are copied H2D asynchronously, so a slot may only be
+    // rewritten once the copy that read it has completed (its event); 3 slots keep 2 frames in flight
+    static constexpr int STAGE_SLOTS = 3;
+    PinnedBuf<DevItem> h_items[STAGE_SLOTS];
+    PinnedBuf<uint2> h_blocks[STAGE_SLOTS];
+    cudaEvent_t stage_done[STAGE_SLOTS]{};
+    bool stage_busy[STAGE_SLOTS]{};
+    int stage_slot = 0;
     DevBuf<RasterRec> d_rrecs;
     DevBuf<ShadeRec> d_srecs;
     DevBuf<uint2> d_clipq;
@@ -106,6 +112,11 @@ struct shsb_context_t
 
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
+
+    // optional per-frame stage timing history (4 events per frame, no host sync while recording)
+    bool timing_on = false;
+    std::vector<cudaEvent_t> timing_ev;
+    size_t timing_used = 0;
 };
 
 namespace
@@ -243,6 +254,16 @@ namespace
     void record(shsb_ctx ctx, int i)
     {
         if (cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess) ctx->ev_valid[i] = true;
+        if (ctx->timing_on && i < 4)
+        {
+            if (ctx->timing_used == ctx->timing_ev.size())
+            {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreate(&e) != cudaSuccess) return;
+                ctx->timing_ev.push_back(e);
+            }
+            cudaEventRecord(ctx->timing_ev[ctx->timing_used++], ctx->stream);
+        }
     }
 
     // Runs geometry -> binning -> tile raster for the draws staged in ctx->h_items[0..n_items).
@@ -274,8 +295,11 @@ namespace
 
             if (job.n_items)
             {
-                CK(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items.p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks.p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+                const int slot = ctx->stage_slot;
+                CK(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items[slot].p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks[slot].p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaEventRecord(ctx->stage_done[slot], ctx->stream));
+                ctx->stage_busy[slot] = true;
             }
             CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream));
             CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
@@ -351,12 +375,16 @@ namespace
 
     int upload_staging(shsb_ctx ctx, const std::vector<DevItem>& items, const std::vector<uint2>& blocks)
     {
-        if (int rc = ensure_pinned(ctx, ctx->h_items, std::max<size_t>(1, items.size()))) return rc;
-        if (int rc = ensure_pinned(ctx, ctx->h_blocks, std::max<size_t>(1, blocks.size()))) return rc;
-        // the previous frame's H2D copy out of these pinned buffers must have completed
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (!items.empty()) std::memcpy(ctx->h_items.p, items.data(), items.size() * sizeof(DevItem));
-        if (!blocks.empty()) std::memcpy(ctx->h_blocks.p, blocks.data(), blocks.size() * sizeof(uint2));
+        const int slot = ctx->stage_slot = (ctx->stage_slot + 1) % shsb_context_t::STAGE_SLOTS;
+        if (ctx->stage_busy[slot])
+        {
+            CK(cudaEventSynchronize(ctx->stage_done[slot])); // the H2D copy that last read this slot has finished
+            ctx->stage_busy[slot] = false;
+        }
+        if (int rc = ensure_pinned(ctx, ctx->h_items[slot], std::max<size_t>(1, items.size()))) return rc;
+        if (int rc = ensure_pinned(ctx, ctx->h_blocks[slot], std::max<size_t>(1, blocks.size()))) return rc;
+        if (!items.empty()) std::memcpy(ctx->h_items[slot].p, items.data(), items.size() * sizeof(DevItem));
+        if (!blocks.empty()) std::memcpy(ctx->h_blocks[slot].p, blocks.data(), blocks.size() * sizeof(uint2));
         return SHSB_OK;
     }
 
@@ -512,6 +540,7 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
     for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < shsb_context_t::STAGE_SLOTS; ++i) ok = cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming) == cudaSuccess;
     if (ok)
     {
         // srgb_to_linear_rgb (shader/builtin_shaders.hpp:25-31) evaluated by the host libm, as the reference does per tap
@@ -541,8 +570,15 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_items.p); cudaFree(ctx->d_blocks.p); cudaFree(ctx->d_rrecs.p); cudaFree(ctx->d_srecs.p); cudaFree(ctx->d_clipq.p);
     cudaFree(ctx->d_tile_count.p); cudaFree(ctx->d_tile_offset.p); cudaFree(ctx->d_tile_fill.p); cudaFree(ctx->d_tile_list.p);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_stats);
-    cudaFreeHost(ctx->h_stats); cudaFreeHost(ctx->h_items.p); cudaFreeHost(ctx->h_blocks.p);
+    cudaFreeHost(ctx->h_stats);
+    for (int i = 0; i < shsb_context_t::STAGE_SLOTS; ++i)
+    {
+        cudaFreeHost(ctx->h_items[i].p);
+        cudaFreeHost(ctx->h_blocks[i].p);
+        if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
+    }
     for (int i = 0; i < NUM_STAGE_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->timing_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SHSB_OK;
@@ -986,6 +1022,34 @@ SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_
     if (counts) CK(cudaMemcpyAsync(counts, ctx->d_tile_counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (indices) CK(cudaMemcpyAsync(indices, ctx->d_tile_indices.p, tiles * ctx->lists_max * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    ctx->timing_on = enable != 0;
+    ctx->timing_used = 0;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames)
+{
+    if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t frames = std::min(ctx->timing_used / 4, cap_frames);
+    for (size_t f = 0; f < frames && out_ms; ++f)
+    {
+        const cudaEvent_t* e = &ctx->timing_ev[f * 4];
+        float g = 0, b = 0, r = 0, t = 0;
+        cudaEventElapsedTime(&g, e[0], e[1]);
+        cudaEventElapsedTime(&b, e[1], e[2]);
+        cudaEventElapsedTime(&r, e[2], e[3]);
+        cudaEventElapsedTime(&t, e[0], e[3]);
+        out_ms[f * 4 + 0] = g; out_ms[f * 4 + 1] = b; out_ms[f * 4 + 2] = r; out_ms[f * 4 + 3] = t;
+    }
+    *out_frames = frames;
+    ctx->timing_used = 0;
     return SHSB_OK;
 }
 

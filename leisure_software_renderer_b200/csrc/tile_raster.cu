@@ -23,7 +23,6 @@ namespace shsb
     {
         constexpr int TILE_THREADS = 256;
         constexpr float PI_F = 3.14159265358979323846f;
-        constexpr int MAX_SMEM_LIGHTS = 128;
 
         struct V3 { float x, y, z; };
         __device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
@@ -291,7 +290,9 @@ namespace shsb
         {
             __shared__ __align__(16) RasterRec s_rec[TILE_THREADS];
             __shared__ uint32_t s_idx[TILE_THREADS];
-            __shared__ __align__(16) SmLight s_light[MAX_SMEM_LIGHTS];
+            __shared__ __align__(16) SmLight s_light[TILE_THREADS]; // one compaction round = 256 candidate lights
+            __shared__ float s_box[TILE_THREADS / 32][6];
+            __shared__ uint32_t s_warp_count[TILE_THREADS / 32];
             __shared__ unsigned long long s_frag[2];
 
             const int tile = blockIdx.x;
@@ -404,73 +405,23 @@ namespace shsb
                 return;
             }
 
-            // ---------------- Forward+: stage this tile's light list (light tile == raster tile when tile_size is 16)
-            const bool use_lights = fc.forward_plus && (fc.shader_id == 0 || fc.shader_id == 1) && fc.n_lights > 0;
-            const bool tile_lights = use_lights && fc.light_tile_size == (uint32_t)TILE;
-            uint32_t light_count = 0;
-            bool saturated = false;
-            if (tile_lights)
-            {
-                const uint32_t list_id = (uint32_t)min(ty, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
-                light_count = min(fc.tile_counts[list_id], fc.max_per_tile);
-                saturated = light_count >= fc.max_per_tile;
-                if (!saturated)
-                {
-                    for (uint32_t i = threadIdx.x; i < light_count; i += TILE_THREADS)
-                    {
-                        const uint32_t idx = fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
-                        SmLight sl;
-                        sl.type = 0u; sl.model = 0u; sl.index = idx; sl.flags = 0u;
-                        sl.pos_range = make_float4(0, 0, 0, 0); sl.radiance = make_float4(0, 0, 0, 0);
-                        sl.dir_cos = make_float4(0, -1, 0, 1); sl.params = make_float4(0, 1, 0.05f, 0);
-                        if (idx < fc.n_lights)
-                        {
-                            const DevLightRec* rec = fc.lights + idx;
-                            const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
-                            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
-                            const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
-                            const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
-                            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
-                            const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
-                            const float range = fmaxf(pr.w, 0.001f);
-                            sl.pos_range = make_float4(pr.x, pr.y, pr.z, range);
-                            sl.radiance = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, range * range);
-                            const float dl = rsqrtf(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
-                            sl.dir_cos = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, ds.w);
-                            sl.params = make_float4(ax.w, sa.y, sa.z, sa.w);
-                            sl.type = tf.x; sl.flags = tf.z; sl.model = tf.w;
-                        }
-                        s_light[i] = sl;
-                    }
-                }
-            }
             __syncthreads();
             if (threadIdx.x == 0)
             {
                 if (s_frag[0]) atomicAdd(&g.stats->frag_covered, s_frag[0]);
                 if (s_frag[1]) atomicAdd(&g.stats->frag_shaded, s_frag[1]);
             }
-            if (!valid) return;
 
-            float out_r, out_g, out_b;
-            if (bkey == KEY_NONE)
+            // ---------------- phase A (per pixel): re-derive the winning fragment and run the builtin program
+            const bool has = valid && bkey != KEY_NONE;
+            const bool lit_shader = fc.shader_id == 0 || fc.shader_id == 1;
+            float out_r = 0.0f, out_g = 0.0f, out_b = 0.0f;
+            Surface surf;
+            surf.P = v3(0, 0, 0); surf.N = v3(0, 1, 0); surf.V = v3(0, 1, 0); surf.albedo = v3(0, 0, 0);
+            surf.metallic = 0.0f; surf.roughness = 1.0f; surf.blinn = fc.shader_id == 1;
+            if (has)
             {
-                if (fc.load_color)
-                {
-                    if (!(fc.fuse_tonemap && fb.ldr)) return;
-                    const float4 c = fb.hdr[pix];
-                    fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
-                    return;
-                }
-                // background gradient, pass_pbr_forward.hpp:73-81
-                const float t = xdiv((float)py, (float)max(1, fc.H - 1));
-                out_r = xadd(0.06f, xmul(0.08f, t));
-                out_g = xadd(0.08f, xmul(0.10f, t));
-                out_b = xadd(0.12f, xmul(0.12f, t));
-            }
-            else
-            {
-                // ---------------- re-derive the winning fragment (bit-identical to the test above)
+                // bit-identical to the coverage test above
                 const float4* rsrc = reinterpret_cast<const float4*>(g.rrecs + bidx);
                 const float4 r0 = __ldg(rsrc + 0), r1 = __ldg(rsrc + 1), r2 = __ldg(rsrc + 2), r3 = __ldg(rsrc + 3);
                 const float v2x = xsub(pxf, r0.x), v2y = xsub(pyf, r0.y);
@@ -485,8 +436,7 @@ namespace shsb
                     const float z_clip = xadd(xadd(xmul(bu, r2.z), xmul(bv, r2.w)), xmul(bw, r3.x));
                     depth01 = gclamp(xadd(xmul(xmul(z_clip, inv_denom), 0.5f), 0.5f), 0.0f, 1.0f);
                 }
-                const ShadeRec* sr = g.srecs + bidx;
-                const float4* ssrc = reinterpret_cast<const float4*>(sr);
+                const float4* ssrc = reinterpret_cast<const float4*>(g.srecs + bidx);
                 float a[28];
 #pragma unroll
                 for (int i = 0; i < 7; ++i)
@@ -501,8 +451,7 @@ namespace shsb
                 const F3 wpos{interp(a[0], a[3], a[6]), interp(a[1], a[4], a[7]), interp(a[2], a[5], a[8])};
                 const F3 nrm_i{interp(a[9], a[12], a[15]), interp(a[10], a[13], a[16]), interp(a[11], a[14], a[17])};
                 const float uvx = interp(a[18], a[20], a[22]), uvy = interp(a[19], a[21], a[23]);
-                const uint32_t item_index = __float_as_uint(a[24]);
-                const DevItem& it = g.items[item_index];
+                const DevItem& it = g.items[__float_as_uint(a[24])];
                 const F3 n_ws = xnormalize3(nrm_i); // rasterizer.hpp:381
 
                 if (fc.shader_id == 2) { out_r = it.base_color[0]; out_g = it.base_color[1]; out_b = it.base_color[2]; }
@@ -533,7 +482,6 @@ namespace shsb
                     const V3 light_color = v3(fc.sun_color[0], fc.sun_color[1], fc.sun_color[2]);
                     const V3 H = normalize_fast(V + L);
                     V3 c;
-                    Surface surf;
                     surf.P = toV3(wpos); surf.N = N; surf.V = V; surf.albedo = albedo;
                     if (fc.shader_id == 1)
                     {
@@ -546,7 +494,7 @@ namespace shsb
                         const V3 diffuse = albedo * ((1.0f - metal) * (NdotL / PI_F));
                         const V3 direct = (diffuse + v3(spec, spec, spec)) * light_color * (fc.sun_intensity * shadow_vis);
                         c = direct + fake_ibl(N, V, albedo, it.metallic, it.roughness, it.ao);
-                        surf.metallic = metal; surf.roughness = rough; surf.blinn = true;
+                        surf.metallic = metal; surf.roughness = rough;
                     }
                     else
                     {
@@ -566,50 +514,155 @@ namespace shsb
                         V3 direct = v3(0, 0, 0);
                         if (NdotL > 0.0f && NdotV > 0.0f) direct = (diff + spec) * light_color * (fc.sun_intensity * NdotL * shadow_vis);
                         c = direct + fake_ibl(N, V, albedo, metal, rough, it.ao);
-                        surf.metallic = metal; surf.roughness = rough; surf.blinn = false;
-                    }
-                    if (use_lights)
-                    {
-                        // Forward+ local lights in ascending list order, fp_stress_scene.frag:644-678
-                        V3 sum = v3(0, 0, 0);
-                        if (tile_lights && !saturated)
-                        {
-                            for (uint32_t i = 0; i < light_count; ++i)
-                            {
-                                const SmLight& lt = s_light[i];
-                                if ((lt.flags & 1u) == 0u) continue;
-                                if (lt.type == 1u || lt.type == 2u) sum = sum + eval_point_spot(surf, lt);
-                                else if (lt.index < fc.n_lights) sum = sum + eval_light_record(surf, fc.lights + lt.index);
-                            }
-                        }
-                        else if (tile_lights)
-                        {
-                            for (uint32_t i = 0; i < fc.n_lights; ++i) sum = sum + eval_light_record(surf, fc.lights + i);
-                        }
-                        else
-                        {
-                            // generic light-tile size: per-pixel list lookup, tile_y counted from the top
-                            const uint32_t ltx = min((uint32_t)px / fc.light_tile_size, fc.light_tiles_x - 1u);
-                            const uint32_t lty = min((uint32_t)fy / fc.light_tile_size, fc.light_tiles_y - 1u);
-                            const uint32_t list_id = lty * fc.light_tiles_x + ltx;
-                            const uint32_t cnt = min(fc.tile_counts[list_id], fc.max_per_tile);
-                            if (cnt >= fc.max_per_tile)
-                            {
-                                for (uint32_t i = 0; i < fc.n_lights; ++i) sum = sum + eval_light_record(surf, fc.lights + i);
-                            }
-                            else
-                            {
-                                for (uint32_t i = 0; i < cnt; ++i)
-                                {
-                                    const uint32_t idx = fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
-                                    if (idx < fc.n_lights) sum = sum + eval_light_record(surf, fc.lights + idx);
-                                }
-                            }
-                        }
-                        c = c + sum;
+                        surf.metallic = metal; surf.roughness = rough;
                     }
                     out_r = c.x; out_g = c.y; out_b = c.z;
                 }
+            }
+
+            // ---------------- phase B (whole CTA): Forward+ local lights, fp_stress_scene.frag:644-678.
+            // Light tile == raster tile when the list tile size is 16.  The tile cell spans all depths, so most listed
+            // lights cannot reach the surfaces actually visible in the tile: lights are first tested against the
+            // world-space AABB of the tile's shaded positions (conservative: a rejected light fails "dist < range"
+            // at every pixel and would add exactly zero) and the survivors are compacted IN ASCENDING ORDER into
+            // shared memory, 256 candidates per round.  A saturated list (count >= max_per_tile) walks ALL lights,
+            // as the GLSL does (:662-668).
+            const bool use_lights = fc.forward_plus && lit_shader && fc.n_lights > 0;
+            if (use_lights && fc.light_tile_size == (uint32_t)TILE)
+            {
+                if (__syncthreads_or(has ? 1 : 0))
+                {
+                    // CTA-wide AABB of shaded world positions
+                    const float INF = 3.0e38f;
+                    float bx0 = has ? surf.P.x : INF, by0 = has ? surf.P.y : INF, bz0 = has ? surf.P.z : INF;
+                    float bx1 = has ? surf.P.x : -INF, by1 = has ? surf.P.y : -INF, bz1 = has ? surf.P.z : -INF;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                    {
+                        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+                        bz0 = fminf(bz0, __shfl_xor_sync(0xffffffffu, bz0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+                        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o)); bz1 = fmaxf(bz1, __shfl_xor_sync(0xffffffffu, bz1, o));
+                    }
+                    if (lane == 0) { s_box[warp][0] = bx0; s_box[warp][1] = by0; s_box[warp][2] = bz0; s_box[warp][3] = bx1; s_box[warp][4] = by1; s_box[warp][5] = bz1; }
+                    __syncthreads();
+#pragma unroll
+                    for (int w = 0; w < TILE_THREADS / 32; ++w)
+                    {
+                        bx0 = fminf(bx0, s_box[w][0]); by0 = fminf(by0, s_box[w][1]); bz0 = fminf(bz0, s_box[w][2]);
+                        bx1 = fmaxf(bx1, s_box[w][3]); by1 = fmaxf(by1, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
+                    }
+
+                    const uint32_t list_id = (uint32_t)min(ty, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
+                    const uint32_t listed = min(fc.tile_counts[list_id], fc.max_per_tile);
+                    const bool saturated = listed >= fc.max_per_tile;
+                    const uint32_t n_src = saturated ? fc.n_lights : listed;
+                    V3 sum = v3(0, 0, 0);
+                    for (uint32_t base = 0; base < n_src; base += TILE_THREADS)
+                    {
+                        const uint32_t i = base + threadIdx.x;
+                        bool keep = false;
+                        uint32_t idx = 0;
+                        float4 pr = make_float4(0, 0, 0, 0);
+                        uint4 tf = make_uint4(0, 0, 0, 0);
+                        if (i < n_src)
+                        {
+                            idx = saturated ? i : fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
+                            if (idx < fc.n_lights)
+                            {
+                                const DevLightRec* rec = fc.lights + idx;
+                                pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
+                                tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
+                                float4 sp = make_float4(pr.x, pr.y, pr.z, fmaxf(pr.w, 0.001f));
+                                if (tf.x > 2u) sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere)); // area lights reach beyond position +- range
+                                const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f);
+                                const float dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
+                                const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
+                                const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;
+                                keep = enabled && (dx * dx + dy * dy + dz * dz) <= sp.w * sp.w * 1.001f + 1e-6f;
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        __syncthreads(); // the previous round's readers are done with s_light / s_warp_count
+                        if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
+                        __syncthreads();
+                        uint32_t before = 0, kept = 0;
+#pragma unroll
+                        for (int w = 0; w < TILE_THREADS / 32; ++w)
+                        {
+                            const uint32_t c = s_warp_count[w];
+                            if (w < warp) before += c;
+                            kept += c;
+                        }
+                        if (keep)
+                        {
+                            const DevLightRec* rec = fc.lights + idx;
+                            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
+                            const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
+                            const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
+                            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
+                            SmLight sl;
+                            const float range = fmaxf(pr.w, 0.001f);
+                            sl.pos_range = make_float4(pr.x, pr.y, pr.z, range);
+                            sl.radiance = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, range * range);
+                            const float dl = rsqrtf(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
+                            sl.dir_cos = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, ds.w);
+                            sl.params = make_float4(ax.w, sa.y, sa.z, sa.w);
+                            sl.type = tf.x; sl.flags = tf.z; sl.model = tf.w; sl.index = idx;
+                            s_light[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = sl;
+                        }
+                        __syncthreads();
+                        if (has)
+                        {
+                            for (uint32_t j = 0; j < kept; ++j)
+                            {
+                                const SmLight& lt = s_light[j];
+                                if (lt.type <= 2u) sum = sum + eval_point_spot(surf, lt);
+                                else sum = sum + eval_light_record(surf, fc.lights + lt.index);
+                            }
+                        }
+                    }
+                    out_r += sum.x; out_g += sum.y; out_b += sum.z;
+                }
+            }
+            else if (use_lights && has)
+            {
+                // generic light-tile size: per-pixel list lookup, tile_y counted from the top
+                V3 sum = v3(0, 0, 0);
+                const uint32_t ltx = min((uint32_t)px / fc.light_tile_size, fc.light_tiles_x - 1u);
+                const uint32_t lty = min((uint32_t)fy / fc.light_tile_size, fc.light_tiles_y - 1u);
+                const uint32_t list_id = lty * fc.light_tiles_x + ltx;
+                const uint32_t cnt = min(fc.tile_counts[list_id], fc.max_per_tile);
+                if (cnt >= fc.max_per_tile)
+                {
+                    for (uint32_t i = 0; i < fc.n_lights; ++i) sum = sum + eval_light_record(surf, fc.lights + i);
+                }
+                else
+                {
+                    for (uint32_t i = 0; i < cnt; ++i)
+                    {
+                        const uint32_t idx = fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
+                        if (idx < fc.n_lights) sum = sum + eval_light_record(surf, fc.lights + idx);
+                    }
+                }
+                out_r += sum.x; out_g += sum.y; out_b += sum.z;
+            }
+
+            // ---------------- phase C (per pixel): resolve colour (+ fused tonemap), each byte written once
+            if (!valid) return;
+            if (!has)
+            {
+                if (fc.load_color)
+                {
+                    if (!(fc.fuse_tonemap && fb.ldr)) return;
+                    const float4 c = fb.hdr[pix];
+                    fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
+                    return;
+                }
+                // background gradient, pass_pbr_forward.hpp:73-81
+                const float t = xdiv((float)py, (float)max(1, fc.H - 1));
+                out_r = xadd(0.06f, xmul(0.08f, t));
+                out_g = xadd(0.08f, xmul(0.10f, t));
+                out_b = xadd(0.12f, xmul(0.12f, t));
             }
             fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);

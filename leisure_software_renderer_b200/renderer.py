@@ -184,6 +184,16 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_launch_count(self.h, C.byref(n)), "shsb_launch_count")
         return n.value
 
+    def timing_enable(self, on=True):
+        _check(self.lib, self.h, self.lib.shsb_timing_enable(self.h, int(on)), "shsb_timing_enable")
+
+    def timing_collect(self, max_frames=4096) -> np.ndarray:
+        """(n_frames, 4) float32: vertex+setup, binning, tile raster+shade, total -- milliseconds."""
+        a = np.zeros((max_frames, 4), dtype=np.float32)
+        n = C.c_size_t()
+        _check(self.lib, self.h, self.lib.shsb_timing_collect(self.h, capi.fptr(a), max_frames, C.byref(n)), "shsb_timing_collect")
+        return a[: n.value]
+
     def last_stage_ms(self):
         a = np.zeros(8, dtype=np.float32)
         _check(self.lib, self.h, self.lib.shsb_last_stage_ms(self.h, capi.fptr(a)), "shsb_last_stage_ms")

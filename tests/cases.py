@@ -1,0 +1,59 @@
+"""Parity cases shared by the CPU (oracle vs reference) and GPU (CUDA vs oracle) tests."""
+from leisure_software_renderer_b200 import capi, scenes
+
+
+def forward_cases():
+    """name -> (SceneData factory, kwargs for harness.*_forward)"""
+    def shadow_scene():
+        sd = scenes.scene_small(w=200, h=120, tex=True)
+        sd.fp.shadow_enable = 1
+        return sd
+
+    def debug(mode):
+        def f():
+            sd = scenes.scene_small(w=128, h=96)
+            sd.fp.debug_view = mode
+            return sd
+        return f
+
+    def cull(mode, ccw=1):
+        def f():
+            sd = scenes.scene_small(w=128, h=96)
+            sd.fp.cull_mode = mode
+            sd.fp.front_face_ccw = ccw
+            return sd
+        return f
+
+    return {
+        "c1_suzanne_blinn_640x480": (scenes.scene_c1, {}),
+        "small_pbr": (lambda: scenes.scene_small(), {}),
+        "small_blinn_tex": (lambda: scenes.scene_small(tex=True, shading=capi.SHADING_BLINN), {}),
+        "ragged_size_pbr": (lambda: scenes.scene_small(w=173, h=99, n_inst=4, seed=3), {}),
+        "nearclip_tex": (lambda: scenes.scene_small(near_clip=True, tex=True), {}),
+        "nearclip_blinn": (lambda: scenes.scene_small(w=200, h=150, near_clip=True, shading=capi.SHADING_BLINN, seed=5), {}),
+        "painter_no_depth": (lambda: scenes.scene_small(), {"depth": False}),
+        "shadow_pcf": (shadow_scene, {"shadow": True}),
+        "debug_albedo": (debug(capi.DEBUG_ALBEDO), {}),
+        "debug_normal": (debug(capi.DEBUG_NORMAL), {}),
+        "debug_depth": (debug(capi.DEBUG_DEPTH), {}),
+        "cull_none": (cull(capi.CULL_NONE), {}),
+        "cull_front": (cull(capi.CULL_FRONT), {}),
+        "front_face_cw": (cull(capi.CULL_BACK, 0), {}),
+        "empty_scene": (lambda: scenes.scene_small(n_inst=0, w=64, h=48), {}),
+        "tiny_target_1x1": (lambda: scenes.scene_small(w=1, h=1), {}),
+    }
+
+
+def forward_plus_cases():
+    return {
+        "fplus_pbr": (lambda: scenes.scene_small(w=320, h=200, lights=64), {"forward_plus": True}),
+        "fplus_blinn_tex": (lambda: scenes.scene_small(w=333, h=207, lights=64, tex=True, shading=capi.SHADING_BLINN), {"forward_plus": True}),
+        "fplus_saturated": (lambda: _saturated(), {"forward_plus": True}),
+        "fplus_c2_small": (lambda: scenes.scene_c2(w=640, h=360, grid=4, n_point=96, n_spot=32), {"forward_plus": True}),
+    }
+
+
+def _saturated():
+    sd = scenes.scene_small(w=160, h=120, lights=96, seed=9)
+    sd.fp.max_lights_per_tile = 8  # forces count >= max -> "walk all lights" fallback (fp_stress_scene.frag:662-668)
+    return sd

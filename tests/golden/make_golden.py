@@ -1,0 +1,55 @@
+"""Generates tests/golden/*.npz by running THE REFERENCE ITSELF (oracle/_ref/libshs_ref.so = the reference's own
+headers compiled from /root/reference) on the deterministic scenes of tests/cases.py.  Run in the container that
+has /root/reference; the committed fixtures let the GPU box (which has no reference tree) check both the oracle and
+the CUDA path against reference outputs.  Light-list goldens come from the restatement (the reference's
+light-culling headers need Jolt and cannot be compiled; 'parity unpinned' for that row)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+import harness  # noqa: E402
+from leisure_software_renderer_b200 import capi, scenes  # noqa: E402
+from oracle.bindings import Oracle  # noqa: E402
+
+GOLDEN = {
+    "golden_pbr_96x72": (lambda: scenes.scene_small(w=96, h=72), {}),
+    "golden_blinn_tex_clip_96x72": (lambda: scenes.scene_small(w=96, h=72, near_clip=True, tex=True, shading=capi.SHADING_BLINN), {}),
+    "golden_painter_96x72": (lambda: scenes.scene_small(w=96, h=72, seed=4), {"depth": False}),
+    "golden_shadow_pcf_96x72": (lambda: _shadow(), {"shadow": True}),
+    "golden_c1_160x120": (lambda: scenes.scene_c1(160, 120), {}),
+}
+
+
+def _shadow():
+    sd = scenes.scene_small(w=96, h=72, tex=True)
+    sd.fp.shadow_enable = 1
+    sd.shadow_size = 128
+    return sd
+
+
+def main():
+    ref = Oracle("reference")
+    port = Oracle("port")
+    for name, (make, kw) in GOLDEN.items():
+        sd = make()
+        f = harness.cpu_forward(ref, sd, aov=False, **kw)
+        out = {"hdr": f.hdr, "ldr": f.ldr, "stats": np.array([f.stats[k] for k in ("tri_input", "tri_after_clip", "tri_raster")], np.uint64)}
+        if f.depth is not None:
+            out["depth"] = f.depth
+        if f.shadow is not None:
+            out["shadow"], out["lvp"] = f.shadow, f.lvp
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+    sd = scenes.scene_small(w=320, h=200, lights=64)
+    counts, indices = port.light_cull(sd.lights, sd.viewproj, sd.w, sd.h, 16, 128)
+    np.savez_compressed(os.path.join(HERE, "golden_light_lists_320x200_port.npz"), counts=counts, indices=indices)
+    print("light lists", counts.shape, int(counts.max()))
+
+
+if __name__ == "__main__":
+    main()
