@@ -85,7 +85,7 @@ struct shsb_context_t
     // lights + tile lists
     DevBuf<DevLightRec> d_lights;
     uint32_t n_lights = 0;
-    DevBuf<uint8_t> d_light_visible;
+    DevBuf<uint32_t> d_cull_scratch; // macro-cell candidate counts + lists
     DevBuf<uint32_t> d_tile_counts, d_tile_indices;
     uint32_t lists_w = 0, lists_h = 0, lists_ts = 0, lists_max = 0;
     bool lists_valid = false;
@@ -104,9 +104,11 @@ struct shsb_context_t
     DevBuf<RasterRec> d_rrecs;
     DevBuf<ShadeRec> d_srecs;
     DevBuf<uint2> d_clipq;
-    DevBuf<uint32_t> d_tile_count, d_tile_offset, d_tile_fill, d_tile_list;
-    uint32_t* d_counters = nullptr; // [0] rec_count, [1] clipq_count
-    DevStats* d_stats = nullptr;
+    DevBuf<uint32_t> d_tile_offset, d_tile_fill, d_tile_list, d_tile_order;
+    // per-frame header, cleared by ONE memset: [0] rec_count [1] clipq_count [2] list_cursor [4..7] class_count |
+    // [8..23] DevStats | [24 ...] tile_count[n_tiles + 1]
+    DevBuf<uint32_t> d_hdr;
+    static constexpr size_t HDR_STATS = 8, HDR_TILE_COUNT = 24;
     DevStats* h_stats = nullptr;    // pinned
     double rec_growth = 1.0;        // multiplier learned from overflow reruns
 
@@ -286,7 +288,8 @@ namespace
             if (int rc = ensure_dev(ctx, ctx->d_rrecs, rec_cap)) return rc;
             if (!fc.shadow_mode) { if (int rc = ensure_dev(ctx, ctx->d_srecs, rec_cap)) return rc; }
             if (int rc = ensure_dev(ctx, ctx->d_clipq, clipq_cap)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_tile_count, n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_hdr, shsb_context_t::HDR_TILE_COUNT + n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_tile_order, (size_t)4 * n_tiles)) return rc;
             if (int rc = ensure_dev(ctx, ctx->d_tile_offset, n_tiles + 2)) return rc;
             if (int rc = ensure_dev(ctx, ctx->d_tile_fill, n_tiles + 1)) return rc;
             if (int rc = ensure_dev(ctx, ctx->d_tile_list, list_cap)) return rc;
@@ -301,9 +304,9 @@ namespace
                 CK(cudaEventRecord(ctx->stage_done[slot], ctx->stream));
                 ctx->stage_busy[slot] = true;
             }
-            CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(uint32_t), ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), ctx->stream));
-            CK(cudaMemsetAsync(ctx->d_tile_count.p, 0, (size_t)(n_tiles + 1) * sizeof(uint32_t), ctx->stream));
+            uint32_t* hdr = ctx->d_hdr.p;
+            DevStats* d_stats = reinterpret_cast<DevStats*>(hdr + shsb_context_t::HDR_STATS);
+            CK(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), ctx->stream));
 
             Geometry g{};
             g.meshes = ctx->d_meshes.p;
@@ -313,16 +316,19 @@ namespace
             g.rrecs = ctx->d_rrecs.p;
             g.srecs = ctx->d_srecs.p;
             g.rec_capacity = (uint32_t)std::min<size_t>(ctx->d_rrecs.cap, fc.shadow_mode ? ctx->d_rrecs.cap : ctx->d_srecs.cap);
-            g.rec_count = ctx->d_counters + 0;
+            g.rec_count = hdr + 0;
             g.clip_queue = ctx->d_clipq.p;
             g.clipq_capacity = (uint32_t)ctx->d_clipq.cap;
-            g.clipq_count = ctx->d_counters + 1;
-            g.tile_count = ctx->d_tile_count.p;
+            g.clipq_count = hdr + 1;
+            g.list_cursor = hdr + 2;
+            g.class_count = hdr + 4;
+            g.tile_order = ctx->d_tile_order.p;
+            g.tile_count = hdr + shsb_context_t::HDR_TILE_COUNT;
             g.tile_offset = ctx->d_tile_offset.p;
             g.tile_fill = ctx->d_tile_fill.p;
             g.tile_list = ctx->d_tile_list.p;
             g.list_capacity = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFFFull);
-            g.stats = ctx->d_stats;
+            g.stats = d_stats;
 
             record(ctx, 0);
             launch_geometry(fc, g, ctx->stream, &ctx->launches);
@@ -334,7 +340,7 @@ namespace
             CK(cudaGetLastError());
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
-            CK(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             const DevStats& st = *ctx->h_stats;
             if (st.overflow_recs || st.overflow_lists || st.overflow_clipq)
@@ -535,8 +541,6 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     shsb_ctx ctx = new shsb_context_t();
     ctx->device = device_ordinal;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counters, 4 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_stats, sizeof(DevStats)) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
     for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
@@ -566,10 +570,9 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& t : ctx->textures) cudaFree(t.texels);
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
-    cudaFree(ctx->d_lights.p); cudaFree(ctx->d_light_visible.p); cudaFree(ctx->d_tile_counts.p); cudaFree(ctx->d_tile_indices.p);
+    cudaFree(ctx->d_lights.p); cudaFree(ctx->d_cull_scratch.p); cudaFree(ctx->d_tile_counts.p); cudaFree(ctx->d_tile_indices.p);
     cudaFree(ctx->d_items.p); cudaFree(ctx->d_blocks.p); cudaFree(ctx->d_rrecs.p); cudaFree(ctx->d_srecs.p); cudaFree(ctx->d_clipq.p);
-    cudaFree(ctx->d_tile_count.p); cudaFree(ctx->d_tile_offset.p); cudaFree(ctx->d_tile_fill.p); cudaFree(ctx->d_tile_list.p);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_hdr.p); cudaFree(ctx->d_tile_order.p); cudaFree(ctx->d_tile_offset.p); cudaFree(ctx->d_tile_fill.p); cudaFree(ctx->d_tile_list.p);
     cudaFreeHost(ctx->h_stats);
     for (int i = 0; i < shsb_context_t::STAGE_SLOTS; ++i)
     {
@@ -981,7 +984,6 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     if (n_lights && !records) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "records is null");
     CK(cudaSetDevice(ctx->device));
     if (int rc = ensure_dev(ctx, ctx->d_lights, std::max(1u, n_lights))) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_light_visible, std::max(1u, n_lights))) return rc;
     if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights.p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_lights = n_lights;
     ctx->lists_valid = false;
@@ -997,13 +999,13 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
     if (int rc = ensure_dev(ctx, ctx->d_tile_counts, tiles)) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_tile_indices, (size_t)tiles * max_per_tile)) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_lights, 1)) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_light_visible, 1)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_cull_scratch, std::max<size_t>(1, light_cull_scratch_words(ctx->n_lights, vw, vh, ts)))) return rc;
     const hm::mat4f vp = hm::load(view_proj);
     const hm::mat4f inv = hm::inverse(vp);
     float planes[24];
     hm::frustum_planes(vp, planes);
     record(ctx, 4);
-    launch_light_cull(ctx->d_lights.p, ctx->n_lights, planes, &inv.col[0].x, vw, vh, ts, max_per_tile, ctx->d_light_visible.p,
+    launch_light_cull(ctx->d_lights.p, ctx->n_lights, planes, &inv.col[0].x, vw, vh, ts, max_per_tile, ctx->d_cull_scratch.p,
                       ctx->d_tile_counts.p, ctx->d_tile_indices.p, ctx->stream, &ctx->launches);
     record(ctx, 5);
     CK(cudaGetLastError());

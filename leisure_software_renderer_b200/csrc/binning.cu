@@ -7,10 +7,14 @@
 // reference iterates is trivially conservative: a pixel outside the bbox is never tested by the reference,
 // and the tile kernel repeats that bbox test per pixel.
 //
-// Three launches: count (atomicAdd per tile), exclusive scan over tiles, fill.  Small triangles (<= 8
-// tiles) are handled by their own lane; larger ones are walked by the whole warp so that a full-screen
-// triangle does not serialise thousands of atomics in one thread.  List order is arbitrary; visibility
-// is resolved by (depth, draw-order key) in the tile kernel.
+// Per-tile list sizes are counted by the geometry kernels when a record is emitted.  Two launches remain:
+//   alloc : one thread per tile reserves its list segment with one atomicAdd on a global cursor (segment
+//           order in memory is arbitrary -- no serial scan) and files the tile into a scheduling class so
+//           that the tile kernel starts the most expensive tiles first;
+//   fill  : every record appends its index to the segment of each tile its bbox touches.  Small triangles
+//           (<= 8 tiles) are handled by their own lane; larger ones are walked by the whole warp so that a
+//           full-screen triangle does not serialise thousands of atomics in one thread.
+// List order is arbitrary; visibility is resolved by (depth, draw-order key) in the tile kernel.
 #include "shsb_dev.cuh"
 
 namespace shsb
@@ -34,7 +38,6 @@ namespace shsb
             return t;
         }
 
-        template <bool FILL>
         __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(const FrameConst fc, const Geometry g)
         {
             const uint32_t n_recs = min(*g.rec_count, g.rec_capacity);
@@ -59,12 +62,8 @@ namespace shsb
                         for (int tx = tr.tx0; tx <= tr.tx1; ++tx)
                         {
                             const uint32_t t = (uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx;
-                            if (FILL)
-                            {
-                                const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
-                                if (pos < g.list_capacity) g.tile_list[pos] = i;
-                            }
-                            else atomicAdd(&g.tile_count[t], 1u);
+                            const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
+                            if (pos < g.list_capacity) g.tile_list[pos] = i;
                         }
                 }
                 unsigned big = __ballot_sync(0xffffffffu, n_tiles > SMALL_TILES);
@@ -81,75 +80,45 @@ namespace shsb
                     {
                         const int ty = ty0 + k / wx, tx = tx0 + k % wx;
                         const uint32_t t = (uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx;
-                        if (FILL)
-                        {
-                            const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
-                            if (pos < g.list_capacity) g.tile_list[pos] = rec;
-                        }
-                        else atomicAdd(&g.tile_count[t], 1u);
+                        const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
+                        if (pos < g.list_capacity) g.tile_list[pos] = rec;
                     }
                 }
             }
         }
 
-        // Exclusive scan of tile_count -> tile_offset (n+1 entries) by one 1024-thread CTA; also zeroes tile_fill.
-        __global__ void __launch_bounds__(1024) scan_kernel(const Geometry g, uint32_t n_tiles)
+        // One thread per tile: reserve the list segment, reset the write cursor, choose the scheduling class.
+        __global__ void __launch_bounds__(BIN_THREADS) alloc_kernel(const FrameConst fc, const Geometry g, uint32_t n_tiles)
         {
-            __shared__ uint32_t warp_sums[32];
-            __shared__ uint32_t carry;
-            const uint32_t per = (n_tiles + 1023u) / 1024u;
-            const uint32_t begin = min(threadIdx.x * per, n_tiles), end = min(begin + per, n_tiles);
-            uint32_t sum = 0;
-            for (uint32_t t = begin; t < end; ++t) sum += g.tile_count[t];
-            // block-wide exclusive scan of the per-thread sums
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
+            const uint32_t t = blockIdx.x * BIN_THREADS + threadIdx.x;
+            if (t >= n_tiles) return;
+            const uint32_t c = g.tile_count[t];
+            uint32_t off = 0;
+            if (c)
             {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+                off = atomicAdd(g.list_cursor, c);
+                if (off + c > g.list_capacity) atomicAdd(&g.stats->overflow_lists, 1u);
             }
-            if (lane == 31) warp_sums[warp] = incl;
-            __syncthreads();
-            if (warp == 0)
+            g.tile_offset[t] = off;
+            g.tile_fill[t] = 0;
+            // class 0: geometry + saturated light list (walks all lights), 1: geometry + long light list,
+            // 2: geometry, 3: background only
+            uint32_t cls = c ? 2u : 3u;
+            if (c && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE)
             {
-                uint32_t w = warp_sums[lane];
-                uint32_t wi = w;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-                    if (lane >= o) wi += v;
-                }
-                warp_sums[lane] = wi - w; // exclusive
-                if (lane == 31) carry = wi;
+                const uint32_t lc = fc.tile_counts[t];
+                if (lc >= fc.max_per_tile) cls = 0u;
+                else if (lc >= 48u) cls = 1u;
             }
-            __syncthreads();
-            uint32_t run = warp_sums[warp] + (incl - sum);
-            for (uint32_t t = begin; t < end; ++t)
-            {
-                const uint32_t c = g.tile_count[t];
-                g.tile_offset[t] = run;
-                g.tile_fill[t] = 0;
-                run += c;
-            }
-            if (threadIdx.x == 0)
-            {
-                g.tile_offset[n_tiles] = carry;
-                if (carry > g.list_capacity) atomicAdd(&g.stats->overflow_lists, 1u);
-            }
+            g.tile_order[(size_t)cls * n_tiles + atomicAdd(&g.class_count[cls], 1u)] = t;
         }
     }
 
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches)
     {
         const uint32_t n_tiles = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
-        // tile_count was zeroed by the frame's arena reset.  Persistent-style grid: 148 SMs x 8 CTAs.
-        const int grid = 148 * 8;
-        bin_kernel<false><<<grid, BIN_THREADS, 0, s>>>(fc, g);
-        scan_kernel<<<1, 1024, 0, s>>>(g, n_tiles);
-        bin_kernel<true><<<grid, BIN_THREADS, 0, s>>>(fc, g);
-        *launches += 3;
+        alloc_kernel<<<(n_tiles + BIN_THREADS - 1) / BIN_THREADS, BIN_THREADS, 0, s>>>(fc, g, n_tiles);
+        bin_kernel<<<148 * 8, BIN_THREADS, 0, s>>>(fc, g); // persistent-style grid: 148 SMs x 8 CTAs, grid-stride
+        *launches += 2;
     }
 }

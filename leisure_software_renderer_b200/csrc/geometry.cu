@@ -162,6 +162,54 @@ namespace shsb
             for (int i = 0; i < 7; ++i) d2[i] = s2[i]; // 25 words used; the pad tail is never read
         }
 
+        // Per-tile list sizes are counted where the record is born (one pass less than a separate count kernel).
+        // Tile rows are TOP-anchored (y is up in the render target): tile_y = (H-1-y) / TILE.
+        struct TileRange { int tx0, tx1, ty0, ty1; };
+        __device__ __forceinline__ TileRange tile_range(uint32_t bbox_x, uint32_t bbox_y, int H)
+        {
+            TileRange t;
+            t.tx0 = (int)(bbox_x & 0xffffu) / TILE;
+            t.tx1 = (int)(bbox_x >> 16) / TILE;
+            t.ty0 = (H - 1 - (int)(bbox_y >> 16)) / TILE;
+            t.ty1 = (H - 1 - (int)(bbox_y & 0xffffu)) / TILE;
+            return t;
+        }
+
+        // all 32 lanes of the warp must call this; `emit` lanes contribute their record's bbox
+        __device__ __forceinline__ void warp_count_tiles(const FrameConst& fc, const Geometry& g, bool emit, uint32_t bbox_x, uint32_t bbox_y)
+        {
+            TileRange tr{0, -1, 0, -1};
+            int n_tiles = 0;
+            if (emit)
+            {
+                tr = tile_range(bbox_x, bbox_y, fc.H);
+                n_tiles = (tr.tx1 - tr.tx0 + 1) * (tr.ty1 - tr.ty0 + 1);
+            }
+            if (n_tiles > 0 && n_tiles <= 8)
+            {
+                for (int ty = tr.ty0; ty <= tr.ty1; ++ty)
+                    for (int tx = tr.tx0; tx <= tr.tx1; ++tx) atomicAdd(&g.tile_count[(uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx], 1u);
+            }
+            unsigned big = __ballot_sync(0xffffffffu, n_tiles > 8);
+            const int lane = threadIdx.x & 31;
+            while (big)
+            {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const int tx0 = __shfl_sync(0xffffffffu, tr.tx0, src), tx1 = __shfl_sync(0xffffffffu, tr.tx1, src);
+                const int ty0 = __shfl_sync(0xffffffffu, tr.ty0, src), ty1 = __shfl_sync(0xffffffffu, tr.ty1, src);
+                const int wx = tx1 - tx0 + 1, total = wx * (ty1 - ty0 + 1);
+                for (int k = lane; k < total; k += 32) atomicAdd(&g.tile_count[(uint32_t)(ty0 + k / wx) * (uint32_t)fc.tiles_x + (uint32_t)(tx0 + k % wx)], 1u);
+            }
+        }
+
+        __device__ __forceinline__ void thread_count_tiles(const FrameConst& fc, const Geometry& g, uint32_t bbox_x, uint32_t bbox_y)
+        {
+            const TileRange tr = tile_range(bbox_x, bbox_y, fc.H);
+            for (int ty = tr.ty0; ty <= tr.ty1; ++ty)
+                for (int tx = tr.tx0; tx <= tr.tx1; ++tx) atomicAdd(&g.tile_count[(uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx], 1u);
+        }
+
         __device__ __forceinline__ void block_add_stats(DevStats* st, unsigned tri_input, unsigned after_clip, unsigned raster)
         {
             // warp reduce, then one atomic per warp and counter
@@ -231,8 +279,9 @@ namespace shsb
                 {
                     const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
                     if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
-                    else atomicAdd(&g.stats->overflow_recs, 1u);
+                    else { atomicAdd(&g.stats->overflow_recs, 1u); emit = false; }
                 }
+                warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
             }
             block_add_stats(g.stats, n_input, n_after, n_raster);
         }
@@ -293,7 +342,7 @@ namespace shsb
                     if (r & 2)
                     {
                         const uint32_t slot = atomicAdd(g.rec_count, 1u);
-                        if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
+                        if (slot < g.rec_capacity) { store_records(g, slot, rr, sr); thread_count_tiles(fc, g, rr.bbox_x, rr.bbox_y); }
                         else atomicAdd(&g.stats->overflow_recs, 1u);
                     }
                 }
@@ -384,8 +433,9 @@ namespace shsb
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d[i] = s[i];
                     }
-                    else atomicAdd(&g.stats->overflow_recs, 1u);
+                    else { atomicAdd(&g.stats->overflow_recs, 1u); emit = false; }
                 }
+                warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
             }
         }
     }

@@ -7,8 +7,10 @@
 // geometry/jolt_culling.hpp:239-257; sphere :129-147; AABB :152-181; eps 1e-5 :118-122).  Bounds come from
 // the CullingLightGPU record's cull_sphere / cull_aabb_min / cull_aabb_max (lighting/light_types.hpp:141-167).
 //
-// One CTA per tile; lights are strided over the CTA's threads 256 at a time and compacted with warp
-// ballots + a per-warp prefix so the list order is the ascending order of the serial reference loop.
+// Two levels: K4a filters the lights once per 8x8-tile macro cell (exact camera-frustum pre-filter + a
+// conservative macro-cell test), K4b runs the exact per-tile test over the macro cell's candidates only
+// (about 6x fewer sphere/AABB-vs-planes tests than tiles x lights).  Both compact with warp ballots + a
+// per-warp prefix, so list order is the ascending light order of the serial reference loop.
 // Output: counts[T] (uncapped) and indices[T * max_per_tile] (first max_per_tile survivors).
 //
 // Every expression decides list membership => exact helpers only (and the TU is built with --fmad=false).
@@ -18,7 +20,7 @@ namespace shsb
 {
     namespace
     {
-        constexpr int CULL_THREADS = 256;
+        constexpr int CULL_THREADS = 128;
 
         struct Planes6 { float4 p[6]; };
 
@@ -54,25 +56,139 @@ namespace shsb
             return inside ? 2 : 1;
         }
 
-        // camera-frustum pre-filter, jolt_light_culling.hpp:152-161
-        __global__ void light_visible_kernel(const DevLightRec* __restrict__ lights, uint32_t n, const Planes6 frustum, uint8_t* __restrict__ visible)
-        {
-            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-            if (i >= n) return;
-            const float4 sp = *reinterpret_cast<const float4*>(lights[i].cull_sphere);
-            const float4 mn = *reinterpret_cast<const float4*>(lights[i].cull_aabb_min);
-            const float4 mx = *reinterpret_cast<const float4*>(lights[i].cull_aabb_max);
-            visible[i] = classify(frustum.p, sp, mn, mx) != 0 ? 1 : 0;
-        }
-
         struct CullParams
         {
             float inv_vp[16];
             uint32_t vw, vh, ts, max_per_tile, tiles_x, tiles_y, n_lights;
+            uint32_t macro_x, macro_y; // macro cells (MACRO x MACRO tiles) per row / column
         };
 
-        __global__ void __launch_bounds__(CULL_THREADS) tile_cull_kernel(const DevLightRec* __restrict__ lights, const uint8_t* __restrict__ visible,
-                                                                         const CullParams cp, uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
+        constexpr uint32_t MACRO = 8; // tiles per macro-cell edge
+
+        // make_screen_tile_cell, jolt_light_culling.hpp:95-133, evaluated by threads 0..7 (corners) and 0..5 (planes)
+        // of the calling CTA; both stages are followed by a __syncthreads() in the caller.
+        __device__ __forceinline__ void cell_corner(const CullParams& cp, uint32_t tx, uint32_t ty, int c, float out[3])
+        {
+            // corner order nbl nbr ntl ntr fbl fbr ftl ftr (:103-117)
+            const float fw = (float)cp.vw, fh = (float)cp.vh;
+            const float x0 = xsub(xmul(xdiv((float)(tx * cp.ts), fw), 2.0f), 1.0f);
+            const float x1 = xsub(xmul(xdiv((float)min((tx + 1u) * cp.ts, cp.vw), fw), 2.0f), 1.0f);
+            const float y_top = xsub(1.0f, xmul(xdiv((float)(ty * cp.ts), fh), 2.0f));
+            const float y_bottom = xsub(1.0f, xmul(xdiv((float)min((ty + 1u) * cp.ts, cp.vh), fh), 2.0f));
+            const float x = (c & 1) ? x1 : x0;
+            const float y = (c & 2) ? y_top : y_bottom;
+            const float z = (c & 4) ? 1.0f : -1.0f;
+            const float4 q = xmat4_mul(cp.inv_vp, x, y, z, 1.0f);
+            out[0] = xdiv(q.x, q.w);
+            out[1] = xdiv(q.y, q.w);
+            out[2] = xdiv(q.z, q.w);
+        }
+
+        __device__ __forceinline__ float4 cell_plane(const float (*corner)[3], int i)
+        {
+            enum { NBL = 0, NBR = 1, NTL = 2, NTR = 3, FBL = 4, FBR = 5, FTL = 6, FTR = 7 };
+            // plane vertex triples, jolt_light_culling.hpp:125-130: near far left right bottom top
+            const int tri[6][3] = {{NBL, NBR, NTR}, {FBR, FBL, FTL}, {NBL, NTL, FTL}, {NBR, FBR, FTR}, {NBL, FBL, FBR}, {NTL, NTR, FTR}};
+            const float* A = corner[tri[i][0]];
+            const float* B = corner[tri[i][1]];
+            const float* Cc = corner[tri[i][2]];
+            // inside = (nbl + ntr + fbl + ftr) * 0.25
+            F3 in;
+            in.x = xmul(xadd(xadd(xadd(corner[NBL][0], corner[NTR][0]), corner[FBL][0]), corner[FTR][0]), 0.25f);
+            in.y = xmul(xadd(xadd(xadd(corner[NBL][1], corner[NTR][1]), corner[FBL][1]), corner[FTR][1]), 0.25f);
+            in.z = xmul(xadd(xadd(xadd(corner[NBL][2], corner[NTR][2]), corner[FBL][2]), corner[FTR][2]), 0.25f);
+            // make_oriented_plane_from_points, :53-68
+            const F3 e1{xsub(B[0], A[0]), xsub(B[1], A[1]), xsub(B[2], A[2])};
+            const F3 e2{xsub(Cc[0], A[0]), xsub(Cc[1], A[1]), xsub(Cc[2], A[2])};
+            F3 nrm{xsub(xmul(e1.y, e2.z), xmul(e2.y, e1.z)), xsub(xmul(e1.z, e2.x), xmul(e2.z, e1.x)), xsub(xmul(e1.x, e2.y), xmul(e2.x, e1.y))};
+            nrm = xnormalize3(nrm);
+            float d = -xdot3(nrm, F3{A[0], A[1], A[2]});
+            if (xadd(xdot3(nrm, in), d) < 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; d = -d; }
+            return make_float4(nrm.x, nrm.y, nrm.z, d);
+        }
+
+        // K4a -- one CTA per macro cell (8x8 tiles): the exact camera-frustum pre-filter of
+        // jolt_light_culling.hpp:152-161 plus a CONSERVATIVE macro-cell test, producing an ascending candidate list
+        // for the tiles of the cell.  Conservative means: every light the exact per-tile test keeps is a candidate.
+        // Each tile plane family (left / right / bottom / top) is a pencil of planes through the eye; over the
+        // few degrees a macro cell spans, a sphere's signed distance to the planes of one family is monotone or has
+        // a positive interior maximum, so a light can pass a tile's plane only if it passes the family's first or
+        // last plane inside the macro cell.  Both are built exactly like tile planes (first and last tile of the
+        // cell) and tested with a slack (1 cm + 0.1 % of the radius) that dwarfs float differences between a tile's
+        // own plane and the family plane built from other corner points.
+        __global__ void __launch_bounds__(CULL_THREADS) macro_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, const Planes6 frustum,
+                                                                          uint32_t* __restrict__ macro_counts, uint32_t* __restrict__ macro_lists)
+        {
+            __shared__ float s_corner[2][8][3];
+            __shared__ float4 s_plane[2][6];
+            __shared__ uint32_t s_warp_count[CULL_THREADS / 32];
+            const uint32_t mc = blockIdx.x;
+            const uint32_t mx = mc % cp.macro_x, my = mc / cp.macro_x;
+            const uint32_t tx0 = mx * MACRO, ty0 = my * MACRO;
+            const uint32_t tx1 = min(tx0 + MACRO, cp.tiles_x) - 1u, ty1 = min(ty0 + MACRO, cp.tiles_y) - 1u;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (threadIdx.x < 16)
+            {
+                const int which = threadIdx.x >> 3;
+                cell_corner(cp, which ? tx1 : tx0, which ? ty1 : ty0, threadIdx.x & 7, s_corner[which][threadIdx.x & 7]);
+            }
+            __syncthreads();
+            if (threadIdx.x < 12)
+            {
+                const int which = threadIdx.x / 6;
+                s_plane[which][threadIdx.x % 6] = cell_plane(s_corner[which], threadIdx.x % 6);
+            }
+            __syncthreads();
+            float4 pa[6], pb[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { pa[i] = s_plane[0][i]; pb[i] = s_plane[1][i]; }
+
+            uint32_t total = 0;
+            uint32_t* list = macro_lists + (size_t)mc * cp.n_lights;
+            for (uint32_t base = 0; base < cp.n_lights; base += CULL_THREADS)
+            {
+                const uint32_t li = base + threadIdx.x;
+                bool keep = false;
+                if (li < cp.n_lights)
+                {
+                    const float4 sp = __ldg(reinterpret_cast<const float4*>(lights[li].cull_sphere));
+                    const float4 mn = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_min));
+                    const float4 mx4 = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_max));
+                    keep = classify(frustum.p, sp, mn, mx4) != 0; // exact frustum_visible[li]
+                    if (keep)
+                    {
+                        const float r = fmaxf(sp.w, 0.0f);
+                        const float slack = -(r * 1.001f + 1e-2f);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+                        {
+                            const float da = plane_dist(pa[i], sp.x, sp.y, sp.z), db = plane_dist(pb[i], sp.x, sp.y, sp.z);
+                            if (da < slack && db < slack) keep = false;
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                __syncthreads();
+                if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
+                __syncthreads();
+                uint32_t before = 0, chunk_total = 0;
+#pragma unroll
+                for (int w = 0; w < CULL_THREADS / 32; ++w)
+                {
+                    const uint32_t c = s_warp_count[w];
+                    if (w < warp) before += c;
+                    chunk_total += c;
+                }
+                if (keep) list[total + before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = li;
+                total += chunk_total;
+            }
+            if (threadIdx.x == 0) macro_counts[mc] = total;
+        }
+
+        // K4b -- one CTA per tile: the exact test of cull_lights_tiled over the macro cell's candidates.
+        __global__ void __launch_bounds__(CULL_THREADS) tile_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp,
+                                                                         const uint32_t* __restrict__ macro_counts, const uint32_t* __restrict__ macro_lists,
+                                                                         uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
         {
             __shared__ float s_corner[8][3];
             __shared__ float4 s_plane[6];
@@ -81,60 +197,26 @@ namespace shsb
             const uint32_t tile = blockIdx.x;
             const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-            if (threadIdx.x < 8)
-            {
-                // make_screen_tile_cell, jolt_light_culling.hpp:103-117: corner order nbl nbr ntl ntr fbl fbr ftl ftr
-                const float fw = (float)cp.vw, fh = (float)cp.vh;
-                const float x0 = xsub(xmul(xdiv((float)(tx * cp.ts), fw), 2.0f), 1.0f);
-                const float x1 = xsub(xmul(xdiv((float)min((tx + 1u) * cp.ts, cp.vw), fw), 2.0f), 1.0f);
-                const float y_top = xsub(1.0f, xmul(xdiv((float)(ty * cp.ts), fh), 2.0f));
-                const float y_bottom = xsub(1.0f, xmul(xdiv((float)min((ty + 1u) * cp.ts, cp.vh), fh), 2.0f));
-                const int c = threadIdx.x;
-                const float x = (c & 1) ? x1 : x0;
-                const float y = (c & 2) ? y_top : y_bottom;
-                const float z = (c & 4) ? 1.0f : -1.0f;
-                const float4 q = xmat4_mul(cp.inv_vp, x, y, z, 1.0f);
-                s_corner[c][0] = xdiv(q.x, q.w);
-                s_corner[c][1] = xdiv(q.y, q.w);
-                s_corner[c][2] = xdiv(q.z, q.w);
-            }
+            if (threadIdx.x < 8) cell_corner(cp, tx, ty, threadIdx.x, s_corner[threadIdx.x]);
             __syncthreads();
-            if (threadIdx.x < 6)
-            {
-                enum { NBL = 0, NBR = 1, NTL = 2, NTR = 3, FBL = 4, FBR = 5, FTL = 6, FTR = 7 };
-                // plane vertex triples, jolt_light_culling.hpp:125-130: near far left right bottom top
-                const int tri[6][3] = {{NBL, NBR, NTR}, {FBR, FBL, FTL}, {NBL, NTL, FTL}, {NBR, FBR, FTR}, {NBL, FBL, FBR}, {NTL, NTR, FTR}};
-                const int i = threadIdx.x;
-                const float* A = s_corner[tri[i][0]];
-                const float* B = s_corner[tri[i][1]];
-                const float* Cc = s_corner[tri[i][2]];
-                // inside = (nbl + ntr + fbl + ftr) * 0.25
-                F3 in;
-                in.x = xmul(xadd(xadd(xadd(s_corner[NBL][0], s_corner[NTR][0]), s_corner[FBL][0]), s_corner[FTR][0]), 0.25f);
-                in.y = xmul(xadd(xadd(xadd(s_corner[NBL][1], s_corner[NTR][1]), s_corner[FBL][1]), s_corner[FTR][1]), 0.25f);
-                in.z = xmul(xadd(xadd(xadd(s_corner[NBL][2], s_corner[NTR][2]), s_corner[FBL][2]), s_corner[FTR][2]), 0.25f);
-                // make_oriented_plane_from_points, :53-68
-                const F3 e1{xsub(B[0], A[0]), xsub(B[1], A[1]), xsub(B[2], A[2])};
-                const F3 e2{xsub(Cc[0], A[0]), xsub(Cc[1], A[1]), xsub(Cc[2], A[2])};
-                F3 nrm{xsub(xmul(e1.y, e2.z), xmul(e2.y, e1.z)), xsub(xmul(e1.z, e2.x), xmul(e2.z, e1.x)), xsub(xmul(e1.x, e2.y), xmul(e2.x, e1.y))};
-                nrm = xnormalize3(nrm);
-                float d = -xdot3(nrm, F3{A[0], A[1], A[2]});
-                if (xadd(xdot3(nrm, in), d) < 0.0f) { nrm.x = -nrm.x; nrm.y = -nrm.y; nrm.z = -nrm.z; d = -d; }
-                s_plane[i] = make_float4(nrm.x, nrm.y, nrm.z, d);
-            }
+            if (threadIdx.x < 6) s_plane[threadIdx.x] = cell_plane(s_corner, threadIdx.x);
             __syncthreads();
             float4 planes[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) planes[i] = s_plane[i];
 
+            const uint32_t mc = (ty / MACRO) * cp.macro_x + (tx / MACRO);
+            const uint32_t n_cand = macro_counts[mc];
+            const uint32_t* cand = macro_lists + (size_t)mc * cp.n_lights;
             uint32_t total = 0;
-            for (uint32_t base = 0; base < cp.n_lights; base += CULL_THREADS)
+            for (uint32_t base = 0; base < n_cand; base += CULL_THREADS)
             {
-                const uint32_t li = base + threadIdx.x;
+                const uint32_t ci = base + threadIdx.x;
                 bool keep = false;
-                if (li < cp.n_lights && visible[li])
+                uint32_t li = 0;
+                if (ci < n_cand)
                 {
+                    li = cand[ci];
                     const float4 sp = __ldg(reinterpret_cast<const float4*>(lights[li].cull_sphere));
                     const float4 mn = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_min));
                     const float4 mx = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_max));
@@ -163,9 +245,16 @@ namespace shsb
         }
     }
 
+    size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts)
+    {
+        const uint32_t tiles_x = (vw + ts - 1) / ts, tiles_y = (vh + ts - 1) / ts;
+        const size_t n_macro = (size_t)((tiles_x + MACRO - 1) / MACRO) * ((tiles_y + MACRO - 1) / MACRO);
+        return n_macro * ((size_t)n_lights + 1);
+    }
+
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
                            uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
-                           uint8_t* visible_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches)
+                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches)
     {
         CullParams cp;
         for (int i = 0; i < 16; ++i) cp.inv_vp[i] = inv_view_proj[i];
@@ -173,14 +262,15 @@ namespace shsb
         cp.tiles_x = (vw + ts - 1) / ts;
         cp.tiles_y = (vh + ts - 1) / ts;
         cp.n_lights = n_lights;
+        cp.macro_x = (cp.tiles_x + MACRO - 1) / MACRO;
+        cp.macro_y = (cp.tiles_y + MACRO - 1) / MACRO;
         Planes6 fr;
         for (int i = 0; i < 6; ++i) fr.p[i] = make_float4(frustum_planes24[i * 4], frustum_planes24[i * 4 + 1], frustum_planes24[i * 4 + 2], frustum_planes24[i * 4 + 3]);
-        if (n_lights)
-        {
-            light_visible_kernel<<<(n_lights + 255) / 256, 256, 0, s>>>(lights, n_lights, fr, visible_scratch);
-            *launches += 1;
-        }
-        tile_cull_kernel<<<cp.tiles_x * cp.tiles_y, CULL_THREADS, 0, s>>>(lights, visible_scratch, cp, counts, indices);
-        *launches += 1;
+        const uint32_t n_macro = cp.macro_x * cp.macro_y;
+        uint32_t* macro_counts = scratch;
+        uint32_t* macro_lists = scratch + n_macro;
+        macro_cull_kernel<<<n_macro, CULL_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
+        tile_cull_kernel<<<cp.tiles_x * cp.tiles_y, CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
+        *launches += 2;
     }
 }

@@ -179,11 +179,14 @@ namespace shsb
         uint2* clip_queue;          // (item, triangle) pairs that need frustum clipping
         uint32_t clipq_capacity;
         uint32_t* clipq_count;
-        uint32_t* tile_count;       // per tile
-        uint32_t* tile_offset;      // exclusive scan of tile_count (+1 entry: total)
+        uint32_t* tile_count;       // per tile: number of list entries (atomically counted by the geometry kernels)
+        uint32_t* tile_offset;      // per tile: start of its segment in tile_list (allocated by atomicAdd on list_cursor)
         uint32_t* tile_fill;        // per tile write cursor
         uint32_t* tile_list;        // RasterRec indices
         uint32_t list_capacity;
+        uint32_t* list_cursor;      // total entries allocated so far
+        uint32_t* class_count;      // [4] tiles per scheduling class (heaviest first)
+        uint32_t* tile_order;       // [4][n_tiles] tile ids per class; CTA b of the tile kernel takes the b-th tile in class order
         DevStats* stats;
     };
 
@@ -204,5 +207,6 @@ namespace shsb
     // frustum_planes24: the 6 normalised camera-frustum planes (nx, ny, nz, d) computed on the host
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
                            uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
-                           uint8_t* visible_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+    size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts); // u32 words of `scratch`
 }

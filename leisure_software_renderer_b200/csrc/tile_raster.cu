@@ -52,38 +52,55 @@ namespace shsb
             V3 P, N, V, albedo;
             float metallic, roughness;
             bool blinn;
+            // per-pixel invariants of the local-light BRDF, hoisted out of the light loop by finish_surface()
+            V3 F0, diffuse;        // mix(0.04, albedo, metallic); PBR: albedo*(1-metallic)/pi, Blinn: albedo/pi
+            float a2, k, NdotV, g1v, spec_a, spec_b; // Blinn: spec_a = shininess, spec_b = spec_strength
         };
 
+        __device__ __forceinline__ void finish_surface(Surface& s)
+        {
+            s.F0 = mix3(v3(0.04f, 0.04f, 0.04f), s.albedo, s.metallic);
+            if (s.blinn)
+            {
+                const float smooth = 1.0f - sat(s.roughness);
+                s.spec_a = mixf(10.0f, 96.0f, smooth);
+                s.spec_b = mixf(0.15f, 0.65f, smooth);
+                s.diffuse = s.albedo * (1.0f / PI_F);
+                s.a2 = s.k = s.NdotV = s.g1v = 0.0f;
+            }
+            else
+            {
+                const float a = s.roughness * s.roughness;
+                s.a2 = a * a;
+                const float rr = s.roughness + 1.0f;
+                s.k = rr * rr * 0.125f;
+                s.NdotV = fmaxf(dot(s.N, s.V), 0.0f);
+                s.g1v = __fdividef(s.NdotV, fmaxf(s.NdotV * (1.0f - s.k) + s.k, 1e-6f));
+                s.diffuse = s.albedo * ((1.0f - s.metallic) * (1.0f / PI_F));
+                s.spec_a = s.spec_b = 0.0f;
+            }
+        }
+
         // ---- eval_pbr_light / eval_blinn_phong_light, shaders/vulkan/fp_stress_scene.frag:132-165
+        // (same formulas; the three quotients NDF, G2 and 1/(4 NdotV NdotL) share one reciprocal)
         __device__ __forceinline__ V3 eval_brdf(const Surface& s, V3 L, V3 radiance)
         {
             const float NdotL = fmaxf(dot(s.N, L), 0.0f);
             if (NdotL <= 0.0f) return v3(0, 0, 0);
             const V3 H = normalize_fast(s.V + L);
+            const float NdotH = fmaxf(dot(s.N, H), 0.0f);
             if (s.blinn)
             {
-                const float smooth = 1.0f - sat(s.roughness);
-                const float shininess = mixf(10.0f, 96.0f, smooth);
-                const float spec = __powf(fmaxf(dot(s.N, H), 0.0f), shininess);
-                const V3 spec_color = mix3(v3(0.04f, 0.04f, 0.04f), s.albedo, s.metallic);
-                const float spec_strength = mixf(0.15f, 0.65f, smooth);
-                return radiance * (s.albedo * ((1.0f / PI_F) * NdotL) + spec_color * (spec * spec_strength));
+                const float spec = __powf(NdotH, s.spec_a);
+                return radiance * (s.diffuse * NdotL + s.F0 * (spec * s.spec_b));
             }
-            const V3 F0 = mix3(v3(0.04f, 0.04f, 0.04f), s.albedo, s.metallic);
             const float fres = pow5(1.0f - fmaxf(dot(H, s.V), 0.0f));
-            const V3 F = F0 + (v3(1, 1, 1) - F0) * fres;
-            const float a = s.roughness * s.roughness, a2 = a * a;
-            const float NdotH = fmaxf(dot(s.N, H), 0.0f);
-            const float dd = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
-            const float NDF = __fdividef(a2, fmaxf(PI_F * dd * dd, 1e-6f));
-            const float NdotV = fmaxf(dot(s.N, s.V), 0.0f);
-            const float rr = s.roughness + 1.0f, k = rr * rr * 0.125f;
-            const float g1 = __fdividef(NdotV, fmaxf(NdotV * (1.0f - k) + k, 1e-6f));
-            const float g2 = __fdividef(NdotL, fmaxf(NdotL * (1.0f - k) + k, 1e-6f));
-            const float inv_denom = __fdividef(1.0f, fmaxf(4.0f * NdotV * NdotL, 1e-6f));
-            const V3 specular = F * (NDF * g1 * g2 * inv_denom);
-            const V3 kD = (v3(1, 1, 1) - F) * (1.0f - s.metallic);
-            return (kD * s.albedo * (1.0f / PI_F) + specular) * radiance * NdotL;
+            const V3 F = s.F0 + (v3(1, 1, 1) - s.F0) * fres;
+            const float dd = NdotH * NdotH * (s.a2 - 1.0f) + 1.0f;
+            const float den = fmaxf(PI_F * dd * dd, 1e-6f) * fmaxf(NdotL * (1.0f - s.k) + s.k, 1e-6f) * fmaxf(4.0f * s.NdotV * NdotL, 1e-6f);
+            const float spec = __fdividef(s.a2 * s.g1v * NdotL, den);
+            // kD = (1 - F) * (1 - metallic); kD * albedo / pi = (1 - F) * diffuse
+            return ((v3(1, 1, 1) - F) * s.diffuse + F * spec) * radiance * NdotL;
         }
 
         // ---- shs_eval_light_attenuation_quadratic, shaders/vulkan/common/light_math.glsl:44-78
@@ -269,33 +286,49 @@ namespace shsb
 
         __device__ __forceinline__ uchar4 tonemap_pixel(float r, float g, float b, float exposure, float inv_gamma)
         {
-            // PassTonemap, passes/pass_tonemap.hpp:58-80
+            // PassTonemap, passes/pass_tonemap.hpp:58-80: max(0, c*exposure) -> x/(1+x) -> pow(x, 1/gamma) -> lround(x*255).
+            // pow through MUFU lg2/ex2 (relative error ~1e-6): the 8-bit result can differ from libm's only when x*255
+            // lands within ~3e-4 of a rounding boundary, i.e. by at most 1 LSB (the north_star colour gate).
             float c[3] = {r, g, b};
             unsigned char o[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
             {
                 float v = fmaxf(0.0f, c[i] * exposure);
-                v = v / (1.0f + v);
-                v = powf(v, inv_gamma);
-                const long q = lroundf(v * 255.0f);
-                o[i] = (unsigned char)min(max(q, 0l), 255l);
+                v = __fdividef(v, 1.0f + v);
+                v = (v > 0.0f) ? exp2f(inv_gamma * __log2f(v)) : ((inv_gamma == 0.0f) ? 1.0f : 0.0f);
+                const float q = floorf(v * 255.0f + 0.5f); // lround: half away from zero (v >= 0)
+                o[i] = (unsigned char)fminf(fmaxf(q, 0.0f), 255.0f);
             }
             return make_uchar4(o[0], o[1], o[2], 255);
         }
 
-        __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
+        __global__ void __launch_bounds__(TILE_THREADS, 4) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
-            __shared__ __align__(16) RasterRec s_rec[TILE_THREADS];
+            // the triangle staging buffer (raster phase) and the light staging buffer (shading phase) are never live at
+            // the same time: they share one 20-KB allocation
+            __shared__ __align__(16) unsigned char s_stage[TILE_THREADS * sizeof(SmLight)];
+            static_assert(sizeof(SmLight) >= sizeof(RasterRec), "staging buffer is sized by SmLight");
+            RasterRec* s_rec = reinterpret_cast<RasterRec*>(s_stage);
+            SmLight* s_light = reinterpret_cast<SmLight*>(s_stage); // one compaction round = 256 candidate lights
             __shared__ uint32_t s_idx[TILE_THREADS];
-            __shared__ __align__(16) SmLight s_light[TILE_THREADS]; // one compaction round = 256 candidate lights
+            __shared__ unsigned s_wmask[TILE_THREADS / 32][TILE_THREADS / 32]; // [consumer warp][staging warp]
             __shared__ float s_box[TILE_THREADS / 32][6];
             __shared__ uint32_t s_warp_count[TILE_THREADS / 32];
             __shared__ unsigned long long s_frag[2];
 
-            const int tile = blockIdx.x;
+            // heaviest scheduling class first (alloc_kernel, binning.cu): the cheap background tiles fill the tail
+            const uint32_t n_tiles_total = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
+            uint32_t ord = blockIdx.x, cls = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+            {
+                const uint32_t cc = g.class_count[c];
+                if (cls == (uint32_t)c && ord >= cc) { ord -= cc; ++cls; }
+            }
+            const int tile = (int)g.tile_order[(size_t)cls * n_tiles_total + ord];
             const int tx = tile % fc.tiles_x, ty = tile / fc.tiles_x;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             // a warp owns an 8x4-pixel block: 128 contiguous bytes of HDR per row
@@ -307,8 +340,6 @@ namespace shsb
             const bool valid = px < fc.W && fy < fc.H;
             const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
             // warp rectangle in RT coordinates (y up)
-            const int wx1 = wx0 + 7;
-            const int wy_hi = fc.H - 1 - wfy0, wy_lo = wy_hi - 3;
 
             if (threadIdx.x < 2) s_frag[threadIdx.x] = 0ull;
             __syncthreads();
@@ -321,26 +352,45 @@ namespace shsb
             const float zrange = xsub(fc.zf, fc.zn);
 
             const uint32_t off0 = g.tile_offset[tile];
-            const uint32_t off1 = min(g.tile_offset[tile + 1], g.list_capacity);
+            const uint32_t off1 = min(off0 + g.tile_count[tile], g.list_capacity);
             for (uint32_t base = off0; base < off1; base += TILE_THREADS)
             {
                 __syncthreads();
                 const uint32_t n = min((uint32_t)TILE_THREADS, off1 - base);
+                int sminx = 0, smaxx = 0, sminy = 0, smaxy = 0;
                 if (threadIdx.x < n)
                 {
                     const uint32_t rec = g.tile_list[base + threadIdx.x];
                     const float4* src = reinterpret_cast<const float4*>(g.rrecs + rec);
                     float4* dst = reinterpret_cast<float4*>(&s_rec[threadIdx.x]);
-                    dst[0] = __ldg(src + 0); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+                    const float4 q3 = __ldg(src + 3);
+                    dst[0] = __ldg(src + 0); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = q3;
                     s_idx[threadIdx.x] = rec;
+                    const uint32_t bx = __float_as_uint(q3.y), by = __float_as_uint(q3.z);
+                    sminx = (int)(bx & 0xffffu); smaxx = (int)(bx >> 16);
+                    sminy = (int)(by & 0xffffu); smaxy = (int)(by >> 16);
+                }
+                // per consumer warp (8x4-pixel block) a 256-bit mask of the staged triangles whose bbox touches it
+#pragma unroll
+                for (int w = 0; w < TILE_THREADS / 32; ++w)
+                {
+                    const int rx0 = tx * TILE + (w & 1) * 8, rx1 = rx0 + 7;
+                    const int ry_hi = fc.H - 1 - (ty * TILE + (w >> 1) * 4), ry_lo = ry_hi - 3;
+                    const bool hit = threadIdx.x < n && !(smaxx < rx0 || sminx > rx1 || smaxy < ry_lo || sminy > ry_hi);
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (lane == 0) s_wmask[w][warp] = m;
                 }
                 __syncthreads();
-                for (uint32_t j = 0; j < n; ++j)
+                for (int k = 0; k < TILE_THREADS / 32; ++k)
                 {
+                  unsigned wm = s_wmask[warp][k];
+                  while (wm)
+                  {
+                    const uint32_t j = (uint32_t)k * 32u + (uint32_t)(__ffs(wm) - 1);
+                    wm &= wm - 1u;
                     const RasterRec& r = s_rec[j];
                     const int minx = (int)(r.bbox_x & 0xffffu), maxx = (int)(r.bbox_x >> 16);
                     const int miny = (int)(r.bbox_y & 0xffffu), maxy = (int)(r.bbox_y >> 16);
-                    if (maxx < wx0 || minx > wx1 || maxy < wy_lo || miny > wy_hi) continue; // warp-uniform reject
                     if (!valid || px < minx || px > maxx || py < miny || py > maxy) continue;  // the reference's bbox loop bounds
                     // barycentric_2d, rasterizer.hpp:167-179
                     const float v2x = xsub(pxf, r.ax), v2y = xsub(pyf, r.ay);
@@ -376,6 +426,7 @@ namespace shsb
                         if (z01 < bz || (z01 == bz && r.key < bkey)) { bz = z01; bkey = r.key; bidx = s_idx[j]; }
                     }
                     else if (r.key > bkey) { bkey = r.key; bidx = s_idx[j]; }
+                  }
                 }
             }
 
@@ -419,6 +470,8 @@ namespace shsb
             Surface surf;
             surf.P = v3(0, 0, 0); surf.N = v3(0, 1, 0); surf.V = v3(0, 1, 0); surf.albedo = v3(0, 0, 0);
             surf.metallic = 0.0f; surf.roughness = 1.0f; surf.blinn = fc.shader_id == 1;
+            surf.F0 = v3(0, 0, 0); surf.diffuse = v3(0, 0, 0);
+            surf.a2 = surf.k = surf.NdotV = surf.g1v = surf.spec_a = surf.spec_b = 0.0f;
             if (has)
             {
                 // bit-identical to the coverage test above
@@ -517,6 +570,7 @@ namespace shsb
                         surf.metallic = metal; surf.roughness = rough;
                     }
                     out_r = c.x; out_g = c.y; out_b = c.z;
+                    if (fc.forward_plus) finish_surface(surf);
                 }
             }
 
