@@ -159,7 +159,7 @@ def run_ours(args):
         hdr, dm, ldr = sets[i % NSETS]
         if e2e:
             ctx.lights_upload(lights_pinned.numpy())          # H2D 160 B x n_lights from pinned memory
-        ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr)   # draw list H2D inside the call
+        ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=False)   # asynchronous; draw list H2D inside the call
         if world > 1:
             ev = torch.cuda.Event()
             ev.record(stream)

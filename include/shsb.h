@@ -320,6 +320,10 @@ SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8]);
 SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable);
 SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames);
 
+/* Accumulated host-side submit cost in microseconds since the last reset: [0] scene -> draw list (model / normal
+ * matrices), [1] staging copy, [2] arena checks, [3] stream capture / enqueue, [4] graph update + launch, [5] frames. */
+SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

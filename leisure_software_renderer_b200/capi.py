@@ -149,6 +149,7 @@ def load_library(path: str | None = None):
         "shsb_light_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
         "shsb_frame_forward_plus": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(Stats)],
         "shsb_last_stage_ms": [vp, P(C.c_float)],
+        "shsb_host_submit_us": [vp, P(C.c_double), C.c_int32],
         "shsb_timing_enable": [vp, C.c_int32],
         "shsb_timing_collect": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
     }

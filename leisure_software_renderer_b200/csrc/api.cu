@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -115,6 +116,20 @@ struct shsb_context_t
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
 
+    // Frame submission as a CUDA graph: the frame's memset / H2D copy / kernels are stream-captured, an existing
+    // executable graph of the same topology is updated in place (cudaGraphExecUpdate) and launched once.  The
+    // light-culling kernels do not depend on geometry / binning, so in the fused Forward+ frame they are
+    // captured on a second stream (fork / join) and run concurrently with those small launch-bound kernels.
+    bool use_graph = true;
+    bool capturing = false;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t graph_exec[4]{}; // [cull branch][shadow mode]
+
+    // host-side submit cost breakdown (microseconds, accumulated): [0] scene -> draw list, [1] staging copy,
+    // [2] arena checks, [3] capture / enqueue, [4] graph update + launch, [5] frames
+    double host_us[8]{};
+
     // optional per-frame stage timing history (4 events per frame, no host sync while recording)
     bool timing_on = false;
     std::vector<cudaEvent_t> timing_ev;
@@ -123,6 +138,11 @@ struct shsb_context_t
 
 namespace
 {
+    inline double now_us()
+    {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+
     int fail(shsb_ctx c, int code, const char* fmt, ...)
     {
         char buf[512];
@@ -253,9 +273,18 @@ namespace
         uint32_t n_blocks = 0;
     };
 
-    void record(shsb_ctx ctx, int i)
+    void record_on(shsb_ctx ctx, cudaEvent_t e, cudaStream_t s)
     {
-        if (cudaEventRecord(ctx->ev[i], ctx->stream) == cudaSuccess) ctx->ev_valid[i] = true;
+        // inside a stream capture a plain cudaEventRecord would only mark a dependency; External makes it a node
+        if (ctx->capturing) cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+        else cudaEventRecord(e, s);
+    }
+
+    void record(shsb_ctx ctx, int i, cudaStream_t s = nullptr)
+    {
+        if (!s) s = ctx->stream;
+        record_on(ctx, ctx->ev[i], s);
+        ctx->ev_valid[i] = true;
         if (ctx->timing_on && i < 4)
         {
             if (ctx->timing_used == ctx->timing_ev.size())
@@ -264,12 +293,46 @@ namespace
                 if (cudaEventCreate(&e) != cudaSuccess) return;
                 ctx->timing_ev.push_back(e);
             }
-            cudaEventRecord(ctx->timing_ev[ctx->timing_used++], ctx->stream);
+            record_on(ctx, ctx->timing_ev[ctx->timing_used++], s);
         }
     }
 
+    // Host half of cull_lights_tiled: inverse(view_proj) and the camera frustum planes (jolt_light_culling.hpp:150-153).
+    struct CullJob
+    {
+        float planes[24];
+        float inv_vp[16];
+        uint32_t vw = 0, vh = 0, ts = 0, max_per_tile = 0;
+    };
+
+    int prepare_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile, CullJob& job)
+    {
+        if (!view_proj || vw == 0 || vh == 0 || ts == 0 || max_per_tile == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad light-cull arguments");
+        const uint32_t tiles = ((vw + ts - 1) / ts) * ((vh + ts - 1) / ts);
+        if (int rc = ensure_dev(ctx, ctx->d_tile_counts, tiles)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_tile_indices, (size_t)tiles * max_per_tile)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_lights, 1)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_cull_scratch, std::max<size_t>(1, light_cull_scratch_words(ctx->n_lights, vw, vh, ts)))) return rc;
+        const hm::mat4f vp = hm::load(view_proj);
+        const hm::mat4f inv = hm::inverse(vp);
+        hm::frustum_planes(vp, job.planes);
+        hm::store(inv, job.inv_vp);
+        job.vw = vw; job.vh = vh; job.ts = ts; job.max_per_tile = max_per_tile;
+        return SHSB_OK;
+    }
+
+    void enqueue_light_cull(shsb_ctx ctx, const CullJob& job, cudaStream_t s)
+    {
+        record(ctx, 4, s);
+        launch_light_cull(ctx->d_lights.p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, ctx->d_cull_scratch.p,
+                          ctx->d_tile_counts.p, ctx->d_tile_indices.p, s, &ctx->launches);
+        record(ctx, 5, s);
+        ctx->lists_w = job.vw; ctx->lists_h = job.vh; ctx->lists_ts = job.ts; ctx->lists_max = job.max_per_tile;
+        ctx->lists_valid = true;
+    }
+
     // Runs geometry -> binning -> tile raster for the draws staged in ctx->h_items[0..n_items).
-    int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats)
+    int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats, const CullJob* cull = nullptr)
     {
         FrameConst& fc = job.fc;
         fc.tiles_x = (fc.W + TILE - 1) / TILE;
@@ -281,6 +344,7 @@ namespace
 
         for (int attempt = 0; attempt < 4; ++attempt)
         {
+            const double t_a = now_us();
             // capacities: every source triangle may emit one record; clipped ones up to 7
             const size_t clipq_cap = std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth));
             const size_t rec_cap = std::max<size_t>(4096, (size_t)(((double)job.n_src_tris + 6.0 * (double)std::min<size_t>(clipq_cap, job.n_src_tris)) * 1.0));
@@ -296,17 +360,10 @@ namespace
             if (int rc = ensure_dev(ctx, ctx->d_items, std::max<size_t>(1, job.n_items))) return rc;
             if (int rc = ensure_dev(ctx, ctx->d_blocks, std::max<size_t>(1, job.n_blocks))) return rc;
 
-            if (job.n_items)
-            {
-                const int slot = ctx->stage_slot;
-                CK(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items[slot].p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks[slot].p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaEventRecord(ctx->stage_done[slot], ctx->stream));
-                ctx->stage_busy[slot] = true;
-            }
             uint32_t* hdr = ctx->d_hdr.p;
             DevStats* d_stats = reinterpret_cast<DevStats*>(hdr + shsb_context_t::HDR_STATS);
-            CK(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), ctx->stream));
+            const double t_b = now_us();
+            ctx->host_us[2] += t_b - t_a;
 
             Geometry g{};
             g.meshes = ctx->d_meshes.p;
@@ -329,15 +386,83 @@ namespace
             g.tile_list = ctx->d_tile_list.p;
             g.list_capacity = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFFFull);
             g.stats = d_stats;
+            if (cull)
+            {
+                // the lists this frame shades with are the ones the cull branch below produces
+                fc.tile_counts = ctx->d_tile_counts.p;
+                fc.tile_indices = ctx->d_tile_indices.p;
+            }
 
+            const int slot = ctx->stage_slot;
+            const bool graph = ctx->use_graph;
+            cudaStream_t s1 = ctx->stream;
+            if (graph)
+            {
+                CK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
+                ctx->capturing = true;
+            }
+            cudaError_t err = cudaSuccess;
+            auto ok = [&](cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; };
+            if (cull)
+            {
+                if (graph)
+                {
+                    ok(cudaEventRecord(ctx->ev_fork, s1));
+                    ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                    enqueue_light_cull(ctx, *cull, ctx->stream2);
+                    ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                }
+                else enqueue_light_cull(ctx, *cull, s1);
+            }
             record(ctx, 0);
-            launch_geometry(fc, g, ctx->stream, &ctx->launches);
+            ok(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), s1));
+            if (job.n_items)
+            {
+                ok(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items[slot].p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, s1));
+                ok(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks[slot].p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, s1));
+            }
+            launch_geometry(fc, g, s1, &ctx->launches);
             record(ctx, 1);
-            launch_binning(fc, g, ctx->stream, &ctx->launches);
+            launch_binning(fc, g, s1, &ctx->launches);
+            if (cull && graph) ok(cudaStreamWaitEvent(s1, ctx->ev_join, 0));
             record(ctx, 2);
-            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, ctx->stream, &ctx->launches);
+            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
             record(ctx, 3);
-            CK(cudaGetLastError());
+            ok(cudaGetLastError());
+            const double t_c = now_us();
+            ctx->host_us[3] += t_c - t_b;
+            if (graph)
+            {
+                ctx->capturing = false;
+                cudaGraph_t captured = nullptr;
+                const cudaError_t ec = cudaStreamEndCapture(s1, &captured);
+                if (err == cudaSuccess) err = ec;
+                if (err == cudaSuccess)
+                {
+                    cudaGraphExec_t& exec = ctx->graph_exec[(cull ? 2 : 0) + (fc.shadow_mode ? 1 : 0)];
+                    if (exec)
+                    {
+                        cudaGraphExecUpdateResultInfo info{};
+                        if (cudaGraphExecUpdate(exec, captured, &info) != cudaSuccess)
+                        {
+                            cudaGetLastError(); // different topology (e.g. no draws this frame): rebuild
+                            cudaGraphExecDestroy(exec);
+                            exec = nullptr;
+                        }
+                    }
+                    if (!exec) err = cudaGraphInstantiate(&exec, captured, 0);
+                    if (err == cudaSuccess) err = cudaGraphLaunch(exec, s1);
+                }
+                if (captured) cudaGraphDestroy(captured);
+            }
+            if (err != cudaSuccess) return fail(ctx, SHSB_E_CUDA, "frame submission failed: %s", cudaGetErrorString(err));
+            if (job.n_items)
+            {
+                CK(cudaEventRecord(ctx->stage_done[slot], s1));
+                ctx->stage_busy[slot] = true;
+            }
+            ctx->host_us[4] += now_us() - t_c;
+            ctx->host_us[5] += 1.0;
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
             CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
@@ -421,7 +546,8 @@ namespace
     }
 
     int forward_common(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt hdr_rt, shsb_rt depth_rt, shsb_rt shadow_rt,
-                       const float* shadow_lvp, int preserve_depth, bool depth_only, shsb_rt ldr_rt, ShsbStats* out_stats)
+                       const float* shadow_lvp, int preserve_depth, bool depth_only, shsb_rt ldr_rt, ShsbStats* out_stats,
+                       const CullJob* cull = nullptr)
     {
         if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
         if (scene->n_items && !scene->items) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene->items is null");
@@ -466,17 +592,18 @@ namespace
         }
         if (!depth_only && fp->light_culling && ctx->n_lights > 0)
         {
-            if (!ctx->lists_valid || ctx->lists_w != (uint32_t)W || ctx->lists_h != (uint32_t)H)
+            if (!cull && (!ctx->lists_valid || ctx->lists_w != (uint32_t)W || ctx->lists_h != (uint32_t)H))
                 return fail(ctx, SHSB_E_INVALID_ARGUMENT, "light_culling is on but shsb_light_cull has not been run for a %dx%d viewport", W, H);
+            const uint32_t ts = cull ? cull->ts : ctx->lists_ts, mx = cull ? cull->max_per_tile : ctx->lists_max;
             fc.forward_plus = 1;
             fc.lights = ctx->d_lights.p;
             fc.n_lights = ctx->n_lights;
             fc.tile_counts = ctx->d_tile_counts.p;
             fc.tile_indices = ctx->d_tile_indices.p;
-            fc.light_tile_size = ctx->lists_ts;
-            fc.max_per_tile = ctx->lists_max;
-            fc.light_tiles_x = (W + ctx->lists_ts - 1) / ctx->lists_ts;
-            fc.light_tiles_y = (H + ctx->lists_ts - 1) / ctx->lists_ts;
+            fc.light_tile_size = ts;
+            fc.max_per_tile = mx;
+            fc.light_tiles_x = (W + ts - 1) / ts;
+            fc.light_tiles_y = (H + ts - 1) / ts;
         }
         if (ldr)
         {
@@ -496,6 +623,7 @@ namespace
             job.fb.aov_coverage = host->coverage;
         }
 
+        const double t_items = now_us();
         std::vector<DevItem> items;
         std::vector<uint2> blocks;
         items.reserve(scene->n_items);
@@ -511,11 +639,14 @@ namespace
             if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex);
             else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u);
         }
+        const double t_stage = now_us();
+        ctx->host_us[0] += t_stage - t_items;
         if (int rc = upload_staging(ctx, items, blocks)) return rc;
+        ctx->host_us[1] += now_us() - t_stage;
         job.n_items = (uint32_t)items.size();
         job.n_blocks = (uint32_t)blocks.size();
         job.n_src_tris = tri_cursor;
-        return run_frame(ctx, job, out_stats);
+        return run_frame(ctx, job, out_stats, cull);
     }
 }
 
@@ -541,6 +672,10 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     shsb_ctx ctx = new shsb_context_t();
     ctx->device = device_ordinal;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats), cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
     for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
@@ -582,6 +717,10 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     }
     for (int i = 0; i < NUM_STAGE_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->timing_ev) cudaEventDestroy(e);
+    for (cudaGraphExec_t e : ctx->graph_exec) if (e) cudaGraphExecDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SHSB_OK;
@@ -901,12 +1040,14 @@ SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, c
     CK(cudaSetDevice(ctx->device));
     RtSlot* hdr = get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
     if (!hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR");
-    if (fp->light_culling && ctx->n_lights > 0)
+    CullJob cull;
+    const bool with_cull = fp->light_culling && ctx->n_lights > 0;
+    if (with_cull)
     {
-        if (int rc = shsb_light_cull(ctx, scene->cam_viewproj, (uint32_t)hdr->w, (uint32_t)hdr->h, std::max(1u, fp->tile_size), std::max(1u, fp->max_lights_per_tile))) return rc;
+        if (int rc = prepare_light_cull(ctx, scene->cam_viewproj, (uint32_t)hdr->w, (uint32_t)hdr->h, std::max(1u, fp->tile_size), std::max(1u, fp->max_lights_per_tile), cull)) return rc;
     }
     if (out_stats) *out_stats = ShsbStats{};
-    return forward_common(ctx, scene, fp, hdr_rt, depth_motion_rt, 0, nullptr, 0, false, ldr_rt, out_stats);
+    return forward_common(ctx, scene, fp, hdr_rt, depth_motion_rt, 0, nullptr, 0, false, ldr_rt, out_stats, with_cull ? &cull : nullptr);
 }
 
 SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp, shsb_rt shadow_rt, float out_light_viewproj[16])
@@ -993,24 +1134,11 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
 SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
-    if (!view_proj || vw == 0 || vh == 0 || ts == 0 || max_per_tile == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad light-cull arguments");
     CK(cudaSetDevice(ctx->device));
-    const uint32_t tiles = ((vw + ts - 1) / ts) * ((vh + ts - 1) / ts);
-    if (int rc = ensure_dev(ctx, ctx->d_tile_counts, tiles)) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_tile_indices, (size_t)tiles * max_per_tile)) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_lights, 1)) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_cull_scratch, std::max<size_t>(1, light_cull_scratch_words(ctx->n_lights, vw, vh, ts)))) return rc;
-    const hm::mat4f vp = hm::load(view_proj);
-    const hm::mat4f inv = hm::inverse(vp);
-    float planes[24];
-    hm::frustum_planes(vp, planes);
-    record(ctx, 4);
-    launch_light_cull(ctx->d_lights.p, ctx->n_lights, planes, &inv.col[0].x, vw, vh, ts, max_per_tile, ctx->d_cull_scratch.p,
-                      ctx->d_tile_counts.p, ctx->d_tile_indices.p, ctx->stream, &ctx->launches);
-    record(ctx, 5);
+    CullJob job;
+    if (int rc = prepare_light_cull(ctx, view_proj, vw, vh, ts, max_per_tile, job)) return rc;
+    enqueue_light_cull(ctx, job, ctx->stream);
     CK(cudaGetLastError());
-    ctx->lists_w = vw; ctx->lists_h = vh; ctx->lists_ts = ts; ctx->lists_max = max_per_tile;
-    ctx->lists_valid = true;
     return SHSB_OK;
 }
 
@@ -1052,6 +1180,14 @@ SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_fra
     }
     *out_frames = frames;
     ctx->timing_used = 0;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t reset)
+{
+    if (!ctx || !out_us) return SHSB_E_INVALID_ARGUMENT;
+    for (int i = 0; i < 8; ++i) out_us[i] = ctx->host_us[i];
+    if (reset) for (double& v : ctx->host_us) v = 0.0;
     return SHSB_OK;
 }
 

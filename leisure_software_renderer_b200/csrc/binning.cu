@@ -88,29 +88,52 @@ namespace shsb
         }
 
         // One thread per tile: reserve the list segment, reset the write cursor, choose the scheduling class.
+        // Atomics are warp-aggregated: one atomicAdd per warp on the list cursor and one per (warp, class).
         __global__ void __launch_bounds__(BIN_THREADS) alloc_kernel(const FrameConst fc, const Geometry g, uint32_t n_tiles)
         {
             const uint32_t t = blockIdx.x * BIN_THREADS + threadIdx.x;
-            if (t >= n_tiles) return;
-            const uint32_t c = g.tile_count[t];
-            uint32_t off = 0;
-            if (c)
+            const int lane = threadIdx.x & 31;
+            const bool live = t < n_tiles;
+            const uint32_t c = live ? g.tile_count[t] : 0u;
+            // warp exclusive scan of the counts -> one cursor atomic per warp
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                off = atomicAdd(g.list_cursor, c);
-                if (off + c > g.list_capacity) atomicAdd(&g.stats->overflow_lists, 1u);
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            g.tile_offset[t] = off;
-            g.tile_fill[t] = 0;
+            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (lane == 31 && warp_total) base = atomicAdd(g.list_cursor, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            const uint32_t off = base + incl - c;
+            if (lane == 31 && warp_total && base + warp_total > g.list_capacity) atomicAdd(&g.stats->overflow_lists, 1u);
             // class 0: geometry + saturated light list (walks all lights), 1: geometry + long light list,
             // 2: geometry, 3: background only
             uint32_t cls = c ? 2u : 3u;
-            if (c && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE)
+            if (live && c && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE)
             {
                 const uint32_t lc = fc.tile_counts[t];
                 if (lc >= fc.max_per_tile) cls = 0u;
                 else if (lc >= 48u) cls = 1u;
             }
-            g.tile_order[(size_t)cls * n_tiles + atomicAdd(&g.class_count[cls], 1u)] = t;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, live && cls == k);
+                if (!m) continue;
+                uint32_t cbase = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) cbase = atomicAdd(&g.class_count[k], (uint32_t)__popc(m));
+                cbase = __shfl_sync(0xffffffffu, cbase, leader);
+                if (live && cls == k) g.tile_order[(size_t)k * n_tiles + cbase + (uint32_t)__popc(m & ((1u << lane) - 1u))] = t;
+            }
+            if (live)
+            {
+                g.tile_offset[t] = off;
+                g.tile_fill[t] = 0;
+            }
         }
     }
 

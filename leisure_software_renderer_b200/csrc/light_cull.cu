@@ -20,7 +20,8 @@ namespace shsb
 {
     namespace
     {
-        constexpr int CULL_THREADS = 128;
+        constexpr int CULL_THREADS = 128;   // per-tile kernel: a macro cell rarely has more than ~250 candidates
+        constexpr int MACRO_THREADS = 512;  // per-macro-cell kernel walks every light
 
         struct Planes6 { float4 p[6]; };
 
@@ -116,12 +117,12 @@ namespace shsb
         // last plane inside the macro cell.  Both are built exactly like tile planes (first and last tile of the
         // cell) and tested with a slack (1 cm + 0.1 % of the radius) that dwarfs float differences between a tile's
         // own plane and the family plane built from other corner points.
-        __global__ void __launch_bounds__(CULL_THREADS) macro_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, const Planes6 frustum,
+        __global__ void __launch_bounds__(MACRO_THREADS) macro_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, const Planes6 frustum,
                                                                           uint32_t* __restrict__ macro_counts, uint32_t* __restrict__ macro_lists)
         {
             __shared__ float s_corner[2][8][3];
             __shared__ float4 s_plane[2][6];
-            __shared__ uint32_t s_warp_count[CULL_THREADS / 32];
+            __shared__ uint32_t s_warp_count[MACRO_THREADS / 32];
             const uint32_t mc = blockIdx.x;
             const uint32_t mx = mc % cp.macro_x, my = mc / cp.macro_x;
             const uint32_t tx0 = mx * MACRO, ty0 = my * MACRO;
@@ -145,7 +146,7 @@ namespace shsb
 
             uint32_t total = 0;
             uint32_t* list = macro_lists + (size_t)mc * cp.n_lights;
-            for (uint32_t base = 0; base < cp.n_lights; base += CULL_THREADS)
+            for (uint32_t base = 0; base < cp.n_lights; base += MACRO_THREADS)
             {
                 const uint32_t li = base + threadIdx.x;
                 bool keep = false;
@@ -173,7 +174,7 @@ namespace shsb
                 __syncthreads();
                 uint32_t before = 0, chunk_total = 0;
 #pragma unroll
-                for (int w = 0; w < CULL_THREADS / 32; ++w)
+                for (int w = 0; w < MACRO_THREADS / 32; ++w)
                 {
                     const uint32_t c = s_warp_count[w];
                     if (w < warp) before += c;
@@ -269,7 +270,7 @@ namespace shsb
         const uint32_t n_macro = cp.macro_x * cp.macro_y;
         uint32_t* macro_counts = scratch;
         uint32_t* macro_lists = scratch + n_macro;
-        macro_cull_kernel<<<n_macro, CULL_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
+        macro_cull_kernel<<<n_macro, MACRO_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
         tile_cull_kernel<<<cp.tiles_x * cp.tiles_y, CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
         *launches += 2;
     }

@@ -160,9 +160,10 @@ class Context:
         _check(self.lib, self.h, rc, "shsb_light_lists_download")
         return counts, indices.reshape(self._tiles, self._max_per_tile)
 
-    def frame_forward_plus(self, scene: Scene, fp: FrameParams, hdr_rt, depth_rt, ldr_rt) -> Stats:
-        st = Stats()
-        rc = self.lib.shsb_frame_forward_plus(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, ldr_rt, C.byref(st))
+    def frame_forward_plus(self, scene: Scene, fp: FrameParams, hdr_rt, depth_rt, ldr_rt, want_stats=True):
+        """want_stats=False submits asynchronously (no stats read-back, no host synchronisation) and returns None."""
+        st = Stats() if want_stats else None
+        rc = self.lib.shsb_frame_forward_plus(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, ldr_rt, C.byref(st) if want_stats else None)
         _check(self.lib, self.h, rc, "shsb_frame_forward_plus")
         if fp.light_culling:
             _, w, h = self._rt_shape[hdr_rt]
@@ -183,6 +184,11 @@ class Context:
         n = C.c_uint64()
         _check(self.lib, self.h, self.lib.shsb_launch_count(self.h, C.byref(n)), "shsb_launch_count")
         return n.value
+
+    def host_submit_us(self, reset=True) -> np.ndarray:
+        a = np.zeros(8, dtype=np.float64)
+        _check(self.lib, self.h, self.lib.shsb_host_submit_us(self.h, a.ctypes.data_as(C.POINTER(C.c_double)), int(reset)), "shsb_host_submit_us")
+        return a
 
     def timing_enable(self, on=True):
         _check(self.lib, self.h, self.lib.shsb_timing_enable(self.h, int(on)), "shsb_timing_enable")
