@@ -126,6 +126,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the raster path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = Context(local_rank)
@@ -153,29 +154,41 @@ def run_ours(args):
 
     ldr_views = [ldr_tensor(s[2]) for s in sets]
     gather_bufs = [torch.empty_like(ldr_views[0]) for _ in range(world)] if (world > 1 and rank == 0) else None
-    host_ldr = torch.empty(W * H * 4, dtype=torch.uint8).pin_memory()
+    host_ldr = [torch.empty(W * H * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    comm_stream = torch.cuda.Stream(device=local_rank) if world > 1 else None
+    gather_done = [None] * NSETS   # per render-target set: the gather that last read its LDR plane
+    last_gather = [None]
 
     def step(i, e2e=False):
-        hdr, dm, ldr = sets[i % NSETS]
+        k = i % NSETS
+        hdr, dm, ldr = sets[k]
         if e2e:
             ctx.lights_upload(lights_pinned.numpy())          # H2D 160 B x n_lights from pinned memory
+        if world > 1 and gather_done[k] is not None:
+            stream.wait_event(gather_done[k])                 # do not overwrite an LDR plane that is still being gathered
         ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=False)   # asynchronous; draw list H2D inside the call
         if world > 1:
+            # frame assembly over NVLink: the gather of frame i runs on its own stream and overlaps with frame i+1
             ev = torch.cuda.Event()
             ev.record(stream)
-            torch.cuda.current_stream().wait_event(ev)
-            dist.gather(ldr_views[i % NSETS], gather_bufs, dst=0)   # frame assembly over NVLink
-            ev2 = torch.cuda.Event()
-            ev2.record(torch.cuda.current_stream())
-            stream.wait_event(ev2)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev)
+                dist.gather(ldr_views[k], gather_bufs, dst=0)
+                done = torch.cuda.Event()
+                done.record(comm_stream)
+            gather_done[k] = done
+            last_gather[0] = done
         if e2e:
-            ctx.rt_download_into(ldr, capi.PLANE_COLOR, host_ldr.data_ptr(), W * H * 4)  # D2H of the step's result
+            # D2H of the step's result into pinned memory (copy stream: overlaps with the next step's rendering)
+            ctx.rt_download_async(ldr, capi.PLANE_COLOR, host_ldr[i % 2].data_ptr(), W * H * 4)
 
     def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ctx.sync()
 
     # one frame with statistics (also sizes the per-frame arena), then warm-up
     st = ctx.frame_forward_plus(sd.scene, fp, *sets[0]).as_dict()
@@ -196,8 +209,10 @@ def run_ours(args):
         e0.record(stream)
         for i in range(args.steps):
             step(i, e2e)
-        if world > 1:
-            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); stream.wait_event(ev)
+        if world > 1 and last_gather[0] is not None:
+            stream.wait_event(last_gather[0])  # the last frame assembly belongs to the timed region
+        if e2e:
+            ctx.sync()  # the last read-backs (copy stream) belong to the timed region
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

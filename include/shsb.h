@@ -247,6 +247,10 @@ SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt);
 SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* value);
 SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* src, size_t bytes);
 SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst, size_t bytes);
+/* Asynchronous download into PINNED host memory on the context's copy stream: the copy starts when everything
+ * submitted so far has finished and overlaps with later submissions; a later pass that writes `rt` waits for
+ * it.  The data is valid after shsb_sync(). */
+SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst_pinned, size_t bytes);
 /* Raw device pointer of a plane (for NCCL frame gather through torch.distributed). */
 SHSB_API int32_t shsb_rt_device_ptr(shsb_ctx ctx, shsb_rt rt, int32_t plane, void** out_ptr, size_t* out_bytes);
 

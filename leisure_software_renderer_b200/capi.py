@@ -136,6 +136,7 @@ def load_library(path: str | None = None):
         "shsb_rt_clear": [vp, C.c_uint32, C.c_int32, vp],
         "shsb_rt_upload": [vp, C.c_uint32, C.c_int32, vp, C.c_size_t],
         "shsb_rt_download": [vp, C.c_uint32, C.c_int32, vp, C.c_size_t],
+        "shsb_rt_download_async": [vp, C.c_uint32, C.c_int32, vp, C.c_size_t],
         "shsb_rt_device_ptr": [vp, C.c_uint32, C.c_int32, P(vp), P(C.c_size_t)],
         "shsb_model_from_transform": [P(Transform), P(C.c_float)],
         "shsb_camera_viewproj": [P(C.c_float), P(C.c_float), P(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, P(C.c_float)],

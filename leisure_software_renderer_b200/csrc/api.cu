@@ -51,6 +51,8 @@ namespace
         float2* motion = nullptr; // DEPTH_MOTION
         uint32_t* tri_id = nullptr;
         uint32_t* coverage = nullptr;
+        cudaEvent_t read_done = nullptr; // last asynchronous download of this RT (copy stream)
+        bool read_pending = false;
     };
 
     template <typename T>
@@ -123,7 +125,8 @@ struct shsb_context_t
     bool use_graph = true;
     bool capturing = false;
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy_stream = nullptr; // asynchronous render-target downloads
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_frame_done = nullptr;
     cudaGraphExec_t graph_exec[4]{}; // [cull branch][shadow mode]
 
     // host-side submit cost breakdown (microseconds, accumulated): [0] scene -> draw list, [1] staging copy,
@@ -519,6 +522,16 @@ namespace
         return SHSB_OK;
     }
 
+    // A pass that is about to overwrite a render target must not overtake an asynchronous download of it.
+    void wait_pending_read(shsb_ctx ctx, RtSlot* r)
+    {
+        if (r && r->read_pending)
+        {
+            cudaStreamWaitEvent(ctx->stream, r->read_done, 0);
+            r->read_pending = false;
+        }
+    }
+
     int shader_from_params(const ShsbFrameParams* fp)
     {
         int shader = (fp->shading_model == SHSB_SHADING_BLINN_PHONG) ? SHSB_SHADER_BLINN_PHONG : SHSB_SHADER_PBR_MR; // pass_pbr_forward.hpp:100-108
@@ -561,6 +574,10 @@ namespace
         const int W = hdr ? hdr->w : dm->w, H = hdr ? hdr->h : dm->h;
         RtSlot* ldr = ldr_rt ? get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR) : nullptr;
         if (ldr_rt && (!ldr || ldr->w != W || ldr->h != H)) return fail(ctx, SHSB_E_INVALID_HANDLE, "ldr_rt is not a live RT_ColorLDR of the HDR target's size");
+
+        wait_pending_read(ctx, hdr);
+        wait_pending_read(ctx, dm);
+        wait_pending_read(ctx, ldr);
 
         FrameJob job;
         FrameConst& fc = job.fc;
@@ -673,6 +690,8 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ctx->device = device_ordinal;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
@@ -720,6 +739,9 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (cudaGraphExec_t e : ctx->graph_exec) if (e) cudaGraphExecDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -732,6 +754,7 @@ SHSB_API int32_t shsb_sync(shsb_ctx ctx)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     return SHSB_OK;
 }
 
@@ -867,7 +890,9 @@ SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     cudaFree(r->color); cudaFree(r->depth); cudaFree(r->motion); cudaFree(r->tri_id); cudaFree(r->coverage);
+    if (r->read_done) cudaEventDestroy(r->read_done);
     *r = RtSlot{};
     return SHSB_OK;
 }
@@ -913,6 +938,25 @@ SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void*
     if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
     CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst_pinned, size_t bytes)
+{
+    if (!ctx || !dst_pinned) return SHSB_E_INVALID_ARGUMENT;
+    RtSlot* r = get_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t want = plane_bytes(*r, plane, &p);
+    if (!want) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
+    if (!r->read_done) CK(cudaEventCreateWithFlags(&r->read_done, cudaEventDisableTiming));
+    // copy stream waits for everything submitted to the render stream so far, then copies while later frames render
+    CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
+    CK(cudaMemcpyAsync(dst_pinned, p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(r->read_done, ctx->copy_stream));
+    r->read_pending = true;
     return SHSB_OK;
 }
 

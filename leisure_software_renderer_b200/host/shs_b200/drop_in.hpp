@@ -1,0 +1,320 @@
+// shs_b200/drop_in.hpp -- the reference-side binding of the B200 raster path (C++20, header-only).
+//
+// A maintainer of leisure-software-renderer adds this header to shs-renderer-lib, links libshsb.so and swaps
+//     shs::rasterize_mesh(...)              ->  shs::b200::rasterize_mesh(dev, ...)
+//     shs::PassPBRForward::execute(...)     ->  shs::b200::PassPBRForward(dev).execute(...)
+//     shs::PassShadowMap::execute(...)      ->  shs::b200::PassShadowMap(dev).execute(...)
+//     shs::PassTonemap::execute(...)        ->  shs::b200::PassTonemap(dev).execute(...)
+// Same argument types (the reference's own MeshData / ShaderUniforms / RasterizerTarget / Scene / FrameParams /
+// RTRegistry), same results, same error convention (invalid input => silent return with zero stats,
+// sw_render/rasterizer.hpp:190-194, passes/pass_pbr_forward.hpp:51-58).
+//
+// It needs the reference's headers (and therefore GLM) on the include path, so it is compiled only inside the
+// reference tree -- in this repository by tests/cpp/Makefile against oracle/glm_shim.
+//
+// Host <-> device: the reference's render targets are std::vector-backed (gfx/rt_types.hpp:35-59).  Device keeps a
+// device twin per host RT object; passes run on the twins and `Device::download(rt)` (or the `sync_host` flag of the
+// pass wrappers, default true) copies results back, so existing code that reads hdr->color.at(x, y) keeps working.
+#pragma once
+
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "shs/core/context.hpp"
+#include "shs/passes/pass_pbr_forward.hpp"
+#include "shs/passes/pass_shadow_map.hpp"
+#include "shs/passes/pass_tonemap.hpp"
+#include "shs/sw_render/rasterizer.hpp"
+
+#include "shsb.h"
+
+namespace shs::b200
+{
+    // The builtin ShaderProgram factories are the only programs that exist on the device (std::function bodies cannot
+    // be shipped to a GPU): shader/builtin_shaders.hpp:105,154,221 and pipeline/pass_adapters.hpp:335.
+    enum class BuiltinProgram : int32_t
+    {
+        PbrMetalRough = SHSB_SHADER_PBR_MR,
+        BlinnPhong = SHSB_SHADER_BLINN_PHONG,
+        DebugAlbedo = SHSB_SHADER_DEBUG_ALBEDO,
+        DebugNormal = SHSB_SHADER_DEBUG_NORMAL,
+        DebugDepth = SHSB_SHADER_DEBUG_DEPTH,
+        DepthOnly = SHSB_SHADER_DEPTH_ONLY
+    };
+
+    class Device
+    {
+    public:
+        explicit Device(int cuda_device = 0) { ok_ = shsb_context_create(cuda_device, &ctx_) == SHSB_OK; }
+        ~Device() { if (ctx_) shsb_context_destroy(ctx_); }
+        Device(const Device&) = delete;
+        Device& operator=(const Device&) = delete;
+
+        bool valid() const { return ok_; }
+        shsb_ctx ctx() const { return ctx_; }
+        const char* last_error() const { return ctx_ ? shsb_last_error_string(ctx_) : "no CUDA device (there is no CPU fallback)"; }
+
+        // ---- assets (uploaded once, keyed by the host object's address like ShadowRuntimeState::mesh_bounds_cache)
+        shsb_mesh mesh(const MeshData& m)
+        {
+            auto it = meshes_.find(&m);
+            if (it != meshes_.end()) return it->second;
+            shsb_mesh h = 0;
+            static_assert(sizeof(glm::vec3) == 12 && sizeof(glm::vec2) == 8, "MeshData streams are tightly packed");
+            shsb_mesh_upload(ctx_, m.positions.empty() ? nullptr : &m.positions[0].x, (uint32_t)m.positions.size(),
+                             m.normals.empty() ? nullptr : &m.normals[0].x, (uint32_t)m.normals.size(),
+                             m.uvs.empty() ? nullptr : &m.uvs[0].x, (uint32_t)m.uvs.size(),
+                             m.indices.empty() ? nullptr : m.indices.data(), (uint32_t)m.indices.size(), &h);
+            meshes_[&m] = h;
+            return h;
+        }
+
+        shsb_tex texture(const Texture2DData* t)
+        {
+            if (!t || !t->valid()) return 0;
+            auto it = textures_.find(t);
+            if (it != textures_.end()) return it->second;
+            shsb_tex h = 0;
+            shsb_texture_upload(ctx_, &t->texels[0].r, t->w, t->h, &h);
+            textures_[t] = h;
+            return h;
+        }
+
+        // ---- render-target twins
+        shsb_rt twin(RT_ColorHDR* rt) { return rt ? twin_of(rt, SHSB_RT_COLOR_HDR, rt->w, rt->h, 0.1f, 1000.0f) : 0; }
+        shsb_rt twin(RT_ColorLDR* rt) { return rt ? twin_of(rt, SHSB_RT_COLOR_LDR, rt->w, rt->h, 0.1f, 1000.0f) : 0; }
+        shsb_rt twin(RT_ColorDepthMotion* rt) { return rt ? twin_of(rt, SHSB_RT_DEPTH_MOTION, rt->w, rt->h, rt->zn, rt->zf) : 0; }
+        shsb_rt twin(RT_ShadowDepth* rt) { return rt ? twin_of(rt, SHSB_RT_SHADOW, rt->w, rt->h, 0.1f, 1000.0f) : 0; }
+
+        void upload(RT_ColorHDR* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(ColorF)); }
+        void upload(RT_ColorDepthMotion* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data.data(), rt->depth.data.size() * sizeof(float)); }
+        void upload(RT_ShadowDepth* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
+        void download(RT_ColorHDR* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(ColorF)); }
+        void download(RT_ColorLDR* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(Color)); }
+        void download(RT_ColorDepthMotion* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data.data(), rt->depth.data.size() * sizeof(float)); }
+        void download(RT_ShadowDepth* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
+
+    private:
+        shsb_rt twin_of(const void* key, int32_t kind, int w, int h, float zn, float zf)
+        {
+            auto it = rts_.find(key);
+            if (it != rts_.end()) return it->second;
+            shsb_rt h_rt = 0;
+            if (w > 0 && h > 0) shsb_rt_create(ctx_, kind, w, h, zn, zf, &h_rt);
+            rts_[key] = h_rt;
+            return h_rt;
+        }
+
+        shsb_ctx ctx_ = nullptr;
+        bool ok_ = false;
+        std::unordered_map<const void*, shsb_mesh> meshes_{};
+        std::unordered_map<const void*, shsb_tex> textures_{};
+        std::unordered_map<const void*, shsb_rt> rts_{};
+    };
+
+    namespace detail
+    {
+        inline void copy_mat(const glm::mat4& m, float out[16]) { std::memcpy(out, &m, 64); }
+        inline void copy_vec(const glm::vec3& v, float out[3]) { out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+
+        inline ShsbFrameParams frame_params(const FrameParams& fp)
+        {
+            ShsbFrameParams o{};
+            o.shading_model = (fp.shading_model == ShadingModel::BlinnPhong) ? SHSB_SHADING_BLINN_PHONG : SHSB_SHADING_PBR_METAL_ROUGH;
+            o.debug_view = (int32_t)fp.debug_view;
+            o.cull_mode = (int32_t)fp.cull_mode;
+            o.front_face_ccw = fp.front_face_ccw ? 1 : 0;
+            o.shadow_enable = fp.pass.shadow.enable ? 1 : 0;
+            o.shadow_bias_const = fp.pass.shadow.bias_const;
+            o.shadow_bias_slope = fp.pass.shadow.bias_slope;
+            o.shadow_pcf_radius = fp.pass.shadow.pcf_radius;
+            o.shadow_pcf_step = fp.pass.shadow.pcf_step;
+            o.shadow_strength = fp.pass.shadow.strength;
+            o.exposure = fp.pass.tonemap.exposure;
+            o.gamma = fp.pass.tonemap.gamma;
+            o.light_culling = fp.technique.light_culling ? 1 : 0;
+            o.tile_size = fp.technique.tile_size;
+            o.max_lights_per_tile = fp.technique.max_lights_per_tile;
+            return o;
+        }
+
+        // Scene + ResourceRegistry -> ShsbScene (items keep Scene::items order; materials resolved like
+        // pass_pbr_forward.hpp:166-184).
+        inline ShsbScene scene(Device& dev, const Scene& s, std::vector<ShsbRenderItem>& items)
+        {
+            ShsbScene o{};
+            copy_mat(s.cam.viewproj, o.cam_viewproj);
+            copy_vec(s.cam.pos, o.cam_pos);
+            copy_vec(s.sun.dir_ws, o.sun_dir_ws);
+            copy_vec(s.sun.color, o.sun_color);
+            o.sun_intensity = s.sun.intensity;
+            items.clear();
+            items.reserve(s.items.size());
+            for (const RenderItem& it : s.items)
+            {
+                ShsbRenderItem r{};
+                copy_vec(it.tr.pos, r.tr.pos);
+                copy_vec(it.tr.rot_euler, r.tr.rot_euler);
+                copy_vec(it.tr.scl, r.tr.scl);
+                const MeshData* mesh = s.resources ? s.resources->get_mesh((MeshAssetHandle)it.mesh) : nullptr;
+                r.mesh = (mesh && !mesh->empty()) ? dev.mesh(*mesh) : 0;
+                const MaterialData* mat = s.resources ? s.resources->get_material((MaterialAssetHandle)it.mat) : nullptr;
+                r.has_material = mat ? 1u : 0u;
+                if (mat)
+                {
+                    copy_vec(mat->base_color, r.base_color);
+                    r.metallic = mat->metallic;
+                    r.roughness = mat->roughness;
+                    r.ao = mat->ao;
+                    r.base_color_tex = mat->base_color_tex ? dev.texture(s.resources->get_texture(mat->base_color_tex)) : 0;
+                }
+                r.casts_shadow = it.casts_shadow ? 1u : 0u;
+                r.visible = it.visible ? 1u : 0u;
+                items.push_back(r);
+            }
+            o.items = items.data();
+            o.n_items = (uint32_t)items.size();
+            return o;
+        }
+    }
+
+    // rasterize_mesh, sw_render/rasterizer.hpp:181-187.  `program` replaces the std::function pair; the job system
+    // fields of RasterizerConfig are accepted and ignored (the device is the job system).
+    inline RasterizerStats rasterize_mesh(Device& dev, const MeshData& mesh, BuiltinProgram program, const ShaderUniforms& u,
+                                          RasterizerTarget target, const RasterizerConfig& config = {}, bool sync_host = true)
+    {
+        RasterizerStats stats{};
+        if (!dev.valid() || !target.hdr) return stats;                 // rasterizer.hpp:190
+        if (mesh.positions.empty()) return stats;                       // :191
+        if (target.hdr->w <= 0 || target.hdr->h <= 0) return stats;     // :194
+        ShsbUniforms su{};
+        detail::copy_mat(u.model, su.model);
+        detail::copy_mat(u.viewproj, su.viewproj);
+        detail::copy_mat(u.light_viewproj, su.light_viewproj);
+        detail::copy_vec(u.light_dir_ws, su.light_dir_ws);
+        detail::copy_vec(u.light_color, su.light_color);
+        su.light_intensity = u.light_intensity;
+        detail::copy_vec(u.camera_pos, su.camera_pos);
+        detail::copy_vec(u.base_color, su.base_color);
+        su.metallic = u.metallic; su.roughness = u.roughness; su.ao = u.ao;
+        su.base_color_tex = dev.texture(u.base_color_tex);
+        if (u.shadow_map)
+        {
+            RT_ShadowDepth* sm = const_cast<RT_ShadowDepth*>(u.shadow_map);
+            su.shadow_map = dev.twin(sm);
+            dev.upload(sm);
+        }
+        su.shadow_bias_const = u.shadow_bias_const; su.shadow_bias_slope = u.shadow_bias_slope;
+        su.shadow_pcf_radius = u.shadow_pcf_radius; su.shadow_pcf_step = u.shadow_pcf_step; su.shadow_strength = u.shadow_strength;
+        ShsbRasterCfg cfg{};
+        cfg.cull_mode = (int32_t)config.cull_mode;
+        cfg.front_face_ccw = config.front_face_ccw ? 1 : 0;
+        // rasterize_mesh composites into whatever the targets hold: mirror the host contents first
+        dev.upload(target.hdr);
+        if (target.depth_motion) dev.upload(target.depth_motion);
+        ShsbStats st{};
+        if (shsb_rasterize_mesh(dev.ctx(), dev.mesh(mesh), (int32_t)program, &su, dev.twin(target.hdr),
+                                target.depth_motion ? dev.twin(target.depth_motion) : 0, &cfg, &st) != SHSB_OK) return stats;
+        if (sync_host)
+        {
+            dev.download(target.hdr);
+            if (target.depth_motion) dev.download(target.depth_motion);
+        }
+        stats.tri_input = st.tri_input; stats.tri_after_clip = st.tri_after_clip; stats.tri_raster = st.tri_raster;
+        return stats;
+    }
+
+    // PassPBRForward, passes/pass_pbr_forward.hpp:31-214 (same Inputs struct, same Context side effects on ctx.debug).
+    class PassPBRForward
+    {
+    public:
+        explicit PassPBRForward(Device& dev, bool sync_host = true) : dev_(dev), sync_host_(sync_host) {}
+        using Inputs = shs::PassPBRForward::Inputs;
+
+        void execute(Context& ctx, const Inputs& in)
+        {
+            if (!in.scene || !in.fp || !in.rtr) return;
+            if (!in.rt_hdr.valid() || !dev_.valid()) return;
+            ctx.debug.tri_input = 0; ctx.debug.tri_after_clip = 0; ctx.debug.tri_raster = 0;
+            auto* hdr = static_cast<RT_ColorHDR*>(in.rtr->get(in.rt_hdr));
+            if (!hdr || hdr->w <= 0 || hdr->h <= 0) return;
+            auto* motion = in.rt_motion.valid() ? static_cast<RT_ColorDepthMotion*>(in.rtr->get(in.rt_motion)) : nullptr;
+            auto* shadow = in.rt_shadow.valid() ? static_cast<RT_ShadowDepth*>(in.rtr->get(in.rt_shadow)) : nullptr;
+            if (in.scene->sky) return; // sky models are a "next" row: not on the device yet, no fallback
+            std::vector<ShsbRenderItem> items;
+            const ShsbScene s = detail::scene(dev_, *in.scene, items);
+            const ShsbFrameParams fp = detail::frame_params(*in.fp);
+            if (motion && in.preserve_existing_depth) dev_.upload(motion);
+            const bool use_shadow = in.fp->pass.shadow.enable && shadow && ctx.shadow.valid;
+            float lvp[16];
+            if (use_shadow) { detail::copy_mat(ctx.shadow.light_viewproj, lvp); dev_.upload(shadow); }
+            ShsbStats st{};
+            if (shsb_pass_pbr_forward(dev_.ctx(), &s, &fp, dev_.twin(hdr), motion ? dev_.twin(motion) : 0, use_shadow ? dev_.twin(shadow) : 0,
+                                      use_shadow ? lvp : nullptr, in.preserve_existing_depth ? 1 : 0, &st) != SHSB_OK) return;
+            if (sync_host_) { dev_.download(hdr); if (motion) dev_.download(motion); }
+            ctx.debug.tri_input = st.tri_input; ctx.debug.tri_after_clip = st.tri_after_clip; ctx.debug.tri_raster = st.tri_raster;
+            ctx.history.has_prev_frame = true;
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_;
+    };
+
+    // PassShadowMap, passes/pass_shadow_map.hpp:27-205.
+    class PassShadowMap
+    {
+    public:
+        explicit PassShadowMap(Device& dev, bool sync_host = true) : dev_(dev), sync_host_(sync_host) {}
+        using Inputs = shs::PassShadowMap::Inputs;
+
+        void execute(Context& ctx, const Inputs& in)
+        {
+            ctx.shadow.reset();
+            if (!in.scene || !in.fp || !in.rtr) return;
+            if (!in.rt_shadow.valid() || !dev_.valid()) return;
+            if (!in.fp->pass.shadow.enable) return;
+            auto* shadow = static_cast<RT_ShadowDepth*>(in.rtr->get(in.rt_shadow));
+            if (!shadow || shadow->w <= 0 || shadow->h <= 0) return;
+            std::vector<ShsbRenderItem> items;
+            const ShsbScene s = detail::scene(dev_, *in.scene, items);
+            const ShsbFrameParams fp = detail::frame_params(*in.fp);
+            float lvp[16];
+            if (shsb_pass_shadow_map(dev_.ctx(), &s, &fp, dev_.twin(shadow), lvp) != SHSB_OK) return;
+            if (sync_host_) dev_.download(shadow);
+            ctx.shadow.map = shadow;
+            std::memcpy(&ctx.shadow.light_viewproj, lvp, 64);
+            ctx.shadow.valid = true;
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_;
+    };
+
+    // PassTonemap, passes/pass_tonemap.hpp:21-84.
+    class PassTonemap
+    {
+    public:
+        explicit PassTonemap(Device& dev, bool sync_host = true, bool hdr_on_device = true) : dev_(dev), sync_host_(sync_host), hdr_on_device_(hdr_on_device) {}
+        using Inputs = shs::PassTonemap::Inputs;
+
+        void execute(Context& ctx, const Inputs& in)
+        {
+            (void)ctx;
+            if (!in.fp || !in.rtr || !dev_.valid()) return;
+            if (!in.rt_hdr.valid() || !in.rt_ldr.valid()) return;
+            auto* hdr = static_cast<RT_ColorHDR*>(in.rtr->get(in.rt_hdr));
+            auto* ldr = static_cast<RT_ColorLDR*>(in.rtr->get(in.rt_ldr));
+            if (!hdr || !ldr || hdr->w <= 0 || hdr->h <= 0 || ldr->w <= 0 || ldr->h <= 0) return;
+            if (!hdr_on_device_) dev_.upload(hdr);
+            if (shsb_pass_tonemap(dev_.ctx(), dev_.twin(hdr), dev_.twin(ldr), in.fp->pass.tonemap.exposure, in.fp->pass.tonemap.gamma) != SHSB_OK) return;
+            if (sync_host_) dev_.download(ldr);
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_, hdr_on_device_;
+    };
+}

@@ -93,6 +93,10 @@ class Context:
     def rt_download_into(self, rt, plane, dst_ptr, nbytes):
         _check(self.lib, self.h, self.lib.shsb_rt_download(self.h, rt, plane, C.c_void_p(dst_ptr), nbytes), "shsb_rt_download")
 
+    def rt_download_async(self, rt, plane, dst_pinned_ptr, nbytes):
+        """D2H into pinned memory on the copy stream; overlaps with later submissions, valid after sync()."""
+        _check(self.lib, self.h, self.lib.shsb_rt_download_async(self.h, rt, plane, C.c_void_p(dst_pinned_ptr), nbytes), "shsb_rt_download_async")
+
     def rt_upload(self, rt, plane, array):
         a = np.ascontiguousarray(array)
         rc = self.lib.shsb_rt_upload(self.h, rt, plane, a.ctypes.data_as(C.c_void_p), a.nbytes)

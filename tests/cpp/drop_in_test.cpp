@@ -1,0 +1,151 @@
+// tests/cpp/drop_in_test.cpp -- the drop-in binding exercised the way the reference's own callers use the path
+// (exp-plumbing/hello_pass_basics.cpp:629-912, exp-plumbing/hello_software_triangle.cpp:116-198): build a Scene with
+// the reference's types, run the reference's CPU passes and the B200 passes, compare.
+//
+// Built only where /root/reference exists (tests/cpp/Makefile); the binary travels to the GPU box.
+// Exit code 0 = parity within the north_star gates, 1 = mismatch, 77 = no CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "shs_b200/drop_in.hpp"
+
+static shs::MeshData make_blob(int rings, int segs, float radius)
+{
+    shs::MeshData m{};
+    for (int r = 0; r <= rings; ++r)
+        for (int s = 0; s <= segs; ++s)
+        {
+            const float v = (float)r / rings, u = (float)s / segs;
+            const float th = v * 3.14159265f, ph = u * 6.2831853f;
+            const glm::vec3 n(std::sin(th) * std::cos(ph), std::cos(th), std::sin(th) * std::sin(ph));
+            m.positions.push_back(n * (radius * (1.0f + 0.15f * std::sin(5.0f * ph) * std::sin(3.0f * th))));
+            m.normals.push_back(n);
+            m.uvs.push_back(glm::vec2(u * 3.0f, v * 2.0f));
+        }
+    for (int r = 0; r < rings; ++r)
+        for (int s = 0; s < segs; ++s)
+        {
+            const uint32_t a = r * (segs + 1) + s, b = a + 1, c = a + segs + 1, d = c + 1;
+            m.indices.insert(m.indices.end(), {a, b, c, b, d, c});
+        }
+    return m;
+}
+
+static int ulp(float a, float b)
+{
+    int32_t x, y;
+    std::memcpy(&x, &a, 4);
+    std::memcpy(&y, &b, 4);
+    return std::abs(x - y);
+}
+
+int main()
+{
+    shs::b200::Device dev(0);
+    if (!dev.valid()) { std::printf("SKIP: %s\n", dev.last_error()); return 77; }
+
+    const int W = 320, H = 200;
+    shs::ResourceRegistry resources{};
+    const shs::MeshAssetHandle blob = resources.add_mesh(make_blob(24, 32, 1.0f));
+    shs::Texture2DData tex(16, 16);
+    for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) tex.at(x, y) = shs::Color{(uint8_t)(x * 16), (uint8_t)(y * 16), (uint8_t)(255 - x * 8), 255};
+    const shs::TextureAssetHandle tex_h = resources.add_texture(tex);
+    const shs::MaterialAssetHandle gold = resources.add_material(shs::MaterialData{"gold", glm::vec3(0.94f, 0.76f, 0.29f), 0.95f, 0.2f, 1.0f});
+    const shs::MaterialAssetHandle textured = resources.add_material(shs::MaterialData{"tex", glm::vec3(1.0f), 0.2f, 0.5f, 1.0f, glm::vec3(0.0f), 0.0f, tex_h, 0, 0, 0});
+
+    shs::Scene scene{};
+    scene.resources = &resources;
+    scene.cam.pos = glm::vec3(0.0f, 2.0f, -6.0f);
+    scene.cam.view = shs::look_at_lh(scene.cam.pos, glm::vec3(0.0f, 0.3f, 0.0f), glm::vec3(0, 1, 0));
+    scene.cam.proj = shs::perspective_lh_no(glm::radians(60.0f), (float)W / (float)H, 0.1f, 100.0f);
+    scene.cam.viewproj = scene.cam.proj * scene.cam.view;
+    scene.sun.dir_ws = glm::normalize(glm::vec3(-0.35f, -1.0f, -0.25f));
+    scene.sun.color = glm::vec3(1.0f, 0.97f, 0.92f);
+    scene.sun.intensity = 2.2f;
+    for (int i = 0; i < 5; ++i)
+    {
+        shs::RenderItem it{};
+        it.tr.pos = glm::vec3(-3.0f + 1.5f * i, 0.2f * i, 0.5f * (i % 2));
+        it.tr.rot_euler = glm::vec3(0.1f * i, 0.7f * i, 0.0f);
+        it.tr.scl = glm::vec3(0.6f + 0.1f * i);
+        it.mesh = blob;
+        it.mat = (i % 3 == 0) ? 0 : ((i % 2) ? gold : textured);
+        scene.items.push_back(it);
+    }
+    shs::FrameParams fp{};
+    fp.w = W; fp.h = H;
+    fp.pass.shadow.enable = true;
+
+    // ---- reference CPU path
+    shs::RT_ColorHDR hdr_ref(W, H), hdr_gpu(W, H);
+    shs::RT_ColorDepthMotion dm_ref(W, H, 0.1f, 100.0f), dm_gpu(W, H, 0.1f, 100.0f);
+    shs::RT_ShadowDepth sm_ref(256, 256), sm_gpu(256, 256);
+    shs::RT_ColorLDR ldr_ref(W, H), ldr_gpu(W, H);
+    auto run = [&](bool gpu, shs::RT_ColorHDR& hdr, shs::RT_ColorDepthMotion& dm, shs::RT_ShadowDepth& sm, shs::RT_ColorLDR& ldr, shs::Context& ctx) {
+        shs::RTRegistry rtr{};
+        const shs::RTHandle h_hdr = rtr.reg<shs::RTHandle>(&hdr);
+        const shs::RTHandle h_dm = rtr.reg<shs::RTHandle>(&dm);
+        const shs::RT_Shadow h_sm = rtr.reg<shs::RT_Shadow>(&sm);
+        const shs::RTHandle h_ldr = rtr.reg<shs::RTHandle>(&ldr);
+        shs::PassShadowMap::Inputs si{&scene, &fp, &rtr, h_sm};
+        shs::PassPBRForward::Inputs fi{};
+        fi.scene = &scene; fi.fp = &fp; fi.rtr = &rtr; fi.rt_hdr = h_hdr; fi.rt_motion = h_dm; fi.rt_shadow = shs::RTHandle{h_sm.id};
+        shs::PassTonemap::Inputs ti{&fp, &rtr, h_hdr, h_ldr};
+        if (gpu)
+        {
+            shs::b200::PassShadowMap(dev).execute(ctx, si);
+            shs::b200::PassPBRForward(dev).execute(ctx, fi);
+            shs::b200::PassTonemap(dev).execute(ctx, ti);
+        }
+        else
+        {
+            shs::PassShadowMap().execute(ctx, si);
+            shs::PassPBRForward().execute(ctx, fi);
+            shs::PassTonemap().execute(ctx, ti);
+        }
+    };
+    shs::Context ctx_ref{}, ctx_gpu{};
+    run(false, hdr_ref, dm_ref, sm_ref, ldr_ref, ctx_ref);
+    run(true, hdr_gpu, dm_gpu, sm_gpu, ldr_gpu, ctx_gpu);
+
+    int bad = 0;
+    int max_depth_ulp = 0, max_shadow_ulp = 0, max_lsb = 0;
+    double se = 0.0, peak = 1.0;
+    for (size_t i = 0; i < dm_ref.depth.data.size(); ++i) max_depth_ulp = std::max(max_depth_ulp, ulp(dm_ref.depth.data[i], dm_gpu.depth.data[i]));
+    for (size_t i = 0; i < sm_ref.depth.size(); ++i) max_shadow_ulp = std::max(max_shadow_ulp, ulp(sm_ref.depth[i], sm_gpu.depth[i]));
+    for (size_t i = 0; i < hdr_ref.color.data.size(); ++i)
+    {
+        const shs::ColorF a = hdr_ref.color.data[i], b = hdr_gpu.color.data[i];
+        se += (a.r - b.r) * (double)(a.r - b.r) + (a.g - b.g) * (double)(a.g - b.g) + (a.b - b.b) * (double)(a.b - b.b);
+        peak = std::max(peak, (double)std::max(a.r, std::max(a.g, a.b)));
+        const shs::Color p = ldr_ref.color.data[i], q = ldr_gpu.color.data[i];
+        max_lsb = std::max(max_lsb, std::max(std::abs(p.r - q.r), std::max(std::abs(p.g - q.g), std::abs(p.b - q.b))));
+    }
+    const double mse = se / (3.0 * hdr_ref.color.data.size());
+    const double psnr = mse == 0.0 ? 999.0 : 10.0 * std::log10(peak * peak / mse);
+    if (ctx_ref.debug.tri_input != ctx_gpu.debug.tri_input || ctx_ref.debug.tri_after_clip != ctx_gpu.debug.tri_after_clip || ctx_ref.debug.tri_raster != ctx_gpu.debug.tri_raster) ++bad;
+    if (std::memcmp(&ctx_ref.shadow.light_viewproj, &ctx_gpu.shadow.light_viewproj, 64) != 0) ++bad;
+    if (max_depth_ulp > 1 || max_shadow_ulp > 1 || max_lsb > 1 || psnr < 60.0) ++bad;
+
+    // ---- rasterize_mesh called directly, like exp-plumbing/hello_software_triangle.cpp:187
+    shs::RT_ColorHDR h2_ref(W, H), h2_gpu(W, H);
+    shs::RT_ColorDepthMotion d2_ref(W, H, 0.1f, 100.0f), d2_gpu(W, H, 0.1f, 100.0f);
+    shs::ShaderUniforms u{};
+    u.model = glm::rotate(glm::translate(glm::mat4(1.0f), glm::vec3(0.2f, 0.1f, 0.0f)), 0.6f, glm::vec3(0, 1, 0));
+    u.viewproj = scene.cam.viewproj;
+    u.light_dir_ws = scene.sun.dir_ws; u.light_color = scene.sun.color; u.light_intensity = 2.0f;
+    u.camera_pos = scene.cam.pos;
+    u.base_color = glm::vec3(0.3f, 0.6f, 0.9f); u.metallic = 0.1f; u.roughness = 0.4f;
+    const shs::RasterizerStats s_ref = shs::rasterize_mesh(*resources.get_mesh(blob), shs::make_blinn_phong_program(), u, shs::RasterizerTarget{&h2_ref, &d2_ref});
+    const shs::RasterizerStats s_gpu = shs::b200::rasterize_mesh(dev, *resources.get_mesh(blob), shs::b200::BuiltinProgram::BlinnPhong, u, shs::RasterizerTarget{&h2_gpu, &d2_gpu});
+    int max_d2 = 0;
+    for (size_t i = 0; i < d2_ref.depth.data.size(); ++i) max_d2 = std::max(max_d2, ulp(d2_ref.depth.data[i], d2_gpu.depth.data[i]));
+    if (s_ref.tri_input != s_gpu.tri_input || s_ref.tri_after_clip != s_gpu.tri_after_clip || s_ref.tri_raster != s_gpu.tri_raster || max_d2 > 1) ++bad;
+
+    std::printf("passes: tris %llu/%llu/%llu  depth<=%d ULP  shadow<=%d ULP  LDR<=%d LSB  HDR PSNR %.1f dB | rasterize_mesh: depth<=%d ULP tris %llu | %s\n",
+                (unsigned long long)ctx_gpu.debug.tri_input, (unsigned long long)ctx_gpu.debug.tri_after_clip, (unsigned long long)ctx_gpu.debug.tri_raster,
+                max_depth_ulp, max_shadow_ulp, max_lsb, psnr, max_d2, (unsigned long long)s_gpu.tri_raster, bad ? "MISMATCH" : "OK");
+    return bad ? 1 : 0;
+}

@@ -1,0 +1,37 @@
+"""The C++ drop-in binding (leisure_software_renderer_b200/host/shs_b200/drop_in.hpp) compiled against the
+reference's own headers: CPU box -> it compiles and refuses to run without a device; GPU box -> reference CPU passes
+vs B200 passes through the reference's types."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "_build", "drop_in_test")
+
+
+def _build():
+    from leisure_software_renderer_b200 import build
+    build.build()
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], check=True, capture_output=True)
+
+
+def test_drop_in_compiles_and_has_no_cpu_fallback():
+    import torch
+    if not os.path.isdir("/root/reference") and not os.path.exists(BIN):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(BIN)
+    if not torch.cuda.is_available():
+        r = subprocess.run([BIN], capture_output=True, text=True)
+        assert r.returncode == 77 and "SKIP" in r.stdout
+
+
+@pytest.mark.gpu
+def test_drop_in_parity_on_gpu():
+    if not os.path.exists(BIN):
+        pytest.skip("tests/cpp/_build/drop_in_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
