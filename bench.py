@@ -99,6 +99,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE tile_kernel launch, from the committed `ncu --set full`
+    capture summarised under profiles/ (not measured live: a run under ncu is never a bench run)."""
+    p = os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")
+    try:
+        t = json.load(open(p))
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t.get("capture")
+    except Exception:
+        return None, None
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -259,8 +270,8 @@ def run_ours(args):
                          "geometry_to_resolve": float(stage_mean[3]), "frames_timed": 0 if stages is None else int(len(stages))},
             "roofline": {"bound": "hbm", "kernel": "tile_kernel (tile raster + Forward+ shade + resolve + tonemap)",
                          "achieved": (b_tile / 1e9) / (tile_ms / 1e3) if tile_ms > 0 else None, "peak": hbm, "unit": "GB/s",
-                         "frac": ((b_tile / 1e9) / (tile_ms / 1e3) / hbm) if tile_ms > 0 else None, "traffic": None,
-                         "algorithmic_bytes": b_tile, "peak_source": peak_src},
+                         "frac": ((b_tile / 1e9) / (tile_ms / 1e3) / hbm) if tile_ms > 0 else None, "traffic": ncu_traffic()[0],
+                         "traffic_source": ncu_traffic()[1], "algorithmic_bytes": b_tile, "peak_source": peak_src},
             "roofline_frame": {"algorithmic_bytes": b_frame, "achieved": (b_frame / 1e9) / (ms_dev / args.steps / 1e3),
                                "frac": (b_frame / 1e9) / (ms_dev / args.steps / 1e3) / hbm, "unit": "GB/s"},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
