@@ -127,7 +127,7 @@ namespace shsb
                 const int leader = __ffs(m) - 1;
                 if (lane == leader) cbase = atomicAdd(&g.class_count[k], (uint32_t)__popc(m));
                 cbase = __shfl_sync(0xffffffffu, cbase, leader);
-                if (live && cls == k) g.tile_order[(size_t)k * n_tiles + cbase + (uint32_t)__popc(m & ((1u << lane) - 1u))] = t;
+                if (live && cls == k) g.tile_order[(size_t)k * n_tiles + cbase + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (t % (uint32_t)fc.tiles_x) | ((t / (uint32_t)fc.tiles_x) << 16);
             }
             if (live)
             {

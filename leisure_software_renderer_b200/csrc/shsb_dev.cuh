@@ -186,7 +186,7 @@ namespace shsb
         uint32_t list_capacity;
         uint32_t* list_cursor;      // total entries allocated so far
         uint32_t* class_count;      // [4] tiles per scheduling class (heaviest first)
-        uint32_t* tile_order;       // [4][n_tiles] tile ids per class; CTA b of the tile kernel takes the b-th tile in class order
+        uint32_t* tile_order;       // [4][n_tiles] tiles per class as (tx | ty << 16); CTA b of the tile kernel takes the b-th tile in class order
         DevStats* stats;
     };
 

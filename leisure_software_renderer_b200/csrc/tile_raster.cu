@@ -34,18 +34,33 @@ namespace shsb
         __device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
         __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
         __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
-        __device__ __forceinline__ V3 normalize_fast(V3 v) { return v * rsqrtf(dot(v, v)); }
+        // Single-MUFU approximations for colour math only (never for coverage / depth / list bits).  The CUDA
+        // intrinsics (__fdividef, rsqrtf, __powf) wrap each MUFU in denormal scaling code when the translation unit is
+        // not compiled with -ftz; the .ftz PTX forms are the bare instruction.
+        __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+        __device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+        __device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+        __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+        // x^p for x >= 0, p > 0: lg2(0) = -inf -> ex2(-inf) = 0
+        __device__ __forceinline__ float fast_pow(float x, float p) { return fast_ex2(p * fast_lg2(x)); }
+        __device__ __forceinline__ V3 normalize_fast(V3 v) { return v * fast_rsqrt(dot(v, v)); }
         __device__ __forceinline__ V3 toV3(F3 v) { return V3{v.x, v.y, v.z}; }
         __device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 
-        struct SmLight // compact per-tile copy of the CullingLightGPU fields the point/spot path reads
+        // Compact per-tile copy of a local light (80 B), built once per tile by the staging threads so that the
+        // per-pixel loop reads pre-digested values: q0 decides the range test, the rest is only read in range.
+        struct SmLight
         {
-            float4 pos_range;     // xyz, max(range, 0.001)
-            float4 radiance;      // color * intensity, w = range^2
-            float4 dir_cos;       // normalised spot direction, inner cos
-            float4 params;        // outer cos, attenuation power, bias, cutoff
-            uint32_t type, model, index, flags;
+            float4 pos_r2;        // xyz, w = range^2 (area lights: cull-sphere centre / radius^2)
+            float4 radiance_ir;   // color * intensity, w = 1 / range
+            float4 atten;         // x = attenuation power, y = max(cutoff, 0), z = max(bias, 1e-5), w = 1 / max(inner_cos - outer_cos, 1e-6)
+            float4 dir_outer;     // normalised spot direction, w = outer cos (clamped)
+            uint32_t kind;        // bits 0-1 attenuation model, bit 2 spot, bit 3 area light (rect / tube -> eval_light_record), bit 4 power != 1
+            uint32_t index;       // light index (area lights re-read their 160-B record)
+            uint32_t pad0, pad1;
         };
+        static_assert(sizeof(SmLight) == 80, "SmLight is 80 bytes");
+        constexpr uint32_t KIND_SPOT = 4u, KIND_AREA = 8u, KIND_POW = 16u;
 
         struct Surface
         {
@@ -54,7 +69,7 @@ namespace shsb
             bool blinn;
             // per-pixel invariants of the local-light BRDF, hoisted out of the light loop by finish_surface()
             V3 F0, diffuse;        // mix(0.04, albedo, metallic); PBR: albedo*(1-metallic)/pi, Blinn: albedo/pi
-            float a2, k, NdotV, g1v, spec_a, spec_b; // Blinn: spec_a = shininess, spec_b = spec_strength
+            float a2, k, NdotV, g1v, spec_a, spec_b; // Blinn: spec_a = shininess, spec_b = spec_strength; PBR: g1v = a2 * G1(V)
         };
 
         __device__ __forceinline__ void finish_surface(Surface& s)
@@ -75,76 +90,87 @@ namespace shsb
                 const float rr = s.roughness + 1.0f;
                 s.k = rr * rr * 0.125f;
                 s.NdotV = fmaxf(dot(s.N, s.V), 0.0f);
-                s.g1v = __fdividef(s.NdotV, fmaxf(s.NdotV * (1.0f - s.k) + s.k, 1e-6f));
+                s.g1v = s.a2 * s.NdotV * fast_rcp(fmaxf(s.NdotV * (1.0f - s.k) + s.k, 1e-6f));
                 s.diffuse = s.albedo * ((1.0f - s.metallic) * (1.0f / PI_F));
                 s.spec_a = s.spec_b = 0.0f;
             }
         }
 
         // ---- eval_pbr_light / eval_blinn_phong_light, shaders/vulkan/fp_stress_scene.frag:132-165
-        // (same formulas; the three quotients NDF, G2 and 1/(4 NdotV NdotL) share one reciprocal)
-        __device__ __forceinline__ V3 eval_brdf(const Surface& s, V3 L, V3 radiance)
+        // (same formulas; the three quotients NDF, G2 and 1/(4 NdotV NdotL) share one reciprocal).  NdotL > 0.
+        __device__ __forceinline__ V3 eval_brdf_lit(const Surface& s, V3 L, float NdotL, V3 radiance)
         {
-            const float NdotL = fmaxf(dot(s.N, L), 0.0f);
-            if (NdotL <= 0.0f) return v3(0, 0, 0);
             const V3 H = normalize_fast(s.V + L);
             const float NdotH = fmaxf(dot(s.N, H), 0.0f);
             if (s.blinn)
             {
-                const float spec = __powf(NdotH, s.spec_a);
+                const float spec = fast_pow(NdotH, s.spec_a);
                 return radiance * (s.diffuse * NdotL + s.F0 * (spec * s.spec_b));
             }
             const float fres = pow5(1.0f - fmaxf(dot(H, s.V), 0.0f));
             const V3 F = s.F0 + (v3(1, 1, 1) - s.F0) * fres;
             const float dd = NdotH * NdotH * (s.a2 - 1.0f) + 1.0f;
             const float den = fmaxf(PI_F * dd * dd, 1e-6f) * fmaxf(NdotL * (1.0f - s.k) + s.k, 1e-6f) * fmaxf(4.0f * s.NdotV * NdotL, 1e-6f);
-            const float spec = __fdividef(s.a2 * s.g1v * NdotL, den);
+            const float spec = s.g1v * NdotL * fast_rcp(den);
             // kD = (1 - F) * (1 - metallic); kD * albedo / pi = (1 - F) * diffuse
             return ((v3(1, 1, 1) - F) * s.diffuse + F * spec) * radiance * NdotL;
+        }
+
+        __device__ __forceinline__ V3 eval_brdf(const Surface& s, V3 L, V3 radiance)
+        {
+            const float NdotL = fmaxf(dot(s.N, L), 0.0f);
+            if (NdotL <= 0.0f) return v3(0, 0, 0);
+            return eval_brdf_lit(s, L, NdotL, radiance);
         }
 
         // ---- shs_eval_light_attenuation_quadratic, shaders/vulkan/common/light_math.glsl:44-78
         __device__ __forceinline__ float attenuation_quadratic(float dist, float range, uint32_t model, float power, float bias, float cutoff)
         {
             const float safe_range = fmaxf(range, 1e-4f);
-            const float t = sat(__fdividef(dist, safe_range));
+            const float t = sat(dist * fast_rcp(safe_range));
             const float edge = 1.0f - t;
             float falloff;
             if (model == 0u) falloff = edge;
             else if (model == 2u)
             {
                 const float denom = fmaxf(dist * dist, fmaxf(bias, 1e-5f));
-                falloff = __fdividef(safe_range * safe_range, denom) * edge * edge;
+                falloff = safe_range * safe_range * fast_rcp(denom) * edge * edge;
             }
             else falloff = edge * edge;
             falloff = fmaxf(falloff, 0.0f);
             const float p = fmaxf(power, 0.001f);
-            if (p != 1.0f) falloff = (falloff > 0.0f) ? __powf(falloff, p) : 0.0f;
+            if (p != 1.0f) falloff = fast_pow(falloff, p);
             return (falloff <= fmaxf(cutoff, 0.0f)) ? 0.0f : falloff;
         }
 
-        // point / spot lights from the shared-memory copy -- eval_local_light, fp_stress_scene.frag:421-523
-        __device__ __forceinline__ V3 eval_point_spot(const Surface& s, const SmLight& lt)
+        // One staged point / spot light against one surface -- eval_local_light, fp_stress_scene.frag:421-523.
+        // The tests run cheapest-first; every early-out is a case where the GLSL adds exactly zero:
+        // out of range (dist >= range), facing away (NdotL <= 0), attenuation at or below the cutoff, outside the cone.
+        __device__ __forceinline__ void accumulate_point_spot(const Surface& s, const SmLight* __restrict__ lt, float dx, float dy, float dz, float dist2,
+                                                              uint32_t kind, V3& sum)
         {
-            const V3 d = v3(lt.pos_range.x, lt.pos_range.y, lt.pos_range.z) - s.P;
-            const float dist2 = dot(d, d);
-            if (!(dist2 < lt.radiance.w) || dist2 <= 1e-10f) return v3(0, 0, 0);
-            const float inv_dist = rsqrtf(dist2);
+            const float nd = s.N.x * dx + s.N.y * dy + s.N.z * dz;
+            if (!(nd > 0.0f)) return;
+            const float4 ri = lt->radiance_ir, at = lt->atten;
+            const float inv_dist = fast_rsqrt(dist2);
             const float dist = dist2 * inv_dist;
-            const V3 L = d * inv_dist;
-            float atten = attenuation_quadratic(dist, lt.pos_range.w, lt.model, lt.params.y, lt.params.z, lt.params.w);
-            if (atten <= 0.0f) return v3(0, 0, 0);
-            if (lt.type == 2u)
+            const float edge = 1.0f - sat(dist * ri.w);
+            const uint32_t model = kind & 3u;
+            float falloff = (model == 0u) ? edge : edge * edge;
+            if (model == 2u) falloff *= lt->pos_r2.w * fast_rcp(fmaxf(dist2, at.z));
+            if (kind & KIND_POW) falloff = fast_pow(falloff, at.x);
+            if (!(falloff > at.y)) return;
+            if (kind & KIND_SPOT)
             {
-                const float inner_cos = fminf(fmaxf(lt.dir_cos.w, -1.0f), 1.0f);
-                const float outer_cos = fminf(fmaxf(lt.params.x, -1.0f), inner_cos);
-                const float cone_cos = -(lt.dir_cos.x * L.x + lt.dir_cos.y * L.y + lt.dir_cos.z * L.z);
-                const float t = sat(__fdividef(cone_cos - outer_cos, fmaxf(inner_cos - outer_cos, 1e-6f)));
+                const float4 dc = lt->dir_outer;
+                const float cone_cos = -(dc.x * dx + dc.y * dy + dc.z * dz) * inv_dist;
+                const float t = sat((cone_cos - dc.w) * at.w);
                 const float spot = t * t * (3.0f - 2.0f * t);
-                if (spot <= 0.0f) return v3(0, 0, 0);
-                atten *= spot;
+                if (!(spot > 0.0f)) return;
+                falloff *= spot;
             }
-            return eval_brdf(s, L, v3(lt.radiance.x, lt.radiance.y, lt.radiance.z) * atten);
+            const V3 L = v3(dx * inv_dist, dy * inv_dist, dz * inv_dist);
+            sum = sum + eval_brdf_lit(s, L, nd * inv_dist, v3(ri.x, ri.y, ri.z) * falloff);
         }
 
         // Any light type straight from the 160-B record (saturated tiles, non-16 light tiles, rect / tube lights).
@@ -295,13 +321,33 @@ namespace shsb
             for (int i = 0; i < 3; ++i)
             {
                 float v = fmaxf(0.0f, c[i] * exposure);
-                v = __fdividef(v, 1.0f + v);
-                v = (v > 0.0f) ? exp2f(inv_gamma * __log2f(v)) : ((inv_gamma == 0.0f) ? 1.0f : 0.0f);
+                v = v * fast_rcp(1.0f + v);
+                v = (inv_gamma == 0.0f) ? 1.0f : fast_pow(v, inv_gamma);       // pow(x, 0) = 1; pow(0, p > 0) = 0
                 const float q = floorf(v * 255.0f + 0.5f); // lround: half away from zero (v >= 0)
                 o[i] = (unsigned char)fminf(fmaxf(q, 0.0f), 255.0f);
             }
             return make_uchar4(o[0], o[1], o[2], 255);
         }
+
+        // Colour resolve of a pixel no fragment reached: background gradient (pass_pbr_forward.hpp:73-81) or, for a
+        // separate draw (load_color), the target's existing colour; fused tonemap if an LDR target is bound.
+        __device__ __forceinline__ void resolve_uncovered(const FrameConst& fc, const FrameBuffers& fb, size_t pix, int py)
+        {
+            if (fc.load_color)
+            {
+                if (!(fc.fuse_tonemap && fb.ldr)) return;
+                const float4 c = fb.hdr[pix];
+                fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
+                return;
+            }
+            const float t = xdiv((float)py, (float)max(1, fc.H - 1));
+            const float r = xadd(0.06f, xmul(0.08f, t)), g = xadd(0.08f, xmul(0.10f, t)), b = xadd(0.12f, xmul(0.12f, t));
+            fb.hdr[pix] = make_float4(r, g, b, 1.0f);
+            if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(r, g, b, fc.exposure, fc.inv_gamma);
+        }
+
+        constexpr int LIGHT_CAP = TILE_THREADS;       // staged lights per pass
+        constexpr int CAND_PER_THREAD = 4;            // candidates filtered per thread per staging round (1024 per CTA)
 
         __global__ void __launch_bounds__(TILE_THREADS, 4) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
@@ -309,15 +355,15 @@ namespace shsb
         {
             // the triangle staging buffer (raster phase) and the light staging buffer (shading phase) are never live at
             // the same time: they share one 20-KB allocation
-            __shared__ __align__(16) unsigned char s_stage[TILE_THREADS * sizeof(SmLight)];
+            __shared__ __align__(16) unsigned char s_stage[LIGHT_CAP * sizeof(SmLight)];
             static_assert(sizeof(SmLight) >= sizeof(RasterRec), "staging buffer is sized by SmLight");
             RasterRec* s_rec = reinterpret_cast<RasterRec*>(s_stage);
-            SmLight* s_light = reinterpret_cast<SmLight*>(s_stage); // one compaction round = 256 candidate lights
+            SmLight* s_light = reinterpret_cast<SmLight*>(s_stage);
             __shared__ uint32_t s_idx[TILE_THREADS];
             __shared__ unsigned s_wmask[TILE_THREADS / 32][TILE_THREADS / 32]; // [consumer warp][staging warp]
+            __shared__ unsigned s_ballot[CAND_PER_THREAD * (TILE_THREADS / 32)]; // light staging: [candidate slot][warp] == ascending light order
             __shared__ float s_box[TILE_THREADS / 32][6];
-            __shared__ uint32_t s_warp_count[TILE_THREADS / 32];
-            __shared__ unsigned long long s_frag[2];
+            __shared__ unsigned long long s_frag[TILE_THREADS / 32][2];
 
             // heaviest scheduling class first (alloc_kernel, binning.cu): the cheap background tiles fill the tail
             const uint32_t n_tiles_total = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
@@ -328,21 +374,29 @@ namespace shsb
                 const uint32_t cc = g.class_count[c];
                 if (cls == (uint32_t)c && ord >= cc) { ord -= cc; ++cls; }
             }
-            const int tile = (int)g.tile_order[(size_t)cls * n_tiles_total + ord];
-            const int tx = tile % fc.tiles_x, ty = tile / fc.tiles_x;
+            const uint32_t packed = g.tile_order[(size_t)cls * n_tiles_total + ord]; // tx | ty << 16
+            const int tx = (int)(packed & 0xffffu), ty = (int)(packed >> 16);
+            const int tile = ty * fc.tiles_x + tx;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             // a warp owns an 8x4-pixel block: 128 contiguous bytes of HDR per row
-            const int wx0 = tx * TILE + (warp & 1) * 8;
-            const int wfy0 = ty * TILE + (warp >> 1) * 4;
-            const int px = wx0 + (lane & 7);
-            const int fy = wfy0 + (lane >> 3);
+            const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+            const int fy = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
             const int py = fc.H - 1 - fy;
             const bool valid = px < fc.W && fy < fc.H;
             const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
-            // warp rectangle in RT coordinates (y up)
 
-            if (threadIdx.x < 2) s_frag[threadIdx.x] = 0ull;
-            __syncthreads();
+            const uint32_t tile_tris = g.tile_count[tile];
+            if (tile_tris == 0u)
+            {
+                // ---------------- empty tile (most of a frame): nothing to rasterise, no barriers, no counters
+                if (!valid) return;
+                if (fb.depth && (fc.has_depth || fc.shadow_mode) && !fc.load_depth) fb.depth[pix] = 1.0f;
+                if (fb.aov_tri_id) fb.aov_tri_id[pix] = 0xFFFFFFFFu;
+                if (fb.aov_coverage) fb.aov_coverage[pix] = 0u;
+                if (fc.shadow_mode || fc.shader_id == 5 || !fb.hdr) return;
+                resolve_uncovered(fc, fb, pix, py);
+                return;
+            }
 
             float bz = 1.0f;
             if (fc.has_depth && fc.load_depth && valid) bz = fb.depth[pix];
@@ -352,10 +406,10 @@ namespace shsb
             const float zrange = xsub(fc.zf, fc.zn);
 
             const uint32_t off0 = g.tile_offset[tile];
-            const uint32_t off1 = min(off0 + g.tile_count[tile], g.list_capacity);
+            const uint32_t off1 = min(off0 + tile_tris, g.list_capacity);
             for (uint32_t base = off0; base < off1; base += TILE_THREADS)
             {
-                __syncthreads();
+                if (base != off0) __syncthreads(); // the previous batch's readers are done with s_rec / s_wmask
                 const uint32_t n = min((uint32_t)TILE_THREADS, off1 - base);
                 int sminx = 0, smaxx = 0, sminy = 0, smaxy = 0;
                 if (threadIdx.x < n)
@@ -437,34 +491,18 @@ namespace shsb
                 if (fb.aov_tri_id) fb.aov_tri_id[pix] = (bkey != KEY_NONE) ? (bkey - 1u) : 0xFFFFFFFFu;
                 if (fb.aov_coverage) fb.aov_coverage[pix] = n_cov;
             }
-            // fragment counters: warp reduce -> shared -> one global atomic per CTA
+            // fragment counters: warp reduce -> one shared slot per warp; thread 0 adds them up behind the next barrier
             {
-                uint32_t c = n_cov, sh = (bkey != KEY_NONE) ? 1u : 0u;
+                unsigned long long c = n_cov;
+                uint32_t sh = (bkey != KEY_NONE) ? 1u : 0u;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); sh += __shfl_down_sync(0xffffffffu, sh, o); }
-                if (lane == 0) { atomicAdd(&s_frag[0], (unsigned long long)c); atomicAdd(&s_frag[1], (unsigned long long)sh); }
+                if (lane == 0) { s_frag[warp][0] = c; s_frag[warp][1] = sh; }
             }
-
-            if (fc.shadow_mode || fc.shader_id == 5 || !fb.hdr)
-            {
-                __syncthreads();
-                if (threadIdx.x == 0)
-                {
-                    if (s_frag[0]) atomicAdd(&g.stats->frag_covered, s_frag[0]);
-                    if (s_frag[1]) atomicAdd(&g.stats->frag_shaded, s_frag[1]);
-                }
-                return;
-            }
-
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                if (s_frag[0]) atomicAdd(&g.stats->frag_covered, s_frag[0]);
-                if (s_frag[1]) atomicAdd(&g.stats->frag_shaded, s_frag[1]);
-            }
+            const bool has = valid && bkey != KEY_NONE;
+            const bool shade = !(fc.shadow_mode || fc.shader_id == 5 || !fb.hdr);
 
             // ---------------- phase A (per pixel): re-derive the winning fragment and run the builtin program
-            const bool has = valid && bkey != KEY_NONE;
             const bool lit_shader = fc.shader_id == 0 || fc.shader_id == 1;
             float out_r = 0.0f, out_g = 0.0f, out_b = 0.0f;
             Surface surf;
@@ -472,7 +510,7 @@ namespace shsb
             surf.metallic = 0.0f; surf.roughness = 1.0f; surf.blinn = fc.shader_id == 1;
             surf.F0 = v3(0, 0, 0); surf.diffuse = v3(0, 0, 0);
             surf.a2 = surf.k = surf.NdotV = surf.g1v = surf.spec_a = surf.spec_b = 0.0f;
-            if (has)
+            if (has && shade)
             {
                 // bit-identical to the coverage test above
                 const float4* rsrc = reinterpret_cast<const float4*>(g.rrecs + bidx);
@@ -574,17 +612,30 @@ namespace shsb
                 }
             }
 
+            // the only barrier every non-empty tile passes: publishes the fragment counters (and tells phase B
+            // whether any pixel of the tile is shaded at all)
+            const int any_has = __syncthreads_or((has && shade) ? 1 : 0);
+            if (threadIdx.x == 0)
+            {
+                unsigned long long c = 0ull, sh = 0ull;
+#pragma unroll
+                for (int w = 0; w < TILE_THREADS / 32; ++w) { c += s_frag[w][0]; sh += s_frag[w][1]; }
+                if (c) atomicAdd(&g.stats->frag_covered, c);
+                if (sh) atomicAdd(&g.stats->frag_shaded, sh);
+            }
+            if (!shade) return;
+
             // ---------------- phase B (whole CTA): Forward+ local lights, fp_stress_scene.frag:644-678.
             // Light tile == raster tile when the list tile size is 16.  The tile cell spans all depths, so most listed
-            // lights cannot reach the surfaces actually visible in the tile: lights are first tested against the
+            // lights cannot reach the surfaces actually visible in the tile: candidates are first tested against the
             // world-space AABB of the tile's shaded positions (conservative: a rejected light fails "dist < range"
             // at every pixel and would add exactly zero) and the survivors are compacted IN ASCENDING ORDER into
-            // shared memory, 256 candidates per round.  A saturated list (count >= max_per_tile) walks ALL lights,
-            // as the GLSL does (:662-668).
+            // shared memory.  A staging round filters up to 1024 candidates (4 per thread) with two barriers; a
+            // saturated list (count >= max_per_tile) walks ALL lights, as the GLSL does (:662-668).
             const bool use_lights = fc.forward_plus && lit_shader && fc.n_lights > 0;
             if (use_lights && fc.light_tile_size == (uint32_t)TILE)
             {
-                if (__syncthreads_or(has ? 1 : 0))
+                if (any_has)
                 {
                     // CTA-wide AABB of shaded world positions
                     const float INF = 3.0e38f;
@@ -610,68 +661,117 @@ namespace shsb
                     const uint32_t listed = min(fc.tile_counts[list_id], fc.max_per_tile);
                     const bool saturated = listed >= fc.max_per_tile;
                     const uint32_t n_src = saturated ? fc.n_lights : listed;
+                    const uint32_t* __restrict__ list = fc.tile_indices + (size_t)list_id * fc.max_per_tile;
                     V3 sum = v3(0, 0, 0);
-                    for (uint32_t base = 0; base < n_src; base += TILE_THREADS)
+                    for (uint32_t sbase = 0; sbase < n_src; sbase += CAND_PER_THREAD * TILE_THREADS)
                     {
-                        const uint32_t i = base + threadIdx.x;
-                        bool keep = false;
-                        uint32_t idx = 0;
-                        float4 pr = make_float4(0, 0, 0, 0);
-                        uint4 tf = make_uint4(0, 0, 0, 0);
-                        if (i < n_src)
-                        {
-                            idx = saturated ? i : fc.tile_indices[(size_t)list_id * fc.max_per_tile + i];
-                            if (idx < fc.n_lights)
-                            {
-                                const DevLightRec* rec = fc.lights + idx;
-                                pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
-                                tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
-                                float4 sp = make_float4(pr.x, pr.y, pr.z, fmaxf(pr.w, 0.001f));
-                                if (tf.x > 2u) sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere)); // area lights reach beyond position +- range
-                                const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f);
-                                const float dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
-                                const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
-                                const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;
-                                keep = enabled && (dx * dx + dy * dy + dz * dz) <= sp.w * sp.w * 1.001f + 1e-6f;
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);
-                        __syncthreads(); // the previous round's readers are done with s_light / s_warp_count
-                        if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
-                        __syncthreads();
-                        uint32_t before = 0, kept = 0;
+                        if (sbase) __syncthreads(); // every warp has finished the previous round (s_ballot readers, light loop)
+                        // ---- filter: candidate slot c of this thread is source position sbase + c*256 + tid
+                        uint32_t cidx[CAND_PER_THREAD];
+                        unsigned cmask[CAND_PER_THREAD];
 #pragma unroll
-                        for (int w = 0; w < TILE_THREADS / 32; ++w)
+                        for (int c = 0; c < CAND_PER_THREAD; ++c)
                         {
-                            const uint32_t c = s_warp_count[w];
-                            if (w < warp) before += c;
-                            kept += c;
-                        }
-                        if (keep)
-                        {
-                            const DevLightRec* rec = fc.lights + idx;
-                            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
-                            const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
-                            const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
-                            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
-                            SmLight sl;
-                            const float range = fmaxf(pr.w, 0.001f);
-                            sl.pos_range = make_float4(pr.x, pr.y, pr.z, range);
-                            sl.radiance = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, range * range);
-                            const float dl = rsqrtf(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
-                            sl.dir_cos = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, ds.w);
-                            sl.params = make_float4(ax.w, sa.y, sa.z, sa.w);
-                            sl.type = tf.x; sl.flags = tf.z; sl.model = tf.w; sl.index = idx;
-                            s_light[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = sl;
-                        }
-                        __syncthreads();
-                        if (has)
-                        {
-                            for (uint32_t j = 0; j < kept; ++j)
+                            cidx[c] = 0xFFFFFFFFu;
+                            cmask[c] = 0u;
+                            if (sbase + (uint32_t)c * TILE_THREADS >= n_src) continue; // CTA-uniform
+                            const uint32_t i = sbase + (uint32_t)c * TILE_THREADS + threadIdx.x;
+                            bool keep = false;
+                            if (i < n_src)
                             {
-                                const SmLight& lt = s_light[j];
-                                if (lt.type <= 2u) sum = sum + eval_point_spot(surf, lt);
-                                else sum = sum + eval_light_record(surf, fc.lights + lt.index);
+                                const uint32_t idx = saturated ? i : list[i];
+                                if (idx < fc.n_lights)
+                                {
+                                    const DevLightRec* rec = fc.lights + idx;
+                                    const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
+                                    const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
+                                    float4 sp = make_float4(pr.x, pr.y, pr.z, fmaxf(pr.w, 0.001f));
+                                    if (tf.x > 2u) sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere)); // area lights reach beyond position +- range
+                                    const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f);
+                                    const float dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
+                                    const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
+                                    const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;
+                                    keep = enabled && (dx * dx + dy * dy + dz * dz) <= sp.w * sp.w * 1.001f + 1e-6f;
+                                    if (keep) cidx[c] = idx;
+                                }
+                            }
+                            cmask[c] = __ballot_sync(0xffffffffu, keep);
+                            if (lane == 0) s_ballot[c * (TILE_THREADS / 32) + warp] = cmask[c];
+                        }
+                        __syncthreads(); // ballots visible
+                        // ---- exclusive prefix over the 32 (slot, warp) ballots, computed redundantly by every warp
+                        const bool slot_live = sbase + (uint32_t)(lane / (TILE_THREADS / 32)) * TILE_THREADS < n_src;
+                        const uint32_t cnt = slot_live ? (uint32_t)__popc(s_ballot[lane]) : 0u;
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1)
+                        {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                        uint32_t dst[CAND_PER_THREAD];
+#pragma unroll
+                        for (int c = 0; c < CAND_PER_THREAD; ++c)
+                        {
+                            const uint32_t before = __shfl_sync(0xffffffffu, incl - cnt, c * (TILE_THREADS / 32) + warp);
+                            dst[c] = before + (uint32_t)__popc(cmask[c] & ((1u << lane) - 1u));
+                        }
+                        for (uint32_t pass = 0; pass < total; pass += LIGHT_CAP)
+                        {
+                            if (pass) __syncthreads(); // the previous pass's light loop is done with s_light
+#pragma unroll
+                            for (int c = 0; c < CAND_PER_THREAD; ++c)
+                            {
+                                if (cidx[c] == 0xFFFFFFFFu || dst[c] < pass || dst[c] >= pass + LIGHT_CAP) continue;
+                                const DevLightRec* rec = fc.lights + cidx[c];
+                                const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
+                                const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
+                                const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
+                                const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
+                                SmLight sl;
+                                const float range = fmaxf(pr.w, 0.001f);
+                                const float power = fmaxf(sa.y, 0.001f);
+                                sl.pos_r2 = make_float4(pr.x, pr.y, pr.z, range * range);
+                                sl.radiance_ir = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, 1.0f / range);
+                                sl.atten = make_float4(power, fmaxf(sa.w, 0.0f), fmaxf(sa.z, 1e-5f), 0.0f);
+                                sl.dir_outer = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                sl.kind = (tf.w == 0u ? 0u : (tf.w == 2u ? 2u : 1u)) | (power != 1.0f ? KIND_POW : 0u);
+                                sl.index = cidx[c]; sl.pad0 = sl.pad1 = 0u;
+                                if (tf.x == 2u)
+                                {
+                                    const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
+                                    const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
+                                    const float dl = fast_rsqrt(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
+                                    const float inner_cos = fminf(fmaxf(ds.w, -1.0f), 1.0f);
+                                    const float outer_cos = fminf(fmaxf(ax.w, -1.0f), inner_cos);
+                                    sl.dir_outer = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, outer_cos);
+                                    sl.atten.w = 1.0f / fmaxf(inner_cos - outer_cos, 1e-6f);
+                                    sl.kind |= KIND_SPOT;
+                                }
+                                else if (tf.x > 2u)
+                                {
+                                    const float4 sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere));
+                                    sl.pos_r2 = make_float4(sp.x, sp.y, sp.z, sp.w * sp.w * 1.001f + 1e-6f);
+                                    sl.kind |= KIND_AREA;
+                                }
+                                s_light[dst[c] - pass] = sl;
+                            }
+                            __syncthreads();
+                            if (has)
+                            {
+                                const uint32_t kept = min(total - pass, (uint32_t)LIGHT_CAP);
+                                const SmLight* lt = s_light;
+                                for (uint32_t j = 0; j < kept; ++j, ++lt)
+                                {
+                                    const float4 q0 = lt->pos_r2;
+                                    const float dx = q0.x - surf.P.x, dy = q0.y - surf.P.y, dz = q0.z - surf.P.z;
+                                    const float dist2 = dx * dx + dy * dy + dz * dz;
+                                    if (!(dist2 < q0.w) || !(dist2 > 1e-10f)) continue;
+                                    const uint32_t kind = lt->kind;
+                                    if (kind & KIND_AREA) sum = sum + eval_light_record(surf, fc.lights + lt->index);
+                                    else accumulate_point_spot(surf, lt, dx, dy, dz, dist2, kind, sum);
+                                }
                             }
                         }
                     }
@@ -703,21 +803,7 @@ namespace shsb
 
             // ---------------- phase C (per pixel): resolve colour (+ fused tonemap), each byte written once
             if (!valid) return;
-            if (!has)
-            {
-                if (fc.load_color)
-                {
-                    if (!(fc.fuse_tonemap && fb.ldr)) return;
-                    const float4 c = fb.hdr[pix];
-                    fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
-                    return;
-                }
-                // background gradient, pass_pbr_forward.hpp:73-81
-                const float t = xdiv((float)py, (float)max(1, fc.H - 1));
-                out_r = xadd(0.06f, xmul(0.08f, t));
-                out_g = xadd(0.08f, xmul(0.10f, t));
-                out_b = xadd(0.12f, xmul(0.12f, t));
-            }
+            if (!has) { resolve_uncovered(fc, fb, pix, py); return; }
             fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);
         }
