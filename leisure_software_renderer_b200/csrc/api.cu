@@ -1,7 +1,14 @@
 // api.cu -- the C-ABI of include/shsb.h: context, device-resident resources / render targets and the
 // pass entry points.  This is the host half of the path; it replaces the reference's job-system dispatch
-// (job/parallel_for.hpp:23-59, job/thread_pool_job_system.hpp:26-110) with kernel launches on one CUDA
-// stream per context, and its std::vector render targets (gfx/rt_types.hpp:35-157) with HBM buffers.
+// (job/parallel_for.hpp:23-59, job/thread_pool_job_system.hpp:26-110) with kernel launches on CUDA streams,
+// and its std::vector render targets (gfx/rt_types.hpp:35-157) with HBM buffers.
+//
+// Frame pipelining.  A submission has a FRONT END (draw-list upload, vertex / clip / set-up, binning, light
+// culling) that touches only per-frame transients, and the TILE KERNEL that touches the render targets.  The
+// front end runs on a high-priority side stream in one of three transient arenas; the tile kernel runs on the
+// context's main stream.  So the front ends of frames f+1 and f+2 overlap frame f's tile kernel, while everything that
+// touches render targets (tile kernels, clears, tonemap, downloads, work the caller orders on shsb_stream())
+// stays in submission order on the main stream.
 //
 // There is no CPU raster path in this file: every pass either launches the kernels or returns an error.
 #include <cstdarg>
@@ -21,7 +28,12 @@ namespace hm = shsb_host;
 
 namespace
 {
-    constexpr int NUM_STAGE_EVENTS = 6; // begin, after geometry, after binning, after raster, (cull begin, cull end)
+    // stage events: 0 front-end begin, 1 after geometry, 2 after binning, 3 tile kernel begin, 4 tile kernel end,
+    // 5 / 6 light cull or standalone tonemap begin / end
+    constexpr int NUM_STAGE_EVENTS = 7;
+    constexpr int TIMING_EVENTS_PER_FRAME = 5;
+    constexpr int NUM_ARENAS = 3;       // transient arenas: the front end may run two frames ahead of the tile kernel
+    constexpr int TILE_DONE_RING = 8;   // per-frame "tile kernel finished" events
 
     struct MeshSlot
     {
@@ -68,6 +80,30 @@ namespace
         T* p = nullptr;
         size_t cap = 0;
     };
+
+    // Per-frame transients (DESIGN.md "Data layout").  The arenas rotate so that front ends can fill the next
+    // ones while the tile kernel of an earlier frame still reads its own.
+    struct Arena
+    {
+        DevBuf<unsigned char> d_draw;   // [DevItem x n_items | uint2 block table], one H2D copy per frame
+        DevBuf<RasterRec> d_rrecs;
+        DevBuf<ShadeRec> d_srecs;
+        DevBuf<uint2> d_clipq;
+        DevBuf<uint32_t> d_tile_offset, d_tile_fill, d_tile_list, d_tile_order;
+        // frame header, cleared by ONE memset: [0] rec_count [1] clipq_count [2] list_cursor [4..7] class_count |
+        // [8..23] DevStats | [24 ...] tile_count[n_tiles + 1]
+        DevBuf<uint32_t> d_hdr;
+    };
+
+    // Tile light lists (LightCullingRuntimePayload, pipeline/render_pass.hpp:32-50): one set per arena for the fused
+    // frame, one for the standalone shsb_light_cull.
+    struct LightLists
+    {
+        DevBuf<uint32_t> counts, indices, scratch;
+        uint32_t w = 0, h = 0, ts = 0, max_per_tile = 0;
+        long long last_reader = -1;     // frame number of the last tile kernel that read these lists
+    };
+    constexpr int LISTS_STANDALONE = NUM_ARENAS;
 }
 
 struct shsb_context_t
@@ -85,32 +121,30 @@ struct shsb_context_t
     bool mesh_table_dirty = true, tex_table_dirty = true;
     float* d_srgb_lut = nullptr;
 
-    // lights + tile lists
-    DevBuf<DevLightRec> d_lights;
+    // lights: a ring of buffers so that an upload for a later frame does not wait for the tile kernel still
+    // reading the current records
+    DevBuf<DevLightRec> d_lights[NUM_ARENAS];
+    int lights_cur = 0;
+    long long lights_last_user[NUM_ARENAS] = {-1, -1, -1}; // frame number of the last tile kernel that read each buffer
     uint32_t n_lights = 0;
-    DevBuf<uint32_t> d_cull_scratch; // macro-cell candidate counts + lists
-    DevBuf<uint32_t> d_tile_counts, d_tile_indices;
-    uint32_t lists_w = 0, lists_h = 0, lists_ts = 0, lists_max = 0;
-    bool lists_valid = false;
+    cudaEvent_t ev_lights_up = nullptr;       // last upload (front stream)
+    cudaEvent_t ev_cull_main = nullptr;       // last standalone cull (main stream)
+    bool cull_main_pending = false;
+    LightLists lists[NUM_ARENAS + 1];
+    int lists_cur = -1;                       // the set produced by the most recent cull, -1 = none
 
-    // per-frame arena
-    DevBuf<DevItem> d_items;
-    DevBuf<uint2> d_blocks;
-    // pinned staging ring: a frame's item / block tables are copied H2D asynchronously, so a slot may only be
-    // rewritten once the copy that read it has completed (its event); 3 slots keep 2 frames in flight
-    static constexpr int STAGE_SLOTS = 3;
-    PinnedBuf<DevItem> h_items[STAGE_SLOTS];
-    PinnedBuf<uint2> h_blocks[STAGE_SLOTS];
+    // per-frame transients
+    Arena arena[NUM_ARENAS];
+    long long frame_no = 0;
+    cudaEvent_t ev_tile_done[TILE_DONE_RING]{};
+    cudaEvent_t ev_front_done[NUM_ARENAS]{};
+    // pinned staging ring: a frame's draw list is copied H2D asynchronously, so a slot may only be rewritten once
+    // the copy that read it has completed (its event)
+    static constexpr int STAGE_SLOTS = 4;
+    PinnedBuf<unsigned char> h_draw[STAGE_SLOTS];
     cudaEvent_t stage_done[STAGE_SLOTS]{};
     bool stage_busy[STAGE_SLOTS]{};
     int stage_slot = 0;
-    DevBuf<RasterRec> d_rrecs;
-    DevBuf<ShadeRec> d_srecs;
-    DevBuf<uint2> d_clipq;
-    DevBuf<uint32_t> d_tile_offset, d_tile_fill, d_tile_list, d_tile_order;
-    // per-frame header, cleared by ONE memset: [0] rec_count [1] clipq_count [2] list_cursor [4..7] class_count |
-    // [8..23] DevStats | [24 ...] tile_count[n_tiles + 1]
-    DevBuf<uint32_t> d_hdr;
     static constexpr size_t HDR_STATS = 8, HDR_TILE_COUNT = 24;
     DevStats* h_stats = nullptr;    // pinned
     double rec_growth = 1.0;        // multiplier learned from overflow reruns
@@ -123,8 +157,10 @@ struct shsb_context_t
     // light-culling kernels do not depend on geometry / binning, so in the fused Forward+ frame they are
     // captured on a second stream (fork / join) and run concurrently with those small launch-bound kernels.
     bool use_graph = true;
+    bool pipeline = true;                // SHSB_NO_PIPELINE=1: front end on the main stream (no frame overlap)
     bool capturing = false;
-    cudaStream_t stream2 = nullptr;
+    cudaStream_t front_stream = nullptr; // front end of each frame (high priority)
+    cudaStream_t stream2 = nullptr;      // light-cull branch of the front end (high priority)
     cudaStream_t copy_stream = nullptr; // asynchronous render-target downloads
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_frame_done = nullptr;
     cudaGraphExec_t graph_exec[4]{}; // [cull branch][shadow mode]
@@ -164,6 +200,14 @@ namespace
         if (e_ != cudaSuccess) return fail(ctx, SHSB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+    void sync_all(shsb_ctx ctx)
+    {
+        cudaStreamSynchronize(ctx->front_stream);
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+    }
+
     template <typename T>
     int ensure_dev(shsb_ctx ctx, DevBuf<T>& b, size_t n)
     {
@@ -174,7 +218,7 @@ namespace
         if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
         if (b.p)
         {
-            cudaStreamSynchronize(ctx->stream);
+            sync_all(ctx);
             cudaFree(b.p);
         }
         b.p = np;
@@ -192,7 +236,7 @@ namespace
         if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaHostAlloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
         if (b.p)
         {
-            cudaStreamSynchronize(ctx->stream);
+            sync_all(ctx);
             cudaFreeHost(b.p);
         }
         b.p = np;
@@ -261,19 +305,14 @@ namespace
         return SHSB_OK;
     }
 
-    struct HostItem
-    {
-        DevItem dev;
-    };
-
     struct FrameJob
     {
         FrameConst fc{};
         FrameBuffers fb{};
-        std::vector<DevItem>* items = nullptr; // in h_items after staging
         uint32_t n_items = 0;
         uint64_t n_src_tris = 0;
         uint32_t n_blocks = 0;
+        int lists_set = -1;     // light-list set the tile kernel reads (Forward+), -1 = none
     };
 
     void record_on(shsb_ctx ctx, cudaEvent_t e, cudaStream_t s)
@@ -283,12 +322,11 @@ namespace
         else cudaEventRecord(e, s);
     }
 
-    void record(shsb_ctx ctx, int i, cudaStream_t s = nullptr)
+    void record(shsb_ctx ctx, int i, cudaStream_t s)
     {
-        if (!s) s = ctx->stream;
         record_on(ctx, ctx->ev[i], s);
         ctx->ev_valid[i] = true;
-        if (ctx->timing_on && i < 4)
+        if (ctx->timing_on && i < TIMING_EVENTS_PER_FRAME)
         {
             if (ctx->timing_used == ctx->timing_ev.size())
             {
@@ -311,11 +349,6 @@ namespace
     int prepare_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile, CullJob& job)
     {
         if (!view_proj || vw == 0 || vh == 0 || ts == 0 || max_per_tile == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad light-cull arguments");
-        const uint32_t tiles = ((vw + ts - 1) / ts) * ((vh + ts - 1) / ts);
-        if (int rc = ensure_dev(ctx, ctx->d_tile_counts, tiles)) return rc;
-        if (int rc = ensure_dev(ctx, ctx->d_tile_indices, (size_t)tiles * max_per_tile)) return rc;
-        if (int rc = ensure_dev(ctx, ctx->d_lights, 1)) return rc;
-        if (int rc = ensure_dev(ctx, ctx->d_cull_scratch, std::max<size_t>(1, light_cull_scratch_words(ctx->n_lights, vw, vh, ts)))) return rc;
         const hm::mat4f vp = hm::load(view_proj);
         const hm::mat4f inv = hm::inverse(vp);
         hm::frustum_planes(vp, job.planes);
@@ -324,17 +357,29 @@ namespace
         return SHSB_OK;
     }
 
-    void enqueue_light_cull(shsb_ctx ctx, const CullJob& job, cudaStream_t s)
+    int ensure_lists(shsb_ctx ctx, LightLists& L, const CullJob& job)
     {
-        record(ctx, 4, s);
-        launch_light_cull(ctx->d_lights.p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, ctx->d_cull_scratch.p,
-                          ctx->d_tile_counts.p, ctx->d_tile_indices.p, s, &ctx->launches);
-        record(ctx, 5, s);
-        ctx->lists_w = job.vw; ctx->lists_h = job.vh; ctx->lists_ts = job.ts; ctx->lists_max = job.max_per_tile;
-        ctx->lists_valid = true;
+        const uint32_t tiles = ((job.vw + job.ts - 1) / job.ts) * ((job.vh + job.ts - 1) / job.ts);
+        if (int rc = ensure_dev(ctx, L.counts, tiles)) return rc;
+        if (int rc = ensure_dev(ctx, L.indices, (size_t)tiles * job.max_per_tile)) return rc;
+        if (int rc = ensure_dev(ctx, L.scratch, std::max<size_t>(1, light_cull_scratch_words(ctx->n_lights, job.vw, job.vh, job.ts)))) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_lights[ctx->lights_cur], 1)) return rc;
+        return SHSB_OK;
     }
 
-    // Runs geometry -> binning -> tile raster for the draws staged in ctx->h_items[0..n_items).
+    void enqueue_light_cull(shsb_ctx ctx, const CullJob& job, int set, cudaStream_t s)
+    {
+        LightLists& L = ctx->lists[set];
+        record(ctx, 5, s);
+        launch_light_cull(ctx->d_lights[ctx->lights_cur].p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, L.scratch.p,
+                          L.counts.p, L.indices.p, s, &ctx->launches);
+        record(ctx, 6, s);
+        L.w = job.vw; L.h = job.vh; L.ts = job.ts; L.max_per_tile = job.max_per_tile;
+        ctx->lists_cur = set;
+    }
+
+    // Submits one frame: front end (draw list staged in ctx->h_draw[stage_slot]) on the front stream in arena
+    // frame_no % NUM_ARENAS, tile kernel on the main stream.
     int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats, const CullJob* cull = nullptr)
     {
         FrameConst& fc = job.fc;
@@ -348,89 +393,92 @@ namespace
         for (int attempt = 0; attempt < 4; ++attempt)
         {
             const double t_a = now_us();
+            const long long f = ctx->frame_no++;
+            const int a = (int)(f % NUM_ARENAS);
+            Arena& A = ctx->arena[a];
             // capacities: every source triangle may emit one record; clipped ones up to 7
             const size_t clipq_cap = std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth));
             const size_t rec_cap = std::max<size_t>(4096, (size_t)(((double)job.n_src_tris + 6.0 * (double)std::min<size_t>(clipq_cap, job.n_src_tris)) * 1.0));
             const size_t list_cap = std::max<size_t>((size_t)n_tiles + 65536, (size_t)((double)rec_cap * 4.0 * ctx->rec_growth) + (size_t)n_tiles * 2);
-            if (int rc = ensure_dev(ctx, ctx->d_rrecs, rec_cap)) return rc;
-            if (!fc.shadow_mode) { if (int rc = ensure_dev(ctx, ctx->d_srecs, rec_cap)) return rc; }
-            if (int rc = ensure_dev(ctx, ctx->d_clipq, clipq_cap)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_hdr, shsb_context_t::HDR_TILE_COUNT + n_tiles + 1)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_tile_order, (size_t)4 * n_tiles)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_tile_offset, n_tiles + 2)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_tile_fill, n_tiles + 1)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_tile_list, list_cap)) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_items, std::max<size_t>(1, job.n_items))) return rc;
-            if (int rc = ensure_dev(ctx, ctx->d_blocks, std::max<size_t>(1, job.n_blocks))) return rc;
+            const size_t items_bytes = (size_t)job.n_items * sizeof(DevItem);
+            const size_t draw_bytes = items_bytes + (size_t)job.n_blocks * sizeof(uint2);
+            if (int rc = ensure_dev(ctx, A.d_rrecs, rec_cap)) return rc;
+            if (!fc.shadow_mode) { if (int rc = ensure_dev(ctx, A.d_srecs, rec_cap)) return rc; }
+            if (int rc = ensure_dev(ctx, A.d_clipq, clipq_cap)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_hdr, shsb_context_t::HDR_TILE_COUNT + n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_tile_order, (size_t)4 * n_tiles)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_tile_offset, n_tiles + 2)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_tile_fill, n_tiles + 1)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_tile_list, list_cap)) return rc;
+            if (int rc = ensure_dev(ctx, A.d_draw, std::max<size_t>(16, draw_bytes))) return rc;
+            if (cull) { if (int rc = ensure_lists(ctx, ctx->lists[a], *cull)) return rc; }
 
-            uint32_t* hdr = ctx->d_hdr.p;
+            uint32_t* hdr = A.d_hdr.p;
             DevStats* d_stats = reinterpret_cast<DevStats*>(hdr + shsb_context_t::HDR_STATS);
             const double t_b = now_us();
             ctx->host_us[2] += t_b - t_a;
 
             Geometry g{};
             g.meshes = ctx->d_meshes.p;
-            g.items = ctx->d_items.p;
-            g.block_table = ctx->d_blocks.p;
+            g.items = reinterpret_cast<const DevItem*>(A.d_draw.p);
+            g.block_table = reinterpret_cast<const uint2*>(A.d_draw.p + items_bytes);
             g.n_blocks = job.n_blocks;
-            g.rrecs = ctx->d_rrecs.p;
-            g.srecs = ctx->d_srecs.p;
-            g.rec_capacity = (uint32_t)std::min<size_t>(ctx->d_rrecs.cap, fc.shadow_mode ? ctx->d_rrecs.cap : ctx->d_srecs.cap);
+            g.rrecs = A.d_rrecs.p;
+            g.srecs = A.d_srecs.p;
+            g.rec_capacity = (uint32_t)std::min<size_t>(A.d_rrecs.cap, fc.shadow_mode ? A.d_rrecs.cap : A.d_srecs.cap);
             g.rec_count = hdr + 0;
-            g.clip_queue = ctx->d_clipq.p;
-            g.clipq_capacity = (uint32_t)ctx->d_clipq.cap;
+            g.clip_queue = A.d_clipq.p;
+            g.clipq_capacity = (uint32_t)A.d_clipq.cap;
             g.clipq_count = hdr + 1;
             g.list_cursor = hdr + 2;
             g.class_count = hdr + 4;
-            g.tile_order = ctx->d_tile_order.p;
+            g.tile_order = A.d_tile_order.p;
             g.tile_count = hdr + shsb_context_t::HDR_TILE_COUNT;
-            g.tile_offset = ctx->d_tile_offset.p;
-            g.tile_fill = ctx->d_tile_fill.p;
-            g.tile_list = ctx->d_tile_list.p;
-            g.list_capacity = (uint32_t)std::min<size_t>(ctx->d_tile_list.cap, 0xFFFFFFFFull);
+            g.tile_offset = A.d_tile_offset.p;
+            g.tile_fill = A.d_tile_fill.p;
+            g.tile_list = A.d_tile_list.p;
+            g.list_capacity = (uint32_t)std::min<size_t>(A.d_tile_list.cap, 0xFFFFFFFFull);
             g.stats = d_stats;
-            if (cull)
+            if (cull) job.lists_set = a; // the lists this frame shades with are the ones its own cull branch produces
+            if (fc.forward_plus)
             {
-                // the lists this frame shades with are the ones the cull branch below produces
-                fc.tile_counts = ctx->d_tile_counts.p;
-                fc.tile_indices = ctx->d_tile_indices.p;
+                const LightLists& L = ctx->lists[job.lists_set];
+                fc.lights = ctx->d_lights[ctx->lights_cur].p;
+                fc.tile_counts = L.counts.p;
+                fc.tile_indices = L.indices.p;
             }
 
             const int slot = ctx->stage_slot;
             const bool graph = ctx->use_graph;
-            cudaStream_t s1 = ctx->stream;
-            if (graph)
-            {
-                CK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
-                ctx->capturing = true;
-            }
+            cudaStream_t s1 = ctx->stream, sf = ctx->pipeline ? ctx->front_stream : s1;
             cudaError_t err = cudaSuccess;
             auto ok = [&](cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; };
+
+            // ---- what the front end must wait for: the tile kernel that last read this arena (NUM_ARENAS frames ago) and,
+            // when it rebuilds light lists, the last tile kernel that read that set
+            if (f >= NUM_ARENAS) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[(f - NUM_ARENAS) % TILE_DONE_RING], 0));
+            if (cull && ctx->lists[a].last_reader >= 0) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[ctx->lists[a].last_reader % TILE_DONE_RING], 0));
+
+            if (graph)
+            {
+                CK(cudaStreamBeginCapture(sf, cudaStreamCaptureModeThreadLocal));
+                ctx->capturing = true;
+            }
             if (cull)
             {
-                if (graph)
-                {
-                    ok(cudaEventRecord(ctx->ev_fork, s1));
-                    ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-                    enqueue_light_cull(ctx, *cull, ctx->stream2);
-                    ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
-                }
-                else enqueue_light_cull(ctx, *cull, s1);
+                ok(cudaEventRecord(ctx->ev_fork, sf));
+                ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                enqueue_light_cull(ctx, *cull, a, ctx->stream2);
+                ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
             }
-            record(ctx, 0);
-            ok(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), s1));
-            if (job.n_items)
-            {
-                ok(cudaMemcpyAsync(ctx->d_items.p, ctx->h_items[slot].p, (size_t)job.n_items * sizeof(DevItem), cudaMemcpyHostToDevice, s1));
-                ok(cudaMemcpyAsync(ctx->d_blocks.p, ctx->h_blocks[slot].p, (size_t)job.n_blocks * sizeof(uint2), cudaMemcpyHostToDevice, s1));
-            }
-            launch_geometry(fc, g, s1, &ctx->launches);
-            record(ctx, 1);
-            launch_binning(fc, g, s1, &ctx->launches);
-            if (cull && graph) ok(cudaStreamWaitEvent(s1, ctx->ev_join, 0));
-            record(ctx, 2);
-            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
-            record(ctx, 3);
+            record(ctx, 0, sf);
+            ok(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), sf));
+            if (draw_bytes) ok(cudaMemcpyAsync(A.d_draw.p, ctx->h_draw[slot].p, draw_bytes, cudaMemcpyHostToDevice, sf));
+            launch_geometry(fc, g, sf, &ctx->launches);
+            record(ctx, 1, sf);
+            if (cull) ok(cudaStreamWaitEvent(sf, ctx->ev_join, 0)); // alloc_kernel reads the tile light counts (scheduling classes)
+            launch_binning(fc, g, sf, &ctx->launches);
+            record(ctx, 2, sf);
             ok(cudaGetLastError());
             const double t_c = now_us();
             ctx->host_us[3] += t_c - t_b;
@@ -438,7 +486,7 @@ namespace
             {
                 ctx->capturing = false;
                 cudaGraph_t captured = nullptr;
-                const cudaError_t ec = cudaStreamEndCapture(s1, &captured);
+                const cudaError_t ec = cudaStreamEndCapture(sf, &captured);
                 if (err == cudaSuccess) err = ec;
                 if (err == cudaSuccess)
                 {
@@ -454,22 +502,36 @@ namespace
                         }
                     }
                     if (!exec) err = cudaGraphInstantiate(&exec, captured, 0);
-                    if (err == cudaSuccess) err = cudaGraphLaunch(exec, s1);
+                    if (err == cudaSuccess) err = cudaGraphLaunch(exec, sf);
                 }
                 if (captured) cudaGraphDestroy(captured);
             }
             if (err != cudaSuccess) return fail(ctx, SHSB_E_CUDA, "frame submission failed: %s", cudaGetErrorString(err));
-            if (job.n_items)
+            CK(cudaEventRecord(ctx->ev_front_done[a], sf));
+            if (draw_bytes)
             {
-                CK(cudaEventRecord(ctx->stage_done[slot], s1));
+                CK(cudaEventRecord(ctx->stage_done[slot], sf));
                 ctx->stage_busy[slot] = true;
+            }
+            // ---- tile kernel: main stream, after this frame's front end (and, by stream order, after every earlier
+            // tile kernel and whatever the caller ordered on the main stream)
+            CK(cudaStreamWaitEvent(s1, ctx->ev_front_done[a], 0));
+            record(ctx, 3, s1);
+            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
+            record(ctx, 4, s1);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev_tile_done[f % TILE_DONE_RING], s1));
+            if (fc.forward_plus)
+            {
+                ctx->lights_last_user[ctx->lights_cur] = f;
+                ctx->lists[job.lists_set].last_reader = f;
             }
             ctx->host_us[4] += now_us() - t_c;
             ctx->host_us[5] += 1.0;
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
-            CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, s1));
+            CK(cudaStreamSynchronize(s1));
             const DevStats& st = *ctx->h_stats;
             if (st.overflow_recs || st.overflow_lists || st.overflow_clipq)
             {
@@ -486,7 +548,7 @@ namespace
         return fail(ctx, SHSB_E_OUT_OF_MEMORY, "per-frame arena overflow persisted after regrowth");
     }
 
-    // Stages one draw into the pinned item / block tables.
+    // Stages one draw into the host item / block tables.
     int stage_item(shsb_ctx ctx, std::vector<DevItem>& items, std::vector<uint2>& blocks, uint64_t& tri_cursor,
                    const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
                    const float base_color[3], float metallic, float roughness, float ao, uint32_t tex)
@@ -507,6 +569,7 @@ namespace
         return SHSB_OK;
     }
 
+    // Copies the draw list ([items | blocks]) into the next slot of the pinned staging ring.
     int upload_staging(shsb_ctx ctx, const std::vector<DevItem>& items, const std::vector<uint2>& blocks)
     {
         const int slot = ctx->stage_slot = (ctx->stage_slot + 1) % shsb_context_t::STAGE_SLOTS;
@@ -515,10 +578,10 @@ namespace
             CK(cudaEventSynchronize(ctx->stage_done[slot])); // the H2D copy that last read this slot has finished
             ctx->stage_busy[slot] = false;
         }
-        if (int rc = ensure_pinned(ctx, ctx->h_items[slot], std::max<size_t>(1, items.size()))) return rc;
-        if (int rc = ensure_pinned(ctx, ctx->h_blocks[slot], std::max<size_t>(1, blocks.size()))) return rc;
-        if (!items.empty()) std::memcpy(ctx->h_items[slot].p, items.data(), items.size() * sizeof(DevItem));
-        if (!blocks.empty()) std::memcpy(ctx->h_blocks[slot].p, blocks.data(), blocks.size() * sizeof(uint2));
+        const size_t items_bytes = items.size() * sizeof(DevItem), blocks_bytes = blocks.size() * sizeof(uint2);
+        if (int rc = ensure_pinned(ctx, ctx->h_draw[slot], std::max<size_t>(16, items_bytes + blocks_bytes))) return rc;
+        if (items_bytes) std::memcpy(ctx->h_draw[slot].p, items.data(), items_bytes);
+        if (blocks_bytes) std::memcpy(ctx->h_draw[slot].p + items_bytes, blocks.data(), blocks_bytes);
         return SHSB_OK;
     }
 
@@ -609,14 +672,13 @@ namespace
         }
         if (!depth_only && fp->light_culling && ctx->n_lights > 0)
         {
-            if (!cull && (!ctx->lists_valid || ctx->lists_w != (uint32_t)W || ctx->lists_h != (uint32_t)H))
+            const LightLists* cur = ctx->lists_cur >= 0 ? &ctx->lists[ctx->lists_cur] : nullptr;
+            if (!cull && (!cur || cur->w != (uint32_t)W || cur->h != (uint32_t)H))
                 return fail(ctx, SHSB_E_INVALID_ARGUMENT, "light_culling is on but shsb_light_cull has not been run for a %dx%d viewport", W, H);
-            const uint32_t ts = cull ? cull->ts : ctx->lists_ts, mx = cull ? cull->max_per_tile : ctx->lists_max;
+            const uint32_t ts = cull ? cull->ts : cur->ts, mx = cull ? cull->max_per_tile : cur->max_per_tile;
             fc.forward_plus = 1;
-            fc.lights = ctx->d_lights.p;
             fc.n_lights = ctx->n_lights;
-            fc.tile_counts = ctx->d_tile_counts.p;
-            fc.tile_indices = ctx->d_tile_indices.p;
+            job.lists_set = ctx->lists_cur; // run_frame points the kernels at the set (its own when it culls)
             fc.light_tile_size = ts;
             fc.max_per_tile = mx;
             fc.light_tiles_x = (W + ts - 1) / ts;
@@ -688,9 +750,19 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     if (cudaSetDevice(device_ordinal) != cudaSuccess) return SHSB_E_NO_DEVICE;
     shsb_ctx ctx = new shsb_context_t();
     ctx->device = device_ordinal;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* e = std::getenv("SHSB_NO_PIPELINE")) ctx->pipeline = !(e[0] == '1');
+    if (const char* e = std::getenv("SHSB_FRONT_PRIORITY")) { if (e[0] == '0') prio_greatest = prio_least; }
+    bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    // the front end is small and latency-bound: at high priority its CTAs slot in between the tile kernel's
+    ok = ok && cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_lights_up, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_cull_main, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < TILE_DONE_RING; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_tile_done[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < NUM_ARENAS; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -719,19 +791,26 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_all(ctx);
     for (auto& m : ctx->meshes) { cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.indices); }
     for (auto& t : ctx->textures) cudaFree(t.texels);
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
-    cudaFree(ctx->d_lights.p); cudaFree(ctx->d_cull_scratch.p); cudaFree(ctx->d_tile_counts.p); cudaFree(ctx->d_tile_indices.p);
-    cudaFree(ctx->d_items.p); cudaFree(ctx->d_blocks.p); cudaFree(ctx->d_rrecs.p); cudaFree(ctx->d_srecs.p); cudaFree(ctx->d_clipq.p);
-    cudaFree(ctx->d_hdr.p); cudaFree(ctx->d_tile_order.p); cudaFree(ctx->d_tile_offset.p); cudaFree(ctx->d_tile_fill.p); cudaFree(ctx->d_tile_list.p);
+    for (auto& l : ctx->d_lights) cudaFree(l.p);
+    for (LightLists& L : ctx->lists) { cudaFree(L.counts.p); cudaFree(L.indices.p); cudaFree(L.scratch.p); }
+    for (Arena& A : ctx->arena)
+    {
+        cudaFree(A.d_draw.p); cudaFree(A.d_rrecs.p); cudaFree(A.d_srecs.p); cudaFree(A.d_clipq.p); cudaFree(A.d_hdr.p);
+        cudaFree(A.d_tile_order.p); cudaFree(A.d_tile_offset.p); cudaFree(A.d_tile_fill.p); cudaFree(A.d_tile_list.p);
+    }
     cudaFreeHost(ctx->h_stats);
+    for (cudaEvent_t e : ctx->ev_tile_done) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_front_done) if (e) cudaEventDestroy(e);
+    if (ctx->ev_lights_up) cudaEventDestroy(ctx->ev_lights_up);
+    if (ctx->ev_cull_main) cudaEventDestroy(ctx->ev_cull_main);
     for (int i = 0; i < shsb_context_t::STAGE_SLOTS; ++i)
     {
-        cudaFreeHost(ctx->h_items[i].p);
-        cudaFreeHost(ctx->h_blocks[i].p);
+        cudaFreeHost(ctx->h_draw[i].p);
         if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
     }
     for (int i = 0; i < NUM_STAGE_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -743,6 +822,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SHSB_OK;
@@ -753,6 +833,7 @@ SHSB_API const char* shsb_last_error_string(shsb_ctx ctx) { return ctx ? ctx->er
 SHSB_API int32_t shsb_sync(shsb_ctx ctx)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(ctx->front_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return SHSB_OK;
@@ -816,7 +897,7 @@ SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh)
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     MeshSlot* m = get_mesh(ctx, mesh);
     if (!m) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh);
-    CK(cudaStreamSynchronize(ctx->stream));
+    sync_all(ctx);
     cudaFree(m->positions); cudaFree(m->normals); cudaFree(m->uvs); cudaFree(m->indices);
     *m = MeshSlot{};
     ctx->mesh_table_dirty = true;
@@ -841,7 +922,7 @@ SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     if (tex == 0 || tex > ctx->textures.size() || !ctx->textures[tex - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", tex);
-    CK(cudaStreamSynchronize(ctx->stream));
+    sync_all(ctx);
     cudaFree(ctx->textures[tex - 1].texels);
     ctx->textures[tex - 1] = TexSlot{};
     ctx->tex_table_dirty = true;
@@ -1156,9 +1237,9 @@ SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt,
     RtSlot* ldr = get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR);
     if (!hdr || !ldr) return fail(ctx, SHSB_E_INVALID_HANDLE, "tonemap needs a live RT_ColorHDR and RT_ColorLDR");
     if (hdr->w != ldr->w || hdr->h != ldr->h) return fail(ctx, SHSB_E_SIZE_MISMATCH, "tonemap targets differ in size"); // reference crops to min(w,h); not needed on this path
-    record(ctx, 4);
+    record(ctx, 5, ctx->stream);
     launch_tonemap((const float4*)hdr->color, (uchar4*)ldr->color, hdr->w * hdr->h, std::max(0.0001f, exposure), 1.0f / std::max(0.001f, gamma), ctx->stream, &ctx->launches);
-    record(ctx, 5);
+    record(ctx, 6, ctx->stream);
     CK(cudaGetLastError());
     return SHSB_OK;
 }
@@ -1168,10 +1249,20 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     if (n_lights && !records) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "records is null");
     CK(cudaSetDevice(ctx->device));
-    if (int rc = ensure_dev(ctx, ctx->d_lights, std::max(1u, n_lights))) return rc;
-    if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights.p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->stream));
+    // The records go into the buffer the in-flight frames are NOT reading, on the front stream: the upload for
+    // frame f+1 overlaps frame f's tile kernel.  It waits only for the last tile kernel / standalone cull that read
+    // that buffer; later culls are ordered behind it on the front stream, and the main stream waits for it too.
+    const int b = (ctx->lights_cur + 1) % NUM_ARENAS;
+    if (int rc = ensure_dev(ctx, ctx->d_lights[b], std::max(1u, n_lights))) return rc;
+    if (ctx->lights_last_user[b] >= 0) CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_tile_done[ctx->lights_last_user[b] % TILE_DONE_RING], 0));
+    if (ctx->cull_main_pending) { CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_cull_main, 0)); ctx->cull_main_pending = false; }
+    if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights[b].p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->front_stream));
+    CK(cudaEventRecord(ctx->ev_lights_up, ctx->front_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lights_up, 0));
+    ctx->lights_cur = b;
+    ctx->lights_last_user[b] = -1;
     ctx->n_lights = n_lights;
-    ctx->lists_valid = false;
+    ctx->lists_cur = -1;
     return SHSB_OK;
 }
 
@@ -1181,20 +1272,27 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
     CK(cudaSetDevice(ctx->device));
     CullJob job;
     if (int rc = prepare_light_cull(ctx, view_proj, vw, vh, ts, max_per_tile, job)) return rc;
-    enqueue_light_cull(ctx, job, ctx->stream);
+    if (int rc = ensure_lists(ctx, ctx->lists[LISTS_STANDALONE], job)) return rc;
+    // main stream: ordered behind every tile kernel that read the standalone set
+    enqueue_light_cull(ctx, job, LISTS_STANDALONE, ctx->stream);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_cull_main, ctx->stream));
+    ctx->cull_main_pending = true;
     return SHSB_OK;
 }
 
 SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
-    if (!ctx->lists_valid) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile light lists: call shsb_light_cull first");
-    const size_t tiles = (size_t)((ctx->lists_w + ctx->lists_ts - 1) / ctx->lists_ts) * ((ctx->lists_h + ctx->lists_ts - 1) / ctx->lists_ts);
+    if (ctx->lists_cur < 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile light lists: call shsb_light_cull first");
+    const LightLists& L = ctx->lists[ctx->lists_cur];
+    const size_t tiles = (size_t)((L.w + L.ts - 1) / L.ts) * ((L.h + L.ts - 1) / L.ts);
     if (counts && n_counts != tiles) return fail(ctx, SHSB_E_SIZE_MISMATCH, "counts has %zu entries, lists have %zu tiles", n_counts, tiles);
-    if (indices && n_indices != tiles * ctx->lists_max) return fail(ctx, SHSB_E_SIZE_MISMATCH, "indices has %zu entries, expected %zu", n_indices, tiles * ctx->lists_max);
-    if (counts) CK(cudaMemcpyAsync(counts, ctx->d_tile_counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (indices) CK(cudaMemcpyAsync(indices, ctx->d_tile_indices.p, tiles * ctx->lists_max * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices && n_indices != tiles * L.max_per_tile) return fail(ctx, SHSB_E_SIZE_MISMATCH, "indices has %zu entries, expected %zu", n_indices, tiles * L.max_per_tile);
+    CK(cudaStreamSynchronize(ctx->front_stream)); // a fused frame builds its lists on the front end
+    CK(cudaStreamSynchronize(ctx->stream2));
+    if (counts) CK(cudaMemcpyAsync(counts, L.counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices) CK(cudaMemcpyAsync(indices, L.indices.p, tiles * L.max_per_tile * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SHSB_OK;
 }
@@ -1211,15 +1309,17 @@ SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_fra
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
     CK(cudaStreamSynchronize(ctx->stream));
-    const size_t frames = std::min(ctx->timing_used / 4, cap_frames);
+    CK(cudaStreamSynchronize(ctx->front_stream));
+    const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
     for (size_t f = 0; f < frames && out_ms; ++f)
     {
-        const cudaEvent_t* e = &ctx->timing_ev[f * 4];
+        // front-end begin, after geometry, after binning (front stream) | tile kernel begin, end (main stream)
+        const cudaEvent_t* e = &ctx->timing_ev[f * TIMING_EVENTS_PER_FRAME];
         float g = 0, b = 0, r = 0, t = 0;
         cudaEventElapsedTime(&g, e[0], e[1]);
         cudaEventElapsedTime(&b, e[1], e[2]);
-        cudaEventElapsedTime(&r, e[2], e[3]);
-        cudaEventElapsedTime(&t, e[0], e[3]);
+        cudaEventElapsedTime(&r, e[3], e[4]);
+        cudaEventElapsedTime(&t, e[0], e[4]);
         out_ms[f * 4 + 0] = g; out_ms[f * 4 + 1] = b; out_ms[f * 4 + 2] = r; out_ms[f * 4 + 3] = t;
     }
     *out_frames = frames;
@@ -1238,6 +1338,7 @@ SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t res
 SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
 {
     if (!ctx || !out_ms) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(ctx->front_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 8; ++i) out_ms[i] = 0.0f;
     auto span = [&](int a, int b) -> float {
@@ -1248,9 +1349,9 @@ SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
     };
     out_ms[0] = span(0, 1);
     out_ms[1] = span(1, 2);
-    out_ms[2] = span(2, 3);
-    out_ms[3] = span(4, 5); // light cull or standalone tonemap, whichever ran last
-    out_ms[5] = span(0, 3);
+    out_ms[2] = span(3, 4);
+    out_ms[3] = span(5, 6); // light cull or standalone tonemap, whichever ran last
+    out_ms[5] = span(0, 4);
     return SHSB_OK;
 }
 

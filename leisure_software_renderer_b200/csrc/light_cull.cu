@@ -20,8 +20,8 @@ namespace shsb
 {
     namespace
     {
-        constexpr int CULL_THREADS = 128;   // per-tile kernel: a macro cell rarely has more than ~250 candidates
-        constexpr int MACRO_THREADS = 512;  // per-macro-cell kernel walks every light
+        constexpr int CULL_THREADS = 128;   // per-tile kernel: 4 tiles per CTA, one warp each
+        constexpr int MACRO_THREADS = 256;  // per-macro-cell kernel walks every light
 
         struct Planes6 { float4 p[6]; };
 
@@ -186,33 +186,36 @@ namespace shsb
             if (threadIdx.x == 0) macro_counts[mc] = total;
         }
 
-        // K4b -- one CTA per tile: the exact test of cull_lights_tiled over the macro cell's candidates.
+        // K4b -- one WARP per tile: the exact test of cull_lights_tiled over the macro cell's candidates.  Lanes 0-7
+        // unproject the cell corners, lanes 0-5 build the planes, then the warp walks the candidates 32 at a time and
+        // compacts with one ballot -- no CTA barrier, so a tile holds 32 threads' worth of registers for its lifetime
+        // (this kernel shares the SMs with the previous frame's tile kernel).
         __global__ void __launch_bounds__(CULL_THREADS) tile_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp,
                                                                          const uint32_t* __restrict__ macro_counts, const uint32_t* __restrict__ macro_lists,
                                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
         {
-            __shared__ float s_corner[8][3];
-            __shared__ float4 s_plane[6];
-            __shared__ uint32_t s_warp_count[CULL_THREADS / 32];
+            __shared__ float s_corner[CULL_THREADS / 32][8][3];
+            __shared__ float4 s_plane[CULL_THREADS / 32][6];
 
-            const uint32_t tile = blockIdx.x;
-            const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            if (threadIdx.x < 8) cell_corner(cp, tx, ty, threadIdx.x, s_corner[threadIdx.x]);
-            __syncthreads();
-            if (threadIdx.x < 6) s_plane[threadIdx.x] = cell_plane(s_corner, threadIdx.x);
-            __syncthreads();
+            const uint32_t tile = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
+            if (tile >= cp.tiles_x * cp.tiles_y) return; // warp-uniform
+            const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
+            if (lane < 8) cell_corner(cp, tx, ty, lane, s_corner[warp][lane]);
+            __syncwarp();
+            if (lane < 6) s_plane[warp][lane] = cell_plane(s_corner[warp], lane);
+            __syncwarp();
             float4 planes[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) planes[i] = s_plane[i];
+            for (int i = 0; i < 6; ++i) planes[i] = s_plane[warp][i];
 
             const uint32_t mc = (ty / MACRO) * cp.macro_x + (tx / MACRO);
             const uint32_t n_cand = macro_counts[mc];
             const uint32_t* cand = macro_lists + (size_t)mc * cp.n_lights;
             uint32_t total = 0;
-            for (uint32_t base = 0; base < n_cand; base += CULL_THREADS)
+            for (uint32_t base = 0; base < n_cand; base += 32u)
             {
-                const uint32_t ci = base + threadIdx.x;
+                const uint32_t ci = base + (uint32_t)lane;
                 bool keep = false;
                 uint32_t li = 0;
                 if (ci < n_cand)
@@ -224,25 +227,14 @@ namespace shsb
                     keep = classify(planes, sp, mn, mx) != 0;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
-                __syncthreads(); // previous iteration's readers are done with s_warp_count
-                if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
-                __syncthreads();
-                uint32_t before = 0, chunk_total = 0;
-#pragma unroll
-                for (int w = 0; w < CULL_THREADS / 32; ++w)
-                {
-                    const uint32_t c = s_warp_count[w];
-                    if (w < warp) before += c;
-                    chunk_total += c;
-                }
                 if (keep)
                 {
-                    const uint32_t pos = total + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    const uint32_t pos = total + (uint32_t)__popc(m & ((1u << lane) - 1u));
                     if (pos < cp.max_per_tile) indices[(size_t)tile * cp.max_per_tile + pos] = li;
                 }
-                total += chunk_total;
+                total += (uint32_t)__popc(m);
             }
-            if (threadIdx.x == 0) counts[tile] = total;
+            if (lane == 0) counts[tile] = total;
         }
     }
 
@@ -271,7 +263,7 @@ namespace shsb
         uint32_t* macro_counts = scratch;
         uint32_t* macro_lists = scratch + n_macro;
         macro_cull_kernel<<<n_macro, MACRO_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
-        tile_cull_kernel<<<cp.tiles_x * cp.tiles_y, CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
+        tile_cull_kernel<<<(cp.tiles_x * cp.tiles_y + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
         *launches += 2;
     }
 }
