@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshsb.so")
+LIB_PATH = os.environ.get("SHSB_LIB") or os.path.join(_HERE, "libshsb.so")  # SHSB_LIB: an alternative BUILD of the same library (kernel experiments)
 
 # ---------------------------------------------------------------- enums (include/shsb.h)
 OK = 0

@@ -22,6 +22,9 @@ namespace shsb
     namespace
     {
         constexpr int TILE_THREADS = 256;
+#ifndef TILE_MIN_CTAS
+#define TILE_MIN_CTAS 4
+#endif
         constexpr float PI_F = 3.14159265358979323846f;
 
         struct V3 { float x, y, z; };
@@ -349,7 +352,7 @@ namespace shsb
         constexpr int LIGHT_CAP = TILE_THREADS;       // staged lights per pass
         constexpr int CAND_PER_THREAD = 4;            // candidates filtered per thread per staging round (1024 per CTA)
 
-        __global__ void __launch_bounds__(TILE_THREADS, 4) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
+        __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
@@ -367,13 +370,55 @@ namespace shsb
 
             // heaviest scheduling class first (alloc_kernel, binning.cu): the cheap background tiles fill the tail
             const uint32_t n_tiles_total = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
-            uint32_t ord = blockIdx.x, cls = 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
+            const uint32_t cc0 = g.class_count[0], cc1 = g.class_count[1], cc2 = g.class_count[2];
+            const uint32_t n_nonempty = cc0 + cc1 + cc2;
+            if (blockIdx.x >= n_nonempty)
             {
-                const uint32_t cc = g.class_count[c];
-                if (cls == (uint32_t)c && ord >= cc) { ord -= cc; ++cls; }
+                // ---------------- empty tiles (class 3; most of a frame): nothing to rasterise, no barriers, no counters.
+                // One CTA resolves FOUR tiles, one thread 4 horizontally adjacent pixels with 128-bit stores; the
+                // background colour depends on the row only, so it is evaluated once per 4 pixels.
+                const uint32_t first = (blockIdx.x - n_nonempty) * 4u + (threadIdx.x >> 6);
+                if (first >= n_tiles_total - n_nonempty) return;
+                const uint32_t packed = g.tile_order[(size_t)3 * n_tiles_total + first];
+                const int q = threadIdx.x & 63;
+                const int x0 = (int)(packed & 0xffffu) * TILE + (q & 3) * 4;
+                const int fy = (int)(packed >> 16) * TILE + (q >> 2);
+                if (x0 >= fc.W || fy >= fc.H) return;
+                const int py = fc.H - 1 - fy;
+                const size_t pix = (size_t)py * (size_t)fc.W + (size_t)x0;
+                const bool clear_depth = fb.depth && (fc.has_depth || fc.shadow_mode) && !fc.load_depth;
+                const bool shade = !(fc.shadow_mode || fc.shader_id == 5 || !fb.hdr);
+                if (x0 - (q & 3) * 4 + TILE <= fc.W && (fc.W & 3) == 0 && !fc.load_color) // whole tile row inside, 16-byte aligned rows
+                {
+                    if (clear_depth) *reinterpret_cast<float4*>(fb.depth + pix) = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                    if (fb.aov_tri_id) *reinterpret_cast<uint4*>(fb.aov_tri_id + pix) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                    if (fb.aov_coverage) *reinterpret_cast<uint4*>(fb.aov_coverage + pix) = make_uint4(0u, 0u, 0u, 0u);
+                    if (!shade) return;
+                    // background gradient, pass_pbr_forward.hpp:73-81
+                    const float t = xdiv((float)py, (float)max(1, fc.H - 1));
+                    const float4 c = make_float4(xadd(0.06f, xmul(0.08f, t)), xadd(0.08f, xmul(0.10f, t)), xadd(0.12f, xmul(0.12f, t)), 1.0f);
+                    // the 4 threads of a row write 64 contiguous bytes per store instruction (whole sectors)
+                    float4* row = fb.hdr + (pix - (size_t)((q & 3) * 4)) + (size_t)(q & 3);
+                    row[0] = c; row[4] = c; row[8] = c; row[12] = c;
+                    if (fc.fuse_tonemap && fb.ldr)
+                    {
+                        const uchar4 l = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
+                        const uint32_t w = (uint32_t)l.x | ((uint32_t)l.y << 8) | ((uint32_t)l.z << 16) | ((uint32_t)l.w << 24);
+                        *reinterpret_cast<uint4*>(fb.ldr + pix) = make_uint4(w, w, w, w);
+                    }
+                    return;
+                }
+                for (int i = 0; i < 4 && x0 + i < fc.W; ++i)
+                {
+                    if (clear_depth) fb.depth[pix + i] = 1.0f;
+                    if (fb.aov_tri_id) fb.aov_tri_id[pix + i] = 0xFFFFFFFFu;
+                    if (fb.aov_coverage) fb.aov_coverage[pix + i] = 0u;
+                    if (shade) resolve_uncovered(fc, fb, pix + i, py);
+                }
+                return;
             }
+            uint32_t ord = blockIdx.x, cls = 0;
+            if (ord >= cc0) { ord -= cc0; cls = 1; if (ord >= cc1) { ord -= cc1; cls = 2; } }
             const uint32_t packed = g.tile_order[(size_t)cls * n_tiles_total + ord]; // tx | ty << 16
             const int tx = (int)(packed & 0xffffu), ty = (int)(packed >> 16);
             const int tile = ty * fc.tiles_x + tx;
@@ -384,19 +429,7 @@ namespace shsb
             const int py = fc.H - 1 - fy;
             const bool valid = px < fc.W && fy < fc.H;
             const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
-
-            const uint32_t tile_tris = g.tile_count[tile];
-            if (tile_tris == 0u)
-            {
-                // ---------------- empty tile (most of a frame): nothing to rasterise, no barriers, no counters
-                if (!valid) return;
-                if (fb.depth && (fc.has_depth || fc.shadow_mode) && !fc.load_depth) fb.depth[pix] = 1.0f;
-                if (fb.aov_tri_id) fb.aov_tri_id[pix] = 0xFFFFFFFFu;
-                if (fb.aov_coverage) fb.aov_coverage[pix] = 0u;
-                if (fc.shadow_mode || fc.shader_id == 5 || !fb.hdr) return;
-                resolve_uncovered(fc, fb, pix, py);
-                return;
-            }
+            const uint32_t tile_tris = g.tile_count[tile]; // > 0: classes 0-2 hold exactly the tiles with triangles
 
             float bz = 1.0f;
             if (fc.has_depth && fc.load_depth && valid) bz = fb.depth[pix];
