@@ -91,7 +91,7 @@ namespace
         DevBuf<uint2> d_clipq;
         DevBuf<uint32_t> d_tile_offset, d_tile_fill, d_tile_list, d_tile_order;
         // frame header, cleared by ONE memset: [0] rec_count [1] clipq_count [2] list_cursor [4..7] class_count |
-        // [8..23] DevStats | [24 ...] tile_count[n_tiles + 1]
+        // [32 ...] DevStats[STAT_SHARDS] | tile_count[n_tiles + 1]
         DevBuf<uint32_t> d_hdr;
     };
 
@@ -145,7 +145,7 @@ struct shsb_context_t
     cudaEvent_t stage_done[STAGE_SLOTS]{};
     bool stage_busy[STAGE_SLOTS]{};
     int stage_slot = 0;
-    static constexpr size_t HDR_STATS = 8, HDR_TILE_COUNT = 24;
+    static constexpr size_t HDR_STATS = 32, HDR_TILE_COUNT = HDR_STATS + STAT_SHARDS * sizeof(DevStats) / 4; // u32 words
     DevStats* h_stats = nullptr;    // pinned
     double rec_growth = 1.0;        // multiplier learned from overflow reruns
 
@@ -530,9 +530,16 @@ namespace
             ctx->host_us[5] += 1.0;
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
-            CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, s1));
+            CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats) * STAT_SHARDS, cudaMemcpyDeviceToHost, s1));
             CK(cudaStreamSynchronize(s1));
-            const DevStats& st = *ctx->h_stats;
+            DevStats st{};
+            for (int k = 0; k < STAT_SHARDS; ++k)
+            {
+                const DevStats& sh = ctx->h_stats[k];
+                st.tri_input += sh.tri_input; st.tri_after_clip += sh.tri_after_clip; st.tri_raster += sh.tri_raster;
+                st.frag_covered += sh.frag_covered; st.frag_shaded += sh.frag_shaded;
+                st.overflow_recs += sh.overflow_recs; st.overflow_lists += sh.overflow_lists; st.overflow_clipq += sh.overflow_clipq;
+            }
             if (st.overflow_recs || st.overflow_lists || st.overflow_clipq)
             {
                 ctx->rec_growth *= 4.0; // arena too small for this scene: grow and re-run the frame
@@ -767,7 +774,7 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
-    ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
     for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < shsb_context_t::STAGE_SLOTS; ++i) ok = cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming) == cudaSuccess;

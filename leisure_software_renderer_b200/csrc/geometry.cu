@@ -210,9 +210,13 @@ namespace shsb
                 for (int tx = tr.tx0; tx <= tr.tx1; ++tx) atomicAdd(&g.tile_count[(uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx], 1u);
         }
 
-        __device__ __forceinline__ void block_add_stats(DevStats* st, unsigned tri_input, unsigned after_clip, unsigned raster)
+        __device__ __forceinline__ DevStats* stats_shard(const Geometry& g) { return g.stats + (blockIdx.x & (STAT_SHARDS - 1)); }
+
+        // CTA-wide statistics: warp reduce -> shared -> ONE atomic per counter and CTA, into the CTA's shard.
+        // Contains a __syncthreads(): every thread of the CTA must call it.
+        __device__ __forceinline__ void block_add_stats(const Geometry& g, unsigned tri_input, unsigned after_clip, unsigned raster)
         {
-            // warp reduce, then one atomic per warp and counter
+            __shared__ unsigned s_stat[GEOM_THREADS / 32][3];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
             {
@@ -220,12 +224,43 @@ namespace shsb
                 after_clip += __shfl_down_sync(0xffffffffu, after_clip, o);
                 raster += __shfl_down_sync(0xffffffffu, raster, o);
             }
-            if ((threadIdx.x & 31) == 0)
+            if ((threadIdx.x & 31) == 0) { s_stat[threadIdx.x >> 5][0] = tri_input; s_stat[threadIdx.x >> 5][1] = after_clip; s_stat[threadIdx.x >> 5][2] = raster; }
+            __syncthreads();
+            if (threadIdx.x == 0)
             {
-                if (tri_input) atomicAdd(&st->tri_input, (unsigned long long)tri_input);
-                if (after_clip) atomicAdd(&st->tri_after_clip, (unsigned long long)after_clip);
-                if (raster) atomicAdd(&st->tri_raster, (unsigned long long)raster);
+                unsigned a = 0, b = 0, c = 0;
+#pragma unroll
+                for (int w = 0; w < GEOM_THREADS / 32; ++w) { a += s_stat[w][0]; b += s_stat[w][1]; c += s_stat[w][2]; }
+                DevStats* st = stats_shard(g);
+                if (a) atomicAdd(&st->tri_input, (unsigned long long)a);
+                if (b) atomicAdd(&st->tri_after_clip, (unsigned long long)b);
+                if (c) atomicAdd(&st->tri_raster, (unsigned long long)c);
             }
+        }
+
+        // CTA-wide record allocation: ONE atomicAdd on the global record counter per CTA (a counter hit once per warp
+        // serialises ~10^5 same-address atomics on a multi-million-triangle frame).  Returns the calling thread's slot
+        // (meaningful where `emit`).  Contains __syncthreads(): every thread of the CTA must call it.
+        __device__ __forceinline__ uint32_t block_alloc_records(const Geometry& g, bool emit)
+        {
+            __shared__ uint32_t s_wcount[GEOM_THREADS / 32];
+            __shared__ uint32_t s_base;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const unsigned mask = __ballot_sync(0xffffffffu, emit);
+            if (lane == 0) s_wcount[warp] = (uint32_t)__popc(mask);
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                uint32_t total = 0;
+#pragma unroll
+                for (int w = 0; w < GEOM_THREADS / 32; ++w) total += s_wcount[w];
+                s_base = total ? atomicAdd(g.rec_count, total) : 0u;
+            }
+            __syncthreads();
+            uint32_t before = 0;
+#pragma unroll
+            for (int w = 0; w < GEOM_THREADS / 32; ++w) if (w < warp) before += s_wcount[w];
+            return s_base + before + (uint32_t)__popc(mask & ((1u << lane) - 1u));
         }
 
         __global__ void __launch_bounds__(GEOM_THREADS) geometry_kernel(const FrameConst fc, const Geometry g)
@@ -263,27 +298,19 @@ namespace shsb
                     {
                         const uint32_t q = atomicAdd(g.clipq_count, 1u);
                         if (q < g.clipq_capacity) g.clip_queue[q] = make_uint2(blk.x, ti);
-                        else atomicAdd(&g.stats->overflow_clipq, 1u);
+                        else atomicAdd(&stats_shard(g)->overflow_clipq, 1u);
                     }
                 }
             }
-            // warp-aggregated append
-            const unsigned mask = __ballot_sync(0xffffffffu, emit);
-            if (mask)
+            // CTA-aggregated append
+            const uint32_t slot = block_alloc_records(g, emit);
+            if (emit)
             {
-                const int lane = threadIdx.x & 31;
-                uint32_t base = 0;
-                if (lane == (__ffs(mask) - 1)) base = atomicAdd(g.rec_count, (uint32_t)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-                if (emit)
-                {
-                    const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                    if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
-                    else { atomicAdd(&g.stats->overflow_recs, 1u); emit = false; }
-                }
-                warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
+                if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
+                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); emit = false; }
             }
-            block_add_stats(g.stats, n_input, n_after, n_raster);
+            if (__ballot_sync(0xffffffffu, emit)) warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
+            block_add_stats(g, n_input, n_after, n_raster);
         }
 
         // Rare path: triangles with at least one corner outside the clip volume.
@@ -343,11 +370,11 @@ namespace shsb
                     {
                         const uint32_t slot = atomicAdd(g.rec_count, 1u);
                         if (slot < g.rec_capacity) { store_records(g, slot, rr, sr); thread_count_tiles(fc, g, rr.bbox_x, rr.bbox_y); }
-                        else atomicAdd(&g.stats->overflow_recs, 1u);
+                        else atomicAdd(&stats_shard(g)->overflow_recs, 1u);
                     }
                 }
             }
-            block_add_stats(g.stats, 0, n_after, n_raster);
+            block_add_stats(g, 0, n_after, n_raster);
         }
 
         // PassShadowMap set-up rules (passes/pass_shadow_map.hpp:155-190): world = vec3(model * p), clip = light_vp * (world, 1),
@@ -416,27 +443,19 @@ namespace shsb
                     }
                 }
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, emit);
-            if (mask)
+            const uint32_t slot = block_alloc_records(g, emit);
+            if (emit)
             {
-                const int lane = threadIdx.x & 31;
-                uint32_t base = 0;
-                if (lane == (__ffs(mask) - 1)) base = atomicAdd(g.rec_count, (uint32_t)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-                if (emit)
+                if (slot < g.rec_capacity)
                 {
-                    const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                    if (slot < g.rec_capacity)
-                    {
-                        float4* d = reinterpret_cast<float4*>(g.rrecs + slot);
-                        const float4* s = reinterpret_cast<const float4*>(&rr);
+                    float4* d = reinterpret_cast<float4*>(g.rrecs + slot);
+                    const float4* s = reinterpret_cast<const float4*>(&rr);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) d[i] = s[i];
-                    }
-                    else { atomicAdd(&g.stats->overflow_recs, 1u); emit = false; }
+                    for (int i = 0; i < 4; ++i) d[i] = s[i];
                 }
-                warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
+                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); emit = false; }
             }
+            if (__ballot_sync(0xffffffffu, emit)) warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
         }
     }
 

@@ -104,11 +104,15 @@ namespace shsb
     };
     static_assert(sizeof(ShadeRec) == 128, "ShadeRec is 128 bytes");
 
-    struct DevStats // device mirror of ShsbStats
+    // Device mirror of ShsbStats.  Counters are SHARDED: a CTA adds to shard (blockIdx.x % STAT_SHARDS), each shard on
+    // its own 128-byte line, so that millions of triangles do not serialise on one L2 atomic unit; the host sums.
+    constexpr int STAT_SHARDS = 32;
+    struct __align__(128) DevStats
     {
         unsigned long long tri_input, tri_after_clip, tri_raster, frag_covered, frag_shaded;
         unsigned int overflow_recs, overflow_lists, overflow_clipq, pad;
     };
+    static_assert(sizeof(DevStats) == 128, "one stats shard per 128-byte line");
 
     struct DevLightRec // CullingLightGPU, lighting/light_types.hpp:141-167
     {
@@ -187,7 +191,7 @@ namespace shsb
         uint32_t* list_cursor;      // total entries allocated so far
         uint32_t* class_count;      // [4] tiles per scheduling class (heaviest first)
         uint32_t* tile_order;       // [4][n_tiles] tiles per class as (tx | ty << 16); CTA b of the tile kernel takes the b-th tile in class order
-        DevStats* stats;
+        DevStats* stats;            // [STAT_SHARDS]
     };
 
     struct DevTexture

@@ -653,8 +653,9 @@ namespace shsb
                 unsigned long long c = 0ull, sh = 0ull;
 #pragma unroll
                 for (int w = 0; w < TILE_THREADS / 32; ++w) { c += s_frag[w][0]; sh += s_frag[w][1]; }
-                if (c) atomicAdd(&g.stats->frag_covered, c);
-                if (sh) atomicAdd(&g.stats->frag_shaded, sh);
+                DevStats* st = g.stats + (blockIdx.x & (STAT_SHARDS - 1));
+                if (c) atomicAdd(&st->frag_covered, c);
+                if (sh) atomicAdd(&st->frag_shaded, sh);
             }
             if (!shade) return;
 
