@@ -77,5 +77,20 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     return OUT
 
 
+def build_phase_clocks() -> str:
+    """Debug variant libshsb_clk.so: tile_raster.cu with -DSHSB_PHASE_CLOCKS (tools/phase_clocks.py, via SHSB_LIB)."""
+    build()
+    cc = nvcc()
+    o = os.path.join(OBJ, "tile_raster_clk.o")
+    subprocess.run([cc, *ARCH, *COMMON, "-DSHSB_PHASE_CLOCKS", "-c", os.path.join(CSRC, "tile_raster.cu"), "-o", o], check=True)
+    out = os.path.join(HERE, "libshsb_clk.so")
+    objs = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "tile_raster.cu"] + [o]
+    subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC"], check=True)
+    return out
+
+
 if __name__ == "__main__":
+    if "--phase-clocks" in sys.argv:
+        print(build_phase_clocks())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_info="--ptxas" in sys.argv))

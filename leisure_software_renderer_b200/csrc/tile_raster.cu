@@ -22,6 +22,17 @@ namespace shsb
     namespace
     {
         constexpr int TILE_THREADS = 256;
+#ifdef SHSB_PHASE_CLOCKS
+        // Debug build only (tools/phase_clocks.py): per scheduling class, cycles thread 0 of each tile CTA spends per phase.
+        __device__ unsigned long long g_phase_clk[4][8];
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_clk[cls][i], (unsigned long long)(t_ - phase_t0)); phase_t0 = t_; } } while (0)
+#define PHASE_BEGIN() long long phase_t0 = clock64()
+#define PHASE_COUNT() do { if (threadIdx.x == 0) atomicAdd(&g_phase_clk[cls][6], 1ull); } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_BEGIN() do { } while (0)
+#define PHASE_COUNT() do { } while (0)
+#endif
 #ifndef TILE_MIN_CTAS
 #define TILE_MIN_CTAS 4
 #endif
@@ -368,6 +379,7 @@ namespace shsb
             __shared__ float s_box[TILE_THREADS / 32][6];
             __shared__ unsigned long long s_frag[TILE_THREADS / 32][2];
 
+            PHASE_BEGIN();
             // heaviest scheduling class first (alloc_kernel, binning.cu): the cheap background tiles fill the tail
             const uint32_t n_tiles_total = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
             const uint32_t cc0 = g.class_count[0], cc1 = g.class_count[1], cc2 = g.class_count[2];
@@ -430,6 +442,8 @@ namespace shsb
             const bool valid = px < fc.W && fy < fc.H;
             const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
             const uint32_t tile_tris = g.tile_count[tile]; // > 0: classes 0-2 hold exactly the tiles with triangles
+            PHASE_MARK(7); // prologue (class / tile lookup)
+            PHASE_COUNT();
 
             float bz = 1.0f;
             if (fc.has_depth && fc.load_depth && valid) bz = fb.depth[pix];
@@ -517,6 +531,7 @@ namespace shsb
                 }
             }
 
+            PHASE_MARK(0); // raster (staging + scan)
             // ---------------- resolve: depth + AOVs
             if (valid)
             {
@@ -645,6 +660,7 @@ namespace shsb
                 }
             }
 
+            PHASE_MARK(1); // resolve + phase A (surface)
             // the only barrier every non-empty tile passes: publishes the fragment counters (and tells phase B
             // whether any pixel of the tile is shaded at all)
             const int any_has = __syncthreads_or((has && shade) ? 1 : 0);
@@ -659,6 +675,7 @@ namespace shsb
             }
             if (!shade) return;
 
+            PHASE_MARK(2); // barrier + stats
             // ---------------- phase B (whole CTA): Forward+ local lights, fp_stress_scene.frag:644-678.
             // Light tile == raster tile when the list tile size is 16.  The tile cell spans all depths, so most listed
             // lights cannot reach the surfaces actually visible in the tile: candidates are first tested against the
@@ -791,6 +808,7 @@ namespace shsb
                                 }
                                 s_light[dst[c] - pass] = sl;
                             }
+                            PHASE_MARK(3); // light staging (AABB, filter, compaction)
                             __syncthreads();
                             if (has)
                             {
@@ -809,6 +827,7 @@ namespace shsb
                             }
                         }
                     }
+                    PHASE_MARK(4); // light loop (+ trailing staging rounds)
                     out_r += sum.x; out_g += sum.y; out_b += sum.z;
                 }
             }
@@ -838,6 +857,7 @@ namespace shsb
             // ---------------- phase C (per pixel): resolve colour (+ fused tonemap), each byte written once
             if (!valid) return;
             if (!has) { resolve_uncovered(fc, fb, pix, py); return; }
+            PHASE_MARK(5);
             fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);
         }
@@ -861,6 +881,16 @@ namespace shsb
             for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
         }
     }
+
+#ifdef SHSB_PHASE_CLOCKS
+    extern "C" __attribute__((visibility("default"))) int shsb_debug_phase_clocks(unsigned long long* out32, int reset)
+    {
+        cudaDeviceSynchronize();
+        if (cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+        if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)); }
+        return 0;
+    }
+#endif
 
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
                             const float* srgb_lut, cudaStream_t s, uint64_t* launches)
