@@ -124,6 +124,7 @@ struct shsb_context_t
     // lights: a ring of buffers so that an upload for a later frame does not wait for the tile kernel still
     // reading the current records
     DevBuf<DevLightRec> d_lights[NUM_ARENAS];
+    DevBuf<SmLight> d_smlights[NUM_ARENAS];   // digested at upload (light_prep_kernel)
     int lights_cur = 0;
     long long lights_last_user[NUM_ARENAS] = {-1, -1, -1}; // frame number of the last tile kernel that read each buffer
     uint32_t n_lights = 0;
@@ -444,6 +445,7 @@ namespace
             {
                 const LightLists& L = ctx->lists[job.lists_set];
                 fc.lights = ctx->d_lights[ctx->lights_cur].p;
+                fc.sm_lights = ctx->d_smlights[ctx->lights_cur].p;
                 fc.tile_counts = L.counts.p;
                 fc.tile_indices = L.indices.p;
             }
@@ -804,6 +806,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
     for (auto& l : ctx->d_lights) cudaFree(l.p);
+    for (auto& l : ctx->d_smlights) cudaFree(l.p);
     for (LightLists& L : ctx->lists) { cudaFree(L.counts.p); cudaFree(L.indices.p); cudaFree(L.scratch.p); }
     for (Arena& A : ctx->arena)
     {
@@ -1261,9 +1264,12 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     // that buffer; later culls are ordered behind it on the front stream, and the main stream waits for it too.
     const int b = (ctx->lights_cur + 1) % NUM_ARENAS;
     if (int rc = ensure_dev(ctx, ctx->d_lights[b], std::max(1u, n_lights))) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_smlights[b], std::max(1u, n_lights))) return rc;
     if (ctx->lights_last_user[b] >= 0) CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_tile_done[ctx->lights_last_user[b] % TILE_DONE_RING], 0));
     if (ctx->cull_main_pending) { CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_cull_main, 0)); ctx->cull_main_pending = false; }
     if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights[b].p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->front_stream));
+    launch_light_prep(ctx->d_lights[b].p, ctx->d_smlights[b].p, n_lights, ctx->front_stream, &ctx->launches);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_lights_up, ctx->front_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lights_up, 0));
     ctx->lights_cur = b;

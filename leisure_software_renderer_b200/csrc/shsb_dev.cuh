@@ -122,6 +122,21 @@ namespace shsb
     };
     static_assert(sizeof(DevLightRec) == 160, "CullingLightGPU is 160 bytes");
 
+    // Compact form of a local light (80 B) for the tile kernel's light loop, digested from the 160-byte record once
+    // per upload: pos_r2 decides the range test, the rest is only read in range.
+    struct SmLight
+    {
+        float4 pos_r2;        // xyz, w = range^2 (area lights: cull-sphere centre / radius^2; disabled lights: -1)
+        float4 radiance_ir;   // color * intensity, w = 1 / range
+        float4 atten;         // x = attenuation power, y = max(cutoff, 0), z = max(bias, 1e-5), w = 1 / max(inner_cos - outer_cos, 1e-6)
+        float4 dir_outer;     // normalised spot direction, w = outer cos (clamped)
+        uint32_t kind;        // bits 0-1 attenuation model, bit 2 spot, bit 3 area light (rect / tube -> eval_light_record), bit 4 power != 1
+        uint32_t index;       // light index (area lights re-read their 160-B record)
+        uint32_t pad0, pad1;
+    };
+    static_assert(sizeof(SmLight) == 80, "SmLight is 80 bytes");
+    constexpr uint32_t KIND_SPOT = 4u, KIND_AREA = 8u, KIND_POW = 16u;
+
     // Everything a frame's kernels need, passed by value as a kernel parameter.
     struct FrameConst
     {
@@ -152,6 +167,7 @@ namespace shsb
         // Forward+
         int forward_plus;
         const DevLightRec* lights;
+        const SmLight* sm_lights;   // digested copies of `lights`
         uint32_t n_lights;
         const uint32_t* tile_counts;
         const uint32_t* tile_indices;
@@ -205,6 +221,7 @@ namespace shsb
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
                             const float* srgb_lut, cudaStream_t s, uint64_t* launches);
+    void launch_light_prep(const DevLightRec* lights, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches);
     void launch_tonemap(const float4* hdr, uchar4* ldr, int n_pixels, float exposure, float inv_gamma, cudaStream_t s, uint64_t* launches);
     void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s, uint64_t* launches);
     void launch_fill_f4(float4* p, float4 v, size_t n, cudaStream_t s, uint64_t* launches);

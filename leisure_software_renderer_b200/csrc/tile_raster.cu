@@ -61,21 +61,6 @@ namespace shsb
         __device__ __forceinline__ V3 toV3(F3 v) { return V3{v.x, v.y, v.z}; }
         __device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 
-        // Compact per-tile copy of a local light (80 B), built once per tile by the staging threads so that the
-        // per-pixel loop reads pre-digested values: q0 decides the range test, the rest is only read in range.
-        struct SmLight
-        {
-            float4 pos_r2;        // xyz, w = range^2 (area lights: cull-sphere centre / radius^2)
-            float4 radiance_ir;   // color * intensity, w = 1 / range
-            float4 atten;         // x = attenuation power, y = max(cutoff, 0), z = max(bias, 1e-5), w = 1 / max(inner_cos - outer_cos, 1e-6)
-            float4 dir_outer;     // normalised spot direction, w = outer cos (clamped)
-            uint32_t kind;        // bits 0-1 attenuation model, bit 2 spot, bit 3 area light (rect / tube -> eval_light_record), bit 4 power != 1
-            uint32_t index;       // light index (area lights re-read their 160-B record)
-            uint32_t pad0, pad1;
-        };
-        static_assert(sizeof(SmLight) == 80, "SmLight is 80 bytes");
-        constexpr uint32_t KIND_SPOT = 4u, KIND_AREA = 8u, KIND_POW = 16u;
-
         struct Surface
         {
             V3 P, N, V, albedo;
@@ -733,16 +718,12 @@ namespace shsb
                                 const uint32_t idx = saturated ? i : list[i];
                                 if (idx < fc.n_lights)
                                 {
-                                    const DevLightRec* rec = fc.lights + idx;
-                                    const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
-                                    const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
-                                    float4 sp = make_float4(pr.x, pr.y, pr.z, fmaxf(pr.w, 0.001f));
-                                    if (tf.x > 2u) sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere)); // area lights reach beyond position +- range
-                                    const float dx = fmaxf(fmaxf(bx0 - sp.x, sp.x - bx1), 0.0f);
-                                    const float dy = fmaxf(fmaxf(by0 - sp.y, sp.y - by1), 0.0f);
-                                    const float dz = fmaxf(fmaxf(bz0 - sp.z, sp.z - bz1), 0.0f);
-                                    const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;
-                                    keep = enabled && (dx * dx + dy * dy + dz * dz) <= sp.w * sp.w * 1.001f + 1e-6f;
+                                    // pos_r2 = (centre, reach^2) of the digested record; reach^2 < 0 marks a disabled light
+                                    const float4 q0 = __ldg(&fc.sm_lights[idx].pos_r2);
+                                    const float dx = fmaxf(fmaxf(bx0 - q0.x, q0.x - bx1), 0.0f);
+                                    const float dy = fmaxf(fmaxf(by0 - q0.y, q0.y - by1), 0.0f);
+                                    const float dz = fmaxf(fmaxf(bz0 - q0.z, q0.z - bz1), 0.0f);
+                                    keep = (dx * dx + dy * dy + dz * dz) <= q0.w * 1.001f + 1e-6f;
                                     if (keep) cidx[c] = idx;
                                 }
                             }
@@ -775,38 +756,11 @@ namespace shsb
                             for (int c = 0; c < CAND_PER_THREAD; ++c)
                             {
                                 if (cidx[c] == 0xFFFFFFFFu || dst[c] < pass || dst[c] >= pass + LIGHT_CAP) continue;
-                                const DevLightRec* rec = fc.lights + cidx[c];
-                                const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
-                                const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
-                                const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
-                                const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
-                                SmLight sl;
-                                const float range = fmaxf(pr.w, 0.001f);
-                                const float power = fmaxf(sa.y, 0.001f);
-                                sl.pos_r2 = make_float4(pr.x, pr.y, pr.z, range * range);
-                                sl.radiance_ir = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, 1.0f / range);
-                                sl.atten = make_float4(power, fmaxf(sa.w, 0.0f), fmaxf(sa.z, 1e-5f), 0.0f);
-                                sl.dir_outer = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                sl.kind = (tf.w == 0u ? 0u : (tf.w == 2u ? 2u : 1u)) | (power != 1.0f ? KIND_POW : 0u);
-                                sl.index = cidx[c]; sl.pad0 = sl.pad1 = 0u;
-                                if (tf.x == 2u)
-                                {
-                                    const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
-                                    const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
-                                    const float dl = fast_rsqrt(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
-                                    const float inner_cos = fminf(fmaxf(ds.w, -1.0f), 1.0f);
-                                    const float outer_cos = fminf(fmaxf(ax.w, -1.0f), inner_cos);
-                                    sl.dir_outer = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, outer_cos);
-                                    sl.atten.w = 1.0f / fmaxf(inner_cos - outer_cos, 1e-6f);
-                                    sl.kind |= KIND_SPOT;
-                                }
-                                else if (tf.x > 2u)
-                                {
-                                    const float4 sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere));
-                                    sl.pos_r2 = make_float4(sp.x, sp.y, sp.z, sp.w * sp.w * 1.001f + 1e-6f);
-                                    sl.kind |= KIND_AREA;
-                                }
-                                s_light[dst[c] - pass] = sl;
+                                // the 80-byte record was digested once at upload (light_prep_kernel): a straight copy
+                                const float4* src = reinterpret_cast<const float4*>(fc.sm_lights + cidx[c]);
+                                float4* dstp = reinterpret_cast<float4*>(s_light + (dst[c] - pass));
+                                const float4 l0 = __ldg(src + 0), l1 = __ldg(src + 1), l2 = __ldg(src + 2), l3 = __ldg(src + 3), l4 = __ldg(src + 4);
+                                dstp[0] = l0; dstp[1] = l1; dstp[2] = l2; dstp[3] = l3; dstp[4] = l4;
                             }
                             PHASE_MARK(3); // light staging (AABB, filter, compaction)
                             __syncthreads();
@@ -862,6 +816,49 @@ namespace shsb
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);
         }
 
+        // Digests the 160-byte CullingLightGPU records into the 80-byte form the tile kernel's light loop reads
+        // (run once per shsb_lights_upload, not per frame or per tile).
+        __global__ void __launch_bounds__(128) light_prep_kernel(const DevLightRec* __restrict__ lights, SmLight* __restrict__ out, uint32_t n)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            const DevLightRec* rec = lights + i;
+            const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
+            const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
+            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
+            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
+            SmLight sl;
+            const float range = fmaxf(pr.w, 0.001f);
+            const float power = fmaxf(sa.y, 0.001f);
+            sl.pos_r2 = make_float4(pr.x, pr.y, pr.z, range * range);
+            sl.radiance_ir = make_float4(ci.x * ci.w, ci.y * ci.w, ci.z * ci.w, 1.0f / range);
+            sl.atten = make_float4(power, fmaxf(sa.w, 0.0f), fmaxf(sa.z, 1e-5f), 0.0f);
+            sl.dir_outer = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            sl.kind = (tf.w == 0u ? 0u : (tf.w == 2u ? 2u : 1u)) | (power != 1.0f ? KIND_POW : 0u);
+            sl.index = i; sl.pad0 = sl.pad1 = 0u;
+            if (tf.x == 2u)
+            {
+                const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
+                const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
+                const float dl = fast_rsqrt(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
+                const float inner_cos = fminf(fmaxf(ds.w, -1.0f), 1.0f);
+                const float outer_cos = fminf(fmaxf(ax.w, -1.0f), inner_cos);
+                sl.dir_outer = make_float4(ds.x * dl, ds.y * dl, ds.z * dl, outer_cos);
+                sl.atten.w = 1.0f / fmaxf(inner_cos - outer_cos, 1e-6f);
+                sl.kind |= KIND_SPOT;
+            }
+            else if (tf.x > 2u)
+            {
+                // area lights reach beyond position +- range: the range test uses their cull sphere
+                const float4 sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere));
+                sl.pos_r2 = make_float4(sp.x, sp.y, sp.z, sp.w * sp.w * 1.001f + 1e-6f); // conservative pre-test; eval_light_record decides
+                sl.kind |= KIND_AREA;
+            }
+            const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;
+            if (!enabled) sl.pos_r2.w = -1.0f; // fails every range test
+            out[i] = sl;
+        }
+
         __global__ void __launch_bounds__(256) tonemap_kernel(const float4* __restrict__ hdr, uchar4* __restrict__ ldr, int n, float exposure, float inv_gamma)
         {
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -898,6 +895,13 @@ namespace shsb
         const int n_tiles = fc.tiles_x * fc.tiles_y;
         if (n_tiles <= 0) return;
         tile_kernel<<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        *launches += 1;
+    }
+
+    void launch_light_prep(const DevLightRec* lights, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches)
+    {
+        if (!n) return;
+        light_prep_kernel<<<(n + 127) / 128, 128, 0, s>>>(lights, out, n);
         *launches += 1;
     }
 
