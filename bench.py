@@ -137,7 +137,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the raster path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL chatter (e.g. its version line) must not share stdout with the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = Context(local_rank)
@@ -217,9 +217,15 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if not e2e:
             ctx.timing_enable(True)
+        ctx.host_submit_us(reset=True)
         e0.record(stream)
+        t_host = time.perf_counter()
         for i in range(args.steps):
             step(i, e2e)
+        host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # host time to SUBMIT a step (includes back-pressure waits on the staging ring)
+        hu = ctx.host_submit_us(reset=True)
+        host_ms = {"total_ms": host_ms, "library_us": {k: float(hu[i] / max(hu[5], 1.0)) for i, k in
+                   enumerate(("draw_list", "staging_incl_ring_wait", "arena_checks", "capture_enqueue", "graph_update_launch_tile_launch"))}}
         if world > 1 and last_gather[0] is not None:
             stream.wait_event(last_gather[0])  # the last frame assembly belongs to the timed region
         if e2e:
@@ -234,10 +240,10 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), stages, clocks, ctx.launch_count() - launches0
+        return float(t.item()), stages, clocks, ctx.launch_count() - launches0, host_ms
 
-    ms_dev, stages, clocks, launches = timed(False)
-    ms_e2e, _, clocks_e2e, _ = timed(True)
+    ms_dev, stages, clocks, launches, host_dev = timed(False)
+    ms_e2e, _, clocks_e2e, _, host_e2e = timed(True)
 
     n_items = len(sd.items)
     n_blocks = sum((len(sd.meshes[it["mesh"] - 1]["indices"]) // 3 + 127) // 128 for it in sd.items)
@@ -264,7 +270,8 @@ def run_ours(args):
             "mtri_per_s": fps * st["tri_input"] / 1e6, "mfrag_per_s": fps * st["frag_covered"] / 1e6,
             "frame_stats": st,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "host_submit_ms_per_step": host_e2e},
+            "host_submit_ms_per_step": host_dev,
             "gpu_launches": int(launches),
             "stage_ms": {"vertex_clip_setup": float(stage_mean[0]), "binning": float(stage_mean[1]), "tile_raster_shade": tile_ms,
                          "geometry_to_resolve": float(stage_mean[3]), "frames_timed": 0 if stages is None else int(len(stages))},
@@ -278,7 +285,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(sd, args.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -346,10 +353,21 @@ def run_reference(args):
                        "resolution": [W, H]},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library may print there (NCCL, torchrun children) goes to stderr
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -323,6 +323,9 @@ SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8]);
  * {vertex+setup, binning, tile raster+shade, total} milliseconds per frame and clears the history. */
 SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable);
 SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames);
+/* Same history as absolute times: 5 floats per frame (front-end begin, after geometry, after binning, tile kernel
+ * begin, tile kernel end), milliseconds since the first recorded event.  For pipeline timelines (tools/e2e_probe.py). */
+SHSB_API int32_t shsb_timing_collect_abs(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames);
 
 /* Accumulated host-side submit cost in microseconds since the last reset: [0] scene -> draw list (model / normal
  * matrices), [1] staging copy, [2] arena checks, [3] stream capture / enqueue, [4] graph update + launch, [5] frames. */

@@ -153,6 +153,7 @@ def load_library(path: str | None = None):
         "shsb_host_submit_us": [vp, P(C.c_double), C.c_int32],
         "shsb_timing_enable": [vp, C.c_int32],
         "shsb_timing_collect": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
+        "shsb_timing_collect_abs": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not export what shsb.h declares

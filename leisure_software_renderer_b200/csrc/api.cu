@@ -32,8 +32,9 @@ namespace
     // 5 / 6 light cull or standalone tonemap begin / end
     constexpr int NUM_STAGE_EVENTS = 7;
     constexpr int TIMING_EVENTS_PER_FRAME = 5;
-    constexpr int NUM_ARENAS = 3;       // transient arenas: the front end may run two frames ahead of the tile kernel
-    constexpr int TILE_DONE_RING = 8;   // per-frame "tile kernel finished" events
+    constexpr int NUM_ARENAS = 6;       // maximum number of transient arenas; ctx->n_arenas of them rotate (SHSB_ARENAS, default 4):
+                                        // the front end may run n_arenas - 1 frames ahead of the tile kernel
+    constexpr int TILE_DONE_RING = 16;  // per-frame "tile kernel finished" events
 
     struct MeshSlot
     {
@@ -75,9 +76,10 @@ namespace
     };
 
     template <typename T>
-    struct PinnedBuf
+    struct PinnedBuf // pinned AND mapped: kernels read it in place through `dp` (zero-copy)
     {
         T* p = nullptr;
+        T* dp = nullptr;
         size_t cap = 0;
     };
 
@@ -125,23 +127,28 @@ struct shsb_context_t
     // reading the current records
     DevBuf<DevLightRec> d_lights[NUM_ARENAS];
     DevBuf<SmLight> d_smlights[NUM_ARENAS];   // digested at upload (light_prep_kernel)
+    PinnedBuf<DevLightRec> h_lights[NUM_ARENAS]; // staging for callers whose records are in pageable memory
+    cudaEvent_t lights_stage_done[NUM_ARENAS]{};
+    bool lights_stage_busy[NUM_ARENAS]{};
     int lights_cur = 0;
-    long long lights_last_user[NUM_ARENAS] = {-1, -1, -1}; // frame number of the last tile kernel that read each buffer
+    long long lights_last_user[NUM_ARENAS] = {-1, -1, -1, -1, -1, -1}; // frame number of the last tile kernel that read each buffer
     uint32_t n_lights = 0;
     cudaEvent_t ev_lights_up = nullptr;       // last upload (front stream)
     cudaEvent_t ev_cull_main = nullptr;       // last standalone cull (main stream)
     bool cull_main_pending = false;
+    bool lights_uploaded = false;
     LightLists lists[NUM_ARENAS + 1];
     int lists_cur = -1;                       // the set produced by the most recent cull, -1 = none
 
     // per-frame transients
     Arena arena[NUM_ARENAS];
+    int n_arenas = 4;
     long long frame_no = 0;
     cudaEvent_t ev_tile_done[TILE_DONE_RING]{};
     cudaEvent_t ev_front_done[NUM_ARENAS]{};
     // pinned staging ring: a frame's draw list is copied H2D asynchronously, so a slot may only be rewritten once
     // the copy that read it has completed (its event)
-    static constexpr int STAGE_SLOTS = 4;
+    static constexpr int STAGE_SLOTS = 8;
     PinnedBuf<unsigned char> h_draw[STAGE_SLOTS];
     cudaEvent_t stage_done[STAGE_SLOTS]{};
     bool stage_busy[STAGE_SLOTS]{};
@@ -160,11 +167,15 @@ struct shsb_context_t
     bool use_graph = true;
     bool pipeline = true;                // SHSB_NO_PIPELINE=1: front end on the main stream (no frame overlap)
     bool capturing = false;
-    cudaStream_t front_stream = nullptr; // front end of each frame (high priority)
-    cudaStream_t stream2 = nullptr;      // light-cull branch of the front end (high priority)
-    cudaStream_t copy_stream = nullptr; // asynchronous render-target downloads
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_frame_done = nullptr;
-    cudaGraphExec_t graph_exec[4]{}; // [cull branch][shadow mode]
+    // One front-end stream (+ one for its light-cull branch) PER ARENA, high priority: the front ends of consecutive
+    // frames are independent of each other, so they overlap instead of queueing behind one another.
+    cudaStream_t front_streams[NUM_ARENAS]{};
+    cudaStream_t cull_streams[NUM_ARENAS]{};
+    cudaStream_t copy_stream = nullptr;  // asynchronous render-target downloads alternate between two streams so that
+    cudaStream_t copy_stream2 = nullptr; // the next copy is already queued on the engine when one finishes
+    int copy_flip = 0;
+    cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr;
+    cudaGraphExec_t graph_exec[NUM_ARENAS][4]{}; // per arena (an executable graph cannot run concurrently with itself): [cull branch][shadow mode]
 
     // host-side submit cost breakdown (microseconds, accumulated): [0] scene -> draw list, [1] staging copy,
     // [2] arena checks, [3] capture / enqueue, [4] graph update + launch, [5] frames
@@ -203,10 +214,11 @@ namespace
 
     void sync_all(shsb_ctx ctx)
     {
-        cudaStreamSynchronize(ctx->front_stream);
-        cudaStreamSynchronize(ctx->stream2);
+        for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamSynchronize(st);
+        for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamSynchronize(st);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->copy_stream2);
     }
 
     template <typename T>
@@ -233,14 +245,17 @@ namespace
         if (n <= b.cap) return SHSB_OK;
         const size_t want = std::max(n, b.cap + b.cap / 2);
         T* np = nullptr;
-        const cudaError_t e = cudaHostAlloc(&np, want * sizeof(T), cudaHostAllocDefault);
-        if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaHostAlloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+        T* ndp = nullptr;
+        cudaError_t e = cudaHostAlloc(&np, want * sizeof(T), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(&ndp, np, 0);
+        if (e != cudaSuccess) return fail(ctx, SHSB_E_OUT_OF_MEMORY, "cudaHostAlloc(%zu bytes, mapped): %s", want * sizeof(T), cudaGetErrorString(e));
         if (b.p)
         {
             sync_all(ctx);
             cudaFreeHost(b.p);
         }
         b.p = np;
+        b.dp = ndp;
         b.cap = want;
         return SHSB_OK;
     }
@@ -395,7 +410,7 @@ namespace
         {
             const double t_a = now_us();
             const long long f = ctx->frame_no++;
-            const int a = (int)(f % NUM_ARENAS);
+            const int a = (int)(f % ctx->n_arenas);
             Arena& A = ctx->arena[a];
             // capacities: every source triangle may emit one record; clipped ones up to 7
             const size_t clipq_cap = std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth));
@@ -411,7 +426,7 @@ namespace
             if (int rc = ensure_dev(ctx, A.d_tile_offset, n_tiles + 2)) return rc;
             if (int rc = ensure_dev(ctx, A.d_tile_fill, n_tiles + 1)) return rc;
             if (int rc = ensure_dev(ctx, A.d_tile_list, list_cap)) return rc;
-            if (int rc = ensure_dev(ctx, A.d_draw, std::max<size_t>(16, draw_bytes))) return rc;
+            if (int rc = ensure_dev(ctx, A.d_draw, std::max<size_t>(16, draw_bytes + 16))) return rc;
             if (cull) { if (int rc = ensure_lists(ctx, ctx->lists[a], *cull)) return rc; }
 
             uint32_t* hdr = A.d_hdr.p;
@@ -452,14 +467,15 @@ namespace
 
             const int slot = ctx->stage_slot;
             const bool graph = ctx->use_graph;
-            cudaStream_t s1 = ctx->stream, sf = ctx->pipeline ? ctx->front_stream : s1;
+            cudaStream_t s1 = ctx->stream, sf = ctx->pipeline ? ctx->front_streams[a] : s1, sc = ctx->cull_streams[a];
             cudaError_t err = cudaSuccess;
             auto ok = [&](cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; };
 
             // ---- what the front end must wait for: the tile kernel that last read this arena (NUM_ARENAS frames ago) and,
             // when it rebuilds light lists, the last tile kernel that read that set
-            if (f >= NUM_ARENAS) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[(f - NUM_ARENAS) % TILE_DONE_RING], 0));
+            if (f >= ctx->n_arenas) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[(f - ctx->n_arenas) % TILE_DONE_RING], 0));
             if (cull && ctx->lists[a].last_reader >= 0) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[ctx->lists[a].last_reader % TILE_DONE_RING], 0));
+            if (cull && ctx->lights_uploaded) ok(cudaStreamWaitEvent(sf, ctx->ev_lights_up, 0)); // the upload ran on some arena's front stream
 
             if (graph)
             {
@@ -468,17 +484,17 @@ namespace
             }
             if (cull)
             {
-                ok(cudaEventRecord(ctx->ev_fork, sf));
-                ok(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-                enqueue_light_cull(ctx, *cull, a, ctx->stream2);
-                ok(cudaEventRecord(ctx->ev_join, ctx->stream2));
+                ok(cudaEventRecord(ctx->ev_fork[a], sf));
+                ok(cudaStreamWaitEvent(sc, ctx->ev_fork[a], 0));
+                enqueue_light_cull(ctx, *cull, a, sc);
+                ok(cudaEventRecord(ctx->ev_join[a], sc));
             }
             record(ctx, 0, sf);
             ok(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), sf));
-            if (draw_bytes) ok(cudaMemcpyAsync(A.d_draw.p, ctx->h_draw[slot].p, draw_bytes, cudaMemcpyHostToDevice, sf));
+            if (draw_bytes) launch_upload(A.d_draw.p, ctx->h_draw[slot].dp, draw_bytes, sf, &ctx->launches); // SM-driven: no copy engine on the frame path
             launch_geometry(fc, g, sf, &ctx->launches);
             record(ctx, 1, sf);
-            if (cull) ok(cudaStreamWaitEvent(sf, ctx->ev_join, 0)); // alloc_kernel reads the tile light counts (scheduling classes)
+            if (cull) ok(cudaStreamWaitEvent(sf, ctx->ev_join[a], 0)); // alloc_kernel reads the tile light counts (scheduling classes)
             launch_binning(fc, g, sf, &ctx->launches);
             record(ctx, 2, sf);
             ok(cudaGetLastError());
@@ -492,7 +508,7 @@ namespace
                 if (err == cudaSuccess) err = ec;
                 if (err == cudaSuccess)
                 {
-                    cudaGraphExec_t& exec = ctx->graph_exec[(cull ? 2 : 0) + (fc.shadow_mode ? 1 : 0)];
+                    cudaGraphExec_t& exec = ctx->graph_exec[a][(cull ? 2 : 0) + (fc.shadow_mode ? 1 : 0)];
                     if (exec)
                     {
                         cudaGraphExecUpdateResultInfo info{};
@@ -588,7 +604,7 @@ namespace
             ctx->stage_busy[slot] = false;
         }
         const size_t items_bytes = items.size() * sizeof(DevItem), blocks_bytes = blocks.size() * sizeof(uint2);
-        if (int rc = ensure_pinned(ctx, ctx->h_draw[slot], std::max<size_t>(16, items_bytes + blocks_bytes))) return rc;
+        if (int rc = ensure_pinned(ctx, ctx->h_draw[slot], std::max<size_t>(16, items_bytes + blocks_bytes + 16))) return rc;
         if (items_bytes) std::memcpy(ctx->h_draw[slot].p, items.data(), items_bytes);
         if (blocks_bytes) std::memcpy(ctx->h_draw[slot].p + items_bytes, blocks.data(), blocks_bytes);
         return SHSB_OK;
@@ -761,20 +777,26 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ctx->device = device_ordinal;
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* e = std::getenv("SHSB_ARENAS")) ctx->n_arenas = std::min(NUM_ARENAS, std::max(2, std::atoi(e)));
     if (const char* e = std::getenv("SHSB_NO_PIPELINE")) ctx->pipeline = !(e[0] == '1');
     if (const char* e = std::getenv("SHSB_FRONT_PRIORITY")) { if (e[0] == '0') prio_greatest = prio_least; }
     bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     // the front end is small and latency-bound: at high priority its CTAs slot in between the tile kernel's
-    ok = ok && cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    for (int i = 0; ok && i < NUM_ARENAS; ++i)
+    {
+        ok = cudaStreamCreateWithPriority(&ctx->front_streams[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->cull_streams[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_lights_up, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_cull_main, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < TILE_DONE_RING; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_tile_done[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < NUM_ARENAS; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < NUM_ARENAS; ++i) ok = cudaEventCreateWithFlags(&ctx->lights_stage_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
@@ -807,6 +829,8 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
+    for (auto& l : ctx->h_lights) cudaFreeHost(l.p);
+    for (cudaEvent_t e : ctx->lights_stage_done) if (e) cudaEventDestroy(e);
     for (LightLists& L : ctx->lists) { cudaFree(L.counts.p); cudaFree(L.indices.p); cudaFree(L.scratch.p); }
     for (Arena& A : ctx->arena)
     {
@@ -825,14 +849,15 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     }
     for (int i = 0; i < NUM_STAGE_EVENTS; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->timing_ev) cudaEventDestroy(e);
-    for (cudaGraphExec_t e : ctx->graph_exec) if (e) cudaGraphExecDestroy(e);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (auto& row : ctx->graph_exec) for (cudaGraphExec_t e : row) if (e) cudaGraphExecDestroy(e);
+    for (cudaEvent_t e : ctx->ev_fork) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_join) if (e) cudaEventDestroy(e);
     if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream2) { cudaStreamSynchronize(ctx->copy_stream2); cudaStreamDestroy(ctx->copy_stream2); }
     for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
+    for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamDestroy(st);
+    for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamDestroy(st);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SHSB_OK;
@@ -843,9 +868,10 @@ SHSB_API const char* shsb_last_error_string(shsb_ctx ctx) { return ctx ? ctx->er
 SHSB_API int32_t shsb_sync(shsb_ctx ctx)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
-    CK(cudaStreamSynchronize(ctx->front_stream));
+    for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream2));
     return SHSB_OK;
 }
 
@@ -980,8 +1006,7 @@ SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->copy_stream));
+    sync_all(ctx);
     cudaFree(r->color); cudaFree(r->depth); cudaFree(r->motion); cudaFree(r->tri_id); cudaFree(r->coverage);
     if (r->read_done) cudaEventDestroy(r->read_done);
     *r = RtSlot{};
@@ -1044,9 +1069,10 @@ SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane,
     if (!r->read_done) CK(cudaEventCreateWithFlags(&r->read_done, cudaEventDisableTiming));
     // copy stream waits for everything submitted to the render stream so far, then copies while later frames render
     CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
-    CK(cudaMemcpyAsync(dst_pinned, p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaEventRecord(r->read_done, ctx->copy_stream));
+    cudaStream_t cs = (ctx->copy_flip ^= 1) ? ctx->copy_stream : ctx->copy_stream2;
+    CK(cudaStreamWaitEvent(cs, ctx->ev_frame_done, 0));
+    CK(cudaMemcpyAsync(dst_pinned, p, bytes, cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(r->read_done, cs));
     r->read_pending = true;
     return SHSB_OK;
 }
@@ -1262,15 +1288,38 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     // The records go into the buffer the in-flight frames are NOT reading, on the front stream: the upload for
     // frame f+1 overlaps frame f's tile kernel.  It waits only for the last tile kernel / standalone cull that read
     // that buffer; later culls are ordered behind it on the front stream, and the main stream waits for it too.
-    const int b = (ctx->lights_cur + 1) % NUM_ARENAS;
+    const int b = (ctx->lights_cur + 1) % ctx->n_arenas;
+    cudaStream_t su = ctx->front_streams[ctx->frame_no % ctx->n_arenas]; // the stream the next frame's front end will use
     if (int rc = ensure_dev(ctx, ctx->d_lights[b], std::max(1u, n_lights))) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_smlights[b], std::max(1u, n_lights))) return rc;
-    if (ctx->lights_last_user[b] >= 0) CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_tile_done[ctx->lights_last_user[b] % TILE_DONE_RING], 0));
-    if (ctx->cull_main_pending) { CK(cudaStreamWaitEvent(ctx->front_stream, ctx->ev_cull_main, 0)); ctx->cull_main_pending = false; }
-    if (n_lights) CK(cudaMemcpyAsync(ctx->d_lights[b].p, records, (size_t)n_lights * sizeof(DevLightRec), cudaMemcpyHostToDevice, ctx->front_stream));
-    launch_light_prep(ctx->d_lights[b].p, ctx->d_smlights[b].p, n_lights, ctx->front_stream, &ctx->launches);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev_lights_up, ctx->front_stream));
+    if (ctx->lights_last_user[b] >= 0) CK(cudaStreamWaitEvent(su, ctx->ev_tile_done[ctx->lights_last_user[b] % TILE_DONE_RING], 0));
+    if (ctx->cull_main_pending) { CK(cudaStreamWaitEvent(su, ctx->ev_cull_main, 0)); ctx->cull_main_pending = false; }
+    if (n_lights)
+    {
+        // The SMs pull the records straight from host memory (zero-copy) while digesting them: no copy-engine H2D that
+        // could queue behind a frame read-back.  Pinned caller memory is read in place (it must stay unchanged until the
+        // upload has run, like any cudaMemcpyAsync source); pageable memory is staged through a pinned ring first.
+        const DevLightRec* src = nullptr;
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, records) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            src = static_cast<const DevLightRec*>(attr.devicePointer);
+        else if (cudaPointerGetAttributes(&attr, records) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+            src = static_cast<const DevLightRec*>(records);
+        else
+        {
+            cudaGetLastError();
+            if (ctx->lights_stage_busy[b]) { CK(cudaEventSynchronize(ctx->lights_stage_done[b])); ctx->lights_stage_busy[b] = false; }
+            if (int rc = ensure_pinned(ctx, ctx->h_lights[b], n_lights)) return rc;
+            std::memcpy(ctx->h_lights[b].p, records, (size_t)n_lights * sizeof(DevLightRec));
+            src = ctx->h_lights[b].dp;
+            ctx->lights_stage_busy[b] = true;
+        }
+        launch_light_prep(src, ctx->d_lights[b].p, ctx->d_smlights[b].p, n_lights, su, &ctx->launches);
+        CK(cudaGetLastError());
+        if (ctx->lights_stage_busy[b]) CK(cudaEventRecord(ctx->lights_stage_done[b], su));
+    }
+    CK(cudaEventRecord(ctx->ev_lights_up, su));
+    ctx->lights_uploaded = true;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lights_up, 0));
     ctx->lights_cur = b;
     ctx->lights_last_user[b] = -1;
@@ -1302,8 +1351,7 @@ SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_
     const size_t tiles = (size_t)((L.w + L.ts - 1) / L.ts) * ((L.h + L.ts - 1) / L.ts);
     if (counts && n_counts != tiles) return fail(ctx, SHSB_E_SIZE_MISMATCH, "counts has %zu entries, lists have %zu tiles", n_counts, tiles);
     if (indices && n_indices != tiles * L.max_per_tile) return fail(ctx, SHSB_E_SIZE_MISMATCH, "indices has %zu entries, expected %zu", n_indices, tiles * L.max_per_tile);
-    CK(cudaStreamSynchronize(ctx->front_stream)); // a fused frame builds its lists on the front end
-    CK(cudaStreamSynchronize(ctx->stream2));
+    sync_all(ctx); // a fused frame builds its lists on its front-end streams
     if (counts) CK(cudaMemcpyAsync(counts, L.counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (indices) CK(cudaMemcpyAsync(indices, L.indices.p, tiles * L.max_per_tile * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1322,7 +1370,7 @@ SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_fra
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->front_stream));
+    for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
     for (size_t f = 0; f < frames && out_ms; ++f)
     {
@@ -1340,6 +1388,26 @@ SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_fra
     return SHSB_OK;
 }
 
+/* Debug: like shsb_timing_collect but absolute times -- per frame the 5 stage events (front-end begin, after
+ * geometry, after binning, tile begin, tile end) in milliseconds since the first recorded event. */
+SHSB_API int32_t shsb_timing_collect_abs(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames)
+{
+    if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
+    for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
+    for (size_t f = 0; f < frames && out_ms; ++f)
+        for (int k = 0; k < TIMING_EVENTS_PER_FRAME; ++k)
+        {
+            float t = 0;
+            cudaEventElapsedTime(&t, ctx->timing_ev[0], ctx->timing_ev[f * TIMING_EVENTS_PER_FRAME + k]);
+            out_ms[f * TIMING_EVENTS_PER_FRAME + k] = t;
+        }
+    *out_frames = frames;
+    ctx->timing_used = 0;
+    return SHSB_OK;
+}
+
 SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t reset)
 {
     if (!ctx || !out_us) return SHSB_E_INVALID_ARGUMENT;
@@ -1351,7 +1419,7 @@ SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t res
 SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
 {
     if (!ctx || !out_ms) return SHSB_E_INVALID_ARGUMENT;
-    CK(cudaStreamSynchronize(ctx->front_stream));
+    for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 8; ++i) out_ms[i] = 0.0f;
     auto span = [&](int a, int b) -> float {

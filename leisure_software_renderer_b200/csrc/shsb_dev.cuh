@@ -221,7 +221,8 @@ namespace shsb
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
                             const float* srgb_lut, cudaStream_t s, uint64_t* launches);
-    void launch_light_prep(const DevLightRec* lights, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches);
+    void launch_light_prep(const DevLightRec* src, DevLightRec* raw, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches);
+    void launch_upload(void* dst, const void* src_mapped, size_t bytes, cudaStream_t s, uint64_t* launches);
     void launch_tonemap(const float4* hdr, uchar4* ldr, int n_pixels, float exposure, float inv_gamma, cudaStream_t s, uint64_t* launches);
     void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s, uint64_t* launches);
     void launch_fill_f4(float4* p, float4 v, size_t n, cudaStream_t s, uint64_t* launches);

@@ -818,15 +818,26 @@ namespace shsb
 
         // Digests the 160-byte CullingLightGPU records into the 80-byte form the tile kernel's light loop reads
         // (run once per shsb_lights_upload, not per frame or per tile).
-        __global__ void __launch_bounds__(128) light_prep_kernel(const DevLightRec* __restrict__ lights, SmLight* __restrict__ out, uint32_t n)
+        // `src` may be pinned HOST memory (zero-copy): the upload is then done by the SMs, not by a copy engine, so it
+        // never queues behind a multi-megabyte frame read-back on the same engine.  `raw` receives the verbatim record.
+        __global__ void __launch_bounds__(128) light_prep_kernel(const DevLightRec* __restrict__ src, DevLightRec* __restrict__ raw, SmLight* __restrict__ out, uint32_t n)
         {
             const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= n) return;
-            const DevLightRec* rec = lights + i;
-            const float4 pr = __ldg(reinterpret_cast<const float4*>(rec->position_range));
-            const uint4 tf = __ldg(reinterpret_cast<const uint4*>(rec->type_shape_flags));
-            const float4 ci = __ldg(reinterpret_cast<const float4*>(rec->color_intensity));
-            const float4 sa = __ldg(reinterpret_cast<const float4*>(rec->shape_attenuation));
+            {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src + i);
+                uint4* d4 = reinterpret_cast<uint4*>(raw + i);
+                uint4 w[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) w[k] = s4[k];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) d4[k] = w[k];
+            }
+            const DevLightRec* rec = raw + i; // this thread's own stores are visible to it
+            const float4 pr = *reinterpret_cast<const float4*>(rec->position_range);
+            const uint4 tf = *reinterpret_cast<const uint4*>(rec->type_shape_flags);
+            const float4 ci = *reinterpret_cast<const float4*>(rec->color_intensity);
+            const float4 sa = *reinterpret_cast<const float4*>(rec->shape_attenuation);
             SmLight sl;
             const float range = fmaxf(pr.w, 0.001f);
             const float power = fmaxf(sa.y, 0.001f);
@@ -838,8 +849,8 @@ namespace shsb
             sl.index = i; sl.pad0 = sl.pad1 = 0u;
             if (tf.x == 2u)
             {
-                const float4 ds = __ldg(reinterpret_cast<const float4*>(rec->direction_spot));
-                const float4 ax = __ldg(reinterpret_cast<const float4*>(rec->axis_spot_outer));
+                const float4 ds = *reinterpret_cast<const float4*>(rec->direction_spot);
+                const float4 ax = *reinterpret_cast<const float4*>(rec->axis_spot_outer);
                 const float dl = fast_rsqrt(ds.x * ds.x + ds.y * ds.y + ds.z * ds.z);
                 const float inner_cos = fminf(fmaxf(ds.w, -1.0f), 1.0f);
                 const float outer_cos = fminf(fmaxf(ax.w, -1.0f), inner_cos);
@@ -850,7 +861,7 @@ namespace shsb
             else if (tf.x > 2u)
             {
                 // area lights reach beyond position +- range: the range test uses their cull sphere
-                const float4 sp = __ldg(reinterpret_cast<const float4*>(rec->cull_sphere));
+                const float4 sp = *reinterpret_cast<const float4*>(rec->cull_sphere);
                 sl.pos_r2 = make_float4(sp.x, sp.y, sp.z, sp.w * sp.w * 1.001f + 1e-6f); // conservative pre-test; eval_light_record decides
                 sl.kind |= KIND_AREA;
             }
@@ -898,10 +909,28 @@ namespace shsb
         *launches += 1;
     }
 
-    void launch_light_prep(const DevLightRec* lights, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches)
+    void launch_light_prep(const DevLightRec* src, DevLightRec* raw, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches)
     {
         if (!n) return;
-        light_prep_kernel<<<(n + 127) / 128, 128, 0, s>>>(lights, out, n);
+        light_prep_kernel<<<(n + 127) / 128, 128, 0, s>>>(src, raw, out, n);
+        *launches += 1;
+    }
+
+    namespace
+    {
+        __global__ void __launch_bounds__(256) upload_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16)
+        {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+        }
+    }
+
+    // Small host -> device upload done by the SMs from mapped pinned memory (see light_prep_kernel).
+    void launch_upload(void* dst, const void* src_mapped, size_t bytes, cudaStream_t s, uint64_t* launches)
+    {
+        const size_t n16 = (bytes + 15) / 16;
+        if (!n16) return;
+        const int grid = (int)min((n16 + 255) / 256, (size_t)64);
+        upload_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src_mapped), n16);
         *launches += 1;
     }
 

@@ -204,6 +204,13 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_timing_collect(self.h, capi.fptr(a), max_frames, C.byref(n)), "shsb_timing_collect")
         return a[: n.value]
 
+    def timing_collect_abs(self, max_frames=4096) -> np.ndarray:
+        """(n_frames, 5) float32 ms since the first event: front begin, after geometry, after binning, tile begin, tile end."""
+        a = np.zeros((max_frames, 5), dtype=np.float32)
+        n = C.c_size_t()
+        _check(self.lib, self.h, self.lib.shsb_timing_collect_abs(self.h, capi.fptr(a), max_frames, C.byref(n)), "shsb_timing_collect_abs")
+        return a[: n.value]
+
     def last_stage_ms(self):
         a = np.zeros(8, dtype=np.float32)
         _check(self.lib, self.h, self.lib.shsb_last_stage_ms(self.h, capi.fptr(a)), "shsb_last_stage_ms")
