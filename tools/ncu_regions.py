@@ -5,12 +5,14 @@ rep = sys.argv[1]
 src_path = "/root/repo/leisure_software_renderer_b200/csrc/tile_raster.cu"
 lines = open(src_path).read().split("\n")
 # region boundaries by marker text -> name
-markers = [("struct Surface", "helpers"), ("eval_brdf(const Surface", "brdf"), ("attenuation_quadratic(float", "attenuation"),
-           ("eval_point_spot(const Surface", "point_spot"), ("eval_light_record(const Surface", "light_record"), ("fake_ibl(V3", "fake_ibl"),
-           ("sample_texture(const", "texture"), ("shadow_visibility(const", "shadow"), ("tonemap_pixel(float", "tonemap"),
-           ("tile_kernel(const FrameConst", "prologue"), ("for (uint32_t base = off0", "raster_loop"), ("// ---------------- resolve: depth", "resolve_depth_counters"),
-           ("// ---------------- phase A", "phaseA_shade"), ("// ---------------- phase B", "phaseB_stage_lights"), ("if (has)\n", "x"),
-           ("// ---------------- phase C", "phaseC_resolve"), ("tonemap_kernel(", "other")]
+markers = [("struct Surface", "helpers"), ("eval_brdf_lit(const Surface", "brdf"), ("attenuation_quadratic(float", "attenuation(generic)"),
+           ("accumulate_point_spot(const Surface", "point_spot(range,N.d,atten)"), ("eval_light_record(const Surface", "light_record"), ("fake_ibl(V3", "fake_ibl"),
+           ("sample_texture(const", "texture"), ("shadow_visibility(const", "shadow"), ("tonemap_pixel(float", "tonemap"), ("resolve_uncovered(const", "resolve_uncovered"),
+           ("tile_kernel(const FrameConst", "prologue"), ("// ---------------- empty tiles", "empty_tiles"), ("uint32_t ord = blockIdx.x, cls = 0;", "prologue"),
+           ("for (uint32_t base = off0", "raster_loop"), ("// ---------------- resolve: depth", "resolve_depth_counters"),
+           ("// ---------------- phase A", "phaseA_shade"), ("// the only barrier every non-empty tile passes", "barrier_stats"), ("// ---------------- phase B", "phaseB_stage_lights"),
+           ("const SmLight* lt = s_light;", "phaseB_light_loop"), ("// generic light-tile size", "generic_light_tiles"),
+           ("// ---------------- phase C", "phaseC_resolve"), ("light_prep_kernel(", "other")]
 bounds = []
 for text, name in markers:
     for i, l in enumerate(lines):
