@@ -33,12 +33,15 @@ namespace shsb
         // 0 = Outside, 1 = Intersecting, 2 = Inside
         __device__ __forceinline__ int classify(const float4* __restrict__ planes, const float4 sphere, const float4 bmin, const float4 bmax)
         {
+            // The result is a pure function of the six per-plane distances (Outside if any fails, Inside if all clear), so
+            // the planes may be visited in any order: the four side planes (2..5) reject far more lights than near / far.
             const float r = fmaxf(sphere.w, 0.0f);
             const float r_eps = xadd(r, 1e-5f);
             bool inside = true;
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 6; ++k)
             {
+                const int i = (k + 2) % 6;
                 const float d = plane_dist(planes[i], sphere.x, sphere.y, sphere.z);
                 if (d < -r_eps) return 0;
                 if (d < r_eps) inside = false;
@@ -46,8 +49,9 @@ namespace shsb
             if (inside) return 2;
             inside = true;
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 6; ++k)
             {
+                const int i = (k + 2) % 6;
                 const float4 pl = planes[i];
                 const float d = plane_dist(pl, (pl.x >= 0.0f) ? bmax.x : bmin.x, (pl.y >= 0.0f) ? bmax.y : bmin.y, (pl.z >= 0.0f) ? bmax.z : bmin.z);
                 if (d < -1e-5f) return 0;
@@ -64,7 +68,10 @@ namespace shsb
             uint32_t macro_x, macro_y; // macro cells (MACRO x MACRO tiles) per row / column
         };
 
-        constexpr uint32_t MACRO = 8; // tiles per macro-cell edge
+#ifndef SHSB_MACRO
+#define SHSB_MACRO 8
+#endif
+        constexpr uint32_t MACRO = SHSB_MACRO; // tiles per macro-cell edge
 
         // make_screen_tile_cell, jolt_light_culling.hpp:95-133, evaluated by threads 0..7 (corners) and 0..5 (planes)
         // of the calling CTA; both stages are followed by a __syncthreads() in the caller.
