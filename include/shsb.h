@@ -96,6 +96,13 @@ enum /* render-target kinds, gfx/rt_types.hpp:61-157, gfx/rt_shadow.hpp:18 */
     SHSB_RT_SHADOW = 4        /* RT_ShadowDepth: f32                                          */
 };
 
+enum /* ISkyModel implementations of the reference (Scene::sky) */
+{
+    SHSB_SKY_NONE = 0,       /* background gradient, pass_pbr_forward.hpp:69-85 */
+    SHSB_SKY_PROCEDURAL = 1, /* ProceduralSky, sky/procedural_sky.hpp:19-47     */
+    SHSB_SKY_CUBEMAP = 2     /* CubemapSky, sky/cubemap_sky.hpp:62-116          */
+};
+
 enum /* planes of a render target for clear / upload / download / device_ptr */
 {
     SHSB_PLANE_COLOR = 0,  /* HDR: float4; LDR: uchar4                                        */
@@ -147,7 +154,9 @@ typedef struct ShsbUniforms /* device-visible subset of ShaderUniforms, shader/t
     int32_t shadow_pcf_radius;
     float shadow_pcf_step;
     float shadow_strength;
-    int32_t reserved;
+    int32_t enable_motion_vectors; /* ShaderUniforms::enable_motion_vectors (shader/types.hpp), rasterizer.hpp:295 */
+    float prev_model[16];          /* ShaderUniforms::prev_model    (rasterizer.hpp:296-307)                      */
+    float prev_viewproj[16];       /* ShaderUniforms::prev_viewproj (rasterizer.hpp:393)                          */
 } ShsbUniforms;
 
 typedef struct ShsbTransform /* Transform, scene/scene_types.hpp:26-31 */
@@ -169,6 +178,7 @@ typedef struct ShsbRenderItem /* RenderItem (scene/scene_types.hpp:62-70) with i
     shsb_tex base_color_tex;
     uint32_t casts_shadow;
     uint32_t visible;
+    uint64_t object_id;    /* RenderItem::object_id: key of the previous-frame model matrix; 0 = derive (pass_pbr_forward.hpp:143-148) */
 } ShsbRenderItem;
 
 typedef struct ShsbScene /* Scene, scene/scene_types.hpp:92-104 (camera + sun + items) */
@@ -181,6 +191,13 @@ typedef struct ShsbScene /* Scene, scene/scene_types.hpp:92-104 (camera + sun + 
     float sun_color[3];
     uint32_t reserved;
     const ShsbRenderItem* items;
+    float cam_prev_viewproj[16]; /* Camera::prev_viewproj (scene/scene_types.hpp:59); used once the context has a previous frame */
+    /* Scene::sky (ISkyModel*, sky/sky_model.hpp:17): the reference's two sky models exist on the device */
+    int32_t sky_kind;            /* SHSB_SKY_*                                                          */
+    float sky_intensity;         /* CubemapSky intensity (sky/cubemap_sky.hpp:66)                       */
+    float sky_sun_dir_ws[3];     /* ProceduralSky sun direction (sky/procedural_sky.hpp:22)             */
+    shsb_tex sky_faces[6];       /* CubemapData::face: +X -X +Y -Y +Z -Z (sky/cubemap_sky.hpp:24)       */
+    uint32_t reserved2;
 } ShsbScene;
 
 typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/frame_params.hpp:117-171 */
@@ -201,6 +218,8 @@ typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/f
     uint32_t tile_size;     /* technique.tile_size (16)                                       */
     uint32_t max_lights_per_tile; /* technique.max_lights_per_tile (128)                      */
     int32_t write_aovs;
+    int32_t motion_vectors_enable; /* pass.motion_vectors.enable (frame/frame_params.hpp:46-49; reference default: true) */
+    int32_t reserved[3];
 } ShsbFrameParams;
 
 /* ------------------------------------------------------------------ context */
@@ -292,6 +311,10 @@ SHSB_API int32_t shsb_pass_depth_prepass(shsb_ctx ctx, const ShsbScene* scene, c
  * out_light_viewproj receives ctx.shadow.light_viewproj. */
 SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, const ShsbFrameParams* fp,
                                       shsb_rt shadow_rt, float out_light_viewproj[16]);
+
+/* Context::history.reset() (core/context.hpp:84-94): forget the previous frame's model matrices, so that the next
+ * PassPBRForward computes motion against the current matrices (zero object motion) like a first frame. */
+SHSB_API int32_t shsb_history_reset(shsb_ctx ctx);
 
 /* PassTonemap::execute (passes/pass_tonemap.hpp:37-84). */
 SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt, float exposure, float gamma);

@@ -18,6 +18,7 @@ OK = 0
 CULL_NONE, CULL_BACK, CULL_FRONT = 0, 1, 2
 SHADER_PBR_MR, SHADER_BLINN_PHONG, SHADER_DEBUG_ALBEDO, SHADER_DEBUG_NORMAL, SHADER_DEBUG_DEPTH, SHADER_DEPTH_ONLY = range(6)
 SHADING_PBR, SHADING_BLINN = 0, 1
+SKY_NONE, SKY_PROCEDURAL, SKY_CUBEMAP = 0, 1, 2
 DEBUG_FINAL, DEBUG_ALBEDO, DEBUG_NORMAL, DEBUG_DEPTH = 0, 1, 2, 3
 RT_COLOR_HDR, RT_COLOR_LDR, RT_DEPTH_MOTION, RT_SHADOW = 1, 2, 3, 4
 PLANE_COLOR, PLANE_DEPTH, PLANE_MOTION, PLANE_TRI_ID, PLANE_COVERAGE = 0, 1, 2, 3, 4
@@ -49,7 +50,8 @@ class Uniforms(C.Structure):
                 ("base_color_tex", C.c_uint32), ("shadow_map", C.c_uint32),
                 ("shadow_bias_const", C.c_float), ("shadow_bias_slope", C.c_float),
                 ("shadow_pcf_radius", C.c_int32), ("shadow_pcf_step", C.c_float),
-                ("shadow_strength", C.c_float), ("reserved", C.c_int32)]
+                ("shadow_strength", C.c_float), ("enable_motion_vectors", C.c_int32),
+                ("prev_model", F16), ("prev_viewproj", F16)]
 
 
 class Transform(C.Structure):
@@ -59,14 +61,17 @@ class Transform(C.Structure):
 class RenderItem(C.Structure):
     _fields_ = [("tr", Transform), ("mesh", C.c_uint32), ("has_material", C.c_uint32),
                 ("base_color", F3), ("metallic", C.c_float), ("roughness", C.c_float), ("ao", C.c_float),
-                ("base_color_tex", C.c_uint32), ("casts_shadow", C.c_uint32), ("visible", C.c_uint32)]
+                ("base_color_tex", C.c_uint32), ("casts_shadow", C.c_uint32), ("visible", C.c_uint32),
+                ("object_id", C.c_uint64)]
 
 
 class Scene(C.Structure):
     _fields_ = [("cam_viewproj", F16), ("cam_pos", F3), ("sun_intensity", C.c_float),
                 ("sun_dir_ws", F3), ("n_items", C.c_uint32),
                 ("sun_color", F3), ("reserved", C.c_uint32),
-                ("items", C.POINTER(RenderItem))]
+                ("items", C.POINTER(RenderItem)),
+                ("cam_prev_viewproj", F16), ("sky_kind", C.c_int32), ("sky_intensity", C.c_float), ("sky_sun_dir_ws", F3),
+                ("sky_faces", C.c_uint32 * 6), ("reserved2", C.c_uint32)]
 
 
 class FrameParams(C.Structure):
@@ -75,7 +80,7 @@ class FrameParams(C.Structure):
                 ("shadow_pcf_radius", C.c_int32), ("shadow_pcf_step", C.c_float), ("shadow_strength", C.c_float),
                 ("exposure", C.c_float), ("gamma", C.c_float),
                 ("light_culling", C.c_int32), ("tile_size", C.c_uint32), ("max_lights_per_tile", C.c_uint32),
-                ("write_aovs", C.c_int32)]
+                ("write_aovs", C.c_int32), ("motion_vectors_enable", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 def default_frame_params(**kw) -> FrameParams:
@@ -83,7 +88,8 @@ def default_frame_params(**kw) -> FrameParams:
     fp = FrameParams(shading_model=SHADING_PBR, debug_view=DEBUG_FINAL, cull_mode=CULL_BACK, front_face_ccw=1,
                      shadow_enable=1, shadow_bias_const=0.0008, shadow_bias_slope=0.0015, shadow_pcf_radius=2,
                      shadow_pcf_step=1.0, shadow_strength=1.0, exposure=1.0, gamma=2.2,
-                     light_culling=0, tile_size=16, max_lights_per_tile=128, write_aovs=0)
+                     light_culling=0, tile_size=16, max_lights_per_tile=128, write_aovs=0,
+                     motion_vectors_enable=0)  # the reference default is true; scenes switch it on explicitly
     for k, v in kw.items():
         setattr(fp, k, v)
     return fp
@@ -144,6 +150,7 @@ def load_library(path: str | None = None):
         "shsb_pass_pbr_forward": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_float), C.c_int32, P(Stats)],
         "shsb_pass_depth_prepass": [vp, P(Scene), P(FrameParams), C.c_uint32, P(Stats)],
         "shsb_pass_shadow_map": [vp, P(Scene), P(FrameParams), C.c_uint32, P(C.c_float)],
+        "shsb_history_reset": [vp],
         "shsb_pass_tonemap": [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float],
         "shsb_lights_upload": [vp, vp, C.c_uint32],
         "shsb_light_cull": [vp, P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32],

@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/shsb.h"
@@ -66,6 +67,7 @@ namespace
         uint32_t* coverage = nullptr;
         cudaEvent_t read_done = nullptr; // last asynchronous download of this RT (copy stream)
         bool read_pending = false;
+        bool motion_dirty = false;       // the motion plane may hold non-zero vectors (a pass that clears it has work to do)
     };
 
     template <typename T>
@@ -139,6 +141,14 @@ struct shsb_context_t
     bool lights_uploaded = false;
     LightLists lists[NUM_ARENAS + 1];
     int lists_cur = -1;                       // the set produced by the most recent cull, -1 = none
+
+    // RenderHistoryState (core/context.hpp:84-94): last frame's model matrix per object, in draw order with its key;
+    // looked up positionally first (the usual case: same scene, same order), through the map otherwise
+    std::vector<uint64_t> hist_keys;
+    std::vector<hm::mat4f> hist_models;
+    std::unordered_map<uint64_t, size_t> hist_index;
+    bool hist_index_valid = false;
+    bool has_prev_frame = false;
 
     // per-frame transients
     Arena arena[NUM_ARENAS];
@@ -576,10 +586,17 @@ namespace
     // Stages one draw into the host item / block tables.
     int stage_item(shsb_ctx ctx, std::vector<DevItem>& items, std::vector<uint2>& blocks, uint64_t& tri_cursor,
                    const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
-                   const float base_color[3], float metallic, float roughness, float ao, uint32_t tex)
+                   const float base_color[3], float metallic, float roughness, float ao, uint32_t tex, const hm::mat4f* prev_model = nullptr)
     {
         DevItem it{};
         hm::store(model, it.model);
+        if (prev_model)
+        {
+            // curr_to_prev_model, rasterizer.hpp:296-307
+            hm::mat4f c2p = hm::identity();
+            if (std::fabs(hm::determinant(model)) > 1e-10f) c2p = hm::mul(*prev_model, hm::inverse(model));
+            hm::store(c2p, it.c2p);
+        }
         hm::normal_matrix(model, it.nrm);
         it.base_color[0] = base_color[0]; it.base_color[1] = base_color[1]; it.base_color[2] = base_color[2];
         it.metallic = metallic; it.roughness = roughness; it.ao = ao;
@@ -716,6 +733,41 @@ namespace
             fc.inv_gamma = 1.0f / std::max(0.001f, fp->gamma);
         }
 
+        // motion vectors + history (pass_pbr_forward.hpp:87-98, 143-166, 212-213); never in the depth pre-pass (pass_adapters.hpp:521)
+        const bool lit_pass = !depth_only;
+        const bool write_motion = lit_pass && dm && dm->motion && fp->motion_vectors_enable != 0;
+        if (lit_pass && dm && dm->motion)
+        {
+            fc.write_motion = write_motion ? 1 : 0;
+            fc.clear_motion = (write_motion || dm->motion_dirty) ? 1 : 0; // both branches of the reference clear the plane
+            job.fb.motion = (write_motion || dm->motion_dirty) ? dm->motion : nullptr;
+            dm->motion_dirty = write_motion;
+            const float* pvp = ctx->has_prev_frame ? scene->cam_prev_viewproj : scene->cam_viewproj;
+            std::memcpy(fc.prev_viewproj, pvp, 64);
+        }
+        // sky model background (Scene::sky)
+        if (lit_pass && scene->sky_kind != SHSB_SKY_NONE)
+        {
+            if (scene->sky_kind != SHSB_SKY_PROCEDURAL && scene->sky_kind != SHSB_SKY_CUBEMAP)
+                return fail(ctx, SHSB_E_UNSUPPORTED, "sky kind %d is not one of the reference's sky models (procedural, cubemap)", scene->sky_kind);
+            fc.sky_kind = scene->sky_kind;
+            hm::store(hm::inverse(hm::load(scene->cam_viewproj)), fc.inv_viewproj);
+            const hm::vec3f sun = hm::normalize(hm::vec3f{scene->sky_sun_dir_ws[0], scene->sky_sun_dir_ws[1], scene->sky_sun_dir_ws[2]});
+            fc.sky_sun[0] = sun.x; fc.sky_sun[1] = sun.y; fc.sky_sun[2] = sun.z;
+            fc.sky_intensity = scene->sky_intensity;
+            if (scene->sky_kind == SHSB_SKY_CUBEMAP)
+            {
+                bool valid = true; // CubemapData::valid(), sky/cubemap_sky.hpp:26-33: an invalid cubemap samples black
+                for (int i = 0; i < 6; ++i)
+                {
+                    const uint32_t t = scene->sky_faces[i];
+                    if (t == 0 || t > ctx->textures.size() || !ctx->textures[t - 1].live) valid = false;
+                    else fc.sky_faces[i] = t - 1;
+                }
+                if (!valid) { fc.sky_kind = SHSB_SKY_CUBEMAP; fc.sky_intensity = 0.0f; for (int i = 0; i < 6; ++i) fc.sky_faces[i] = 0; if (ctx->textures.empty()) return fail(ctx, SHSB_E_INVALID_HANDLE, "cubemap sky without any texture uploaded"); }
+            }
+        }
+
         job.fb.hdr = hdr ? (float4*)hdr->color : nullptr;
         job.fb.depth = dm ? dm->depth : nullptr;
         job.fb.ldr = ldr ? (uchar4*)ldr->color : nullptr;
@@ -732,6 +784,9 @@ namespace
         std::vector<uint2> blocks;
         items.reserve(scene->n_items);
         uint64_t tri_cursor = 0;
+        std::vector<uint64_t> next_keys;
+        std::vector<hm::mat4f> next_models;
+        if (lit_pass) { next_keys.reserve(scene->n_items); next_models.reserve(scene->n_items); }
         for (uint32_t i = 0; i < scene->n_items; ++i)
         {
             const ShsbRenderItem& it = scene->items[i];
@@ -739,9 +794,48 @@ namespace
             const MeshSlot* mesh = get_mesh(ctx, it.mesh);
             if (!mesh || mesh->n_positions == 0 || mesh->n_indices == 0) continue; // MeshData::empty(), resources/mesh.hpp:32-35
             const hm::mat4f model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
+            const hm::mat4f* prev = nullptr;
+            hm::mat4f prev_model = model;
+            if (lit_pass)
+            {
+                // motion key, pass_pbr_forward.hpp:143-148 (the reference's material handle is 0 for "no material"; items with a
+                // material resolved on the caller's side are told apart by object_id or by their position)
+                uint64_t key = it.object_id;
+                if (key == 0)
+                {
+                    key = ((uint64_t)it.mesh << 32) ^ (uint64_t)(it.has_material ? 1u : 0u) ^ ((uint64_t)i + 1u);
+                    if (key == 0) key = 1;
+                }
+                if (ctx->has_prev_frame)
+                {
+                    const size_t k = next_keys.size();
+                    if (k < ctx->hist_keys.size() && ctx->hist_keys[k] == key) prev_model = ctx->hist_models[k];
+                    else
+                    {
+                        if (!ctx->hist_index_valid)
+                        {
+                            ctx->hist_index.clear();
+                            for (size_t q = 0; q < ctx->hist_keys.size(); ++q) ctx->hist_index[ctx->hist_keys[q]] = q; // a later duplicate key wins, like the map assignment
+                            ctx->hist_index_valid = true;
+                        }
+                        const auto f = ctx->hist_index.find(key);
+                        if (f != ctx->hist_index.end()) prev_model = ctx->hist_models[f->second];
+                    }
+                }
+                next_keys.push_back(key);
+                next_models.push_back(model);
+                if (write_motion) prev = &prev_model;
+            }
             const float def_color[3] = {0.8f, 0.5f, 0.2f}; // pass_pbr_forward.hpp:179-184
-            if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex);
-            else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u);
+            if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex, prev);
+            else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u, prev);
+        }
+        if (lit_pass)
+        {
+            ctx->hist_keys.swap(next_keys);
+            ctx->hist_models.swap(next_models);
+            ctx->hist_index_valid = false;
+            ctx->has_prev_frame = true;
         }
         const double t_stage = now_us();
         ctx->host_us[0] += t_stage - t_items;
@@ -1025,6 +1119,7 @@ SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const vo
     if (bytes == n * 16) { float4 v; std::memcpy(&v, value, 16); launch_fill_f4((float4*)p, v, n, ctx->stream, &ctx->launches); }
     else if (bytes == n * 8) { uint32_t v[2]; std::memcpy(v, value, 8); if (v[0] == v[1]) launch_fill_u32((uint32_t*)p, v[0], n * 2, ctx->stream, &ctx->launches); else return fail(ctx, SHSB_E_UNSUPPORTED, "motion clear needs x == y"); }
     else { uint32_t v; std::memcpy(&v, value, 4); launch_fill_u32((uint32_t*)p, v, n, ctx->stream, &ctx->launches); }
+    if (plane == SHSB_PLANE_MOTION) r->motion_dirty = true;
     CK(cudaGetLastError());
     return SHSB_OK;
 }
@@ -1040,6 +1135,7 @@ SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const v
     if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
     CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (plane == SHSB_PLANE_MOTION) r->motion_dirty = true;
     return SHSB_OK;
 }
 
@@ -1159,6 +1255,14 @@ SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh_h, int32_t sha
     }
     job.fb.hdr = (float4*)hdr->color;
     job.fb.depth = dm ? dm->depth : nullptr;
+    const bool write_motion = dm && dm->motion && u->enable_motion_vectors != 0; // rasterizer.hpp:295
+    if (write_motion)
+    {
+        fc.write_motion = 1;
+        std::memcpy(fc.prev_viewproj, u->prev_viewproj, 64);
+        job.fb.motion = dm->motion;
+        dm->motion_dirty = true;
+    }
     if (cfg->write_aovs)
     {
         if (int rc = ensure_aovs(ctx, hdr)) return rc;
@@ -1168,7 +1272,9 @@ SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh_h, int32_t sha
     std::vector<DevItem> items;
     std::vector<uint2> blocks;
     uint64_t tri_cursor = 0;
-    stage_item(ctx, items, blocks, tri_cursor, hm::load(u->model), *mesh, mesh_h - 1, u->base_color, u->metallic, u->roughness, u->ao, u->base_color_tex);
+    const hm::mat4f prev_model = hm::load(u->prev_model);
+    stage_item(ctx, items, blocks, tri_cursor, hm::load(u->model), *mesh, mesh_h - 1, u->base_color, u->metallic, u->roughness, u->ao, u->base_color_tex,
+               write_motion ? &prev_model : nullptr);
     if (int rc = upload_staging(ctx, items, blocks)) return rc;
     job.n_items = 1;
     job.n_blocks = (uint32_t)blocks.size();
@@ -1263,6 +1369,17 @@ SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, cons
     job.n_src_tris = tri_cursor;
     ShsbStats st{};
     return run_frame(ctx, job, &st);
+}
+
+SHSB_API int32_t shsb_history_reset(shsb_ctx ctx)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    ctx->hist_keys.clear();
+    ctx->hist_models.clear();
+    ctx->hist_index.clear();
+    ctx->hist_index_valid = false;
+    ctx->has_prev_frame = false;
+    return SHSB_OK;
 }
 
 SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt, float exposure, float gamma)

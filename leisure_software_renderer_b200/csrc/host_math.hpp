@@ -106,6 +106,24 @@ namespace shsb_host
         return m;
     }
 
+    // glm::determinant(mat4) (func_matrix.inl compute_determinant<4,4>)
+    inline float determinant(const mat4f& mm)
+    {
+        const float* M = &mm.col[0].x;
+        auto m = [&](int c, int r) { return M[c * 4 + r]; };
+        const float s00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3);
+        const float s01 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3);
+        const float s02 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2);
+        const float s03 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3);
+        const float s04 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2);
+        const float s05 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1);
+        const float d0 = +(m(1, 1) * s00 - m(1, 2) * s01 + m(1, 3) * s02);
+        const float d1 = -(m(1, 0) * s00 - m(1, 2) * s03 + m(1, 3) * s04);
+        const float d2 = +(m(1, 0) * s01 - m(1, 1) * s03 + m(1, 3) * s05);
+        const float d3 = -(m(1, 0) * s02 - m(1, 1) * s04 + m(1, 2) * s05);
+        return m(0, 0) * d0 + m(0, 1) * d1 + m(0, 2) * d2 + m(0, 3) * d3;
+    }
+
     inline void normal_matrix(const mat4f& model, float n9[9])
     {
         const float* M = &model.col[0].x;

@@ -77,8 +77,9 @@ namespace shsb
         uint32_t tri_offset;   // global index of this draw's triangle 0 (draw-order key = (tri_offset + ti) * 8 + fan)
         uint32_t tri_count;
         uint32_t pad[10];
+        float c2p[16];         // curr_to_prev_model = prev_model * inverse(model), host-computed (rasterizer.hpp:296-307)
     };
-    static_assert(sizeof(DevItem) == 192, "DevItem is 192 bytes");
+    static_assert(sizeof(DevItem) == 256, "DevItem is 256 bytes");
 
     struct __align__(16) RasterRec
     {
@@ -175,6 +176,16 @@ namespace shsb
         // fused tonemap (PassTonemap, pass_tonemap.hpp:49-81)
         int fuse_tonemap;
         float exposure, inv_gamma;
+        // motion vectors (rasterizer.hpp:295-307, 388-411)
+        int write_motion;       // winning fragments write their screen-space velocity
+        int clear_motion;       // pixels no fragment reached get (0, 0): PassPBRForward clears the plane (pass_pbr_forward.hpp:87-98)
+        float prev_viewproj[16];
+        // sky background (Scene::sky, sky/skybox_renderer.hpp:25-57)
+        int sky_kind;           // SHSB_SKY_*
+        float inv_viewproj[16]; // host-computed glm::inverse(cam.viewproj)
+        float sky_sun[3];       // normalised ProceduralSky sun direction
+        float sky_intensity;
+        uint32_t sky_faces[6];  // indices into the texture table (cubemap), all valid when sky_kind == cubemap
     };
 
     struct FrameBuffers
@@ -184,6 +195,7 @@ namespace shsb
         uchar4* ldr;              // W*H or null
         uint32_t* aov_tri_id;     // W*H or null
         uint32_t* aov_coverage;   // W*H or null
+        float2* motion;           // W*H or null
     };
 
     struct Geometry // per-frame transient arena

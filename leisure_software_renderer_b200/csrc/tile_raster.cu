@@ -328,10 +328,91 @@ namespace shsb
             return make_uchar4(o[0], o[1], o[2], 255);
         }
 
-        // Colour resolve of a pixel no fragment reached: background gradient (pass_pbr_forward.hpp:73-81) or, for a
-        // separate draw (load_color), the target's existing colour; fused tonemap if an LDR target is bound.
-        __device__ __forceinline__ void resolve_uncovered(const FrameConst& fc, const FrameBuffers& fb, size_t pix, int py)
+        // ---- sky models (Scene::sky): exact arithmetic, they select texels and feed an HDR target compared at PSNR >= 60 dB
+        __device__ __forceinline__ float xmix(float a, float b, float t) { return xadd(xmul(a, xsub(1.0f, t)), xmul(b, t)); } // glm::mix
+        __device__ __forceinline__ F3 xmix3(F3 a, F3 b, float t) { return F3{xmix(a.x, b.x, t), xmix(a.y, b.y, t), xmix(a.z, b.z, t)}; }
+
+        // ProceduralSky::sample, sky/procedural_sky.hpp:25-45
+        __device__ __forceinline__ F3 sky_procedural(F3 dir, const float* __restrict__ sun)
         {
+            const F3 d = xnormalize3(dir);
+            const float t = gclamp(xadd(xmul(d.y, 0.5f), 0.5f), 0.0f, 1.0f);
+            F3 sky = xmix3(F3{0.30f, 0.60f, 1.00f}, F3{0.05f, 0.20f, 0.50f}, t);
+            const float sun_dot = xdot3(d, F3{-sun[0], -sun[1], -sun[2]});
+            if (sun_dot > 0.9998f) sky = F3{15.0f, 15.0f, 15.0f};
+            else if (sun_dot > 0.9990f)
+            {
+                const float glow = xdiv(xsub(sun_dot, 0.9990f), xsub(0.9998f, 0.9990f));
+                sky = xmix3(sky, F3{10.0f, 8.0f, 4.0f}, glow);
+            }
+            return sky;
+        }
+
+        // sample_face_bilinear_linear, sky/cubemap_sky.hpp:39-60 (clamped addressing; lut[i] = powf(i/255, 2.2) from the host libm)
+        __device__ __forceinline__ F3 sample_face_clamped(const DevTexture& tex, const float* __restrict__ lut, float u, float v)
+        {
+            u = gclamp(u, 0.0f, 1.0f);
+            v = gclamp(v, 0.0f, 1.0f);
+            const float fx = xmul(u, (float)(tex.w - 1)), fy = xmul(v, (float)(tex.h - 1));
+            const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+            const int x1 = min(x0 + 1, tex.w - 1), y1 = min(y0 + 1, tex.h - 1);
+            const float tx = xsub(fx, (float)x0), ty = xsub(fy, (float)y0);
+            const uchar4 t00 = tex.texels[(size_t)y0 * tex.w + x0], t10 = tex.texels[(size_t)y0 * tex.w + x1];
+            const uchar4 t01 = tex.texels[(size_t)y1 * tex.w + x0], t11 = tex.texels[(size_t)y1 * tex.w + x1];
+            const F3 v00{lut[t00.x], lut[t00.y], lut[t00.z]}, v10{lut[t10.x], lut[t10.y], lut[t10.z]};
+            const F3 v01{lut[t01.x], lut[t01.y], lut[t01.z]}, v11{lut[t11.x], lut[t11.y], lut[t11.z]};
+            return xmix3(xmix3(v00, v10, tx), xmix3(v01, v11, tx), ty);
+        }
+
+        // CubemapSky::sample, sky/cubemap_sky.hpp:69-109
+        __device__ __forceinline__ F3 sky_cubemap(const FrameConst& fc, const DevTexture* __restrict__ textures, const float* __restrict__ lut, F3 d)
+        {
+            const float len = xsqrt(xdot3(d, d));
+            if (len < 1e-8f) return F3{0.0f, 0.0f, 0.0f};
+            d.x = xdiv(d.x, len); d.y = xdiv(d.y, len); d.z = xdiv(d.z, len);
+            const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+            int face;
+            float u, v;
+            if (ax >= ay && ax >= az)
+            {
+                if (d.x > 0.0f) { face = 0; u = xdiv(-d.z, ax); v = xdiv(d.y, ax); }
+                else { face = 1; u = xdiv(d.z, ax); v = xdiv(d.y, ax); }
+            }
+            else if (ay >= ax && ay >= az)
+            {
+                if (d.y > 0.0f) { face = 2; u = xdiv(d.x, ay); v = xdiv(-d.z, ay); }
+                else { face = 3; u = xdiv(d.x, ay); v = xdiv(d.z, ay); }
+            }
+            else
+            {
+                if (d.z > 0.0f) { face = 4; u = xdiv(d.x, az); v = xdiv(d.y, az); }
+                else { face = 5; u = xdiv(-d.x, az); v = xdiv(d.y, az); }
+            }
+            u = xmul(0.5f, xadd(u, 1.0f));
+            v = xmul(0.5f, xadd(v, 1.0f));
+            const F3 c = sample_face_clamped(textures[fc.sky_faces[face]], lut, u, v);
+            return F3{xmul(c.x, fc.sky_intensity), xmul(c.y, fc.sky_intensity), xmul(c.z, fc.sky_intensity)};
+        }
+
+        // render_skybox_to_hdr, sky/skybox_renderer.hpp:25-57, for one pixel
+        __device__ __forceinline__ F3 sky_pixel(const FrameConst& fc, const DevTexture* __restrict__ textures, const float* __restrict__ lut, int px, int py)
+        {
+            const float ndc_x = xsub(xdiv(xmul(2.0f, xadd((float)px, 0.5f)), (float)fc.W), 1.0f);
+            const float ndc_y = xsub(xdiv(xmul(2.0f, xadd((float)py, 0.5f)), (float)fc.H), 1.0f);
+            const float4 world = xmat4_mul(fc.inv_viewproj, ndc_x, ndc_y, 1.0f, 1.0f);
+            if (fabsf(world.w) < 1e-8f) return F3{0.0f, 0.0f, 0.0f};
+            const F3 dir = xnormalize3(F3{xsub(xdiv(world.x, world.w), fc.camera_pos[0]), xsub(xdiv(world.y, world.w), fc.camera_pos[1]),
+                                          xsub(xdiv(world.z, world.w), fc.camera_pos[2])});
+            return (fc.sky_kind == 1) ? sky_procedural(dir, fc.sky_sun) : sky_cubemap(fc, textures, lut, dir);
+        }
+
+        // Resolve of a pixel no fragment reached: motion (0, 0) when the pass clears the plane; colour = sky model or
+        // background gradient (pass_pbr_forward.hpp:64-85) or, for a separate draw (load_color), the target's existing
+        // colour; fused tonemap if an LDR target is bound.
+        __device__ __forceinline__ void resolve_uncovered(const FrameConst& fc, const FrameBuffers& fb, const DevTexture* __restrict__ textures,
+                                                          const float* __restrict__ lut, size_t pix, int px, int py)
+        {
+            if (fc.clear_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f);
             if (fc.load_color)
             {
                 if (!(fc.fuse_tonemap && fb.ldr)) return;
@@ -339,8 +420,17 @@ namespace shsb
                 fb.ldr[pix] = tonemap_pixel(c.x, c.y, c.z, fc.exposure, fc.inv_gamma);
                 return;
             }
-            const float t = xdiv((float)py, (float)max(1, fc.H - 1));
-            const float r = xadd(0.06f, xmul(0.08f, t)), g = xadd(0.08f, xmul(0.10f, t)), b = xadd(0.12f, xmul(0.12f, t));
+            float r, g, b;
+            if (fc.sky_kind != 0)
+            {
+                const F3 c = sky_pixel(fc, textures, lut, px, py);
+                r = c.x; g = c.y; b = c.z;
+            }
+            else
+            {
+                const float t = xdiv((float)py, (float)max(1, fc.H - 1));
+                r = xadd(0.06f, xmul(0.08f, t)); g = xadd(0.08f, xmul(0.10f, t)); b = xadd(0.12f, xmul(0.12f, t));
+            }
             fb.hdr[pix] = make_float4(r, g, b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(r, g, b, fc.exposure, fc.inv_gamma);
         }
@@ -385,12 +475,17 @@ namespace shsb
                 const size_t pix = (size_t)py * (size_t)fc.W + (size_t)x0;
                 const bool clear_depth = fb.depth && (fc.has_depth || fc.shadow_mode) && !fc.load_depth;
                 const bool shade = !(fc.shadow_mode || fc.shader_id == 5 || !fb.hdr);
-                if (x0 - (q & 3) * 4 + TILE <= fc.W && (fc.W & 3) == 0 && !fc.load_color) // whole tile row inside, 16-byte aligned rows
+                if (x0 - (q & 3) * 4 + TILE <= fc.W && (fc.W & 3) == 0 && !fc.load_color && fc.sky_kind == 0) // whole tile row inside, 16-byte aligned rows, row-constant colour
                 {
                     if (clear_depth) *reinterpret_cast<float4*>(fb.depth + pix) = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                     if (fb.aov_tri_id) *reinterpret_cast<uint4*>(fb.aov_tri_id + pix) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                     if (fb.aov_coverage) *reinterpret_cast<uint4*>(fb.aov_coverage + pix) = make_uint4(0u, 0u, 0u, 0u);
                     if (!shade) return;
+                    if (fc.clear_motion && fb.motion)
+                    {
+                        float4* m = reinterpret_cast<float4*>(fb.motion + pix);
+                        m[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); m[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
                     // background gradient, pass_pbr_forward.hpp:73-81
                     const float t = xdiv((float)py, (float)max(1, fc.H - 1));
                     const float4 c = make_float4(xadd(0.06f, xmul(0.08f, t)), xadd(0.08f, xmul(0.10f, t)), xadd(0.12f, xmul(0.12f, t)), 1.0f);
@@ -410,7 +505,7 @@ namespace shsb
                     if (clear_depth) fb.depth[pix + i] = 1.0f;
                     if (fb.aov_tri_id) fb.aov_tri_id[pix + i] = 0xFFFFFFFFu;
                     if (fb.aov_coverage) fb.aov_coverage[pix + i] = 0u;
-                    if (shade) resolve_uncovered(fc, fb, pix + i, py);
+                    if (shade) resolve_uncovered(fc, fb, textures, srgb_lut, pix + i, x0 + i, py);
                 }
                 return;
             }
@@ -577,6 +672,22 @@ namespace shsb
                 const float uvx = interp(a[18], a[20], a[22]), uvy = interp(a[19], a[21], a[23]);
                 const DevItem& it = g.items[__float_as_uint(a[24])];
                 const F3 n_ws = xnormalize3(nrm_i); // rasterizer.hpp:381
+                if (fc.write_motion && fb.motion)
+                {
+                    // rasterizer.hpp:388-411: the winning fragment is the last one the serial loop lets past the depth test
+                    const float4 pw = xmat4_mul(it.c2p, wpos.x, wpos.y, wpos.z, 1.0f);
+                    const float4 cc = xmat4_mul(fc.viewproj, wpos.x, wpos.y, wpos.z, 1.0f);
+                    const float4 pc = xmat4_mul(fc.prev_viewproj, pw.x, pw.y, pw.z, pw.w);
+                    float mx = 0.0f, my = 0.0f;
+                    if (fabsf(cc.w) > 1e-8f && fabsf(pc.w) > 1e-8f)
+                    {
+                        mx = xmul(xmul(xsub(xdiv(cc.x, cc.w), xdiv(pc.x, pc.w)), 0.5f), (float)fc.W);
+                        my = xmul(xmul(xsub(xdiv(cc.y, cc.w), xdiv(pc.y, pc.w)), 0.5f), (float)fc.H);
+                        const float len = xsqrt(xadd(xmul(mx, mx), xmul(my, my)));
+                        if (len > 96.0f && len > 1e-6f) { const float k = xdiv(96.0f, len); mx = xmul(mx, k); my = xmul(my, k); }
+                    }
+                    fb.motion[pix] = make_float2(mx, my);
+                }
 
                 if (fc.shader_id == 2) { out_r = it.base_color[0]; out_g = it.base_color[1]; out_b = it.base_color[2]; }
                 else if (fc.shader_id == 3)
@@ -810,7 +921,8 @@ namespace shsb
 
             // ---------------- phase C (per pixel): resolve colour (+ fused tonemap), each byte written once
             if (!valid) return;
-            if (!has) { resolve_uncovered(fc, fb, pix, py); return; }
+            if (!has) { resolve_uncovered(fc, fb, textures, srgb_lut, pix, px, py); return; }
+            if (fc.clear_motion && !fc.write_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f); // plane cleared, vectors disabled
             PHASE_MARK(5);
             fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);

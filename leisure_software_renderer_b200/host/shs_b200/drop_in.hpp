@@ -25,6 +25,8 @@
 #include "shs/passes/pass_pbr_forward.hpp"
 #include "shs/passes/pass_shadow_map.hpp"
 #include "shs/passes/pass_tonemap.hpp"
+#include "shs/sky/cubemap_sky.hpp"
+#include "shs/sky/procedural_sky.hpp"
 #include "shs/sw_render/rasterizer.hpp"
 
 #include "shsb.h"
@@ -92,7 +94,28 @@ namespace shs::b200
         void upload(RT_ShadowDepth* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
         void download(RT_ColorHDR* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(ColorF)); }
         void download(RT_ColorLDR* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(Color)); }
-        void download(RT_ColorDepthMotion* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data.data(), rt->depth.data.size() * sizeof(float)); }
+        void download(RT_ColorDepthMotion* rt)
+        {
+            if (!rt) return;
+            shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data.data(), rt->depth.data.size() * sizeof(float));
+            shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_MOTION, rt->motion.data.data(), rt->motion.data.size() * sizeof(Motion2f));
+        }
+
+        // ---- sky models.  ISkyModel implementations keep their parameters private, so a Scene::sky pointer has to be
+        // introduced once: the reference's two models exist on the device, any other ISkyModel is refused (no fallback).
+        struct SkyDesc { int32_t kind = SHSB_SKY_NONE; float intensity = 1.0f; glm::vec3 sun_dir{0.0f}; shsb_tex faces[6]{}; };
+        void register_sky(const ProceduralSky* sky, const glm::vec3& sun_dir_ws)
+        {
+            SkyDesc d; d.kind = SHSB_SKY_PROCEDURAL; d.sun_dir = sun_dir_ws;
+            skies_[sky] = d;
+        }
+        void register_sky(const CubemapSky* sky, const CubemapData& cubemap, float intensity = 1.0f)
+        {
+            SkyDesc d; d.kind = SHSB_SKY_CUBEMAP; d.intensity = intensity;
+            for (int i = 0; i < 6; ++i) d.faces[i] = texture(&cubemap.face[(size_t)i]);
+            skies_[sky] = d;
+        }
+        const SkyDesc* sky(const ISkyModel* s) const { const auto it = skies_.find(s); return it == skies_.end() ? nullptr : &it->second; }
         void download(RT_ShadowDepth* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
 
     private:
@@ -111,6 +134,7 @@ namespace shs::b200
         std::unordered_map<const void*, shsb_mesh> meshes_{};
         std::unordered_map<const void*, shsb_tex> textures_{};
         std::unordered_map<const void*, shsb_rt> rts_{};
+        std::unordered_map<const ISkyModel*, SkyDesc> skies_{};
     };
 
     namespace detail
@@ -136,6 +160,7 @@ namespace shs::b200
             o.light_culling = fp.technique.light_culling ? 1 : 0;
             o.tile_size = fp.technique.tile_size;
             o.max_lights_per_tile = fp.technique.max_lights_per_tile;
+            o.motion_vectors_enable = fp.pass.motion_vectors.enable ? 1 : 0;
             return o;
         }
 
@@ -145,7 +170,19 @@ namespace shs::b200
         {
             ShsbScene o{};
             copy_mat(s.cam.viewproj, o.cam_viewproj);
+            copy_mat(s.cam.prev_viewproj, o.cam_prev_viewproj);
             copy_vec(s.cam.pos, o.cam_pos);
+            if (s.sky)
+            {
+                if (const Device::SkyDesc* d = dev.sky(s.sky))
+                {
+                    o.sky_kind = d->kind;
+                    o.sky_intensity = d->intensity;
+                    copy_vec(d->sun_dir, o.sky_sun_dir_ws);
+                    for (int i = 0; i < 6; ++i) o.sky_faces[i] = d->faces[i];
+                }
+                else o.sky_kind = -1; // unknown ISkyModel: the pass refuses it
+            }
             copy_vec(s.sun.dir_ws, o.sun_dir_ws);
             copy_vec(s.sun.color, o.sun_color);
             o.sun_intensity = s.sun.intensity;
@@ -171,6 +208,7 @@ namespace shs::b200
                 }
                 r.casts_shadow = it.casts_shadow ? 1u : 0u;
                 r.visible = it.visible ? 1u : 0u;
+                r.object_id = it.object_id;
                 items.push_back(r);
             }
             o.items = items.data();
@@ -207,6 +245,9 @@ namespace shs::b200
         }
         su.shadow_bias_const = u.shadow_bias_const; su.shadow_bias_slope = u.shadow_bias_slope;
         su.shadow_pcf_radius = u.shadow_pcf_radius; su.shadow_pcf_step = u.shadow_pcf_step; su.shadow_strength = u.shadow_strength;
+        su.enable_motion_vectors = u.enable_motion_vectors ? 1 : 0;    // rasterizer.hpp:295
+        detail::copy_mat(u.prev_model, su.prev_model);
+        detail::copy_mat(u.prev_viewproj, su.prev_viewproj);
         ShsbRasterCfg cfg{};
         cfg.cull_mode = (int32_t)config.cull_mode;
         cfg.front_face_ccw = config.front_face_ccw ? 1 : 0;
@@ -241,10 +282,11 @@ namespace shs::b200
             if (!hdr || hdr->w <= 0 || hdr->h <= 0) return;
             auto* motion = in.rt_motion.valid() ? static_cast<RT_ColorDepthMotion*>(in.rtr->get(in.rt_motion)) : nullptr;
             auto* shadow = in.rt_shadow.valid() ? static_cast<RT_ShadowDepth*>(in.rtr->get(in.rt_shadow)) : nullptr;
-            if (in.scene->sky) return; // sky models are a "next" row: not on the device yet, no fallback
             std::vector<ShsbRenderItem> items;
             const ShsbScene s = detail::scene(dev_, *in.scene, items);
+            if (s.sky_kind < 0) return; // an ISkyModel that was not introduced with Device::register_sky: no fallback
             const ShsbFrameParams fp = detail::frame_params(*in.fp);
+            if (!ctx.history.has_prev_frame) shsb_history_reset(dev_.ctx()); // Context::history owns the notion of "first frame"
             if (motion && in.preserve_existing_depth) dev_.upload(motion);
             const bool use_shadow = in.fp->pass.shadow.enable && shadow && ctx.shadow.valid;
             float lvp[16];

@@ -144,6 +144,10 @@ class Context:
                "shsb_pass_shadow_map")
         return lvp
 
+    def history_reset(self):
+        """Context::history.reset(): the next lit pass behaves like a first frame (zero object motion)."""
+        _check(self.lib, self.h, self.lib.shsb_history_reset(self.h), "shsb_history_reset")
+
     def pass_tonemap(self, hdr_rt, ldr_rt, exposure=1.0, gamma=2.2):
         _check(self.lib, self.h, self.lib.shsb_pass_tonemap(self.h, hdr_rt, ldr_rt, exposure, gamma), "shsb_pass_tonemap")
 

@@ -190,6 +190,8 @@ class SceneData:
     aspect: float | None = None
     shadow_size: int = 0
     viewproj: np.ndarray | None = None
+    prev_viewproj: np.ndarray | None = None   # Camera::prev_viewproj (defaults to viewproj)
+    sky: dict | None = None                    # {"kind": "procedural", "sun_dir": (x, y, z)} | {"kind": "cubemap", "faces": [6 texture handles], "intensity": f}
 
     def __post_init__(self):
         if self.viewproj is None:
@@ -210,6 +212,7 @@ class SceneData:
                 ri.base_color_tex = mat.get("tex", 0)
             ri.casts_shadow = 1 if it.get("casts_shadow", True) else 0
             ri.visible = 1 if it.get("visible", True) else 0
+            ri.object_id = int(it.get("object_id", 0))
         self.scene = Scene()
         capi.set_f(self.scene.cam_viewproj, self.viewproj)
         capi.set_f(self.scene.cam_pos, self.cam_pos)
@@ -218,6 +221,16 @@ class SceneData:
         self.scene.sun_intensity = self.sun_intensity
         self.scene.n_items = len(self.items)
         self.scene.items = C.cast(self._items_c, C.POINTER(RenderItem))
+        capi.set_f(self.scene.cam_prev_viewproj, self.prev_viewproj if self.prev_viewproj is not None else self.viewproj)
+        if self.sky:
+            if self.sky["kind"] == "procedural":
+                self.scene.sky_kind = capi.SKY_PROCEDURAL
+                capi.set_f(self.scene.sky_sun_dir_ws, self.sky.get("sun_dir", (0.4668, -0.3487, 0.8127)))
+            else:
+                self.scene.sky_kind = capi.SKY_CUBEMAP
+                self.scene.sky_intensity = float(self.sky.get("intensity", 1.0))
+                for k, t in enumerate(self.sky["faces"]):
+                    self.scene.sky_faces[k] = int(t)
 
     @property
     def n_triangles(self) -> int:
@@ -226,7 +239,26 @@ class SceneData:
     def with_camera(self, cam_pos, cam_target):
         return SceneData(self.name, self.w, self.h, self.zn, self.zf, self.meshes, self.textures, self.items, tuple(cam_pos),
                          tuple(cam_target), self.fovy, self.sun_dir, self.sun_color, self.sun_intensity, self.fp, self.lights,
-                         self.aspect, self.shadow_size)
+                         self.aspect, self.shadow_size, sky=self.sky)
+
+    def models(self, oracle) -> np.ndarray:
+        """(n_items, 16) model matrices in items order (for Context::history in the CPU checkers)."""
+        return np.stack([oracle.model_from_transform(it["pos"], it.get("rot", (0, 0, 0)), it.get("scl", (1, 1, 1))) for it in self.items])
+
+    def moved(self, dpos=(0.3, 0.0, -0.2), drot=(0.0, 0.15, 0.05), cam_pos=None, cam_target=None):
+        """The next frame of an animation: every k-th item translated / rotated a little, optionally a new camera whose
+        prev_viewproj is this frame's viewproj."""
+        items = []
+        for k, it in enumerate(self.items):
+            it2 = dict(it)
+            if k % 2 == 1:
+                it2["pos"] = tuple(float(a) + float(b) * (1 + 0.25 * k) for a, b in zip(it["pos"], dpos))
+                it2["rot"] = tuple(float(a) + float(b) for a, b in zip(it.get("rot", (0, 0, 0)), drot))
+            items.append(it2)
+        return SceneData(self.name + "_next", self.w, self.h, self.zn, self.zf, self.meshes, self.textures, items,
+                         tuple(cam_pos) if cam_pos is not None else self.cam_pos, tuple(cam_target) if cam_target is not None else self.cam_target,
+                         self.fovy, self.sun_dir, self.sun_color, self.sun_intensity, self.fp, self.lights, self.aspect, self.shadow_size,
+                         prev_viewproj=self.viewproj, sky=self.sky)
 
 
 _SUN_DIR = tuple(_norm((-0.35, -1.0, -0.25)))  # exp-plumbing/hello_pass_basics.cpp:669-671
@@ -312,18 +344,41 @@ def camera_ring(scene: SceneData, n_cameras: int, radius=28.0, height=12.0):
     return out
 
 
-def scene_small(w=160, h=120, shading=capi.SHADING_PBR, n_inst=3, lights=0, tex=False, seed=1, near_clip=False) -> SceneData:
+def make_sky_faces(size=16, seed=3) -> list:
+    """Six small RGBA faces with distinct hues and a gradient (a stand-in for the reference's 2048^2 skybox PNGs)."""
+    faces = []
+    y, x = np.mgrid[0:size, 0:size]
+    for f in range(6):
+        t = np.zeros((size, size, 4), np.uint8)
+        r = (pseudo_random01((y * size + x + seed * 977 + f * 131).astype(np.uint64)) * 40).astype(np.int32)
+        t[..., 0] = np.clip(40 + 35 * f + 4 * x + r, 0, 255)
+        t[..., 1] = np.clip(200 - 25 * f + 3 * y - r, 0, 255)
+        t[..., 2] = np.clip(90 + 20 * ((f * 3) % 6) + 2 * (x + y), 0, 255)
+        t[..., 3] = 255
+        faces.append(t)
+    return faces
+
+
+def scene_small(w=160, h=120, shading=capi.SHADING_PBR, n_inst=3, lights=0, tex=False, seed=1, near_clip=False, sky=None, motion=False) -> SceneData:
     """Small parity scene: a few Suzannes + floor; optional texture, lights and a camera that forces frustum clipping."""
     meshes = [load_suzanne(), make_grid_plane(24.0, 8)]
     textures = [make_checker_texture(32)] if tex else []
-    items = [{"pos": (0, -1.0, 0), "mesh": 2, "material": dict(_MATERIALS[1], tex=1 if tex else 0), "casts_shadow": False}]
+    sky_desc = None
+    if sky == "procedural":
+        sky_desc = {"kind": "procedural", "sun_dir": (0.2, -0.35, 0.9)}
+    elif sky == "cubemap":
+        first = len(textures) + 1
+        textures = textures + make_sky_faces()
+        sky_desc = {"kind": "cubemap", "faces": list(range(first, first + 6)), "intensity": 1.25}
+    items = [{"pos": (0, -1.0, 0), "mesh": 2, "material": dict(_MATERIALS[1], tex=1 if tex else 0), "casts_shadow": False, "object_id": 1000}]
     for k in range(n_inst):
         r = pseudo_random01(np.arange(4, dtype=np.uint64) + np.uint64(seed * 131 + k * 17))
         items.append({"pos": (float(r[0] * 8 - 4), float(r[1] * 1.5), float(r[2] * 8 - 4)), "rot": (0.1 * k, float(r[3] * 6.28), 0.05 * k),
                       "scl": (1.0 + 0.3 * k, 1.0 + 0.3 * k, 1.0 + 0.3 * k), "mesh": 1,
-                      "material": (dict(_MATERIALS[k % 4], tex=1) if (tex and k % 2 == 0) else (_MATERIALS[k % 4] if k % 3 else None))})
+                      "material": (dict(_MATERIALS[k % 4], tex=1) if (tex and k % 2 == 0) else (_MATERIALS[k % 4] if k % 3 else None)),
+                      "object_id": 1001 + k})
     lt = make_lights(max(1, lights * 3 // 4), lights - max(1, lights * 3 // 4), (-6, 0.2, -6), (6, 3.0, 6), seed=seed) if lights else None
-    fp = capi.default_frame_params(shading_model=shading, shadow_enable=0, light_culling=1 if lights else 0)
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=0, light_culling=1 if lights else 0, motion_vectors_enable=1 if motion else 0)
     cam = (0.5, 1.2, -2.2) if near_clip else (0, 4, -8)
     return SceneData(f"small_{w}x{h}", w, h, 0.1, 100.0, meshes, textures, items, cam, (0, 0.5, 0), math.radians(60.0),
-                     _SUN_DIR, _SUN_COLOR, 2.2, fp, lt, shadow_size=256)
+                     _SUN_DIR, _SUN_COLOR, 2.2, fp, lt, shadow_size=256, sky=sky_desc)

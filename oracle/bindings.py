@@ -39,7 +39,7 @@ class Target(C.Structure):
     _fields_ = [("hdr", C.POINTER(C.c_float)), ("depth", C.POINTER(C.c_float)), ("shadow", C.POINTER(C.c_float)),
                 ("tri_id", C.POINTER(C.c_uint32)), ("coverage", C.POINTER(C.c_uint32)),
                 ("w", C.c_int32), ("h", C.c_int32), ("shadow_w", C.c_int32), ("shadow_h", C.c_int32),
-                ("zn", C.c_float), ("zf", C.c_float)]
+                ("zn", C.c_float), ("zf", C.c_float), ("motion", C.POINTER(C.c_float))]
 
 
 def _records_u8(records) -> np.ndarray:
@@ -128,7 +128,7 @@ class Oracle:
 
     # ---- target plumbing
     @staticmethod
-    def make_target(w, h, hdr, depth=None, shadow=None, tri_id=None, coverage=None, zn=0.1, zf=1000.0):
+    def make_target(w, h, hdr, depth=None, shadow=None, tri_id=None, coverage=None, zn=0.1, zf=1000.0, motion=None):
         t = Target()
         t.hdr = capi.fptr(hdr)
         t.depth = capi.fptr(depth) if depth is not None else None
@@ -138,6 +138,7 @@ class Oracle:
         t.tri_id = capi.u32ptr(tri_id) if tri_id is not None else None
         t.coverage = capi.u32ptr(coverage) if coverage is not None else None
         t.w, t.h, t.zn, t.zf = w, h, zn, zf
+        t.motion = capi.fptr(motion) if motion is not None else None
         return t
 
     # ---- passes
@@ -150,11 +151,15 @@ class Oracle:
         assert rc == 0, rc
         return st
 
-    def pass_pbr_forward(self, assets: HostAssets, scene: Scene, fp: FrameParams, tgt: Target, shadow_lvp=None, preserve_depth=False):
+    def pass_pbr_forward(self, assets: HostAssets, scene: Scene, fp: FrameParams, tgt: Target, shadow_lvp=None, preserve_depth=False,
+                         prev_models=None):
+        """prev_models: (n_items, 16) model matrices of the previous frame (Context::history), None = first frame."""
         st = Stats()
         lvp = np.ascontiguousarray(shadow_lvp, dtype=np.float32) if shadow_lvp is not None else None
-        rc = self.fn("pass_pbr_forward")(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt),
-                                         capi.fptr(lvp) if lvp is not None else None, C.c_int32(int(preserve_depth)), C.byref(st))
+        pm = np.ascontiguousarray(prev_models, dtype=np.float32) if prev_models is not None else None
+        rc = self.fn("pass_pbr_forward_history")(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt),
+                                                 capi.fptr(lvp) if lvp is not None else None, C.c_int32(int(preserve_depth)),
+                                                 capi.fptr(pm) if pm is not None else None, C.byref(st))
         assert rc == 0, rc
         return st
 

@@ -120,6 +120,24 @@ namespace
 #undef M
     }
 
+    // glm::determinant(mat4): Laplace expansion along column 0 of the cofactors of rows 2,3 (func_matrix.inl compute_determinant<4,4>)
+    float mat4_determinant(const float* m)
+    {
+#define M(c, r) m[(c) * 4 + (r)]
+        const float s00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+        const float s01 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+        const float s02 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+        const float s03 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+        const float s04 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+        const float s05 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+        const float d0 = +(M(1, 1) * s00 - M(1, 2) * s01 + M(1, 3) * s02);
+        const float d1 = -(M(1, 0) * s00 - M(1, 2) * s03 + M(1, 3) * s04);
+        const float d2 = +(M(1, 0) * s01 - M(1, 1) * s03 + M(1, 3) * s05);
+        const float d3 = -(M(1, 0) * s02 - M(1, 1) * s04 + M(1, 2) * s05);
+        return M(0, 0) * d0 + M(0, 1) * d1 + M(0, 2) * d2 + M(0, 3) * d3;
+#undef M
+    }
+
     // normal matrix of make_default_vertex_out, shader/builtin_shaders.hpp:92-95:
     // mat3(model); if |det| > 1e-8 -> transpose(inverse(.)).  Returns column-major 3x3.
     void normal_matrix(const float* model, float* n9)
@@ -172,7 +190,26 @@ namespace
         float viewproj[16];
         float nrm[9];
         bool has_varyings; // false for the depth-prepass program (pass_adapters.hpp:335-353)
+        // motion vectors (rasterizer.hpp:295-307): curr_to_prev_model = prev_model * inverse(model) when |det(model)| > 1e-10
+        bool write_motion = false;
+        float curr_to_prev_model[16];
+        float prev_viewproj[16];
     };
+
+    inline void set_motion(DrawConst& dc, bool enable, const float* prev_model, const float* prev_viewproj)
+    {
+        dc.write_motion = enable;
+        if (!enable) return;
+        const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        if (std::fabs(mat4_determinant(dc.model)) > 1e-10f)
+        {
+            float inv[16];
+            mat4_inverse(dc.model, inv);
+            mat4_mul_mat4(prev_model, inv, dc.curr_to_prev_model);
+        }
+        else std::memcpy(dc.curr_to_prev_model, ident, 64);
+        std::memcpy(dc.prev_viewproj, prev_viewproj, 64);
+    }
 
     inline Corner run_vs(const DrawConst& dc, const ShsoMesh& mesh, uint32_t idx)
     {
@@ -329,6 +366,77 @@ namespace
         const V3 c01 = srgb_to_linear(at(x0, y1));
         const V3 c11 = srgb_to_linear(at(x1, y1));
         return mix3(mix3(c00, c10, tx), mix3(c01, c11, tx), ty);
+    }
+
+    // ---------------------------------------------------------------- sky models (Scene::sky)
+    // ProceduralSky::sample, sky/procedural_sky.hpp:25-45.  sun = normalize(ctor argument).
+    V3 sky_procedural(V3 dir, V3 sun)
+    {
+        const V3 d = normalize3(dir);
+        const float t = clampf(d.y * 0.5f + 0.5f, 0.0f, 1.0f);
+        const V3 zenith{0.05f, 0.20f, 0.50f}, horizon{0.30f, 0.60f, 1.00f};
+        V3 sky = mix3(horizon, zenith, t);
+        const float sun_dot = dot3(d, V3{-sun.x, -sun.y, -sun.z});
+        if (sun_dot > 0.9998f) sky = V3{15.0f, 15.0f, 15.0f};
+        else if (sun_dot > 0.9990f)
+        {
+            const float glow = (sun_dot - 0.9990f) / (0.9998f - 0.9990f);
+            sky = mix3(sky, V3{10.0f, 8.0f, 4.0f}, glow);
+        }
+        return sky;
+    }
+
+    // sample_face_bilinear_linear, sky/cubemap_sky.hpp:39-60 (clamped, not repeated; same per-tap pow as the material sampler)
+    V3 sample_face_clamped(const ShsoTexture* tex, float u, float v)
+    {
+        if (!tex || tex->w <= 0 || tex->h <= 0 || !tex->rgba) return V3{0.0f, 0.0f, 0.0f};
+        u = clampf(u, 0.0f, 1.0f);
+        v = clampf(v, 0.0f, 1.0f);
+        const float fx = u * (float)(tex->w - 1);
+        const float fy = v * (float)(tex->h - 1);
+        const int x0 = (int)std::floor(fx);
+        const int y0 = (int)std::floor(fy);
+        const int x1 = std::min(x0 + 1, tex->w - 1);
+        const int y1 = std::min(y0 + 1, tex->h - 1);
+        const float tx = fx - (float)x0;
+        const float ty = fy - (float)y0;
+        auto at = [&](int x, int y) { return tex->rgba + ((size_t)y * (size_t)tex->w + (size_t)x) * 4; };
+        const V3 v00 = srgb_to_linear(at(x0, y0));
+        const V3 v10 = srgb_to_linear(at(x1, y0));
+        const V3 v01 = srgb_to_linear(at(x0, y1));
+        const V3 v11 = srgb_to_linear(at(x1, y1));
+        return mix3(mix3(v00, v10, tx), mix3(v01, v11, tx), ty);
+    }
+
+    // CubemapSky::sample, sky/cubemap_sky.hpp:69-109.  faces: +X -X +Y -Y +Z -Z; nullptr face => CubemapData::valid() false.
+    V3 sky_cubemap(V3 dir, const ShsoTexture* const faces[6], float intensity)
+    {
+        for (int i = 0; i < 6; ++i) if (!faces[i] || faces[i]->w <= 0 || faces[i]->h <= 0 || !faces[i]->rgba) return V3{0.0f, 0.0f, 0.0f};
+        V3 d = dir;
+        const float len = std::sqrt(dot3(d, d));
+        if (len < 1e-8f) return V3{0.0f, 0.0f, 0.0f};
+        d.x /= len; d.y /= len; d.z /= len;
+        const float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+        int face = 0;
+        float u = 0.5f, v = 0.5f;
+        if (ax >= ay && ax >= az)
+        {
+            if (d.x > 0.0f) { face = 0; u = (-d.z / ax); v = (d.y / ax); }
+            else { face = 1; u = (d.z / ax); v = (d.y / ax); }
+        }
+        else if (ay >= ax && ay >= az)
+        {
+            if (d.y > 0.0f) { face = 2; u = (d.x / ay); v = (-d.z / ay); }
+            else { face = 3; u = (d.x / ay); v = (d.z / ay); }
+        }
+        else
+        {
+            if (d.z > 0.0f) { face = 4; u = (d.x / az); v = (d.y / az); }
+            else { face = 5; u = (-d.x / az); v = (d.y / az); }
+        }
+        u = 0.5f * (u + 1.0f);
+        v = 0.5f * (v + 1.0f);
+        return scale(sample_face_clamped(faces[face], u, v), intensity);
     }
 
     V3 fake_ibl(V3 N, V3 V, V3 base_color, float metallic, float roughness, float ao)
@@ -804,6 +912,25 @@ namespace
                         {
                             f.world_pos = V3{0, 0, 0}; f.normal_ws = V3{0, 1, 0}; f.u = f.v = 0.0f;
                         }
+                        if (dc.write_motion && tgt.motion && tgt.depth)
+                        {
+                            // rasterizer.hpp:388-411
+                            const V4 pw = mat4_mul(dc.curr_to_prev_model, f.world_pos.x, f.world_pos.y, f.world_pos.z, 1.0f);
+                            const V4 cc = mat4_mul(dc.viewproj, f.world_pos.x, f.world_pos.y, f.world_pos.z, 1.0f);
+                            const V4 pc = mat4_mul(dc.prev_viewproj, pw.x, pw.y, pw.z, pw.w);
+                            float mx = 0.0f, my = 0.0f;
+                            if (std::fabs(cc.w) > 1e-8f && std::fabs(pc.w) > 1e-8f)
+                            {
+                                const float cnx = cc.x / cc.w, cny = cc.y / cc.w, pnx = pc.x / pc.w, pny = pc.y / pc.w;
+                                mx = ((cnx - pnx) * 0.5f) * (float)W;
+                                my = ((cny - pny) * 0.5f) * (float)H;
+                                const float len = std::sqrt(mx * mx + my * my);
+                                const float max_vel = 96.0f;
+                                if (len > max_vel && len > 1e-6f) { const float k = max_vel / len; mx *= k; my *= k; }
+                            }
+                            tgt.motion[pix * 2 + 0] = mx;
+                            tgt.motion[pix * 2 + 1] = my;
+                        }
                         run_fs(env, f, tgt.hdr + pix * 4);
                     }
                 }
@@ -896,7 +1023,7 @@ namespace
     int32_t forward_impl(const ShsoAssets* assets, const ShsbScene* s, const ShsbFrameParams* fp, const ShsoTarget* tgt,
                          const float* shadow_lvp, int32_t preserve_depth, bool depth_only,
                          const void* lights, uint32_t n_lights, const uint32_t* counts, const uint32_t* indices,
-                         ShsbStats* out_stats)
+                         ShsbStats* out_stats, const float* prev_models16 = nullptr)
     {
         if (!s || !fp || !tgt) return SHSB_E_INVALID_ARGUMENT;
         const int W = tgt->w, H = tgt->h;
@@ -915,6 +1042,36 @@ namespace
         else
         {
             if (!T.hdr) return SHSB_E_INVALID_ARGUMENT;
+            if (s->sky_kind == SHSB_SKY_PROCEDURAL || s->sky_kind == SHSB_SKY_CUBEMAP)
+            {
+                // render_skybox_to_hdr, sky/skybox_renderer.hpp:25-57
+                float inv_vp[16];
+                mat4_inverse(s->cam_viewproj, inv_vp);
+                const V3 cam = load3(s->cam_pos);
+                const ShsoTexture* faces[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                for (int i = 0; i < 6; ++i)
+                    if (assets && s->sky_faces[i] >= 1 && s->sky_faces[i] <= assets->n_textures) faces[i] = &assets->textures[s->sky_faces[i] - 1];
+                const V3 sun = normalize3(load3(s->sky_sun_dir_ws));
+                for (int y = 0; y < H; ++y)
+                {
+                    const float ndc_y = (2.0f * ((float)y + 0.5f) / (float)H) - 1.0f;
+                    float* row = T.hdr + (size_t)y * W * 4;
+                    for (int x = 0; x < W; ++x)
+                    {
+                        const float ndc_x = (2.0f * ((float)x + 0.5f) / (float)W) - 1.0f;
+                        V4 world = mat4_mul(inv_vp, ndc_x, ndc_y, 1.0f, 1.0f);
+                        V3 c{0.0f, 0.0f, 0.0f};
+                        if (!(std::fabs(world.w) < 1e-8f))
+                        {
+                            world.x /= world.w; world.y /= world.w; world.z /= world.w;
+                            const V3 dir = normalize3(V3{world.x - cam.x, world.y - cam.y, world.z - cam.z});
+                            c = (s->sky_kind == SHSB_SKY_PROCEDURAL) ? sky_procedural(dir, sun) : sky_cubemap(dir, faces, s->sky_intensity);
+                        }
+                        row[x * 4 + 0] = c.x; row[x * 4 + 1] = c.y; row[x * 4 + 2] = c.z; row[x * 4 + 3] = 1.0f;
+                    }
+                }
+            }
+            else
             // background gradient, pass_pbr_forward.hpp:69-85 (scene.sky == nullptr)
             for (int y = 0; y < H; ++y)
             {
@@ -925,6 +1082,7 @@ namespace
             }
             // depth clear policy, pass_pbr_forward.hpp:87-98
             if (T.depth && !preserve_depth) for (size_t i = 0; i < (size_t)W * H; ++i) T.depth[i] = 1.0f;
+            if (T.depth && T.motion) for (size_t i = 0; i < (size_t)W * H * 2; ++i) T.motion[i] = 0.0f; // both branches clear the motion plane
         }
         if (T.tri_id) for (size_t i = 0; i < (size_t)W * H; ++i) T.tri_id[i] = SHSB_TRI_ID_NONE;
         if (T.coverage) for (size_t i = 0; i < (size_t)W * H; ++i) T.coverage[i] = 0u;
@@ -949,6 +1107,10 @@ namespace
             std::memcpy(dc.viewproj, s->cam_viewproj, 64);
             normal_matrix(dc.model, dc.nrm);
             dc.has_varyings = !depth_only;
+            // history: prev_model = last frame's model of this object if there was a frame, else the current one; prev_viewproj
+            // likewise (pass_pbr_forward.hpp:149-161).  The depth pre-pass never writes motion (pass_adapters.hpp:521).
+            set_motion(dc, !depth_only && fp->motion_vectors_enable != 0 && T.depth && T.motion,
+                       prev_models16 ? prev_models16 + (size_t)ii * 16 : dc.model, prev_models16 ? s->cam_prev_viewproj : s->cam_viewproj);
 
             const ItemMaterial mat = resolve_material(it);
             ShsbUniforms u{};
@@ -1093,6 +1255,7 @@ int32_t shso_rasterize_mesh(const ShsoAssets* assets, shsb_mesh mesh_h, int32_t 
     std::memcpy(dc.viewproj, u->viewproj, 64);
     normal_matrix(dc.model, dc.nrm);
     dc.has_varyings = shader_id != SHSB_SHADER_DEPTH_ONLY;
+    set_motion(dc, u->enable_motion_vectors != 0 && tgt->depth && tgt->motion, u->prev_model, u->prev_viewproj); // rasterizer.hpp:295
     FsEnv env;
     fill_env_from_uniforms(env, shader_id, u, assets, tgt);
     ShsbStats st{};
@@ -1112,6 +1275,13 @@ int32_t shso_pass_pbr_forward(const ShsoAssets* assets, const ShsbScene* scene, 
                               int32_t preserve_existing_depth, ShsbStats* out_stats)
 {
     return forward_impl(assets, scene, fp, tgt, shadow_light_viewproj, preserve_existing_depth, false, nullptr, 0, nullptr, nullptr, out_stats);
+}
+
+int32_t shso_pass_pbr_forward_history(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                      const ShsoTarget* tgt, const float* shadow_light_viewproj, int32_t preserve_existing_depth,
+                                      const float* prev_models16, ShsbStats* out_stats)
+{
+    return forward_impl(assets, scene, fp, tgt, shadow_light_viewproj, preserve_existing_depth, false, nullptr, 0, nullptr, nullptr, out_stats, prev_models16);
 }
 
 int32_t shso_pass_pbr_forward_plus(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,

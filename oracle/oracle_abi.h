@@ -54,6 +54,7 @@ typedef struct ShsoTarget /* RasterizerTarget + the RTs behind it, all host memo
     int32_t w, h;
     int32_t shadow_w, shadow_h;
     float zn, zf;
+    float* motion;       /* optional W*H*2: RT_ColorDepthMotion::motion (needs depth)           */
 } ShsoTarget;
 
 #define SHSO_FN(ret, name, args) ret shso_##name args; ret shsref_##name args
@@ -83,6 +84,13 @@ SHSO_FN(int32_t, rasterize_mesh, (const ShsoAssets* assets, shsb_mesh mesh, int3
 SHSO_FN(int32_t, pass_pbr_forward, (const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
                                     const ShsoTarget* tgt, const float* shadow_light_viewproj,
                                     int32_t preserve_existing_depth, ShsbStats* out_stats));
+
+/* The same pass with Context::history populated (core/context.hpp:84-94): prev_models16 = n_items model matrices of
+ * the previous frame in scene->items order (has_prev_frame = true), or NULL for a first frame.  Writes tgt->motion when
+ * fp->motion_vectors_enable and the target has depth + motion planes (rasterizer.hpp:295-307, 388-411). */
+SHSO_FN(int32_t, pass_pbr_forward_history, (const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
+                                            const ShsoTarget* tgt, const float* shadow_light_viewproj,
+                                            int32_t preserve_existing_depth, const float* prev_models16, ShsbStats* out_stats));
 
 /* PassShadowMap::execute, passes/pass_shadow_map.hpp:44 */
 SHSO_FN(int32_t, pass_shadow_map, (const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,

@@ -24,6 +24,8 @@
 #include "shs/passes/pass_shadow_map.hpp"
 #include "shs/passes/pass_tonemap.hpp"
 #include "shs/shader/builtin_shaders.hpp"
+#include "shs/sky/cubemap_sky.hpp"
+#include "shs/sky/procedural_sky.hpp"
 #include "shs/sw_render/rasterizer.hpp"
 
 #include "oracle_abi.h"
@@ -123,14 +125,32 @@ namespace
         out.pass.shadow.strength = fp->shadow_strength;
         out.pass.tonemap.exposure = fp->exposure;
         out.pass.tonemap.gamma = fp->gamma;
-        out.pass.motion_vectors.enable = false;
+        out.pass.motion_vectors.enable = fp->motion_vectors_enable != 0;
+    }
+
+    // Scene::sky from the POD scene: the reference's own ProceduralSky / CubemapSky objects (kept alive in `holder`)
+    void fill_sky(const ShsbScene* s, shs::Scene& scene, const shs::ResourceRegistry& reg, std::unique_ptr<shs::ISkyModel>& holder)
+    {
+        holder.reset();
+        if (s->sky_kind == SHSB_SKY_PROCEDURAL) holder = std::make_unique<shs::ProceduralSky>(load_vec3(s->sky_sun_dir_ws));
+        else if (s->sky_kind == SHSB_SKY_CUBEMAP)
+        {
+            shs::CubemapData cm{};
+            for (int i = 0; i < 6; ++i)
+            {
+                const shs::Texture2DData* t = reg.get_texture((shs::TextureAssetHandle)s->sky_faces[i]);
+                if (t) cm.face[(size_t)i] = *t;
+            }
+            holder = std::make_unique<shs::CubemapSky>(std::move(cm), s->sky_intensity);
+        }
+        scene.sky = holder.get();
     }
 
     void fill_scene(const ShsbScene* s, shs::Scene& scene, shs::ResourceRegistry& reg)
     {
         scene.resources = &reg;
         scene.cam.viewproj = load_mat4(s->cam_viewproj);
-        scene.cam.prev_viewproj = scene.cam.viewproj;
+        scene.cam.prev_viewproj = load_mat4(s->cam_prev_viewproj);
         scene.cam.pos = load_vec3(s->cam_pos);
         scene.sun.dir_ws = load_vec3(s->sun_dir_ws);
         scene.sun.color = load_vec3(s->sun_color);
@@ -159,6 +179,7 @@ namespace
             }
             ri.casts_shadow = it.casts_shadow != 0;
             ri.visible = it.visible != 0;
+            ri.object_id = it.object_id;
             scene.items.push_back(ri);
         }
     }
@@ -290,7 +311,9 @@ int32_t shsref_rasterize_mesh(const ShsoAssets* assets, shsb_mesh mesh, int32_t 
     su.shadow_pcf_radius = u->shadow_pcf_radius;
     su.shadow_pcf_step = u->shadow_pcf_step;
     su.shadow_strength = u->shadow_strength;
-    su.enable_motion_vectors = false;
+    su.enable_motion_vectors = u->enable_motion_vectors != 0;
+    su.prev_model = load_mat4(u->prev_model);
+    su.prev_viewproj = load_mat4(u->prev_viewproj);
 
     shs::ShaderProgram prog = program_for(shader_id);
     if (!prog.valid()) return SHSB_E_UNSUPPORTED_SHADER;
@@ -343,6 +366,7 @@ int32_t shsref_rasterize_mesh(const ShsoAssets* assets, shsb_mesh mesh, int32_t 
 
     std::memcpy(tgt->hdr, hdr.color.data.data(), (size_t)W * H * 16);
     if (dm) std::memcpy(tgt->depth, dm->depth.data.data(), (size_t)W * H * 4);
+    if (dm && tgt->motion) std::memcpy(tgt->motion, dm->motion.data.data(), (size_t)W * H * 8);
     if (out_stats)
     {
         out_stats->tri_input += st.tri_input;
@@ -355,6 +379,13 @@ int32_t shsref_rasterize_mesh(const ShsoAssets* assets, shsb_mesh mesh, int32_t 
 int32_t shsref_pass_pbr_forward(const ShsoAssets* assets, const ShsbScene* s, const ShsbFrameParams* fp,
                                 const ShsoTarget* tgt, const float* shadow_light_viewproj,
                                 int32_t preserve_existing_depth, ShsbStats* out_stats)
+{
+    return shsref_pass_pbr_forward_history(assets, s, fp, tgt, shadow_light_viewproj, preserve_existing_depth, nullptr, out_stats);
+}
+
+int32_t shsref_pass_pbr_forward_history(const ShsoAssets* assets, const ShsbScene* s, const ShsbFrameParams* fp,
+                                        const ShsoTarget* tgt, const float* shadow_light_viewproj,
+                                        int32_t preserve_existing_depth, const float* prev_models16, ShsbStats* out_stats)
 {
     if (!s || !fp || !tgt || !tgt->hdr) return SHSB_E_INVALID_ARGUMENT;
     Assets base(nullptr);
@@ -393,10 +424,28 @@ int32_t shsref_pass_pbr_forward(const ShsoAssets* assets, const ShsbScene* s, co
 
     shs::Scene scene{};
     fill_scene(s, scene, reg);
+    std::unique_ptr<shs::ISkyModel> sky_holder;
+    fill_sky(s, scene, reg, sky_holder);
     shs::FrameParams f{};
     f.w = W;
     f.h = H;
     fill_frame_params(fp, f);
+    if (prev_models16)
+    {
+        // Context::history as the previous PassPBRForward::execute left it (pass_pbr_forward.hpp:143-155, 212-213)
+        for (size_t i = 0; i < scene.items.size(); ++i)
+        {
+            const auto& item = scene.items[i];
+            uint64_t key = item.object_id;
+            if (key == 0)
+            {
+                key = ((uint64_t)item.mesh << 32) ^ (uint64_t)item.mat ^ ((uint64_t)i + 1u);
+                if (key == 0) key = 1;
+            }
+            ctx.history.prev_model_by_object[key] = load_mat4(prev_models16 + i * 16);
+        }
+        ctx.history.has_prev_frame = true;
+    }
 
     shs::PassPBRForward pass{};
     shs::PassPBRForward::Inputs in{};
@@ -411,6 +460,7 @@ int32_t shsref_pass_pbr_forward(const ShsoAssets* assets, const ShsbScene* s, co
 
     std::memcpy(tgt->hdr, hdr.color.data.data(), (size_t)W * H * 16);
     if (tgt->depth) std::memcpy(tgt->depth, dm.depth.data.data(), (size_t)W * H * 4);
+    if (tgt->depth && tgt->motion) std::memcpy(tgt->motion, dm.motion.data.data(), (size_t)W * H * 8);
     if (out_stats)
     {
         out_stats->tri_input = ctx.debug.tri_input;

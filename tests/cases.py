@@ -39,6 +39,9 @@ def forward_cases():
         "cull_none": (cull(capi.CULL_NONE), {}),
         "cull_front": (cull(capi.CULL_FRONT), {}),
         "front_face_cw": (cull(capi.CULL_BACK, 0), {}),
+        "sky_procedural": (lambda: scenes.scene_small(w=192, h=108, sky="procedural"), {}),
+        "sky_cubemap_tex": (lambda: scenes.scene_small(w=176, h=100, sky="cubemap", tex=True), {}),
+        "sky_cubemap_nearclip_blinn": (lambda: scenes.scene_small(w=150, h=90, sky="cubemap", near_clip=True, shading=capi.SHADING_BLINN), {}),
         "empty_scene": (lambda: scenes.scene_small(n_inst=0, w=64, h=48), {}),
         "tiny_target_1x1": (lambda: scenes.scene_small(w=1, h=1), {}),
     }
@@ -57,3 +60,26 @@ def _saturated():
     sd = scenes.scene_small(w=160, h=120, lights=96, seed=9)
     sd.fp.max_lights_per_tile = 8  # forces count >= max -> "walk all lights" fallback (fp_stress_scene.frag:662-668)
     return sd
+
+
+def motion_cases():
+    """name -> (factory of (previous frame, current frame), kwargs).  The current frame's Camera::prev_viewproj is the previous
+    frame's viewproj; Context::history holds the previous frame's model matrices (keyed by RenderItem::object_id)."""
+    def moving_objects():
+        a = scenes.scene_small(w=192, h=120, motion=True, n_inst=4, seed=2)
+        return a, a.moved()
+
+    def moving_camera_and_objects():
+        a = scenes.scene_small(w=200, h=113, motion=True, tex=True, near_clip=True)
+        return a, a.moved(dpos=(0.05, 0.0, 0.1), cam_pos=(0.65, 1.25, -2.3), cam_target=(0.0, 0.55, 0.1))
+
+    def fast_motion_clamped():
+        a = scenes.scene_small(w=160, h=100, motion=True, n_inst=3, seed=4)
+        return a, a.moved(dpos=(6.0, 0.5, -3.0), drot=(0.3, 1.2, 0.0), cam_pos=(3.0, 4.0, -8.0))   # > 96 px: velocity clamp
+
+    def first_frame():
+        a = scenes.scene_small(w=128, h=80, motion=True)
+        return None, a                                                                                # no history: zero object motion
+
+    return {"moving_objects": (moving_objects, {}), "moving_camera_and_objects": (moving_camera_and_objects, {}),
+            "fast_motion_clamped": (fast_motion_clamped, {}), "first_frame": (first_frame, {})}

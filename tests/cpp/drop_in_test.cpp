@@ -72,6 +72,7 @@ int main()
         it.tr.scl = glm::vec3(0.6f + 0.1f * i);
         it.mesh = blob;
         it.mat = (i % 3 == 0) ? 0 : ((i % 2) ? gold : textured);
+        it.object_id = 100u + (uint64_t)i; // explicit motion keys (the derived key mixes in the material handle, pass_pbr_forward.hpp:143-148)
         scene.items.push_back(it);
     }
     shs::FrameParams fp{};
@@ -128,6 +129,43 @@ int main()
     if (ctx_ref.debug.tri_input != ctx_gpu.debug.tri_input || ctx_ref.debug.tri_after_clip != ctx_gpu.debug.tri_after_clip || ctx_ref.debug.tri_raster != ctx_gpu.debug.tri_raster) ++bad;
     if (std::memcmp(&ctx_ref.shadow.light_viewproj, &ctx_gpu.shadow.light_viewproj, 64) != 0) ++bad;
     if (max_depth_ulp > 1 || max_shadow_ulp > 1 || max_lsb > 1 || psnr < 60.0) ++bad;
+
+    // ---- second frame: objects and camera moved, ProceduralSky background, motion vectors against the first frame
+    // (FrameParams::pass.motion_vectors.enable defaults to true; Context::history carries the previous model matrices)
+    shs::ProceduralSky sky(glm::vec3(0.2f, -0.35f, 0.9f));
+    dev.register_sky(&sky, glm::vec3(0.2f, -0.35f, 0.9f));
+    scene.sky = &sky;
+    scene.cam.prev_viewproj = scene.cam.viewproj;
+    scene.cam.pos = glm::vec3(0.25f, 2.1f, -6.1f);
+    scene.cam.view = shs::look_at_lh(scene.cam.pos, glm::vec3(0.0f, 0.3f, 0.0f), glm::vec3(0, 1, 0));
+    scene.cam.viewproj = scene.cam.proj * scene.cam.view;
+    for (size_t i = 0; i < scene.items.size(); ++i)
+    {
+        scene.items[i].tr.pos += glm::vec3(0.15f * (float)i, 0.05f, -0.1f * (float)i);
+        scene.items[i].tr.rot_euler.y += 0.2f;
+    }
+    run(false, hdr_ref, dm_ref, sm_ref, ldr_ref, ctx_ref);
+    run(true, hdr_gpu, dm_gpu, sm_gpu, ldr_gpu, ctx_gpu);
+    size_t motion_diff = 0, motion_nonzero = 0;
+    for (size_t i = 0; i < dm_ref.motion.data.size(); ++i)
+    {
+        if (std::memcmp(&dm_ref.motion.data[i], &dm_gpu.motion.data[i], sizeof(shs::Motion2f)) != 0) ++motion_diff;
+        if (dm_ref.motion.data[i].x != 0.0f || dm_ref.motion.data[i].y != 0.0f) ++motion_nonzero;
+    }
+    double se2 = 0.0, peak2 = 1.0;
+    int max_depth_ulp2 = 0;
+    for (size_t i = 0; i < hdr_ref.color.data.size(); ++i)
+    {
+        const shs::ColorF a = hdr_ref.color.data[i], b = hdr_gpu.color.data[i];
+        se2 += (a.r - b.r) * (double)(a.r - b.r) + (a.g - b.g) * (double)(a.g - b.g) + (a.b - b.b) * (double)(a.b - b.b);
+        peak2 = std::max(peak2, (double)std::max(a.r, std::max(a.g, a.b)));
+        max_depth_ulp2 = std::max(max_depth_ulp2, ulp(dm_ref.depth.data[i], dm_gpu.depth.data[i]));
+    }
+    const double mse2 = se2 / (3.0 * hdr_ref.color.data.size());
+    const double psnr2 = mse2 == 0.0 ? 999.0 : 10.0 * std::log10(peak2 * peak2 / mse2);
+    if (motion_diff != 0 || motion_nonzero == 0 || psnr2 < 60.0 || max_depth_ulp2 > 1) ++bad;
+    std::printf("frame 2 (sky + motion): motion vectors differing %zu of %zu (non-zero %zu)  depth<=%d ULP  HDR PSNR %.1f dB\n",
+                motion_diff, dm_ref.motion.data.size(), motion_nonzero, max_depth_ulp2, psnr2);
 
     // ---- rasterize_mesh called directly, like exp-plumbing/hello_software_triangle.cpp:187
     shs::RT_ColorHDR h2_ref(W, H), h2_gpu(W, H);

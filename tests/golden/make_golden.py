@@ -22,7 +22,19 @@ GOLDEN = {
     "golden_painter_96x72": (lambda: scenes.scene_small(w=96, h=72, seed=4), {"depth": False}),
     "golden_shadow_pcf_96x72": (lambda: _shadow(), {"shadow": True}),
     "golden_c1_160x120": (lambda: scenes.scene_c1(160, 120), {}),
+    "golden_sky_cubemap_96x72": (lambda: scenes.scene_small(w=96, h=72, sky="cubemap", tex=True), {}),
+    "golden_sky_procedural_96x72": (lambda: scenes.scene_small(w=96, h=72, sky="procedural", seed=6), {}),
 }
+
+# motion-vector fixtures: (previous frame, current frame) -> reference output of the current frame with the previous one as history
+GOLDEN_MOTION = {
+    "golden_motion_96x72": lambda: _motion(),
+}
+
+
+def _motion():
+    a = scenes.scene_small(w=96, h=72, motion=True, tex=True, n_inst=4, seed=2)
+    return a, a.moved(cam_pos=(0.2, 4.05, -7.9))
 
 
 def _shadow():
@@ -45,6 +57,11 @@ def main():
             out["shadow"], out["lvp"] = f.shadow, f.lvp
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})
+    for name, make in GOLDEN_MOTION.items():
+        prev, cur = make()
+        f = harness.cpu_forward(ref, cur, aov=False, motion=True, prev_models=prev.models(ref))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), hdr=f.hdr, ldr=f.ldr, depth=f.depth, motion=f.motion)
+        print(name, f.motion.shape, float(np.abs(f.motion).max()))
     sd = scenes.scene_small(w=320, h=200, lights=64)
     counts, indices = port.light_cull(sd.lights, sd.viewproj, sd.w, sd.h, 16, 128)
     np.savez_compressed(os.path.join(HERE, "golden_light_lists_320x200_port.npz"), counts=counts, indices=indices)

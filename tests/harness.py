@@ -21,13 +21,15 @@ def psnr(a: np.ndarray, b: np.ndarray) -> float:
 
 
 class CpuFrame:
-    def __init__(self, hdr, depth, tri_id, coverage, stats, ldr=None, shadow=None, lvp=None, counts=None, indices=None):
+    def __init__(self, hdr, depth, tri_id, coverage, stats, ldr=None, shadow=None, lvp=None, counts=None, indices=None, motion=None):
         self.hdr, self.depth, self.tri_id, self.coverage, self.stats = hdr, depth, tri_id, coverage, stats
-        self.ldr, self.shadow, self.lvp, self.counts, self.indices = ldr, shadow, lvp, counts, indices
+        self.ldr, self.shadow, self.lvp, self.counts, self.indices, self.motion = ldr, shadow, lvp, counts, indices, motion
 
 
-def cpu_forward(o, sd, depth=True, aov=True, shadow=False, forward_plus=False, preserve_depth=False, init_depth=None, tonemap=True):
-    """PassShadowMap (optional) -> light cull (optional) -> PassPBRForward -> PassTonemap on a CPU checker."""
+def cpu_forward(o, sd, depth=True, aov=True, shadow=False, forward_plus=False, preserve_depth=False, init_depth=None, tonemap=True,
+                prev_models=None, motion=False):
+    """PassShadowMap (optional) -> light cull (optional) -> PassPBRForward -> PassTonemap on a CPU checker.
+    motion: also return the motion plane; prev_models: Context::history of the previous frame (None = first frame)."""
     A = HostAssets(sd.meshes, sd.textures)
     hdr = np.zeros((sd.h, sd.w, 4), np.float32)
     dep = (np.ones((sd.h, sd.w), np.float32) if init_depth is None else init_depth.copy()) if depth else None
@@ -36,15 +38,16 @@ def cpu_forward(o, sd, depth=True, aov=True, shadow=False, forward_plus=False, p
     sh = lvp = None
     if shadow:
         sh, lvp = o.pass_shadow_map(A, sd.scene, sd.fp, sd.shadow_size, sd.shadow_size)
-    tgt = o.make_target(sd.w, sd.h, hdr, dep, shadow=sh, tri_id=tri, coverage=cov, zn=sd.zn, zf=sd.zf)
+    mot = np.full((sd.h, sd.w, 2), 7.0, np.float32) if (motion and depth) else None   # the pass must clear it
+    tgt = o.make_target(sd.w, sd.h, hdr, dep, shadow=sh, tri_id=tri, coverage=cov, zn=sd.zn, zf=sd.zf, motion=mot)
     counts = indices = None
     if forward_plus:
         counts, indices = o.light_cull(sd.lights, sd.viewproj, sd.w, sd.h, sd.fp.tile_size, sd.fp.max_lights_per_tile)
         st = o.pass_pbr_forward_plus(A, sd.scene, sd.fp, tgt, sd.lights, counts, indices, shadow_lvp=lvp, preserve_depth=preserve_depth)
     else:
-        st = o.pass_pbr_forward(A, sd.scene, sd.fp, tgt, shadow_lvp=lvp, preserve_depth=preserve_depth)
+        st = o.pass_pbr_forward(A, sd.scene, sd.fp, tgt, shadow_lvp=lvp, preserve_depth=preserve_depth, prev_models=prev_models)
     ldr = o.pass_tonemap(hdr, sd.fp.exposure, sd.fp.gamma) if tonemap else None
-    return CpuFrame(hdr, dep, tri, cov, st.as_dict(), ldr, sh, lvp, counts, indices)
+    return CpuFrame(hdr, dep, tri, cov, st.as_dict(), ldr, sh, lvp, counts, indices, mot)
 
 
 class GpuScene:
@@ -59,12 +62,8 @@ class GpuScene:
         self.mesh_offset = handles[0] - 1 if handles else 0
         self.tex_offset = tex[0] - 1 if tex else 0
         # remap item handles if this context already held other assets
-        if self.mesh_offset or self.tex_offset:
-            for i in range(sd.scene.n_items):
-                it = sd.scene.items[i]
-                it.mesh += self.mesh_offset
-                if it.base_color_tex:
-                    it.base_color_tex += self.tex_offset
+        self._remapped = []
+        self.remap(sd)
         self.hdr = ctx.rt_create(capi.RT_COLOR_HDR, sd.w, sd.h)
         self.dm = ctx.rt_create(capi.RT_DEPTH_MOTION, sd.w, sd.h, sd.zn, sd.zf)
         self.ldr = ctx.rt_create(capi.RT_COLOR_LDR, sd.w, sd.h)
@@ -72,22 +71,44 @@ class GpuScene:
         if sd.lights is not None:
             ctx.lights_upload(sd.lights.view(np.uint8))
 
-    def release(self):
-        # undo the handle remap so the SceneData can be reused
+    def remap(self, sd, sign=1):
+        """Shifts the asset handles of a SceneData that uses this scene's meshes / textures (undone by release())."""
         if self.mesh_offset or self.tex_offset:
-            for i in range(self.sd.scene.n_items):
-                it = self.sd.scene.items[i]
-                it.mesh -= self.mesh_offset
+            for i in range(sd.scene.n_items):
+                it = sd.scene.items[i]
+                it.mesh += sign * self.mesh_offset
                 if it.base_color_tex:
-                    it.base_color_tex -= self.tex_offset
+                    it.base_color_tex += sign * self.tex_offset
+            for k in range(6):
+                if sd.scene.sky_faces[k]:
+                    sd.scene.sky_faces[k] += sign * self.tex_offset
+        if sign > 0:
+            self._remapped.append(sd)
+
+    def release(self):
+        # undo the handle remaps so the SceneData objects can be reused
+        for sd in self._remapped:
+            self.remap(sd, -1)
+        self._remapped = []
         for rt in (self.hdr, self.dm, self.ldr, self.shadow):
             if rt:
                 self.ctx.rt_destroy(rt)
 
 
-def gpu_forward(ctx, sd, depth=True, aov=True, shadow=False, forward_plus=False, preserve_depth=False, init_depth=None, fused=False):
+def gpu_forward(ctx, sd, depth=True, aov=True, shadow=False, forward_plus=False, preserve_depth=False, init_depth=None, fused=False,
+                prev_scene=None, motion=False):
+    """prev_scene: a SceneData rendered first into the same targets (it becomes the context's history); without it the
+    history is reset so that the frame is a first frame."""
     g = GpuScene(ctx, sd)
     try:
+        ctx.history_reset()
+        if prev_scene is not None:
+            g.remap(prev_scene)
+            pfp = capi.FrameParams.from_buffer_copy(prev_scene.fp)
+            pfp.light_culling = 0
+            ctx.pass_pbr_forward(prev_scene.scene, pfp, g.hdr, g.dm if depth else 0)
+        if motion and depth:
+            ctx.rt_upload(g.dm, capi.PLANE_MOTION, np.full((sd.h, sd.w, 2), 7.0, np.float32))  # the pass must clear it
         fp = capi.FrameParams.from_buffer_copy(sd.fp)
         fp.write_aovs = 1 if aov else 0
         fp.light_culling = 1 if forward_plus else 0
@@ -114,7 +135,8 @@ def gpu_forward(ctx, sd, depth=True, aov=True, shadow=False, forward_plus=False,
         ldr = ctx.rt_download(g.ldr)
         tri = ctx.rt_download(g.hdr, capi.PLANE_TRI_ID) if aov else None
         cov = ctx.rt_download(g.hdr, capi.PLANE_COVERAGE) if aov else None
-        return CpuFrame(hdr, dep, tri, cov, st.as_dict(), ldr, sh_img, lvp, counts, indices)
+        mot = ctx.rt_download(g.dm, capi.PLANE_MOTION) if (motion and depth) else None
+        return CpuFrame(hdr, dep, tri, cov, st.as_dict(), ldr, sh_img, lvp, counts, indices, mot)
     finally:
         g.release()
 
@@ -137,6 +159,10 @@ def assert_frame_parity(gpu_f: CpuFrame, cpu_f: CpuFrame, depth=True, name=""):
         m = gpu_f.indices.shape[1]
         valid = np.arange(m)[None, :] < np.minimum(cpu_f.counts, m)[:, None]
         assert np.array_equal(gpu_f.indices[valid], cpu_f.indices[valid]), f"{name}: tile light lists differ"
+    if cpu_f.motion is not None and gpu_f.motion is not None:
+        # exact arithmetic end to end: the velocity of the winning fragment, (0, 0) elsewhere
+        assert np.array_equal(gpu_f.motion.view(np.uint32), cpu_f.motion.view(np.uint32)), \
+            f"{name}: motion vectors differ at {int(np.count_nonzero(gpu_f.motion != cpu_f.motion))} components"
     p = psnr(gpu_f.hdr[..., :3], cpu_f.hdr[..., :3])
     assert p >= 60.0, f"{name}: HDR PSNR {p:.1f} dB < 60 dB"
     d = np.abs(gpu_f.ldr.astype(np.int32) - cpu_f.ldr.astype(np.int32))

@@ -27,15 +27,30 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(bound._shsb_symbols), set(names) ^ set(bound._shsb_symbols)
 
 
-def test_struct_sizes_match_header():
-    # sizes implied by include/shsb.h on LP64
-    assert C.sizeof(capi.Stats) == 40
-    assert C.sizeof(capi.RasterCfg) == 16
-    assert C.sizeof(capi.Uniforms) == 3 * 64 + 4 * 16 + 8 * 4
-    assert C.sizeof(capi.Transform) == 36
-    assert C.sizeof(capi.RenderItem) == 36 + 8 + 12 + 12 + 12
-    assert C.sizeof(capi.Scene) == 64 + 16 + 16 + 16 + 8
-    assert C.sizeof(capi.FrameParams) == 64
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors in capi.py against the C compiler's own view of include/shsb.h: sizes and the offsets of the
+    last field and of the fields behind alignment holes."""
+    import subprocess
+    probes = {"ShsbStats": (capi.Stats, ["frag_shaded"]), "ShsbRasterCfg": (capi.RasterCfg, ["reserved"]),
+              "ShsbUniforms": (capi.Uniforms, ["base_color_tex", "enable_motion_vectors", "prev_model", "prev_viewproj"]),
+              "ShsbTransform": (capi.Transform, ["scl"]), "ShsbRenderItem": (capi.RenderItem, ["visible", "object_id"]),
+              "ShsbScene": (capi.Scene, ["items", "cam_prev_viewproj", "sky_kind", "sky_faces", "reserved2"]),
+              "ShsbFrameParams": (capi.FrameParams, ["write_aovs", "motion_vectors_enable", "reserved"])}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{os.path.join(ROOT, "include", "shsb.h")}"', "int main(void) {"]
+    for cname, (_, fields) in probes.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, (cls, fields) in probes.items():
+        assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
 
 
 def test_no_cpu_fallback_when_no_device():

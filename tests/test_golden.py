@@ -28,6 +28,15 @@ def test_port_matches_reference_golden(port, name):
     assert [f.stats[k] for k in ("tri_input", "tri_after_clip", "tri_raster")] == list(g["stats"])
 
 
+@pytest.mark.parametrize("name", list(make_golden.GOLDEN_MOTION))
+def test_port_matches_reference_motion_golden(port, name):
+    prev, cur = make_golden.GOLDEN_MOTION[name]()
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    f = harness.cpu_forward(port, cur, aov=False, motion=True, prev_models=prev.models(port))
+    assert np.array_equal(f.motion.view(np.uint32), g["motion"].view(np.uint32))
+    assert np.array_equal(f.hdr.view(np.uint32), g["hdr"].view(np.uint32)) and np.array_equal(f.depth.view(np.uint32), g["depth"].view(np.uint32))
+
+
 def test_light_lists_golden(port):
     from leisure_software_renderer_b200 import scenes
     sd = scenes.scene_small(w=320, h=200, lights=64)

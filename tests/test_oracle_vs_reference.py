@@ -31,6 +31,26 @@ def test_forward_pass_bit_exact(port, reference, name):
         assert a.stats[k] == b.stats[k], (name, k, a.stats[k], b.stats[k])
 
 
+@pytest.mark.parametrize("name", list(cases.motion_cases()))
+def test_motion_vectors_bit_exact(port, reference, name):
+    """RT_ColorDepthMotion::motion (rasterizer.hpp:295-307, 388-411) with Context::history from a previous frame."""
+    make, kw = cases.motion_cases()[name]
+    prev, cur = make()
+    pm = prev.models(port) if prev is not None else None
+    a = harness.cpu_forward(port, cur, aov=False, motion=True, prev_models=pm, **kw)
+    b = harness.cpu_forward(reference, cur, aov=False, motion=True, prev_models=pm, **kw)
+    assert _same_bits(a.hdr, b.hdr) and _same_bits(a.depth, b.depth), f"{name}: colour / depth differ"
+    assert _same_bits(a.motion, b.motion), f"{name}: motion differs at {int(np.count_nonzero(a.motion != b.motion))} components"
+    covered = a.depth < 1.0
+    assert np.all(a.motion[~covered] == 0.0), "the pass clears the motion plane where nothing is drawn"
+    if prev is not None:
+        assert np.count_nonzero(a.motion[covered]) > 0, "moving objects must produce non-zero vectors"
+        assert float(np.sqrt((a.motion.astype(np.float64) ** 2).sum(axis=2)).max()) <= 96.0 + 1e-3   # max_vel clamp
+    else:
+        # first frame: prev_model = model and prev_viewproj = viewproj; prev_model * inverse(model) is the identity only up to rounding
+        assert float(np.abs(a.motion).max()) < 1e-2
+
+
 def _uniforms(sd, model, mat):
     u = capi.Uniforms()
     capi.set_f(u.model, model)
