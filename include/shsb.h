@@ -222,6 +222,31 @@ typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/f
     int32_t reserved[3];
 } ShsbFrameParams;
 
+typedef struct ShsbMotionBlurParams /* MotionBlurPassParams (frame/frame_params.hpp:51-59) + FrameParams::dt */
+{
+    int32_t enable;        /* 0: the pass only copies input -> output (pass_motion_blur.hpp:56-60)   */
+    int32_t samples;       /* clamped to 4..32 (pass_motion_blur.hpp:79)                              */
+    float strength;
+    float max_velocity_px;
+    float min_velocity_px;
+    float depth_reject;
+    float dt;              /* FrameParams::dt, seconds (pass_motion_blur.hpp:84)                      */
+    int32_t reserved;
+} ShsbMotionBlurParams;
+
+typedef struct ShsbLightShaftsParams /* LightShaftsPassParams (frame/frame_params.hpp:35-42) + the Scene fields the pass reads */
+{
+    int32_t enable;
+    int32_t steps;         /* max(8, steps) (pass_light_shafts.hpp:135)                               */
+    float density;
+    float weight;
+    float decay;
+    float cam_pos[3];      /* Scene::cam.pos       (pass_light_shafts.hpp:81)                          */
+    float sun_dir_ws[3];   /* Scene::sun.dir_ws                                                       */
+    float reserved;
+    float cam_viewproj[16];/* Scene::cam.viewproj  (pass_light_shafts.hpp:82)                          */
+} ShsbLightShaftsParams;
+
 /* ------------------------------------------------------------------ context */
 
 /* Creates a device context on CUDA device `device_ordinal`.  Replaces the reference's
@@ -318,6 +343,26 @@ SHSB_API int32_t shsb_history_reset(shsb_ctx ctx);
 
 /* PassTonemap::execute (passes/pass_tonemap.hpp:37-84). */
 SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt, float exposure, float gamma);
+
+/* ---- post passes that consume the path's outputs; RGBA8 in, RGBA8 out, bit-exact.
+ * Targets of different sizes are cropped to the common minimum like the reference does. */
+
+/* PassMotionBlur::execute (passes/pass_motion_blur.hpp:40-184): velocity-directed gather over the LDR frame with a
+ * per-tap depth rejection; depth_motion_rt supplies RT_ColorDepthMotion::motion and ::depth.  input == output is
+ * allowed (the reference's scratch path, :72-76,166-183). */
+SHSB_API int32_t shsb_pass_motion_blur(shsb_ctx ctx, const ShsbMotionBlurParams* params, shsb_rt input_ldr, shsb_rt output_ldr,
+                                       shsb_rt depth_motion_rt);
+
+/* PassLightShafts::execute (passes/pass_light_shafts.hpp:43-214): screen-space march towards the projected sun over
+ * the frame's luma, weighted by depth (depth_like_rt, 0 = none).  input == output is allowed. */
+SHSB_API int32_t shsb_pass_light_shafts(shsb_ctx ctx, const ShsbLightShaftsParams* params, shsb_rt input_ldr, shsb_rt output_ldr,
+                                        shsb_rt depth_like_rt);
+
+/* PassTemporalAAAdapter::execute_resolved (pipeline/pass_adapters.hpp:1438-1491): blends the frame with the context's
+ * colour history (Context::temporal_aa, core/context.hpp:99-113); the first frame after a reset only seeds it. */
+SHSB_API int32_t shsb_pass_taa(shsb_ctx ctx, shsb_rt ldr_rt);
+/* TemporalAARuntimeState::reset (core/context.hpp:106-112) == PassTemporalAAAdapter::reset_history. */
+SHSB_API int32_t shsb_taa_reset(shsb_ctx ctx);
 
 /* Local lights: n records of CullingLightGPU (lighting/light_types.hpp:141-167, 160 B each). */
 SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t n_lights);

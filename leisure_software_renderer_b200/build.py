@@ -3,6 +3,7 @@
 nvcc cross-compiles without a GPU, so this runs on the CPU build box; the .so travels to the GPU box.
 Per-file flags:
   geometry.cu, light_cull.cu   --fmad=false   (every expression decides coverage / depth / list bits)
+  post_passes.cu               --fmad=false   (RGBA8 outputs of the post passes are bit-exact)
   tile_raster.cu, binning.cu   FMA allowed; exact expressions use __fmul_rn/__fadd_rn/__fdiv_rn explicitly
   api.cu                       host code with -ffp-contract=off (host float math must equal the reference's)
 """
@@ -24,6 +25,7 @@ SOURCES = {
     "geometry.cu": ["--fmad=false"],
     "light_cull.cu": ["--fmad=false"],
     "binning.cu": [],
+    "post_passes.cu": ["--fmad=false"],
     "tile_raster.cu": [],
     "api.cu": [],
 }

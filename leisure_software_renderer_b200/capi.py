@@ -54,6 +54,29 @@ class Uniforms(C.Structure):
                 ("prev_model", F16), ("prev_viewproj", F16)]
 
 
+class MotionBlurParams(C.Structure):
+    """ShsbMotionBlurParams; defaults = MotionBlurPassParams (frame/frame_params.hpp:51-59) with the pass enabled."""
+    _fields_ = [("enable", C.c_int32), ("samples", C.c_int32), ("strength", C.c_float), ("max_velocity_px", C.c_float),
+                ("min_velocity_px", C.c_float), ("depth_reject", C.c_float), ("dt", C.c_float), ("reserved", C.c_int32)]
+
+    def __init__(self, enable=1, samples=10, strength=1.0, max_velocity_px=20.0, min_velocity_px=0.25, depth_reject=0.08, dt=1.0 / 60.0):
+        super().__init__(int(enable), int(samples), strength, max_velocity_px, min_velocity_px, depth_reject, dt, 0)
+
+
+class LightShaftsParams(C.Structure):
+    """ShsbLightShaftsParams; defaults = LightShaftsPassParams (frame/frame_params.hpp:35-42)."""
+    _fields_ = [("enable", C.c_int32), ("steps", C.c_int32), ("density", C.c_float), ("weight", C.c_float), ("decay", C.c_float),
+                ("cam_pos", F3), ("sun_dir_ws", F3), ("reserved", C.c_float), ("cam_viewproj", F16)]
+
+    def __init__(self, cam_viewproj=None, cam_pos=(0, 0, 0), sun_dir_ws=(0, -1, 0), enable=1, steps=48, density=0.8, weight=0.9, decay=0.95):
+        super().__init__()
+        self.enable, self.steps, self.density, self.weight, self.decay = int(enable), int(steps), density, weight, decay
+        set_f(self.cam_pos, cam_pos)
+        set_f(self.sun_dir_ws, sun_dir_ws)
+        if cam_viewproj is not None:
+            set_f(self.cam_viewproj, cam_viewproj)
+
+
 class Transform(C.Structure):
     _fields_ = [("pos", F3), ("rot_euler", F3), ("scl", F3)]
 
@@ -152,6 +175,10 @@ def load_library(path: str | None = None):
         "shsb_pass_shadow_map": [vp, P(Scene), P(FrameParams), C.c_uint32, P(C.c_float)],
         "shsb_history_reset": [vp],
         "shsb_pass_tonemap": [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float],
+        "shsb_pass_motion_blur": [vp, P(MotionBlurParams), C.c_uint32, C.c_uint32, C.c_uint32],
+        "shsb_pass_light_shafts": [vp, P(LightShaftsParams), C.c_uint32, C.c_uint32, C.c_uint32],
+        "shsb_pass_taa": [vp, C.c_uint32],
+        "shsb_taa_reset": [vp],
         "shsb_lights_upload": [vp, vp, C.c_uint32],
         "shsb_light_cull": [vp, P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32],
         "shsb_light_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],

@@ -187,6 +187,13 @@ struct shsb_context_t
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr;
     cudaGraphExec_t graph_exec[NUM_ARENAS][4]{}; // per arena (an executable graph cannot run concurrently with itself): [cull branch][shadow mode]
 
+    // post passes: scratch for in-place operation, the light-shaft luma plane, TAA colour history
+    DevBuf<uchar4> d_post_scratch;
+    DevBuf<float> d_post_luma;
+    DevBuf<uchar4> d_taa_hist;      // TemporalAARuntimeState::history (core/context.hpp:101)
+    int taa_w = 0, taa_h = 0;
+    bool taa_valid = false;
+
     // host-side submit cost breakdown (microseconds, accumulated): [0] scene -> draw list, [1] staging copy,
     // [2] arena checks, [3] capture / enqueue, [4] graph update + launch, [5] frames
     double host_us[8]{};
@@ -921,6 +928,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& t : ctx->textures) cudaFree(t.texels);
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
+    cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p);
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
     for (auto& l : ctx->h_lights) cudaFreeHost(l.p);
@@ -1394,6 +1402,157 @@ SHSB_API int32_t shsb_pass_tonemap(shsb_ctx ctx, shsb_rt hdr_rt, shsb_rt ldr_rt,
     launch_tonemap((const float4*)hdr->color, (uchar4*)ldr->color, hdr->w * hdr->h, std::max(0.0001f, exposure), 1.0f / std::max(0.001f, gamma), ctx->stream, &ctx->launches);
     record(ctx, 6, ctx->stream);
     CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- post passes
+namespace
+{
+    // copy_ldr of the reference (pass_motion_blur.hpp:187-199, pass_light_shafts.hpp:59-66): cropped copy, no-op in place
+    int copy_ldr(shsb_ctx ctx, RtSlot* src, RtSlot* dst, int w, int h)
+    {
+        if (src == dst) return SHSB_OK;
+        wait_pending_read(ctx, dst);
+        launch_copy_ldr((const uchar4*)src->color, src->w, (uchar4*)dst->color, dst->w, w, h, ctx->stream, &ctx->launches);
+        CK(cudaGetLastError());
+        return SHSB_OK;
+    }
+}
+
+SHSB_API int32_t shsb_pass_motion_blur(shsb_ctx ctx, const ShsbMotionBlurParams* p, shsb_rt input_ldr, shsb_rt output_ldr, shsb_rt depth_motion_rt)
+{
+    if (!ctx || !p) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* src = get_rt(ctx, input_ldr, SHSB_RT_COLOR_LDR);
+    RtSlot* dst = get_rt(ctx, output_ldr, SHSB_RT_COLOR_LDR);
+    RtSlot* mot = get_rt(ctx, depth_motion_rt, SHSB_RT_DEPTH_MOTION);
+    if (!src || !dst || !mot) return fail(ctx, SHSB_E_INVALID_HANDLE, "motion blur needs live input / output RT_ColorLDR and an RT_ColorDepthMotion"); // :49
+    const int w = std::min({src->w, dst->w, mot->w}), h = std::min({src->h, dst->h, mot->h}); // :51-53
+    if (w <= 0 || h <= 0) return SHSB_OK;
+    if (!p->enable) return copy_ldr(ctx, src, dst, w, h); // :56-60
+    PostMotionBlur a{};
+    a.src = (const uchar4*)src->color; a.src_w = src->w;
+    a.motion = mot->motion; a.depth = mot->depth; a.mot_w = mot->w;
+    a.w = w; a.h = h;
+    a.samples = std::clamp(p->samples, 4, 32);                                   // :79
+    a.strength = std::max(0.0f, p->strength);                                    // :80
+    a.max_vel = std::max(1.0f, p->max_velocity_px);                              // :81
+    a.min_vel = std::max(0.0f, p->min_velocity_px);                              // :82
+    a.depth_eps = std::max(0.0f, p->depth_reject);                               // :83
+    a.dt_scale = std::clamp(std::max(p->dt, 1e-4f) * 60.0f, 0.5f, 2.5f);         // :84
+    const bool in_place = (src == dst);
+    if (in_place)
+    {
+        if (int rc = ensure_dev(ctx, ctx->d_post_scratch, (size_t)w * h)) return rc;
+        a.dst = ctx->d_post_scratch.p; a.dst_w = w;
+    }
+    else
+    {
+        wait_pending_read(ctx, dst);
+        a.dst = (uchar4*)dst->color; a.dst_w = dst->w;
+    }
+    launch_motion_blur(a, ctx->stream, &ctx->launches);
+    if (in_place)
+    {
+        wait_pending_read(ctx, dst);
+        launch_copy_ldr(ctx->d_post_scratch.p, w, (uchar4*)dst->color, dst->w, w, h, ctx->stream, &ctx->launches); // :166-183
+    }
+    CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_pass_light_shafts(shsb_ctx ctx, const ShsbLightShaftsParams* p, shsb_rt input_ldr, shsb_rt output_ldr, shsb_rt depth_like_rt)
+{
+    if (!ctx || !p) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* src = get_rt(ctx, input_ldr, SHSB_RT_COLOR_LDR);
+    RtSlot* dst = get_rt(ctx, output_ldr, SHSB_RT_COLOR_LDR);
+    if (!src || !dst) return fail(ctx, SHSB_E_INVALID_HANDLE, "light shafts need live input / output RT_ColorLDR"); // :50
+    RtSlot* dep = depth_like_rt ? get_rt(ctx, depth_like_rt, SHSB_RT_DEPTH_MOTION) : nullptr;
+    if (depth_like_rt && !dep) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth_like_rt %u is not a live RT_ColorDepthMotion", depth_like_rt);
+    const int w = std::min(src->w, dst->w), h = std::min(src->h, dst->h);
+    if (w <= 0 || h <= 0) return SHSB_OK;
+    if (!p->enable) return copy_ldr(ctx, src, dst, w, h); // :53-67
+
+    // sun position on screen, pass_light_shafts.hpp:77-93 (host arithmetic in the reference's order)
+    float sun_u = 0.5f, sun_v = 0.2f;
+    bool sun_valid = false;
+    {
+        const hm::vec3f sun_pos{p->cam_pos[0] + (-p->sun_dir_ws[0]) * 100.0f, p->cam_pos[1] + (-p->sun_dir_ws[1]) * 100.0f, p->cam_pos[2] + (-p->sun_dir_ws[2]) * 100.0f};
+        const hm::vec4f clip = hm::mul_v(hm::load(p->cam_viewproj), hm::vec4f{sun_pos.x, sun_pos.y, sun_pos.z, 1.0f});
+        if (std::abs(clip.w) > 1e-6f)
+        {
+            const float nx = clip.x / clip.w, ny = clip.y / clip.w, nz = clip.z / clip.w;
+            sun_u = nx * 0.5f + 0.5f;
+            sun_v = ny * 0.5f + 0.5f;
+            sun_valid = (clip.w > 0.0f) && (nz >= -1.0f && nz <= 1.0f) && (sun_u >= 0.0f && sun_u <= 1.0f) && (sun_v >= 0.0f && sun_v <= 1.0f);
+        }
+    }
+    if (!sun_valid) return copy_ldr(ctx, src, dst, w, h); // :96-108
+
+    PostLightShafts a{};
+    a.src = (const uchar4*)src->color; a.src_w = src->w;
+    a.w = w; a.h = h;
+    a.steps = std::max(8, p->steps);                    // :135
+    a.density = std::max(0.0f, p->density);             // :136
+    a.weight = std::max(0.0f, p->weight);               // :137
+    a.decay = std::clamp(p->decay, 0.0f, 1.0f);         // :138
+    a.sun_u = sun_u; a.sun_v = sun_v;
+    if (int rc = ensure_dev(ctx, ctx->d_post_luma, (size_t)w * h)) return rc;
+    const bool use_depth = dep && dep->w == w && dep->h == h; // :165
+    const bool in_place = (src == dst);
+    if (in_place)
+    {
+        if (int rc = ensure_dev(ctx, ctx->d_post_scratch, (size_t)w * h)) return rc;
+        a.dst = ctx->d_post_scratch.p; a.dst_w = w;
+    }
+    else
+    {
+        wait_pending_read(ctx, dst);
+        a.dst = (uchar4*)dst->color; a.dst_w = dst->w;
+    }
+    launch_light_shafts(a, use_depth ? dep->depth : nullptr, use_depth ? dep->w : 0, ctx->d_post_luma.p, ctx->stream, &ctx->launches);
+    if (in_place)
+    {
+        wait_pending_read(ctx, dst);
+        launch_copy_ldr(ctx->d_post_scratch.p, w, (uchar4*)dst->color, dst->w, w, h, ctx->stream, &ctx->launches); // :197-211
+    }
+    CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_pass_taa(shsb_ctx ctx, shsb_rt ldr_rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* ldr = get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR);
+    if (!ldr) return fail(ctx, SHSB_E_INVALID_HANDLE, "TAA needs a live RT_ColorLDR"); // pass_adapters.hpp:1444-1445
+    const size_t count = (size_t)ldr->w * ldr->h;
+    if (ctx->taa_w != ldr->w || ctx->taa_h != ldr->h) // :1451-1457
+    {
+        if (int rc = ensure_dev(ctx, ctx->d_taa_hist, count)) return rc;
+        ctx->taa_w = ldr->w;
+        ctx->taa_h = ldr->h;
+        ctx->taa_valid = false;
+    }
+    if (!ctx->taa_valid) // :1461-1469: seed the history, leave the frame untouched
+    {
+        CK(cudaMemcpyAsync(ctx->d_taa_hist.p, ldr->color, count * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->taa_valid = true;
+        return SHSB_OK;
+    }
+    wait_pending_read(ctx, ldr);
+    const float blend = 0.12f, keep = 1.0f - blend; // :1459-1460
+    launch_taa((uchar4*)ldr->color, ctx->d_taa_hist.p, count, keep, blend, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_taa_reset(shsb_ctx ctx)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    ctx->taa_w = ctx->taa_h = 0;
+    ctx->taa_valid = false;
     return SHSB_OK;
 }
 

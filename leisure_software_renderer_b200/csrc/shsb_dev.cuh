@@ -228,6 +228,28 @@ namespace shsb
         int w, h;
     };
 
+    // ---------------------------------------------------------------- post passes (post_passes.cu)
+    struct PostMotionBlur // PassMotionBlur, passes/pass_motion_blur.hpp:40-184 (parameters already clamped on the host, :79-84)
+    {
+        const uchar4* src; int src_w;
+        uchar4* dst; int dst_w;
+        const float2* motion; const float* depth; int mot_w;
+        int w, h;
+        int samples;
+        float strength, dt_scale, max_vel, min_vel, depth_eps;
+    };
+
+    struct PostLightShafts // PassLightShafts, passes/pass_light_shafts.hpp:43-214 (parameters clamped on the host, :135-138)
+    {
+        const uchar4* src; int src_w;
+        uchar4* dst; int dst_w;
+        const float* lumad; // luma * clamp(depth,0,1) plane, w * h
+        int w, h;
+        int steps;
+        float density, weight, decay;
+        float sun_u, sun_v;
+    };
+
     // ---------------------------------------------------------------- kernel launchers (one per .cu)
     void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
@@ -242,5 +264,9 @@ namespace shsb
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
                            uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
                            uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+    void launch_motion_blur(const PostMotionBlur& a, cudaStream_t s, uint64_t* launches);
+    void launch_light_shafts(const PostLightShafts& a, const float* depth, int depth_w, float* lumad, cudaStream_t s, uint64_t* launches);
+    void launch_taa(uchar4* ldr, uchar4* hist, size_t n_pixels, float keep, float blend, cudaStream_t s, uint64_t* launches);
+    void launch_copy_ldr(const uchar4* src, int src_w, uchar4* dst, int dst_w, int w, int h, cudaStream_t s, uint64_t* launches);
     size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts); // u32 words of `scratch`
 }

@@ -5,6 +5,9 @@
 //     shs::PassPBRForward::execute(...)     ->  shs::b200::PassPBRForward(dev).execute(...)
 //     shs::PassShadowMap::execute(...)      ->  shs::b200::PassShadowMap(dev).execute(...)
 //     shs::PassTonemap::execute(...)        ->  shs::b200::PassTonemap(dev).execute(...)
+//     shs::PassMotionBlur::execute(...)     ->  shs::b200::PassMotionBlur(dev).execute(...)
+//     shs::PassLightShafts::execute(...)    ->  shs::b200::PassLightShafts(dev).execute(...)
+//     PassTemporalAAAdapter (taa)           ->  shs::b200::PassTemporalAA(dev).execute(ctx, rtr, rt_ldr)
 // Same argument types (the reference's own MeshData / ShaderUniforms / RasterizerTarget / Scene / FrameParams /
 // RTRegistry), same results, same error convention (invalid input => silent return with zero stats,
 // sw_render/rasterizer.hpp:190-194, passes/pass_pbr_forward.hpp:51-58).
@@ -22,6 +25,8 @@
 #include <vector>
 
 #include "shs/core/context.hpp"
+#include "shs/passes/pass_light_shafts.hpp"
+#include "shs/passes/pass_motion_blur.hpp"
 #include "shs/passes/pass_pbr_forward.hpp"
 #include "shs/passes/pass_shadow_map.hpp"
 #include "shs/passes/pass_tonemap.hpp"
@@ -90,6 +95,8 @@ namespace shs::b200
         shsb_rt twin(RT_ShadowDepth* rt) { return rt ? twin_of(rt, SHSB_RT_SHADOW, rt->w, rt->h, 0.1f, 1000.0f) : 0; }
 
         void upload(RT_ColorHDR* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(ColorF)); }
+        void upload(RT_ColorLDR* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(Color)); }
+        void upload_motion(RT_ColorDepthMotion* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_MOTION, rt->motion.data.data(), rt->motion.data.size() * sizeof(Motion2f)); }
         void upload(RT_ColorDepthMotion* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data.data(), rt->depth.data.size() * sizeof(float)); }
         void upload(RT_ShadowDepth* rt) { if (rt) shsb_rt_upload(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
         void download(RT_ColorHDR* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_COLOR, rt->color.data.data(), rt->color.data.size() * sizeof(ColorF)); }
@@ -358,5 +365,107 @@ namespace shs::b200
     private:
         Device& dev_;
         bool sync_host_, hdr_on_device_;
+    };
+    // PassMotionBlur, passes/pass_motion_blur.hpp:25-200.  `inputs_on_device` = the LDR frame and the depth / motion planes
+    // were produced by the b200 passes and already live in the twins (the normal case); false uploads the host copies first.
+    class PassMotionBlur
+    {
+    public:
+        explicit PassMotionBlur(Device& dev, bool sync_host = true, bool inputs_on_device = true) : dev_(dev), sync_host_(sync_host), on_device_(inputs_on_device) {}
+        using Inputs = shs::PassMotionBlur::Inputs;
+
+        void execute(Context& ctx, const Inputs& in)
+        {
+            (void)ctx;
+            if (!in.fp || !in.rtr || !dev_.valid()) return;
+            if (!in.rt_input_ldr.valid() || !in.rt_output_ldr.valid()) return;
+            auto* src = static_cast<RT_ColorLDR*>(in.rtr->get(in.rt_input_ldr));
+            auto* dst = static_cast<RT_ColorLDR*>(in.rtr->get(in.rt_output_ldr));
+            auto* motion = in.rt_motion.valid() ? static_cast<RT_ColorDepthMotion*>(in.rtr->get(in.rt_motion)) : nullptr;
+            if (!src || !dst || !motion) return; // rt_tmp is only scratch in the reference; the device owns its own
+            if (!on_device_) { dev_.upload(src); dev_.upload(motion); dev_.upload_motion(motion); }
+            const MotionBlurPassParams& mb = in.fp->pass.motion_blur;
+            ShsbMotionBlurParams p{};
+            p.enable = mb.enable ? 1 : 0;
+            p.samples = mb.samples;
+            p.strength = mb.strength;
+            p.max_velocity_px = mb.max_velocity_px;
+            p.min_velocity_px = mb.min_velocity_px;
+            p.depth_reject = mb.depth_reject;
+            p.dt = in.fp->dt;
+            if (shsb_pass_motion_blur(dev_.ctx(), &p, dev_.twin(src), dev_.twin(dst), dev_.twin(motion)) != SHSB_OK) return;
+            if (sync_host_) dev_.download(dst);
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_, on_device_;
+    };
+
+    // PassLightShafts, passes/pass_light_shafts.hpp:27-216.
+    class PassLightShafts
+    {
+    public:
+        explicit PassLightShafts(Device& dev, bool sync_host = true, bool inputs_on_device = true) : dev_(dev), sync_host_(sync_host), on_device_(inputs_on_device) {}
+        using Inputs = shs::PassLightShafts::Inputs;
+
+        void execute(Context& ctx, const Inputs& in)
+        {
+            (void)ctx;
+            if (!in.scene || !in.fp || !in.rtr || !dev_.valid()) return;
+            if (!in.rt_input_ldr.valid() || !in.rt_output_ldr.valid()) return;
+            auto* src = static_cast<RT_ColorLDR*>(in.rtr->get(in.rt_input_ldr));
+            auto* dst = static_cast<RT_ColorLDR*>(in.rtr->get(in.rt_output_ldr));
+            if (!src || !dst || src->w <= 0 || src->h <= 0 || dst->w <= 0 || dst->h <= 0) return;
+            auto* depth_like = in.rt_depth_like.valid() ? static_cast<RT_ColorDepthMotion*>(in.rtr->get(in.rt_depth_like)) : nullptr;
+            if (!on_device_) { dev_.upload(src); if (depth_like) dev_.upload(depth_like); }
+            const LightShaftsPassParams& ls = in.fp->pass.light_shafts;
+            ShsbLightShaftsParams p{};
+            p.enable = ls.enable ? 1 : 0;
+            p.steps = ls.steps;
+            p.density = ls.density;
+            p.weight = ls.weight;
+            p.decay = ls.decay;
+            std::memcpy(p.cam_pos, &in.scene->cam.pos, 12);
+            std::memcpy(p.sun_dir_ws, &in.scene->sun.dir_ws, 12);
+            std::memcpy(p.cam_viewproj, &in.scene->cam.viewproj, 64);
+            if (shsb_pass_light_shafts(dev_.ctx(), &p, dev_.twin(src), dev_.twin(dst), depth_like ? dev_.twin(depth_like) : 0) != SHSB_OK) return;
+            if (sync_host_) dev_.download(dst);
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_, on_device_;
+    };
+
+    // PassTemporalAAAdapter::execute_resolved / reset_history, pipeline/pass_adapters.hpp:1402-1496.  The colour history
+    // (Context::temporal_aa) lives on the device; ctx.temporal_aa only mirrors its size / validity flags.
+    class PassTemporalAA
+    {
+    public:
+        explicit PassTemporalAA(Device& dev, bool sync_host = true, bool inputs_on_device = true) : dev_(dev), sync_host_(sync_host), on_device_(inputs_on_device) {}
+
+        void execute(Context& ctx, RTRegistry& rtr, RTHandle rt_ldr)
+        {
+            auto* ldr = static_cast<RT_ColorLDR*>(rtr.get(rt_ldr));
+            if (!ldr || ldr->w <= 0 || ldr->h <= 0 || !dev_.valid()) return;
+            if (!on_device_) dev_.upload(ldr);
+            if (!ctx.temporal_aa.history_valid) shsb_taa_reset(dev_.ctx()); // someone called ctx.temporal_aa.reset()
+            if (shsb_pass_taa(dev_.ctx(), dev_.twin(ldr)) != SHSB_OK) return;
+            ctx.temporal_aa.history_w = ldr->w;
+            ctx.temporal_aa.history_h = ldr->h;
+            ctx.temporal_aa.history_valid = true;
+            if (sync_host_) dev_.download(ldr);
+        }
+
+        void reset_history(Context& ctx)
+        {
+            ctx.temporal_aa.reset();
+            shsb_taa_reset(dev_.ctx());
+        }
+
+    private:
+        Device& dev_;
+        bool sync_host_, on_device_;
     };
 }

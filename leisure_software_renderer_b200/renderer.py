@@ -151,6 +151,20 @@ class Context:
     def pass_tonemap(self, hdr_rt, ldr_rt, exposure=1.0, gamma=2.2):
         _check(self.lib, self.h, self.lib.shsb_pass_tonemap(self.h, hdr_rt, ldr_rt, exposure, gamma), "shsb_pass_tonemap")
 
+    def pass_motion_blur(self, params: "capi.MotionBlurParams", input_ldr, output_ldr, depth_motion_rt):
+        rc = self.lib.shsb_pass_motion_blur(self.h, C.byref(params), input_ldr, output_ldr, depth_motion_rt)
+        _check(self.lib, self.h, rc, "shsb_pass_motion_blur")
+
+    def pass_light_shafts(self, params: "capi.LightShaftsParams", input_ldr, output_ldr, depth_like_rt=0):
+        rc = self.lib.shsb_pass_light_shafts(self.h, C.byref(params), input_ldr, output_ldr, depth_like_rt)
+        _check(self.lib, self.h, rc, "shsb_pass_light_shafts")
+
+    def pass_taa(self, ldr_rt):
+        _check(self.lib, self.h, self.lib.shsb_pass_taa(self.h, ldr_rt), "shsb_pass_taa")
+
+    def taa_reset(self):
+        _check(self.lib, self.h, self.lib.shsb_taa_reset(self.h), "shsb_taa_reset")
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")

@@ -178,6 +178,29 @@ class Oracle:
         assert rc == 0, rc
         return ldr
 
+    def pass_motion_blur(self, params, src_ldr, motion, depth):
+        h, w = src_ldr.shape[:2]
+        src = np.ascontiguousarray(src_ldr, dtype=np.uint8)
+        mot = np.ascontiguousarray(motion, dtype=np.float32)
+        dep = np.ascontiguousarray(depth, dtype=np.float32)
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        rc = self.fn("pass_motion_blur")(C.byref(params), src.ctypes.data_as(u8), capi.fptr(mot), capi.fptr(dep), C.c_int32(w), C.c_int32(h),
+                                         out.ctypes.data_as(u8))
+        assert rc == 0, rc
+        return out
+
+    def pass_light_shafts(self, params, src_ldr, depth=None):
+        h, w = src_ldr.shape[:2]
+        src = np.ascontiguousarray(src_ldr, dtype=np.uint8)
+        dep = np.ascontiguousarray(depth, dtype=np.float32) if depth is not None else None
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        rc = self.fn("pass_light_shafts")(C.byref(params), src.ctypes.data_as(u8), capi.fptr(dep) if dep is not None else None,
+                                          C.c_int32(w), C.c_int32(h), out.ctypes.data_as(u8))
+        assert rc == 0, rc
+        return out
+
     # ---- restatement-only
     def light_cull(self, records, view_proj, w, h, tile_size=16, max_per_tile=128):
         assert self.kind == "port"
@@ -190,6 +213,15 @@ class Oracle:
                                       C.c_uint32(tile_size), C.c_uint32(max_per_tile), capi.u32ptr(counts), capi.u32ptr(indices))
         assert rc == 0, rc
         return counts, indices
+
+    def pass_taa(self, ldr, history, history_valid):
+        """In place on both arrays (PassTemporalAAAdapter); returns them."""
+        assert self.kind == "port"
+        assert ldr.dtype == np.uint8 and history.dtype == np.uint8 and ldr.flags.c_contiguous and history.flags.c_contiguous
+        u8 = C.POINTER(C.c_uint8)
+        rc = self.lib.shso_pass_taa(ldr.ctypes.data_as(u8), history.ctypes.data_as(u8), C.c_int32(int(history_valid)), C.c_size_t(ldr.size // 4))
+        assert rc == 0, rc
+        return ldr, history
 
     def pass_pbr_forward_plus(self, assets, scene, fp, tgt, records, counts, indices, shadow_lvp=None, preserve_depth=False):
         assert self.kind == "port"

@@ -1471,6 +1471,133 @@ int32_t shso_pass_tonemap(const float* hdr, int32_t w, int32_t h, float exposure
     return SHSB_OK;
 }
 
+int32_t shso_pass_motion_blur(const ShsbMotionBlurParams* p, const uint8_t* src, const float* motion, const float* depth,
+                              int32_t w, int32_t h, uint8_t* out)
+{
+    // PassMotionBlur::execute, passes/pass_motion_blur.hpp:40-184
+    if (!p || !src || !motion || !depth || !out || w <= 0 || h <= 0) return SHSB_E_INVALID_ARGUMENT;
+    const size_t n = (size_t)w * h;
+    if (!p->enable) { std::memcpy(out, src, n * 4); return SHSB_OK; } // :56-60
+    const int samples = std::clamp(p->samples, 4, 32);                              // :79
+    const float strength = std::max(0.0f, p->strength);                             // :80
+    const float max_vel = std::max(1.0f, p->max_velocity_px);                       // :81
+    const float min_vel = std::max(0.0f, p->min_velocity_px);                       // :82
+    const float depth_eps = std::max(0.0f, p->depth_reject);                        // :83
+    const float dt_scale = std::clamp(std::max(p->dt, 1e-4f) * 60.0f, 0.5f, 2.5f);  // :84
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            const size_t i = (size_t)y * w + x;
+            float vx = motion[i * 2 + 0] * strength * dt_scale; // :116-117
+            float vy = motion[i * 2 + 1] * strength * dt_scale;
+            const float len = std::sqrt(vx * vx + vy * vy);
+            uint8_t* o = out + i * 4;
+            if (len < min_vel) { std::memcpy(o, src + i * 4, 4); continue; } // :119-123
+            if (len > max_vel && len > 1e-6f) // :124-129
+            {
+                const float s = max_vel / len;
+                vx *= s;
+                vy *= s;
+            }
+            const float zc = depth[i];
+            float acc[3] = {0.0f, 0.0f, 0.0f}, kept = 0.0f;
+            for (int k = 0; k < samples; ++k) // :136-149
+            {
+                const float t = ((float)k / (float)(samples - 1) - 0.5f);
+                const int sx = std::clamp((int)std::lround((float)x + vx * t), 0, w - 1);
+                const int sy = std::clamp((int)std::lround((float)y + vy * t), 0, h - 1);
+                const size_t j = (size_t)sy * w + sx;
+                if (std::abs(depth[j] - zc) > depth_eps) continue;
+                acc[0] += (float)src[j * 4 + 0];
+                acc[1] += (float)src[j * 4 + 1];
+                acc[2] += (float)src[j * 4 + 2];
+                kept += 1.0f;
+            }
+            if (kept < 1.0f) { std::memcpy(o, src + i * 4, 4); continue; } // :151-155
+            for (int c = 0; c < 3; ++c) o[c] = (uint8_t)std::clamp((int)std::lround(acc[c] / kept), 0, 255); // :157-162
+            o[3] = 255;
+        }
+    return SHSB_OK;
+}
+
+int32_t shso_pass_light_shafts(const ShsbLightShaftsParams* p, const uint8_t* src, const float* depth, int32_t w, int32_t h, uint8_t* out)
+{
+    // PassLightShafts::execute, passes/pass_light_shafts.hpp:43-214
+    if (!p || !src || !out || w <= 0 || h <= 0) return SHSB_E_INVALID_ARGUMENT;
+    const size_t n = (size_t)w * h;
+    if (!p->enable) { std::memcpy(out, src, n * 4); return SHSB_OK; } // :53-67
+    // projected sun, :77-93
+    float sun_u = 0.5f, sun_v = 0.2f;
+    bool sun_valid = false;
+    {
+        const V3 sp = add(load3(p->cam_pos), scale(neg(load3(p->sun_dir_ws)), 100.0f));
+        const V4 clip = mat4_mul(p->cam_viewproj, sp.x, sp.y, sp.z, 1.0f);
+        if (std::abs(clip.w) > 1e-6f)
+        {
+            const float nx = clip.x / clip.w, ny = clip.y / clip.w, nz = clip.z / clip.w;
+            sun_u = nx * 0.5f + 0.5f;
+            sun_v = ny * 0.5f + 0.5f;
+            sun_valid = clip.w > 0.0f && nz >= -1.0f && nz <= 1.0f && sun_u >= 0.0f && sun_u <= 1.0f && sun_v >= 0.0f && sun_v <= 1.0f;
+        }
+    }
+    if (!sun_valid) { std::memcpy(out, src, n * 4); return SHSB_OK; } // :96-108
+    std::vector<float> luma(n); // :112-126
+    for (size_t i = 0; i < n; ++i)
+    {
+        const float r = (float)src[i * 4 + 0] / 255.0f, g = (float)src[i * 4 + 1] / 255.0f, b = (float)src[i * 4 + 2] / 255.0f;
+        luma[i] = 0.2126f * r + 0.7152f * g + 0.0722f * b;
+    }
+    const int steps = std::max(8, p->steps);                 // :135
+    const float density = std::max(0.0f, p->density);        // :136
+    const float weight = std::max(0.0f, p->weight);          // :137
+    const float decay = std::clamp(p->decay, 0.0f, 1.0f);    // :138
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            const float u = (float)x / (float)std::max(1, w - 1);
+            const float v = (float)y / (float)std::max(1, h - 1);
+            float fall = 1.0f, sum = 0.0f;
+            for (int k = 0; k < steps; ++k) // :152-176
+            {
+                const float t = (float)k / (float)steps;
+                const float su = u + (sun_u - u) * t * density;
+                const float sv = v + (sun_v - v) * t * density;
+                const int sx = std::clamp((int)std::lround(su * (float)(w - 1)), 0, w - 1);
+                const int sy = std::clamp((int)std::lround(sv * (float)(h - 1)), 0, h - 1);
+                float s = luma[(size_t)sy * w + sx];
+                if (depth) s *= std::clamp(depth[(size_t)sy * w + sx], 0.0f, 1.0f); // :165-171
+                sum += s * fall * weight;
+                fall *= decay;
+            }
+            const uint8_t* b = src + ((size_t)y * w + x) * 4;
+            uint8_t* o = out + ((size_t)y * w + x) * 4;
+            const int boost = std::clamp((int)std::lround(sum * 80.0f), 0, 120); // :179
+            o[0] = (uint8_t)std::clamp((int)b[0] + boost, 0, 255);
+            o[1] = (uint8_t)std::clamp((int)b[1] + boost, 0, 255);
+            o[2] = (uint8_t)std::clamp((int)b[2] + boost / 2, 0, 255);
+            o[3] = 255;
+        }
+    return SHSB_OK;
+}
+
+int32_t shso_pass_taa(uint8_t* ldr, uint8_t* history, int32_t history_valid, size_t n_pixels)
+{
+    // PassTemporalAAAdapter::execute_resolved, pipeline/pass_adapters.hpp:1438-1491
+    if (!ldr || !history) return SHSB_E_INVALID_ARGUMENT;
+    if (!history_valid) { std::memcpy(history, ldr, n_pixels * 4); return SHSB_OK; } // :1461-1469
+    const float blend = 0.12f, keep = 1.0f - blend;
+    for (size_t i = 0; i < n_pixels; ++i)
+    {
+        for (int c = 0; c < 3; ++c)
+        {
+            const float v = keep * (float)ldr[i * 4 + c] + blend * (float)history[i * 4 + c]; // :1477-1481
+            ldr[i * 4 + c] = (uint8_t)std::clamp((int)(v + 0.5f), 0, 255);
+        }
+        std::memcpy(history + i * 4, ldr + i * 4, 4); // alpha stays cur.a (:1486), history = out (:1488)
+    }
+    return SHSB_OK;
+}
+
 int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float view_proj[16],
                         uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
                         uint32_t* counts, uint32_t* indices)

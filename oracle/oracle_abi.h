@@ -99,6 +99,14 @@ SHSO_FN(int32_t, pass_shadow_map, (const ShsoAssets* assets, const ShsbScene* sc
 /* PassTonemap::execute, passes/pass_tonemap.hpp:37 */
 SHSO_FN(int32_t, pass_tonemap, (const float* hdr, int32_t w, int32_t h, float exposure, float gamma, uint8_t* out_ldr));
 
+/* PassMotionBlur::execute, passes/pass_motion_blur.hpp:40 (input != output; all planes w x h; motion = 2 floats / px) */
+SHSO_FN(int32_t, pass_motion_blur, (const ShsbMotionBlurParams* p, const uint8_t* src_ldr, const float* motion, const float* depth,
+                                    int32_t w, int32_t h, uint8_t* out_ldr));
+
+/* PassLightShafts::execute, passes/pass_light_shafts.hpp:43 (depth may be NULL: no rt_depth_like) */
+SHSO_FN(int32_t, pass_light_shafts, (const ShsbLightShaftsParams* p, const uint8_t* src_ldr, const float* depth,
+                                     int32_t w, int32_t h, uint8_t* out_ldr));
+
 #undef SHSO_FN
 
 /* ---- restatement-only entry points (no compilable reference: Jolt-guarded headers / GLSL spec) ---- */
@@ -121,6 +129,10 @@ int32_t shso_pass_pbr_forward_plus(const ShsoAssets* assets, const ShsbScene* sc
 /* PassDepthPrepassAdapter, pipeline/pass_adapters.hpp:401-528 */
 int32_t shso_pass_depth_prepass(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,
                                 const ShsoTarget* tgt, ShsbStats* out_stats);
+
+/* PassTemporalAAAdapter::execute_resolved, pipeline/pass_adapters.hpp:1438-1491 (that header needs Jolt types, so
+ * restatement only).  history_valid == 0: seeds `history` from `ldr` and leaves the frame untouched. */
+int32_t shso_pass_taa(uint8_t* ldr_inout, uint8_t* history_inout, int32_t history_valid, size_t n_pixels);
 
 /* ThreadPoolJobSystem(n) handed to the reference passes as ctx.job_system / RasterizerConfig::job_system
  * (exp-plumbing/hello_pass_basics.cpp:629-630); n <= 1 means no job system (serial). */

@@ -20,6 +20,8 @@
 #include "shs/core/context.hpp"
 #include "shs/job/thread_pool_job_system.hpp"
 #include "shs/lighting/light_types.hpp"
+#include "shs/passes/pass_light_shafts.hpp"
+#include "shs/passes/pass_motion_blur.hpp"
 #include "shs/passes/pass_pbr_forward.hpp"
 #include "shs/passes/pass_shadow_map.hpp"
 #include "shs/passes/pass_tonemap.hpp"
@@ -519,6 +521,67 @@ int32_t shsref_pass_tonemap(const float* hdr_in, int32_t w, int32_t h, float exp
     in.rt_ldr = h_ldr;
     pass.execute(ctx, in);
     std::memcpy(out_ldr, ldr.color.data.data(), (size_t)w * h * 4);
+    return SHSB_OK;
+}
+
+int32_t shsref_pass_motion_blur(const ShsbMotionBlurParams* p, const uint8_t* src_ldr, const float* motion, const float* depth,
+                                int32_t w, int32_t h, uint8_t* out_ldr)
+{
+    shs::RT_ColorLDR src(w, h), dst(w, h);
+    std::memcpy(src.color.data.data(), src_ldr, (size_t)w * h * 4);
+    shs::RT_ColorDepthMotion dm(w, h, 0.1f, 1000.0f);
+    std::memcpy(dm.depth.data.data(), depth, (size_t)w * h * 4);
+    std::memcpy(dm.motion.data.data(), motion, (size_t)w * h * 8);
+    shs::RTRegistry rtr{};
+    shs::Context ctx{};
+    ctx.job_system = g_jobs.get();
+    shs::FrameParams f{};
+    f.dt = p->dt;
+    f.pass.motion_blur.enable = p->enable != 0;
+    f.pass.motion_blur.samples = p->samples;
+    f.pass.motion_blur.strength = p->strength;
+    f.pass.motion_blur.max_velocity_px = p->max_velocity_px;
+    f.pass.motion_blur.min_velocity_px = p->min_velocity_px;
+    f.pass.motion_blur.depth_reject = p->depth_reject;
+    shs::PassMotionBlur::Inputs in{};
+    in.fp = &f;
+    in.rtr = &rtr;
+    in.rt_input_ldr = rtr.reg<shs::RTHandle>(&src);
+    in.rt_output_ldr = rtr.reg<shs::RTHandle>(&dst);
+    in.rt_motion = rtr.reg<shs::RTHandle>(&dm);
+    shs::PassMotionBlur{}.execute(ctx, in);
+    std::memcpy(out_ldr, dst.color.data.data(), (size_t)w * h * 4);
+    return SHSB_OK;
+}
+
+int32_t shsref_pass_light_shafts(const ShsbLightShaftsParams* p, const uint8_t* src_ldr, const float* depth, int32_t w, int32_t h, uint8_t* out_ldr)
+{
+    shs::RT_ColorLDR src(w, h), dst(w, h);
+    std::memcpy(src.color.data.data(), src_ldr, (size_t)w * h * 4);
+    shs::RT_ColorDepthMotion dm(w, h, 0.1f, 1000.0f);
+    if (depth) std::memcpy(dm.depth.data.data(), depth, (size_t)w * h * 4);
+    shs::RTRegistry rtr{};
+    shs::Context ctx{};
+    ctx.job_system = g_jobs.get();
+    shs::FrameParams f{};
+    f.pass.light_shafts.enable = p->enable != 0;
+    f.pass.light_shafts.steps = p->steps;
+    f.pass.light_shafts.density = p->density;
+    f.pass.light_shafts.weight = p->weight;
+    f.pass.light_shafts.decay = p->decay;
+    shs::Scene scene{};
+    scene.cam.pos = load_vec3(p->cam_pos);
+    scene.cam.viewproj = load_mat4(p->cam_viewproj);
+    scene.sun.dir_ws = load_vec3(p->sun_dir_ws);
+    shs::PassLightShafts::Inputs in{};
+    in.scene = &scene;
+    in.fp = &f;
+    in.rtr = &rtr;
+    in.rt_input_ldr = rtr.reg<shs::RTHandle>(&src);
+    in.rt_output_ldr = rtr.reg<shs::RTHandle>(&dst);
+    if (depth) in.rt_depth_like = rtr.reg<shs::RTHandle>(&dm);
+    shs::PassLightShafts{}.execute(ctx, in);
+    std::memcpy(out_ldr, dst.color.data.data(), (size_t)w * h * 4);
     return SHSB_OK;
 }
 

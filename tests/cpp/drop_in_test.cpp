@@ -167,6 +167,41 @@ int main()
     std::printf("frame 2 (sky + motion): motion vectors differing %zu of %zu (non-zero %zu)  depth<=%d ULP  HDR PSNR %.1f dB\n",
                 motion_diff, dm_ref.motion.data.size(), motion_nonzero, max_depth_ulp2, psnr2);
 
+    // ---- post passes on frame 2: PassLightShafts -> PassMotionBlur (reference order, hello_pass_basics.cpp) on the reference's
+    // own LDR / depth / motion (uploaded, so that both sides start from identical bytes); RGBA8 must be bit-equal
+    {
+        fp.dt = 1.0f / 30.0f;
+        fp.pass.motion_blur.enable = true;
+        fp.pass.motion_blur.samples = 12;
+        fp.pass.light_shafts.enable = true;
+        // look towards the sun so that it projects inside the frame (pass_light_shafts.hpp:77-93)
+        shs::Scene sc2 = scene;
+        sc2.cam.view = shs::look_at_lh(sc2.cam.pos, sc2.cam.pos - sc2.sun.dir_ws * 10.0f + glm::vec3(0.4f, -0.3f, 0.0f), glm::vec3(0, 1, 0));
+        sc2.cam.viewproj = sc2.cam.proj * sc2.cam.view;
+        shs::RT_ColorLDR shafts_ref(W, H), shafts_gpu(W, H), blur_ref(W, H), blur_gpu(W, H);
+        shs::RTRegistry rtr{};
+        const shs::RTHandle h_in = rtr.reg<shs::RTHandle>(&ldr_ref);
+        const shs::RTHandle h_dm = rtr.reg<shs::RTHandle>(&dm_ref);
+        const shs::RTHandle h_sr = rtr.reg<shs::RTHandle>(&shafts_ref), h_sg = rtr.reg<shs::RTHandle>(&shafts_gpu);
+        const shs::RTHandle h_br = rtr.reg<shs::RTHandle>(&blur_ref), h_bg = rtr.reg<shs::RTHandle>(&blur_gpu);
+        shs::PassLightShafts::Inputs li{}; li.scene = &sc2; li.fp = &fp; li.rtr = &rtr; li.rt_input_ldr = h_in; li.rt_depth_like = h_dm;
+        shs::PassMotionBlur::Inputs mi{}; mi.fp = &fp; mi.rtr = &rtr; mi.rt_motion = h_dm;
+        li.rt_output_ldr = h_sr; shs::PassLightShafts().execute(ctx_ref, li);
+        mi.rt_input_ldr = h_sr; mi.rt_output_ldr = h_br; shs::PassMotionBlur().execute(ctx_ref, mi);
+        li.rt_output_ldr = h_sg; shs::b200::PassLightShafts(dev, true, false).execute(ctx_gpu, li);
+        mi.rt_input_ldr = h_sg; mi.rt_output_ldr = h_bg; shs::b200::PassMotionBlur(dev, true, false).execute(ctx_gpu, mi);
+        size_t shafts_diff = 0, blur_diff = 0, shafts_changed = 0, blur_changed = 0;
+        for (size_t i = 0; i < shafts_ref.color.data.size(); ++i)
+        {
+            if (std::memcmp(&shafts_ref.color.data[i], &shafts_gpu.color.data[i], 4) != 0) ++shafts_diff;
+            if (std::memcmp(&blur_ref.color.data[i], &blur_gpu.color.data[i], 4) != 0) ++blur_diff;
+            if (std::memcmp(&shafts_ref.color.data[i], &ldr_ref.color.data[i], 3) != 0) ++shafts_changed;
+            if (std::memcmp(&blur_ref.color.data[i], &shafts_ref.color.data[i], 3) != 0) ++blur_changed;
+        }
+        if (shafts_diff || blur_diff || !shafts_changed || !blur_changed) ++bad;
+        std::printf("post passes: light shafts differing %zu (changed %zu px)  motion blur differing %zu (changed %zu px)\n", shafts_diff, shafts_changed, blur_diff, blur_changed);
+    }
+
     // ---- rasterize_mesh called directly, like exp-plumbing/hello_software_triangle.cpp:187
     shs::RT_ColorHDR h2_ref(W, H), h2_gpu(W, H);
     shs::RT_ColorDepthMotion d2_ref(W, H, 0.1f, 100.0f), d2_gpu(W, H, 0.1f, 100.0f);

@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(HERE, ".."))
 
 import harness  # noqa: E402
+import post_cases  # noqa: E402
 from leisure_software_renderer_b200 import capi, scenes  # noqa: E402
 from oracle.bindings import Oracle  # noqa: E402
 
@@ -62,6 +63,15 @@ def main():
         f = harness.cpu_forward(ref, cur, aov=False, motion=True, prev_models=prev.models(ref))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), hdr=f.hdr, ldr=f.ldr, depth=f.depth, motion=f.motion)
         print(name, f.motion.shape, float(np.abs(f.motion).max()))
+    post = {}
+    for name, (make, p) in post_cases.blur_cases().items():
+        ldr, depth, motion = make()
+        post["blur_" + name] = ref.pass_motion_blur(p, ldr, motion, depth)
+    for name, (make, p, with_depth) in post_cases.shafts_cases().items():
+        ldr, depth, _ = make()
+        post["shafts_" + name] = ref.pass_light_shafts(p, ldr, depth if with_depth else None)
+    np.savez_compressed(os.path.join(HERE, "golden_post_passes.npz"), **post)
+    print("post passes", sorted(post))
     sd = scenes.scene_small(w=320, h=200, lights=64)
     counts, indices = port.light_cull(sd.lights, sd.viewproj, sd.w, sd.h, 16, 128)
     np.savez_compressed(os.path.join(HERE, "golden_light_lists_320x200_port.npz"), counts=counts, indices=indices)
