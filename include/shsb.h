@@ -247,6 +247,25 @@ typedef struct ShsbLightShaftsParams /* LightShaftsPassParams (frame/frame_param
     float cam_viewproj[16];/* Scene::cam.viewproj  (pass_light_shafts.hpp:82)                          */
 } ShsbLightShaftsParams;
 
+enum /* LightCullingMode (lighting/light_culling_mode.hpp) as the bin builders of lighting/jolt_light_culling.hpp */
+{
+    SHSB_LIGHT_CULL_TILED = 0,            /* cull_lights_tiled                    :135-187 */
+    SHSB_LIGHT_CULL_TILED_DEPTH01 = 1,    /* cull_lights_tiled_depth01_range      :196-258 */
+    SHSB_LIGHT_CULL_TILED_VIEW_DEPTH = 2, /* cull_lights_tiled_view_depth_range   :261-324 */
+    SHSB_LIGHT_CULL_CLUSTERED = 3         /* cull_lights_clustered                :341-412 */
+};
+
+typedef struct ShsbLightCullDesc /* arguments of the bin builders + LightBinCullingConfig (lighting/light_culling_runtime.hpp:29-36) */
+{
+    float view_proj[16];
+    uint32_t viewport_w, viewport_h;
+    uint32_t tile_size;
+    uint32_t max_per_bin;   /* entries kept per bin in `indices` (counts stay uncapped)            */
+    int32_t mode;           /* SHSB_LIGHT_CULL_*                                                    */
+    uint32_t depth_slices;  /* clustered: cluster_depth_slices (16)                                 */
+    float z_near, z_far;    /* view-depth and clustered modes                                       */
+} ShsbLightCullDesc;
+
 /* ------------------------------------------------------------------ context */
 
 /* Creates a device context on CUDA device `device_ordinal`.  Replaces the reference's
@@ -375,6 +394,21 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
                                  uint32_t tile_size, uint32_t max_per_tile);
 SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts,
                                            uint32_t* indices, size_t n_indices);
+
+/* The other bin builders of lighting/jolt_light_culling.hpp.  Depth-range modes take the
+ * per-tile ranges from host memory (range_min / range_max, one float per tile, tile (0,0) = top-left) or, when both are
+ * NULL, from the context's last shsb_tile_depth_range result (view depth: use SHSB_LIGHT_CULL_TILED_VIEW_DEPTH).
+ * Tiled modes (0-2) produce lists the Forward+ pass can use and shsb_light_lists_download returns; clustered bins
+ * (bin = cz * tiles + ty * tiles_x + tx) are returned by shsb_cluster_lists_download. */
+SHSB_API int32_t shsb_light_cull_ex(shsb_ctx ctx, const ShsbLightCullDesc* desc, const float* range_min, const float* range_max);
+SHSB_API int32_t shsb_cluster_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices);
+
+/* Per-tile [min, max] linear view depth of a z-buffer written by the raster path (z01 = (view_z - zn) / (zf - zn),
+ * sw_render/rasterizer.hpp:352-354); cleared pixels are skipped, empty tiles get [zn, zf]
+ * (build_tile_view_depth_range_from_scene, lighting/light_culling_runtime.hpp:254-261).  The software analogue of
+ * shaders/vulkan/fp_stress_depth_reduce.comp.  The result stays on the device for shsb_light_cull_ex. */
+SHSB_API int32_t shsb_tile_depth_range(shsb_ctx ctx, shsb_rt depth_motion_rt, uint32_t tile_size);
+SHSB_API int32_t shsb_tile_depth_range_download(shsb_ctx ctx, float* out_min, float* out_max, size_t n_tiles);
 
 /* Fused Forward+ frame = light cull + PassPBRForward (Forward+) + PassTonemap in one submission
  * with HDR, depth and LDR each written once (SURVEY.md section 8d B_frame). */

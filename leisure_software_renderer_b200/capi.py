@@ -24,6 +24,7 @@ RT_COLOR_HDR, RT_COLOR_LDR, RT_DEPTH_MOTION, RT_SHADOW = 1, 2, 3, 4
 PLANE_COLOR, PLANE_DEPTH, PLANE_MOTION, PLANE_TRI_ID, PLANE_COVERAGE = 0, 1, 2, 3, 4
 TRI_ID_NONE = 0xFFFFFFFF
 LIGHT_RECORD_BYTES = 160
+LIGHT_CULL_TILED, LIGHT_CULL_TILED_DEPTH01, LIGHT_CULL_TILED_VIEW_DEPTH, LIGHT_CULL_CLUSTERED = 0, 1, 2, 3
 
 F16 = C.c_float * 16
 F3 = C.c_float * 3
@@ -75,6 +76,25 @@ class LightShaftsParams(C.Structure):
         set_f(self.sun_dir_ws, sun_dir_ws)
         if cam_viewproj is not None:
             set_f(self.cam_viewproj, cam_viewproj)
+
+
+class LightCullDesc(C.Structure):
+    """ShsbLightCullDesc: arguments of the bin builders of lighting/jolt_light_culling.hpp."""
+    _fields_ = [("view_proj", F16), ("viewport_w", C.c_uint32), ("viewport_h", C.c_uint32), ("tile_size", C.c_uint32),
+                ("max_per_bin", C.c_uint32), ("mode", C.c_int32), ("depth_slices", C.c_uint32), ("z_near", C.c_float), ("z_far", C.c_float)]
+
+    def __init__(self, view_proj=None, w=0, h=0, mode=0, tile_size=16, max_per_bin=128, depth_slices=16, z_near=0.1, z_far=1000.0):
+        super().__init__()
+        if view_proj is not None:
+            set_f(self.view_proj, view_proj)
+        self.viewport_w, self.viewport_h, self.tile_size, self.max_per_bin = w, h, tile_size, max_per_bin
+        self.mode, self.depth_slices, self.z_near, self.z_far = mode, depth_slices, z_near, z_far
+
+    def tiles(self):
+        return ((self.viewport_w + self.tile_size - 1) // self.tile_size) * ((self.viewport_h + self.tile_size - 1) // self.tile_size)
+
+    def bins(self):
+        return self.tiles() * (self.depth_slices if self.mode == LIGHT_CULL_CLUSTERED else 1)
 
 
 class Transform(C.Structure):
@@ -181,6 +201,10 @@ def load_library(path: str | None = None):
         "shsb_taa_reset": [vp],
         "shsb_lights_upload": [vp, vp, C.c_uint32],
         "shsb_light_cull": [vp, P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32],
+        "shsb_light_cull_ex": [vp, P(LightCullDesc), P(C.c_float), P(C.c_float)],
+        "shsb_cluster_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
+        "shsb_tile_depth_range": [vp, C.c_uint32, C.c_uint32],
+        "shsb_tile_depth_range_download": [vp, P(C.c_float), P(C.c_float), C.c_size_t],
         "shsb_light_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
         "shsb_frame_forward_plus": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(Stats)],
         "shsb_last_stage_ms": [vp, P(C.c_float)],

@@ -187,6 +187,15 @@ struct shsb_context_t
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr;
     cudaGraphExec_t graph_exec[NUM_ARENAS][4]{}; // per arena (an executable graph cannot run concurrently with itself): [cull branch][shadow mode]
 
+    // depth-range / clustered light culling (shsb_light_cull_ex): per-tile view-depth ranges, per-slice NDC bounds, cluster bins
+    DevBuf<float> d_range_min, d_range_max;   // last shsb_tile_depth_range result
+    uint32_t range_w = 0, range_h = 0, range_ts = 0;
+    DevBuf<float> d_range_up_min, d_range_up_max; // caller-provided ranges
+    DevBuf<float2> d_slice_ndc;
+    DevBuf<uint32_t> d_vis;                   // frustum-visible light list
+    LightLists cluster_lists;
+    uint32_t cluster_slices = 0;
+
     // post passes: scratch for in-place operation, the light-shaft luma plane, TAA colour history
     DevBuf<uchar4> d_post_scratch;
     DevBuf<float> d_post_luma;
@@ -928,6 +937,8 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& t : ctx->textures) cudaFree(t.texels);
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
+    cudaFree(ctx->d_range_min.p); cudaFree(ctx->d_range_max.p); cudaFree(ctx->d_range_up_min.p); cudaFree(ctx->d_range_up_max.p);
+    cudaFree(ctx->d_slice_ndc.p); cudaFree(ctx->d_vis.p); cudaFree(ctx->cluster_lists.counts.p); cudaFree(ctx->cluster_lists.indices.p);
     cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p);
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
@@ -1616,6 +1627,117 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_cull_main, ctx->stream));
     ctx->cull_main_pending = true;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_tile_depth_range(shsb_ctx ctx, shsb_rt depth_motion_rt, uint32_t tile_size)
+{
+    if (!ctx || tile_size == 0) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* dm = get_rt(ctx, depth_motion_rt, SHSB_RT_DEPTH_MOTION);
+    if (!dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "tile depth range needs a live RT_ColorDepthMotion");
+    const size_t tiles = (size_t)((dm->w + tile_size - 1) / tile_size) * ((dm->h + tile_size - 1) / tile_size);
+    if (int rc = ensure_dev(ctx, ctx->d_range_min, tiles)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_range_max, tiles)) return rc;
+    launch_tile_depth_range(dm->depth, dm->w, dm->h, tile_size, dm->zn, dm->zf, ctx->d_range_min.p, ctx->d_range_max.p, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    ctx->range_w = (uint32_t)dm->w; ctx->range_h = (uint32_t)dm->h; ctx->range_ts = tile_size;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_tile_depth_range_download(shsb_ctx ctx, float* out_min, float* out_max, size_t n_tiles)
+{
+    if (!ctx || !out_min || !out_max) return SHSB_E_INVALID_ARGUMENT;
+    if (!ctx->range_ts) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile depth ranges: call shsb_tile_depth_range first");
+    const size_t tiles = (size_t)((ctx->range_w + ctx->range_ts - 1) / ctx->range_ts) * ((ctx->range_h + ctx->range_ts - 1) / ctx->range_ts);
+    if (n_tiles != tiles) return fail(ctx, SHSB_E_SIZE_MISMATCH, "caller passed %zu tiles, ranges have %zu", n_tiles, tiles);
+    CK(cudaMemcpyAsync(out_min, ctx->d_range_min.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_max, ctx->d_range_max.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_light_cull_ex(shsb_ctx ctx, const ShsbLightCullDesc* d, const float* range_min, const float* range_max)
+{
+    if (!ctx || !d) return SHSB_E_INVALID_ARGUMENT;
+    if (d->mode == SHSB_LIGHT_CULL_TILED) return shsb_light_cull(ctx, d->view_proj, d->viewport_w, d->viewport_h, d->tile_size, d->max_per_bin);
+    if (d->mode < 0 || d->mode > SHSB_LIGHT_CULL_CLUSTERED) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "unknown light culling mode %d", d->mode);
+    CK(cudaSetDevice(ctx->device));
+    CullJob job;
+    if (int rc = prepare_light_cull(ctx, d->view_proj, d->viewport_w, d->viewport_h, d->tile_size, d->max_per_bin, job)) return rc;
+    const uint32_t tiles = ((job.vw + job.ts - 1) / job.ts) * ((job.vh + job.ts - 1) / job.ts);
+    const bool clustered = d->mode == SHSB_LIGHT_CULL_CLUSTERED;
+    const uint32_t slices = clustered ? d->depth_slices : 1u;
+    if (slices == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "depth_slices must be > 0");
+    const float* dev_min = nullptr;
+    const float* dev_max = nullptr;
+    if (!clustered)
+    {
+        if ((range_min == nullptr) != (range_max == nullptr)) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "range_min and range_max must both be given or both be NULL");
+        if (range_min)
+        {
+            if (int rc = ensure_dev(ctx, ctx->d_range_up_min, tiles)) return rc;
+            if (int rc = ensure_dev(ctx, ctx->d_range_up_max, tiles)) return rc;
+            CK(cudaMemcpyAsync(ctx->d_range_up_min.p, range_min, (size_t)tiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_range_up_max.p, range_max, (size_t)tiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream)); // the caller's arrays may be pageable and short-lived
+            dev_min = ctx->d_range_up_min.p; dev_max = ctx->d_range_up_max.p;
+        }
+        else
+        {
+            if (ctx->range_ts != job.ts || ctx->range_w != job.vw || ctx->range_h != job.vh)
+                return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no device tile depth ranges for a %ux%u viewport with %u-px tiles: call shsb_tile_depth_range first", job.vw, job.vh, job.ts);
+            dev_min = ctx->d_range_min.p; dev_max = ctx->d_range_max.p;
+        }
+    }
+    else
+    {
+        // slice boundaries on the host (std::log / std::exp of the host libm, exactly like the reference: jolt_light_culling.hpp:373-382)
+        std::vector<float2> ndc(slices);
+        const float log_ratio = std::log(d->z_far / d->z_near);
+        for (uint32_t cz = 0; cz < slices; ++cz)
+        {
+            const float slice_near = d->z_near * std::exp(log_ratio * static_cast<float>(cz) / static_cast<float>(slices));
+            const float slice_far = d->z_near * std::exp(log_ratio * static_cast<float>(cz + 1) / static_cast<float>(slices));
+            ndc[cz] = make_float2(hm::ndc_from_view_depth_lh_no(slice_near, d->z_near, d->z_far), hm::ndc_from_view_depth_lh_no(slice_far, d->z_near, d->z_far));
+        }
+        if (int rc = ensure_dev(ctx, ctx->d_slice_ndc, slices)) return rc;
+        CK(cudaMemcpyAsync(ctx->d_slice_ndc.p, ndc.data(), (size_t)slices * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    LightLists& L = clustered ? ctx->cluster_lists : ctx->lists[LISTS_STANDALONE];
+    const size_t bins = (size_t)tiles * slices;
+    if (int rc = ensure_dev(ctx, L.counts, bins)) return rc;
+    if (int rc = ensure_dev(ctx, L.indices, bins * job.max_per_tile)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_vis, (size_t)ctx->n_lights + 1)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_lights[ctx->lights_cur], 1)) return rc;
+    record(ctx, 5, ctx->stream);
+    launch_light_cull_cells(ctx->d_lights[ctx->lights_cur].p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, d->mode, slices,
+                            dev_min, dev_max, ctx->d_slice_ndc.p, d->z_near, d->z_far, ctx->d_vis.p, L.counts.p, L.indices.p, ctx->stream, &ctx->launches);
+    record(ctx, 6, ctx->stream);
+    CK(cudaGetLastError());
+    L.w = job.vw; L.h = job.vh; L.ts = job.ts; L.max_per_tile = job.max_per_tile;
+    if (clustered) ctx->cluster_slices = slices;
+    else
+    {
+        ctx->lists_cur = LISTS_STANDALONE;
+        CK(cudaEventRecord(ctx->ev_cull_main, ctx->stream));
+        ctx->cull_main_pending = true;
+    }
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_cluster_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!ctx->cluster_slices) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no cluster bins: call shsb_light_cull_ex(SHSB_LIGHT_CULL_CLUSTERED) first");
+    const LightLists& L = ctx->cluster_lists;
+    const size_t bins = (size_t)((L.w + L.ts - 1) / L.ts) * ((L.h + L.ts - 1) / L.ts) * ctx->cluster_slices;
+    if (counts && n_counts != bins) return fail(ctx, SHSB_E_SIZE_MISMATCH, "counts has %zu entries, there are %zu bins", n_counts, bins);
+    if (indices && n_indices != bins * L.max_per_tile) return fail(ctx, SHSB_E_SIZE_MISMATCH, "indices has %zu entries, expected %zu", n_indices, bins * L.max_per_tile);
+    if (counts) CK(cudaMemcpyAsync(counts, L.counts.p, bins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indices) CK(cudaMemcpyAsync(indices, L.indices.p, bins * L.max_per_tile * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return SHSB_OK;
 }
 

@@ -277,4 +277,14 @@ namespace shsb_host
         }
         return mul(ortho_lh_no(l, r, b, t, n, f), view);
     }
+
+    // ndc_from_view_depth_lh_no, lighting/jolt_light_culling.hpp:85-93
+    inline float ndc_from_view_depth_lh_no(float view_depth, float z_near, float z_far)
+    {
+        const float n = std::max(z_near, 1e-4f);
+        const float f = std::max(z_far, n + 1e-3f);
+        const float z = std::clamp(view_depth, n, f);
+        const float denom = std::max(f - n, 1e-6f);
+        return ((f + n) / denom) - ((2.0f * f * n) / (denom * z));
+    }
 }

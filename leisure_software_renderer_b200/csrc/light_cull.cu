@@ -75,7 +75,7 @@ namespace shsb
 
         // make_screen_tile_cell, jolt_light_culling.hpp:95-133, evaluated by threads 0..7 (corners) and 0..5 (planes)
         // of the calling CTA; both stages are followed by a __syncthreads() in the caller.
-        __device__ __forceinline__ void cell_corner(const CullParams& cp, uint32_t tx, uint32_t ty, int c, float out[3])
+        __device__ __forceinline__ void cell_corner(const CullParams& cp, uint32_t tx, uint32_t ty, int c, float out[3], float near_ndc = -1.0f, float far_ndc = 1.0f)
         {
             // corner order nbl nbr ntl ntr fbl fbr ftl ftr (:103-117)
             const float fw = (float)cp.vw, fh = (float)cp.vh;
@@ -85,7 +85,7 @@ namespace shsb
             const float y_bottom = xsub(1.0f, xmul(xdiv((float)min((ty + 1u) * cp.ts, cp.vh), fh), 2.0f));
             const float x = (c & 1) ? x1 : x0;
             const float y = (c & 2) ? y_top : y_bottom;
-            const float z = (c & 4) ? 1.0f : -1.0f;
+            const float z = (c & 4) ? far_ndc : near_ndc; // tile_near_ndc / tile_far_ndc, :101-102
             const float4 q = xmat4_mul(cp.inv_vp, x, y, z, 1.0f);
             out[0] = xdiv(q.x, q.w);
             out[1] = xdiv(q.y, q.w);
@@ -245,6 +245,156 @@ namespace shsb
         }
     }
 
+    namespace
+    {
+        // ---------------------------------------------------------------- depth-range and clustered modes
+        // cull_lights_tiled_depth01_range / _view_depth_range / cull_lights_clustered (jolt_light_culling.hpp:196-412) share
+        // make_screen_tile_cell with a per-cell near / far NDC.  A thin depth range makes the side planes of a cell
+        // numerically unrelated to the tile's geometric planes (and a zero range makes them NaN, which the reference's
+        // comparisons then treat as "not outside"), so no conservative pre-filter is valid here: every cell runs the
+        // exact test over the camera-frustum-visible lights.
+
+        // ndc_from_depth01_lh_no, :79-83
+        __device__ __forceinline__ float ndc_from_depth01(float depth01) { return xsub(xmul(sclamp(depth01, 0.0f, 1.0f), 2.0f), 1.0f); }
+
+        // ndc_from_view_depth_lh_no, :85-93
+        __device__ __forceinline__ float ndc_from_view_depth(float view_depth, float z_near, float z_far)
+        {
+            const float n = gmax(z_near, 1e-4f);
+            const float f = gmax(z_far, xadd(n, 1e-3f));
+            const float z = sclamp(view_depth, n, f);
+            const float denom = gmax(xsub(f, n), 1e-6f);
+            return xsub(xdiv(xadd(f, n), denom), xdiv(xmul(xmul(2.0f, f), n), xmul(denom, z)));
+        }
+
+        // frustum_visible[] of :150-161 as an ascending list: vis[0] = count, vis[1..] = light indices.  One CTA.
+        __global__ void __launch_bounds__(MACRO_THREADS) frustum_list_kernel(const DevLightRec* __restrict__ lights, uint32_t n_lights, const Planes6 frustum,
+                                                                            uint32_t* __restrict__ vis)
+        {
+            __shared__ uint32_t s_warp_count[MACRO_THREADS / 32];
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            uint32_t total = 0;
+            for (uint32_t base = 0; base < n_lights; base += MACRO_THREADS)
+            {
+                const uint32_t li = base + threadIdx.x;
+                bool keep = false;
+                if (li < n_lights)
+                {
+                    const float4 sp = __ldg(reinterpret_cast<const float4*>(lights[li].cull_sphere));
+                    const float4 mn = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_min));
+                    const float4 mx4 = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_max));
+                    keep = classify(frustum.p, sp, mn, mx4) != 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                __syncthreads();
+                if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
+                __syncthreads();
+                uint32_t before = 0, chunk_total = 0;
+#pragma unroll
+                for (int w = 0; w < MACRO_THREADS / 32; ++w)
+                {
+                    const uint32_t c = s_warp_count[w];
+                    if (w < warp) before += c;
+                    chunk_total += c;
+                }
+                if (keep) vis[1 + total + before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = li;
+                total += chunk_total;
+            }
+            if (threadIdx.x == 0) vis[0] = total;
+        }
+
+        // One WARP per cell (tile, or tile x depth slice): exact classify_vs_cell over the frustum-visible lights,
+        // ascending, ballot-compacted.  Cell index = cz * tiles + ty * tiles_x + tx (:394-396).
+        __global__ void __launch_bounds__(CULL_THREADS) cell_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, int mode, uint32_t n_slices,
+                                                                         const float* __restrict__ range_min, const float* __restrict__ range_max,
+                                                                         const float2* __restrict__ slice_ndc, float z_near, float z_far,
+                                                                         const uint32_t* __restrict__ vis, uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
+        {
+            __shared__ float s_corner[CULL_THREADS / 32][8][3];
+            __shared__ float4 s_plane[CULL_THREADS / 32][6];
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const uint32_t tiles = cp.tiles_x * cp.tiles_y;
+            const uint32_t cell = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
+            if (cell >= tiles * n_slices) return; // warp-uniform
+            const uint32_t tile = cell % tiles, cz = cell / tiles;
+            const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
+            float near_ndc = -1.0f, far_ndc = 1.0f;
+            if (mode == 1) { near_ndc = ndc_from_depth01(__ldg(range_min + tile)); far_ndc = ndc_from_depth01(__ldg(range_max + tile)); }                                  // :232-235
+            else if (mode == 2) { near_ndc = ndc_from_view_depth(__ldg(range_min + tile), z_near, z_far); far_ndc = ndc_from_view_depth(__ldg(range_max + tile), z_near, z_far); } // :300-303
+            else if (mode == 3) { const float2 sl = __ldg(slice_ndc + cz); near_ndc = sl.x; far_ndc = sl.y; }                                                                 // :375-379
+            if (lane < 8) cell_corner(cp, tx, ty, lane, s_corner[warp][lane], near_ndc, far_ndc);
+            __syncwarp();
+            if (lane < 6) s_plane[warp][lane] = cell_plane(s_corner[warp], lane);
+            __syncwarp();
+            float4 planes[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) planes[i] = s_plane[warp][i];
+            const uint32_t n_cand = vis[0];
+            uint32_t total = 0;
+            for (uint32_t base = 0; base < n_cand; base += 32u)
+            {
+                const uint32_t ci = base + (uint32_t)lane;
+                bool keep = false;
+                uint32_t li = 0;
+                if (ci < n_cand)
+                {
+                    li = vis[1 + ci];
+                    const float4 sp = __ldg(reinterpret_cast<const float4*>(lights[li].cull_sphere));
+                    const float4 mn = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_min));
+                    const float4 mx = __ldg(reinterpret_cast<const float4*>(lights[li].cull_aabb_max));
+                    keep = classify(planes, sp, mn, mx) != 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep)
+                {
+                    const uint32_t pos = total + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (pos < cp.max_per_tile) indices[(size_t)cell * cp.max_per_tile + pos] = li;
+                }
+                total += (uint32_t)__popc(m);
+            }
+            if (lane == 0) counts[cell] = total;
+        }
+
+        // Per-tile depth range of the z-buffer, as linear view depth (the inverse of rasterizer.hpp:352-354:
+        // view_z = zn + z01 * (zf - zn)); pixels still at the clear value (>= 1.0) are skipped and a tile without any
+        // geometry gets [zn, zf] like build_tile_view_depth_range_from_scene (light_culling_runtime.hpp:254-261).  The
+        // software analogue of shaders/vulkan/fp_stress_depth_reduce.comp.  Light tiles are top-anchored
+        // (jolt_light_culling.hpp:105-107) while the framebuffer is y-up: tile row ty covers rows H-1-py in [ty*ts, (ty+1)*ts).
+        __global__ void __launch_bounds__(CULL_THREADS) tile_depth_range_kernel(const float* __restrict__ depth, int W, int H, uint32_t ts, uint32_t tiles_x, uint32_t tiles_y,
+                                                                                float zn, float zf, float* __restrict__ out_min, float* __restrict__ out_max)
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const uint32_t tile = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
+            if (tile >= tiles_x * tiles_y) return;
+            const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+            const int x0 = (int)(tx * ts), x1 = min((int)((tx + 1u) * ts), W);
+            const int r0 = (int)(ty * ts), r1 = min((int)((ty + 1u) * ts), H); // rows counted from the top
+            const int tw = x1 - x0, n = tw * (r1 - r0);
+            float lo = 2.0f, hi = -1.0f;
+            for (int i = lane; i < n; i += 32)
+            {
+                const int px = x0 + i % tw, py = H - 1 - (r0 + i / tw);
+                const float d = __ldg(depth + (size_t)py * W + px);
+                if (d >= 1.0f) continue;
+                lo = fminf(lo, d);
+                hi = fmaxf(hi, d);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0)
+            {
+                const bool any = hi >= 0.0f;
+                const float k = xsub(zf, zn);
+                out_min[tile] = any ? xadd(zn, xmul(lo, k)) : zn; // monotone in d, so min / max commute with the mapping
+                out_max[tile] = any ? xadd(zn, xmul(hi, k)) : zf;
+            }
+        }
+    }
+
     size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts)
     {
         const uint32_t tiles_x = (vw + ts - 1) / ts, tiles_y = (vh + ts - 1) / ts;
@@ -272,5 +422,35 @@ namespace shsb
         macro_cull_kernel<<<n_macro, MACRO_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
         tile_cull_kernel<<<(cp.tiles_x * cp.tiles_y + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
         *launches += 2;
+    }
+
+    void launch_light_cull_cells(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
+                                 uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_bin, int mode, uint32_t n_slices,
+                                 const float* range_min, const float* range_max, const float2* slice_ndc, float z_near, float z_far,
+                                 uint32_t* vis_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches)
+    {
+        CullParams cp;
+        for (int i = 0; i < 16; ++i) cp.inv_vp[i] = inv_view_proj[i];
+        cp.vw = vw; cp.vh = vh; cp.ts = ts; cp.max_per_tile = max_per_bin;
+        cp.tiles_x = (vw + ts - 1) / ts;
+        cp.tiles_y = (vh + ts - 1) / ts;
+        cp.n_lights = n_lights;
+        cp.macro_x = cp.macro_y = 0;
+        Planes6 fr;
+        for (int i = 0; i < 6; ++i) fr.p[i] = make_float4(frustum_planes24[i * 4], frustum_planes24[i * 4 + 1], frustum_planes24[i * 4 + 2], frustum_planes24[i * 4 + 3]);
+        frustum_list_kernel<<<1, MACRO_THREADS, 0, s>>>(lights, n_lights, fr, vis_scratch);
+        const uint32_t cells = cp.tiles_x * cp.tiles_y * n_slices;
+        cell_cull_kernel<<<(cells + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(lights, cp, mode, n_slices, range_min, range_max, slice_ndc, z_near, z_far,
+                                                                                                      vis_scratch, counts, indices);
+        *launches += 2;
+    }
+
+    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches)
+    {
+        const uint32_t tiles_x = ((uint32_t)W + ts - 1) / ts, tiles_y = ((uint32_t)H + ts - 1) / ts;
+        const uint32_t tiles = tiles_x * tiles_y;
+        if (!tiles) return;
+        tile_depth_range_kernel<<<(tiles + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(depth, W, H, ts, tiles_x, tiles_y, zn, zf, out_min, out_max);
+        *launches += 1;
     }
 }

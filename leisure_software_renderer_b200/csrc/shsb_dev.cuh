@@ -268,5 +268,12 @@ namespace shsb
     void launch_light_shafts(const PostLightShafts& a, const float* depth, int depth_w, float* lumad, cudaStream_t s, uint64_t* launches);
     void launch_taa(uchar4* ldr, uchar4* hist, size_t n_pixels, float keep, float blend, cudaStream_t s, uint64_t* launches);
     void launch_copy_ldr(const uchar4* src, int src_w, uchar4* dst, int dst_w, int w, int h, cudaStream_t s, uint64_t* launches);
+    // depth-range / clustered modes (jolt_light_culling.hpp:196-412): mode 1 depth01 range, 2 view-depth range, 3 clustered;
+    // vis_scratch holds n_lights + 1 words; counts[cells], indices[cells * max_per_bin], cells = tiles * n_slices
+    void launch_light_cull_cells(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
+                                 uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_bin, int mode, uint32_t n_slices,
+                                 const float* range_min, const float* range_max, const float2* slice_ndc, float z_near, float z_far,
+                                 uint32_t* vis_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches);
     size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts); // u32 words of `scratch`
 }

@@ -175,6 +175,33 @@ class Context:
         self._tiles = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
         self._max_per_tile = max_per_tile
 
+    def light_cull_ex(self, desc: "capi.LightCullDesc", range_min=None, range_max=None):
+        """Depth-range / clustered bin builders; returns (counts, indices[bins, max_per_bin])."""
+        lo = np.ascontiguousarray(range_min, dtype=np.float32).reshape(-1) if range_min is not None else None
+        hi = np.ascontiguousarray(range_max, dtype=np.float32).reshape(-1) if range_max is not None else None
+        if lo is not None:
+            assert lo.size == desc.tiles() and hi is not None and hi.size == desc.tiles()
+        rc = self.lib.shsb_light_cull_ex(self.h, C.byref(desc), capi.fptr(lo) if lo is not None else None, capi.fptr(hi) if hi is not None else None)
+        _check(self.lib, self.h, rc, "shsb_light_cull_ex")
+        bins, mx = desc.bins(), desc.max_per_bin
+        if desc.mode == capi.LIGHT_CULL_CLUSTERED:
+            counts = np.zeros(bins, dtype=np.uint32)
+            indices = np.zeros(bins * mx, dtype=np.uint32)
+            rc = self.lib.shsb_cluster_lists_download(self.h, capi.u32ptr(counts), counts.size, capi.u32ptr(indices), indices.size)
+            _check(self.lib, self.h, rc, "shsb_cluster_lists_download")
+            return counts, indices.reshape(bins, mx)
+        self._tiles, self._max_per_tile = bins, mx
+        return self.light_lists_download()
+
+    def tile_depth_range(self, depth_motion_rt, tile_size=16):
+        """Per-tile [min, max] view depth of the z-buffer (kept on the device for light_cull_ex); returns both arrays."""
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range(self.h, depth_motion_rt, tile_size), "shsb_tile_depth_range")
+        _, w, h = self._rt_shape[depth_motion_rt]
+        n = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        lo, hi = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range_download(self.h, capi.fptr(lo), capi.fptr(hi), n), "shsb_tile_depth_range_download")
+        return lo, hi
+
     def light_lists_download(self):
         counts = np.zeros(self._tiles, dtype=np.uint32)
         indices = np.zeros(self._tiles * self._max_per_tile, dtype=np.uint32)

@@ -214,6 +214,31 @@ class Oracle:
         assert rc == 0, rc
         return counts, indices
 
+    def light_cull_ex(self, records, desc, range_min=None, range_max=None):
+        assert self.kind == "port"
+        r = _records_u8(records)
+        lo = np.ascontiguousarray(range_min, dtype=np.float32).reshape(-1) if range_min is not None else None
+        hi = np.ascontiguousarray(range_max, dtype=np.float32).reshape(-1) if range_max is not None else None
+        bins, mx = desc.bins(), desc.max_per_bin
+        counts = np.zeros(bins, dtype=np.uint32)
+        indices = np.zeros((bins, mx), dtype=np.uint32)
+        rc = self.lib.shso_light_cull_ex(r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), C.byref(desc),
+                                         capi.fptr(lo) if lo is not None else None, capi.fptr(hi) if hi is not None else None,
+                                         capi.u32ptr(counts), capi.u32ptr(indices))
+        assert rc == 0, rc
+        return counts, indices
+
+    def tile_depth_range(self, depth, tile_size, zn, zf):
+        assert self.kind == "port"
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        h, w = d.shape
+        n = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        lo, hi = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        rc = self.lib.shso_tile_depth_range(capi.fptr(d), C.c_int32(w), C.c_int32(h), C.c_uint32(tile_size), C.c_float(zn), C.c_float(zf),
+                                            capi.fptr(lo), capi.fptr(hi))
+        assert rc == 0, rc
+        return lo, hi
+
     def pass_taa(self, ldr, history, history_valid):
         """In place on both arrays (PassTemporalAAAdapter); returns them."""
         assert self.kind == "port"

@@ -1598,14 +1598,34 @@ int32_t shso_pass_taa(uint8_t* ldr, uint8_t* history, int32_t history_valid, siz
     return SHSB_OK;
 }
 
-int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float view_proj[16],
-                        uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
-                        uint32_t* counts, uint32_t* indices)
+namespace
 {
-    // cull_lights_tiled, lighting/jolt_light_culling.hpp:135-187 (restated; headers need Jolt)
+    // ndc_from_depth01_lh_no / ndc_from_view_depth_lh_no, lighting/jolt_light_culling.hpp:79-93
+    inline float ndc_from_depth01(float depth01) { return std_clampf(depth01, 0.0f, 1.0f) * 2.0f - 1.0f; }
+    inline float ndc_from_view_depth(float view_depth, float z_near, float z_far)
+    {
+        const float n = std::max(z_near, 1e-4f);
+        const float f = std::max(z_far, n + 1e-3f);
+        const float z = std_clampf(view_depth, n, f);
+        const float denom = std::max(f - n, 1e-6f);
+        return ((f + n) / denom) - ((2.0f * f * n) / (denom * z));
+    }
+}
+
+// All four bin builders of lighting/jolt_light_culling.hpp share one loop: mode 0 = cull_lights_tiled (:135-187),
+// 1 = cull_lights_tiled_depth01_range (:196-258), 2 = cull_lights_tiled_view_depth_range (:261-324),
+// 3 = cull_lights_clustered (:341-412; bin = cz * tiles + ty * tiles_x + tx).  Restated; the headers need Jolt.
+static int32_t light_cull_bins(const void* records160, uint32_t n_lights, const float view_proj[16],
+                               uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
+                               int mode, uint32_t n_slices, const float* range_min, const float* range_max, float z_near, float z_far,
+                               uint32_t* counts, uint32_t* indices)
+{
     if (!view_proj || vw == 0 || vh == 0 || ts == 0 || max_per_tile == 0 || !counts || !indices) return SHSB_E_INVALID_ARGUMENT;
+    if ((mode == 1 || mode == 2) && (!range_min || !range_max)) return SHSB_E_INVALID_ARGUMENT;
+    if (mode != 3) n_slices = 1;
+    if (n_slices == 0) return SHSB_E_INVALID_ARGUMENT;
     const uint32_t tiles_x = (vw + ts - 1) / ts, tiles_y = (vh + ts - 1) / ts;
-    for (uint32_t t = 0; t < tiles_x * tiles_y; ++t) counts[t] = 0;
+    for (size_t t = 0; t < (size_t)tiles_x * tiles_y * n_slices; ++t) counts[t] = 0;
     if (n_lights == 0) return SHSB_OK;
     const uint8_t* recs = (const uint8_t*)records160;
 
@@ -1680,18 +1700,31 @@ int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float v
         return p;
     };
 
+    const float log_ratio = (mode == 3) ? std::log(z_far / z_near) : 0.0f; // :373
+    for (uint32_t cz = 0; cz < n_slices; ++cz)
     for (uint32_t ty = 0; ty < tiles_y; ++ty)
         for (uint32_t tx = 0; tx < tiles_x; ++tx)
         {
+            float zn_ndc = -1.0f, zf_ndc = 1.0f;
+            const uint32_t tile2d = ty * tiles_x + tx;
+            if (mode == 1) { zn_ndc = ndc_from_depth01(range_min[tile2d]); zf_ndc = ndc_from_depth01(range_max[tile2d]); }                             // :232-235
+            else if (mode == 2) { zn_ndc = ndc_from_view_depth(range_min[tile2d], z_near, z_far); zf_ndc = ndc_from_view_depth(range_max[tile2d], z_near, z_far); } // :300-303
+            else if (mode == 3)
+            {
+                const float slice_near = z_near * std::exp(log_ratio * (float)cz / (float)n_slices);        // :377
+                const float slice_far = z_near * std::exp(log_ratio * (float)(cz + 1) / (float)n_slices);   // :378
+                zn_ndc = ndc_from_view_depth(slice_near, z_near, z_far);
+                zf_ndc = ndc_from_view_depth(slice_far, z_near, z_far);
+            }
             // make_screen_tile_cell, jolt_light_culling.hpp:95-133
             const float x0 = (float)(tx * ts) / (float)vw * 2.0f - 1.0f;
             const float x1 = (float)std::min((tx + 1) * ts, vw) / (float)vw * 2.0f - 1.0f;
             const float y_top = 1.0f - (float)(ty * ts) / (float)vh * 2.0f;
             const float y_bottom = 1.0f - (float)std::min((ty + 1) * ts, vh) / (float)vh * 2.0f;
-            const V3 nbl = unproject(x0, y_bottom, -1.0f), nbr = unproject(x1, y_bottom, -1.0f);
-            const V3 ntl = unproject(x0, y_top, -1.0f), ntr = unproject(x1, y_top, -1.0f);
-            const V3 fbl = unproject(x0, y_bottom, 1.0f), fbr = unproject(x1, y_bottom, 1.0f);
-            const V3 ftl = unproject(x0, y_top, 1.0f), ftr = unproject(x1, y_top, 1.0f);
+            const V3 nbl = unproject(x0, y_bottom, zn_ndc), nbr = unproject(x1, y_bottom, zn_ndc);
+            const V3 ntl = unproject(x0, y_top, zn_ndc), ntr = unproject(x1, y_top, zn_ndc);
+            const V3 fbl = unproject(x0, y_bottom, zf_ndc), fbr = unproject(x1, y_bottom, zf_ndc);
+            const V3 ftl = unproject(x0, y_top, zf_ndc), ftr = unproject(x1, y_top, zf_ndc);
             const V3 inside = scale(add(add(add(nbl, ntr), fbl), ftr), 0.25f);
             Pl cell[6];
             cell[0] = oriented(nbl, nbr, ntr, inside);
@@ -1700,16 +1733,60 @@ int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float v
             cell[3] = oriented(nbr, fbr, ftr, inside);
             cell[4] = oriented(nbl, fbl, fbr, inside);
             cell[5] = oriented(ntl, ntr, ftr, inside);
-            const uint32_t tile = ty * tiles_x + tx;
+            const size_t tile = (size_t)cz * tiles_x * tiles_y + tile2d;
             uint32_t cnt = 0;
             for (uint32_t li = 0; li < n_lights; ++li)
             {
                 if (!visible[li]) continue;
                 if (classify(cell, 6, L[li]) == 0) continue;
-                if (cnt < max_per_tile) indices[(size_t)tile * max_per_tile + cnt] = li;
+                if (cnt < max_per_tile) indices[tile * max_per_tile + cnt] = li;
                 ++cnt;
             }
             counts[tile] = cnt;
+        }
+    return SHSB_OK;
+}
+
+int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float view_proj[16],
+                        uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
+                        uint32_t* counts, uint32_t* indices)
+{
+    return light_cull_bins(records160, n_lights, view_proj, vw, vh, ts, max_per_tile, 0, 1, nullptr, nullptr, 0.1f, 1000.0f, counts, indices);
+}
+
+int32_t shso_light_cull_ex(const void* records160, uint32_t n_lights, const ShsbLightCullDesc* d,
+                           const float* range_min, const float* range_max, uint32_t* counts, uint32_t* indices)
+{
+    if (!d || d->mode < 0 || d->mode > 3) return SHSB_E_INVALID_ARGUMENT;
+    return light_cull_bins(records160, n_lights, d->view_proj, d->viewport_w, d->viewport_h, d->tile_size, d->max_per_bin, d->mode, d->depth_slices,
+                           range_min, range_max, d->z_near, d->z_far, counts, indices);
+}
+
+int32_t shso_tile_depth_range(const float* depth, int32_t w, int32_t h, uint32_t ts, float zn, float zf, float* out_min, float* out_max)
+{
+    // Per-tile [min, max] linear view depth of a z-buffer written by rasterize_mesh (z01 = (view_z - zn) / (zf - zn),
+    // sw_render/rasterizer.hpp:352-354, inverted as zn + z01 * (zf - zn)); cleared pixels (>= 1.0) are skipped, tiles
+    // without geometry get [zn, zf] (light_culling_runtime.hpp:254-261).  Tile rows are top-anchored
+    // (jolt_light_culling.hpp:105-107), framebuffer rows are y-up (gfx/rt_types.hpp:35-59).  This DEFINES the software
+    // analogue of shaders/vulkan/fp_stress_depth_reduce.comp; the reference has no CPU depth reduce.
+    if (!depth || !out_min || !out_max || w <= 0 || h <= 0 || ts == 0) return SHSB_E_INVALID_ARGUMENT;
+    const uint32_t tiles_x = ((uint32_t)w + ts - 1) / ts, tiles_y = ((uint32_t)h + ts - 1) / ts;
+    for (uint32_t ty = 0; ty < tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx)
+        {
+            bool any = false;
+            float lo = zf, hi = zn;
+            for (uint32_t r = ty * ts; r < std::min((ty + 1) * ts, (uint32_t)h); ++r)
+                for (uint32_t x = tx * ts; x < std::min((tx + 1) * ts, (uint32_t)w); ++x)
+                {
+                    const float d = depth[(size_t)((uint32_t)h - 1 - r) * w + x];
+                    if (d >= 1.0f) continue;
+                    const float vz = zn + d * (zf - zn);
+                    if (!any) { lo = hi = vz; any = true; }
+                    else { lo = std::min(lo, vz); hi = std::max(hi, vz); }
+                }
+            out_min[ty * tiles_x + tx] = any ? lo : zn;
+            out_max[ty * tiles_x + tx] = any ? hi : zf;
         }
     return SHSB_OK;
 }

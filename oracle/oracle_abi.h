@@ -117,6 +117,17 @@ int32_t shso_light_cull(const void* records160, uint32_t n_lights, const float v
                         uint32_t viewport_w, uint32_t viewport_h, uint32_t tile_size, uint32_t max_per_tile,
                         uint32_t* counts, uint32_t* indices);
 
+/* cull_lights_tiled_depth01_range / cull_lights_tiled_view_depth_range / cull_lights_clustered
+ * (lighting/jolt_light_culling.hpp:196-412) and mode 0 = cull_lights_tiled.  counts[bins], indices[bins * max_per_bin],
+ * bins = tiles (* depth_slices for clustered), bin = cz * tiles + ty * tiles_x + tx. */
+int32_t shso_light_cull_ex(const void* records160, uint32_t n_lights, const ShsbLightCullDesc* desc,
+                           const float* range_min, const float* range_max, uint32_t* counts, uint32_t* indices);
+
+/* Per-tile [min, max] view depth of a z-buffer (software analogue of shaders/vulkan/fp_stress_depth_reduce.comp;
+ * semantics defined in oracle.cpp). */
+int32_t shso_tile_depth_range(const float* depth, int32_t w, int32_t h, uint32_t tile_size, float zn, float zf,
+                              float* out_min, float* out_max);
+
 /* Forward+ frame: PassPBRForward with the local-light loop of fp_stress_scene.frag:644-678 added to
  * the builtin fragment program.  counts/indices as produced by shso_light_cull. */
 int32_t shso_pass_pbr_forward_plus(const ShsoAssets* assets, const ShsbScene* scene, const ShsbFrameParams* fp,

@@ -63,6 +63,23 @@ def main():
         f = harness.cpu_forward(ref, cur, aov=False, motion=True, prev_models=prev.models(ref))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), hdr=f.hdr, ldr=f.ldr, depth=f.depth, motion=f.motion)
         print(name, f.motion.shape, float(np.abs(f.motion).max()))
+    # depth-range / clustered bins: restatement only (the reference's headers need Jolt) -> "_port" fixture
+    import test_light_bins_cpu as lb
+    sd = lb.bins_scene()
+    f = harness.cpu_forward(port, sd, aov=False)
+    lo, hi = port.tile_depth_range(f.depth, 16, sd.zn, sd.zf)
+    rng = np.random.default_rng(3)
+    n = lo.size
+    r01_min = (rng.random(n, dtype=np.float32) * np.float32(0.6)).astype(np.float32)
+    r01_max = (r01_min + rng.random(n, dtype=np.float32) * np.float32(0.5)).astype(np.float32)
+    r01_max[::7] = r01_min[::7]          # zero-thickness cells: NaN side planes keep every light touching the slab (classify_* never reject on NaN)
+    bins = {"range_min": lo, "range_max": hi, "range01_min": r01_min, "range01_max": r01_max}
+    for name, d in lb.descs(sd, mx=32).items():
+        r = (lo, hi) if name == "view_depth" else ((r01_min, r01_max) if name == "depth01" else (None, None))
+        c, i = port.light_cull_ex(sd.lights, d, *r)
+        bins[name + "_counts"], bins[name + "_indices"] = c, i
+    np.savez_compressed(os.path.join(HERE, "golden_light_bins_port.npz"), **bins)
+    print("light bins", {k: int(v.sum()) for k, v in bins.items() if k.endswith("_counts")})
     post = {}
     for name, (make, p) in post_cases.blur_cases().items():
         ldr, depth, motion = make()
