@@ -416,12 +416,15 @@ SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, c
                                          shsb_rt hdr_rt, shsb_rt depth_motion_rt, shsb_rt ldr_rt,
                                          ShsbStats* out_stats);
 
-/* Last frame's per-stage device times in milliseconds (CUDA events on the context stream):
+/* Last frame's per-stage device times in milliseconds (CUDA events on the context stream; recorded for synchronous
+ * submissions -- out_stats != NULL -- and for frames sampled by shsb_timing_enable, zero otherwise):
  * [0] vertex+setup, [1] binning, [2] tile raster+shade, [3] light cull, [4] tonemap, [5] total. */
 SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8]);
 
-/* Per-frame stage timing history for benchmarks: while enabled every frame submission records four CUDA
- * events on the context stream (no host synchronisation).  shsb_timing_collect synchronises, writes
+/* Per-frame stage timing history for benchmarks: while enabled, frame submissions record five CUDA events on
+ * their streams (no host synchronisation).  enable = n > 1 samples every n-th frame only: each event is one more
+ * command for the GPU's host interface to fetch, and five per frame lengthen a 135 us frame by ~15 us
+ * (profiles/r1_pcie_command_latency_s4.md).  shsb_timing_collect synchronises, writes
  * {vertex+setup, binning, tile raster+shade, total} milliseconds per frame and clears the history. */
 SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable);
 SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames);

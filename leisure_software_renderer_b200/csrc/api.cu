@@ -169,6 +169,8 @@ struct shsb_context_t
 
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
+    bool stage_events = true;            // false while an asynchronous frame without timing history is submitted
+    bool main_needs_lights = false;      // the render stream has not yet been ordered behind the last light upload
 
     // Frame submission as a CUDA graph: the frame's memset / H2D copy / kernels are stream-captured, an existing
     // executable graph of the same topology is updated in place (cudaGraphExecUpdate) and launched once.  The
@@ -185,7 +187,7 @@ struct shsb_context_t
     cudaStream_t copy_stream2 = nullptr; // the next copy is already queued on the engine when one finishes
     int copy_flip = 0;
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr;
-    cudaGraphExec_t graph_exec[NUM_ARENAS][4]{}; // per arena (an executable graph cannot run concurrently with itself): [cull branch][shadow mode]
+    cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
 
     // depth-range / clustered light culling (shsb_light_cull_ex): per-tile view-depth ranges, per-slice NDC bounds, cluster bins
     DevBuf<float> d_range_min, d_range_max;   // last shsb_tile_depth_range result
@@ -209,6 +211,7 @@ struct shsb_context_t
 
     // optional per-frame stage timing history (4 events per frame, no host sync while recording)
     bool timing_on = false;
+    long long timing_stride = 1;         // record the stage events of every n-th frame only
     std::vector<cudaEvent_t> timing_ev;
     size_t timing_used = 0;
 };
@@ -364,8 +367,12 @@ namespace
         else cudaEventRecord(e, s);
     }
 
+    // Stage events feed shsb_last_stage_ms / the timing history.  An asynchronous submission without the timing history has
+    // no reader for them, and every extra command on the render stream is a separate fetch by the GPU's host interface
+    // over PCIe -- microseconds each once a frame read-back saturates the link (profiles/r1_pcie_command_latency_s4.md).
     void record(shsb_ctx ctx, int i, cudaStream_t s)
     {
+        if (!ctx->stage_events) { ctx->ev_valid[i] = false; return; }
         record_on(ctx, ctx->ev[i], s);
         ctx->ev_valid[i] = true;
         if (ctx->timing_on && i < TIMING_EVENTS_PER_FRAME)
@@ -420,6 +427,8 @@ namespace
         ctx->lists_cur = set;
     }
 
+    int main_wait_lights(shsb_ctx ctx);
+
     // Submits one frame: front end (draw list staged in ctx->h_draw[stage_slot]) on the front stream in arena
     // frame_no % NUM_ARENAS, tile kernel on the main stream.
     int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats, const CullJob* cull = nullptr)
@@ -431,6 +440,8 @@ namespace
         if (fc.W > 65535 || fc.H > 65535) return fail(ctx, SHSB_E_UNSUPPORTED, "render target larger than 65535 pixels on a side");
         if ((job.n_src_tris + 1) * 8ull >= 0xFFFFFFFFull) return fail(ctx, SHSB_E_UNSUPPORTED, "more than 2^29 source triangles in one submission");
         if (int rc = sync_tables(ctx)) return rc;
+        struct StageEventScope { shsb_ctx c; ~StageEventScope() { c->stage_events = true; } } stage_scope{ctx};
+        ctx->stage_events = out_stats != nullptr || (ctx->timing_on && ctx->frame_no % ctx->timing_stride == 0);
 
         for (int attempt = 0; attempt < 4; ++attempt)
         {
@@ -534,7 +545,7 @@ namespace
                 if (err == cudaSuccess) err = ec;
                 if (err == cudaSuccess)
                 {
-                    cudaGraphExec_t& exec = ctx->graph_exec[a][(cull ? 2 : 0) + (fc.shadow_mode ? 1 : 0)];
+                    cudaGraphExec_t& exec = ctx->graph_exec[a][(ctx->stage_events ? 4 : 0) + (cull ? 2 : 0) + (fc.shadow_mode ? 1 : 0)];
                     if (exec)
                     {
                         cudaGraphExecUpdateResultInfo info{};
@@ -559,6 +570,7 @@ namespace
             }
             // ---- tile kernel: main stream, after this frame's front end (and, by stream order, after every earlier
             // tile kernel and whatever the caller ordered on the main stream)
+            if (fc.forward_plus && !cull) { if (int rc = main_wait_lights(ctx)) return rc; } // lists built earlier: the records are read directly
             CK(cudaStreamWaitEvent(s1, ctx->ev_front_done[a], 0));
             record(ctx, 3, s1);
             launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
@@ -643,14 +655,32 @@ namespace
         return SHSB_OK;
     }
 
-    // A pass that is about to overwrite a render target must not overtake an asynchronous download of it.
+    // A pass that is about to overwrite a render target must not overtake an asynchronous download of it.  A download
+    // that has already finished (the usual case with a few render-target sets in rotation) needs no command at all.
     void wait_pending_read(shsb_ctx ctx, RtSlot* r)
     {
         if (r && r->read_pending)
         {
-            cudaStreamWaitEvent(ctx->stream, r->read_done, 0);
+            if (cudaEventQuery(r->read_done) != cudaSuccess)
+            {
+                cudaGetLastError();
+                cudaStreamWaitEvent(ctx->stream, r->read_done, 0);
+            }
             r->read_pending = false;
         }
+    }
+
+    // Orders the render stream behind the last light upload (which ran on a front-end stream).  Needed by work on the
+    // render stream that reads the light records directly: a standalone cull, or the tile kernel of a frame whose lists
+    // were built earlier.  A frame that culls itself is ordered through its own front end instead.
+    int main_wait_lights(shsb_ctx ctx)
+    {
+        if (ctx->main_needs_lights)
+        {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lights_up, 0));
+            ctx->main_needs_lights = false;
+        }
+        return SHSB_OK;
     }
 
     int shader_from_params(const ShsbFrameParams* fp)
@@ -1607,7 +1637,7 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     }
     CK(cudaEventRecord(ctx->ev_lights_up, su));
     ctx->lights_uploaded = true;
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lights_up, 0));
+    ctx->main_needs_lights = true; // ordered lazily: a frame that culls reaches the records through its front end (main_wait_lights)
     ctx->lights_cur = b;
     ctx->lights_last_user[b] = -1;
     ctx->n_lights = n_lights;
@@ -1622,6 +1652,7 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
     CullJob job;
     if (int rc = prepare_light_cull(ctx, view_proj, vw, vh, ts, max_per_tile, job)) return rc;
     if (int rc = ensure_lists(ctx, ctx->lists[LISTS_STANDALONE], job)) return rc;
+    if (int rc = main_wait_lights(ctx)) return rc;
     // main stream: ordered behind every tile kernel that read the standalone set
     enqueue_light_cull(ctx, job, LISTS_STANDALONE, ctx->stream);
     CK(cudaGetLastError());
@@ -1711,6 +1742,7 @@ SHSB_API int32_t shsb_light_cull_ex(shsb_ctx ctx, const ShsbLightCullDesc* d, co
     if (int rc = ensure_dev(ctx, L.indices, bins * job.max_per_tile)) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_vis, (size_t)ctx->n_lights + 1)) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_lights[ctx->lights_cur], 1)) return rc;
+    if (int rc = main_wait_lights(ctx)) return rc;
     record(ctx, 5, ctx->stream);
     launch_light_cull_cells(ctx->d_lights[ctx->lights_cur].p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, d->mode, slices,
                             dev_min, dev_max, ctx->d_slice_ndc.p, d->z_near, d->z_far, ctx->d_vis.p, L.counts.p, L.indices.p, ctx->stream, &ctx->launches);
@@ -1760,6 +1792,7 @@ SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     ctx->timing_on = enable != 0;
+    ctx->timing_stride = std::max(1, enable);
     ctx->timing_used = 0;
     return SHSB_OK;
 }

@@ -25,6 +25,16 @@ for _ in range(3):
 out = (C.c_ulonglong * 32)()
 ctx.lib.shsb_debug_phase_clocks(out, 1)
 N = 10
+if len(sys.argv) > 2 and sys.argv[2] == "d2h":
+    # a back-to-back 8.3 MB device -> pinned-host copy loop on another stream while the frames run
+    import torch
+    copy = torch.cuda.Stream()
+    d_small = torch.empty(1920 * 1080 * 4, dtype=torch.uint8, device="cuda")
+    h_small = [torch.empty(1920 * 1080 * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    with torch.cuda.stream(copy):
+        for i in range(200):
+            h_small[i % 2].copy_(d_small, non_blocking=True)
+    print("with a concurrent D2H copy loop")
 for _ in range(N):
     ctx.frame_forward_plus(sd.scene, sd.fp, hdr, dm, ldr)
 ctx.lib.shsb_debug_phase_clocks(out, 1)
