@@ -53,5 +53,44 @@ def main():
         print(json.dumps({"pass": name, "w": w, "h": h, "ms": ms, "algorithmic_bytes": w * h * bpp, "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / peak}))
 
 
+def bins():
+    """Depth reduce + the depth-range / clustered bin builders on the C2 scene (1080p, 1024 lights)."""
+    from leisure_software_renderer_b200 import scenes
+    sd = scenes.scene_c2()
+    gpu = Context(0)
+    for m in sd.meshes:
+        gpu.mesh_upload(m["positions"], m["normals"], m["uvs"], m["indices"])
+    gpu.lights_upload(sd.lights.view(np.uint8))
+    hdr = gpu.rt_create(capi.RT_COLOR_HDR, sd.w, sd.h); dm = gpu.rt_create(capi.RT_DEPTH_MOTION, sd.w, sd.h, sd.zn, sd.zf)
+    fp = capi.FrameParams.from_buffer_copy(sd.fp)
+    fp.light_culling = 0
+    gpu.pass_pbr_forward(sd.scene, fp, hdr, dm)
+    stream = torch.cuda.ExternalStream(gpu.stream())
+    import ctypes as C
+    mk = lambda mode, **kw: capi.LightCullDesc(sd.viewproj, sd.w, sd.h, mode, 16, 128, z_near=sd.zn, z_far=sd.zf, **kw)
+    descs = {"tiled (two-level, shsb_light_cull)": mk(capi.LIGHT_CULL_TILED), "tiled view-depth range": mk(capi.LIGHT_CULL_TILED_VIEW_DEPTH),
+             "clustered x16": mk(capi.LIGHT_CULL_CLUSTERED, depth_slices=16)}
+    calls = {"tile_depth_range": lambda: gpu.lib.shsb_tile_depth_range(gpu.h, dm, 16)}
+    gpu.lib.shsb_tile_depth_range(gpu.h, dm, 16)
+    for name, d in descs.items():
+        calls["light_cull_ex " + name] = (lambda d=d: gpu.lib.shsb_light_cull_ex(gpu.h, C.byref(d), None, None))
+    for name, fn in calls.items():
+        for _ in range(3):
+            assert fn() == 0
+        gpu.sync()
+        n = 30
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                fn()
+            e1.record(stream)
+        gpu.sync()
+        print(json.dumps({"call": name, "w": sd.w, "h": sd.h, "lights": len(sd.lights), "ms": e0.elapsed_time(e1) / n}))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bins":
+        bins()
+    else:
+        main()
