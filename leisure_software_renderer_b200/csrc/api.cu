@@ -169,6 +169,8 @@ struct shsb_context_t
 
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
+    uint64_t launches_at_tile = ~0ull;   // value of `launches` right after the last frame's tile kernel was submitted
+    int tile_event_at_tile = -1;         // ring index of that frame's "tile done" event
     bool stage_events = true;            // false while an asynchronous frame without timing history is submitted
     bool main_needs_lights = false;      // the render stream has not yet been ordered behind the last light upload
 
@@ -584,6 +586,8 @@ namespace
             }
             ctx->host_us[4] += now_us() - t_c;
             ctx->host_us[5] += 1.0;
+            ctx->launches_at_tile = ctx->launches; // shsb_rt_download_async reuses this frame's "tile done" event while nothing else has been launched
+            ctx->tile_event_at_tile = (int)(f % TILE_DONE_RING);
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
             CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats) * STAT_SHARDS, cudaMemcpyDeviceToHost, s1));
@@ -1213,9 +1217,18 @@ SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane,
     if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
     if (!r->read_done) CK(cudaEventCreateWithFlags(&r->read_done, cudaEventDisableTiming));
     // copy stream waits for everything submitted to the render stream so far, then copies while later frames render
-    CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
     cudaStream_t cs = (ctx->copy_flip ^= 1) ? ctx->copy_stream : ctx->copy_stream2;
-    CK(cudaStreamWaitEvent(cs, ctx->ev_frame_done, 0));
+    if (ctx->launches == ctx->launches_at_tile && ctx->tile_event_at_tile >= 0)
+    {
+        // the last thing this library put on the render stream is a frame's tile kernel, which already recorded an event:
+        // no further command on the (critical) render stream
+        CK(cudaStreamWaitEvent(cs, ctx->ev_tile_done[ctx->tile_event_at_tile], 0));
+    }
+    else
+    {
+        CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_frame_done, 0));
+    }
     CK(cudaMemcpyAsync(dst_pinned, p, bytes, cudaMemcpyDeviceToHost, cs));
     CK(cudaEventRecord(r->read_done, cs));
     r->read_pending = true;
@@ -1579,6 +1592,7 @@ SHSB_API int32_t shsb_pass_taa(shsb_ctx ctx, shsb_rt ldr_rt)
     if (!ctx->taa_valid) // :1461-1469: seed the history, leave the frame untouched
     {
         CK(cudaMemcpyAsync(ctx->d_taa_hist.p, ldr->color, count * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches += 1; // a device operation on the render stream (see shsb_rt_download_async)
         ctx->taa_valid = true;
         return SHSB_OK;
     }

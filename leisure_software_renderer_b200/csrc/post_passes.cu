@@ -23,6 +23,22 @@ namespace shsb
         }
         __device__ __forceinline__ int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+        // clamp((int)std::lround(v), 0, hi) for 0 <= hi < 2^22, without the conversion unit.  lround is monotone and
+        // maps 0 -> 0 and hi -> hi, so clamping FIRST (in float) gives the same integer; the clamped value is >= 0 and
+        // small, so adding 1.5 * 2^23 rounds it to an integer (ties to even) whose value sits in the low mantissa bits,
+        // and the one case where ties-to-even differs from half-away-from-zero (remainder exactly +0.5) is fixed up.
+        // FRND / F2I run at a quarter of the FP32 rate and four of them per tap made the march conversion-bound.
+        // (|v| beyond the int range is undefined behaviour in the reference's (int) cast; here it clamps like any other value.)
+        __device__ __forceinline__ int lround_clamp0(float v, float hi_f)
+        {
+            const float MAGIC = 12582912.0f; // 1.5 * 2^23
+            const float vc = fminf(fmaxf(v, 0.0f), hi_f);
+            const float t = vc + MAGIC;
+            int r = __float_as_int(t) - 0x4B400000;
+            if (vc - (t - MAGIC) == 0.5f) r += 1;
+            return r;
+        }
+
         // ------------------------------------------------------------------ PassMotionBlur
         // pass_motion_blur.hpp:109-161: per pixel, `samples` taps along the (scaled, clamped) velocity, each
         // rejected when its depth differs from the centre's by more than depth_reject; mean of the kept taps.
@@ -51,12 +67,12 @@ namespace shsb
                 }
                 const float centre_depth = a.depth[(size_t)y * a.mot_w + x];
                 float ar = 0.0f, ag = 0.0f, ab = 0.0f, aw = 0.0f;
-                const float fx = (float)x, fy = (float)y;
+                const float fx = (float)x, fy = (float)y, wm1 = (float)(a.w - 1), hm1 = (float)(a.h - 1);
                 for (int i = 0; i < a.samples; ++i) // :136-149
                 {
                     const float t = t_tab[i];
-                    const int sx = iclamp(lround_f(fx + vx * t), 0, a.w - 1);
-                    const int sy = iclamp(lround_f(fy + vy * t), 0, a.h - 1);
+                    const int sx = lround_clamp0(fx + vx * t, wm1);
+                    const int sy = lround_clamp0(fy + vy * t, hm1);
                     const float sd = __ldg(a.depth + (size_t)sy * a.mot_w + sx);
                     if (fabsf(sd - centre_depth) > a.depth_eps) continue;
                     const uchar4 sc = __ldg(a.src + (size_t)sy * a.src_w + sx);
@@ -83,11 +99,14 @@ namespace shsb
         __global__ void __launch_bounds__(256) shafts_luma_kernel(const uchar4* __restrict__ src, int src_w, const float* __restrict__ depth, int depth_w,
                                                                   float* __restrict__ lumad, int w, int h)
         {
+            __shared__ float unorm[256]; // (float)c / 255.0f, one exact division per value per CTA instead of three per pixel
+            unorm[threadIdx.x] = (float)threadIdx.x / 255.0f;
+            __syncthreads();
             const int x = blockIdx.x * 32 + (threadIdx.x & 31);
             const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
             if (x >= w || y >= h) return;
             const uchar4 c = src[(size_t)y * src_w + x];
-            const float r = (float)c.x / 255.0f, g = (float)c.y / 255.0f, b = (float)c.z / 255.0f;
+            const float r = unorm[c.x], g = unorm[c.y], b = unorm[c.z];
             float s = 0.2126f * r + 0.7152f * g + 0.0722f * b;
             if (depth) s *= sclamp(depth[(size_t)y * depth_w + x], 0.0f, 1.0f);
             lumad[(size_t)y * w + x] = s;
@@ -114,9 +133,9 @@ namespace shsb
                 const float t = (i < SHAFT_TABLE) ? t_tab[i] : (float)i / fsteps;
                 const float su = u + du * t * a.density;
                 const float sv = v + dv * t * a.density;
-                const int sx = iclamp(lround_f(su * wm1), 0, a.w - 1);
-                const int sy = iclamp(lround_f(sv * hm1), 0, a.h - 1);
-                const float s = __ldg(a.lumad + (size_t)sy * a.w + sx);
+                const int sx = lround_clamp0(su * wm1, wm1);
+                const int sy = lround_clamp0(sv * hm1, hm1);
+                const float s = __ldg(a.lumad + (sy * a.w + sx));
                 accum += s * illum_decay * a.weight;
                 illum_decay *= a.decay;
             }
