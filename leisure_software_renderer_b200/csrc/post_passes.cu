@@ -128,9 +128,7 @@ namespace shsb
             const float du = a.sun_u - u, dv = a.sun_v - v;
             const float wm1 = (float)(a.w - 1), hm1 = (float)(a.h - 1), fsteps = (float)a.steps;
             float illum_decay = 1.0f, accum = 0.0f;
-            for (int i = 0; i < a.steps; ++i)
-            {
-                const float t = (i < SHAFT_TABLE) ? t_tab[i] : (float)i / fsteps;
+            auto tap = [&](float t) {
                 const float su = u + du * t * a.density;
                 const float sv = v + dv * t * a.density;
                 const int sx = lround_clamp0(su * wm1, wm1);
@@ -138,7 +136,10 @@ namespace shsb
                 const float s = __ldg(a.lumad + (sy * a.w + sx));
                 accum += s * illum_decay * a.weight;
                 illum_decay *= a.decay;
-            }
+            };
+            const int n_tab = min(a.steps, SHAFT_TABLE);
+            for (int i = 0; i < n_tab; ++i) tap(t_tab[i]);
+            for (int i = n_tab; i < a.steps; ++i) tap((float)i / fsteps); // beyond the table: divide per pixel
             const uchar4 base = a.src[(size_t)y * a.src_w + x];
             const int boost = iclamp(lround_f(accum * 80.0f), 0, 120);
             uchar4 out;

@@ -382,3 +382,42 @@ def scene_small(w=160, h=120, shading=capi.SHADING_PBR, n_inst=3, lights=0, tex=
     cam = (0.5, 1.2, -2.2) if near_clip else (0, 4, -8)
     return SceneData(f"small_{w}x{h}", w, h, 0.1, 100.0, meshes, textures, items, cam, (0, 0.5, 0), math.radians(60.0),
                      _SUN_DIR, _SUN_COLOR, 2.2, fp, lt, shadow_size=256, sky=sky_desc)
+
+
+def scene_ragged(w=150, h=110, shading=capi.SHADING_PBR, shadow=False, nonfinite=True) -> SceneData:
+    """Ragged / hostile inputs the reference's triangle loop accepts (sw_render/rasterizer.hpp:196-230, 260-290):
+    a NON-indexed mesh; normal / uv arrays shorter than the position array (defaults (0,1,0) / (0,0)); indices beyond
+    the position array (triangle counted in tri_input, then skipped); zero-area and repeated-vertex triangles; a vertex
+    at infinity and a NaN vertex (non-finite reject); an invisible item; an item without a material; a zero-scale item
+    (singular normal matrix: builtin_shaders.hpp:93-96 falls back to mat3(model)); an item that casts no shadow."""
+    rng = np.random.default_rng(12)
+    # mesh 1: non-indexed soup of 40 triangles around the origin, normals for the first 70 vertices only, uvs for 50
+    pos = (rng.random((120, 3), dtype=np.float32) - 0.5) * np.float32(3.0)
+    pos[9] = pos[10]                                   # repeated vertex -> zero area
+    pos[12:15] = pos[12]                               # a point
+    if nonfinite:                                      # (they also poison the scene AABB of PassShadowMap: keep them out of shadow cases)
+        pos[30] = (np.float32(np.inf), 0.0, 0.0)       # vertex at infinity
+        pos[45] = (np.float32(np.nan), 1.0, 1.0)       # NaN vertex
+    nrm = rng.random((70, 3), dtype=np.float32) - 0.5
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    soup = {"positions": pos, "normals": nrm.astype(np.float32), "uvs": rng.random((50, 2), dtype=np.float32), "indices": np.zeros((0,), np.uint32)}
+    # mesh 2: indexed quad grid with some indices out of range and a trailing partial triangle
+    grid = make_grid_plane(6.0, 4)
+    idx = grid["indices"].copy()
+    idx[7] = 10_000                                    # beyond positions.size(): triangle skipped after tri_input++
+    idx[20] = len(grid["positions"])                   # == size: also out of range
+    idx = np.concatenate([idx, np.array([0, 1], np.uint32)])   # 2 dangling indices: indices.size() / 3 truncates
+    ragged_grid = dict(grid, indices=idx, uvs=grid["uvs"][:5])
+    meshes = [soup, ragged_grid, load_suzanne()]
+    textures = [make_checker_texture(16)]
+    items = [
+        {"pos": (0, -0.8, 0), "mesh": 2, "material": dict(_MATERIALS[1], tex=1), "casts_shadow": False, "object_id": 1},
+        {"pos": (-0.5, 0.6, 0.5), "rot": (0.3, 0.8, 0.1), "scl": (1.2, 0.9, 1.1), "mesh": 1, "material": dict(_MATERIALS[0], tex=1), "object_id": 2},
+        {"pos": (1.8, 0.4, 0.2), "rot": (0.0, 2.5, 0.0), "mesh": 3, "material": None, "object_id": 3},                     # no material: reference defaults
+        {"pos": (-2.0, 0.5, 1.0), "mesh": 3, "material": _MATERIALS[2], "visible": False, "object_id": 4},               # invisible
+        {"pos": (0.2, 1.4, -0.4), "scl": (1.0, 0.0, 1.0), "mesh": 3, "material": _MATERIALS[3], "object_id": 5},          # flattened: det(model) = 0
+        {"pos": (0.0, 0.2, 1.5), "scl": (0.0, 0.0, 0.0), "mesh": 3, "material": _MATERIALS[3], "object_id": 6},           # collapsed to a point
+    ]
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=1 if shadow else 0, light_culling=0, motion_vectors_enable=0)
+    return SceneData(f"ragged_{w}x{h}", w, h, 0.1, 60.0, meshes, textures, items, (0.3, 2.2, -4.5), (0, 0.4, 0), math.radians(55.0),
+                     _SUN_DIR, _SUN_COLOR, 2.0, fp, None, shadow_size=160)

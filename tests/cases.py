@@ -42,6 +42,8 @@ def forward_cases():
         "sky_procedural": (lambda: scenes.scene_small(w=192, h=108, sky="procedural"), {}),
         "sky_cubemap_tex": (lambda: scenes.scene_small(w=176, h=100, sky="cubemap", tex=True), {}),
         "sky_cubemap_nearclip_blinn": (lambda: scenes.scene_small(w=150, h=90, sky="cubemap", near_clip=True, shading=capi.SHADING_BLINN), {}),
+        "ragged_inputs_pbr": (lambda: scenes.scene_ragged(), {}),
+        "ragged_inputs_blinn_shadow": (lambda: scenes.scene_ragged(w=131, h=97, shading=capi.SHADING_BLINN, shadow=True, nonfinite=False), {"shadow": True}),
         "empty_scene": (lambda: scenes.scene_small(n_inst=0, w=64, h=48), {}),
         "tiny_target_1x1": (lambda: scenes.scene_small(w=1, h=1), {}),
     }
