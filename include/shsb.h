@@ -219,7 +219,15 @@ typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/f
     uint32_t max_lights_per_tile; /* technique.max_lights_per_tile (128)                      */
     int32_t write_aovs;
     int32_t motion_vectors_enable; /* pass.motion_vectors.enable (frame/frame_params.hpp:46-49; reference default: true) */
-    int32_t reserved[3];
+    /* Sort-first screen partition (no reference counterpart -- the CPU renderer draws whole frames):
+     * this submission rasterises, shades and writes ONLY the 16-px tile rows it owns, row ty (0 = top of the frame) being
+     * owned iff ty >= own_row_first and (ty - own_row_first) % own_row_stride < own_row_count.  own_row_count = 0 means the
+     * whole frame.  Pixels of other rows are left untouched in every plane, so the union of the ranks' submissions is
+     * bit-identical to one whole-frame submission.  Draws whose projected bounds cannot reach an owned row are skipped on the host,
+     * so triangle statistics cover the remaining draws; fragment statistics are per owner and add up to the whole frame's. */
+    int32_t own_row_first;
+    int32_t own_row_count;
+    int32_t own_row_stride;
 } ShsbFrameParams;
 
 typedef struct ShsbMotionBlurParams /* MotionBlurPassParams (frame/frame_params.hpp:51-59) + FrameParams::dt */

@@ -123,7 +123,8 @@ class FrameParams(C.Structure):
                 ("shadow_pcf_radius", C.c_int32), ("shadow_pcf_step", C.c_float), ("shadow_strength", C.c_float),
                 ("exposure", C.c_float), ("gamma", C.c_float),
                 ("light_culling", C.c_int32), ("tile_size", C.c_uint32), ("max_lights_per_tile", C.c_uint32),
-                ("write_aovs", C.c_int32), ("motion_vectors_enable", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("write_aovs", C.c_int32), ("motion_vectors_enable", C.c_int32),
+                ("own_row_first", C.c_int32), ("own_row_count", C.c_int32), ("own_row_stride", C.c_int32)]
 
 
 def default_frame_params(**kw) -> FrameParams:

@@ -615,6 +615,32 @@ namespace
         return fail(ctx, SHSB_E_OUT_OF_MEMORY, "per-frame arena overflow persisted after regrowth");
     }
 
+    // Sort-first partitions (ShsbFrameParams::own_row_*): can any triangle of this draw reach a tile row this submission owns?
+    // Conservative: the 8 corners of the mesh's local bounds are projected like vertices (rasterizer.hpp:260-269); if all lie in
+    // front of the camera, every triangle's clamped pixel bbox lies within the corners' screen-y range (+- one pixel of rounding
+    // slack, then whole tile rows).  Any corner at w <= 0 or non-finite means "cannot bound": keep the draw.  A skipped draw
+    // contributes no pixels to the owned rows, so the frame is unchanged; only the whole-scene triangle counters shrink.
+    bool item_touches_owned_rows(const FrameConst& fc, const hm::mat4f& viewproj, const hm::mat4f& model, const MeshSlot& mesh)
+    {
+        float ymin = 3.0e38f, ymax = -3.0e38f;
+        for (int c = 0; c < 8; ++c)
+        {
+            const hm::vec4f wp = hm::mul_v(model, {(c & 1) ? mesh.bmax.x : mesh.bmin.x, (c & 2) ? mesh.bmax.y : mesh.bmin.y, (c & 4) ? mesh.bmax.z : mesh.bmin.z, 1.0f});
+            const hm::vec4f clip = hm::mul_v(viewproj, {wp.x, wp.y, wp.z, 1.0f});
+            if (!(clip.w > 1e-4f) || !std::isfinite(clip.y) || !std::isfinite(clip.w)) return true;
+            const float sy = (clip.y / clip.w * 0.5f + 0.5f) * (float)(fc.H - 1);
+            if (!std::isfinite(sy)) return true;
+            ymin = std::min(ymin, sy);
+            ymax = std::max(ymax, sy);
+        }
+        ymin -= 2.0f; ymax += 2.0f;
+        if (ymax < 0.0f || ymin > (float)(fc.H - 1)) return false; // entirely above or below the frame: no pixels at all
+        const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(fc.H - 1)));
+        const int ty0 = (fc.H - 1 - py1) / TILE, ty1 = (fc.H - 1 - py0) / TILE; // tile rows count from the top
+        for (int ty = ty0; ty <= ty1; ++ty) if (owned_row(fc, ty)) return true;
+        return false;
+    }
+
     // Stages one draw into the host item / block tables.
     int stage_item(shsb_ctx ctx, std::vector<DevItem>& items, std::vector<uint2>& blocks, uint64_t& tri_cursor,
                    const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
@@ -743,6 +769,11 @@ namespace
         fc.shader_id = depth_only ? SHSB_SHADER_DEPTH_ONLY : shader_from_params(fp);
         fc.cull_mode = fp->cull_mode;
         fc.front_face_ccw = fp->front_face_ccw;
+        if (fp->own_row_count > 0)
+        {
+            if (fp->own_row_first < 0 || fp->own_row_stride < fp->own_row_count) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "own_row_first must be >= 0 and own_row_stride >= own_row_count");
+            fc.own_first = fp->own_row_first; fc.own_count = fp->own_row_count; fc.own_stride = fp->own_row_stride;
+        }
         fc.has_depth = dm ? 1 : 0;
         fc.linear_depth = (dm && (dm->zf > dm->zn + 1e-6f)) ? 1 : 0;
         fc.load_depth = (!depth_only && preserve_depth) ? 1 : 0;
@@ -875,6 +906,13 @@ namespace
                 next_keys.push_back(key);
                 next_models.push_back(model);
                 if (write_motion) prev = &prev_model;
+            }
+            if (fc.own_count > 0 && !item_touches_owned_rows(fc, hm::load(scene->cam_viewproj), model, *mesh))
+            {
+                // sort-first: this draw can only reach another rank's rows.  Its triangles keep their place in the draw order
+                // (the triangle-id AOV and depth ties are defined by the whole scene's order, not by what this rank draws).
+                tri_cursor += mesh->n_indices ? mesh->n_indices / 3 : mesh->n_positions / 3;
+                continue;
             }
             const float def_color[3] = {0.8f, 0.5f, 0.2f}; // pass_pbr_forward.hpp:179-184
             if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex, prev);

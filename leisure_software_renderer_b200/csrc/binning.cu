@@ -59,12 +59,15 @@ namespace shsb
                 if (n_tiles > 0 && n_tiles <= SMALL_TILES)
                 {
                     for (int ty = tr.ty0; ty <= tr.ty1; ++ty)
+                    {
+                        if (!owned_row(fc, ty)) continue; // must mirror the counting in geometry.cu exactly
                         for (int tx = tr.tx0; tx <= tr.tx1; ++tx)
                         {
                             const uint32_t t = (uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx;
                             const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
                             if (pos < g.list_capacity) g.tile_list[pos] = i;
                         }
+                    }
                 }
                 unsigned big = __ballot_sync(0xffffffffu, n_tiles > SMALL_TILES);
                 while (big)
@@ -79,6 +82,7 @@ namespace shsb
                     for (int k = lane; k < total; k += 32)
                     {
                         const int ty = ty0 + k / wx, tx = tx0 + k % wx;
+                        if (!owned_row(fc, ty)) continue;
                         const uint32_t t = (uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx;
                         const uint32_t pos = g.tile_offset[t] + atomicAdd(&g.tile_fill[t], 1u);
                         if (pos < g.list_capacity) g.tile_list[pos] = rec;
@@ -93,7 +97,8 @@ namespace shsb
         {
             const uint32_t t = blockIdx.x * BIN_THREADS + threadIdx.x;
             const int lane = threadIdx.x & 31;
-            const bool live = t < n_tiles;
+            const bool in_frame = t < n_tiles;
+            const bool live = in_frame && owned_row(fc, (int)(t / (uint32_t)fc.tiles_x)); // rows of other ranks are not scheduled at all
             const uint32_t c = live ? g.tile_count[t] : 0u;
             // warp exclusive scan of the counts -> one cursor atomic per warp
             uint32_t incl = c;
@@ -129,7 +134,7 @@ namespace shsb
                 cbase = __shfl_sync(0xffffffffu, cbase, leader);
                 if (live && cls == k) g.tile_order[(size_t)k * n_tiles + cbase + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (t % (uint32_t)fc.tiles_x) | ((t / (uint32_t)fc.tiles_x) << 16);
             }
-            if (live)
+            if (in_frame)
             {
                 g.tile_offset[t] = off;
                 g.tile_fill[t] = 0;

@@ -188,7 +188,10 @@ namespace shsb
             if (n_tiles > 0 && n_tiles <= 8)
             {
                 for (int ty = tr.ty0; ty <= tr.ty1; ++ty)
+                {
+                    if (!owned_row(fc, ty)) continue; // sort-first: another rank's tile row
                     for (int tx = tr.tx0; tx <= tr.tx1; ++tx) atomicAdd(&g.tile_count[(uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx], 1u);
+                }
             }
             unsigned big = __ballot_sync(0xffffffffu, n_tiles > 8);
             const int lane = threadIdx.x & 31;
@@ -199,7 +202,8 @@ namespace shsb
                 const int tx0 = __shfl_sync(0xffffffffu, tr.tx0, src), tx1 = __shfl_sync(0xffffffffu, tr.tx1, src);
                 const int ty0 = __shfl_sync(0xffffffffu, tr.ty0, src), ty1 = __shfl_sync(0xffffffffu, tr.ty1, src);
                 const int wx = tx1 - tx0 + 1, total = wx * (ty1 - ty0 + 1);
-                for (int k = lane; k < total; k += 32) atomicAdd(&g.tile_count[(uint32_t)(ty0 + k / wx) * (uint32_t)fc.tiles_x + (uint32_t)(tx0 + k % wx)], 1u);
+                for (int k = lane; k < total; k += 32)
+                    if (owned_row(fc, ty0 + k / wx)) atomicAdd(&g.tile_count[(uint32_t)(ty0 + k / wx) * (uint32_t)fc.tiles_x + (uint32_t)(tx0 + k % wx)], 1u);
             }
         }
 
@@ -207,7 +211,10 @@ namespace shsb
         {
             const TileRange tr = tile_range(bbox_x, bbox_y, fc.H);
             for (int ty = tr.ty0; ty <= tr.ty1; ++ty)
+            {
+                if (!owned_row(fc, ty)) continue;
                 for (int tx = tr.tx0; tx <= tr.tx1; ++tx) atomicAdd(&g.tile_count[(uint32_t)ty * (uint32_t)fc.tiles_x + (uint32_t)tx], 1u);
+            }
         }
 
         __device__ __forceinline__ DevStats* stats_shard(const Geometry& g) { return g.stats + (blockIdx.x & (STAT_SHARDS - 1)); }

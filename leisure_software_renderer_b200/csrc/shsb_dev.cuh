@@ -186,7 +186,14 @@ namespace shsb
         float sky_sun[3];       // normalised ProceduralSky sun direction
         float sky_intensity;
         uint32_t sky_faces[6];  // indices into the texture table (cubemap), all valid when sky_kind == cubemap
+        // sort-first screen partition: the tile rows this submission owns (ShsbFrameParams::own_row_*); count 0 = all rows
+        int own_first, own_count, own_stride;
     };
+
+    __host__ __device__ __forceinline__ bool owned_row(const FrameConst& fc, int ty)
+    {
+        return fc.own_count <= 0 || (ty >= fc.own_first && ((ty - fc.own_first) % fc.own_stride) < fc.own_count);
+    }
 
     struct FrameBuffers
     {

@@ -465,7 +465,7 @@ namespace shsb
                 // One CTA resolves FOUR tiles, one thread 4 horizontally adjacent pixels with 128-bit stores; the
                 // background colour depends on the row only, so it is evaluated once per 4 pixels.
                 const uint32_t first = (blockIdx.x - n_nonempty) * 4u + (threadIdx.x >> 6);
-                if (first >= n_tiles_total - n_nonempty) return;
+                if (first >= g.class_count[3]) return; // owned empty tiles only (sort-first partitions leave other rows untouched)
                 const uint32_t packed = g.tile_order[(size_t)3 * n_tiles_total + first];
                 const int q = threadIdx.x & 63;
                 const int x0 = (int)(packed & 0xffffu) * TILE + (q & 3) * 4;

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header(tmp_path):
               "ShsbUniforms": (capi.Uniforms, ["base_color_tex", "enable_motion_vectors", "prev_model", "prev_viewproj"]),
               "ShsbTransform": (capi.Transform, ["scl"]), "ShsbRenderItem": (capi.RenderItem, ["visible", "object_id"]),
               "ShsbScene": (capi.Scene, ["items", "cam_prev_viewproj", "sky_kind", "sky_faces", "reserved2"]),
-              "ShsbFrameParams": (capi.FrameParams, ["write_aovs", "motion_vectors_enable", "reserved"]),
+              "ShsbFrameParams": (capi.FrameParams, ["write_aovs", "motion_vectors_enable", "own_row_first", "own_row_stride"]),
               "ShsbMotionBlurParams": (capi.MotionBlurParams, ["depth_reject", "dt", "reserved"]),
               "ShsbLightShaftsParams": (capi.LightShaftsParams, ["decay", "cam_pos", "sun_dir_ws", "cam_viewproj"])}
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{os.path.join(ROOT, "include", "shsb.h")}"', "int main(void) {"]
