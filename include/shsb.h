@@ -224,7 +224,9 @@ typedef struct ShsbFrameParams /* the FrameParams fields the path reads, frame/f
      * owned iff ty >= own_row_first and (ty - own_row_first) % own_row_stride < own_row_count.  own_row_count = 0 means the
      * whole frame.  Pixels of other rows are left untouched in every plane, so the union of the ranks' submissions is
      * bit-identical to one whole-frame submission.  Draws whose projected bounds cannot reach an owned row are skipped on the host,
-     * so triangle statistics cover the remaining draws; fragment statistics are per owner and add up to the whole frame's. */
+     * so triangle statistics cover the remaining draws; fragment statistics are per owner and add up to the whole frame's.
+     * With 16-px light tiles the fused frame builds only the owned rows' light lists.  A partition that does not write motion
+     * vectors leaves the motion history empty (it drops draws before their model matrix exists). */
     int32_t own_row_first;
     int32_t own_row_count;
     int32_t own_row_stride;

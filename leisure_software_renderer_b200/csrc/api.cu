@@ -395,6 +395,7 @@ namespace
         float planes[24];
         float inv_vp[16];
         uint32_t vw = 0, vh = 0, ts = 0, max_per_tile = 0;
+        int own_first = 0, own_count = 0, own_stride = 1; // sort-first: light-tile rows whose lists are needed (count 0 = all)
     };
 
     int prepare_light_cull(shsb_ctx ctx, const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile, CullJob& job)
@@ -423,7 +424,7 @@ namespace
         LightLists& L = ctx->lists[set];
         record(ctx, 5, s);
         launch_light_cull(ctx->d_lights[ctx->lights_cur].p, ctx->n_lights, job.planes, job.inv_vp, job.vw, job.vh, job.ts, job.max_per_tile, L.scratch.p,
-                          L.counts.p, L.indices.p, s, &ctx->launches);
+                          L.counts.p, L.indices.p, s, &ctx->launches, job.own_first, job.own_count, job.own_stride);
         record(ctx, 6, s);
         L.w = job.vw; L.h = job.vh; L.ts = job.ts; L.max_per_tile = job.max_per_tile;
         ctx->lists_cur = set;
@@ -637,6 +638,36 @@ namespace
         if (ymax < 0.0f || ymin > (float)(fc.H - 1)) return false; // entirely above or below the frame: no pixels at all
         const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(fc.H - 1)));
         const int ty0 = (fc.H - 1 - py1) / TILE, ty1 = (fc.H - 1 - py0) / TILE; // tile rows count from the top
+        for (int ty = ty0; ty <= ty1; ++ty) if (owned_row(fc, ty)) return true;
+        return false;
+    }
+
+    struct VpRows { float y[4], w[4], gy, gw; };
+
+    // The same question as item_touches_owned_rows, answered without building the model matrix: model = T * R * S maps the
+    // mesh's local bounds into the sphere (tr.pos, max|scl| * max distance of a bounds corner from the local origin),
+    // whatever the rotation.  Over that sphere clip.y and clip.w vary by at most radius * |gradient|, so ndc.y lies
+    // between the extreme ratios of the two intervals (all w > 0, else "cannot bound").  Conservative, never exact:
+    // a draw it keeps is tested again with its real matrix.
+    bool sphere_may_touch_owned_rows(const FrameConst& fc, const VpRows& v, const ShsbTransform& tr, const MeshSlot& mesh)
+    {
+        const float ex = std::max(std::fabs(mesh.bmin.x), std::fabs(mesh.bmax.x)), ey = std::max(std::fabs(mesh.bmin.y), std::fabs(mesh.bmax.y)),
+                    ez = std::max(std::fabs(mesh.bmin.z), std::fabs(mesh.bmax.z));
+        const float smax = std::max(std::fabs(tr.scl[0]), std::max(std::fabs(tr.scl[1]), std::fabs(tr.scl[2])));
+        const float radius = smax * std::sqrt(ex * ex + ey * ey + ez * ez) * 1.001f + 1e-4f;
+        const float yc = v.y[0] * tr.pos[0] + v.y[1] * tr.pos[1] + v.y[2] * tr.pos[2] + v.y[3];
+        const float wc = v.w[0] * tr.pos[0] + v.w[1] * tr.pos[1] + v.w[2] * tr.pos[2] + v.w[3];
+        const float dy = radius * v.gy, dw = radius * v.gw;
+        const float w0 = wc - dw, w1 = wc + dw;
+        if (!(w0 > 1e-3f) || !std::isfinite(yc) || !std::isfinite(w1) || !std::isfinite(dy)) return true;
+        const float y0 = yc - dy, y1 = yc + dy;
+        const float nlo = std::min(std::min(y0 / w0, y0 / w1), std::min(y1 / w0, y1 / w1));
+        const float nhi = std::max(std::max(y0 / w0, y0 / w1), std::max(y1 / w0, y1 / w1));
+        const float ymin = (nlo * 0.5f + 0.5f) * (float)(fc.H - 1) - 2.0f, ymax = (nhi * 0.5f + 0.5f) * (float)(fc.H - 1) + 2.0f;
+        if (!std::isfinite(ymin) || !std::isfinite(ymax)) return true;
+        if (ymax < 0.0f || ymin > (float)(fc.H - 1)) return false;
+        const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(fc.H - 1)));
+        const int ty0 = (fc.H - 1 - py1) / TILE, ty1 = (fc.H - 1 - py0) / TILE;
         for (int ty = ty0; ty <= ty1; ++ty) if (owned_row(fc, ty)) return true;
         return false;
     }
@@ -868,12 +899,33 @@ namespace
         std::vector<uint64_t> next_keys;
         std::vector<hm::mat4f> next_models;
         if (lit_pass) { next_keys.reserve(scene->n_items); next_models.reserve(scene->n_items); }
+        // rows of cam.viewproj that produce clip.y and clip.w, with the norms of their xyz parts (sphere_may_touch_owned_rows)
+        VpRows vp_rows{};
+        {
+            const float* m = scene->cam_viewproj;
+            vp_rows.y[0] = m[1]; vp_rows.y[1] = m[5]; vp_rows.y[2] = m[9]; vp_rows.y[3] = m[13];
+            vp_rows.w[0] = m[3]; vp_rows.w[1] = m[7]; vp_rows.w[2] = m[11]; vp_rows.w[3] = m[15];
+            vp_rows.gy = std::sqrt(m[1] * m[1] + m[5] * m[5] + m[9] * m[9]);
+            vp_rows.gw = std::sqrt(m[3] * m[3] + m[7] * m[7] + m[11] * m[11]);
+        }
+        // Motion vectors need last frame's model matrix of every item, so a partition that writes motion builds every matrix;
+        // one that does not may drop a draw before its matrix exists, and then leaves the history empty (the next frame that
+        // asks for motion vectors starts like a first frame) rather than half-filled.
+        const bool precull = fc.own_count > 0 && !write_motion;
+        bool history_partial = false;
         for (uint32_t i = 0; i < scene->n_items; ++i)
         {
             const ShsbRenderItem& it = scene->items[i];
             if (!it.visible) continue;
             const MeshSlot* mesh = get_mesh(ctx, it.mesh);
             if (!mesh || mesh->n_positions == 0 || mesh->n_indices == 0) continue; // MeshData::empty(), resources/mesh.hpp:32-35
+            if (precull && !sphere_may_touch_owned_rows(fc, vp_rows, it.tr, *mesh))
+            {
+                // sort-first, cheap test first (no trigonometry, no matrix products): see item_touches_owned_rows
+                tri_cursor += mesh->n_indices ? mesh->n_indices / 3 : mesh->n_positions / 3;
+                history_partial = true;
+                continue;
+            }
             const hm::mat4f model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
             const hm::mat4f* prev = nullptr;
             hm::mat4f prev_model = model;
@@ -918,7 +970,14 @@ namespace
             if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex, prev);
             else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u, prev);
         }
-        if (lit_pass)
+        if (lit_pass && history_partial)
+        {
+            ctx->hist_keys.clear();
+            ctx->hist_models.clear();
+            ctx->hist_index_valid = false;
+            ctx->has_prev_frame = false;
+        }
+        else if (lit_pass)
         {
             ctx->hist_keys.swap(next_keys);
             ctx->hist_models.swap(next_models);
@@ -1412,6 +1471,11 @@ SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, c
     if (with_cull)
     {
         if (int rc = prepare_light_cull(ctx, scene->cam_viewproj, (uint32_t)hdr->w, (uint32_t)hdr->h, std::max(1u, fp->tile_size), std::max(1u, fp->max_lights_per_tile), cull)) return rc;
+        if (fp->own_row_count > 0 && cull.ts == (uint32_t)TILE && fp->own_row_first >= 0 && fp->own_row_stride >= fp->own_row_count)
+        {
+            // sort-first partition: only the owned tile rows' lists are ever read (light tile == raster tile)
+            cull.own_first = fp->own_row_first; cull.own_count = fp->own_row_count; cull.own_stride = fp->own_row_stride;
+        }
     }
     if (out_stats) *out_stats = ShsbStats{};
     return forward_common(ctx, scene, fp, hdr_rt, depth_motion_rt, 0, nullptr, 0, false, ldr_rt, out_stats, with_cull ? &cull : nullptr);

@@ -66,7 +66,13 @@ namespace shsb
             float inv_vp[16];
             uint32_t vw, vh, ts, max_per_tile, tiles_x, tiles_y, n_lights;
             uint32_t macro_x, macro_y; // macro cells (MACRO x MACRO tiles) per row / column
+            int own_first, own_count, own_stride; // sort-first partition: tile rows whose lists are needed (count 0 = all)
         };
+
+        __device__ __forceinline__ bool cull_row_owned(const CullParams& cp, uint32_t ty)
+        {
+            return cp.own_count <= 0 || ((int)ty >= cp.own_first && (((int)ty - cp.own_first) % cp.own_stride) < cp.own_count);
+        }
 
 #ifndef SHSB_MACRO
 #define SHSB_MACRO 8
@@ -135,6 +141,11 @@ namespace shsb
             const uint32_t tx0 = mx * MACRO, ty0 = my * MACRO;
             const uint32_t tx1 = min(tx0 + MACRO, cp.tiles_x) - 1u, ty1 = min(ty0 + MACRO, cp.tiles_y) - 1u;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            {
+                bool any_owned = false; // CTA-uniform
+                for (uint32_t ty = ty0; ty <= ty1; ++ty) any_owned = any_owned || cull_row_owned(cp, ty);
+                if (!any_owned) { if (threadIdx.x == 0) macro_counts[mc] = 0; return; }
+            }
             if (threadIdx.x < 16)
             {
                 const int which = threadIdx.x >> 3;
@@ -208,6 +219,7 @@ namespace shsb
             const uint32_t tile = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
             if (tile >= cp.tiles_x * cp.tiles_y) return; // warp-uniform
             const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
+            if (!cull_row_owned(cp, ty)) { if (lane == 0) counts[tile] = 0; return; } // another rank's row: nobody reads this list
             if (lane < 8) cell_corner(cp, tx, ty, lane, s_corner[warp][lane]);
             __syncwarp();
             if (lane < 6) s_plane[warp][lane] = cell_plane(s_corner[warp], lane);
@@ -404,7 +416,8 @@ namespace shsb
 
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
                            uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
-                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches)
+                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches,
+                           int own_first, int own_count, int own_stride)
     {
         CullParams cp;
         for (int i = 0; i < 16; ++i) cp.inv_vp[i] = inv_view_proj[i];
@@ -412,6 +425,7 @@ namespace shsb
         cp.tiles_x = (vw + ts - 1) / ts;
         cp.tiles_y = (vh + ts - 1) / ts;
         cp.n_lights = n_lights;
+        cp.own_first = own_first; cp.own_count = own_count; cp.own_stride = own_stride > 0 ? own_stride : 1;
         cp.macro_x = (cp.tiles_x + MACRO - 1) / MACRO;
         cp.macro_y = (cp.tiles_y + MACRO - 1) / MACRO;
         Planes6 fr;
@@ -435,6 +449,7 @@ namespace shsb
         cp.tiles_x = (vw + ts - 1) / ts;
         cp.tiles_y = (vh + ts - 1) / ts;
         cp.n_lights = n_lights;
+        cp.own_first = 0; cp.own_count = 0; cp.own_stride = 1;
         cp.macro_x = cp.macro_y = 0;
         Planes6 fr;
         for (int i = 0; i < 6; ++i) fr.p[i] = make_float4(frustum_planes24[i * 4], frustum_planes24[i * 4 + 1], frustum_planes24[i * 4 + 2], frustum_planes24[i * 4 + 3]);

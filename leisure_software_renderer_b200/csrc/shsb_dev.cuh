@@ -270,7 +270,8 @@ namespace shsb
     // frustum_planes24: the 6 normalised camera-frustum planes (nx, ny, nz, d) computed on the host
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
                            uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
-                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
+                           uint32_t* scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches,
+                           int own_first = 0, int own_count = 0, int own_stride = 1); // sort-first: only these tile rows' lists are built
     void launch_motion_blur(const PostMotionBlur& a, cudaStream_t s, uint64_t* launches);
     void launch_light_shafts(const PostLightShafts& a, const float* depth, int depth_w, float* lumad, cudaStream_t s, uint64_t* launches);
     void launch_taa(uchar4* ldr, uchar4* hist, size_t n_pixels, float keep, float blend, cudaStream_t s, uint64_t* launches);

@@ -45,7 +45,7 @@ def main():
     for m in sd.meshes:
         ctx.mesh_upload(m["positions"], m["normals"], m["uvs"], m["indices"])
     ctx.lights_upload(sd.lights.view(np.uint8))
-    NSETS = 2
+    NSETS = 3
     sets = [(ctx.rt_create(capi.RT_COLOR_HDR, W, H), ctx.rt_create(capi.RT_DEPTH_MOTION, W, H, sd.zn, sd.zf), ctx.rt_create(capi.RT_COLOR_LDR, W, H)) for _ in range(NSETS)]
     tile_rows = (H + 15) // 16
 
@@ -54,8 +54,21 @@ def main():
     depth = ctx.rt_download(sets[0][1], capi.PLANE_DEPTH)
     shaded_rows = (depth[::-1] < 1.0).sum(axis=1)                                   # per pixel row, from the top
     pad = tile_rows * 16 - H
-    cost = np.concatenate([shaded_rows, np.zeros(pad, shaded_rows.dtype)]).reshape(tile_rows, 16).sum(axis=1).astype(np.float64) + 0.02 * W * 16
+    px_cost = np.concatenate([shaded_rows, np.zeros(pad, shaded_rows.dtype)]).reshape(tile_rows, 16).sum(axis=1).astype(np.float64)
     del depth
+    # triangles per tile row: every draw's triangle count at the tile row its origin projects to (instances are small on screen)
+    vp = np.asarray(sd.viewproj, dtype=np.float64).reshape(4, 4).T                     # row-major
+    tri_cost = np.zeros(tile_rows)
+    for it in sd.items:
+        m = sd.meshes[it["mesh"] - 1]
+        c = vp @ np.array([*it["pos"], 1.0])
+        if c[3] <= 1e-3:
+            continue
+        py = (c[1] / c[3] * 0.5 + 0.5) * (H - 1)
+        ty = int(np.clip((H - 1 - py) // 16, 0, tile_rows - 1))
+        tri_cost[ty] += len(m["indices"]) // 3
+    # a frame's time is about half per-pixel work (shading) and half per-triangle work (set-up, binning, coverage)
+    cost = px_cost / max(px_cost.sum(), 1.0) + tri_cost / max(tri_cost.sum(), 1.0) + 0.02 / tile_rows
     fp = capi.FrameParams.from_buffer_copy(sd.fp)
     if world > 1:
         if args.layout == "bands":
@@ -103,6 +116,12 @@ def main():
     frame_out = torch.empty((H, W * 4), dtype=torch.uint8, device=f"cuda:{local}") if rank == 0 else None
     recv_bufs = [torch.empty((rows_of[r], W * 4), dtype=torch.uint8, device="cuda:0") for r in range(world)] if (rank == 0 and world > 1) else None
     gather_done = [None] * NSETS
+    comm_events = []
+    pack_buf = torch.empty((my_rows.numel(), W * 4), dtype=torch.uint8, device=f"cuda:{local}") if (world > 1 and rank != 0 and args.layout != "bands") else None
+    # framebuffer row range [a, b) of every rank's band (rows are bottom-origin, tile rows count from the top)
+    fb_range = None
+    if world > 1 and args.layout == "bands":
+        fb_range = [(max(0, H - cuts[r + 1] * 16), H - cuts[r] * 16) for r in range(world)]
 
     def step(i):
         k = i % NSETS
@@ -113,16 +132,32 @@ def main():
             ev = torch.cuda.Event(); ev.record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                if rank == 0:
+                c0 = torch.cuda.Event(enable_timing=True); c0.record(comm)
+                if args.layout == "bands":
+                    # a band is a contiguous range of framebuffer rows: receive straight into the assembled frame, all peers in ONE grouped NCCL call
+                    if rank == 0:
+                        a, b = fb_range[0]
+                        frame_out[a:b].copy_(views[k][a:b], non_blocking=True)
+                        ops = [dist.P2POp(dist.irecv, frame_out[fb_range[r][0]:fb_range[r][1]], r) for r in range(1, world)]
+                        for q in dist.batch_isend_irecv(ops):
+                            q.wait()
+                    else:
+                        a, b = fb_range[rank]
+                        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, views[k][a:b], 0)]):
+                            q.wait()
+                elif rank == 0:
                     frame_out[all_rows[0]] = views[k][all_rows[0]]
-                    reqs = [dist.irecv(recv_bufs[r], src=r) for r in range(1, world)]
-                    for q in reqs:
+                    ops = [dist.P2POp(dist.irecv, recv_bufs[r], r) for r in range(1, world)]
+                    for q in dist.batch_isend_irecv(ops):
                         q.wait()
                     for r in range(1, world):
                         frame_out[all_rows[r]] = recv_bufs[r]
                 else:
-                    dist.send(views[k][my_rows].contiguous(), dst=0)
-                done = torch.cuda.Event(); done.record(comm)
+                    pack_buf.copy_(views[k][my_rows])
+                    for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, pack_buf, 0)]):
+                        q.wait()
+                done = torch.cuda.Event(enable_timing=True); done.record(comm)
+                comm_events.append((c0, done))
             gather_done[k] = done
 
     def barrier():
@@ -132,20 +167,29 @@ def main():
         torch.cuda.synchronize()
 
     st = ctx.frame_forward_plus(sd.scene, fp, *sets[0]).as_dict()
+    sm = ctx.last_stage_ms()  # stage times of this synchronous frame (this rank's partition alone on its GPU)
     for i in range(args.warmup):
         step(i)
     barrier()
+    import time
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.host_submit_us(reset=True)
     e0.record(stream)
+    t_host = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps
+    hu = ctx.host_submit_us(reset=True)
+    lib_ms = float(hu[:5].sum() / max(hu[5], 1.0)) / 1e3
     for d in gather_done:
         if d is not None:
             stream.wait_event(d)
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    mine = torch.tensor([float(owned.sum()), float(st["frag_shaded"]), float(st["tri_input"])], dtype=torch.float64, device="cuda")
+    comm_ms = float(np.mean([a.elapsed_time(b) for a, b in comm_events[-args.steps:]])) if comm_events else 0.0
+    mine = torch.tensor([float(owned.sum()), float(st["frag_shaded"]), float(st["tri_input"]), host_ms, lib_ms, float(sm[0]), float(sm[1]), float(sm[2]), comm_ms],
+                        dtype=torch.float64, device="cuda")
     per_rank = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -162,7 +206,12 @@ def main():
         print(json.dumps({"metric": "frames/s", "config": sd.name, "resolution": [W, H], "n_gpus": world, "layout": args.layout if world > 1 else "whole frame",
                           "value": 1e3 / t, "ms_per_frame": t, "steps": args.steps, "scaling": "strong",
                           "tile_rows_per_rank": [int(p[0].item()) for p in per_rank], "frag_shaded_per_rank": [int(p[1].item()) for p in per_rank],
-                          "tri_input_per_rank": [int(p[2].item()) for p in per_rank], "whole_frame_stats": whole,
+                          "tri_input_per_rank": [int(p[2].item()) for p in per_rank],
+                          "host_submit_ms_per_rank": [round(float(p[3].item()), 3) for p in per_rank], "library_host_ms_per_rank": [round(float(p[4].item()), 3) for p in per_rank],
+                          "gpu_stage_ms_per_rank": {"vertex_clip_setup": [round(float(p[5].item()), 3) for p in per_rank], "binning": [round(float(p[6].item()), 3) for p in per_rank],
+                                                    "tile": [round(float(p[7].item()), 3) for p in per_rank]},
+                          "frame_assembly_ms_per_rank": [round(float(p[8].item()), 3) for p in per_rank],
+                          "whole_frame_stats": whole,
                           "assembled_frame_equals_whole_frame": ok}), flush=True)
     ctx.close()
     if world > 1:
