@@ -1,6 +1,5 @@
 mkdir -p gpurun_out/s4i
-for cfg in "8 0" "1 0" "1000000 0" "8 1" "1000000 1"; do set -- $cfg; 
-  if [ "$2" = "1" ]; then export SHSB_BENCH_NOCLOCKS=1; else unset SHSB_BENCH_NOCLOCKS; fi
+for cfg in "8 0" "1 0" "1000000 0"; do set -- $cfg;
   SHSB_BENCH_STRIDE=$1 python bench.py --steps 300 --warmup 10 --no-cpu-baseline > gpurun_out/s4i/b_$1_$2.json 2> gpurun_out/s4i/b_$1_$2.err
   python - <<PY
 import json
