@@ -11,12 +11,17 @@
 // stays in submission order on the main stream.
 //
 // There is no CPU raster path in this file: every pass either launches the kernels or returns an error.
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -110,6 +115,91 @@ namespace
     constexpr int LISTS_STANDALONE = NUM_ARENAS;
 }
 
+namespace
+{
+    // Fork-join helper for the host half of a submission (per-draw model / normal matrices in the reference's exact GLM
+    // order are ~200 ns each: 2 ms for the 10 k draws of the 8K config).  It takes the place ThreadPoolJobSystem +
+    // parallel_for_1d (job/thread_pool_job_system.hpp:26-110, job/parallel_for.hpp:23-59) have in the reference, for the one
+    // loop that stays on the host.  Workers sleep on a condition variable between submissions; the caller works too.
+    class HostPool
+    {
+    public:
+        explicit HostPool(int n_workers)
+        {
+            for (int i = 0; i < n_workers; ++i) workers_.emplace_back([this, i] { run(i + 1); });
+        }
+        ~HostPool()
+        {
+            stop_.store(true);
+            gen_.fetch_add(1);
+            { std::lock_guard<std::mutex> lk(m_); }
+            cv_.notify_all();
+            for (std::thread& t : workers_) t.join();
+        }
+        int parts() const { return (int)workers_.size() + 1; }
+        // fn(part, n_parts) is called once per part, part 0 on the calling thread; returns when all parts are done.
+        // Workers spin for a couple of milliseconds after a job before they go to sleep: frames arrive every millisecond or
+        // so, and waking a sleeping thread costs more than the whole job.
+        void run_parts(const std::function<void(int, int)>& fn)
+        {
+            if (workers_.empty()) { fn(0, 1); return; }
+            fn_ = &fn;
+            pending_.store((int)workers_.size());
+            gen_.fetch_add(1);
+            { std::lock_guard<std::mutex> lk(m_); } // a worker between its predicate check and its wait holds m_
+            cv_.notify_all();
+            fn(0, parts());
+            while (pending_.load() != 0) std::this_thread::yield();
+            fn_ = nullptr;
+        }
+
+    private:
+        void run(int part)
+        {
+            uint64_t seen = 0;
+            for (;;)
+            {
+                const auto t0 = std::chrono::steady_clock::now();
+                int spins = 0;
+                while (gen_.load() == seen)
+                {
+                    __builtin_ia32_pause();
+                    if ((++spins & 63) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2))
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return gen_.load() != seen; });
+                        break;
+                    }
+                }
+                seen = gen_.load();
+                if (stop_.load()) return;
+                (*fn_)(part, parts());
+                pending_.fetch_sub(1);
+            }
+        }
+        std::vector<std::thread> workers_;
+        std::mutex m_;
+        std::condition_variable cv_;
+        const std::function<void(int, int)>* fn_ = nullptr;
+        std::atomic<int> pending_{0};
+        std::atomic<uint64_t> gen_{0};
+        std::atomic<bool> stop_{false};
+    };
+}
+
+namespace
+{
+    // Per-item scratch of a scene submission (forward_common): filled in parallel, consumed in draw order.
+    struct DrawPrep
+    {
+        uint8_t state;        // 0 not a draw, 1 preculled (sphere), 2 culled by the exact bounds test, 3 kept
+        uint32_t hist_slot;   // position among the draws (the motion history is positional first)
+        int64_t prev_src;     // index into hist_models, or -1
+        hm::mat4f model;
+        DevItem item;         // everything but tri_offset
+    };
+}
+
 struct shsb_context_t
 {
     int device = 0;
@@ -171,6 +261,9 @@ struct shsb_context_t
     bool ev_valid[NUM_STAGE_EVENTS]{};
     uint64_t launches_at_tile = ~0ull;   // value of `launches` right after the last frame's tile kernel was submitted
     int tile_event_at_tile = -1;         // ring index of that frame's "tile done" event
+    std::vector<DrawPrep> prep;
+    HostPool* host_pool = nullptr;       // created on first use by a submission with >= 2048 draws
+    int host_threads = 1;                // SHSB_HOST_THREADS, default clamp(hardware threads / 8, 1, 4): a share of an 8-GPU box
     bool stage_events = true;            // false while an asynchronous frame without timing history is submitted
     bool main_needs_lights = false;      // the render stream has not yet been ordered behind the last light upload
 
@@ -672,6 +765,27 @@ namespace
         return false;
     }
 
+    // One draw's device record (everything but its place in the draw order).  Thread-safe: reads the context only.
+    void fill_item(shsb_ctx ctx, DevItem& it, const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
+                   const float base_color[3], float metallic, float roughness, float ao, uint32_t tex, const hm::mat4f* prev_model = nullptr)
+    {
+        it = DevItem{};
+        hm::store(model, it.model);
+        if (prev_model)
+        {
+            // curr_to_prev_model, rasterizer.hpp:296-307
+            hm::mat4f c2p = hm::identity();
+            if (std::fabs(hm::determinant(model)) > 1e-10f) c2p = hm::mul(*prev_model, hm::inverse(model));
+            hm::store(c2p, it.c2p);
+        }
+        hm::normal_matrix(model, it.nrm);
+        it.base_color[0] = base_color[0]; it.base_color[1] = base_color[1]; it.base_color[2] = base_color[2];
+        it.metallic = metallic; it.roughness = roughness; it.ao = ao;
+        it.tex = (tex >= 1 && tex <= ctx->textures.size() && ctx->textures[tex - 1].live) ? tex : 0u;
+        it.mesh = mesh_index;
+        it.tri_count = mesh.n_indices ? mesh.n_indices / 3 : mesh.n_positions / 3;
+    }
+
     // Stages one draw into the host item / block tables.
     int stage_item(shsb_ctx ctx, std::vector<DevItem>& items, std::vector<uint2>& blocks, uint64_t& tri_cursor,
                    const hm::mat4f& model, const MeshSlot& mesh, uint32_t mesh_index,
@@ -913,22 +1027,24 @@ namespace
         // asks for motion vectors starts like a first frame) rather than half-filled.
         const bool precull = fc.own_count > 0 && !write_motion;
         bool history_partial = false;
+
+        // ---- pass 0 (serial, integer work only): which items are draws at all, their motion keys and history slots
+        using Prep = DrawPrep;
+        std::vector<Prep>& prep = ctx->prep;
+        prep.resize(scene->n_items);
+        uint32_t n_draws = 0;
+        const bool want_prev = lit_pass && write_motion && ctx->has_prev_frame;
         for (uint32_t i = 0; i < scene->n_items; ++i)
         {
             const ShsbRenderItem& it = scene->items[i];
+            Prep& p = prep[i];
+            p.state = 0;
             if (!it.visible) continue;
             const MeshSlot* mesh = get_mesh(ctx, it.mesh);
             if (!mesh || mesh->n_positions == 0 || mesh->n_indices == 0) continue; // MeshData::empty(), resources/mesh.hpp:32-35
-            if (precull && !sphere_may_touch_owned_rows(fc, vp_rows, it.tr, *mesh))
-            {
-                // sort-first, cheap test first (no trigonometry, no matrix products): see item_touches_owned_rows
-                tri_cursor += mesh->n_indices ? mesh->n_indices / 3 : mesh->n_positions / 3;
-                history_partial = true;
-                continue;
-            }
-            const hm::mat4f model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
-            const hm::mat4f* prev = nullptr;
-            hm::mat4f prev_model = model;
+            p.state = 3;
+            p.hist_slot = n_draws++;
+            p.prev_src = -1;
             if (lit_pass)
             {
                 // motion key, pass_pbr_forward.hpp:143-148 (the reference's material handle is 0 for "no material"; items with a
@@ -939,10 +1055,11 @@ namespace
                     key = ((uint64_t)it.mesh << 32) ^ (uint64_t)(it.has_material ? 1u : 0u) ^ ((uint64_t)i + 1u);
                     if (key == 0) key = 1;
                 }
-                if (ctx->has_prev_frame)
+                next_keys.push_back(key);
+                if (want_prev)
                 {
-                    const size_t k = next_keys.size();
-                    if (k < ctx->hist_keys.size() && ctx->hist_keys[k] == key) prev_model = ctx->hist_models[k];
+                    const size_t k = p.hist_slot;
+                    if (k < ctx->hist_keys.size() && ctx->hist_keys[k] == key) p.prev_src = (int64_t)k;
                     else
                     {
                         if (!ctx->hist_index_valid)
@@ -952,23 +1069,64 @@ namespace
                             ctx->hist_index_valid = true;
                         }
                         const auto f = ctx->hist_index.find(key);
-                        if (f != ctx->hist_index.end()) prev_model = ctx->hist_models[f->second];
+                        if (f != ctx->hist_index.end()) p.prev_src = (int64_t)f->second;
                     }
                 }
-                next_keys.push_back(key);
-                next_models.push_back(model);
-                if (write_motion) prev = &prev_model;
             }
-            if (fc.own_count > 0 && !item_touches_owned_rows(fc, hm::load(scene->cam_viewproj), model, *mesh))
+        }
+
+        // ---- pass 1 (parallel over items for large scenes): culling tests and the per-draw matrices, all in the reference's
+        // operation order (host_math.hpp); items are independent of each other here
+        const hm::mat4f cam_vp = hm::load(scene->cam_viewproj);
+        std::atomic<uint32_t> next_chunk{0};
+        constexpr uint32_t CHUNK = 64; // items are claimed in small chunks: kept draws (200 ns) cluster in index ranges, dropped ones cost 40 ns
+        auto prepare = [&](int, int)
+        {
+            for (;;)
             {
-                // sort-first: this draw can only reach another rank's rows.  Its triangles keep their place in the draw order
-                // (the triangle-id AOV and depth ties are defined by the whole scene's order, not by what this rank draws).
-                tri_cursor += mesh->n_indices ? mesh->n_indices / 3 : mesh->n_positions / 3;
-                continue;
+            const uint32_t lo = next_chunk.fetch_add(1) * CHUNK;
+            if (lo >= scene->n_items) break;
+            const uint32_t hi = std::min(scene->n_items, lo + CHUNK);
+            for (uint32_t i = lo; i < hi; ++i)
+            {
+                Prep& p = prep[i];
+                if (p.state == 0) continue;
+                const ShsbRenderItem& it = scene->items[i];
+                const MeshSlot& mesh = ctx->meshes[it.mesh - 1];
+                if (precull && !sphere_may_touch_owned_rows(fc, vp_rows, it.tr, mesh)) { p.state = 1; continue; } // cheap test first: no trigonometry, no matrix products
+                p.model = hm::model_from_transform(it.tr.pos, it.tr.rot_euler, it.tr.scl);
+                if (fc.own_count > 0 && !item_touches_owned_rows(fc, cam_vp, p.model, mesh)) { p.state = 2; continue; }
+                const hm::mat4f prev_model = p.prev_src >= 0 ? ctx->hist_models[(size_t)p.prev_src] : p.model;
+                const float def_color[3] = {0.8f, 0.5f, 0.2f}; // pass_pbr_forward.hpp:179-184
+                const hm::mat4f* prev = (lit_pass && write_motion) ? &prev_model : nullptr;
+                if (it.has_material) fill_item(ctx, p.item, p.model, mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex, prev);
+                else fill_item(ctx, p.item, p.model, mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u, prev);
             }
-            const float def_color[3] = {0.8f, 0.5f, 0.2f}; // pass_pbr_forward.hpp:179-184
-            if (it.has_material) stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, it.base_color, it.metallic, it.roughness, it.ao, it.base_color_tex, prev);
-            else stage_item(ctx, items, blocks, tri_cursor, model, *mesh, it.mesh - 1, def_color, 0.1f, 0.5f, 1.0f, 0u, prev);
+            }
+        };
+        if (n_draws >= 2048 && ctx->host_threads > 1)
+        {
+            if (!ctx->host_pool) ctx->host_pool = new HostPool(ctx->host_threads - 1);
+            ctx->host_pool->run_parts(prepare);
+        }
+        else prepare(0, 1);
+
+        // ---- pass 2 (serial): draw order -- triangle offsets (culled draws keep their place: depth ties and the triangle-id
+        // AOV are defined by the whole scene's order), the item and block tables, the motion history
+        for (uint32_t i = 0; i < scene->n_items; ++i)
+        {
+            Prep& p = prep[i];
+            if (p.state == 0) continue;
+            const MeshSlot& mesh = ctx->meshes[scene->items[i].mesh - 1];
+            const uint32_t tri_count = mesh.n_indices ? mesh.n_indices / 3 : mesh.n_positions / 3;
+            if (p.state == 1) history_partial = true;              // dropped before its model matrix existed
+            else if (lit_pass) next_models.push_back(p.model);
+            if (p.state != 3) { tri_cursor += tri_count; continue; }
+            p.item.tri_offset = (uint32_t)tri_cursor;
+            const uint32_t item_index = (uint32_t)items.size();
+            items.push_back(p.item);
+            for (uint32_t t = 0; t < p.item.tri_count; t += 128) blocks.push_back(make_uint2(item_index, t));
+            tri_cursor += p.item.tri_count;
         }
         if (lit_pass && history_partial)
         {
@@ -1020,6 +1178,8 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     if (const char* e = std::getenv("SHSB_ARENAS")) ctx->n_arenas = std::min(NUM_ARENAS, std::max(2, std::atoi(e)));
     if (const char* e = std::getenv("SHSB_NO_PIPELINE")) ctx->pipeline = !(e[0] == '1');
+    ctx->host_threads = std::min(4, std::max(1, (int)std::thread::hardware_concurrency() / 8));
+    if (const char* e = std::getenv("SHSB_HOST_THREADS")) ctx->host_threads = std::min(32, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("SHSB_FRONT_PRIORITY")) { if (e[0] == '0') prio_greatest = prio_least; }
     bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     // the front end is small and latency-bound: at high priority its CTAs slot in between the tile kernel's
@@ -1064,6 +1224,8 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
+    delete ctx->host_pool;
+    ctx->host_pool = nullptr;
     for (auto& m : ctx->meshes) { cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.indices); }
     for (auto& t : ctx->textures) cudaFree(t.texels);
     for (auto& r : ctx->rts) { cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion); cudaFree(r.tri_id); cudaFree(r.coverage); }

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c5", choices=["c5", "c2"])
+    ap.add_argument("--emulate", type=int, nargs=2, metavar=("WORLD", "RANK"), default=None,
+                    help="single process: render only the partition rank RANK of WORLD would own (no frame assembly) -- the period one rank can sustain")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -70,16 +72,18 @@ def main():
     # a frame's time is about half per-pixel work (shading) and half per-triangle work (set-up, binning, coverage)
     cost = px_cost / max(px_cost.sum(), 1.0) + tri_cost / max(tri_cost.sum(), 1.0) + 0.02 / tile_rows
     fp = capi.FrameParams.from_buffer_copy(sd.fp)
-    if world > 1:
+    emu_world, emu_rank = (args.emulate if args.emulate else (world, rank))
+    if emu_world > 1:
+        part_world, part_rank = emu_world, emu_rank
         if args.layout == "bands":
             cum = np.concatenate([[0.0], np.cumsum(cost)])
-            cuts = [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(world + 1)]
+            cuts = [int(np.searchsorted(cum, cum[-1] * r / part_world)) for r in range(part_world + 1)]
             cuts[0], cuts[-1] = 0, tile_rows
-            for r in range(1, world + 1):
-                cuts[r] = max(cuts[r], cuts[r - 1] + 1) if r < world else tile_rows
-            first, count, stride = cuts[rank], cuts[rank + 1] - cuts[rank], 1 << 24
+            for r in range(1, part_world + 1):
+                cuts[r] = max(cuts[r], cuts[r - 1] + 1) if r < part_world else tile_rows
+            first, count, stride = cuts[part_rank], cuts[part_rank + 1] - cuts[part_rank], 1 << 24
         else:
-            first, count, stride = rank * 2, 2, world * 2
+            first, count, stride = part_rank * 2, 2, part_world * 2
         fp.own_row_first, fp.own_row_count, fp.own_row_stride = first, count, stride
     else:
         first, count, stride = 0, tile_rows, 1 << 24
@@ -203,7 +207,8 @@ def main():
         ok = bool(torch.equal(frame_out, views[1]))
     if rank == 0:
         t = float(ms.item()) / args.steps
-        print(json.dumps({"metric": "frames/s", "config": sd.name, "resolution": [W, H], "n_gpus": world, "layout": args.layout if world > 1 else "whole frame",
+        print(json.dumps({"metric": "frames/s", "config": sd.name, "resolution": [W, H], "n_gpus": world, "layout": args.layout if emu_world > 1 else "whole frame", "emulated_partition": args.emulate,
+                          "host_threads": os.environ.get("SHSB_HOST_THREADS", "default: clamp(cores / 8, 1, 4)"),
                           "value": 1e3 / t, "ms_per_frame": t, "steps": args.steps, "scaling": "strong",
                           "tile_rows_per_rank": [int(p[0].item()) for p in per_rank], "frag_shaded_per_rank": [int(p[1].item()) for p in per_rank],
                           "tri_input_per_rank": [int(p[2].item()) for p in per_rank],
