@@ -421,3 +421,77 @@ def scene_ragged(w=150, h=110, shading=capi.SHADING_PBR, shadow=False, nonfinite
     fp = capi.default_frame_params(shading_model=shading, shadow_enable=1 if shadow else 0, light_culling=0, motion_vectors_enable=0)
     return SceneData(f"ragged_{w}x{h}", w, h, 0.1, 60.0, meshes, textures, items, (0.3, 2.2, -4.5), (0, 0.4, 0), math.radians(55.0),
                      _SUN_DIR, _SUN_COLOR, 2.0, fp, None, shadow_size=160)
+
+
+def scene_adversarial(w=96, h=64, shading=capi.SHADING_PBR) -> SceneData:
+    """Geometry chosen to sit ON the decision boundaries of the reference's raster loop (sw_render/rasterizer.hpp:260-361),
+    drawn with viewproj = identity (clip = world position, w = 1) so that screen coordinates are under direct control:
+      * a fan of triangles whose shared edges and vertices pass exactly through pixel centres (the reference has no fill
+        rule: bc >= 0 on both sides, :336-338 -- shared-edge pixels are covered twice and the depth tie goes to the
+        earlier triangle, :359);
+      * two coplanar quads at the same depth with different materials (tie -> earlier draw);
+      * a triangle far larger than the frame (clipped by all four side planes, :232-250);
+      * a cloud of sub-pixel triangles, most of which cover no sample;
+      * a triangle with one vertex exactly on w = 0 and one behind the camera (perspective matrix item), :111-164;
+      * a sliver whose |area| is just above / below the 1e-10 reject (:273-274)."""
+    def sx(px):  # NDC x that maps to screen x = px
+        return np.float32(2.0 * px / (w - 1) - 1.0)
+
+    def sy(py):
+        return np.float32(2.0 * py / (h - 1) - 1.0)
+
+    meshes = []
+    # 1. fan around a pixel centre, rim vertices on pixel centres too
+    cx, cy = 20.5, 30.5
+    rim = [(cx + 8, cy), (cx + 8, cy + 8), (cx, cy + 8), (cx - 8, cy + 8), (cx - 8, cy), (cx - 8, cy - 8), (cx, cy - 8), (cx + 8, cy - 8)]
+    pos = [(sx(cx), sy(cy), 0.2)] + [(sx(x), sy(y), 0.2) for x, y in rim]
+    idx = []
+    for k in range(8):
+        idx += [0, 1 + k, 1 + (k + 1) % 8]
+    meshes.append({"positions": np.array(pos, np.float32), "normals": np.tile(np.array([[0, 0, -1]], np.float32), (9, 1)),
+                   "uvs": np.zeros((9, 2), np.float32), "indices": np.array(idx, np.uint32)})
+    # 2. coplanar quads (two meshes, same depth, overlapping)
+    def quad(x0, y0, x1, y1, z):
+        p = np.array([(sx(x0), sy(y0), z), (sx(x1), sy(y0), z), (sx(x1), sy(y1), z), (sx(x0), sy(y1), z)], np.float32)
+        return {"positions": p, "normals": np.tile(np.array([[0, 0, -1]], np.float32), (4, 1)), "uvs": np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32),
+                "indices": np.array([0, 1, 2, 0, 2, 3], np.uint32)}
+    meshes.append(quad(40.0, 10.0, 70.0, 40.0, 0.4))
+    meshes.append(quad(55.5, 25.5, 90.5, 55.5, 0.4))
+    # 3. far larger than the frame
+    meshes.append({"positions": np.array([(-40.0, -30.0, 0.9), (50.0, -35.0, 0.9), (3.0, 60.0, 0.9)], np.float32),
+                   "normals": np.tile(np.array([[0, 0, -1]], np.float32), (3, 1)), "uvs": np.zeros((3, 2), np.float32), "indices": np.array([0, 1, 2], np.uint32)})
+    # 4. sub-pixel cloud
+    rng = np.random.default_rng(5)
+    c = np.stack([rng.uniform(2, w - 3, 600), rng.uniform(2, h - 3, 600)], axis=1)
+    tri = np.repeat(c, 3, axis=0) + rng.uniform(-0.6, 0.6, (1800, 2))
+    p4 = np.stack([sx(tri[:, 0]), sy(tri[:, 1]), np.full(1800, 0.1, np.float32)], axis=1).astype(np.float32)
+    meshes.append({"positions": p4, "normals": np.tile(np.array([[0, 0, -1]], np.float32), (1800, 1)), "uvs": np.zeros((1800, 2), np.float32),
+                   "indices": np.arange(1800, dtype=np.uint32)})
+    # 6. slivers around the area threshold (screen-space area2 ~ 1e-10 needs NDC offsets ~1e-7)
+    base = np.array([(sx(10.0), sy(50.0), 0.3), (sx(30.0), sy(50.0), 0.3)], np.float32)
+    sl = []
+    for eps in (0.0, 1e-9, 1e-7, 1e-5):
+        sl += [base[0], base[1], (np.float32(base[0][0] + 0.3), np.float32(base[0][1] + eps), np.float32(0.3))]
+    sl = np.array(sl, np.float32)
+    meshes.append({"positions": sl, "normals": np.tile(np.array([[0, 0, -1]], np.float32), (len(sl), 1)), "uvs": np.zeros((len(sl), 2), np.float32),
+                   "indices": np.arange(len(sl), dtype=np.uint32)})
+    items = [{"pos": (0, 0, 0), "mesh": k + 1, "material": _MATERIALS[k % 4], "object_id": 10 + k} for k in range(len(meshes))]
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=0, light_culling=0, motion_vectors_enable=0, cull_mode=capi.CULL_NONE)
+    sd = SceneData(f"adversarial_{w}x{h}", w, h, 0.1, 10.0, meshes, [], items, (0.0, 0.0, -3.0), (0, 0, 0), math.radians(60.0),
+                   _SUN_DIR, _SUN_COLOR, 2.0, fp, None, shadow_size=0, viewproj=np.eye(4, dtype=np.float32).reshape(16))
+    return sd
+
+
+def scene_w_zero(w=120, h=80) -> SceneData:
+    """A real perspective camera with triangles that have a vertex exactly ON the camera plane (clip.w = 0) and behind it:
+    the near-plane clip's t = da / (da - db) and the |da - db| <= 1e-8 skip (rasterizer.hpp:133-138) decide the topology."""
+    eye = (0.0, 0.0, -2.0)
+    p = np.array([(-1.0, -0.5, 1.0), (1.0, -0.5, 1.0), (0.0, 0.8, -2.0),        # apex exactly on the camera plane (view z = 0)
+                  (-1.5, 0.2, 0.5), (-0.5, 0.9, -3.5), (-0.2, -0.1, 0.5),        # apex behind the camera
+                  (0.3, 0.1, -1.9), (1.2, 0.2, -1.9), (0.8, 0.9, -1.9),          # whole triangle 0.1 in front of the eye (zn = 0.1: on the near plane)
+                  (0.3, -0.9, -1.95), (1.2, -0.8, -1.95), (0.8, -0.2, 3.0)], np.float32)  # crosses the near plane
+    mesh = {"positions": p, "normals": np.tile(np.array([[0, 0, -1]], np.float32), (len(p), 1)), "uvs": np.zeros((len(p), 2), np.float32),
+            "indices": np.arange(len(p), dtype=np.uint32)}
+    items = [{"pos": (0, 0, 0), "mesh": 1, "material": _MATERIALS[2], "object_id": 1}]
+    fp = capi.default_frame_params(shading_model=capi.SHADING_BLINN, shadow_enable=0, light_culling=0, motion_vectors_enable=0, cull_mode=capi.CULL_NONE)
+    return SceneData(f"w_zero_{w}x{h}", w, h, 0.1, 50.0, [mesh], [], items, eye, (0, 0, 1.0), math.radians(70.0), _SUN_DIR, _SUN_COLOR, 2.0, fp, None)

@@ -44,6 +44,9 @@ def forward_cases():
         "sky_cubemap_nearclip_blinn": (lambda: scenes.scene_small(w=150, h=90, sky="cubemap", near_clip=True, shading=capi.SHADING_BLINN), {}),
         "ragged_inputs_pbr": (lambda: scenes.scene_ragged(), {}),
         "ragged_inputs_blinn_shadow": (lambda: scenes.scene_ragged(w=131, h=97, shading=capi.SHADING_BLINN, shadow=True, nonfinite=False), {"shadow": True}),
+        "adversarial_boundaries": (lambda: scenes.scene_adversarial(), {}),
+        "adversarial_boundaries_painter": (lambda: scenes.scene_adversarial(w=81, h=57, shading=capi.SHADING_BLINN), {"depth": False}),
+        "vertex_on_camera_plane": (lambda: scenes.scene_w_zero(), {}),
         "empty_scene": (lambda: scenes.scene_small(n_inst=0, w=64, h=48), {}),
         "tiny_target_1x1": (lambda: scenes.scene_small(w=1, h=1), {}),
     }
