@@ -972,9 +972,16 @@ namespace shsb
             }
             else if (tf.x > 2u)
             {
-                // area lights reach beyond position +- range: the range test uses their cull sphere
-                const float4 sp = *reinterpret_cast<const float4*>(rec->cull_sphere);
-                sl.pos_r2 = make_float4(sp.x, sp.y, sp.z, sp.w * sp.w * 1.001f + 1e-6f); // conservative pre-test; eval_light_record decides
+                // Area lights light a point only if it is closer than `range` to the nearest point of the rectangle / segment
+                // (eval_light_record: dist < range), so the pre-test sphere is (position, range + the emitter's half diagonal /
+                // half length).  NOT the record's cull sphere: make_rect_area_culling_light stores direction_spot = -axis_z
+                // (lighting/light_types.hpp:383) while its bounds extend along +axis_z, so the reference's cull bounds and the
+                // side the GLSL lights do not coincide; the tile lists follow the bounds (like the reference), the fragment
+                // loop follows the GLSL, and this filter must be conservative for the latter.
+                const float4 ux = *reinterpret_cast<const float4*>(rec->up_shape_x);
+                const float ext = (tf.x == 3u) ? sqrtf(fmaxf(ux.w, 1e-4f) * fmaxf(ux.w, 1e-4f) + fmaxf(sa.x, 1e-4f) * fmaxf(sa.x, 1e-4f)) : fmaxf(ux.w, 1e-4f);
+                const float reach = (range + ext) * 1.001f + 1e-4f;
+                sl.pos_r2 = make_float4(pr.x, pr.y, pr.z, reach * reach); // conservative pre-test; eval_light_record decides
                 sl.kind |= KIND_AREA;
             }
             const bool enabled = (tf.z & 1u) != 0u && tf.x >= 1u && tf.x <= 4u;

@@ -495,3 +495,13 @@ def scene_w_zero(w=120, h=80) -> SceneData:
     items = [{"pos": (0, 0, 0), "mesh": 1, "material": _MATERIALS[2], "object_id": 1}]
     fp = capi.default_frame_params(shading_model=capi.SHADING_BLINN, shadow_enable=0, light_culling=0, motion_vectors_enable=0, cull_mode=capi.CULL_NONE)
     return SceneData(f"w_zero_{w}x{h}", w, h, 0.1, 50.0, [mesh], [], items, eye, (0, 0, 1.0), math.radians(70.0), _SUN_DIR, _SUN_COLOR, 2.0, fp, None)
+
+
+def scene_mixed_lights(records_u8, w=288, h=180, shading=capi.SHADING_PBR, max_per_tile=128) -> SceneData:
+    """The small parity scene lit by a caller-supplied set of CullingLightGPU records (tests/golden/golden_area_lights.npz:
+    point lights with all three attenuation models, spot, rect-area and tube-area lights, disabled / zero lights)."""
+    sd = scene_small(w=w, h=h, shading=shading, n_inst=4, lights=0, tex=True, seed=8)
+    sd.lights = np.ascontiguousarray(records_u8, dtype=np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES).view(LIGHT_DTYPE).reshape(-1)
+    sd.fp.light_culling = 1
+    sd.fp.max_lights_per_tile = max_per_tile
+    return sd

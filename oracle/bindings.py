@@ -122,6 +122,24 @@ class Oracle:
           C.c_uint32(model), C.c_float(power), C.c_float(bias), C.c_float(cutoff), out.ctypes.data_as(C.c_void_p))
         return out
 
+    def pack_rect_light(self, pos, rng, color, intensity, direction, right, half_x, half_y, flags=7, model=1, power=1.0, bias=0.05, cutoff=0.0):
+        assert self.kind == "reference"
+        p, c, d, r = (np.asarray(v, dtype=np.float32) for v in (pos, color, direction, right))
+        out = np.zeros(160, dtype=np.uint8)
+        f = self.lib.shsref_pack_rect_light; f.restype = None
+        f(capi.fptr(p), C.c_float(rng), capi.fptr(c), C.c_float(intensity), capi.fptr(d), capi.fptr(r), C.c_float(half_x), C.c_float(half_y),
+          C.c_uint32(flags), C.c_uint32(model), C.c_float(power), C.c_float(bias), C.c_float(cutoff), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def pack_tube_light(self, pos, rng, color, intensity, axis, half_length, radius, flags=7, model=1, power=1.0, bias=0.05, cutoff=0.0):
+        assert self.kind == "reference"
+        p, c, a = (np.asarray(v, dtype=np.float32) for v in (pos, color, axis))
+        out = np.zeros(160, dtype=np.uint8)
+        f = self.lib.shsref_pack_tube_light; f.restype = None
+        f(capi.fptr(p), C.c_float(rng), capi.fptr(c), C.c_float(intensity), capi.fptr(a), C.c_float(half_length), C.c_float(radius),
+          C.c_uint32(flags), C.c_uint32(model), C.c_float(power), C.c_float(bias), C.c_float(cutoff), out.ctypes.data_as(C.c_void_p))
+        return out
+
     def set_threads(self, n):
         if self.kind == "reference":
             self.lib.shsref_set_threads(C.c_int32(n))

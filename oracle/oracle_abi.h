@@ -145,6 +145,14 @@ int32_t shso_pass_depth_prepass(const ShsoAssets* assets, const ShsbScene* scene
  * restatement only).  history_valid == 0: seeds `history` from `ldr` and leaves the frame untouched. */
 int32_t shso_pass_taa(uint8_t* ldr_inout, uint8_t* history_inout, int32_t history_valid, size_t n_pixels);
 
+/* make_rect_area_culling_light / make_tube_area_culling_light, lighting/light_types.hpp:379-436 (reference only). */
+void shsref_pack_rect_light(const float pos[3], float range, const float color[3], float intensity,
+                            const float dir[3], const float right[3], float half_x, float half_y,
+                            uint32_t flags, uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff, void* out_record160);
+void shsref_pack_tube_light(const float pos[3], float range, const float color[3], float intensity,
+                            const float axis[3], float half_length, float radius,
+                            uint32_t flags, uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff, void* out_record160);
+
 /* ThreadPoolJobSystem(n) handed to the reference passes as ctx.job_system / RasterizerConfig::job_system
  * (exp-plumbing/hello_pass_basics.cpp:629-630); n <= 1 means no job system (serial). */
 int32_t shsref_set_threads(int32_t n_threads);

@@ -268,6 +268,50 @@ void shsref_pack_spot_light(const float pos[3], float range, const float color[3
     std::memcpy(out_record160, &rec, sizeof(rec));
 }
 
+// Area lights: the reference's own packers (lighting/light_types.hpp:379-436).  Reference-only entry points: the restatement has
+// no packer of its own for these, the records they produce are committed as a fixture (tests/golden/golden_area_lights.npz).
+void shsref_pack_rect_light(const float pos[3], float range, const float color[3], float intensity,
+                            const float dir[3], const float right[3], float half_x, float half_y,
+                            uint32_t flags, uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff, void* out_record160)
+{
+    shs::RectAreaLight r{};
+    r.common.position_ws = load_vec3(pos);
+    r.common.range = range;
+    r.common.color = load_vec3(color);
+    r.common.intensity = intensity;
+    r.common.flags = flags;
+    r.common.attenuation_model = (shs::LightAttenuationModel)atten_model;
+    r.common.attenuation_power = atten_power;
+    r.common.attenuation_bias = atten_bias;
+    r.common.attenuation_cutoff = atten_cutoff;
+    r.direction_ws = load_vec3(dir);
+    r.right_ws = load_vec3(right);
+    r.half_extents = glm::vec2(half_x, half_y);
+    const shs::CullingLightGPU rec = shs::make_rect_area_culling_light(r);
+    std::memcpy(out_record160, &rec, sizeof(rec));
+}
+
+void shsref_pack_tube_light(const float pos[3], float range, const float color[3], float intensity,
+                            const float axis[3], float half_length, float radius,
+                            uint32_t flags, uint32_t atten_model, float atten_power, float atten_bias, float atten_cutoff, void* out_record160)
+{
+    shs::TubeAreaLight t{};
+    t.common.position_ws = load_vec3(pos);
+    t.common.range = range;
+    t.common.color = load_vec3(color);
+    t.common.intensity = intensity;
+    t.common.flags = flags;
+    t.common.attenuation_model = (shs::LightAttenuationModel)atten_model;
+    t.common.attenuation_power = atten_power;
+    t.common.attenuation_bias = atten_bias;
+    t.common.attenuation_cutoff = atten_cutoff;
+    t.axis_ws = load_vec3(axis);
+    t.half_length = half_length;
+    t.radius = radius;
+    const shs::CullingLightGPU rec = shs::make_tube_area_culling_light(t);
+    std::memcpy(out_record160, &rec, sizeof(rec));
+}
+
 int32_t shsref_rasterize_mesh(const ShsoAssets* assets, shsb_mesh mesh, int32_t shader_id,
                               const ShsbUniforms* u, const ShsoTarget* tgt, const ShsbRasterCfg* cfg,
                               uint32_t key_base, ShsbStats* out_stats)

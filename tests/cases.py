@@ -58,7 +58,17 @@ def forward_plus_cases():
         "fplus_blinn_tex": (lambda: scenes.scene_small(w=333, h=207, lights=64, tex=True, shading=capi.SHADING_BLINN), {"forward_plus": True}),
         "fplus_saturated": (lambda: _saturated(), {"forward_plus": True}),
         "fplus_c2_small": (lambda: scenes.scene_c2(w=640, h=360, grid=4, n_point=96, n_spot=32), {"forward_plus": True}),
+        # every light type and attenuation model the reference can pack (records from its own packers), incl. disabled / zero lights
+        "fplus_mixed_light_types_pbr": (lambda: _mixed(), {"forward_plus": True}),
+        "fplus_mixed_light_types_blinn_saturated": (lambda: _mixed(w=200, h=120, shading=capi.SHADING_BLINN, max_per_tile=6), {"forward_plus": True}),
     }
+
+
+def _mixed(**kw):
+    import os
+    import numpy as np
+    rec = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_area_lights.npz"))["records"]
+    return scenes.scene_mixed_lights(rec, **kw)
 
 
 def _saturated():

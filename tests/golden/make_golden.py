@@ -80,6 +80,35 @@ def main():
         bins[name + "_counts"], bins[name + "_indices"] = c, i
     np.savez_compressed(os.path.join(HERE, "golden_light_bins_port.npz"), **bins)
     print("light bins", {k: int(v.sum()) for k, v in bins.items() if k.endswith("_counts")})
+    # mixed light set (point x 3 attenuation models, spot, rect area, tube area, disabled, zero-intensity, zero-range):
+    # the RECORDS come from the reference's own packers; how area lights shade is the oracle's (GLSL-derived) definition
+    recs = []
+    rng = np.random.default_rng(17)
+    def P(lo, hi):
+        return rng.uniform(lo, hi, 3).astype(np.float32)
+    for k in range(60):
+        pos = P((-5, 0.3, -5), (5, 2.5, 5)); col = rng.uniform(0.2, 1.0, 3).astype(np.float32)
+        kind = k % 6
+        model, power, bias, cutoff = k % 3, float(rng.uniform(0.5, 2.5)), float(rng.uniform(0.01, 0.3)), float(rng.uniform(0.0, 0.05) if k % 4 == 0 else 0.0)
+        flags = 7 if k % 11 else 6          # every 11th light has LightFlagEnabled cleared
+        inten = 0.0 if k == 7 else float(rng.uniform(1.5, 4.0))
+        rad = 0.0 if k == 13 else float(rng.uniform(2.0, 5.0))
+        if kind in (0, 1, 2):
+            r = ref.pack_point_light(pos, rad, col, inten, model=model, power=power, bias=bias, cutoff=cutoff, jolt_bounds=(kind == 2))
+            if flags != 7:
+                r.view(np.uint32)[26] = flags   # type_shape_flags.z
+        elif kind == 3:
+            d = P((-1, -2, -1), (1, -0.5, 1))
+            r = ref.pack_spot_light(pos, rad, col, inten, d, float(rng.uniform(0.1, 0.5)), float(rng.uniform(0.3, 0.9)), model=model, power=power, bias=bias, cutoff=cutoff)
+        elif kind == 4:
+            d = P((-0.4, -1, -0.4), (0.4, -0.6, 0.4)); right = P((0.6, -0.2, -0.4), (1.0, 0.2, 0.4))
+            r = ref.pack_rect_light(pos, rad, col, inten, d, right, float(rng.uniform(0.3, 1.5)), float(rng.uniform(0.2, 1.0)), flags=flags, model=model, power=power, bias=bias, cutoff=cutoff)
+        else:
+            ax = P((-1, -0.3, -1), (1, 0.3, 1))
+            r = ref.pack_tube_light(pos, rad, col, inten, ax, float(rng.uniform(0.3, 2.0)), float(rng.uniform(0.05, 0.4)), flags=flags, model=model, power=power, bias=bias, cutoff=cutoff)
+        recs.append(r)
+    np.savez_compressed(os.path.join(HERE, "golden_area_lights.npz"), records=np.stack(recs))
+    print("mixed light records", len(recs))
     post = {}
     for name, (make, p) in post_cases.blur_cases().items():
         ldr, depth, motion = make()
