@@ -505,3 +505,53 @@ def scene_mixed_lights(records_u8, w=288, h=180, shading=capi.SHADING_PBR, max_p
     sd.fp.light_culling = 1
     sd.fp.max_lights_per_tile = max_per_tile
     return sd
+
+
+def scene_odd_texture(w=140, h=100, shading=capi.SHADING_PBR) -> SceneData:
+    """Texture sampling corners (shader/builtin_shaders.hpp:25-55): a 5 x 3 and a 1 x 1 texture, uvs far outside [0, 1] and negative
+    (repeat wrap via floor), bilinear taps that straddle the wrap seam."""
+    rng = np.random.default_rng(21)
+    t53 = rng.integers(0, 256, size=(3, 5, 4)).astype(np.uint8)
+    t53[..., 3] = 255
+    t11 = np.array([[[200, 40, 90, 255]]], np.uint8)
+    plane = make_grid_plane(10.0, 6)
+    plane["uvs"] = ((plane["uvs"] / 8.0) * np.float32(6.0) - np.float32(2.3)).astype(np.float32)     # uv in [-2.3, 3.7]
+    suz = load_suzanne()
+    suz = dict(suz, uvs=(suz["uvs"] * np.float32(-3.0) + np.float32(0.5)).astype(np.float32))        # negative, scaled
+    items = [{"pos": (0, -1.0, 0), "mesh": 1, "material": dict(_MATERIALS[1], tex=1), "object_id": 1},
+             {"pos": (-1.2, 0.2, 0.5), "rot": (0.2, 0.9, 0.0), "mesh": 2, "material": dict(_MATERIALS[0], tex=1), "object_id": 2},
+             {"pos": (1.4, 0.1, 0.0), "rot": (0.0, -0.7, 0.1), "mesh": 2, "material": dict(_MATERIALS[3], tex=2), "object_id": 3}]
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=0, light_culling=0, motion_vectors_enable=0)
+    return SceneData(f"odd_texture_{w}x{h}", w, h, 0.1, 60.0, [plane, suz], [t53, t11], items, (0.2, 2.0, -4.2), (0, 0.2, 0), math.radians(55.0),
+                     _SUN_DIR, _SUN_COLOR, 2.2, fp, None)
+
+
+def scene_ndc_depth(w=150, h=96) -> SceneData:
+    """A depth target whose zf <= zn + 1e-6: the rasteriser falls back from linear view depth to NDC z * 0.5 + 0.5
+    (sw_render/rasterizer.hpp:354-357).  The camera keeps a normal near / far; only the RENDER TARGET's zn / zf are equal."""
+    sd = scene_small(w=w, h=h, near_clip=True, tex=True, seed=7)
+    vp = sd.viewproj
+    return SceneData(f"ndc_depth_{w}x{h}", w, h, 5.0, 5.0, sd.meshes, sd.textures, sd.items, sd.cam_pos, sd.cam_target, sd.fovy,
+                     sd.sun_dir, sd.sun_color, sd.sun_intensity, sd.fp, None, viewproj=vp)
+
+
+def scene_shadow_variants(variant: int, w=180, h=110) -> SceneData:
+    """PCF corners (lighting/shadow_sample.hpp:65-104): radius 0 (one tap), a fractional step that rounds to 2 or 3, partial strength,
+    large biases, a shadow map far smaller / larger than the frame."""
+    sd = scene_small(w=w, h=h, tex=True, seed=3 + variant)
+    sd.fp.shadow_enable = 1
+    r, step, strength, bc, bs, size = [(0, 1.0, 1.0, 0.0008, 0.0015, 64), (1, 2.5, 0.35, 0.004, 0.02, 96), (3, 1.49, 0.8, 0.0, 0.0, 33), (2, 0.2, 1.7, 0.0008, 0.0015, 512)][variant]
+    sd.fp.shadow_pcf_radius, sd.fp.shadow_pcf_step, sd.fp.shadow_strength = r, step, strength
+    sd.fp.shadow_bias_const, sd.fp.shadow_bias_slope = bc, bs
+    sd.shadow_size = size
+    return sd
+
+
+def scene_many_lights(w=128, h=96, n_lights=2600, max_per_tile=8) -> SceneData:
+    """More lights than one staging round of the tile kernel holds (1024 candidates) and, with every list saturated, more survivors
+    than one pass stages (256): the light loop runs several rounds and passes.  Lights crowd the objects so that they matter."""
+    sd = scene_small(w=w, h=h, n_inst=3, lights=0, tex=False, seed=6)
+    sd.lights = make_lights(n_lights * 3 // 4, n_lights - n_lights * 3 // 4, (-4, 0.1, -4), (4, 2.5, 4), seed=11, range_lo=1.5, range_hi=4.0)
+    sd.fp.light_culling = 1
+    sd.fp.max_lights_per_tile = max_per_tile
+    return sd

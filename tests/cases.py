@@ -44,6 +44,13 @@ def forward_cases():
         "sky_cubemap_nearclip_blinn": (lambda: scenes.scene_small(w=150, h=90, sky="cubemap", near_clip=True, shading=capi.SHADING_BLINN), {}),
         "ragged_inputs_pbr": (lambda: scenes.scene_ragged(), {}),
         "ragged_inputs_blinn_shadow": (lambda: scenes.scene_ragged(w=131, h=97, shading=capi.SHADING_BLINN, shadow=True, nonfinite=False), {"shadow": True}),
+        "odd_textures_wrap_pbr": (lambda: scenes.scene_odd_texture(), {}),
+        "odd_textures_wrap_blinn": (lambda: scenes.scene_odd_texture(w=97, h=71, shading=capi.SHADING_BLINN), {}),
+        "ndc_depth_when_zf_equals_zn": (lambda: scenes.scene_ndc_depth(), {}),
+        "shadow_pcf_radius0": (lambda: scenes.scene_shadow_variants(0), {"shadow": True}),
+        "shadow_pcf_step2_5_strength": (lambda: scenes.scene_shadow_variants(1), {"shadow": True}),
+        "shadow_pcf_radius3_tiny_map": (lambda: scenes.scene_shadow_variants(2), {"shadow": True}),
+        "shadow_pcf_step_below_1_strength_above_1": (lambda: scenes.scene_shadow_variants(3), {"shadow": True}),
         "adversarial_boundaries": (lambda: scenes.scene_adversarial(), {}),
         "adversarial_boundaries_painter": (lambda: scenes.scene_adversarial(w=81, h=57, shading=capi.SHADING_BLINN), {"depth": False}),
         "vertex_on_camera_plane": (lambda: scenes.scene_w_zero(), {}),
@@ -58,6 +65,8 @@ def forward_plus_cases():
         "fplus_blinn_tex": (lambda: scenes.scene_small(w=333, h=207, lights=64, tex=True, shading=capi.SHADING_BLINN), {"forward_plus": True}),
         "fplus_saturated": (lambda: _saturated(), {"forward_plus": True}),
         "fplus_c2_small": (lambda: scenes.scene_c2(w=640, h=360, grid=4, n_point=96, n_spot=32), {"forward_plus": True}),
+        "fplus_2600_lights_saturated": (lambda: scenes.scene_many_lights(), {"forward_plus": True}),
+        "fplus_1500_lights_long_lists": (lambda: scenes.scene_many_lights(w=96, h=64, n_lights=1500, max_per_tile=2048), {"forward_plus": True}),
         # every light type and attenuation model the reference can pack (records from its own packers), incl. disabled / zero lights
         "fplus_mixed_light_types_pbr": (lambda: _mixed(), {"forward_plus": True}),
         "fplus_mixed_light_types_blinn_saturated": (lambda: _mixed(w=200, h=120, shading=capi.SHADING_BLINN, max_per_tile=6), {"forward_plus": True}),
