@@ -967,7 +967,7 @@ namespace
             fc.write_motion = write_motion ? 1 : 0;
             fc.clear_motion = (write_motion || dm->motion_dirty) ? 1 : 0; // both branches of the reference clear the plane
             job.fb.motion = (write_motion || dm->motion_dirty) ? dm->motion : nullptr;
-            dm->motion_dirty = write_motion;
+            dm->motion_dirty = write_motion || (fp->own_row_count > 0 && dm->motion_dirty); // a partition cleans only its own rows
             const float* pvp = ctx->has_prev_frame ? scene->cam_prev_viewproj : scene->cam_viewproj;
             std::memcpy(fc.prev_viewproj, pvp, 64);
         }
