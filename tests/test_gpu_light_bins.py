@@ -105,3 +105,23 @@ def test_bins_full_1080p(gpu, port):
             assert np.array_equal(i[keep], oi[keep])
     finally:
         g.release()
+
+
+def test_bins_with_every_light_type(gpu, port):
+    """The reference-packed mixed light set (rect / tube area lights carry OBB- and capsule-derived cull boxes, Jolt-bounded points a
+    sqrt(3)-inflated sphere): all four bin builders against the oracle."""
+    import cases
+    sd = cases._mixed(w=208, h=120)
+    g, depth = _render_depth(gpu, sd)
+    try:
+        lo, hi = gpu.tile_depth_range(g.dm, 16)
+        for name, d in lb.descs(sd, mx=64).items():
+            rng = (lo, hi) if name in ("view_depth",) else ((np.clip(lo / np.float32(sd.zf), 0, 1), np.clip(hi / np.float32(sd.zf), 0, 1)) if name == "depth01" else (None, None))
+            c, i = gpu.light_cull_ex(d, *rng)
+            oc, oi = port.light_cull_ex(sd.lights, d, *rng)
+            assert np.array_equal(c, oc), f"{name}: counts differ in {int(np.count_nonzero(c != oc))} bins"
+            keep = np.arange(64)[None, :] < np.minimum(oc, 64)[:, None]
+            assert np.array_equal(i[keep], oi[keep]), f"{name}: indices differ"
+            assert int(oc.sum()) > 0
+    finally:
+        g.release()
