@@ -709,60 +709,20 @@ namespace
         return fail(ctx, SHSB_E_OUT_OF_MEMORY, "per-frame arena overflow persisted after regrowth");
     }
 
-    // Sort-first partitions (ShsbFrameParams::own_row_*): can any triangle of this draw reach a tile row this submission owns?
-    // Conservative: the 8 corners of the mesh's local bounds are projected like vertices (rasterizer.hpp:260-269); if all lie in
-    // front of the camera, every triangle's clamped pixel bbox lies within the corners' screen-y range (+- one pixel of rounding
-    // slack, then whole tile rows).  Any corner at w <= 0 or non-finite means "cannot bound": keep the draw.  A skipped draw
-    // contributes no pixels to the owned rows, so the frame is unchanged; only the whole-scene triangle counters shrink.
+    // Sort-first partitions (ShsbFrameParams::own_row_*): the two conservative "can this draw reach an owned tile row?" tests live in
+    // host_math.hpp (pure host arithmetic, property-tested on the CPU by tests/cpp/host_cull_test.cpp).
+    using VpRows = hm::VpRows;
+
+    inline hm::RowOwnership ownership(const FrameConst& fc) { return hm::RowOwnership{fc.H, TILE, fc.own_first, fc.own_count, fc.own_stride}; }
+
     bool item_touches_owned_rows(const FrameConst& fc, const hm::mat4f& viewproj, const hm::mat4f& model, const MeshSlot& mesh)
     {
-        float ymin = 3.0e38f, ymax = -3.0e38f;
-        for (int c = 0; c < 8; ++c)
-        {
-            const hm::vec4f wp = hm::mul_v(model, {(c & 1) ? mesh.bmax.x : mesh.bmin.x, (c & 2) ? mesh.bmax.y : mesh.bmin.y, (c & 4) ? mesh.bmax.z : mesh.bmin.z, 1.0f});
-            const hm::vec4f clip = hm::mul_v(viewproj, {wp.x, wp.y, wp.z, 1.0f});
-            if (!(clip.w > 1e-4f) || !std::isfinite(clip.y) || !std::isfinite(clip.w)) return true;
-            const float sy = (clip.y / clip.w * 0.5f + 0.5f) * (float)(fc.H - 1);
-            if (!std::isfinite(sy)) return true;
-            ymin = std::min(ymin, sy);
-            ymax = std::max(ymax, sy);
-        }
-        ymin -= 2.0f; ymax += 2.0f;
-        if (ymax < 0.0f || ymin > (float)(fc.H - 1)) return false; // entirely above or below the frame: no pixels at all
-        const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(fc.H - 1)));
-        const int ty0 = (fc.H - 1 - py1) / TILE, ty1 = (fc.H - 1 - py0) / TILE; // tile rows count from the top
-        for (int ty = ty0; ty <= ty1; ++ty) if (owned_row(fc, ty)) return true;
-        return false;
+        return hm::bounds_touch_owned_rows(ownership(fc), viewproj, model, mesh.bmin, mesh.bmax);
     }
 
-    struct VpRows { float y[4], w[4], gy, gw; };
-
-    // The same question as item_touches_owned_rows, answered without building the model matrix: model = T * R * S maps the
-    // mesh's local bounds into the sphere (tr.pos, max|scl| * max distance of a bounds corner from the local origin),
-    // whatever the rotation.  Over that sphere clip.y and clip.w vary by at most radius * |gradient|, so ndc.y lies
-    // between the extreme ratios of the two intervals (all w > 0, else "cannot bound").  Conservative, never exact:
-    // a draw it keeps is tested again with its real matrix.
     bool sphere_may_touch_owned_rows(const FrameConst& fc, const VpRows& v, const ShsbTransform& tr, const MeshSlot& mesh)
     {
-        const float ex = std::max(std::fabs(mesh.bmin.x), std::fabs(mesh.bmax.x)), ey = std::max(std::fabs(mesh.bmin.y), std::fabs(mesh.bmax.y)),
-                    ez = std::max(std::fabs(mesh.bmin.z), std::fabs(mesh.bmax.z));
-        const float smax = std::max(std::fabs(tr.scl[0]), std::max(std::fabs(tr.scl[1]), std::fabs(tr.scl[2])));
-        const float radius = smax * std::sqrt(ex * ex + ey * ey + ez * ez) * 1.001f + 1e-4f;
-        const float yc = v.y[0] * tr.pos[0] + v.y[1] * tr.pos[1] + v.y[2] * tr.pos[2] + v.y[3];
-        const float wc = v.w[0] * tr.pos[0] + v.w[1] * tr.pos[1] + v.w[2] * tr.pos[2] + v.w[3];
-        const float dy = radius * v.gy, dw = radius * v.gw;
-        const float w0 = wc - dw, w1 = wc + dw;
-        if (!(w0 > 1e-3f) || !std::isfinite(yc) || !std::isfinite(w1) || !std::isfinite(dy)) return true;
-        const float y0 = yc - dy, y1 = yc + dy;
-        const float nlo = std::min(std::min(y0 / w0, y0 / w1), std::min(y1 / w0, y1 / w1));
-        const float nhi = std::max(std::max(y0 / w0, y0 / w1), std::max(y1 / w0, y1 / w1));
-        const float ymin = (nlo * 0.5f + 0.5f) * (float)(fc.H - 1) - 2.0f, ymax = (nhi * 0.5f + 0.5f) * (float)(fc.H - 1) + 2.0f;
-        if (!std::isfinite(ymin) || !std::isfinite(ymax)) return true;
-        if (ymax < 0.0f || ymin > (float)(fc.H - 1)) return false;
-        const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(fc.H - 1)));
-        const int ty0 = (fc.H - 1 - py1) / TILE, ty1 = (fc.H - 1 - py0) / TILE;
-        for (int ty = ty0; ty <= ty1; ++ty) if (owned_row(fc, ty)) return true;
-        return false;
+        return hm::sphere_may_touch_owned_rows(ownership(fc), v, tr.pos, tr.scl, mesh.bmin, mesh.bmax);
     }
 
     // One draw's device record (everything but its place in the draw order).  Thread-safe: reads the context only.
@@ -1014,14 +974,7 @@ namespace
         std::vector<hm::mat4f> next_models;
         if (lit_pass) { next_keys.reserve(scene->n_items); next_models.reserve(scene->n_items); }
         // rows of cam.viewproj that produce clip.y and clip.w, with the norms of their xyz parts (sphere_may_touch_owned_rows)
-        VpRows vp_rows{};
-        {
-            const float* m = scene->cam_viewproj;
-            vp_rows.y[0] = m[1]; vp_rows.y[1] = m[5]; vp_rows.y[2] = m[9]; vp_rows.y[3] = m[13];
-            vp_rows.w[0] = m[3]; vp_rows.w[1] = m[7]; vp_rows.w[2] = m[11]; vp_rows.w[3] = m[15];
-            vp_rows.gy = std::sqrt(m[1] * m[1] + m[5] * m[5] + m[9] * m[9]);
-            vp_rows.gw = std::sqrt(m[3] * m[3] + m[7] * m[7] + m[11] * m[11]);
-        }
+        const VpRows vp_rows = hm::vp_rows_of(scene->cam_viewproj);
         // Motion vectors need last frame's model matrix of every item, so a partition that writes motion builds every matrix;
         // one that does not may drop a draw before its matrix exists, and then leaves the history empty (the next frame that
         // asks for motion vectors starts like a first frame) rather than half-filled.

@@ -287,4 +287,76 @@ namespace shsb_host
         const float denom = std::max(f - n, 1e-6f);
         return ((f + n) / denom) - ((2.0f * f * n) / (denom * z));
     }
+
+    // ---------------------------------------------------------------- sort-first partitions (ShsbFrameParams::own_row_*)
+    // Tile row ty (0 = top of the frame, `tile` pixels high) is owned iff ty >= first and (ty - first) % stride < count; count <= 0 owns all.
+    struct RowOwnership
+    {
+        int H, tile, first, count, stride;
+        bool owns(int ty) const { return count <= 0 || (ty >= first && ((ty - first) % stride) < count); }
+        // any owned tile row among the rows that framebuffer (bottom-origin) pixel rows [ymin, ymax] fall into?
+        bool any_owned(float ymin, float ymax) const
+        {
+            if (ymax < 0.0f || ymin > (float)(H - 1)) return false; // entirely above or below the frame: no pixels at all
+            const int py0 = (int)std::floor(std::max(ymin, 0.0f)), py1 = (int)std::ceil(std::min(ymax, (float)(H - 1)));
+            const int ty0 = (H - 1 - py1) / tile, ty1 = (H - 1 - py0) / tile; // tile rows count from the top
+            for (int ty = ty0; ty <= ty1; ++ty) if (owns(ty)) return true;
+            return false;
+        }
+    };
+
+    // Can any triangle of a draw reach a tile row this submission owns?  Conservative: the 8 corners of the mesh's local bounds are
+    // projected like vertices (sw_render/rasterizer.hpp:260-269); if all lie in front of the camera, every triangle's clamped pixel
+    // bbox lies within the corners' screen-y range (+- two pixels of rounding slack, then whole tile rows).  Any corner at w <= 0 or
+    // non-finite means "cannot bound": keep the draw.  A dropped draw contributes no pixels to the owned rows.
+    inline bool bounds_touch_owned_rows(const RowOwnership& own, const mat4f& viewproj, const mat4f& model, vec3f bmin, vec3f bmax)
+    {
+        float ymin = 3.0e38f, ymax = -3.0e38f;
+        for (int c = 0; c < 8; ++c)
+        {
+            const vec4f wp = mul_v(model, {(c & 1) ? bmax.x : bmin.x, (c & 2) ? bmax.y : bmin.y, (c & 4) ? bmax.z : bmin.z, 1.0f});
+            const vec4f clip = mul_v(viewproj, {wp.x, wp.y, wp.z, 1.0f});
+            if (!(clip.w > 1e-4f) || !std::isfinite(clip.y) || !std::isfinite(clip.w)) return true;
+            const float sy = (clip.y / clip.w * 0.5f + 0.5f) * (float)(own.H - 1);
+            if (!std::isfinite(sy)) return true;
+            ymin = std::min(ymin, sy);
+            ymax = std::max(ymax, sy);
+        }
+        return own.any_owned(ymin - 2.0f, ymax + 2.0f);
+    }
+
+    // rows of a view-projection matrix that produce clip.y and clip.w, with the norms of their xyz parts
+    struct VpRows { float y[4], w[4], gy, gw; };
+    inline VpRows vp_rows_of(const float* m)
+    {
+        VpRows v{};
+        v.y[0] = m[1]; v.y[1] = m[5]; v.y[2] = m[9]; v.y[3] = m[13];
+        v.w[0] = m[3]; v.w[1] = m[7]; v.w[2] = m[11]; v.w[3] = m[15];
+        v.gy = std::sqrt(m[1] * m[1] + m[5] * m[5] + m[9] * m[9]);
+        v.gw = std::sqrt(m[3] * m[3] + m[7] * m[7] + m[11] * m[11]);
+        return v;
+    }
+
+    // The same question answered without building the model matrix: model = T * R * S maps the mesh's local bounds into the sphere
+    // (pos, max|scl| * max distance of a bounds corner from the local origin), whatever the rotation.  Over that sphere clip.y and
+    // clip.w vary by at most radius * |gradient|, so ndc.y lies between the extreme ratios of the two intervals (all w > 0, else
+    // "cannot bound").  Conservative, never exact: a draw it keeps is tested again with its real matrix.
+    inline bool sphere_may_touch_owned_rows(const RowOwnership& own, const VpRows& v, const float pos[3], const float scl[3], vec3f bmin, vec3f bmax)
+    {
+        const float ex = std::max(std::fabs(bmin.x), std::fabs(bmax.x)), ey = std::max(std::fabs(bmin.y), std::fabs(bmax.y)),
+                    ez = std::max(std::fabs(bmin.z), std::fabs(bmax.z));
+        const float smax = std::max(std::fabs(scl[0]), std::max(std::fabs(scl[1]), std::fabs(scl[2])));
+        const float radius = smax * std::sqrt(ex * ex + ey * ey + ez * ez) * 1.001f + 1e-4f;
+        const float yc = v.y[0] * pos[0] + v.y[1] * pos[1] + v.y[2] * pos[2] + v.y[3];
+        const float wc = v.w[0] * pos[0] + v.w[1] * pos[1] + v.w[2] * pos[2] + v.w[3];
+        const float dy = radius * v.gy, dw = radius * v.gw;
+        const float w0 = wc - dw, w1 = wc + dw;
+        if (!(w0 > 1e-3f) || !std::isfinite(yc) || !std::isfinite(w1) || !std::isfinite(dy)) return true;
+        const float y0 = yc - dy, y1 = yc + dy;
+        const float nlo = std::min(std::min(y0 / w0, y0 / w1), std::min(y1 / w0, y1 / w1));
+        const float nhi = std::max(std::max(y0 / w0, y0 / w1), std::max(y1 / w0, y1 / w1));
+        const float ymin = (nlo * 0.5f + 0.5f) * (float)(own.H - 1) - 2.0f, ymax = (nhi * 0.5f + 0.5f) * (float)(own.H - 1) + 2.0f;
+        if (!std::isfinite(ymin) || !std::isfinite(ymax)) return true;
+        return own.any_owned(ymin, ymax);
+    }
 }
