@@ -31,6 +31,45 @@ def band_sizes(height: int, width: int, world: int, bytes_per_pixel: int, tile: 
     return [(band_of_rank(height, world, r, tile)[1] - band_of_rank(height, world, r, tile)[0]) * width * bytes_per_pixel for r in range(world)]
 
 
+def owned_rows(tile_rows: int, first: int, count: int, stride: int) -> List[bool]:
+    """ShsbFrameParams::own_row_* as a mask over tile rows (row 0 = top): owned iff ty >= first and (ty - first) % stride < count;
+    count <= 0 owns every row."""
+    return [count <= 0 or (ty >= first and (ty - first) % stride < count) for ty in range(tile_rows)]
+
+
+def stripes_of_rank(world: int, rank: int, rows_per_stripe: int = 2) -> Tuple[int, int, int]:
+    """Interleaved stripes: (own_row_first, own_row_count, own_row_stride) of rank r -- balanced by construction, no draw can be dropped."""
+    return rank * rows_per_stripe, rows_per_stripe, world * rows_per_stripe
+
+
+def balanced_band_cuts(row_cost: Sequence[float], world: int) -> List[int]:
+    """Cost-balanced contiguous bands: cuts[r] .. cuts[r + 1] are rank r's tile rows, every rank gets at least one row and about
+    1 / world of sum(row_cost) (e.g. last frame's shaded pixels + triangles per tile row).  Deterministic, so every rank computes
+    the same partition from the same costs."""
+    n = len(row_cost)
+    if world <= 0 or n < world:
+        raise ValueError("need at least one tile row per rank")
+    cum = [0.0]
+    for c in row_cost:
+        cum.append(cum[-1] + max(float(c), 0.0))
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = cuts[-1] + 1
+        while k < n - (world - r) and cum[k] < target:   # leave a row for every later rank
+            k += 1
+        cuts.append(k)
+    cuts.append(n)
+    return cuts
+
+
+def band_framebuffer_rows(height: int, cuts: Sequence[int], rank: int, tile: int = TILE) -> Tuple[int, int]:
+    """Framebuffer (bottom-origin) pixel rows [a, b) of rank r's band: a band of top-anchored tile rows is one contiguous range of
+    render-target memory, so it can be sent / received in place."""
+    return max(0, height - cuts[rank + 1] * tile), height - cuts[rank] * tile
+
+
 def gather_frames(local, world: int, rank: int, root: int = 0):
     """Gathers equally-sized per-rank frame tensors on `root` (camera batch).  Returns a list on root, None elsewhere."""
     import torch

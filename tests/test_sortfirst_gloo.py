@@ -62,3 +62,39 @@ def test_partitions_cover_frame_exactly():
         for world in (1, 2, 8):
             got = sorted(c for r in range(world) for c in sortfirst.cameras_of_rank(n, world, r))
             assert got == list(range(n))
+
+
+def test_ownership_layouts_cover_every_row_once():
+    for tile_rows in (1, 7, 13, 68, 270):
+        for world in (1, 2, 3, 4, 8):
+            if tile_rows < world:
+                continue
+            # interleaved stripes
+            for rows_per_stripe in (1, 2, 3):
+                count = [0] * tile_rows
+                for r in range(world):
+                    for ty, o in enumerate(sortfirst.owned_rows(tile_rows, *sortfirst.stripes_of_rank(world, r, rows_per_stripe))):
+                        count[ty] += int(o)
+                assert count == [1] * tile_rows
+            # cost-balanced bands
+            rng = np.random.default_rng(tile_rows * 31 + world)
+            for cost in (np.ones(tile_rows), rng.random(tile_rows) ** 4, np.concatenate([np.zeros(tile_rows - 1), [5.0]]), np.zeros(tile_rows)):
+                cuts = sortfirst.balanced_band_cuts(cost, world)
+                assert cuts[0] == 0 and cuts[-1] == tile_rows and len(cuts) == world + 1
+                assert all(b > a for a, b in zip(cuts, cuts[1:])), "every rank owns at least one tile row"
+                count = [0] * tile_rows
+                for r in range(world):
+                    for ty, o in enumerate(sortfirst.owned_rows(tile_rows, cuts[r], cuts[r + 1] - cuts[r], 1 << 24)):
+                        count[ty] += int(o)
+                assert count == [1] * tile_rows
+    # balance: with a smooth cost no band exceeds its fair share by more than one row's cost
+    cost = np.linspace(1.0, 3.0, 270)
+    cuts = sortfirst.balanced_band_cuts(cost, 8)
+    shares = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+    assert max(shares) <= cost.sum() / 8 + cost.max()
+    # framebuffer rows of the bands tile the frame bottom-up without gaps (ragged last tile row included)
+    H = 4320 + 5
+    cuts = sortfirst.balanced_band_cuts(np.ones((H + 15) // 16), 8)
+    spans = [sortfirst.band_framebuffer_rows(H, cuts, r) for r in range(8)]
+    assert spans[0][1] == H and spans[-1][0] == 0
+    assert all(spans[r][0] == spans[r + 1][1] for r in range(7))
