@@ -274,10 +274,15 @@ namespace shs::b200
     }
 
     // PassPBRForward, passes/pass_pbr_forward.hpp:31-214 (same Inputs struct, same Context side effects on ctx.debug).
+    // `inputs_on_device`: the shadow map and (with preserve_existing_depth) the depth plane were produced by the b200 passes
+    // and already live in the twins; false (default) mirrors the host copies first.  `local_lights`: -1 = as FrameParams says
+    // (technique.light_culling), 0 = sun only like the reference's CPU lit pass (quirk Q2, pass_pbr_forward.hpp:157-195 never
+    // reads tile lists), 1 = walk the tile lists of the last shsb_light_cull (fp_stress_scene.frag:644-678).
     class PassPBRForward
     {
     public:
-        explicit PassPBRForward(Device& dev, bool sync_host = true) : dev_(dev), sync_host_(sync_host) {}
+        explicit PassPBRForward(Device& dev, bool sync_host = true, bool inputs_on_device = false, int local_lights = -1)
+            : dev_(dev), sync_host_(sync_host), on_device_(inputs_on_device), local_lights_(local_lights) {}
         using Inputs = shs::PassPBRForward::Inputs;
 
         void execute(Context& ctx, const Inputs& in)
@@ -292,12 +297,13 @@ namespace shs::b200
             std::vector<ShsbRenderItem> items;
             const ShsbScene s = detail::scene(dev_, *in.scene, items);
             if (s.sky_kind < 0) return; // an ISkyModel that was not introduced with Device::register_sky: no fallback
-            const ShsbFrameParams fp = detail::frame_params(*in.fp);
+            ShsbFrameParams fp = detail::frame_params(*in.fp);
+            if (local_lights_ >= 0) fp.light_culling = local_lights_;
             if (!ctx.history.has_prev_frame) shsb_history_reset(dev_.ctx()); // Context::history owns the notion of "first frame"
-            if (motion && in.preserve_existing_depth) dev_.upload(motion);
+            if (motion && in.preserve_existing_depth && !on_device_) dev_.upload(motion);
             const bool use_shadow = in.fp->pass.shadow.enable && shadow && ctx.shadow.valid;
             float lvp[16];
-            if (use_shadow) { detail::copy_mat(ctx.shadow.light_viewproj, lvp); dev_.upload(shadow); }
+            if (use_shadow) { detail::copy_mat(ctx.shadow.light_viewproj, lvp); if (!on_device_) dev_.upload(shadow); }
             ShsbStats st{};
             if (shsb_pass_pbr_forward(dev_.ctx(), &s, &fp, dev_.twin(hdr), motion ? dev_.twin(motion) : 0, use_shadow ? dev_.twin(shadow) : 0,
                                       use_shadow ? lvp : nullptr, in.preserve_existing_depth ? 1 : 0, &st) != SHSB_OK) return;
@@ -308,7 +314,8 @@ namespace shs::b200
 
     private:
         Device& dev_;
-        bool sync_host_;
+        bool sync_host_, on_device_;
+        int local_lights_;
     };
 
     // PassShadowMap, passes/pass_shadow_map.hpp:27-205.

@@ -1,0 +1,396 @@
+// tests/cpp/plugin_test.cpp -- the B200 passes driven by the reference's OWN pipeline machinery: PassFactoryRegistry ->
+// PluggablePipeline::configure_for_technique -> PipelineExecutionPlanner -> PipelineRuntimeExecutor
+// (pipeline/pluggable_pipeline.hpp), exactly the way exp-plumbing/hello_pass_basics.cpp:700-760 assembles a software frame.
+//
+// Part 1 (no GPU needed): every id is registered and creatable, the technique profiles assemble, the planner accepts the
+// contracts / IO of every pass with a SoftwareRenderBackend, roles match the reference's standard contracts.
+// Part 2 (GPU): frames rendered through the pipeline equal the reference's CPU pass classes run in the order and with the
+// flags its adapters use (pass_adapters.hpp:356-1496; the adapters themselves need JoltPhysics and cannot be compiled here).
+//
+// Exit code 0 = OK, 1 = mismatch, 77 = part 1 OK but no CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "shs/pipeline/pluggable_pipeline.hpp"
+#include "shs/rhi/drivers/software/sw_backend.hpp"
+
+#include "shs_b200/plugin.hpp"
+
+static int g_bad = 0;
+#define EXPECT(cond, ...) do { if (!(cond)) { ++g_bad; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } } while (0)
+
+static shs::MeshData make_blob(int rings, int segs, float radius)
+{
+    shs::MeshData m{};
+    for (int r = 0; r <= rings; ++r)
+        for (int s = 0; s <= segs; ++s)
+        {
+            const float v = (float)r / rings, u = (float)s / segs;
+            const float th = v * 3.14159265f, ph = u * 6.2831853f;
+            const glm::vec3 n(std::sin(th) * std::cos(ph), std::cos(th), std::sin(th) * std::sin(ph));
+            m.positions.push_back(n * (radius * (1.0f + 0.2f * std::sin(4.0f * ph) * std::sin(3.0f * th))));
+            m.normals.push_back(n);
+            m.uvs.push_back(glm::vec2(u, v));
+        }
+    for (int r = 0; r < rings; ++r)
+        for (int s = 0; s < segs; ++s)
+        {
+            const uint32_t a = r * (segs + 1) + s, b = a + 1, c = a + segs + 1, d = c + 1;
+            m.indices.insert(m.indices.end(), {a, b, c, b, d, c});
+        }
+    return m;
+}
+
+static int ulp(float a, float b)
+{
+    int32_t x, y;
+    std::memcpy(&x, &a, 4);
+    std::memcpy(&y, &b, 4);
+    return std::abs(x - y);
+}
+
+struct Targets
+{
+    shs::RT_ColorHDR hdr;
+    shs::RT_ColorDepthMotion dm;
+    shs::RT_ShadowDepth sm;
+    shs::RT_ColorLDR ldr, shafts_tmp, mb_tmp;
+    shs::RTRegistry rtr{};
+    shs::RTHandle h_hdr{}, h_ldr{}, h_shafts{}, h_mb{};
+    shs::RT_Motion h_dm{};
+    shs::RT_Shadow h_sm{};
+    Targets(int w, int h) : hdr(w, h), dm(w, h, 0.1f, 100.0f), sm(128, 128), ldr(w, h), shafts_tmp(w, h), mb_tmp(w, h)
+    {
+        h_hdr = rtr.reg<shs::RTHandle>(&hdr);
+        h_dm = rtr.reg<shs::RT_Motion>(&dm);
+        h_sm = rtr.reg<shs::RT_Shadow>(&sm);
+        h_ldr = rtr.reg<shs::RTHandle>(&ldr);
+        h_shafts = rtr.reg<shs::RTHandle>(&shafts_tmp);
+        h_mb = rtr.reg<shs::RTHandle>(&mb_tmp);
+    }
+};
+
+// PassDepthPrepassAdapter::execute_with_scratch (pass_adapters.hpp:470-525) with the reference's rasterizer
+static void reference_depth_prepass(shs::Context& ctx, const shs::Scene& scene, const shs::FrameParams& fp, Targets& t)
+{
+    shs::RT_ColorHDR scratch(t.dm.w, t.dm.h);
+    t.dm.depth.clear(1.0f);
+    t.dm.motion.clear(shs::Motion2f{});
+    scratch.clear(shs::ColorF{0.0f, 0.0f, 0.0f, 1.0f});
+    shs::ShaderProgram prog{};
+    prog.vs = [](const shs::ShaderVertex& vin, const shs::ShaderUniforms& u) -> shs::VertexOut {
+        shs::VertexOut out{};
+        const glm::vec4 wp4 = u.model * glm::vec4(vin.position, 1.0f);
+        out.world_pos = glm::vec3(wp4);
+        out.clip = u.viewproj * wp4;
+        return out;
+    };
+    prog.fs = [](const shs::FragmentIn&, const shs::ShaderUniforms&) -> shs::FragmentOut { shs::FragmentOut o{}; o.color = shs::ColorF{0, 0, 0, 1}; return o; };
+    shs::RasterizerConfig cfg{};
+    cfg.front_face_ccw = fp.front_face_ccw;
+    cfg.job_system = ctx.job_system;
+    cfg.cull_mode = fp.cull_mode == shs::CullMode::None ? shs::RasterizerCullMode::None : (fp.cull_mode == shs::CullMode::Front ? shs::RasterizerCullMode::Front : shs::RasterizerCullMode::Back);
+    for (const auto& item : scene.items)
+    {
+        if (!item.visible || !scene.resources) continue;
+        const shs::MeshData* mesh = scene.resources->get_mesh((shs::MeshAssetHandle)item.mesh);
+        if (!mesh || mesh->empty()) continue;
+        shs::ShaderUniforms u{};
+        glm::mat4 model(1.0f);
+        model = glm::translate(model, item.tr.pos);
+        model = glm::rotate(model, item.tr.rot_euler.x, glm::vec3(1, 0, 0));
+        model = glm::rotate(model, item.tr.rot_euler.y, glm::vec3(0, 1, 0));
+        model = glm::rotate(model, item.tr.rot_euler.z, glm::vec3(0, 0, 1));
+        model = glm::scale(model, item.tr.scl);
+        u.model = model;
+        u.viewproj = scene.cam.viewproj;
+        u.enable_motion_vectors = false;
+        (void)shs::rasterize_mesh(*mesh, prog, u, shs::RasterizerTarget{&scratch, &t.dm}, cfg);
+    }
+}
+
+struct Diff { int depth_ulp = 0, shadow_ulp = 0, ldr_lsb = 0; double psnr = 999.0; size_t motion_diff = 0; };
+static Diff compare(const Targets& a, const Targets& b)
+{
+    Diff d{};
+    double se = 0.0, peak = 1.0;
+    for (size_t i = 0; i < a.dm.depth.data.size(); ++i) d.depth_ulp = std::max(d.depth_ulp, ulp(a.dm.depth.data[i], b.dm.depth.data[i]));
+    for (size_t i = 0; i < a.sm.depth.size(); ++i) d.shadow_ulp = std::max(d.shadow_ulp, ulp(a.sm.depth[i], b.sm.depth[i]));
+    for (size_t i = 0; i < a.hdr.color.data.size(); ++i)
+    {
+        const shs::ColorF p = a.hdr.color.data[i], q = b.hdr.color.data[i];
+        se += (p.r - q.r) * (double)(p.r - q.r) + (p.g - q.g) * (double)(p.g - q.g) + (p.b - q.b) * (double)(p.b - q.b);
+        peak = std::max(peak, (double)std::max(p.r, std::max(p.g, p.b)));
+        const shs::Color x = a.ldr.color.data[i], y = b.ldr.color.data[i];
+        d.ldr_lsb = std::max(d.ldr_lsb, std::max(std::abs(x.r - y.r), std::max(std::abs(x.g - y.g), std::abs(x.b - y.b))));
+        if (std::memcmp(&a.dm.motion.data[i], &b.dm.motion.data[i], sizeof(shs::Motion2f)) != 0) ++d.motion_diff;
+    }
+    const double mse = se / (3.0 * a.hdr.color.data.size());
+    if (mse > 0.0) d.psnr = 10.0 * std::log10(peak * peak / mse);
+    return d;
+}
+
+int main()
+{
+    const int W = 256, H = 160;
+    shs::b200::Device dev(0);
+    Targets gpu(W, H), ref(W, H);
+
+    // ------------------------------------------------------------------ part 1: registry, profiles, planner
+    const shs::PassFactoryRegistry reg = shs::b200::make_b200_pass_factory_registry(dev, gpu.h_sm, gpu.h_hdr, gpu.h_dm, gpu.h_ldr, gpu.h_shafts, gpu.h_mb);
+    const char* ids[] = {"shadow_map", "depth_prepass", "light_culling", "cluster_build", "cluster_light_assign", "pbr_forward", "pbr_forward_plus",
+                         "pbr_forward_clustered", "tonemap", "light_shafts", "motion_blur", "depth_of_field", "taa"};
+    for (const char* id : ids)
+    {
+        EXPECT(reg.has(std::string(id)), "id '%s' is not registered", id);
+        const std::unique_ptr<shs::IRenderPass> p = reg.create(std::string(id));
+        EXPECT(p && std::string(p->id()) == id, "factory of '%s' creates a pass with another id", id);
+        if (!p) continue;
+        EXPECT(p->supports_backend(shs::RenderBackendType::Software) && !p->supports_backend(shs::RenderBackendType::Vulkan), "'%s' backend support", id);
+        shs::TechniquePassContract std_c{};
+        const shs::PassId pid = shs::parse_pass_id(id);
+        if (shs::pass_id_is_standard(pid) && shs::lookup_standard_pass_contract(pid, std_c))
+        {
+            // (the pass's own contract mirrors the reference's ADAPTER, which is not always its standard-contract table:
+            // PassTonemapAdapter says Composite, pass_adapters.hpp:1147, the table says PostProcess)
+            const shs::TechniquePassContract c = p->describe_contract();
+            EXPECT(c.role != shs::TechniquePassRole::Custom && !c.semantics.empty(), "'%s': contract carries no metadata", id);
+            EXPECT(c.requires_depth_prepass == std_c.requires_depth_prepass || !std_c.requires_depth_prepass, "'%s': requires_depth_prepass", id);
+            shs::PassFactoryDescriptor desc{};
+            EXPECT(reg.try_get_descriptor(pid, desc) && desc.backend_mask == shs::PassFactoryRegistry::backend_bit(shs::RenderBackendType::Software), "'%s': descriptor", id);
+        }
+    }
+    EXPECT(!reg.has(std::string("gbuffer")) && !reg.has(std::string("deferred_lighting")), "deferred passes are outside the path and must not be claimed");
+
+    shs::SoftwareRenderBackend sw_backend{};
+    const shs::TechniqueMode modes[] = {shs::TechniqueMode::Forward, shs::TechniqueMode::ForwardPlus, shs::TechniqueMode::ClusteredForward};
+    const size_t expected_passes[] = {4, 6, 7};
+    for (int mi = 0; mi < 3; ++mi)
+    {
+        shs::PluggablePipeline pipe{};
+        std::vector<std::string> missing{};
+        const bool ok = pipe.configure_for_technique(reg, modes[mi], &missing);
+        EXPECT(ok && missing.empty(), "technique %d: profile does not assemble (%zu ids missing)", mi, missing.size());
+        shs::Context ctx{};
+        ctx.register_backend(&sw_backend);
+        shs::FrameParams fp{};
+        fp.w = W; fp.h = H;
+        fp.technique.mode = modes[mi];
+        const shs::PipelineExecutionPlan plan = pipe.build_execution_plan(ctx, fp, gpu.rtr);
+        EXPECT(plan.valid, "technique %d: the reference's planner rejects the plan", mi);
+        for (const std::string& e : plan.report.errors) std::printf("  planner error: %s\n", e.c_str());
+        for (const std::string& w : plan.report.warnings) std::printf("  planner warning: %s\n", w.c_str());
+        // the one warning the reference's own adapters produce as well: tonemap writes rt_ldr, motion_blur read-writes it
+        size_t unexpected = 0;
+        for (const std::string& w : plan.report.warnings) if (w.find("Multiple writers") == std::string::npos) ++unexpected;
+        EXPECT(plan.report.errors.empty() && unexpected == 0, "technique %d: planner report is not clean", mi);
+        EXPECT(plan.passes.size() == expected_passes[mi], "technique %d: %zu passes planned, expected %zu", mi, plan.passes.size(), expected_passes[mi]);
+        std::printf("technique %-18s:", shs::technique_mode_name(modes[mi]));
+        for (const shs::PipelineExecutionPass& p : plan.passes) std::printf(" %s", p.label.c_str());
+        std::printf("\n");
+    }
+    {
+        // a pass without a device refuses to run instead of falling back to the CPU
+        shs::b200::Device* none = nullptr; (void)none;
+        if (!dev.valid())
+        {
+            shs::Context ctx{};
+            shs::Scene scene{};
+            shs::FrameParams fp{};
+            fp.w = W; fp.h = H;
+            for (const char* id : ids)
+            {
+                if (std::string(id) == "depth_of_field") continue; // a no-op in the reference too
+                const std::unique_ptr<shs::IRenderPass> p = reg.create(std::string(id));
+                shs::PassExecutionRequest rq = p->build_execution_request(ctx, scene, fp, gpu.rtr);
+                shs::LightCullingRuntimePayload payload{};
+                rq.inputs.light_culling = &payload;
+                rq.depth_prepass_ready = true;
+                EXPECT(!p->execute_resolved(ctx, rq).executed, "'%s' claims to have executed without a device", id);
+            }
+        }
+    }
+    std::printf("part 1 (registry / profiles / planner): %s\n", g_bad ? "FAILED" : "OK");
+    if (g_bad) return 1;
+    if (!dev.valid()) { std::printf("SKIP part 2: %s\n", dev.last_error()); return 77; }
+
+    // ------------------------------------------------------------------ part 2: frames through the reference's executor
+    shs::ResourceRegistry resources{};
+    const shs::MeshAssetHandle blob = resources.add_mesh(make_blob(20, 28, 1.0f));
+    const shs::MaterialAssetHandle red = resources.add_material(shs::MaterialData{"red", glm::vec3(0.9f, 0.25f, 0.2f), 0.3f, 0.45f, 1.0f});
+    shs::Scene scene{};
+    scene.resources = &resources;
+    scene.cam.pos = glm::vec3(0.0f, 2.5f, -7.0f);
+    scene.cam.view = shs::look_at_lh(scene.cam.pos, glm::vec3(0.0f, 0.2f, 0.0f), glm::vec3(0, 1, 0));
+    scene.cam.proj = shs::perspective_lh_no(glm::radians(60.0f), (float)W / (float)H, 0.1f, 100.0f);
+    scene.cam.viewproj = scene.cam.proj * scene.cam.view;
+    scene.cam.prev_viewproj = scene.cam.viewproj;
+    scene.sun.dir_ws = glm::normalize(glm::vec3(-0.4f, -1.0f, 0.3f));
+    scene.sun.color = glm::vec3(1.0f, 0.96f, 0.9f);
+    scene.sun.intensity = 2.0f;
+    for (int i = 0; i < 6; ++i)
+    {
+        shs::RenderItem it{};
+        it.tr.pos = glm::vec3(-3.5f + 1.4f * i, 0.15f * (i % 3), 0.8f * (i % 2));
+        it.tr.rot_euler = glm::vec3(0.0f, 0.5f * i, 0.1f * i);
+        it.tr.scl = glm::vec3(0.7f);
+        it.mesh = blob;
+        it.mat = (i % 2) ? red : 0;
+        it.object_id = 10u + (uint64_t)i;
+        scene.items.push_back(it);
+    }
+    shs::LightSet lights{};
+    for (int i = 0; i < 24; ++i)
+    {
+        shs::PointLight pl{};
+        pl.common.position_ws = glm::vec3(-4.0f + 0.35f * i, 1.2f + 0.3f * (i % 3), -1.0f + 0.5f * (i % 4));
+        pl.common.range = 2.5f;
+        pl.common.color = glm::vec3(0.3f + 0.1f * (i % 5), 0.8f, 1.0f - 0.1f * (i % 4));
+        pl.common.intensity = 3.0f;
+        lights.points.push_back(pl);
+    }
+    scene.local_lights = &lights;
+
+    auto move_scene = [&]() {
+        scene.cam.prev_viewproj = scene.cam.viewproj;
+        scene.cam.pos += glm::vec3(0.2f, 0.05f, -0.1f);
+        scene.cam.view = shs::look_at_lh(scene.cam.pos, glm::vec3(0.0f, 0.2f, 0.0f), glm::vec3(0, 1, 0));
+        scene.cam.viewproj = scene.cam.proj * scene.cam.view;
+        for (size_t i = 0; i < scene.items.size(); ++i) scene.items[i].tr.rot_euler.y += 0.15f;
+    };
+
+    // reference sequence of one frame = the adapters' bodies in pipeline order
+    auto reference_frame = [&](shs::Context& ctx, const shs::FrameParams& fp, bool depth_prepass, bool preserve_depth, bool motion_blur) {
+        shs::PassShadowMap::Inputs si{&scene, &fp, &ref.rtr, ref.h_sm};
+        shs::PassShadowMap().execute(ctx, si);
+        if (depth_prepass) reference_depth_prepass(ctx, scene, fp, ref);
+        shs::PassPBRForward::Inputs fi{};
+        fi.scene = &scene; fi.fp = &fp; fi.rtr = &ref.rtr; fi.rt_hdr = ref.h_hdr; fi.rt_motion = ref.h_dm; fi.rt_shadow = shs::RTHandle{ref.h_sm.id};
+        fi.preserve_existing_depth = preserve_depth;
+        shs::PassPBRForward().execute(ctx, fi);
+        shs::PassTonemap::Inputs ti{&fp, &ref.rtr, ref.h_hdr, ref.h_ldr};
+        shs::PassTonemap().execute(ctx, ti);
+        if (motion_blur)
+        {
+            shs::PassMotionBlur::Inputs mi{};
+            mi.fp = &fp; mi.rtr = &ref.rtr; mi.rt_input_ldr = ref.h_ldr; mi.rt_output_ldr = ref.h_ldr; mi.rt_motion = ref.h_dm; mi.rt_tmp = ref.h_mb;
+            shs::PassMotionBlur().execute(ctx, mi);
+        }
+    };
+
+    struct Case { const char* name; shs::TechniqueMode mode; bool emulate_vk; bool expect_preserve; };
+    // Forward+ with the deferred-queue emulation (the reference's default) runs light culling after the graphics passes, so
+    // the lit pass re-clears depth; executed strictly in order it keeps the pre-pass depth and the strict LESS test rejects
+    // every surface (quirk Q1).  Both behaviours are the reference's and both must be reproduced.
+    const Case cases[] = {
+        {"forward", shs::TechniqueMode::Forward, false, false},
+        {"forward, vk-like queues", shs::TechniqueMode::Forward, true, false},
+        {"forward+, vk-like queues", shs::TechniqueMode::ForwardPlus, true, false},
+        {"forward+, in order (Q1)", shs::TechniqueMode::ForwardPlus, false, true},
+        {"clustered, in order (Q1)", shs::TechniqueMode::ClusteredForward, false, true},
+    };
+    for (const Case& c : cases)
+    {
+        shs::PluggablePipeline pipe{};
+        pipe.configure_for_technique(reg, c.mode);
+        shs::Context ctx_gpu{}, ctx_ref{};
+        ctx_gpu.register_backend(&sw_backend);
+        shs::FrameParams fp{};
+        fp.w = W; fp.h = H;
+        fp.dt = 1.0f / 30.0f;
+        fp.technique.mode = c.mode;
+        fp.hybrid.emulate_vulkan_runtime = c.emulate_vk;
+        fp.pass.motion_blur.enable = true;
+        const bool prepass = c.mode != shs::TechniqueMode::Forward;
+        for (int frame = 0; frame < 2; ++frame)
+        {
+            pipe.execute(ctx_gpu, scene, fp, gpu.rtr);
+            EXPECT(pipe.execution_report().valid, "%s: execution report invalid", c.name);
+            reference_frame(ctx_ref, fp, prepass, c.expect_preserve, true);
+            const Diff d = compare(ref, gpu);
+            size_t lit = 0;
+            for (const shs::ColorF& px : ref.hdr.color.data) if (px.r > 0.3f) ++lit;
+            std::printf("%-26s frame %d: depth<=%d ULP shadow<=%d ULP LDR<=%d LSB HDR PSNR %.1f dB motion diff %zu  tris %llu (ref %llu)  bright px %zu\n", c.name, frame,
+                        d.depth_ulp, d.shadow_ulp, d.ldr_lsb, d.psnr, d.motion_diff, (unsigned long long)ctx_gpu.debug.tri_raster, (unsigned long long)ctx_ref.debug.tri_raster, lit);
+            EXPECT(d.depth_ulp <= 1 && d.shadow_ulp <= 1 && d.ldr_lsb <= 1 && d.psnr >= 60.0 && d.motion_diff == 0, "%s frame %d: parity gates", c.name, frame);
+            EXPECT(ctx_gpu.debug.tri_input == ctx_ref.debug.tri_input && ctx_gpu.debug.tri_raster == ctx_ref.debug.tri_raster, "%s frame %d: stats", c.name, frame);
+            EXPECT(ctx_gpu.history.has_prev_frame && ctx_gpu.shadow.valid, "%s: Context side effects", c.name);
+            move_scene();
+        }
+        pipe.reset_history(ctx_gpu, gpu.rtr);
+        EXPECT(!ctx_gpu.history.has_prev_frame, "%s: reset_history", c.name);
+    }
+
+    // ---- light_culling called directly (the executor keeps its payload private): counts follow pass_adapters.hpp:292-330
+    {
+        shs::FrameParams fp{};
+        fp.w = W; fp.h = H;
+        fp.technique.mode = shs::TechniqueMode::ForwardPlus;
+        fp.technique.max_lights_per_tile = 8;
+        shs::Context ctx{};
+        const std::unique_ptr<shs::IRenderPass> cull = reg.create(shs::PassId::LightCulling);
+        shs::PassExecutionRequest rq = cull->build_execution_request(ctx, scene, fp, gpu.rtr);
+        shs::LightCullingRuntimePayload payload{};
+        rq.inputs.light_culling = &payload;
+        rq.depth_prepass_ready = false;
+        EXPECT(!cull->execute_resolved(ctx, rq).executed, "light_culling must wait for the depth pre-pass (pass_adapters.hpp:241)");
+        rq.depth_prepass_ready = true;
+        const shs::PassExecutionResult r = cull->execute_resolved(ctx, rq);
+        EXPECT(r.executed && r.produced_light_grid && r.produced_light_index_list, "light_culling result flags");
+        EXPECT(payload.tile_count_x == (uint32_t)(W + 15) / 16 && payload.tile_count_y == (uint32_t)(H + 15) / 16 && payload.tile_size == 16 && payload.max_lights_per_tile == 8, "payload grid");
+        EXPECT(payload.tile_light_counts.size() == (size_t)payload.tile_count_x * payload.tile_count_y, "payload counts size");
+        uint32_t mx = 0, mn = 1000; uint64_t sum = 0;
+        for (uint32_t v : payload.tile_light_counts) { mx = std::max(mx, v); mn = std::min(mn, v); sum += v; }
+        EXPECT(mn >= 1 && mx == 8, "counts include the directional light and saturate at the cap (min %u max %u)", mn, mx);
+        EXPECT(payload.visible_light_count >= 2 && payload.visible_light_count <= 25, "visible_light_count %u", payload.visible_light_count);
+        std::printf("light_culling payload: %ux%u tiles, counts min %u max %u sum %llu, visible lights %u\n", payload.tile_count_x, payload.tile_count_y, mn, mx,
+                    (unsigned long long)sum, payload.visible_light_count);
+    }
+
+    // ---- opt-in: Forward+ that really shades Scene::local_lights (the reference's GPU behaviour); radiance only adds
+    for (int with_shadow = 1; with_shadow >= 0; --with_shadow)
+    {
+        shs::b200::PluginOptions opt{};
+        opt.shade_local_lights = true;
+        const shs::PassFactoryRegistry reg2 = shs::b200::make_b200_pass_factory_registry(dev, gpu.h_sm, gpu.h_hdr, gpu.h_dm, gpu.h_ldr, gpu.h_shafts, gpu.h_mb, opt);
+        shs::PluggablePipeline pipe{};
+        pipe.configure_for_technique(reg2, shs::TechniqueMode::ForwardPlus);
+        shs::Context ctx{};
+        ctx.register_backend(&sw_backend);
+        shs::FrameParams fp{};
+        fp.w = W; fp.h = H;
+        fp.technique.mode = shs::TechniqueMode::ForwardPlus;
+        fp.technique.depth_prepass = false; // without the pre-pass the lit pass draws normally and culling is ready in order
+        fp.hybrid.emulate_vulkan_runtime = false;
+        fp.pass.shadow.enable = with_shadow != 0;
+        pipe.execute(ctx, scene, fp, gpu.rtr);
+        shs::Context ctx_ref{};
+        reference_frame(ctx_ref, fp, false, false, false);
+        size_t brighter = 0, darker = 0, depth_diff = 0, shadow_diff = 0;
+        float max_darker = 0.0f;
+        int dx0 = W, dx1 = -1, dy0 = H, dy1 = -1;
+        for (size_t i = 0; i < ref.hdr.color.data.size(); ++i)
+        {
+            const shs::ColorF a = ref.hdr.color.data[i], b = gpu.hdr.color.data[i];
+            if (b.r > a.r + 1e-3f || b.g > a.g + 1e-3f || b.b > a.b + 1e-3f) ++brighter;
+            if (b.r < a.r - 1e-3f || b.g < a.g - 1e-3f || b.b < a.b - 1e-3f)
+            {
+                ++darker;
+                max_darker = std::max(max_darker, std::max(a.r - b.r, std::max(a.g - b.g, a.b - b.b)));
+                const int x = (int)(i % W), y = (int)(i / W);
+                dx0 = std::min(dx0, x); dx1 = std::max(dx1, x); dy0 = std::min(dy0, y); dy1 = std::max(dy1, y);
+            }
+            if (ulp(ref.dm.depth.data[i], gpu.dm.depth.data[i]) > 1) ++depth_diff;
+        }
+        for (size_t i = 0; i < ref.sm.depth.size(); ++i) if (ulp(ref.sm.depth[i], gpu.sm.depth[i]) > 1) ++shadow_diff;
+        std::printf("forward+ with local lights (shadows %d): %zu px brighter than the sun-only reference frame, %zu darker (max %.4f, x %d..%d y %d..%d), depth diff %zu, shadow map diff %zu\n",
+                    with_shadow, brighter, darker, max_darker, dx0, dx1, dy0, dy1, depth_diff, shadow_diff);
+        EXPECT(brighter > 500 && darker == 0 && depth_diff == 0 && shadow_diff == 0, "local lights must add radiance and never remove it");
+    }
+
+    std::printf("%s\n", g_bad ? "MISMATCH" : "OK");
+    return g_bad ? 1 : 0;
+}

@@ -8,6 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "_build", "drop_in_test")
+PLUGIN_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "plugin_test")
 
 
 def _build():
@@ -33,5 +34,30 @@ def test_drop_in_parity_on_gpu():
     if not os.path.exists(BIN):
         pytest.skip("tests/cpp/_build/drop_in_test was not built (needs /root/reference at build time)")
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_plugin_registry_profiles_and_planner():
+    """host/shs_b200/plugin.hpp: the B200 passes behind the reference's IRenderPass / PassFactoryRegistry interface, assembled by
+    the reference's own PluggablePipeline and accepted by its planner (part 1 of tests/cpp/plugin_test.cpp; no device needed)."""
+    import torch
+    if not os.path.isdir("/root/reference") and not os.path.exists(PLUGIN_BIN):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(PLUGIN_BIN)
+    if not torch.cuda.is_available():
+        r = subprocess.run([PLUGIN_BIN], capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        assert r.returncode == 77 and "part 1 (registry / profiles / planner): OK" in r.stdout and "SKIP part 2" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plugin_pipeline_parity_on_gpu():
+    """Frames rendered through the reference's PipelineRuntimeExecutor with the B200 registry equal the reference's CPU passes
+    (Forward, Forward+ with and without the queue emulation -- quirk Q1 --, clustered), payload counts, opt-in local lights."""
+    if not os.path.exists(PLUGIN_BIN):
+        pytest.skip("tests/cpp/_build/plugin_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([PLUGIN_BIN], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
