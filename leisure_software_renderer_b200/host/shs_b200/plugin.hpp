@@ -51,7 +51,10 @@ namespace shs::b200
         // tile lists; execute_generic_light_culling, pass_adapters.hpp:228-333, only counts).  false keeps that -- results
         // equal the reference's.  true makes pbr_forward_plus / pbr_forward_clustered walk the tile lists built by
         // light_culling / cluster_light_assign over Scene::local_lights the way the reference's GPU path does
-        // (shaders/vulkan/fp_stress_scene.frag:644-678).
+        // (shaders/vulkan/fp_stress_scene.frag:644-678).  The lists are used only when the executor reports them ready
+        // (PassExecutionRequest::light_culling_ready); with the reference's pipeline semantics that means an in-order frame,
+        // and -- because an in-order frame WITH the depth pre-pass draws nothing (quirk Q1) -- technique.depth_prepass = false
+        // with PluggablePipeline::set_strict_graph_validation(false) (tests/cpp/plugin_test.cpp).
         bool shade_local_lights = false;
         // Fill LightCullingRuntimePayload::tile_light_counts / visible_light_count (a device -> host read of 4 B per tile).
         bool fill_light_culling_payload = true;

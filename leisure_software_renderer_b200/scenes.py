@@ -555,3 +555,91 @@ def scene_many_lights(w=128, h=96, n_lights=2600, max_per_tile=8) -> SceneData:
     sd.fp.light_culling = 1
     sd.fp.max_lights_per_tile = max_per_tile
     return sd
+
+
+def make_triangle_soup(n_tris: int, seed: int, extent=3.0, indexed=True, zero_normals=True) -> dict:
+    """Random triangles for the fuzz scenes: a mix of small, large (frustum-crossing) and sliver triangles with random
+    per-vertex normals (not unit length, sometimes zero) and uvs outside [0, 1]."""
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-extent, extent, (n_tris, 1, 3))
+    size = rng.choice([0.05, 0.4, 2.5, 12.0], (n_tris, 1, 1), p=[0.2, 0.5, 0.25, 0.05])
+    pos = (centers + rng.uniform(-1, 1, (n_tris, 3, 3)) * size).astype(np.float32)
+    sl = rng.random(n_tris) < 0.15                                       # slivers: third vertex almost on the first edge
+    t = rng.random((n_tris, 1)).astype(np.float32)
+    pos[sl, 2] = pos[sl, 0] * (1 - t[sl]) + pos[sl, 1] * t[sl] + rng.normal(0, 1e-4, (int(sl.sum()), 3)).astype(np.float32)
+    nrm = rng.normal(0, 1, (n_tris * 3, 3)).astype(np.float32)
+    zero = rng.random(n_tris * 3) < 0.03
+    if zero_normals:
+        nrm[zero] = 0.0                                                  # normalize(0) = NaN colour in the reference: CPU-vs-CPU bit tests only
+    uv = rng.uniform(-2.5, 3.5, (n_tris * 3, 2)).astype(np.float32)
+    pos = pos.reshape(-1, 3)
+    if indexed:
+        idx = np.arange(n_tris * 3, dtype=np.uint32)
+        rng.shuffle(idx.reshape(-1, 3))                                  # triangle order != vertex order
+        return {"positions": pos, "normals": nrm, "uvs": uv, "indices": idx}
+    return {"positions": pos, "normals": nrm, "uvs": uv, "indices": np.zeros(0, np.uint32)}
+
+
+def scene_fuzz(seed: int, lights: bool = False, zero_normals: bool = True) -> SceneData:
+    """Seeded random parity scene (tests/test_fuzz_*.py): random target size, camera (often inside or grazing geometry, so the
+    near / side planes clip), fov, depth range, shading model, cull mode / winding, shadow parameters, sky model, materials,
+    textures of odd sizes, non-uniform and mirrored instance scales, triangle soups.  Everything is a function of `seed`."""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(17, 230)), int(rng.integers(13, 170))
+    meshes = [load_suzanne(), make_grid_plane(float(rng.uniform(6, 30)), int(rng.integers(1, 9))),
+              make_triangle_soup(int(rng.integers(8, 120)), seed * 7 + 1, indexed=True, zero_normals=zero_normals),
+              make_triangle_soup(int(rng.integers(3, 40)), seed * 7 + 2, extent=1.5, indexed=bool(rng.random() < 0.5), zero_normals=zero_normals)]
+    tw, th = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+    tex = rng.integers(0, 256, (th, tw, 4), dtype=np.uint8)
+    textures = [make_checker_texture(32, seed), tex]
+    sky_desc = None
+    sk = rng.random()
+    if sk < 0.2:
+        sky_desc = {"kind": "procedural", "sun_dir": tuple(float(v) for v in rng.normal(0, 1, 3))}
+    elif sk < 0.4:
+        textures = textures + make_sky_faces(int(rng.integers(1, 12)), seed)
+        sky_desc = {"kind": "cubemap", "faces": list(range(3, 9)), "intensity": float(rng.uniform(0.2, 2.0))}
+    items = []
+    for k in range(int(rng.integers(0, 7))):
+        mesh = int(rng.choice([1, 2, 3, 4], p=[0.35, 0.2, 0.3, 0.15]))
+        scl = rng.uniform(0.3, 2.0, 3) if rng.random() < 0.5 else np.repeat(rng.uniform(0.3, 2.0), 3)
+        if rng.random() < 0.15:
+            scl = scl * np.array([-1.0, 1.0, 1.0])                        # mirrored: winding flips on screen
+        mat = None
+        if rng.random() < 0.8:
+            mat = {"base_color": tuple(float(v) for v in rng.uniform(0, 1, 3)), "metallic": float(rng.uniform(-0.2, 1.2)),
+                   "roughness": float(rng.uniform(-0.1, 1.3)), "ao": float(rng.uniform(0, 1)), "tex": int(rng.choice([0, 0, 1, 2]))}
+        items.append({"pos": tuple(float(v) for v in rng.uniform(-4, 4, 3) * np.array([1, 0.4, 1])), "rot": tuple(float(v) for v in rng.uniform(-3.2, 3.2, 3)),
+                      "scl": tuple(float(v) for v in scl), "mesh": mesh, "material": mat, "visible": bool(rng.random() < 0.92),
+                      "casts_shadow": bool(rng.random() < 0.8), "object_id": 500 + k})
+    shading = capi.SHADING_BLINN if rng.random() < 0.4 else capi.SHADING_PBR
+    fp = capi.default_frame_params(shading_model=shading, shadow_enable=1 if rng.random() < 0.4 else 0,
+                                   cull_mode=int(rng.choice([capi.CULL_NONE, capi.CULL_BACK, capi.CULL_FRONT], p=[0.3, 0.5, 0.2])),
+                                   front_face_ccw=int(rng.random() < 0.7), shadow_pcf_radius=int(rng.integers(0, 4)),
+                                   shadow_pcf_step=float(rng.uniform(0.3, 3.0)), shadow_strength=float(rng.uniform(0.0, 1.2)),
+                                   shadow_bias_const=float(rng.uniform(0, 0.004)), shadow_bias_slope=float(rng.uniform(0, 0.004)),
+                                   exposure=float(rng.uniform(0.2, 3.0)), gamma=float(rng.uniform(1.0, 2.6)),
+                                   light_culling=1 if lights else 0, tile_size=16, max_lights_per_tile=int(rng.choice([4, 16, 128])) if lights else 128)
+    if rng.random() < 0.1:
+        fp.debug_view = int(rng.choice([capi.DEBUG_ALBEDO, capi.DEBUG_NORMAL, capi.DEBUG_DEPTH]))
+    mode = rng.random()
+    if mode < 0.35:      # orbit camera looking at the cluster
+        cam = tuple(float(v) for v in rng.uniform(-9, 9, 3) * np.array([1, 0.5, 1]) + np.array([0, 2.5, 0]))
+        tgt = tuple(float(v) for v in rng.uniform(-1, 1, 3))
+    elif mode < 0.8:     # inside the cluster: near- and side-plane clipping of large triangles
+        cam = tuple(float(v) for v in rng.uniform(-3, 3, 3) * np.array([1, 0.3, 1]))
+        tgt = tuple(float(v) for v in np.array(cam) + rng.normal(0, 1, 3))
+    else:                # grazing the floor plane
+        cam = (float(rng.uniform(-3, 3)), float(rng.uniform(-0.02, 0.05)), float(rng.uniform(-3, 3)))
+        tgt = (float(rng.uniform(-3, 3)), float(rng.uniform(-0.5, 0.5)), float(rng.uniform(-3, 3)))
+    zn = float(rng.choice([0.01, 0.1, 0.5]))
+    zf = float(rng.choice([20.0, 100.0, 1000.0]))
+    lt = None
+    if lights:
+        n = int(rng.integers(1, 90))
+        n_spot = int(n * rng.uniform(0, 0.6))
+        lt = make_lights(max(1, n - n_spot), n_spot, (-6, -0.5, -6), (6, 3.0, 6), seed=seed, range_lo=0.5, range_hi=6.0)
+    return SceneData(f"fuzz{seed}_{w}x{h}", w, h, zn, zf, meshes, textures, items, cam, tgt, math.radians(float(rng.uniform(25, 110))),
+                     tuple(_norm(rng.normal(0, 1, 3) * np.array([1, 0.5, 1]) - np.array([0, 0.8, 0]))), tuple(float(v) for v in rng.uniform(0.3, 1.0, 3)),
+                     float(rng.uniform(0.0, 4.0)), fp, lt, aspect=None if rng.random() < 0.7 else float(rng.uniform(0.6, 2.2)),
+                     shadow_size=int(rng.choice([16, 64, 200])), sky=sky_desc)

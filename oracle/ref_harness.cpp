@@ -75,23 +75,51 @@ namespace
         }
     };
 
-    // Assets are rebuilt only when the caller passes a different descriptor block, so that a
-    // timed loop (bench.py --impl reference) does not re-copy meshes every frame.
+    // Assets are rebuilt only when their CONTENT changes, so that a timed loop (bench.py --impl reference) does not re-copy
+    // meshes every frame.  The key is a hash of every byte the descriptor block points at, not the block's address: a test
+    // that builds one scene after another gets freed addresses handed back with different meshes behind them.
     struct AssetCache
     {
-        const ShsoAssets* key = nullptr;
-        const ShsoMesh* meshes = nullptr;
-        uint32_t n_meshes = 0, n_textures = 0;
+        uint64_t key = 0;
         std::unique_ptr<Assets> assets{};
+        static void mix(uint64_t& h, const void* p, size_t n)
+        {
+            const unsigned char* b = static_cast<const unsigned char*>(p);
+            size_t i = 0;
+            for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, b + i, 8); h = (h ^ w) * 0x100000001b3ull; h ^= h >> 29; }
+            for (; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+            h = (h ^ (uint64_t)n) * 0x100000001b3ull;
+        }
+        static uint64_t fingerprint(const ShsoAssets* a)
+        {
+            uint64_t h = 0xcbf29ce484222325ull;
+            if (!a) return h;
+            mix(h, &a->n_meshes, 4);
+            mix(h, &a->n_textures, 4);
+            for (uint32_t i = 0; i < a->n_meshes; ++i)
+            {
+                const ShsoMesh& m = a->meshes[i];
+                mix(h, m.positions, (size_t)m.n_positions * 12);
+                mix(h, m.normals, (size_t)m.n_normals * 12);
+                mix(h, m.uvs, (size_t)m.n_uvs * 8);
+                mix(h, m.indices, (size_t)m.n_indices * 4);
+            }
+            for (uint32_t i = 0; i < a->n_textures; ++i)
+            {
+                const ShsoTexture& t = a->textures[i];
+                mix(h, &t.w, sizeof(t.w));
+                mix(h, &t.h, sizeof(t.h));
+                mix(h, t.rgba, (size_t)t.w * (size_t)t.h * 4);
+            }
+            return h;
+        }
         Assets& get(const ShsoAssets* a)
         {
-            if (!assets || key != a || meshes != a->meshes || n_meshes != a->n_meshes || n_textures != a->n_textures)
+            const uint64_t k = fingerprint(a);
+            if (!assets || key != k)
             {
                 assets = std::make_unique<Assets>(a);
-                key = a;
-                meshes = a->meshes;
-                n_meshes = a->n_meshes;
-                n_textures = a->n_textures;
+                key = k;
             }
             return *assets;
         }
