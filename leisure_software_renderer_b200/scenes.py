@@ -243,6 +243,8 @@ class SceneData:
 
     def models(self, oracle) -> np.ndarray:
         """(n_items, 16) model matrices in items order (for Context::history in the CPU checkers)."""
+        if not self.items:
+            return np.zeros((0, 16), np.float32)
         return np.stack([oracle.model_from_transform(it["pos"], it.get("rot", (0, 0, 0)), it.get("scl", (1, 1, 1))) for it in self.items])
 
     def moved(self, dpos=(0.3, 0.0, -0.2), drot=(0.0, 0.15, 0.05), cam_pos=None, cam_target=None):

@@ -1,0 +1,40 @@
+"""Seeded random inputs shared by the CPU fuzz suite (oracle vs compiled reference, bit-exact) and the GPU fuzz suite (CUDA vs
+oracle).  Scenes themselves come from leisure_software_renderer_b200.scenes.scene_fuzz."""
+import numpy as np
+
+import post_cases
+from leisure_software_renderer_b200 import capi, scenes
+
+
+def motion_pair(seed, zero_normals=True):
+    """Two consecutive random frames: every second item moves (sometimes far beyond the 96-px velocity clamp), the camera
+    moves in 60 % of the cases; the second frame's prev_viewproj is the first frame's viewproj."""
+    rng = np.random.default_rng(7000 + seed)
+    prev = scenes.scene_fuzz(seed, zero_normals=zero_normals)
+    prev.fp.motion_vectors_enable = 1
+    kw = {}
+    if rng.random() < 0.6:
+        kw = {"cam_pos": tuple(float(a) + float(d) for a, d in zip(prev.cam_pos, rng.normal(0, 0.3, 3))), "cam_target": prev.cam_target}
+    cur = prev.moved(dpos=tuple(float(v) for v in rng.normal(0, 1.0 if seed % 5 else 8.0, 3)), drot=tuple(float(v) for v in rng.normal(0, 0.4, 3)), **kw)
+    return prev, cur
+
+
+def post_inputs(seed):
+    """Random planes + PassMotionBlur / PassLightShafts parameters, also outside their sane ranges (negative sample / step
+    counts, negative strengths, dt = 0): returns (ldr, depth, motion, blur params, shafts params, shafts use depth)."""
+    rng = np.random.default_rng(9000 + seed)
+    w, h = int(rng.integers(3, 120)), int(rng.integers(3, 90))
+    ldr, depth, motion = post_cases.planes(w, h, seed, max_motion=float(rng.choice([0.3, 8.0, 60.0, 300.0])))
+    p = capi.MotionBlurParams(samples=int(rng.integers(-2, 70)), strength=float(rng.uniform(-0.5, 3.0)), max_velocity_px=float(rng.uniform(-1.0, 64.0)),
+                              min_velocity_px=float(rng.uniform(0.0, 2.0)), depth_reject=float(rng.uniform(-0.05, 0.5)),
+                              dt=float(rng.choice([0.0, 1e-6, 1 / 144, 1 / 30, 0.5])))
+    eye = tuple(float(v) for v in rng.uniform(-5, 5, 3))
+    tgt = tuple(float(v) for v in rng.uniform(-2, 2, 3))
+    vp = scenes.camera_viewproj(eye, tgt, (0.0, 1.0, 0.0), float(np.radians(rng.uniform(30, 100))), w / h, 0.1, 200.0)
+    sun = rng.normal(0, 1, 3)
+    if seed % 3 == 0:   # the sun direction points away from where the sun is: aim it so that the sun projects into the view and the march runs
+        sun = (np.asarray(tgt) - np.asarray(eye)) * -1.0 + rng.normal(0, 0.4, 3)
+        sun = -sun
+    q = capi.LightShaftsParams(cam_viewproj=vp, cam_pos=eye, sun_dir_ws=tuple(float(v) for v in sun / np.linalg.norm(sun)), steps=int(rng.integers(-1, 120)),
+                               density=float(rng.uniform(-0.2, 2.0)), weight=float(rng.uniform(0.0, 2.5)), decay=float(rng.uniform(0.3, 1.6)))
+    return ldr, depth, motion, p, q, bool(rng.random() < 0.8)

@@ -6,6 +6,7 @@ parameters.  Same machine, same libm, no FMA: every plane must be BIT-equal."""
 import numpy as np
 import pytest
 
+import fuzz_cases
 import harness
 from leisure_software_renderer_b200 import scenes
 
@@ -43,3 +44,27 @@ def test_fuzz_scenes_are_not_trivial(port):
         drawn += f.stats["tri_raster"] > 0
         clipped += f.stats["tri_after_clip"] != f.stats["tri_input"]
     assert drawn >= 10 and clipped >= 6, (drawn, clipped)
+
+
+@pytest.mark.parametrize("seed", list(range(60)))
+def test_fuzz_motion_vectors_bit_exact(port, reference, seed):
+    """Two consecutive random frames: Context::history of frame 1 feeds the motion vectors of frame 2 (rasterizer.hpp:295-307,
+    388-411); random per-item motion, sometimes far beyond the 96-px clamp, sometimes a moved camera."""
+    prev, cur = fuzz_cases.motion_pair(seed)
+    pm = prev.models(port)
+    a = harness.cpu_forward(port, cur, aov=False, motion=True, prev_models=pm)
+    b = harness.cpu_forward(reference, cur, aov=False, motion=True, prev_models=pm)
+    assert _same_bits(a.depth, b.depth) and _same_bits(a.hdr, b.hdr), f"{cur.name}: colour / depth differ"
+    assert _same_bits(a.motion, b.motion), f"{cur.name}: motion differs at {int(np.count_nonzero(a.motion.view(np.uint32) != b.motion.view(np.uint32)))} components"
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_fuzz_post_passes_bit_exact(port, reference, seed):
+    """PassMotionBlur / PassLightShafts with random parameters (also outside their sane ranges) on random planes."""
+    ldr, depth, motion, p, q, with_depth = fuzz_cases.post_inputs(seed)
+    a = port.pass_motion_blur(p, ldr, motion, depth)
+    b = reference.pass_motion_blur(p, ldr, motion, depth)
+    assert np.array_equal(a, b), f"blur seed {seed}: {int(np.count_nonzero((a != b).any(axis=2)))} pixels differ"
+    a = port.pass_light_shafts(q, ldr, depth if with_depth else None)
+    b = reference.pass_light_shafts(q, ldr, depth if with_depth else None)
+    assert np.array_equal(a, b), f"shafts seed {seed}: {int(np.count_nonzero((a != b).any(axis=2)))} pixels differ"

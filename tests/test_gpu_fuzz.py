@@ -5,6 +5,7 @@ shadow depth <= 1 ULP, LDR <= 1 LSB, HDR PSNR >= 60 dB."""
 import numpy as np
 import pytest
 
+import fuzz_cases
 import harness
 from leisure_software_renderer_b200 import scenes
 
@@ -30,3 +31,32 @@ def test_fuzz_forward_plus_parity(gpu, port, seed):
     g = harness.gpu_forward(gpu, sd, forward_plus=True, fused=bool(seed & 1))
     c = harness.cpu_forward(port, sd, forward_plus=True)
     harness.assert_frame_parity(g, c, name=sd.name)
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_fuzz_motion_vectors_parity(gpu, port, seed):
+    """Two consecutive random frames: the context's history comes from rendering the first one; motion vectors bit-exact."""
+    prev, cur = fuzz_cases.motion_pair(seed, zero_normals=False)
+    g = harness.gpu_forward(gpu, cur, prev_scene=prev, motion=True)
+    c = harness.cpu_forward(port, cur, prev_models=prev.models(port), motion=True)
+    harness.assert_frame_parity(g, c, name=cur.name)
+    assert g.motion is not None and np.array_equal(g.motion.view(np.uint32), c.motion.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_fuzz_post_passes_parity(gpu, port, seed):
+    """PassMotionBlur / PassLightShafts with random (also out-of-range) parameters: RGBA8, bit-exact."""
+    from test_gpu_post_passes import Targets
+    ldr, depth, motion, p, q, with_depth = fuzz_cases.post_inputs(seed)
+    t = Targets(gpu, ldr, depth, motion)
+    try:
+        want = port.pass_motion_blur(p, ldr, motion, depth)
+        gpu.pass_motion_blur(p, t.src, t.dst, t.dm)
+        got = gpu.rt_download(t.dst)
+        assert np.array_equal(got, want), f"blur seed {seed}: {int(np.count_nonzero((got != want).any(axis=2)))} pixels differ"
+        want = port.pass_light_shafts(q, ldr, depth if with_depth else None)
+        gpu.pass_light_shafts(q, t.src, t.dst, t.dm if with_depth else 0)
+        got = gpu.rt_download(t.dst)
+        assert np.array_equal(got, want), f"shafts seed {seed}: {int(np.count_nonzero((got != want).any(axis=2)))} pixels differ"
+    finally:
+        t.close()
