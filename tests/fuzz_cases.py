@@ -38,3 +38,35 @@ def post_inputs(seed):
     q = capi.LightShaftsParams(cam_viewproj=vp, cam_pos=eye, sun_dir_ws=tuple(float(v) for v in sun / np.linalg.norm(sun)), steps=int(rng.integers(-1, 120)),
                                density=float(rng.uniform(-0.2, 2.0)), weight=float(rng.uniform(0.0, 2.5)), decay=float(rng.uniform(0.3, 1.6)))
     return ldr, depth, motion, p, q, bool(rng.random() < 0.8)
+
+
+def light_bins(seed):
+    """Random light set + camera + bin-builder arguments: returns (records, [(name, LightCullDesc, range_min, range_max)]) over
+    the plain tiled builder's arguments and all four modes of shsb_light_cull_ex.  Viewports that are not tile multiples, tile
+    sizes 8 / 16 / 20 / 32, caps from 1 to 128, ranges from centimetres to beyond the far plane, lights behind the camera, the
+    sqrt(3)-inflated Jolt sphere bounds for a third of the sets, depth ranges that are thin, inverted-free and partly outside [0, 1]."""
+    rng = np.random.default_rng(11000 + seed)
+    w, h = int(rng.integers(20, 300)), int(rng.integers(16, 200))
+    ts = int(rng.choice([8, 16, 20, 32]))
+    cap = int(rng.choice([1, 4, 32, 128]))
+    n = int(rng.integers(1, 260))
+    n_spot = int(n * rng.uniform(0, 0.5))
+    ext = float(rng.choice([4.0, 12.0, 40.0]))
+    rl = float(rng.choice([0.05, 0.5, 2.0]))
+    lights = scenes.make_lights(max(1, n - n_spot), n_spot, (-ext, -2.0, -ext), (ext, 4.0, ext), seed=seed, range_lo=rl,
+                                range_hi=rl * float(rng.choice([2.0, 10.0, 200.0])), jolt_bounds=bool(seed % 3 == 0))
+    eye = tuple(float(v) for v in rng.uniform(-ext, ext, 3) * np.array([1, 0.3, 1]))
+    tgt = tuple(float(v) for v in rng.uniform(-ext / 2, ext / 2, 3))
+    zn, zf = float(rng.choice([0.05, 0.1, 1.0])), float(rng.choice([15.0, 100.0, 1000.0]))
+    vp = scenes.camera_viewproj(eye, tgt, (0.0, 1.0, 0.0), float(np.radians(rng.uniform(30, 110))), w / h, zn, zf)
+    tiles = ((w + ts - 1) // ts) * ((h + ts - 1) // ts)
+    a = rng.uniform(-0.1, 1.0, tiles).astype(np.float32)
+    b = (a + rng.choice([0.0, 1e-6, 0.02, 0.5], tiles) * rng.uniform(0, 1, tiles)).astype(np.float32)
+    va = (zn + (zf - zn) * np.clip(a, 0, 1) ** 2).astype(np.float32)
+    vb = (va + rng.choice([0.0, 1e-4, 0.5, 30.0], tiles).astype(np.float32)).astype(np.float32)
+    mk = lambda mode, **kw: capi.LightCullDesc(vp, w, h, mode, ts, cap, z_near=zn, z_far=zf, **kw)
+    descs = [("tiled", mk(capi.LIGHT_CULL_TILED), None, None),
+             ("depth01", mk(capi.LIGHT_CULL_TILED_DEPTH01), a, b),
+             ("view_depth", mk(capi.LIGHT_CULL_TILED_VIEW_DEPTH), va, vb),
+             ("clustered", mk(capi.LIGHT_CULL_CLUSTERED, depth_slices=int(rng.choice([1, 3, 16]))), None, None)]
+    return lights, descs

@@ -68,3 +68,37 @@ def test_fuzz_post_passes_bit_exact(port, reference, seed):
     a = port.pass_light_shafts(q, ldr, depth if with_depth else None)
     b = reference.pass_light_shafts(q, ldr, depth if with_depth else None)
     assert np.array_equal(a, b), f"shafts seed {seed}: {int(np.count_nonzero((a != b).any(axis=2)))} pixels differ"
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_fuzz_light_bins_properties(port, seed):
+    """The bin builders have no compilable reference (jolt_light_culling.hpp needs JoltPhysics: parity unpinned), so the fuzzed
+    restatement is held to the structure the reference's code implies: the plain builder == mode 0 of the _ex entry; strictly
+    ascending lists; counts are uncapped and a capped call keeps exactly the first max_per_bin entries; a bin never lists a light
+    the camera frustum rejects.  (Set relations between the modes -- a depth range only removes lights, a tile's clusters cover its
+    plain list -- are properties of the geometry, not of the float arithmetic: a sub-cell's side planes are rebuilt from its own
+    corners and differ from the tile's by more than the 1e-5 tolerance, so borderline lights flip.  They are checked on the
+    well-conditioned scene of tests/test_light_bins_cpu.py, not under fuzz.)"""
+    lights, descs = fuzz_cases.light_bins(seed)
+    d0 = descs[0][1]
+    pc, pi = port.light_cull(lights, np.array(list(d0.view_proj), np.float32), d0.viewport_w, d0.viewport_h, d0.tile_size, 1024)
+    out = {}
+    for name, d, lo, hi in descs:
+        big = type(d).from_buffer_copy(d)
+        big.max_per_bin = 1024                                   # uncapped view of the lists for the set relations
+        out[name] = port.light_cull_ex(lights, big, lo, hi)
+        c, i = out[name]
+        for b in np.nonzero(c > 1)[0][:200]:
+            row = i[b, : min(int(c[b]), 1024)]
+            assert np.all(np.diff(row.astype(np.int64)) > 0), f"{name}: list of bin {b} is not strictly ascending"
+        cc, ci = port.light_cull_ex(lights, d, lo, hi)          # the capped call keeps the uncapped counts and the first entries
+        assert np.array_equal(cc, c)
+        keep = np.arange(d.max_per_bin)[None, :] < np.minimum(c, d.max_per_bin)[:, None]
+        assert np.array_equal(ci[keep], i[:, : d.max_per_bin][keep])
+    assert np.array_equal(out["tiled"][0], pc) and np.array_equal(out["tiled"][1], pi)
+    n_lights = len(np.frombuffer(lights.tobytes(), np.uint8)) // 160
+    for name in out:
+        c, i = out[name]
+        assert int(c.max()) <= n_lights
+        used = i[np.arange(1024)[None, :] < np.minimum(c, 1024)[:, None]]
+        assert used.size == 0 or int(used.max()) < n_lights, f"{name}: index beyond the light set"
