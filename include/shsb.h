@@ -446,6 +446,42 @@ SHSB_API int32_t shsb_timing_collect_abs(shsb_ctx ctx, float* out_ms, size_t cap
  * matrices), [1] staging copy, [2] arena checks, [3] stream capture / enqueue, [4] graph update + launch, [5] frames. */
 SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t reset);
 
+/* ------------------------------------------------------------------ legacy tile-job variant
+ *
+ * BASELINE.json configs[0] "as shipped": the demo cpp-folders/src/hello-3d-primitives/hello_pipeline_blinn_phong_shading.cpp with
+ * the helpers of cpp-folders/src/hello-shs-renderer/shs_renderer.hpp -- a rasterizer of its own, not the library path: y-flipped
+ * screen map, no clipping, `area <= 0` cull, dot-product barycentrics, affine NDC depth tested LESS against FLT_MAX, affine
+ * varyings, RGBA8 by truncation (:189-242, shs_renderer.hpp:802-831).  Host helpers restate the demo's matrix set-up. */
+
+typedef struct ShsbLegacyUniforms /* struct Uniforms, hello_pipeline_blinn_phong_shading.cpp:35-41 (+ the job-tile size :28-29) */
+{
+    float mvp[16];          /* proj * view * model (:273); build it with shsb_legacy_mvp for the reference's product order */
+    float model[16];
+    float light_dir[3];     /* HelloScene::light_direction (:152): the direction the light travels */
+    float camera_pos[3];    /* Viewer::position */
+    uint8_t color[4];       /* MonkeyObject::color, RGBA8 */
+    int32_t job_tile_w;     /* TILE_SIZE_X / TILE_SIZE_Y (80): the demo's unit of work; 0 = 80.  It shows in the result only for   */
+    int32_t job_tile_h;     /* ill-conditioned slivers at job-tile borders (see csrc/legacy.cu), and is honoured exactly.          */
+} ShsbLegacyUniforms;
+
+/* Viewer(position, speed, w, h) + Camera3D::update (shs_renderer.hpp:1210-1236, 1322-1346): fov 60 deg, aspect hard-coded 4/3,
+ * z 0.1 .. 1000, left-handed; angles in degrees. */
+SHSB_API int32_t shsb_legacy_camera(const float position[3], float horizontal_angle_deg, float vertical_angle_deg,
+                                    float out_view[16], float out_proj[16]);
+/* MonkeyObject::get_world_matrix (:122-128): translate * rotate(y, degrees) * scale, each built from the identity. */
+SHSB_API int32_t shsb_legacy_world_matrix(const float position[3], const float scale[3], float rotation_angle_deg, float out_model[16]);
+/* uniforms.mvp = proj * view * model (:273), evaluated left to right. */
+SHSB_API int32_t shsb_legacy_mvp(const float proj[16], const float view[16], const float model[16], float out_mvp[16]);
+
+/* One object of RendererSystem::process (:244-313) = draw_triangle_tile (:189-242) over every job tile and every triangle of
+ * `mesh` (indexed meshes are expanded by their indices like ModelGeometry's loader does, shs_renderer.hpp:1262-1295; the mesh
+ * needs a normal per position) with blinn_phong_vertex_shader / blinn_phong_fragment_shader (:48-96).
+ * canvas_ldr: SHSB_RT_COLOR_LDR in shs::Canvas order (row 0 = bottom of the screen; uncovered pixels keep their content).
+ * zbuffer:    the depth plane of a SHSB_RT_SHADOW or SHSB_RT_DEPTH_MOTION target in shs::ZBuffer order (row = screen y, top
+ *             down), same size as the canvas; clear it to FLT_MAX with shsb_rt_clear like ZBuffer::clear (:671-674). */
+SHSB_API int32_t shsb_legacy_draw_blinn_phong(shsb_ctx ctx, shsb_mesh mesh, const ShsbLegacyUniforms* uniforms,
+                                              shsb_rt canvas_ldr, shsb_rt zbuffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,24 @@ class LightShaftsParams(C.Structure):
             set_f(self.cam_viewproj, cam_viewproj)
 
 
+class LegacyUniforms(C.Structure):
+    """ShsbLegacyUniforms: struct Uniforms of the legacy tile-job demo (hello_pipeline_blinn_phong_shading.cpp:35-41) + its job-tile size."""
+    _fields_ = [("mvp", F16), ("model", F16), ("light_dir", F3), ("camera_pos", F3), ("color", C.c_uint8 * 4),
+                ("job_tile_w", C.c_int32), ("job_tile_h", C.c_int32)]
+
+    def __init__(self, mvp=None, model=None, light_dir=(0, -1, 0), camera_pos=(0, 0, 0), color=(255, 255, 255, 255), job_tile_w=0, job_tile_h=0):
+        super().__init__()
+        if mvp is not None:
+            set_f(self.mvp, mvp)
+        if model is not None:
+            set_f(self.model, model)
+        set_f(self.light_dir, light_dir)
+        set_f(self.camera_pos, camera_pos)
+        for i, v in enumerate(color):
+            self.color[i] = int(v)
+        self.job_tile_w, self.job_tile_h = int(job_tile_w), int(job_tile_h)
+
+
 class LightCullDesc(C.Structure):
     """ShsbLightCullDesc: arguments of the bin builders of lighting/jolt_light_culling.hpp."""
     _fields_ = [("view_proj", F16), ("viewport_w", C.c_uint32), ("viewport_h", C.c_uint32), ("tile_size", C.c_uint32),
@@ -210,6 +228,10 @@ def load_library(path: str | None = None):
         "shsb_frame_forward_plus": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(Stats)],
         "shsb_last_stage_ms": [vp, P(C.c_float)],
         "shsb_host_submit_us": [vp, P(C.c_double), C.c_int32],
+        "shsb_legacy_camera": [P(C.c_float), C.c_float, C.c_float, P(C.c_float), P(C.c_float)],
+        "shsb_legacy_world_matrix": [P(C.c_float), P(C.c_float), C.c_float, P(C.c_float)],
+        "shsb_legacy_mvp": [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)],
+        "shsb_legacy_draw_blinn_phong": [vp, C.c_uint32, P(LegacyUniforms), C.c_uint32, C.c_uint32],
         "shsb_timing_enable": [vp, C.c_int32],
         "shsb_timing_collect": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
         "shsb_timing_collect_abs": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],

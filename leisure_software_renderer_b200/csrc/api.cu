@@ -297,6 +297,7 @@ struct shsb_context_t
     DevBuf<uchar4> d_post_scratch;
     DevBuf<float> d_post_luma;
     DevBuf<uchar4> d_taa_hist;      // TemporalAARuntimeState::history (core/context.hpp:101)
+    DevBuf<LegacyTri> d_legacy_tris; // set-up records of the legacy tile-job variant (legacy.cu)
     int taa_w = 0, taa_h = 0;
     bool taa_valid = false;
 
@@ -1185,7 +1186,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_textures.p); cudaFree(ctx->d_srgb_lut);
     cudaFree(ctx->d_range_min.p); cudaFree(ctx->d_range_max.p); cudaFree(ctx->d_range_up_min.p); cudaFree(ctx->d_range_up_max.p);
     cudaFree(ctx->d_slice_ndc.p); cudaFree(ctx->d_vis.p); cudaFree(ctx->cluster_lists.counts.p); cudaFree(ctx->cluster_lists.indices.p);
-    cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p);
+    cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p); cudaFree(ctx->d_legacy_tris.p);
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
     for (auto& l : ctx->h_lights) cudaFreeHost(l.p);
@@ -1475,6 +1476,90 @@ SHSB_API int32_t shsb_camera_viewproj(const float eye[3], const float target[3],
     const hm::mat4f view = hm::look_at_lh({eye[0], eye[1], eye[2]}, {target[0], target[1], target[2]}, {up[0], up[1], up[2]});
     const hm::mat4f proj = hm::perspective_lh_no(fovy_radians, aspect, znear, zfar);
     hm::store(hm::mul(proj, view), out_viewproj);
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- legacy tile-job variant (row L1)
+SHSB_API int32_t shsb_legacy_camera(const float position[3], float horizontal_angle_deg, float vertical_angle_deg, float out_view[16], float out_proj[16])
+{
+    if (!position || !out_view || !out_proj) return SHSB_E_INVALID_ARGUMENT;
+    // Camera3D::update, shs_renderer.hpp:1223-1236.  The reference calls the unqualified C functions cos / sin on float
+    // arguments: with <cmath> alone those are the DOUBLE functions, the products are formed in double and narrowed by the
+    // glm::vec3 constructor (checked bit for bit against the compiled reference in tests/test_legacy_cpu.py).
+    const float deg = 0.01745329251994329576923690768489f;
+    const float va = vertical_angle_deg * deg, ha = horizontal_angle_deg * deg;
+    hm::vec3f dir{(float)(std::cos((double)va) * std::sin((double)ha)), (float)std::sin((double)va), (float)(std::cos((double)va) * std::cos((double)ha))};
+    dir = hm::normalize(dir);
+    const hm::vec3f world_up{0.0f, 1.0f, 0.0f};
+    const hm::vec3f right = hm::normalize(hm::cross(world_up, dir));
+    const hm::vec3f up = hm::normalize(hm::cross(dir, right));
+    const hm::vec3f pos{position[0], position[1], position[2]};
+    // field_of_view is a run-time member in the reference: tan() must be libm's at run time, not the compiler's folded constant
+    volatile float field_of_view = 60.0f;
+    hm::store(hm::perspective_lh_no(field_of_view * deg, 4.0f / 3.0f, 0.1f, 1000.0f), out_proj);
+    hm::store(hm::look_at_lh(pos, pos + dir, up), out_view);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_legacy_world_matrix(const float position[3], const float scale[3], float rotation_angle_deg, float out_model[16])
+{
+    if (!position || !scale || !out_model) return SHSB_E_INVALID_ARGUMENT;
+    const hm::mat4f t = hm::translate(hm::identity(), {position[0], position[1], position[2]});
+    const hm::mat4f r = hm::rotate(hm::identity(), rotation_angle_deg * 0.01745329251994329576923690768489f, {0.0f, 1.0f, 0.0f});
+    const hm::mat4f sc = hm::scale(hm::identity(), {scale[0], scale[1], scale[2]});
+    hm::store(hm::mul(hm::mul(t, r), sc), out_model);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_legacy_mvp(const float proj[16], const float view[16], const float model[16], float out_mvp[16])
+{
+    if (!proj || !view || !model || !out_mvp) return SHSB_E_INVALID_ARGUMENT;
+    hm::store(hm::mul(hm::mul(hm::load(proj), hm::load(view)), hm::load(model)), out_mvp);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_legacy_draw_blinn_phong(shsb_ctx ctx, shsb_mesh mesh_h, const ShsbLegacyUniforms* u, shsb_rt canvas_rt, shsb_rt zbuffer_rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!u) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "uniforms are null");
+    CK(cudaSetDevice(ctx->device));
+    const MeshSlot* mesh = get_mesh(ctx, mesh_h);
+    if (!mesh) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh %u is not live", mesh_h);
+    RtSlot* canvas = get_rt(ctx, canvas_rt, SHSB_RT_COLOR_LDR);
+    if (!canvas) return fail(ctx, SHSB_E_INVALID_HANDLE, "canvas_ldr is not a live RT_ColorLDR");
+    RtSlot* zb = get_rt(ctx, zbuffer_rt);
+    if (!zb || !zb->depth || (zb->kind != SHSB_RT_SHADOW && zb->kind != SHSB_RT_DEPTH_MOTION))
+        return fail(ctx, SHSB_E_INVALID_HANDLE, "zbuffer is not a live target with a depth plane (RT_ShadowDepth / RT_ColorDepthMotion)");
+    if (zb->w != canvas->w || zb->h != canvas->h) return fail(ctx, SHSB_E_SIZE_MISMATCH, "canvas is %dx%d, z-buffer %dx%d", canvas->w, canvas->h, zb->w, zb->h);
+    if (u->job_tile_w < 0 || u->job_tile_h < 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "job tile size must be positive (0 = the demo's 80)");
+    if (mesh->n_normals < mesh->n_positions)
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "the legacy vertex shader needs a normal per position (ModelGeometry emits both streams)");
+    LegacyDraw d{};
+    d.positions = mesh->positions;
+    d.normals = mesh->normals;
+    d.indices = mesh->n_indices ? mesh->indices : nullptr;
+    d.n_positions = mesh->n_positions;
+    d.n_normals = mesh->n_normals;
+    d.n_tris = (mesh->n_indices ? mesh->n_indices : mesh->n_positions) / 3;
+    d.W = canvas->w; d.H = canvas->h;
+    d.job_w = u->job_tile_w ? u->job_tile_w : 80;
+    d.job_h = u->job_tile_h ? u->job_tile_h : 80;
+    std::memcpy(d.mvp, u->mvp, 64);
+    std::memcpy(d.model, u->model, 64);
+    // glm::mat3(glm::transpose(glm::inverse(u.model))) (:55): the 4x4 cofactor inverse, transposed, upper-left 3x3
+    const hm::mat4f inv = hm::inverse(hm::load(u->model));
+    const float* c = reinterpret_cast<const float*>(&inv);
+    for (int col = 0; col < 3; ++col)
+        for (int row = 0; row < 3; ++row) d.normal_matrix[col * 3 + row] = c[row * 4 + col]; // transpose(inv)[col][row] = inv[row][col]
+    std::memcpy(d.light_dir, u->light_dir, 12);
+    std::memcpy(d.camera_pos, u->camera_pos, 12);
+    std::memcpy(d.color, u->color, 4);
+    if (d.n_tris == 0) return SHSB_OK;
+    wait_pending_read(ctx, canvas);
+    wait_pending_read(ctx, zb);
+    if (int rc = ensure_dev(ctx, ctx->d_legacy_tris, d.n_tris)) return rc;
+    launch_legacy_draw(d, ctx->d_legacy_tris.p, (uchar4*)canvas->color, zb->depth, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
     return SHSB_OK;
 }
 

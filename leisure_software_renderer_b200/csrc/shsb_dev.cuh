@@ -257,7 +257,33 @@ namespace shsb
         float sun_u, sun_v;
     };
 
+    // ---------------------------------------------------------------- legacy tile-job variant (legacy.cu)
+    struct LegacyDraw // one object of RendererSystem::process, hello_pipeline_blinn_phong_shading.cpp:262-305
+    {
+        const float* positions;   // MeshData streams of the mesh handle (ModelGeometry::triangles / normals once expanded by `indices`)
+        const float* normals;
+        const uint32_t* indices;  // nullptr: non-indexed soup
+        uint32_t n_positions, n_normals, n_tris;
+        int W, H;
+        int job_w, job_h;         // TILE_SIZE_X / TILE_SIZE_Y of the demo (80 x 80): see legacy.cu
+        float mvp[16], model[16];
+        float normal_matrix[9];   // mat3(transpose(inverse(model))), column-major, computed on the host
+        float light_dir[3], camera_pos[3];
+        unsigned char color[4];
+    };
+
+    struct LegacyTri // set-up output, one per source triangle
+    {
+        uint32_t valid;
+        float ax, ay, v0x, v0y, v1x, v1y;   // screen-space A and the edge vectors B - A, C - A
+        float d00, d01, d11, denom;         // the P-independent dot products of Canvas::barycentric_coordinate
+        float z[3];                         // NDC z per corner (affine depth)
+        float minx, maxx, miny, maxy;       // float bounding box of the three screen positions
+        float normal[3][3], world[3][3];    // vertex-shader outputs, interpolated affinely
+    };
+
     // ---------------------------------------------------------------- kernel launchers (one per .cu)
+    void launch_legacy_draw(const LegacyDraw& d, LegacyTri* tris, uchar4* canvas, float* zbuf, cudaStream_t s, uint64_t* launches);
     void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,

@@ -165,6 +165,12 @@ class Context:
     def taa_reset(self):
         _check(self.lib, self.h, self.lib.shsb_taa_reset(self.h), "shsb_taa_reset")
 
+    # ---- legacy tile-job variant (BASELINE configs[0] as shipped)
+    def legacy_draw_blinn_phong(self, mesh, uniforms: "capi.LegacyUniforms", canvas_ldr, zbuffer):
+        """One object of the legacy demo's RendererSystem::process on the device (canvas in shs::Canvas order, z in ZBuffer order)."""
+        _check(self.lib, self.h, self.lib.shsb_legacy_draw_blinn_phong(self.h, mesh, C.byref(uniforms), canvas_ldr, zbuffer),
+               "shsb_legacy_draw_blinn_phong")
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")
@@ -280,4 +286,29 @@ def camera_viewproj(eye, target, up, fovy, aspect, zn, zf) -> np.ndarray:
     u = np.asarray(up, dtype=np.float32)
     out = np.zeros(16, dtype=np.float32)
     lib.shsb_camera_viewproj(capi.fptr(e), capi.fptr(t), capi.fptr(u), fovy, aspect, zn, zf, capi.fptr(out))
+    return out
+
+
+def legacy_camera(position, horizontal_angle_deg=0.0, vertical_angle_deg=0.0):
+    """(view, proj) of the legacy demo's Viewer / Camera3D (host-side helper of the C-ABI; needs no device)."""
+    lib = capi.load_library()
+    pos = np.ascontiguousarray(position, dtype=np.float32)
+    view, proj = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    assert lib.shsb_legacy_camera(capi.fptr(pos), float(horizontal_angle_deg), float(vertical_angle_deg), capi.fptr(view), capi.fptr(proj)) == 0
+    return view, proj
+
+
+def legacy_world_matrix(position, scale, rotation_angle_deg=0.0):
+    lib = capi.load_library()
+    p, sc = np.ascontiguousarray(position, dtype=np.float32), np.ascontiguousarray(scale, dtype=np.float32)
+    out = np.zeros(16, np.float32)
+    assert lib.shsb_legacy_world_matrix(capi.fptr(p), capi.fptr(sc), float(rotation_angle_deg), capi.fptr(out)) == 0
+    return out
+
+
+def legacy_mvp(proj, view, model):
+    lib = capi.load_library()
+    a, b, c = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (proj, view, model))
+    out = np.zeros(16, np.float32)
+    assert lib.shsb_legacy_mvp(capi.fptr(a), capi.fptr(b), capi.fptr(c), capi.fptr(out)) == 0
     return out

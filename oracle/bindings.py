@@ -3,6 +3,7 @@
 ctypes bindings of the two CPU checkers declared in oracle/oracle_abi.h:
   Oracle("port")      -> oracle/liboracle.so        (this repo's restatement, shso_*)
   Oracle("reference") -> oracle/_ref/libshs_ref.so  (the reference's own headers, shsref_*)
+                         oracle/_ref/libshs_legacy_ref.so (the reference's legacy tile-job demo sources, shsref_legacy_*)
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 """
 from __future__ import annotations
@@ -19,6 +20,7 @@ from leisure_software_renderer_b200.capi import FrameParams, RasterCfg, Scene, S
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(_HERE, "liboracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libshs_ref.so")
+REF_LEGACY_LIB = os.path.join(_HERE, "_ref", "libshs_legacy_ref.so")
 
 
 class Mesh(C.Structure):
@@ -284,3 +286,65 @@ class Oracle:
         rc = self.lib.shso_pass_depth_prepass(C.byref(assets.block), C.byref(scene), C.byref(fp), C.byref(tgt), C.byref(st))
         assert rc == 0, rc
         return st
+
+
+class LegacyOracle:
+    """The legacy tile-job rasterizer (BASELINE configs[0] as shipped) on the CPU:
+    LegacyOracle("port") = oracle/oracle_legacy.cpp, LegacyOracle("reference") = the reference's own demo sources
+    (hello_pipeline_blinn_phong_shading.cpp + shs_renderer.hpp) compiled by oracle/ref_legacy_harness.cpp."""
+
+    def __init__(self, kind: str = "port"):
+        assert kind in ("port", "reference")
+        self.kind = kind
+        path = PORT_LIB if kind == "port" else REF_LEGACY_LIB
+        if not os.path.exists(path):
+            build(kind)
+        self.lib = C.CDLL(path)
+        self.prefix = "shso_legacy_" if kind == "port" else "shsref_legacy_"
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        return os.path.exists(PORT_LIB if kind == "port" else REF_LEGACY_LIB)
+
+    def fn(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        return f
+
+    def camera(self, position, horizontal_angle_deg=0.0, vertical_angle_deg=0.0):
+        pos = np.ascontiguousarray(position, dtype=np.float32)
+        view, proj = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        f = self.fn("camera"); f.restype = None
+        f(capi.fptr(pos), C.c_float(horizontal_angle_deg), C.c_float(vertical_angle_deg), capi.fptr(view), capi.fptr(proj))
+        return view, proj
+
+    def world_matrix(self, position, scale, rotation_angle_deg=0.0):
+        p, s = np.ascontiguousarray(position, dtype=np.float32), np.ascontiguousarray(scale, dtype=np.float32)
+        out = np.zeros(16, np.float32)
+        f = self.fn("world_matrix"); f.restype = None
+        f(capi.fptr(p), capi.fptr(s), C.c_float(rotation_angle_deg), capi.fptr(out))
+        return out
+
+    def mvp(self, proj, view, model):
+        a, b, c = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (proj, view, model))
+        out = np.zeros(16, np.float32)
+        f = self.fn("mvp"); f.restype = None
+        f(capi.fptr(a), capi.fptr(b), capi.fptr(c), capi.fptr(out))
+        return out
+
+    def draw(self, positions, normals, mvp, model, light_dir, camera_pos, color, canvas, zbuffer, tile_w=80, tile_h=80):
+        """In place on canvas (H, W, 4) uint8 in shs::Canvas order and zbuffer (H, W) float32 in shs::ZBuffer order.
+        positions / normals: (n_vertices, 3) float32 triangle soup (ModelGeometry::triangles / normals)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        assert len(pos) == len(nrm)
+        assert canvas.dtype == np.uint8 and canvas.flags.c_contiguous and zbuffer.dtype == np.float32 and zbuffer.flags.c_contiguous
+        h, w = zbuffer.shape
+        m0 = np.ascontiguousarray(mvp, dtype=np.float32).reshape(16)
+        m1 = np.ascontiguousarray(model, dtype=np.float32).reshape(16)
+        ld, cp = np.ascontiguousarray(light_dir, dtype=np.float32), np.ascontiguousarray(camera_pos, dtype=np.float32)
+        col = np.ascontiguousarray(color, dtype=np.uint8)
+        rc = self.fn("draw")(capi.fptr(pos), capi.fptr(nrm), C.c_uint32(len(pos)), capi.fptr(m0), capi.fptr(m1), capi.fptr(ld), capi.fptr(cp),
+                             col.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h),
+                             canvas.ctypes.data_as(C.POINTER(C.c_uint8)), capi.fptr(zbuffer))
+        assert rc == 0, rc
+        return canvas, zbuffer

@@ -1,0 +1,249 @@
+// oracle/oracle_legacy.cpp -- TEST INFRASTRUCTURE ONLY (never linked into, imported by or shipped with the product).
+//
+// CPU restatement of the reference's LEGACY tile-job rasterizer (BASELINE configs[0] as shipped):
+//   cpp-folders/src/hello-3d-primitives/hello_pipeline_blinn_phong_shading.cpp   Uniforms :35-41, blinn_phong_vertex_shader :48-58,
+//       blinn_phong_fragment_shader :64-96, RendererSystem::draw_triangle_tile :189-242, ::process :244-313
+//   cpp-folders/src/hello-shs-renderer/shs_renderer.hpp   Canvas::barycentric_coordinate :803-820, clip_to_screen :822-831,
+//       ZBuffer::test_and_set_depth :659-669, Canvas::draw_pixel_screen_space :792-796, Camera3D::update :1223-1236
+// Plain floats, explicit operation order (GLM's scalar path as stated in oracle/glm_shim).  PINNED: tests/test_legacy_cpu.py demands
+// bit-equality with the reference's own sources compiled into oracle/_ref/libshs_legacy_ref.so (oracle/ref_legacy_harness.cpp).
+// Part of liboracle.so (oracle/Makefile).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace
+{
+    struct V3 { float x, y, z; };
+    inline V3 add(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+    inline V3 sub(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+    inline V3 kmul(float k, V3 a) { return V3{k * a.x, k * a.y, k * a.z}; }      // float * vec3
+    inline V3 mulk(V3 a, float k) { return V3{a.x * k, a.y * k, a.z * k}; }      // vec3 * float
+    inline float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+    inline V3 normalize3(V3 v) { return mulk(v, 1.0f / std::sqrt(dot3(v, v))); }
+    inline V3 cross3(V3 x, V3 y) { return V3{x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y}; }
+    inline float gmax(float a, float b) { return (a < b) ? b : a; }
+    inline float gmin(float a, float b) { return (b < a) ? b : a; }
+
+    // column-major 4x4 helpers in GLM's scalar order
+    inline void mat_mul_point(const float* m, V3 p, float out[4])
+    {
+        for (int r = 0; r < 4; ++r) out[r] = (m[r] * p.x + m[4 + r] * p.y) + (m[8 + r] * p.z + m[12 + r] * 1.0f);
+    }
+    inline void mat_mul(const float* a, const float* b, float* out) // a * b: column i = a0*b[i][0] + a1*b[i][1] + a2*b[i][2] + a3*b[i][3]
+    {
+        float r[16];
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 4; ++k)
+                r[i * 4 + k] = a[k] * b[i * 4] + a[4 + k] * b[i * 4 + 1] + a[8 + k] * b[i * 4 + 2] + a[12 + k] * b[i * 4 + 3];
+        std::memcpy(out, r, 64);
+    }
+    void mat_identity(float* m) { std::memset(m, 0, 64); m[0] = m[5] = m[10] = m[15] = 1.0f; }
+
+    void mat_inverse(const float* src, float* out) // glm::inverse(mat4), cofactor expansion times 1 / det
+    {
+        float m[4][4];
+        std::memcpy(m, src, 64);
+        const float c00 = m[2][2] * m[3][3] - m[3][2] * m[2][3], c02 = m[1][2] * m[3][3] - m[3][2] * m[1][3], c03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+        const float c04 = m[2][1] * m[3][3] - m[3][1] * m[2][3], c06 = m[1][1] * m[3][3] - m[3][1] * m[1][3], c07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+        const float c08 = m[2][1] * m[3][2] - m[3][1] * m[2][2], c10 = m[1][1] * m[3][2] - m[3][1] * m[1][2], c11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+        const float c12 = m[2][0] * m[3][3] - m[3][0] * m[2][3], c14 = m[1][0] * m[3][3] - m[3][0] * m[1][3], c15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+        const float c16 = m[2][0] * m[3][2] - m[3][0] * m[2][2], c18 = m[1][0] * m[3][2] - m[3][0] * m[1][2], c19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+        const float c20 = m[2][0] * m[3][1] - m[3][0] * m[2][1], c22 = m[1][0] * m[3][1] - m[3][0] * m[1][1], c23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+        const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+        const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+        const float v0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, v1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+        const float v2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, v3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+        float inv[4][4];
+        const float sa[4] = {+1, -1, +1, -1}, sb[4] = {-1, +1, -1, +1};
+        for (int i = 0; i < 4; ++i)
+        {
+            const float i0 = v1[i] * f0[i] - v2[i] * f1[i] + v3[i] * f2[i];
+            const float i1 = v0[i] * f0[i] - v2[i] * f3[i] + v3[i] * f4[i];
+            const float i2 = v0[i] * f1[i] - v1[i] * f3[i] + v3[i] * f5[i];
+            const float i3 = v0[i] * f2[i] - v1[i] * f4[i] + v2[i] * f5[i];
+            inv[0][i] = i0 * sa[i]; inv[1][i] = i1 * sb[i]; inv[2][i] = i2 * sa[i]; inv[3][i] = i3 * sb[i];
+        }
+        const float row0[4] = {inv[0][0], inv[1][0], inv[2][0], inv[3][0]};
+        const float d0 = m[0][0] * row0[0], d1 = m[0][1] * row0[1], d2 = m[0][2] * row0[2], d3 = m[0][3] * row0[3];
+        const float det = (d0 + d1) + (d2 + d3);
+        const float one_over = 1.0f / det;
+        for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) out[c * 4 + r] = inv[c][r] * one_over;
+    }
+}
+
+extern "C"
+{
+    // Camera3D::update (shs_renderer.hpp:1223-1236) under Viewer(position, speed, w, h) (:1322-1346): fov 60, aspect 4/3, z 0.1..1000
+    void shso_legacy_camera(const float position[3], float horizontal_angle_deg, float vertical_angle_deg, float out_view[16], float out_proj[16])
+    {
+        const float deg = 0.01745329251994329576923690768489f; // glm::radians
+        const float va = vertical_angle_deg * deg, ha = horizontal_angle_deg * deg;
+        // unqualified cos / sin on floats = the C double functions; the products are narrowed by glm::vec3's converting constructor
+        V3 dir{(float)(std::cos((double)va) * std::sin((double)ha)), (float)std::sin((double)va), (float)(std::cos((double)va) * std::cos((double)ha))};
+        dir = normalize3(dir);
+        const V3 world_up{0.0f, 1.0f, 0.0f};
+        const V3 right = normalize3(cross3(world_up, dir));
+        const V3 up = normalize3(cross3(dir, right));
+        const V3 pos{position[0], position[1], position[2]};
+        // glm::perspectiveLH_NO
+        // (field_of_view is a run-time member in the reference: keep the compiler from folding tan() with its own, correctly
+        // rounded, arithmetic -- libm's tanf is not always correctly rounded and is what the reference calls)
+        volatile float field_of_view = 60.0f;
+        const float fovy = field_of_view * deg, aspect = 4.0f / 3.0f, zn = 0.1f, zf = 1000.0f;
+        const float thf = std::tan(fovy / 2.0f);
+        std::memset(out_proj, 0, 64);
+        out_proj[0] = 1.0f / (aspect * thf);
+        out_proj[5] = 1.0f / thf;
+        out_proj[10] = (zf + zn) / (zf - zn);
+        out_proj[11] = 1.0f;
+        out_proj[14] = -(2.0f * zf * zn) / (zf - zn);
+        // glm::lookAtLH(eye, center, up)
+        const V3 center = add(pos, dir);
+        const V3 f = normalize3(sub(center, pos));
+        const V3 s = normalize3(cross3(up, f));
+        const V3 u = cross3(f, s);
+        mat_identity(out_view);
+        out_view[0] = s.x; out_view[4] = s.y; out_view[8] = s.z;
+        out_view[1] = u.x; out_view[5] = u.y; out_view[9] = u.z;
+        out_view[2] = f.x; out_view[6] = f.y; out_view[10] = f.z;
+        out_view[12] = -dot3(s, pos); out_view[13] = -dot3(u, pos); out_view[14] = -dot3(f, pos);
+    }
+
+    // MonkeyObject::get_world_matrix (:122-128)
+    void shso_legacy_world_matrix(const float position[3], const float scale[3], float rotation_angle_deg, float out_model[16])
+    {
+        float t[16], r[16], s[16], tr[16];
+        mat_identity(t);
+        // glm::translate(I, v): col3 = I0*v.x + I1*v.y + I2*v.z + I3
+        for (int k = 0; k < 4; ++k) t[12 + k] = ((k == 0 ? 1.0f : 0.0f) * position[0] + (k == 1 ? 1.0f : 0.0f) * position[1]) + (k == 2 ? 1.0f : 0.0f) * position[2] + (k == 3 ? 1.0f : 0.0f);
+        // glm::rotate(I, a, (0,1,0))
+        const float a = rotation_angle_deg * 0.01745329251994329576923690768489f;
+        const float c = std::cos(a), sn = std::sin(a);
+        const V3 axis = normalize3(V3{0.0f, 1.0f, 0.0f});
+        const V3 temp = mulk(axis, 1.0f - c);
+        float R[3][3];
+        R[0][0] = c + temp.x * axis.x; R[0][1] = temp.x * axis.y + sn * axis.z; R[0][2] = temp.x * axis.z - sn * axis.y;
+        R[1][0] = temp.y * axis.x - sn * axis.z; R[1][1] = c + temp.y * axis.y; R[1][2] = temp.y * axis.z + sn * axis.x;
+        R[2][0] = temp.z * axis.x + sn * axis.y; R[2][1] = temp.z * axis.y - sn * axis.x; R[2][2] = c + temp.z * axis.z;
+        float I[16];
+        mat_identity(I);
+        mat_identity(r);
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 4; ++k) r[j * 4 + k] = I[k] * R[j][0] + I[4 + k] * R[j][1] + I[8 + k] * R[j][2];
+        // glm::scale(I, v)
+        mat_identity(s);
+        for (int k = 0; k < 4; ++k) { s[k] = I[k] * scale[0]; s[4 + k] = I[4 + k] * scale[1]; s[8 + k] = I[8 + k] * scale[2]; }
+        mat_mul(t, r, tr);
+        mat_mul(tr, s, out_model);
+    }
+
+    void shso_legacy_mvp(const float proj[16], const float view[16], const float model[16], float out_mvp[16])
+    {
+        float pv[16];
+        mat_mul(proj, view, pv);
+        mat_mul(pv, model, out_mvp);
+    }
+
+    int32_t shso_legacy_draw(const float* positions, const float* normals, uint32_t n_vertices, const float mvp[16], const float model[16],
+                             const float light_dir[3], const float camera_pos[3], const uint8_t color[4], int32_t W, int32_t H,
+                             int32_t tile_w, int32_t tile_h, uint8_t* canvas_rgba, float* zbuffer)
+    {
+        if (!positions || !normals || !canvas_rgba || !zbuffer || W <= 0 || H <= 0 || tile_w <= 0 || tile_h <= 0) return 1;
+        float inv[16], nm[9];
+        mat_inverse(model, inv);
+        for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row) nm[col * 3 + row] = inv[row * 4 + col]; // mat3(transpose(inverse(model)))
+        const int cols = (W + tile_w - 1) / tile_w, rows = (H + tile_h - 1) / tile_h;
+        for (int ty = 0; ty < rows; ++ty)
+            for (int tx = 0; tx < cols; ++tx)
+            {
+                const int tminx = tx * tile_w, tminy = ty * tile_h;
+                const int tmaxx = std::min((tx + 1) * tile_w, W) - 1, tmaxy = std::min((ty + 1) * tile_h, H) - 1;
+                for (uint32_t i = 0; i + 2 < n_vertices; i += 3)
+                {
+                    // ---- vertex stage (:199-204)
+                    float sx[3], sy[3], sz[3];
+                    V3 vn[3], vw[3];
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const V3 p{positions[3 * (i + k)], positions[3 * (i + k) + 1], positions[3 * (i + k) + 2]};
+                        const V3 n{normals[3 * (i + k)], normals[3 * (i + k) + 1], normals[3 * (i + k) + 2]};
+                        float clip[4], wp[4];
+                        mat_mul_point(mvp, p, clip);
+                        mat_mul_point(model, p, wp);
+                        vw[k] = V3{wp[0], wp[1], wp[2]};
+                        vn[k] = normalize3(V3{nm[0] * n.x + nm[3] * n.y + nm[6] * n.z, nm[1] * n.x + nm[4] * n.y + nm[7] * n.z, nm[2] * n.x + nm[5] * n.y + nm[8] * n.z});
+                        const float ndx = clip[0] / clip[3], ndy = clip[1] / clip[3], ndz = clip[2] / clip[3];
+                        sx[k] = (ndx + 1.0f) * 0.5f * float(W - 1);
+                        sy[k] = (1.0f - ndy) * 0.5f * float(H - 1);
+                        sz[k] = ndz;
+                    }
+                    // non-finite screen positions: the reference casts them to int (undefined behaviour); dropped (as in csrc/legacy.cu)
+                    bool finite = true;
+                    for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sx[k]) && std::isfinite(sy[k]);
+                    if (!finite) continue;
+                    // ---- bounding box clamped INTO the job tile (:206-214)
+                    float bminx = (float)tmaxx, bminy = (float)tmaxy, bmaxx = (float)tminx, bmaxy = (float)tminy;
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        bminx = gmax((float)tminx, gmin(bminx, sx[k])); bminy = gmax((float)tminy, gmin(bminy, sy[k]));
+                        bmaxx = gmin((float)tmaxx, gmax(bmaxx, sx[k])); bmaxy = gmin((float)tmaxy, gmax(bmaxy, sy[k]));
+                    }
+                    if (bminx > bmaxx || bminy > bmaxy) continue;
+                    const float area = (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sy[1] - sy[0]) * (sx[2] - sx[0]);
+                    if (area <= 0) continue;
+                    // ---- fragment stage (:222-241), the reference's column-major pixel order
+                    const float v0x = sx[1] - sx[0], v0y = sy[1] - sy[0], v1x = sx[2] - sx[0], v1y = sy[2] - sy[0];
+                    for (int px = (int)bminx; px <= (int)bmaxx; ++px)
+                        for (int py = (int)bminy; py <= (int)bmaxy; ++py)
+                        {
+                            const float Px = px + 0.5f, Py = py + 0.5f;
+                            const float v2x = Px - sx[0], v2y = Py - sy[0];
+                            const float d00 = v0x * v0x + v0y * v0y, d01 = v0x * v1x + v0y * v1y, d11 = v1x * v1x + v1y * v1y;
+                            const float d20 = v2x * v0x + v2y * v0y, d21 = v2x * v1x + v2y * v1y;
+                            const float denom = d00 * d11 - d01 * d01;
+                            float bu, bv, bw;
+                            if (std::abs(denom) < 1e-5) { bu = bv = bw = -1.0f; }
+                            else
+                            {
+                                bv = (d11 * d20 - d01 * d21) / denom;
+                                bw = (d00 * d21 - d01 * d20) / denom;
+                                bu = 1.0f - bv - bw;
+                            }
+                            if (bu < 0 || bv < 0 || bw < 0) continue;
+                            const float z = bu * sz[0] + bv * sz[1] + bw * sz[2];
+                            if (px < 0 || px >= W || py < 0 || py >= H) continue;      // ZBuffer::test_and_set_depth bounds
+                            float& d = zbuffer[(size_t)py * W + px];
+                            if (!(z < d)) continue;
+                            d = z;
+                            const V3 in_normal = normalize3(add(add(kmul(bu, vn[0]), kmul(bv, vn[1])), kmul(bw, vn[2])));
+                            const V3 world_pos = add(add(kmul(bu, vw[0]), kmul(bv, vw[1])), kmul(bw, vw[2]));
+                            // blinn_phong_fragment_shader (:64-96)
+                            const V3 norm = normalize3(in_normal);
+                            const V3 ldir = normalize3(V3{-light_dir[0], -light_dir[1], -light_dir[2]});
+                            const V3 vdir = normalize3(sub(V3{camera_pos[0], camera_pos[1], camera_pos[2]}, world_pos));
+                            const float ambient = 0.15f * 1.0f;
+                            const float diff = gmax(dot3(norm, ldir), 0.0f);
+                            const float diffuse = diff * 1.0f;
+                            const V3 halfway = normalize3(add(ldir, vdir));
+                            const float spec = std::pow(gmax(dot3(norm, halfway), 0.0f), 64.0f);
+                            const float specular = (0.5f * spec) * 1.0f;
+                            const float lit = (ambient + diffuse) + specular;
+                            const float oc[3] = {(float)color[0] / 255.0f, (float)color[1] / 255.0f, (float)color[2] / 255.0f};
+                            uint8_t out[4];
+                            for (int c = 0; c < 3; ++c)
+                            {
+                                const float r = gmin(gmax(lit * oc[c], 0.0f), 1.0f);
+                                out[c] = (uint8_t)(r * 255);
+                            }
+                            out[3] = 255;
+                            const int y_canvas = (H - 1) - py;                            // Canvas::draw_pixel_screen_space
+                            std::memcpy(canvas_rgba + ((size_t)y_canvas * W + px) * 4, out, 4);
+                        }
+                }
+            }
+        return 0;
+    }
+}

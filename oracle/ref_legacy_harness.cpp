@@ -1,0 +1,140 @@
+// oracle/ref_legacy_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into, imported by or shipped with the product).
+//
+// The reference's LEGACY tile-job rasterizer -- BASELINE.json configs[0] "as shipped", SURVEY.md section 8a row L1 -- compiled from
+// the reference's own sources where they lie under /root/reference:
+//     cpp-folders/src/hello-3d-primitives/hello_pipeline_blinn_phong_shading.cpp   (the demo program: Uniforms, the Blinn-Phong
+//         vertex / fragment shaders :48-96, RendererSystem::draw_triangle_tile :189-242, the tile fan-out of ::process :244-313)
+//     cpp-folders/src/hello-shs-renderer/shs_renderer.hpp                          (Canvas, ZBuffer, barycentric_coordinate,
+//         clip_to_screen :802-831, Camera3D / Viewer :1210-1355)
+// The demo's `main` is renamed and never called; SDL2 / SDL2_image / Assimp / GLM are third-party dependencies of the reference
+// that are absent from this container: oracle/legacy_shim declares the names the two sources mention (no behaviour), this file
+// defines them as aborting stubs so that the library loads, and oracle/glm_shim states GLM's arithmetic.
+// The raster functions pinned here touch none of them.  No reference source is copied: the .cpp is #included from its own tree.
+//
+// Built by oracle/Makefile (`make ref`) into oracle/_ref/libshs_legacy_ref.so (git-ignored; travels to the GPU box as a binary).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define main shs_legacy_demo_main
+#include "hello_pipeline_blinn_phong_shading.cpp"
+#undef main
+
+// ---- aborting definitions of the declared-only third-party names (ctypes loads with RTLD_NOW)
+namespace
+{
+    [[noreturn]] void third_party_stub(const char* name)
+    {
+        std::fprintf(stderr, "oracle/ref_legacy_harness: %s is a declaration-only stub (SDL2 / Assimp are absent) and must never be called\n", name);
+        std::abort();
+    }
+}
+#define SHS_STUB(name) third_party_stub(#name)
+int SDL_Init(Uint32) { SHS_STUB(SDL_Init); }
+void SDL_Quit() { SHS_STUB(SDL_Quit); }
+Uint32 SDL_GetTicks() { SHS_STUB(SDL_GetTicks); }
+int SDL_PollEvent(SDL_Event*) { SHS_STUB(SDL_PollEvent); }
+int SDL_CreateWindowAndRenderer(int, int, Uint32, SDL_Window**, SDL_Renderer**) { SHS_STUB(SDL_CreateWindowAndRenderer); }
+void SDL_DestroyWindow(SDL_Window*) { SHS_STUB(SDL_DestroyWindow); }
+void SDL_DestroyRenderer(SDL_Renderer*) { SHS_STUB(SDL_DestroyRenderer); }
+void SDL_DestroyTexture(SDL_Texture*) { SHS_STUB(SDL_DestroyTexture); }
+SDL_Texture* SDL_CreateTextureFromSurface(SDL_Renderer*, SDL_Surface*) { SHS_STUB(SDL_CreateTextureFromSurface); }
+int SDL_UpdateTexture(SDL_Texture*, const SDL_Rect*, const void*, int) { SHS_STUB(SDL_UpdateTexture); }
+int SDL_RenderCopy(SDL_Renderer*, SDL_Texture*, const SDL_Rect*, const SDL_Rect*) { SHS_STUB(SDL_RenderCopy); }
+void SDL_RenderPresent(SDL_Renderer*) { SHS_STUB(SDL_RenderPresent); }
+SDL_Surface* SDL_ConvertSurfaceFormat(SDL_Surface*, Uint32, Uint32) { SHS_STUB(SDL_ConvertSurfaceFormat); }
+SDL_Surface* SDL_CreateRGBSurface(Uint32, int, int, int, Uint32, Uint32, Uint32, Uint32) { SHS_STUB(SDL_CreateRGBSurface); }
+void SDL_FreeSurface(SDL_Surface*) { SHS_STUB(SDL_FreeSurface); }
+const char* SDL_GetError() { SHS_STUB(SDL_GetError); }
+void SDL_GetRGBA(Uint32, const SDL_PixelFormat*, Uint8*, Uint8*, Uint8*, Uint8*) { SHS_STUB(SDL_GetRGBA); }
+Uint32 SDL_MapRGBA(const SDL_PixelFormat*, Uint8, Uint8, Uint8, Uint8) { SHS_STUB(SDL_MapRGBA); }
+SDL_Surface* IMG_Load(const char*) { SHS_STUB(IMG_Load); }
+const char* IMG_GetError() { SHS_STUB(IMG_GetError); }
+const aiScene* Assimp::Importer::ReadFile(const char*, unsigned int) { SHS_STUB(Assimp::Importer::ReadFile); }
+const char* Assimp::Importer::GetErrorString() const { SHS_STUB(Assimp::Importer::GetErrorString); }
+float glm::simplex(const glm::vec2&) { SHS_STUB(glm::simplex); }
+
+namespace
+{
+    glm::mat4 load_mat4(const float* m) { glm::mat4 r; std::memcpy(&r, m, 64); return r; }
+    void store_mat4(const glm::mat4& m, float* out) { std::memcpy(out, &m, 64); }
+}
+
+extern "C"
+{
+    // Viewer(position, speed, width, height) + Camera3D::update (shs_renderer.hpp:1210-1236, 1322-1346) as the demo builds them
+    // (hello_pipeline_blinn_phong_shading.cpp:384): fov 60 deg, aspect hard-coded 4/3, z 0.1 .. 1000, LH.
+    void shsref_legacy_camera(const float position[3], float horizontal_angle_deg, float vertical_angle_deg, float out_view[16], float out_proj[16])
+    {
+        shs::Viewer viewer(glm::vec3(position[0], position[1], position[2]), 50.0f, 10.0f, 10.0f);
+        viewer.horizontal_angle = horizontal_angle_deg;
+        viewer.vertical_angle = vertical_angle_deg;
+        viewer.update();
+        store_mat4(viewer.camera->view_matrix, out_view);
+        store_mat4(viewer.camera->projection_matrix, out_proj);
+    }
+
+    // MonkeyObject::get_world_matrix (:122-128): t * r * s from three separate identity-based matrices.
+    void shsref_legacy_world_matrix(const float position[3], const float scale[3], float rotation_angle_deg, float out_model[16])
+    {
+        const glm::mat4 t = glm::translate(glm::mat4(1.0f), glm::vec3(position[0], position[1], position[2]));
+        const glm::mat4 r = glm::rotate(glm::mat4(1.0f), glm::radians(rotation_angle_deg), glm::vec3(0.0f, 1.0f, 0.0f));
+        const glm::mat4 s = glm::scale(glm::mat4(1.0f), glm::vec3(scale[0], scale[1], scale[2]));
+        store_mat4(t * r * s, out_model);
+    }
+
+    // uniforms.mvp = proj * view * uniforms.model (:273)
+    void shsref_legacy_mvp(const float proj[16], const float view[16], const float model[16], float out_mvp[16])
+    {
+        store_mat4(load_mat4(proj) * load_mat4(view) * load_mat4(model), out_mvp);
+    }
+
+    // One object through RendererSystem::process's tile fan-out (:244-313), serially: for every (tile_w x tile_h) tile, for every
+    // triangle, the reference's own static RendererSystem::draw_triangle_tile with the reference's own shaders.  `canvas_rgba` is
+    // shs::Canvas's buffer (row 0 = bottom of the screen, draw_pixel_screen_space flips y), `zbuffer` is shs::ZBuffer's buffer
+    // (row = screen y, top-down; cleared to FLT_MAX by the demo); both are read and written.
+    int32_t shsref_legacy_draw(const float* positions, const float* normals, uint32_t n_vertices, const float mvp[16], const float model[16],
+                               const float light_dir[3], const float camera_pos[3], const uint8_t color[4], int32_t width, int32_t height,
+                               int32_t tile_w, int32_t tile_h, uint8_t* canvas_rgba, float* zbuffer)
+    {
+        if (!positions || !normals || !canvas_rgba || !zbuffer || width <= 0 || height <= 0 || tile_w <= 0 || tile_h <= 0) return 1;
+        shs::Canvas canvas(width, height);
+        shs::ZBuffer zbuf(width, height, 0.1f, 1000.0f);
+        static_assert(sizeof(shs::Color) == 4, "Canvas texels are RGBA8");
+        std::memcpy(canvas.buffer().raw(), canvas_rgba, (size_t)width * height * 4);
+        std::memcpy(zbuf.buffer().raw(), zbuffer, (size_t)width * height * 4);
+
+        Uniforms uniforms;
+        uniforms.model = load_mat4(model);
+        uniforms.mvp = load_mat4(mvp);
+        uniforms.light_dir = glm::vec3(light_dir[0], light_dir[1], light_dir[2]);
+        uniforms.camera_pos = glm::vec3(camera_pos[0], camera_pos[1], camera_pos[2]);
+        uniforms.color = shs::Color{color[0], color[1], color[2], color[3]};
+
+        const int cols = (width + tile_w - 1) / tile_w, rows = (height + tile_h - 1) / tile_h;
+        for (int ty = 0; ty < rows; ++ty)
+            for (int tx = 0; tx < cols; ++tx)
+            {
+                const glm::ivec2 t_min(tx * tile_w, ty * tile_h);
+                const glm::ivec2 t_max(std::min((tx + 1) * tile_w, width) - 1, std::min((ty + 1) * tile_h, height) - 1);
+                for (uint32_t i = 0; i + 2 < n_vertices; i += 3)
+                {
+                    const std::vector<glm::vec3> tri_verts = {glm::vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]),
+                                                              glm::vec3(positions[3 * i + 3], positions[3 * i + 4], positions[3 * i + 5]),
+                                                              glm::vec3(positions[3 * i + 6], positions[3 * i + 7], positions[3 * i + 8])};
+                    const std::vector<glm::vec3> tri_norms = {glm::vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]),
+                                                              glm::vec3(normals[3 * i + 3], normals[3 * i + 4], normals[3 * i + 5]),
+                                                              glm::vec3(normals[3 * i + 6], normals[3 * i + 7], normals[3 * i + 8])};
+                    RendererSystem::draw_triangle_tile(
+                        canvas, zbuf, tri_verts, tri_norms,
+                        [&uniforms](const glm::vec3& p, const glm::vec3& n) { return blinn_phong_vertex_shader(p, n, uniforms); },
+                        [&uniforms](const shs::Varyings& v) { return blinn_phong_fragment_shader(v, uniforms); },
+                        t_min, t_max);
+                }
+            }
+        std::memcpy(canvas_rgba, canvas.buffer().raw(), (size_t)width * height * 4);
+        std::memcpy(zbuffer, zbuf.buffer().raw(), (size_t)width * height * 4);
+        return 0;
+    }
+}

@@ -70,3 +70,36 @@ def light_bins(seed):
              ("view_depth", mk(capi.LIGHT_CULL_TILED_VIEW_DEPTH), va, vb),
              ("clustered", mk(capi.LIGHT_CULL_CLUSTERED, depth_slices=int(rng.choice([1, 3, 16]))), None, None)]
     return lights, descs
+
+
+def legacy_draws(seed):
+    """Random inputs of the legacy tile-job rasterizer (BASELINE configs[0] as shipped): canvas size, job-tile size, one to three
+    objects (Suzanne or a triangle soup with slivers and frustum-crossing triangles, expanded to per-corner streams like the demo's
+    ModelGeometry), the demo's camera / world-matrix construction with random parameters -- often with geometry behind or
+    around the camera, which this rasterizer projects through instead of clipping.
+    Returns (W, H, tile_w, tile_h, camera_pos, light_dir, [(positions, normals, model_args, color)], view_args)."""
+    rng = np.random.default_rng(13000 + seed)
+    W, H = int(rng.integers(9, 200)), int(rng.integers(7, 150))
+    tile_w, tile_h = (80, 80) if seed % 3 == 0 else (int(rng.integers(1, 90)), int(rng.integers(1, 90)))
+    cam = tuple(float(v) for v in rng.uniform(-6, 6, 3))
+    if seed % 4 == 0:
+        cam = (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)))   # inside the objects
+    h_ang, v_ang = float(rng.uniform(-180, 180)), float(rng.uniform(-70, 70))
+    if seed % 2 == 0:  # look roughly at the origin
+        d = -np.asarray(cam) / max(1e-3, np.linalg.norm(cam))
+        h_ang = float(np.degrees(np.arctan2(d[0], d[2])) + rng.normal(0, 8))
+        v_ang = float(np.degrees(np.arcsin(np.clip(d[1], -1, 1))) + rng.normal(0, 5))
+    light = rng.normal(0, 1, 3)
+    light = tuple(float(v) for v in light / np.linalg.norm(light))
+    objs = []
+    for k in range(int(rng.integers(1, 4))):
+        if rng.random() < 0.5:
+            m = scenes.load_suzanne()
+            pos, nrm = m["positions"][m["indices"]], m["normals"][m["indices"]]
+        else:
+            m = scenes.make_triangle_soup(int(rng.integers(4, 80)), seed * 11 + k, extent=2.0, indexed=False, zero_normals=False)
+            pos, nrm = m["positions"], m["normals"]
+        scl = float(rng.uniform(0.3, 3.0))
+        model_args = (tuple(float(v) for v in rng.uniform(-2, 2, 3)), (scl, scl * float(rng.choice([1.0, 1.0, 0.4])), scl), float(rng.uniform(-360, 360)))
+        objs.append((np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32), model_args, tuple(int(v) for v in rng.integers(0, 256, 3)) + (255,)))
+    return W, H, tile_w, tile_h, cam, light, objs, (h_ang, v_ang)

@@ -37,7 +37,8 @@ def test_struct_layouts_match_header(tmp_path):
               "ShsbScene": (capi.Scene, ["items", "cam_prev_viewproj", "sky_kind", "sky_faces", "reserved2"]),
               "ShsbFrameParams": (capi.FrameParams, ["write_aovs", "motion_vectors_enable", "own_row_first", "own_row_stride"]),
               "ShsbMotionBlurParams": (capi.MotionBlurParams, ["depth_reject", "dt", "reserved"]),
-              "ShsbLightShaftsParams": (capi.LightShaftsParams, ["decay", "cam_pos", "sun_dir_ws", "cam_viewproj"])}
+              "ShsbLightShaftsParams": (capi.LightShaftsParams, ["decay", "cam_pos", "sun_dir_ws", "cam_viewproj"]),
+              "ShsbLegacyUniforms": (capi.LegacyUniforms, ["model", "camera_pos", "color", "job_tile_w", "job_tile_h"])}
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{os.path.join(ROOT, "include", "shsb.h")}"', "int main(void) {"]
     for cname, (_, fields) in probes.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
