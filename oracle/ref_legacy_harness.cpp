@@ -12,6 +12,7 @@
 // The raster functions pinned here touch none of them.  No reference source is copied: the .cpp is #included from its own tree.
 //
 // Built by oracle/Makefile (`make ref`) into oracle/_ref/libshs_legacy_ref.so (git-ignored; travels to the GPU box as a binary).
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -136,5 +137,65 @@ extern "C"
         std::memcpy(canvas_rgba, canvas.buffer().raw(), (size_t)width * height * 4);
         std::memcpy(zbuffer, zbuf.buffer().raw(), (size_t)width * height * 4);
         return 0;
+    }
+
+    // The CPU baseline of SURVEY.md section 8d (B2): RendererSystem::process as shipped -- z-buffer clear, then ONE JOB PER TILE on the
+    // reference's own shs::Job::ThreadedPriorityJobSystem with `n_threads` workers and its WaitGroup (:244-313) -- repeated `frames`
+    // times on one object.  Returns the mean milliseconds per frame; the last frame is left in canvas_rgba / zbuffer.
+    double shsref_legacy_frames_threaded(const float* positions, const float* normals, uint32_t n_vertices, const float mvp[16], const float model[16],
+                                         const float light_dir[3], const float camera_pos[3], const uint8_t color[4], int32_t width, int32_t height,
+                                         int32_t tile_w, int32_t tile_h, int32_t n_threads, int32_t frames, uint8_t* canvas_rgba, float* zbuffer)
+    {
+        if (!positions || !normals || !canvas_rgba || !zbuffer || width <= 0 || height <= 0 || tile_w <= 0 || tile_h <= 0 || n_threads <= 0 || frames <= 0) return -1.0;
+        shs::Canvas canvas(width, height);
+        shs::ZBuffer zbuf(width, height, 0.1f, 1000.0f);
+        std::vector<glm::vec3> verts(n_vertices), norms(n_vertices);
+        for (uint32_t i = 0; i < n_vertices; ++i)
+        {
+            verts[i] = glm::vec3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+            norms[i] = glm::vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        }
+        Uniforms uniforms;
+        uniforms.model = load_mat4(model);
+        uniforms.mvp = load_mat4(mvp);
+        uniforms.light_dir = glm::vec3(light_dir[0], light_dir[1], light_dir[2]);
+        uniforms.camera_pos = glm::vec3(camera_pos[0], camera_pos[1], camera_pos[2]);
+        uniforms.color = shs::Color{color[0], color[1], color[2], color[3]};
+        auto* jobs = new shs::Job::ThreadedPriorityJobSystem(n_threads);
+        shs::Job::WaitGroup wait_group;
+        const int cols = (width + tile_w - 1) / tile_w, rows = (height + tile_h - 1) / tile_h;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int f = 0; f < frames; ++f)
+        {
+            shs::Canvas::fill_pixel(canvas, 0, 0, width, height, shs::Color::black()); // the demo's main loop (:452)
+            zbuf.clear();
+            wait_group.reset();
+            for (int ty = 0; ty < rows; ++ty)
+                for (int tx = 0; tx < cols; ++tx)
+                {
+                    wait_group.add(1);
+                    jobs->submit({[&, tx, ty]() {
+                        const glm::ivec2 t_min(tx * tile_w, ty * tile_h);
+                        const glm::ivec2 t_max(std::min((tx + 1) * tile_w, width) - 1, std::min((ty + 1) * tile_h, height) - 1);
+                        for (size_t i = 0; i + 2 < verts.size(); i += 3)
+                        {
+                            const std::vector<glm::vec3> tri_verts = {verts[i], verts[i + 1], verts[i + 2]};
+                            const std::vector<glm::vec3> tri_norms = {norms[i], norms[i + 1], norms[i + 2]};
+                            RendererSystem::draw_triangle_tile(
+                                canvas, zbuf, tri_verts, tri_norms,
+                                [&uniforms](const glm::vec3& p, const glm::vec3& n) { return blinn_phong_vertex_shader(p, n, uniforms); },
+                                [&uniforms](const shs::Varyings& v) { return blinn_phong_fragment_shader(v, uniforms); },
+                                t_min, t_max);
+                        }
+                        wait_group.done();
+                    }, shs::Job::PRIORITY_HIGH});
+                }
+            wait_group.wait();
+        }
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / frames;
+        delete jobs;
+        std::memcpy(canvas_rgba, canvas.buffer().raw(), (size_t)width * height * 4);
+        std::memcpy(zbuffer, zbuf.buffer().raw(), (size_t)width * height * 4);
+        return ms;
     }
 }
