@@ -22,39 +22,7 @@
 #include "hello_pipeline_blinn_phong_shading.cpp"
 #undef main
 
-// ---- aborting definitions of the declared-only third-party names (ctypes loads with RTLD_NOW)
-namespace
-{
-    [[noreturn]] void third_party_stub(const char* name)
-    {
-        std::fprintf(stderr, "oracle/ref_legacy_harness: %s is a declaration-only stub (SDL2 / Assimp are absent) and must never be called\n", name);
-        std::abort();
-    }
-}
-#define SHS_STUB(name) third_party_stub(#name)
-int SDL_Init(Uint32) { SHS_STUB(SDL_Init); }
-void SDL_Quit() { SHS_STUB(SDL_Quit); }
-Uint32 SDL_GetTicks() { SHS_STUB(SDL_GetTicks); }
-int SDL_PollEvent(SDL_Event*) { SHS_STUB(SDL_PollEvent); }
-int SDL_CreateWindowAndRenderer(int, int, Uint32, SDL_Window**, SDL_Renderer**) { SHS_STUB(SDL_CreateWindowAndRenderer); }
-void SDL_DestroyWindow(SDL_Window*) { SHS_STUB(SDL_DestroyWindow); }
-void SDL_DestroyRenderer(SDL_Renderer*) { SHS_STUB(SDL_DestroyRenderer); }
-void SDL_DestroyTexture(SDL_Texture*) { SHS_STUB(SDL_DestroyTexture); }
-SDL_Texture* SDL_CreateTextureFromSurface(SDL_Renderer*, SDL_Surface*) { SHS_STUB(SDL_CreateTextureFromSurface); }
-int SDL_UpdateTexture(SDL_Texture*, const SDL_Rect*, const void*, int) { SHS_STUB(SDL_UpdateTexture); }
-int SDL_RenderCopy(SDL_Renderer*, SDL_Texture*, const SDL_Rect*, const SDL_Rect*) { SHS_STUB(SDL_RenderCopy); }
-void SDL_RenderPresent(SDL_Renderer*) { SHS_STUB(SDL_RenderPresent); }
-SDL_Surface* SDL_ConvertSurfaceFormat(SDL_Surface*, Uint32, Uint32) { SHS_STUB(SDL_ConvertSurfaceFormat); }
-SDL_Surface* SDL_CreateRGBSurface(Uint32, int, int, int, Uint32, Uint32, Uint32, Uint32) { SHS_STUB(SDL_CreateRGBSurface); }
-void SDL_FreeSurface(SDL_Surface*) { SHS_STUB(SDL_FreeSurface); }
-const char* SDL_GetError() { SHS_STUB(SDL_GetError); }
-void SDL_GetRGBA(Uint32, const SDL_PixelFormat*, Uint8*, Uint8*, Uint8*, Uint8*) { SHS_STUB(SDL_GetRGBA); }
-Uint32 SDL_MapRGBA(const SDL_PixelFormat*, Uint8, Uint8, Uint8, Uint8) { SHS_STUB(SDL_MapRGBA); }
-SDL_Surface* IMG_Load(const char*) { SHS_STUB(IMG_Load); }
-const char* IMG_GetError() { SHS_STUB(IMG_GetError); }
-const aiScene* Assimp::Importer::ReadFile(const char*, unsigned int) { SHS_STUB(Assimp::Importer::ReadFile); }
-const char* Assimp::Importer::GetErrorString() const { SHS_STUB(Assimp::Importer::GetErrorString); }
-float glm::simplex(const glm::vec2&) { SHS_STUB(glm::simplex); }
+#include "legacy_shim/stubs.inc" // aborting definitions of the declared-only third-party names (ctypes loads with RTLD_NOW)
 
 namespace
 {

@@ -9,6 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "_build", "drop_in_test")
 PLUGIN_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "plugin_test")
+LEGACY_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "legacy_drop_in_test")
 
 
 def _build():
@@ -59,5 +60,30 @@ def test_plugin_pipeline_parity_on_gpu():
     if not os.path.exists(PLUGIN_BIN):
         pytest.skip("tests/cpp/_build/plugin_test was not built (needs /root/reference at build time)")
     r = subprocess.run([PLUGIN_BIN], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_legacy_drop_in_compiles_and_has_no_cpu_fallback():
+    """host/shs_b200/legacy_drop_in.hpp compiled INTO the reference's config-1 demo source (hello_pipeline_blinn_phong_shading.cpp,
+    main renamed): without a device every call of the binding refuses and nothing is rendered on the CPU."""
+    import torch
+    if not os.path.isdir("/root/reference") and not os.path.exists(LEGACY_BIN):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(LEGACY_BIN)
+    if not torch.cuda.is_available():
+        r = subprocess.run([LEGACY_BIN], capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        assert r.returncode == 77 and "every call refused" in r.stdout
+
+
+@pytest.mark.gpu
+def test_legacy_drop_in_parity_on_gpu():
+    """The demo's own RendererSystem::draw_triangle_tile loops on the CPU vs shs::b200::legacy::Renderer over the same shs::Canvas /
+    shs::ZBuffer / geometry: z-buffer bit-equal, canvas within 1 LSB."""
+    if not os.path.exists(LEGACY_BIN):
+        pytest.skip("tests/cpp/_build/legacy_drop_in_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([LEGACY_BIN], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
