@@ -82,9 +82,19 @@ namespace
     {
         uint64_t key = 0;
         std::unique_ptr<Assets> assets{};
+        // arrays up to 1 MiB are hashed whole; larger ones (4K cubemap faces in a timed loop) by their size, their first and
+        // last 64 KiB and every 4099th 8-byte word in between
         static void mix(uint64_t& h, const void* p, size_t n)
         {
             const unsigned char* b = static_cast<const unsigned char*>(p);
+            if (n > (1u << 20))
+            {
+                mix(h, b, 65536);
+                mix(h, b + n - 65536, 65536);
+                for (size_t i = 65536; i + 8 <= n - 65536; i += 8 * 4099) { uint64_t w; std::memcpy(&w, b + i, 8); h = (h ^ w) * 0x100000001b3ull; h ^= h >> 29; }
+                h = (h ^ (uint64_t)n) * 0x100000001b3ull;
+                return;
+            }
             size_t i = 0;
             for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, b + i, 8); h = (h ^ w) * 0x100000001b3ull; h ^= h >> 29; }
             for (; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;

@@ -102,3 +102,50 @@ def test_fuzz_light_bins_properties(port, seed):
         assert int(c.max()) <= n_lights
         used = i[np.arange(1024)[None, :] < np.minimum(c, 1024)[:, None]]
         assert used.size == 0 or int(used.max()) < n_lights, f"{name}: index beyond the light set"
+
+
+@pytest.mark.parametrize("seed", list(range(60)))
+def test_fuzz_triangle_ids_through_reference_callbacks(port, reference, seed):
+    """Triangle ids and per-pixel fragment counts are bit-exact gates of the north_star.  The reference has no such outputs: its
+    side obtains them through its OWN shader-callback API (a counting VS wrapper + a recording FS wrapper around the builtin
+    program, oracle/ref_harness.cpp), drawing the fuzz scene item by item with rasterize_mesh -- including the NON-indexed soups
+    that PassPBRForward would skip as MeshData::empty()."""
+    from oracle.bindings import HostAssets
+    from leisure_software_renderer_b200 import capi
+    from test_oracle_vs_reference import _uniforms
+    sd = scenes.scene_fuzz(seed)
+    depth = seed % 5 != 2
+    A = HostAssets(sd.meshes, sd.textures)
+    shader = capi.SHADER_BLINN_PHONG if sd.fp.shading_model == capi.SHADING_BLINN else capi.SHADER_PBR_MR
+    outs = []
+    for o in (port, reference):
+        hdr = np.zeros((sd.h, sd.w, 4), np.float32)
+        dep = np.ones((sd.h, sd.w), np.float32) if depth else None
+        tri = np.full((sd.h, sd.w), capi.TRI_ID_NONE, np.uint32)
+        cov = np.zeros((sd.h, sd.w), np.uint32)
+        tgt = o.make_target(sd.w, sd.h, hdr, dep, tri_id=tri, coverage=cov, zn=sd.zn, zf=sd.zf)
+        key = 0
+        tot = {"tri_input": 0, "tri_after_clip": 0, "tri_raster": 0}
+        for it in sd.items:
+            if not it.get("visible", True):
+                continue
+            model = o.model_from_transform(it["pos"], it.get("rot", (0, 0, 0)), it.get("scl", (1, 1, 1)))
+            mat = it.get("material") or {"base_color": (0.8, 0.5, 0.2), "metallic": 0.1, "roughness": 0.5}
+            mesh = sd.meshes[it["mesh"] - 1]
+            n_tris = (len(mesh["indices"]) if len(mesh["indices"]) else len(mesh["positions"])) // 3
+            st = o.rasterize_mesh(A, it["mesh"], shader, _uniforms(sd, model, mat), tgt, key_base=key,
+                                  cull_mode=sd.fp.cull_mode, front_face_ccw=bool(sd.fp.front_face_ccw))
+            key += n_tris * 8
+            for k in tot:
+                tot[k] += getattr(st, k)
+        outs.append((hdr, dep, tri, cov, tot))
+    (h0, d0, t0, c0, s0), (h1, d1, t1, c1, s1) = outs
+    assert s0 == s1, (sd.name, s0, s1)
+    assert _same_bits(h0, h1), f"{sd.name}: HDR differs"
+    if depth:
+        assert _same_bits(d0, d1)
+    assert np.array_equal(t0 >> 3, t1 >> 3), f"{sd.name}: {int(np.count_nonzero((t0 >> 3) != (t1 >> 3)))} pixels have another winning (item, triangle)"
+    if not depth:
+        assert np.array_equal(c0, c1), f"{sd.name}: fragment counts differ"
+    else:
+        assert np.all(c1 <= c0) and np.array_equal(c1 > 0, c0 > 0)
