@@ -77,6 +77,23 @@ namespace shs::b200
             return h;
         }
 
+        // A MeshData / Texture2DData whose CONTENT changed in place (procedural or streamed assets) must be announced: the device
+        // copy is keyed by the host object's address.
+        void invalidate(const MeshData& m)
+        {
+            const auto it = meshes_.find(&m);
+            if (it == meshes_.end()) return;
+            shsb_mesh_destroy(ctx_, it->second);
+            meshes_.erase(it);
+        }
+        void invalidate(const Texture2DData* t)
+        {
+            const auto it = textures_.find(t);
+            if (it == textures_.end()) return;
+            shsb_texture_destroy(ctx_, it->second);
+            textures_.erase(it);
+        }
+
         shsb_tex texture(const Texture2DData* t)
         {
             if (!t || !t->valid()) return 0;
@@ -126,21 +143,30 @@ namespace shs::b200
         void download(RT_ShadowDepth* rt) { if (rt) shsb_rt_download(ctx_, twin(rt), SHSB_PLANE_DEPTH, rt->depth.data(), rt->depth.size() * sizeof(float)); }
 
     private:
+        // A host RT object that was resized (RTRegistry::ensure_*, a window resize: same address, new extent) or whose depth
+        // range changed gets a fresh twin; the old contents are gone on the host side as well (PixelBuffer2D reallocates).
+        struct Twin { shsb_rt rt = 0; int w = 0, h = 0; float zn = 0.0f, zf = 0.0f; };
         shsb_rt twin_of(const void* key, int32_t kind, int w, int h, float zn, float zf)
         {
             auto it = rts_.find(key);
-            if (it != rts_.end()) return it->second;
-            shsb_rt h_rt = 0;
-            if (w > 0 && h > 0) shsb_rt_create(ctx_, kind, w, h, zn, zf, &h_rt);
-            rts_[key] = h_rt;
-            return h_rt;
+            if (it != rts_.end())
+            {
+                const Twin& t = it->second;
+                if (t.w == w && t.h == h && t.zn == zn && t.zf == zf) return t.rt;
+                if (t.rt) shsb_rt_destroy(ctx_, t.rt);
+            }
+            Twin t{};
+            t.w = w; t.h = h; t.zn = zn; t.zf = zf;
+            if (w > 0 && h > 0) shsb_rt_create(ctx_, kind, w, h, zn, zf, &t.rt);
+            rts_[key] = t;
+            return t.rt;
         }
 
         shsb_ctx ctx_ = nullptr;
         bool ok_ = false;
         std::unordered_map<const void*, shsb_mesh> meshes_{};
         std::unordered_map<const void*, shsb_tex> textures_{};
-        std::unordered_map<const void*, shsb_rt> rts_{};
+        std::unordered_map<const void*, Twin> rts_{};
         std::unordered_map<const ISkyModel*, SkyDesc> skies_{};
     };
 
