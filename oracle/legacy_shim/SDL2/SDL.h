@@ -39,6 +39,8 @@ SDL_Texture* SDL_CreateTextureFromSurface(SDL_Renderer*, SDL_Surface*);
 int SDL_UpdateTexture(SDL_Texture*, const SDL_Rect*, const void*, int);
 int SDL_RenderCopy(SDL_Renderer*, SDL_Texture*, const SDL_Rect*, const SDL_Rect*);
 void SDL_RenderPresent(SDL_Renderer*);
+int SDL_RenderClear(SDL_Renderer*);
+void SDL_SetWindowTitle(SDL_Window*, const char*);
 SDL_Surface* SDL_ConvertSurfaceFormat(SDL_Surface*, Uint32, Uint32);
 SDL_Surface* SDL_CreateRGBSurface(Uint32, int, int, int, Uint32, Uint32, Uint32, Uint32);
 void SDL_FreeSurface(SDL_Surface*);

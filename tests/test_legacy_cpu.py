@@ -85,3 +85,16 @@ def test_host_helpers_match_the_reference(lref):
         m0, m1 = lref.world_matrix(*margs), Host.world_matrix(*margs)
         assert np.array_equal(m0.view(np.uint32), m1.view(np.uint32)), i
         assert np.array_equal(lref.mvp(p0, v0, m0).view(np.uint32), Host.mvp(p0, v0, m0).view(np.uint32)), i
+
+
+def test_legacy_goldens(lport):
+    """The restatement against the committed fixture written by tests/golden/make_golden_legacy.py from the reference's own code."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_legacy as mg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_legacy.npz"))
+    for name, make in mg.CASES.items():
+        canvas, z = render(lport, *make())
+        assert np.array_equal(z.view(np.uint32), g[name + "_z"].view(np.uint32)), name
+        assert np.array_equal(canvas, g[name + "_canvas"]), name
