@@ -13,3 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:tile_kernel -s 12 -c 1 -f -o $OUT/tile_kernel \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json
+# legacy tile-job variant (configs[0] as shipped): frames/s next to the reference's threaded CPU path, and its two kernels under ncu
+python tools/bench_legacy.py 300 > $OUT/bench_legacy.jsonl 2> $OUT/bench_legacy.err; echo "legacy bench rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:legacy_ -s 8 -c 2 -f -o $OUT/legacy_kernels \
+    python tools/bench_legacy.py 20 > $OUT/ncu_legacy.log 2>&1; echo "ncu legacy rc=$?"
