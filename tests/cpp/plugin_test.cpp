@@ -193,6 +193,24 @@ int main()
         std::printf("\n");
     }
     {
+        // The deferred techniques ask for passes outside the raster path (gbuffer, ssao, deferred lighting): the profile machinery
+        // must report exactly those as missing and still assemble every pass this registry owns (tonemap is the only required one;
+        // cf. the reference's own test_profile_config_uses_mode_hints_before_instantiation, tests/vop_core_tests.cpp:279).
+        const shs::TechniqueMode deferred[] = {shs::TechniqueMode::Deferred, shs::TechniqueMode::TiledDeferred};
+        for (const shs::TechniqueMode m : deferred)
+        {
+            shs::PluggablePipeline pipe{};
+            std::vector<std::string> missing{};
+            const bool ok = pipe.configure_for_technique(reg, m, &missing);
+            EXPECT(ok, "%s: a required pass is missing", shs::technique_mode_name(m));
+            for (const std::string& id : missing)
+                EXPECT(id == "gbuffer" || id == "ssao" || id == "deferred_lighting" || id == "deferred_lighting_tiled", "%s: '%s' reported missing", shs::technique_mode_name(m), id.c_str());
+            EXPECT(missing.size() == 3, "%s: %zu passes missing, expected the three deferred-only ones", shs::technique_mode_name(m), missing.size());
+            EXPECT(pipe.find(shs::PassId::Tonemap) && pipe.find(shs::PassId::ShadowMap) && pipe.find(shs::PassId::TAA) && pipe.find(shs::PassId::MotionBlur),
+                   "%s: passes of the path were not assembled", shs::technique_mode_name(m));
+        }
+    }
+    {
         // a pass without a device refuses to run instead of falling back to the CPU
         shs::b200::Device* none = nullptr; (void)none;
         if (!dev.valid())
