@@ -21,6 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(_HERE, "liboracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libshs_ref.so")
 REF_LEGACY_LIB = os.path.join(_HERE, "_ref", "libshs_legacy_ref.so")
+REF_LEGACY2_LIB = os.path.join(_HERE, "_ref", "libshs_legacy2_ref.so")
 
 
 class Mesh(C.Structure):
@@ -346,5 +347,58 @@ class LegacyOracle:
         rc = self.fn("draw")(capi.fptr(pos), capi.fptr(nrm), C.c_uint32(len(pos)), capi.fptr(m0), capi.fptr(m1), capi.fptr(ld), capi.fptr(cp),
                              col.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h),
                              canvas.ctypes.data_as(C.POINTER(C.c_uint8)), capi.fptr(zbuffer))
+        assert rc == 0, rc
+        return canvas, zbuffer
+
+
+class L2Uniforms(C.Structure):
+    """struct Uniforms of the legacy soft-shadow demo (hello_shadow_mapping_soft.cpp:714-732) as plain data."""
+    _fields_ = [("mvp", C.c_float * 16), ("model", C.c_float * 16), ("mv", C.c_float * 16), ("normal_mat", C.c_float * 9), ("light_vp", C.c_float * 16),
+                ("light_dir_world", C.c_float * 3), ("camera_pos", C.c_float * 3), ("base_color", C.c_uint8 * 4), ("use_texture", C.c_int32)]
+
+
+class Legacy2Oracle:
+    """The legacy soft-shadow demo (config-3 flavour) on the CPU: "port" = oracle/oracle_legacy.cpp (second
+    half), "reference" = hello_shadow_mapping_soft.cpp compiled by oracle/ref_legacy2_harness.cpp.  CPU only: the CUDA path of this
+    row is not built yet."""
+
+    def __init__(self, kind: str = "port"):
+        assert kind in ("port", "reference")
+        self.kind = kind
+        path = PORT_LIB if kind == "port" else REF_LEGACY2_LIB
+        if not os.path.exists(path):
+            build(kind)
+        self.lib = C.CDLL(path)
+        self.prefix = "shso_l2_" if kind == "port" else "shsref_l2_"
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        return os.path.exists(PORT_LIB if kind == "port" else REF_LEGACY2_LIB)
+
+    def shadow_draw(self, positions, model, light_vp, shadow, tile_w=160, tile_h=160):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        m, lvp = (np.ascontiguousarray(a, dtype=np.float32).reshape(16) for a in (model, light_vp))
+        assert shadow.dtype == np.float32 and shadow.flags.c_contiguous
+        h, w = shadow.shape
+        rc = getattr(self.lib, self.prefix + "shadow_draw")(capi.fptr(pos), C.c_uint32(len(pos)), capi.fptr(m), capi.fptr(lvp), C.c_int32(w), C.c_int32(h),
+                                                            C.c_int32(tile_w), C.c_int32(tile_h), capi.fptr(shadow))
+        assert rc == 0, rc
+        return shadow
+
+    def camera_draw(self, positions, normals, uvs, uniforms: L2Uniforms, canvas, zbuffer, texture=None, shadow=None, tile_w=160, tile_h=160):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        assert len(pos) == len(nrm) == len(uv)
+        assert canvas.dtype == np.uint8 and canvas.flags.c_contiguous and zbuffer.dtype == np.float32 and zbuffer.flags.c_contiguous
+        h, w = zbuffer.shape
+        u8 = C.POINTER(C.c_uint8)
+        tex = np.ascontiguousarray(texture, dtype=np.uint8) if texture is not None else None
+        sm = np.ascontiguousarray(shadow, dtype=np.float32) if shadow is not None else None
+        rc = getattr(self.lib, self.prefix + "camera_draw")(
+            capi.fptr(pos), capi.fptr(nrm), capi.fptr(uv), C.c_uint32(len(pos)), C.byref(uniforms),
+            tex.ctypes.data_as(u8) if tex is not None else None, C.c_int32(tex.shape[1] if tex is not None else 0), C.c_int32(tex.shape[0] if tex is not None else 0),
+            capi.fptr(sm) if sm is not None else None, C.c_int32(sm.shape[1] if sm is not None else 0), C.c_int32(sm.shape[0] if sm is not None else 0),
+            C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h), canvas.ctypes.data_as(u8), capi.fptr(zbuffer))
         assert rc == 0, rc
         return canvas, zbuffer

@@ -8,6 +8,13 @@
 // Plain floats, explicit operation order (GLM's scalar path as stated in oracle/glm_shim).  PINNED: tests/test_legacy_cpu.py demands
 // bit-equality with the reference's own sources compiled into oracle/_ref/libshs_legacy_ref.so (oracle/ref_legacy_harness.cpp).
 // Part of liboracle.so (oracle/Makefile).
+//
+// Second half of the file: the legacy SOFT-SHADOW demo (config-3 flavour),
+//   cpp-folders/src/hello-render-target/hello_shadow_mapping_soft.cpp   ShadowMap :191-229, shadow_uvz_from_world :231-250,
+//       PCSS :252-445, vertex shaders :746-784, draw_triangle_tile_shadow :796-839, draw_triangle_tile_color_depth_softshadow :845-986,
+//       fragment_shader_softshadow :991-1040
+// PINNED the same way (oracle/ref_legacy2_harness.cpp -> oracle/_ref/libshs_legacy2_ref.so, tests/test_legacy2_cpu.py).  The CUDA
+// path of this row is NOT built yet: this restatement is the checker it will be built against.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -242,6 +249,356 @@ extern "C"
                             const int y_canvas = (H - 1) - py;                            // Canvas::draw_pixel_screen_space
                             std::memcpy(canvas_rgba + ((size_t)y_canvas * W + px) * 4, out, 4);
                         }
+                }
+            }
+        return 0;
+    }
+}
+
+// =====================================================================================================================
+// L2: the legacy soft-shadow demo (hello_shadow_mapping_soft.cpp)
+// =====================================================================================================================
+namespace
+{
+    const float FLT_MAXV = std::numeric_limits<float>::max();
+    inline float clampf_l2(float v, float lo, float hi) { if (v < lo) return lo; if (v > hi) return hi; return v; }   // the demo's clampf :127-132
+    inline int clampi_l2(int v, int lo, int hi) { if (v < lo) return lo; if (v > hi) return hi; return v; }
+    inline float saturate_hdr(float v) { return (v < 0.0f) ? 0.0f : (v > 1.0f ? 1.0f : v); }                            // shs::Math::saturate
+
+    // Canvas::barycentric_coordinate, shs_renderer.hpp:803-820
+    inline void bary_legacy(float Px, float Py, const float sx[3], const float sy[3], float& bu, float& bv, float& bw)
+    {
+        const float v0x = sx[1] - sx[0], v0y = sy[1] - sy[0], v1x = sx[2] - sx[0], v1y = sy[2] - sy[0];
+        const float v2x = Px - sx[0], v2y = Py - sy[0];
+        const float d00 = v0x * v0x + v0y * v0y, d01 = v0x * v1x + v0y * v1y, d11 = v1x * v1x + v1y * v1y;
+        const float d20 = v2x * v0x + v2y * v0y, d21 = v2x * v1x + v2y * v1y;
+        const float denom = d00 * d11 - d01 * d01;
+        if (std::abs(denom) < 1e-5) { bu = bv = bw = -1.0f; return; }
+        bv = (d11 * d20 - d01 * d21) / denom;
+        bw = (d00 * d21 - d01 * d20) / denom;
+        bu = 1.0f - bv - bw;
+    }
+
+    // the job tile's clamped bounding box (:806-814 / :917-925); false = empty
+    inline bool job_bbox(const float sx[3], const float sy[3], int tminx, int tminy, int tmaxx, int tmaxy, float& bminx, float& bminy, float& bmaxx, float& bmaxy)
+    {
+        bminx = (float)tmaxx; bminy = (float)tmaxy; bmaxx = (float)tminx; bmaxy = (float)tminy;
+        for (int k = 0; k < 3; ++k)
+        {
+            bminx = gmax((float)tminx, gmin(bminx, sx[k])); bminy = gmax((float)tminy, gmin(bminy, sy[k]));
+            bmaxx = gmin((float)tmaxx, gmax(bmaxx, sx[k])); bmaxy = gmin((float)tmaxy, gmax(bmaxy, sy[k]));
+        }
+        return !(bminx > bmaxx || bminy > bmaxy);
+    }
+
+    struct ShadowView { const float* depth; int w, h; };
+
+    inline float shadow_sample_depth_uv(const ShadowView& sm, float u, float v) // :252-262 + ShadowMap::sample :223-228
+    {
+        if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return FLT_MAXV;
+        int x = (int)std::lround(u * float(sm.w - 1));
+        int y = (int)std::lround(v * float(sm.h - 1));
+        x = clampi_l2(x, 0, sm.w - 1);
+        y = clampi_l2(y, 0, sm.h - 1);
+        return sm.depth[(size_t)y * sm.w + x];
+    }
+
+    const float POISSON_32[32][2] = {
+        {-0.613392f, 0.617481f}, {0.170019f, -0.040254f}, {-0.299417f, 0.791925f}, {0.645680f, 0.493210f}, {-0.651784f, 0.717887f},
+        {0.421003f, 0.027070f}, {-0.817194f, -0.271096f}, {-0.705374f, -0.668203f}, {0.977050f, -0.108615f}, {0.063326f, 0.142369f},
+        {0.203528f, 0.214331f}, {-0.667531f, 0.326090f}, {-0.098422f, -0.295755f}, {-0.885922f, 0.215369f}, {0.566637f, 0.605213f},
+        {0.039766f, -0.396100f}, {0.751946f, 0.453352f}, {0.078707f, -0.715323f}, {-0.075838f, -0.529344f}, {0.724479f, -0.580798f},
+        {0.222999f, -0.215125f}, {-0.467574f, -0.405438f}, {-0.248268f, -0.814753f}, {0.354411f, -0.887570f}, {0.175817f, 0.382366f},
+        {0.487472f, -0.063082f}, {-0.084078f, 0.898312f}, {0.488876f, -0.783441f}, {0.470016f, 0.217933f}, {-0.696890f, -0.549791f},
+        {-0.149693f, 0.605762f}, {0.034211f, 0.979980f}};
+
+    inline uint32_t hash_u32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+    inline float hash01(uint32_t x) { return float(hash_u32(x) & 0x00FFFFFFu) / float(0x01000000u); }
+    inline void rotate2(float px, float py, float a, float& ox, float& oy)
+    {
+        const float c = std::cos(a), s = std::sin(a); // float overloads = libm cosf / sinf
+        ox = c * px - s * py;
+        oy = s * px + c * py;
+    }
+
+    float pcss_shadow_factor(const ShadowView& sm, float u, float v, float z_receiver, float bias, int px, int py) // :333-445
+    {
+        if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return 1.0f;
+        const float center = shadow_sample_depth_uv(sm, u, v);
+        if (center == FLT_MAXV) return 1.0f;
+        const float texelU = 1.0f / float(sm.w), texelV = 1.0f / float(sm.h);
+        const float searchU = 18.0f * texelU, searchV = 18.0f * texelV;
+        const uint32_t seed = (uint32_t)(px * 1973u ^ py * 9277u ^ 0x9e3779b9u);
+        const float ang = hash01(seed) * 6.2831853f;
+        float blocker_sum = 0.0f;
+        int blocker_cnt = 0;
+        const float z_test = z_receiver - bias;
+        for (int i = 0; i < 12; ++i)
+        {
+            float ox, oy;
+            rotate2(POISSON_32[i & 31][0], POISSON_32[i & 31][1], ang, ox, oy);
+            const float d = shadow_sample_depth_uv(sm, u + ox * searchU, v + oy * searchV);
+            if (d == FLT_MAXV) continue;
+            if (d < z_test) { blocker_sum += d; blocker_cnt++; }
+        }
+        if (blocker_cnt <= 0) return 1.0f;
+        const float avg = blocker_sum / float(blocker_cnt);
+        const float zB = gmax(1e-5f, avg), zR = gmax(1e-5f, z_receiver);
+        float ratio = (zR - zB) / zB;
+        ratio = gmax(0.0f, ratio);
+        float fU = 0.0035f * ratio, fV = 0.0035f * ratio;
+        const float ftU = fU / texelU, ftV = fV / texelV;
+        float ft = 0.5f * (ftU + ftV);
+        ft = clampf_l2(ft, 1.0f, 28.0f);
+        fU = ft * texelU;
+        fV = ft * texelV;
+        float lit_sum = 0.0f;
+        int lit_cnt = 0;
+        const float ang2 = hash01(seed ^ 0xB5297A4Du) * 6.2831853f;
+        for (int i = 0; i < 24; ++i)
+        {
+            float ox, oy;
+            rotate2(POISSON_32[i & 31][0], POISSON_32[i & 31][1], ang2, ox, oy);
+            const float d = shadow_sample_depth_uv(sm, u + ox * fU, v + oy * fV);
+            if (d == FLT_MAXV) { lit_sum += 1.0f; lit_cnt++; continue; }
+            lit_sum += (z_receiver <= d + bias) ? 1.0f : 0.0f;
+            lit_cnt++;
+        }
+        if (lit_cnt <= 0) return 1.0f;
+        return lit_sum / float(lit_cnt);
+    }
+
+    struct L2Vary { float pos[4]; V3 world, normal; float u, v, view_z; };
+
+    inline L2Vary lerp_vary(const L2Vary& a, const L2Vary& b, float t) // :859-867: a + (b - a) * t
+    {
+        L2Vary o;
+        for (int k = 0; k < 4; ++k) o.pos[k] = a.pos[k] + (b.pos[k] - a.pos[k]) * t;
+        o.world = add(a.world, mulk(sub(b.world, a.world), t));
+        o.normal = add(a.normal, mulk(sub(b.normal, a.normal), t));
+        o.u = a.u + (b.u - a.u) * t;
+        o.v = a.v + (b.v - a.v) * t;
+        o.view_z = a.view_z + (b.view_z - a.view_z) * t;
+        return o;
+    }
+}
+
+extern "C"
+{
+    struct ShsoL2Uniforms // struct Uniforms, hello_shadow_mapping_soft.cpp:714-732, as plain data (same layout as in ref_legacy2_harness.cpp)
+    {
+        float mvp[16], model[16], mv[16], normal_mat[9], light_vp[16];
+        float light_dir_world[3], camera_pos[3];
+        uint8_t base_color[4];
+        int32_t use_texture;
+    };
+
+    int32_t shso_l2_shadow_draw(const float* positions, uint32_t n_vertices, const float model[16], const float light_vp[16],
+                                int32_t sm_w, int32_t sm_h, int32_t tile_w, int32_t tile_h, float* shadow_depth)
+    {
+        if (!positions || !shadow_depth || sm_w <= 0 || sm_h <= 0 || tile_w <= 0 || tile_h <= 0) return 1;
+        float lm[16];
+        mat_mul(light_vp, model, lm); // u.light_vp * u.model * vec4: the matrix product first (:779)
+        const int cols = (sm_w + tile_w - 1) / tile_w, rows = (sm_h + tile_h - 1) / tile_h;
+        for (int ty = 0; ty < rows; ++ty)
+            for (int tx = 0; tx < cols; ++tx)
+            {
+                const int tminx = tx * tile_w, tminy = ty * tile_h;
+                const int tmaxx = std::min((tx + 1) * tile_w, sm_w) - 1, tmaxy = std::min((ty + 1) * tile_h, sm_h) - 1;
+                for (uint32_t i = 0; i + 2 < n_vertices; i += 3)
+                {
+                    float sx[3], sy[3], sz[3];
+                    bool ok = true;
+                    for (int k = 0; k < 3 && ok; ++k)
+                    {
+                        const V3 p{positions[3 * (i + k)], positions[3 * (i + k) + 1], positions[3 * (i + k) + 2]};
+                        float clip[4];
+                        mat_mul_point(lm, p, clip);
+                        if (std::abs(clip[3]) < 1e-6f) { ok = false; break; }
+                        const float ndx = clip[0] / clip[3], ndy = clip[1] / clip[3], ndz = clip[2] / clip[3];
+                        sx[k] = (ndx * 0.5f + 0.5f) * float(sm_w - 1);
+                        sy[k] = (1.0f - (ndy * 0.5f + 0.5f)) * float(sm_h - 1);
+                        sz[k] = ndz;
+                    }
+                    if (!ok) continue;
+                    bool finite = true;
+                    for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sx[k]) && std::isfinite(sy[k]);
+                    if (!finite) continue; // the reference casts them to int: undefined behaviour
+                    float bminx, bminy, bmaxx, bmaxy;
+                    if (!job_bbox(sx, sy, tminx, tminy, tmaxx, tmaxy, bminx, bminy, bmaxx, bmaxy)) continue;
+                    const float area = (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sy[1] - sy[0]) * (sx[2] - sx[0]);
+                    if (std::abs(area) < 1e-8f) continue;
+                    for (int px = (int)bminx; px <= (int)bmaxx; ++px)
+                        for (int py = (int)bminy; py <= (int)bmaxy; ++py)
+                        {
+                            float bu, bv, bw;
+                            bary_legacy(px + 0.5f, py + 0.5f, sx, sy, bu, bv, bw);
+                            if (bu < 0 || bv < 0 || bw < 0) continue;
+                            const float z = bu * sz[0] + bv * sz[1] + bw * sz[2];
+                            if (z < 0.0f || z > 1.0f) continue;
+                            if (px < 0 || px >= sm_w || py < 0 || py >= sm_h) continue;
+                            float& d = shadow_depth[(size_t)py * sm_w + px];
+                            if (z < d) d = z;
+                        }
+                }
+            }
+        return 0;
+    }
+
+    int32_t shso_l2_camera_draw(const float* positions, const float* normals, const float* uvs, uint32_t n_vertices, const ShsoL2Uniforms* un,
+                                const uint8_t* texture_rgba, int32_t tex_w, int32_t tex_h, const float* shadow_depth, int32_t sm_w, int32_t sm_h,
+                                int32_t W, int32_t H, int32_t tile_w, int32_t tile_h, uint8_t* canvas_rgba, float* zbuffer)
+    {
+        if (!positions || !normals || !uvs || !un || !canvas_rgba || !zbuffer || W <= 0 || H <= 0 || tile_w <= 0 || tile_h <= 0) return 1;
+        const bool has_tex = texture_rgba && tex_w > 0 && tex_h > 0;
+        const bool has_shadow = shadow_depth && sm_w > 0 && sm_h > 0;
+        const ShadowView sm{shadow_depth, sm_w, sm_h};
+        const float* nm = un->normal_mat;
+        const int cols = (W + tile_w - 1) / tile_w, rows = (H + tile_h - 1) / tile_h;
+        for (int ty = 0; ty < rows; ++ty)
+            for (int tx = 0; tx < cols; ++tx)
+            {
+                const int tminx = tx * tile_w, tminy = ty * tile_h;
+                const int tmaxx = std::min((tx + 1) * tile_w, W) - 1, tmaxy = std::min((ty + 1) * tile_h, H) - 1;
+                for (uint32_t i = 0; i + 2 < n_vertices; i += 3)
+                {
+                    // ---- vertex_shader_full x 3 (:746-766)
+                    L2Vary vin[3];
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const V3 p{positions[3 * (i + k)], positions[3 * (i + k) + 1], positions[3 * (i + k) + 2]};
+                        const V3 n{normals[3 * (i + k)], normals[3 * (i + k) + 1], normals[3 * (i + k) + 2]};
+                        float wh[4], vp[4];
+                        mat_mul_point(un->mvp, p, vin[k].pos);
+                        mat_mul_point(un->model, p, wh);
+                        vin[k].world = V3{wh[0], wh[1], wh[2]};
+                        vin[k].normal = normalize3(V3{nm[0] * n.x + nm[3] * n.y + nm[6] * n.z, nm[1] * n.x + nm[4] * n.y + nm[7] * n.z, nm[2] * n.x + nm[5] * n.y + nm[8] * n.z});
+                        vin[k].u = uvs[2 * (i + k)];
+                        vin[k].v = uvs[2 * (i + k) + 1];
+                        mat_mul_point(un->mv, p, vp);
+                        vin[k].view_z = vp[2];
+                    }
+                    // ---- clip_poly_near_z (:869-905): Sutherland-Hodgman against z >= 0 (and w > 1e-6)
+                    std::vector<L2Vary> poly;
+                    poly.reserve(6);
+                    auto inside = [](const L2Vary& v) { return (v.pos[3] > 1e-6f) && (v.pos[2] >= 0.0f); };
+                    auto intersect = [](const L2Vary& a, const L2Vary& b) {
+                        const float az = a.pos[2], bz = b.pos[2];
+                        const float denom = (bz - az);
+                        float t = (std::abs(denom) < 1e-8f) ? 0.0f : ((0.0f - az) / denom);
+                        t = clampf_l2(t, 0.0f, 1.0f);
+                        return lerp_vary(a, b, t);
+                    };
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const L2Vary& A = vin[k];
+                        const L2Vary& B = vin[(k + 1) % 3];
+                        const bool a_in = inside(A), b_in = inside(B);
+                        if (a_in && b_in) poly.push_back(B);
+                        else if (a_in && !b_in) poly.push_back(intersect(A, B));
+                        else if (!a_in && b_in) { poly.push_back(intersect(A, B)); poly.push_back(B); }
+                    }
+                    if (poly.size() < 3) continue;
+                    for (int ti = 1; ti + 1 < (int)poly.size(); ++ti)
+                    {
+                        const L2Vary tv[3] = {poly[0], poly[(size_t)ti], poly[(size_t)ti + 1]};
+                        bool tri_ok = true;
+                        float sx[3], sy[3];
+                        for (int k = 0; k < 3; ++k)
+                        {
+                            if (tv[k].pos[3] <= 1e-6f) { tri_ok = false; break; }
+                            const float ndx = tv[k].pos[0] / tv[k].pos[3], ndy = tv[k].pos[1] / tv[k].pos[3];
+                            sx[k] = (ndx + 1.0f) * 0.5f * float(W - 1);       // Canvas::clip_to_screen
+                            sy[k] = (1.0f - ndy) * 0.5f * float(H - 1);
+                        }
+                        if (!tri_ok) continue;
+                        bool finite = true;
+                        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sx[k]) && std::isfinite(sy[k]);
+                        if (!finite) continue; // undefined behaviour in the reference ((int) of a non-finite float)
+                        float bminx, bminy, bmaxx, bmaxy;
+                        if (!job_bbox(sx, sy, tminx, tminy, tmaxx, tmaxy, bminx, bminy, bmaxx, bmaxy)) continue;
+                        const float area = (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sy[1] - sy[0]) * (sx[2] - sx[0]);
+                        if (std::abs(area) < 1e-8f) continue;
+                        for (int px = (int)bminx; px <= (int)bmaxx; ++px)
+                            for (int py = (int)bminy; py <= (int)bmaxy; ++py)
+                            {
+                                float bu, bv, bw;
+                                bary_legacy(px + 0.5f, py + 0.5f, sx, sy, bu, bv, bw);
+                                if (bu < 0 || bv < 0 || bw < 0) continue;
+                                const float vz = bu * tv[0].view_z + bv * tv[1].view_z + bw * tv[2].view_z;
+                                // ZBuffer::test_and_set_depth_screen_space: the z-buffer is indexed with the FLIPPED row here
+                                const int y_canvas = (H - 1) - py;
+                                if (px < 0 || px >= W || y_canvas < 0 || y_canvas >= H) continue;
+                                float& d = zbuffer[(size_t)y_canvas * W + px];
+                                if (!(vz < d)) continue;
+                                d = vz;
+                                const float w0 = tv[0].pos[3], w1 = tv[1].pos[3], w2 = tv[2].pos[3];
+                                const float iw0 = (std::abs(w0) < 1e-6f) ? 0.0f : 1.0f / w0;
+                                const float iw1 = (std::abs(w1) < 1e-6f) ? 0.0f : 1.0f / w1;
+                                const float iw2 = (std::abs(w2) < 1e-6f) ? 0.0f : 1.0f / w2;
+                                const float iw_sum = bu * iw0 + bv * iw1 + bw * iw2;
+                                if (iw_sum <= 1e-8f) continue; // depth already written (:951-961)
+                                const V3 in_normal = normalize3(add(add(kmul(bu, tv[0].normal), kmul(bv, tv[1].normal)), kmul(bw, tv[2].normal)));
+                                const V3 wp_over_w = add(add(kmul(bu, mulk(tv[0].world, iw0)), kmul(bv, mulk(tv[1].world, iw1))), kmul(bw, mulk(tv[2].world, iw2)));
+                                const V3 world_pos{wp_over_w.x / iw_sum, wp_over_w.y / iw_sum, wp_over_w.z / iw_sum};
+                                const float uw = bu * (tv[0].u * iw0) + bv * (tv[1].u * iw1) + bw * (tv[2].u * iw2);
+                                const float vw = bu * (tv[0].v * iw0) + bv * (tv[1].v * iw1) + bw * (tv[2].v * iw2);
+                                const float fu = uw / iw_sum, fv = vw / iw_sum;
+
+                                // ---- fragment_shader_softshadow (:991-1040)
+                                const V3 N = normalize3(in_normal);
+                                const V3 L = normalize3(V3{-un->light_dir_world[0], -un->light_dir_world[1], -un->light_dir_world[2]});
+                                const V3 Vd = normalize3(sub(V3{un->camera_pos[0], un->camera_pos[1], un->camera_pos[2]}, world_pos));
+                                V3 base;
+                                if (un->use_texture && has_tex)
+                                {
+                                    // shs::sample_nearest (shs_renderer.hpp:367-377)
+                                    const float su = saturate_hdr(fu), sv = saturate_hdr(fv);
+                                    int x = (int)std::lround(su * (float)(tex_w - 1));
+                                    int y = (int)std::lround(sv * (float)(tex_h - 1));
+                                    x = clampi_l2(x, 0, tex_w - 1);
+                                    y = clampi_l2(y, 0, tex_h - 1);
+                                    const uint8_t* t = texture_rgba + ((size_t)y * tex_w + x) * 4;
+                                    base = V3{float(t[0]) / 255.0f, float(t[1]) / 255.0f, float(t[2]) / 255.0f};
+                                }
+                                else base = V3{float(un->base_color[0]) / 255.0f, float(un->base_color[1]) / 255.0f, float(un->base_color[2]) / 255.0f};
+                                const float ndl = dot3(N, L);
+                                const float diff = gmax(ndl, 0.0f);
+                                const V3 Hh = normalize3(add(L, Vd));
+                                const float spec = std::pow(gmax(dot3(N, Hh), 0.0f), 64.0f);
+                                const float specular = (0.45f * spec) * 1.0f;
+                                float shadow = 1.0f;
+                                if (has_shadow)
+                                {
+                                    float clip[4];
+                                    mat_mul_point(un->light_vp, world_pos, clip);          // shadow_uvz_from_world :231-250
+                                    if (!(std::abs(clip[3]) < 1e-6f))
+                                    {
+                                        const float ndx = clip[0] / clip[3], ndy = clip[1] / clip[3], ndz = clip[2] / clip[3];
+                                        if (!(ndz < 0.0f || ndz > 1.0f))
+                                        {
+                                            const float suvx = ndx * 0.5f + 0.5f, suvy = 1.0f - (ndy * 0.5f + 0.5f);
+                                            const float slope = 1.0f - gmin(gmax(ndl, 0.0f), 1.0f);
+                                            const float bias = 0.0025f + 0.0100f * slope;
+                                            shadow = pcss_shadow_factor(sm, suvx, suvy, ndz, bias, px, py);
+                                        }
+                                    }
+                                }
+                                const float dcol = diff * 1.0f;
+                                uint8_t out[4];
+                                const float bc3[3] = {base.x, base.y, base.z};
+                                for (int c = 0; c < 3; ++c)
+                                {
+                                    const float amb = 0.22f * bc3[c];
+                                    const float direct = shadow * (dcol * bc3[c] + specular);
+                                    const float r = gmin(gmax(amb + direct, 0.0f), 1.0f);   // glm::clamp(amb + direct, 0, 1)
+                                    const float r2 = gmin(gmax(r, 0.0f), 1.0f) * 255.0f;    // rgb01_to_color clamps again, then scales
+                                    out[c] = (uint8_t)r2;
+                                }
+                                out[3] = 255;
+                                std::memcpy(canvas_rgba + ((size_t)y_canvas * W + px) * 4, out, 4);
+                            }
+                    }
                 }
             }
         return 0;

@@ -103,3 +103,59 @@ def legacy_draws(seed):
         model_args = (tuple(float(v) for v in rng.uniform(-2, 2, 3)), (scl, scl * float(rng.choice([1.0, 1.0, 0.4])), scl), float(rng.uniform(-360, 360)))
         objs.append((np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(nrm, np.float32), model_args, tuple(int(v) for v in rng.integers(0, 256, 3)) + (255,)))
     return W, H, tile_w, tile_h, cam, light, objs, (h_ang, v_ang)
+
+
+def _mat_look_at_lh(eye, center, up=(0.0, 1.0, 0.0)):
+    eye, center, up = (np.asarray(v, np.float64) for v in (eye, center, up))
+    f = center - eye
+    f /= np.linalg.norm(f)
+    s = np.cross(up, f)
+    s /= np.linalg.norm(s)
+    u = np.cross(f, s)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, f
+    m[0, 3], m[1, 3], m[2, 3] = -s @ eye, -u @ eye, -f @ eye
+    return m
+
+
+def legacy2_scene(seed):
+    """Random inputs of the legacy soft-shadow demo: a floor quad grid + one to three objects (Suzanne or a
+    soup), an orthographic light (z in 0..1 like the demo's ortho_lh_zo), a perspective camera that often clips the floor at the near
+    plane, an optional random texture, random canvas / shadow-map / job-tile sizes.  All matrices are INPUTS of the path (float32,
+    column-major when flattened): they only have to be the same for both sides.
+    Returns dict(W, H, sm, tile, objs=[(pos, nrm, uv, model, color, use_tex)], view, proj, light_vp, light_dir, cam, texture)."""
+    rng = np.random.default_rng(17000 + seed)
+    W, H = int(rng.integers(24, 150)), int(rng.integers(20, 110))
+    sm = int(rng.choice([24, 64, 150]))
+    tile = (160, 160) if seed % 3 == 0 else (int(rng.integers(5, 90)), int(rng.integers(5, 90)))
+    cam = np.array([rng.uniform(-6, 6), rng.uniform(0.3, 5), rng.uniform(-9, -2)])
+    view = _mat_look_at_lh(cam, rng.uniform(-1, 1, 3) + np.array([0, 0.5, 0]))
+    fov, asp, zn, zf = np.radians(rng.uniform(40, 90)), W / H, 0.1, 200.0
+    t = np.tan(fov / 2)
+    proj = np.zeros((4, 4))
+    proj[0, 0], proj[1, 1], proj[2, 2], proj[3, 2], proj[2, 3] = 1 / (asp * t), 1 / t, zf / (zf - zn), 1.0, -zn * zf / (zf - zn)   # LH, z in 0..1
+    ldir = rng.normal(0, 1, 3) * np.array([1, 0.3, 1]) - np.array([0, 0.9, 0])
+    ldir /= np.linalg.norm(ldir)
+    lview = _mat_look_at_lh(-ldir * 30.0, np.zeros(3))
+    ext, lzn, lzf = float(rng.uniform(6, 14)), 0.1, 80.0
+    lproj = np.eye(4)
+    lproj[0, 0], lproj[1, 1], lproj[2, 2], lproj[2, 3] = 1 / ext, 1 / ext, 1 / (lzf - lzn), -lzn / (lzf - lzn)
+    f32 = lambda m: np.ascontiguousarray(np.asarray(m, np.float32).T).reshape(16)     # row-major math -> column-major floats
+    objs = []
+    g = scenes.make_grid_plane(float(rng.uniform(8, 30)), int(rng.integers(1, 5)))
+    objs.append((g["positions"][g["indices"]], g["normals"][g["indices"]], g["uvs"][g["indices"]] / 8.0, np.eye(4), tuple(int(v) for v in rng.integers(40, 256, 3)) + (255,), bool(rng.random() < 0.5)))
+    for k in range(int(rng.integers(1, 4))):
+        if rng.random() < 0.5:
+            m = scenes.load_suzanne()
+            pos, nrm, uv = m["positions"][m["indices"]], m["normals"][m["indices"]], m["uvs"][m["indices"]]
+        else:
+            m = scenes.make_triangle_soup(int(rng.integers(4, 60)), seed * 13 + k, extent=1.5, indexed=False, zero_normals=False)
+            pos, nrm, uv = m["positions"], m["normals"], m["uvs"]
+        model = np.eye(4)
+        a, sc = rng.uniform(0, 6.28), rng.uniform(0.4, 2.0)
+        model[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]) * sc * np.array([1, rng.choice([1.0, 0.5]), 1])
+        model[:3, 3] = rng.uniform(-3, 3, 3) * np.array([1, 0.2, 1]) + np.array([0, 1.0, 0])
+        objs.append((pos, nrm, uv, model, tuple(int(v) for v in rng.integers(0, 256, 3)) + (255,), bool(rng.random() < 0.4)))
+    tw, th = int(rng.integers(1, 24)), int(rng.integers(1, 24))
+    return {"W": W, "H": H, "sm": sm, "tile": tile, "objs": objs, "view": view, "proj": proj, "light_vp": f32(lproj @ lview), "light_dir": tuple(float(v) for v in ldir),
+            "cam": tuple(float(v) for v in cam), "texture": rng.integers(0, 256, (th, tw, 4), dtype=np.uint8), "f32": f32}
