@@ -22,6 +22,7 @@ PORT_LIB = os.path.join(_HERE, "liboracle.so")
 REF_LIB = os.path.join(_HERE, "_ref", "libshs_ref.so")
 REF_LEGACY_LIB = os.path.join(_HERE, "_ref", "libshs_legacy_ref.so")
 REF_LEGACY2_LIB = os.path.join(_HERE, "_ref", "libshs_legacy2_ref.so")
+REF_LEGACY3_LIB = os.path.join(_HERE, "_ref", "libshs_legacy3_ref.so")
 
 
 class Mesh(C.Structure):
@@ -402,3 +403,70 @@ class Legacy2Oracle:
             C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h), canvas.ctypes.data_as(u8), capi.fptr(zbuffer))
         assert rc == 0, rc
         return canvas, zbuffer
+
+
+class L3Uniforms(C.Structure):
+    """struct Uniforms + MaterialPBR of the legacy PBR / IBL demo (hello_pbr.cpp:474-519) as plain data."""
+    _fields_ = [("mvp", C.c_float * 16), ("prev_mvp", C.c_float * 16), ("model", C.c_float * 16), ("mv", C.c_float * 16), ("normal_mat", C.c_float * 9),
+                ("light_vp", C.c_float * 16), ("light_dir_world", C.c_float * 3), ("camera_pos", C.c_float * 3), ("base_color_srgb", C.c_uint8 * 4),
+                ("metallic", C.c_float), ("roughness", C.c_float), ("ao", C.c_float), ("use_texture", C.c_int32),
+                ("ibl_diffuse_intensity", C.c_float), ("ibl_specular_intensity", C.c_float), ("ibl_reflection_strength", C.c_float)]
+
+
+class Legacy3Oracle:
+    """The legacy PBR / IBL demo (config-4 flavour) on the CPU: "port" = oracle/oracle_legacy.cpp (third part),
+    "reference" = hello_pbr.cpp compiled by oracle/ref_legacy3_harness.cpp.  CPU only: the CUDA path of this row is not built."""
+
+    def __init__(self, kind: str = "port"):
+        assert kind in ("port", "reference")
+        self.kind = kind
+        path = PORT_LIB if kind == "port" else REF_LEGACY3_LIB
+        if not os.path.exists(path):
+            build(kind)
+        self.lib = C.CDLL(path)
+        self.prefix = "shso_l3_" if kind == "port" else "shsref_l3_"
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        return os.path.exists(PORT_LIB if kind == "port" else REF_LEGACY3_LIB)
+
+    def shadow_draw(self, positions, model, light_vp, shadow, tile_w=160, tile_h=160):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        m, lvp = (np.ascontiguousarray(a, dtype=np.float32).reshape(16) for a in (model, light_vp))
+        assert shadow.dtype == np.float32 and shadow.flags.c_contiguous
+        h, w = shadow.shape
+        rc = getattr(self.lib, self.prefix + "shadow_draw")(capi.fptr(pos), C.c_uint32(len(pos)), capi.fptr(m), capi.fptr(lvp), C.c_int32(w), C.c_int32(h),
+                                                            C.c_int32(tile_w), C.c_int32(tile_h), capi.fptr(shadow))
+        assert rc == 0, rc
+        return shadow
+
+    def camera_draw(self, positions, normals, uvs, uniforms: L3Uniforms, canvas, zbuffer, velocity, texture=None, shadow=None, irradiance=None,
+                    prefiltered=None, tile_w=160, tile_h=160):
+        """In place on canvas (H, W, 4) uint8, zbuffer (H, W) float32 and velocity (H, W, 2) float32 (shs::Buffer order).
+        irradiance: (6, n, n, 3) float32; prefiltered: list of (6, n_m, n_m, 3) float32 mips."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        assert len(pos) == len(nrm) == len(uv)
+        for a, dt in ((canvas, np.uint8), (zbuffer, np.float32), (velocity, np.float32)):
+            assert a.dtype == dt and a.flags.c_contiguous
+        h, w = zbuffer.shape
+        u8 = C.POINTER(C.c_uint8)
+        tex = np.ascontiguousarray(texture, dtype=np.uint8) if texture is not None else None
+        sm = np.ascontiguousarray(shadow, dtype=np.float32) if shadow is not None else None
+        irr = np.ascontiguousarray(irradiance, dtype=np.float32) if irradiance is not None else None
+        if prefiltered is not None:
+            sizes = np.array([m.shape[1] for m in prefiltered], np.int32)
+            pre = np.concatenate([np.ascontiguousarray(m, dtype=np.float32).reshape(-1) for m in prefiltered])
+        else:
+            sizes = pre = None
+        rc = getattr(self.lib, self.prefix + "camera_draw")(
+            capi.fptr(pos), capi.fptr(nrm), capi.fptr(uv), C.c_uint32(len(pos)), C.byref(uniforms),
+            tex.ctypes.data_as(u8) if tex is not None else None, C.c_int32(tex.shape[1] if tex is not None else 0), C.c_int32(tex.shape[0] if tex is not None else 0),
+            capi.fptr(sm) if sm is not None else None, C.c_int32(sm.shape[1] if sm is not None else 0), C.c_int32(sm.shape[0] if sm is not None else 0),
+            capi.fptr(irr) if irr is not None else None, C.c_int32(irr.shape[1] if irr is not None else 0),
+            capi.fptr(pre) if pre is not None else None, sizes.ctypes.data_as(C.POINTER(C.c_int32)) if sizes is not None else None,
+            C.c_int32(len(sizes) if sizes is not None else 0),
+            C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h), canvas.ctypes.data_as(u8), capi.fptr(zbuffer), capi.fptr(velocity))
+        assert rc == 0, rc
+        return canvas, zbuffer, velocity

@@ -15,6 +15,11 @@
 //       fragment_shader_softshadow :991-1040
 // PINNED the same way (oracle/ref_legacy2_harness.cpp -> oracle/_ref/libshs_legacy2_ref.so, tests/test_legacy2_cpu.py).  The CUDA
 // path of this row is NOT built yet: this restatement is the checker it will be built against.
+//
+// Third part: the legacy PBR / IBL demo (config-4 flavour, row L3), cpp-folders/src/hello-render-target/hello_pbr.cpp
+//   PBR:: :238-279, shadow_factor_pcf_2x2 :599-621, fragment_shader_pbr :627-727, draw_triangle_tile_color_depth_motion :883-1045,
+//   with shs-renderer-lib/include/shs/resources/ibl.hpp:215-287 (cube-map sampling).  Pinned by oracle/ref_legacy3_harness.cpp,
+//   tests/test_legacy3_cpu.py.  CUDA path not built yet either.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -595,6 +600,338 @@ extern "C"
                                     const float r2 = gmin(gmax(r, 0.0f), 1.0f) * 255.0f;    // rgb01_to_color clamps again, then scales
                                     out[c] = (uint8_t)r2;
                                 }
+                                out[3] = 255;
+                                std::memcpy(canvas_rgba + ((size_t)y_canvas * W + px) * 4, out, 4);
+                            }
+                    }
+                }
+            }
+        return 0;
+    }
+}
+
+// =====================================================================================================================
+// L3: the legacy PBR / IBL demo (hello_pbr.cpp)
+// =====================================================================================================================
+namespace
+{
+    inline float std_clamp(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); } // std::clamp
+    inline int std_clampi(int v, int lo, int hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+    inline V3 mul3(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+    inline V3 mix3(V3 a, V3 b, float t) { return add(mulk(a, 1.0f - t), mulk(b, t)); }                   // glm::mix
+
+    struct CubeView { const float* data; int size; }; // 6 faces x size^2 x RGB
+
+    inline V3 cube_at(const CubeView& c, int f, int x, int y)
+    {
+        const float* p = c.data + (((size_t)f * c.size + (size_t)y) * c.size + (size_t)x) * 3;
+        return V3{p[0], p[1], p[2]};
+    }
+
+    V3 sample_face_bilinear(const CubeView& cm, int face, float u, float v) // ibl.hpp:215-235
+    {
+        u = std_clamp(u, 0.0f, 1.0f);
+        v = std_clamp(v, 0.0f, 1.0f);
+        const float fx = u * float(cm.size - 1), fy = v * float(cm.size - 1);
+        const int x0 = std_clampi((int)std::floor(fx), 0, cm.size - 1), y0 = std_clampi((int)std::floor(fy), 0, cm.size - 1);
+        const int x1 = std_clampi(x0 + 1, 0, cm.size - 1), y1 = std_clampi(y0 + 1, 0, cm.size - 1);
+        const float tx = fx - float(x0), ty = fy - float(y0);
+        const V3 cx0 = mix3(cube_at(cm, face, x0, y0), cube_at(cm, face, x1, y0), tx);
+        const V3 cx1 = mix3(cube_at(cm, face, x0, y1), cube_at(cm, face, x1, y1), tx);
+        return mix3(cx0, cx1, ty);
+    }
+
+    V3 sample_cubemap_linear(const CubeView& cm, V3 dir) // ibl.hpp:237-270
+    {
+        if (cm.size <= 0) return V3{0, 0, 0};
+        V3 d = dir;
+        const float len = std::sqrt(dot3(d, d));
+        if (len < 1e-8f) return V3{0, 0, 0};
+        d = V3{d.x / len, d.y / len, d.z / len};
+        const float ax = std::abs(d.x), ay = std::abs(d.y), az = std::abs(d.z);
+        int face = 0;
+        float u = 0.5f, v = 0.5f;
+        if (ax >= ay && ax >= az)
+        {
+            if (d.x > 0.0f) { face = 0; u = (-d.z / ax); v = (d.y / ax); }
+            else { face = 1; u = (d.z / ax); v = (d.y / ax); }
+        }
+        else if (ay >= ax && ay >= az)
+        {
+            if (d.y > 0.0f) { face = 2; u = (d.x / ay); v = (-d.z / ay); }
+            else { face = 3; u = (d.x / ay); v = (d.z / ay); }
+        }
+        else
+        {
+            if (d.z > 0.0f) { face = 4; u = (d.x / az); v = (d.y / az); }
+            else { face = 5; u = (-d.x / az); v = (d.y / az); }
+        }
+        u = 0.5f * (u + 1.0f);
+        v = 0.5f * (v + 1.0f);
+        return sample_face_bilinear(cm, face, u, v);
+    }
+
+    struct L3Vary { float pos[4], prev[4]; V3 world, normal; float u, v, view_z; };
+
+    inline L3Vary lerp_vary3(const L3Vary& a, const L3Vary& b, float t)
+    {
+        L3Vary o;
+        for (int k = 0; k < 4; ++k) { o.pos[k] = a.pos[k] + (b.pos[k] - a.pos[k]) * t; o.prev[k] = a.prev[k] + (b.prev[k] - a.prev[k]) * t; }
+        o.world = add(a.world, mulk(sub(b.world, a.world), t));
+        o.normal = add(a.normal, mulk(sub(b.normal, a.normal), t));
+        o.u = a.u + (b.u - a.u) * t;
+        o.v = a.v + (b.v - a.v) * t;
+        o.view_z = a.view_z + (b.view_z - a.view_z) * t;
+        return o;
+    }
+}
+
+extern "C"
+{
+    struct ShsoL3Uniforms // same layout as in ref_legacy3_harness.cpp
+    {
+        float mvp[16], prev_mvp[16], model[16], mv[16], normal_mat[9], light_vp[16];
+        float light_dir_world[3], camera_pos[3];
+        uint8_t base_color_srgb[4];
+        float metallic, roughness, ao;
+        int32_t use_texture;
+        float ibl_diffuse_intensity, ibl_specular_intensity, ibl_reflection_strength;
+    };
+
+    // draw_triangle_tile_shadow of hello_pbr.cpp:827-875 is the same function as the soft-shadow demo's
+    int32_t shso_l3_shadow_draw(const float* positions, uint32_t n_vertices, const float model[16], const float light_vp[16],
+                                int32_t sm_w, int32_t sm_h, int32_t tile_w, int32_t tile_h, float* shadow_depth)
+    {
+        return shso_l2_shadow_draw(positions, n_vertices, model, light_vp, sm_w, sm_h, tile_w, tile_h, shadow_depth);
+    }
+
+    int32_t shso_l3_camera_draw(const float* positions, const float* normals, const float* uvs, uint32_t n_vertices, const ShsoL3Uniforms* un,
+                                const uint8_t* texture_rgba, int32_t tex_w, int32_t tex_h, const float* shadow_depth, int32_t sm_w, int32_t sm_h,
+                                const float* irradiance, int32_t irr_size, const float* prefiltered, const int32_t* spec_sizes, int32_t n_mips,
+                                int32_t W, int32_t H, int32_t tile_w, int32_t tile_h, uint8_t* canvas_rgba, float* zbuffer, float* velocity)
+    {
+        if (!positions || !normals || !uvs || !un || !canvas_rgba || !zbuffer || !velocity || W <= 0 || H <= 0 || tile_w <= 0 || tile_h <= 0) return 1;
+        const bool has_tex = texture_rgba && tex_w > 0 && tex_h > 0;
+        const bool has_shadow = shadow_depth && sm_w > 0 && sm_h > 0;
+        const bool has_ibl = irradiance && irr_size > 0 && prefiltered && spec_sizes && n_mips > 0;
+        const CubeView irr{irradiance, irr_size};
+        std::vector<CubeView> mips;
+        if (has_ibl)
+        {
+            size_t off = 0;
+            for (int m = 0; m < n_mips; ++m) { mips.push_back(CubeView{prefiltered + off, spec_sizes[m]}); off += (size_t)6 * spec_sizes[m] * spec_sizes[m] * 3; }
+        }
+        const float PI = 3.14159265358979323846f;
+        const float* nm = un->normal_mat;
+        const int cols = (W + tile_w - 1) / tile_w, rows = (H + tile_h - 1) / tile_h;
+        for (int ty = 0; ty < rows; ++ty)
+            for (int tx = 0; tx < cols; ++tx)
+            {
+                const int tminx = tx * tile_w, tminy = ty * tile_h;
+                const int tmaxx = std::min((tx + 1) * tile_w, W) - 1, tmaxy = std::min((ty + 1) * tile_h, H) - 1;
+                for (uint32_t i = 0; i + 2 < n_vertices; i += 3)
+                {
+                    L3Vary vin[3];
+                    for (int k = 0; k < 3; ++k) // vertex_shader_full :535-556
+                    {
+                        const V3 p{positions[3 * (i + k)], positions[3 * (i + k) + 1], positions[3 * (i + k) + 2]};
+                        const V3 n{normals[3 * (i + k)], normals[3 * (i + k) + 1], normals[3 * (i + k) + 2]};
+                        float wh[4], vp[4];
+                        mat_mul_point(un->mvp, p, vin[k].pos);
+                        mat_mul_point(un->prev_mvp, p, vin[k].prev);
+                        mat_mul_point(un->model, p, wh);
+                        vin[k].world = V3{wh[0], wh[1], wh[2]};
+                        vin[k].normal = normalize3(V3{nm[0] * n.x + nm[3] * n.y + nm[6] * n.z, nm[1] * n.x + nm[4] * n.y + nm[7] * n.z, nm[2] * n.x + nm[5] * n.y + nm[8] * n.z});
+                        vin[k].u = uvs[2 * (i + k)];
+                        vin[k].v = uvs[2 * (i + k) + 1];
+                        mat_mul_point(un->mv, p, vp);
+                        vin[k].view_z = vp[2];
+                    }
+                    std::vector<L3Vary> poly;
+                    poly.reserve(6);
+                    auto inside = [](const L3Vary& v) { return (v.pos[3] > 1e-6f) && (v.pos[2] >= 0.0f); };
+                    auto intersect = [](const L3Vary& a, const L3Vary& b) {
+                        const float az = a.pos[2], bz = b.pos[2];
+                        const float denom = (bz - az);
+                        float t = (std::abs(denom) < 1e-8f) ? 0.0f : ((0.0f - az) / denom);
+                        t = saturate_hdr(t); // shs::Math::clampf(t, 0, 1)
+                        return lerp_vary3(a, b, t);
+                    };
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const L3Vary& A = vin[k];
+                        const L3Vary& B = vin[(k + 1) % 3];
+                        const bool a_in = inside(A), b_in = inside(B);
+                        if (a_in && b_in) poly.push_back(B);
+                        else if (a_in && !b_in) poly.push_back(intersect(A, B));
+                        else if (!a_in && b_in) { poly.push_back(intersect(A, B)); poly.push_back(B); }
+                    }
+                    if (poly.size() < 3) continue;
+                    for (int ti = 1; ti + 1 < (int)poly.size(); ++ti)
+                    {
+                        const L3Vary tv[3] = {poly[0], poly[(size_t)ti], poly[(size_t)ti + 1]};
+                        bool tri_ok = true;
+                        float sx[3], sy[3];
+                        for (int k = 0; k < 3; ++k)
+                        {
+                            if (tv[k].pos[3] <= 1e-6f) { tri_ok = false; break; }
+                            sx[k] = (tv[k].pos[0] / tv[k].pos[3] + 1.0f) * 0.5f * float(W - 1);
+                            sy[k] = (1.0f - tv[k].pos[1] / tv[k].pos[3]) * 0.5f * float(H - 1);
+                        }
+                        if (!tri_ok) continue;
+                        bool finite = true;
+                        for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(sx[k]) && std::isfinite(sy[k]);
+                        if (!finite) continue;
+                        float bminx, bminy, bmaxx, bmaxy;
+                        if (!job_bbox(sx, sy, tminx, tminy, tmaxx, tmaxy, bminx, bminy, bmaxx, bmaxy)) continue;
+                        const float area = (sx[1] - sx[0]) * (sy[2] - sy[0]) - (sy[1] - sy[0]) * (sx[2] - sx[0]);
+                        if (std::abs(area) < 1e-8f) continue;
+                        for (int px = (int)bminx; px <= (int)bmaxx; ++px)
+                            for (int py = (int)bminy; py <= (int)bmaxy; ++py)
+                            {
+                                float bu, bv, bw;
+                                bary_legacy(px + 0.5f, py + 0.5f, sx, sy, bu, bv, bw);
+                                if (bu < 0 || bv < 0 || bw < 0) continue;
+                                const float vz = bu * tv[0].view_z + bv * tv[1].view_z + bw * tv[2].view_z;
+                                const int y_canvas = (H - 1) - py;
+                                if (px < 0 || px >= W || y_canvas < 0 || y_canvas >= H) continue;
+                                float& d = zbuffer[(size_t)y_canvas * W + px];
+                                if (!(vz < d)) continue;
+                                d = vz;
+                                const float w0 = tv[0].pos[3], w1 = tv[1].pos[3], w2 = tv[2].pos[3];
+                                const float iw0 = (std::abs(w0) < 1e-6f) ? 0.0f : 1.0f / w0;
+                                const float iw1 = (std::abs(w1) < 1e-6f) ? 0.0f : 1.0f / w1;
+                                const float iw2 = (std::abs(w2) < 1e-6f) ? 0.0f : 1.0f / w2;
+                                const float iw_sum = bu * iw0 + bv * iw1 + bw * iw2;
+                                if (iw_sum <= 1e-8f) continue;
+                                float cpos[4], ppos[4];
+                                for (int k = 0; k < 4; ++k)
+                                {
+                                    cpos[k] = bu * tv[0].pos[k] + bv * tv[1].pos[k] + bw * tv[2].pos[k];
+                                    ppos[k] = bu * tv[0].prev[k] + bv * tv[1].prev[k] + bw * tv[2].prev[k];
+                                }
+                                const V3 in_normal = normalize3(add(add(kmul(bu, tv[0].normal), kmul(bv, tv[1].normal)), kmul(bw, tv[2].normal)));
+                                const V3 wp_over_w = add(add(kmul(bu, mulk(tv[0].world, iw0)), kmul(bv, mulk(tv[1].world, iw1))), kmul(bw, mulk(tv[2].world, iw2)));
+                                const V3 world_pos{wp_over_w.x / iw_sum, wp_over_w.y / iw_sum, wp_over_w.z / iw_sum};
+                                const float fu = (bu * (tv[0].u * iw0) + bv * (tv[1].u * iw1) + bw * (tv[2].u * iw2)) / iw_sum;
+                                const float fv = (bu * (tv[0].v * iw0) + bv * (tv[1].v * iw1) + bw * (tv[2].v * iw2)) / iw_sum;
+
+                                // ---- motion vector (:1018-1030): screen-space difference of the affinely interpolated clip positions
+                                const float csx = (cpos[0] / cpos[3] + 1.0f) * 0.5f * float(W - 1), csy = (1.0f - cpos[1] / cpos[3]) * 0.5f * float(H - 1);
+                                const float psx = (ppos[0] / ppos[3] + 1.0f) * 0.5f * float(W - 1), psy = (1.0f - ppos[1] / ppos[3]) * 0.5f * float(H - 1);
+                                float vx = csx - psx, vy = -(csy - psy);
+                                const float vlen = std::sqrt(vx * vx + vy * vy);
+                                if (vlen > 22.0f && vlen > 1e-6f) { const float k = 22.0f / vlen; vx *= k; vy *= k; }
+                                velocity[((size_t)y_canvas * W + px) * 2] = vx;
+                                velocity[((size_t)y_canvas * W + px) * 2 + 1] = vy;
+
+                                // ---- fragment_shader_pbr (:627-727)
+                                const V3 N = normalize3(in_normal);
+                                const V3 Vd = normalize3(sub(V3{un->camera_pos[0], un->camera_pos[1], un->camera_pos[2]}, world_pos));
+                                const V3 L = normalize3(V3{-un->light_dir_world[0], -un->light_dir_world[1], -un->light_dir_world[2]});
+                                const V3 Hh = normalize3(add(Vd, L));
+                                const float NoV = gmax(0.0f, dot3(N, Vd)), NoL = gmax(0.0f, dot3(N, L)), NoH = gmax(0.0f, dot3(N, Hh));
+                                V3 srgb;
+                                if (un->use_texture && has_tex)
+                                {
+                                    const float su = saturate_hdr(fu), sv = saturate_hdr(fv);
+                                    int x = (int)std::lround(su * (float)(tex_w - 1));
+                                    int y = (int)std::lround(sv * (float)(tex_h - 1));
+                                    x = clampi_l2(x, 0, tex_w - 1);
+                                    y = clampi_l2(y, 0, tex_h - 1);
+                                    const uint8_t* t = texture_rgba + ((size_t)y * tex_w + x) * 4;
+                                    srgb = V3{float(t[0]) / 255.0f, float(t[1]) / 255.0f, float(t[2]) / 255.0f};
+                                }
+                                else srgb = V3{float(un->base_color_srgb[0]) / 255.0f, float(un->base_color_srgb[1]) / 255.0f, float(un->base_color_srgb[2]) / 255.0f};
+                                // srgb_to_linear: pow(clamp(x, 0, 1), 2.2)
+                                const V3 base{std::pow(gmin(gmax(srgb.x, 0.0f), 1.0f), 2.2f), std::pow(gmin(gmax(srgb.y, 0.0f), 1.0f), 2.2f), std::pow(gmin(gmax(srgb.z, 0.0f), 1.0f), 2.2f)};
+                                const float metallic = saturate_hdr(un->metallic);
+                                const float roughness = saturate_hdr(un->roughness) < 0.04f ? 0.04f : (un->roughness > 1.0f ? 1.0f : un->roughness); // clampf(r, 0.04, 1)
+                                const float ao = saturate_hdr(un->ao);
+                                const V3 F0 = mix3(V3{0.04f, 0.04f, 0.04f}, base, metallic);
+                                // PBR::fresnel_schlick
+                                const float fx = 1.0f - saturate_hdr(NoV);
+                                const float fx2 = fx * fx;
+                                const float fx5 = fx2 * fx2 * fx;
+                                V3 F = add(F0, mulk(sub(V3{1.0f, 1.0f, 1.0f}, F0), fx5));
+                                F = mul3(F, V3{1.0f, 0.96f, 0.90f});
+                                const V3 kd = mulk(sub(V3{1.0f, 1.0f, 1.0f}, F), 1.0f - metallic);
+                                const float alpha = roughness * roughness;
+                                // PBR::ndf_ggx
+                                const float nh = saturate_hdr(NoH);
+                                const float a2 = alpha * alpha;
+                                const float dd = (nh * nh) * (a2 - 1.0f) + 1.0f;
+                                const float D = a2 / (PI * dd * dd);
+                                // PBR::g_smith
+                                const float rr = (roughness < 0.04f ? 0.04f : (roughness > 1.0f ? 1.0f : roughness)) + 1.0f;
+                                const float kk = (rr * rr) / 8.0f;
+                                const float nv = saturate_hdr(NoV), nl = saturate_hdr(NoL);
+                                const float gv = nv / (nv * (1.0f - kk) + kk), gl = nl / (nl * (1.0f - kk) + kk);
+                                const float G = gv * gl;
+                                const V3 direct_diffuse = mulk(mul3(kd, base), 1.0f / PI);
+                                const float spec_den = gmax(1e-6f, (4.0f * NoV * NoL));
+                                const V3 dgf = kmul(D * G, F);
+                                const V3 direct_specular{dgf.x / spec_den, dgf.y / spec_den, dgf.z / spec_den};
+                                V3 direct = mulk(mul3(add(direct_diffuse, direct_specular), V3{3.0f, 3.0f, 3.0f}), NoL);
+                                float shadow = 1.0f;
+                                if (has_shadow)
+                                {
+                                    float clip[4];
+                                    mat_mul_point(un->light_vp, world_pos, clip);
+                                    if (!(std::abs(clip[3]) < 1e-6f))
+                                    {
+                                        const float ndx = clip[0] / clip[3], ndy = clip[1] / clip[3], ndz = clip[2] / clip[3];
+                                        if (!(ndz < 0.0f || ndz > 1.0f))
+                                        {
+                                            const float suvx = ndx * 0.5f + 0.5f, suvy = 1.0f - (ndy * 0.5f + 0.5f);
+                                            const float slope = 1.0f - gmin(gmax(dot3(N, L), 0.0f), 1.0f);
+                                            const float bias = 0.0025f + 0.0100f * slope;
+                                            // shadow_factor_pcf_2x2 (:599-621); shs::ShadowMap::sample returns FLT_MAX out of bounds
+                                            const float sfx = suvx * float(sm_w - 1), sfy = suvy * float(sm_h - 1);
+                                            const int x0 = std_clampi((int)std::floor(sfx), 0, sm_w - 1);
+                                            const int y0 = std_clampi((int)std::floor(sfy), 0, sm_h - 1);
+                                            const int x1 = std_clampi(x0 + 1, 0, sm_w - 1), y1 = std_clampi(y0 + 1, 0, sm_h - 1);
+                                            auto smp = [&](int x, int y) { return shadow_depth[(size_t)y * sm_w + x]; };
+                                            const float s00 = (ndz <= smp(x0, y0) + bias) ? 1.0f : 0.0f;
+                                            const float s10 = (ndz <= smp(x1, y0) + bias) ? 1.0f : 0.0f;
+                                            const float s01 = (ndz <= smp(x0, y1) + bias) ? 1.0f : 0.0f;
+                                            const float s11 = (ndz <= smp(x1, y1) + bias) ? 1.0f : 0.0f;
+                                            shadow = 0.25f * (s00 + s10 + s01 + s11);
+                                        }
+                                    }
+                                }
+                                direct = mulk(direct, shadow);
+                                V3 ibl{0.0f, 0.0f, 0.0f};
+                                if (has_ibl)
+                                {
+                                    const V3 irradiance_c = sample_cubemap_linear(irr, N);
+                                    V3 diffuse_ibl = mul3(mul3(irradiance_c, base), kd);
+                                    diffuse_ibl = mulk(diffuse_ibl, saturate_hdr(un->ibl_diffuse_intensity));
+                                    // glm::reflect(-V, N) = I - N * dot(N, I) * 2
+                                    const V3 I{-Vd.x, -Vd.y, -Vd.z};
+                                    const V3 R = sub(I, mulk(mulk(N, dot3(N, I)), 2.0f));
+                                    float lod = roughness * float(n_mips - 1);
+                                    // sample_prefiltered_spec_trilinear (ibl.hpp:272-287)
+                                    const float mmax = float(n_mips - 1);
+                                    lod = std_clamp(lod, 0.0f, mmax);
+                                    const int m0 = (int)std::floor(lod);
+                                    const int m1 = std::min(m0 + 1, n_mips - 1);
+                                    const float tl = lod - float(m0);
+                                    const V3 prefiltered_c = mix3(sample_cubemap_linear(mips[(size_t)m0], R), sample_cubemap_linear(mips[(size_t)m1], R), tl);
+                                    V3 spec_ibl = mul3(prefiltered_c, F);
+                                    spec_ibl = mulk(spec_ibl, saturate_hdr(un->ibl_specular_intensity) * saturate_hdr(un->ibl_reflection_strength));
+                                    ibl = add(diffuse_ibl, spec_ibl);
+                                }
+                                ibl = mulk(ibl, ao);
+                                V3 color = add(direct, ibl);
+                                color = add(color, mulk(mulk(base, 0.03f), ao));
+                                color = mulk(color, 1.75f);
+                                color = V3{color.x / (1.0f + color.x), color.y / (1.0f + color.y), color.z / (1.0f + color.z)}; // tonemap_reinhard
+                                const float inv_gamma = 1.0f / 2.2f;
+                                const float cs[3] = {std::pow(gmin(gmax(color.x, 0.0f), 1.0f), inv_gamma), std::pow(gmin(gmax(color.y, 0.0f), 1.0f), inv_gamma),
+                                                     std::pow(gmin(gmax(color.z, 0.0f), 1.0f), inv_gamma)};
+                                uint8_t out[4];
+                                for (int c = 0; c < 3; ++c) out[c] = (uint8_t)(gmin(gmax(cs[c], 0.0f), 1.0f) * 255.0f);
                                 out[3] = 255;
                                 std::memcpy(canvas_rgba + ((size_t)y_canvas * W + px) * 4, out, 4);
                             }

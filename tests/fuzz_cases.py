@@ -159,3 +159,24 @@ def legacy2_scene(seed):
     tw, th = int(rng.integers(1, 24)), int(rng.integers(1, 24))
     return {"W": W, "H": H, "sm": sm, "tile": tile, "objs": objs, "view": view, "proj": proj, "light_vp": f32(lproj @ lview), "light_dir": tuple(float(v) for v in ldir),
             "cam": tuple(float(v) for v in cam), "texture": rng.integers(0, 256, (th, tw, 4), dtype=np.uint8), "f32": f32}
+
+
+def legacy3_scene(seed):
+    """Random inputs of the legacy PBR / IBL demo: the L2 scene plus a previous-frame camera (motion vectors),
+    per-object metallic / roughness / ao (also out of range), a random irradiance cube and a prefiltered-specular mip chain
+    (HDR values; the library's cube-map sampling only reads them), IBL intensities.  Returns the L2 dict with extra keys."""
+    sc = legacy2_scene(seed)
+    rng = np.random.default_rng(23000 + seed)
+    cam = np.asarray(sc["cam"])
+    sc["prev_view"] = _mat_look_at_lh(cam + rng.normal(0, 0.15 if seed % 4 else 1.5, 3), rng.uniform(-1, 1, 3) + np.array([0, 0.5, 0])) if seed % 5 else sc["view"]
+    sc["pbr"] = [(float(rng.uniform(-0.2, 1.2)), float(rng.uniform(-0.1, 1.3)), float(rng.uniform(-0.2, 1.2))) for _ in sc["objs"]]
+    if seed % 7 == 6:
+        sc["irradiance"], sc["prefiltered"] = None, None
+    else:
+        n_irr = int(rng.choice([1, 2, 8, 16]))
+        sc["irradiance"] = rng.uniform(0, 2.5, (6, n_irr, n_irr, 3)).astype(np.float32)
+        base = int(rng.choice([1, 4, 16, 32]))
+        n_mips = int(rng.integers(1, 7))
+        sc["prefiltered"] = [rng.uniform(0, 4.0, (6, max(1, base >> m), max(1, base >> m), 3)).astype(np.float32) for m in range(n_mips)]
+    sc["ibl_k"] = (float(rng.uniform(-0.2, 1.4)), float(rng.uniform(-0.2, 1.4)), float(rng.uniform(0, 1.2)))
+    return sc
