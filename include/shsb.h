@@ -482,6 +482,62 @@ SHSB_API int32_t shsb_legacy_mvp(const float proj[16], const float view[16], con
 SHSB_API int32_t shsb_legacy_draw_blinn_phong(shsb_ctx ctx, shsb_mesh mesh, const ShsbLegacyUniforms* uniforms,
                                               shsb_rt canvas_ldr, shsb_rt zbuffer);
 
+/* ------------------------------------------------------------------ legacy render-target demos
+ *
+ * cpp-folders/src/hello-render-target/hello_shadow_mapping_soft.cpp (config-3 flavour: 2048^2 shadow map + PCSS soft-shadow lit
+ * pass) and hello_pbr.cpp (config-4 flavour: Cook-Torrance + IBL lit pass with motion vectors).  Both are rasterizers of their own
+ * on top of hello-shs-renderer/shs_renderer.hpp: y-flipped screen map, near-plane Sutherland-Hodgman clip + fan (:869-905), no
+ * back-face cull, dot-product barycentrics, depth = affine VIEW-space z tested LESS against FLT_MAX with the z-buffer stored in
+ * canvas order (row 0 = bottom), perspective-correct world position / uv, affine normal, RGBA8 by truncation.  One call = one object
+ * of one pass = the demo's `for tile: for triangle: draw_triangle_tile_*` loops (soft :1130-1200 / :1223-1360). */
+
+typedef uint32_t shsb_ibl; /* EnvIBL of hello_pbr.cpp:455-461: an irradiance cube + a prefiltered-specular mip chain (shs::CubeMapLinear) */
+
+typedef struct ShsbLegacy2Uniforms /* struct Uniforms, hello_shadow_mapping_soft.cpp:714-732 / hello_pbr.cpp:474-519 (+ MaterialPBR, job tile) */
+{
+    float mvp[16];
+    float prev_mvp[16];        /* pbr only (motion vectors) */
+    float model[16];
+    float mv[16];              /* view * model: its third row gives the depth that is tested */
+    float normal_mat[9];       /* mat3, column-major: the demo sets transpose(inverse(mat3(model))) or the identity */
+    float light_vp[16];
+    float light_dir_world[3];  /* the direction the light travels */
+    float camera_pos[3];
+    uint8_t base_color[4];     /* Uniforms::base_color / MaterialPBR::baseColor_srgb */
+    int32_t use_texture;
+    shsb_tex albedo;           /* 0 = none; sampled with shs::sample_nearest (shs_renderer.hpp:367-377) */
+    float metallic, roughness, ao;                                                      /* pbr only */
+    float ibl_diffuse_intensity, ibl_specular_intensity, ibl_reflection_strength;       /* pbr only */
+    int32_t job_tile_w;        /* TILE_SIZE_X / TILE_SIZE_Y (160); 0 = 160.  Honoured exactly, see csrc/legacy.cu */
+    int32_t job_tile_h;
+} ShsbLegacy2Uniforms;
+
+/* draw_triangle_tile_shadow over every job tile and triangle of `mesh` (soft :796-839, pbr :827-875; identical) with
+ * shadow_vertex_shader (light_vp * model taken first, :779).  shadow_map: SHSB_RT_SHADOW, any size; clear it to FLT_MAX with
+ * shsb_rt_clear like ShadowMap::clear.  Rows are light-space screen rows (top down), as ShadowMap stores them. */
+SHSB_API int32_t shsb_legacy2_shadow_draw(shsb_ctx ctx, shsb_mesh mesh, const float model[16], const float light_vp[16],
+                                          int32_t job_tile_w, int32_t job_tile_h, shsb_rt shadow_map);
+
+/* draw_triangle_tile_color_depth_softshadow (:845-986) with vertex_shader_full (:746-766) and fragment_shader_softshadow (:991-1040;
+ * PCSS :333-445).  shadow_map: 0 = Uniforms::shadow == nullptr.  canvas_ldr: SHSB_RT_COLOR_LDR in shs::Canvas order; zbuffer: the
+ * depth plane of a SHSB_RT_SHADOW / SHSB_RT_DEPTH_MOTION target of the same size, in CANVAS order (this demo's
+ * ZBuffer::test_and_set_depth_screen_space flips the row), cleared to FLT_MAX. */
+SHSB_API int32_t shsb_legacy2_draw_softshadow(shsb_ctx ctx, shsb_mesh mesh, const ShsbLegacy2Uniforms* uniforms, shsb_rt shadow_map,
+                                              shsb_rt canvas_ldr, shsb_rt zbuffer);
+
+/* EnvIBL as plain data: irradiance = 6 faces x irr_size^2 x RGB float32 (face order +X -X +Y -Y +Z -Z, shs/resources/ibl.hpp:237-262);
+ * prefiltered = n_mips such cube maps of sizes spec_sizes[m], concatenated (n_mips <= 16). */
+SHSB_API int32_t shsb_legacy3_ibl_upload(shsb_ctx ctx, const float* irradiance, int32_t irr_size, const float* prefiltered,
+                                         const int32_t* spec_sizes, int32_t n_mips, shsb_ibl* out_ibl);
+SHSB_API int32_t shsb_legacy3_ibl_destroy(shsb_ctx ctx, shsb_ibl ibl);
+
+/* draw_triangle_tile_color_depth_motion (hello_pbr.cpp:883-1045) with vertex_shader_full (:535-556) and fragment_shader_pbr (:627-727;
+ * shadow_factor_pcf_2x2 :599-621, cube-map sampling shs/resources/ibl.hpp:215-287).  ibl: 0 = Uniforms::ibl == nullptr.
+ * depth_motion: SHSB_RT_DEPTH_MOTION of the canvas size = RT_ColorDepthMotion's depth + velocity planes, both in canvas order;
+ * velocity in pixels, +y up, clamped to 22 px (:1018-1030). */
+SHSB_API int32_t shsb_legacy3_draw_pbr(shsb_ctx ctx, shsb_mesh mesh, const ShsbLegacy2Uniforms* uniforms, shsb_rt shadow_map, shsb_ibl ibl,
+                                       shsb_rt canvas_ldr, shsb_rt depth_motion);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,16 @@ class LegacyUniforms(C.Structure):
         self.job_tile_w, self.job_tile_h = int(job_tile_w), int(job_tile_h)
 
 
+class Legacy2Uniforms(C.Structure):
+    """ShsbLegacy2Uniforms: struct Uniforms of the legacy render-target demos (hello_shadow_mapping_soft.cpp:714-732, hello_pbr.cpp:474-519)
+    as plain data + MaterialPBR + the job-tile size."""
+    _fields_ = [("mvp", F16), ("prev_mvp", F16), ("model", F16), ("mv", F16), ("normal_mat", C.c_float * 9), ("light_vp", F16),
+                ("light_dir_world", F3), ("camera_pos", F3), ("base_color", C.c_uint8 * 4), ("use_texture", C.c_int32), ("albedo", C.c_uint32),
+                ("metallic", C.c_float), ("roughness", C.c_float), ("ao", C.c_float),
+                ("ibl_diffuse_intensity", C.c_float), ("ibl_specular_intensity", C.c_float), ("ibl_reflection_strength", C.c_float),
+                ("job_tile_w", C.c_int32), ("job_tile_h", C.c_int32)]
+
+
 class LightCullDesc(C.Structure):
     """ShsbLightCullDesc: arguments of the bin builders of lighting/jolt_light_culling.hpp."""
     _fields_ = [("view_proj", F16), ("viewport_w", C.c_uint32), ("viewport_h", C.c_uint32), ("tile_size", C.c_uint32),
@@ -232,6 +242,11 @@ def load_library(path: str | None = None):
         "shsb_legacy_world_matrix": [P(C.c_float), P(C.c_float), C.c_float, P(C.c_float)],
         "shsb_legacy_mvp": [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)],
         "shsb_legacy_draw_blinn_phong": [vp, C.c_uint32, P(LegacyUniforms), C.c_uint32, C.c_uint32],
+        "shsb_legacy2_shadow_draw": [vp, C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32, C.c_int32, C.c_uint32],
+        "shsb_legacy2_draw_softshadow": [vp, C.c_uint32, P(Legacy2Uniforms), C.c_uint32, C.c_uint32, C.c_uint32],
+        "shsb_legacy3_ibl_upload": [vp, P(C.c_float), C.c_int32, P(C.c_float), P(C.c_int32), C.c_int32, P(C.c_uint32)],
+        "shsb_legacy3_ibl_destroy": [vp, C.c_uint32],
+        "shsb_legacy3_draw_pbr": [vp, C.c_uint32, P(Legacy2Uniforms), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32],
         "shsb_timing_enable": [vp, C.c_int32],
         "shsb_timing_collect": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
         "shsb_timing_collect_abs": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],

@@ -298,6 +298,11 @@ struct shsb_context_t
     DevBuf<float> d_post_luma;
     DevBuf<uchar4> d_taa_hist;      // TemporalAARuntimeState::history (core/context.hpp:101)
     DevBuf<LegacyTri> d_legacy_tris; // set-up records of the legacy tile-job variant (legacy.cu)
+    DevBuf<l2::RasterRec> d_l2_raster; // slot records of the legacy render-target demos (legacy2.cu)
+    DevBuf<l2::BoxRec> d_l2_box;
+    DevBuf<l2::ShadeRec> d_l2_shade;
+    struct IblSlot { bool live = false; float* irradiance = nullptr; float* prefiltered = nullptr; int irr_size = 0, n_mips = 0; int spec_size[l2::MAX_SPEC_MIPS] = {}; uint32_t spec_off[l2::MAX_SPEC_MIPS] = {}; };
+    std::vector<IblSlot> ibls;        // EnvIBL of the legacy PBR demo
     int taa_w = 0, taa_h = 0;
     bool taa_valid = false;
 
@@ -1187,6 +1192,8 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_range_min.p); cudaFree(ctx->d_range_max.p); cudaFree(ctx->d_range_up_min.p); cudaFree(ctx->d_range_up_max.p);
     cudaFree(ctx->d_slice_ndc.p); cudaFree(ctx->d_vis.p); cudaFree(ctx->cluster_lists.counts.p); cudaFree(ctx->cluster_lists.indices.p);
     cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p); cudaFree(ctx->d_legacy_tris.p);
+    cudaFree(ctx->d_l2_raster.p); cudaFree(ctx->d_l2_box.p); cudaFree(ctx->d_l2_shade.p);
+    for (auto& e : ctx->ibls) { cudaFree(e.irradiance); cudaFree(e.prefiltered); }
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
     for (auto& l : ctx->h_lights) cudaFreeHost(l.p);
@@ -1561,6 +1568,174 @@ SHSB_API int32_t shsb_legacy_draw_blinn_phong(shsb_ctx ctx, shsb_mesh mesh_h, co
     launch_legacy_draw(d, ctx->d_legacy_tris.p, (uchar4*)canvas->color, zb->depth, ctx->stream, &ctx->launches);
     CK(cudaGetLastError());
     return SHSB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------- legacy render-target demos (rows L2, L3)
+namespace
+{
+    int legacy2_fill_mesh(shsb_ctx ctx, shsb_mesh mesh_h, bool camera, l2::Draw& d)
+    {
+        const MeshSlot* mesh = get_mesh(ctx, mesh_h);
+        if (!mesh) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh %u is not live", mesh_h);
+        if (camera && mesh->n_normals < mesh->n_positions)
+            return fail(ctx, SHSB_E_INVALID_ARGUMENT, "the legacy vertex shader needs a normal per position (ModelGeometry emits both streams)");
+        d.positions = mesh->positions;
+        d.normals = mesh->normals;
+        d.uvs = mesh->n_uvs ? mesh->uvs : nullptr;
+        d.indices = mesh->n_indices ? mesh->indices : nullptr;
+        d.n_positions = mesh->n_positions;
+        d.n_normals = mesh->n_normals;
+        d.n_uvs = mesh->n_uvs;
+        d.n_tris = (mesh->n_indices ? mesh->n_indices : mesh->n_positions) / 3;
+        return SHSB_OK;
+    }
+
+    int legacy2_launch(shsb_ctx ctx, const l2::Draw& d, uchar4* canvas, float* zbuf, float2* velocity)
+    {
+        if (d.n_tris == 0) return SHSB_OK;
+        const size_t slots = legacy2_slots(d);
+        if (int rc = ensure_dev(ctx, ctx->d_l2_raster, slots)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_l2_box, slots)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_l2_shade, d.mode == l2::MODE_SHADOW ? 1 : slots)) return rc;
+        launch_legacy2_draw(d, ctx->d_l2_raster.p, ctx->d_l2_box.p, ctx->d_l2_shade.p, canvas, zbuf, velocity, ctx->stream, &ctx->launches);
+        CK(cudaGetLastError());
+        return SHSB_OK;
+    }
+
+    // the parts of a camera-pass draw that the soft-shadow and the PBR demo share
+    int legacy2_fill_camera(shsb_ctx ctx, shsb_mesh mesh_h, const ShsbLegacy2Uniforms* u, shsb_rt shadow_rt, shsb_rt canvas_rt, shsb_rt zbuffer_rt,
+                            bool need_motion, l2::Draw& d, RtSlot*& canvas, RtSlot*& zb)
+    {
+        if (!u) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "uniforms are null");
+        if (int rc = legacy2_fill_mesh(ctx, mesh_h, true, d)) return rc;
+        canvas = get_rt(ctx, canvas_rt, SHSB_RT_COLOR_LDR);
+        if (!canvas) return fail(ctx, SHSB_E_INVALID_HANDLE, "canvas_ldr is not a live RT_ColorLDR");
+        zb = get_rt(ctx, zbuffer_rt);
+        if (!zb || !zb->depth || (zb->kind != SHSB_RT_DEPTH_MOTION && (need_motion || zb->kind != SHSB_RT_SHADOW)))
+            return fail(ctx, SHSB_E_INVALID_HANDLE, need_motion ? "depth_motion is not a live RT_ColorDepthMotion" : "zbuffer is not a live target with a depth plane (RT_ShadowDepth / RT_ColorDepthMotion)");
+        if (zb->w != canvas->w || zb->h != canvas->h) return fail(ctx, SHSB_E_SIZE_MISMATCH, "canvas is %dx%d, z-buffer %dx%d", canvas->w, canvas->h, zb->w, zb->h);
+        if (u->job_tile_w < 0 || u->job_tile_h < 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "job tile size must be positive (0 = the demo's 160)");
+        d.W = canvas->w; d.H = canvas->h;
+        d.job_w = u->job_tile_w ? u->job_tile_w : 160;
+        d.job_h = u->job_tile_h ? u->job_tile_h : 160;
+        std::memcpy(d.mvp, u->mvp, 64); std::memcpy(d.prev_mvp, u->prev_mvp, 64); std::memcpy(d.model, u->model, 64); std::memcpy(d.mv, u->mv, 64);
+        std::memcpy(d.normal_mat, u->normal_mat, 36); std::memcpy(d.light_vp, u->light_vp, 64);
+        std::memcpy(d.light_dir, u->light_dir_world, 12); std::memcpy(d.camera_pos, u->camera_pos, 12); std::memcpy(d.color, u->base_color, 4);
+        d.use_texture = u->use_texture;
+        if (u->albedo)
+        {
+            if (u->albedo > ctx->textures.size() || !ctx->textures[u->albedo - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", u->albedo);
+            const TexSlot& t = ctx->textures[u->albedo - 1];
+            d.tex = reinterpret_cast<const unsigned char*>(t.texels); d.tex_w = t.w; d.tex_h = t.h;
+        }
+        if (shadow_rt)
+        {
+            RtSlot* sh = get_rt(ctx, shadow_rt, SHSB_RT_SHADOW);
+            if (!sh) return fail(ctx, SHSB_E_INVALID_HANDLE, "shadow_map is not a live RT_ShadowDepth");
+            if (sh == zb) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "the shadow map and the z-buffer are the same target");
+            wait_pending_read(ctx, sh);
+            d.shadow = sh->depth; d.sm_w = sh->w; d.sm_h = sh->h;
+        }
+        return SHSB_OK;
+    }
+}
+
+SHSB_API int32_t shsb_legacy2_shadow_draw(shsb_ctx ctx, shsb_mesh mesh_h, const float model[16], const float light_vp[16], int32_t job_tile_w, int32_t job_tile_h,
+                                          shsb_rt shadow_rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!model || !light_vp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "model / light_vp are null");
+    if (job_tile_w < 0 || job_tile_h < 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "job tile size must be positive (0 = the demo's 160)");
+    CK(cudaSetDevice(ctx->device));
+    l2::Draw d{};
+    d.mode = l2::MODE_SHADOW;
+    if (int rc = legacy2_fill_mesh(ctx, mesh_h, false, d)) return rc;
+    RtSlot* sh = get_rt(ctx, shadow_rt, SHSB_RT_SHADOW);
+    if (!sh) return fail(ctx, SHSB_E_INVALID_HANDLE, "shadow_map is not a live RT_ShadowDepth");
+    d.W = sh->w; d.H = sh->h;
+    d.job_w = job_tile_w ? job_tile_w : 160;
+    d.job_h = job_tile_h ? job_tile_h : 160;
+    hm::store(hm::mul(hm::load(light_vp), hm::load(model)), d.light_model); // u.light_vp * u.model * vec4: the matrix product first (:779)
+    wait_pending_read(ctx, sh);
+    return legacy2_launch(ctx, d, nullptr, sh->depth, nullptr);
+}
+
+SHSB_API int32_t shsb_legacy2_draw_softshadow(shsb_ctx ctx, shsb_mesh mesh_h, const ShsbLegacy2Uniforms* u, shsb_rt shadow_rt, shsb_rt canvas_rt, shsb_rt zbuffer_rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    l2::Draw d{};
+    d.mode = l2::MODE_SOFTSHADOW;
+    RtSlot *canvas = nullptr, *zb = nullptr;
+    if (int rc = legacy2_fill_camera(ctx, mesh_h, u, shadow_rt, canvas_rt, zbuffer_rt, false, d, canvas, zb)) return rc;
+    wait_pending_read(ctx, canvas);
+    wait_pending_read(ctx, zb);
+    return legacy2_launch(ctx, d, (uchar4*)canvas->color, zb->depth, nullptr);
+}
+
+SHSB_API int32_t shsb_legacy3_ibl_upload(shsb_ctx ctx, const float* irradiance, int32_t irr_size, const float* prefiltered, const int32_t* spec_sizes, int32_t n_mips,
+                                         shsb_ibl* out_ibl)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (!out_ibl || !irradiance || !prefiltered || !spec_sizes || irr_size <= 0 || n_mips <= 0 || n_mips > l2::MAX_SPEC_MIPS)
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad IBL arguments (1 <= n_mips <= %d)", l2::MAX_SPEC_MIPS);
+    CK(cudaSetDevice(ctx->device));
+    shsb_context_t::IblSlot e;
+    e.live = true; e.irr_size = irr_size; e.n_mips = n_mips;
+    size_t off = 0;
+    for (int m = 0; m < n_mips; ++m)
+    {
+        if (spec_sizes[m] <= 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "prefiltered mip %d has size %d", m, spec_sizes[m]);
+        e.spec_size[m] = spec_sizes[m];
+        e.spec_off[m] = (uint32_t)off;
+        off += (size_t)6 * spec_sizes[m] * spec_sizes[m] * 3;
+        if (off > 0xFFFFFFFFull) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "prefiltered chain too large");
+    }
+    const size_t irr_bytes = (size_t)6 * irr_size * irr_size * 3 * sizeof(float);
+    CK(cudaMalloc(&e.irradiance, irr_bytes));
+    CK(cudaMalloc(&e.prefiltered, off * sizeof(float)));
+    CK(cudaMemcpyAsync(e.irradiance, irradiance, irr_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(e.prefiltered, prefiltered, off * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ibls.push_back(e);
+    *out_ibl = (shsb_ibl)ctx->ibls.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_legacy3_ibl_destroy(shsb_ctx ctx, shsb_ibl ibl)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (ibl == 0 || ibl > ctx->ibls.size() || !ctx->ibls[ibl - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "IBL handle %u is not live", ibl);
+    sync_all(ctx);
+    cudaFree(ctx->ibls[ibl - 1].irradiance);
+    cudaFree(ctx->ibls[ibl - 1].prefiltered);
+    ctx->ibls[ibl - 1] = shsb_context_t::IblSlot{};
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_legacy3_draw_pbr(shsb_ctx ctx, shsb_mesh mesh_h, const ShsbLegacy2Uniforms* u, shsb_rt shadow_rt, shsb_ibl ibl, shsb_rt canvas_rt, shsb_rt depth_motion_rt)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    l2::Draw d{};
+    d.mode = l2::MODE_PBR;
+    RtSlot *canvas = nullptr, *dm = nullptr;
+    if (int rc = legacy2_fill_camera(ctx, mesh_h, u, shadow_rt, canvas_rt, depth_motion_rt, true, d, canvas, dm)) return rc;
+    d.metallic = u->metallic; d.roughness = u->roughness; d.ao = u->ao;
+    d.ibl_diffuse = u->ibl_diffuse_intensity; d.ibl_specular = u->ibl_specular_intensity; d.ibl_reflection = u->ibl_reflection_strength;
+    if (ibl)
+    {
+        if (ibl > ctx->ibls.size() || !ctx->ibls[ibl - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "IBL handle %u is not live", ibl);
+        const shsb_context_t::IblSlot& e = ctx->ibls[ibl - 1];
+        d.irradiance = e.irradiance; d.irr_size = e.irr_size; d.prefiltered = e.prefiltered; d.n_mips = e.n_mips;
+        std::memcpy(d.spec_size, e.spec_size, sizeof(d.spec_size));
+        std::memcpy(d.spec_off, e.spec_off, sizeof(d.spec_off));
+    }
+    wait_pending_read(ctx, canvas);
+    wait_pending_read(ctx, dm);
+    dm->motion_dirty = true;
+    return legacy2_launch(ctx, d, (uchar4*)canvas->color, dm->depth, dm->motion);
 }
 
 // ---------------------------------------------------------------------------------------- passes

@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "legacy2_core.cuh"
 
 namespace shsb
 {
@@ -283,6 +284,9 @@ namespace shsb
     };
 
     // ---------------------------------------------------------------- kernel launchers (one per .cu)
+    uint32_t legacy2_slots(const l2::Draw& d);
+    void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
+                             cudaStream_t s, uint64_t* launches);
     void launch_legacy_draw(const LegacyDraw& d, LegacyTri* tris, uchar4* canvas, float* zbuf, cudaStream_t s, uint64_t* launches);
     void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);

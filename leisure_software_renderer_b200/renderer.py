@@ -171,6 +171,35 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_legacy_draw_blinn_phong(self.h, mesh, C.byref(uniforms), canvas_ldr, zbuffer),
                "shsb_legacy_draw_blinn_phong")
 
+    def legacy2_shadow_draw(self, mesh, model, light_vp, shadow_map, job_tile_w=0, job_tile_h=0):
+        """One object of the legacy render-target demos' shadow pass (draw_triangle_tile_shadow over every job tile)."""
+        m, lvp = (np.ascontiguousarray(a, dtype=np.float32).reshape(16) for a in (model, light_vp))
+        _check(self.lib, self.h, self.lib.shsb_legacy2_shadow_draw(self.h, mesh, capi.fptr(m), capi.fptr(lvp), job_tile_w, job_tile_h, shadow_map),
+               "shsb_legacy2_shadow_draw")
+
+    def legacy2_draw_softshadow(self, mesh, uniforms: "capi.Legacy2Uniforms", shadow_map, canvas_ldr, zbuffer):
+        """One object of the soft-shadow demo's lit pass (canvas and z-buffer in shs::Canvas order)."""
+        _check(self.lib, self.h, self.lib.shsb_legacy2_draw_softshadow(self.h, mesh, C.byref(uniforms), shadow_map, canvas_ldr, zbuffer),
+               "shsb_legacy2_draw_softshadow")
+
+    def legacy3_ibl_upload(self, irradiance, prefiltered) -> int:
+        """irradiance: (6, n, n, 3) float32; prefiltered: list of (6, n_m, n_m, 3) float32 mips."""
+        irr = np.ascontiguousarray(irradiance, dtype=np.float32)
+        sizes = np.array([m.shape[1] for m in prefiltered], np.int32)
+        pre = np.concatenate([np.ascontiguousarray(m, dtype=np.float32).reshape(-1) for m in prefiltered])
+        out = C.c_uint32()
+        _check(self.lib, self.h, self.lib.shsb_legacy3_ibl_upload(self.h, capi.fptr(irr), irr.shape[1], capi.fptr(pre), sizes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                                 len(sizes), C.byref(out)), "shsb_legacy3_ibl_upload")
+        return out.value
+
+    def legacy3_ibl_destroy(self, ibl):
+        _check(self.lib, self.h, self.lib.shsb_legacy3_ibl_destroy(self.h, ibl), "shsb_legacy3_ibl_destroy")
+
+    def legacy3_draw_pbr(self, mesh, uniforms: "capi.Legacy2Uniforms", shadow_map, ibl, canvas_ldr, depth_motion):
+        """One object of the PBR / IBL demo's lit pass (canvas, depth and velocity in shs::Canvas order)."""
+        _check(self.lib, self.h, self.lib.shsb_legacy3_draw_pbr(self.h, mesh, C.byref(uniforms), shadow_map, ibl, canvas_ldr, depth_motion),
+               "shsb_legacy3_draw_pbr")
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")
