@@ -335,16 +335,26 @@ namespace shsb
         L2_HD uint32_t hash_u32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
         L2_HD float hash01(uint32_t x) { return float(hash_u32(x) & 0x00FFFFFFu) / float(0x01000000u); }
 
-        L2_HD void poisson(int i, float& x, float& y) // POISSON_32 (:264-281); only the first 24 are ever read
+#define L2_POISSON_24                                                                                                                         \
+    {-0.613392f, 0.617481f}, {0.170019f, -0.040254f}, {-0.299417f, 0.791925f}, {0.645680f, 0.493210f}, {-0.651784f, 0.717887f},                \
+    {0.421003f, 0.027070f}, {-0.817194f, -0.271096f}, {-0.705374f, -0.668203f}, {0.977050f, -0.108615f}, {0.063326f, 0.142369f},               \
+    {0.203528f, 0.214331f}, {-0.667531f, 0.326090f}, {-0.098422f, -0.295755f}, {-0.885922f, 0.215369f}, {0.566637f, 0.605213f},                \
+    {0.039766f, -0.396100f}, {0.751946f, 0.453352f}, {0.078707f, -0.715323f}, {-0.075838f, -0.529344f}, {0.724479f, -0.580798f},               \
+    {0.222999f, -0.215125f}, {-0.467574f, -0.405438f}, {-0.248268f, -0.814753f}, {0.354411f, -0.887570f}
+        // POISSON_32 (:264-281); only the first 24 are ever read.  Constant bank on the device, a plain table on the host.
+        static const float h_poisson[24][2] = {L2_POISSON_24};
+#ifdef __CUDACC__
+        static __constant__ float c_poisson[24][2] = {L2_POISSON_24};
+#endif
+        L2_HD void poisson(int i, float& x, float& y)
         {
-            const float P[24][2] = {
-                {-0.613392f, 0.617481f}, {0.170019f, -0.040254f}, {-0.299417f, 0.791925f}, {0.645680f, 0.493210f}, {-0.651784f, 0.717887f},
-                {0.421003f, 0.027070f}, {-0.817194f, -0.271096f}, {-0.705374f, -0.668203f}, {0.977050f, -0.108615f}, {0.063326f, 0.142369f},
-                {0.203528f, 0.214331f}, {-0.667531f, 0.326090f}, {-0.098422f, -0.295755f}, {-0.885922f, 0.215369f}, {0.566637f, 0.605213f},
-                {0.039766f, -0.396100f}, {0.751946f, 0.453352f}, {0.078707f, -0.715323f}, {-0.075838f, -0.529344f}, {0.724479f, -0.580798f},
-                {0.222999f, -0.215125f}, {-0.467574f, -0.405438f}, {-0.248268f, -0.814753f}, {0.354411f, -0.887570f}};
-            x = P[i][0];
-            y = P[i][1];
+#ifdef __CUDA_ARCH__
+            x = c_poisson[i][0];
+            y = c_poisson[i][1];
+#else
+            x = h_poisson[i][0];
+            y = h_poisson[i][1];
+#endif
         }
 
         L2_HD float pcss_shadow_factor(const Draw& d, float u, float v, float z_receiver, float bias, int px, int py) // :333-445

@@ -87,3 +87,20 @@ def test_legacy_drop_in_parity_on_gpu():
     r = subprocess.run([LEGACY_BIN], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", ["legacy2_drop_in_test", "legacy3_drop_in_test"])
+def test_legacy2_drop_in_compiles_and_has_no_cpu_fallback(name):
+    """host/shs_b200/legacy2_drop_in.hpp compiled INTO the reference's render-target demo sources (hello_shadow_mapping_soft.cpp /
+    hello_pbr.cpp, main renamed): the reference side renders a non-trivial frame with the demo's own loops; without a device every
+    call of the binding refuses and nothing is rendered on the CPU.  (GPU half: tests/test_zz_gpu_legacy2.py.)"""
+    import torch
+    path = os.path.join(ROOT, "tests", "cpp", "_build", name)
+    if not os.path.isdir("/root/reference") and not os.path.exists(path):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([path], capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        assert r.returncode == 77 and "every call refused" in r.stdout and "reference side: 18598 of 30000 px covered" in r.stdout

@@ -162,3 +162,17 @@ def test_legacy2_error_behaviour(gpu):
     finally:
         for rt in (c_rt, z_small, z_ok, dm_ok, hdr):
             gpu.rt_destroy(rt)
+
+
+@pytest.mark.parametrize("name", ["legacy2_drop_in_test", "legacy3_drop_in_test"])
+def test_legacy2_drop_in_parity_on_gpu(name):
+    """The demos' own draw_triangle_tile_* loops on the CPU vs shs::b200::legacy2::Renderer fed with the same Uniforms objects
+    (tests/cpp/legacy2_drop_in_test.cpp): shadow map, z-buffer and velocity bit-equal, canvas within 1 LSB."""
+    import os
+    import subprocess
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", name)
+    if not os.path.exists(path):
+        pytest.skip(f"tests/cpp/_build/{name} was not built (needs /root/reference at build time)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
