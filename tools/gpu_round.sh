@@ -17,3 +17,7 @@ tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json
 python tools/bench_legacy.py 300 > $OUT/bench_legacy.jsonl 2> $OUT/bench_legacy.err; echo "legacy bench rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:legacy_ -s 8 -c 2 -f -o $OUT/legacy_kernels \
     python tools/bench_legacy.py 20 > $OUT/ncu_legacy.log 2>&1; echo "ncu legacy rc=$?"
+# legacy render-target demos (rows L2 / L3): parity + frames/s at the shipped sizes, and their kernels under ncu
+python tools/bench_legacy2.py 100 > $OUT/bench_legacy2.jsonl 2> $OUT/bench_legacy2.err; echo "legacy2 bench rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:legacy2_ -s 12 -c 4 -f -o $OUT/legacy2_kernels \
+    python tools/bench_legacy2.py 4 > $OUT/ncu_legacy2.log 2>&1; echo "ncu legacy2 rc=$?"
