@@ -38,7 +38,9 @@ def test_struct_layouts_match_header(tmp_path):
               "ShsbFrameParams": (capi.FrameParams, ["write_aovs", "motion_vectors_enable", "own_row_first", "own_row_stride"]),
               "ShsbMotionBlurParams": (capi.MotionBlurParams, ["depth_reject", "dt", "reserved"]),
               "ShsbLightShaftsParams": (capi.LightShaftsParams, ["decay", "cam_pos", "sun_dir_ws", "cam_viewproj"]),
-              "ShsbLegacyUniforms": (capi.LegacyUniforms, ["model", "camera_pos", "color", "job_tile_w", "job_tile_h"])}
+              "ShsbLegacyUniforms": (capi.LegacyUniforms, ["model", "camera_pos", "color", "job_tile_w", "job_tile_h"]),
+              "ShsbLegacy2Uniforms": (capi.Legacy2Uniforms, ["prev_mvp", "mv", "normal_mat", "light_vp", "light_dir_world", "camera_pos", "base_color", "use_texture",
+                                                             "albedo", "metallic", "ao", "ibl_diffuse_intensity", "ibl_reflection_strength", "job_tile_w", "job_tile_h"])}
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{os.path.join(ROOT, "include", "shsb.h")}"', "int main(void) {"]
     for cname, (_, fields) in probes.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -72,3 +74,35 @@ def test_built_for_sm_100a_only():
     out = os.popen(f"cuobjdump -lelf {capi.LIB_PATH} 2>/dev/null").read()
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_legacy2_wrappers_marshal_their_arguments_without_a_device():
+    """The numpy-facing wrappers of the legacy render-target demo entries (rows L2 / L3) called on a NULL context: every argument
+    must pass ctypes' conversion and the library must answer SHSB_E_INVALID_ARGUMENT (1) -- not crash, not compute.  Catches wrapper /
+    signature drift on the CPU box, where no context can be created."""
+    import ctypes as C
+
+    import numpy as np
+
+    from leisure_software_renderer_b200 import capi
+    from leisure_software_renderer_b200.renderer import Context
+
+    ctx = Context.__new__(Context)            # no device: skip __init__, keep the methods
+    ctx.lib, ctx.h, ctx._rt_shape = capi.load_library(), C.c_void_p(), {}
+    u = capi.Legacy2Uniforms()
+    u.mvp[:] = list(np.eye(4, dtype=np.float32).ravel())
+    u.base_color[:] = [1, 2, 3, 255]
+    u.albedo, u.use_texture, u.job_tile_w, u.job_tile_h = 3, 1, 160, 160
+    u.metallic, u.roughness, u.ao = 0.5, 0.25, 1.0
+    eye = np.eye(4)
+    irr = np.zeros((6, 2, 2, 3), np.float32)
+    calls = [lambda: ctx.legacy2_shadow_draw(1, eye, eye.astype(np.float32).ravel(), 2, 160, 160),
+             lambda: ctx.legacy2_draw_softshadow(1, u, 0, 2, 3),
+             lambda: ctx.legacy3_ibl_upload(irr, [np.zeros((6, 4, 4, 3), np.float32), np.zeros((6, 2, 2, 3), np.float32)]),
+             lambda: ctx.legacy3_ibl_destroy(1),
+             lambda: ctx.legacy3_draw_pbr(1, u, 2, 1, 3, 4)]
+    for call in calls:
+        with pytest.raises(capi.ShsbError, match="status 1"):
+            call()
+    ctx.h = None                              # keep __del__ from touching the library
+    assert C.sizeof(capi.Legacy2Uniforms) == 4 * (16 * 5 + 9 + 3 + 3) + 4 + 4 + 4 + 4 * 6 + 8
