@@ -23,6 +23,7 @@ REF_LIB = os.path.join(_HERE, "_ref", "libshs_ref.so")
 REF_LEGACY_LIB = os.path.join(_HERE, "_ref", "libshs_legacy_ref.so")
 REF_LEGACY2_LIB = os.path.join(_HERE, "_ref", "libshs_legacy2_ref.so")
 REF_LEGACY3_LIB = os.path.join(_HERE, "_ref", "libshs_legacy3_ref.so")
+REF_LIGHTCULL_LIB = os.path.join(_HERE, "_ref", "libshs_lightcull_ref.so")
 
 
 class Mesh(C.Structure):
@@ -470,3 +471,40 @@ class Legacy3Oracle:
             C.c_int32(w), C.c_int32(h), C.c_int32(tile_w), C.c_int32(tile_h), canvas.ctypes.data_as(u8), capi.fptr(zbuffer), capi.fptr(velocity))
         assert rc == 0, rc
         return canvas, zbuffer, velocity
+
+
+class LightCullReference:
+    """The reference's own light-list builders (lighting/jolt_light_culling.hpp:135-412) compiled with SHS_HAS_JOLT=1 against the
+    JoltPhysics declaration shim (oracle/jolt_shim) by oracle/ref_lightcull_harness.cpp.  A light is its world AABB (SHS space)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_LIGHTCULL_LIB):
+            build("reference")
+        self.lib = C.CDLL(REF_LIGHTCULL_LIB)
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_LIGHTCULL_LIB)
+
+    def bounds(self, aabbs):
+        """(n, 6) AABBs -> (n, 10): sphere centre xyz + radius, AABB min xyz, max xyz as SceneShape reports them."""
+        a = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        out = np.zeros((len(a), 10), np.float32)
+        assert self.lib.shsref_light_bounds(capi.fptr(a), C.c_uint32(len(a)), capi.fptr(out)) == 0
+        return out
+
+    def light_cull(self, aabbs, desc, range_min=None, range_max=None):
+        a = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+        lo = np.ascontiguousarray(range_min, dtype=np.float32).reshape(-1) if range_min is not None else None
+        hi = np.ascontiguousarray(range_max, dtype=np.float32).reshape(-1) if range_max is not None else None
+        bins, mx = desc.bins(), desc.max_per_bin
+        counts = np.zeros(bins, dtype=np.uint32)
+        indices = np.zeros((bins, mx), dtype=np.uint32)
+        vp = np.ascontiguousarray(np.frombuffer(bytes(desc.view_proj), dtype=np.float32))
+        rc = self.lib.shsref_light_cull(capi.fptr(a), C.c_uint32(len(a)), capi.fptr(vp), C.c_uint32(desc.viewport_w), C.c_uint32(desc.viewport_h),
+                                        C.c_uint32(desc.tile_size), C.c_uint32(mx), C.c_int32(desc.mode), C.c_uint32(desc.depth_slices),
+                                        C.c_float(desc.z_near), C.c_float(desc.z_far), capi.fptr(lo) if lo is not None else None,
+                                        capi.fptr(hi) if hi is not None else None, C.c_uint32(len(lo) if lo is not None else 0),
+                                        capi.u32ptr(counts), capi.u32ptr(indices))
+        assert rc == 0, rc
+        return counts, indices
