@@ -24,6 +24,7 @@ REF_LEGACY_LIB = os.path.join(_HERE, "_ref", "libshs_legacy_ref.so")
 REF_LEGACY2_LIB = os.path.join(_HERE, "_ref", "libshs_legacy2_ref.so")
 REF_LEGACY3_LIB = os.path.join(_HERE, "_ref", "libshs_legacy3_ref.so")
 REF_LIGHTCULL_LIB = os.path.join(_HERE, "_ref", "libshs_lightcull_ref.so")
+REF_TAA_LIB = os.path.join(_HERE, "_ref", "libshs_taa_ref.so")
 
 
 class Mesh(C.Structure):
@@ -508,3 +509,16 @@ class LightCullReference:
                                         capi.u32ptr(counts), capi.u32ptr(indices))
         assert rc == 0, rc
         return counts, indices
+
+
+def reference_pass_taa(ldr, history, history_valid):
+    """The reference's own PassTemporalAAAdapter (pipeline/pass_adapters.hpp:1402-1491, compiled by oracle/ref_taa_harness.cpp against
+    the JoltPhysics declaration shim); in place on ldr / history (H, W, 4) uint8 like Oracle.pass_taa."""
+    if not os.path.exists(REF_TAA_LIB):
+        build("reference")
+    lib = C.CDLL(REF_TAA_LIB)
+    assert ldr.dtype == np.uint8 and history.dtype == np.uint8 and ldr.flags.c_contiguous and history.flags.c_contiguous and ldr.shape == history.shape
+    u8 = C.POINTER(C.c_uint8)
+    rc = lib.shsref_pass_taa(ldr.ctypes.data_as(u8), history.ctypes.data_as(u8), C.c_int32(int(history_valid)), C.c_int32(ldr.shape[1]), C.c_int32(ldr.shape[0]))
+    assert rc == 0, rc
+    return ldr, history

@@ -12,11 +12,16 @@
 // oracle/_ref/libshs_ref.so (oracle/ref_harness.cpp = the reference's own headers compiled
 // from /root/reference) is run on the same inputs by tests/test_oracle_vs_reference.py
 // (bit-exact HDR/depth/shadow/LDR/stats) and the resulting fixtures are committed under
-// tests/golden/.  Two parts have NO compilable reference and stay "parity unpinned":
-//   * tile light lists (A11): lighting/jolt_light_culling.hpp + geometry/jolt_culling.hpp are
-//     guarded by SHS_HAS_JOLT and need JoltPhysics v5.2.0 (absent); restated line by line here.
+// tests/golden/.  The tile / depth-range / clustered light lists (A11; lighting/jolt_light_culling.hpp +
+// geometry/jolt_culling.hpp) and the temporal-AA adapter (pipeline/pass_adapters.hpp) are guarded by
+// SHS_HAS_JOLT and need JoltPhysics v5.2.0 (absent): they are pinned against the reference's headers compiled
+// with a JoltPhysics DECLARATION shim (oracle/jolt_shim, oracle/ref_lightcull_harness.cpp,
+// oracle/ref_taa_harness.cpp; tests/test_light_cull_pinned_cpu.py, tests/test_post_passes_cpu.py) --
+// the headers use Jolt only to turn a light's shape into bounds, and bounds are an input here.
+// One part has NO compilable reference and stays "parity unpinned":
 //   * the Forward+ per-fragment local-light loop (A9): exists only as GLSL
-//     (shaders/vulkan/fp_stress_scene.frag:421-523,644-678); this file DEFINES the CPU semantics.
+//     (shaders/vulkan/fp_stress_scene.frag:421-523,644-678); this file DEFINES the CPU semantics
+//     (and likewise the per-tile depth reduce, a GLSL compute shader in the reference).
 //
 // All arithmetic is IEEE-754 binary32, round-to-nearest, no FMA (-ffp-contract=off), evaluated
 // in the order the reference (and GLM's scalar path, see oracle/glm_shim/glm/glm.hpp) evaluates it.
@@ -1614,7 +1619,7 @@ namespace
 
 // All four bin builders of lighting/jolt_light_culling.hpp share one loop: mode 0 = cull_lights_tiled (:135-187),
 // 1 = cull_lights_tiled_depth01_range (:196-258), 2 = cull_lights_tiled_view_depth_range (:261-324),
-// 3 = cull_lights_clustered (:341-412; bin = cz * tiles + ty * tiles_x + tx).  Restated; the headers need Jolt.
+// 3 = cull_lights_clustered (:341-412; bin = cz * tiles + ty * tiles_x + tx).  Pinned through oracle/ref_lightcull_harness.cpp.
 static int32_t light_cull_bins(const void* records160, uint32_t n_lights, const float view_proj[16],
                                uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_tile,
                                int mode, uint32_t n_slices, const float* range_min, const float* range_max, float z_near, float z_far,

@@ -109,7 +109,8 @@ SHSO_FN(int32_t, pass_light_shafts, (const ShsbLightShaftsParams* p, const uint8
 
 #undef SHSO_FN
 
-/* ---- restatement-only entry points (no compilable reference: Jolt-guarded headers / GLSL spec) ---- */
+/* ---- entry points without a twin in ref_harness.cpp: the light-list builders and TAA are pinned through the Jolt declaration
+ * shim (ref_lightcull_harness.cpp / ref_taa_harness.cpp); the depth reduce and the Forward+ fragment loop follow a GLSL spec ---- */
 
 /* cull_lights_tiled, lighting/jolt_light_culling.hpp:135-187 over CullingLightGPU cull_sphere/cull_aabb.
  * counts[T] uncapped; indices[T*max_per_tile] first max_per_tile entries, ascending. */

@@ -1,6 +1,7 @@
 """CPU suite for the depth-range / clustered bin builders.  The reference's headers for these
-(lighting/jolt_light_culling.hpp) need JoltPhysics, so parity is UNPINNED: the restatement is checked through structural
-properties that follow from the reference's definition, and committed as a fixture for the GPU box."""
+(lighting/jolt_light_culling.hpp) need JoltPhysics; they are pinned in tests/test_light_cull_pinned_cpu.py (compiled against a
+JoltPhysics declaration shim).  Here: structural properties that follow from the reference's definition, the per-tile depth reduce
+(defined by this repository: the reference has it only as GLSL), and the fixture for the GPU box."""
 import os
 
 import numpy as np

@@ -49,8 +49,8 @@ def test_post_goldens(port):
 
 
 def test_taa_restatement_properties(port):
-    """PassTemporalAAAdapter has no compilable reference (pass_adapters.hpp needs Jolt): the restatement is checked
-    against an independent numpy statement of pass_adapters.hpp:1471-1489."""
+    """The restatement against an independent numpy statement of pass_adapters.hpp:1471-1489 (the pin against the compiled
+    reference is test_taa_restatement_equals_the_reference below)."""
     frames = post_cases.taa_frames()
     hist = np.zeros_like(frames[0])
     valid = False
@@ -67,3 +67,37 @@ def test_taa_restatement_properties(port):
         port.pass_taa(cur, hist, valid)
         valid = True
         assert np.array_equal(cur, want) and np.array_equal(hist, want_hist)
+
+
+def test_taa_restatement_equals_the_reference(port):
+    """PINNED: the reference's own PassTemporalAAAdapter (pipeline/pass_adapters.hpp:1402-1491) compiled against the JoltPhysics
+    declaration shim (oracle/ref_taa_harness.cpp) vs the restatement, frame after frame with the history carried over -- including
+    every (current, history) byte pair at least once (a 256 x 256 frame), so the rounding rule is covered exhaustively."""
+    import os
+
+    from oracle import bindings
+    if not os.path.exists(bindings.REF_TAA_LIB) and not os.path.isdir("/root/reference"):
+        pytest.skip("oracle/_ref/libshs_taa_ref.so not built and /root/reference absent")
+    for frames in (post_cases.taa_frames(), post_cases.taa_frames(w=33, h=7, n=6, seed=3)):
+        hp, hr = np.zeros_like(frames[0]), np.zeros_like(frames[0])
+        valid = False
+        for f in frames:
+            a, b = f.copy(), f.copy()
+            port.pass_taa(a, hp, valid)
+            bindings.reference_pass_taa(b, hr, valid)
+            valid = True
+            assert np.array_equal(a, b) and np.array_equal(hp, hr)
+    cur = np.zeros((256, 256, 4), np.uint8)
+    cur[..., 0] = np.arange(256)[:, None]
+    cur[..., 1] = np.arange(256)[:, None]
+    cur[..., 2] = 255 - np.arange(256)[:, None]
+    cur[..., 3] = 77
+    hist = np.zeros((256, 256, 4), np.uint8)
+    hist[..., 0] = np.arange(256)[None, :]
+    hist[..., 1] = 255 - np.arange(256)[None, :]
+    hist[..., 2] = np.arange(256)[None, :]
+    hist[..., 3] = 255
+    a, b, hp, hr = cur.copy(), cur.copy(), hist.copy(), hist.copy()
+    port.pass_taa(a, hp, True)
+    bindings.reference_pass_taa(b, hr, True)
+    assert np.array_equal(a, b) and np.array_equal(hp, hr) and not np.array_equal(a, cur)
