@@ -538,6 +538,32 @@ SHSB_API int32_t shsb_legacy3_ibl_destroy(shsb_ctx ctx, shsb_ibl ibl);
 SHSB_API int32_t shsb_legacy3_draw_pbr(shsb_ctx ctx, shsb_mesh mesh, const ShsbLegacy2Uniforms* uniforms, shsb_rt shadow_map, shsb_ibl ibl,
                                        shsb_rt canvas_ldr, shsb_rt depth_motion);
 
+/* ------------------------------------------------------------------ scene-level culling upstream of the path
+ *
+ * The two data-parallel steps the reference runs on the CPU right before draw submission.  Synchronous host-buffer calls (upload,
+ * kernels, download): they sit outside the frame pipeline.  The strictly serial software-occlusion loop
+ * (geometry/culling_software.hpp) is not offered. */
+
+/* cull_vs_frustum over FastCullable + HasWorldAABB objects (geometry/jolt_culling.hpp:279-306; classify_vs_frustum :258-275) against
+ * extract_frustum_planes(view_proj) (geometry/frustum_culling.hpp:47-65).
+ * bounds10: n x (bounding-sphere centre xyz, radius, world AABB min xyz, max xyz) = SceneShape::bounding_sphere / world_aabb
+ *           (geometry/scene_shape.hpp:56-81; the Jolt shape -> bounds step stays with the caller).
+ * out_classes[n]: CullClass (0 outside, 1 intersecting, 2 inside); out_visible[<= n]: CullResult::visible_indices (ascending);
+ * out_counts5: tested, outside, intersecting, inside, visible. */
+SHSB_API int32_t shsb_cull_objects_frustum(shsb_ctx ctx, const float* bounds10, uint32_t n_objects, const float view_proj[16],
+                                           uint8_t* out_classes, uint32_t* out_visible, uint32_t out_counts5[5]);
+
+enum ShsbLightObjectCullMode { SHSB_LIGHT_OBJECT_CULL_NONE = 0, SHSB_LIGHT_OBJECT_CULL_SPHERE_AABB = 1, SHSB_LIGHT_OBJECT_CULL_VOLUME_AABB = 2 }; /* lighting/light_runtime.hpp:24-29 */
+
+/* collect_object_lights (lighting/light_runtime.hpp:592-616) for n_objects objects at once: per object the up-to-8 nearest lights
+ * (kLightSelectionCapacity) among those of `visible_lights` (visited in order; entries >= n_lights are skipped) that affect its
+ * AABB under `cull_mode`, in the reference's slot order (add_light_candidate :263-289).
+ * records160: CullingLightGPU records (LightInstance::packed; position_range.xyz is the light position).
+ * out_counts[n_objects], out_indices8[n_objects * 8], out_dist2_8[n_objects * 8] (unused slots zero). */
+SHSB_API int32_t shsb_collect_object_lights(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible_lights,
+                                            uint32_t n_visible, const void* records160, uint32_t n_lights, int32_t cull_mode,
+                                            uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,6 +298,7 @@ struct shsb_context_t
     DevBuf<float> d_post_luma;
     DevBuf<uchar4> d_taa_hist;      // TemporalAARuntimeState::history (core/context.hpp:101)
     DevBuf<LegacyTri> d_legacy_tris; // set-up records of the legacy tile-job variant (legacy.cu)
+    DevBuf<uint8_t> d_sc_bytes;      // scratch of the scene-level culling calls (scene_cull.cu): inputs and outputs, one allocation
     DevBuf<l2::RasterRec> d_l2_raster; // slot records of the legacy render-target demos (legacy2.cu)
     DevBuf<l2::BoxRec> d_l2_box;
     DevBuf<l2::ShadeRec> d_l2_shade;
@@ -1192,6 +1193,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_range_min.p); cudaFree(ctx->d_range_max.p); cudaFree(ctx->d_range_up_min.p); cudaFree(ctx->d_range_up_max.p);
     cudaFree(ctx->d_slice_ndc.p); cudaFree(ctx->d_vis.p); cudaFree(ctx->cluster_lists.counts.p); cudaFree(ctx->cluster_lists.indices.p);
     cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p); cudaFree(ctx->d_legacy_tris.p);
+    cudaFree(ctx->d_sc_bytes.p);
     cudaFree(ctx->d_l2_raster.p); cudaFree(ctx->d_l2_box.p); cudaFree(ctx->d_l2_shade.p);
     for (auto& e : ctx->ibls) { cudaFree(e.irradiance); cudaFree(e.prefiltered); }
     for (auto& l : ctx->d_lights) cudaFree(l.p);
@@ -1736,6 +1738,59 @@ SHSB_API int32_t shsb_legacy3_draw_pbr(shsb_ctx ctx, shsb_mesh mesh_h, const Shs
     wait_pending_read(ctx, dm);
     dm->motion_dirty = true;
     return legacy2_launch(ctx, d, (uchar4*)canvas->color, dm->depth, dm->motion);
+}
+
+// ---------------------------------------------------------------------------------------- scene-level culling
+namespace
+{
+    inline size_t sc_align(size_t n) { return (n + 255) & ~(size_t)255; }
+}
+
+SHSB_API int32_t shsb_cull_objects_frustum(shsb_ctx ctx, const float* bounds10, uint32_t n, const float view_proj[16], uint8_t* out_classes, uint32_t* out_visible,
+                                           uint32_t out_counts5[5])
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if ((n && (!bounds10 || !out_classes || !out_visible)) || !view_proj || !out_counts5) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    float planes[24];
+    hm::frustum_planes(hm::load(view_proj), planes); // extract_frustum_planes, on the host like the light-list builders' pre-filter
+    const size_t o_bounds = 0, o_classes = sc_align((size_t)n * 40), o_visible = o_classes + sc_align(n), o_counts = o_visible + sc_align((size_t)n * 4);
+    if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, o_counts + 256)) return rc;
+    uint8_t* base = ctx->d_sc_bytes.p;
+    if (n) CK(cudaMemcpyAsync(base + o_bounds, bounds10, (size_t)n * 40, cudaMemcpyHostToDevice, ctx->stream));
+    launch_cull_objects((const float*)(base + o_bounds), n, planes, base + o_classes, (uint32_t*)(base + o_visible), (uint32_t*)(base + o_counts), ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_counts5, base + o_counts, 20, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(out_classes, base + o_classes, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out_counts5[4]) CK(cudaMemcpy(out_visible, base + o_visible, (size_t)out_counts5[4] * 4, cudaMemcpyDeviceToHost));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_collect_object_lights(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible_lights, uint32_t n_visible,
+                                            const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if ((n_objects && (!object_aabbs6 || !out_counts || !out_indices8 || !out_dist2_8)) || (n_visible && !visible_lights) || (n_lights && !records160))
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+    if (cull_mode < SHSB_LIGHT_OBJECT_CULL_NONE || cull_mode > SHSB_LIGHT_OBJECT_CULL_VOLUME_AABB) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "unknown LightObjectCullMode %d", cull_mode);
+    if (n_objects == 0) return SHSB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t o_boxes = 0, o_vis = sc_align((size_t)n_objects * 24), o_recs = o_vis + sc_align((size_t)n_visible * 4), o_counts = o_recs + sc_align((size_t)n_lights * 160);
+    const size_t o_idx = o_counts + sc_align((size_t)n_objects * 4), o_d2 = o_idx + sc_align((size_t)n_objects * 32), total = o_d2 + sc_align((size_t)n_objects * 32);
+    if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, total)) return rc;
+    uint8_t* base = ctx->d_sc_bytes.p;
+    CK(cudaMemcpyAsync(base + o_boxes, object_aabbs6, (size_t)n_objects * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_visible) CK(cudaMemcpyAsync(base + o_vis, visible_lights, (size_t)n_visible * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_lights) CK(cudaMemcpyAsync(base + o_recs, records160, (size_t)n_lights * 160, cudaMemcpyHostToDevice, ctx->stream));
+    launch_collect_object_lights((const float*)(base + o_boxes), n_objects, (const uint32_t*)(base + o_vis), n_visible, (const float*)(base + o_recs), n_lights, cull_mode,
+                                 (uint32_t*)(base + o_counts), (uint32_t*)(base + o_idx), (float*)(base + o_d2), ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_counts, base + o_counts, (size_t)n_objects * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_indices8, base + o_idx, (size_t)n_objects * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_dist2_8, base + o_d2, (size_t)n_objects * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
 }
 
 // ---------------------------------------------------------------------------------------- passes

@@ -1,0 +1,91 @@
+// scene_cull.cu -- scene-level culling steps upstream of draw submission: objects against the camera
+// frustum (cull_vs_frustum, geometry/jolt_culling.hpp:279-306: classes, the ordered visible list, the four counters) and per-object
+// light selection (collect_object_lights, lighting/light_runtime.hpp:592-616).  Arithmetic in scene_cull_core.cuh; --fmad=false.
+// The software-occlusion loop of culling_software.hpp is strictly serial (each object's test reads the depth the previous ones
+// wrote) and is not part of this file.
+#include "shsb_dev.cuh"
+#include "scene_cull_core.cuh"
+
+namespace shsb
+{
+    namespace
+    {
+        struct Planes { float p[24]; };
+
+        __global__ void __launch_bounds__(256) classify_objects_kernel(const float* __restrict__ bounds10, uint32_t n, const Planes planes, uint8_t* __restrict__ classes)
+        {
+            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            float b[10];
+            for (int k = 0; k < 10; ++k) b[k] = bounds10[(size_t)i * 10 + k];
+            classes[i] = (uint8_t)sc::classify_object(b, planes.p);
+        }
+
+        // one CTA: the visible list keeps object order (CullResult::visible_indices is filled by a serial loop), so the compaction is
+        // an ordered ballot scan over 1024 objects per round; counts[0..3] = tested, outside, intersecting, inside
+        __global__ void __launch_bounds__(1024) compact_visible_kernel(const uint8_t* __restrict__ classes, uint32_t n, uint32_t* __restrict__ visible, uint32_t* __restrict__ counts)
+        {
+            __shared__ uint32_t s_warp[32];
+            __shared__ uint32_t s_base;
+            __shared__ uint32_t s_cls[3];
+            if (threadIdx.x == 0) { s_base = 0; s_cls[0] = s_cls[1] = s_cls[2] = 0; }
+            __syncthreads();
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (uint32_t base = 0; base < n; base += 1024)
+            {
+                const uint32_t i = base + threadIdx.x;
+                const int c = (i < n) ? (int)classes[i] : -1;
+                const bool vis = c == sc::INTERSECTING || c == sc::INSIDE;
+                const unsigned ballot = __ballot_sync(0xffffffffu, vis);
+                if (lane == 0) s_warp[warp] = __popc(ballot);
+                if (c >= 0) atomicAdd(&s_cls[c], 1u);
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    uint32_t acc = s_base;
+                    for (int w = 0; w < 32; ++w) { const uint32_t k = s_warp[w]; s_warp[w] = acc; acc += k; }
+                    s_base = acc;
+                }
+                __syncthreads();
+                if (vis) visible[s_warp[warp] + __popc(ballot & ((1u << lane) - 1u))] = i;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) { counts[0] = n; counts[1] = s_cls[0]; counts[2] = s_cls[1]; counts[3] = s_cls[2]; counts[4] = s_base; }
+        }
+
+        __global__ void __launch_bounds__(128) collect_object_lights_kernel(const float* __restrict__ boxes6, uint32_t n_objects, const uint32_t* __restrict__ visible,
+                                                                             uint32_t n_visible, const float* __restrict__ records, uint32_t n_lights, int mode,
+                                                                             uint32_t* __restrict__ out_counts, uint32_t* __restrict__ out_idx, float* __restrict__ out_d2)
+        {
+            const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+            if (o >= n_objects) return;
+            float box[6];
+            for (int k = 0; k < 6; ++k) box[k] = boxes6[(size_t)o * 6 + k];
+            uint32_t idx[sc::LIGHT_SELECTION_CAPACITY];
+            float d2[sc::LIGHT_SELECTION_CAPACITY];
+            out_counts[o] = sc::collect_lights(box, visible, n_visible, records, n_lights, mode, idx, d2);
+            for (uint32_t k = 0; k < sc::LIGHT_SELECTION_CAPACITY; ++k)
+            {
+                out_idx[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = idx[k];
+                out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = d2[k];
+            }
+        }
+    }
+
+    void launch_cull_objects(const float* bounds10, uint32_t n, const float planes24[24], uint8_t* classes, uint32_t* visible, uint32_t* counts5, cudaStream_t s, uint64_t* launches)
+    {
+        Planes pl;
+        for (int i = 0; i < 24; ++i) pl.p[i] = planes24[i];
+        if (n) classify_objects_kernel<<<(n + 255) / 256, 256, 0, s>>>(bounds10, n, pl, classes);
+        compact_visible_kernel<<<1, 1024, 0, s>>>(classes, n, visible, counts5);
+        if (launches) *launches += n ? 2 : 1;
+    }
+
+    void launch_collect_object_lights(const float* boxes6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float* records, uint32_t n_lights, int mode,
+                                      uint32_t* out_counts, uint32_t* out_idx, float* out_d2, cudaStream_t s, uint64_t* launches)
+    {
+        if (n_objects == 0) return;
+        collect_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, records, n_lights, mode, out_counts, out_idx, out_d2);
+        if (launches) *launches += 1;
+    }
+}

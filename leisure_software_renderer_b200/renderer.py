@@ -200,6 +200,26 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_legacy3_draw_pbr(self.h, mesh, C.byref(uniforms), shadow_map, ibl, canvas_ldr, depth_motion),
                "shsb_legacy3_draw_pbr")
 
+    def cull_objects_frustum(self, bounds10, view_proj):
+        """cull_vs_frustum over objects given as (n, 10) sphere + AABB bounds: classes (n,) uint8, visible indices, counts
+        (tested, outside, intersecting, inside, visible)."""
+        b = np.ascontiguousarray(bounds10, dtype=np.float32).reshape(-1, 10)
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        classes, visible, counts = np.zeros(len(b), np.uint8), np.zeros(max(1, len(b)), np.uint32), np.zeros(5, np.uint32)
+        _check(self.lib, self.h, self.lib.shsb_cull_objects_frustum(self.h, capi.fptr(b), len(b), capi.fptr(vp), classes.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                                   capi.u32ptr(visible), capi.u32ptr(counts)), "shsb_cull_objects_frustum")
+        return classes, visible[:int(counts[4])].copy(), counts
+
+    def collect_object_lights(self, object_aabbs, visible, records, cull_mode):
+        """collect_object_lights per object: counts (n,), light indices (n, 8), squared distances (n, 8)."""
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        v = np.ascontiguousarray(visible, dtype=np.uint32).reshape(-1)
+        r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
+        counts, idx, d2 = np.zeros(len(a), np.uint32), np.zeros((len(a), 8), np.uint32), np.zeros((len(a), 8), np.float32)
+        _check(self.lib, self.h, self.lib.shsb_collect_object_lights(self.h, capi.fptr(a), len(a), capi.u32ptr(v), len(v), r.ctypes.data_as(C.c_void_p), len(r), int(cull_mode),
+                                                                    capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2)), "shsb_collect_object_lights")
+        return counts, idx, d2
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")

@@ -522,3 +522,36 @@ def reference_pass_taa(ldr, history, history_valid):
     rc = lib.shsref_pass_taa(ldr.ctypes.data_as(u8), history.ctypes.data_as(u8), C.c_int32(int(history_valid)), C.c_int32(ldr.shape[1]), C.c_int32(ldr.shape[0]))
     assert rc == 0, rc
     return ldr, history
+
+
+class SceneCull:
+    """Scene-level steps upstream of draw submission: "port" = oracle/oracle_scene_cull.cpp, "reference" = the
+    reference's cull_vs_frustum / collect_object_lights compiled by oracle/ref_lightcull_harness.cpp (Jolt declaration shim)."""
+
+    def __init__(self, kind="port"):
+        assert kind in ("port", "reference")
+        path = PORT_LIB if kind == "port" else REF_LIGHTCULL_LIB
+        if not os.path.exists(path):
+            build(kind)
+        self.kind, self.lib, self.prefix = kind, C.CDLL(path), ("shso_" if kind == "port" else "shsref_")
+
+    def cull_objects(self, bounds, view_proj):
+        """bounds: (n, 10) sphere + AABB for the port, (n, 6) AABBs for the reference (it derives the sphere itself).
+        Returns classes (n,) uint8, visible indices, counts (tested, outside, intersecting, inside, visible)."""
+        b = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 10 if self.kind == "port" else 6)
+        vp = np.ascontiguousarray(view_proj, dtype=np.float32).reshape(16)
+        classes, visible, counts = np.zeros(len(b), np.uint8), np.zeros(max(1, len(b)), np.uint32), np.zeros(5, np.uint32)
+        rc = getattr(self.lib, self.prefix + "cull_objects")(capi.fptr(b), C.c_uint32(len(b)), capi.fptr(vp), classes.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                             capi.u32ptr(visible), capi.u32ptr(counts))
+        assert rc == 0, rc
+        return classes, visible[:int(counts[4])].copy(), counts
+
+    def collect_object_lights(self, object_aabbs, visible, records, cull_mode):
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        v = np.ascontiguousarray(visible, dtype=np.uint32).reshape(-1)
+        r = _records_u8(records)
+        counts, idx, d2 = np.zeros(len(a), np.uint32), np.zeros((len(a), 8), np.uint32), np.zeros((len(a), 8), np.float32)
+        rc = getattr(self.lib, self.prefix + "collect_object_lights")(capi.fptr(a), C.c_uint32(len(a)), capi.u32ptr(v), C.c_uint32(len(v)), r.ctypes.data_as(C.c_void_p),
+                                                                      C.c_uint32(len(r)), C.c_int32(cull_mode), capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2))
+        assert rc == 0, rc
+        return counts, idx, d2

@@ -7,6 +7,8 @@
 // obtain a light's world bounds (SceneShape::bounding_sphere / world_aabb); a light is therefore a shim Shape that carries its
 // world AABox.  Everything the lists depend on after that point is the reference's code.  The bounds the reference derived
 // (sphere + AABB in SHS space, after its LH <-> RH conversions) are returned so that the restatement is fed the same numbers.
+// Also here, compiled the same way: cull_vs_frustum over SceneShapes (geometry/jolt_culling.hpp:279-306)
+// and collect_object_lights (lighting/light_runtime.hpp:592-616).
 // Built by oracle/Makefile (`make ref`) into oracle/_ref/libshs_lightcull_ref.so.
 #include <cstdint>
 #include <cstring>
@@ -14,6 +16,7 @@
 
 #define SHS_HAS_JOLT 1
 #include "shs/lighting/jolt_light_culling.hpp"
+#include "shs/lighting/light_runtime.hpp"
 
 namespace
 {
@@ -90,5 +93,55 @@ extern "C"
         case 3: write_lists(shs::cull_lights_clustered(shapes, vp, w, h, tile_size, depth_slices, z_near, z_far).cluster_light_lists, max_per_bin, counts, indices); return 0;
         default: return 1;
         }
+    }
+}
+
+extern "C"
+{
+    // cull_vs_frustum(objects, extract_frustum_planes(view_proj)); objects enter as world AABBs like the lights above.
+    int32_t shsref_cull_objects(const float* aabb6, uint32_t n, const float view_proj[16], uint8_t* classes, uint32_t* visible, uint32_t counts5[5])
+    {
+        if (!view_proj || !classes || !visible || !counts5) return 1;
+        Lights L(aabb6, n);
+        glm::mat4 vp;
+        std::memcpy(&vp, view_proj, 64);
+        const shs::Frustum fr = shs::extract_frustum_planes(vp);
+        const shs::CullResult r = shs::cull_vs_frustum(std::span<const shs::SceneShape>(L.scene.data(), L.scene.size()), fr);
+        for (uint32_t i = 0; i < n; ++i) classes[i] = (uint8_t)r.classes[i];
+        for (size_t i = 0; i < r.visible_indices.size(); ++i) visible[i] = (uint32_t)r.visible_indices[i];
+        counts5[0] = (uint32_t)r.tested; counts5[1] = (uint32_t)r.outside; counts5[2] = (uint32_t)r.intersecting; counts5[3] = (uint32_t)r.inside;
+        counts5[4] = (uint32_t)r.visible_indices.size();
+        return 0;
+    }
+
+    // collect_object_lights per object.  records160: CullingLightGPU records -> LightInstance::packed; LightProperties::position_ws is
+    // set from position_range.xyz (what the reference's packers copy there).  The light scene is the identity mapping
+    // (scene element i -> user_index i), so `visible` holds light indices.
+    int32_t shsref_collect_object_lights(const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const void* records160, uint32_t n_lights,
+                                         int32_t cull_mode, uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8)
+    {
+        if (!out_counts || !out_indices8 || !out_dist2_8 || cull_mode < 0 || cull_mode > 2) return 1;
+        static_assert(sizeof(shs::CullingLightGPU) == 160, "CullingLightGPU is 160 bytes");
+        static_assert(shs::kLightSelectionCapacity == 8u, "LightSelection holds 8 lights");
+        std::vector<shs::LightInstance> lights(n_lights);
+        shs::SceneElementSet light_scene;
+        for (uint32_t i = 0; i < n_lights; ++i)
+        {
+            std::memcpy(&lights[i].packed, (const uint8_t*)records160 + (size_t)i * 160, 160);
+            lights[i].props.position_ws = glm::vec3(lights[i].packed.position_range);
+            shs::SceneElement e{};
+            e.user_index = i;
+            light_scene.add(e);
+        }
+        for (uint32_t o = 0; o < n_objects; ++o)
+        {
+            shs::AABB box{};
+            box.minv = glm::vec3(object_aabbs6[6 * o], object_aabbs6[6 * o + 1], object_aabbs6[6 * o + 2]);
+            box.maxv = glm::vec3(object_aabbs6[6 * o + 3], object_aabbs6[6 * o + 4], object_aabbs6[6 * o + 5]);
+            const shs::LightSelection sel = shs::collect_object_lights(box, std::span<const uint32_t>(visible, n_visible), light_scene, lights, (shs::LightObjectCullMode)cull_mode);
+            out_counts[o] = sel.count;
+            for (uint32_t k = 0; k < 8; ++k) { out_indices8[8 * o + k] = sel.indices[k]; out_dist2_8[8 * o + k] = sel.dist2[k]; }
+        }
+        return 0;
     }
 }

@@ -1,0 +1,48 @@
+// tests/cpp/scene_cull_emul.cpp -- TEST INFRASTRUCTURE ONLY.  The device functions of leisure_software_renderer_b200/csrc/scene_cull_core.cuh
+// compiled by g++ (-ffp-contract=off == nvcc --fmad=false) and driven like scene_cull.cu drives them (one object per thread; an
+// ordered compaction of the non-outside objects), with the C signatures of oracle/oracle_scene_cull.cpp under the prefix shsemu_.
+// Nothing in the product links or loads it.
+#include <cmath>
+#include <cstring>
+#include "scene_cull_core.cuh"
+
+using namespace shsb::sc;
+
+extern "C"
+{
+    int32_t shsemu_cull_objects(const float* bounds10, uint32_t n, const float view_proj[16], uint8_t* classes, uint32_t* visible, uint32_t counts5[5])
+    {
+        // the planes are computed on the host by the product too (hm::frustum_planes in api.cu); restated here in the same order
+        const float* m = view_proj;
+        const float r0[4] = {m[0], m[4], m[8], m[12]}, r1[4] = {m[1], m[5], m[9], m[13]}, r2[4] = {m[2], m[6], m[10], m[14]}, r3[4] = {m[3], m[7], m[11], m[15]};
+        const float* rows[3] = {r0, r1, r2};
+        float planes[24];
+        for (int i = 0; i < 6; ++i)
+        {
+            float eq[4];
+            for (int k = 0; k < 4; ++k) eq[k] = (i & 1) ? (r3[k] - rows[i / 2][k]) : (r3[k] + rows[i / 2][k]);
+            const float len = std::sqrt(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2]);
+            if (len <= 1e-8f) { planes[4 * i] = 0; planes[4 * i + 1] = 1; planes[4 * i + 2] = 0; planes[4 * i + 3] = eq[3]; }
+            else { planes[4 * i] = eq[0] / len; planes[4 * i + 1] = eq[1] / len; planes[4 * i + 2] = eq[2] / len; planes[4 * i + 3] = eq[3] / len; }
+        }
+        uint32_t cnt[3] = {0, 0, 0}, nv = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            const int c = classify_object(bounds10 + (size_t)i * 10, planes);
+            classes[i] = (uint8_t)c;
+            ++cnt[c];
+            if (c != OUTSIDE) visible[nv++] = i;
+        }
+        counts5[0] = n; counts5[1] = cnt[0]; counts5[2] = cnt[1]; counts5[3] = cnt[2]; counts5[4] = nv;
+        return 0;
+    }
+
+    int32_t shsemu_collect_object_lights(const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const void* records160, uint32_t n_lights,
+                                         int32_t cull_mode, uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8)
+    {
+        for (uint32_t o = 0; o < n_objects; ++o)
+            out_counts[o] = collect_lights(object_aabbs6 + (size_t)o * 6, visible, n_visible, (const float*)records160, n_lights, cull_mode, out_indices8 + (size_t)o * 8,
+                                           out_dist2_8 + (size_t)o * 8);
+        return 0;
+    }
+}

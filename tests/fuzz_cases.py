@@ -180,3 +180,30 @@ def legacy3_scene(seed):
         sc["prefiltered"] = [rng.uniform(0, 4.0, (6, max(1, base >> m), max(1, base >> m), 3)).astype(np.float32) for m in range(n_mips)]
     sc["ibl_k"] = (float(rng.uniform(-0.2, 1.4)), float(rng.uniform(-0.2, 1.4)), float(rng.uniform(0, 1.2)))
     return sc
+
+
+def scene_cull(seed):
+    """Random inputs of the scene-level steps upstream of draw submission: object AABBs around / inside / behind
+    the camera frustum (thin slabs, huge boxes that contain the camera, point-sized boxes, boxes touching a plane), a camera, a
+    light set and a visible-light list with repeats, gaps and out-of-range entries; ties in distance come from lights sharing a position.
+    Returns dict(aabbs (n, 6), view_proj, lights, visible, n_lights)."""
+    rng = np.random.default_rng(29000 + seed)
+    n = int(rng.integers(1, 400))
+    ext = float(rng.choice([3.0, 15.0, 60.0]))
+    c = rng.uniform(-ext, ext, (n, 3)) * np.array([1, 0.4, 1])
+    half = np.abs(rng.normal(0, 1, (n, 3))) * rng.choice([0.01, 0.5, 3.0, 30.0], (n, 1)) * rng.choice([1.0, 1.0, 0.02], (n, 3))
+    half[rng.random(n) < 0.05] = 0.0
+    aabbs = np.concatenate([c - half, c + half], axis=1).astype(np.float32)
+    eye = tuple(float(v) for v in rng.uniform(-ext, ext, 3) * np.array([1, 0.3, 1]))
+    tgt = tuple(float(v) for v in rng.uniform(-ext / 2, ext / 2, 3))
+    zn, zf = float(rng.choice([0.05, 0.1, 1.0])), float(rng.choice([15.0, 100.0, 1000.0]))
+    vp = scenes.camera_viewproj(eye, tgt, (0.0, 1.0, 0.0), float(np.radians(rng.uniform(30, 110))), float(rng.uniform(0.6, 2.2)), zn, zf)
+    nl = int(rng.integers(1, 200))
+    lights = scenes.make_lights(max(1, nl - nl // 4), nl // 4, (-ext, -2.0, -ext), (ext, 4.0, ext), seed=seed + 7, range_lo=0.2,
+                                range_hi=float(rng.choice([1.0, 8.0, 80.0])), jolt_bounds=bool(seed % 2))
+    if len(lights) > 12:                                  # equal positions -> equal squared distances (the strict-less rule decides)
+        for k in range(0, len(lights) - 1, 5):
+            lights["position_range"][k + 1, :3] = lights["position_range"][k, :3]
+    nv = int(rng.integers(0, 3 * len(lights)))
+    visible = rng.integers(0, len(lights) + 3, nv).astype(np.uint32) if seed % 3 else np.arange(len(lights), dtype=np.uint32)
+    return {"aabbs": aabbs, "view_proj": vp, "lights": lights, "visible": visible}

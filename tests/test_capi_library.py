@@ -100,7 +100,9 @@ def test_legacy2_wrappers_marshal_their_arguments_without_a_device():
              lambda: ctx.legacy2_draw_softshadow(1, u, 0, 2, 3),
              lambda: ctx.legacy3_ibl_upload(irr, [np.zeros((6, 4, 4, 3), np.float32), np.zeros((6, 2, 2, 3), np.float32)]),
              lambda: ctx.legacy3_ibl_destroy(1),
-             lambda: ctx.legacy3_draw_pbr(1, u, 2, 1, 3, 4)]
+             lambda: ctx.legacy3_draw_pbr(1, u, 2, 1, 3, 4),
+             lambda: ctx.cull_objects_frustum(np.zeros((3, 10), np.float32), eye),
+             lambda: ctx.collect_object_lights(np.zeros((3, 6), np.float32), np.arange(4, dtype=np.uint32), np.zeros((4, 160), np.uint8), 1)]
     for call in calls:
         with pytest.raises(capi.ShsbError, match="status 1"):
             call()

@@ -1,0 +1,81 @@
+"""Scene-level steps upstream of draw submission on the CPU: the restatement
+(oracle/oracle_scene_cull.cpp) PINNED against the reference's own cull_vs_frustum (geometry/jolt_culling.hpp:279-306) and
+collect_object_lights (lighting/light_runtime.hpp:592-616), compiled where they lie against the JoltPhysics declaration shim
+(oracle/ref_lightcull_harness.cpp) -- classes, the ordered visible list, the counters, and per object the selected light slots and
+squared distances bit for bit -- and the DEVICE functions of csrc/scene_cull_core.cuh compiled by g++ (tests/cpp/scene_cull_emul.cpp)
+against the restatement."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fuzz_cases
+from leisure_software_renderer_b200 import capi
+from oracle.bindings import LightCullReference, SceneCull
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "..", "leisure_software_renderer_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def refs():
+    if not LightCullReference.available() and not os.path.isdir("/root/reference"):
+        pytest.skip("oracle/_ref/libshs_lightcull_ref.so not built and /root/reference absent")
+    return SceneCull("port"), SceneCull("reference"), LightCullReference()
+
+
+class Emul(SceneCull):
+    def __init__(self):
+        out, src, hdr = os.path.join(HERE, "cpp", "_build", "libscene_cull_emul.so"), os.path.join(HERE, "cpp", "scene_cull_emul.cpp"), os.path.join(CSRC, "scene_cull_core.cuh")
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-I" + CSRC, src, "-o", out], check=True)
+        self.kind, self.lib, self.prefix = "port", C.CDLL(out), "shsemu_"
+
+
+def object_bounds(light_ref, aabbs):
+    """(n, 10) bounds as SceneShape reports them for these AABBs (the sphere is the reference's derivation)."""
+    return light_ref.bounds(aabbs)
+
+
+@pytest.mark.parametrize("seed", list(range(50)))
+def test_fuzz_object_culling_equals_the_reference(refs, seed):
+    port, ref, lref = refs
+    sc = fuzz_cases.scene_cull(seed)
+    b = object_bounds(lref, sc["aabbs"])
+    pc, pv, pn = port.cull_objects(b, sc["view_proj"])
+    rc, rv, rn = ref.cull_objects(sc["aabbs"], sc["view_proj"])
+    assert np.array_equal(pc, rc) and np.array_equal(pv, rv) and np.array_equal(pn, rn), (seed, pn, rn)
+    ec, ev, en = Emul().cull_objects(b, sc["view_proj"])
+    assert np.array_equal(ec, pc) and np.array_equal(ev, pv) and np.array_equal(en, pn)
+
+
+@pytest.mark.parametrize("seed", list(range(50)))
+def test_fuzz_object_light_selection_equals_the_reference(refs, seed):
+    port, ref, _ = refs
+    sc = fuzz_cases.scene_cull(seed)
+    for mode in (0, 1, 2):
+        p = port.collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], mode)
+        r = ref.collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], mode)
+        e = Emul().collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], mode)
+        for k, what in enumerate(("counts", "indices", "dist2")):
+            assert np.array_equal(p[k].view(np.uint32), r[k].view(np.uint32)), f"seed {seed} mode {mode}: {what} differ from the reference"
+            assert np.array_equal(e[k].view(np.uint32), p[k].view(np.uint32)), f"seed {seed} mode {mode}: device functions: {what} differ"
+
+
+def test_scene_cull_scenes_are_not_trivial(refs):
+    port, _, lref = refs
+    seen = np.zeros(3, np.int64)
+    full = replaced = 0
+    for seed in range(20):
+        sc = fuzz_cases.scene_cull(seed)
+        cls, _, _ = port.cull_objects(object_bounds(lref, sc["aabbs"]), sc["view_proj"])
+        seen += np.bincount(cls, minlength=3)
+        counts, idx, d2 = port.collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], 1)
+        full += int((counts == 8).sum())
+        none = port.collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], 0)
+        replaced += int(np.count_nonzero((none[1] != idx).any(axis=1)))
+    assert (seen > 50).all(), seen
+    assert full > 100 and replaced > 100, (full, replaced)

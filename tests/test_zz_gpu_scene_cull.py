@@ -1,0 +1,62 @@
+"""GPU parity (`-m gpu`) of the scene-level culling steps behind the C-ABI (shsb_cull_objects_frustum, shsb_collect_object_lights;
+csrc/scene_cull.cu) against the CPU oracle (oracle/oracle_scene_cull.cpp, pinned bit for bit against the
+reference's own cull_vs_frustum / collect_object_lights by tests/test_scene_cull_cpu.py): classes, the ordered visible list, the
+counters, and per object the selected light slots and squared distances, all bit-exact.
+(Sorts last on purpose: written after the round's GPU budget was spent, checked so far through the CPU emulation of its device
+functions only.)"""
+import numpy as np
+import pytest
+
+import fuzz_cases
+from oracle.bindings import LightCullReference, SceneCull
+
+pytestmark = pytest.mark.gpu
+
+
+def bounds_of(aabbs):
+    """(n, 10) sphere + AABB as SceneShape reports them: centre and half-extent length of the AABB."""
+    if LightCullReference.available():
+        return LightCullReference().bounds(aabbs)
+    a = np.ascontiguousarray(aabbs, np.float32)
+    half = np.float32(0.5) * (a[:, 3:] - a[:, :3])
+    r = np.sqrt((half[:, 0] * half[:, 0] + half[:, 1] * half[:, 1]) + half[:, 2] * half[:, 2]).astype(np.float32)
+    return np.concatenate([np.float32(0.5) * (a[:, :3] + a[:, 3:]), r[:, None], a], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", list(range(30)))
+def test_fuzz_object_culling_parity(gpu, seed):
+    sc = fuzz_cases.scene_cull(seed)
+    b = bounds_of(sc["aabbs"])
+    g = gpu.cull_objects_frustum(b, sc["view_proj"])
+    c = SceneCull("port").cull_objects(b, sc["view_proj"])
+    assert np.array_equal(g[0], c[0]) and np.array_equal(g[1], c[1]) and np.array_equal(g[2], c[2]), (seed, g[2], c[2])
+
+
+@pytest.mark.parametrize("seed", list(range(30)))
+def test_fuzz_object_light_selection_parity(gpu, seed):
+    sc = fuzz_cases.scene_cull(seed)
+    for mode in (0, 1, 2):
+        g = gpu.collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], mode)
+        c = SceneCull("port").collect_object_lights(sc["aabbs"], sc["visible"], sc["lights"], mode)
+        for k, what in enumerate(("counts", "indices", "dist2")):
+            assert np.array_equal(g[k].view(np.uint32), c[k].view(np.uint32)), f"seed {seed} mode {mode}: {what}"
+
+
+def test_scene_cull_large_and_empty(gpu):
+    """More objects than one compaction round (1024) and the empty cases."""
+    rng = np.random.default_rng(3)
+    sc = fuzz_cases.scene_cull(4)
+    c = rng.uniform(-40, 40, (5000, 3))
+    half = np.abs(rng.normal(0, 2.0, (5000, 3)))
+    aabbs = np.concatenate([c - half, c + half], axis=1).astype(np.float32)
+    b = bounds_of(aabbs)
+    g, p = gpu.cull_objects_frustum(b, sc["view_proj"]), SceneCull("port").cull_objects(b, sc["view_proj"])
+    assert np.array_equal(g[0], p[0]) and np.array_equal(g[1], p[1]) and np.array_equal(g[2], p[2]) and 0 < int(p[2][4]) < 5000
+    g, p = gpu.collect_object_lights(aabbs, sc["visible"], sc["lights"], 1), SceneCull("port").collect_object_lights(aabbs, sc["visible"], sc["lights"], 1)
+    assert all(np.array_equal(x.view(np.uint32), y.view(np.uint32)) for x, y in zip(g, p))
+    e = gpu.cull_objects_frustum(np.zeros((0, 10), np.float32), sc["view_proj"])
+    assert e[0].size == 0 and e[1].size == 0 and not e[2].any()
+    e = gpu.collect_object_lights(aabbs[:3], np.zeros(0, np.uint32), sc["lights"], 2)
+    assert not e[0].any() and not e[1].any()
+    with pytest.raises(Exception, match="status 1"):
+        gpu.collect_object_lights(aabbs[:3], sc["visible"], sc["lights"], 7)
