@@ -564,6 +564,15 @@ SHSB_API int32_t shsb_collect_object_lights(shsb_ctx ctx, const float* object_aa
                                             uint32_t n_visible, const void* records160, uint32_t n_lights, int32_t cull_mode,
                                             uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8);
 
+/* build_tile_view_depth_range_from_scene (lighting/light_culling_runtime.hpp:188-264; project_aabb_bounds :92-153): per-tile
+ * [min, max] view depth from the world AABBs of the visible objects -- the reference's CPU source of the ranges that
+ * cull_lights_tiled_view_depth_range consumes.  visible_objects: scene indices (entries >= n_objects are skipped); view / view_proj:
+ * the camera matrices.  The result stays on the device for shsb_light_cull_ex (range_min = range_max = NULL,
+ * SHSB_LIGHT_CULL_TILED_VIEW_DEPTH) and is returned by shsb_tile_depth_range_download, like shsb_tile_depth_range's. */
+SHSB_API int32_t shsb_tile_depth_range_from_scene(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible_objects,
+                                                  uint32_t n_visible, const float view[16], const float view_proj[16], uint32_t viewport_w,
+                                                  uint32_t viewport_h, uint32_t tile_size, float z_near, float z_far);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1793,6 +1793,30 @@ SHSB_API int32_t shsb_collect_object_lights(shsb_ctx ctx, const float* object_aa
     return SHSB_OK;
 }
 
+SHSB_API int32_t shsb_tile_depth_range_from_scene(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible_objects, uint32_t n_visible,
+                                                  const float view[16], const float view_proj[16], uint32_t vw, uint32_t vh, uint32_t tile_size, float z_near, float z_far)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if ((n_objects && !object_aabbs6) || (n_visible && !visible_objects) || !view || !view_proj) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+    if (vw == 0 || vh == 0 || tile_size == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "viewport %ux%u, tile size %u", vw, vh, tile_size);
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t tiles_x = (vw + tile_size - 1) / tile_size, tiles_y = (vh + tile_size - 1) / tile_size;
+    const size_t tiles = (size_t)tiles_x * tiles_y;
+    if (int rc = ensure_dev(ctx, ctx->d_range_min, tiles)) return rc;
+    if (int rc = ensure_dev(ctx, ctx->d_range_max, tiles)) return rc;
+    const size_t o_boxes = 0, o_vis = sc_align((size_t)n_objects * 24), o_scratch = o_vis + sc_align((size_t)n_visible * 4), total = o_scratch + sc_align(tiles * 12);
+    if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, total)) return rc;
+    uint8_t* base = ctx->d_sc_bytes.p;
+    if (n_objects) CK(cudaMemcpyAsync(base + o_boxes, object_aabbs6, (size_t)n_objects * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_visible) CK(cudaMemcpyAsync(base + o_vis, visible_objects, (size_t)n_visible * 4, cudaMemcpyHostToDevice, ctx->stream));
+    launch_scene_tile_depth_range((const float*)(base + o_boxes), n_objects, (const uint32_t*)(base + o_vis), n_objects ? n_visible : 0, view, view_proj, z_near, z_far, tiles_x, tiles_y,
+                                  (uint32_t*)(base + o_scratch), ctx->d_range_min.p, ctx->d_range_max.p, ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream)); // the host arrays may go away after the call
+    ctx->range_w = vw; ctx->range_h = vh; ctx->range_ts = tile_size;
+    return SHSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------- passes
 SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh_h, int32_t shader_id, const ShsbUniforms* u,
                                      shsb_rt hdr_rt, shsb_rt depth_motion_rt, const ShsbRasterCfg* cfg, ShsbStats* out_stats)

@@ -70,6 +70,49 @@ namespace shsb
                 out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = d2[k];
             }
         }
+
+        __global__ void __launch_bounds__(256) scene_range_init_kernel(uint32_t tiles, float z_near, float z_far, uint32_t* __restrict__ kmin, uint32_t* __restrict__ kmax, uint32_t* __restrict__ has)
+        {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            if (t >= tiles) return;
+            kmin[t] = sc::depth_key(z_far);
+            kmax[t] = sc::depth_key(z_near);
+            has[t] = 0u;
+        }
+
+        struct ViewMats { float view[16], view_proj[16]; };
+
+        // one thread per visible object: project, then fold its depth range into every tile of its rectangle
+        __global__ void __launch_bounds__(128) scene_range_scatter_kernel(const float* __restrict__ boxes6, uint32_t n_objects, const uint32_t* __restrict__ visible, uint32_t n_visible,
+                                                                           const ViewMats m, float z_near, float z_far, uint32_t tiles_x, uint32_t tiles_y,
+                                                                           uint32_t* __restrict__ kmin, uint32_t* __restrict__ kmax, uint32_t* __restrict__ has)
+        {
+            const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+            if (v >= n_visible) return;
+            const uint32_t o = visible[v];
+            if (o >= n_objects) return;
+            float box[6];
+            for (int k = 0; k < 6; ++k) box[k] = boxes6[(size_t)o * 6 + k];
+            sc::TileRect r;
+            if (!sc::project_object(box, m.view, m.view_proj, z_near, z_far, tiles_x, tiles_y, r)) return;
+            const uint32_t lo = sc::depth_key(r.min_depth), hi = sc::depth_key(r.max_depth);
+            for (uint32_t ty = r.ty0; ty <= r.ty1; ++ty)
+                for (uint32_t tx = r.tx0; tx <= r.tx1; ++tx)
+                {
+                    const uint32_t t = ty * tiles_x + tx;
+                    atomicMin(&kmin[t], lo);
+                    atomicMax(&kmax[t], hi);
+                    has[t] = 1u;
+                }
+        }
+
+        __global__ void __launch_bounds__(256) scene_range_finish_kernel(uint32_t tiles, float z_near, float z_far, const uint32_t* __restrict__ kmin, const uint32_t* __restrict__ kmax,
+                                                                          const uint32_t* __restrict__ has, float* __restrict__ out_min, float* __restrict__ out_max)
+        {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            if (t >= tiles) return;
+            sc::finish_tile(has[t], sc::key_depth(kmin[t]), sc::key_depth(kmax[t]), z_near, z_far, out_min[t], out_max[t]);
+        }
     }
 
     void launch_cull_objects(const float* bounds10, uint32_t n, const float planes24[24], uint8_t* classes, uint32_t* visible, uint32_t* counts5, cudaStream_t s, uint64_t* launches)
@@ -87,5 +130,23 @@ namespace shsb
         if (n_objects == 0) return;
         collect_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, records, n_lights, mode, out_counts, out_idx, out_d2);
         if (launches) *launches += 1;
+    }
+}
+
+namespace shsb
+{
+    // build_tile_view_depth_range_from_scene; scratch3: 3 x tiles uint32 (min keys, max keys, has-depth flags)
+    void launch_scene_tile_depth_range(const float* boxes6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16], const float view_proj[16],
+                                       float z_near, float z_far, uint32_t tiles_x, uint32_t tiles_y, uint32_t* scratch3, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches)
+    {
+        const uint32_t tiles = tiles_x * tiles_y;
+        if (tiles == 0) return;
+        uint32_t *kmin = scratch3, *kmax = scratch3 + tiles, *has = scratch3 + 2 * (size_t)tiles;
+        ViewMats m;
+        for (int i = 0; i < 16; ++i) { m.view[i] = view[i]; m.view_proj[i] = view_proj[i]; }
+        scene_range_init_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(tiles, z_near, z_far, kmin, kmax, has);
+        if (n_visible) scene_range_scatter_kernel<<<(n_visible + 127) / 128, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, m, z_near, z_far, tiles_x, tiles_y, kmin, kmax, has);
+        scene_range_finish_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(tiles, z_near, z_far, kmin, kmax, has, out_min, out_max);
+        if (launches) *launches += n_visible ? 3 : 2;
     }
 }

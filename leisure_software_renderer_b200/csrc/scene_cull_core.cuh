@@ -6,9 +6,13 @@
 //   collect_lights       collect_object_lights + light_affects_object + add_light_candidate, lighting/light_runtime.hpp:239-252,
 //                        263-289, 570-616: up to 8 nearest affecting lights per object; the SLOT a light lands in depends on visit
 //                        order (replace the first farthest slot when strictly nearer), so each object walks its candidates serially
+//   project_object       project_aabb_bounds + the tile rectangle of build_tile_view_depth_range_from_scene,
+//                        lighting/light_culling_runtime.hpp:92-168, 188-264: an object's screen-tile rectangle and view-depth range;
+//                        the per-tile min / max over objects is order-independent and is taken with atomics on ordered keys
 // IEEE binary32, unfused, GLM's scalar order (compiled --fmad=false / -ffp-contract=off).
 #pragma once
 #include <cstdint>
+#include <cstring>
 
 #ifdef __CUDACC__
 #define SC_HD __host__ __device__ __forceinline__
@@ -97,6 +101,69 @@ namespace shsb
                 if (d2 < far_d2) { out_idx[farthest] = li; out_d2[farthest] = d2; }
             }
             return count;
+        }
+
+        SC_HD float std_clampf(float v, float lo, float hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); } // std::clamp
+        SC_HD float std_minf(float a, float b) { return (b < a) ? b : a; }                                  // std::min
+        SC_HD float std_maxf(float a, float b) { return (a < b) ? b : a; }                                  // std::max
+
+        SC_HD uint32_t ndc_x_to_bin(float ndc_x, uint32_t bins) // :155-160
+        {
+            const float u = std_clampf(ndc_x * 0.5f + 0.5f, 0.0f, 0.999999f);
+            const uint32_t b = (uint32_t)(u * (float)bins);
+            return b < bins - 1u ? b : bins - 1u;
+        }
+        SC_HD uint32_t ndc_y_to_bin_top(float ndc_y, uint32_t bins) // :162-167
+        {
+            const float v = std_clampf(1.0f - (ndc_y * 0.5f + 0.5f), 0.0f, 0.999999f);
+            const uint32_t b = (uint32_t)(v * (float)bins);
+            return b < bins - 1u ? b : bins - 1u;
+        }
+
+        struct TileRect { uint32_t tx0, tx1, ty0, ty1; float min_depth, max_depth; };
+
+        // false: no corner in front of the camera (the object contributes nothing)
+        SC_HD bool project_object(const float* box6, const float* view, const float* view_proj, float z_near, float z_far, uint32_t tiles_x, uint32_t tiles_y, TileRect& r)
+        {
+            bool any = false;
+            float min_x = 1.0f, max_x = -1.0f, min_y = 1.0f, max_y = -1.0f, min_d = z_far, max_d = z_near;
+            for (int c = 0; c < 8; ++c) // aabb_corners order (:80-90): x fastest, then y, then z
+            {
+                const float x = box6[(c & 1) ? 3 : 0], y = box6[(c & 2) ? 4 : 1], z = box6[(c & 4) ? 5 : 2];
+                const float* m = view_proj;
+                const float cw = (m[3] * x + m[7] * y) + (m[11] * z + m[15] * 1.0f);
+                if (cw <= 1e-5f) continue;
+                const float cx = (m[0] * x + m[4] * y) + (m[8] * z + m[12] * 1.0f), cy = (m[1] * x + m[5] * y) + (m[9] * z + m[13] * 1.0f);
+                const float nx = cx / cw, ny = cy / cw;
+                min_x = std_minf(min_x, nx); max_x = std_maxf(max_x, nx);
+                min_y = std_minf(min_y, ny); max_y = std_maxf(max_y, ny);
+                const float vd = (view[2] * x + view[6] * y) + (view[10] * z + view[14] * 1.0f);
+                if (vd > 1e-5f) { min_d = std_minf(min_d, vd); max_d = std_maxf(max_d, vd); }
+                any = true;
+            }
+            if (!any) return false;
+            min_x = std_clampf(min_x, -1.0f, 1.0f); max_x = std_clampf(max_x, -1.0f, 1.0f);
+            min_y = std_clampf(min_y, -1.0f, 1.0f); max_y = std_clampf(max_y, -1.0f, 1.0f);
+            if (min_x > max_x) { const float t = min_x; min_x = max_x; max_x = t; }
+            if (min_y > max_y) { const float t = min_y; min_y = max_y; max_y = t; }
+            min_d = std_clampf(min_d, z_near, z_far);
+            max_d = std_clampf(max_d, z_near, z_far);
+            if (min_d > max_d) { min_d = z_near; max_d = z_far; }
+            r.tx0 = ndc_x_to_bin(min_x, tiles_x); r.tx1 = ndc_x_to_bin(max_x, tiles_x);
+            r.ty0 = ndc_y_to_bin_top(max_y, tiles_y); r.ty1 = ndc_y_to_bin_top(min_y, tiles_y);
+            r.min_depth = min_d; r.max_depth = max_d;
+            return true;
+        }
+
+        // order-preserving float <-> uint32 keys (so that integer atomicMin / atomicMax give the float min / max)
+        SC_HD uint32_t depth_key(float f) { uint32_t b; memcpy(&b, &f, 4); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+        SC_HD float key_depth(uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k; float f; memcpy(&f, &b, 4); return f; }
+
+        // the closing loop of build_tile_view_depth_range_from_scene (:254-261)
+        SC_HD void finish_tile(uint32_t has, float mn, float mx, float z_near, float z_far, float& out_min, float& out_max)
+        {
+            if (has == 0u || mn > mx) { out_min = z_near; out_max = z_far; }
+            else { out_min = mn; out_max = mx; }
         }
     }
 }

@@ -287,6 +287,8 @@ namespace shsb
     void launch_cull_objects(const float* bounds10, uint32_t n, const float planes24[24], uint8_t* classes, uint32_t* visible, uint32_t* counts5, cudaStream_t s, uint64_t* launches);
     void launch_collect_object_lights(const float* boxes6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float* records, uint32_t n_lights, int mode,
                                       uint32_t* out_counts, uint32_t* out_idx, float* out_d2, cudaStream_t s, uint64_t* launches);
+    void launch_scene_tile_depth_range(const float* boxes6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16], const float view_proj[16],
+                                       float z_near, float z_far, uint32_t tiles_x, uint32_t tiles_y, uint32_t* scratch3, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches);
     uint32_t legacy2_slots(const l2::Draw& d);
     void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
                              cudaStream_t s, uint64_t* launches);

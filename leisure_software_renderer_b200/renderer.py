@@ -220,6 +220,18 @@ class Context:
                                                                     capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2)), "shsb_collect_object_lights")
         return counts, idx, d2
 
+    def tile_depth_range_from_scene(self, object_aabbs, visible_objects, view, view_proj, w, h, tile_size, z_near, z_far):
+        """build_tile_view_depth_range_from_scene on the device; the ranges stay there for light_cull_ex and are returned as two arrays."""
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        v = np.ascontiguousarray(visible_objects, dtype=np.uint32).reshape(-1)
+        mv, mvp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range_from_scene(self.h, capi.fptr(a), len(a), capi.u32ptr(v), len(v), capi.fptr(mv), capi.fptr(mvp), int(w), int(h),
+                                                                          int(tile_size), float(z_near), float(z_far)), "shsb_tile_depth_range_from_scene")
+        n = ((int(w) + int(tile_size) - 1) // int(tile_size)) * ((int(h) + int(tile_size) - 1) // int(tile_size))
+        lo, hi = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range_download(self.h, capi.fptr(lo), capi.fptr(hi), n), "shsb_tile_depth_range_download")
+        return lo, hi
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")

@@ -555,3 +555,15 @@ class SceneCull:
                                                                       C.c_uint32(len(r)), C.c_int32(cull_mode), capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2))
         assert rc == 0, rc
         return counts, idx, d2
+
+    def tile_depth_range_from_scene(self, object_aabbs, visible, view, view_proj, w, h, tile_size, z_near, z_far):
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        v = np.ascontiguousarray(visible, dtype=np.uint32).reshape(-1)
+        mv, mvp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        tiles = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        lo, hi = np.zeros(tiles, np.float32), np.zeros(tiles, np.float32)
+        rc = getattr(self.lib, self.prefix + "tile_depth_range_from_scene")(capi.fptr(a), C.c_uint32(len(a)), capi.u32ptr(v), C.c_uint32(len(v)), capi.fptr(mv), capi.fptr(mvp),
+                                                                            C.c_uint32(w), C.c_uint32(h), C.c_uint32(tile_size), C.c_float(z_near), C.c_float(z_far),
+                                                                            capi.fptr(lo), capi.fptr(hi))
+        assert rc == 0, rc
+        return lo, hi

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 namespace
 {
@@ -133,6 +134,63 @@ extern "C"
             }
             out_counts[o] = count;
         }
+        return 0;
+    }
+
+    // build_tile_view_depth_range_from_scene (lighting/light_culling_runtime.hpp:188-264) with project_aabb_bounds (:92-153),
+    // aabb_corners (:78-90), ndc_x_to_bin / ndc_y_to_bin_top_origin (:155-167).  Objects enter as world AABBs (SceneShape::world_aabb);
+    // visible: scene indices in visit order (entries >= n_objects are skipped).  out_min / out_max: one float per tile, tile (0,0) top-left.
+    int32_t shso_tile_depth_range_from_scene(const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16],
+                                             const float view_proj[16], uint32_t viewport_w, uint32_t viewport_h, uint32_t tile_size, float z_near, float z_far,
+                                             float* out_min, float* out_max)
+    {
+        if (!view || !view_proj || !out_min || !out_max || viewport_w == 0 || viewport_h == 0 || tile_size == 0) return 1;
+        const uint32_t tiles_x = (viewport_w + tile_size - 1u) / tile_size, tiles_y = (viewport_h + tile_size - 1u) / tile_size, total = tiles_x * tiles_y;
+        std::vector<uint8_t> has(total, 0);
+        for (uint32_t t = 0; t < total; ++t) { out_min[t] = z_far; out_max[t] = z_near; }
+        auto mul = [](const float* m, int row, float x, float y, float z) { return (m[row] * x + m[4 + row] * y) + (m[8 + row] * z + m[12 + row] * 1.0f); }; // mat4 * vec4(p, 1), GLM scalar order
+        auto xbin = [](float ndc_x, uint32_t bins) { const float u = std::clamp(ndc_x * 0.5f + 0.5f, 0.0f, 0.999999f); return std::min((uint32_t)(u * (float)bins), bins - 1u); };
+        auto ybin = [](float ndc_y, uint32_t bins) { const float v = std::clamp(1.0f - (ndc_y * 0.5f + 0.5f), 0.0f, 0.999999f); return std::min((uint32_t)(v * (float)bins), bins - 1u); };
+        for (uint32_t vi = 0; vi < n_visible; ++vi)
+        {
+            const uint32_t o = visible[vi];
+            if (o >= n_objects) continue;
+            const float* b = object_aabbs6 + (size_t)o * 6;
+            bool any = false;
+            float min_x = 1.0f, max_x = -1.0f, min_y = 1.0f, max_y = -1.0f, min_d = z_far, max_d = z_near;
+            for (int c = 0; c < 8; ++c)
+            {
+                const float x = (c & 1) ? b[3] : b[0], y = (c & 2) ? b[4] : b[1], z = (c & 4) ? b[5] : b[2];
+                const float cw = mul(view_proj, 3, x, y, z);
+                if (cw <= 1e-5f) continue;
+                const float nx = mul(view_proj, 0, x, y, z) / cw, ny = mul(view_proj, 1, x, y, z) / cw;
+                min_x = std::min(min_x, nx); max_x = std::max(max_x, nx);
+                min_y = std::min(min_y, ny); max_y = std::max(max_y, ny);
+                const float vd = mul(view, 2, x, y, z);
+                if (vd > 1e-5f) { min_d = std::min(min_d, vd); max_d = std::max(max_d, vd); }
+                any = true;
+            }
+            if (!any) continue;
+            min_x = std::clamp(min_x, -1.0f, 1.0f); max_x = std::clamp(max_x, -1.0f, 1.0f);
+            min_y = std::clamp(min_y, -1.0f, 1.0f); max_y = std::clamp(max_y, -1.0f, 1.0f);
+            if (min_x > max_x) std::swap(min_x, max_x);
+            if (min_y > max_y) std::swap(min_y, max_y);
+            min_d = std::clamp(min_d, z_near, z_far);
+            max_d = std::clamp(max_d, z_near, z_far);
+            if (min_d > max_d) { min_d = z_near; max_d = z_far; }
+            const uint32_t tx0 = xbin(min_x, tiles_x), tx1 = xbin(max_x, tiles_x), ty0 = ybin(max_y, tiles_y), ty1 = ybin(min_y, tiles_y);
+            for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                for (uint32_t tx = tx0; tx <= tx1; ++tx)
+                {
+                    const uint32_t t = ty * tiles_x + tx;
+                    if (t >= total) continue;
+                    out_min[t] = std::min(out_min[t], min_d);
+                    out_max[t] = std::max(out_max[t], max_d);
+                    has[t] = 1;
+                }
+        }
+        for (uint32_t t = 0; t < total; ++t)
+            if (!has[t] || out_min[t] > out_max[t]) { out_min[t] = z_near; out_max[t] = z_far; }
         return 0;
     }
 }

@@ -17,6 +17,7 @@
 #define SHS_HAS_JOLT 1
 #include "shs/lighting/jolt_light_culling.hpp"
 #include "shs/lighting/light_runtime.hpp"
+#include "shs/lighting/light_culling_runtime.hpp"
 
 namespace
 {
@@ -144,4 +145,27 @@ extern "C"
         }
         return 0;
     }
+}
+
+extern "C" int32_t shsref_tile_depth_range_from_scene(const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16],
+                                                       const float view_proj[16], uint32_t viewport_w, uint32_t viewport_h, uint32_t tile_size, float z_near, float z_far,
+                                                       float* out_min, float* out_max)
+{
+    // build_tile_view_depth_range_from_scene (lighting/light_culling_runtime.hpp:188-264) over a SceneElementSet whose geometries carry the AABBs
+    if (!view || !view_proj || !out_min || !out_max) return 1;
+    Lights L(object_aabbs6, n_objects);
+    shs::SceneElementSet scene;
+    for (uint32_t i = 0; i < n_objects; ++i)
+    {
+        shs::SceneElement e{};
+        e.geometry = L.scene[i];
+        e.geometry.stable_id = i + 1u;
+        scene.add(e);
+    }
+    glm::mat4 v, vp;
+    std::memcpy(&v, view, 64);
+    std::memcpy(&vp, view_proj, 64);
+    const shs::TileViewDepthRange r = shs::build_tile_view_depth_range_from_scene(std::span<const uint32_t>(visible, n_visible), scene, v, vp, viewport_w, viewport_h, tile_size, z_near, z_far);
+    for (size_t t = 0; t < r.min_view_depth.size(); ++t) { out_min[t] = r.min_view_depth[t]; out_max[t] = r.max_view_depth[t]; }
+    return 0;
 }

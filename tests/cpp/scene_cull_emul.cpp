@@ -4,6 +4,7 @@
 // Nothing in the product links or loads it.
 #include <cmath>
 #include <cstring>
+#include <vector>
 #include "scene_cull_core.cuh"
 
 using namespace shsb::sc;
@@ -45,4 +46,32 @@ extern "C"
                                            out_dist2_8 + (size_t)o * 8);
         return 0;
     }
+}
+
+extern "C" int32_t shsemu_tile_depth_range_from_scene(const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16],
+                                                       const float view_proj[16], uint32_t viewport_w, uint32_t viewport_h, uint32_t tile_size, float z_near, float z_far,
+                                                       float* out_min, float* out_max)
+{
+    // like scene_cull.cu: keys initialised, every visible object folds its range into its rectangle (atomicMin / atomicMax on ordered
+    // keys -- visited here in REVERSE order to show that the order does not matter), then the closing pass
+    const uint32_t tiles_x = (viewport_w + tile_size - 1u) / tile_size, tiles_y = (viewport_h + tile_size - 1u) / tile_size, tiles = tiles_x * tiles_y;
+    std::vector<uint32_t> kmin(tiles, depth_key(z_far)), kmax(tiles, depth_key(z_near)), has(tiles, 0u);
+    for (uint32_t v = n_visible; v-- > 0;)
+    {
+        const uint32_t o = visible[v];
+        if (o >= n_objects) continue;
+        TileRect r;
+        if (!project_object(object_aabbs6 + (size_t)o * 6, view, view_proj, z_near, z_far, tiles_x, tiles_y, r)) continue;
+        const uint32_t lo = depth_key(r.min_depth), hi = depth_key(r.max_depth);
+        for (uint32_t ty = r.ty0; ty <= r.ty1; ++ty)
+            for (uint32_t tx = r.tx0; tx <= r.tx1; ++tx)
+            {
+                const uint32_t t = ty * tiles_x + tx;
+                if (lo < kmin[t]) kmin[t] = lo;
+                if (hi > kmax[t]) kmax[t] = hi;
+                has[t] = 1u;
+            }
+    }
+    for (uint32_t t = 0; t < tiles; ++t) finish_tile(has[t], key_depth(kmin[t]), key_depth(kmax[t]), z_near, z_far, out_min[t], out_max[t]);
+    return 0;
 }

@@ -186,7 +186,7 @@ def scene_cull(seed):
     """Random inputs of the scene-level steps upstream of draw submission: object AABBs around / inside / behind
     the camera frustum (thin slabs, huge boxes that contain the camera, point-sized boxes, boxes touching a plane), a camera, a
     light set and a visible-light list with repeats, gaps and out-of-range entries; ties in distance come from lights sharing a position.
-    Returns dict(aabbs (n, 6), view_proj, lights, visible, n_lights)."""
+    Returns dict(aabbs (n, 6), view_proj, view, lights, visible (lights), visible_objects, w, h, ts, zn, zf)."""
     rng = np.random.default_rng(29000 + seed)
     n = int(rng.integers(1, 400))
     ext = float(rng.choice([3.0, 15.0, 60.0]))
@@ -206,4 +206,9 @@ def scene_cull(seed):
             lights["position_range"][k + 1, :3] = lights["position_range"][k, :3]
     nv = int(rng.integers(0, 3 * len(lights)))
     visible = rng.integers(0, len(lights) + 3, nv).astype(np.uint32) if seed % 3 else np.arange(len(lights), dtype=np.uint32)
-    return {"aabbs": aabbs, "view_proj": vp, "lights": lights, "visible": visible}
+    view = np.ascontiguousarray(scenes.look_at_lh(eye, tgt, (0.0, 1.0, 0.0)).astype(np.float32).T).reshape(16)
+    w, h, ts = int(rng.integers(20, 400)), int(rng.integers(16, 260)), int(rng.choice([8, 16, 20, 32]))
+    nvo = int(rng.integers(0, 2 * n))
+    visible_objects = rng.integers(0, n + 2, nvo).astype(np.uint32) if seed % 4 else np.arange(n, dtype=np.uint32)
+    return {"aabbs": aabbs, "view_proj": vp, "lights": lights, "visible": visible, "view": view, "w": w, "h": h, "ts": ts, "zn": zn, "zf": zf,
+            "visible_objects": visible_objects}

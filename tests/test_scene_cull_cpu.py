@@ -65,6 +65,31 @@ def test_fuzz_object_light_selection_equals_the_reference(refs, seed):
             assert np.array_equal(e[k].view(np.uint32), p[k].view(np.uint32)), f"seed {seed} mode {mode}: device functions: {what} differ"
 
 
+@pytest.mark.parametrize("seed", list(range(50)))
+def test_fuzz_scene_tile_depth_range_equals_the_reference(refs, seed):
+    """build_tile_view_depth_range_from_scene (lighting/light_culling_runtime.hpp:188-264): restatement == compiled reference, and the
+    device functions (projection per object, ordered-key min / max folded in REVERSE object order, closing pass) == restatement."""
+    port, ref, _ = refs
+    sc = fuzz_cases.scene_cull(seed)
+    args = (sc["aabbs"], sc["visible_objects"], sc["view"], sc["view_proj"], sc["w"], sc["h"], sc["ts"], sc["zn"], sc["zf"])
+    p, r, e = port.tile_depth_range_from_scene(*args), ref.tile_depth_range_from_scene(*args), Emul().tile_depth_range_from_scene(*args)
+    for k in (0, 1):
+        assert np.array_equal(p[k].view(np.uint32), r[k].view(np.uint32)), f"seed {seed}: {'min' if k == 0 else 'max'} differs from the reference in {int(np.count_nonzero(p[k] != r[k]))} tiles"
+        assert np.array_equal(e[k].view(np.uint32), p[k].view(np.uint32)), f"seed {seed}: device functions differ"
+
+
+def test_scene_tile_depth_ranges_are_not_trivial(refs):
+    port = refs[0]
+    tight = full = 0
+    for seed in range(20):
+        sc = fuzz_cases.scene_cull(seed)
+        lo, hi = port.tile_depth_range_from_scene(sc["aabbs"], sc["visible_objects"], sc["view"], sc["view_proj"], sc["w"], sc["h"], sc["ts"], sc["zn"], sc["zf"])
+        assert np.all(lo <= hi)
+        tight += int(np.count_nonzero((lo > np.float32(sc["zn"])) | (hi < np.float32(sc["zf"]))))
+        full += int(np.count_nonzero((lo == np.float32(sc["zn"])) & (hi == np.float32(sc["zf"]))))
+    assert tight > 500 and full > 500, (tight, full)
+
+
 def test_scene_cull_scenes_are_not_trivial(refs):
     port, _, lref = refs
     seen = np.zeros(3, np.int64)

@@ -60,3 +60,28 @@ def test_scene_cull_large_and_empty(gpu):
     assert not e[0].any() and not e[1].any()
     with pytest.raises(Exception, match="status 1"):
         gpu.collect_object_lights(aabbs[:3], sc["visible"], sc["lights"], 7)
+
+
+@pytest.mark.parametrize("seed", list(range(30)))
+def test_fuzz_scene_tile_depth_range_parity(gpu, seed):
+    """build_tile_view_depth_range_from_scene: the device's atomic min / max over ordered keys == the reference's serial loop."""
+    sc = fuzz_cases.scene_cull(seed)
+    args = (sc["aabbs"], sc["visible_objects"], sc["view"], sc["view_proj"], sc["w"], sc["h"], sc["ts"], sc["zn"], sc["zf"])
+    g, c = gpu.tile_depth_range_from_scene(*args), SceneCull("port").tile_depth_range_from_scene(*args)
+    assert np.array_equal(g[0].view(np.uint32), c[0].view(np.uint32)) and np.array_equal(g[1].view(np.uint32), c[1].view(np.uint32)), seed
+
+
+def test_scene_depth_ranges_feed_the_view_depth_bin_builder(gpu):
+    """The ranges left on the device are what shsb_light_cull_ex consumes with NULL range pointers."""
+    from leisure_software_renderer_b200 import capi
+    from oracle.bindings import Oracle
+    sc = fuzz_cases.scene_cull(2)
+    args = (sc["aabbs"], sc["visible_objects"], sc["view"], sc["view_proj"], sc["w"], sc["h"], sc["ts"], sc["zn"], sc["zf"])
+    lo, hi = gpu.tile_depth_range_from_scene(*args)
+    desc = capi.LightCullDesc(sc["view_proj"], sc["w"], sc["h"], capi.LIGHT_CULL_TILED_VIEW_DEPTH, sc["ts"], 64, z_near=sc["zn"], z_far=sc["zf"])
+    gpu.lights_upload(sc["lights"])
+    gc, gi = gpu.light_cull_ex(desc)
+    pc, pi = Oracle("port").light_cull_ex(sc["lights"], desc, lo, hi)
+    assert np.array_equal(gc, pc)
+    keep = np.arange(64)[None, :] < np.minimum(pc, 64)[:, None]
+    assert np.array_equal(gi[keep], pi[keep])
