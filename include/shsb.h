@@ -573,6 +573,19 @@ SHSB_API int32_t shsb_tile_depth_range_from_scene(shsb_ctx ctx, const float* obj
                                                   uint32_t n_visible, const float view[16], const float view_proj[16], uint32_t viewport_w,
                                                   uint32_t viewport_h, uint32_t tile_size, float z_near, float z_far);
 
+/* gather_light_scene_candidates_for_aabb (lighting/light_culling_runtime.hpp:373-449) followed by collect_object_lights, per object
+ * -- the chain of exp-plumbing/hello_light_types_culling_sw.cpp:968-996 -- over the light bins the context built last:
+ * clustered = 0: the tile lists of shsb_light_cull / shsb_light_cull_ex (tiled modes); clustered = 1: the cluster bins of
+ * shsb_light_cull_ex(SHSB_LIGHT_CULL_CLUSTERED).  view / view_proj: the camera the bins were built for; z_near / z_far:
+ * LightBinCullingConfig's.  records160 / n_lights: the records that were uploaded with shsb_lights_upload (the visible-light list
+ * is the identity).  A bin contributes its first max_per_bin entries: build the bins with a cap no smaller than the largest count
+ * to match the reference's uncapped lists.  out_candidates[n_objects]: the gathered list's length per object (the demo's
+ * light_candidates statistic); the other outputs as shsb_collect_object_lights. */
+SHSB_API int32_t shsb_select_object_lights_from_bins(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const float view[16],
+                                                     const float view_proj[16], int32_t clustered, float z_near, float z_far,
+                                                     const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts,
+                                                     uint32_t* out_indices8, float* out_dist2_8, uint32_t* out_candidates);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,6 +250,8 @@ def load_library(path: str | None = None):
         "shsb_cull_objects_frustum": [vp, P(C.c_float), C.c_uint32, P(C.c_float), P(C.c_uint8), P(C.c_uint32), P(C.c_uint32)],
         "shsb_collect_object_lights": [vp, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, vp, C.c_uint32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_float)],
         "shsb_tile_depth_range_from_scene": [vp, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_float), P(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float],
+        "shsb_select_object_lights_from_bins": [vp, P(C.c_float), C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32, C.c_float, C.c_float, vp, C.c_uint32, C.c_int32,
+                                                P(C.c_uint32), P(C.c_uint32), P(C.c_float), P(C.c_uint32)],
         "shsb_timing_enable": [vp, C.c_int32],
         "shsb_timing_collect": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],
         "shsb_timing_collect_abs": [vp, P(C.c_float), C.c_size_t, P(C.c_size_t)],

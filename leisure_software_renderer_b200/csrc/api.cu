@@ -1817,6 +1817,47 @@ SHSB_API int32_t shsb_tile_depth_range_from_scene(shsb_ctx ctx, const float* obj
     return SHSB_OK;
 }
 
+SHSB_API int32_t shsb_select_object_lights_from_bins(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const float view[16], const float view_proj[16], int32_t clustered,
+                                                     float z_near, float z_far, const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts,
+                                                     uint32_t* out_indices8, float* out_dist2_8, uint32_t* out_candidates)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if ((n_objects && (!object_aabbs6 || !out_counts || !out_indices8 || !out_dist2_8 || !out_candidates)) || !view || !view_proj || (n_lights && !records160))
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+    if (cull_mode < SHSB_LIGHT_OBJECT_CULL_NONE || cull_mode > SHSB_LIGHT_OBJECT_CULL_VOLUME_AABB) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "unknown LightObjectCullMode %d", cull_mode);
+    const LightLists& L = clustered ? ctx->cluster_lists : ctx->lists[LISTS_STANDALONE];
+    if (!L.ts || !L.counts.p || !L.indices.p || (clustered && !ctx->cluster_slices))
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, clustered ? "no cluster bins: call shsb_light_cull_ex(SHSB_LIGHT_CULL_CLUSTERED) first" : "no tile light lists: call shsb_light_cull / shsb_light_cull_ex first");
+    if (n_objects == 0) return SHSB_OK;
+    CK(cudaSetDevice(ctx->device));
+    sc::BinGrid g{};
+    g.bins_x = (L.w + L.ts - 1) / L.ts;
+    g.bins_y = (L.h + L.ts - 1) / L.ts;
+    g.bins_z = clustered ? ctx->cluster_slices : 1u;
+    g.clustered = clustered ? 1 : 0;
+    g.z_near = std::max(z_near, 1e-4f);            // LightBinCullingData::z_near / z_far, light_culling_runtime.hpp:278-279
+    g.z_far = std::max(z_far, g.z_near + 1e-3f);
+    g.max_per_bin = L.max_per_tile;
+    const uint32_t words = (n_lights + 31u) / 32u + 1u;
+    const size_t o_boxes = 0, o_recs = sc_align((size_t)n_objects * 24), o_seen = o_recs + sc_align((size_t)n_lights * 160), o_counts = o_seen + sc_align((size_t)n_objects * words * 4);
+    const size_t o_idx = o_counts + sc_align((size_t)n_objects * 4), o_d2 = o_idx + sc_align((size_t)n_objects * 32), o_cand = o_d2 + sc_align((size_t)n_objects * 32);
+    const size_t total = o_cand + sc_align((size_t)n_objects * 4);
+    if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, total)) return rc;
+    uint8_t* base = ctx->d_sc_bytes.p;
+    CK(cudaMemcpyAsync(base + o_boxes, object_aabbs6, (size_t)n_objects * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_lights) CK(cudaMemcpyAsync(base + o_recs, records160, (size_t)n_lights * 160, cudaMemcpyHostToDevice, ctx->stream));
+    launch_select_object_lights((const float*)(base + o_boxes), n_objects, view, view_proj, g, L.counts.p, L.indices.p, (const float*)(base + o_recs), n_lights, cull_mode,
+                                (uint32_t*)(base + o_seen), words, (uint32_t*)(base + o_counts), (uint32_t*)(base + o_idx), (float*)(base + o_d2), (uint32_t*)(base + o_cand),
+                                ctx->stream, &ctx->launches);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_counts, base + o_counts, (size_t)n_objects * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_indices8, base + o_idx, (size_t)n_objects * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_dist2_8, base + o_d2, (size_t)n_objects * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_candidates, base + o_cand, (size_t)n_objects * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------- passes
 SHSB_API int32_t shsb_rasterize_mesh(shsb_ctx ctx, shsb_mesh mesh_h, int32_t shader_id, const ShsbUniforms* u,
                                      shsb_rt hdr_rt, shsb_rt depth_motion_rt, const ShsbRasterCfg* cfg, ShsbStats* out_stats)

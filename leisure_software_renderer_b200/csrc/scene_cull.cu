@@ -4,7 +4,6 @@
 // The software-occlusion loop of culling_software.hpp is strictly serial (each object's test reads the depth the previous ones
 // wrote) and is not part of this file.
 #include "shsb_dev.cuh"
-#include "scene_cull_core.cuh"
 
 namespace shsb
 {
@@ -148,5 +147,47 @@ namespace shsb
         if (n_visible) scene_range_scatter_kernel<<<(n_visible + 127) / 128, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, m, z_near, z_far, tiles_x, tiles_y, kmin, kmax, has);
         scene_range_finish_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(tiles, z_near, z_far, kmin, kmax, has, out_min, out_max);
         if (launches) *launches += n_visible ? 3 : 2;
+    }
+}
+
+namespace shsb
+{
+    namespace
+    {
+        struct SelectArgs { float view[16], view_proj[16]; sc::BinGrid grid; };
+
+        // one thread per object; seen: n_objects x words_per_object, zeroed by the launcher
+        __global__ void __launch_bounds__(128) select_object_lights_kernel(const float* __restrict__ boxes6, uint32_t n_objects, const SelectArgs a, const uint32_t* __restrict__ bin_counts,
+                                                                            const uint32_t* __restrict__ bin_indices, const float* __restrict__ records, uint32_t n_lights, int mode,
+                                                                            uint32_t* __restrict__ seen, uint32_t words_per_object, uint32_t* __restrict__ out_counts,
+                                                                            uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_candidates)
+        {
+            const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+            if (o >= n_objects) return;
+            float box[6];
+            for (int k = 0; k < 6; ++k) box[k] = boxes6[(size_t)o * 6 + k];
+            sc::Selection sel;
+            out_candidates[o] = sc::select_from_bins(box, a.view, a.view_proj, a.grid, bin_counts, bin_indices, records, n_lights, mode, seen + (size_t)o * words_per_object, sel);
+            out_counts[o] = sel.count;
+            for (uint32_t k = 0; k < sc::LIGHT_SELECTION_CAPACITY; ++k)
+            {
+                out_idx[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.idx[k];
+                out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.d2[k];
+            }
+        }
+    }
+
+    void launch_select_object_lights(const float* boxes6, uint32_t n_objects, const float view[16], const float view_proj[16], const sc::BinGrid& grid, const uint32_t* bin_counts,
+                                     const uint32_t* bin_indices, const float* records, uint32_t n_lights, int mode, uint32_t* seen, uint32_t words_per_object, uint32_t* out_counts,
+                                     uint32_t* out_idx, float* out_d2, uint32_t* out_candidates, cudaStream_t s, uint64_t* launches)
+    {
+        if (n_objects == 0) return;
+        SelectArgs a;
+        for (int i = 0; i < 16; ++i) { a.view[i] = view[i]; a.view_proj[i] = view_proj[i]; }
+        a.grid = grid;
+        cudaMemsetAsync(seen, 0, (size_t)n_objects * words_per_object * 4, s);
+        select_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, a, bin_counts, bin_indices, records, n_lights, mode, seen, words_per_object, out_counts, out_idx,
+                                                                             out_d2, out_candidates);
+        if (launches) *launches += 1;
     }
 }

@@ -9,10 +9,19 @@
 //   project_object       project_aabb_bounds + the tile rectangle of build_tile_view_depth_range_from_scene,
 //                        lighting/light_culling_runtime.hpp:92-168, 188-264: an object's screen-tile rectangle and view-depth range;
 //                        the per-tile min / max over objects is order-independent and is taken with atomics on ordered keys
+//   select_from_bins     gather_light_scene_candidates_for_aabb (lighting/light_culling_runtime.hpp:373-449) fused with
+//                        collect_object_lights: the bins an object's projected AABB touches are walked in (z, y, x) order, each light
+//                        is considered at its FIRST occurrence (a per-object bit set replaces the reference's std::find) and fed to
+//                        the selection in that order.  The cluster slice uses logf: CUDA's double log rounded to float on the device.
 // IEEE binary32, unfused, GLM's scalar order (compiled --fmad=false / -ffp-contract=off).
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <cstring>
+
+#ifndef SC_LOGF
+#define SC_LOGF(x) ((float)log((double)(x)))
+#endif
 
 #ifdef __CUDACC__
 #define SC_HD __host__ __device__ __forceinline__
@@ -164,6 +173,86 @@ namespace shsb
         {
             if (has == 0u || mn > mx) { out_min = z_near; out_max = z_far; }
             else { out_min = mn; out_max = mx; }
+        }
+
+        // ---- light selection state shared by collect_lights and select_from_bins
+        struct Selection { uint32_t idx[LIGHT_SELECTION_CAPACITY]; float d2[LIGHT_SELECTION_CAPACITY]; uint32_t count; };
+        SC_HD void selection_clear(Selection& s) { s.count = 0; for (uint32_t k = 0; k < LIGHT_SELECTION_CAPACITY; ++k) { s.idx[k] = 0u; s.d2[k] = 0.0f; } }
+        SC_HD void consider_light(Selection& s, uint32_t li, const float* rec, const float* box6, float cx, float cy, float cz, int mode)
+        {
+            if (!light_affects_object(rec, box6, mode)) return;
+            const float dx = rec[REC_POSITION] - cx, dy = rec[REC_POSITION + 1] - cy, dz = rec[REC_POSITION + 2] - cz;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (s.count < LIGHT_SELECTION_CAPACITY) { s.idx[s.count] = li; s.d2[s.count] = d2; ++s.count; return; }
+            uint32_t farthest = 0;
+            float far_d2 = s.d2[0];
+            for (uint32_t i = 1; i < LIGHT_SELECTION_CAPACITY; ++i)
+                if (s.d2[i] > far_d2) { farthest = i; far_d2 = s.d2[i]; }
+            if (d2 < far_d2) { s.idx[farthest] = li; s.d2[farthest] = d2; }
+        }
+
+        SC_HD uint32_t view_depth_to_cluster_slice(float view_depth, float z_near, float z_far, uint32_t slices) // :170-186
+        {
+            if (slices <= 1u) return 0u;
+            const float zn = std_maxf(z_near, 1e-4f);
+            const float zf = std_maxf(z_far, zn + 1e-3f);
+            const float d = std_clampf(view_depth, zn, zf);
+            const float log_ratio = SC_LOGF(zf / zn);
+            if (log_ratio <= 1e-6f) return 0u;
+            const float t = std_clampf(SC_LOGF(d / zn) / log_ratio, 0.0f, 0.999999f);
+            const uint32_t b = (uint32_t)(t * (float)slices);
+            return b < slices - 1u ? b : slices - 1u;
+        }
+
+        struct BinGrid
+        {
+            uint32_t bins_x, bins_y, bins_z; // bins_z = 1 for the tiled builders
+            int clustered;                   // LightCullingMode::Clustered
+            float z_near, z_far;             // LightBinCullingData::z_near / z_far (already max(.., 1e-4) / max(.., zn + 1e-3), :278-279)
+            uint32_t max_per_bin;            // row stride of bin_indices; a bin holds min(count, max_per_bin) entries
+        };
+
+        // seen: ceil(n_lights / 32) words of scratch owned by this object, zeroed on entry.  Returns the number of candidates
+        // (gather's list length); the selection is what collect_object_lights makes of that list.
+        SC_HD uint32_t select_from_bins(const float* box6, const float* view, const float* view_proj, const BinGrid& g, const uint32_t* bin_counts, const uint32_t* bin_indices,
+                                        const float* records, uint32_t n_lights, int mode, uint32_t* seen, Selection& sel)
+        {
+            selection_clear(sel);
+            const float cx = 0.5f * (box6[0] + box6[3]), cy = 0.5f * (box6[1] + box6[4]), cz = 0.5f * (box6[2] + box6[5]);
+            TileRect r;
+            const bool has_bins = g.bins_x > 0u && g.bins_y > 0u && g.bins_z > 0u;
+            if (!has_bins || !project_object(box6, view, view_proj, g.z_near, g.z_far, g.bins_x, g.bins_y, r))
+            {
+                // fallback_light_scene_candidates: every visible light, in order
+                for (uint32_t li = 0; li < n_lights; ++li) consider_light(sel, li, records + (size_t)li * LIGHT_RECORD_FLOATS, box6, cx, cy, cz, mode);
+                return n_lights;
+            }
+            uint32_t tz0 = 0u, tz1 = (g.bins_z > 1u ? g.bins_z : 1u) - 1u;
+            if (g.clustered && g.bins_z > 1u)
+            {
+                tz0 = view_depth_to_cluster_slice(r.min_depth, g.z_near, g.z_far, g.bins_z);
+                tz1 = view_depth_to_cluster_slice(r.max_depth, g.z_near, g.z_far, g.bins_z);
+                if (tz0 > tz1) { const uint32_t t = tz0; tz0 = tz1; tz1 = t; }
+            }
+            uint32_t n_candidates = 0;
+            for (uint32_t tz = tz0; tz <= tz1; ++tz)
+                for (uint32_t ty = r.ty0; ty <= r.ty1; ++ty)
+                    for (uint32_t tx = r.tx0; tx <= r.tx1; ++tx)
+                    {
+                        const uint32_t bin = tz * (g.bins_x * g.bins_y) + ty * g.bins_x + tx;
+                        const uint32_t n = bin_counts[bin] < g.max_per_bin ? bin_counts[bin] : g.max_per_bin;
+                        for (uint32_t k = 0; k < n; ++k)
+                        {
+                            const uint32_t li = bin_indices[(size_t)bin * g.max_per_bin + k];
+                            if (li >= n_lights) continue;
+                            const uint32_t bit = 1u << (li & 31u);
+                            if (seen[li >> 5] & bit) continue;
+                            seen[li >> 5] |= bit;
+                            ++n_candidates;
+                            consider_light(sel, li, records + (size_t)li * LIGHT_RECORD_FLOATS, box6, cx, cy, cz, mode);
+                        }
+                    }
+            return n_candidates;
         }
     }
 }

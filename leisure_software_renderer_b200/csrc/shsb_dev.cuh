@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "legacy2_core.cuh"
+#include "scene_cull_core.cuh"
 
 namespace shsb
 {
@@ -289,6 +290,9 @@ namespace shsb
                                       uint32_t* out_counts, uint32_t* out_idx, float* out_d2, cudaStream_t s, uint64_t* launches);
     void launch_scene_tile_depth_range(const float* boxes6, uint32_t n_objects, const uint32_t* visible, uint32_t n_visible, const float view[16], const float view_proj[16],
                                        float z_near, float z_far, uint32_t tiles_x, uint32_t tiles_y, uint32_t* scratch3, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches);
+    void launch_select_object_lights(const float* boxes6, uint32_t n_objects, const float view[16], const float view_proj[16], const sc::BinGrid& grid, const uint32_t* bin_counts,
+                                     const uint32_t* bin_indices, const float* records, uint32_t n_lights, int mode, uint32_t* seen, uint32_t words_per_object, uint32_t* out_counts,
+                                     uint32_t* out_idx, float* out_d2, uint32_t* out_candidates, cudaStream_t s, uint64_t* launches);
     uint32_t legacy2_slots(const l2::Draw& d);
     void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
                              cudaStream_t s, uint64_t* launches);

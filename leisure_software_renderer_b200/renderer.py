@@ -232,6 +232,18 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_tile_depth_range_download(self.h, capi.fptr(lo), capi.fptr(hi), n), "shsb_tile_depth_range_download")
         return lo, hi
 
+    def select_object_lights_from_bins(self, object_aabbs, view, view_proj, clustered, z_near, z_far, records, cull_mode):
+        """gather_light_scene_candidates_for_aabb + collect_object_lights per object over the context's last light bins:
+        counts (n,), light indices (n, 8), squared distances (n, 8), candidate counts (n,)."""
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        mv, mvp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
+        counts, idx, d2, cand = np.zeros(len(a), np.uint32), np.zeros((len(a), 8), np.uint32), np.zeros((len(a), 8), np.float32), np.zeros(len(a), np.uint32)
+        _check(self.lib, self.h, self.lib.shsb_select_object_lights_from_bins(self.h, capi.fptr(a), len(a), capi.fptr(mv), capi.fptr(mvp), int(bool(clustered)), float(z_near),
+                                                                             float(z_far), r.ctypes.data_as(C.c_void_p), len(r), int(cull_mode), capi.u32ptr(counts),
+                                                                             capi.u32ptr(idx), capi.fptr(d2), capi.u32ptr(cand)), "shsb_select_object_lights_from_bins")
+        return counts, idx, d2, cand
+
     def lights_upload(self, records: np.ndarray):
         r = np.ascontiguousarray(records).view(np.uint8).reshape(-1, capi.LIGHT_RECORD_BYTES)
         _check(self.lib, self.h, self.lib.shsb_lights_upload(self.h, r.ctypes.data_as(C.c_void_p), len(r)), "shsb_lights_upload")

@@ -567,3 +567,36 @@ class SceneCull:
                                                                             capi.fptr(lo), capi.fptr(hi))
         assert rc == 0, rc
         return lo, hi
+
+    def select_object_lights_from_bins(self, object_aabbs, view, view_proj, bins_xyz, clustered, z_near, z_far, bin_counts, bin_indices, records, cull_mode):
+        """port / device-function flavour: bins in the capped device layout (counts[bins], indices[bins, max_per_bin])."""
+        assert self.kind == "port"
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        mv, mvp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        bc = np.ascontiguousarray(bin_counts, dtype=np.uint32).reshape(-1)
+        bi = np.ascontiguousarray(bin_indices, dtype=np.uint32).reshape(len(bc), -1)
+        r = _records_u8(records)
+        counts, idx, d2, cand = np.zeros(len(a), np.uint32), np.zeros((len(a), 8), np.uint32), np.zeros((len(a), 8), np.float32), np.zeros(len(a), np.uint32)
+        rc = getattr(self.lib, self.prefix + "select_object_lights_from_bins")(
+            capi.fptr(a), C.c_uint32(len(a)), capi.fptr(mv), capi.fptr(mvp), C.c_uint32(bins_xyz[0]), C.c_uint32(bins_xyz[1]), C.c_uint32(bins_xyz[2]), C.c_int32(int(clustered)),
+            C.c_float(z_near), C.c_float(z_far), C.c_uint32(bi.shape[1]), capi.u32ptr(bc), capi.u32ptr(bi), r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), C.c_int32(cull_mode),
+            capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2), capi.u32ptr(cand))
+        assert rc == 0, rc
+        return counts, idx, d2, cand
+
+    def reference_select_object_lights(self, object_aabbs, view, view_proj, w, h, culling_mode, tile_size, depth_slices, z_near, z_far, range_min, range_max, light_aabbs, records, cull_mode):
+        """reference flavour: build_light_bin_culling + gather + collect_object_lights from the reference's own headers."""
+        assert self.kind == "reference"
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        la = np.ascontiguousarray(light_aabbs, dtype=np.float32).reshape(-1, 6)
+        mv, mvp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        lo = np.ascontiguousarray(range_min, dtype=np.float32).reshape(-1) if range_min is not None else None
+        hi = np.ascontiguousarray(range_max, dtype=np.float32).reshape(-1) if range_max is not None else None
+        r = _records_u8(records)
+        counts, idx, d2, cand = np.zeros(len(a), np.uint32), np.zeros((len(a), 8), np.uint32), np.zeros((len(a), 8), np.float32), np.zeros(len(a), np.uint32)
+        rc = self.lib.shsref_select_object_lights_from_bins(
+            capi.fptr(a), C.c_uint32(len(a)), capi.fptr(mv), capi.fptr(mvp), C.c_uint32(w), C.c_uint32(h), C.c_int32(culling_mode), C.c_uint32(tile_size), C.c_uint32(depth_slices),
+            C.c_float(z_near), C.c_float(z_far), capi.fptr(lo) if lo is not None else None, capi.fptr(hi) if hi is not None else None, C.c_uint32(len(lo) if lo is not None else 0),
+            capi.fptr(la), r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), C.c_int32(cull_mode), capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2), capi.u32ptr(cand))
+        assert rc == 0, rc
+        return counts, idx, d2, cand

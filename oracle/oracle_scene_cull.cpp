@@ -193,4 +193,93 @@ extern "C"
             if (!has[t] || out_min[t] > out_max[t]) { out_min[t] = z_near; out_max[t] = z_far; }
         return 0;
     }
+
+    // gather_light_scene_candidates_for_aabb (lighting/light_culling_runtime.hpp:373-449) followed by collect_object_lights
+    // (lighting/light_runtime.hpp:592-616), per object, as exp-plumbing/hello_light_types_culling_sw.cpp:968-996 chains them.
+    // The bins are LightBinCullingData::bin_local_light_lists in the capped device layout (bin_counts[bins], bin_indices[bins * max_per_bin],
+    // bin = tz * bins_x * bins_y + ty * bins_x + tx); the visible-light list is the identity, so local index == scene index == light index
+    // and the fallback (no bins / nothing of the box in front of the camera) is every light in order.  z_near / z_far are
+    // LightBinCullingData's (max(cfg.z_near, 1e-4), max(cfg.z_far, z_near + 1e-3), :278-279).  out_candidates: the gathered list's length.
+    int32_t shso_select_object_lights_from_bins(const float* object_aabbs6, uint32_t n_objects, const float view[16], const float view_proj[16], uint32_t bins_x, uint32_t bins_y,
+                                                uint32_t bins_z, int32_t clustered, float z_near, float z_far, uint32_t max_per_bin, const uint32_t* bin_counts,
+                                                const uint32_t* bin_indices, const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts,
+                                                uint32_t* out_indices8, float* out_dist2_8, uint32_t* out_candidates)
+    {
+        if (!view || !view_proj || !out_counts || !out_indices8 || !out_dist2_8 || !out_candidates || cull_mode < 0 || cull_mode > 2) return 1;
+        auto mul = [](const float* m, int row, float x, float y, float z) { return (m[row] * x + m[4 + row] * y) + (m[8 + row] * z + m[12 + row] * 1.0f); };
+        auto xbin = [](float ndc_x, uint32_t bins) { const float u = std::clamp(ndc_x * 0.5f + 0.5f, 0.0f, 0.999999f); return std::min((uint32_t)(u * (float)bins), bins - 1u); };
+        auto ybin = [](float ndc_y, uint32_t bins) { const float v = std::clamp(1.0f - (ndc_y * 0.5f + 0.5f), 0.0f, 0.999999f); return std::min((uint32_t)(v * (float)bins), bins - 1u); };
+        auto slice = [](float view_depth, float zn_, float zf_, uint32_t slices) -> uint32_t { // view_depth_to_cluster_slice :170-186
+            if (slices <= 1u) return 0u;
+            const float zn = std::max(zn_, 1e-4f), zf = std::max(zf_, zn + 1e-3f);
+            const float d = std::clamp(view_depth, zn, zf);
+            const float log_ratio = std::log(zf / zn);
+            if (log_ratio <= 1e-6f) return 0u;
+            const float t = std::clamp(std::log(d / zn) / log_ratio, 0.0f, 0.999999f);
+            return std::min((uint32_t)(t * (float)slices), slices - 1u);
+        };
+        const bool has_bins = bins_x > 0 && bins_y > 0 && bins_z > 0 && bin_counts && bin_indices;
+        std::vector<uint32_t> cand, identity(n_lights);
+        for (uint32_t i = 0; i < n_lights; ++i) identity[i] = i;
+        for (uint32_t o = 0; o < n_objects; ++o)
+        {
+            const float* b = object_aabbs6 + (size_t)o * 6;
+            const std::vector<uint32_t>* list = &identity;
+            bool any = false;
+            float min_x = 1.0f, max_x = -1.0f, min_y = 1.0f, max_y = -1.0f, min_d = z_far, max_d = z_near;
+            if (has_bins)
+            {
+                for (int c = 0; c < 8; ++c) // project_aabb_bounds :92-153
+                {
+                    const float x = (c & 1) ? b[3] : b[0], y = (c & 2) ? b[4] : b[1], z = (c & 4) ? b[5] : b[2];
+                    const float cw = mul(view_proj, 3, x, y, z);
+                    if (cw <= 1e-5f) continue;
+                    const float nx = mul(view_proj, 0, x, y, z) / cw, ny = mul(view_proj, 1, x, y, z) / cw;
+                    min_x = std::min(min_x, nx); max_x = std::max(max_x, nx);
+                    min_y = std::min(min_y, ny); max_y = std::max(max_y, ny);
+                    const float vd = mul(view, 2, x, y, z);
+                    if (vd > 1e-5f) { min_d = std::min(min_d, vd); max_d = std::max(max_d, vd); }
+                    any = true;
+                }
+            }
+            if (any)
+            {
+                min_x = std::clamp(min_x, -1.0f, 1.0f); max_x = std::clamp(max_x, -1.0f, 1.0f);
+                min_y = std::clamp(min_y, -1.0f, 1.0f); max_y = std::clamp(max_y, -1.0f, 1.0f);
+                if (min_x > max_x) std::swap(min_x, max_x);
+                if (min_y > max_y) std::swap(min_y, max_y);
+                min_d = std::clamp(min_d, z_near, z_far);
+                max_d = std::clamp(max_d, z_near, z_far);
+                if (min_d > max_d) { min_d = z_near; max_d = z_far; }
+                const uint32_t tx0 = xbin(min_x, bins_x), tx1 = xbin(max_x, bins_x), ty0 = ybin(max_y, bins_y), ty1 = ybin(min_y, bins_y);
+                uint32_t tz0 = 0u, tz1 = std::max(bins_z, 1u) - 1u;
+                if (clustered && bins_z > 1u)
+                {
+                    tz0 = slice(min_d, z_near, z_far, bins_z);
+                    tz1 = slice(max_d, z_near, z_far, bins_z);
+                    if (tz0 > tz1) std::swap(tz0, tz1);
+                }
+                cand.clear();
+                for (uint32_t tz = tz0; tz <= tz1; ++tz)
+                    for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                        for (uint32_t tx = tx0; tx <= tx1; ++tx)
+                        {
+                            const uint32_t bin = tz * (bins_x * bins_y) + ty * bins_x + tx;
+                            const uint32_t n = std::min(bin_counts[bin], max_per_bin);
+                            for (uint32_t k = 0; k < n; ++k)
+                            {
+                                const uint32_t li = bin_indices[(size_t)bin * max_per_bin + k];
+                                if (li >= n_lights) continue;
+                                if (std::find(cand.begin(), cand.end(), li) == cand.end()) cand.push_back(li);
+                            }
+                        }
+                list = &cand;
+            }
+            out_candidates[o] = (uint32_t)list->size();
+            if (int32_t rc = shso_collect_object_lights(b, 1, list->data(), (uint32_t)list->size(), records160, n_lights, cull_mode, out_counts + o, out_indices8 + (size_t)o * 8,
+                                                        out_dist2_8 + (size_t)o * 8))
+                return rc;
+        }
+        return 0;
+    }
 }

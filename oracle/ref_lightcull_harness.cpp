@@ -169,3 +169,53 @@ extern "C" int32_t shsref_tile_depth_range_from_scene(const float* object_aabbs6
     for (size_t t = 0; t < r.min_view_depth.size(); ++t) { out_min[t] = r.min_view_depth[t]; out_max[t] = r.max_view_depth[t]; }
     return 0;
 }
+
+extern "C" int32_t shsref_select_object_lights_from_bins(const float* object_aabbs6, uint32_t n_objects, const float view[16], const float view_proj[16], uint32_t viewport_w,
+                                                          uint32_t viewport_h, int32_t culling_mode /* LightCullingMode 0..3 */, uint32_t tile_size, uint32_t depth_slices, float z_near,
+                                                          float z_far, const float* range_min, const float* range_max, uint32_t n_ranges, const float* light_aabbs6,
+                                                          const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts, uint32_t* out_indices8,
+                                                          float* out_dist2_8, uint32_t* out_candidates)
+{
+    // build_light_bin_culling (lighting/light_culling_runtime.hpp:266-371) over all lights, then per object
+    // gather_light_scene_candidates_for_aabb (:373-449) -> collect_object_lights, as hello_light_types_culling_sw.cpp:968-996 does
+    if (!view || !view_proj || !out_counts || !out_indices8 || !out_dist2_8 || !out_candidates) return 1;
+    Lights L(light_aabbs6, n_lights);
+    std::vector<shs::LightInstance> lights(n_lights);
+    shs::SceneElementSet light_scene;
+    std::vector<uint32_t> visible(n_lights);
+    for (uint32_t i = 0; i < n_lights; ++i)
+    {
+        std::memcpy(&lights[i].packed, (const uint8_t*)records160 + (size_t)i * 160, 160);
+        lights[i].props.position_ws = glm::vec3(lights[i].packed.position_range);
+        shs::SceneElement e{};
+        e.geometry = L.scene[i];
+        e.geometry.stable_id = i + 1u;
+        e.user_index = i;
+        light_scene.add(e);
+        visible[i] = i;
+    }
+    glm::mat4 v, vp;
+    std::memcpy(&v, view, 64);
+    std::memcpy(&vp, view_proj, 64);
+    shs::LightBinCullingConfig cfg{};
+    cfg.mode = (shs::LightCullingMode)culling_mode;
+    cfg.tile_size = tile_size;
+    cfg.cluster_depth_slices = depth_slices;
+    cfg.z_near = z_near;
+    cfg.z_far = z_far;
+    const shs::LightBinCullingData data = shs::build_light_bin_culling(std::span<const uint32_t>(visible.data(), visible.size()), light_scene, vp, viewport_w, viewport_h, cfg,
+                                                                       std::span<const float>(range_min, range_min ? n_ranges : 0), std::span<const float>(range_max, range_max ? n_ranges : 0));
+    std::vector<uint32_t> scratch;
+    for (uint32_t o = 0; o < n_objects; ++o)
+    {
+        shs::AABB box{};
+        box.minv = glm::vec3(object_aabbs6[6 * o], object_aabbs6[6 * o + 1], object_aabbs6[6 * o + 2]);
+        box.maxv = glm::vec3(object_aabbs6[6 * o + 3], object_aabbs6[6 * o + 4], object_aabbs6[6 * o + 5]);
+        const std::span<const uint32_t> cand = shs::gather_light_scene_candidates_for_aabb(data, box, v, vp, scratch);
+        out_candidates[o] = (uint32_t)cand.size();
+        const shs::LightSelection sel = shs::collect_object_lights(box, cand, light_scene, lights, (shs::LightObjectCullMode)cull_mode);
+        out_counts[o] = sel.count;
+        for (uint32_t k = 0; k < 8; ++k) { out_indices8[8 * o + k] = sel.indices[k]; out_dist2_8[8 * o + k] = sel.dist2[k]; }
+    }
+    return 0;
+}

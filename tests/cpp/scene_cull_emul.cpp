@@ -4,6 +4,8 @@
 // Nothing in the product links or loads it.
 #include <cmath>
 #include <cstring>
+#define SC_LOGF(x) logf(x) /* the host libm flavour (the device narrows a double log); see scene_cull_core.cuh */
+#include <algorithm>
 #include <vector>
 #include "scene_cull_core.cuh"
 
@@ -73,5 +75,23 @@ extern "C" int32_t shsemu_tile_depth_range_from_scene(const float* object_aabbs6
             }
     }
     for (uint32_t t = 0; t < tiles; ++t) finish_tile(has[t], key_depth(kmin[t]), key_depth(kmax[t]), z_near, z_far, out_min[t], out_max[t]);
+    return 0;
+}
+
+extern "C" int32_t shsemu_select_object_lights_from_bins(const float* object_aabbs6, uint32_t n_objects, const float view[16], const float view_proj[16], uint32_t bins_x, uint32_t bins_y,
+                                                          uint32_t bins_z, int32_t clustered, float z_near, float z_far, uint32_t max_per_bin, const uint32_t* bin_counts,
+                                                          const uint32_t* bin_indices, const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts,
+                                                          uint32_t* out_indices8, float* out_dist2_8, uint32_t* out_candidates)
+{
+    BinGrid g{bins_x, bins_y, bins_z, clustered, z_near, z_far, max_per_bin};
+    std::vector<uint32_t> seen((n_lights + 31) / 32 + 1);
+    for (uint32_t o = 0; o < n_objects; ++o)
+    {
+        std::fill(seen.begin(), seen.end(), 0u);
+        Selection sel;
+        out_candidates[o] = select_from_bins(object_aabbs6 + (size_t)o * 6, view, view_proj, g, bin_counts, bin_indices, (const float*)records160, n_lights, cull_mode, seen.data(), sel);
+        out_counts[o] = sel.count;
+        for (uint32_t k = 0; k < 8; ++k) { out_indices8[8 * o + k] = sel.idx[k]; out_dist2_8[8 * o + k] = sel.d2[k]; }
+    }
     return 0;
 }

@@ -103,6 +103,7 @@ def test_legacy2_wrappers_marshal_their_arguments_without_a_device():
              lambda: ctx.legacy3_draw_pbr(1, u, 2, 1, 3, 4),
              lambda: ctx.cull_objects_frustum(np.zeros((3, 10), np.float32), eye),
              lambda: ctx.tile_depth_range_from_scene(np.zeros((3, 6), np.float32), np.arange(3, dtype=np.uint32), eye, eye, 64, 48, 16, 0.1, 100.0),
+             lambda: ctx.select_object_lights_from_bins(np.zeros((3, 6), np.float32), eye, eye, True, 0.1, 100.0, np.zeros((4, 160), np.uint8), 2),
              lambda: ctx.collect_object_lights(np.zeros((3, 6), np.float32), np.arange(4, dtype=np.uint32), np.zeros((4, 160), np.uint8), 1)]
     for call in calls:
         with pytest.raises(capi.ShsbError, match="status 1"):

@@ -104,3 +104,59 @@ def test_scene_cull_scenes_are_not_trivial(refs):
         replaced += int(np.count_nonzero((none[1] != idx).any(axis=1)))
     assert (seen > 50).all(), seen
     assert full > 100 and replaced > 100, (full, replaced)
+
+
+def _bins_for(sc, lref, culling_mode, slices):
+    """The light bins of build_light_bin_culling for this scene in the capped device layout, from the PINNED bin builders of the
+    restatement (cap = n_lights, so nothing is cut), plus the reference-derived light records and AABBs."""
+    import test_light_cull_pinned_cpu as lp
+    from oracle.bindings import Oracle
+    recs, light_aabbs = lp.with_reference_bounds(lref, sc["lights"])
+    zn, zf = max(sc["zn"], 1e-4), None
+    zn32 = np.float32(max(np.float32(sc["zn"]), np.float32(1e-4)))
+    zf32 = np.float32(max(np.float32(sc["zf"]), zn32 + np.float32(1e-3)))
+    ts = max(sc["ts"], 1)
+    mode = {1: capi.LIGHT_CULL_TILED, 2: capi.LIGHT_CULL_TILED_VIEW_DEPTH, 3: capi.LIGHT_CULL_CLUSTERED}[culling_mode]
+    desc = capi.LightCullDesc(sc["view_proj"], sc["w"], sc["h"], mode, ts, len(recs), depth_slices=max(slices, 1), z_near=float(zn32), z_far=float(zf32))
+    return recs, light_aabbs, desc, float(zn32), float(zf32), Oracle("port")
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_fuzz_bin_gather_and_selection_equals_the_reference(refs, seed):
+    """build_light_bin_culling -> gather_light_scene_candidates_for_aabb -> collect_object_lights, per object, as the reference's
+    software light-culling demo chains them (exp-plumbing/hello_light_types_culling_sw.cpp:968-996): candidate counts, selected slots
+    and squared distances of the restatement (fed with the pinned restatement's bins) and of the device functions, against the
+    compiled reference, bit for bit -- tiled, tiled + scene depth ranges, clustered."""
+    port, ref, lref = refs
+    sc = fuzz_cases.scene_cull(seed)
+    slices = [1, 3, 16][seed % 3]
+    objs = sc["aabbs"][:120]
+    for culling_mode in (1, 2, 3):
+        recs, light_aabbs, desc, zn, zf, oport = _bins_for(sc, lref, culling_mode, slices)
+        lo = hi = None
+        if culling_mode == 2:
+            lo, hi = port.tile_depth_range_from_scene(sc["aabbs"], sc["visible_objects"], sc["view"], sc["view_proj"], sc["w"], sc["h"], desc.tile_size, zn, zf)
+        bc, bi = oport.light_cull_ex(recs, desc, lo, hi)
+        tiles_x, tiles_y = (sc["w"] + desc.tile_size - 1) // desc.tile_size, (sc["h"] + desc.tile_size - 1) // desc.tile_size
+        bins = (tiles_x, tiles_y, desc.depth_slices if culling_mode == 3 else 1)
+        for cull_mode in (1, 2):
+            r = ref.reference_select_object_lights(objs, sc["view"], sc["view_proj"], sc["w"], sc["h"], culling_mode, desc.tile_size, slices, sc["zn"], sc["zf"], lo, hi,
+                                                   light_aabbs, recs, cull_mode)
+            for who, impl in (("restatement", port), ("device functions", Emul())):
+                p = impl.select_object_lights_from_bins(objs, sc["view"], sc["view_proj"], bins, culling_mode == 3, zn, zf, bc, bi, recs, cull_mode)
+                for k, what in enumerate(("counts", "indices", "dist2", "candidates")):
+                    assert np.array_equal(p[k].view(np.uint32), r[k].view(np.uint32)), f"seed {seed} bins {culling_mode} cull {cull_mode}: {who}: {what} differ"
+
+
+def test_bin_gather_is_not_trivial(refs):
+    port, _, lref = refs
+    fewer = fallback = 0
+    for seed in range(12):
+        sc = fuzz_cases.scene_cull(seed)
+        recs, light_aabbs, desc, zn, zf, oport = _bins_for(sc, lref, 3, 16)
+        bc, bi = oport.light_cull_ex(recs, desc)
+        tiles_x, tiles_y = (sc["w"] + desc.tile_size - 1) // desc.tile_size, (sc["h"] + desc.tile_size - 1) // desc.tile_size
+        p = port.select_object_lights_from_bins(sc["aabbs"], sc["view"], sc["view_proj"], (tiles_x, tiles_y, 16), True, zn, zf, bc, bi, recs, 1)
+        fewer += int(np.count_nonzero(p[3] < len(recs)))
+        fallback += int(np.count_nonzero(p[3] == len(recs)))
+    assert fewer > 300 and fallback > 20, (fewer, fallback)

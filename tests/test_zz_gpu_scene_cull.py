@@ -85,3 +85,27 @@ def test_scene_depth_ranges_feed_the_view_depth_bin_builder(gpu):
     assert np.array_equal(gc, pc)
     keep = np.arange(64)[None, :] < np.minimum(pc, 64)[:, None]
     assert np.array_equal(gi[keep], pi[keep])
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_fuzz_bin_gather_and_selection_parity(gpu, seed):
+    """shsb_select_object_lights_from_bins over the bins the context built (tiled and clustered) == the restatement fed with the
+    restatement's bins (which tests/test_scene_cull_cpu.py pins against the reference's build_light_bin_culling -> gather -> collect)."""
+    from leisure_software_renderer_b200 import capi
+    from oracle.bindings import Oracle
+    sc = fuzz_cases.scene_cull(seed)
+    lights = sc["lights"]
+    zn = float(np.float32(max(np.float32(sc["zn"]), np.float32(1e-4))))
+    zf = float(np.float32(max(np.float32(sc["zf"]), np.float32(zn) + np.float32(1e-3))))
+    gpu.lights_upload(lights)
+    tiles_x, tiles_y = (sc["w"] + sc["ts"] - 1) // sc["ts"], (sc["h"] + sc["ts"] - 1) // sc["ts"]
+    for clustered, slices in ((False, 1), (True, [1, 3, 16][seed % 3])):
+        mode = capi.LIGHT_CULL_CLUSTERED if clustered else capi.LIGHT_CULL_TILED
+        desc = capi.LightCullDesc(sc["view_proj"], sc["w"], sc["h"], mode, sc["ts"], max(1, len(lights)), depth_slices=slices, z_near=zn, z_far=zf)
+        gpu.light_cull_ex(desc)
+        bc, bi = Oracle("port").light_cull_ex(lights, desc)
+        for cull_mode in (0, 1, 2):
+            g = gpu.select_object_lights_from_bins(sc["aabbs"], sc["view"], sc["view_proj"], clustered, sc["zn"], sc["zf"], lights, cull_mode)
+            c = SceneCull("port").select_object_lights_from_bins(sc["aabbs"], sc["view"], sc["view_proj"], (tiles_x, tiles_y, slices), clustered, zn, zf, bc, bi, lights, cull_mode)
+            for k, what in enumerate(("counts", "indices", "dist2", "candidates")):
+                assert np.array_equal(g[k].view(np.uint32), c[k].view(np.uint32)), f"seed {seed} clustered {clustered} cull {cull_mode}: {what}"
