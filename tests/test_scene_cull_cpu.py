@@ -112,7 +112,6 @@ def _bins_for(sc, lref, culling_mode, slices):
     import test_light_cull_pinned_cpu as lp
     from oracle.bindings import Oracle
     recs, light_aabbs = lp.with_reference_bounds(lref, sc["lights"])
-    zn, zf = max(sc["zn"], 1e-4), None
     zn32 = np.float32(max(np.float32(sc["zn"]), np.float32(1e-4)))
     zf32 = np.float32(max(np.float32(sc["zf"]), zn32 + np.float32(1e-3)))
     ts = max(sc["ts"], 1)
