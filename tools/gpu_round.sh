@@ -21,3 +21,5 @@ ncu --set full --clock-control none --import-source on -k regex:legacy_ -s 8 -c 
 python tools/bench_legacy2.py 100 > $OUT/bench_legacy2.jsonl 2> $OUT/bench_legacy2.err; echo "legacy2 bench rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:legacy2_ -s 12 -c 4 -f -o $OUT/legacy2_kernels \
     python tools/bench_legacy2.py 4 > $OUT/ncu_legacy2.log 2>&1; echo "ncu legacy2 rc=$?"
+# scene-level culling calls (8f row 1): parity against the reference's own functions + calls/s through the C-ABI with host buffers
+python tools/bench_scene_cull.py 20 > $OUT/bench_scene_cull.jsonl 2> $OUT/bench_scene_cull.err; echo "scene cull bench rc=$?"
