@@ -71,3 +71,16 @@ def test_c2_shaped_light_lists_equal_the_reference(port, ref):
     assert np.array_equal(pc, rc) and int(pc.sum()) > 1000
     keep = np.arange(128)[None, :] < np.minimum(pc, 128)[:, None]
     assert np.array_equal(pi[keep], ri[keep])
+
+
+def test_c2_full_size_light_lists_equal_the_reference(port, ref):
+    """BASELINE configs[1] at its full size: 1920x1080, 16-px tiles (8160 tiles), 1024 point / spot lights, cap 128 -- about 548 k list
+    entries, up to ~300 lights in a tile (so the cap cuts lists: counts stay uncapped on both sides, the first 128 entries agree)."""
+    sd = scenes.scene_c2()
+    r, aabbs = with_reference_bounds(ref, sd.lights)
+    desc = capi.LightCullDesc(sd.viewproj, sd.w, sd.h, capi.LIGHT_CULL_TILED, 16, 128, z_near=sd.zn, z_far=sd.zf)
+    pc, pi = port.light_cull_ex(r, desc)
+    rc, ri = ref.light_cull(aabbs, desc)
+    assert np.array_equal(pc, rc) and int(pc.sum()) > 400000 and int(pc.max()) > 128
+    keep = np.arange(128)[None, :] < np.minimum(pc, 128)[:, None]
+    assert np.array_equal(pi[keep], ri[keep])
