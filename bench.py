@@ -315,8 +315,10 @@ def run_reference(args):
     """The reference's OWN CPU code for this path (oracle/_ref = its headers compiled from /root/reference):
     PassPBRForward::execute + PassTonemap::execute with ThreadPoolJobSystem(all host cores), as
     exp-plumbing/hello_pass_basics.cpp drives them.  NOTE the reference's CPU Forward+ lit pass shades the sun
-    only (passes/pass_pbr_forward.hpp:157-195 never reads tile lists) and its tile-list builder needs Jolt
-    (not compilable here), so this arm does strictly LESS work per frame than the CUDA arm."""
+    only (passes/pass_pbr_forward.hpp:157-195 never reads tile lists), so this arm does strictly LESS work per frame than the
+    CUDA arm.  Its tile-list builder (cull_lights_tiled, lighting/jolt_light_culling.hpp:135-187 -- a serial loop in the reference)
+    is part of the frame when oracle/_ref/libshs_lightcull_ref.so exists (the reference's header compiled against the JoltPhysics
+    declaration shim, oracle/ref_lightcull_harness.cpp); the `sample` text says whether it was."""
     rank, _, world = dist_env()
     if rank != 0:
         return
@@ -329,9 +331,23 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     o.set_threads(cores)
     sd = scenes.scene_c2(W, H)
+    cull = None
+    if kind == "reference":
+        try:  # the reference's own tile-list builder over the frame's 1024 lights (A11), serial like in the reference
+            import numpy as np
+            from leisure_software_renderer_b200 import capi
+            lref = bindings.LightCullReference()
+            light_aabbs = np.ascontiguousarray(np.concatenate([sd.lights["cull_aabb_min"][:, :3], sd.lights["cull_aabb_max"][:, :3]], axis=1), dtype=np.float32)
+            desc = capi.LightCullDesc(sd.viewproj, W, H, capi.LIGHT_CULL_TILED, 16, 128, z_near=sd.zn, z_far=sd.zf)
+            lref.light_cull(light_aabbs, desc)
+            cull = lambda: lref.light_cull(light_aabbs, desc)
+        except Exception as e:  # library not built and no reference tree: the lit pass alone, as before
+            print(f"reference arm: cull_lights_tiled unavailable ({e}); timing the lit pass only", file=sys.stderr)
 
     def frame():
         if kind == "reference":
+            if cull is not None:
+                cull()
             harness.cpu_forward(o, sd, forward_plus=False, aov=False)
         else:
             harness.cpu_forward(o, sd, forward_plus=True, aov=False)
@@ -345,7 +361,8 @@ def run_reference(args):
         frame()
     dt = time.perf_counter() - t0
     fps = steps / dt
-    sample = (f"{steps} full C2 frames: PassPBRForward (sun + fake IBL only; the reference CPU path never shades tile light lists) + PassTonemap "
+    sample = (f"{steps} full C2 frames: " + ("cull_lights_tiled over 1024 lights (the reference's serial builder, Jolt declaration shim) + " if cull is not None else "") +
+              f"PassPBRForward (sun + fake IBL only; the reference CPU path never shades tile light lists) + PassTonemap "
               f"via oracle/_ref/libshs_ref.so, ThreadPoolJobSystem({cores})" if kind == "reference"
               else f"{steps} full C2 Forward+ frames via oracle/liboracle.so (single thread)")
     line = {"impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps,
