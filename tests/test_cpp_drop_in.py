@@ -104,3 +104,18 @@ def test_legacy2_drop_in_compiles_and_has_no_cpu_fallback(name):
         r = subprocess.run([path], capture_output=True, text=True)
         print(r.stdout, r.stderr)
         assert r.returncode == 77 and "every call refused" in r.stdout and "reference side: 18598 of 30000 px covered" in r.stdout
+
+
+def test_scene_cull_drop_in_compiles_and_has_no_cpu_fallback():
+    """host/shs_b200/scene_cull_drop_in.hpp compiled against the reference's Jolt-guarded headers (JoltPhysics declaration shim): the
+    reference side culls / selects / builds ranges with its own functions; without a device the binding refuses every call."""
+    import torch
+    path = os.path.join(ROOT, "tests", "cpp", "_build", "scene_cull_drop_in_test")
+    if not os.path.isdir("/root/reference") and not os.path.exists(path):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([path], capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        assert r.returncode == 77 and "every call refused" in r.stdout and "417 of 600 objects visible" in r.stdout

@@ -109,3 +109,16 @@ def test_fuzz_bin_gather_and_selection_parity(gpu, seed):
             c = SceneCull("port").select_object_lights_from_bins(sc["aabbs"], sc["view"], sc["view_proj"], (tiles_x, tiles_y, slices), clustered, zn, zf, bc, bi, lights, cull_mode)
             for k, what in enumerate(("counts", "indices", "dist2", "candidates")):
                 assert np.array_equal(g[k].view(np.uint32), c[k].view(np.uint32)), f"seed {seed} clustered {clustered} cull {cull_mode}: {what}"
+
+
+def test_scene_cull_drop_in_parity_on_gpu():
+    """shs::b200::cull_vs_frustum / collect_object_lights / build_tile_view_depth_range_from_scene over the reference's own types vs the
+    reference functions (tests/cpp/scene_cull_drop_in_test.cpp): every result equal."""
+    import os
+    import subprocess
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", "scene_cull_drop_in_test")
+    if not os.path.exists(path):
+        pytest.skip("tests/cpp/_build/scene_cull_drop_in_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
