@@ -362,8 +362,7 @@ class L2Uniforms(C.Structure):
 
 class Legacy2Oracle:
     """The legacy soft-shadow demo (config-3 flavour) on the CPU: "port" = oracle/oracle_legacy.cpp (second
-    half), "reference" = hello_shadow_mapping_soft.cpp compiled by oracle/ref_legacy2_harness.cpp.  CPU only: the CUDA path of this
-    row is not built yet."""
+    half), "reference" = hello_shadow_mapping_soft.cpp compiled by oracle/ref_legacy2_harness.cpp.  The CUDA path of this row (csrc/legacy2.cu) is compared with the port by tests/test_zz_gpu_legacy2.py."""
 
     def __init__(self, kind: str = "port"):
         assert kind in ("port", "reference")
@@ -417,7 +416,7 @@ class L3Uniforms(C.Structure):
 
 class Legacy3Oracle:
     """The legacy PBR / IBL demo (config-4 flavour) on the CPU: "port" = oracle/oracle_legacy.cpp (third part),
-    "reference" = hello_pbr.cpp compiled by oracle/ref_legacy3_harness.cpp.  CPU only: the CUDA path of this row is not built."""
+    "reference" = hello_pbr.cpp compiled by oracle/ref_legacy3_harness.cpp.  The CUDA path (csrc/legacy2.cu, MODE_PBR) is compared with the port by tests/test_zz_gpu_legacy2.py."""
 
     def __init__(self, kind: str = "port"):
         assert kind in ("port", "reference")

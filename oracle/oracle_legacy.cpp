@@ -14,12 +14,12 @@
 //       PCSS :252-445, vertex shaders :746-784, draw_triangle_tile_shadow :796-839, draw_triangle_tile_color_depth_softshadow :845-986,
 //       fragment_shader_softshadow :991-1040
 // PINNED the same way (oracle/ref_legacy2_harness.cpp -> oracle/_ref/libshs_legacy2_ref.so, tests/test_legacy2_cpu.py).  The CUDA
-// path of this row is NOT built yet: this restatement is the checker it will be built against.
+// path of this row (csrc/legacy2.cu) is checked against this restatement (tests/test_zz_gpu_legacy2.py).
 //
 // Third part: the legacy PBR / IBL demo (config-4 flavour, row L3), cpp-folders/src/hello-render-target/hello_pbr.cpp
 //   PBR:: :238-279, shadow_factor_pcf_2x2 :599-621, fragment_shader_pbr :627-727, draw_triangle_tile_color_depth_motion :883-1045,
 //   with shs-renderer-lib/include/shs/resources/ibl.hpp:215-287 (cube-map sampling).  Pinned by oracle/ref_legacy3_harness.cpp,
-//   tests/test_legacy3_cpu.py.  CUDA path not built yet either.
+//   tests/test_legacy3_cpu.py.  CUDA path: csrc/legacy2.cu (MODE_PBR), same GPU test file.
 #include <cmath>
 #include <cstdint>
 #include <cstring>

@@ -1,7 +1,7 @@
 """The legacy soft-shadow demo (config-3 flavour) on the CPU: the restatement (second half of
 oracle/oracle_legacy.cpp) against the reference's OWN source, hello_shadow_mapping_soft.cpp, compiled where it lies by
-oracle/ref_legacy2_harness.cpp -- shadow map, canvas and z-buffer bit for bit.  (The CUDA path of this row is not built yet; this
-is the checker it will be built against.)"""
+oracle/ref_legacy2_harness.cpp -- shadow map, canvas and z-buffer bit for bit.  (This is the checker the CUDA path of the row, csrc/legacy2.cu, is compared with:
+tests/test_zz_gpu_legacy2.py.)"""
 import os
 
 import numpy as np

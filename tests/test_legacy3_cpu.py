@@ -1,7 +1,7 @@
 """The legacy PBR / IBL demo (config-4 flavour) on the CPU: the restatement (third part of
 oracle/oracle_legacy.cpp) against the reference's OWN source, hello_pbr.cpp with the library's shs/resources/ibl.hpp, compiled where
-it lies by oracle/ref_legacy3_harness.cpp -- shadow map, z-buffer and velocity buffer bit for bit, canvas identical.  (The CUDA path
-of this row is not built; this is the checker it will be built against.)"""
+it lies by oracle/ref_legacy3_harness.cpp -- shadow map, z-buffer and velocity buffer bit for bit, canvas identical.  (This is the checker the CUDA path of the row,
+csrc/legacy2.cu in MODE_PBR, is compared with: tests/test_zz_gpu_legacy2.py.)"""
 import os
 
 import numpy as np
