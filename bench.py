@@ -152,7 +152,6 @@ def run_ours(args):
 
     # Rotating render-target sets: 4 x (33.2 + 8.3 + 8.3 MB) = 199 MB > 126 MB L2, so a frame's output lines
     # cannot still be dirty-resident in L2 when the same buffers are written again.
-    NSETS = 4
     sets = [(ctx.rt_create(capi.RT_COLOR_HDR, W, H), ctx.rt_create(capi.RT_DEPTH_MOTION, W, H, sd.zn, sd.zf), ctx.rt_create(capi.RT_COLOR_LDR, W, H))
             for _ in range(NSETS)]
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
@@ -205,11 +204,25 @@ def run_ours(args):
     # one frame with statistics (also sizes the per-frame arena), then warm-up
     st = ctx.frame_forward_plus(sd.scene, fp, *sets[0]).as_dict()
     counts, _ = ctx.light_lists_download()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
+    n_warm = max(args.warmup, 3)
+
+    def warm(e2e):
+        """Warm-up of the path that is timed next: the same calls as the timed loop (both executable-graph topologies of the
+        front end -- with and without stage events --, the light-upload ring, the read-back streams and their pinned buffers),
+        at least 2 x NSETS frames so that every render-target set and every transient arena has been through it once."""
+        if not e2e:
+            ctx.timing_enable(TIMING_STRIDE)
+        for i in range(max(n_warm, 2 * NSETS)):
+            step(i, e2e)
+        if e2e:
+            ctx.sync()
+        barrier()
+        if not e2e:
+            ctx.timing_collect()
+            ctx.timing_enable(False)
 
     def timed(e2e):
+        warm(e2e)
         launches0 = ctx.launch_count()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -263,11 +276,7 @@ def run_ours(args):
             "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: 1080p Forward+ frame, 100 Suzanne instances ({st['tri_input']} tris), 1024 point/spot lights, 16-px tiles, <=128 lights/tile"
-                                   + (f"; camera batch of {world}, one camera per GPU, LDR frames gathered to rank 0 over NCCL" if world > 1 else ""),
-                       "resolution": [W, H], "tile_size": int(fp.tile_size), "max_lights_per_tile": int(fp.max_lights_per_tile),
-                       "parallelism": f"sort-first camera batch x{world}" if world > 1 else "single GPU",
-                       "l2": f"{NSETS} rotating render-target sets ({NSETS * W * H * 24 / 1e6:.0f} MB) > 126 MB L2"},
+            "config": workload_config(sd, world),
             "mtri_per_s": fps * st["tri_input"] / 1e6, "mfrag_per_s": fps * st["frag_covered"] / 1e6,
             "frame_stats": st,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -291,6 +300,21 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+NSETS = 4
+
+
+def workload_config(sd, world):
+    """The `config` object of the JSON line -- the same dict from both arms (the driver compares them)."""
+    tris = sum(len(sd.meshes[it["mesh"] - 1]["indices"]) // 3 for it in sd.items)
+    n_lights = 0 if sd.lights is None else len(sd.lights)
+    return {"workload": f"C2: 1080p Forward+ frame, {len(sd.items)} Suzanne instances ({tris} tris), {n_lights} point/spot lights, "
+                        f"{int(sd.fp.tile_size)}-px tiles, <={int(sd.fp.max_lights_per_tile)} lights/tile"
+                        + (f"; camera batch of {world}, one camera per GPU, LDR frames gathered to rank 0 over NCCL" if world > 1 else ""),
+            "resolution": [W, H], "tile_size": int(sd.fp.tile_size), "max_lights_per_tile": int(sd.fp.max_lights_per_tile),
+            "parallelism": f"sort-first camera batch x{world}" if world > 1 else "single GPU",
+            "l2": f"{NSETS} rotating render-target sets ({NSETS * W * H * 24 / 1e6:.0f} MB) > 126 MB L2"}
 
 
 def cpu_baseline_port(sd, budget_s):
@@ -353,8 +377,9 @@ def run_reference(args):
             harness.cpu_forward(o, sd, forward_plus=True, aov=False)
 
     t0 = time.perf_counter(); frame(); t1 = time.perf_counter() - t0
+    n_warm = max(args.warmup, 3)                                      # the CUDA arm's rule, so that both lines carry the same `warmup`
     steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(n_warm if t1 * n_warm < 30.0 else 1):
         frame()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -366,10 +391,9 @@ def run_reference(args):
               f"via oracle/_ref/libshs_ref.so, ThreadPoolJobSystem({cores})" if kind == "reference"
               else f"{steps} full C2 Forward+ frames via oracle/liboracle.so (single thread)")
     line = {"impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps,
-            "steps_requested": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "steps_requested": args.steps, "warmup": n_warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 1080p Forward+ frame, 100 Suzanne instances (96700 tris), 1024 point/spot lights, 16-px tiles, <=128 lights/tile",
-                       "resolution": [W, H]},
+            "config": workload_config(sd, world),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
