@@ -599,3 +599,60 @@ class SceneCull:
             capi.fptr(la), r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), C.c_int32(cull_mode), capi.u32ptr(counts), capi.u32ptr(idx), capi.fptr(d2), capi.u32ptr(cand))
         assert rc == 0, rc
         return counts, idx, d2, cand
+
+
+REF_GLSL_A9_LIB = os.path.join(_HERE, "_ref", "libshs_glsl_a9_ref.so")
+
+
+class LocalLightEvaluator:
+    """Row A9 for ONE surface point through either checker:
+      kind "glsl" -> oracle/_ref/libshs_glsl_a9_ref.so: the reference's fp_stress_scene.frag text compiled as C++
+                     (oracle/extract_glsl_a9.py + oracle/ref_glsl_a9_harness.cpp),
+      kind "port" -> oracle/liboracle.so: this repo's restatement (oracle.cpp eval_local_light / forward_plus_lights)."""
+
+    def __init__(self, kind: str):
+        self.kind = kind
+        if kind == "glsl":
+            if not os.path.exists(REF_GLSL_A9_LIB):
+                build("reference")
+            self.lib, self.pfx = C.CDLL(REF_GLSL_A9_LIB), "shsglsl_"
+        else:
+            if not os.path.exists(PORT_LIB):
+                build("port")
+            self.lib, self.pfx = C.CDLL(PORT_LIB), "shso_"
+        self._att = getattr(self.lib, self.pfx + "attenuation_quadratic")
+        self._att.restype = C.c_float
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_GLSL_A9_LIB) or os.path.isdir("/root/reference")
+
+    @staticmethod
+    def _f3(v):
+        return (C.c_float * 3)(*[float(x) for x in v])
+
+    def eval_local_light(self, records, idx, P, N, V, albedo, metallic, roughness, technique=0):
+        r = _records_u8(records)
+        out = (C.c_float * 3)()
+        getattr(self.lib, self.pfx + "eval_local_light")(r.ctypes.data_as(C.c_void_p), C.c_uint32(idx), self._f3(P), self._f3(N), self._f3(V), self._f3(albedo),
+                                                          C.c_float(metallic), C.c_float(roughness), C.c_uint32(technique), out)
+        return np.array(out[:], dtype=np.float32)
+
+    def attenuation(self, distance, rng, model, power, bias, cutoff):
+        return np.float32(self._att(C.c_float(distance), C.c_float(rng), C.c_uint32(model), C.c_float(power), C.c_float(bias), C.c_float(cutoff)))
+
+    def light_loop(self, records, counts, indices, tiles_x, tiles_y, max_per_tile, tile_size, px, py, H, P, N, V, albedo, metallic, roughness, technique=0, culling_mode=1):
+        r = _records_u8(records)
+        cnt = np.ascontiguousarray(counts, dtype=np.uint32).reshape(-1)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        out = (C.c_float * 3)()
+        tail = (C.c_int32(px), C.c_int32(py), C.c_int32(H), self._f3(P), self._f3(N), self._f3(V), self._f3(albedo), C.c_float(metallic), C.c_float(roughness),
+                C.c_uint32(technique), out)
+        head = (r.ctypes.data_as(C.c_void_p), C.c_uint32(len(r)), capi.u32ptr(cnt), capi.u32ptr(idx), C.c_uint32(tiles_x), C.c_uint32(tiles_y), C.c_uint32(max_per_tile),
+                C.c_uint32(tile_size))
+        if self.kind == "glsl":
+            self.lib.shsglsl_local_light_loop(*head, C.c_uint32(culling_mode), C.c_uint32(1), None, C.c_float(0.1), C.c_float(100.0), *tail)
+        else:
+            assert culling_mode == 1, "the restatement walks tile lists"
+            self.lib.shso_local_light_loop(*head, *tail)
+        return np.array(out[:], dtype=np.float32)

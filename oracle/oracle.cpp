@@ -18,10 +18,15 @@
 // with a JoltPhysics DECLARATION shim (oracle/jolt_shim, oracle/ref_lightcull_harness.cpp,
 // oracle/ref_taa_harness.cpp; tests/test_light_cull_pinned_cpu.py, tests/test_post_passes_cpu.py) --
 // the headers use Jolt only to turn a light's shape into bounds, and bounds are an input here.
-// One part has NO compilable reference and stays "parity unpinned":
-//   * the Forward+ per-fragment local-light loop (A9): exists only as GLSL
-//     (shaders/vulkan/fp_stress_scene.frag:421-523,644-678); this file DEFINES the CPU semantics
-//     (and likewise the per-tile depth reduce, a GLSL compute shader in the reference).
+// The Forward+ per-fragment local-light loop (A9) exists in the reference only as GLSL
+// (shaders/vulkan/fp_stress_scene.frag:132-165, 421-523, 644-678; common/light_math.glsl:44-78): it is pinned against that
+// text compiled as C++ (oracle/extract_glsl_a9.py lifts it with lexical rewrites only, oracle/ref_glsl_a9_harness.cpp compiles it
+// against oracle/glsl_shim; tests/test_a9_pinned_cpu.py: per-light radiance, attenuation and the list walk bit for bit, plus the
+// committed fixture tests/golden/golden_a9_glsl.npz).  What stays DEFINED here: how the CPU rasterizer's fragment (bottom-up rows)
+// maps to the shader's gl_FragCoord (Vulkan: top-down) -- tile_y = (H-1-py) / tile_size -- and that the loop's radiance is ADDED to
+// the CPU builtin program's colour (the shader's own ambient / sun terms are not the CPU path's).
+// One part has NO compilable reference and stays "parity unpinned": the per-tile depth reduce (a GLSL compute shader on a
+// different depth encoding in the reference, shaders/vulkan/fp_stress_depth_reduce.comp).
 //
 // All arithmetic is IEEE-754 binary32, round-to-nearest, no FMA (-ffp-contract=off), evaluated
 // in the order the reference (and GLM's scalar path, see oracle/glm_shim/glm/glm.hpp) evaluates it.
@@ -503,7 +508,7 @@ namespace
         return (count > 0) ? (float)lit / (float)count : 1.0f;
     }
 
-    // ---- Forward+ local lights (A9).  DEFINED HERE: semantics follow the GLSL
+    // ---- Forward+ local lights (A9).  PINNED against the GLSL compiled as C++ (tests/test_a9_pinned_cpu.py): semantics follow
     // fp_stress_scene.frag:421-523 (eval_local_light), :132-165 (eval_pbr_light /
     // eval_blinn_phong_light), common/light_math.glsl:44-78 (attenuation_quadratic).
     struct LightRec // CullingLightGPU, lighting/light_types.hpp:141-167
@@ -1794,6 +1799,36 @@ int32_t shso_tile_depth_range(const float* depth, int32_t w, int32_t h, uint32_t
             out_max[ty * tiles_x + tx] = any ? hi : zf;
         }
     return SHSB_OK;
+}
+
+// ---- test hooks of row A9 (tests/test_a9_pinned_cpu.py): the restatement's per-light radiance, attenuation and list walk for
+// ONE surface point, so that they can be held against the reference's GLSL compiled as C++ (oracle/ref_glsl_a9_harness.cpp)
+void shso_eval_local_light(const void* records160, uint32_t idx, const float P[3], const float N[3], const float V[3], const float albedo[3],
+                           float metallic, float roughness, uint32_t technique, float out3[3])
+{
+    FsEnv e{};
+    e.lights = static_cast<const uint8_t*>(records160);
+    const V3 r = eval_local_light(e, idx, load3(P), load3(N), load3(V), load3(albedo), metallic, roughness, technique == 1u);
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+
+float shso_attenuation_quadratic(float distance, float range, uint32_t model, float power, float bias, float cutoff)
+{
+    return attenuation_quadratic(distance, range, model, power, bias, cutoff);
+}
+
+void shso_local_light_loop(const void* records160, uint32_t n_lights, const uint32_t* counts, const uint32_t* indices, uint32_t tiles_x, uint32_t tiles_y,
+                           uint32_t max_per_tile, uint32_t tile_size, int32_t px, int32_t py, int32_t H, const float P[3], const float N[3], const float V[3],
+                           const float albedo[3], float metallic, float roughness, uint32_t technique, float out3[3])
+{
+    FsEnv e{};
+    e.lights = static_cast<const uint8_t*>(records160);
+    e.n_lights = n_lights; e.tile_counts = counts; e.tile_indices = indices;
+    e.tiles_x = tiles_x; e.tiles_y = tiles_y; e.max_per_tile = max_per_tile; e.tile_size = tile_size; e.H = H;
+    Frag f{};
+    f.world_pos = load3(P); f.px = px; f.py = py;
+    const V3 r = forward_plus_lights(e, f, load3(N), load3(V), load3(albedo), metallic, roughness, technique == 1u);
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
 
 } // extern "C"
