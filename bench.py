@@ -178,9 +178,11 @@ def run_ours(args):
             ctx.lights_upload(lights_pinned.numpy())          # H2D 160 B x n_lights from pinned memory
         if world > 1 and gather_done[k] is not None:
             stream.wait_event(gather_done[k])                 # do not overwrite an LDR plane that is still being gathered
+            ctx.fence()
         ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=False)   # asynchronous; draw list H2D inside the call
         if world > 1:
             # frame assembly over NVLink: the gather of frame i runs on its own stream and overlaps with frame i+1
+            ctx.fence()
             ev = torch.cuda.Event()
             ev.record(stream)
             with torch.cuda.stream(comm_stream):
@@ -244,6 +246,7 @@ def run_ours(args):
             stream.wait_event(last_gather[0])  # the last frame assembly belongs to the timed region
         if e2e:
             ctx.sync()  # the last read-backs (copy stream) belong to the timed region
+        ctx.fence()     # frames run on several render streams: the main stream (and e1) behind all of them
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

@@ -13,8 +13,10 @@
  *   - no exceptions: the reference silently returns zero stats on bad input
  *     (sw_render/rasterizer.hpp:190-194); here every call returns an int32 status, SHSB_OK = 0,
  *     and shsb_last_error_string() explains a failure.
- *   - one host thread per context; calls are asynchronous on the context's CUDA stream until
- *     shsb_sync / a download.
+ *   - one host thread per context; calls are asynchronous on the context's CUDA streams until
+ *     shsb_sync / a download.  Results are ordered as submitted: the library tracks hazards per render
+ *     target, so asynchronous frames into DIFFERENT targets may overlap on the device while every
+ *     operation on one target sees the operations submitted before it.
  *
  * There is NO CPU fallback: if no CUDA device is usable shsb_context_create fails with
  * SHSB_E_NO_DEVICE, and arbitrary host std::function shaders are rejected with
@@ -285,8 +287,19 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx);
 SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx);
 SHSB_API const char* shsb_last_error_string(shsb_ctx ctx);
 SHSB_API int32_t shsb_sync(shsb_ctx ctx);
-/* CUDA stream handle (cudaStream_t as void*) so callers can record their own events on it. */
+/* The context's main CUDA stream (cudaStream_t as void*) so callers can order their own work / events on it.
+ * Asynchronous frames (out_stats == NULL) into different render targets may run on internal side streams; the
+ * call therefore first does what shsb_fence does.  A caller that caches the handle calls shsb_fence before it
+ * records an event that must cover frames submitted since, and after it has put work of its own on the stream
+ * that later frames must not overtake. */
 SHSB_API int32_t shsb_stream(shsb_ctx ctx, void** out_stream);
+/* Two-way ordering point, no host synchronisation: the main stream waits for every frame submitted so far, and
+ * every frame submitted afterwards starts behind whatever is on the main stream now.  Replaces nothing in the
+ * reference (its passes run serially on the calling thread, pluggable_pipeline.hpp:125-136). */
+SHSB_API int32_t shsb_fence(shsb_ctx ctx);
+/* Number of render streams asynchronous frames are spread over (1..4, default 2; environment SHSB_TILE_STREAMS).
+ * 1 = every tile kernel on the main stream, back to back (what bench.py uses to time the tile kernel alone). */
+SHSB_API int32_t shsb_set_tile_streams(shsb_ctx ctx, int32_t n);
 /* Number of kernels this context launched since creation (bench.py's gpu_launches). */
 SHSB_API int32_t shsb_launch_count(shsb_ctx ctx, uint64_t* out_count);
 /* Library build info string (arch, flags). */

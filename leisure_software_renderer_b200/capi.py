@@ -204,6 +204,8 @@ def load_library(path: str | None = None):
         "shsb_context_destroy": [vp],
         "shsb_sync": [vp],
         "shsb_stream": [vp, P(vp)],
+        "shsb_fence": [vp],
+        "shsb_set_tile_streams": [vp, C.c_int32],
         "shsb_launch_count": [vp, P(C.c_uint64)],
         "shsb_mesh_upload": [vp, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32)],
         "shsb_mesh_destroy": [vp, C.c_uint32],

@@ -41,6 +41,7 @@ namespace
     constexpr int NUM_ARENAS = 6;       // maximum number of transient arenas; ctx->n_arenas of them rotate (SHSB_ARENAS, default 4):
                                         // the front end may run n_arenas - 1 frames ahead of the tile kernel
     constexpr int TILE_DONE_RING = 16;  // per-frame "tile kernel finished" events
+    constexpr int MAX_TILE_STREAMS = 4; // render streams: [0] = the context's main stream, [1..] side streams for asynchronous frames
 
     struct MeshSlot
     {
@@ -73,6 +74,12 @@ namespace
         cudaEvent_t read_done = nullptr; // last asynchronous download of this RT (copy stream)
         bool read_pending = false;
         bool motion_dirty = false;       // the motion plane may hold non-zero vectors (a pass that clears it has work to do)
+        // hazard tracking across render streams: the last frame (run_frame) that used this target
+        long long last_frame = -1;       // its frame number (-> ctx->ev_tile_done[last_frame % TILE_DONE_RING]), -1 = none
+        int last_stream = 0;             // render stream that frame ran on
+        bool frame_is_last = false;      // nothing on the main stream has touched the target since that frame
+        unsigned long long main_seq = 0; // stamp of the last main-stream operation that touched it (ctx->main_seq)
+        int affinity = -1;               // render stream its asynchronous frames go to
     };
 
     template <typename T>
@@ -203,7 +210,18 @@ namespace
 struct shsb_context_t
 {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // main render stream == tile_streams[0]
+    // Asynchronous frames into DIFFERENT render targets are independent: their tile kernels go to different render streams
+    // so that the head of frame f+1 fills the SMs the tail of frame f leaves idle.  Hazards are tracked per render target.
+    cudaStream_t tile_streams[MAX_TILE_STREAMS]{};
+    int n_tile_streams = 2;                 // SHSB_TILE_STREAMS / shsb_set_tile_streams (1 = everything on the main stream)
+    int affinity_next = 0;
+    unsigned long long main_seq = 0;        // counts main-stream operations that touch render targets
+    unsigned long long fence_seq = 0;       // main_seq at the last shsb_fence / shsb_stream
+    unsigned long long side_synced[MAX_TILE_STREAMS]{}; // main_seq up to which each side stream is ordered behind the main stream
+    long long side_last_frame[MAX_TILE_STREAMS] = {-1, -1, -1, -1}; // last frame submitted to each render stream
+    bool side_joined[MAX_TILE_STREAMS] = {true, true, true, true};  // the main stream already waits for side_last_frame[k]
+    cudaEvent_t ev_main_sync[MAX_TILE_STREAMS]{};
     std::string error;
     uint64_t launches = 0;
 
@@ -223,7 +241,7 @@ struct shsb_context_t
     cudaEvent_t lights_stage_done[NUM_ARENAS]{};
     bool lights_stage_busy[NUM_ARENAS]{};
     int lights_cur = 0;
-    long long lights_last_user[NUM_ARENAS] = {-1, -1, -1, -1, -1, -1}; // frame number of the last tile kernel that read each buffer
+    long long lights_last_user[NUM_ARENAS][MAX_TILE_STREAMS]; // per buffer and render stream: frame number of the last tile kernel that read it (-1 = none)
     uint32_t n_lights = 0;
     cudaEvent_t ev_lights_up = nullptr;       // last upload (front stream)
     cudaEvent_t ev_cull_main = nullptr;       // last standalone cull (main stream)
@@ -259,8 +277,6 @@ struct shsb_context_t
 
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
-    uint64_t launches_at_tile = ~0ull;   // value of `launches` right after the last frame's tile kernel was submitted
-    int tile_event_at_tile = -1;         // ring index of that frame's "tile done" event
     std::vector<DrawPrep> prep;
     HostPool* host_pool = nullptr;       // created on first use by a submission with >= 2048 draws
     int host_threads = 1;                // SHSB_HOST_THREADS, default clamp(hardware threads / 8, 1, 4): a share of an 8-GPU box
@@ -347,7 +363,7 @@ namespace
     {
         for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamSynchronize(st);
         for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamSynchronize(st);
-        cudaStreamSynchronize(ctx->stream);
+        for (cudaStream_t st : ctx->tile_streams) if (st) cudaStreamSynchronize(st);
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->copy_stream2);
     }
@@ -391,12 +407,46 @@ namespace
         return SHSB_OK;
     }
 
-    RtSlot* get_rt(shsb_ctx ctx, shsb_rt h, int kind = 0)
+    // Handle lookup only.
+    RtSlot* peek_rt(shsb_ctx ctx, shsb_rt h, int kind = 0)
     {
         if (h == 0 || h > ctx->rts.size()) return nullptr;
         RtSlot* r = &ctx->rts[h - 1];
         if (!r->live) return nullptr;
         if (kind && r->kind != kind) return nullptr;
+        return r;
+    }
+
+    // The main stream is about to use target r: order it behind the side-stream frame that last used r, if any.
+    void join_rt_to_main(shsb_ctx ctx, RtSlot* r)
+    {
+        if (r->last_frame >= 0 && r->last_stream > 0)
+        {
+            cudaStreamWaitEvent(ctx->stream, ctx->ev_tile_done[r->last_frame % TILE_DONE_RING], 0);
+            r->last_stream = 0;
+        }
+        r->frame_is_last = false;
+        r->main_seq = ++ctx->main_seq;
+    }
+
+    // Lookup for an operation that is about to touch the target ON THE MAIN STREAM (every entry point but the frame
+    // submissions, which choose their own render stream): joins pending side-stream work on it, orders the main stream
+    // behind an asynchronous download still reading it, and stamps it so that later side-stream frames order themselves
+    // behind this operation.
+    RtSlot* get_rt(shsb_ctx ctx, shsb_rt h, int kind = 0)
+    {
+        RtSlot* r = peek_rt(ctx, h, kind);
+        if (!r) return nullptr;
+        join_rt_to_main(ctx, r);
+        if (r->read_pending)
+        {
+            if (cudaEventQuery(r->read_done) != cudaSuccess)
+            {
+                cudaGetLastError();
+                cudaStreamWaitEvent(ctx->stream, r->read_done, 0);
+            }
+            r->read_pending = false;
+        }
         return r;
     }
 
@@ -460,6 +510,8 @@ namespace
         uint64_t n_src_tris = 0;
         uint32_t n_blocks = 0;
         int lists_set = -1;     // light-list set the tile kernel reads (Forward+), -1 = none
+        int tile_stream = 0;    // render stream of the tile kernel (0 = main)
+        long long frame_no = -1; // out: the frame number the submission got
     };
 
     void record_on(shsb_ctx ctx, cudaEvent_t e, cudaStream_t s)
@@ -607,7 +659,10 @@ namespace
 
             const int slot = ctx->stage_slot;
             const bool graph = ctx->use_graph;
-            cudaStream_t s1 = ctx->stream, sf = ctx->pipeline ? ctx->front_streams[a] : s1, sc = ctx->cull_streams[a];
+            cudaStream_t s1 = ctx->tile_streams[job.tile_stream], sf = ctx->pipeline ? ctx->front_streams[a] : s1, sc = ctx->cull_streams[a];
+            // the ring slot this frame records into belonged to frame f - TILE_DONE_RING: make "slot re-recorded => that frame
+            // has finished" an invariant (it finished long ago; this is a query, not a wait, in steady state)
+            if (f >= TILE_DONE_RING) CK(cudaEventSynchronize(ctx->ev_tile_done[f % TILE_DONE_RING]));
             cudaError_t err = cudaSuccess;
             auto ok = [&](cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; };
 
@@ -682,13 +737,14 @@ namespace
             CK(cudaEventRecord(ctx->ev_tile_done[f % TILE_DONE_RING], s1));
             if (fc.forward_plus)
             {
-                ctx->lights_last_user[ctx->lights_cur] = f;
+                ctx->lights_last_user[ctx->lights_cur][job.tile_stream] = f;
                 ctx->lists[job.lists_set].last_reader = f;
             }
             ctx->host_us[4] += now_us() - t_c;
             ctx->host_us[5] += 1.0;
-            ctx->launches_at_tile = ctx->launches; // shsb_rt_download_async reuses this frame's "tile done" event while nothing else has been launched
-            ctx->tile_event_at_tile = (int)(f % TILE_DONE_RING);
+            job.frame_no = f;
+            ctx->side_last_frame[job.tile_stream] = f;
+            ctx->side_joined[job.tile_stream] = job.tile_stream == 0;
 
             if (!out_stats) return SHSB_OK; // asynchronous submission; overflow would surface at the next stats read
             CK(cudaMemcpyAsync(ctx->h_stats, d_stats, sizeof(DevStats) * STAT_SHARDS, cudaMemcpyDeviceToHost, s1));
@@ -799,17 +855,58 @@ namespace
 
     // A pass that is about to overwrite a render target must not overtake an asynchronous download of it.  A download
     // that has already finished (the usual case with a few render-target sets in rotation) needs no command at all.
-    void wait_pending_read(shsb_ctx ctx, RtSlot* r)
+    void wait_pending_read(shsb_ctx ctx, RtSlot* r, cudaStream_t s = nullptr)
     {
         if (r && r->read_pending)
         {
             if (cudaEventQuery(r->read_done) != cudaSuccess)
             {
                 cudaGetLastError();
-                cudaStreamWaitEvent(ctx->stream, r->read_done, 0);
+                cudaStreamWaitEvent(s ? s : ctx->stream, r->read_done, 0);
             }
             r->read_pending = false;
         }
+    }
+
+    // Orders render stream k behind everything that last touched the given targets: frames on OTHER render streams (their
+    // "tile done" events), main-stream operations (one lazily recorded event per side stream), asynchronous downloads.
+    int order_frame_on(shsb_ctx ctx, int k, RtSlot* const* targets, int n)
+    {
+        cudaStream_t s = ctx->tile_streams[k];
+        bool need_main = k != 0 && ctx->fence_seq > ctx->side_synced[k];
+        for (int i = 0; i < n; ++i)
+        {
+            RtSlot* r = targets[i];
+            if (!r) continue;
+            if (r->last_frame >= 0 && r->last_stream != k) CK(cudaStreamWaitEvent(s, ctx->ev_tile_done[r->last_frame % TILE_DONE_RING], 0));
+            if (k != 0 && r->main_seq > ctx->side_synced[k]) need_main = true;
+            wait_pending_read(ctx, r, s);
+        }
+        if (need_main)
+        {
+            CK(cudaEventRecord(ctx->ev_main_sync[k], ctx->stream));
+            CK(cudaStreamWaitEvent(s, ctx->ev_main_sync[k], 0));
+            ctx->side_synced[k] = ctx->main_seq;
+        }
+        return SHSB_OK;
+    }
+
+    void frame_used_targets(int k, long long frame_no, RtSlot* const* targets, int n)
+    {
+        for (int i = 0; i < n; ++i)
+            if (targets[i]) { targets[i]->last_frame = frame_no; targets[i]->last_stream = k; targets[i]->frame_is_last = true; }
+    }
+
+    // Main stream waits for the last frame of every side stream (shsb_fence, shsb_stream, shsb_sync callers that go on
+    // to order their own work on the main stream).
+    void join_side_streams(shsb_ctx ctx)
+    {
+        for (int k = 1; k < MAX_TILE_STREAMS; ++k)
+            if (!ctx->side_joined[k] && ctx->side_last_frame[k] >= 0)
+            {
+                cudaStreamWaitEvent(ctx->stream, ctx->ev_tile_done[ctx->side_last_frame[k] % TILE_DONE_RING], 0);
+                ctx->side_joined[k] = true;
+            }
     }
 
     // Orders the render stream behind the last light upload (which ran on a front-end stream).  Needed by work on the
@@ -857,22 +954,35 @@ namespace
     {
         if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
         if (scene->n_items && !scene->items) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene->items is null");
-        RtSlot* hdr = depth_only ? nullptr : get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+        RtSlot* hdr = depth_only ? nullptr : peek_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
         if (!depth_only && !hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR");
-        RtSlot* dm = depth_rt ? get_rt(ctx, depth_rt, SHSB_RT_DEPTH_MOTION) : nullptr;
+        RtSlot* dm = depth_rt ? peek_rt(ctx, depth_rt, SHSB_RT_DEPTH_MOTION) : nullptr;
         if (depth_rt && !dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth_motion_rt is not a live RT_ColorDepthMotion");
         if (depth_only && !dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth prepass needs a depth target");
         // the reference ignores a motion RT whose size differs from the HDR target (pass_pbr_forward.hpp:87,111)
         if (hdr && dm && (dm->w != hdr->w || dm->h != hdr->h)) dm = nullptr;
         const int W = hdr ? hdr->w : dm->w, H = hdr ? hdr->h : dm->h;
-        RtSlot* ldr = ldr_rt ? get_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR) : nullptr;
+        RtSlot* ldr = ldr_rt ? peek_rt(ctx, ldr_rt, SHSB_RT_COLOR_LDR) : nullptr;
         if (ldr_rt && (!ldr || ldr->w != W || ldr->h != H)) return fail(ctx, SHSB_E_INVALID_HANDLE, "ldr_rt is not a live RT_ColorLDR of the HDR target's size");
+        RtSlot* sh = (!depth_only && shadow_rt) ? peek_rt(ctx, shadow_rt, SHSB_RT_SHADOW) : nullptr;
+        RtSlot* const dm_arg = depth_rt ? peek_rt(ctx, depth_rt, SHSB_RT_DEPTH_MOTION) : nullptr; // tracked even when its size mismatch makes the pass ignore it
 
-        wait_pending_read(ctx, hdr);
-        wait_pending_read(ctx, dm);
-        wait_pending_read(ctx, ldr);
-
+        // Render stream of the tile kernel.  A synchronous submission (statistics) and a frame that shades with lists built
+        // earlier on the main stream stay on the main stream; an asynchronous frame goes to the stream its primary target
+        // has an affinity to (assigned round-robin at first use), so frames into different target sets overlap while
+        // frames into the same set keep their order without any cross-stream command.
         FrameJob job;
+        const bool lists_from_main = !depth_only && fp->light_culling && ctx->n_lights > 0 && !cull;
+        if (!out_stats && ctx->pipeline && ctx->n_tile_streams > 1 && !lists_from_main)
+        {
+            RtSlot* prim = hdr ? hdr : dm;
+            if (prim->affinity < 0 || prim->affinity >= ctx->n_tile_streams) prim->affinity = ctx->affinity_next++ % ctx->n_tile_streams;
+            job.tile_stream = prim->affinity;
+        }
+        RtSlot* const used[5] = {hdr, dm, ldr, sh, dm_arg != dm ? dm_arg : nullptr};
+        if (int rc = order_frame_on(ctx, job.tile_stream, used, 5)) return rc;
+        if (job.tile_stream == 0) ctx->main_seq++; // a main-stream frame is a main-stream operation for fences
+
         FrameConst& fc = job.fc;
         fill_camera_sun(fc, scene);
         fc.W = W; fc.H = H;
@@ -893,7 +1003,6 @@ namespace
         fc.write_aovs = fp->write_aovs;
         fc.shadow_mode = 0;
 
-        RtSlot* sh = (!depth_only && shadow_rt) ? get_rt(ctx, shadow_rt, SHSB_RT_SHADOW) : nullptr;
         if (fp->shadow_enable && sh && shadow_lvp) // pass_pbr_forward.hpp:185-194
         {
             fc.shadow_map = sh->depth;
@@ -1109,7 +1218,9 @@ namespace
         job.n_items = (uint32_t)items.size();
         job.n_blocks = (uint32_t)blocks.size();
         job.n_src_tris = tri_cursor;
-        return run_frame(ctx, job, out_stats, cull);
+        const int rc = run_frame(ctx, job, out_stats, cull);
+        if (rc == SHSB_OK) frame_used_targets(job.tile_stream, job.frame_no, used, 5);
+        return rc;
     }
 }
 
@@ -1134,6 +1245,7 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     if (cudaSetDevice(device_ordinal) != cudaSuccess) return SHSB_E_NO_DEVICE;
     shsb_ctx ctx = new shsb_context_t();
     ctx->device = device_ordinal;
+    for (auto& row : ctx->lights_last_user) for (long long& u : row) u = -1;
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     if (const char* e = std::getenv("SHSB_ARENAS")) ctx->n_arenas = std::min(NUM_ARENAS, std::max(2, std::atoi(e)));
@@ -1142,6 +1254,13 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     if (const char* e = std::getenv("SHSB_HOST_THREADS")) ctx->host_threads = std::min(32, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("SHSB_FRONT_PRIORITY")) { if (e[0] == '0') prio_greatest = prio_least; }
     bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    ctx->tile_streams[0] = ctx->stream;
+    for (int i = 1; ok && i < MAX_TILE_STREAMS; ++i)
+    {
+        ok = cudaStreamCreateWithPriority(&ctx->tile_streams[i], cudaStreamNonBlocking, prio_least) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_main_sync[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (const char* e = std::getenv("SHSB_TILE_STREAMS")) ctx->n_tile_streams = std::min(MAX_TILE_STREAMS, std::max(1, std::atoi(e)));
     // the front end is small and latency-bound: at high priority its CTAs slot in between the tile kernel's
     for (int i = 0; ok && i < NUM_ARENAS; ++i)
     {
@@ -1227,6 +1346,11 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
     for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamDestroy(st);
     for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamDestroy(st);
+    for (int i = 1; i < MAX_TILE_STREAMS; ++i)
+    {
+        if (ctx->tile_streams[i]) cudaStreamDestroy(ctx->tile_streams[i]);
+        if (ctx->ev_main_sync[i]) cudaEventDestroy(ctx->ev_main_sync[i]);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SHSB_OK;
@@ -1237,17 +1361,39 @@ SHSB_API const char* shsb_last_error_string(shsb_ctx ctx) { return ctx ? ctx->er
 SHSB_API int32_t shsb_sync(shsb_ctx ctx)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream2));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_fence(shsb_ctx ctx)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    join_side_streams(ctx);                  // main stream: behind every frame submitted so far
+    ctx->fence_seq = ++ctx->main_seq;        // side streams: their next frame orders itself behind the main stream's tail
+    CK(cudaGetLastError());
     return SHSB_OK;
 }
 
 SHSB_API int32_t shsb_stream(shsb_ctx ctx, void** out_stream)
 {
     if (!ctx || !out_stream) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = shsb_fence(ctx)) return rc;
     *out_stream = (void*)ctx->stream;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_set_tile_streams(shsb_ctx ctx, int32_t n)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (n < 1 || n > MAX_TILE_STREAMS) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render-stream count must be 1..%d", MAX_TILE_STREAMS);
+    ctx->n_tile_streams = n;
+    for (RtSlot& r : ctx->rts) r.affinity = -1;
+    ctx->affinity_next = 0;
     return SHSB_OK;
 }
 
@@ -1373,7 +1519,7 @@ SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h
 SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
-    RtSlot* r = get_rt(ctx, rt);
+    RtSlot* r = peek_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     sync_all(ctx);
     cudaFree(r->color); cudaFree(r->depth); cudaFree(r->motion); cudaFree(r->tri_id); cudaFree(r->coverage);
@@ -1431,23 +1577,24 @@ SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void*
 SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst_pinned, size_t bytes)
 {
     if (!ctx || !dst_pinned) return SHSB_E_INVALID_ARGUMENT;
-    RtSlot* r = get_rt(ctx, rt);
+    CK(cudaSetDevice(ctx->device));
+    RtSlot* r = peek_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     void* p = nullptr;
     const size_t want = plane_bytes(*r, plane, &p);
     if (!want) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
     if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
     if (!r->read_done) CK(cudaEventCreateWithFlags(&r->read_done, cudaEventDisableTiming));
-    // copy stream waits for everything submitted to the render stream so far, then copies while later frames render
+    // the copy stream waits for whatever wrote the target last, then copies while later frames render
     cudaStream_t cs = (ctx->copy_flip ^= 1) ? ctx->copy_stream : ctx->copy_stream2;
-    if (ctx->launches == ctx->launches_at_tile && ctx->tile_event_at_tile >= 0)
+    if (r->frame_is_last && r->last_frame >= 0)
     {
-        // the last thing this library put on the render stream is a frame's tile kernel, which already recorded an event:
-        // no further command on the (critical) render stream
-        CK(cudaStreamWaitEvent(cs, ctx->ev_tile_done[ctx->tile_event_at_tile], 0));
+        // a frame's tile kernel, which already recorded an event on its render stream: no further command on a (critical) render stream
+        CK(cudaStreamWaitEvent(cs, ctx->ev_tile_done[r->last_frame % TILE_DONE_RING], 0));
     }
     else
     {
+        // main-stream work touched it since (that work joined any side-stream frame when it looked the target up)
         CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
         CK(cudaStreamWaitEvent(cs, ctx->ev_frame_done, 0));
     }
@@ -1959,7 +2106,7 @@ SHSB_API int32_t shsb_frame_forward_plus(shsb_ctx ctx, const ShsbScene* scene, c
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     if (!scene || !fp) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "scene / frame params are null");
     CK(cudaSetDevice(ctx->device));
-    RtSlot* hdr = get_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
+    RtSlot* hdr = peek_rt(ctx, hdr_rt, SHSB_RT_COLOR_HDR);
     if (!hdr) return fail(ctx, SHSB_E_INVALID_HANDLE, "hdr_rt is not a live RT_ColorHDR");
     CullJob cull;
     const bool with_cull = fp->light_culling && ctx->n_lights > 0;
@@ -2220,7 +2367,8 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     cudaStream_t su = ctx->front_streams[ctx->frame_no % ctx->n_arenas]; // the stream the next frame's front end will use
     if (int rc = ensure_dev(ctx, ctx->d_lights[b], std::max(1u, n_lights))) return rc;
     if (int rc = ensure_dev(ctx, ctx->d_smlights[b], std::max(1u, n_lights))) return rc;
-    if (ctx->lights_last_user[b] >= 0) CK(cudaStreamWaitEvent(su, ctx->ev_tile_done[ctx->lights_last_user[b] % TILE_DONE_RING], 0));
+    for (int k = 0; k < MAX_TILE_STREAMS; ++k) // frames on different render streams finish in any order: wait for the last reader on each
+        if (ctx->lights_last_user[b][k] >= 0) CK(cudaStreamWaitEvent(su, ctx->ev_tile_done[ctx->lights_last_user[b][k] % TILE_DONE_RING], 0));
     if (ctx->cull_main_pending) { CK(cudaStreamWaitEvent(su, ctx->ev_cull_main, 0)); ctx->cull_main_pending = false; }
     if (n_lights)
     {
@@ -2250,7 +2398,7 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
     ctx->lights_uploaded = true;
     ctx->main_needs_lights = true; // ordered lazily: a frame that culls reaches the records through its front end (main_wait_lights)
     ctx->lights_cur = b;
-    ctx->lights_last_user[b] = -1;
+    for (long long& u : ctx->lights_last_user[b]) u = -1;
     ctx->n_lights = n_lights;
     ctx->lists_cur = -1;
     return SHSB_OK;
@@ -2411,7 +2559,7 @@ SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable)
 SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames)
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
     for (size_t f = 0; f < frames && out_ms; ++f)
@@ -2436,7 +2584,7 @@ SHSB_API int32_t shsb_timing_collect_abs(shsb_ctx ctx, float* out_ms, size_t cap
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
     for (size_t f = 0; f < frames && out_ms; ++f)
         for (int k = 0; k < TIMING_EVENTS_PER_FRAME; ++k)
@@ -2462,7 +2610,7 @@ SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
 {
     if (!ctx || !out_ms) return SHSB_E_INVALID_ARGUMENT;
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
-    CK(cudaStreamSynchronize(ctx->stream));
+    for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     for (int i = 0; i < 8; ++i) out_ms[i] = 0.0f;
     auto span = [&](int a, int b) -> float {
         float ms = 0.0f;

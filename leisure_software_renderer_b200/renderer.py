@@ -122,13 +122,14 @@ class Context:
         return st
 
     def pass_pbr_forward(self, scene: Scene, fp: FrameParams, hdr_rt, depth_rt=0, shadow_rt=0, shadow_light_viewproj=None,
-                         preserve_existing_depth=False) -> Stats:
+                         preserve_existing_depth=False, want_stats=True) -> Stats:
+        """want_stats=False: asynchronous submission (no host synchronisation, may run on a side render stream)."""
         st = Stats()
         lvp = None
         if shadow_light_viewproj is not None:
             lvp = np.ascontiguousarray(shadow_light_viewproj, dtype=np.float32).reshape(16)
         rc = self.lib.shsb_pass_pbr_forward(self.h, C.byref(scene), C.byref(fp), hdr_rt, depth_rt, shadow_rt,
-                                            capi.fptr(lvp) if lvp is not None else None, int(preserve_existing_depth), C.byref(st))
+                                            capi.fptr(lvp) if lvp is not None else None, int(preserve_existing_depth), C.byref(st) if want_stats else None)
         _check(self.lib, self.h, rc, "shsb_pass_pbr_forward")
         return st
 
@@ -302,6 +303,13 @@ class Context:
 
     def sync(self):
         _check(self.lib, self.h, self.lib.shsb_sync(self.h), "shsb_sync")
+
+    def fence(self):
+        """Main stream behind every frame submitted so far; later frames behind the main stream's current tail."""
+        _check(self.lib, self.h, self.lib.shsb_fence(self.h), "shsb_fence")
+
+    def set_tile_streams(self, n: int):
+        _check(self.lib, self.h, self.lib.shsb_set_tile_streams(self.h, int(n)), "shsb_set_tile_streams")
 
     def stream(self) -> int:
         p = C.c_void_p()

@@ -153,3 +153,139 @@ def test_full_size_configs_properties(gpu, name):
             assert np.array_equal(gpu.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32), dep1.view(np.uint32))
     finally:
         g.release()
+
+
+# ---------------------------------------------------------------------------------- render streams (hazards per render target)
+def _target_sets(gpu, base, n):
+    return [(gpu.rt_create(capi.RT_COLOR_HDR, base.w, base.h), gpu.rt_create(capi.RT_DEPTH_MOTION, base.w, base.h, base.zn, base.zf),
+             gpu.rt_create(capi.RT_COLOR_LDR, base.w, base.h)) for _ in range(n)]
+
+
+@pytest.mark.parametrize("n_streams", [1, 2, 3, 4])
+def test_render_streams_frames_into_different_targets(gpu, n_streams):
+    """Asynchronous frames into different target sets are spread over n render streams and may overlap on the device;
+    every frame equals its one-at-a-time synchronous rendering bit for bit, for every stream count."""
+    base = scenes.scene_small(w=300, h=180, lights=40, tex=True)
+    cams = scenes.camera_ring(base, 10, radius=9.0, height=4.0)
+    g = harness.GpuScene(gpu, base)
+    sets = _target_sets(gpu, base, 5)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 1
+        want = []
+        for cam in cams:
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr)
+            want.append(_download(gpu, g))
+        gpu.set_tile_streams(n_streams)
+        for rnd in range(2):                                           # 10 frames over 5 sets: every set is written twice
+            for k in range(5):
+                hdr, dm, ldr = sets[k]
+                gpu.frame_forward_plus(cams[rnd * 5 + k].scene, fp, hdr, dm, ldr, want_stats=False)
+        gpu.sync()
+        for k, (hdr, dm, ldr) in enumerate(sets):
+            got = (gpu.rt_download(hdr).view(np.uint32), gpu.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32), gpu.rt_download(ldr))
+            for a, b, what in zip(got, want[5 + k], ("hdr", "depth", "ldr")):
+                assert np.array_equal(a, b), f"{n_streams} streams, set {k}: {what} differs"
+    finally:
+        gpu.set_tile_streams(2)
+        for rts in sets:
+            for rt in rts:
+                gpu.rt_destroy(rt)
+        g.release()
+
+
+def test_main_stream_operations_see_side_stream_frames_and_vice_versa(gpu):
+    """A frame on a side render stream followed by main-stream work on the same targets (tonemap, clear, a synchronous
+    frame that keeps the depth) and main-stream work followed by a side-stream frame: results are those of submission order."""
+    base = scenes.scene_small(w=260, h=150, lights=0)
+    cams = scenes.camera_ring(base, 4, radius=9.0, height=4.0)
+    g = harness.GpuScene(gpu, base)
+    sets = _target_sets(gpu, base, 4)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 0
+        want = []
+        for cam in cams:                                                # reference: everything synchronous on one target set
+            gpu.pass_pbr_forward(cam.scene, fp, g.hdr, g.dm)
+            gpu.pass_tonemap(g.hdr, g.ldr, 1.3, 2.0)
+            want.append((gpu.rt_download(g.hdr).view(np.uint32), gpu.rt_download(g.ldr)))
+        gpu.set_tile_streams(4)
+        for (hdr, dm, ldr), cam in zip(sets, cams):                     # side-stream lit pass, then main-stream tonemap of its output
+            gpu.pass_pbr_forward(cam.scene, fp, hdr, dm, want_stats=False)
+            gpu.pass_tonemap(hdr, ldr, 1.3, 2.0)
+        for k, (hdr, dm, ldr) in enumerate(sets):
+            assert np.array_equal(gpu.rt_download(ldr), want[k][1]), f"set {k}: tonemap ran ahead of the side-stream frame"
+            assert np.array_equal(gpu.rt_download(hdr).view(np.uint32), want[k][0])
+        # main-stream clear of the depth plane to 0.5, then a side-stream frame that PRESERVES depth: only nearer fragments land
+        half = np.float32(0.5)
+        gpu.rt_clear(g.dm, capi.PLANE_DEPTH, half)
+        ref = gpu.pass_pbr_forward(cams[0].scene, fp, g.hdr, g.dm, preserve_existing_depth=True).as_dict()
+        want_depth = gpu.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32)
+        want_hdr = gpu.rt_download(g.hdr).view(np.uint32)
+        assert ref["frag_covered"] > 0
+        for hdr, dm, ldr in sets:
+            gpu.pass_pbr_forward(cams[0].scene, fp, hdr, dm)             # same colour history as the reference targets
+            gpu.rt_clear(dm, capi.PLANE_DEPTH, half)
+            gpu.pass_pbr_forward(cams[0].scene, fp, hdr, dm, preserve_existing_depth=True, want_stats=False)
+        for k, (hdr, dm, ldr) in enumerate(sets):
+            assert np.array_equal(gpu.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32), want_depth), f"set {k}: the frame overtook the clear"
+        # asynchronous read-back of a side-stream frame, then the next frame into the same targets must not overtake the copy
+        import torch
+        bufs = [torch.empty(base.w * base.h * 4, dtype=torch.uint8).pin_memory() for _ in range(8)]
+        fused = []
+        for cam in cams:
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr)
+            fused.append(gpu.rt_download(g.ldr))
+        for i in range(8):
+            hdr, dm, ldr = sets[i % 2]
+            gpu.frame_forward_plus(cams[i % 4].scene, fp, hdr, dm, ldr, want_stats=False)
+            gpu.rt_download_async(ldr, capi.PLANE_COLOR, bufs[i].data_ptr(), bufs[i].numel())
+        gpu.sync()
+        for i in range(8):
+            assert np.array_equal(bufs[i].numpy().reshape(fused[0].shape), fused[i % 4]), f"read-back {i} torn or stale"
+        assert want_hdr is not None
+    finally:
+        gpu.set_tile_streams(2)
+        for rts in sets:
+            for rt in rts:
+                gpu.rt_destroy(rt)
+        g.release()
+
+
+def test_fence_orders_caller_work_on_the_main_stream(gpu):
+    """shsb_fence: an event the caller records on shsb_stream() after the fence covers frames that ran on side streams."""
+    import torch
+    base = scenes.scene_small(w=320, h=200, lights=32)
+    cams = scenes.camera_ring(base, 6, radius=9.0, height=4.0)
+    g = harness.GpuScene(gpu, base)
+    sets = _target_sets(gpu, base, 3)
+    try:
+        fp = capi.FrameParams.from_buffer_copy(base.fp)
+        fp.light_culling = 1
+        want = []
+        for cam in cams[:3]:
+            gpu.frame_forward_plus(cam.scene, fp, g.hdr, g.dm, g.ldr)
+            want.append(gpu.rt_download(g.ldr))
+        gpu.set_tile_streams(3)
+        stream = torch.cuda.ExternalStream(gpu.stream(), device=0)
+        views = []
+        for hdr, dm, ldr in sets:
+            ptr, nbytes = gpu.rt_device_ptr(ldr, capi.PLANE_COLOR)
+
+            class _Cai:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            views.append(torch.as_tensor(_Cai(), device="cuda:0"))
+        for (hdr, dm, ldr), cam in zip(sets, cams[:3]):
+            gpu.frame_forward_plus(cam.scene, fp, hdr, dm, ldr, want_stats=False)
+        gpu.fence()
+        with torch.cuda.stream(stream):
+            copies = [v.clone() for v in views]                        # caller's own work on the main stream
+        stream.synchronize()
+        for k in range(3):
+            assert np.array_equal(copies[k].cpu().numpy().reshape(want[k].shape), want[k]), f"set {k}: the caller's copy ran ahead of the frame"
+    finally:
+        gpu.set_tile_streams(2)
+        for rts in sets:
+            for rt in rts:
+                gpu.rt_destroy(rt)
+        g.release()
