@@ -128,13 +128,23 @@ namespace shsb
         // few degrees a macro cell spans, a sphere's signed distance to the planes of one family is monotone or has
         // a positive interior maximum, so a light can pass a tile's plane only if it passes the family's first or
         // last plane inside the macro cell.  Both are built exactly like tile planes (first and last tile of the
-        // cell) and tested with a slack (1 cm + 0.1 % of the radius) that dwarfs float differences between a tile's
-        // own plane and the family plane built from other corner points.
+        // cell) and tested with a slack of 1 cm + 0.1 % of the radius + a NOISE term.
+        //
+        // The noise term: the reference builds every tile's planes from the tile's OWN unprojected corners, and the
+        // near corners of a tile are sub-millimetre apart at coordinates of tens to hundreds of metres, so a tile's
+        // plane is tilted about its corner ray by (corner rounding error) / (near-edge length): 1e-3 rad on the 1080p
+        // frame, several 1e-2 rad on the 8K frame with its far camera -- the exact per-tile test reproduces that tilt
+        // bit for bit (same operations), the pre-filter must allow for it.  It is MEASURED per macro cell: the near
+        // (far) planes of all tiles of a cell are one geometric plane, the left / right planes of a tile column and
+        // the bottom / top planes of a tile row likewise, so the spread of their computed normals is the tilt.  A tilt
+        // dn moves a plane by dn * (distance of the point from the tilt axis); the slack adds 4 x that bound.
         __global__ void __launch_bounds__(MACRO_THREADS) macro_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, const Planes6 frustum,
                                                                           uint32_t* __restrict__ macro_counts, uint32_t* __restrict__ macro_lists)
         {
             __shared__ float s_corner[2][8][3];
             __shared__ float4 s_plane[2][6];
+            __shared__ float4 s_tile_n[MACRO * MACRO][6];
+            __shared__ unsigned s_dev[6];
             __shared__ uint32_t s_warp_count[MACRO_THREADS / 32];
             const uint32_t mc = blockIdx.x;
             const uint32_t mx = mc % cp.macro_x, my = mc / cp.macro_x;
@@ -151,16 +161,61 @@ namespace shsb
                 const int which = threadIdx.x >> 3;
                 cell_corner(cp, which ? tx1 : tx0, which ? ty1 : ty0, threadIdx.x & 7, s_corner[which][threadIdx.x & 7]);
             }
+            if (threadIdx.x < 6) s_dev[threadIdx.x] = 0u;
+            // every tile of the cell builds its own six planes, exactly as the per-tile kernel will
+            const uint32_t t_col = threadIdx.x % MACRO, t_row = threadIdx.x / MACRO;
+            const bool t_valid = threadIdx.x < MACRO * MACRO && tx0 + t_col <= tx1 && ty0 + t_row <= ty1;
+            if (t_valid)
+            {
+                float c8[8][3];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) cell_corner(cp, tx0 + t_col, ty0 + t_row, c, c8[c]);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s_tile_n[threadIdx.x][i] = cell_plane(c8, i);
+            }
             __syncthreads();
             if (threadIdx.x < 12)
             {
                 const int which = threadIdx.x / 6;
                 s_plane[which][threadIdx.x % 6] = cell_plane(s_corner[which], threadIdx.x % 6);
             }
+            if (t_valid)
+            {
+                // reference copy of the same geometric plane: near / far -> tile (0, 0); left / right -> same column, row 0;
+                // bottom / top -> same row, column 0
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                {
+                    const uint32_t ref = (i < 2) ? 0u : ((i < 4) ? t_col : t_row * MACRO);
+                    const float4 a = s_tile_n[threadIdx.x][i], b = s_tile_n[ref][i];
+                    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+                    const float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+                    if (dn == dn) atomicMax(&s_dev[i], __float_as_uint(dn)); // non-negative floats order like their bit patterns
+                }
+            }
             __syncthreads();
             float4 pa[6], pb[6];
+            float dev[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) { pa[i] = s_plane[0][i]; pb[i] = s_plane[1][i]; }
+            {
+                // the tilt of the near plane (its three corners are the closest together) bounds the side planes' where a
+                // cell has a single row / column of tiles and nothing to compare them with
+                const float dn_near = __uint_as_float(s_dev[0]);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dev[i] = fmaxf(__uint_as_float(s_dev[i]), (i >= 2) ? dn_near : 0.0f) + 1e-7f;
+            }
+            // tilt axes: the corner rays of the first and of the last tile of the cell; points are measured from the near corner
+            const float ax0 = s_corner[0][0][0], ay0 = s_corner[0][0][1], az0 = s_corner[0][0][2];
+            float ux = s_corner[0][4][0] - ax0, uy = s_corner[0][4][1] - ay0, uz = s_corner[0][4][2] - az0;
+            float vx = s_corner[1][7][0] - s_corner[1][3][0], vy = s_corner[1][7][1] - s_corner[1][3][1], vz = s_corner[1][7][2] - s_corner[1][3][2];
+            {
+                const float ul = rsqrtf(ux * ux + uy * uy + uz * uz), vl = rsqrtf(vx * vx + vy * vy + vz * vz);
+                ux *= ul; uy *= ul; uz *= ul; vx *= vl; vy *= vl; vz *= vl;
+            }
+            const float cxx = uy * vz - uz * vy, cxy = uz * vx - ux * vz, cxz = ux * vy - uy * vx;
+            const float sin_span = fminf(1.0f, sqrtf(cxx * cxx + cxy * cxy + cxz * cxz) * 1.25f + 1e-4f); // angle the cell's corner rays span
+            const float fx0 = s_corner[0][4][0], fy0 = s_corner[0][4][1], fz0 = s_corner[0][4][2];            // a far corner (far plane's anchor)
 
             uint32_t total = 0;
             uint32_t* list = macro_lists + (size_t)mc * cp.n_lights;
@@ -177,10 +232,19 @@ namespace shsb
                     if (keep)
                     {
                         const float r = fmaxf(sp.w, 0.0f);
-                        const float slack = -(r * 1.001f + 1e-2f);
+                        const float wx = sp.x - ax0, wy = sp.y - ay0, wz = sp.z - az0;
+                        const float wl = sqrtf(wx * wx + wy * wy + wz * wz);
+                        const float along = wx * ux + wy * uy + wz * uz;
+                        // distance from the tilt axis of ANY tile of the cell: from the first corner ray, plus what the rays diverge by
+                        const float rho = sqrtf(fmaxf(wl * wl - along * along, 0.0f)) + wl * sin_span + 0.5f;
+                        const float gx = sp.x - fx0, gy = sp.y - fy0, gz = sp.z - fz0;
+                        const float far_l = sqrtf(gx * gx + gy * gy + gz * gz) + 0.5f;
+                        const float base_slack = r * 1.001f + 1e-2f;
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
                         {
+                            const float arm = (i == 0) ? (wl + 0.5f) : ((i == 1) ? far_l : rho);
+                            const float slack = -(base_slack + 4.0f * dev[i] * arm);
                             const float da = plane_dist(pa[i], sp.x, sp.y, sp.z), db = plane_dist(pb[i], sp.x, sp.y, sp.z);
                             if (da < slack && db < slack) keep = false;
                         }

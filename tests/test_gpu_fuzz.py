@@ -82,3 +82,36 @@ def test_fuzz_light_bins_parity(gpu, port, seed):
         assert np.array_equal(c, oc), f"seed {seed} {name}: counts differ in {int(np.count_nonzero(c != oc))} of {c.size} bins"
         keep = np.arange(d.max_per_bin)[None, :] < np.minimum(oc, d.max_per_bin)[:, None]
         assert np.array_equal(i[keep], oi[keep]), f"seed {seed} {name}: lists differ"
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_fuzz_light_lists_far_camera_high_resolution(gpu, port, seed):
+    """The regime the full-size 8K frame exposed: a camera hundreds of metres from the origin, a small near distance and a
+    viewport thousands of pixels wide make the near corners of a tile sub-millimetre apart at large coordinates, so the planes
+    the reference builds from them are tilted by up to degrees -- numerically, per tile.  The per-tile test reproduces that bit
+    for bit; the two-level builder's conservative macro-cell pre-filter has to allow for it (it measures the tilt per macro cell).
+    Wide, short viewports keep the oracle's O(tiles x lights) loop at a few seconds."""
+    rng = np.random.default_rng(17000 + seed)
+    w = int(rng.choice([3840, 7680, 5120, 2560]))
+    h = int(rng.choice([64, 96, 160]))
+    dist = float(rng.choice([150.0, 400.0, 1200.0]))
+    zn = float(rng.choice([0.05, 0.1, 0.5]))
+    zf = float(rng.choice([2000.0, 5000.0]))
+    n = int(rng.integers(200, 700))
+    ext = dist * 0.4
+    lights = scenes.make_lights(n - n // 4, n // 4, (-ext, -0.1 * ext, -ext), (ext, 0.1 * ext, ext), seed=seed, range_lo=0.01 * dist, range_hi=0.06 * dist,
+                                jolt_bounds=bool(seed % 2))
+    ang = rng.uniform(0, 2 * np.pi)
+    eye = (dist * np.sin(ang) + float(rng.uniform(-1000, 1000)) * (seed % 3 == 0), 0.25 * dist, -dist * np.cos(ang))
+    off = (eye[0] - dist * np.sin(ang), 0.0, 0.0)
+    lights["position_range"][:, 0] += np.float32(off[0]); lights["cull_sphere"][:, 0] += np.float32(off[0])
+    lights["cull_aabb_min"][:, 0] += np.float32(off[0]); lights["cull_aabb_max"][:, 0] += np.float32(off[0])
+    vp = scenes.camera_viewproj(tuple(float(v) for v in eye), (float(off[0]), 0.0, 0.0), (0.0, 1.0, 0.0), float(np.radians(rng.uniform(8, 25))), w / h, zn, zf)
+    gpu.lights_upload(lights.view(np.uint8))
+    gpu.light_cull(vp, w, h, 16, 128)
+    c, i = gpu.light_lists_download()
+    oc, oi = port.light_cull(lights, vp, w, h, 16, 128)
+    assert int(oc.sum()) > 0
+    keep = np.arange(128)[None, :] < np.minimum(oc, 128)[:, None]
+    assert np.array_equal(c, oc), f"seed {seed}: counts differ in {int(np.count_nonzero(c != oc))} of {c.size} tiles ({w}x{h}, camera at {dist} m)"
+    assert np.array_equal(i[keep], oi[keep]), f"seed {seed}: lists differ"
