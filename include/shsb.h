@@ -49,7 +49,8 @@ enum
     SHSB_E_UNSUPPORTED_SHADER = 5,
     SHSB_E_OUT_OF_MEMORY = 6,
     SHSB_E_SIZE_MISMATCH = 7,
-    SHSB_E_UNSUPPORTED = 8
+    SHSB_E_UNSUPPORTED = 8,
+    SHSB_E_TIMEOUT = 9
 };
 
 typedef struct shsb_context_t* shsb_ctx; /* opaque */
@@ -339,6 +340,54 @@ SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void*
 SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst_pinned, size_t bytes);
 /* Raw device pointer of a plane (for NCCL frame gather through torch.distributed). */
 SHSB_API int32_t shsb_rt_device_ptr(shsb_ctx ctx, shsb_rt rt, int32_t plane, void** out_ptr, size_t* out_bytes);
+
+/* ------------------------------------------------------------------ sort-first frame assembly (multi-GPU, one process per GPU) */
+
+/* The reference renders one frame on one CPU; it has no counterpart of this section (screen tiles / cameras are
+ * partitioned over the GPUs of one box, scene replicated, and the only exchange step is the assembly of disjoint pixels on a
+ * root GPU).  The assembly is a PUSH: every rank copies the planes (or row bands) it rendered straight into the root GPU's
+ * assembly memory with copy-engine peer writes over NVLink -- no SMs besides one-thread flag kernels, no collective library,
+ * no host synchronisation.  Memory is shared through CUDA IPC handles, which the caller ships to the other processes over
+ * whatever host channel it has (MPI, torch.distributed, a pipe); ranks living in the root's own process use the raw pointers.
+ *
+ * Steps are numbered 1, 2, 3, ...; step s uses slot (s - 1) % slots of the assembly memory, so `slots` steps may be in flight.
+ *   every rank : shsb_frame_gather(step, ...) once per plane / band, then shsb_gather_commit(step)
+ *   root       : shsb_gather_wait(step) -> read the slot (shsb_gather_device_ptr / shsb_gather_download) -> shsb_gather_release(step)
+ * All of it is stream-ordered on the context's gather stream: a push starts when the frame that wrote the render target has
+ * finished, a later frame into that target waits for the push, a rank reusing a slot waits (on the device, bounded by a
+ * time-out that surfaces as SHSB_E_TIMEOUT) for the root's release of the step that used it before. */
+typedef uint32_t shsb_gather;
+#define SHSB_GATHER_MAX_RANKS 16
+typedef struct ShsbGatherExport
+{
+    unsigned char mem_handle[64]; /* cudaIpcMemHandle_t of the assembly memory (slots x slot_bytes) */
+    unsigned char ctl_handle[64]; /* cudaIpcMemHandle_t of the control block (step counters)        */
+    uint64_t mem_ptr, ctl_ptr;    /* the same two allocations as raw device pointers (same-process ranks) */
+    uint64_t slot_bytes;
+    uint32_t n_ranks, slots;
+    int32_t root_device;
+    int32_t root_pid;
+} ShsbGatherExport;
+/* Root (rank 0): allocates the assembly memory and fills `out_export` for the other ranks. */
+SHSB_API int32_t shsb_gather_create(shsb_ctx ctx, uint32_t n_ranks, uint32_t slots, size_t slot_bytes, shsb_gather* out_gather, ShsbGatherExport* out_export);
+/* Rank 1 .. n_ranks-1: maps the root's memory (peer access over NVLink is enabled on first use). */
+SHSB_API int32_t shsb_gather_open(shsb_ctx ctx, const ShsbGatherExport* exp, uint32_t rank, shsb_gather* out_gather);
+SHSB_API int32_t shsb_gather_destroy(shsb_ctx ctx, shsb_gather gather);
+/* Pushes `bytes` of a plane of `rt`, from byte `src_offset` of the plane, to byte `dst_offset` of the step's slot.  Rows are
+ * contiguous (row-major targets), so a screen band is one call; a camera of a batch is one call with src_offset 0. */
+SHSB_API int32_t shsb_frame_gather(shsb_ctx ctx, shsb_gather gather, uint64_t step, shsb_rt rt, int32_t plane, size_t src_offset, size_t bytes, size_t dst_offset);
+/* This rank has enqueued all its pushes of `step`. */
+SHSB_API int32_t shsb_gather_commit(shsb_ctx ctx, shsb_gather gather, uint64_t step);
+/* Root: orders the gather stream behind every rank's commit of `step` (asynchronous). */
+SHSB_API int32_t shsb_gather_wait(shsb_ctx ctx, shsb_gather gather, uint64_t step);
+/* Root: the slot of `step` may be overwritten (asynchronous, ordered behind whatever the root enqueued to read it). */
+SHSB_API int32_t shsb_gather_release(shsb_ctx ctx, shsb_gather gather, uint64_t step);
+/* Root: device pointer of the slot of `step`; synchronous / asynchronous (pinned destination, gather stream) read of it. */
+SHSB_API int32_t shsb_gather_device_ptr(shsb_ctx ctx, shsb_gather gather, uint64_t step, void** out_ptr);
+SHSB_API int32_t shsb_gather_download(shsb_ctx ctx, shsb_gather gather, uint64_t step, size_t offset, void* dst, size_t bytes);
+SHSB_API int32_t shsb_gather_download_async(shsb_ctx ctx, shsb_gather gather, uint64_t step, size_t offset, void* dst_pinned, size_t bytes);
+/* The context's gather stream (cudaStream_t as void*), e.g. to record timing events behind a wait. */
+SHSB_API int32_t shsb_gather_stream(shsb_ctx ctx, void** out_stream);
 
 /* ------------------------------------------------------------------ host helpers (bit-exact restatements) */
 

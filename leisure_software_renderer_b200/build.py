@@ -32,6 +32,7 @@ SOURCES = {
     "legacy2.cu": ["--fmad=false"],
     "scene_cull.cu": ["--fmad=false"],
     "tile_raster.cu": [],
+    "gather.cu": [],
     "api.cu": [],
 }
 

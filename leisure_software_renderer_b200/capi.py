@@ -187,6 +187,13 @@ class ShsbError(RuntimeError):
 _lib = None
 
 
+class GatherExport(C.Structure):
+    """ShsbGatherExport: what the root of a sort-first frame assembly hands to the other ranks (184 bytes, plain bytes: ship it
+    over any host channel, e.g. torch.distributed.broadcast_object_list(bytes(export)))."""
+    _fields_ = [("mem_handle", C.c_ubyte * 64), ("ctl_handle", C.c_ubyte * 64), ("mem_ptr", C.c_uint64), ("ctl_ptr", C.c_uint64),
+                ("slot_bytes", C.c_uint64), ("n_ranks", C.c_uint32), ("slots", C.c_uint32), ("root_device", C.c_int32), ("root_pid", C.c_int32)]
+
+
 def load_library(path: str | None = None):
     """Loads libshsb.so; raises (never falls back) when it has not been built."""
     global _lib
@@ -207,6 +214,17 @@ def load_library(path: str | None = None):
         "shsb_fence": [vp],
         "shsb_set_tile_streams": [vp, C.c_int32],
         "shsb_launch_count": [vp, P(C.c_uint64)],
+        "shsb_gather_create": [vp, C.c_uint32, C.c_uint32, C.c_size_t, P(C.c_uint32), P(GatherExport)],
+        "shsb_gather_open": [vp, P(GatherExport), C.c_uint32, P(C.c_uint32)],
+        "shsb_gather_destroy": [vp, C.c_uint32],
+        "shsb_frame_gather": [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int32, C.c_size_t, C.c_size_t, C.c_size_t],
+        "shsb_gather_commit": [vp, C.c_uint32, C.c_uint64],
+        "shsb_gather_wait": [vp, C.c_uint32, C.c_uint64],
+        "shsb_gather_release": [vp, C.c_uint32, C.c_uint64],
+        "shsb_gather_device_ptr": [vp, C.c_uint32, C.c_uint64, P(vp)],
+        "shsb_gather_download": [vp, C.c_uint32, C.c_uint64, C.c_size_t, vp, C.c_size_t],
+        "shsb_gather_download_async": [vp, C.c_uint32, C.c_uint64, C.c_size_t, vp, C.c_size_t],
+        "shsb_gather_stream": [vp, P(vp)],
         "shsb_mesh_upload": [vp, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32)],
         "shsb_mesh_destroy": [vp, C.c_uint32],
         "shsb_texture_upload": [vp, P(C.c_uint8), C.c_int32, C.c_int32, P(C.c_uint32)],

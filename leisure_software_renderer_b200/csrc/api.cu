@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/shsb.h"
@@ -207,6 +208,27 @@ namespace
     };
 }
 
+namespace
+{
+    // Sort-first frame assembly (shsb_gather_*): the root's assembly memory and its control block of step counters.
+    struct GatherCtl
+    {
+        unsigned long long arrive[SHSB_GATHER_MAX_RANKS]; // arrive[r] = last step rank r committed
+        unsigned long long released;                      // last step whose slot the root released
+        unsigned long long pad[15];
+    };
+    struct GatherSlot
+    {
+        bool live = false, root = false, ipc = false;
+        uint32_t n_ranks = 0, rank = 0, slots = 0;
+        size_t slot_bytes = 0;
+        unsigned char* base = nullptr;
+        GatherCtl* ctl = nullptr;
+        uint64_t begun = 0, committed = 0, waited = 0, released = 0; // highest step this rank has begun / committed / (root) waited for / released
+    };
+    constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+}
+
 struct shsb_context_t
 {
     int device = 0;
@@ -222,6 +244,11 @@ struct shsb_context_t
     long long side_last_frame[MAX_TILE_STREAMS] = {-1, -1, -1, -1}; // last frame submitted to each render stream
     bool side_joined[MAX_TILE_STREAMS] = {true, true, true, true};  // the main stream already waits for side_last_frame[k]
     cudaEvent_t ev_main_sync[MAX_TILE_STREAMS]{};
+    // sort-first frame assembly
+    std::vector<GatherSlot> gathers;
+    cudaStream_t gather_stream = nullptr;
+    uint32_t* h_gather_timeout = nullptr;   // pinned + mapped: raised by a flag wait that ran out of time
+    uint32_t* d_gather_timeout = nullptr;
     std::string error;
     uint64_t launches = 0;
 
@@ -364,6 +391,7 @@ namespace
         for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamSynchronize(st);
         for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamSynchronize(st);
         for (cudaStream_t st : ctx->tile_streams) if (st) cudaStreamSynchronize(st);
+        if (ctx->gather_stream) cudaStreamSynchronize(ctx->gather_stream);
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->copy_stream2);
     }
@@ -1346,6 +1374,9 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
     for (cudaStream_t st : ctx->cull_streams) if (st) cudaStreamDestroy(st);
     for (cudaStream_t st : ctx->front_streams) if (st) cudaStreamDestroy(st);
+    for (size_t i = 0; i < ctx->gathers.size(); ++i) if (ctx->gathers[i].live) shsb_gather_destroy(ctx, (shsb_gather)(i + 1));
+    if (ctx->gather_stream) cudaStreamDestroy(ctx->gather_stream);
+    if (ctx->h_gather_timeout) cudaFreeHost(ctx->h_gather_timeout);
     for (int i = 1; i < MAX_TILE_STREAMS; ++i)
     {
         if (ctx->tile_streams[i]) cudaStreamDestroy(ctx->tile_streams[i]);
@@ -1364,8 +1395,10 @@ SHSB_API int32_t shsb_sync(shsb_ctx ctx)
     CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
+    if (ctx->gather_stream) CK(cudaStreamSynchronize(ctx->gather_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream2));
+    if (ctx->h_gather_timeout && *ctx->h_gather_timeout) return fail(ctx, SHSB_E_TIMEOUT, "a frame-assembly wait timed out (a rank never committed / the root never released a step)");
     return SHSB_OK;
 }
 
@@ -1598,6 +1631,7 @@ SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane,
         CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
         CK(cudaStreamWaitEvent(cs, ctx->ev_frame_done, 0));
     }
+    if (r->read_pending) CK(cudaStreamWaitEvent(cs, r->read_done, 0)); // an earlier reader on another stream: the one event then covers both
     CK(cudaMemcpyAsync(dst_pinned, p, bytes, cudaMemcpyDeviceToHost, cs));
     CK(cudaEventRecord(r->read_done, cs));
     r->read_pending = true;
@@ -2544,6 +2578,240 @@ SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_
     if (counts) CK(cudaMemcpyAsync(counts, L.counts.p, tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (indices) CK(cudaMemcpyAsync(indices, L.indices.p, tiles * L.max_per_tile * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- sort-first frame assembly
+namespace
+{
+    GatherSlot* get_gather(shsb_ctx ctx, shsb_gather g)
+    {
+        if (g == 0 || g > ctx->gathers.size() || !ctx->gathers[g - 1].live) return nullptr;
+        return &ctx->gathers[g - 1];
+    }
+
+    int gather_prepare(shsb_ctx ctx)
+    {
+        CK(cudaSetDevice(ctx->device));
+        if (!ctx->gather_stream) CK(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+        if (!ctx->h_gather_timeout)
+        {
+            CK(cudaHostAlloc(&ctx->h_gather_timeout, sizeof(uint32_t), cudaHostAllocMapped));
+            *ctx->h_gather_timeout = 0u;
+            CK(cudaHostGetDevicePointer(&ctx->d_gather_timeout, ctx->h_gather_timeout, 0));
+        }
+        if (*ctx->h_gather_timeout) return fail(ctx, SHSB_E_TIMEOUT, "a frame-assembly wait timed out (a rank never committed / the root never released a step)");
+        return SHSB_OK;
+    }
+}
+
+SHSB_API int32_t shsb_gather_create(shsb_ctx ctx, uint32_t n_ranks, uint32_t slots, size_t slot_bytes, shsb_gather* out_gather, ShsbGatherExport* out_export)
+{
+    if (!ctx || !out_gather || !out_export) return SHSB_E_INVALID_ARGUMENT;
+    if (n_ranks == 0 || n_ranks > SHSB_GATHER_MAX_RANKS || slots == 0 || slot_bytes == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad frame-assembly description");
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot g;
+    g.live = true; g.root = true; g.n_ranks = n_ranks; g.rank = 0; g.slots = slots; g.slot_bytes = slot_bytes;
+    if (cudaMalloc(&g.base, slot_bytes * slots) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SHSB_E_OUT_OF_MEMORY, "assembly memory: %zu bytes", slot_bytes * slots); }
+    if (cudaMalloc(&g.ctl, sizeof(GatherCtl)) != cudaSuccess) { cudaGetLastError(); cudaFree(g.base); return fail(ctx, SHSB_E_OUT_OF_MEMORY, "assembly control block"); }
+    CK(cudaMemset(g.ctl, 0, sizeof(GatherCtl)));
+    CK(cudaDeviceSynchronize());
+    *out_export = ShsbGatherExport{};
+    cudaIpcMemHandle_t hm{}, hc{};
+    // legacy IPC handles: valid for other processes; ranks of this process use the raw pointers below
+    if (cudaIpcGetMemHandle(&hm, g.base) == cudaSuccess && cudaIpcGetMemHandle(&hc, g.ctl) == cudaSuccess)
+    {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(out_export->mem_handle, &hm, 64);
+        std::memcpy(out_export->ctl_handle, &hc, 64);
+    }
+    else cudaGetLastError();
+    out_export->mem_ptr = (uint64_t)(uintptr_t)g.base;
+    out_export->ctl_ptr = (uint64_t)(uintptr_t)g.ctl;
+    out_export->slot_bytes = slot_bytes;
+    out_export->n_ranks = n_ranks; out_export->slots = slots;
+    out_export->root_device = ctx->device;
+    out_export->root_pid = (int32_t)getpid();
+    ctx->gathers.push_back(g);
+    *out_gather = (shsb_gather)ctx->gathers.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_open(shsb_ctx ctx, const ShsbGatherExport* exp, uint32_t rank, shsb_gather* out_gather)
+{
+    if (!ctx || !exp || !out_gather) return SHSB_E_INVALID_ARGUMENT;
+    if (rank == 0 || rank >= exp->n_ranks || exp->n_ranks > SHSB_GATHER_MAX_RANKS || exp->slots == 0 || exp->slot_bytes == 0)
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad frame-assembly export / rank %u of %u", rank, exp->n_ranks);
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot g;
+    g.live = true; g.root = false; g.n_ranks = exp->n_ranks; g.rank = rank; g.slots = exp->slots; g.slot_bytes = (size_t)exp->slot_bytes;
+    if (exp->root_pid == (int32_t)getpid())
+    {
+        // same process (several contexts of one host program): the allocations are directly addressable (unified addressing)
+        if (exp->root_device != ctx->device)
+        {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, exp->root_device));
+            if (!can) return fail(ctx, SHSB_E_UNSUPPORTED, "device %d cannot access device %d's memory (no peer-to-peer path)", ctx->device, exp->root_device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(exp->root_device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, SHSB_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        g.base = (unsigned char*)(uintptr_t)exp->mem_ptr;
+        g.ctl = (GatherCtl*)(uintptr_t)exp->ctl_ptr;
+    }
+    else
+    {
+        cudaIpcMemHandle_t hm{}, hc{};
+        std::memcpy(&hm, exp->mem_handle, 64);
+        std::memcpy(&hc, exp->ctl_handle, 64);
+        void* pm = nullptr; void* pc = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pm, hm, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); if (pm) cudaIpcCloseMemHandle(pm); return fail(ctx, SHSB_E_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+        g.base = (unsigned char*)pm;
+        g.ctl = (GatherCtl*)pc;
+        g.ipc = true;
+    }
+    ctx->gathers.push_back(g);
+    *out_gather = (shsb_gather)ctx->gathers.size();
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_destroy(shsb_ctx ctx, shsb_gather gather)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not live", gather);
+    cudaSetDevice(ctx->device);
+    sync_all(ctx);
+    if (g->root) { cudaFree(g->base); cudaFree(g->ctl); }
+    else if (g->ipc) { cudaIpcCloseMemHandle(g->base); cudaIpcCloseMemHandle(g->ctl); }
+    *g = GatherSlot{};
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_frame_gather(shsb_ctx ctx, shsb_gather gather, uint64_t step, shsb_rt rt, int32_t plane, size_t src_offset, size_t bytes, size_t dst_offset)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not live", gather);
+    RtSlot* r = peek_rt(ctx, rt);
+    if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
+    void* p = nullptr;
+    const size_t have = plane_bytes(*r, plane, &p);
+    if (!have) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "render target %u has no plane %d", rt, plane);
+    if (src_offset > have || bytes > have - src_offset) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, push asks for [%zu, %zu)", have, src_offset, src_offset + bytes);
+    if (dst_offset > g->slot_bytes || bytes > g->slot_bytes - dst_offset) return fail(ctx, SHSB_E_SIZE_MISMATCH, "slot is %zu bytes, push targets [%zu, %zu)", g->slot_bytes, dst_offset, dst_offset + bytes);
+    if (step == 0 || step < g->begun || step <= g->committed) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "steps are numbered from 1 and never go back (step %llu after %llu)", (unsigned long long)step, (unsigned long long)g->begun);
+    cudaStream_t gs = ctx->gather_stream;
+    if (step > g->begun)
+    {
+        // first push of a new step: its slot was last used by step - slots, which the root must have released
+        if (step > g->slots)
+        {
+            if (g->root)
+            {
+                if (g->released < step - g->slots) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "step %llu reuses the slot of step %llu, which has not been released", (unsigned long long)step, (unsigned long long)(step - g->slots));
+            }
+            else launch_gather_wait(&g->ctl->released, 1, step - g->slots, GATHER_TIMEOUT_NS, ctx->d_gather_timeout, gs, &ctx->launches);
+        }
+        g->begun = step;
+    }
+    // the push starts when whatever wrote the target last has finished (same rule as shsb_rt_download_async)
+    if (r->frame_is_last && r->last_frame >= 0) CK(cudaStreamWaitEvent(gs, ctx->ev_tile_done[r->last_frame % TILE_DONE_RING], 0));
+    else
+    {
+        CK(cudaEventRecord(ctx->ev_frame_done, ctx->stream));
+        CK(cudaStreamWaitEvent(gs, ctx->ev_frame_done, 0));
+    }
+    if (!r->read_done) CK(cudaEventCreateWithFlags(&r->read_done, cudaEventDisableTiming));
+    if (r->read_pending) CK(cudaStreamWaitEvent(gs, r->read_done, 0));
+    unsigned char* dst = g->base + (size_t)((step - 1) % g->slots) * g->slot_bytes + dst_offset;
+    if (bytes) CK(cudaMemcpyAsync(dst, (const unsigned char*)p + src_offset, bytes, cudaMemcpyDeviceToDevice, gs)); // copy engine; peer write over NVLink for a remote root
+    CK(cudaEventRecord(r->read_done, gs));
+    r->read_pending = true; // a later pass that writes the target waits for the push
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_commit(shsb_ctx ctx, shsb_gather gather, uint64_t step)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not live", gather);
+    if (step == 0 || step <= g->committed || step < g->begun) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "commit of step %llu after step %llu", (unsigned long long)step, (unsigned long long)std::max(g->committed, g->begun));
+    if (step > g->begun && step > g->slots && !g->root)
+        launch_gather_wait(&g->ctl->released, 1, step - g->slots, GATHER_TIMEOUT_NS, ctx->d_gather_timeout, ctx->gather_stream, &ctx->launches); // a step without pushes still keeps the ring order
+    launch_gather_signal(&g->ctl->arrive[g->rank], step, ctx->gather_stream, &ctx->launches);
+    CK(cudaGetLastError());
+    g->begun = g->committed = step;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_wait(shsb_ctx ctx, shsb_gather gather, uint64_t step)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g || !g->root) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not a live root handle", gather);
+    if (step == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "steps are numbered from 1");
+    launch_gather_wait(g->ctl->arrive, g->n_ranks, step, GATHER_TIMEOUT_NS, ctx->d_gather_timeout, ctx->gather_stream, &ctx->launches);
+    CK(cudaGetLastError());
+    g->waited = std::max<uint64_t>(g->waited, step);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_release(shsb_ctx ctx, shsb_gather gather, uint64_t step)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g || !g->root) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not a live root handle", gather);
+    if (step == 0 || step <= g->released) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "release of step %llu after step %llu", (unsigned long long)step, (unsigned long long)g->released);
+    if (g->waited < step) { if (int rc = shsb_gather_wait(ctx, gather, step)) return rc; } // releasing a step nobody waited for would let ranks overwrite pushes still in flight
+    launch_gather_signal(&g->ctl->released, step, ctx->gather_stream, &ctx->launches);
+    CK(cudaGetLastError());
+    g->released = step;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_device_ptr(shsb_ctx ctx, shsb_gather gather, uint64_t step, void** out_ptr)
+{
+    if (!ctx || !out_ptr) return SHSB_E_INVALID_ARGUMENT;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g || !g->root) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not a live root handle", gather);
+    if (step == 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "steps are numbered from 1");
+    *out_ptr = g->base + (size_t)((step - 1) % g->slots) * g->slot_bytes;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_download_async(shsb_ctx ctx, shsb_gather gather, uint64_t step, size_t offset, void* dst_pinned, size_t bytes)
+{
+    if (!ctx || !dst_pinned) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    GatherSlot* g = get_gather(ctx, gather);
+    if (!g || !g->root) return fail(ctx, SHSB_E_INVALID_HANDLE, "frame-assembly handle %u is not a live root handle", gather);
+    if (step == 0 || offset > g->slot_bytes || bytes > g->slot_bytes - offset) return fail(ctx, SHSB_E_SIZE_MISMATCH, "slot is %zu bytes, read asks for [%zu, %zu)", g->slot_bytes, offset, offset + bytes);
+    if (g->waited < step) { if (int rc = shsb_gather_wait(ctx, gather, step)) return rc; }
+    CK(cudaMemcpyAsync(dst_pinned, g->base + (size_t)((step - 1) % g->slots) * g->slot_bytes + offset, bytes, cudaMemcpyDeviceToHost, ctx->gather_stream));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_download(shsb_ctx ctx, shsb_gather gather, uint64_t step, size_t offset, void* dst, size_t bytes)
+{
+    if (int rc = shsb_gather_download_async(ctx, gather, step, offset, dst, bytes)) return rc;
+    CK(cudaStreamSynchronize(ctx->gather_stream));
+    if (*ctx->h_gather_timeout) return fail(ctx, SHSB_E_TIMEOUT, "a frame-assembly wait timed out (a rank never committed step %llu)", (unsigned long long)step);
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_gather_stream(shsb_ctx ctx, void** out_stream)
+{
+    if (!ctx || !out_stream) return SHSB_E_INVALID_ARGUMENT;
+    if (int rc = gather_prepare(ctx)) return rc;
+    *out_stream = (void*)ctx->gather_stream;
     return SHSB_OK;
 }
 

@@ -311,6 +311,47 @@ class Context:
     def set_tile_streams(self, n: int):
         _check(self.lib, self.h, self.lib.shsb_set_tile_streams(self.h, int(n)), "shsb_set_tile_streams")
 
+    # ---- sort-first frame assembly (include/shsb.h "sort-first frame assembly")
+    def gather_create(self, n_ranks: int, slots: int, slot_bytes: int):
+        """Root: returns (handle, export); bytes(export) goes to the other ranks."""
+        g, exp = C.c_uint32(), capi.GatherExport()
+        _check(self.lib, self.h, self.lib.shsb_gather_create(self.h, n_ranks, slots, slot_bytes, C.byref(g), C.byref(exp)), "shsb_gather_create")
+        return g.value, exp
+
+    def gather_open(self, export, rank: int) -> int:
+        exp = export if isinstance(export, capi.GatherExport) else capi.GatherExport.from_buffer_copy(bytes(export))
+        g = C.c_uint32()
+        _check(self.lib, self.h, self.lib.shsb_gather_open(self.h, C.byref(exp), rank, C.byref(g)), "shsb_gather_open")
+        return g.value
+
+    def gather_destroy(self, g):
+        _check(self.lib, self.h, self.lib.shsb_gather_destroy(self.h, g), "shsb_gather_destroy")
+
+    def frame_gather(self, g, step, rt, plane, src_offset, nbytes, dst_offset):
+        _check(self.lib, self.h, self.lib.shsb_frame_gather(self.h, g, step, rt, plane, src_offset, nbytes, dst_offset), "shsb_frame_gather")
+
+    def gather_commit(self, g, step):
+        _check(self.lib, self.h, self.lib.shsb_gather_commit(self.h, g, step), "shsb_gather_commit")
+
+    def gather_wait(self, g, step):
+        _check(self.lib, self.h, self.lib.shsb_gather_wait(self.h, g, step), "shsb_gather_wait")
+
+    def gather_release(self, g, step):
+        _check(self.lib, self.h, self.lib.shsb_gather_release(self.h, g, step), "shsb_gather_release")
+
+    def gather_download(self, g, step, offset, nbytes) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        _check(self.lib, self.h, self.lib.shsb_gather_download(self.h, g, step, offset, out.ctypes.data_as(C.c_void_p), nbytes), "shsb_gather_download")
+        return out
+
+    def gather_download_async(self, g, step, offset, dst_ptr, nbytes):
+        _check(self.lib, self.h, self.lib.shsb_gather_download_async(self.h, g, step, offset, C.c_void_p(dst_ptr), nbytes), "shsb_gather_download_async")
+
+    def gather_stream(self) -> int:
+        p = C.c_void_p()
+        _check(self.lib, self.h, self.lib.shsb_gather_stream(self.h, C.byref(p)), "shsb_gather_stream")
+        return p.value
+
     def stream(self) -> int:
         p = C.c_void_p()
         _check(self.lib, self.h, self.lib.shsb_stream(self.h, C.byref(p)), "shsb_stream")

@@ -119,3 +119,19 @@ def test_scene_cull_drop_in_compiles_and_has_no_cpu_fallback():
         r = subprocess.run([path], capture_output=True, text=True)
         print(r.stdout, r.stderr)
         assert r.returncode == 77 and "every call refused" in r.stdout and "417 of 600 objects visible" in r.stdout
+
+
+def test_gather_test_compiles_against_the_c_abi_alone_and_refuses_without_a_device():
+    """tests/cpp/gather_test.cpp includes nothing but include/shsb.h; without a device both of its processes stop at
+    shsb_context_create (SHSB_E_NO_DEVICE -> exit code 77)."""
+    import torch
+    from leisure_software_renderer_b200 import build
+    build.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "gather_test")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/gather_test"], check=True, capture_output=True)
+    assert os.path.exists(exe)
+    src = open(os.path.join(ROOT, "tests", "cpp", "gather_test.cpp")).read()
+    assert '#include "shsb.h"' in src and "torch" not in src.split("#include", 1)[1] and "nccl" not in src.lower().split("#include", 1)[1]
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 77 and "SKIP" in r.stdout
