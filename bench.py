@@ -137,13 +137,25 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the raster path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    batch = world > 1
+    if batch:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL chatter (e.g. its version line) must not share stdout with the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = Context(local_rank)
     base = scenes.scene_c2(W, H)
-    sd = scenes.camera_ring(base, world)[rank] if world > 1 else base
+    # N = 1: the C2 frame, one camera, a step = one frame.  N > 1: BASELINE configs[4]'s 64-camera batch over the same scene, a step = the
+    # whole batch (fixed total work => strong scaling), rank r renders cameras {c : c mod N == r} and pushes every LDR frame into the
+    # assembly memory on rank 0's GPU (shsb_frame_gather: copy-engine peer writes over NVLink, no collective on the data path).
+    if batch:
+        ring = scenes.camera_ring(base, N_CAMERAS)
+        from leisure_software_renderer_b200 import sortfirst
+        my_cams = sortfirst.cameras_of_rank(N_CAMERAS, world, rank)
+        views = [ring[c] for c in my_cams]
+    else:
+        my_cams, views = [0], [base]
+    frames_per_step = N_CAMERAS if batch else 1
+    sd = views[0]
     for m in sd.meshes:
         ctx.mesh_upload(m["positions"], m["normals"], m["uvs"], m["indices"])
     lights_pinned = torch.from_numpy(np.ascontiguousarray(sd.lights).view(np.uint8).copy()).pin_memory()
@@ -155,51 +167,48 @@ def run_ours(args):
     sets = [(ctx.rt_create(capi.RT_COLOR_HDR, W, H), ctx.rt_create(capi.RT_DEPTH_MOTION, W, H, sd.zn, sd.zf), ctx.rt_create(capi.RT_COLOR_LDR, W, H))
             for _ in range(NSETS)]
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+    frame_bytes = W * H * 4
+    host_ldr = [torch.empty(frame_bytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
 
-    def ldr_tensor(rt):
-        ptr, nbytes = ctx.rt_device_ptr(rt, capi.PLANE_COLOR)
+    gather = None
+    gstream = None
+    if batch:
+        # the root allocates 2 slots x 64 frames of assembly memory; its CUDA IPC export travels as bytes (an NCCL broadcast of a uint8 tensor)
+        exp_t = torch.zeros(C_sizeof_export(capi), dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            gather, exp = ctx.gather_create(world, GATHER_SLOTS, N_CAMERAS * frame_bytes)
+            exp_t.copy_(torch.frombuffer(bytearray(bytes(exp)), dtype=torch.uint8))
+        dist.broadcast(exp_t, src=0)
+        if rank != 0:
+            gather = ctx.gather_open(bytes(exp_t.cpu().numpy().tobytes()), rank)
+        gstream = torch.cuda.ExternalStream(ctx.gather_stream(), device=local_rank)
+    counters = {"step": 0, "frame": 0}
 
-        class _Cai:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        return torch.as_tensor(_Cai(), device=torch.device("cuda", local_rank))
-
-    ldr_views = [ldr_tensor(s[2]) for s in sets]
-    gather_bufs = [torch.empty_like(ldr_views[0]) for _ in range(world)] if (world > 1 and rank == 0) else None
-    host_ldr = [torch.empty(W * H * 4, dtype=torch.uint8).pin_memory() for _ in range(2)]
-
-    comm_stream = torch.cuda.Stream(device=local_rank) if world > 1 else None
-    gather_done = [None] * NSETS   # per render-target set: the gather that last read its LDR plane
-    last_gather = [None]
-
-    def step(i, e2e=False):
-        k = i % NSETS
-        hdr, dm, ldr = sets[k]
+    def step(_i, e2e=False):
+        counters["step"] += 1
+        s_no = counters["step"]
         if e2e:
-            ctx.lights_upload(lights_pinned.numpy())          # H2D 160 B x n_lights from pinned memory
-        if world > 1 and gather_done[k] is not None:
-            stream.wait_event(gather_done[k])                 # do not overwrite an LDR plane that is still being gathered
-            ctx.fence()
-        ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=False)   # asynchronous; draw list H2D inside the call
-        if world > 1:
-            # frame assembly over NVLink: the gather of frame i runs on its own stream and overlaps with frame i+1
-            ctx.fence()
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                dist.gather(ldr_views[k], gather_bufs, dst=0)
-                done = torch.cuda.Event()
-                done.record(comm_stream)
-            gather_done[k] = done
-            last_gather[0] = done
-        if e2e:
-            # D2H of the step's result into pinned memory (copy stream: overlaps with the next step's rendering)
-            ctx.rt_download_async(ldr, capi.PLANE_COLOR, host_ldr[i % 2].data_ptr(), W * H * 4)
+            ctx.lights_upload(lights_pinned.numpy())          # H2D 160 B x n_lights from pinned memory, once per step
+        for c, v in zip(my_cams, views):
+            k = counters["frame"] % NSETS
+            counters["frame"] += 1
+            hdr, dm, ldr = sets[k]
+            ctx.frame_forward_plus(v.scene, fp, hdr, dm, ldr, want_stats=False)   # asynchronous; draw list H2D inside the call
+            if batch:
+                ctx.frame_gather(gather, s_no, ldr, capi.PLANE_COLOR, 0, frame_bytes, c * frame_bytes)   # frame assembly over NVLink, behind the frame
+            if e2e:
+                # D2H of the frame into pinned memory (copy stream: overlaps with the next frames' rendering)
+                ctx.rt_download_async(ldr, capi.PLANE_COLOR, host_ldr[counters["frame"] % 4].data_ptr(), frame_bytes)
+        if batch:
+            ctx.gather_commit(gather, s_no)
+            if rank == 0:
+                ctx.gather_wait(gather, s_no)                 # the assembled batch is complete on the root's GPU ...
+                ctx.gather_release(gather, s_no)              # ... and its slot may be reused two steps later
 
     def barrier():
         torch.cuda.synchronize()
         ctx.sync()
-        if world > 1:
+        if batch:
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -210,11 +219,11 @@ def run_ours(args):
 
     def warm(e2e):
         """Warm-up of the path that is timed next: the same calls as the timed loop (both executable-graph topologies of the
-        front end -- with and without stage events --, the light-upload ring, the read-back streams and their pinned buffers),
-        at least 2 x NSETS frames so that every render-target set and every transient arena has been through it once."""
+        front end -- with and without stage events --, the light-upload ring, the read-back streams and their pinned buffers, the
+        assembly ring), enough frames that every render-target set and every transient arena has been through it once."""
         if not e2e:
             ctx.timing_enable(TIMING_STRIDE)
-        for i in range(max(n_warm, 2 * NSETS)):
+        for i in range(n_warm if batch else max(n_warm, 2 * NSETS)):
             step(i, e2e)
         if e2e:
             ctx.sync()
@@ -230,7 +239,7 @@ def run_ours(args):
         if rank == 0:
             sampler.start()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e1g = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         if not e2e:
             ctx.timing_enable(TIMING_STRIDE)   # stage events on every 8th frame only: they are extra commands on the critical stream
         ctx.host_submit_us(reset=True)
@@ -242,32 +251,46 @@ def run_ours(args):
         hu = ctx.host_submit_us(reset=True)
         host_ms = {"total_ms": host_ms, "library_us": {k: float(hu[i] / max(hu[5], 1.0)) for i, k in
                    enumerate(("draw_list", "staging_incl_ring_wait", "arena_checks", "capture_enqueue", "graph_update_launch_tile_launch"))}}
-        if world > 1 and last_gather[0] is not None:
-            stream.wait_event(last_gather[0])  # the last frame assembly belongs to the timed region
         if e2e:
             ctx.sync()  # the last read-backs (copy stream) belong to the timed region
         ctx.fence()     # frames run on several render streams: the main stream (and e1) behind all of them
         e1.record(stream)
+        if batch:
+            e1g.record(gstream)  # the last pushes / the root's wait for every rank's last commit belong to the timed region
         barrier()
         ms = e0.elapsed_time(e1)
+        if batch:
+            ms = max(ms, e0.elapsed_time(e1g))
         stages = ctx.timing_collect() if not e2e else None
         if not e2e:
             ctx.timing_enable(False)
         clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if world > 1:
+        if batch:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), stages, clocks, ctx.launch_count() - launches0, host_ms
 
     ms_dev, stages, clocks, launches, host_dev = timed(False)
     ms_e2e, _, clocks_e2e, _, host_e2e = timed(True)
 
+    # The tile kernel timed ALONE for the roofline: every tile kernel on the main stream, back to back (front ends of later frames
+    # still overlap it, as in round 1), CUDA events around each launch.  In the timed regions above tile kernels of consecutive
+    # frames overlap on two render streams, so an event pair around one of them also spans its neighbour's share of the SMs.
+    ctx.set_tile_streams(1)
+    ctx.timing_enable(2)
+    for i in range(48):
+        ctx.frame_forward_plus(sd.scene, fp, *sets[i % NSETS], want_stats=False)
+    alone = ctx.timing_collect()
+    ctx.timing_enable(False)
+    ctx.set_tile_streams(2)
+    tile_alone_ms = float(np.median(alone[4:, 2])) if len(alone) > 8 else float("nan")
+
     n_items = len(sd.items)
     n_blocks = sum((len(sd.meshes[it["mesh"] - 1]["indices"]) // 3 + 127) // 128 for it in sd.items)
-    h2d = n_items * 192 + n_blocks * 8 + len(sd.lights) * 160
-    d2h = W * H * 4
-    fps = world * args.steps / (ms_dev / 1e3)
-    fps_e2e = world * args.steps / (ms_e2e / 1e3)
+    h2d = frames_per_step * (n_items * 256 + n_blocks * 8) + world * len(sd.lights) * 160
+    d2h = frames_per_step * frame_bytes
+    fps = frames_per_step * args.steps / (ms_dev / 1e3)
+    fps_e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
     hbm, peak_src = peaks()
     mesh = sd.meshes[0]
     b_frame, b_tile = algorithmic_bytes(sd, counts, len(mesh["positions"]), len(mesh["indices"]))
@@ -276,47 +299,67 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if batch else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(sd, world),
+            "config": workload_config(base, world),
+            "frames_per_step": frames_per_step,
             "mtri_per_s": fps * st["tri_input"] / 1e6, "mfrag_per_s": fps * st["frag_covered"] / 1e6,
             "frame_stats": st,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "host_submit_ms_per_step": host_e2e},
             "host_submit_ms_per_step": host_dev,
             "gpu_launches": int(launches),
-            "stage_ms": {"vertex_clip_setup": float(stage_mean[0]), "binning": float(stage_mean[1]), "tile_raster_shade": tile_ms,
+            "stage_ms": {"vertex_clip_setup": float(stage_mean[0]), "binning": float(stage_mean[1]), "tile_raster_shade_overlapped": tile_ms,
+                         "tile_raster_shade_alone": tile_alone_ms,
                          "geometry_to_resolve": float(stage_mean[3]), "frames_timed": 0 if stages is None else int(len(stages)),
-                         "note": f"CUDA events around the stages of every {TIMING_STRIDE}th frame of the timed region"},
+                         "note": f"CUDA events around the stages of every {TIMING_STRIDE}th frame of the timed region (tile kernels of consecutive frames "
+                                 f"overlap on 2 render streams there); `alone` = median over {max(0, len(alone) - 4)} launches of a separate pass with every "
+                                 f"tile kernel on one stream"},
             "roofline": {"bound": "hbm", "kernel": "tile_kernel (tile raster + Forward+ shade + resolve + tonemap)",
-                         "achieved": (b_tile / 1e9) / (tile_ms / 1e3) if tile_ms > 0 else None, "peak": hbm, "unit": "GB/s",
-                         "frac": ((b_tile / 1e9) / (tile_ms / 1e3) / hbm) if tile_ms > 0 else None, "traffic": ncu_traffic()[0],
-                         "traffic_source": ncu_traffic()[1], "algorithmic_bytes": b_tile, "peak_source": peak_src},
-            "roofline_frame": {"algorithmic_bytes": b_frame, "achieved": (b_frame / 1e9) / (ms_dev / args.steps / 1e3),
-                               "frac": (b_frame / 1e9) / (ms_dev / args.steps / 1e3) / hbm, "unit": "GB/s"},
+                         "achieved": (b_tile / 1e9) / (tile_alone_ms / 1e3) if tile_alone_ms > 0 else None, "peak": hbm, "unit": "GB/s",
+                         "frac": ((b_tile / 1e9) / (tile_alone_ms / 1e3) / hbm) if tile_alone_ms > 0 else None, "traffic": ncu_traffic()[0],
+                         "traffic_source": ncu_traffic()[1], "algorithmic_bytes": b_tile, "peak_source": peak_src,
+                         "launch_ms": tile_alone_ms, "how": "kernel timed alone on its stream (CUDA events around each launch, back-to-back frames)"},
+            "roofline_frame": {"algorithmic_bytes": b_frame, "achieved": (b_frame / 1e9) / (ms_dev / args.steps / frames_per_step * world / 1e3),
+                               "frac": (b_frame / 1e9) / (ms_dev / args.steps / frames_per_step * world / 1e3) / hbm, "unit": "GB/s",
+                               "note": "whole frame (front end + tile kernel, pipelined) per GPU: algorithmic bytes / steady-state period"},
             "clocks": clocks, "clocks_e2e": clocks_e2e,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if not batch and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(sd, args.cpu_seconds)
         emit(line)
+    if gather is not None:
+        barrier()
+        ctx.gather_destroy(gather)
     ctx.close()
-    if world > 1:
+    if batch:
         dist.destroy_process_group()
 
 
+def C_sizeof_export(capi):
+    import ctypes
+    return ctypes.sizeof(capi.GatherExport)
+
+
 NSETS = 4
+N_CAMERAS = 64     # BASELINE configs[4]: the 64-camera batch
+GATHER_SLOTS = 2
 
 
 def workload_config(sd, world):
     """The `config` object of the JSON line -- the same dict from both arms (the driver compares them)."""
     tris = sum(len(sd.meshes[it["mesh"] - 1]["indices"]) // 3 for it in sd.items)
     n_lights = 0 if sd.lights is None else len(sd.lights)
-    return {"workload": f"C2: 1080p Forward+ frame, {len(sd.items)} Suzanne instances ({tris} tris), {n_lights} point/spot lights, "
-                        f"{int(sd.fp.tile_size)}-px tiles, <={int(sd.fp.max_lights_per_tile)} lights/tile"
-                        + (f"; camera batch of {world}, one camera per GPU, LDR frames gathered to rank 0 over NCCL" if world > 1 else ""),
-            "resolution": [W, H], "tile_size": int(sd.fp.tile_size), "max_lights_per_tile": int(sd.fp.max_lights_per_tile),
-            "parallelism": f"sort-first camera batch x{world}" if world > 1 else "single GPU",
+    frame = (f"1080p Forward+ frame, {len(sd.items)} Suzanne instances ({tris} tris), {n_lights} point/spot lights, "
+             f"{int(sd.fp.tile_size)}-px tiles, <={int(sd.fp.max_lights_per_tile)} lights/tile")
+    if world > 1:
+        workload = (f"C5b: {N_CAMERAS}-camera batch (cameras on a ring around the C2 scene), each camera one {frame}; a step = the whole batch; sort-first: "
+                    f"cameras c mod {world} per GPU, every LDR frame assembled on rank 0's GPU over NVLink (copy-engine peer pushes, shsb_frame_gather)")
+    else:
+        workload = "C2: " + frame
+    return {"workload": workload, "resolution": [W, H], "tile_size": int(sd.fp.tile_size), "max_lights_per_tile": int(sd.fp.max_lights_per_tile),
+            "parallelism": f"sort-first camera batch, {N_CAMERAS} cameras over {world} GPUs" if world > 1 else "single GPU",
             "l2": f"{NSETS} rotating render-target sets ({NSETS * W * H * 24 / 1e6:.0f} MB) > 126 MB L2"}
 
 
@@ -357,7 +400,11 @@ def run_reference(args):
     o = bindings.Oracle(kind)
     cores = os.cpu_count() or 1
     o.set_threads(cores)
-    sd = scenes.scene_c2(W, H)
+    base = scenes.scene_c2(W, H)
+    # N = 1: the C2 frame.  N > 1: the CUDA arm's workload is the 64-camera batch; a reference step is a bounded sample of it -- one
+    # camera of the ring per step, in ring order (64 full frames per step would take 16 s of CPU each).
+    views = scenes.camera_ring(base, N_CAMERAS) if world > 1 else [base]
+    sd = views[0]
     cull = None
     if kind == "reference":
         try:  # the reference's own tile-list builder over the frame's 1024 lights (A11), serial like in the reference
@@ -365,19 +412,22 @@ def run_reference(args):
             from leisure_software_renderer_b200 import capi
             lref = bindings.LightCullReference()
             light_aabbs = np.ascontiguousarray(np.concatenate([sd.lights["cull_aabb_min"][:, :3], sd.lights["cull_aabb_max"][:, :3]], axis=1), dtype=np.float32)
-            desc = capi.LightCullDesc(sd.viewproj, W, H, capi.LIGHT_CULL_TILED, 16, 128, z_near=sd.zn, z_far=sd.zf)
-            lref.light_cull(light_aabbs, desc)
-            cull = lambda: lref.light_cull(light_aabbs, desc)
+            descs = [capi.LightCullDesc(v.viewproj, W, H, capi.LIGHT_CULL_TILED, 16, 128, z_near=v.zn, z_far=v.zf) for v in views]
+            lref.light_cull(light_aabbs, descs[0])
+            cull = lambda k: lref.light_cull(light_aabbs, descs[k])
         except Exception as e:  # library not built and no reference tree: the lit pass alone, as before
             print(f"reference arm: cull_lights_tiled unavailable ({e}); timing the lit pass only", file=sys.stderr)
+    frame_no = [0]
 
     def frame():
+        k = frame_no[0] % len(views)
+        frame_no[0] += 1
         if kind == "reference":
             if cull is not None:
-                cull()
-            harness.cpu_forward(o, sd, forward_plus=False, aov=False)
+                cull(k)
+            harness.cpu_forward(o, views[k], forward_plus=False, aov=False)
         else:
-            harness.cpu_forward(o, sd, forward_plus=True, aov=False)
+            harness.cpu_forward(o, views[k], forward_plus=True, aov=False)
 
     t0 = time.perf_counter(); frame(); t1 = time.perf_counter() - t0
     n_warm = max(args.warmup, 3)                                      # the CUDA arm's rule, so that both lines carry the same `warmup`
@@ -389,14 +439,14 @@ def run_reference(args):
         frame()
     dt = time.perf_counter() - t0
     fps = steps / dt
-    sample = (f"{steps} full C2 frames: " + ("cull_lights_tiled over 1024 lights (the reference's serial builder, Jolt declaration shim) + " if cull is not None else "") +
+    sample = ((f"{steps} frames = one camera of the {N_CAMERAS}-camera batch per step, in ring order: " if world > 1 else f"{steps} full C2 frames: ") + ("cull_lights_tiled over 1024 lights (the reference's serial builder, Jolt declaration shim) + " if cull is not None else "") +
               f"PassPBRForward (sun + fake IBL only; the reference CPU path never shades tile light lists) + PassTonemap "
               f"via oracle/_ref/libshs_ref.so, ThreadPoolJobSystem({cores})" if kind == "reference"
               else f"{steps} full C2 Forward+ frames via oracle/liboracle.so (single thread)")
     line = {"impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps,
             "steps_requested": args.steps, "warmup": n_warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(sd, world),
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(base, world),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
