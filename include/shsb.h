@@ -50,7 +50,8 @@ enum
     SHSB_E_OUT_OF_MEMORY = 6,
     SHSB_E_SIZE_MISMATCH = 7,
     SHSB_E_UNSUPPORTED = 8,
-    SHSB_E_TIMEOUT = 9
+    SHSB_E_TIMEOUT = 9,
+    SHSB_E_OVERFLOW = 10 /* an earlier ASYNCHRONOUS submission did not fit its per-frame arena (see ShsbStats below) */
 };
 
 typedef struct shsb_context_t* shsb_ctx; /* opaque */
@@ -120,6 +121,12 @@ enum /* planes of a render target for clear / upload / download / device_ptr */
 
 /* ------------------------------------------------------------------ POD mirrors of reference structs */
 
+/* Passing `out_stats` makes a submission SYNCHRONOUS (the call returns when the frame is done, and re-runs the frame with larger
+ * per-frame arenas if the set-up records / tile lists did not fit).  Passing NULL makes it asynchronous: such a frame cannot re-run
+ * itself; if it overflows its arena it renders with geometry missing, raises a sticky flag, and the NEXT frame submission,
+ * shsb_sync or shsb_rt_download returns SHSB_E_OVERFLOW once (capacities are grown x4 at that point: submit the frame again).
+ * The arenas are sized from the submission (every source triangle one record, a quarter of them clipped into 7); a first frame
+ * with statistics sizes them for good. */
 typedef struct ShsbStats /* RasterizerStats, sw_render/rasterizer.hpp:48-53 (+ fragment counters) */
 {
     uint64_t tri_input;

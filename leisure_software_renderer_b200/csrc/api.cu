@@ -301,6 +301,9 @@ struct shsb_context_t
     static constexpr size_t HDR_STATS = 32, HDR_TILE_COUNT = HDR_STATS + STAT_SHARDS * sizeof(DevStats) / 4; // u32 words
     DevStats* h_stats = nullptr;    // pinned
     double rec_growth = 1.0;        // multiplier learned from overflow reruns
+    uint32_t* h_overflow = nullptr; // pinned + mapped, sticky: [0] a kernel of some frame had to drop a record / list / clip-queue entry, [1] / [2] its demand
+    uint32_t* d_overflow = nullptr;
+    size_t min_list_cap = 0, min_rec_cap = 0; // learned from overflows: what a frame of this context has needed
 
     cudaEvent_t ev[NUM_STAGE_EVENTS]{};
     bool ev_valid[NUM_STAGE_EVENTS]{};
@@ -612,6 +615,29 @@ namespace
 
     int main_wait_lights(shsb_ctx ctx);
 
+    // An asynchronous submission (out_stats == NULL) cannot re-run itself when its arena turns out too small: the kernels raise
+    // a sticky flag in mapped host memory instead, and the next submission / shsb_sync / synchronous download reports it --
+    // after growing the capacities, so that re-submitting the frame succeeds.
+    void learn_from_overflow(shsb_ctx ctx)
+    {
+        // the demand words lag the flag by at most one kernel (the tile kernel writes them): whatever is there is a lower bound
+        ctx->min_list_cap = std::max(ctx->min_list_cap, (size_t)ctx->h_overflow[1] + (size_t)ctx->h_overflow[1] / 4);
+        ctx->min_rec_cap = std::max(ctx->min_rec_cap, (size_t)ctx->h_overflow[2] + (size_t)ctx->h_overflow[2] / 4);
+        ctx->rec_growth *= 4.0;
+        std::memset(ctx->h_overflow, 0, 4 * sizeof(uint32_t));
+    }
+
+    int check_async_overflow(shsb_ctx ctx)
+    {
+        if (ctx->h_overflow && *ctx->h_overflow)
+        {
+            learn_from_overflow(ctx);
+            return fail(ctx, SHSB_E_OVERFLOW, "an asynchronous frame submitted earlier overflowed its per-frame arena (records / tile lists / clip queue) and is missing "
+                                              "geometry; capacities have been grown x4: submit it again (or pass out_stats to let the call re-run itself)");
+        }
+        return SHSB_OK;
+    }
+
     // Submits one frame: front end (draw list staged in ctx->h_draw[stage_slot]) on the front stream in arena
     // frame_no % NUM_ARENAS, tile kernel on the main stream.
     int run_frame(shsb_ctx ctx, FrameJob& job, ShsbStats* out_stats, const CullJob* cull = nullptr)
@@ -623,6 +649,7 @@ namespace
         if (fc.W > 65535 || fc.H > 65535) return fail(ctx, SHSB_E_UNSUPPORTED, "render target larger than 65535 pixels on a side");
         if ((job.n_src_tris + 1) * 8ull >= 0xFFFFFFFFull) return fail(ctx, SHSB_E_UNSUPPORTED, "more than 2^29 source triangles in one submission");
         if (int rc = sync_tables(ctx)) return rc;
+        if (int rc = check_async_overflow(ctx)) return rc;
         struct StageEventScope { shsb_ctx c; ~StageEventScope() { c->stage_events = true; } } stage_scope{ctx};
         ctx->stage_events = out_stats != nullptr || (ctx->timing_on && ctx->frame_no % ctx->timing_stride == 0);
 
@@ -633,9 +660,12 @@ namespace
             const int a = (int)(f % ctx->n_arenas);
             Arena& A = ctx->arena[a];
             // capacities: every source triangle may emit one record; clipped ones up to 7
-            const size_t clipq_cap = std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth));
-            const size_t rec_cap = std::max<size_t>(4096, (size_t)(((double)job.n_src_tris + 6.0 * (double)std::min<size_t>(clipq_cap, job.n_src_tris)) * 1.0));
-            const size_t list_cap = std::max<size_t>((size_t)n_tiles + 65536, (size_t)((double)rec_cap * 4.0 * ctx->rec_growth) + (size_t)n_tiles * 2);
+            // the clip queue takes every source triangle (8 bytes each: it cannot overflow); records are sized for a quarter of the
+            // triangles being clipped into the maximum of 7 fan triangles, x the growth learned from overflows
+            const size_t clipq_cap = std::max<size_t>(4096, (size_t)job.n_src_tris);
+            const size_t clipped_est = std::min<size_t>(job.n_src_tris, std::max<size_t>(4096, (size_t)((double)job.n_src_tris * 0.25 * ctx->rec_growth)));
+            const size_t rec_cap = std::max<size_t>(std::max<size_t>(4096, ctx->min_rec_cap), (size_t)((double)job.n_src_tris + 6.0 * (double)clipped_est));
+            const size_t list_cap = std::max<size_t>(std::max<size_t>((size_t)n_tiles + 65536, ctx->min_list_cap), (size_t)((double)rec_cap * 4.0 * ctx->rec_growth) + (size_t)n_tiles * 2);
             const size_t items_bytes = (size_t)job.n_items * sizeof(DevItem);
             const size_t draw_bytes = items_bytes + (size_t)job.n_blocks * sizeof(uint2);
             if (int rc = ensure_dev(ctx, A.d_rrecs, rec_cap)) return rc;
@@ -675,6 +705,7 @@ namespace
             g.tile_list = A.d_tile_list.p;
             g.list_capacity = (uint32_t)std::min<size_t>(A.d_tile_list.cap, 0xFFFFFFFFull);
             g.stats = d_stats;
+            g.overflow_flag = ctx->d_overflow;
             if (cull) job.lists_set = a; // the lists this frame shades with are the ones its own cull branch produces
             if (fc.forward_plus)
             {
@@ -787,7 +818,7 @@ namespace
             }
             if (st.overflow_recs || st.overflow_lists || st.overflow_clipq)
             {
-                ctx->rec_growth *= 4.0; // arena too small for this scene: grow and re-run the frame
+                learn_from_overflow(ctx); // arena too small for this scene: grow (x4, and at least to what this frame needed) and re-run the frame
                 continue;
             }
             out_stats->tri_input += st.tri_input;
@@ -1307,6 +1338,8 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_overflow, 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess;
+    if (ok) { std::memset(ctx->h_overflow, 0, 4 * sizeof(uint32_t)); ok = cudaHostGetDevicePointer(&ctx->d_overflow, ctx->h_overflow, 0) == cudaSuccess; }
     ok = ok && cudaMalloc(&ctx->d_srgb_lut, 256 * sizeof(float)) == cudaSuccess;
     for (int i = 0; ok && i < NUM_STAGE_EVENTS; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < shsb_context_t::STAGE_SLOTS; ++i) ok = cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1354,6 +1387,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
         cudaFree(A.d_tile_order.p); cudaFree(A.d_tile_offset.p); cudaFree(A.d_tile_fill.p); cudaFree(A.d_tile_list.p);
     }
     cudaFreeHost(ctx->h_stats);
+    cudaFreeHost(ctx->h_overflow);
     for (cudaEvent_t e : ctx->ev_tile_done) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_front_done) if (e) cudaEventDestroy(e);
     if (ctx->ev_lights_up) cudaEventDestroy(ctx->ev_lights_up);
@@ -1399,7 +1433,7 @@ SHSB_API int32_t shsb_sync(shsb_ctx ctx)
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream2));
     if (ctx->h_gather_timeout && *ctx->h_gather_timeout) return fail(ctx, SHSB_E_TIMEOUT, "a frame-assembly wait timed out (a rank never committed / the root never released a step)");
-    return SHSB_OK;
+    return check_async_overflow(ctx);
 }
 
 SHSB_API int32_t shsb_fence(shsb_ctx ctx)
@@ -1604,7 +1638,7 @@ SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void*
     if (bytes != want) return fail(ctx, SHSB_E_SIZE_MISMATCH, "plane is %zu bytes, caller passed %zu", want, bytes);
     CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return SHSB_OK;
+    return check_async_overflow(ctx); // the pixels just read may come from an asynchronous frame that dropped geometry
 }
 
 SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst_pinned, size_t bytes)

@@ -113,7 +113,7 @@ namespace shsb
             if (lane == 31 && warp_total) base = atomicAdd(g.list_cursor, warp_total);
             base = __shfl_sync(0xffffffffu, base, 31);
             const uint32_t off = base + incl - c;
-            if (lane == 31 && warp_total && base + warp_total > g.list_capacity) atomicAdd(&g.stats[blockIdx.x & (STAT_SHARDS - 1)].overflow_lists, 1u);
+            if (lane == 31 && warp_total && base + warp_total > g.list_capacity) { atomicAdd(&g.stats[blockIdx.x & (STAT_SHARDS - 1)].overflow_lists, 1u); *g.overflow_flag = 1u; }
             // class 0: geometry + saturated light list (walks all lights), 1: geometry + long light list,
             // 2: geometry, 3: background only
             uint32_t cls = c ? 2u : 3u;

@@ -303,9 +303,26 @@ namespace shsb
                     }
                     else
                     {
-                        const uint32_t q = atomicAdd(g.clipq_count, 1u);
-                        if (q < g.clipq_capacity) g.clip_queue[q] = make_uint2(blk.x, ti);
-                        else atomicAdd(&stats_shard(g)->overflow_clipq, 1u);
+                        // A triangle whose three corners are beyond the SAME clip plane leaves the Sutherland-Hodgman loop
+                        // (rasterizer.hpp:111-164) empty: every vertex an earlier plane inserts is a convex combination of
+                        // corners, so it is beyond that plane too.  Such triangles -- most of what a camera inside a large scene
+                        // does not see -- are dropped here instead of being queued; the margin (1e-4 of the operands) keeps
+                        // the shortcut away from every case where rounding in the interpolation could decide differently.
+                        bool beyond = false;
+#pragma unroll
+                        for (int p = 0; p < 6; ++p)
+                        {
+                            const int a = p >> 1;
+                            const float m0 = 1e-4f * (fabsf(c0.clip[3]) + fabsf(c0.clip[a])), m1 = 1e-4f * (fabsf(c1.clip[3]) + fabsf(c1.clip[a])),
+                                        m2 = 1e-4f * (fabsf(c2.clip[3]) + fabsf(c2.clip[a]));
+                            if (plane_dist(c0, p) < -m0 && plane_dist(c1, p) < -m1 && plane_dist(c2, p) < -m2) beyond = true;
+                        }
+                        if (!beyond)
+                        {
+                            const uint32_t q = atomicAdd(g.clipq_count, 1u);
+                            if (q < g.clipq_capacity) g.clip_queue[q] = make_uint2(blk.x, ti);
+                            else { atomicAdd(&stats_shard(g)->overflow_clipq, 1u); *g.overflow_flag = 1u; }
+                        }
                     }
                 }
             }
@@ -314,7 +331,7 @@ namespace shsb
             if (emit)
             {
                 if (slot < g.rec_capacity) store_records(g, slot, rr, sr);
-                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); emit = false; }
+                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); *g.overflow_flag = 1u; emit = false; }
             }
             if (__ballot_sync(0xffffffffu, emit)) warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
             block_add_stats(g, n_input, n_after, n_raster);
@@ -377,7 +394,7 @@ namespace shsb
                     {
                         const uint32_t slot = atomicAdd(g.rec_count, 1u);
                         if (slot < g.rec_capacity) { store_records(g, slot, rr, sr); thread_count_tiles(fc, g, rr.bbox_x, rr.bbox_y); }
-                        else atomicAdd(&stats_shard(g)->overflow_recs, 1u);
+                        else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); *g.overflow_flag = 1u; }
                     }
                 }
             }
@@ -460,7 +477,7 @@ namespace shsb
 #pragma unroll
                     for (int i = 0; i < 4; ++i) d[i] = s[i];
                 }
-                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); emit = false; }
+                else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); *g.overflow_flag = 1u; emit = false; }
             }
             if (__ballot_sync(0xffffffffu, emit)) warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
         }

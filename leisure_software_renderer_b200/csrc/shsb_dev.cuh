@@ -229,6 +229,8 @@ namespace shsb
         uint32_t* class_count;      // [4] tiles per scheduling class (heaviest first)
         uint32_t* tile_order;       // [4][n_tiles] tiles per class as (tx | ty << 16); CTA b of the tile kernel takes the b-th tile in class order
         DevStats* stats;            // [STAT_SHARDS]
+        uint32_t* overflow_flag;    // mapped host words, sticky: [0] set by any kernel that had to drop a record / list entry / clip-queue entry,
+                                    // [1] / [2] the tile-list entries / records the frame needed (written by the tile kernel when above capacity)
     };
 
     struct DevTexture

@@ -455,6 +455,13 @@ namespace shsb
             __shared__ unsigned long long s_frag[TILE_THREADS / 32][2];
 
             PHASE_BEGIN();
+            // the frame's total demand, for the host to size the arenas from when a front-end kernel had to drop something
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+            {
+                const uint32_t need_lists = *g.list_cursor, need_recs = *g.rec_count;
+                if (need_lists > g.list_capacity) g.overflow_flag[1] = need_lists;
+                if (need_recs > g.rec_capacity) g.overflow_flag[2] = need_recs;
+            }
             // heaviest scheduling class first (alloc_kernel, binning.cu): the cheap background tiles fill the tail
             const uint32_t n_tiles_total = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
             const uint32_t cc0 = g.class_count[0], cc1 = g.class_count[1], cc2 = g.class_count[2];

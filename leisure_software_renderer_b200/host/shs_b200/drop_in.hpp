@@ -286,7 +286,9 @@ namespace shs::b200
         cfg.front_face_ccw = config.front_face_ccw ? 1 : 0;
         // rasterize_mesh composites into whatever the targets hold: mirror the host contents first
         dev.upload(target.hdr);
-        if (target.depth_motion) dev.upload(target.depth_motion);
+        // depth AND motion: the draw touches only covered pixels of both planes (rasterizer.hpp:359-411), and the read-back below
+        // copies both planes whole, so a twin with a stale motion plane would overwrite the host's vectors on uncovered pixels
+        if (target.depth_motion) { dev.upload(target.depth_motion); dev.upload_motion(target.depth_motion); }
         ShsbStats st{};
         if (shsb_rasterize_mesh(dev.ctx(), dev.mesh(mesh), (int32_t)program, &su, dev.twin(target.hdr),
                                 target.depth_motion ? dev.twin(target.depth_motion) : 0, &cfg, &st) != SHSB_OK) return stats;

@@ -217,6 +217,33 @@ int main()
     for (size_t i = 0; i < d2_ref.depth.data.size(); ++i) max_d2 = std::max(max_d2, ulp(d2_ref.depth.data[i], d2_gpu.depth.data[i]));
     if (s_ref.tri_input != s_gpu.tri_input || s_ref.tri_after_clip != s_gpu.tri_after_clip || s_ref.tri_raster != s_gpu.tri_raster || max_d2 > 1) ++bad;
 
+    // ---- the usual caller pattern: the host clears / refills its targets between draws.  The motion plane of BOTH sides is
+    // filled with a marker the draw must leave alone on uncovered pixels and overwrite on covered ones (rasterizer.hpp:388-411
+    // touches covered pixels only); a device twin that kept a stale motion plane would bring old vectors back here.
+    {
+        for (size_t i = 0; i < d2_ref.motion.data.size(); ++i)
+        {
+            d2_ref.motion.data[i] = shs::Motion2f{3.0f + (float)(i % 7), -2.0f};
+            d2_gpu.motion.data[i] = d2_ref.motion.data[i];
+            d2_ref.depth.data[i] = 1.0f; d2_gpu.depth.data[i] = 1.0f;
+        }
+        shs::ShaderUniforms u2 = u;
+        u2.enable_motion_vectors = true;
+        u2.prev_model = glm::translate(u.model, glm::vec3(0.05f, -0.02f, 0.0f));
+        u2.prev_viewproj = scene.cam.viewproj;
+        shs::rasterize_mesh(*resources.get_mesh(blob), shs::make_blinn_phong_program(), u2, shs::RasterizerTarget{&h2_ref, &d2_ref});
+        shs::b200::rasterize_mesh(dev, *resources.get_mesh(blob), shs::b200::BuiltinProgram::BlinnPhong, u2, shs::RasterizerTarget{&h2_gpu, &d2_gpu});
+        size_t mdiff = 0, kept = 0, written = 0;
+        for (size_t i = 0; i < d2_ref.motion.data.size(); ++i)
+        {
+            if (std::memcmp(&d2_ref.motion.data[i], &d2_gpu.motion.data[i], sizeof(shs::Motion2f)) != 0) ++mdiff;
+            const bool marker = d2_ref.motion.data[i].x == 3.0f + (float)(i % 7) && d2_ref.motion.data[i].y == -2.0f;
+            if (marker) ++kept; else ++written;
+        }
+        if (mdiff != 0 || kept == 0 || written == 0) ++bad;
+        std::printf("rasterize_mesh with motion vectors over a pre-filled plane: %zu differing, %zu pixels kept, %zu written\n", mdiff, kept, written);
+    }
+
     std::printf("passes: tris %llu/%llu/%llu  depth<=%d ULP  shadow<=%d ULP  LDR<=%d LSB  HDR PSNR %.1f dB | rasterize_mesh: depth<=%d ULP tris %llu | %s\n",
                 (unsigned long long)ctx_gpu.debug.tri_input, (unsigned long long)ctx_gpu.debug.tri_after_clip, (unsigned long long)ctx_gpu.debug.tri_raster,
                 max_depth_ulp, max_shadow_ulp, max_lsb, psnr, max_d2, (unsigned long long)s_gpu.tri_raster, bad ? "MISMATCH" : "OK");

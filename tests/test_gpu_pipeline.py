@@ -289,3 +289,46 @@ def test_fence_orders_caller_work_on_the_main_stream(gpu):
             for rt in rts:
                 gpu.rt_destroy(rt)
         g.release()
+
+
+def test_asynchronous_overflow_is_reported_not_silent():
+    """an asynchronous submission (no statistics) that overflows its per-frame arena used to drop triangles with
+    SHSB_OK.  Twelve screen-filling triangles at 4096 x 4096 need 786 k tile-list entries against the 147 k a fresh context
+    sizes for 12 source triangles: the frame raises the sticky flag, the next shsb_sync returns SHSB_E_OVERFLOW (10) once and
+    grows the capacities, and the re-submitted frame equals the synchronous rendering bit for bit."""
+    from leisure_software_renderer_b200.renderer import Context
+    ctx = Context(0)
+    try:
+        n = 12
+        pos = np.zeros((n * 3, 3), np.float32)
+        for k in range(n):
+            z = 0.5 + 0.1 * k
+            pos[3 * k:3 * k + 3] = [[-40, -40, z], [40, -40, z], [0, 60, z]]
+        nrm = np.tile(np.array([[0, 0, -1]], np.float32), (n * 3, 1))
+        uv = np.zeros((n * 3, 2), np.float32)
+        idx = np.arange(n * 3, dtype=np.uint32)
+        sd = scenes.scene_small(w=4096, h=4096, n_inst=0).with_camera((0.0, 0.0, -2.0), (0.0, 0.0, 10.0))   # looking down +z at the triangles
+        mesh = ctx.mesh_upload(pos, nrm, uv, idx)
+        item = capi.RenderItem()
+        capi.set_f(item.tr.scl, (1, 1, 1)); capi.set_f(item.tr.pos, (0, 0, 6))
+        item.mesh, item.visible, item.casts_shadow, item.has_material = mesh, 1, 1, 1
+        capi.set_f(item.base_color, (0.7, 0.3, 0.2)); item.metallic, item.roughness, item.ao = 0.1, 0.6, 1.0
+        import ctypes as C
+        items = (capi.RenderItem * 1)(item)
+        sc = capi.Scene.from_buffer_copy(sd.scene)
+        sc.items, sc.n_items = C.cast(items, C.POINTER(capi.RenderItem)), 1
+        fp = capi.FrameParams.from_buffer_copy(sd.fp)
+        fp.light_culling, fp.cull_mode = 0, capi.CULL_NONE
+        hdr, dm = ctx.rt_create(capi.RT_COLOR_HDR, 4096, 4096), ctx.rt_create(capi.RT_DEPTH_MOTION, 4096, 4096, sd.zn, sd.zf)
+        ctx.pass_pbr_forward(sc, fp, hdr, dm, want_stats=False)          # overflows: no error yet, it is asynchronous
+        with pytest.raises(capi.ShsbError, match="status 10"):
+            ctx.sync()
+        ctx.sync()                                                       # reported once
+        ctx.pass_pbr_forward(sc, fp, hdr, dm, want_stats=False)          # capacities were grown: fits now
+        ctx.sync()
+        got = (ctx.rt_download(hdr).view(np.uint32), ctx.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32))
+        st = ctx.pass_pbr_forward(sc, fp, hdr, dm).as_dict()
+        assert st["tri_input"] == n and st["frag_shaded"] > 4096 * 4096 // 2
+        assert np.array_equal(got[0], ctx.rt_download(hdr).view(np.uint32)) and np.array_equal(got[1], ctx.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32))
+    finally:
+        ctx.close()

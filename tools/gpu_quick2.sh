@@ -10,6 +10,6 @@ for n in ${STREAMS:-1 2}; do
   python - <<PY
 import json
 d=json.load(open("$OUT/bench_ts$n.json"))
-print("streams $n: value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "tile_ms", d["stage_ms"]["tile_raster_shade"], "host", d["host_submit_ms_per_step"]["total_ms"])
+print("streams $n: value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "tile_ms", d["stage_ms"]["tile_raster_shade_alone"], "host", d["host_submit_ms_per_step"]["total_ms"])
 PY
 done
