@@ -610,8 +610,30 @@ SHSB_API int32_t shsb_legacy3_draw_pbr(shsb_ctx ctx, shsb_mesh mesh, const ShsbL
 /* ------------------------------------------------------------------ scene-level culling upstream of the path
  *
  * The two data-parallel steps the reference runs on the CPU right before draw submission.  Synchronous host-buffer calls (upload,
- * kernels, download): they sit outside the frame pipeline.  The strictly serial software-occlusion loop
- * (geometry/culling_software.hpp) is not offered. */
+ * kernels, download): they sit outside the frame pipeline.  The software-occlusion pass (geometry/culling_software.hpp) is serial
+ * in the order of objects only: shsb_software_occlusion walks that order on one persistent CTA. */
+
+/* run_software_occlusion_pass (geometry/culling_software.hpp:253-333) as SceneCullingContext::run_software_occlusion drives it
+ * (scene/scene_culling.hpp:186-222): the frustum-visible objects are sorted front to back by the view depth of their AABB centre
+ * (std::sort with the reference's comparator, on the host: ties fall as they do there), then, in that order, an object whose
+ * projected AABB rectangle is hidden at every texel of the occlusion depth buffer (z_near > depth + epsilon) is occluded, and every
+ * other object rasterises its occluder mesh into the buffer (rasterize_mesh_depth_transformed :116-143, minimum depth per texel).
+ *   object_aabbs6      n_objects x (min xyz, max xyz), world space          (get_world_aabb)
+ *   frustum_visible    CullResult::visible_indices (indices >= n_objects are skipped, :294)
+ *   object_mesh        per object: index into mesh_table, or 0xFFFFFFFF for "rasterises nothing" (the demos' guard, e.g.
+ *                      exp-plumbing/hello_occlusion_culling_sw.cpp:361-363)
+ *   object_models16    per object: the model matrix the occluder mesh is drawn with
+ *   mesh_table3        per mesh: first index, index count, base vertex into occluder_indices / occluder_vertices (DebugMesh,
+ *                      geometry/jolt_debug_draw.hpp:36-52, concatenated)
+ *   enable_occlusion   0: every frustum-visible object is visible, in the given order (:270-284)
+ * Outputs: out_occluded[n_objects] (0 / 1; objects outside frustum_visible keep 0), out_visible[<= n_visible] in the pass's order,
+ * out_counts4 = CullingStats scene / frustum-visible / visible / occluded counts (culling_runtime.hpp:59-100), out_depth (optional,
+ * occ_w x occ_h) = the occlusion depth buffer after the pass. */
+SHSB_API int32_t shsb_software_occlusion(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* frustum_visible, uint32_t n_visible,
+                                         const uint32_t* object_mesh, const float* object_models16, const uint32_t* mesh_table3, uint32_t n_meshes,
+                                         const float* occluder_vertices, uint32_t n_vertices, const uint32_t* occluder_indices, uint32_t n_indices,
+                                         const float view[16], const float view_proj[16], int32_t occ_w, int32_t occ_h, float depth_epsilon, int32_t enable_occlusion,
+                                         uint8_t* out_occluded, uint32_t* out_visible, uint32_t out_counts4[4], float* out_depth);
 
 /* cull_vs_frustum over FastCullable + HasWorldAABB objects (geometry/jolt_culling.hpp:279-306; classify_vs_frustum :258-275) against
  * extract_frustum_planes(view_proj) (geometry/frustum_culling.hpp:47-65).

@@ -214,6 +214,9 @@ def load_library(path: str | None = None):
         "shsb_fence": [vp],
         "shsb_set_tile_streams": [vp, C.c_int32],
         "shsb_launch_count": [vp, P(C.c_uint64)],
+        "shsb_software_occlusion": [vp, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32), P(C.c_float), P(C.c_uint32), C.c_uint32, P(C.c_float), C.c_uint32,
+                                    P(C.c_uint32), C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32, C.c_int32, C.c_float, C.c_int32, P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),
+                                    P(C.c_float)],
         "shsb_gather_create": [vp, C.c_uint32, C.c_uint32, C.c_size_t, P(C.c_uint32), P(GatherExport)],
         "shsb_gather_open": [vp, P(GatherExport), C.c_uint32, P(C.c_uint32)],
         "shsb_gather_destroy": [vp, C.c_uint32],

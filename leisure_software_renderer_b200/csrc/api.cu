@@ -327,7 +327,8 @@ struct shsb_context_t
     cudaStream_t copy_stream = nullptr;  // asynchronous render-target downloads alternate between two streams so that
     cudaStream_t copy_stream2 = nullptr; // the next copy is already queued on the engine when one finishes
     int copy_flip = 0;
-    cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr;
+    cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr, ev_front_sync = nullptr;
+    bool shadow_direct = true;           // SHSB_SHADOW_DIRECT=0: every shadow-pass triangle through the binned tile path
     cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
 
     // depth-range / clustered light culling (shsb_light_cull_ex): per-tile view-depth ranges, per-slice NDC bounds, cluster bins
@@ -543,6 +544,10 @@ namespace
         int lists_set = -1;     // light-list set the tile kernel reads (Forward+), -1 = none
         int tile_stream = 0;    // render stream of the tile kernel (0 = main)
         long long frame_no = -1; // out: the frame number the submission got
+        // shadow pass: its set-up kernel rasterises small triangles straight into the depth plane, so the FRONT END touches a render
+        // target here: it is ordered behind the main stream and starts by filling the plane with the clear value
+        float* prefill_depth = nullptr;
+        size_t prefill_n = 0;
     };
 
     void record_on(shsb_ctx ctx, cudaEvent_t e, cudaStream_t s)
@@ -731,6 +736,11 @@ namespace
             if (cull && ctx->lists[a].last_reader >= 0) ok(cudaStreamWaitEvent(sf, ctx->ev_tile_done[ctx->lists[a].last_reader % TILE_DONE_RING], 0));
             if (cull && ctx->lights_uploaded) ok(cudaStreamWaitEvent(sf, ctx->ev_lights_up, 0)); // the upload ran on some arena's front stream
 
+            if (job.prefill_depth && sf != s1)
+            {
+                ok(cudaEventRecord(ctx->ev_front_sync, s1));
+                ok(cudaStreamWaitEvent(sf, ctx->ev_front_sync, 0));
+            }
             if (graph)
             {
                 CK(cudaStreamBeginCapture(sf, cudaStreamCaptureModeThreadLocal));
@@ -745,11 +755,20 @@ namespace
             }
             record(ctx, 0, sf);
             ok(cudaMemsetAsync(hdr, 0, (shsb_context_t::HDR_TILE_COUNT + n_tiles + 1) * sizeof(uint32_t), sf));
+            if (job.prefill_depth)
+            {
+                // shadow->clear(1.0f), pass_shadow_map.hpp:55 -- on the forked stream, next to the draw-list upload (which waits on PCIe)
+                ok(cudaEventRecord(ctx->ev_fork[a], sf));
+                ok(cudaStreamWaitEvent(sc, ctx->ev_fork[a], 0));
+                launch_fill_u32(reinterpret_cast<uint32_t*>(job.prefill_depth), 0x3F800000u, job.prefill_n, sc, &ctx->launches);
+                ok(cudaEventRecord(ctx->ev_join[a], sc));
+            }
             if (draw_bytes) launch_upload(A.d_draw.p, ctx->h_draw[slot].dp, draw_bytes, sf, &ctx->launches); // SM-driven: no copy engine on the frame path
+            if (job.prefill_depth) ok(cudaStreamWaitEvent(sf, ctx->ev_join[a], 0));
             launch_geometry(fc, g, sf, &ctx->launches);
             record(ctx, 1, sf);
             if (cull) ok(cudaStreamWaitEvent(sf, ctx->ev_join[a], 0)); // alloc_kernel reads the tile light counts (scheduling classes)
-            launch_binning(fc, g, sf, &ctx->launches);
+            if (!fc.direct_depth) launch_binning(fc, g, sf, &ctx->launches); // the direct shadow pass has no tile stage
             record(ctx, 2, sf);
             ok(cudaGetLastError());
             const double t_c = now_us();
@@ -790,7 +809,7 @@ namespace
             if (fc.forward_plus && !cull) { if (int rc = main_wait_lights(ctx)) return rc; } // lists built earlier: the records are read directly
             CK(cudaStreamWaitEvent(s1, ctx->ev_front_done[a], 0));
             record(ctx, 3, s1);
-            launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
+            if (!fc.direct_depth) launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
             record(ctx, 4, s1);
             CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->ev_tile_done[f % TILE_DONE_RING], s1));
@@ -1336,6 +1355,8 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     for (int i = 0; ok && i < NUM_ARENAS; ++i) ok = cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < NUM_ARENAS; ++i) ok = cudaEventCreateWithFlags(&ctx->lights_stage_done[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_front_sync, cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e = std::getenv("SHSB_SHADOW_DIRECT")) ctx->shadow_direct = !(e[0] == '0');
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_overflow, 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess;
@@ -1403,6 +1424,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     for (cudaEvent_t e : ctx->ev_fork) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_join) if (e) cudaEventDestroy(e);
     if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
+    if (ctx->ev_front_sync) cudaEventDestroy(ctx->ev_front_sync);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_stream2) { cudaStreamSynchronize(ctx->copy_stream2); cudaStreamDestroy(ctx->copy_stream2); }
     for (auto& r : ctx->rts) if (r.read_done) cudaEventDestroy(r.read_done);
@@ -1982,6 +2004,76 @@ SHSB_API int32_t shsb_cull_objects_frustum(shsb_ctx ctx, const float* bounds10, 
     return SHSB_OK;
 }
 
+SHSB_API int32_t shsb_software_occlusion(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* frustum_visible, uint32_t n_visible,
+                                         const uint32_t* object_mesh, const float* object_models16, const uint32_t* mesh_table3, uint32_t n_meshes,
+                                         const float* occluder_vertices, uint32_t n_vertices, const uint32_t* occluder_indices, uint32_t n_indices,
+                                         const float view[16], const float view_proj[16], int32_t occ_w, int32_t occ_h, float depth_epsilon, int32_t enable_occlusion,
+                                         uint8_t* out_occluded, uint32_t* out_visible, uint32_t out_counts4[4], float* out_depth)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    if ((n_objects && (!object_aabbs6 || !out_occluded)) || (n_visible && (!frustum_visible || !out_visible)) || !view || !view_proj || !out_counts4)
+        return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+    if (n_objects && (!object_mesh || !object_models16)) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "object_mesh / object_models16 are null");
+    if ((n_meshes && !mesh_table3) || (n_vertices && !occluder_vertices) || (n_indices && !occluder_indices)) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null occluder mesh data");
+    if (occ_w <= 0 || occ_h <= 0 || (size_t)occ_w * (size_t)occ_h > (1u << 26)) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad occlusion buffer size %d x %d", occ_w, occ_h);
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        if ((uint64_t)mesh_table3[3 * m] + mesh_table3[3 * m + 1] > n_indices) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "mesh %u reaches beyond the index array", m);
+    CK(cudaSetDevice(ctx->device));
+    if (n_objects) std::memset(out_occluded, 0, n_objects);
+    out_counts4[0] = n_objects; out_counts4[1] = n_visible; out_counts4[2] = 0; out_counts4[3] = 0;
+    if (!enable_occlusion)
+    {
+        // :270-284: nothing to rasterise or test -- the visible list is the frustum list minus out-of-range entries
+        uint32_t nv = 0;
+        for (uint32_t k = 0; k < n_visible; ++k) if (frustum_visible[k] < n_objects) out_visible[nv++] = frustum_visible[k];
+        out_counts4[2] = nv;
+        out_counts4[1] = std::max(out_counts4[1], nv); // normalize_culling_stats
+        out_counts4[3] = out_counts4[1] - nv;
+        if (out_depth) std::fill(out_depth, out_depth + (size_t)occ_w * occ_h, 1.0f); // the buffer is not touched by the reference in this mode; 1.0 = cleared
+        return SHSB_OK;
+    }
+    // front-to-back order: the reference's std::sort with its comparator (:289-297), same library, same ties
+    std::vector<float> key(n_objects);
+    for (uint32_t i = 0; i < n_objects; ++i) key[i] = sc::occ_view_depth(object_aabbs6 + (size_t)i * 6, view);
+    std::vector<uint32_t> sorted(frustum_visible, frustum_visible + n_visible);
+    std::sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) {
+        if (a >= n_objects) return false;
+        if (b >= n_objects) return true;
+        return key[a] < key[b];
+    });
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += sc_align(std::max<size_t>(bytes, 4)); return o; };
+    const size_t o_boxes = take((size_t)n_objects * 24), o_sorted = take((size_t)n_visible * 4), o_omesh = take((size_t)n_objects * 4), o_models = take((size_t)n_objects * 64),
+                 o_table = take((size_t)n_meshes * 12), o_verts = take((size_t)n_vertices * 12), o_idx = take((size_t)n_indices * 4), o_depth = take((size_t)occ_w * occ_h * 4),
+                 o_occ = take(n_objects), o_vis = take((size_t)n_visible * 4), o_counts = take(8);
+    if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, off + 256)) return rc;
+    uint8_t* base = ctx->d_sc_bytes.p;
+    cudaStream_t st = ctx->stream;
+    auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t { return bytes ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    CK(up(o_boxes, object_aabbs6, (size_t)n_objects * 24));
+    CK(up(o_sorted, sorted.data(), (size_t)n_visible * 4));
+    CK(up(o_omesh, object_mesh, (size_t)n_objects * 4));
+    CK(up(o_models, object_models16, (size_t)n_objects * 64));
+    CK(up(o_table, mesh_table3, (size_t)n_meshes * 12));
+    CK(up(o_verts, occluder_vertices, (size_t)n_vertices * 12));
+    CK(up(o_idx, occluder_indices, (size_t)n_indices * 4));
+    CK(cudaMemsetAsync(base + o_occ, 0, std::max<size_t>(n_objects, 4), st));
+    launch_software_occlusion((const float*)(base + o_boxes), n_objects, (const uint32_t*)(base + o_sorted), n_visible, (const uint32_t*)(base + o_omesh), (const float*)(base + o_models),
+                              (const uint32_t*)(base + o_table), n_meshes, (const float*)(base + o_verts), n_vertices, (const uint32_t*)(base + o_idx), n_indices, view_proj, occ_w, occ_h,
+                              depth_epsilon, (float*)(base + o_depth), base + o_occ, (uint32_t*)(base + o_vis), (uint32_t*)(base + o_counts), st, &ctx->launches);
+    CK(cudaGetLastError());
+    uint32_t c2[2] = {0, 0};
+    CK(cudaMemcpyAsync(c2, base + o_counts, 8, cudaMemcpyDeviceToHost, st));
+    if (n_objects) CK(cudaMemcpyAsync(out_occluded, base + o_occ, n_objects, cudaMemcpyDeviceToHost, st));
+    if (out_depth) CK(cudaMemcpyAsync(out_depth, base + o_depth, (size_t)occ_w * occ_h * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (c2[0]) CK(cudaMemcpy(out_visible, base + o_vis, (size_t)c2[0] * 4, cudaMemcpyDeviceToHost));
+    out_counts4[2] = c2[0];
+    out_counts4[1] = std::max(out_counts4[1], c2[0]); // normalize_culling_stats, culling_runtime.hpp:59-75
+    out_counts4[3] = out_counts4[1] - c2[0];
+    return SHSB_OK;
+}
+
 SHSB_API int32_t shsb_collect_object_lights(shsb_ctx ctx, const float* object_aabbs6, uint32_t n_objects, const uint32_t* visible_lights, uint32_t n_visible,
                                             const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts, uint32_t* out_indices8, float* out_dist2_8)
 {
@@ -2237,6 +2329,15 @@ SHSB_API int32_t shsb_pass_shadow_map(shsb_ctx ctx, const ShsbScene* scene, cons
     fc.shader_id = SHSB_SHADER_DEPTH_ONLY;
     fc.load_depth = 0; // shadow->clear(1.0f), pass_shadow_map.hpp:55
     job.fb.depth = sh->depth;
+    if (ctx->shadow_direct)
+    {
+        // small and medium triangles (nearly all of a shadow map's) are rasterised by the set-up kernel into the pre-cleared plane,
+        // what is larger than 64x64 texels by a chunked second kernel: no bins, no tile kernel
+        fc.direct_depth = sh->depth;
+        fc.load_depth = 1;
+        job.prefill_depth = sh->depth;
+        job.prefill_n = (size_t)sh->w * (size_t)sh->h;
+    }
     if (int rc = upload_staging(ctx, items, blocks)) return rc;
     job.n_items = (uint32_t)items.size();
     job.n_blocks = (uint32_t)blocks.size();

@@ -403,6 +403,33 @@ namespace shsb
 
         // PassShadowMap set-up rules (passes/pass_shadow_map.hpp:155-190): world = vec3(model * p), clip = light_vp * (world, 1),
         // reject |w| < 1e-8, reject only if all three corners are beyond the same NDC bound, NO clipping, NO culling.
+        // One texel of PassShadowMap's inline raster (pass_shadow_map.hpp:185-201) for one set-up triangle: the same operations, in the
+        // same order, as the tile kernel's shadow mode.  The pass keeps the MINIMUM depth per texel, which does not depend on the
+        // order triangles arrive in, so an atomic minimum on the float's bit pattern (depths are in [0, 1]: bit order == value
+        // order) reproduces the serial loop bit for bit.  NaN depths fail `z01 < 1` exactly as they fail the reference's `z01 < zbuf`.
+        __device__ __forceinline__ void shadow_texel(const RasterRec& r, int x, int y, uint32_t* __restrict__ depth_bits, int W)
+        {
+            const float pxf = xadd((float)x, 0.5f), pyf = xadd((float)y, 0.5f);
+            const float v2x = xsub(pxf, r.ax), v2y = xsub(pyf, r.ay);
+            const float bv = xmul(xsub(xmul(v2x, r.v1y), xmul(r.v1x, v2y)), r.inv_den);
+            const float bw = xmul(xsub(xmul(r.v0x, v2y), xmul(v2x, r.v0y)), r.inv_den);
+            const float bu = xsub(xsub(1.0f, bv), bw);
+            if (bu < 0.0f || bv < 0.0f || bw < 0.0f) return;
+            const float z_ndc = xadd(xadd(xmul(bu, r.zw0), xmul(bv, r.zw1)), xmul(bw, r.zw2));
+            const float z01 = sclamp(xadd(xmul(z_ndc, 0.5f), 0.5f), 0.0f, 1.0f);
+            if (z01 < 1.0f) atomicMin(depth_bits + (size_t)y * (size_t)W + (size_t)x, __float_as_uint(z01));
+        }
+
+        constexpr int SHADOW_SMALL_AREA = 64;     // clamped bbox of at most this many texels: walked by the triangle's own lane
+        constexpr int SHADOW_MEDIUM_AREA = 4096;  // up to this many: walked by the whole warp; larger triangles go through the tile bins
+
+        // PassShadowMap::execute, pass_shadow_map.hpp:144-203: one thread per caster triangle.  Vertex transform, the all-outside
+        // reject, the screen map and the bbox are the reference's; what happens to a surviving triangle depends on its size.  A
+        // shadow map sees the scene from far away, so nearly all of its triangles cover a handful of texels: binning them into
+        // 16x16 tiles and testing 32 texels per (block, triangle) pair spends 250 instructions on a triangle that covers 8 texels.
+        // With `fc.direct_depth` the kernel rasterises them itself into the pre-cleared depth plane -- small ones in the lane that
+        // set them up, medium ones by the whole warp -- and only what is larger than 64x64 texels is emitted as a record for the
+        // binned tile kernel (which then LOADS the plane, load_depth = 1).
         __global__ void __launch_bounds__(GEOM_THREADS) shadow_geometry_kernel(const FrameConst fc, const Geometry g)
         {
             const uint2 blk = g.block_table[blockIdx.x];
@@ -411,6 +438,7 @@ namespace shsb
             const uint32_t ti = blk.y + threadIdx.x;
             bool emit = false;
             RasterRec rr;
+            int minx = 0, maxx = -1, miny = 0, maxy = -1;
             if (ti < it.tri_count)
             {
                 uint32_t id[3];
@@ -445,10 +473,10 @@ namespace shsb
                         // floor/ceil of +-inf/NaN are UB on the CPU side as well; a sane light camera never produces them.
                         const float minxf = fminf(fminf(sx[0], sx[1]), sx[2]), maxxf = fmaxf(fmaxf(sx[0], sx[1]), sx[2]);
                         const float minyf = fminf(fminf(sy[0], sy[1]), sy[2]), maxyf = fmaxf(fmaxf(sy[0], sy[1]), sy[2]);
-                        const int minx = max(0, (int)floorf(minxf));
-                        const int maxx = min(fc.W - 1, (int)ceilf(maxxf));
-                        const int miny = max(0, (int)floorf(minyf));
-                        const int maxy = min(fc.H - 1, (int)ceilf(maxyf));
+                        minx = max(0, (int)floorf(minxf));
+                        maxx = min(fc.W - 1, (int)ceilf(maxxf));
+                        miny = max(0, (int)floorf(minyf));
+                        maxy = min(fc.H - 1, (int)ceilf(maxyf));
                         const float v0x = xsub(sx[1], sx[0]), v0y = xsub(sy[1], sy[0]);
                         const float v1x = xsub(sx[2], sx[0]), v1y = xsub(sy[2], sy[0]);
                         const float den = xsub(xmul(v0x, v1y), xmul(v1x, v0y));
@@ -467,7 +495,49 @@ namespace shsb
                     }
                 }
             }
-            const uint32_t slot = block_alloc_records(g, emit);
+            if (fc.direct_depth)
+            {
+                uint32_t* depth_bits = reinterpret_cast<uint32_t*>(fc.direct_depth);
+                const int bw = maxx - minx + 1, bh = maxy - miny + 1;
+                const long long area = emit ? (long long)bw * (long long)bh : 0;
+                if (emit && area <= SHADOW_SMALL_AREA)
+                {
+                    for (int y = miny; y <= maxy; ++y)
+                        for (int x = minx; x <= maxx; ++x) shadow_texel(rr, x, y, depth_bits, fc.W);
+                    emit = false;
+                }
+                // medium triangles: the warp walks each one's bbox together (a serial walk of a 40x40 bbox by one lane would stall 31 others)
+                unsigned med = __ballot_sync(0xffffffffu, emit && area <= SHADOW_MEDIUM_AREA);
+                const int lane = threadIdx.x & 31;
+                if (emit && area <= SHADOW_MEDIUM_AREA) emit = false;
+                while (med)
+                {
+                    const int src = __ffs(med) - 1;
+                    med &= med - 1;
+                    RasterRec q;
+                    q.ax = __shfl_sync(0xffffffffu, rr.ax, src); q.ay = __shfl_sync(0xffffffffu, rr.ay, src);
+                    q.v0x = __shfl_sync(0xffffffffu, rr.v0x, src); q.v0y = __shfl_sync(0xffffffffu, rr.v0y, src);
+                    q.v1x = __shfl_sync(0xffffffffu, rr.v1x, src); q.v1y = __shfl_sync(0xffffffffu, rr.v1y, src);
+                    q.inv_den = __shfl_sync(0xffffffffu, rr.inv_den, src);
+                    q.zw0 = __shfl_sync(0xffffffffu, rr.zw0, src); q.zw1 = __shfl_sync(0xffffffffu, rr.zw1, src); q.zw2 = __shfl_sync(0xffffffffu, rr.zw2, src);
+                    const int x0 = __shfl_sync(0xffffffffu, minx, src), y0 = __shfl_sync(0xffffffffu, miny, src);
+                    const int w = __shfl_sync(0xffffffffu, bw, src), total = w * __shfl_sync(0xffffffffu, bh, src);
+                    for (int k = lane; k < total; k += 32) shadow_texel(q, x0 + k % w, y0 + k / w, depth_bits, fc.W);
+                }
+            }
+            uint32_t slot;
+            if (fc.direct_depth)
+            {
+                // what is left are the few triangles larger than 64x64 texels: one counter atomic per warp that has any, no CTA
+                // barrier (the lanes of a CTA finish their texel walks at very different times)
+                const unsigned mask = __ballot_sync(0xffffffffu, emit);
+                if (!mask) return;
+                const int lane = threadIdx.x & 31;
+                uint32_t base = 0;
+                if (lane == __ffs(mask) - 1) base = atomicAdd(g.rec_count, (uint32_t)__popc(mask));
+                slot = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1) + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            }
+            else slot = block_alloc_records(g, emit);
             if (emit)
             {
                 if (slot < g.rec_capacity)
@@ -479,7 +549,45 @@ namespace shsb
                 }
                 else { atomicAdd(&stats_shard(g)->overflow_recs, 1u); *g.overflow_flag = 1u; emit = false; }
             }
+            if (fc.direct_depth) return; // large triangles are walked by shadow_large_kernel, not binned
             if (__ballot_sync(0xffffffffu, emit)) warp_count_tiles(fc, g, emit, rr.bbox_x, rr.bbox_y);
+        }
+
+        // The shadow pass's large triangles (bbox above 64x64 texels; a ground plane under the casters is the typical one): their
+        // records are cut into 64x64-texel chunks and the chunks dealt round-robin over a fixed grid, so that one triangle spanning
+        // the whole map is walked by every SM.  Every CTA scans the (short) record list and keeps a running chunk count; a chunk is
+        // walked by the 256 threads of its CTA, 16 texels each, with the same exact per-texel test and atomic minimum as above.
+        constexpr int SHADOW_CHUNK = 64;
+        __global__ void __launch_bounds__(256) shadow_large_kernel(const FrameConst fc, const Geometry g)
+        {
+            const uint32_t n = min(*g.rec_count, g.rec_capacity);
+            uint32_t* depth_bits = reinterpret_cast<uint32_t*>(fc.direct_depth);
+            uint32_t seen = 0; // chunks of the records before this one
+            for (uint32_t ri = 0; ri < n; ++ri)
+            {
+                const RasterRec* rp = g.rrecs + ri;
+                const uint32_t bx = rp->bbox_x, by = rp->bbox_y;
+                const int minx = (int)(bx & 0xffffu), maxx = (int)(bx >> 16), miny = (int)(by & 0xffffu), maxy = (int)(by >> 16);
+                const uint32_t cx = (uint32_t)(maxx - minx) / SHADOW_CHUNK + 1u, cy = (uint32_t)(maxy - miny) / SHADOW_CHUNK + 1u;
+                const uint32_t chunks = cx * cy;
+                // first chunk of this record that falls to this CTA: global chunk index == blockIdx.x (mod gridDim.x)
+                uint32_t c = (blockIdx.x + gridDim.x - seen % gridDim.x) % gridDim.x;
+                if (c < chunks)
+                {
+                    const RasterRec r = *rp;
+                    for (; c < chunks; c += gridDim.x)
+                    {
+                        const int x0 = minx + (int)(c % cx) * SHADOW_CHUNK, y0 = miny + (int)(c / cx) * SHADOW_CHUNK;
+#pragma unroll 4
+                        for (int k = threadIdx.x; k < SHADOW_CHUNK * SHADOW_CHUNK; k += 256)
+                        {
+                            const int x = x0 + (k % SHADOW_CHUNK), y = y0 + (k / SHADOW_CHUNK);
+                            if (x <= maxx && y <= maxy) shadow_texel(r, x, y, depth_bits, fc.W);
+                        }
+                    }
+                }
+                seen += chunks;
+            }
         }
     }
 
@@ -490,6 +598,11 @@ namespace shsb
         {
             shadow_geometry_kernel<<<g.n_blocks, GEOM_THREADS, 0, s>>>(fc, g);
             *launches += 1;
+            if (fc.direct_depth)
+            {
+                shadow_large_kernel<<<148 * 2, 256, 0, s>>>(fc, g);
+                *launches += 1;
+            }
             return;
         }
         geometry_kernel<<<g.n_blocks, GEOM_THREADS, 0, s>>>(fc, g);

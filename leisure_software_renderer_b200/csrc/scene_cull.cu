@@ -1,8 +1,8 @@
 // scene_cull.cu -- scene-level culling steps upstream of draw submission: objects against the camera
 // frustum (cull_vs_frustum, geometry/jolt_culling.hpp:279-306: classes, the ordered visible list, the four counters) and per-object
 // light selection (collect_object_lights, lighting/light_runtime.hpp:592-616).  Arithmetic in scene_cull_core.cuh; --fmad=false.
-// The software-occlusion loop of culling_software.hpp is strictly serial (each object's test reads the depth the previous ones
-// wrote) and is not part of this file.
+// The software-occlusion pass of culling_software.hpp is serial in the ORDER of objects (each object's test reads the depth the
+// previous ones wrote); one persistent CTA walks that order and spreads the work of each object over its threads.
 #include "shsb_dev.cuh"
 
 namespace shsb
@@ -189,5 +189,110 @@ namespace shsb
         select_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, a, bin_counts, bin_indices, records, n_lights, mode, seen, words_per_object, out_counts, out_idx,
                                                                              out_d2, out_candidates);
         if (launches) *launches += 1;
+    }
+    namespace
+    {
+        struct OccParams
+        {
+            const float* boxes6; uint32_t n_objects;
+            const uint32_t* sorted; uint32_t n_sorted;           // frustum-visible indices in the host's front-to-back order
+            const uint32_t* object_mesh;                         // per object: index into mesh_table, 0xFFFFFFFF = no occluder mesh
+            const float* object_models;                          // per object: model matrix (16 floats)
+            const uint32_t* mesh_table;                          // per mesh: first index, index count, base vertex
+            uint32_t n_meshes;
+            const float* vertices; uint32_t n_vertices;          // local-space positions of all occluder meshes
+            const uint32_t* indices; uint32_t n_indices;
+            float view_proj[16];
+            int width, height;
+            float epsilon;
+            uint32_t* depth_bits;                                // width * height, pre-filled with 1.0f
+            uint8_t* occluded;                                   // per object
+            uint32_t* visible;                                   // output list (sorted order)
+            uint32_t* counts;                                    // [0] visible, [1] occluded
+        };
+
+        // run_software_occlusion_pass, geometry/culling_software.hpp:292-322, on ONE CTA: per object (in order) thread 0 projects the
+        // AABB, the CTA ANDs "hidden" over the rectangle's texels (is_rect_occluded), and -- if the object shows -- rasterises its
+        // occluder mesh (rasterize_mesh_depth_transformed) a warp per triangle, lanes over the bbox texels, with an atomic minimum on
+        // the depth's bit pattern (depths are in [0, 1]; the minimum does not depend on the order within one object).  Texel reads
+        // bypass L1 (the buffer is rewritten between barriers by other SMs' ... by this CTA's own atomics, which live in L2).
+        __global__ void __launch_bounds__(1024) software_occlusion_kernel(const OccParams p)
+        {
+            __shared__ sc::OccRect s_rect;
+            __shared__ uint32_t s_nvis, s_nocc;
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+            if (tid == 0) { s_nvis = 0; s_nocc = 0; }
+            __syncthreads();
+            for (uint32_t k = 0; k < p.n_sorted; ++k)
+            {
+                const uint32_t idx = p.sorted[k];
+                if (idx >= p.n_objects) continue; // CTA-uniform
+                if (tid == 0) s_rect = sc::occ_project_rect(p.boxes6 + (size_t)idx * 6, p.view_proj, p.width, p.height);
+                __syncthreads();
+                const sc::OccRect r = s_rect;
+                bool shows = false;
+                if (r.valid)
+                {
+                    const int rw = r.x_max - r.x_min + 1, total = rw * (r.y_max - r.y_min + 1);
+                    for (int i = tid; i < total && !shows; i += blockDim.x)
+                    {
+                        const int x = r.x_min + i % rw, y = r.y_min + i / rw;
+                        shows = sc::occ_texel_shows(r.z_near, __uint_as_float(__ldcg(p.depth_bits + (size_t)y * p.width + x)), p.epsilon);
+                    }
+                }
+                const bool occluded = r.valid && !__syncthreads_or(shows ? 1 : 0); // an invalid rectangle is never occluded (:208)
+                if (tid == 0)
+                {
+                    p.occluded[idx] = occluded ? 1 : 0;
+                    if (occluded) ++s_nocc; else p.visible[s_nvis++] = idx;
+                }
+                if (occluded) continue; // CTA-uniform
+                const uint32_t m = p.object_mesh[idx];
+                if (m < p.n_meshes)
+                {
+                    const uint32_t first = p.mesh_table[3 * m], count = p.mesh_table[3 * m + 1], base_v = p.mesh_table[3 * m + 2];
+                    const float* model = p.object_models + (size_t)idx * 16;
+                    for (uint32_t t = (uint32_t)warp * 3u; t + 2u < count; t += (uint32_t)n_warps * 3u) // `i + 2 < indices.size()`, :125
+                    {
+                        float xy[3][2], z[3];
+                        bool ok = true;
+                        for (int v = 0; v < 3; ++v)
+                        {
+                            const uint32_t vi = base_v + p.indices[first + t + v];
+                            ok = ok && vi < p.n_vertices && sc::occ_project_vertex(model, p.vertices + (size_t)vi * 3, p.view_proj, p.width, p.height, xy[v], z[v]);
+                        }
+                        if (!ok) continue; // warp-uniform
+                        const sc::OccTri tri = sc::occ_setup_triangle(xy[0], z[0], xy[1], z[1], xy[2], z[2], p.width, p.height);
+                        if (!tri.valid) continue;
+                        const int bw = tri.max_x - tri.min_x + 1, total = bw * (tri.max_y - tri.min_y + 1);
+                        for (int i = lane; i < total; i += 32)
+                        {
+                            const int x = tri.min_x + i % bw, y = tri.min_y + i / bw;
+                            float d;
+                            if (sc::occ_texel_depth(tri, x, y, d)) atomicMin(p.depth_bits + (size_t)y * p.width + x, __float_as_uint(d == 0.0f ? 0.0f : d)); // -0 -> +0
+                        }
+                    }
+                }
+                __syncthreads(); // the next object's test must see this object's depths
+            }
+            __syncthreads();
+            if (tid == 0) { p.counts[0] = s_nvis; p.counts[1] = s_nocc; }
+        }
+    }
+
+    void launch_software_occlusion(const float* boxes6, uint32_t n_objects, const uint32_t* sorted, uint32_t n_sorted, const uint32_t* object_mesh, const float* object_models,
+                                   const uint32_t* mesh_table, uint32_t n_meshes, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
+                                   const float view_proj[16], int width, int height, float epsilon, float* depth, uint8_t* occluded, uint32_t* visible, uint32_t* counts2,
+                                   cudaStream_t s, uint64_t* launches)
+    {
+        OccParams p{};
+        p.boxes6 = boxes6; p.n_objects = n_objects; p.sorted = sorted; p.n_sorted = n_sorted; p.object_mesh = object_mesh; p.object_models = object_models;
+        p.mesh_table = mesh_table; p.n_meshes = n_meshes; p.vertices = vertices; p.n_vertices = n_vertices; p.indices = indices; p.n_indices = n_indices;
+        for (int i = 0; i < 16; ++i) p.view_proj[i] = view_proj[i];
+        p.width = width; p.height = height; p.epsilon = epsilon;
+        p.depth_bits = reinterpret_cast<uint32_t*>(depth); p.occluded = occluded; p.visible = visible; p.counts = counts2;
+        launch_fill_u32(p.depth_bits, 0x3F800000u, (size_t)width * (size_t)height, s, launches); // std::fill(occlusion_depth, 1.0f), :286
+        software_occlusion_kernel<<<1, 1024, 0, s>>>(p);
+        *launches += 1;
     }
 }

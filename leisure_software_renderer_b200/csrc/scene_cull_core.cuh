@@ -254,5 +254,109 @@ namespace shsb
                     }
             return n_candidates;
         }
+
+        // ---------------------------------------------------------------- software occlusion (geometry/culling_software.hpp:41-222)
+        // The pass of run_software_occlusion_pass (:253-333) walks the frustum-visible objects front to back; each object's screen
+        // rectangle is tested against the occlusion depth buffer the objects before it rasterised their occluder meshes into.  The
+        // ORDER of objects is serial; the work of one object -- an AND over the rectangle's texels, a minimum-write per triangle
+        // texel -- is order-free and is what the device spreads over a CTA.
+        SC_HD void mul4(const float* m, float x, float y, float z, float w, float out[4]) // glm's scalar mat4 * vec4
+        {
+            for (int r = 0; r < 4; ++r) out[r] = (m[r] * x + m[4 + r] * y) + (m[8 + r] * z + m[12 + r] * w);
+        }
+
+        struct OccRect { int x_min, y_min, x_max, y_max; float z_near; bool valid; };
+
+        // project_aabb_to_screen_rect, :145-199
+        SC_HD OccRect occ_project_rect(const float* box6, const float* view_proj, int width, int height)
+        {
+            OccRect out{0, 0, -1, -1, 1.0f, false};
+            if (width <= 0 || height <= 0) return out;
+            float min_x = (float)width, min_y = (float)height, max_x = -1.0f, max_y = -1.0f, near_depth = 1.0f;
+            bool any = false;
+            for (int c = 0; c < 8; ++c)
+            {
+                float clip[4];
+                mul4(view_proj, box6[(c & 1) ? 3 : 0], box6[(c & 2) ? 4 : 1], box6[(c & 4) ? 5 : 2], 1.0f, clip);
+                if (clip[3] <= 0.001f) continue;
+                const float nx = clip[0] / clip[3], ny = clip[1] / clip[3], nz = clip[2] / clip[3];
+                const float z01 = nz * 0.5f + 0.5f;
+                if (z01 < 0.0f || z01 > 1.0f) continue;
+                const float sx = (nx + 1.0f) * 0.5f * (float)width;
+                const float sy = (ny + 1.0f) * 0.5f * (float)height;
+                min_x = std_minf(min_x, sx); min_y = std_minf(min_y, sy);
+                max_x = std_maxf(max_x, sx); max_y = std_maxf(max_y, sy);
+                near_depth = std_minf(near_depth, z01);
+                any = true;
+            }
+            if (!any) return out;
+            const int fx = (int)floorf(min_x), fy = (int)floorf(min_y), cx = (int)ceilf(max_x), cy = (int)ceilf(max_y);
+            out.x_min = fx > 0 ? fx : 0; out.y_min = fy > 0 ? fy : 0;
+            out.x_max = cx < width - 1 ? cx : width - 1; out.y_max = cy < height - 1 ? cy : height - 1;
+            out.z_near = std_clampf(near_depth, 0.0f, 1.0f);
+            out.valid = out.x_min <= out.x_max && out.y_min <= out.y_max;
+            return out;
+        }
+
+        // one texel of is_rect_occluded, :201-222: true = the rectangle is NOT hidden at this texel
+        SC_HD bool occ_texel_shows(float z_near, float depth, float epsilon) { return z_near <= depth + epsilon; }
+
+        // project_world_to_screen, :46-63, after vec3(model * vec4(local, 1)) of rasterize_mesh_depth_transformed :131-133
+        SC_HD bool occ_project_vertex(const float* model, const float* local3, const float* view_proj, int width, int height, float xy[2], float& depth01)
+        {
+            float wp[4], clip[4];
+            mul4(model, local3[0], local3[1], local3[2], 1.0f, wp);
+            mul4(view_proj, wp[0], wp[1], wp[2], 1.0f, clip);
+            if (clip[3] <= 0.001f) return false;
+            const float nx = clip[0] / clip[3], ny = clip[1] / clip[3], nz = clip[2] / clip[3];
+            if (nz < -1.0f || nz > 1.0f) return false;
+            xy[0] = (nx + 1.0f) * 0.5f * (float)width;
+            xy[1] = (ny + 1.0f) * 0.5f * (float)height;
+            depth01 = nz * 0.5f + 0.5f;
+            return true;
+        }
+
+        SC_HD float occ_edge(const float* a, const float* b, float px, float py) { return (px - a[0]) * (b[1] - a[1]) - (py - a[1]) * (b[0] - a[0]); } // :41-44
+
+        struct OccTri { float p0[2], p1[2], p2[2], z0, z1, z2, area; int min_x, min_y, max_x, max_y; bool valid; };
+
+        // the per-triangle part of rasterize_depth_triangle, :65-90
+        SC_HD OccTri occ_setup_triangle(const float* p0, float z0, const float* p1, float z1, const float* p2, float z2, int width, int height)
+        {
+            OccTri t;
+            t.p0[0] = p0[0]; t.p0[1] = p0[1]; t.p1[0] = p1[0]; t.p1[1] = p1[1]; t.p2[0] = p2[0]; t.p2[1] = p2[1];
+            t.z0 = z0; t.z1 = z1; t.z2 = z2;
+            t.area = occ_edge(p0, p1, p2[0], p2[1]);
+            t.valid = false;
+            t.min_x = t.min_y = 0; t.max_x = t.max_y = -1;
+            if (fabsf(t.area) <= 1e-6f) return t;
+            const float min_xf = std_minf(p0[0], std_minf(p1[0], p2[0])), min_yf = std_minf(p0[1], std_minf(p1[1], p2[1]));
+            const float max_xf = std_maxf(p0[0], std_maxf(p1[0], p2[0])), max_yf = std_maxf(p0[1], std_maxf(p1[1], p2[1]));
+            const int fx = (int)floorf(min_xf), fy = (int)floorf(min_yf), cx = (int)ceilf(max_xf), cy = (int)ceilf(max_yf);
+            t.min_x = fx > 0 ? fx : 0; t.min_y = fy > 0 ? fy : 0;
+            t.max_x = cx < width - 1 ? cx : width - 1; t.max_y = cy < height - 1 ? cy : height - 1;
+            t.valid = t.min_x <= t.max_x && t.min_y <= t.max_y;
+            return t;
+        }
+
+        // the per-texel part, :92-114: true + depth when the texel takes part in the minimum
+        SC_HD bool occ_texel_depth(const OccTri& t, int x, int y, float& depth)
+        {
+            const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+            const float w0 = occ_edge(t.p1, t.p2, px, py), w1 = occ_edge(t.p2, t.p0, px, py), w2 = occ_edge(t.p0, t.p1, px, py);
+            const bool inside = (t.area > 0.0f) ? (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) : (w0 <= 0.0f && w1 <= 0.0f && w2 <= 0.0f);
+            if (!inside) return false;
+            const float iw0 = w0 / t.area, iw1 = w1 / t.area, iw2 = w2 / t.area;
+            depth = iw0 * t.z0 + iw1 * t.z1 + iw2 * t.z2;
+            return !(depth < 0.0f || depth > 1.0f);
+        }
+
+        // view_depth_of_aabb_center, :224-231 (the sort key)
+        SC_HD float occ_view_depth(const float* box6, const float* view)
+        {
+            float v[4];
+            mul4(view, 0.5f * (box6[0] + box6[3]), 0.5f * (box6[1] + box6[4]), 0.5f * (box6[2] + box6[5]), 1.0f, v);
+            return v[2];
+        }
     }
 }

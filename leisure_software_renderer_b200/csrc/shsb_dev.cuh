@@ -162,6 +162,8 @@ namespace shsb
         int load_color;         // 1: keep RT colour where nothing is drawn; 0: write the background gradient (pass_pbr_forward.hpp:69-85)
         int write_aovs;
         int shadow_mode;        // PassShadowMap raster rules (pass_shadow_map.hpp:144-203)
+        float* direct_depth;    // shadow mode: the depth plane, pre-filled with 1.0, that the set-up kernel rasterises small and medium
+                                // triangles into directly (atomic minimum); null = every triangle goes through the binned tile path
         // shadow sampling (shadow_sample.hpp)
         const float* shadow_map;
         int shadow_w, shadow_h;
@@ -295,6 +297,10 @@ namespace shsb
     void launch_select_object_lights(const float* boxes6, uint32_t n_objects, const float view[16], const float view_proj[16], const sc::BinGrid& grid, const uint32_t* bin_counts,
                                      const uint32_t* bin_indices, const float* records, uint32_t n_lights, int mode, uint32_t* seen, uint32_t words_per_object, uint32_t* out_counts,
                                      uint32_t* out_idx, float* out_d2, uint32_t* out_candidates, cudaStream_t s, uint64_t* launches);
+    void launch_software_occlusion(const float* boxes6, uint32_t n_objects, const uint32_t* sorted, uint32_t n_sorted, const uint32_t* object_mesh, const float* object_models,
+                                   const uint32_t* mesh_table, uint32_t n_meshes, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
+                                   const float view_proj[16], int width, int height, float epsilon, float* depth, uint8_t* occluded, uint32_t* visible, uint32_t* counts2,
+                                   cudaStream_t s, uint64_t* launches);
     uint32_t legacy2_slots(const l2::Draw& d);
     void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
                              cudaStream_t s, uint64_t* launches);

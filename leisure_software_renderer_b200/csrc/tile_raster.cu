@@ -533,7 +533,7 @@ namespace shsb
             PHASE_COUNT();
 
             float bz = 1.0f;
-            if (fc.has_depth && fc.load_depth && valid) bz = fb.depth[pix];
+            if ((fc.has_depth || fc.shadow_mode) && fc.load_depth && valid) bz = fb.depth[pix];
             uint32_t bkey = KEY_NONE, bidx = 0;
             uint32_t n_cov = 0;
             const float pxf = xadd((float)px, 0.5f), pyf = xadd((float)py, 0.5f);

@@ -211,6 +211,25 @@ class Context:
                                                                    capi.u32ptr(visible), capi.u32ptr(counts)), "shsb_cull_objects_frustum")
         return classes, visible[:int(counts[4])].copy(), counts
 
+    def software_occlusion(self, object_aabbs, frustum_visible, object_mesh, models, mesh_table, vertices, indices, view, view_proj, occ_w, occ_h, eps=1e-4, enable=True):
+        """run_software_occlusion_pass on the device: occluded flags (n,), the ordered visible list, counts (scene, frustum-visible,
+        visible, occluded) and the occlusion depth buffer (occ_h, occ_w)."""
+        a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)
+        vis = np.ascontiguousarray(frustum_visible, dtype=np.uint32).reshape(-1)
+        om = np.ascontiguousarray(object_mesh, dtype=np.uint32).reshape(-1)
+        mo = np.ascontiguousarray(models, dtype=np.float32).reshape(-1, 16)
+        mt = np.ascontiguousarray(mesh_table, dtype=np.uint32).reshape(-1, 3)
+        vt = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        ix = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        v, vp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (view, view_proj))
+        occ, out_vis, counts = np.zeros(max(1, len(a)), np.uint8), np.zeros(max(1, len(vis)), np.uint32), np.zeros(4, np.uint32)
+        depth = np.zeros((int(occ_h), int(occ_w)), np.float32)
+        rc = self.lib.shsb_software_occlusion(self.h, capi.fptr(a), len(a), capi.u32ptr(vis), len(vis), capi.u32ptr(om), capi.fptr(mo), capi.u32ptr(mt), len(mt), capi.fptr(vt), len(vt),
+                                              capi.u32ptr(ix), len(ix), capi.fptr(v), capi.fptr(vp), int(occ_w), int(occ_h), float(eps), int(bool(enable)),
+                                              occ.ctypes.data_as(C.POINTER(C.c_uint8)), capi.u32ptr(out_vis), capi.u32ptr(counts), capi.fptr(depth))
+        _check(self.lib, self.h, rc, "shsb_software_occlusion")
+        return occ[:len(a)], out_vis[:int(counts[2])].copy(), counts, depth
+
     def collect_object_lights(self, object_aabbs, visible, records, cull_mode):
         """collect_object_lights per object: counts (n,), light indices (n, 8), squared distances (n, 8)."""
         a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)

@@ -656,3 +656,53 @@ class LocalLightEvaluator:
             assert culling_mode == 1, "the restatement walks tile lists"
             self.lib.shso_local_light_loop(*head, *tail)
         return np.array(out[:], dtype=np.float32)
+
+
+REF_OCCLUSION_LIB = os.path.join(_HERE, "_ref", "libshs_occlusion_ref.so")
+
+
+class SoftwareOcclusion:
+    """run_software_occlusion_pass (geometry/culling_software.hpp:253-333) through a checker:
+      "reference" -> oracle/_ref/libshs_occlusion_ref.so (the reference's own header, oracle/ref_occlusion_harness.cpp)
+      "port"      -> oracle/liboracle.so (oracle_scene_cull.cpp: shso_software_occlusion)
+      a path      -> a library exporting the same signature under `prefix` (the g++ build of the device functions)."""
+
+    def __init__(self, kind="port", prefix=None):
+        if kind == "reference":
+            if not os.path.exists(REF_OCCLUSION_LIB):
+                build("reference")
+            self.lib, self.prefix = C.CDLL(REF_OCCLUSION_LIB), "shsref_"
+        elif kind == "port":
+            if not os.path.exists(PORT_LIB):
+                build("port")
+            self.lib, self.prefix = C.CDLL(PORT_LIB), "shso_"
+        else:
+            self.lib, self.prefix = C.CDLL(kind), prefix
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_OCCLUSION_LIB) or os.path.isdir("/root/reference")
+
+    def run(self, sc, enable=True):
+        """sc: dict of aabbs (n, 6), visible, object_mesh (n,), models (n, 16), mesh_table (m, 3), vertices (v, 3), indices, view, view_proj,
+        occ_w, occ_h, eps.  Returns occluded (n,) uint8, visible list, counts4, depth (occ_h, occ_w)."""
+        return run_software_occlusion(getattr(self.lib, self.prefix + "software_occlusion"), None, sc, enable)
+
+
+def run_software_occlusion(fn, ctx_handle, sc, enable=True):
+    a = np.ascontiguousarray(sc["aabbs"], dtype=np.float32).reshape(-1, 6)
+    vis = np.ascontiguousarray(sc["visible"], dtype=np.uint32).reshape(-1)
+    om = np.ascontiguousarray(sc["object_mesh"], dtype=np.uint32).reshape(-1)
+    mo = np.ascontiguousarray(sc["models"], dtype=np.float32).reshape(-1, 16)
+    mt = np.ascontiguousarray(sc["mesh_table"], dtype=np.uint32).reshape(-1, 3)
+    vt = np.ascontiguousarray(sc["vertices"], dtype=np.float32).reshape(-1, 3)
+    ix = np.ascontiguousarray(sc["indices"], dtype=np.uint32).reshape(-1)
+    v, vp = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (sc["view"], sc["view_proj"]))
+    w, h = int(sc["occ_w"]), int(sc["occ_h"])
+    occ, out_vis, counts, depth = np.zeros(max(1, len(a)), np.uint8), np.zeros(max(1, len(vis)), np.uint32), np.zeros(4, np.uint32), np.zeros((h, w), np.float32)
+    args = [capi.fptr(a), C.c_uint32(len(a)), capi.u32ptr(vis), C.c_uint32(len(vis)), capi.u32ptr(om), capi.fptr(mo), capi.u32ptr(mt), C.c_uint32(len(mt)), capi.fptr(vt),
+            C.c_uint32(len(vt)), capi.u32ptr(ix), C.c_uint32(len(ix)), capi.fptr(v), capi.fptr(vp), C.c_int32(w), C.c_int32(h), C.c_float(sc.get("eps", 1e-4)), C.c_int32(int(enable)),
+            occ.ctypes.data_as(C.POINTER(C.c_uint8)), capi.u32ptr(out_vis), capi.u32ptr(counts), capi.fptr(depth)]
+    rc = fn(*([ctx_handle] if ctx_handle is not None else []), *args)
+    assert rc == 0, rc
+    return occ[:len(a)], out_vis[:int(counts[2])].copy(), counts, depth

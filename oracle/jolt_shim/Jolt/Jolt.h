@@ -58,6 +58,8 @@ namespace JPH
         Mat44(const Vec4& c0, const Vec4& c1, const Vec4& c2, const Vec4& c3) : c_{c0, c1, c2, c3} {}
         static Mat44 sIdentity() { return Mat44(Vec4(1, 0, 0, 0), Vec4(0, 1, 0, 0), Vec4(0, 0, 1, 0), Vec4(0, 0, 0, 1)); }
         Vec4 GetColumn4(unsigned i) const { return c_[i]; }
+        Vec3 GetTranslation() const { return Vec3(c_[3].GetX(), c_[3].GetY(), c_[3].GetZ()); }
+        class Quat GetQuaternion() const; // declared for jolt_debug_draw.hpp, never called (see Shape::GetTriangles*)
     private:
         Vec4 c_[4];
     };
@@ -84,11 +86,33 @@ namespace JPH
         Vec3 mMin, mMax;
     };
 
+    // geometry/jolt_debug_draw.hpp (included by geometry/culling_software.hpp for its DebugMesh type) walks a shape's triangles through
+    // Shape::GetTrianglesStart / GetTrianglesNext.  Declarations only: the occlusion harness hands the reference ready-made DebugMesh
+    // data (vertices + indices are the INPUT of rasterize_mesh_depth_transformed), so these are never called.
+    struct Float3 { float x, y, z; Float3() = default; Float3(float a, float b, float c) : x(a), y(b), z(c) {} };
+    class Quat
+    {
+    public:
+        Quat() = default;
+        Quat(float x, float y, float z, float w) : x_(x), y_(y), z_(z), w_(w) {}
+        static Quat sIdentity() { return Quat(0, 0, 0, 1); }
+        float GetX() const { return x_; }
+        float GetY() const { return y_; }
+        float GetZ() const { return z_; }
+        float GetW() const { return w_; }
+    private:
+        float x_ = 0, y_ = 0, z_ = 0, w_ = 1;
+    };
+    class PhysicsMaterial;
+
     class Shape
     {
     public:
         virtual ~Shape() = default;
         virtual AABox GetWorldSpaceBounds(const Mat44& center_of_mass_transform, const Vec3& scale) const = 0;
+        struct GetTrianglesContext { unsigned char opaque[4288]; };
+        virtual void GetTrianglesStart(GetTrianglesContext&, const AABox&, const Vec3&, const Quat&, const Vec3&) const {}
+        virtual int GetTrianglesNext(GetTrianglesContext&, int, Float3*, const PhysicsMaterial** = nullptr) const { return 0; }
     };
 
     // RefConst<Shape>: a non-owning stand-in (the harness keeps the shapes alive)
@@ -98,6 +122,7 @@ namespace JPH
         ShapeRefC() = default;
         ShapeRefC(const Shape* s) : s_(s) {}
         const Shape* operator->() const { return s_; }
+        const Shape& operator*() const { return *s_; }
         const Shape* GetPtr() const { return s_; }
         explicit operator bool() const { return s_ != nullptr; }
         bool operator!() const { return s_ == nullptr; }

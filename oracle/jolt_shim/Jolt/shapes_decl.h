@@ -9,7 +9,7 @@
 
 namespace JPH
 {
-    struct Float3 { float x, y, z; Float3() = default; Float3(float a, float b, float c) : x(a), y(b), z(c) {} };
+    // Float3 lives in Jolt/Jolt.h (geometry/jolt_debug_draw.hpp needs it as well)
     struct Triangle { Float3 mV[3]; Triangle() = default; Triangle(const Float3& a, const Float3& b, const Float3& c) : mV{a, b, c} {} Triangle(const Vec3& a, const Vec3& b, const Vec3& c) : mV{Float3(a.GetX(), a.GetY(), a.GetZ()), Float3(b.GetX(), b.GetY(), b.GetZ()), Float3(c.GetX(), c.GetY(), c.GetZ())} {} };
     using TriangleList = std::vector<Triangle>;
 

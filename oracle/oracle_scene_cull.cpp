@@ -283,3 +283,142 @@ extern "C"
         return 0;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Software occlusion, geometry/culling_software.hpp:41-333, as scene/scene_culling.hpp:186-222 drives it.  PINNED against the
+// reference's own header compiled with the JoltPhysics declaration shim (oracle/ref_occlusion_harness.cpp; tests/test_occlusion_cpu.py).
+namespace
+{
+    inline void mul4(const float* m, float x, float y, float z, float w, float out[4]) // glm's scalar mat4 * vec4
+    {
+        for (int r = 0; r < 4; ++r) out[r] = (m[r] * x + m[4 + r] * y) + (m[8 + r] * z + m[12 + r] * w);
+    }
+    inline float edge_fn(const float* a, const float* b, const float* p) { return (p[0] - a[0]) * (b[1] - a[1]) - (p[1] - a[1]) * (b[0] - a[0]); } // :41-44
+
+    bool world_to_screen(const float* world, const float* vp, int w, int h, float xy[2], float& depth01) // :46-63
+    {
+        float clip[4];
+        mul4(vp, world[0], world[1], world[2], 1.0f, clip);
+        if (clip[3] <= 0.001f) return false;
+        const float ndc[3] = {clip[0] / clip[3], clip[1] / clip[3], clip[2] / clip[3]};
+        if (ndc[2] < -1.0f || ndc[2] > 1.0f) return false;
+        xy[0] = (ndc[0] + 1.0f) * 0.5f * (float)w;
+        xy[1] = (ndc[1] + 1.0f) * 0.5f * (float)h;
+        depth01 = ndc[2] * 0.5f + 0.5f;
+        return true;
+    }
+
+    void depth_triangle(float* depth, int w, int h, const float* p0, float z0, const float* p1, float z1, const float* p2, float z2) // :65-115
+    {
+        const float area = edge_fn(p0, p1, p2);
+        if (std::abs(area) <= 1e-6f) return;
+        const int min_x = std::max(0, (int)std::floor(std::min(p0[0], std::min(p1[0], p2[0]))));
+        const int min_y = std::max(0, (int)std::floor(std::min(p0[1], std::min(p1[1], p2[1]))));
+        const int max_x = std::min(w - 1, (int)std::ceil(std::max(p0[0], std::max(p1[0], p2[0]))));
+        const int max_y = std::min(h - 1, (int)std::ceil(std::max(p0[1], std::max(p1[1], p2[1]))));
+        if (min_x > max_x || min_y > max_y) return;
+        const bool ccw = area > 0.0f;
+        for (int y = min_y; y <= max_y; ++y)
+            for (int x = min_x; x <= max_x; ++x)
+            {
+                const float p[2] = {(float)x + 0.5f, (float)y + 0.5f};
+                const float w0 = edge_fn(p1, p2, p), w1 = edge_fn(p2, p0, p), w2 = edge_fn(p0, p1, p);
+                if (!(ccw ? (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) : (w0 <= 0.0f && w1 <= 0.0f && w2 <= 0.0f))) continue;
+                const float d = (w0 / area) * z0 + (w1 / area) * z1 + (w2 / area) * z2;
+                if (d < 0.0f || d > 1.0f) continue;
+                float& dst = depth[(size_t)y * w + x];
+                if (d < dst) dst = d;
+            }
+    }
+}
+
+extern "C" int32_t shso_software_occlusion(const float* object_aabbs6, uint32_t n_objects, const uint32_t* frustum_visible, uint32_t n_visible, const uint32_t* object_mesh,
+                                           const float* object_models16, const uint32_t* mesh_table3, uint32_t n_meshes, const float* vertices, uint32_t n_vertices,
+                                           const uint32_t* indices, uint32_t n_indices, const float view[16], const float view_proj[16], int32_t occ_w, int32_t occ_h,
+                                           float depth_epsilon, int32_t enable_occlusion, uint8_t* out_occluded, uint32_t* out_visible, uint32_t out_counts4[4], float* out_depth)
+{
+    (void)n_vertices; (void)n_indices;
+    std::vector<float> depth((size_t)occ_w * occ_h, 1.0f);
+    for (uint32_t i = 0; i < n_objects; ++i) out_occluded[i] = 0;
+    uint32_t nv = 0;
+    if (!enable_occlusion) // :270-284
+    {
+        for (uint32_t k = 0; k < n_visible; ++k) if (frustum_visible[k] < n_objects) out_visible[nv++] = frustum_visible[k];
+    }
+    else
+    {
+        auto view_depth = [&](uint32_t i) { // view_depth_of_aabb_center, :224-231
+            const float* b = object_aabbs6 + (size_t)i * 6;
+            float v[4];
+            mul4(view, 0.5f * (b[0] + b[3]), 0.5f * (b[1] + b[4]), 0.5f * (b[2] + b[5]), 1.0f, v);
+            return v[2];
+        };
+        std::vector<uint32_t> sorted(frustum_visible, frustum_visible + n_visible);
+        std::sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) { // :288-297
+            if (a >= n_objects) return false;
+            if (b >= n_objects) return true;
+            return view_depth(a) < view_depth(b);
+        });
+        for (const uint32_t idx : sorted)
+        {
+            if (idx >= n_objects) continue;
+            // project_aabb_to_screen_rect, :145-199
+            const float* b = object_aabbs6 + (size_t)idx * 6;
+            float min_x = (float)occ_w, min_y = (float)occ_h, max_x = -1.0f, max_y = -1.0f, near_depth = 1.0f;
+            bool any = false;
+            for (int c = 0; c < 8; ++c)
+            {
+                float clip[4];
+                mul4(view_proj, b[(c & 1) ? 3 : 0], b[(c & 2) ? 4 : 1], b[(c & 4) ? 5 : 2], 1.0f, clip);
+                if (clip[3] <= 0.001f) continue;
+                const float ndc[3] = {clip[0] / clip[3], clip[1] / clip[3], clip[2] / clip[3]};
+                const float z01 = ndc[2] * 0.5f + 0.5f;
+                if (z01 < 0.0f || z01 > 1.0f) continue;
+                const float sx = (ndc[0] + 1.0f) * 0.5f * (float)occ_w, sy = (ndc[1] + 1.0f) * 0.5f * (float)occ_h;
+                min_x = std::min(min_x, sx); min_y = std::min(min_y, sy); max_x = std::max(max_x, sx); max_y = std::max(max_y, sy);
+                near_depth = std::min(near_depth, z01);
+                any = true;
+            }
+            bool occluded = false;
+            if (any)
+            {
+                const int x0 = std::max(0, (int)std::floor(min_x)), y0 = std::max(0, (int)std::floor(min_y));
+                const int x1 = std::min(occ_w - 1, (int)std::ceil(max_x)), y1 = std::min(occ_h - 1, (int)std::ceil(max_y));
+                const float z_near = std::clamp(near_depth, 0.0f, 1.0f);
+                if (x0 <= x1 && y0 <= y1) // is_rect_occluded, :201-222
+                {
+                    occluded = true;
+                    for (int y = y0; y <= y1 && occluded; ++y)
+                        for (int x = x0; x <= x1; ++x)
+                            if (z_near <= depth[(size_t)y * occ_w + x] + depth_epsilon) { occluded = false; break; }
+                }
+            }
+            out_occluded[idx] = occluded ? 1 : 0;
+            if (occluded) continue;
+            out_visible[nv++] = idx;
+            const uint32_t m = object_mesh[idx];
+            if (m >= n_meshes) continue;
+            const uint32_t first = mesh_table3[3 * m], count = mesh_table3[3 * m + 1], base_v = mesh_table3[3 * m + 2];
+            const float* model = object_models16 + (size_t)idx * 16;
+            for (uint32_t i = 0; i + 2 < count; i += 3) // rasterize_mesh_depth_transformed, :116-143
+            {
+                float s[3][2], z[3];
+                bool ok = true;
+                for (int v = 0; v < 3 && ok; ++v)
+                {
+                    const float* lp = vertices + (size_t)(base_v + indices[first + i + v]) * 3;
+                    float wp[4];
+                    mul4(model, lp[0], lp[1], lp[2], 1.0f, wp);
+                    ok = world_to_screen(wp, view_proj, occ_w, occ_h, s[v], z[v]);
+                }
+                if (ok) depth_triangle(depth.data(), occ_w, occ_h, s[0], z[0], s[1], z[1], s[2], z[2]);
+            }
+        }
+    }
+    out_counts4[0] = n_objects;
+    out_counts4[1] = std::max(n_visible, nv);
+    out_counts4[2] = nv;
+    out_counts4[3] = out_counts4[1] - nv;
+    if (out_depth) std::memcpy(out_depth, depth.data(), depth.size() * sizeof(float));
+    return 0;
+}

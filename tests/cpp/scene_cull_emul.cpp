@@ -95,3 +95,76 @@ extern "C" int32_t shsemu_select_object_lights_from_bins(const float* object_aab
     }
     return 0;
 }
+
+// The software-occlusion kernel's walk (scene_cull.cu: software_occlusion_kernel) with the device functions: objects in the host's
+// sorted order; per object the rectangle test over its texels, then every triangle's bbox texels through occ_texel_depth with a
+// minimum on the depth's BIT PATTERN (what the device's atomicMin does) -- triangles and texels visited in REVERSE order to show
+// that the minimum does not care.
+extern "C" int32_t shsemu_software_occlusion(const float* object_aabbs6, uint32_t n_objects, const uint32_t* frustum_visible, uint32_t n_visible, const uint32_t* object_mesh,
+                                             const float* object_models16, const uint32_t* mesh_table3, uint32_t n_meshes, const float* vertices, uint32_t n_vertices,
+                                             const uint32_t* indices, uint32_t n_indices, const float view[16], const float view_proj[16], int32_t occ_w, int32_t occ_h,
+                                             float depth_epsilon, int32_t enable_occlusion, uint8_t* out_occluded, uint32_t* out_visible, uint32_t out_counts4[4], float* out_depth)
+{
+    (void)n_indices;
+    std::vector<uint32_t> bits((size_t)occ_w * occ_h, 0x3F800000u);
+    auto as_float = [](uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; };
+    auto as_bits = [](float f) { uint32_t b; std::memcpy(&b, &f, 4); return b; };
+    for (uint32_t i = 0; i < n_objects; ++i) out_occluded[i] = 0;
+    uint32_t nv = 0;
+    if (!enable_occlusion)
+    {
+        for (uint32_t k = 0; k < n_visible; ++k) if (frustum_visible[k] < n_objects) out_visible[nv++] = frustum_visible[k];
+    }
+    else
+    {
+        std::vector<float> key(n_objects);
+        for (uint32_t i = 0; i < n_objects; ++i) key[i] = occ_view_depth(object_aabbs6 + (size_t)i * 6, view);
+        std::vector<uint32_t> sorted(frustum_visible, frustum_visible + n_visible);
+        std::sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) { if (a >= n_objects) return false; if (b >= n_objects) return true; return key[a] < key[b]; });
+        for (const uint32_t idx : sorted)
+        {
+            if (idx >= n_objects) continue;
+            const OccRect r = occ_project_rect(object_aabbs6 + (size_t)idx * 6, view_proj, occ_w, occ_h);
+            bool shows = false;
+            if (r.valid)
+                for (int y = r.y_max; y >= r.y_min; --y)
+                    for (int x = r.x_max; x >= r.x_min; --x) shows = shows || occ_texel_shows(r.z_near, as_float(bits[(size_t)y * occ_w + x]), depth_epsilon);
+            const bool occluded = r.valid && !shows;
+            out_occluded[idx] = occluded ? 1 : 0;
+            if (occluded) continue;
+            out_visible[nv++] = idx;
+            const uint32_t m = object_mesh[idx];
+            if (m >= n_meshes) continue;
+            const uint32_t first = mesh_table3[3 * m], count = mesh_table3[3 * m + 1], base_v = mesh_table3[3 * m + 2];
+            const float* model = object_models16 + (size_t)idx * 16;
+            const uint32_t n_tri = count / 3;
+            for (uint32_t ti = n_tri; ti-- > 0;)
+            {
+                const uint32_t t = ti * 3;
+                if (!(t + 2 < count)) continue;
+                float xy[3][2], z[3];
+                bool ok = true;
+                for (int v = 0; v < 3; ++v)
+                {
+                    const uint32_t vi = base_v + indices[first + t + v];
+                    ok = ok && vi < n_vertices && occ_project_vertex(model, vertices + (size_t)vi * 3, view_proj, occ_w, occ_h, xy[v], z[v]);
+                }
+                if (!ok) continue;
+                const OccTri tri = occ_setup_triangle(xy[0], z[0], xy[1], z[1], xy[2], z[2], occ_w, occ_h);
+                if (!tri.valid) continue;
+                for (int y = tri.max_y; y >= tri.min_y; --y)
+                    for (int x = tri.max_x; x >= tri.min_x; --x)
+                    {
+                        float d;
+                        if (!occ_texel_depth(tri, x, y, d)) continue;
+                        const uint32_t b = as_bits(d == 0.0f ? 0.0f : d);
+                        uint32_t& dst = bits[(size_t)y * occ_w + x];
+                        if (b < dst) dst = b;
+                    }
+            }
+        }
+    }
+    out_counts4[0] = n_objects; out_counts4[1] = std::max(n_visible, nv); out_counts4[2] = nv; out_counts4[3] = out_counts4[1] - nv;
+    if (out_depth) for (size_t i = 0; i < bits.size(); ++i) out_depth[i] = as_float(bits[i]);
+    return 0;
+}

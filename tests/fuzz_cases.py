@@ -212,3 +212,48 @@ def scene_cull(seed):
     visible_objects = rng.integers(0, n + 2, nvo).astype(np.uint32) if seed % 4 else np.arange(n, dtype=np.uint32)
     return {"aabbs": aabbs, "view_proj": vp, "lights": lights, "visible": visible, "view": view, "w": w, "h": h, "ts": ts, "zn": zn, "zf": zf,
             "visible_objects": visible_objects}
+
+
+def occlusion_scene(seed):
+    """Random input of the software-occlusion pass (geometry/culling_software.hpp): a camera looking down a corridor of boxes and
+    spheres-as-boxes of very different sizes -- big walls near the camera that hide what is behind them, small props, objects
+    behind / around the camera, objects with no occluder mesh, a mesh with a dangling index pair (indices.size() % 3 != 0), stale
+    entries in the frustum-visible list (indices >= n_objects) -- and occlusion buffers from 8 x 6 to 320 x 180.  Occluder meshes
+    are DebugMesh-like: a unit box (12 triangles), an octahedron (8), a thin quad (2), each drawn with the object's model matrix."""
+    rng = np.random.default_rng(19000 + seed)
+    box_v = np.array([[x, y, z] for z in (-.5, .5) for y in (-.5, .5) for x in (-.5, .5)], np.float32)
+    box_i = np.array([0, 1, 3, 0, 3, 2, 4, 6, 7, 4, 7, 5, 0, 4, 5, 0, 5, 1, 2, 3, 7, 2, 7, 6, 0, 2, 6, 0, 6, 4, 1, 5, 7, 1, 7, 3], np.uint32)
+    oct_v = np.array([[.5, 0, 0], [-.5, 0, 0], [0, .5, 0], [0, -.5, 0], [0, 0, .5], [0, 0, -.5]], np.float32)
+    oct_i = np.array([0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5], np.uint32)
+    quad_v = np.array([[-.5, -.5, 0], [.5, -.5, 0], [.5, .5, 0], [-.5, .5, 0]], np.float32)
+    quad_i = np.array([0, 1, 2, 0, 2, 3, 1, 2], np.uint32)            # 8 indices: the trailing pair is ignored (i + 2 < size)
+    vertices = np.concatenate([box_v, oct_v, quad_v])
+    indices = np.concatenate([box_i, oct_i, quad_i])
+    mesh_table = np.array([[0, 36, 0], [36, 24, 8], [60, 8, 14]], np.uint32)
+    n = int(rng.integers(1, 120))
+    ext = float(rng.choice([6.0, 20.0, 60.0]))
+    aabbs, models, omesh = [], [], []
+    for i in range(n):
+        c = rng.uniform(-ext, ext, 3) * np.array([1.0, 0.4, 1.0])
+        big = rng.random() < 0.15
+        half = rng.uniform(0.1, 1.5, 3) * (float(rng.uniform(3, 10)) if big else 1.0)
+        m = int(rng.choice([0, 0, 1, 2, 0xFFFFFFFF])) if not big else 0
+        model = np.eye(4, dtype=np.float32)
+        model[0, 0], model[1, 1], model[2, 2] = 2 * half          # column-major storage below: scale then translate
+        model[:3, 3] = c
+        aabbs.append(np.concatenate([c - half, c + half]))
+        models.append(model.T.reshape(16))                          # glm column-major
+        omesh.append(m)
+    aabbs = np.array(aabbs, np.float32)
+    eye = tuple(float(v) for v in rng.uniform(-ext, ext, 3) * np.array([1.0, 0.3, 1.0]))
+    tgt = tuple(float(v) for v in rng.uniform(-ext / 3, ext / 3, 3))
+    w, h = [(8, 6), (64, 36), (160, 90), (320, 180), (97, 53)][int(rng.integers(0, 5))]
+    zn, zf = float(rng.choice([0.05, 0.1, 1.0])), float(rng.choice([50.0, 300.0, 1000.0]))
+    view_proj = scenes.camera_viewproj(eye, tgt, (0.0, 1.0, 0.0), float(np.radians(rng.uniform(40, 90))), w / h, zn, zf)
+    view = np.ascontiguousarray(scenes.look_at_lh(eye, tgt, (0.0, 1.0, 0.0)).astype(np.float32).T).reshape(16)
+    visible = rng.permutation(n)[: int(rng.integers(0, n + 1))].astype(np.uint32)
+    if seed % 4 == 0 and len(visible):
+        visible = np.concatenate([visible, np.array([n + 3, 0xFFFFFFF0], np.uint32)])      # stale indices
+        rng.shuffle(visible)
+    return {"aabbs": aabbs, "visible": visible, "object_mesh": np.array(omesh, np.uint32), "models": np.array(models, np.float32), "mesh_table": mesh_table,
+            "vertices": vertices, "indices": indices, "view": view, "view_proj": view_proj, "occ_w": w, "occ_h": h, "eps": float(rng.choice([1e-4, 0.0, 1e-2]))}

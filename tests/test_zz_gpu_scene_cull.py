@@ -122,3 +122,32 @@ def test_scene_cull_drop_in_parity_on_gpu():
     r = subprocess.run([path], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_fuzz_software_occlusion_equals_the_oracle(gpu, seed):
+    """shsb_software_occlusion (one persistent CTA walking the reference's front-to-back order, atomic-minimum occluder raster) against
+    the pinned restatement: occluded flags, the ordered visible list, CullingStats counters and the occlusion depth buffer bit for bit,
+    with occlusion on and off."""
+    from oracle import bindings
+    sc = fuzz_cases.occlusion_scene(seed)
+    port = bindings.SoftwareOcclusion("port")
+    for enable in (True, False):
+        want = port.run(sc, enable)
+        got = gpu.software_occlusion(sc["aabbs"], sc["visible"], sc["object_mesh"], sc["models"], sc["mesh_table"], sc["vertices"], sc["indices"], sc["view"], sc["view_proj"],
+                                     sc["occ_w"], sc["occ_h"], sc["eps"], enable)
+        for g, w, name in zip(got, want, ("occluded flags", "visible list", "counts", "depth buffer")):
+            if name == "depth buffer" and not enable:
+                continue
+            assert np.array_equal(np.asarray(g) + 0, np.asarray(w) + 0), f"seed {seed} enable {enable}: {name} differ"
+
+
+def test_software_occlusion_argument_checks(gpu):
+    import ctypes as C
+    lib = gpu.lib
+    z = np.zeros(16, np.float32)
+    c4 = np.zeros(4, np.uint32)
+    f = capi.fptr(z)
+    assert lib.shsb_software_occlusion(gpu.h, None, 0, None, 0, None, None, None, 0, None, 0, None, 0, f, f, 0, 10, C.c_float(1e-4), 1, None, None, capi.u32ptr(c4), None) == 1   # empty buffer
+    assert lib.shsb_software_occlusion(gpu.h, None, 0, None, 0, None, None, None, 0, None, 0, None, 0, f, f, 16, 8, C.c_float(1e-4), 1, None, None, capi.u32ptr(c4), None) == 0   # empty scene
+    assert list(c4) == [0, 0, 0, 0]
