@@ -2045,7 +2045,7 @@ SHSB_API int32_t shsb_software_occlusion(shsb_ctx ctx, const float* object_aabbs
     auto take = [&](size_t bytes) { const size_t o = off; off += sc_align(std::max<size_t>(bytes, 4)); return o; };
     const size_t o_boxes = take((size_t)n_objects * 24), o_sorted = take((size_t)n_visible * 4), o_omesh = take((size_t)n_objects * 4), o_models = take((size_t)n_objects * 64),
                  o_table = take((size_t)n_meshes * 12), o_verts = take((size_t)n_vertices * 12), o_idx = take((size_t)n_indices * 4), o_depth = take((size_t)occ_w * occ_h * 4),
-                 o_occ = take(n_objects), o_vis = take((size_t)n_visible * 4), o_counts = take(8);
+                 o_occ = take(n_objects), o_vis = take((size_t)n_visible * 4), o_counts = take(8), o_rects = take((size_t)n_visible * 32);
     if (int rc = ensure_dev(ctx, ctx->d_sc_bytes, off + 256)) return rc;
     uint8_t* base = ctx->d_sc_bytes.p;
     cudaStream_t st = ctx->stream;
@@ -2060,7 +2060,7 @@ SHSB_API int32_t shsb_software_occlusion(shsb_ctx ctx, const float* object_aabbs
     CK(cudaMemsetAsync(base + o_occ, 0, std::max<size_t>(n_objects, 4), st));
     launch_software_occlusion((const float*)(base + o_boxes), n_objects, (const uint32_t*)(base + o_sorted), n_visible, (const uint32_t*)(base + o_omesh), (const float*)(base + o_models),
                               (const uint32_t*)(base + o_table), n_meshes, (const float*)(base + o_verts), n_vertices, (const uint32_t*)(base + o_idx), n_indices, view_proj, occ_w, occ_h,
-                              depth_epsilon, (float*)(base + o_depth), base + o_occ, (uint32_t*)(base + o_vis), (uint32_t*)(base + o_counts), st, &ctx->launches);
+                              depth_epsilon, (float*)(base + o_depth), base + o_occ, (uint32_t*)(base + o_vis), (uint32_t*)(base + o_counts), base + o_rects, st, &ctx->launches);
     CK(cudaGetLastError());
     uint32_t c2[2] = {0, 0};
     CK(cudaMemcpyAsync(c2, base + o_counts, 8, cudaMemcpyDeviceToHost, st));

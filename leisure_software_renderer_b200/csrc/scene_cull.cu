@@ -211,69 +211,119 @@ namespace shsb
             uint32_t* counts;                                    // [0] visible, [1] occluded
         };
 
-        // run_software_occlusion_pass, geometry/culling_software.hpp:292-322, on ONE CTA: per object (in order) thread 0 projects the
-        // AABB, the CTA ANDs "hidden" over the rectangle's texels (is_rect_occluded), and -- if the object shows -- rasterises its
-        // occluder mesh (rasterize_mesh_depth_transformed) a warp per triangle, lanes over the bbox texels, with an atomic minimum on
-        // the depth's bit pattern (depths are in [0, 1]; the minimum does not depend on the order within one object).  Texel reads
-        // bypass L1 (the buffer is rewritten between barriers by other SMs' ... by this CTA's own atomics, which live in L2).
-        __global__ void __launch_bounds__(1024) software_occlusion_kernel(const OccParams p)
+        // project_aabb_to_screen_rect for every entry of the sorted list, in parallel: a rectangle depends on the object and the camera
+        // only, not on the depth buffer
+        __global__ void __launch_bounds__(256) occlusion_rects_kernel(const OccParams p, sc::OccRect* __restrict__ rects)
         {
-            __shared__ sc::OccRect s_rect;
+            const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+            if (k >= p.n_sorted) return;
+            const uint32_t idx = p.sorted[k];
+            if (idx < p.n_objects) rects[k] = sc::occ_project_rect(p.boxes6 + (size_t)idx * 6, p.view_proj, p.width, p.height);
+        }
+
+        // run_software_occlusion_pass, geometry/culling_software.hpp:292-322, on ONE CTA of 32 warps.  The order of objects is serial,
+        // but the depth buffer only ever gets NEARER (minimum writes), so "occluded" is monotone: an object hidden by the buffer as it
+        // is now is still hidden when its turn comes.  Each round therefore tests the next 32 entries at once (one warp per entry,
+        // lanes over the rectangle's texels): every entry before the first one that shows is occluded for good -- occluded objects
+        // rasterise nothing, so the buffer that first showing object sees is the current one, and it is visible for good too.  It
+        // rasterises its occluder mesh (rasterize_mesh_depth_transformed: a warp per triangle, lanes over the bbox texels, atomic
+        // minimum on the depth's bit pattern -- depths are in [0, 1]), and the next round starts behind it.  A round thus settles one
+        // visible object plus all occluded ones in front of it; the results are those of the serial loop.
+        __global__ void __launch_bounds__(1024) software_occlusion_kernel(const OccParams p, const sc::OccRect* __restrict__ rects, uint8_t* __restrict__ settled)
+        {
+            __shared__ int s_state[32];       // per window entry: 0 occluded, 1 shows, 2 not an object (stale index), 3 large rectangle, not tested yet
             __shared__ uint32_t s_nvis, s_nocc;
-            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            constexpr int WARP_RECT_MAX = 2048; // texels a single warp scans; larger rectangles are scanned by the whole CTA
             if (tid == 0) { s_nvis = 0; s_nocc = 0; }
-            __syncthreads();
-            for (uint32_t k = 0; k < p.n_sorted; ++k)
+            uint32_t pos = 0;
+            while (pos < p.n_sorted)
             {
-                const uint32_t idx = p.sorted[k];
-                if (idx >= p.n_objects) continue; // CTA-uniform
-                if (tid == 0) s_rect = sc::occ_project_rect(p.boxes6 + (size_t)idx * 6, p.view_proj, p.width, p.height);
+                const uint32_t e = pos + (uint32_t)warp;
+                int state = 2;
+                uint32_t idx = 0xFFFFFFFFu;
+                if (e < p.n_sorted)
+                {
+                    idx = p.sorted[e];
+                    if (idx < p.n_objects)
+                    {
+                        const sc::OccRect r = rects[e];
+                        const int rw = r.x_max - r.x_min + 1, total = r.valid ? rw * (r.y_max - r.y_min + 1) : 0;
+                        if (settled[e]) state = 0;               // found hidden in an earlier round: hidden for good (the buffer only gets nearer)
+                        else if (!r.valid) state = 1;            // an invalid rectangle is never occluded (:208)
+                        else if (total > WARP_RECT_MAX) state = 3;
+                        else
+                        {
+                            bool shows = false;
+                            for (int base = 0; base < total && !shows; base += 32)
+                            {
+                                const int i = base + lane;
+                                bool mine = false;
+                                if (i < total)
+                                    mine = sc::occ_texel_shows(r.z_near, __uint_as_float(__ldcg(p.depth_bits + (size_t)(r.y_min + i / rw) * p.width + (r.x_min + i % rw))), p.epsilon);
+                                shows = __any_sync(0xffffffffu, mine);
+                            }
+                            state = shows ? 1 : 0;
+                            if (!shows && lane == 0) settled[e] = 1;
+                        }
+                    }
+                }
+                if (lane == 0) s_state[warp] = state;
                 __syncthreads();
-                const sc::OccRect r = s_rect;
-                bool shows = false;
-                if (r.valid)
+                const uint32_t window = min(32u, p.n_sorted - pos);
+                int first = 32;
+                for (int w = 0; w < (int)window; ++w) // CTA-uniform walk in order; large rectangles are scanned by all threads, only while no earlier entry shows
                 {
+                    const int st = s_state[w];
+                    if (st == 1) { first = w; break; }
+                    if (st != 3) continue;
+                    const sc::OccRect r = rects[pos + (uint32_t)w];
                     const int rw = r.x_max - r.x_min + 1, total = rw * (r.y_max - r.y_min + 1);
-                    for (int i = tid; i < total && !shows; i += blockDim.x)
-                    {
-                        const int x = r.x_min + i % rw, y = r.y_min + i / rw;
-                        shows = sc::occ_texel_shows(r.z_near, __uint_as_float(__ldcg(p.depth_bits + (size_t)y * p.width + x)), p.epsilon);
-                    }
+                    bool mine = false;
+                    for (int i = tid; i < total && !mine; i += 1024)
+                        mine = sc::occ_texel_shows(r.z_near, __uint_as_float(__ldcg(p.depth_bits + (size_t)(r.y_min + i / rw) * p.width + (r.x_min + i % rw))), p.epsilon);
+                    const int shows = __syncthreads_or(mine ? 1 : 0);
+                    if (shows) { first = w; break; }
+                    if (tid == 0) { s_state[w] = 0; settled[pos + (uint32_t)w] = 1; }
                 }
-                const bool occluded = r.valid && !__syncthreads_or(shows ? 1 : 0); // an invalid rectangle is never occluded (:208)
-                if (tid == 0)
+                __syncthreads();
+                state = ((uint32_t)warp < window) ? s_state[warp] : 2;
+                // entries in front of the first showing one are settled: occluded (or stale)
+                if (lane == 0 && (uint32_t)warp < window && warp < first && state == 0) { p.occluded[idx] = 1; atomicAdd(&s_nocc, 1u); }
+                if (first < 32)
                 {
-                    p.occluded[idx] = occluded ? 1 : 0;
-                    if (occluded) ++s_nocc; else p.visible[s_nvis++] = idx;
-                }
-                if (occluded) continue; // CTA-uniform
-                const uint32_t m = p.object_mesh[idx];
-                if (m < p.n_meshes)
-                {
-                    const uint32_t first = p.mesh_table[3 * m], count = p.mesh_table[3 * m + 1], base_v = p.mesh_table[3 * m + 2];
-                    const float* model = p.object_models + (size_t)idx * 16;
-                    for (uint32_t t = (uint32_t)warp * 3u; t + 2u < count; t += (uint32_t)n_warps * 3u) // `i + 2 < indices.size()`, :125
+                    const uint32_t vidx = p.sorted[pos + (uint32_t)first];
+                    if (tid == 0) { p.occluded[vidx] = 0; p.visible[s_nvis++] = vidx; }
+                    const uint32_t m = p.object_mesh[vidx];
+                    if (m < p.n_meshes)
                     {
-                        float xy[3][2], z[3];
-                        bool ok = true;
-                        for (int v = 0; v < 3; ++v)
+                        const uint32_t firsti = p.mesh_table[3 * m], count = p.mesh_table[3 * m + 1], base_v = p.mesh_table[3 * m + 2];
+                        const float* model = p.object_models + (size_t)vidx * 16;
+                        for (uint32_t t = (uint32_t)warp * 3u; t + 2u < count; t += 32u * 3u) // `i + 2 < indices.size()`, :125
                         {
-                            const uint32_t vi = base_v + p.indices[first + t + v];
-                            ok = ok && vi < p.n_vertices && sc::occ_project_vertex(model, p.vertices + (size_t)vi * 3, p.view_proj, p.width, p.height, xy[v], z[v]);
-                        }
-                        if (!ok) continue; // warp-uniform
-                        const sc::OccTri tri = sc::occ_setup_triangle(xy[0], z[0], xy[1], z[1], xy[2], z[2], p.width, p.height);
-                        if (!tri.valid) continue;
-                        const int bw = tri.max_x - tri.min_x + 1, total = bw * (tri.max_y - tri.min_y + 1);
-                        for (int i = lane; i < total; i += 32)
-                        {
-                            const int x = tri.min_x + i % bw, y = tri.min_y + i / bw;
-                            float d;
-                            if (sc::occ_texel_depth(tri, x, y, d)) atomicMin(p.depth_bits + (size_t)y * p.width + x, __float_as_uint(d == 0.0f ? 0.0f : d)); // -0 -> +0
+                            float xy[3][2], z[3];
+                            bool ok = true;
+                            for (int v = 0; v < 3; ++v)
+                            {
+                                const uint32_t vi = base_v + p.indices[firsti + t + v];
+                                ok = ok && vi < p.n_vertices && sc::occ_project_vertex(model, p.vertices + (size_t)vi * 3, p.view_proj, p.width, p.height, xy[v], z[v]);
+                            }
+                            if (!ok) continue; // warp-uniform
+                            const sc::OccTri tri = sc::occ_setup_triangle(xy[0], z[0], xy[1], z[1], xy[2], z[2], p.width, p.height);
+                            if (!tri.valid) continue;
+                            const int bw = tri.max_x - tri.min_x + 1, total = bw * (tri.max_y - tri.min_y + 1);
+                            for (int i = lane; i < total; i += 32)
+                            {
+                                const int x = tri.min_x + i % bw, y = tri.min_y + i / bw;
+                                float d;
+                                if (sc::occ_texel_depth(tri, x, y, d)) atomicMin(p.depth_bits + (size_t)y * p.width + x, __float_as_uint(d == 0.0f ? 0.0f : d)); // -0 -> +0
+                            }
                         }
                     }
+                    pos += (uint32_t)first + 1u;
                 }
-                __syncthreads(); // the next object's test must see this object's depths
+                else pos += window;
+                __syncthreads(); // the next round's tests must see this object's depths; s_state is rewritten
             }
             __syncthreads();
             if (tid == 0) { p.counts[0] = s_nvis; p.counts[1] = s_nocc; }
@@ -283,8 +333,9 @@ namespace shsb
     void launch_software_occlusion(const float* boxes6, uint32_t n_objects, const uint32_t* sorted, uint32_t n_sorted, const uint32_t* object_mesh, const float* object_models,
                                    const uint32_t* mesh_table, uint32_t n_meshes, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
                                    const float view_proj[16], int width, int height, float epsilon, float* depth, uint8_t* occluded, uint32_t* visible, uint32_t* counts2,
-                                   cudaStream_t s, uint64_t* launches)
+                                   void* rect_scratch, cudaStream_t s, uint64_t* launches)
     {
+        sc::OccRect* rects = static_cast<sc::OccRect*>(rect_scratch); // n_sorted x (sizeof(sc::OccRect) = 24 bytes + 1 "settled" byte)
         OccParams p{};
         p.boxes6 = boxes6; p.n_objects = n_objects; p.sorted = sorted; p.n_sorted = n_sorted; p.object_mesh = object_mesh; p.object_models = object_models;
         p.mesh_table = mesh_table; p.n_meshes = n_meshes; p.vertices = vertices; p.n_vertices = n_vertices; p.indices = indices; p.n_indices = n_indices;
@@ -292,7 +343,11 @@ namespace shsb
         p.width = width; p.height = height; p.epsilon = epsilon;
         p.depth_bits = reinterpret_cast<uint32_t*>(depth); p.occluded = occluded; p.visible = visible; p.counts = counts2;
         launch_fill_u32(p.depth_bits, 0x3F800000u, (size_t)width * (size_t)height, s, launches); // std::fill(occlusion_depth, 1.0f), :286
-        software_occlusion_kernel<<<1, 1024, 0, s>>>(p);
-        *launches += 1;
+        if (n_sorted == 0) { cudaMemsetAsync(counts2, 0, 8, s); return; }
+        uint8_t* settled = reinterpret_cast<uint8_t*>(rects + n_sorted);
+        cudaMemsetAsync(settled, 0, n_sorted, s);
+        occlusion_rects_kernel<<<(n_sorted + 255) / 256, 256, 0, s>>>(p, rects);
+        software_occlusion_kernel<<<1, 1024, 0, s>>>(p, rects, settled);
+        *launches += 2;
     }
 }

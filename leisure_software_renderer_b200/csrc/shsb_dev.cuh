@@ -300,7 +300,7 @@ namespace shsb
     void launch_software_occlusion(const float* boxes6, uint32_t n_objects, const uint32_t* sorted, uint32_t n_sorted, const uint32_t* object_mesh, const float* object_models,
                                    const uint32_t* mesh_table, uint32_t n_meshes, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
                                    const float view_proj[16], int width, int height, float epsilon, float* depth, uint8_t* occluded, uint32_t* visible, uint32_t* counts2,
-                                   cudaStream_t s, uint64_t* launches);
+                                   void* rect_scratch /* n_sorted x 32 bytes */, cudaStream_t s, uint64_t* launches);
     uint32_t legacy2_slots(const l2::Draw& d);
     void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
                              cudaStream_t s, uint64_t* launches);

@@ -144,6 +144,7 @@ def test_fuzz_software_occlusion_equals_the_oracle(gpu, seed):
 
 def test_software_occlusion_argument_checks(gpu):
     import ctypes as C
+    from leisure_software_renderer_b200 import capi
     lib = gpu.lib
     z = np.zeros(16, np.float32)
     c4 = np.zeros(4, np.uint32)
