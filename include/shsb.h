@@ -330,6 +330,20 @@ SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh);
 SHSB_API int32_t shsb_texture_upload(shsb_ctx ctx, const uint8_t* rgba, int32_t w, int32_t h, shsb_tex* out_tex);
 SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex);
 
+/* On-disk fixtures -> device.  The reference reads meshes through Assimp
+ * (resources/loaders/mesh_loader_assimp.hpp:42-101) and textures through SDL_image (resources/loaders/texture_loader_sdl.hpp:21-56);
+ * these two calls read the formats its fixtures use -- Wavefront OBJ (cpp-folders/src/assets/obj/...) and PNG -- with the same
+ * conventions (one vertex per distinct v/vt/vn triple, file face order, fan triangulation, default normal (0,1,0) / uv (0,0);
+ * RGBA8 with the vertical flip load_texture2d_sdl_image applies by default) and upload the result.  Other formats:
+ * SHSB_E_UNSUPPORTED; unreadable / malformed files: SHSB_E_INVALID_ARGUMENT with the reason in shsb_last_error_string. */
+SHSB_API int32_t shsb_mesh_load_obj(shsb_ctx ctx, const char* path, shsb_mesh* out_mesh);
+SHSB_API int32_t shsb_texture_load_png(shsb_ctx ctx, const char* path, int32_t flip_y, shsb_tex* out_tex);
+/* Sizes of a mesh (positions, normals, uvs, indices) / a texture (w, h), and their contents back on the host. */
+SHSB_API int32_t shsb_mesh_info(shsb_ctx ctx, shsb_mesh mesh, uint32_t out_counts4[4]);
+SHSB_API int32_t shsb_mesh_download(shsb_ctx ctx, shsb_mesh mesh, float* positions, float* normals, float* uvs, uint32_t* indices);
+SHSB_API int32_t shsb_texture_info(shsb_ctx ctx, shsb_tex tex, int32_t out_wh2[2]);
+SHSB_API int32_t shsb_texture_download(shsb_ctx ctx, shsb_tex tex, uint8_t* rgba, size_t bytes);
+
 /* ------------------------------------------------------------------ render targets */
 
 /* RT_ColorHDR / RT_ColorLDR / RT_ColorDepthVelocity / RT_ShadowDepth constructors

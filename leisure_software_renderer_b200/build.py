@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             print(f"--- {src}\n{out}")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [cc, *ARCH, "-shared", "-o", OUT, *objs, "-Xcompiler", "-fPIC"]
+    link = [cc, *ARCH, "-shared", "-o", OUT, *objs, "-Xcompiler", "-fPIC", "-lz"]  # zlib: PNG fixtures (asset_loaders.hpp)
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
@@ -93,7 +93,7 @@ def build_phase_clocks() -> str:
     subprocess.run([cc, *ARCH, *COMMON, "-DSHSB_PHASE_CLOCKS", "-c", os.path.join(CSRC, "tile_raster.cu"), "-o", o], check=True)
     out = os.path.join(HERE, "libshsb_clk.so")
     objs = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "tile_raster.cu"] + [o]
-    subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC"], check=True)
+    subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC", "-lz"], check=True)
     return out
 
 

@@ -230,6 +230,12 @@ def load_library(path: str | None = None):
         "shsb_gather_stream": [vp, P(vp)],
         "shsb_mesh_upload": [vp, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32)],
         "shsb_mesh_destroy": [vp, C.c_uint32],
+        "shsb_mesh_load_obj": [vp, C.c_char_p, P(C.c_uint32)],
+        "shsb_texture_load_png": [vp, C.c_char_p, C.c_int32, P(C.c_uint32)],
+        "shsb_mesh_info": [vp, C.c_uint32, P(C.c_uint32)],
+        "shsb_mesh_download": [vp, C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_uint32)],
+        "shsb_texture_info": [vp, C.c_uint32, P(C.c_int32)],
+        "shsb_texture_download": [vp, C.c_uint32, P(C.c_uint8), C.c_size_t],
         "shsb_texture_upload": [vp, P(C.c_uint8), C.c_int32, C.c_int32, P(C.c_uint32)],
         "shsb_texture_destroy": [vp, C.c_uint32],
         "shsb_rt_create": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, P(C.c_uint32)],

@@ -28,6 +28,7 @@
 
 #include "../../include/shsb.h"
 #include "host_math.hpp"
+#include "asset_loaders.hpp"
 #include "shsb_dev.cuh"
 
 using namespace shsb;
@@ -171,7 +172,11 @@ namespace
                 int spins = 0;
                 while (gen_.load() == seen)
                 {
+#if defined(__x86_64__) || defined(__i386__)
                     __builtin_ia32_pause();
+#else
+                    std::this_thread::yield(); // aarch64 (Grace) hosts have no pause intrinsic of that name
+#endif
                     if ((++spins & 63) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2))
                     {
                         std::unique_lock<std::mutex> lk(m_);
@@ -1275,6 +1280,17 @@ namespace
             for (uint32_t t = 0; t < p.item.tri_count; t += 128) blocks.push_back(make_uint2(item_index, t));
             tri_cursor += p.item.tri_count;
         }
+        const double t_stage = now_us();
+        ctx->host_us[0] += t_stage - t_items;
+        if (int rc = upload_staging(ctx, items, blocks)) return rc;
+        ctx->host_us[1] += now_us() - t_stage;
+        job.n_items = (uint32_t)items.size();
+        job.n_blocks = (uint32_t)blocks.size();
+        job.n_src_tris = tri_cursor;
+        const int rc = run_frame(ctx, job, out_stats, cull);
+        if (rc != SHSB_OK) return rc; // a failed submission leaves the motion history as it was
+        frame_used_targets(job.tile_stream, job.frame_no, used, 5);
+        // Context::history (pass_pbr_forward.hpp:212-213): committed once the frame is on its way
         if (lit_pass && history_partial)
         {
             ctx->hist_keys.clear();
@@ -1289,15 +1305,6 @@ namespace
             ctx->hist_index_valid = false;
             ctx->has_prev_frame = true;
         }
-        const double t_stage = now_us();
-        ctx->host_us[0] += t_stage - t_items;
-        if (int rc = upload_staging(ctx, items, blocks)) return rc;
-        ctx->host_us[1] += now_us() - t_stage;
-        job.n_items = (uint32_t)items.size();
-        job.n_blocks = (uint32_t)blocks.size();
-        job.n_src_tris = tri_cursor;
-        const int rc = run_frame(ctx, job, out_stats, cull);
-        if (rc == SHSB_OK) frame_used_targets(job.tile_stream, job.frame_no, used, 5);
         return rc;
     }
 }
@@ -1535,6 +1542,7 @@ SHSB_API int32_t shsb_mesh_upload(shsb_ctx ctx, const float* positions, uint32_t
 SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     MeshSlot* m = get_mesh(ctx, mesh);
     if (!m) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh);
     sync_all(ctx);
@@ -1547,6 +1555,7 @@ SHSB_API int32_t shsb_mesh_destroy(shsb_ctx ctx, shsb_mesh mesh)
 SHSB_API int32_t shsb_texture_upload(shsb_ctx ctx, const uint8_t* rgba, int32_t w, int32_t h, shsb_tex* out_tex)
 {
     if (!ctx || !out_tex || !rgba || w <= 0 || h <= 0) return ctx ? fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad texture arguments") : SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     TexSlot t;
     t.live = true; t.w = w; t.h = h;
     CK(cudaMalloc(&t.texels, (size_t)w * h * 4));
@@ -1561,6 +1570,7 @@ SHSB_API int32_t shsb_texture_upload(shsb_ctx ctx, const uint8_t* rgba, int32_t 
 SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     if (tex == 0 || tex > ctx->textures.size() || !ctx->textures[tex - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", tex);
     sync_all(ctx);
     cudaFree(ctx->textures[tex - 1].texels);
@@ -1569,10 +1579,73 @@ SHSB_API int32_t shsb_texture_destroy(shsb_ctx ctx, shsb_tex tex)
     return SHSB_OK;
 }
 
+// ---------------------------------------------------------------------------------------- on-disk fixtures
+SHSB_API int32_t shsb_mesh_load_obj(shsb_ctx ctx, const char* path, shsb_mesh* out_mesh)
+{
+    if (!ctx || !path || !out_mesh) return SHSB_E_INVALID_ARGUMENT;
+    shsb_loaders::ObjMesh m;
+    const std::string err = shsb_loaders::load_obj(path, m);
+    if (!err.empty()) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "%s", err.c_str());
+    const uint32_t nv = (uint32_t)(m.positions.size() / 3);
+    return shsb_mesh_upload(ctx, m.positions.data(), nv, m.normals.data(), nv, m.uvs.data(), nv, m.indices.data(), (uint32_t)m.indices.size(), out_mesh);
+}
+
+SHSB_API int32_t shsb_texture_load_png(shsb_ctx ctx, const char* path, int32_t flip_y, shsb_tex* out_tex)
+{
+    if (!ctx || !path || !out_tex) return SHSB_E_INVALID_ARGUMENT;
+    std::vector<unsigned char> rgba;
+    int w = 0, h = 0;
+    const std::string err = shsb_loaders::load_png(path, flip_y != 0, rgba, w, h);
+    if (!err.empty()) return fail(ctx, err.find("not supported") != std::string::npos || err.find("unsupported") != std::string::npos ? SHSB_E_UNSUPPORTED : SHSB_E_INVALID_ARGUMENT, "%s", err.c_str());
+    return shsb_texture_upload(ctx, rgba.data(), w, h, out_tex);
+}
+
+SHSB_API int32_t shsb_mesh_info(shsb_ctx ctx, shsb_mesh mesh, uint32_t out_counts4[4])
+{
+    if (!ctx || !out_counts4) return SHSB_E_INVALID_ARGUMENT;
+    MeshSlot* m = get_mesh(ctx, mesh);
+    if (!m) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh);
+    out_counts4[0] = m->n_positions; out_counts4[1] = m->n_normals; out_counts4[2] = m->n_uvs; out_counts4[3] = m->n_indices;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_mesh_download(shsb_ctx ctx, shsb_mesh mesh, float* positions, float* normals, float* uvs, uint32_t* indices)
+{
+    if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    MeshSlot* m = get_mesh(ctx, mesh);
+    if (!m) return fail(ctx, SHSB_E_INVALID_HANDLE, "mesh handle %u is not live", mesh);
+    CK(cudaSetDevice(ctx->device));
+    if (positions && m->n_positions) CK(cudaMemcpy(positions, m->positions, (size_t)m->n_positions * 12, cudaMemcpyDeviceToHost));
+    if (normals && m->n_normals) CK(cudaMemcpy(normals, m->normals, (size_t)m->n_normals * 12, cudaMemcpyDeviceToHost));
+    if (uvs && m->n_uvs) CK(cudaMemcpy(uvs, m->uvs, (size_t)m->n_uvs * 8, cudaMemcpyDeviceToHost));
+    if (indices && m->n_indices) CK(cudaMemcpy(indices, m->indices, (size_t)m->n_indices * 4, cudaMemcpyDeviceToHost));
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_texture_info(shsb_ctx ctx, shsb_tex tex, int32_t out_wh2[2])
+{
+    if (!ctx || !out_wh2) return SHSB_E_INVALID_ARGUMENT;
+    if (tex == 0 || tex > ctx->textures.size() || !ctx->textures[tex - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", tex);
+    out_wh2[0] = ctx->textures[tex - 1].w; out_wh2[1] = ctx->textures[tex - 1].h;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_texture_download(shsb_ctx ctx, shsb_tex tex, uint8_t* rgba, size_t bytes)
+{
+    if (!ctx || !rgba) return SHSB_E_INVALID_ARGUMENT;
+    if (tex == 0 || tex > ctx->textures.size() || !ctx->textures[tex - 1].live) return fail(ctx, SHSB_E_INVALID_HANDLE, "texture handle %u is not live", tex);
+    const TexSlot& t = ctx->textures[tex - 1];
+    if (bytes != (size_t)t.w * t.h * 4) return fail(ctx, SHSB_E_SIZE_MISMATCH, "texture is %zu bytes, caller passed %zu", (size_t)t.w * t.h * 4, bytes);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(rgba, t.texels, bytes, cudaMemcpyDeviceToHost));
+    return SHSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------- render targets
 SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h, float zn, float zf, shsb_rt* out_rt)
 {
     if (!ctx || !out_rt) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     if (w <= 0 || h <= 0 || kind < SHSB_RT_COLOR_HDR || kind > SHSB_RT_SHADOW) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "bad render-target description");
     RtSlot r;
     r.live = true; r.kind = kind; r.w = w; r.h = h; r.zn = zn; r.zf = zf;
@@ -1608,6 +1681,7 @@ SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h
 SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     RtSlot* r = peek_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     sync_all(ctx);
@@ -1620,6 +1694,7 @@ SHSB_API int32_t shsb_rt_destroy(shsb_ctx ctx, shsb_rt rt)
 SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* value)
 {
     if (!ctx || !value) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     void* p = nullptr;
@@ -1637,6 +1712,7 @@ SHSB_API int32_t shsb_rt_clear(shsb_ctx ctx, shsb_rt rt, int32_t plane, const vo
 SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const void* src, size_t bytes)
 {
     if (!ctx || !src) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     void* p = nullptr;
@@ -1652,6 +1728,7 @@ SHSB_API int32_t shsb_rt_upload(shsb_ctx ctx, shsb_rt rt, int32_t plane, const v
 SHSB_API int32_t shsb_rt_download(shsb_ctx ctx, shsb_rt rt, int32_t plane, void* dst, size_t bytes)
 {
     if (!ctx || !dst) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     void* p = nullptr;
@@ -1697,6 +1774,7 @@ SHSB_API int32_t shsb_rt_download_async(shsb_ctx ctx, shsb_rt rt, int32_t plane,
 SHSB_API int32_t shsb_rt_device_ptr(shsb_ctx ctx, shsb_rt rt, int32_t plane, void** out_ptr, size_t* out_bytes)
 {
     if (!ctx || !out_ptr) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     RtSlot* r = get_rt(ctx, rt);
     if (!r) return fail(ctx, SHSB_E_INVALID_HANDLE, "render target %u is not live", rt);
     void* p = nullptr;
@@ -2607,6 +2685,7 @@ SHSB_API int32_t shsb_tile_depth_range(shsb_ctx ctx, shsb_rt depth_motion_rt, ui
 SHSB_API int32_t shsb_tile_depth_range_download(shsb_ctx ctx, float* out_min, float* out_max, size_t n_tiles)
 {
     if (!ctx || !out_min || !out_max) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     if (!ctx->range_ts) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile depth ranges: call shsb_tile_depth_range first");
     const size_t tiles = (size_t)((ctx->range_w + ctx->range_ts - 1) / ctx->range_ts) * ((ctx->range_h + ctx->range_ts - 1) / ctx->range_ts);
     if (n_tiles != tiles) return fail(ctx, SHSB_E_SIZE_MISMATCH, "caller passed %zu tiles, ranges have %zu", n_tiles, tiles);
@@ -2690,6 +2769,7 @@ SHSB_API int32_t shsb_light_cull_ex(shsb_ctx ctx, const ShsbLightCullDesc* d, co
 SHSB_API int32_t shsb_cluster_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     if (!ctx->cluster_slices) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no cluster bins: call shsb_light_cull_ex(SHSB_LIGHT_CULL_CLUSTERED) first");
     const LightLists& L = ctx->cluster_lists;
     const size_t bins = (size_t)((L.w + L.ts - 1) / L.ts) * ((L.h + L.ts - 1) / L.ts) * ctx->cluster_slices;
@@ -2704,6 +2784,7 @@ SHSB_API int32_t shsb_cluster_lists_download(shsb_ctx ctx, uint32_t* counts, siz
 SHSB_API int32_t shsb_light_lists_download(shsb_ctx ctx, uint32_t* counts, size_t n_counts, uint32_t* indices, size_t n_indices)
 {
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     if (ctx->lists_cur < 0) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "no tile light lists: call shsb_light_cull first");
     const LightLists& L = ctx->lists[ctx->lists_cur];
     const size_t tiles = (size_t)((L.w + L.ts - 1) / L.ts) * ((L.h + L.ts - 1) / L.ts);
@@ -2962,6 +3043,7 @@ SHSB_API int32_t shsb_timing_enable(shsb_ctx ctx, int32_t enable)
 SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames)
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
@@ -2986,6 +3068,7 @@ SHSB_API int32_t shsb_timing_collect(shsb_ctx ctx, float* out_ms, size_t cap_fra
 SHSB_API int32_t shsb_timing_collect_abs(shsb_ctx ctx, float* out_ms, size_t cap_frames, size_t* out_frames)
 {
     if (!ctx || !out_frames) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     const size_t frames = std::min(ctx->timing_used / TIMING_EVENTS_PER_FRAME, cap_frames);
@@ -3012,6 +3095,7 @@ SHSB_API int32_t shsb_host_submit_us(shsb_ctx ctx, double out_us[8], int32_t res
 SHSB_API int32_t shsb_last_stage_ms(shsb_ctx ctx, float out_ms[8])
 {
     if (!ctx || !out_ms) return SHSB_E_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
     for (cudaStream_t st : ctx->front_streams) CK(cudaStreamSynchronize(st));
     for (cudaStream_t st : ctx->tile_streams) CK(cudaStreamSynchronize(st));
     for (int i = 0; i < 8; ++i) out_ms[i] = 0.0f;

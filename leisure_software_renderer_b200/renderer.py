@@ -6,6 +6,7 @@ Everything here forwards to libshsb.so; nothing is computed in Python.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -111,6 +112,31 @@ class Context:
         n = C.c_size_t()
         _check(self.lib, self.h, self.lib.shsb_rt_device_ptr(self.h, rt, plane, C.byref(p), C.byref(n)), "shsb_rt_device_ptr")
         return p.value, n.value
+
+    # ---- on-disk fixtures (Wavefront OBJ / PNG)
+    def mesh_load_obj(self, path: str) -> int:
+        out = C.c_uint32()
+        _check(self.lib, self.h, self.lib.shsb_mesh_load_obj(self.h, os.fsencode(path), C.byref(out)), "shsb_mesh_load_obj")
+        return out.value
+
+    def texture_load_png(self, path: str, flip_y=True) -> int:
+        out = C.c_uint32()
+        _check(self.lib, self.h, self.lib.shsb_texture_load_png(self.h, os.fsencode(path), int(bool(flip_y)), C.byref(out)), "shsb_texture_load_png")
+        return out.value
+
+    def mesh_download(self, mesh) -> dict:
+        n = np.zeros(4, np.uint32)
+        _check(self.lib, self.h, self.lib.shsb_mesh_info(self.h, mesh, capi.u32ptr(n)), "shsb_mesh_info")
+        pos, nrm, uv, idx = np.zeros((n[0], 3), np.float32), np.zeros((n[1], 3), np.float32), np.zeros((n[2], 2), np.float32), np.zeros(n[3], np.uint32)
+        _check(self.lib, self.h, self.lib.shsb_mesh_download(self.h, mesh, capi.fptr(pos), capi.fptr(nrm), capi.fptr(uv), capi.u32ptr(idx)), "shsb_mesh_download")
+        return {"positions": pos, "normals": nrm, "uvs": uv, "indices": idx}
+
+    def texture_download(self, tex) -> np.ndarray:
+        wh = np.zeros(2, np.int32)
+        _check(self.lib, self.h, self.lib.shsb_texture_info(self.h, tex, wh.ctypes.data_as(C.POINTER(C.c_int32))), "shsb_texture_info")
+        out = np.zeros((int(wh[1]), int(wh[0]), 4), np.uint8)
+        _check(self.lib, self.h, self.lib.shsb_texture_download(self.h, tex, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size), "shsb_texture_download")
+        return out
 
     # ---- passes
     def rasterize_mesh(self, mesh, shader_id, uniforms: Uniforms, hdr_rt, depth_rt=0, cull_mode=capi.CULL_BACK,
