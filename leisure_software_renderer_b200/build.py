@@ -97,7 +97,22 @@ def build_phase_clocks() -> str:
     return out
 
 
+def build_no_stores() -> str:
+    """Debug variant libshsb_nostore.so: tile_raster.cu with -DSHSB_NO_STORES (tools/gpu_store_bound.sh, via SHSB_LIB)."""
+    build()
+    cc = nvcc()
+    o = os.path.join(OBJ, "tile_raster_nostore.o")
+    subprocess.run([cc, *ARCH, *COMMON, "-DSHSB_NO_STORES", "-c", os.path.join(CSRC, "tile_raster.cu"), "-o", o], check=True)
+    out = os.path.join(HERE, "libshsb_nostore.so")
+    objs = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "tile_raster.cu"] + [o]
+    subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC", "-lz"], check=True)
+    return out
+
+
 if __name__ == "__main__":
+    if "--no-stores" in sys.argv:
+        print(build_no_stores())
+        sys.exit(0)
     if "--phase-clocks" in sys.argv:
         print(build_phase_clocks())
         sys.exit(0)

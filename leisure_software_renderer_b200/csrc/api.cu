@@ -334,6 +334,7 @@ struct shsb_context_t
     int copy_flip = 0;
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr, ev_front_sync = nullptr;
     bool shadow_direct = true;           // SHSB_SHADOW_DIRECT=0: every shadow-pass triangle through the binned tile path
+    bool hiz = false;                    // SHSB_HIZ=1: hierarchical-Z early reject in the tile kernel for asynchronous frames without AOVs
     cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
 
     // depth-range / clustered light culling (shsb_light_cull_ex): per-tile view-depth ranges, per-slice NDC bounds, cluster bins
@@ -655,6 +656,7 @@ namespace
         FrameConst& fc = job.fc;
         fc.tiles_x = (fc.W + TILE - 1) / TILE;
         fc.tiles_y = (fc.H + TILE - 1) / TILE;
+        fc.hiz = (ctx->hiz && !out_stats && !fc.write_aovs) ? 1 : 0; // hidden fragments a Hi-Z reject skips are not counted: only where nobody reads the counters
         const uint32_t n_tiles = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
         if (fc.W > 65535 || fc.H > 65535) return fail(ctx, SHSB_E_UNSUPPORTED, "render target larger than 65535 pixels on a side");
         if ((job.n_src_tris + 1) * 8ull >= 0xFFFFFFFFull) return fail(ctx, SHSB_E_UNSUPPORTED, "more than 2^29 source triangles in one submission");
@@ -1364,6 +1366,7 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_front_sync, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_SHADOW_DIRECT")) ctx->shadow_direct = !(e[0] == '0');
+    if (const char* e = std::getenv("SHSB_HIZ")) ctx->hiz = e[0] == '1';
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_overflow, 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess;

@@ -192,6 +192,10 @@ namespace shsb
         uint32_t sky_faces[6];  // indices into the texture table (cubemap), all valid when sky_kind == cubemap
         // sort-first screen partition: the tile rows this submission owns (ShsbFrameParams::own_row_*); count 0 = all rows
         int own_first, own_count, own_stride;
+        // hierarchical-Z early reject in the tile kernel (per 8x4 block: skip a staged triangle whose conservative nearest depth is
+        // behind everything the block holds).  Only for submissions nobody reads fragment counters / AOVs of: a skipped triangle's
+        // hidden fragments are not counted.
+        int hiz;
     };
 
     __host__ __device__ __forceinline__ bool owned_row(const FrameConst& fc, int ty)

@@ -36,6 +36,15 @@ namespace shsb
 #ifndef TILE_MIN_CTAS
 #define TILE_MIN_CTAS 4
 #endif
+        // Debug build only (tools/gpu_store_bound.sh, libshsb_nostore.so): the tile kernel's render-target stores of tiles WITH geometry
+        // are predicated on a value no computation produces, so that everything is still computed but nothing is written -- the time
+        // difference to the normal build bounds what any other store mechanism (TMA bulk tensor stores from a shared-memory tile)
+        // could gain.  Frames rendered by that build are garbage by construction.
+#ifdef SHSB_NO_STORES
+#define STORE_IF(v) if (__float_as_uint(v) == 0x7fc12345u)
+#else
+#define STORE_IF(v)
+#endif
         constexpr float PI_F = 3.14159265358979323846f;
 
         struct V3 { float x, y, z; };
@@ -431,8 +440,8 @@ namespace shsb
                 const float t = xdiv((float)py, (float)max(1, fc.H - 1));
                 r = xadd(0.06f, xmul(0.08f, t)); g = xadd(0.08f, xmul(0.10f, t)); b = xadd(0.12f, xmul(0.12f, t));
             }
-            fb.hdr[pix] = make_float4(r, g, b, 1.0f);
-            if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(r, g, b, fc.exposure, fc.inv_gamma);
+            STORE_IF(r) fb.hdr[pix] = make_float4(r, g, b, 1.0f);
+            if (fc.fuse_tonemap && fb.ldr) { const uchar4 l = tonemap_pixel(r, g, b, fc.exposure, fc.inv_gamma); STORE_IF(__uint_as_float((uint32_t)l.x * 0x01010101u + 0x7fc12000u)) fb.ldr[pix] = l; }
         }
 
         constexpr int LIGHT_CAP = TILE_THREADS;       // staged lights per pass
@@ -449,6 +458,7 @@ namespace shsb
             RasterRec* s_rec = reinterpret_cast<RasterRec*>(s_stage);
             SmLight* s_light = reinterpret_cast<SmLight*>(s_stage);
             __shared__ uint32_t s_idx[TILE_THREADS];
+            __shared__ float s_znear[TILE_THREADS];               // hierarchical Z: conservative nearest z01 of each staged triangle
             __shared__ unsigned s_wmask[TILE_THREADS / 32][TILE_THREADS / 32]; // [consumer warp][staging warp]
             __shared__ unsigned s_ballot[CAND_PER_THREAD * (TILE_THREADS / 32)]; // light staging: [candidate slot][warp] == ascending light order
             __shared__ float s_box[TILE_THREADS / 32][6];
@@ -539,6 +549,12 @@ namespace shsb
             const float pxf = xadd((float)px, 0.5f), pyf = xadd((float)py, 0.5f);
             const float zrange = xsub(fc.zf, fc.zn);
 
+            // hierarchical Z (north_star): the farthest depth the warp's 8x4 block holds; a staged triangle that cannot be nearer than
+            // that anywhere is skipped before its bbox is even decoded.  Linear view-depth targets only (the bound below is for them).
+            const bool hiz = fc.hiz && fc.has_depth && fc.linear_depth && !fc.shadow_mode;
+            float blk_zmax = 1.0f;
+            bool z_dirty = fc.load_depth != 0; // loaded depths: take the block maximum before the first test
+
             const uint32_t off0 = g.tile_offset[tile];
             const uint32_t off1 = min(off0 + tile_tris, g.list_capacity);
             for (uint32_t base = off0; base < off1; base += TILE_THREADS)
@@ -554,6 +570,17 @@ namespace shsb
                     const float4 q3 = __ldg(src + 3);
                     dst[0] = __ldg(src + 0); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = q3;
                     s_idx[threadIdx.x] = rec;
+                    if (hiz)
+                    {
+                        // z01 = clamp((1 / denom - zn) / (zf - zn)) with denom a (rounded) convex combination of the corners' 1 / w: it cannot
+                        // exceed the largest of them by more than a few ULP, so 1 / max(1 / w) -- shrunk by 1e-5 relative, twice, and 1e-6
+                        // absolute, orders of magnitude above any rounding in the per-pixel expression -- is a lower bound of every
+                        // fragment's depth.  (All 1 / w are positive: records exist only for triangles inside / clipped to w > 0.)
+                        const float4 q1 = dst[1], q2 = dst[2];
+                        const float max_iw = fmaxf(fmaxf(q1.w, q2.x), q2.y);
+                        const float zb = (max_iw > 0.0f) ? ((__fdividef(0.99999f, max_iw) - fc.zn) * __fdividef(0.99999f, fc.zf - fc.zn) - 1e-6f) : 0.0f;
+                        s_znear[threadIdx.x] = zb;
+                    }
                     const uint32_t bx = __float_as_uint(q3.y), by = __float_as_uint(q3.z);
                     sminx = (int)(bx & 0xffffu); smaxx = (int)(bx >> 16);
                     sminy = (int)(by & 0xffffu); smaxy = (int)(by >> 16);
@@ -576,6 +603,16 @@ namespace shsb
                   {
                     const uint32_t j = (uint32_t)k * 32u + (uint32_t)(__ffs(wm) - 1);
                     wm &= wm - 1u;
+                    if (hiz)
+                    {
+                        __syncwarp(); // wm is warp-uniform: every lane is back here once per staged triangle
+                        if (__any_sync(0xffffffffu, z_dirty))
+                        {
+                            blk_zmax = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(bz) : 0u)); // depths are in [0, 1]: bit order == value order
+                            z_dirty = false;
+                        }
+                        if (s_znear[j] > blk_zmax) continue; // strictly behind every pixel of the block: no fragment of it can win (ties need equality)
+                    }
                     const RasterRec& r = s_rec[j];
                     const int minx = (int)(r.bbox_x & 0xffffu), maxx = (int)(r.bbox_x >> 16);
                     const int miny = (int)(r.bbox_y & 0xffffu), maxy = (int)(r.bbox_y >> 16);
@@ -611,7 +648,7 @@ namespace shsb
                             const float z_clip = xadd(xadd(xmul(bu, r.zw0), xmul(bv, r.zw1)), xmul(bw, r.zw2));
                             z01 = gclamp(xadd(xmul(xmul(z_clip, xrcp(denom)), 0.5f), 0.5f), 0.0f, 1.0f);
                         }
-                        if (z01 < bz || (z01 == bz && r.key < bkey)) { bz = z01; bkey = r.key; bidx = s_idx[j]; }
+                        if (z01 < bz || (z01 == bz && r.key < bkey)) { bz = z01; bkey = r.key; bidx = s_idx[j]; z_dirty = true; }
                     }
                     else if (r.key > bkey) { bkey = r.key; bidx = s_idx[j]; }
                   }
@@ -622,7 +659,7 @@ namespace shsb
             // ---------------- resolve: depth + AOVs
             if (valid)
             {
-                if (fb.depth && (fc.has_depth || fc.shadow_mode) && (bkey != KEY_NONE || !fc.load_depth)) fb.depth[pix] = bz;
+                if (fb.depth && (fc.has_depth || fc.shadow_mode) && (bkey != KEY_NONE || !fc.load_depth)) { STORE_IF(bz) fb.depth[pix] = bz; }
                 if (fb.aov_tri_id) fb.aov_tri_id[pix] = (bkey != KEY_NONE) ? (bkey - 1u) : 0xFFFFFFFFu;
                 if (fb.aov_coverage) fb.aov_coverage[pix] = n_cov;
             }
@@ -931,8 +968,8 @@ namespace shsb
             if (!has) { resolve_uncovered(fc, fb, textures, srgb_lut, pix, px, py); return; }
             if (fc.clear_motion && !fc.write_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f); // plane cleared, vectors disabled
             PHASE_MARK(5);
-            fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
-            if (fc.fuse_tonemap && fb.ldr) fb.ldr[pix] = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma);
+            STORE_IF(out_r) fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
+            if (fc.fuse_tonemap && fb.ldr) { const uchar4 l = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma); STORE_IF(__uint_as_float((uint32_t)l.x * 0x01010101u + 0x7fc12000u)) fb.ldr[pix] = l; }
         }
 
         // Digests the 160-byte CullingLightGPU records into the 80-byte form the tile kernel's light loop reads

@@ -332,3 +332,35 @@ def test_asynchronous_overflow_is_reported_not_silent():
         assert np.array_equal(got[0], ctx.rt_download(hdr).view(np.uint32)) and np.array_equal(got[1], ctx.rt_download(dm, capi.PLANE_DEPTH).view(np.uint32))
     finally:
         ctx.close()
+
+
+def test_hierarchical_z_reject_changes_no_pixel(monkeypatch):
+    """SHSB_HIZ=1: asynchronous frames skip, per 8x4-pixel block, staged triangles whose conservative nearest depth is behind
+    everything the block already holds.  A scene with heavy overdraw (a dense grid of Suzannes seen at a grazing angle, plus a frame
+    that PRESERVES a pre-pass depth) must come out bit-identical in depth, HDR and LDR with and without it."""
+    from leisure_software_renderer_b200.renderer import Context
+    base = scenes.scene_c5(w=640, h=360, nx=24, nz=24).with_camera((0, 0.6, -38), (0, 0.4, 40))   # grazing: rows of Suzannes behind each other, overdraw 4
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SHSB_HIZ", flag)
+        ctx = Context(0)
+        try:
+            g = harness.GpuScene(ctx, base)
+            fp = capi.FrameParams.from_buffer_copy(base.fp)
+            fp.light_culling = 1
+            ctx.frame_forward_plus(base.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)
+            ctx.sync()
+            a = (ctx.rt_download(g.hdr).view(np.uint32), ctx.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32), ctx.rt_download(g.ldr))
+            fp.light_culling = 0
+            ctx.pass_depth_prepass(base.scene, fp, g.dm)
+            ctx.pass_pbr_forward(base.scene, fp, g.hdr, g.dm, preserve_existing_depth=True, want_stats=False)   # loads the depth plane: Hi-Z starts from it
+            ctx.sync()
+            b = (ctx.rt_download(g.hdr).view(np.uint32), ctx.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32))
+            st = ctx.frame_forward_plus(base.scene, fp, g.hdr, g.dm, g.ldr).as_dict()
+            out[flag] = (a, b, st)
+            g.release()
+        finally:
+            ctx.close()
+    assert out["0"][2]["frag_covered"] > 1.5 * out["0"][2]["frag_shaded"] > 0, "the scene has no overdraw to reject"
+    for x, y, what in zip(out["0"][0] + out["0"][1], out["1"][0] + out["1"][1], ("hdr", "depth", "ldr", "hdr (preserved depth)", "depth (preserved)")):
+        assert np.array_equal(x, y), f"Hi-Z changed the {what} plane"

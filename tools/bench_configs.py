@@ -49,7 +49,7 @@ def run(name, sd, iters, shadow=False, forward_plus=False):
         if shadow:
             lvp = ctx.pass_shadow_map(sd.scene, fp, sh)
             out["shadow_ms"] = float(ctx.last_stage_ms()[5]) if stats else 0.0
-            st = ctx.pass_pbr_forward(sd.scene, fp, hdr, dm, sh, lvp)
+            st = ctx.pass_pbr_forward(sd.scene, fp, hdr, dm, sh, lvp, want_stats=stats)
             ctx.pass_tonemap(hdr, ldr, fp.exposure, fp.gamma)
         else:
             st = ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=stats)
