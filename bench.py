@@ -50,7 +50,10 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The driver's 20-step run times a
+    3 ms region, far below nvidia-smi's sampling period, so the samples come from NVML directly (nvidia_ml_py: one query is ~0.1 ms)
+    on a helper thread, about one per millisecond; nvidia-smi is the fall-back.  `post_roll` keeps sampling while the caller
+    runs more (untimed) steps under the same load when the region itself was too short for a handful of samples."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -58,8 +61,44 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.samples = []          # (sm_mhz, reasons bitmask) from NVML
+        self.nvml = None
+        self._stop = threading.Event()
+        self.in_region = 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative ordinal -> NVML handle through the CUDA device's UUID when torch can tell it
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, reasons))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,7 +115,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def n_samples(self) -> int:
+        return len(self.samples) if self.nvml is not None else len(self.lines)
+
+    def mark_region_end(self):
+        self.in_region = self.n_samples()
+
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            n = self.nvml
+            names = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)), ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)), ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+            reasons = sorted({name for _, r in self.samples for name, bit in names if r & bit})
+            sm = [m for m, _ in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "samples_in_timed_region": self.in_region, "source": "NVML, ~1 sample / ms; samples beyond the timed region were taken while the same steps kept running"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": self.in_region, "source": "nvidia-smi -lms 20"}
 
 
 def ncu_traffic():
@@ -264,11 +319,21 @@ def run_ours(args):
         stages = ctx.timing_collect() if not e2e else None
         if not e2e:
             ctx.timing_enable(False)
-        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            sampler.mark_region_end()
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if batch:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), stages, clocks, ctx.launch_count() - launches0, host_ms
+        launches = ctx.launch_count() - launches0
+        # A 20-step region lasts a few milliseconds: keep the same steps running (untimed) for about 60 ms so that the sampler sees
+        # the load for more than a handful of samples.  The count is derived from the all-reduced time: every rank runs the same
+        # number of steps (a batch step ends in the root's wait for every rank's commit).
+        n_roll = int(min(2000, max(8, 60.0 / max(float(t.item()) / args.steps, 1e-3))))
+        for i in range(n_roll):
+            step(i, e2e)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        return float(t.item()), stages, clocks, launches, host_ms
 
     ms_dev, stages, clocks, launches, host_dev = timed(False)
     ms_e2e, _, clocks_e2e, _, host_e2e = timed(True)
