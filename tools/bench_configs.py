@@ -55,7 +55,7 @@ def run(name, sd, iters, shadow=False, forward_plus=False):
             st = ctx.frame_forward_plus(sd.scene, fp, hdr, dm, ldr, want_stats=stats)
         if stats:
             ms = ctx.last_stage_ms()
-            out.update({"vertex_clip_setup_ms": float(ms[0]), "binning_ms": float(ms[1]), "tile_ms": float(ms[2]), "stats": st.as_dict()})
+            out.update({"vertex_clip_setup_ms": float(ms[0]), "binning_ms": float(ms[1]), "tile_ms": float(ms[2]), "light_cull_ms": float(ms[3]), "front_to_tile_end_ms": float(ms[5]), "stats": st.as_dict()})
         return out
 
     info = frame(stats=True)   # sizes the arenas
