@@ -118,6 +118,13 @@ class ClockSampler:
     def n_samples(self) -> int:
         return len(self.samples) if self.nvml is not None else len(self.lines)
 
+    def mark_region_start(self):
+        """Samples taken before this point (the warm-up) are dropped."""
+        if self.nvml is not None:
+            del self.samples[:]
+        else:
+            self.lines.clear()
+
     def mark_region_end(self):
         self.in_region = self.n_samples()
 
@@ -288,16 +295,18 @@ def run_ours(args):
             ctx.timing_enable(False)
 
     def timed(e2e):
-        warm(e2e)
-        launches0 = ctx.launch_count()
         sampler = ClockSampler(local_rank)
         if rank == 0:
-            sampler.start()
+            sampler.start()          # the helper thread is up and sampling before the region starts (the warm-up runs under the same load)
+        warm(e2e)
+        launches0 = ctx.launch_count()
         barrier()
         e0, e1, e1g = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         if not e2e:
             ctx.timing_enable(TIMING_STRIDE)   # stage events on every 8th frame only: they are extra commands on the critical stream
         ctx.host_submit_us(reset=True)
+        if rank == 0:
+            sampler.mark_region_start()
         e0.record(stream)
         t_host = time.perf_counter()
         for i in range(args.steps):
