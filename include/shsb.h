@@ -691,6 +691,57 @@ SHSB_API int32_t shsb_select_object_lights_from_bins(shsb_ctx ctx, const float* 
                                                      const void* records160, uint32_t n_lights, int32_t cull_mode, uint32_t* out_counts,
                                                      uint32_t* out_indices8, float* out_dist2_8, uint32_t* out_candidates);
 
+/* ------------------------------------------------------------------ flat-shaded mesh draws: the consumer of the light selections
+ *
+ * The reference's software draws of a DebugMesh (geometry/jolt_debug_draw.hpp:36-52; vertices + indices) with ONE colour per
+ * triangle, depth-tested into an RT_ColorLDR and a float depth buffer (sw_render/debug_draw.hpp:64-112: a fragment replaces the texel
+ * when its depth is strictly below the stored one; depths outside [0, 1] are dropped).  The device takes a whole BATCH of draws per
+ * call -- the demos issue one per visible object -- and resolves every texel to the minimum of (depth, draw order, triangle order),
+ * which is what the reference's serial loop leaves.  Stream-ordered on the context's main stream like every other target writer;
+ * the call returns after the set-up pass (one 4-byte read), the raster and resolve kernels are still in flight.
+ *   canvas_ldr   SHSB_RT_COLOR_LDR, texel (x, y) = RT_ColorLDR::set_rgba(x, y): canvas_w / canvas_h of the reference are its size
+ *   depth        depth plane of a SHSB_RT_SHADOW / SHSB_RT_DEPTH_MOTION target of the same size = the std::span<float> depth buffer,
+ *                non-negative; clear it to 1.0f with shsb_rt_clear like the demos' std::fill
+ * Meshes: shsb_mesh_upload(positions, indices) (no normals / uvs needed); an index beyond the vertices skips its triangle. */
+typedef struct ShsbFlatDraw
+{
+    shsb_mesh mesh;
+    uint32_t selection_count;  /* LightSelection::count (lighting/light_runtime.hpp:126-131), <= 8; multi-light draw only */
+    float model[16];
+    float base_color[3];
+    uint32_t selection[8];     /* LightSelection::indices = one row of shsb_collect_object_lights / shsb_select_object_lights_from_bins */
+} ShsbFlatDraw;
+
+/* shs::LightProperties (lighting/light_runtime.hpp:52-71) as plain data, plus the LightType (light_types.hpp:24-32) of the
+ * LightInstance's model, which selects the ILightModel::sample the draw evaluates: 1 Point, 2 Spot, 3 RectArea, 4 TubeArea (other
+ * types contribute nothing: the demo registers no model for them). */
+typedef struct ShsbLightProperties
+{
+    float color[3], intensity;
+    float position_ws[3], range;
+    float direction_ws[3], inner_angle_rad;
+    float right_ws[3], outer_angle_rad;
+    float up_ws[3], tube_half_length;
+    float rect_half_extents[2], tube_radius, attenuation_power;
+    float attenuation_bias, attenuation_cutoff;
+    uint32_t attenuation_model;  /* LightAttenuationModel: 0 Linear, 1 Smooth, 2 InverseSquare */
+    uint32_t flags;
+    uint32_t light_type;
+    uint32_t reserved[3];
+} ShsbLightProperties; /* 128 bytes */
+
+/* debug_draw::draw_mesh_blinn_phong_transformed (sw_render/debug_draw.hpp:153-203) for n_draws meshes in order: per triangle
+ * ambient 0.18 + 0.72 N.L + 0.35 (N.H)^32 against one directional light, face normal cross(p2 - p0, p1 - p0). */
+SHSB_API int32_t shsb_flat_draw_blinn_phong(shsb_ctx ctx, const ShsbFlatDraw* draws, uint32_t n_draws, const float view_proj[16], const float camera_pos[3],
+                                            const float light_dir_ws[3], shsb_rt canvas_ldr, shsb_rt depth);
+
+/* draw_mesh_multi_light_transformed (exp-plumbing/hello_light_types_culling_sw.cpp:366-422) for n_draws objects in order: per
+ * triangle the ambient + hemisphere term, then light.model->sample(props, centroid, n, V) of every light of the draw's selection
+ * (entries >= n_lights are skipped, :411): Point / Spot / RectArea / TubeArea models of lighting/light_runtime.hpp:291-520 with
+ * eval_local_light_brdf / eval_distance_attenuation (:182-237).  std::pow / std::cos are evaluated in double and rounded once. */
+SHSB_API int32_t shsb_flat_draw_multi_light(shsb_ctx ctx, const ShsbFlatDraw* draws, uint32_t n_draws, const float view_proj[16], const float camera_pos[3],
+                                            const ShsbLightProperties* lights, uint32_t n_lights, shsb_rt canvas_ldr, shsb_rt depth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ Per-file flags:
   geometry.cu, light_cull.cu   --fmad=false   (every expression decides coverage / depth / list bits)
   post_passes.cu               --fmad=false   (RGBA8 outputs of the post passes are bit-exact)
   scene_cull.cu                --fmad=false   (object classes / light selections are bit-exact)
+  flat_draw.cu                 --fmad=false   (flat-shaded draws: depth bit-exact, colours the reference's expressions)
   legacy.cu, legacy2.cu        --fmad=false   (the legacy demo variants: every expression is the reference's, unfused)
   tile_raster.cu, binning.cu   FMA allowed; exact expressions use __fmul_rn/__fadd_rn/__fdiv_rn explicitly
   api.cu                       host code with -ffp-contract=off (host float math must equal the reference's)
@@ -31,6 +32,7 @@ SOURCES = {
     "legacy.cu": ["--fmad=false"],
     "legacy2.cu": ["--fmad=false"],
     "scene_cull.cu": ["--fmad=false"],
+    "flat_draw.cu": ["--fmad=false"],
     "tile_raster.cu": [],
     "gather.cu": [],
     "api.cu": [],

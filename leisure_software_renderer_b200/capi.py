@@ -106,6 +106,20 @@ class Legacy2Uniforms(C.Structure):
                 ("job_tile_w", C.c_int32), ("job_tile_h", C.c_int32)]
 
 
+class FlatDraw(C.Structure):
+    """ShsbFlatDraw: one flat-shaded draw of a batch (a DebugMesh, its model matrix and base colour, the object's LightSelection)."""
+    _fields_ = [("mesh", C.c_uint32), ("selection_count", C.c_uint32), ("model", F16), ("base_color", F3), ("selection", C.c_uint32 * 8)]
+
+
+# ShsbLightProperties (128 bytes): shs::LightProperties (lighting/light_runtime.hpp:53-72) + the LightType of the instance's model
+LIGHT_PROPS_DTYPE = np.dtype([("color", "<f4", 3), ("intensity", "<f4"), ("position_ws", "<f4", 3), ("range", "<f4"), ("direction_ws", "<f4", 3), ("inner_angle_rad", "<f4"),
+                              ("right_ws", "<f4", 3), ("outer_angle_rad", "<f4"), ("up_ws", "<f4", 3), ("tube_half_length", "<f4"), ("rect_half_extents", "<f4", 2),
+                              ("tube_radius", "<f4"), ("attenuation_power", "<f4"), ("attenuation_bias", "<f4"), ("attenuation_cutoff", "<f4"), ("attenuation_model", "<u4"),
+                              ("flags", "<u4"), ("light_type", "<u4"), ("reserved", "<u4", 3)])
+assert LIGHT_PROPS_DTYPE.itemsize == 128
+LIGHT_TYPE_POINT, LIGHT_TYPE_SPOT, LIGHT_TYPE_RECT_AREA, LIGHT_TYPE_TUBE_AREA = 1, 2, 3, 4
+
+
 class LightCullDesc(C.Structure):
     """ShsbLightCullDesc: arguments of the bin builders of lighting/jolt_light_culling.hpp."""
     _fields_ = [("view_proj", F16), ("viewport_w", C.c_uint32), ("viewport_h", C.c_uint32), ("tile_size", C.c_uint32),
@@ -217,6 +231,8 @@ def load_library(path: str | None = None):
         "shsb_software_occlusion": [vp, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32), P(C.c_float), P(C.c_uint32), C.c_uint32, P(C.c_float), C.c_uint32,
                                     P(C.c_uint32), C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32, C.c_int32, C.c_float, C.c_int32, P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),
                                     P(C.c_float)],
+        "shsb_flat_draw_blinn_phong": [vp, P(FlatDraw), C.c_uint32, P(C.c_float), P(C.c_float), P(C.c_float), C.c_uint32, C.c_uint32],
+        "shsb_flat_draw_multi_light": [vp, P(FlatDraw), C.c_uint32, P(C.c_float), P(C.c_float), vp, C.c_uint32, C.c_uint32, C.c_uint32],
         "shsb_gather_create": [vp, C.c_uint32, C.c_uint32, C.c_size_t, P(C.c_uint32), P(GatherExport)],
         "shsb_gather_open": [vp, P(GatherExport), C.c_uint32, P(C.c_uint32)],
         "shsb_gather_destroy": [vp, C.c_uint32],

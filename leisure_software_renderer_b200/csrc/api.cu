@@ -352,6 +352,8 @@ struct shsb_context_t
     DevBuf<uchar4> d_taa_hist;      // TemporalAARuntimeState::history (core/context.hpp:101)
     DevBuf<LegacyTri> d_legacy_tris; // set-up records of the legacy tile-job variant (legacy.cu)
     DevBuf<uint8_t> d_sc_bytes;      // scratch of the scene-level culling calls (scene_cull.cu): inputs and outputs, one allocation
+    DevBuf<uint8_t> d_fd_bytes;      // scratch of the flat-shaded draws (flat_draw.cu): draw / light tables, triangle records, work list, depth keys
+    uint32_t fd_item_cap = 0;        // work-list capacity the last batches needed
     DevBuf<l2::RasterRec> d_l2_raster; // slot records of the legacy render-target demos (legacy2.cu)
     DevBuf<l2::BoxRec> d_l2_box;
     DevBuf<l2::ShadeRec> d_l2_shade;
@@ -1405,6 +1407,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_slice_ndc.p); cudaFree(ctx->d_vis.p); cudaFree(ctx->cluster_lists.counts.p); cudaFree(ctx->cluster_lists.indices.p);
     cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p); cudaFree(ctx->d_legacy_tris.p);
     cudaFree(ctx->d_sc_bytes.p);
+    cudaFree(ctx->d_fd_bytes.p);
     cudaFree(ctx->d_l2_raster.p); cudaFree(ctx->d_l2_box.p); cudaFree(ctx->d_l2_shade.p);
     for (auto& e : ctx->ibls) { cudaFree(e.irradiance); cudaFree(e.prefiltered); }
     for (auto& l : ctx->d_lights) cudaFree(l.p);
@@ -2244,6 +2247,106 @@ SHSB_API int32_t shsb_select_object_lights_from_bins(shsb_ctx ctx, const float* 
     CK(cudaMemcpyAsync(out_candidates, base + o_cand, (size_t)n_objects * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SHSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- flat-shaded mesh draws (sw_render/debug_draw.hpp)
+namespace
+{
+    // One batch of flat-shaded draws into (canvas, depth): see flat_draw.cu.  mode: fd::MODE_BLINN_PHONG / fd::MODE_MULTI_LIGHT.
+    int flat_draw_batch(shsb_ctx ctx, int mode, const ShsbFlatDraw* draws, uint32_t n_draws, const float view_proj[16], const float camera_pos[3], const float light_dir_ws[3],
+                        const ShsbLightProperties* lights, uint32_t n_lights, shsb_rt canvas_rt, shsb_rt depth_rt)
+    {
+        if (!ctx) return SHSB_E_INVALID_ARGUMENT;
+        if ((n_draws && !draws) || !view_proj || !camera_pos || (mode == fd::MODE_BLINN_PHONG && !light_dir_ws) || (n_lights && !lights))
+            return fail(ctx, SHSB_E_INVALID_ARGUMENT, "null argument");
+        CK(cudaSetDevice(ctx->device));
+        RtSlot* canvas = get_rt(ctx, canvas_rt, SHSB_RT_COLOR_LDR);
+        if (!canvas) return fail(ctx, SHSB_E_INVALID_HANDLE, "canvas_ldr is not a live RT_ColorLDR");
+        RtSlot* zb = get_rt(ctx, depth_rt);
+        if (!zb || !zb->depth) return fail(ctx, SHSB_E_INVALID_HANDLE, "depth is not a live target with a depth plane (RT_ShadowDepth / RT_ColorDepthMotion)");
+        if (zb->w != canvas->w || zb->h != canvas->h) return fail(ctx, SHSB_E_SIZE_MISMATCH, "canvas is %dx%d, depth buffer %dx%d", canvas->w, canvas->h, zb->w, zb->h);
+        if (canvas->w > 65535 * 64 || canvas->h > 65535 * 64) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "canvas too large");
+
+        fd::BatchDesc bd{};
+        std::memcpy(bd.view_proj, view_proj, 64);
+        std::memcpy(bd.camera, camera_pos, 12);
+        if (mode == fd::MODE_BLINN_PHONG)
+        {
+            // const glm::vec3 L = glm::normalize(-light_dir_ws), debug_draw.hpp:165
+            const fd::V3 L = fd::glm_normalize(-fd::v3(light_dir_ws));
+            bd.L[0] = L.x; bd.L[1] = L.y; bd.L[2] = L.z;
+        }
+        bd.W = canvas->w; bd.H = canvas->h; bd.mode = mode; bd.n_lights = n_lights;
+
+        std::vector<fd::DrawRec> recs;
+        recs.reserve(n_draws);
+        uint64_t n_tris = 0;
+        for (uint32_t i = 0; i < n_draws; ++i)
+        {
+            const ShsbFlatDraw& d = draws[i];
+            const MeshSlot* mesh = get_mesh(ctx, d.mesh);
+            if (!mesh) return fail(ctx, SHSB_E_INVALID_HANDLE, "draw %u: mesh handle %u is not live", i, d.mesh);
+            if (d.selection_count > 8) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "draw %u: a LightSelection holds at most 8 lights", i);
+            // for (i = 0; i + 2 < indices.size(); i += 3): whole triangles of the index list only (debug_draw.hpp:166)
+            const uint32_t tris = mesh->n_indices / 3;
+            if (tris == 0) continue;
+            fd::DrawRec r{};
+            r.positions = mesh->positions; r.indices = mesh->indices; r.n_positions = mesh->n_positions; r.n_tris = tris;
+            r.tri_base = (uint32_t)n_tris; r.selection_count = d.selection_count;
+            std::memcpy(r.model, d.model, 64); std::memcpy(r.base, d.base_color, 12); std::memcpy(r.selection, d.selection, 32);
+            recs.push_back(r);
+            n_tris += tris;
+            if (n_tris >= 0xFFFFFFFEull) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "more than 2^32 - 2 triangles in one batch");
+        }
+        if (recs.empty()) return SHSB_OK;
+        bd.n_draws = (uint32_t)recs.size(); bd.n_tris = (uint32_t)n_tris;
+
+        const size_t n_px = (size_t)canvas->w * canvas->h;
+        const size_t tri_bytes = flat_tri_record_bytes();
+        if (ctx->fd_item_cap < bd.n_tris + 4096u) ctx->fd_item_cap = bd.n_tris + bd.n_tris / 2 + 4096u;
+        wait_pending_read(ctx, canvas);
+        wait_pending_read(ctx, zb);
+        for (int attempt = 0; attempt < 2; ++attempt)
+        {
+            const size_t o_draws = 0, o_lights = sc_align(recs.size() * sizeof(fd::DrawRec)), o_tris = o_lights + sc_align((size_t)n_lights * sizeof(fd::LightProps)),
+                         o_colours = o_tris + sc_align((size_t)bd.n_tris * tri_bytes), o_items = o_colours + sc_align((size_t)bd.n_tris * 4),
+                         o_total = o_items + sc_align((size_t)ctx->fd_item_cap * 8), o_zkey = o_total + 256, total = o_zkey + n_px * 8;
+            if (int rc = ensure_dev(ctx, ctx->d_fd_bytes, total)) return rc;
+            uint8_t* base = ctx->d_fd_bytes.p;
+            CK(cudaMemcpyAsync(base + o_draws, recs.data(), recs.size() * sizeof(fd::DrawRec), cudaMemcpyHostToDevice, ctx->stream));
+            if (n_lights) CK(cudaMemcpyAsync(base + o_lights, lights, (size_t)n_lights * sizeof(fd::LightProps), cudaMemcpyHostToDevice, ctx->stream));
+            launch_flat_draw_batch(bd, (const fd::DrawRec*)(base + o_draws), (const fd::LightProps*)(base + o_lights), base + o_tris, (uint32_t*)(base + o_colours),
+                                   (uint2*)(base + o_items), ctx->fd_item_cap, (uint32_t*)(base + o_total), (unsigned long long*)(base + o_zkey), zb->depth, true, ctx->stream,
+                                   &ctx->launches);
+            CK(cudaGetLastError());
+            uint32_t n_items = 0;
+            CK(cudaMemcpyAsync(&n_items, base + o_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (n_items > ctx->fd_item_cap)
+            {
+                if (attempt) return fail(ctx, SHSB_E_OVERFLOW, "flat draw: work list still too small (%u > %u)", n_items, ctx->fd_item_cap);
+                ctx->fd_item_cap = n_items + n_items / 4; // the set-up pass told how many 64 x 64 chunks the batch covers: run it again with room
+                continue;
+            }
+            launch_flat_raster_resolve(bd, base + o_tris, (const uint32_t*)(base + o_colours), (const uint2*)(base + o_items), n_items, (unsigned long long*)(base + o_zkey),
+                                       zb->depth, (uchar4*)canvas->color, ctx->stream, &ctx->launches);
+            CK(cudaGetLastError());
+            break;
+        }
+        return SHSB_OK;
+    }
+}
+
+SHSB_API int32_t shsb_flat_draw_blinn_phong(shsb_ctx ctx, const ShsbFlatDraw* draws, uint32_t n_draws, const float view_proj[16], const float camera_pos[3],
+                                            const float light_dir_ws[3], shsb_rt canvas_ldr, shsb_rt depth)
+{
+    return flat_draw_batch(ctx, fd::MODE_BLINN_PHONG, draws, n_draws, view_proj, camera_pos, light_dir_ws, nullptr, 0, canvas_ldr, depth);
+}
+
+SHSB_API int32_t shsb_flat_draw_multi_light(shsb_ctx ctx, const ShsbFlatDraw* draws, uint32_t n_draws, const float view_proj[16], const float camera_pos[3],
+                                            const ShsbLightProperties* lights, uint32_t n_lights, shsb_rt canvas_ldr, shsb_rt depth)
+{
+    return flat_draw_batch(ctx, fd::MODE_MULTI_LIGHT, draws, n_draws, view_proj, camera_pos, nullptr, lights, n_lights, canvas_ldr, depth);
 }
 
 // ---------------------------------------------------------------------------------------- passes

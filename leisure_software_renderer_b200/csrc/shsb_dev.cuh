@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include "legacy2_core.cuh"
 #include "scene_cull_core.cuh"
+#include "flat_draw_core.cuh"
 
 namespace shsb
 {
@@ -305,6 +306,11 @@ namespace shsb
                                    const uint32_t* mesh_table, uint32_t n_meshes, const float* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
                                    const float view_proj[16], int width, int height, float epsilon, float* depth, uint8_t* occluded, uint32_t* visible, uint32_t* counts2,
                                    void* rect_scratch /* n_sorted x 32 bytes */, cudaStream_t s, uint64_t* launches);
+    void launch_flat_draw_batch(const fd::BatchDesc& bd, const fd::DrawRec* draws, const fd::LightProps* lights, void* tris, uint32_t* colours, uint2* items, uint32_t item_cap,
+                                uint32_t* item_total, unsigned long long* zkey, float* depth, bool init_keys, cudaStream_t s, uint64_t* launches);
+    void launch_flat_raster_resolve(const fd::BatchDesc& bd, const void* tris, const uint32_t* colours, const uint2* items, uint32_t n_items, unsigned long long* zkey,
+                                    float* depth, uchar4* canvas, cudaStream_t s, uint64_t* launches);
+    size_t flat_tri_record_bytes();
     uint32_t legacy2_slots(const l2::Draw& d);
     void launch_legacy2_draw(const l2::Draw& d, l2::RasterRec* rr, l2::BoxRec* bb, l2::ShadeRec* ss, uchar4* canvas, float* zbuf, float2* velocity,
                              cudaStream_t s, uint64_t* launches);

@@ -256,6 +256,36 @@ class Context:
         _check(self.lib, self.h, rc, "shsb_software_occlusion")
         return occ[:len(a)], out_vis[:int(counts[2])].copy(), counts, depth
 
+    @staticmethod
+    def _flat_draws(draws):
+        """draws: iterable of dicts mesh, model (16,), base_color (3,), optional selection (<= 8 light indices)."""
+        arr = (capi.FlatDraw * max(1, len(draws)))()
+        for i, d in enumerate(draws):
+            arr[i].mesh = int(d["mesh"])
+            capi.set_f(arr[i].model, d["model"])
+            capi.set_f(arr[i].base_color, d["base_color"])
+            sel = [int(v) for v in d.get("selection", ())]
+            arr[i].selection_count = int(d.get("selection_count", len(sel)))
+            for k, v in enumerate(sel[:8]):
+                arr[i].selection[k] = v
+        return arr
+
+    def flat_draw_blinn_phong(self, draws, view_proj, camera_pos, light_dir_ws, canvas_ldr, depth):
+        """debug_draw::draw_mesh_blinn_phong_transformed for a batch of draws, in order, into (canvas_ldr, depth plane of `depth`)."""
+        arr = self._flat_draws(draws)
+        vp, cam, ld = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in (view_proj, camera_pos, light_dir_ws))
+        _check(self.lib, self.h, self.lib.shsb_flat_draw_blinn_phong(self.h, arr, len(draws), capi.fptr(vp), capi.fptr(cam), capi.fptr(ld), canvas_ldr, depth),
+               "shsb_flat_draw_blinn_phong")
+
+    def flat_draw_multi_light(self, draws, view_proj, camera_pos, lights, canvas_ldr, depth):
+        """draw_mesh_multi_light_transformed (the consumer of the per-object LightSelections) for a batch of draws, in order.
+        lights: array of capi.LIGHT_PROPS_DTYPE."""
+        arr = self._flat_draws(draws)
+        vp, cam = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in (view_proj, camera_pos))
+        li = np.ascontiguousarray(lights, dtype=capi.LIGHT_PROPS_DTYPE).reshape(-1)
+        _check(self.lib, self.h, self.lib.shsb_flat_draw_multi_light(self.h, arr, len(draws), capi.fptr(vp), capi.fptr(cam), li.ctypes.data_as(C.c_void_p), len(li),
+                                                                    canvas_ldr, depth), "shsb_flat_draw_multi_light")
+
     def collect_object_lights(self, object_aabbs, visible, records, cull_mode):
         """collect_object_lights per object: counts (n,), light indices (n, 8), squared distances (n, 8)."""
         a = np.ascontiguousarray(object_aabbs, dtype=np.float32).reshape(-1, 6)

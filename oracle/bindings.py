@@ -706,3 +706,56 @@ def run_software_occlusion(fn, ctx_handle, sc, enable=True):
     rc = fn(*([ctx_handle] if ctx_handle is not None else []), *args)
     assert rc == 0, rc
     return occ[:len(a)], out_vis[:int(counts[2])].copy(), counts, depth
+
+
+# ---------------------------------------------------------------- flat-shaded mesh draws (the consumer of the light selections)
+REF_FLAT_DRAW_LIB = os.path.join(_HERE, "_ref", "libshs_flat_draw_ref.so")
+
+
+class FlatDraw:
+    """debug_draw::draw_mesh_blinn_phong_transformed (mode 0, sw_render/debug_draw.hpp:153-203) and draw_mesh_multi_light_transformed
+    (mode 1, exp-plumbing/hello_light_types_culling_sw.cpp:366-422) over a batch of draws through a checker:
+      "reference" -> oracle/_ref/libshs_flat_draw_ref.so (the reference's own text, oracle/ref_flat_draw_harness.cpp)
+      "port"      -> oracle/liboracle.so (oracle_flat_draw.cpp: shso_flat_draw)
+      a path      -> a library exporting the same signature under `prefix` (the g++ build of the device functions)."""
+
+    def __init__(self, kind="port", prefix=None):
+        if kind == "reference":
+            if not os.path.exists(REF_FLAT_DRAW_LIB):
+                build("reference")
+            self.lib, self.prefix = C.CDLL(REF_FLAT_DRAW_LIB), "shsref_"
+        elif kind == "port":
+            if not os.path.exists(PORT_LIB):
+                build("port")
+            self.lib, self.prefix = C.CDLL(PORT_LIB), "shso_"
+        else:
+            self.lib, self.prefix = C.CDLL(kind), prefix
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_FLAT_DRAW_LIB) or os.path.isdir("/root/reference")
+
+    def run(self, sc, mode):
+        """sc: dict of draw_mesh (d,), models (d, 16), base (d, 3), sel_counts (d,), sel_idx (d, 8), mesh_table (m, 3), vertices (v, 3),
+        indices, view_proj, camera, light_dir, lights (capi.LIGHT_PROPS_DTYPE), W, H, canvas (H, W, 4) uint8, depth (H, W) float32.
+        Returns the canvas and the depth buffer after the batch."""
+        dm = np.ascontiguousarray(sc["draw_mesh"], dtype=np.uint32).reshape(-1)
+        mo = np.ascontiguousarray(sc["models"], dtype=np.float32).reshape(-1, 16)
+        ba = np.ascontiguousarray(sc["base"], dtype=np.float32).reshape(-1, 3)
+        scn = np.ascontiguousarray(sc["sel_counts"], dtype=np.uint32).reshape(-1)
+        six = np.ascontiguousarray(sc["sel_idx"], dtype=np.uint32).reshape(-1, 8)
+        mt = np.ascontiguousarray(sc["mesh_table"], dtype=np.uint32).reshape(-1, 3)
+        vt = np.ascontiguousarray(sc["vertices"], dtype=np.float32).reshape(-1, 3)
+        ix = np.ascontiguousarray(sc["indices"], dtype=np.uint32).reshape(-1)
+        vp, cam, ld = (np.ascontiguousarray(sc[k], dtype=np.float32).reshape(-1) for k in ("view_proj", "camera", "light_dir"))
+        li = np.ascontiguousarray(sc["lights"], dtype=capi.LIGHT_PROPS_DTYPE).reshape(-1)
+        w, h = int(sc["W"]), int(sc["H"])
+        canvas = np.ascontiguousarray(sc["canvas"], dtype=np.uint8).reshape(h, w, 4).copy()
+        depth = np.ascontiguousarray(sc["depth"], dtype=np.float32).reshape(h, w).copy()
+        fn = getattr(self.lib, self.prefix + "flat_draw")
+        fn.restype = C.c_int32
+        rc = fn(C.c_int32(int(mode)), C.c_uint32(len(dm)), capi.u32ptr(dm), capi.fptr(mo), capi.fptr(ba), capi.u32ptr(scn), capi.u32ptr(six), capi.u32ptr(mt), C.c_uint32(len(mt)),
+                capi.fptr(vt), C.c_uint32(len(vt)), capi.u32ptr(ix), C.c_uint32(len(ix)), capi.fptr(vp), capi.fptr(cam), capi.fptr(ld), li.ctypes.data_as(C.c_void_p), C.c_uint32(len(li)),
+                C.c_int32(w), C.c_int32(h), canvas.ctypes.data_as(C.POINTER(C.c_uint8)), capi.fptr(depth))
+        assert rc == 0, rc
+        return canvas, depth

@@ -52,6 +52,13 @@ namespace glm
         vec2& operator/=(float k) { x /= k; y /= k; return *this; }
     };
 
+    struct ivec2 // only what sw_render/debug_draw.hpp's wireframe draw stores: two ints
+    {
+        int x = 0, y = 0;
+        ivec2() = default;
+        ivec2(int X, int Y) : x(X), y(Y) {}
+    };
+
     struct vec3
     {
         union { float x, r, s; };

@@ -257,3 +257,129 @@ def occlusion_scene(seed):
         rng.shuffle(visible)
     return {"aabbs": aabbs, "visible": visible, "object_mesh": np.array(omesh, np.uint32), "models": np.array(models, np.float32), "mesh_table": mesh_table,
             "vertices": vertices, "indices": indices, "view": view, "view_proj": view_proj, "occ_w": w, "occ_h": h, "eps": float(rng.choice([1e-4, 0.0, 1e-2]))}
+
+
+def _uv_sphere(n_lon=14, n_lat=9):
+    """A DebugMesh-like unit sphere (radius 0.5): the tessellated shapes the demos draw (spheres, capsules) are of this kind."""
+    v = [[0.0, 0.5, 0.0]]
+    for j in range(1, n_lat):
+        th = np.pi * j / n_lat
+        for i in range(n_lon):
+            ph = 2 * np.pi * i / n_lon
+            v.append([0.5 * np.sin(th) * np.cos(ph), 0.5 * np.cos(th), 0.5 * np.sin(th) * np.sin(ph)])
+    v.append([0.0, -0.5, 0.0])
+    idx = []
+    ring = lambda j, i: 1 + (j - 1) * n_lon + (i % n_lon)
+    for i in range(n_lon):
+        idx += [0, ring(1, i + 1), ring(1, i)]
+        idx += [len(v) - 1, ring(n_lat - 1, i), ring(n_lat - 1, i + 1)]
+    for j in range(1, n_lat - 1):
+        for i in range(n_lon):
+            idx += [ring(j, i), ring(j, i + 1), ring(j + 1, i + 1), ring(j, i), ring(j + 1, i + 1), ring(j + 1, i)]
+    return np.array(v, np.float32), np.array(idx, np.uint32)
+
+
+def _rotation(rng):
+    a = rng.normal(size=3)
+    a /= max(np.linalg.norm(a), 1e-6)
+    t = rng.uniform(0, 2 * np.pi)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * (K @ K)
+
+
+def flat_draw_lights(rng, n, ext):
+    """n lights of the four local light models (lighting/light_runtime.hpp:291-535) with properties around and beyond the
+    clamps their sample() functions apply: ranges from smaller than the scene to larger, every attenuation model, powers
+    below / at / above 1, cut-offs, negative colours and intensities, zero direction / axis vectors (the fallbacks), cone angles
+    outside [0.02, pi/2 - 0.02] and outer < inner."""
+    li = np.zeros(n, capi.LIGHT_PROPS_DTYPE)
+    for i in range(n):
+        l = li[i]
+        l["light_type"] = int(rng.integers(1, 5))
+        l["color"] = rng.uniform(0.1, 1.0, 3) if rng.random() > 0.08 else rng.uniform(-0.5, 1.0, 3)
+        l["intensity"] = float(rng.uniform(0.3, 6.0)) if rng.random() > 0.05 else -1.0
+        l["position_ws"] = rng.uniform(-ext, ext, 3) * np.array([1.0, 0.35, 1.0]) + np.array([0.0, 0.3 * ext, 0.0])
+        l["range"] = float(rng.choice([0.4, 1.0, 2.0, 4.0]) * ext * rng.uniform(0.3, 1.0))
+        d = rng.normal(size=3)
+        l["direction_ws"] = d / np.linalg.norm(d) * float(rng.choice([1.0, 1.0, 3.0])) if rng.random() > 0.06 else np.zeros(3)
+        l["inner_angle_rad"] = float(rng.choice([0.0, 0.2, 0.5, 1.0, 1.7]))
+        l["outer_angle_rad"] = float(rng.choice([0.1, 0.4, 0.8, 1.3, 2.0]))
+        r = rng.normal(size=3)
+        l["right_ws"] = r / np.linalg.norm(r) if rng.random() > 0.06 else np.zeros(3)
+        # an up hint that is never parallel to the direction: the parallel case divides by zero inside right_from_forward and ends in a
+        # float -> uint8 conversion of NaN, which C++ leaves undefined
+        u = np.cross(l["direction_ws"] if np.any(l["direction_ws"]) else np.array([0.0, -1.0, 0.0]), rng.normal(size=3))
+        l["up_ws"] = u / max(np.linalg.norm(u), 1e-6) + 0.2 * rng.normal(size=3)
+        l["tube_half_length"] = float(rng.choice([0.02, 0.5, 1.5, 4.0]))
+        l["rect_half_extents"] = rng.choice([0.01, 0.4, 1.0, 3.0], 2)
+        l["tube_radius"] = 0.25
+        l["attenuation_model"] = int(rng.integers(0, 3)) if rng.random() > 0.04 else 7
+        l["attenuation_power"] = float(rng.choice([1.0, 1.0, 0.5, 2.0, 3.3, 0.0]))
+        l["attenuation_bias"] = float(rng.choice([0.05, 0.0, 1.0]))
+        l["attenuation_cutoff"] = float(rng.choice([0.0, 0.0, 0.02, 0.3]))
+        l["flags"] = 1
+    return li
+
+
+def flat_draw_scene(seed, dangling=False, size=None):
+    """Random batch of flat-shaded draws (sw_render/debug_draw.hpp:153-203; hello_light_types_culling_sw.cpp:366-422): boxes,
+    octahedra, quads (with a trailing index pair that is ignored), tessellated spheres and a floor that covers the canvas, under
+    rotated / non-uniformly scaled model matrices; objects behind and across the near plane (a triangle with one rejected vertex is
+    skipped whole); duplicated draws with another colour (equal depths: the earlier draw stays); degenerate triangles; per-draw
+    light selections of 0..8 entries with stale indices; a canvas that is not empty and a depth buffer that already holds a
+    near block.  dangling=True adds a mesh whose indices point beyond the vertex array (skipped by the restatement and the device; the
+    reference would read out of bounds, so those scenes are not fed to it)."""
+    rng = np.random.default_rng(23000 + seed)
+    box_v = np.array([[x, y, z] for z in (-.5, .5) for y in (-.5, .5) for x in (-.5, .5)], np.float32)
+    box_i = np.array([0, 1, 3, 0, 3, 2, 4, 6, 7, 4, 7, 5, 0, 4, 5, 0, 5, 1, 2, 3, 7, 2, 7, 6, 0, 2, 6, 0, 6, 4, 1, 5, 7, 1, 7, 3], np.uint32)
+    oct_v = np.array([[.5, 0, 0], [-.5, 0, 0], [0, .5, 0], [0, -.5, 0], [0, 0, .5], [0, 0, -.5]], np.float32)
+    oct_i = np.array([0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5], np.uint32)
+    quad_v = np.array([[-.5, 0, -.5], [.5, 0, -.5], [.5, 0, .5], [-.5, 0, .5]], np.float32)
+    quad_i = np.array([0, 2, 1, 0, 3, 2, 1, 2], np.uint32)             # 8 indices: the trailing pair is ignored (i + 2 < size)
+    sph_v, sph_i = _uv_sphere()
+    deg_v = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0]], np.float32)
+    deg_i = np.array([0, 1, 2, 0, 0, 3, 0, 1, 3], np.uint32)           # collinear, repeated vertex, one proper triangle
+    meshes = [(box_v, box_i), (oct_v, oct_i), (quad_v, quad_i), (sph_v, sph_i), (deg_v, deg_i)]
+    if dangling:
+        meshes.append((oct_v, np.array([0, 2, 4, 2, 1, 40, 1, 3, 4, 0xFFFFFFFF, 0, 4, 2, 0, 5], np.uint32)))  # LAST mesh: indices beyond the array
+    vertices = np.concatenate([m[0] for m in meshes])
+    indices = np.concatenate([m[1] for m in meshes])
+    table, fi, bv = [], 0, 0
+    for v, i in meshes:
+        table.append([fi, len(i), bv])
+        fi += len(i); bv += len(v)
+    ext = float(rng.choice([5.0, 12.0, 30.0]))
+    n = int(rng.integers(1, 50))
+    draw_mesh, models, base = [], [], []
+    for k in range(n):
+        if k and rng.random() < 0.12:                                   # the same object again in another colour: every depth ties
+            draw_mesh.append(draw_mesh[-1]); models.append(models[-1]); base.append(rng.uniform(0, 1, 3))
+            continue
+        floor = rng.random() < 0.08
+        m = 2 if floor else int(rng.choice([0, 0, 1, 2, 3, 3, 4] + ([5] if dangling else [])))
+        scl = np.array([4 * ext, 1.0, 4 * ext]) if floor else rng.uniform(0.2, 2.5, 3) * float(rng.choice([1.0, 1.0, 3.0]))
+        R = np.eye(3) if floor else _rotation(rng)
+        M = np.eye(4)
+        M[:3, :3] = R @ np.diag(scl)
+        M[:3, 3] = np.array([0.0, -0.2 * ext, 0.0]) if floor else rng.uniform(-ext, ext, 3) * np.array([1.0, 0.35, 1.0])
+        draw_mesh.append(m); models.append(M.T.astype(np.float32).reshape(16)); base.append(rng.uniform(0, 1.1, 3))
+    eye = rng.uniform(-ext, ext, 3) * np.array([1.0, 0.3, 1.0]) + np.array([0.0, 0.25 * ext, 0.0])
+    tgt = rng.uniform(-ext / 3, ext / 3, 3)
+    w, h = size or [(16, 12), (97, 53), (160, 90), (320, 180), (200, 150)][int(rng.integers(0, 5))]
+    zn, zf = float(rng.choice([0.05, 0.1, 1.0])), float(rng.choice([50.0, 300.0]))
+    view_proj = scenes.camera_viewproj(tuple(map(float, eye)), tuple(map(float, tgt)), (0.0, 1.0, 0.0), float(np.radians(rng.uniform(40, 90))), w / h, zn, zf)
+    n_lights = int(rng.integers(0, 25))
+    lights = flat_draw_lights(rng, n_lights, ext)
+    sel_counts = rng.integers(0, 9, n).astype(np.uint32)
+    sel_idx = rng.integers(0, n_lights + 2, (n, 8)).astype(np.uint32)  # n_lights, n_lights + 1: stale entries (skipped, :411)
+    if seed % 7 == 0:
+        sel_idx[0, 0] = 0xFFFFFFFF
+    canvas = np.empty((h, w, 4), np.uint8)
+    canvas[:] = np.array([int(rng.integers(0, 60)), int(rng.integers(0, 60)), int(rng.integers(0, 80)), 255], np.uint8)
+    depth = np.ones((h, w), np.float32)
+    if seed % 3 == 0:
+        depth[h // 4: h // 2, w // 3: 2 * w // 3] = np.float32(rng.choice([0.0, 0.5, 0.97]))
+    ld = rng.normal(size=3)
+    return {"draw_mesh": np.array(draw_mesh, np.uint32), "models": np.array(models, np.float32), "base": np.array(base, np.float32), "sel_counts": sel_counts, "sel_idx": sel_idx,
+            "mesh_table": np.array(table, np.uint32), "vertices": vertices, "indices": indices, "view_proj": view_proj, "camera": eye.astype(np.float32),
+            "light_dir": (ld / np.linalg.norm(ld)).astype(np.float32) * np.float32(rng.choice([1.0, 2.5])), "lights": lights, "W": w, "H": h, "canvas": canvas, "depth": depth}
