@@ -357,6 +357,7 @@ struct shsb_context_t
     DevBuf<l2::RasterRec> d_l2_raster; // slot records of the legacy render-target demos (legacy2.cu)
     DevBuf<l2::BoxRec> d_l2_box;
     DevBuf<l2::ShadeRec> d_l2_shade;
+    float* d_l2_rot = nullptr;         // (sin, cos) of the 2^24 PCSS kernel rotation angles, tabulated by the host's libm on first use (128 MB)
     struct IblSlot { bool live = false; float* irradiance = nullptr; float* prefiltered = nullptr; int irr_size = 0, n_mips = 0; int spec_size[l2::MAX_SPEC_MIPS] = {}; uint32_t spec_off[l2::MAX_SPEC_MIPS] = {}; };
     std::vector<IblSlot> ibls;        // EnvIBL of the legacy PBR demo
     int taa_w = 0, taa_h = 0;
@@ -1408,7 +1409,7 @@ SHSB_API int32_t shsb_context_destroy(shsb_ctx ctx)
     cudaFree(ctx->d_post_scratch.p); cudaFree(ctx->d_post_luma.p); cudaFree(ctx->d_taa_hist.p); cudaFree(ctx->d_legacy_tris.p);
     cudaFree(ctx->d_sc_bytes.p);
     cudaFree(ctx->d_fd_bytes.p);
-    cudaFree(ctx->d_l2_raster.p); cudaFree(ctx->d_l2_box.p); cudaFree(ctx->d_l2_shade.p);
+    cudaFree(ctx->d_l2_raster.p); cudaFree(ctx->d_l2_box.p); cudaFree(ctx->d_l2_shade.p); cudaFree(ctx->d_l2_rot);
     for (auto& e : ctx->ibls) { cudaFree(e.irradiance); cudaFree(e.prefiltered); }
     for (auto& l : ctx->d_lights) cudaFree(l.p);
     for (auto& l : ctx->d_smlights) cudaFree(l.p);
@@ -1926,6 +1927,37 @@ namespace
         return SHSB_OK;
     }
 
+    // rotate2 (hello_shadow_mapping_soft.cpp:320-325) turns the PCSS kernels by ang = hash01(seed) * 6.2831853f with std::cos / std::sin
+    // of a float, i.e. the platform libm's cosf / sinf, which no device function reproduces bit for bit (glibc's are not correctly
+    // rounded, and its x86-64 build picks an FMA or a non-FMA variant at load time).  hash01 has a 24-bit numerator, so there are 2^24
+    // angles: the host evaluates the SAME libm calls the reference makes for all of them once per context (a few hundred ms over the
+    // host's threads, 128 MB on the device) and the kernels look the pair up (legacy2_core.cuh: rotation()).
+    int ensure_l2_rotation(shsb_ctx ctx)
+    {
+        if (ctx->d_l2_rot) return SHSB_OK;
+        constexpr uint32_t N = 0x01000000u;
+        std::vector<float> table((size_t)N * 2);
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned n_threads = std::max(1u, std::min(hw ? hw : 1u, 32u));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; ++t)
+            pool.emplace_back([&table, t, n_threads]() {
+                const uint32_t lo = (uint32_t)((uint64_t)N * t / n_threads), hi = (uint32_t)((uint64_t)N * (t + 1) / n_threads);
+                for (uint32_t k = lo; k < hi; ++k)
+                {
+                    const float ang = (float(k) / float(0x01000000u)) * 6.2831853f; // hash01(seed) * 6.2831853f, :316-319, :360
+                    table[2 * (size_t)k] = std::sin(ang);
+                    table[2 * (size_t)k + 1] = std::cos(ang);
+                }
+            });
+        for (auto& th : pool) th.join();
+        float* dev = nullptr;
+        if (cudaMalloc((void**)&dev, table.size() * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, SHSB_E_OUT_OF_MEMORY, "PCSS rotation table (128 MB)"); }
+        if (cudaMemcpy(dev, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return fail(ctx, SHSB_E_CUDA, "PCSS rotation table upload"); }
+        ctx->d_l2_rot = dev;
+        return SHSB_OK;
+    }
+
     // the parts of a camera-pass draw that the soft-shadow and the PBR demo share
     int legacy2_fill_camera(shsb_ctx ctx, shsb_mesh mesh_h, const ShsbLegacy2Uniforms* u, shsb_rt shadow_rt, shsb_rt canvas_rt, shsb_rt zbuffer_rt,
                             bool need_motion, l2::Draw& d, RtSlot*& canvas, RtSlot*& zb)
@@ -1992,6 +2024,11 @@ SHSB_API int32_t shsb_legacy2_draw_softshadow(shsb_ctx ctx, shsb_mesh mesh_h, co
     d.mode = l2::MODE_SOFTSHADOW;
     RtSlot *canvas = nullptr, *zb = nullptr;
     if (int rc = legacy2_fill_camera(ctx, mesh_h, u, shadow_rt, canvas_rt, zbuffer_rt, false, d, canvas, zb)) return rc;
+    if (d.shadow)
+    {
+        if (int rc = ensure_l2_rotation(ctx)) return rc;
+        d.rot = ctx->d_l2_rot;
+    }
     wait_pending_read(ctx, canvas);
     wait_pending_read(ctx, zb);
     return legacy2_launch(ctx, d, (uchar4*)canvas->color, zb->depth, nullptr);

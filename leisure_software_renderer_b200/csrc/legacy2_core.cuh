@@ -18,9 +18,11 @@
 // reproduced by visiting the candidate triangles in draw order and keeping (running minimum depth, last shadeable prefix minimum).
 //
 // Approximate operations (everything else is IEEE binary32, unfused, in the reference's order): powf (CUDA's, not glibc's; reaches
-// the canvas through an 8-bit truncation -> the <= 1 LSB colour gate) and the PCSS kernel rotation's sinf / cosf, evaluated as the
-// double-precision sin / cos rounded to float (equal to glibc's sinf / cosf on 98.7 % of the 2^24 possible angles and 1 ULP off on
-// the rest -- counted exhaustively on the CPU; it reaches the image only where a rotated tap lands within 1e-9 of a texel boundary).
+// the canvas through an 8-bit truncation -> the <= 1 LSB colour gate).  The PCSS kernel rotation's sinf / cosf are NOT approximated:
+// the angle is hash01() * 6.2831853f, one of 2^24 values, and the product reads (sin, cos) from a table the host's libm filled
+// (Draw::rot, api.cu) -- the double-precision sin / cos rounded to float would equal glibc's sinf / cosf on only 98.7 % of those
+// angles (1 ULP off on the rest, counted exhaustively on the CPU), which moved a rotated tap across a texel boundary in a few pixels
+// per frame.  L2_SINCOSF remains for builds without the table (the CPU emulator overrides it with libm's).
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -90,6 +92,8 @@ namespace shsb
             int tex_w, tex_h;
             const float* shadow;       // shadow map depths (row = light-space screen y), null = no shadow term
             int sm_w, sm_h;
+            const float* rot;          // PCSS kernel rotations: (sin, cos) of the 2^24 angles hash01() * 6.2831853f can take, tabulated by the
+                                       // HOST's libm (api.cu: the sinf / cosf the reference itself calls); null = evaluate L2_SINCOSF
             // MODE_PBR
             float metallic, roughness, ao, ibl_diffuse, ibl_specular, ibl_reflection;
             const float* irradiance;   // 6 faces x irr_size^2 x RGB
@@ -357,6 +361,19 @@ namespace shsb
 #endif
         }
 
+        // rotate2's std::cos / std::sin (:320-325) of ang = hash01(x) * 6.2831853f
+        L2_HD void rotation(const Draw& d, uint32_t x, float ang, float& s, float& c)
+        {
+            if (d.rot)
+            {
+                const uint32_t k = hash_u32(x) & 0x00FFFFFFu; // hash01's numerator
+                s = d.rot[2u * k];
+                c = d.rot[2u * k + 1u];
+                return;
+            }
+            L2_SINCOSF(ang, s, c);
+        }
+
         L2_HD float pcss_shadow_factor(const Draw& d, float u, float v, float z_receiver, float bias, int px, int py) // :333-445
         {
             if (u < 0.0f || u > 1.0f || v < 0.0f || v > 1.0f) return 1.0f;
@@ -367,7 +384,7 @@ namespace shsb
             const uint32_t seed = (uint32_t)(px * 1973u ^ py * 9277u ^ 0x9e3779b9u);
             const float ang = hash01(seed) * 6.2831853f;
             float c, s;
-            L2_SINCOSF(ang, s, c);
+            rotation(d, seed, ang, s, c);
             float blocker_sum = 0.0f;
             int blocker_cnt = 0;
             const float z_test = z_receiver - bias;
@@ -394,7 +411,7 @@ namespace shsb
             float lit_sum = 0.0f;
             int lit_cnt = 0;
             const float ang2 = hash01(seed ^ 0xB5297A4Du) * 6.2831853f;
-            L2_SINCOSF(ang2, s, c);
+            rotation(d, seed ^ 0xB5297A4Du, ang2, s, c);
             for (int i = 0; i < 24; ++i)
             {
                 float qx, qy;

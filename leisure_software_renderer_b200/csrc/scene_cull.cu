@@ -52,22 +52,50 @@ namespace shsb
             if (threadIdx.x == 0) { counts[0] = n; counts[1] = s_cls[0]; counts[2] = s_cls[1]; counts[3] = s_cls[2]; counts[4] = s_base; }
         }
 
+        // ---- one WARP per object.  The selection's slot layout depends on the order in which the affecting lights arrive
+        // (add_light_candidate, light_runtime.hpp:263-289), so that part stays serial; what is order-free -- reading a light's
+        // record, the light-affects-object test, the squared distance -- is done 32 candidates at a time, one per lane, and the
+        // survivors are fed to the (redundantly held, register-resident) selection in ascending lane order = the reference's visit order.
+        __device__ __forceinline__ void warp_consider(sc::Selection& sel, bool live, uint32_t li, const float* __restrict__ records, const float* box, float cx, float cy, float cz, int mode)
+        {
+            float d2 = 0.0f;
+            const bool hit = live && sc::light_candidate(records + (size_t)li * sc::LIGHT_RECORD_FLOATS, box, cx, cy, cz, mode, d2);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m)
+            {
+                const int src = __ffs(m) - 1;
+                m &= m - 1u;
+                sc::selection_insert(sel, __shfl_sync(0xffffffffu, li, src), __shfl_sync(0xffffffffu, d2, src));
+            }
+        }
+
+        __device__ __forceinline__ void warp_store_selection(const sc::Selection& sel, uint32_t o, uint32_t lane, uint32_t* __restrict__ out_counts, uint32_t* __restrict__ out_idx,
+                                                             float* __restrict__ out_d2)
+        {
+            if (lane == 0) out_counts[o] = sel.count;
+#pragma unroll
+            for (uint32_t k = 0; k < sc::LIGHT_SELECTION_CAPACITY; ++k)
+                if (lane == k) { out_idx[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.idx[k]; out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.d2[k]; }
+        }
+
         __global__ void __launch_bounds__(128) collect_object_lights_kernel(const float* __restrict__ boxes6, uint32_t n_objects, const uint32_t* __restrict__ visible,
                                                                              uint32_t n_visible, const float* __restrict__ records, uint32_t n_lights, int mode,
                                                                              uint32_t* __restrict__ out_counts, uint32_t* __restrict__ out_idx, float* __restrict__ out_d2)
         {
-            const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-            if (o >= n_objects) return;
+            const uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+            if (o >= n_objects) return; // whole warps leave together
             float box[6];
             for (int k = 0; k < 6; ++k) box[k] = boxes6[(size_t)o * 6 + k];
-            uint32_t idx[sc::LIGHT_SELECTION_CAPACITY];
-            float d2[sc::LIGHT_SELECTION_CAPACITY];
-            out_counts[o] = sc::collect_lights(box, visible, n_visible, records, n_lights, mode, idx, d2);
-            for (uint32_t k = 0; k < sc::LIGHT_SELECTION_CAPACITY; ++k)
+            const float cx = 0.5f * (box[0] + box[3]), cy = 0.5f * (box[1] + box[4]), cz = 0.5f * (box[2] + box[5]);
+            sc::Selection sel;
+            sc::selection_clear(sel);
+            for (uint32_t v0 = 0; v0 < n_visible; v0 += 32u)
             {
-                out_idx[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = idx[k];
-                out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = d2[k];
+                const uint32_t v = v0 + lane;
+                const uint32_t li = v < n_visible ? visible[v] : 0xFFFFFFFFu;
+                warp_consider(sel, li < n_lights, li, records, box, cx, cy, cz, mode); // entries >= n_lights are skipped (:604-606)
             }
+            warp_store_selection(sel, o, lane, out_counts, out_idx, out_d2);
         }
 
         __global__ void __launch_bounds__(256) scene_range_init_kernel(uint32_t tiles, float z_near, float z_far, uint32_t* __restrict__ kmin, uint32_t* __restrict__ kmax, uint32_t* __restrict__ has)
@@ -127,7 +155,7 @@ namespace shsb
                                       uint32_t* out_counts, uint32_t* out_idx, float* out_d2, cudaStream_t s, uint64_t* launches)
     {
         if (n_objects == 0) return;
-        collect_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, records, n_lights, mode, out_counts, out_idx, out_d2);
+        collect_object_lights_kernel<<<(n_objects + 3) / 4, 128, 0, s>>>(boxes6, n_objects, visible, n_visible, records, n_lights, mode, out_counts, out_idx, out_d2);
         if (launches) *launches += 1;
     }
 }
@@ -156,24 +184,65 @@ namespace shsb
     {
         struct SelectArgs { float view[16], view_proj[16]; sc::BinGrid grid; };
 
-        // one thread per object; seen: n_objects x words_per_object, zeroed by the launcher
+        // one WARP per object (see collect_object_lights_kernel).  A bin lists a light at most once, so the 32 entries a warp reads from one
+        // bin are distinct lights: their "seen" bits are tested together, set together, and the fresh ones considered in entry order.
+        // seen: ceil(n_lights / 32) words per object -- in shared memory when the CTA's four objects fit (the launcher decides), else in the
+        // zeroed global scratch (volatile reads: the bits are set by other lanes' atomics).
         __global__ void __launch_bounds__(128) select_object_lights_kernel(const float* __restrict__ boxes6, uint32_t n_objects, const SelectArgs a, const uint32_t* __restrict__ bin_counts,
                                                                             const uint32_t* __restrict__ bin_indices, const float* __restrict__ records, uint32_t n_lights, int mode,
-                                                                            uint32_t* __restrict__ seen, uint32_t words_per_object, uint32_t* __restrict__ out_counts,
-                                                                            uint32_t* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t* __restrict__ out_candidates)
+                                                                            uint32_t* __restrict__ seen_global, uint32_t words_per_object, int seen_in_shared,
+                                                                            uint32_t* __restrict__ out_counts, uint32_t* __restrict__ out_idx, float* __restrict__ out_d2,
+                                                                            uint32_t* __restrict__ out_candidates)
         {
-            const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-            if (o >= n_objects) return;
+            extern __shared__ uint32_t s_seen[];
+            const uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+            if (o >= n_objects) return; // whole warps leave together
             float box[6];
             for (int k = 0; k < 6; ++k) box[k] = boxes6[(size_t)o * 6 + k];
+            const float cx = 0.5f * (box[0] + box[3]), cy = 0.5f * (box[1] + box[4]), cz = 0.5f * (box[2] + box[5]);
             sc::Selection sel;
-            out_candidates[o] = sc::select_from_bins(box, a.view, a.view_proj, a.grid, bin_counts, bin_indices, records, n_lights, mode, seen + (size_t)o * words_per_object, sel);
-            out_counts[o] = sel.count;
-            for (uint32_t k = 0; k < sc::LIGHT_SELECTION_CAPACITY; ++k)
+            sc::selection_clear(sel);
+            sc::TileRect r;
+            uint32_t tz0, tz1, n_candidates = 0;
+            if (!sc::object_bin_range(box, a.view, a.view_proj, a.grid, r, tz0, tz1))
             {
-                out_idx[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.idx[k];
-                out_d2[(size_t)o * sc::LIGHT_SELECTION_CAPACITY + k] = sel.d2[k];
+                // fallback_light_scene_candidates: every visible light, in order
+                for (uint32_t l0 = 0; l0 < n_lights; l0 += 32u) warp_consider(sel, l0 + lane < n_lights, l0 + lane, records, box, cx, cy, cz, mode);
+                n_candidates = n_lights;
             }
+            else
+            {
+                volatile uint32_t* seen;
+                if (seen_in_shared)
+                {
+                    seen = s_seen + (size_t)(threadIdx.x >> 5) * words_per_object;
+                    for (uint32_t w = lane; w < words_per_object; w += 32u) seen[w] = 0u;
+                    __syncwarp();
+                }
+                else seen = seen_global + (size_t)o * words_per_object;
+                const sc::BinGrid& g = a.grid;
+                for (uint32_t tz = tz0; tz <= tz1; ++tz)
+                    for (uint32_t ty = r.ty0; ty <= r.ty1; ++ty)
+                        for (uint32_t tx = r.tx0; tx <= r.tx1; ++tx)
+                        {
+                            const uint32_t bin = tz * (g.bins_x * g.bins_y) + ty * g.bins_x + tx;
+                            const uint32_t n = min(bin_counts[bin], g.max_per_bin);
+                            for (uint32_t k0 = 0; k0 < n; k0 += 32u)
+                            {
+                                const uint32_t k = k0 + lane;
+                                const uint32_t li = k < n ? bin_indices[(size_t)bin * g.max_per_bin + k] : 0xFFFFFFFFu;
+                                const uint32_t bit = 1u << (li & 31u);
+                                const bool fresh = li < n_lights && !(seen[li >> 5] & bit);
+                                __syncwarp(); // every lane has read the bits before any is set
+                                if (fresh) atomicOr(const_cast<uint32_t*>(&seen[li >> 5]), bit);
+                                __syncwarp();
+                                n_candidates += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
+                                warp_consider(sel, fresh, li, records, box, cx, cy, cz, mode);
+                            }
+                        }
+            }
+            if (lane == 0) out_candidates[o] = n_candidates;
+            warp_store_selection(sel, o, lane, out_counts, out_idx, out_d2);
         }
     }
 
@@ -185,9 +254,11 @@ namespace shsb
         SelectArgs a;
         for (int i = 0; i < 16; ++i) { a.view[i] = view[i]; a.view_proj[i] = view_proj[i]; }
         a.grid = grid;
-        cudaMemsetAsync(seen, 0, (size_t)n_objects * words_per_object * 4, s);
-        select_object_lights_kernel<<<(n_objects + 127) / 128, 128, 0, s>>>(boxes6, n_objects, a, bin_counts, bin_indices, records, n_lights, mode, seen, words_per_object, out_counts, out_idx,
-                                                                             out_d2, out_candidates);
+        const size_t shared = (size_t)4 * words_per_object * sizeof(uint32_t); // 4 warps = 4 objects per CTA
+        const int in_shared = shared <= 40 * 1024;                             // up to 81 920 lights; beyond that the zeroed global scratch
+        if (!in_shared) cudaMemsetAsync(seen, 0, (size_t)n_objects * words_per_object * 4, s);
+        select_object_lights_kernel<<<(n_objects + 3) / 4, 128, in_shared ? shared : 0, s>>>(boxes6, n_objects, a, bin_counts, bin_indices, records, n_lights, mode, seen, words_per_object,
+                                                                                            in_shared, out_counts, out_idx, out_d2, out_candidates);
         if (launches) *launches += 1;
     }
     namespace

@@ -178,17 +178,28 @@ namespace shsb
         // ---- light selection state shared by collect_lights and select_from_bins
         struct Selection { uint32_t idx[LIGHT_SELECTION_CAPACITY]; float d2[LIGHT_SELECTION_CAPACITY]; uint32_t count; };
         SC_HD void selection_clear(Selection& s) { s.count = 0; for (uint32_t k = 0; k < LIGHT_SELECTION_CAPACITY; ++k) { s.idx[k] = 0u; s.d2[k] = 0.0f; } }
-        SC_HD void consider_light(Selection& s, uint32_t li, const float* rec, const float* box6, float cx, float cy, float cz, int mode)
+        // add_light_candidate, light_runtime.hpp:263-289: the order-dependent part (the kernels feed it in the reference's visit order)
+        SC_HD void selection_insert(Selection& s, uint32_t li, float d2)
         {
-            if (!light_affects_object(rec, box6, mode)) return;
-            const float dx = rec[REC_POSITION] - cx, dy = rec[REC_POSITION + 1] - cy, dz = rec[REC_POSITION + 2] - cz;
-            const float d2 = dx * dx + dy * dy + dz * dz;
             if (s.count < LIGHT_SELECTION_CAPACITY) { s.idx[s.count] = li; s.d2[s.count] = d2; ++s.count; return; }
             uint32_t farthest = 0;
             float far_d2 = s.d2[0];
             for (uint32_t i = 1; i < LIGHT_SELECTION_CAPACITY; ++i)
                 if (s.d2[i] > far_d2) { farthest = i; far_d2 = s.d2[i]; }
             if (d2 < far_d2) { s.idx[farthest] = li; s.d2[farthest] = d2; }
+        }
+        // the order-free part: does the light reach the object, and how far is it from the box centre
+        SC_HD bool light_candidate(const float* rec, const float* box6, float cx, float cy, float cz, int mode, float& d2)
+        {
+            if (!light_affects_object(rec, box6, mode)) return false;
+            const float dx = rec[REC_POSITION] - cx, dy = rec[REC_POSITION + 1] - cy, dz = rec[REC_POSITION + 2] - cz;
+            d2 = dx * dx + dy * dy + dz * dz;
+            return true;
+        }
+        SC_HD void consider_light(Selection& s, uint32_t li, const float* rec, const float* box6, float cx, float cy, float cz, int mode)
+        {
+            float d2;
+            if (light_candidate(rec, box6, cx, cy, cz, mode, d2)) selection_insert(s, li, d2);
         }
 
         SC_HD uint32_t view_depth_to_cluster_slice(float view_depth, float z_near, float z_far, uint32_t slices) // :170-186
@@ -212,6 +223,21 @@ namespace shsb
             uint32_t max_per_bin;            // row stride of bin_indices; a bin holds min(count, max_per_bin) entries
         };
 
+        // The bins an object's projected AABB touches (:389-420): false = no bins / nothing in front of the camera -> every light is a candidate
+        SC_HD bool object_bin_range(const float* box6, const float* view, const float* view_proj, const BinGrid& g, TileRect& r, uint32_t& tz0, uint32_t& tz1)
+        {
+            const bool has_bins = g.bins_x > 0u && g.bins_y > 0u && g.bins_z > 0u;
+            if (!has_bins || !project_object(box6, view, view_proj, g.z_near, g.z_far, g.bins_x, g.bins_y, r)) return false;
+            tz0 = 0u; tz1 = (g.bins_z > 1u ? g.bins_z : 1u) - 1u;
+            if (g.clustered && g.bins_z > 1u)
+            {
+                tz0 = view_depth_to_cluster_slice(r.min_depth, g.z_near, g.z_far, g.bins_z);
+                tz1 = view_depth_to_cluster_slice(r.max_depth, g.z_near, g.z_far, g.bins_z);
+                if (tz0 > tz1) { const uint32_t t = tz0; tz0 = tz1; tz1 = t; }
+            }
+            return true;
+        }
+
         // seen: ceil(n_lights / 32) words of scratch owned by this object, zeroed on entry.  Returns the number of candidates
         // (gather's list length); the selection is what collect_object_lights makes of that list.
         SC_HD uint32_t select_from_bins(const float* box6, const float* view, const float* view_proj, const BinGrid& g, const uint32_t* bin_counts, const uint32_t* bin_indices,
@@ -220,19 +246,12 @@ namespace shsb
             selection_clear(sel);
             const float cx = 0.5f * (box6[0] + box6[3]), cy = 0.5f * (box6[1] + box6[4]), cz = 0.5f * (box6[2] + box6[5]);
             TileRect r;
-            const bool has_bins = g.bins_x > 0u && g.bins_y > 0u && g.bins_z > 0u;
-            if (!has_bins || !project_object(box6, view, view_proj, g.z_near, g.z_far, g.bins_x, g.bins_y, r))
+            uint32_t tz0, tz1;
+            if (!object_bin_range(box6, view, view_proj, g, r, tz0, tz1))
             {
                 // fallback_light_scene_candidates: every visible light, in order
                 for (uint32_t li = 0; li < n_lights; ++li) consider_light(sel, li, records + (size_t)li * LIGHT_RECORD_FLOATS, box6, cx, cy, cz, mode);
                 return n_lights;
-            }
-            uint32_t tz0 = 0u, tz1 = (g.bins_z > 1u ? g.bins_z : 1u) - 1u;
-            if (g.clustered && g.bins_z > 1u)
-            {
-                tz0 = view_depth_to_cluster_slice(r.min_depth, g.z_near, g.z_far, g.bins_z);
-                tz1 = view_depth_to_cluster_slice(r.max_depth, g.z_near, g.z_far, g.bins_z);
-                if (tz0 > tz1) { const uint32_t t = tz0; tz0 = tz1; tz1 = t; }
             }
             uint32_t n_candidates = 0;
             for (uint32_t tz = tz0; tz <= tz1; ++tz)
