@@ -93,8 +93,10 @@ def build_phase_clocks() -> str:
     cc = nvcc()
     o = os.path.join(OBJ, "tile_raster_clk.o")
     subprocess.run([cc, *ARCH, *COMMON, "-DSHSB_PHASE_CLOCKS", "-c", os.path.join(CSRC, "tile_raster.cu"), "-o", o], check=True)
+    o2 = os.path.join(OBJ, "legacy2_clk.o")  # per-CTA clocks of the legacy render-target demos' raster kernel (tools/l2_clocks.py)
+    subprocess.run([cc, *ARCH, *COMMON, *SOURCES["legacy2.cu"], "-DSHSB_PHASE_CLOCKS", "-c", os.path.join(CSRC, "legacy2.cu"), "-o", o2], check=True)
     out = os.path.join(HERE, "libshsb_clk.so")
-    objs = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f != "tile_raster.cu"] + [o]
+    objs = [os.path.join(OBJ, f.replace(".cu", ".o")) for f in SOURCES if f not in ("tile_raster.cu", "legacy2.cu")] + [o, o2]
     subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC", "-lz"], check=True)
     return out
 

@@ -132,13 +132,47 @@ namespace shsb
             i1 = (int)gmin(f1, gmax(f0, hi));
         }
 
+        // Does any job tile J overlapping the pixel rectangle T = [tx0, tx1] x [ty0, ty1] test one of T's pixels for a triangle whose float box
+        // is [lox, hix] x [loy, hiy]?  J tests the columns [i0, i1] = [(int)max(j0, min(j1, lox)), (int)min(j1, max(j0, hix))]
+        // (legacy_job_range), a non-empty interval inside J; with [a0, a1] = T's columns inside J and all operands non-negative,
+        //     i0 <= a1  <=>  max(j0, min(j1, lox)) < a1 + 1  <=>  lox < a1 + 1  or  a1 == j1      (j0 <= a1 always)
+        //     i1 >= a0  <=>  min(j1, max(j0, hix)) >= a0     <=>  hix >= a0     or  a0 == j0      (j1 >= a0 always)
+        // -- the same decisions as evaluating legacy_job_range and intersecting, in four float compares per axis.
+        __device__ __forceinline__ bool legacy_tile_tests_box(const LegacyDraw& d, int tx0, int tx1, int ty0, int ty1, float lox, float hix, float loy, float hiy)
+        {
+            for (int jy = (ty0 / d.job_h) * d.job_h; jy <= ty1; jy += d.job_h)
+            {
+                const int jy1 = min(jy + d.job_h, d.H) - 1, a0 = max(ty0, jy), a1 = min(ty1, jy1);
+                if (!((loy < (float)(a1 + 1) || a1 == jy1) && (hiy >= (float)a0 || a0 == jy))) continue;
+                for (int jx = (tx0 / d.job_w) * d.job_w; jx <= tx1; jx += d.job_w)
+                {
+                    const int jx1 = min(jx + d.job_w, d.W) - 1, c0 = max(tx0, jx), c1 = min(tx1, jx1);
+                    if ((lox < (float)(c1 + 1) || c1 == jx1) && (hix >= (float)c0 || c0 == jx)) return true;
+                }
+            }
+            return false;
+        }
+
+        // one triangle at one pixel of job tile [jx0, jx1] x [jy0, jy1]: the job's pixel loops (:223-224), the inside test (:226-227), the depth (:230)
+        __device__ __forceinline__ bool legacy_probe(const LegacyStage& s, int px, int py, int jx0, int jx1, int jy0, int jy1, float& z)
+        {
+            // px in [ix0, ix1] of legacy_job_range(minx, maxx, jx0, jx1), in the compare form derived at legacy_tile_tests_box
+            if (!((s.minx < (float)(px + 1) || px == jx1) && (s.maxx >= (float)px || px == jx0))) return false;
+            if (!((s.miny < (float)(py + 1) || py == jy1) && (s.maxy >= (float)py || py == jy0))) return false;
+            float u, v, w;
+            if (!legacy_bary(s, (float)px + 0.5f, (float)py + 0.5f, u, v, w)) return false;
+            z = u * s.z0 + v * s.z1 + w * s.z2;
+            return true;
+        }
+
         // ---- raster + shade: one CTA per 16x16 tile, one pixel per thread (screen space, y down)
         __global__ void __launch_bounds__(LEGACY_TILE * LEGACY_TILE) legacy_raster_kernel(const LegacyDraw d, const LegacyTri* __restrict__ tris,
                                                                                             uchar4* __restrict__ canvas, float* __restrict__ zbuf)
         {
-            __shared__ LegacyStage s_tri[LEGACY_CHUNK];
-            __shared__ uint32_t s_warp_base[LEGACY_TILE * LEGACY_TILE / 32];
-            __shared__ uint32_t s_count;
+            // two staging buffers: a chunk needs two barriers (counts published; records published) and none at its end, because the next
+            // chunk fills the OTHER buffer and the one after that is behind two more barriers
+            __shared__ LegacyStage s_tri[2][LEGACY_CHUNK];
+            __shared__ uint32_t s_warp_cnt[2][LEGACY_TILE * LEGACY_TILE / 32];
             const int tx0 = blockIdx.x * LEGACY_TILE, ty0 = blockIdx.y * LEGACY_TILE;
             const int tx1 = min(tx0 + LEGACY_TILE, d.W) - 1, ty1 = min(ty0 + LEGACY_TILE, d.H) - 1; // last pixel of this CTA's tile
             const int px = tx0 + (int)(threadIdx.x % LEGACY_TILE), py = ty0 + (int)(threadIdx.x / LEGACY_TILE);
@@ -150,65 +184,77 @@ namespace shsb
             float best_z = inside ? zbuf[(size_t)py * d.W + px] : 0.0f;
             uint32_t best_tri = 0xFFFFFFFFu;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const bool corner = (px == jx0 || px == jx1) && (py == jy0 || py == jy1); // a corner texel of its job tile
 
-            for (uint32_t base = 0; base < d.n_tris; base += LEGACY_CHUNK)
+            int buf = 0;
+            for (uint32_t base = 0; base < d.n_tris; base += LEGACY_CHUNK, buf ^= 1)
             {
                 const uint32_t t = base + threadIdx.x;
                 bool keep = false;
-                LegacyTri r;
-                if (t < d.n_tris)
+                float minx = 0.0f, maxx = 0.0f, miny = 0.0f, maxy = 0.0f;
+                if (t < d.n_tris && tris[t].valid)
                 {
-                    r = tris[t];
-                    if (r.valid)
-                    {
-                        // does any job tile overlapping this CTA's 16x16 tile test a pixel of the 16x16 tile for this triangle?
-                        for (int jy = (ty0 / d.job_h) * d.job_h; jy <= ty1 && !keep; jy += d.job_h)
-                            for (int jx = (tx0 / d.job_w) * d.job_w; jx <= tx1 && !keep; jx += d.job_w)
-                            {
-                                int ix0, ix1, iy0, iy1;
-                                legacy_job_range(r.minx, r.maxx, jx, min(jx + d.job_w, d.W) - 1, ix0, ix1);
-                                legacy_job_range(r.miny, r.maxy, jy, min(jy + d.job_h, d.H) - 1, iy0, iy1);
-                                keep = max(ix0, tx0) <= min(ix1, tx1) && max(iy0, ty0) <= min(iy1, ty1);
-                            }
-                    }
+                    // the filter reads the box only (16 of the record's 156 bytes); kept triangles fetch the rest below
+                    minx = tris[t].minx; maxx = tris[t].maxx; miny = tris[t].miny; maxy = tris[t].maxy;
+                    // does any job tile overlapping this CTA's 16x16 tile test a pixel of the 16x16 tile for this triangle?
+                    keep = legacy_tile_tests_box(d, tx0, tx1, ty0, ty1, minx, maxx, miny, maxy);
                 }
                 // order-preserving compaction (ties are broken by triangle index, candidates are visited in draw order)
                 const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) s_warp_base[warp] = __popc(ballot);
+                if (lane == 0) s_warp_cnt[buf][warp] = __popc(ballot);
                 __syncthreads();
-                if (threadIdx.x == 0)
-                {
-                    uint32_t acc = 0;
-                    for (int i = 0; i < LEGACY_TILE * LEGACY_TILE / 32; ++i) { const uint32_t c = s_warp_base[i]; s_warp_base[i] = acc; acc += c; }
-                    s_count = acc;
-                }
-                __syncthreads();
+                uint32_t before = 0, n = 0;
+#pragma unroll
+                for (int i = 0; i < LEGACY_TILE * LEGACY_TILE / 32; ++i) { const uint32_t c = s_warp_cnt[buf][i]; if (i < warp) before += c; n += c; }
+                if (n == 0) continue; // CTA-uniform: nothing of this chunk reaches the tile
                 if (keep)
                 {
-                    LegacyStage& s = s_tri[s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u))];
+                    const LegacyTri& r = tris[t];
+                    LegacyStage& s = s_tri[buf][before + __popc(ballot & ((1u << lane) - 1u))];
                     s.ax = r.ax; s.ay = r.ay; s.v0x = r.v0x; s.v0y = r.v0y; s.v1x = r.v1x; s.v1y = r.v1y;
                     s.d00 = r.d00; s.d01 = r.d01; s.d11 = r.d11; s.denom = r.denom;
                     s.z0 = r.z[0]; s.z1 = r.z[1]; s.z2 = r.z[2];
-                    s.minx = r.minx; s.maxx = r.maxx; s.miny = r.miny; s.maxy = r.maxy; s.tri = t;
+                    s.minx = minx; s.maxx = maxx; s.miny = miny; s.maxy = maxy; s.tri = t;
                 }
                 __syncthreads();
-                const uint32_t n = s_count;
-                if (inside)
+                if (inside && !corner)
                 {
                     for (uint32_t i = 0; i < n; ++i)
                     {
-                        const LegacyStage& s = s_tri[i];
-                        int ix0, ix1, iy0, iy1;
-                        legacy_job_range(s.minx, s.maxx, jx0, jx1, ix0, ix1);
-                        legacy_job_range(s.miny, s.maxy, jy0, jy1, iy0, iy1);
-                        if (px < ix0 || px > ix1 || py < iy0 || py > iy1) continue;  // the job's pixel loops, :223-224
-                        float u, v, w;
-                        if (!legacy_bary(s, Px, Py, u, v, w)) continue;             // :226-227
-                        const float z = u * s.z0 + v * s.z1 + w * s.z2;              // :230
-                        if (z < best_z) { best_z = z; best_tri = s.tri; }             // ZBuffer::test_and_set_depth: strict LESS, in order
+                        const LegacyStage& s = s_tri[buf][i];
+                        float z;
+                        if (legacy_probe(s, px, py, jx0, jx1, jy0, jy1, z) && z < best_z) { best_z = z; best_tri = s.tri; } // ZBuffer::test_and_set_depth: strict LESS, in order
                     }
                 }
-                __syncthreads(); // s_tri / s_warp_base are rewritten by the next chunk
+                // The corner pixels of a job tile are tested for EVERY triangle that lies outside the job tile in both directions
+                // (legacy_job_range clamps such a box to the corner texel): one lane walking ~all triangles of the draw is the kernel's
+                // critical path.  Their warp probes 32 triangles at a time for them and applies the few hits in draw order.
+                unsigned hot = __ballot_sync(0xffffffffu, inside && corner);
+                while (hot)
+                {
+                    const int src = __ffs(hot) - 1;
+                    hot &= hot - 1u;
+                    const int cpx = __shfl_sync(0xffffffffu, px, src), cpy = __shfl_sync(0xffffffffu, py, src);
+                    const int cjx0 = __shfl_sync(0xffffffffu, jx0, src), cjx1 = __shfl_sync(0xffffffffu, jx1, src);
+                    const int cjy0 = __shfl_sync(0xffffffffu, jy0, src), cjy1 = __shfl_sync(0xffffffffu, jy1, src);
+                    float cz = __shfl_sync(0xffffffffu, best_z, src);
+                    uint32_t ctri = __shfl_sync(0xffffffffu, best_tri, src);
+                    for (uint32_t i0 = 0; i0 < n; i0 += 32u)
+                    {
+                        const uint32_t i = i0 + (uint32_t)lane;
+                        float z = 0.0f;
+                        const bool cand = i < n && legacy_probe(s_tri[buf][i], cpx, cpy, cjx0, cjx1, cjy0, cjy1, z);
+                        unsigned m = __ballot_sync(0xffffffffu, cand);
+                        while (m)
+                        {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1u;
+                            const float zl = __shfl_sync(0xffffffffu, z, l);
+                            if (zl < cz) { cz = zl; ctri = s_tri[buf][i0 + (uint32_t)l].tri; }
+                        }
+                    }
+                    if (lane == src) { best_z = cz; best_tri = ctri; }
+                }
             }
             if (!inside || best_tri == 0xFFFFFFFFu) return;
             zbuf[(size_t)py * d.W + px] = best_z;

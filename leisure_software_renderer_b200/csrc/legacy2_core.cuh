@@ -294,6 +294,16 @@ namespace shsb
             return !(u < 0.0f || v < 0.0f || w < 0.0f);
         }
 
+        // MODE_SHADOW, one texel of one slot: the body of draw_triangle_tile_shadow's pixel loop (:816-836) up to the depth test.  The
+        // shadow pass keeps a plain minimum per texel, so its result does not depend on the order of slots or texels.
+        L2_HD bool shadow_texel_depth(const RasterRec& s, int px, int py, float& z)
+        {
+            float bu, bv, bw;
+            if (!bary(s, (float)px + 0.5f, (float)py + 0.5f, bu, bv, bw)) return false;
+            z = bu * s.z0 + bv * s.z1 + bw * s.z2;
+            return !(z < 0.0f || z > 1.0f);
+        }
+
         struct PixelState
         {
             float best_z;        // running minimum, starts as the buffer's content
@@ -301,28 +311,43 @@ namespace shsb
             bool wrote;          // the depth changed
         };
 
-        // one candidate, in draw order.  (jx0..jy1): the job tile of this pixel, inclusive.
-        L2_HD void pixel_visit(int mode, const RasterRec& s, const BoxRec& b, uint32_t slot, int px, int py, int jx0, int jx1, int jy0, int jy1, PixelState& st)
+        // One candidate at one pixel, split in two: the order-free PROBE (does the job tile test the pixel for this slot, is the pixel
+        // inside, its depth and whether the fragment's 1/w sum is usable) and the order-dependent UPDATE of the pixel's state, which must
+        // see the probes that passed in draw order.  (jx0..jy1): the job tile of the pixel, inclusive.
+        L2_HD bool pixel_probe(int mode, const RasterRec& s, const BoxRec& b, int px, int py, int jx0, int jx1, int jy0, int jy1, float& z, bool& usable)
         {
-            int ix0, ix1, iy0, iy1;
-            job_range(b.minx, b.maxx, jx0, jx1, ix0, ix1);
-            job_range(b.miny, b.maxy, jy0, jy1, iy0, iy1);
-            if (px < ix0 || px > ix1 || py < iy0 || py > iy1) return; // the job's pixel loops
+            // the job's pixel loops: px in [ix0, ix1] = [(int)max(jx0, min(jx1, minx)), (int)min(jx1, max(jx0, maxx))] (job_range), written as
+            // compares -- with jx0 <= px <= jx1 and non-negative operands, ix0 <= px <=> minx < px + 1 or px == jx1, and ix1 >= px <=> maxx >= px
+            // or px == jx0 (tests/test_legacy2_emul_cpu.py holds this form to the oracle's clamps and casts bit for bit)
+            if (!((b.minx < (float)(px + 1) || px == jx1) && (b.maxx >= (float)px || px == jx0))) return false;
+            if (!((b.miny < (float)(py + 1) || py == jy1) && (b.maxy >= (float)py || py == jy0))) return false;
             float bu, bv, bw;
-            if (!bary(s, (float)px + 0.5f, (float)py + 0.5f, bu, bv, bw)) return;
-            const float z = bu * s.z0 + bv * s.z1 + bw * s.z2;
+            if (!bary(s, (float)px + 0.5f, (float)py + 0.5f, bu, bv, bw)) return false;
+            z = bu * s.z0 + bv * s.z1 + bw * s.z2;
+            usable = true;
+            if (mode == MODE_SHADOW) return !(z < 0.0f || z > 1.0f);
+            const float iw_sum = bu * s.iw0 + bv * s.iw1 + bw * s.iw2;
+            usable = !(iw_sum <= 1e-8f);
+            return true;
+        }
+        L2_HD void pixel_update(int mode, float z, bool usable, uint32_t slot, PixelState& st)
+        {
             if (mode == MODE_SHADOW)
             {
-                if (z < 0.0f || z > 1.0f) return;
                 if (z < st.best_z) { st.best_z = z; st.wrote = true; }
                 return;
             }
             if (!(z < st.best_z)) return;
             st.best_z = z;
             st.wrote = true;
-            const float iw_sum = bu * s.iw0 + bv * s.iw1 + bw * s.iw2;
-            if (iw_sum <= 1e-8f) return; // the depth stays written (:951-961)
+            if (!usable) return; // the depth stays written (:951-961)
             st.shade_slot = slot;
+        }
+        L2_HD void pixel_visit(int mode, const RasterRec& s, const BoxRec& b, uint32_t slot, int px, int py, int jx0, int jx1, int jy0, int jy1, PixelState& st)
+        {
+            float z;
+            bool usable;
+            if (pixel_probe(mode, s, b, px, py, jx0, jx1, jy0, jy1, z, usable)) pixel_update(mode, z, usable, slot, st);
         }
 
         // ---- shading helpers
