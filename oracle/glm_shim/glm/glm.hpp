@@ -52,11 +52,12 @@ namespace glm
         vec2& operator/=(float k) { x /= k; y /= k; return *this; }
     };
 
-    struct ivec2 // only what sw_render/debug_draw.hpp's wireframe draw stores: two ints
+    struct ivec2 // what sw_render/debug_draw.hpp's wireframe draw and the legacy demos' job-tile bounds store: two ints
     {
-        int x = 0, y = 0;
-        ivec2() = default;
+        int x, y;
+        ivec2() : x(0), y(0) {}
         ivec2(int X, int Y) : x(X), y(Y) {}
+        explicit operator vec2() const { return vec2((float)x, (float)y); } // glm::vec2(ivec2): int -> float per component
     };
 
     struct vec3

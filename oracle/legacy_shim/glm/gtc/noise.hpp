@@ -12,13 +12,7 @@ namespace glm
     inline float pow(float b, float e) { return std::pow(b, e); }
     inline vec3 pow(const vec3& b, const vec3& e) { return vec3(std::pow(b.x, e.x), std::pow(b.y, e.y), std::pow(b.z, e.z)); }
     inline float sin(float x) { return std::sin(x); }
-    struct ivec2
-    {
-        int x, y;
-        ivec2() : x(0), y(0) {}
-        ivec2(int X, int Y) : x(X), y(Y) {}
-        explicit operator vec2() const { return vec2((float)x, (float)y); } // glm::vec2(ivec2): int -> float per component
-    };
+    // ivec2: oracle/glm_shim/glm/glm.hpp
     inline float fract(float x) { return x - std::floor(x); }
     inline float smoothstep(float e0, float e1, float x) { const float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f); return t * t * (3.0f - 2.0f * t); }
     float simplex(const vec2& p); // declared only: never called by the harness

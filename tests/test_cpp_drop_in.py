@@ -121,6 +121,22 @@ def test_scene_cull_drop_in_compiles_and_has_no_cpu_fallback():
         assert r.returncode == 77 and "every call refused" in r.stdout and "417 of 600 objects visible" in r.stdout
 
 
+def test_flat_draw_drop_in_compiles_and_has_no_cpu_fallback():
+    """host/shs_b200/flat_draw_drop_in.hpp compiled against the reference's debug_draw.hpp / light_runtime.hpp (JoltPhysics declaration
+    shim) and the demo's own draw function: the reference side draws a frame with its per-object calls; without a device the binding
+    refuses every call and draws nothing."""
+    import torch
+    path = os.path.join(ROOT, "tests", "cpp", "_build", "flat_draw_drop_in_test")
+    if not os.path.isdir("/root/reference") and not os.path.exists(path):
+        pytest.skip("reference tree absent and no prebuilt binary")
+    _build()
+    assert os.path.exists(path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([path], capture_output=True, text=True)
+        print(r.stdout, r.stderr)
+        assert r.returncode == 77 and "every call refused" in r.stdout and "26721 of 120000 texels covered" in r.stdout
+
+
 def test_gather_test_compiles_against_the_c_abi_alone_and_refuses_without_a_device():
     """tests/cpp/gather_test.cpp includes nothing but include/shsb.h; without a device both of its processes stop at
     shsb_context_create (SHSB_E_NO_DEVICE -> exit code 77)."""

@@ -168,3 +168,16 @@ def test_flat_draw_argument_checks(gpu):
     finally:
         gpu.rt_destroy(other)
         t.close()
+
+
+def test_flat_draw_drop_in_parity_on_gpu():
+    """shs::b200::FlatDrawBatch over the reference's own types (DebugMesh, RT_ColorLDR, LightInstance with its four light models,
+    LightSelection) vs the reference's per-object draws (tests/cpp/flat_draw_drop_in_test.cpp): depth bit for bit, canvas <= 1 LSB."""
+    import os
+    import subprocess
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "_build", "flat_draw_drop_in_test")
+    if not os.path.exists(path):
+        pytest.skip("tests/cpp/_build/flat_draw_drop_in_test was not built (needs /root/reference at build time)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
