@@ -501,6 +501,14 @@ SHSB_API int32_t shsb_cluster_lists_download(shsb_ctx ctx, uint32_t* counts, siz
  * (build_tile_view_depth_range_from_scene, lighting/light_culling_runtime.hpp:254-261).  The software analogue of
  * shaders/vulkan/fp_stress_depth_reduce.comp.  The result stays on the device for shsb_light_cull_ex. */
 SHSB_API int32_t shsb_tile_depth_range(shsb_ctx ctx, shsb_rt depth_motion_rt, uint32_t tile_size);
+/* shaders/vulkan/fp_stress_depth_reduce.comp itself (:40-81), for a depth plane that holds the HARDWARE's zero-to-one projective depth
+ * of the reference's LH projection, d = f / (f - n) - n f / ((f - n) view_z) -- the depth attachment of the reference's Vulkan path, here
+ * uploaded with shsb_rt_upload (the software rasteriser never writes this encoding: its fallback for zf <= zn is the interpolated clip z
+ * * 0.5 + 0.5, sw_render/rasterizer.hpp:345-347): view_z = near * far / max(far - clamp(d, 0, 1) * (far - near), 1e-5) with
+ * near = max(z_near, 0.001), far = max(z_far, near + 0.01) (depth01_to_view_lh_no, :31-38; z_near / z_far = ubo.depth_params.xy); texels
+ * >= 1 are skipped, a tile without any other texel gets (0, 0) as in the shader.  Any target with a depth plane; the result stays on the
+ * device like shsb_tile_depth_range's. */
+SHSB_API int32_t shsb_tile_depth_range_ndc01(shsb_ctx ctx, shsb_rt depth_rt, uint32_t tile_size, float z_near, float z_far);
 SHSB_API int32_t shsb_tile_depth_range_download(shsb_ctx ctx, float* out_min, float* out_max, size_t n_tiles);
 
 /* Fused Forward+ frame = light cull + PassPBRForward (Forward+) + PassTonemap in one submission

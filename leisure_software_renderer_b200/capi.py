@@ -278,6 +278,7 @@ def load_library(path: str | None = None):
         "shsb_light_cull_ex": [vp, P(LightCullDesc), P(C.c_float), P(C.c_float)],
         "shsb_cluster_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
         "shsb_tile_depth_range": [vp, C.c_uint32, C.c_uint32],
+        "shsb_tile_depth_range_ndc01": [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float],
         "shsb_tile_depth_range_download": [vp, P(C.c_float), P(C.c_float), C.c_size_t],
         "shsb_light_lists_download": [vp, P(C.c_uint32), C.c_size_t, P(C.c_uint32), C.c_size_t],
         "shsb_frame_forward_plus": [vp, P(Scene), P(FrameParams), C.c_uint32, C.c_uint32, C.c_uint32, P(Stats)],

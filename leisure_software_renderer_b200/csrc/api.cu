@@ -2810,19 +2810,33 @@ SHSB_API int32_t shsb_light_cull(shsb_ctx ctx, const float view_proj[16], uint32
     return SHSB_OK;
 }
 
+namespace
+{
+    int tile_depth_range_common(shsb_ctx ctx, shsb_rt depth_rt, uint32_t tile_size, bool ndc01, float z_near, float z_far)
+    {
+        if (!ctx || tile_size == 0) return SHSB_E_INVALID_ARGUMENT;
+        CK(cudaSetDevice(ctx->device));
+        RtSlot* dm = ndc01 ? get_rt(ctx, depth_rt) : get_rt(ctx, depth_rt, SHSB_RT_DEPTH_MOTION);
+        if (!dm || !dm->depth) return fail(ctx, SHSB_E_INVALID_HANDLE, ndc01 ? "tile depth range needs a live target with a depth plane" : "tile depth range needs a live RT_ColorDepthMotion");
+        const size_t tiles = (size_t)((dm->w + tile_size - 1) / tile_size) * ((dm->h + tile_size - 1) / tile_size);
+        if (int rc = ensure_dev(ctx, ctx->d_range_min, tiles)) return rc;
+        if (int rc = ensure_dev(ctx, ctx->d_range_max, tiles)) return rc;
+        launch_tile_depth_range(dm->depth, dm->w, dm->h, tile_size, ndc01 ? z_near : dm->zn, ndc01 ? z_far : dm->zf, ndc01 ? 1 : 0, ctx->d_range_min.p, ctx->d_range_max.p, ctx->stream,
+                                &ctx->launches);
+        CK(cudaGetLastError());
+        ctx->range_w = (uint32_t)dm->w; ctx->range_h = (uint32_t)dm->h; ctx->range_ts = tile_size;
+        return SHSB_OK;
+    }
+}
+
 SHSB_API int32_t shsb_tile_depth_range(shsb_ctx ctx, shsb_rt depth_motion_rt, uint32_t tile_size)
 {
-    if (!ctx || tile_size == 0) return SHSB_E_INVALID_ARGUMENT;
-    CK(cudaSetDevice(ctx->device));
-    RtSlot* dm = get_rt(ctx, depth_motion_rt, SHSB_RT_DEPTH_MOTION);
-    if (!dm) return fail(ctx, SHSB_E_INVALID_HANDLE, "tile depth range needs a live RT_ColorDepthMotion");
-    const size_t tiles = (size_t)((dm->w + tile_size - 1) / tile_size) * ((dm->h + tile_size - 1) / tile_size);
-    if (int rc = ensure_dev(ctx, ctx->d_range_min, tiles)) return rc;
-    if (int rc = ensure_dev(ctx, ctx->d_range_max, tiles)) return rc;
-    launch_tile_depth_range(dm->depth, dm->w, dm->h, tile_size, dm->zn, dm->zf, ctx->d_range_min.p, ctx->d_range_max.p, ctx->stream, &ctx->launches);
-    CK(cudaGetLastError());
-    ctx->range_w = (uint32_t)dm->w; ctx->range_h = (uint32_t)dm->h; ctx->range_ts = tile_size;
-    return SHSB_OK;
+    return tile_depth_range_common(ctx, depth_motion_rt, tile_size, false, 0.0f, 0.0f);
+}
+
+SHSB_API int32_t shsb_tile_depth_range_ndc01(shsb_ctx ctx, shsb_rt depth_rt, uint32_t tile_size, float z_near, float z_far)
+{
+    return tile_depth_range_common(ctx, depth_rt, tile_size, true, z_near, z_far);
 }
 
 SHSB_API int32_t shsb_tile_depth_range_download(shsb_ctx ctx, float* out_min, float* out_max, size_t n_tiles)

@@ -436,8 +436,12 @@ namespace shsb
         // geometry gets [zn, zf] like build_tile_view_depth_range_from_scene (light_culling_runtime.hpp:254-261).  The
         // software analogue of shaders/vulkan/fp_stress_depth_reduce.comp.  Light tiles are top-anchored
         // (jolt_light_culling.hpp:105-107) while the framebuffer is y-up: tile row ty covers rows H-1-py in [ty*ts, (ty+1)*ts).
+        // ndc01 != 0: the buffer holds the hardware's zero-to-one projective depth (uploaded by the caller) and the result is the compute shader's own:
+        // view_z = near * far / max(far - clamp(d) * (far - near), 1e-5) with near = max(zn, 0.001), far = max(zf, near + 0.01)
+        // (fp_stress_depth_reduce.comp:31-38), min / max starting at 1e30 / 0, (0, 0) for a tile without geometry (:56-57, :73-77).  Every
+        // step of that mapping is monotone in d under IEEE rounding, so it commutes with the reduction here as well.
         __global__ void __launch_bounds__(CULL_THREADS) tile_depth_range_kernel(const float* __restrict__ depth, int W, int H, uint32_t ts, uint32_t tiles_x, uint32_t tiles_y,
-                                                                                float zn, float zf, float* __restrict__ out_min, float* __restrict__ out_max)
+                                                                                float zn, float zf, int ndc01, float* __restrict__ out_min, float* __restrict__ out_max)
         {
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             const uint32_t tile = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
@@ -446,7 +450,7 @@ namespace shsb
             const int x0 = (int)(tx * ts), x1 = min((int)((tx + 1u) * ts), W);
             const int r0 = (int)(ty * ts), r1 = min((int)((ty + 1u) * ts), H); // rows counted from the top
             const int tw = x1 - x0, n = tw * (r1 - r0);
-            float lo = 2.0f, hi = -1.0f;
+            float lo = INFINITY, hi = -INFINITY; // any value below 1 takes part, negative ones included
             for (int i = lane; i < n; i += 32)
             {
                 const int px = x0 + i % tw, py = H - 1 - (r0 + i / tw);
@@ -463,7 +467,17 @@ namespace shsb
             }
             if (lane == 0)
             {
-                const bool any = hi >= 0.0f;
+                const bool any = hi > -INFINITY;
+                if (ndc01)
+                {
+                    const float near_z = gmax(zn, 0.001f), far_z = gmax(zf, xadd(near_z, 0.01f));
+                    const float span = xsub(far_z, near_z), nf = xmul(near_z, far_z);
+                    const float vlo = xdiv(nf, gmax(xsub(far_z, xmul(gclamp(lo, 0.0f, 1.0f), span)), 1e-5f));
+                    const float vhi = xdiv(nf, gmax(xsub(far_z, xmul(gclamp(hi, 0.0f, 1.0f), span)), 1e-5f));
+                    out_min[tile] = any ? gmin(1e30f, vlo) : 0.0f;
+                    out_max[tile] = any ? gmax(0.0f, vhi) : 0.0f;
+                    return;
+                }
                 const float k = xsub(zf, zn);
                 out_min[tile] = any ? xadd(zn, xmul(lo, k)) : zn; // monotone in d, so min / max commute with the mapping
                 out_max[tile] = any ? xadd(zn, xmul(hi, k)) : zf;
@@ -524,12 +538,12 @@ namespace shsb
         *launches += 2;
     }
 
-    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches)
+    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, int ndc01, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches)
     {
         const uint32_t tiles_x = ((uint32_t)W + ts - 1) / ts, tiles_y = ((uint32_t)H + ts - 1) / ts;
         const uint32_t tiles = tiles_x * tiles_y;
         if (!tiles) return;
-        tile_depth_range_kernel<<<(tiles + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(depth, W, H, ts, tiles_x, tiles_y, zn, zf, out_min, out_max);
+        tile_depth_range_kernel<<<(tiles + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(depth, W, H, ts, tiles_x, tiles_y, zn, zf, ndc01, out_min, out_max);
         *launches += 1;
     }
 }

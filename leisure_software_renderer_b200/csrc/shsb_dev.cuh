@@ -339,7 +339,7 @@ namespace shsb
                                  uint32_t vw, uint32_t vh, uint32_t ts, uint32_t max_per_bin, int mode, uint32_t n_slices,
                                  const float* range_min, const float* range_max, const float2* slice_ndc, float z_near, float z_far,
                                  uint32_t* vis_scratch, uint32_t* counts, uint32_t* indices, cudaStream_t s, uint64_t* launches);
-    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches);
+    void launch_tile_depth_range(const float* depth, int W, int H, uint32_t ts, float zn, float zf, int ndc01, float* out_min, float* out_max, cudaStream_t s, uint64_t* launches);
     size_t light_cull_scratch_words(uint32_t n_lights, uint32_t vw, uint32_t vh, uint32_t ts); // u32 words of `scratch`
     // sort-first frame assembly (gather.cu): publish / await monotonic 64-bit step counters in (peer) device memory
     void launch_gather_signal(unsigned long long* flag, unsigned long long value, cudaStream_t s, uint64_t* launches);

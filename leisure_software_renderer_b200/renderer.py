@@ -357,6 +357,15 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_tile_depth_range_download(self.h, capi.fptr(lo), capi.fptr(hi), n), "shsb_tile_depth_range_download")
         return lo, hi
 
+    def tile_depth_range_ndc01(self, depth_rt, tile_size, z_near, z_far):
+        """fp_stress_depth_reduce.comp on a depth plane that holds projective depth in [0, 1]; returns (min, max) view depth per tile."""
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range_ndc01(self.h, depth_rt, tile_size, float(z_near), float(z_far)), "shsb_tile_depth_range_ndc01")
+        _, w, h = self._rt_shape[depth_rt]
+        n = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+        lo, hi = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        _check(self.lib, self.h, self.lib.shsb_tile_depth_range_download(self.h, capi.fptr(lo), capi.fptr(hi), n), "shsb_tile_depth_range_download")
+        return lo, hi
+
     def light_lists_download(self):
         counts = np.zeros(self._tiles, dtype=np.uint32)
         indices = np.zeros(self._tiles * self._max_per_tile, dtype=np.uint32)

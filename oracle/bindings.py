@@ -62,6 +62,29 @@ def available(kind: str) -> bool:
     return os.path.exists(PORT_LIB if kind == "port" else REF_LIB)
 
 
+def _tile_depth_range_ndc01(fn, depth, tile_size, z_near, z_far):
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    h, w = d.shape
+    n = ((w + tile_size - 1) // tile_size) * ((h + tile_size - 1) // tile_size)
+    lo, hi = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    rc = fn(capi.fptr(d), C.c_int32(w), C.c_int32(h), C.c_uint32(tile_size), C.c_float(z_near), C.c_float(z_far), capi.fptr(lo), capi.fptr(hi))
+    assert rc == 0, rc
+    return lo, hi
+
+
+def glsl_depth_reduce_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libshs_glsl_a9_ref.so")) or os.path.isdir("/root/reference")
+
+
+def glsl_tile_depth_range_ndc01(depth, tile_size, z_near, z_far):
+    """shaders/vulkan/fp_stress_depth_reduce.comp, the shader's own text compiled as C++ (oracle/extract_glsl_a9.py +
+    oracle/ref_glsl_a9_harness.cpp: shsglsl_tile_depth_range_ndc01)."""
+    path = os.path.join(_HERE, "_ref", "libshs_glsl_a9_ref.so")
+    if not os.path.exists(path):
+        build("reference")
+    return _tile_depth_range_ndc01(C.CDLL(path).shsglsl_tile_depth_range_ndc01, depth, tile_size, z_near, z_far)
+
+
 class HostAssets:
     """Keeps numpy arrays alive behind a ShsoAssets block (1-based handles like ResourceRegistry)."""
 
@@ -262,6 +285,11 @@ class Oracle:
                                             capi.fptr(lo), capi.fptr(hi))
         assert rc == 0, rc
         return lo, hi
+
+    def tile_depth_range_ndc01(self, depth, tile_size, z_near, z_far):
+        """fp_stress_depth_reduce.comp restated (shso_tile_depth_range_ndc01); glsl_tile_depth_range_ndc01 below is the shader's own text."""
+        assert self.kind == "port"
+        return _tile_depth_range_ndc01(self.lib.shso_tile_depth_range_ndc01, depth, tile_size, z_near, z_far)
 
     def pass_taa(self, ldr, history, history_valid):
         """In place on both arrays (PassTemporalAAAdapter); returns them."""

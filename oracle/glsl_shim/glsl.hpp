@@ -60,6 +60,14 @@ namespace glsl
         explicit uvec2(vec2 v) : x((uint)v.x), y((uint)v.y) {} // float -> uint conversion truncates toward zero
     };
     struct uvec4 { uint x, y, z, w; };
+    struct uvec3 { uint x, y, z; };
+    struct ivec2 // fp_stress_depth_reduce.comp: texel coordinates
+    {
+        int x, y;
+        ivec2() : x(0), y(0) {}
+        ivec2(int a, int b) : x(a), y(b) {}
+        ivec2(uint a, uint b) : x((int)a), y((int)b) {} // uint -> int conversion keeps the bit pattern
+    };
 
     struct mat4
     {

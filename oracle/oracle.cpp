@@ -1801,6 +1801,40 @@ int32_t shso_tile_depth_range(const float* depth, int32_t w, int32_t h, uint32_t
     return SHSB_OK;
 }
 
+int32_t shso_tile_depth_range_ndc01(const float* depth, int32_t w, int32_t h, uint32_t ts, float z_near, float z_far, float* out_min, float* out_max)
+{
+    // shaders/vulkan/fp_stress_depth_reduce.comp restated: per-tile [min, max] view depth of a depth plane in the hardware's zero-to-one
+    // encoding of the LH projection (the Vulkan path's depth attachment; the software rasteriser does not write it), inverted by
+    // depth01_to_view_lh_no (:31-38).  Texels >= 1 are skipped (:64-65), a tile without any other texel gets (0, 0) (:73-77), min / max
+    // start at 1e30 / 0 (:56-57).  Tile rows are top-anchored, buffer rows y-up.
+    // PINNED against the shader's own text compiled as C++ (oracle/ref_glsl_a9_harness.cpp; tests/test_light_bins_cpu.py).
+    if (!depth || !out_min || !out_max || w <= 0 || h <= 0 || ts == 0) return SHSB_E_INVALID_ARGUMENT;
+    const uint32_t tiles_x = ((uint32_t)w + ts - 1) / ts, tiles_y = ((uint32_t)h + ts - 1) / ts;
+    auto gmaxf = [](float a, float b) { return (a < b) ? b : a; };
+    auto gminf = [](float a, float b) { return (b < a) ? b : a; };
+    const float near_z = gmaxf(z_near, 0.001f), far_z = gmaxf(z_far, near_z + 0.01f);
+    for (uint32_t ty = 0; ty < tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx)
+        {
+            bool any = false;
+            float lo = 1e30f, hi = 0.0f;
+            for (uint32_t r = ty * ts; r < std::min((ty + 1) * ts, (uint32_t)h); ++r)
+                for (uint32_t x = tx * ts; x < std::min((tx + 1) * ts, (uint32_t)w); ++x)
+                {
+                    const float d01 = depth[(size_t)((uint32_t)h - 1 - r) * w + x];
+                    if (d01 >= 1.0f) continue;
+                    const float d = gminf(gmaxf(d01, 0.0f), 1.0f);
+                    const float denom = gmaxf(far_z - d * (far_z - near_z), 1e-5f);
+                    const float vz = (near_z * far_z) / denom;
+                    lo = gminf(lo, vz); hi = gmaxf(hi, vz);
+                    any = true;
+                }
+            out_min[ty * tiles_x + tx] = any ? lo : 0.0f;
+            out_max[ty * tiles_x + tx] = any ? hi : 0.0f;
+        }
+    return SHSB_OK;
+}
+
 // ---- test hooks of row A9 (tests/test_a9_pinned_cpu.py): the restatement's per-light radiance, attenuation and list walk for
 // ONE surface point, so that they can be held against the reference's GLSL compiled as C++ (oracle/ref_glsl_a9_harness.cpp)
 void shso_eval_local_light(const void* records160, uint32_t idx, const float P[3], const float N[3], const float V[3], const float albedo[3],

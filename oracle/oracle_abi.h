@@ -128,6 +128,9 @@ int32_t shso_light_cull_ex(const void* records160, uint32_t n_lights, const Shsb
  * semantics defined in oracle.cpp). */
 int32_t shso_tile_depth_range(const float* depth, int32_t w, int32_t h, uint32_t tile_size, float zn, float zf,
                               float* out_min, float* out_max);
+/* shaders/vulkan/fp_stress_depth_reduce.comp itself, for a z-buffer that holds projective depth in [0, 1] (pinned against the shader's text) */
+int32_t shso_tile_depth_range_ndc01(const float* depth, int32_t w, int32_t h, uint32_t tile_size, float z_near, float z_far,
+                                    float* out_min, float* out_max);
 
 /* Forward+ frame: PassPBRForward with the local-light loop of fp_stress_scene.frag:644-678 added to
  * the builtin fragment program.  counts/indices as produced by shso_light_cull. */

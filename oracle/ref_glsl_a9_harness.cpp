@@ -15,6 +15,7 @@
 //   * gl_FragCoord: Vulkan's window origin is the UPPER-left corner with pixel centres at +0.5, the software rasterizer's rows
 //     run bottom-up (rasterizer.hpp:267-269), so pixel (px, py) of an H-row target is gl_FragCoord = (px + 0.5, (H - 1 - py) + 0.5).
 #include <cstring>
+#include <vector>
 
 #include "glsl_shim/glsl.hpp"
 
@@ -79,3 +80,42 @@ void shsglsl_local_light_loop(const void* records160, uint32_t n_lights, const u
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// The per-tile depth reduce: shaders/vulkan/fp_stress_depth_reduce.comp, lifted the same way into
+// oracle/_ref/glsl_depth_reduce_generated.inc (its CameraUBO block, depth01_to_view_lh_no, main() renamed shs_depth_reduce_main).
+// The harness supplies the shader's interface: gl_GlobalInvocationID, the tile_depth_ranges buffer, and texelFetch on depth_tex --
+// Vulkan image rows run top-down, the software z-buffer's rows bottom-up (gfx/rt_types.hpp:35-59), so texel (px, py) is
+// depth[(H - 1 - py) * W + px], the same flip the light tiles use (jolt_light_culling.hpp:105-107).
+namespace shs_glsl_reduce
+{
+    using namespace glsl;
+    uvec3 gl_GlobalInvocationID;
+    vec2* tile_depth_ranges = nullptr;
+    struct DepthTex { const float* texels; int w, h; } depth_tex{nullptr, 0, 0};
+    inline vec4 texelFetch(const DepthTex& t, ivec2 p, int) { return vec4(t.texels[(size_t)(t.h - 1 - p.y) * (size_t)t.w + (size_t)p.x], 0.0f, 0.0f, 1.0f); }
+
+#include "_ref/glsl_depth_reduce_generated.inc"
+}
+
+extern "C" int32_t shsglsl_tile_depth_range_ndc01(const float* depth, int32_t w, int32_t h, uint32_t ts, float z_near, float z_far, float* out_min, float* out_max)
+{
+    using namespace shs_glsl_reduce;
+    if (!depth || !out_min || !out_max || w <= 0 || h <= 0 || ts == 0) return 1;
+    const uint32_t tiles_x = ((uint32_t)w + ts - 1) / ts, tiles_y = ((uint32_t)h + ts - 1) / ts;
+    ubo = CameraUBO{};
+    ubo.screen_tile_lightcount.x = (uint32_t)w; ubo.screen_tile_lightcount.y = (uint32_t)h; ubo.screen_tile_lightcount.z = tiles_x;
+    ubo.params.x = tiles_y; ubo.params.z = ts;
+    ubo.depth_params.x = z_near; ubo.depth_params.y = z_far;
+    depth_tex = DepthTex{depth, w, h};
+    std::vector<vec2> ranges((size_t)tiles_x * tiles_y);
+    tile_depth_ranges = ranges.data();
+    for (uint32_t ty = 0; ty < tiles_y; ++ty) // the dispatch: one invocation per tile (local_size 1 x 1 x 1)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx)
+        {
+            gl_GlobalInvocationID = uvec3{tx, ty, 0u};
+            shs_depth_reduce_main();
+        }
+    for (size_t i = 0; i < ranges.size(); ++i) { out_min[i] = ranges[i].x; out_max[i] = ranges[i].y; }
+    return 0;
+}

@@ -125,3 +125,22 @@ def test_bins_with_every_light_type(gpu, port):
             assert int(oc.sum()) > 0
     finally:
         g.release()
+
+
+@pytest.mark.parametrize("seed", list(range(25)))
+def test_depth_reduce_ndc01_equals_the_pinned_restatement(gpu, port, seed):
+    """shsb_tile_depth_range_ndc01 (the reference's fp_stress_depth_reduce.comp as a device path) against the restatement that
+    tests/test_light_bins_cpu.py pins to the shader's own text: per-tile (min, max) bit for bit, for three tile sizes, on depth planes
+    with cleared / out-of-range / negative texels, empty tiles, ragged sizes and the shader's near / far clamps."""
+    d, zn, zf = lb.ndc01_depth_buffers(seed)
+    h, w = d.shape
+    rt = gpu.rt_create(capi.RT_SHADOW if seed % 2 else capi.RT_DEPTH_MOTION, w, h)
+    try:
+        gpu.rt_upload(rt, capi.PLANE_DEPTH, d)
+        for ts in (16, 8, 32):
+            lo, hi = gpu.tile_depth_range_ndc01(rt, ts, zn, zf)
+            olo, ohi = port.tile_depth_range_ndc01(d, ts, zn, zf)
+            assert np.array_equal(lo.view(np.uint32), olo.view(np.uint32)) and np.array_equal(hi.view(np.uint32), ohi.view(np.uint32)), (seed, ts)
+    finally:
+        gpu.rt_destroy(rt)
+    assert gpu.lib.shsb_tile_depth_range_ndc01(gpu.h, 9999, 16, 0.1, 100.0) == 2 and gpu.lib.shsb_tile_depth_range_ndc01(gpu.h, 1, 0, 0.1, 100.0) == 1
