@@ -113,7 +113,35 @@ def build_no_stores() -> str:
     return out
 
 
+def build_variant(tag: str, defines: list) -> str:
+    """Experiment variant libshsb_<tag>.so: EVERY translation unit recompiled with extra -D flags (tools/gpu_ab_lib.sh, via SHSB_LIB)."""
+    cc = nvcc()
+    obj = os.path.join(OBJ, tag)
+    os.makedirs(obj, exist_ok=True)
+    procs, objs = [], []
+    for src, extra in SOURCES.items():
+        o = os.path.join(obj, src.replace(".cu", ".o"))
+        procs.append((src, subprocess.Popen([cc, *ARCH, *COMMON, *extra, *defines, "-c", os.path.join(CSRC, src), "-o", o], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    out = os.path.join(HERE, f"libshsb_{tag}.so")
+    subprocess.run([cc, *ARCH, "-shared", "-o", out, *objs, "-Xcompiler", "-fPIC", "-lz"], check=True)
+    return out
+
+
 if __name__ == "__main__":
+    if "--tile-h8" in sys.argv:
+        print(build_variant("h8", ["-DSHSB_TILE_H=8"]))
+        sys.exit(0)
+    if "--tile-h4" in sys.argv:
+        print(build_variant("h4", ["-DSHSB_TILE_H=4"]))
+        sys.exit(0)
+    if "--tile-h16" in sys.argv:
+        print(build_variant("h16", ["-DSHSB_TILE_H=16"]))
+        sys.exit(0)
     if "--no-stores" in sys.argv:
         print(build_no_stores())
         sys.exit(0)

@@ -658,7 +658,7 @@ namespace
     {
         FrameConst& fc = job.fc;
         fc.tiles_x = (fc.W + TILE - 1) / TILE;
-        fc.tiles_y = (fc.H + TILE - 1) / TILE;
+        fc.tiles_y = (fc.H + TILE_H - 1) / TILE_H;
         fc.hiz = (ctx->hiz && !out_stats && !fc.write_aovs) ? 1 : 0; // hidden fragments a Hi-Z reject skips are not counted: only where nobody reads the counters
         const uint32_t n_tiles = (uint32_t)fc.tiles_x * (uint32_t)fc.tiles_y;
         if (fc.W > 65535 || fc.H > 65535) return fail(ctx, SHSB_E_UNSUPPORTED, "render target larger than 65535 pixels on a side");

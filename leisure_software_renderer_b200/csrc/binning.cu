@@ -33,8 +33,8 @@ namespace shsb
             TileRange t;
             t.tx0 = minx / TILE;
             t.tx1 = maxx / TILE;
-            t.ty0 = (H - 1 - maxy) / TILE; // tile rows are anchored at the TOP of the frame (y is up in the RT)
-            t.ty1 = (H - 1 - miny) / TILE;
+            t.ty0 = (H - 1 - maxy) / TILE_H; // tile rows are anchored at the TOP of the frame (y is up in the RT)
+            t.ty1 = (H - 1 - miny) / TILE_H;
             return t;
         }
 
@@ -119,7 +119,9 @@ namespace shsb
             uint32_t cls = c ? 2u : 3u;
             if (live && c && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE)
             {
-                const uint32_t lc = fc.tile_counts[t];
+                // the light tile (16 x 16) this raster tile lies in
+                const uint32_t lc = fc.tile_counts[min((t / (uint32_t)fc.tiles_x) * (uint32_t)TILE_H / (uint32_t)TILE, fc.light_tiles_y - 1u) * fc.light_tiles_x +
+                                                   min(t % (uint32_t)fc.tiles_x, fc.light_tiles_x - 1u)];
                 if (lc >= fc.max_per_tile) cls = 0u;
                 else if (lc >= 48u) cls = 1u;
             }

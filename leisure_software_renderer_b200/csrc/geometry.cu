@@ -170,8 +170,8 @@ namespace shsb
             TileRange t;
             t.tx0 = (int)(bbox_x & 0xffffu) / TILE;
             t.tx1 = (int)(bbox_x >> 16) / TILE;
-            t.ty0 = (H - 1 - (int)(bbox_y >> 16)) / TILE;
-            t.ty1 = (H - 1 - (int)(bbox_y & 0xffffu)) / TILE;
+            t.ty0 = (H - 1 - (int)(bbox_y >> 16)) / TILE_H;
+            t.ty1 = (H - 1 - (int)(bbox_y & 0xffffu)) / TILE_H;
             return t;
         }
 

@@ -24,8 +24,15 @@
 
 namespace shsb
 {
-    constexpr int TILE = 16;           // raster tile edge in pixels (== Forward+ light tile of the reference default)
-    constexpr int TILE_PIXELS = TILE * TILE;
+    constexpr int TILE = 16;           // raster tile WIDTH in pixels == Forward+ light tile of the reference default == unit of the own-row partition
+#ifndef SHSB_TILE_H
+#define SHSB_TILE_H 8
+#endif
+    // raster tile HEIGHT.  Measured on B200 (profiles/r2_tile_height_ab.md): 16 x 8 tiles -- two raster tiles per light tile, 4 instead of 8
+    // warps waiting for the slowest 8x4 block of their tile -- beat 16 x 16 by 2.6 % (C2 frames/s) to 9-13 % (C3-C5 tile kernel); 16 x 4 loses on C2.
+    constexpr int TILE_H = SHSB_TILE_H;
+    static_assert(TILE_H == 16 || TILE_H == 8 || TILE_H == 4, "a raster tile is 16 x 16, 16 x 8 or 16 x 4 pixels");
+    constexpr int TILE_PIXELS = TILE * TILE_H;
     constexpr uint32_t KEY_NONE = 0u;  // internal draw-order key = public key + 1; 0 = "no fragment yet"
 
     // ---------------------------------------------------------------- exact binary32 ops (never fused)
@@ -199,9 +206,11 @@ namespace shsb
         int hiz;
     };
 
+    // ty: RASTER tile row; the partition is stated in rows of TILE (16) pixels (ShsbFrameParams::own_row_*)
     __host__ __device__ __forceinline__ bool owned_row(const FrameConst& fc, int ty)
     {
-        return fc.own_count <= 0 || (ty >= fc.own_first && ((ty - fc.own_first) % fc.own_stride) < fc.own_count);
+        const int row = ty * TILE_H / TILE;
+        return fc.own_count <= 0 || (row >= fc.own_first && ((row - fc.own_first) % fc.own_stride) < fc.own_count);
     }
 
     struct FrameBuffers

@@ -21,7 +21,8 @@ namespace shsb
 {
     namespace
     {
-        constexpr int TILE_THREADS = 256;
+        constexpr int TILE_THREADS = TILE_PIXELS; // 256 (16 x 16) or 128 (16 x 8): one thread per pixel
+        constexpr int TILE_WARPS = TILE_THREADS / 32;
 #ifdef SHSB_PHASE_CLOCKS
         // Debug build only (tools/phase_clocks.py): per scheduling class, cycles thread 0 of each tile CTA spends per phase.
         __device__ unsigned long long g_phase_clk[4][8];
@@ -34,7 +35,7 @@ namespace shsb
 #define PHASE_COUNT() do { } while (0)
 #endif
 #ifndef TILE_MIN_CTAS
-#define TILE_MIN_CTAS 4
+#define TILE_MIN_CTAS (1024 / TILE_PIXELS) /* 32 warps per SM either way (64 registers per thread) */
 #endif
         // Debug build only (tools/gpu_store_bound.sh, libshsb_nostore.so): the tile kernel's render-target stores of tiles WITH geometry
         // are predicated on a value no computation produces, so that everything is still computed but nothing is written -- the time
@@ -481,12 +482,13 @@ namespace shsb
                 // ---------------- empty tiles (class 3; most of a frame): nothing to rasterise, no barriers, no counters.
                 // One CTA resolves FOUR tiles, one thread 4 horizontally adjacent pixels with 128-bit stores; the
                 // background colour depends on the row only, so it is evaluated once per 4 pixels.
-                const uint32_t first = (blockIdx.x - n_nonempty) * 4u + (threadIdx.x >> 6);
+                constexpr int Q = TILE_PIXELS / 4; // threads per empty tile: 4 per row
+                const uint32_t first = (blockIdx.x - n_nonempty) * 4u + (threadIdx.x / Q);
                 if (first >= g.class_count[3]) return; // owned empty tiles only (sort-first partitions leave other rows untouched)
                 const uint32_t packed = g.tile_order[(size_t)3 * n_tiles_total + first];
-                const int q = threadIdx.x & 63;
+                const int q = threadIdx.x % Q;
                 const int x0 = (int)(packed & 0xffffu) * TILE + (q & 3) * 4;
-                const int fy = (int)(packed >> 16) * TILE + (q >> 2);
+                const int fy = (int)(packed >> 16) * TILE_H + (q >> 2);
                 if (x0 >= fc.W || fy >= fc.H) return;
                 const int py = fc.H - 1 - fy;
                 const size_t pix = (size_t)py * (size_t)fc.W + (size_t)x0;
@@ -534,7 +536,7 @@ namespace shsb
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             // a warp owns an 8x4-pixel block: 128 contiguous bytes of HDR per row
             const int px = tx * TILE + (warp & 1) * 8 + (lane & 7);
-            const int fy = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+            const int fy = ty * TILE_H + (warp >> 1) * 4 + (lane >> 3);
             const int py = fc.H - 1 - fy;
             const bool valid = px < fc.W && fy < fc.H;
             const size_t pix = valid ? ((size_t)py * (size_t)fc.W + (size_t)px) : 0;
@@ -590,7 +592,7 @@ namespace shsb
                 for (int w = 0; w < TILE_THREADS / 32; ++w)
                 {
                     const int rx0 = tx * TILE + (w & 1) * 8, rx1 = rx0 + 7;
-                    const int ry_hi = fc.H - 1 - (ty * TILE + (w >> 1) * 4), ry_lo = ry_hi - 3;
+                    const int ry_hi = fc.H - 1 - (ty * TILE_H + (w >> 1) * 4), ry_lo = ry_hi - 3;
                     const bool hit = threadIdx.x < n && !(smaxx < rx0 || sminx > rx1 || smaxy < ry_lo || sminy > ry_hi);
                     const unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (lane == 0) s_wmask[w][warp] = m;
@@ -848,7 +850,7 @@ namespace shsb
                         bx1 = fmaxf(bx1, s_box[w][3]); by1 = fmaxf(by1, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
                     }
 
-                    const uint32_t list_id = (uint32_t)min(ty, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
+                    const uint32_t list_id = (uint32_t)min(ty * TILE_H / TILE, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
                     const uint32_t listed = min(fc.tile_counts[list_id], fc.max_per_tile);
                     const bool saturated = listed >= fc.max_per_tile;
                     const uint32_t n_src = saturated ? fc.n_lights : listed;
@@ -887,7 +889,7 @@ namespace shsb
                         }
                         __syncthreads(); // ballots visible
                         // ---- exclusive prefix over the 32 (slot, warp) ballots, computed redundantly by every warp
-                        const bool slot_live = sbase + (uint32_t)(lane / (TILE_THREADS / 32)) * TILE_THREADS < n_src;
+                        const bool slot_live = lane < CAND_PER_THREAD * TILE_WARPS && sbase + (uint32_t)(lane / TILE_WARPS) * TILE_THREADS < n_src;
                         const uint32_t cnt = slot_live ? (uint32_t)__popc(s_ballot[lane]) : 0u;
                         uint32_t incl = cnt;
 #pragma unroll
