@@ -139,6 +139,9 @@ if __name__ == "__main__":
     if "--tile-h4" in sys.argv:
         print(build_variant("h4", ["-DSHSB_TILE_H=4"]))
         sys.exit(0)
+    if "--cand8" in sys.argv:
+        print(build_variant("cand8", ["-DSHSB_CAND_PER_THREAD=8"]))
+        sys.exit(0)
     if "--tile-h16" in sys.argv:
         print(build_variant("h16", ["-DSHSB_TILE_H=16"]))
         sys.exit(0)

@@ -446,7 +446,11 @@ namespace shsb
         }
 
         constexpr int LIGHT_CAP = TILE_THREADS;       // staged lights per pass
-        constexpr int CAND_PER_THREAD = 4;            // candidates filtered per thread per staging round (1024 per CTA)
+#ifndef SHSB_CAND_PER_THREAD
+#define SHSB_CAND_PER_THREAD 4
+#endif
+        constexpr int CAND_PER_THREAD = SHSB_CAND_PER_THREAD; // candidates filtered per thread per staging round (x TILE_THREADS per CTA)
+        static_assert(CAND_PER_THREAD * (TILE_PIXELS / 32) <= 32, "the (slot, warp) ballots of a round are scanned by one warp");
 
         __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
