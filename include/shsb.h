@@ -180,7 +180,8 @@ typedef struct ShsbRenderItem /* RenderItem (scene/scene_types.hpp:62-70) with i
 {
     ShsbTransform tr;
     shsb_mesh mesh;
-    uint32_t has_material; /* 0: reference defaults (0.8,0.5,0.2) m=0.1 r=0.5 ao=1; pass_pbr_forward.hpp:179-184 */
+    uint32_t has_material; /* RenderItem::mat, the material handle: 0 = none -> reference defaults (0.8,0.5,0.2) m=0.1 r=0.5 ao=1, pass_pbr_forward.hpp:179-184;
+                              any other value = the MaterialData resolved below (the value itself enters the derived motion key like item.mat, :146) */
     float base_color[3];
     float metallic;
     float roughness;

@@ -285,6 +285,8 @@ struct shsb_context_t
     // RenderHistoryState (core/context.hpp:84-94): last frame's model matrix per object, in draw order with its key;
     // looked up positionally first (the usual case: same scene, same order), through the map otherwise
     std::vector<uint64_t> hist_keys;
+    bool hist_has_duplicates = false;       // two draws of the previous frame shared a motion key: the reference's map then holds the LAST one's model for both
+    std::vector<uint64_t> key_set;          // scratch of the duplicate test (open addressing, a power of two of slots)
     std::vector<hm::mat4f> hist_models;
     std::unordered_map<uint64_t, size_t> hist_index;
     bool hist_index_valid = false;
@@ -1209,14 +1211,16 @@ namespace
                 uint64_t key = it.object_id;
                 if (key == 0)
                 {
-                    key = ((uint64_t)it.mesh << 32) ^ (uint64_t)(it.has_material ? 1u : 0u) ^ ((uint64_t)i + 1u);
+                    key = ((uint64_t)it.mesh << 32) ^ (uint64_t)it.has_material ^ ((uint64_t)i + 1u); // has_material carries RenderItem::mat (0 = none)
                     if (key == 0) key = 1;
                 }
                 next_keys.push_back(key);
                 if (want_prev)
                 {
                     const size_t k = p.hist_slot;
-                    if (k < ctx->hist_keys.size() && ctx->hist_keys[k] == key) p.prev_src = (int64_t)k;
+                    // same position, same key: the usual frame-to-frame case, no map needed -- unless the previous frame held the key more
+                    // than once, where prev_model_by_object[key] is the LAST such draw's model for every one of them
+                    if (!ctx->hist_has_duplicates && k < ctx->hist_keys.size() && ctx->hist_keys[k] == key) p.prev_src = (int64_t)k;
                     else
                     {
                         if (!ctx->hist_index_valid)
@@ -1301,10 +1305,27 @@ namespace
             ctx->hist_keys.clear();
             ctx->hist_models.clear();
             ctx->hist_index_valid = false;
+            ctx->hist_has_duplicates = false;
             ctx->has_prev_frame = false;
         }
         else if (lit_pass)
         {
+            // does any key occur twice?  (object ids are the caller's; derived keys can collide as well)
+            bool dup = false;
+            if (next_keys.size() > 1)
+            {
+                size_t slots = 16;
+                while (slots < next_keys.size() * 2) slots <<= 1;
+                ctx->key_set.assign(slots, 0ull); // keys are never 0 (a derived 0 becomes 1; object_id 0 means "derive")
+                for (const uint64_t key : next_keys)
+                {
+                    size_t at = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 17) & (slots - 1);
+                    while (ctx->key_set[at] != 0ull && ctx->key_set[at] != key) at = (at + 1) & (slots - 1);
+                    if (ctx->key_set[at] == key) { dup = true; break; }
+                    ctx->key_set[at] = key;
+                }
+            }
+            ctx->hist_has_duplicates = dup;
             ctx->hist_keys.swap(next_keys);
             ctx->hist_models.swap(next_models);
             ctx->hist_index_valid = false;
@@ -2572,6 +2593,7 @@ SHSB_API int32_t shsb_history_reset(shsb_ctx ctx)
     if (!ctx) return SHSB_E_INVALID_ARGUMENT;
     ctx->hist_keys.clear();
     ctx->hist_models.clear();
+    ctx->hist_has_duplicates = false;
     ctx->hist_index.clear();
     ctx->hist_index_valid = false;
     ctx->has_prev_frame = false;

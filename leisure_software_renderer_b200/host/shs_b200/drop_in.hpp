@@ -230,7 +230,7 @@ namespace shs::b200
                 const MeshData* mesh = s.resources ? s.resources->get_mesh((MeshAssetHandle)it.mesh) : nullptr;
                 r.mesh = (mesh && !mesh->empty()) ? dev.mesh(*mesh) : 0;
                 const MaterialData* mat = s.resources ? s.resources->get_material((MaterialAssetHandle)it.mat) : nullptr;
-                r.has_material = mat ? 1u : 0u;
+                r.has_material = mat ? (uint32_t)it.mat : 0u; // the handle itself: it enters the derived motion key (pass_pbr_forward.hpp:146)
                 if (mat)
                 {
                     copy_vec(mat->base_color, r.base_color);

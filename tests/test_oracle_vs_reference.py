@@ -161,3 +161,40 @@ def test_preserve_existing_depth(port, reference):
     b = harness.cpu_forward(reference, sd, aov=False, preserve_depth=True, init_depth=half)
     assert _same_bits(a.hdr, b.hdr) and _same_bits(a.depth, b.depth)
 
+
+
+def duplicate_id_pair():
+    """Two frames in which two (and then three) items share one RenderItem::object_id: the reference keeps ONE previous model per key
+    (Context::history.prev_model_by_object[key] = model, pass_pbr_forward.hpp:212: the last item with that key wins), so every item with
+    the key gets that model as its prev_model in the next frame."""
+    from leisure_software_renderer_b200 import scenes
+    import dataclasses
+    a = scenes.scene_small(w=176, h=110, motion=True, n_inst=4, seed=3)
+    items = [dict(it) for it in a.items]
+    for it, oid in zip(items[1:], (77, 77, 5, 77)):
+        it["object_id"] = oid
+    a = dataclasses.replace(a, items=items)
+    b = a.moved(dpos=(0.3, 0.05, -0.2), drot=(0.0, 0.4, 0.1))
+    return a, b
+
+
+def last_duplicate_models(prev, cur, models):
+    """prev_models per item of `cur` under the reference's map rule: the model of the LAST item of `prev` with the same key."""
+    keys = [int(it.get("object_id", 0)) for it in prev.items]
+    out = models.copy().reshape(len(keys), 16)
+    last = {k: i for i, k in enumerate(keys) if k}
+    for i, it in enumerate(cur.items):
+        k = int(it.get("object_id", 0))
+        if k in last:
+            out[i] = models.reshape(len(keys), 16)[last[k]]
+    return out
+
+
+def test_duplicate_object_ids_share_the_last_previous_model(port, reference):
+    prev, cur = duplicate_id_pair()
+    pm = prev.models(port)
+    ref = harness.cpu_forward(reference, cur, aov=False, motion=True, prev_models=pm)          # the reference's own map
+    own = harness.cpu_forward(port, cur, aov=False, motion=True, prev_models=pm)               # every item its own previous model
+    mapped = harness.cpu_forward(port, cur, aov=False, motion=True, prev_models=last_duplicate_models(prev, cur, pm))
+    assert np.array_equal(mapped.motion.view(np.uint32), ref.motion.view(np.uint32))
+    assert not np.array_equal(own.motion.view(np.uint32), ref.motion.view(np.uint32)), "the case must tell the two rules apart"
