@@ -1545,11 +1545,18 @@ SHSB_API int32_t shsb_mesh_upload(shsb_ctx ctx, const float* positions, uint32_t
         if (e != cudaSuccess) return e;
         return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
-    CK(up(&m.positions, positions, (size_t)n_positions * 12));
-    CK(up(&m.normals, normals, (size_t)n_normals * 12));
-    CK(up(&m.uvs, uvs, (size_t)n_uvs * 8));
-    CK(up(&m.indices, indices, (size_t)n_indices * 4));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // a failing step releases what the earlier ones allocated
+    auto step = [&](cudaError_t e) -> int {
+        if (e == cudaSuccess) return SHSB_OK;
+        cudaFree(m.positions); cudaFree(m.normals); cudaFree(m.uvs); cudaFree(m.indices);
+        cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SHSB_E_OUT_OF_MEMORY : SHSB_E_CUDA, "mesh upload: %s", cudaGetErrorString(e));
+    };
+    if (int rc = step(up(&m.positions, positions, (size_t)n_positions * 12))) return rc;
+    if (int rc = step(up(&m.normals, normals, (size_t)n_normals * 12))) return rc;
+    if (int rc = step(up(&m.uvs, uvs, (size_t)n_uvs * 8))) return rc;
+    if (int rc = step(up(&m.indices, indices, (size_t)n_indices * 4))) return rc;
+    if (int rc = step(cudaStreamSynchronize(ctx->stream))) return rc;
     if (n_positions)
     {
         hm::vec3f mn{3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx{-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
@@ -1678,29 +1685,36 @@ SHSB_API int32_t shsb_rt_create(shsb_ctx ctx, int32_t kind, int32_t w, int32_t h
     RtSlot r;
     r.live = true; r.kind = kind; r.w = w; r.h = h; r.zn = zn; r.zf = zf;
     const size_t n = (size_t)w * h;
+    // a failing step releases what the earlier ones allocated
+    auto step = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) return SHSB_OK;
+        cudaFree(r.color); cudaFree(r.depth); cudaFree(r.motion);
+        cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? SHSB_E_OUT_OF_MEMORY : SHSB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
     if (kind == SHSB_RT_COLOR_HDR)
     {
-        CK(cudaMalloc(&r.color, n * 16));
+        if (int rc = step(cudaMalloc(&r.color, n * 16), "render target colour plane")) return rc;
         launch_fill_f4((float4*)r.color, make_float4(0, 0, 0, 1), n, ctx->stream, &ctx->launches); // RT_ColorHDR ctor, rt_types.hpp:85
     }
     else if (kind == SHSB_RT_COLOR_LDR)
     {
-        CK(cudaMalloc(&r.color, n * 4));
+        if (int rc = step(cudaMalloc(&r.color, n * 4), "render target colour plane")) return rc;
         launch_fill_u32((uint32_t*)r.color, 0xFF000000u, n, ctx->stream, &ctx->launches);          // {0,0,0,255}, rt_types.hpp:68
     }
     else if (kind == SHSB_RT_DEPTH_MOTION)
     {
-        CK(cudaMalloc(&r.depth, n * 4));
-        CK(cudaMalloc(&r.motion, n * 8));
+        if (int rc = step(cudaMalloc(&r.depth, n * 4), "render target depth plane")) return rc;
+        if (int rc = step(cudaMalloc(&r.motion, n * 8), "render target motion plane")) return rc;
         launch_fill_u32((uint32_t*)r.depth, 0x3F800000u, n, ctx->stream, &ctx->launches);          // depth 1.0, rt_types.hpp:144
-        CK(cudaMemsetAsync(r.motion, 0, n * 8, ctx->stream));
+        if (int rc = step(cudaMemsetAsync(r.motion, 0, n * 8, ctx->stream), "render target motion clear")) return rc;
     }
     else
     {
-        CK(cudaMalloc(&r.depth, n * 4));
+        if (int rc = step(cudaMalloc(&r.depth, n * 4), "render target depth plane")) return rc;
         launch_fill_u32((uint32_t*)r.depth, 0x3F800000u, n, ctx->stream, &ctx->launches);          // rt_shadow.hpp:26-29
     }
-    CK(cudaGetLastError());
+    if (int rc = step(cudaGetLastError(), "render target clear")) return rc;
     ctx->rts.push_back(r);
     *out_rt = (shsb_rt)ctx->rts.size();
     return SHSB_OK;
@@ -2074,11 +2088,18 @@ SHSB_API int32_t shsb_legacy3_ibl_upload(shsb_ctx ctx, const float* irradiance, 
         if (off > 0xFFFFFFFFull) return fail(ctx, SHSB_E_INVALID_ARGUMENT, "prefiltered chain too large");
     }
     const size_t irr_bytes = (size_t)6 * irr_size * irr_size * 3 * sizeof(float);
-    CK(cudaMalloc(&e.irradiance, irr_bytes));
-    CK(cudaMalloc(&e.prefiltered, off * sizeof(float)));
-    CK(cudaMemcpyAsync(e.irradiance, irradiance, irr_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(e.prefiltered, prefiltered, off * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // a failing step releases what the earlier ones allocated
+    auto step = [&](cudaError_t err) -> int {
+        if (err == cudaSuccess) return SHSB_OK;
+        cudaFree(e.irradiance); cudaFree(e.prefiltered);
+        cudaGetLastError();
+        return fail(ctx, err == cudaErrorMemoryAllocation ? SHSB_E_OUT_OF_MEMORY : SHSB_E_CUDA, "IBL upload: %s", cudaGetErrorString(err));
+    };
+    if (int rc = step(cudaMalloc(&e.irradiance, irr_bytes))) return rc;
+    if (int rc = step(cudaMalloc(&e.prefiltered, off * sizeof(float)))) return rc;
+    if (int rc = step(cudaMemcpyAsync(e.irradiance, irradiance, irr_bytes, cudaMemcpyHostToDevice, ctx->stream))) return rc;
+    if (int rc = step(cudaMemcpyAsync(e.prefiltered, prefiltered, off * sizeof(float), cudaMemcpyHostToDevice, ctx->stream))) return rc;
+    if (int rc = step(cudaStreamSynchronize(ctx->stream))) return rc;
     ctx->ibls.push_back(e);
     *out_ibl = (shsb_ibl)ctx->ibls.size();
     return SHSB_OK;
