@@ -336,6 +336,7 @@ struct shsb_context_t
     int copy_flip = 0;
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr, ev_front_sync = nullptr;
     bool shadow_direct = true;           // SHSB_SHADOW_DIRECT=0: every shadow-pass triangle through the binned tile path
+    bool fast_tile = true;               // SHSB_NO_FAST_TILE=1: the tile kernel's general instantiation for every frame (tile_raster.cu: launch_tile_raster)
     bool hiz = false;                    // SHSB_HIZ=1: hierarchical-Z early reject in the tile kernel for asynchronous frames without AOVs
     cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
 
@@ -821,7 +822,7 @@ namespace
             if (fc.forward_plus && !cull) { if (int rc = main_wait_lights(ctx)) return rc; } // lists built earlier: the records are read directly
             CK(cudaStreamWaitEvent(s1, ctx->ev_front_done[a], 0));
             record(ctx, 3, s1);
-            if (!fc.direct_depth) launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches);
+            if (!fc.direct_depth) launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches, ctx->fast_tile);
             record(ctx, 4, s1);
             CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->ev_tile_done[f % TILE_DONE_RING], s1));
@@ -1391,6 +1392,7 @@ SHSB_API int32_t shsb_context_create(int32_t device_ordinal, shsb_ctx* out_ctx)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_front_sync, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = std::getenv("SHSB_SHADOW_DIRECT")) ctx->shadow_direct = !(e[0] == '0');
     if (const char* e = std::getenv("SHSB_HIZ")) ctx->hiz = e[0] == '1';
+    if (const char* e = std::getenv("SHSB_NO_FAST_TILE")) ctx->fast_tile = e[0] != '1';
     if (const char* e = std::getenv("SHSB_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
     ok = ok && cudaHostAlloc(&ctx->h_stats, sizeof(DevStats) * STAT_SHARDS, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_overflow, 4 * sizeof(uint32_t), cudaHostAllocMapped) == cudaSuccess;

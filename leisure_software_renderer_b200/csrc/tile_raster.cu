@@ -419,11 +419,13 @@ namespace shsb
         // Resolve of a pixel no fragment reached: motion (0, 0) when the pass clears the plane; colour = sky model or
         // background gradient (pass_pbr_forward.hpp:64-85) or, for a separate draw (load_color), the target's existing
         // colour; fused tonemap if an LDR target is bound.
+        template <bool FAST>
         __device__ __forceinline__ void resolve_uncovered(const FrameConst& fc, const FrameBuffers& fb, const DevTexture* __restrict__ textures,
                                                           const float* __restrict__ lut, size_t pix, int px, int py)
         {
-            if (fc.clear_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f);
-            if (fc.load_color)
+            const int F_clear_motion = FAST ? 0 : fc.clear_motion, F_load_color = FAST ? 0 : fc.load_color, F_sky_kind = FAST ? 0 : fc.sky_kind;
+            if (F_clear_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f);
+            if (F_load_color)
             {
                 if (!(fc.fuse_tonemap && fb.ldr)) return;
                 const float4 c = fb.hdr[pix];
@@ -431,7 +433,7 @@ namespace shsb
                 return;
             }
             float r, g, b;
-            if (fc.sky_kind != 0)
+            if (F_sky_kind != 0)
             {
                 const F3 c = sky_pixel(fc, textures, lut, px, py);
                 r = c.x; g = c.y; b = c.z;
@@ -452,10 +454,26 @@ namespace shsb
         constexpr int CAND_PER_THREAD = SHSB_CAND_PER_THREAD; // candidates filtered per thread per staging round (x TILE_THREADS per CTA)
         static_assert(CAND_PER_THREAD * (TILE_PIXELS / 32) <= 32, "the (slot, warp) ballots of a round are scanned by one warp");
 
+        // FAST: the instantiation for the plain Forward+ frame (the benchmarked one) -- linear-depth target cleared by the pass, lit builtin
+        // program, 16-pixel light tiles with lights, no shadow-map pass mode, no sky model, no motion plane traffic, no AOVs, no Hi-Z.  The
+        // mode flags are compile-time constants there, so the other modes' code is not in the kernel at all (instruction cache, uniform
+        // branches); launch_tile_raster picks the instantiation, every other frame runs the general one.  Same source, same arithmetic.
+        // MODE: 0 = general, 1 = FAST with the PBR program, 2 = FAST with the Blinn-Phong program
+        template <int MODE>
         __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
+            constexpr bool FAST = MODE != 0;
+            const int F_shadow_mode = FAST ? 0 : fc.shadow_mode, F_has_depth = FAST ? 1 : fc.has_depth, F_linear_depth = FAST ? 1 : fc.linear_depth;
+            const int F_load_depth = FAST ? 0 : fc.load_depth, F_load_color = FAST ? 0 : fc.load_color, F_write_motion = FAST ? 0 : fc.write_motion;
+            const int F_clear_motion = FAST ? 0 : fc.clear_motion, F_hiz = FAST ? 0 : fc.hiz, F_sky_kind = FAST ? 0 : fc.sky_kind;
+            const int F_shader_id = MODE == 1 ? 0 : (MODE == 2 ? 1 : fc.shader_id), F_forward_plus = FAST ? 1 : fc.forward_plus;
+            const float* const F_shadow_map = FAST ? nullptr : fc.shadow_map;
+            const uint32_t F_light_tile_size = FAST ? (uint32_t)TILE : fc.light_tile_size;
+            uint32_t* const F_aov_tri_id = FAST ? nullptr : fb.aov_tri_id;
+            uint32_t* const F_aov_coverage = FAST ? nullptr : fb.aov_coverage;
+            float2* const F_motion = FAST ? nullptr : fb.motion;
             // the triangle staging buffer (raster phase) and the light staging buffer (shading phase) are never live at
             // the same time: they share one 20-KB allocation
             __shared__ __align__(16) unsigned char s_stage[LIGHT_CAP * sizeof(SmLight)];
@@ -496,17 +514,17 @@ namespace shsb
                 if (x0 >= fc.W || fy >= fc.H) return;
                 const int py = fc.H - 1 - fy;
                 const size_t pix = (size_t)py * (size_t)fc.W + (size_t)x0;
-                const bool clear_depth = fb.depth && (fc.has_depth || fc.shadow_mode) && !fc.load_depth;
-                const bool shade = !(fc.shadow_mode || fc.shader_id == 5 || !fb.hdr);
-                if (x0 - (q & 3) * 4 + TILE <= fc.W && (fc.W & 3) == 0 && !fc.load_color && fc.sky_kind == 0) // whole tile row inside, 16-byte aligned rows, row-constant colour
+                const bool clear_depth = fb.depth && (F_has_depth || F_shadow_mode) && !F_load_depth;
+                const bool shade = !(F_shadow_mode || F_shader_id == 5 || !fb.hdr);
+                if (x0 - (q & 3) * 4 + TILE <= fc.W && (fc.W & 3) == 0 && !F_load_color && F_sky_kind == 0) // whole tile row inside, 16-byte aligned rows, row-constant colour
                 {
                     if (clear_depth) *reinterpret_cast<float4*>(fb.depth + pix) = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-                    if (fb.aov_tri_id) *reinterpret_cast<uint4*>(fb.aov_tri_id + pix) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                    if (fb.aov_coverage) *reinterpret_cast<uint4*>(fb.aov_coverage + pix) = make_uint4(0u, 0u, 0u, 0u);
+                    if (F_aov_tri_id) *reinterpret_cast<uint4*>(F_aov_tri_id + pix) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                    if (F_aov_coverage) *reinterpret_cast<uint4*>(F_aov_coverage + pix) = make_uint4(0u, 0u, 0u, 0u);
                     if (!shade) return;
-                    if (fc.clear_motion && fb.motion)
+                    if (F_clear_motion && F_motion)
                     {
-                        float4* m = reinterpret_cast<float4*>(fb.motion + pix);
+                        float4* m = reinterpret_cast<float4*>(F_motion + pix);
                         m[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); m[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     }
                     // background gradient, pass_pbr_forward.hpp:73-81
@@ -526,9 +544,9 @@ namespace shsb
                 for (int i = 0; i < 4 && x0 + i < fc.W; ++i)
                 {
                     if (clear_depth) fb.depth[pix + i] = 1.0f;
-                    if (fb.aov_tri_id) fb.aov_tri_id[pix + i] = 0xFFFFFFFFu;
-                    if (fb.aov_coverage) fb.aov_coverage[pix + i] = 0u;
-                    if (shade) resolve_uncovered(fc, fb, textures, srgb_lut, pix + i, x0 + i, py);
+                    if (F_aov_tri_id) F_aov_tri_id[pix + i] = 0xFFFFFFFFu;
+                    if (F_aov_coverage) F_aov_coverage[pix + i] = 0u;
+                    if (shade) resolve_uncovered<FAST>(fc, fb, textures, srgb_lut, pix + i, x0 + i, py);
                 }
                 return;
             }
@@ -549,7 +567,7 @@ namespace shsb
             PHASE_COUNT();
 
             float bz = 1.0f;
-            if ((fc.has_depth || fc.shadow_mode) && fc.load_depth && valid) bz = fb.depth[pix];
+            if ((F_has_depth || F_shadow_mode) && F_load_depth && valid) bz = fb.depth[pix];
             uint32_t bkey = KEY_NONE, bidx = 0;
             uint32_t n_cov = 0;
             const float pxf = xadd((float)px, 0.5f), pyf = xadd((float)py, 0.5f);
@@ -557,9 +575,9 @@ namespace shsb
 
             // hierarchical Z (north_star): the farthest depth the warp's 8x4 block holds; a staged triangle that cannot be nearer than
             // that anywhere is skipped before its bbox is even decoded.  Linear view-depth targets only (the bound below is for them).
-            const bool hiz = fc.hiz && fc.has_depth && fc.linear_depth && !fc.shadow_mode;
+            const bool hiz = F_hiz && F_has_depth && F_linear_depth && !F_shadow_mode;
             float blk_zmax = 1.0f;
-            bool z_dirty = fc.load_depth != 0; // loaded depths: take the block maximum before the first test
+            bool z_dirty = F_load_depth != 0; // loaded depths: take the block maximum before the first test
 
             const uint32_t off0 = g.tile_offset[tile];
             const uint32_t off1 = min(off0 + tile_tris, g.list_capacity);
@@ -629,7 +647,7 @@ namespace shsb
                     const float bw = xmul(xsub(xmul(r.v0x, v2y), xmul(v2x, r.v0y)), r.inv_den);
                     const float bu = xsub(xsub(1.0f, bv), bw);
                     if (bu < 0.0f || bv < 0.0f || bw < 0.0f) continue;
-                    if (fc.shadow_mode)
+                    if (F_shadow_mode)
                     {
                         // pass_shadow_map.hpp:197-200: affine NDC z, keep the minimum
                         const float z_ndc = xadd(xadd(xmul(bu, r.zw0), xmul(bv, r.zw1)), xmul(bw, r.zw2));
@@ -641,10 +659,10 @@ namespace shsb
                     const float denom = xadd(xadd(xmul(bu, r.iw0), xmul(bv, r.iw1)), xmul(bw, r.iw2));
                     if (denom <= 1e-10f) continue;
                     ++n_cov;
-                    if (fc.has_depth)
+                    if (F_has_depth)
                     {
                         float z01;
-                        if (fc.linear_depth)
+                        if (F_linear_depth)
                         {
                             const float view_z = xrcp(denom);
                             z01 = gclamp(xdiv(xsub(view_z, fc.zn), zrange), 0.0f, 1.0f);
@@ -665,9 +683,9 @@ namespace shsb
             // ---------------- resolve: depth + AOVs
             if (valid)
             {
-                if (fb.depth && (fc.has_depth || fc.shadow_mode) && (bkey != KEY_NONE || !fc.load_depth)) { STORE_IF(bz) fb.depth[pix] = bz; }
-                if (fb.aov_tri_id) fb.aov_tri_id[pix] = (bkey != KEY_NONE) ? (bkey - 1u) : 0xFFFFFFFFu;
-                if (fb.aov_coverage) fb.aov_coverage[pix] = n_cov;
+                if (fb.depth && (F_has_depth || F_shadow_mode) && (bkey != KEY_NONE || !F_load_depth)) { STORE_IF(bz) fb.depth[pix] = bz; }
+                if (F_aov_tri_id) F_aov_tri_id[pix] = (bkey != KEY_NONE) ? (bkey - 1u) : 0xFFFFFFFFu;
+                if (F_aov_coverage) F_aov_coverage[pix] = n_cov;
             }
             // fragment counters: warp reduce -> one shared slot per warp; thread 0 adds them up behind the next barrier
             {
@@ -678,14 +696,14 @@ namespace shsb
                 if (lane == 0) { s_frag[warp][0] = c; s_frag[warp][1] = sh; }
             }
             const bool has = valid && bkey != KEY_NONE;
-            const bool shade = !(fc.shadow_mode || fc.shader_id == 5 || !fb.hdr);
+            const bool shade = !(F_shadow_mode || F_shader_id == 5 || !fb.hdr);
 
             // ---------------- phase A (per pixel): re-derive the winning fragment and run the builtin program
-            const bool lit_shader = fc.shader_id == 0 || fc.shader_id == 1;
+            const bool lit_shader = F_shader_id == 0 || F_shader_id == 1;
             float out_r = 0.0f, out_g = 0.0f, out_b = 0.0f;
             Surface surf;
             surf.P = v3(0, 0, 0); surf.N = v3(0, 1, 0); surf.V = v3(0, 1, 0); surf.albedo = v3(0, 0, 0);
-            surf.metallic = 0.0f; surf.roughness = 1.0f; surf.blinn = fc.shader_id == 1;
+            surf.metallic = 0.0f; surf.roughness = 1.0f; surf.blinn = F_shader_id == 1;
             surf.F0 = v3(0, 0, 0); surf.diffuse = v3(0, 0, 0);
             surf.a2 = surf.k = surf.NdotV = surf.g1v = surf.spec_a = surf.spec_b = 0.0f;
             if (has && shade)
@@ -700,7 +718,7 @@ namespace shsb
                 const float denom = xadd(xadd(xmul(bu, r1.w), xmul(bv, r2.x)), xmul(bw, r2.y));
                 const float inv_denom = xrcp(denom);
                 float depth01 = bz;
-                if (!fc.has_depth)
+                if (!F_has_depth)
                 {
                     const float z_clip = xadd(xadd(xmul(bu, r2.z), xmul(bv, r2.w)), xmul(bw, r3.x));
                     depth01 = gclamp(xadd(xmul(xmul(z_clip, inv_denom), 0.5f), 0.5f), 0.0f, 1.0f);
@@ -722,7 +740,7 @@ namespace shsb
                 const float uvx = interp(a[18], a[20], a[22]), uvy = interp(a[19], a[21], a[23]);
                 const DevItem& it = g.items[__float_as_uint(a[24])];
                 const F3 n_ws = xnormalize3(nrm_i); // rasterizer.hpp:381
-                if (fc.write_motion && fb.motion)
+                if (F_write_motion && F_motion)
                 {
                     // rasterizer.hpp:388-411: the winning fragment is the last one the serial loop lets past the depth test
                     const float4 pw = xmat4_mul(it.c2p, wpos.x, wpos.y, wpos.z, 1.0f);
@@ -736,16 +754,16 @@ namespace shsb
                         const float len = xsqrt(xadd(xmul(mx, mx), xmul(my, my)));
                         if (len > 96.0f && len > 1e-6f) { const float k = xdiv(96.0f, len); mx = xmul(mx, k); my = xmul(my, k); }
                     }
-                    fb.motion[pix] = make_float2(mx, my);
+                    F_motion[pix] = make_float2(mx, my);
                 }
 
-                if (fc.shader_id == 2) { out_r = it.base_color[0]; out_g = it.base_color[1]; out_b = it.base_color[2]; }
-                else if (fc.shader_id == 3)
+                if (F_shader_id == 2) { out_r = it.base_color[0]; out_g = it.base_color[1]; out_b = it.base_color[2]; }
+                else if (F_shader_id == 3)
                 {
                     const F3 n = xnormalize3(n_ws);
                     out_r = xadd(xmul(n.x, 0.5f), 0.5f); out_g = xadd(xmul(n.y, 0.5f), 0.5f); out_b = xadd(xmul(n.z, 0.5f), 0.5f);
                 }
-                else if (fc.shader_id == 4) { const float d = sclamp(depth01, 0.0f, 1.0f); out_r = out_g = out_b = d; }
+                else if (F_shader_id == 4) { const float d = sclamp(depth01, 0.0f, 1.0f); out_r = out_g = out_b = d; }
                 else
                 {
                     // ---- builtin lit programs.  N, L, NdotL stay exact: they feed the shadow bias and the NdotL > 0 branches.
@@ -759,7 +777,7 @@ namespace shsb
                     const V3 base = v3(it.base_color[0], it.base_color[1], it.base_color[2]);
                     const V3 albedo = v3(fmaxf(base.x * albedo_tex.x, 0.0f), fmaxf(base.y * albedo_tex.y, 0.0f), fmaxf(base.z * albedo_tex.z, 0.0f));
                     float shadow_vis = 1.0f;
-                    if (fc.shadow_map && NdotL > 0.0f)
+                    if (F_shadow_map && NdotL > 0.0f)
                     {
                         shadow_vis = shadow_visibility(fc, wpos, NdotL);
                         shadow_vis = mixf(1.0f, shadow_vis, sat(fc.shadow_strength));
@@ -768,7 +786,7 @@ namespace shsb
                     const V3 H = normalize_fast(V + L);
                     V3 c;
                     surf.P = toV3(wpos); surf.N = N; surf.V = V; surf.albedo = albedo;
-                    if (fc.shader_id == 1)
+                    if (F_shader_id == 1)
                     {
                         // make_blinn_phong_program, builtin_shaders.hpp:105-152
                         const float NdotH = fmaxf(0.0f, dot(N, H));
@@ -802,7 +820,7 @@ namespace shsb
                         surf.metallic = metal; surf.roughness = rough;
                     }
                     out_r = c.x; out_g = c.y; out_b = c.z;
-                    if (fc.forward_plus) finish_surface(surf);
+                    if (F_forward_plus) finish_surface(surf);
                 }
             }
 
@@ -829,8 +847,8 @@ namespace shsb
             // at every pixel and would add exactly zero) and the survivors are compacted IN ASCENDING ORDER into
             // shared memory.  A staging round filters up to 1024 candidates (4 per thread) with two barriers; a
             // saturated list (count >= max_per_tile) walks ALL lights, as the GLSL does (:662-668).
-            const bool use_lights = fc.forward_plus && lit_shader && fc.n_lights > 0;
-            if (use_lights && fc.light_tile_size == (uint32_t)TILE)
+            const bool use_lights = F_forward_plus && lit_shader && fc.n_lights > 0;
+            if (use_lights && F_light_tile_size == (uint32_t)TILE)
             {
                 if (any_has)
                 {
@@ -950,8 +968,8 @@ namespace shsb
             {
                 // generic light-tile size: per-pixel list lookup, tile_y counted from the top
                 V3 sum = v3(0, 0, 0);
-                const uint32_t ltx = min((uint32_t)px / fc.light_tile_size, fc.light_tiles_x - 1u);
-                const uint32_t lty = min((uint32_t)fy / fc.light_tile_size, fc.light_tiles_y - 1u);
+                const uint32_t ltx = min((uint32_t)px / F_light_tile_size, fc.light_tiles_x - 1u);
+                const uint32_t lty = min((uint32_t)fy / F_light_tile_size, fc.light_tiles_y - 1u);
                 const uint32_t list_id = lty * fc.light_tiles_x + ltx;
                 const uint32_t cnt = min(fc.tile_counts[list_id], fc.max_per_tile);
                 if (cnt >= fc.max_per_tile)
@@ -971,8 +989,8 @@ namespace shsb
 
             // ---------------- phase C (per pixel): resolve colour (+ fused tonemap), each byte written once
             if (!valid) return;
-            if (!has) { resolve_uncovered(fc, fb, textures, srgb_lut, pix, px, py); return; }
-            if (fc.clear_motion && !fc.write_motion && fb.motion) fb.motion[pix] = make_float2(0.0f, 0.0f); // plane cleared, vectors disabled
+            if (!has) { resolve_uncovered<FAST>(fc, fb, textures, srgb_lut, pix, px, py); return; }
+            if (F_clear_motion && !F_write_motion && F_motion) F_motion[pix] = make_float2(0.0f, 0.0f); // plane cleared, vectors disabled
             PHASE_MARK(5);
             STORE_IF(out_r) fb.hdr[pix] = make_float4(out_r, out_g, out_b, 1.0f);
             if (fc.fuse_tonemap && fb.ldr) { const uchar4 l = tonemap_pixel(out_r, out_g, out_b, fc.exposure, fc.inv_gamma); STORE_IF(__uint_as_float((uint32_t)l.x * 0x01010101u + 0x7fc12000u)) fb.ldr[pix] = l; }
@@ -1070,11 +1088,20 @@ namespace shsb
 #endif
 
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
-                            const float* srgb_lut, cudaStream_t s, uint64_t* launches)
+                            const float* srgb_lut, cudaStream_t s, uint64_t* launches, bool allow_fast)
     {
         const int n_tiles = fc.tiles_x * fc.tiles_y;
         if (n_tiles <= 0) return;
-        tile_kernel<<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        // allow_fast = false (SHSB_NO_FAST_TILE=1 at context creation): always the general instantiation -- the A/B knob, and what a
+        // caller sets who needs the LAST BITS of the colour planes to agree between frames of different modes: the instantiations share
+        // their source, but the compiler contracts and schedules the colour arithmetic of each on its own, so HDR values may differ by
+        // an ULP or two between them (depth, coverage, triangle ids and light lists are exact in both)
+        const bool fast = allow_fast && !fc.shadow_map && !fc.shadow_mode && fc.has_depth && fc.linear_depth && !fc.load_depth && !fc.load_color && !fc.write_motion && !fc.clear_motion && !fc.hiz &&
+                          fc.sky_kind == 0 && (fc.shader_id == 0 || fc.shader_id == 1) && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE && fc.n_lights > 0 &&
+                          !fb.aov_tri_id && !fb.aov_coverage && fb.hdr && fb.depth;
+        if (fast && fc.shader_id == 0) tile_kernel<1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (fast) tile_kernel<2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else tile_kernel<0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
         *launches += 1;
     }
 

@@ -341,6 +341,7 @@ def test_hierarchical_z_reject_changes_no_pixel(monkeypatch):
     from leisure_software_renderer_b200.renderer import Context
     base = scenes.scene_c5(w=640, h=360, nx=24, nz=24).with_camera((0, 0.6, -38), (0, 0.4, 40))   # grazing: rows of Suzannes behind each other, overdraw 4
     out = {}
+    monkeypatch.setenv("SHSB_NO_FAST_TILE", "1")   # Hi-Z lives in the general instantiation only: compare like with like (see launch_tile_raster)
     for flag in ("0", "1"):
         monkeypatch.setenv("SHSB_HIZ", flag)
         ctx = Context(0)
@@ -364,3 +365,31 @@ def test_hierarchical_z_reject_changes_no_pixel(monkeypatch):
     assert out["0"][2]["frag_covered"] > 1.5 * out["0"][2]["frag_shaded"] > 0, "the scene has no overdraw to reject"
     for x, y, what in zip(out["0"][0] + out["0"][1], out["1"][0] + out["1"][1], ("hdr", "depth", "ldr", "hdr (preserved depth)", "depth (preserved)")):
         assert np.array_equal(x, y), f"Hi-Z changed the {what} plane"
+
+
+def test_fast_tile_instantiation_agrees_with_the_general_one(monkeypatch):
+    """The plain Forward+ frame runs a specialised instantiation of the tile kernel (mode flags as compile-time constants, one per
+    shading program); SHSB_NO_FAST_TILE=1 renders the same frame with the general one.  Depth must be equal bit for bit, LDR within
+    1 LSB, HDR beyond 100 dB -- the two share their source; only the compiler's contraction of the colour arithmetic may differ."""
+    from leisure_software_renderer_b200.renderer import Context
+    for shading in (capi.SHADING_PBR, capi.SHADING_BLINN):
+        sd = scenes.scene_small(w=320, h=200, shading=shading, n_inst=4, lights=160, seed=5)
+        out = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("SHSB_NO_FAST_TILE", flag)
+            ctx = Context(0)
+            try:
+                g = harness.GpuScene(ctx, sd)
+                fp = capi.FrameParams.from_buffer_copy(sd.fp)
+                fp.light_culling = 1
+                ctx.frame_forward_plus(sd.scene, fp, g.hdr, g.dm, g.ldr, want_stats=False)
+                ctx.sync()
+                out[flag] = (ctx.rt_download(g.hdr), ctx.rt_download(g.dm, capi.PLANE_DEPTH).view(np.uint32), ctx.rt_download(g.ldr))
+                g.release()
+            finally:
+                ctx.close()
+        assert np.array_equal(out["0"][1], out["1"][1]), "depth differs between the instantiations"
+        assert int(np.abs(out["0"][2].astype(np.int32) - out["1"][2].astype(np.int32)).max()) <= 1
+        psnr = harness.psnr(out["0"][0][..., :3], out["1"][0][..., :3])
+        print(f"shading {shading}: HDR PSNR fast vs general {psnr:.1f} dB, LDR pixels off by 1: {int(np.count_nonzero((out['0'][2] != out['1'][2]).any(axis=-1)))}")
+        assert psnr >= 100.0
