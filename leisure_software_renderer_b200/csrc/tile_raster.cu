@@ -458,18 +458,20 @@ namespace shsb
         // program, 16-pixel light tiles with lights, no shadow-map pass mode, no sky model, no motion plane traffic, no AOVs, no Hi-Z.  The
         // mode flags are compile-time constants there, so the other modes' code is not in the kernel at all (instruction cache, uniform
         // branches); launch_tile_raster picks the instantiation, every other frame runs the general one.  Same source, same arithmetic.
-        // MODE: 0 = general, 1 = FAST with the PBR program, 2 = FAST with the Blinn-Phong program
-        template <int MODE>
+        // PROG: 0 = general (every mode flag read from fc), 1 = FAST with the PBR program, 2 = FAST with the Blinn-Phong program.
+        // LIGHTS (FAST only): 1 = Forward+ over 16-pixel light tiles, no sun shadow map; 2 = no local lights (sun shadow map allowed).
+        template <int PROG, int LIGHTS>
         __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
-            constexpr bool FAST = MODE != 0;
+            constexpr bool FAST = PROG != 0;
+            static_assert(FAST ? (LIGHTS == 1 || LIGHTS == 2) : LIGHTS == 0, "FAST instantiations fix the light mode");
             const int F_shadow_mode = FAST ? 0 : fc.shadow_mode, F_has_depth = FAST ? 1 : fc.has_depth, F_linear_depth = FAST ? 1 : fc.linear_depth;
             const int F_load_depth = FAST ? 0 : fc.load_depth, F_load_color = FAST ? 0 : fc.load_color, F_write_motion = FAST ? 0 : fc.write_motion;
             const int F_clear_motion = FAST ? 0 : fc.clear_motion, F_hiz = FAST ? 0 : fc.hiz, F_sky_kind = FAST ? 0 : fc.sky_kind;
-            const int F_shader_id = MODE == 1 ? 0 : (MODE == 2 ? 1 : fc.shader_id), F_forward_plus = FAST ? 1 : fc.forward_plus;
-            const float* const F_shadow_map = FAST ? nullptr : fc.shadow_map;
+            const int F_shader_id = PROG == 1 ? 0 : (PROG == 2 ? 1 : fc.shader_id), F_forward_plus = FAST ? (LIGHTS == 1 ? 1 : 0) : fc.forward_plus;
+            const float* const F_shadow_map = (FAST && LIGHTS == 1) ? nullptr : fc.shadow_map;
             const uint32_t F_light_tile_size = FAST ? (uint32_t)TILE : fc.light_tile_size;
             uint32_t* const F_aov_tri_id = FAST ? nullptr : fb.aov_tri_id;
             uint32_t* const F_aov_coverage = FAST ? nullptr : fb.aov_coverage;
@@ -1096,12 +1098,16 @@ namespace shsb
         // caller sets who needs the LAST BITS of the colour planes to agree between frames of different modes: the instantiations share
         // their source, but the compiler contracts and schedules the colour arithmetic of each on its own, so HDR values may differ by
         // an ULP or two between them (depth, coverage, triangle ids and light lists are exact in both)
-        const bool fast = allow_fast && !fc.shadow_map && !fc.shadow_mode && fc.has_depth && fc.linear_depth && !fc.load_depth && !fc.load_color && !fc.write_motion && !fc.clear_motion && !fc.hiz &&
-                          fc.sky_kind == 0 && (fc.shader_id == 0 || fc.shader_id == 1) && fc.forward_plus && fc.light_tile_size == (uint32_t)TILE && fc.n_lights > 0 &&
-                          !fb.aov_tri_id && !fb.aov_coverage && fb.hdr && fb.depth;
-        if (fast && fc.shader_id == 0) tile_kernel<1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (fast) tile_kernel<2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else tile_kernel<0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        const bool fast = allow_fast && !fc.shadow_mode && fc.has_depth && fc.linear_depth && !fc.load_depth && !fc.load_color && !fc.write_motion && !fc.clear_motion &&
+                          !fc.hiz && fc.sky_kind == 0 && (fc.shader_id == 0 || fc.shader_id == 1) && !fb.aov_tri_id && !fb.aov_coverage && fb.hdr && fb.depth;
+        const bool lights = fc.forward_plus && fc.n_lights > 0;
+        const int light_mode = !fast ? 0 : ((lights && fc.light_tile_size == (uint32_t)TILE && !fc.shadow_map) ? 1 : (!lights ? 2 : 0));
+        const bool blinn = fc.shader_id == 1;
+        if (light_mode == 1 && !blinn) tile_kernel<1, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 1) tile_kernel<2, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 2 && !blinn) tile_kernel<1, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 2) tile_kernel<2, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else tile_kernel<0, 0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
         *launches += 1;
     }
 
