@@ -139,6 +139,10 @@ if __name__ == "__main__":
     if "--tile-h4" in sys.argv:
         print(build_variant("h4", ["-DSHSB_TILE_H=4"]))
         sys.exit(0)
+    for n in (10, 12):
+        if f"--nolight-ctas{n}" in sys.argv:
+            print(build_variant(f"nl{n}", [f"-DSHSB_NOLIGHT_CTAS={n}"]))
+            sys.exit(0)
     if "--cand8" in sys.argv:
         print(build_variant("cand8", ["-DSHSB_CAND_PER_THREAD=8"]))
         sys.exit(0)

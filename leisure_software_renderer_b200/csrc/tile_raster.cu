@@ -460,8 +460,14 @@ namespace shsb
         // branches); launch_tile_raster picks the instantiation, every other frame runs the general one.  Same source, same arithmetic.
         // PROG: 0 = general (every mode flag read from fc), 1 = FAST with the PBR program, 2 = FAST with the Blinn-Phong program.
         // LIGHTS (FAST only): 1 = Forward+ over 16-pixel light tiles, no sun shadow map; 2 = no local lights (sun shadow map allowed).
+        // The instantiations without local lights need 56 registers uncapped; capped at 48 (10 CTAs of 128 threads per SM) they do not
+        // spill and hide more latency: -4 % (C3) / -7 % (C4) on the tile kernel against 8 CTAs, 12 CTAs (40 registers) give no more
+        // (profiles/r2_tile_kernel_specialisation.md)
+#ifndef SHSB_NOLIGHT_CTAS
+#define SHSB_NOLIGHT_CTAS 10
+#endif
         template <int PROG, int LIGHTS>
-        __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
+        __global__ void __launch_bounds__(TILE_THREADS, (LIGHTS == 2 ? SHSB_NOLIGHT_CTAS : TILE_MIN_CTAS)) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
