@@ -336,6 +336,7 @@ struct shsb_context_t
     int copy_flip = 0;
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr, ev_front_sync = nullptr;
     bool shadow_direct = true;           // SHSB_SHADOW_DIRECT=0: every shadow-pass triangle through the binned tile path
+    bool area_lights = true;             // the current light set may hold rect / tube lights (decides the tile kernel's instantiation)
     bool fast_tile = true;               // SHSB_NO_FAST_TILE=1: the tile kernel's general instantiation for every frame (tile_raster.cu: launch_tile_raster)
     bool hiz = false;                    // SHSB_HIZ=1: hierarchical-Z early reject in the tile kernel for asynchronous frames without AOVs
     cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
@@ -1113,6 +1114,7 @@ namespace
             const uint32_t ts = cull ? cull->ts : cur->ts, mx = cull ? cull->max_per_tile : cur->max_per_tile;
             fc.forward_plus = 1;
             fc.n_lights = ctx->n_lights;
+            fc.area_lights = ctx->area_lights ? 1 : 0;
             job.lists_set = ctx->lists_cur; // run_frame points the kernels at the set (its own when it culls)
             fc.light_tile_size = ts;
             fc.max_per_tile = mx;
@@ -2812,10 +2814,14 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
         // upload has run, like any cudaMemcpyAsync source); pageable memory is staged through a pinned ring first.
         const DevLightRec* src = nullptr;
         cudaPointerAttributes attr{};
+        bool host_readable = true;
         if (cudaPointerGetAttributes(&attr, records) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             src = static_cast<const DevLightRec*>(attr.devicePointer);
         else if (cudaPointerGetAttributes(&attr, records) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+        {
             src = static_cast<const DevLightRec*>(records);
+            host_readable = attr.type == cudaMemoryTypeManaged;
+        }
         else
         {
             cudaGetLastError();
@@ -2825,6 +2831,15 @@ SHSB_API int32_t shsb_lights_upload(shsb_ctx ctx, const void* records, uint32_t 
             src = ctx->h_lights[b].dp;
             ctx->lights_stage_busy[b] = true;
         }
+        // rect / tube lights go through the general per-record evaluation in the tile kernel; a set without any lets the frame run an
+        // instantiation that does not carry that code (one word per record read here; device-resident records are not looked at)
+        bool area = !host_readable;
+        if (host_readable)
+        {
+            const DevLightRec* h = static_cast<const DevLightRec*>(records);
+            for (uint32_t i = 0; i < n_lights && !area; ++i) area = h[i].type_shape_flags[0] > 2u;
+        }
+        ctx->area_lights = area;
         launch_light_prep(src, ctx->d_lights[b].p, ctx->d_smlights[b].p, n_lights, su, &ctx->launches);
         CK(cudaGetLastError());
         if (ctx->lights_stage_busy[b]) CK(cudaEventRecord(ctx->lights_stage_done[b], su));

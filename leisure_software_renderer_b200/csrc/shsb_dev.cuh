@@ -182,6 +182,7 @@ namespace shsb
         const DevLightRec* lights;
         const SmLight* sm_lights;   // digested copies of `lights`
         uint32_t n_lights;
+        int area_lights;        // the uploaded set may hold rect / tube lights (unknown for device-resident records: assumed)
         const uint32_t* tile_counts;
         const uint32_t* tile_indices;
         uint32_t light_tile_size, max_per_tile, light_tiles_x, light_tiles_y;

@@ -459,7 +459,9 @@ namespace shsb
         // mode flags are compile-time constants there, so the other modes' code is not in the kernel at all (instruction cache, uniform
         // branches); launch_tile_raster picks the instantiation, every other frame runs the general one.  Same source, same arithmetic.
         // PROG: 0 = general (every mode flag read from fc), 1 = FAST with the PBR program, 2 = FAST with the Blinn-Phong program.
-        // LIGHTS (FAST only): 1 = Forward+ over 16-pixel light tiles, no sun shadow map; 2 = no local lights (sun shadow map allowed).
+        // LIGHTS (FAST only): 1 = Forward+ over 16-pixel light tiles, point / spot lights only, no sun shadow map; 3 = the same with rect /
+        // tube lights possible (they are evaluated from the 160-byte record by a function that is CALLED with the surface by reference, which
+        // keeps the surface addressable: stack frame, spills in the staging code); 2 = no local lights (sun shadow map allowed).
         // The instantiations without local lights need 56 registers uncapped; capped at 48 (10 CTAs of 128 threads per SM) they do not
         // spill and hide more latency: -4 % (C3) / -7 % (C4) on the tile kernel against 8 CTAs, 12 CTAs (40 registers) give no more
         // (profiles/r2_tile_kernel_specialisation.md)
@@ -472,12 +474,12 @@ namespace shsb
                                                                     const float* __restrict__ srgb_lut)
         {
             constexpr bool FAST = PROG != 0;
-            static_assert(FAST ? (LIGHTS == 1 || LIGHTS == 2) : LIGHTS == 0, "FAST instantiations fix the light mode");
+            static_assert(FAST ? (LIGHTS >= 1 && LIGHTS <= 3) : LIGHTS == 0, "FAST instantiations fix the light mode");
             const int F_shadow_mode = FAST ? 0 : fc.shadow_mode, F_has_depth = FAST ? 1 : fc.has_depth, F_linear_depth = FAST ? 1 : fc.linear_depth;
             const int F_load_depth = FAST ? 0 : fc.load_depth, F_load_color = FAST ? 0 : fc.load_color, F_write_motion = FAST ? 0 : fc.write_motion;
             const int F_clear_motion = FAST ? 0 : fc.clear_motion, F_hiz = FAST ? 0 : fc.hiz, F_sky_kind = FAST ? 0 : fc.sky_kind;
-            const int F_shader_id = PROG == 1 ? 0 : (PROG == 2 ? 1 : fc.shader_id), F_forward_plus = FAST ? (LIGHTS == 1 ? 1 : 0) : fc.forward_plus;
-            const float* const F_shadow_map = (FAST && LIGHTS == 1) ? nullptr : fc.shadow_map;
+            const int F_shader_id = PROG == 1 ? 0 : (PROG == 2 ? 1 : fc.shader_id), F_forward_plus = FAST ? (LIGHTS != 2 ? 1 : 0) : fc.forward_plus;
+            const float* const F_shadow_map = (FAST && LIGHTS != 2) ? nullptr : fc.shadow_map;
             const uint32_t F_light_tile_size = FAST ? (uint32_t)TILE : fc.light_tile_size;
             uint32_t* const F_aov_tri_id = FAST ? nullptr : fb.aov_tri_id;
             uint32_t* const F_aov_coverage = FAST ? nullptr : fb.aov_coverage;
@@ -962,7 +964,7 @@ namespace shsb
                                     const float dist2 = dx * dx + dy * dy + dz * dz;
                                     if (!(dist2 < q0.w) || !(dist2 > 1e-10f)) continue;
                                     const uint32_t kind = lt->kind;
-                                    if (kind & KIND_AREA) sum = sum + eval_light_record(surf, fc.lights + lt->index);
+                                    if (LIGHTS != 1 && (kind & KIND_AREA)) sum = sum + eval_light_record(surf, fc.lights + lt->index);
                                     else accumulate_point_spot(surf, lt, dx, dy, dz, dist2, kind, sum);
                                 }
                             }
@@ -1109,8 +1111,10 @@ namespace shsb
         const bool lights = fc.forward_plus && fc.n_lights > 0;
         const int light_mode = !fast ? 0 : ((lights && fc.light_tile_size == (uint32_t)TILE && !fc.shadow_map) ? 1 : (!lights ? 2 : 0));
         const bool blinn = fc.shader_id == 1;
-        if (light_mode == 1 && !blinn) tile_kernel<1, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 1) tile_kernel<2, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        if (light_mode == 1 && !fc.area_lights && !blinn) tile_kernel<1, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 1 && !fc.area_lights) tile_kernel<2, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 1 && !blinn) tile_kernel<1, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        else if (light_mode == 1) tile_kernel<2, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
         else if (light_mode == 2 && !blinn) tile_kernel<1, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
         else if (light_mode == 2) tile_kernel<2, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
         else tile_kernel<0, 0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
