@@ -143,6 +143,10 @@ if __name__ == "__main__":
         if f"--nolight-ctas{n}" in sys.argv:
             print(build_variant(f"nl{n}", [f"-DSHSB_NOLIGHT_CTAS={n}"]))
             sys.exit(0)
+    for n in (6, 7, 9, 10, 11, 12, 14):
+        if f"--tile-ctas{n}" in sys.argv:
+            print(build_variant(f"ctas{n}", [f"-DSHSB_FPLUS_CTAS={n}"]))
+            sys.exit(0)
     if "--cand8" in sys.argv:
         print(build_variant("cand8", ["-DSHSB_CAND_PER_THREAD=8"]))
         sys.exit(0)

@@ -468,8 +468,14 @@ namespace shsb
 #ifndef SHSB_NOLIGHT_CTAS
 #define SHSB_NOLIGHT_CTAS 10
 #endif
+        // The point / spot Forward+ instantiations at 10 CTAs per SM (48 registers, 104 bytes of spills in the STAGING code, none in the light
+        // loop): 10 195 frames/s on C2 against 9610 at 8 CTAs (64 registers), 9870 at 9, 10 035 at 11-12, 9205 at 14 (same file).  The
+        // general kernel and the area-light instantiations keep 8: round 1 measured more CTAs as a loss for the kernel that carries everything.
+#ifndef SHSB_FPLUS_CTAS
+#define SHSB_FPLUS_CTAS 10
+#endif
         template <int PROG, int LIGHTS>
-        __global__ void __launch_bounds__(TILE_THREADS, (LIGHTS == 2 ? SHSB_NOLIGHT_CTAS : TILE_MIN_CTAS)) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
+        __global__ void __launch_bounds__(TILE_THREADS, (LIGHTS == 2 ? SHSB_NOLIGHT_CTAS : (LIGHTS == 1 ? SHSB_FPLUS_CTAS : TILE_MIN_CTAS))) tile_kernel(const FrameConst fc, const Geometry g, const FrameBuffers fb,
                                                                     const DevTexture* __restrict__ textures,
                                                                     const float* __restrict__ srgb_lut)
         {
