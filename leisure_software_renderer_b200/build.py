@@ -147,6 +147,13 @@ if __name__ == "__main__":
         if f"--tile-ctas{n}" in sys.argv:
             print(build_variant(f"ctas{n}", [f"-DSHSB_FPLUS_CTAS={n}"]))
             sys.exit(0)
+    for n in (4, 6, 12, 16):
+        if f"--macro{n}" in sys.argv:
+            print(build_variant(f"macro{n}", [f"-DSHSB_MACRO={n}"]))
+            sys.exit(0)
+    if "--cand2" in sys.argv:
+        print(build_variant("cand2", ["-DSHSB_CAND_PER_THREAD=2"]))
+        sys.exit(0)
     if "--cand8" in sys.argv:
         print(build_variant("cand8", ["-DSHSB_CAND_PER_THREAD=8"]))
         sys.exit(0)

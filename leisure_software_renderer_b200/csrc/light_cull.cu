@@ -7,7 +7,7 @@
 // geometry/jolt_culling.hpp:239-257; sphere :129-147; AABB :152-181; eps 1e-5 :118-122).  Bounds come from
 // the CullingLightGPU record's cull_sphere / cull_aabb_min / cull_aabb_max (lighting/light_types.hpp:141-167).
 //
-// Two levels: K4a filters the lights once per 8x8-tile macro cell (exact camera-frustum pre-filter + a
+// Two levels: K4a filters the lights once per 12x12-tile macro cell (exact camera-frustum pre-filter + a
 // conservative macro-cell test), K4b runs the exact per-tile test over the macro cell's candidates only
 // (about 6x fewer sphere/AABB-vs-planes tests than tiles x lights).  Both compact with warp ballots + a
 // per-warp prefix, so list order is the ascending light order of the serial reference loop.
@@ -74,8 +74,10 @@ namespace shsb
             return cp.own_count <= 0 || ((int)ty >= cp.own_first && (((int)ty - cp.own_first) % cp.own_stride) < cp.own_count);
         }
 
+        // Tiles per macro-cell edge.  Measured on the C2 bench (profiles/r2_tile_kernel_specialisation.md): every macro cell walks ALL lights,
+        // and that work shares the SMs with the previous frame's tile kernel -- 4: 8973 frames/s, 6: 9814, 8: 10 200, 12: 10 365, 16: 10 347.
 #ifndef SHSB_MACRO
-#define SHSB_MACRO 8
+#define SHSB_MACRO 12
 #endif
         constexpr uint32_t MACRO = SHSB_MACRO; // tiles per macro-cell edge
 
