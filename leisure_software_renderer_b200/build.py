@@ -151,6 +151,10 @@ if __name__ == "__main__":
         if f"--macro{n}" in sys.argv:
             print(build_variant(f"macro{n}", [f"-DSHSB_MACRO={n}"]))
             sys.exit(0)
+    for n in (8, 10, 12):
+        if f"--geom-ctas{n}" in sys.argv:
+            print(build_variant(f"geom{n}", [f"-DSHSB_GEOM_CTAS={n}"]))
+            sys.exit(0)
     if "--cand2" in sys.argv:
         print(build_variant("cand2", ["-DSHSB_CAND_PER_THREAD=2"]))
         sys.exit(0)

@@ -270,7 +270,10 @@ namespace shsb
             return s_base + before + (uint32_t)__popc(mask & ((1u << lane) - 1u));
         }
 
-        __global__ void __launch_bounds__(GEOM_THREADS) geometry_kernel(const FrameConst fc, const Geometry g)
+#ifndef SHSB_GEOM_CTAS
+#define SHSB_GEOM_CTAS 1
+#endif
+        __global__ void __launch_bounds__(GEOM_THREADS, SHSB_GEOM_CTAS) geometry_kernel(const FrameConst fc, const Geometry g)
         {
             const uint2 blk = g.block_table[blockIdx.x];
             const DevItem& it = g.items[blk.x];
