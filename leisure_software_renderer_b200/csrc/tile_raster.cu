@@ -709,7 +709,18 @@ namespace shsb
                 uint32_t sh = (bkey != KEY_NONE) ? 1u : 0u;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); sh += __shfl_down_sync(0xffffffffu, sh, o); }
-                if (lane == 0) { s_frag[warp][0] = c; s_frag[warp][1] = sh; }
+                if (FAST && LIGHTS == 2)
+                {
+                    // no local lights: nothing after this point needs the other warps of the tile, so the counters go out per warp and the
+                    // tile has no barrier at all behind its raster loop
+                    if (lane == 0)
+                    {
+                        DevStats* st = g.stats + (blockIdx.x & (STAT_SHARDS - 1));
+                        if (c) atomicAdd(&st->frag_covered, c);
+                        if (sh) atomicAdd(&st->frag_shaded, (unsigned long long)sh);
+                    }
+                }
+                else if (lane == 0) { s_frag[warp][0] = c; s_frag[warp][1] = sh; }
             }
             const bool has = valid && bkey != KEY_NONE;
             const bool shade = !(F_shadow_mode || F_shader_id == 5 || !fb.hdr);
@@ -843,8 +854,11 @@ namespace shsb
             PHASE_MARK(1); // resolve + phase A (surface)
             // the only barrier every non-empty tile passes: publishes the fragment counters (and tells phase B
             // whether any pixel of the tile is shaded at all)
-            const int any_has = __syncthreads_or((has && shade) ? 1 : 0);
-            if (threadIdx.x == 0)
+            // (FAST Forward+ instantiations: the barrier of the position box below publishes the counters as well -- one barrier instead of two;
+            // FAST without local lights: none, see above)
+            int any_has = 1;
+            if (!FAST) any_has = __syncthreads_or((has && shade) ? 1 : 0);
+            if (!FAST && threadIdx.x == 0)
             {
                 unsigned long long c = 0ull, sh = 0ull;
 #pragma unroll
@@ -881,17 +895,27 @@ namespace shsb
                     }
                     if (lane == 0) { s_box[warp][0] = bx0; s_box[warp][1] = by0; s_box[warp][2] = bz0; s_box[warp][3] = bx1; s_box[warp][4] = by1; s_box[warp][5] = bz1; }
                     __syncthreads();
+                    if (FAST && threadIdx.x == 0)
+                    {
+                        unsigned long long c = 0ull, sh = 0ull;
+#pragma unroll
+                        for (int w = 0; w < TILE_THREADS / 32; ++w) { c += s_frag[w][0]; sh += s_frag[w][1]; }
+                        DevStats* st = g.stats + (blockIdx.x & (STAT_SHARDS - 1));
+                        if (c) atomicAdd(&st->frag_covered, c);
+                        if (sh) atomicAdd(&st->frag_shaded, sh);
+                    }
 #pragma unroll
                     for (int w = 0; w < TILE_THREADS / 32; ++w)
                     {
                         bx0 = fminf(bx0, s_box[w][0]); by0 = fminf(by0, s_box[w][1]); bz0 = fminf(bz0, s_box[w][2]);
                         bx1 = fmaxf(bx1, s_box[w][3]); by1 = fmaxf(by1, s_box[w][4]); bz1 = fmaxf(bz1, s_box[w][5]);
                     }
+                    if (FAST) any_has = bx0 <= bx1; // no shaded pixel in the tile: the box is empty (+INF .. -INF), CTA-uniform
 
                     const uint32_t list_id = (uint32_t)min(ty * TILE_H / TILE, (int)fc.light_tiles_y - 1) * fc.light_tiles_x + (uint32_t)min(tx, (int)fc.light_tiles_x - 1);
                     const uint32_t listed = min(fc.tile_counts[list_id], fc.max_per_tile);
                     const bool saturated = listed >= fc.max_per_tile;
-                    const uint32_t n_src = saturated ? fc.n_lights : listed;
+                    const uint32_t n_src = !any_has ? 0u : (saturated ? fc.n_lights : listed); // (FAST: any_has is known only here)
                     const uint32_t* __restrict__ list = fc.tile_indices + (size_t)list_id * fc.max_per_tile;
                     V3 sum = v3(0, 0, 0);
                     for (uint32_t sbase = 0; sbase < n_src; sbase += CAND_PER_THREAD * TILE_THREADS)
