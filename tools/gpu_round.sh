@@ -23,3 +23,5 @@ ncu --set full --clock-control none --import-source on -k regex:legacy2_ -s 12 -
     python tools/bench_legacy2.py 4 > $OUT/ncu_legacy2.log 2>&1; echo "ncu legacy2 rc=$?"
 # scene-level culling calls (8f row 1): parity against the reference's own functions + calls/s through the C-ABI with host buffers
 python tools/bench_scene_cull.py 20 > $OUT/bench_scene_cull.jsonl 2> $OUT/bench_scene_cull.err; echo "scene cull bench rc=$?"
+# flat-shaded multi-light draws (8f row 1, the consumer of the light selections): parity + ms per frame next to the reference's own loop
+python tools/bench_flat_draw.py 10 > $OUT/bench_flat_draw.jsonl 2> $OUT/bench_flat_draw.err; echo "flat draw bench rc=$?"
