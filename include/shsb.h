@@ -311,6 +311,10 @@ SHSB_API int32_t shsb_fence(shsb_ctx ctx);
 SHSB_API int32_t shsb_set_tile_streams(shsb_ctx ctx, int32_t n);
 /* Number of kernels this context launched since creation (bench.py's gpu_launches). */
 SHSB_API int32_t shsb_launch_count(shsb_ctx ctx, uint64_t* out_count);
+/* Diagnostics: which instantiation of the tile kernel the last frame / draw of this context launched -- 0 the general one, else
+ * PROGRAM * 10 + LIGHTS with PROGRAM 1 = PBR, 2 = Blinn-Phong and LIGHTS 1 = Forward+ over point / spot lights, 3 = Forward+ with area
+ * lights possible, 2 = no local lights (csrc/tile_raster.cu); -1 before the first launch.  No reference counterpart. */
+SHSB_API int32_t shsb_last_tile_kernel(shsb_ctx ctx, int32_t* out_mode);
 /* Library build info string (arch, flags). */
 SHSB_API const char* shsb_version(void);
 

@@ -228,6 +228,7 @@ def load_library(path: str | None = None):
         "shsb_fence": [vp],
         "shsb_set_tile_streams": [vp, C.c_int32],
         "shsb_launch_count": [vp, P(C.c_uint64)],
+        "shsb_last_tile_kernel": [vp, P(C.c_int32)],
         "shsb_software_occlusion": [vp, P(C.c_float), C.c_uint32, P(C.c_uint32), C.c_uint32, P(C.c_uint32), P(C.c_float), P(C.c_uint32), C.c_uint32, P(C.c_float), C.c_uint32,
                                     P(C.c_uint32), C.c_uint32, P(C.c_float), P(C.c_float), C.c_int32, C.c_int32, C.c_float, C.c_int32, P(C.c_uint8), P(C.c_uint32), P(C.c_uint32),
                                     P(C.c_float)],

@@ -337,6 +337,7 @@ struct shsb_context_t
     cudaEvent_t ev_fork[NUM_ARENAS]{}, ev_join[NUM_ARENAS]{}, ev_frame_done = nullptr, ev_front_sync = nullptr;
     bool shadow_direct = true;           // SHSB_SHADOW_DIRECT=0: every shadow-pass triangle through the binned tile path
     bool area_lights = true;             // the current light set may hold rect / tube lights (decides the tile kernel's instantiation)
+    int last_tile_mode = -1;             // instantiation of the last tile kernel launched: PROG * 10 + LIGHTS (tile_raster.cu), 0 = general
     bool fast_tile = true;               // SHSB_NO_FAST_TILE=1: the tile kernel's general instantiation for every frame (tile_raster.cu: launch_tile_raster)
     bool hiz = false;                    // SHSB_HIZ=1: hierarchical-Z early reject in the tile kernel for asynchronous frames without AOVs
     cudaGraphExec_t graph_exec[NUM_ARENAS][8]{}; // per arena (an executable graph cannot run concurrently with itself): [stage events][cull branch][shadow mode] -- one executable per topology, so that a sampled (timed) frame does not force a re-instantiation
@@ -823,7 +824,7 @@ namespace
             if (fc.forward_plus && !cull) { if (int rc = main_wait_lights(ctx)) return rc; } // lists built earlier: the records are read directly
             CK(cudaStreamWaitEvent(s1, ctx->ev_front_done[a], 0));
             record(ctx, 3, s1);
-            if (!fc.direct_depth) launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches, ctx->fast_tile);
+            if (!fc.direct_depth) launch_tile_raster(fc, g, job.fb, ctx->d_textures.p, ctx->d_srgb_lut, s1, &ctx->launches, ctx->fast_tile, &ctx->last_tile_mode);
             record(ctx, 4, s1);
             CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->ev_tile_done[f % TILE_DONE_RING], s1));
@@ -1522,6 +1523,13 @@ SHSB_API int32_t shsb_set_tile_streams(shsb_ctx ctx, int32_t n)
     ctx->n_tile_streams = n;
     for (RtSlot& r : ctx->rts) r.affinity = -1;
     ctx->affinity_next = 0;
+    return SHSB_OK;
+}
+
+SHSB_API int32_t shsb_last_tile_kernel(shsb_ctx ctx, int32_t* out_mode)
+{
+    if (!ctx || !out_mode) return SHSB_E_INVALID_ARGUMENT;
+    *out_mode = ctx->last_tile_mode;
     return SHSB_OK;
 }
 

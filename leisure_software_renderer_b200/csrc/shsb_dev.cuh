@@ -328,7 +328,7 @@ namespace shsb
     void launch_geometry(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_binning(const FrameConst& fc, const Geometry& g, cudaStream_t s, uint64_t* launches);
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
-                            const float* srgb_lut, cudaStream_t s, uint64_t* launches, bool allow_fast = true);
+                            const float* srgb_lut, cudaStream_t s, uint64_t* launches, bool allow_fast = true, int* mode_out = nullptr);
     void launch_light_prep(const DevLightRec* src, DevLightRec* raw, SmLight* out, uint32_t n, cudaStream_t s, uint64_t* launches);
     void launch_upload(void* dst, const void* src_mapped, size_t bytes, cudaStream_t s, uint64_t* launches);
     void launch_tonemap(const float4* hdr, uchar4* ldr, int n_pixels, float exposure, float inv_gamma, cudaStream_t s, uint64_t* launches);

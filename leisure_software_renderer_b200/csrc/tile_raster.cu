@@ -1128,7 +1128,7 @@ namespace shsb
 #endif
 
     void launch_tile_raster(const FrameConst& fc, const Geometry& g, const FrameBuffers& fb, const DevTexture* textures,
-                            const float* srgb_lut, cudaStream_t s, uint64_t* launches, bool allow_fast)
+                            const float* srgb_lut, cudaStream_t s, uint64_t* launches, bool allow_fast, int* mode_out)
     {
         const int n_tiles = fc.tiles_x * fc.tiles_y;
         if (n_tiles <= 0) return;
@@ -1141,13 +1141,20 @@ namespace shsb
         const bool lights = fc.forward_plus && fc.n_lights > 0;
         const int light_mode = !fast ? 0 : ((lights && fc.light_tile_size == (uint32_t)TILE && !fc.shadow_map) ? 1 : (!lights ? 2 : 0));
         const bool blinn = fc.shader_id == 1;
-        if (light_mode == 1 && !fc.area_lights && !blinn) tile_kernel<1, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 1 && !fc.area_lights) tile_kernel<2, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 1 && !blinn) tile_kernel<1, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 1) tile_kernel<2, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 2 && !blinn) tile_kernel<1, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else if (light_mode == 2) tile_kernel<2, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
-        else tile_kernel<0, 0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut);
+        int prog = 0, lights_t = 0;
+        if (light_mode == 1) { prog = blinn ? 2 : 1; lights_t = fc.area_lights ? 3 : 1; }
+        else if (light_mode == 2) { prog = blinn ? 2 : 1; lights_t = 2; }
+        if (mode_out) *mode_out = prog * 10 + lights_t;
+        switch (prog * 10 + lights_t)
+        {
+            case 11: tile_kernel<1, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            case 21: tile_kernel<2, 1><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            case 13: tile_kernel<1, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            case 23: tile_kernel<2, 3><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            case 12: tile_kernel<1, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            case 22: tile_kernel<2, 2><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+            default: tile_kernel<0, 0><<<n_tiles, TILE_THREADS, 0, s>>>(fc, g, fb, textures, srgb_lut); break;
+        }
         *launches += 1;
     }
 

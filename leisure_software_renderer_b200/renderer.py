@@ -441,6 +441,12 @@ class Context:
         _check(self.lib, self.h, self.lib.shsb_stream(self.h, C.byref(p)), "shsb_stream")
         return p.value or 0
 
+    def last_tile_kernel(self) -> int:
+        """Instantiation of the tile kernel the last frame launched: 0 general, else PROGRAM * 10 + LIGHTS (include/shsb.h)."""
+        m = C.c_int32()
+        _check(self.lib, self.h, self.lib.shsb_last_tile_kernel(self.h, C.byref(m)), "shsb_last_tile_kernel")
+        return m.value
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         _check(self.lib, self.h, self.lib.shsb_launch_count(self.h, C.byref(n)), "shsb_launch_count")

@@ -115,3 +115,30 @@ def test_fuzz_light_lists_far_camera_high_resolution(gpu, port, seed):
     keep = np.arange(128)[None, :] < np.minimum(oc, 128)[:, None]
     assert np.array_equal(c, oc), f"seed {seed}: counts differ in {int(np.count_nonzero(c != oc))} of {c.size} tiles ({w}x{h}, camera at {dist} m)"
     assert np.array_equal(i[keep], oi[keep]), f"seed {seed}: lists differ"
+
+
+@pytest.mark.parametrize("seed", list(range(24)) + list(range(100, 116)))
+def test_fuzz_specialised_tile_instantiations_parity(gpu, port, seed):
+    """The random scenes again WITHOUT AOVs, so that the frames run the specialised instantiations of the tile kernel (Forward+ over
+    point / spot lights or with area lights, no local lights with or without the sun shadow map, both programs) instead of the general
+    one: depth <= 1 ULP, light lists and statistics exact, LDR <= 1 LSB, HDR >= 60 dB against the oracle."""
+    lights = seed >= 100
+    sd = scenes.scene_fuzz(seed, lights=lights, zero_normals=False)
+    shadow = bool(sd.fp.shadow_enable) and not lights
+    kw = {"forward_plus": True, "fused": bool(seed & 1)} if lights else {"shadow": shadow}
+    g = harness.gpu_forward(gpu, sd, aov=False, **kw)
+    mode = gpu.last_tile_kernel()
+    kw.pop("fused", None)
+    c = harness.cpu_forward(port, sd, aov=False, **kw)
+    harness.assert_frame_parity(g, c, name=f"{sd.name} (instantiation {mode})")
+    print(f"{sd.name}: tile kernel instantiation {mode}")
+    FAST_SEEN.add(mode)
+
+
+FAST_SEEN = set()
+
+
+def test_fuzz_specialised_instantiations_were_exercised():
+    """Runs after the parametrised test above (same file, same process): the seeds must have reached the Forward+ and the no-lights
+    instantiations of both programs, not only the general kernel."""
+    assert {11, 12} <= FAST_SEEN and (FAST_SEEN & {21, 22}), FAST_SEEN
