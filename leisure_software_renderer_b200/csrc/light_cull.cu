@@ -141,7 +141,8 @@ namespace shsb
         // the bottom / top planes of a tile row likewise, so the spread of their computed normals is the tilt.  A tilt
         // dn moves a plane by dn * (distance of the point from the tilt axis); the slack adds 4 x that bound.
         __global__ void __launch_bounds__(MACRO_THREADS) macro_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp, const Planes6 frustum,
-                                                                          uint32_t* __restrict__ macro_counts, uint32_t* __restrict__ macro_lists)
+                                                                          uint32_t* __restrict__ macro_counts, uint32_t* __restrict__ macro_lists,
+                                                                          float4* __restrict__ tile_planes)
         {
             __shared__ float s_corner[2][8][3];
             __shared__ float4 s_plane[2][6];
@@ -172,8 +173,10 @@ namespace shsb
                 float c8[8][3];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) cell_corner(cp, tx0 + t_col, ty0 + t_row, c, c8[c]);
+                // ... and the per-tile kernel reads them back instead of building them a second time (same functions, same bits)
+                float4* out = tile_planes + (size_t)((ty0 + t_row) * cp.tiles_x + (tx0 + t_col)) * 6;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) s_tile_n[threadIdx.x][i] = cell_plane(c8, i);
+                for (int i = 0; i < 6; ++i) { const float4 pl = cell_plane(c8, i); s_tile_n[threadIdx.x][i] = pl; out[i] = pl; }
             }
             __syncthreads();
             if (threadIdx.x < 12)
@@ -270,29 +273,23 @@ namespace shsb
             if (threadIdx.x == 0) macro_counts[mc] = total;
         }
 
-        // K4b -- one WARP per tile: the exact test of cull_lights_tiled over the macro cell's candidates.  Lanes 0-7
-        // unproject the cell corners, lanes 0-5 build the planes, then the warp walks the candidates 32 at a time and
+        // K4b -- one WARP per tile: the exact test of cull_lights_tiled over the macro cell's candidates.  The tile's planes come
+        // from K4a (which builds every tile's planes anyway, to measure their tilt); the warp walks the candidates 32 at a time and
         // compacts with one ballot -- no CTA barrier, so a tile holds 32 threads' worth of registers for its lifetime
         // (this kernel shares the SMs with the previous frame's tile kernel).
         __global__ void __launch_bounds__(CULL_THREADS) tile_cull_kernel(const DevLightRec* __restrict__ lights, const CullParams cp,
                                                                          const uint32_t* __restrict__ macro_counts, const uint32_t* __restrict__ macro_lists,
-                                                                         uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
+                                                                         const float4* __restrict__ tile_planes, uint32_t* __restrict__ counts, uint32_t* __restrict__ indices)
         {
-            __shared__ float s_corner[CULL_THREADS / 32][8][3];
-            __shared__ float4 s_plane[CULL_THREADS / 32][6];
-
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             const uint32_t tile = blockIdx.x * (CULL_THREADS / 32) + (uint32_t)warp;
             if (tile >= cp.tiles_x * cp.tiles_y) return; // warp-uniform
             const uint32_t tx = tile % cp.tiles_x, ty = tile / cp.tiles_x;
             if (!cull_row_owned(cp, ty)) { if (lane == 0) counts[tile] = 0; return; } // another rank's row: nobody reads this list
-            if (lane < 8) cell_corner(cp, tx, ty, lane, s_corner[warp][lane]);
-            __syncwarp();
-            if (lane < 6) s_plane[warp][lane] = cell_plane(s_corner[warp], lane);
-            __syncwarp();
+            // the tile's six planes (make_screen_tile_cell) as the macro-cell kernel built and kept them
             float4 planes[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) planes[i] = s_plane[warp][i];
+            for (int i = 0; i < 6; ++i) planes[i] = __ldg(tile_planes + (size_t)tile * 6 + i);
 
             const uint32_t mc = (ty / MACRO) * cp.macro_x + (tx / MACRO);
             const uint32_t n_cand = macro_counts[mc];
@@ -491,7 +488,7 @@ namespace shsb
     {
         const uint32_t tiles_x = (vw + ts - 1) / ts, tiles_y = (vh + ts - 1) / ts;
         const size_t n_macro = (size_t)((tiles_x + MACRO - 1) / MACRO) * ((tiles_y + MACRO - 1) / MACRO);
-        return n_macro * ((size_t)n_lights + 1);
+        return n_macro * ((size_t)n_lights + 1) + 4 + (size_t)tiles_x * tiles_y * 24; // + the tiles' planes (6 x float4 each, 16-byte aligned)
     }
 
     void launch_light_cull(const DevLightRec* lights, uint32_t n_lights, const float* frustum_planes24, const float* inv_view_proj,
@@ -513,8 +510,11 @@ namespace shsb
         const uint32_t n_macro = cp.macro_x * cp.macro_y;
         uint32_t* macro_counts = scratch;
         uint32_t* macro_lists = scratch + n_macro;
-        macro_cull_kernel<<<n_macro, MACRO_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists);
-        tile_cull_kernel<<<(cp.tiles_x * cp.tiles_y + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, counts, indices);
+        const size_t planes_at = ((size_t)n_macro * ((size_t)n_lights + 1) + 3) & ~(size_t)3; // in words, from a 256-byte aligned allocation
+        float4* tile_planes = reinterpret_cast<float4*>(scratch + planes_at);
+        macro_cull_kernel<<<n_macro, MACRO_THREADS, 0, s>>>(lights, cp, fr, macro_counts, macro_lists, tile_planes);
+        tile_cull_kernel<<<(cp.tiles_x * cp.tiles_y + CULL_THREADS / 32 - 1) / (CULL_THREADS / 32), CULL_THREADS, 0, s>>>(lights, cp, macro_counts, macro_lists, tile_planes, counts,
+                                                                                                                          indices);
         *launches += 2;
     }
 
